@@ -1,0 +1,198 @@
+"""ctypes binding of libdartray_gpu.so (include/drt.h) — the same symbols a dart:ffi binding looks up.
+
+The library is the only execution path: if it is missing or no CUDA device is present the calls
+raise; nothing here falls back to a CPU implementation."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libdartray_gpu.so")
+
+DEVICE_NONE = -1
+SPLIT_MIDDLE, SPLIT_EQUAL_COUNTS, SPLIT_SAH = 0, 1, 2
+
+HIT_DTYPE = np.dtype([("t", np.float32), ("b1", np.float32), ("b2", np.float32), ("prim", np.int32)])
+
+# every symbol include/drt.h declares (tests/test_abi.py checks the header against this list)
+SYMBOLS = [
+    "drt_version", "drt_create", "drt_destroy", "drt_last_error", "drt_set_triangles", "drt_set_spheres",
+    "drt_set_build_order", "drt_build_bvh", "drt_bvh_info_get", "drt_bvh_export", "drt_trace_closest",
+    "drt_trace_any", "drt_trace_closest_device", "drt_trace_any_device", "drt_set_counting", "drt_get_counters",
+    "drt_last_kernel_ms", "drt_kernel_launches",
+]
+
+
+class DrtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libdartray_gpu error {code}: {msg}")
+        self.code = code
+
+
+class BvhInfo(C.Structure):
+    _fields_ = [("n_nodes", C.c_uint32), ("n_prims", C.c_uint32), ("n_leaves", C.c_uint32),
+                ("max_leaf_prims", C.c_uint32), ("max_depth", C.c_uint32), ("device_bytes", C.c_uint64),
+                ("build_seconds", C.c_double)]
+
+
+class Counters(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("nodes_visited", C.c_uint64), ("prims_tested", C.c_uint64),
+                ("hits", C.c_uint64)]
+
+
+_lib = None
+
+
+def load():
+    """Load libdartray_gpu.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(dartray_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    L.drt_version.restype = i32
+    L.drt_create.restype = vp
+    L.drt_create.argtypes = [i32]
+    L.drt_destroy.argtypes = [vp]
+    L.drt_last_error.restype = C.c_char_p
+    L.drt_last_error.argtypes = [vp]
+    L.drt_set_triangles.argtypes = [vp, vp, u32, vp, u32, vp, vp, vp]
+    L.drt_set_spheres.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
+    L.drt_set_build_order.argtypes = [vp, vp, u32]
+    L.drt_build_bvh.argtypes = [vp, i32, i32]
+    L.drt_bvh_info_get.argtypes = [vp, C.POINTER(BvhInfo)]
+    L.drt_bvh_export.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.drt_trace_closest.argtypes = [vp, vp, vp, u64, vp]
+    L.drt_trace_any.argtypes = [vp, vp, vp, u64, vp]
+    L.drt_trace_closest_device.argtypes = [vp, vp, vp, u64, vp, vp]
+    L.drt_trace_any_device.argtypes = [vp, vp, vp, u64, vp, vp]
+    L.drt_set_counting.argtypes = [vp, i32]
+    L.drt_get_counters.argtypes = [vp, C.POINTER(Counters)]
+    L.drt_last_kernel_ms.restype = C.c_double
+    L.drt_last_kernel_ms.argtypes = [vp]
+    L.drt_kernel_launches.restype = u64
+    L.drt_kernel_launches.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _arr(a, dtype):
+    return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+
+
+class Context:
+    """One drt_ctx: a scene resident on one CUDA device."""
+
+    def __init__(self, device: int = 0):
+        self.L = load()
+        self.h = self.L.drt_create(device)
+        if not self.h:
+            raise DrtError(-4, self.L.drt_last_error(None).decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.drt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise DrtError(rc, self.L.drt_last_error(self.h).decode())
+
+    # -- scene ---------------------------------------------------------------------------------
+    def set_triangles(self, P, idx, material=None, light=None, reverse=None):
+        P = _arr(P, np.float32).reshape(-1, 3)
+        idx = _arr(idx, np.uint32).reshape(-1, 3)
+        m, l, r = _arr(material, np.int32), _arr(light, np.int32), _arr(reverse, np.uint8)
+        self._ck(self.L.drt_set_triangles(self.h, _p(P), P.shape[0], _p(idx), idx.shape[0], _p(m), _p(l), _p(r)))
+
+    def set_spheres(self, o2w, w2o, params, material=None, light=None, reverse=None):
+        o2w = _arr(o2w, np.float32).reshape(-1, 16)
+        w2o = _arr(w2o, np.float32).reshape(-1, 16)
+        params = _arr(params, np.float64).reshape(-1, 4)
+        m, l, r = _arr(material, np.int32), _arr(light, np.int32), _arr(reverse, np.uint8)
+        self._ck(self.L.drt_set_spheres(self.h, o2w.shape[0], _p(o2w), _p(w2o), _p(params), _p(m), _p(l), _p(r)))
+
+    def set_build_order(self, order):
+        if order is None:
+            self._ck(self.L.drt_set_build_order(self.h, None, 0))
+        else:
+            o = _arr(order, np.uint32)
+            self._ck(self.L.drt_set_build_order(self.h, _p(o), o.shape[0]))
+
+    def build_bvh(self, split: int = SPLIT_SAH, max_node_prims: int = 4):
+        self._ck(self.L.drt_build_bvh(self.h, split, max_node_prims))
+
+    def bvh_info(self) -> dict:
+        info = BvhInfo()
+        self._ck(self.L.drt_bvh_info_get(self.h, C.byref(info)))
+        return {k: getattr(info, k) for k, _ in BvhInfo._fields_}
+
+    def bvh_export(self) -> dict:
+        info = self.bvh_info()
+        n, npr = info["n_nodes"], info["n_prims"]
+        bounds = np.empty((n, 6), np.float32)
+        offset = np.empty(n, np.int32)
+        nprims = np.empty(n, np.int32)
+        axis = np.empty(n, np.int32)
+        ordered = np.empty(npr, np.uint32)
+        self._ck(self.L.drt_bvh_export(self.h, _p(bounds), _p(offset), _p(nprims), _p(axis), _p(ordered)))
+        return dict(bounds=bounds, offset=offset, n_primitives=nprims, axis=axis, ordered=ordered)
+
+    # -- queries (host buffers) ----------------------------------------------------------------
+    def trace_closest(self, ro, rd, out=None):
+        ro, rd = _arr(ro, np.float32), _arr(rd, np.float32)
+        n = ro.shape[0]
+        hits = out if out is not None else np.empty(n, HIT_DTYPE)
+        self._ck(self.L.drt_trace_closest(self.h, _p(ro), _p(rd), n, _p(hits)))
+        return hits
+
+    def trace_any(self, ro, rd, out=None):
+        ro, rd = _arr(ro, np.float32), _arr(rd, np.float32)
+        n = ro.shape[0]
+        occ = out if out is not None else np.empty(n, np.uint8)
+        self._ck(self.L.drt_trace_any(self.h, _p(ro), _p(rd), n, _p(occ)))
+        return occ
+
+    # -- queries (device pointers, e.g. torch tensors' data_ptr()) ------------------------------
+    def trace_closest_device(self, d_ro: int, d_rd: int, n: int, d_hits: int, stream: int = 0):
+        self._ck(self.L.drt_trace_closest_device(self.h, d_ro, d_rd, n, d_hits, stream))
+
+    def trace_any_device(self, d_ro: int, d_rd: int, n: int, d_occ: int, stream: int = 0):
+        self._ck(self.L.drt_trace_any_device(self.h, d_ro, d_rd, n, d_occ, stream))
+
+    def set_counting(self, enabled: bool):
+        self._ck(self.L.drt_set_counting(self.h, 1 if enabled else 0))
+
+    def counters(self) -> dict:
+        c = Counters()
+        self._ck(self.L.drt_get_counters(self.h, C.byref(c)))
+        return {k: int(getattr(c, k)) for k, _ in Counters._fields_}
+
+    @property
+    def last_kernel_ms(self) -> float:
+        return self.L.drt_last_kernel_ms(self.h)
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.L.drt_kernel_launches(self.h))

@@ -1,0 +1,337 @@
+// Host BVH builder: reference-identical topology, GPU-oriented output.  See bvh_builder.h.
+#include "bvh_builder.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <future>
+#include <limits>
+
+namespace drt {
+namespace {
+
+constexpr float kFInf = std::numeric_limits<float>::infinity();
+constexpr int kBuckets = 12;  // bvh_accel.dart:319
+
+struct Box {
+  float lo[3], hi[3];
+  void clear() {
+    for (int a = 0; a < 3; ++a) { lo[a] = kFInf; hi[a] = -kFInf; }
+  }
+  void grow(const float* l, const float* h) {
+    for (int a = 0; a < 3; ++a) { lo[a] = l[a] < lo[a] ? l[a] : lo[a]; hi[a] = h[a] > hi[a] ? h[a] : hi[a]; }
+  }
+  void growPoint(const float* p) { grow(p, p); }
+  // bbox.dart:164-167: the diagonal is a float32 Vector, the area expression is float64.
+  double area() const {
+    double dx = (float)((double)hi[0] - lo[0]), dy = (float)((double)hi[1] - lo[1]), dz = (float)((double)hi[2] - lo[2]);
+    return 2.0 * (dx * dy + dx * dz + dy * dz);
+  }
+};
+
+struct PrimRef {
+  float lo[3], hi[3];
+  float cen[3];
+  uint32_t id;
+};
+
+struct TNode {
+  Box box;
+  int32_t left = -1, right = -1;  // pool indices; -1 -> leaf
+  uint32_t first = 0, count = 0;  // leaf: range in the builder's PrimRef array
+  int32_t axis = 0;
+};
+
+struct Arena {
+  std::vector<TNode> pool;
+};
+
+class TreeBuilder {
+ public:
+  TreeBuilder(std::vector<PrimRef>& refs, int split, int maxPrims) : refs_(refs), split_(split), maxPrims_(maxPrims) {}
+
+  // Builds [start, end) into `arena`, returns the node's index in that arena.
+  int32_t build(Arena& arena, uint32_t start, uint32_t end, int depth) {
+    int32_t me = (int32_t)arena.pool.size();
+    arena.pool.emplace_back();
+    Box box;
+    box.clear();
+    for (uint32_t i = start; i < end; ++i) box.grow(refs_[i].lo, refs_[i].hi);
+    arena.pool[me].box = box;
+    uint32_t n = end - start;
+    if (n == 1) return makeLeaf(arena, me, start, end);
+
+    Box cb;
+    cb.clear();
+    for (uint32_t i = start; i < end; ++i) cb.growPoint(refs_[i].cen);
+    int dim = maxExtent(cb);
+    if (cb.hi[dim] == cb.lo[dim]) return makeLeaf(arena, me, start, end);  // bvh_accel.dart:265-274
+
+    uint32_t mid = (start + end) / 2;
+    const double cmin = cb.lo[dim], cmax = cb.hi[dim];
+    bool needEqual = false;
+    if (split_ == 0) {  // SPLIT_MIDDLE, bvh_accel.dart:282-304
+      double pmid = 0.5 * (cmin + cmax);
+      mid = hoarePartition(start, end, [&](const PrimRef& r) { return (double)r.cen[dim] < pmid; });
+      if (mid == start || mid == end) needEqual = true;
+    } else if (split_ == 1) {
+      needEqual = true;
+    } else if (n <= 4) {  // bvh_accel.dart:313-316
+      needEqual = true;
+    } else {
+      // 12-bucket SAH, bvh_accel.dart:318-403
+      uint32_t cnt[kBuckets] = {0};
+      Box bb[kBuckets];
+      for (auto& b : bb) b.clear();
+      const double inv = cmax - cmin;
+      for (uint32_t i = start; i < end; ++i) {
+        int b = (int)(kBuckets * (((double)refs_[i].cen[dim] - cmin) / inv));
+        if (b == kBuckets) b = kBuckets - 1;
+        cnt[b]++;
+        bb[b].grow(refs_[i].lo, refs_[i].hi);
+      }
+      // prefix / suffix sweeps give the same unions as the reference's O(B^2) loops (min/max are exact)
+      Box pre[kBuckets], suf[kBuckets];
+      uint32_t preN[kBuckets], sufN[kBuckets];
+      Box acc;
+      acc.clear();
+      uint32_t accN = 0;
+      for (int i = 0; i < kBuckets; ++i) { acc.grow(bb[i].lo, bb[i].hi); accN += cnt[i]; pre[i] = acc; preN[i] = accN; }
+      acc.clear();
+      accN = 0;
+      for (int i = kBuckets - 1; i >= 0; --i) { acc.grow(bb[i].lo, bb[i].hi); accN += cnt[i]; suf[i] = acc; sufN[i] = accN; }
+      const double total = box.area();
+      float cost[kBuckets - 1];  // Float32List in the reference (:345): costs are rounded to float32
+      for (int i = 0; i < kBuckets - 1; ++i)
+        cost[i] = (float)(0.125 + ((double)preN[i] * pre[i].area() + (double)sufN[i + 1] * suf[i + 1].area()) / total);
+      double minCost = cost[0];
+      int minSplit = 0;
+      for (int i = 1; i < kBuckets - 1; ++i)
+        if ((double)cost[i] < minCost) { minCost = cost[i]; minSplit = i; }
+      if (n > (uint32_t)maxPrims_ || minCost < (double)n) {
+        mid = hoarePartition(start, end, [&](const PrimRef& r) {
+          int b = (int)std::floor(kBuckets * (((double)r.cen[dim] - cmin) / inv));
+          if (b == kBuckets) b = kBuckets - 1;
+          return b <= minSplit;
+        });
+      } else {
+        return makeLeaf(arena, me, start, end);
+      }
+    }
+    if (needEqual) {
+      mid = (start + end) / 2;
+      sortByCentroid(start, end, dim);
+    }
+
+    // Large subtrees are built concurrently; each child uses a private arena that is spliced in
+    // afterwards, so the result does not depend on thread timing.
+    int32_t l, r;
+    if (n >= (1u << 16) && depth < 4) {
+      Arena right;
+      auto fut = std::async(std::launch::async, [&] { return build(right, mid, end, depth + 1); });
+      l = build(arena, start, mid, depth + 1);
+      int32_t rLocal = fut.get();
+      r = splice(arena, right, rLocal);
+    } else {
+      l = build(arena, start, mid, depth + 1);
+      r = build(arena, mid, end, depth + 1);
+    }
+    TNode& node = arena.pool[me];
+    node.left = l;
+    node.right = r;
+    node.axis = dim;
+    // bvh_accel.dart:521 — union of the children's boxes (equals `box`: min/max are exact)
+    return me;
+  }
+
+ private:
+  std::vector<PrimRef>& refs_;
+  int split_, maxPrims_;
+
+  static int maxExtent(const Box& b) {  // bbox.dart:174-183 on the float32 diagonal
+    float dx = (float)((double)b.hi[0] - b.lo[0]), dy = (float)((double)b.hi[1] - b.lo[1]),
+          dz = (float)((double)b.hi[2] - b.lo[2]);
+    if (dx > dy && dx > dz) return 0;
+    if (dy > dz) return 1;
+    return 2;
+  }
+
+  int32_t makeLeaf(Arena& arena, int32_t me, uint32_t start, uint32_t end) {
+    arena.pool[me].first = start;
+    arena.pool[me].count = end - start;
+    return me;
+  }
+
+  // common.dart:256-284: element order after the call matters for later equal-count sorts.
+  template <class Pred>
+  uint32_t hoarePartition(uint32_t first, uint32_t last, Pred pred) {
+    while (first < last) {
+      while (pred(refs_[first])) {
+        if (++first == last) return first;
+      }
+      do {
+        if (first == --last) return first;
+      } while (!pred(refs_[last]));
+      std::swap(refs_[first], refs_[last]);
+      ++first;
+    }
+    return first;
+  }
+
+  // common.dart:289-297 + Dart List.sort on a comparator that never returns 0: for the <= 32
+  // element ranges the SAH path produces this is Dart's insertion sort, which moves an element in
+  // front of every predecessor that is NOT strictly smaller.
+  void sortByCentroid(uint32_t first, uint32_t last, int dim) {
+    if (last - first > 32) {
+      // splitmethod middle/equal on big ranges: same ordering rule, O(n log n).  Elements with
+      // equal keys end up in reverse input order under the insertion rule above.
+      std::reverse(refs_.begin() + first, refs_.begin() + last);
+      std::stable_sort(refs_.begin() + first, refs_.begin() + last,
+                       [dim](const PrimRef& a, const PrimRef& b) { return a.cen[dim] < b.cen[dim]; });
+      return;
+    }
+    for (uint32_t i = first + 1; i < last; ++i) {
+      PrimRef el = refs_[i];
+      uint32_t j = i;
+      while (j > first && !(refs_[j - 1].cen[dim] < el.cen[dim])) {
+        refs_[j] = refs_[j - 1];
+        --j;
+      }
+      refs_[j] = el;
+    }
+  }
+
+  static int32_t splice(Arena& dst, Arena& src, int32_t srcRoot) {
+    int32_t base = (int32_t)dst.pool.size();
+    for (TNode n : src.pool) {
+      if (n.left >= 0) { n.left += base; n.right += base; }
+      dst.pool.push_back(n);
+    }
+    return srcRoot + base;
+  }
+};
+
+struct Flattener {
+  const std::vector<TNode>& pool;
+  const std::vector<PrimRef>& refs;
+  BuiltBvh* out;
+
+  // Reference numbering: depth first, first child at n+1 (bvh_accel.dart:419-437).
+  int32_t numberRef(int32_t t, std::vector<int32_t>& refIndexOf) {
+    int32_t my = (int32_t)out->refNodes.size();
+    refIndexOf[t] = my;
+    out->refNodes.emplace_back();
+    const TNode& n = pool[t];
+    RefNode rn;
+    std::memcpy(rn.bmin, n.box.lo, 12);
+    std::memcpy(rn.bmax, n.box.hi, 12);
+    rn.axis = 0;
+    rn.offset = 0;
+    rn.nPrimitives = (int32_t)n.count;
+    if (n.left >= 0) {
+      rn.axis = n.axis;
+      rn.nPrimitives = 0;
+      out->refNodes[my] = rn;
+      numberRef(n.left, refIndexOf);
+      int32_t second = numberRef(n.right, refIndexOf);
+      out->refNodes[my].offset = second;
+    } else {
+      out->refNodes[my] = rn;
+    }
+    return my;
+  }
+
+  // The reference appends a leaf's primitives to `orderedPrims` when the leaf is created and
+  // builds the SECOND child first (bvh_accel.dart:407-411) -> right-first leaf order.
+  void orderRef(int32_t t, const std::vector<int32_t>& refIndexOf) {
+    const TNode& n = pool[t];
+    if (n.left < 0) {
+      out->refNodes[refIndexOf[t]].offset = (int32_t)out->refOrdered.size();
+      for (uint32_t i = 0; i < n.count; ++i) out->refOrdered.push_back(refs[n.first + i].id);
+      return;
+    }
+    orderRef(n.right, refIndexOf);
+    orderRef(n.left, refIndexOf);
+  }
+
+  // GPU layout: interior nodes in DFS order, leaf records in DFS (left-first) order.
+  int32_t emit(int32_t t, uint32_t depth, const std::vector<int32_t>& refIndexOf) {
+    const TNode& n = pool[t];
+    if (depth > out->maxDepth) out->maxDepth = depth;
+    if (n.left < 0) {
+      uint32_t off = (uint32_t)out->leafPrimIds.size();
+      for (uint32_t i = 0; i < n.count; ++i) {
+        out->leafPrimIds.push_back(refs[n.first + i].id);
+        out->leafCounts.push_back(i == 0 ? n.count : 0);
+      }
+      out->nLeaves++;
+      if (n.count > out->maxLeafPrims) out->maxLeafPrims = n.count;
+      return makeLeafRef(off, n.count);
+    }
+    int32_t my = (int32_t)out->nodes.size();
+    out->nodes.emplace_back();
+    int32_t r0 = emit(n.left, depth + 1, refIndexOf);
+    int32_t r1 = emit(n.right, depth + 1, refIndexOf);
+    GNode g;
+    const TNode &a = pool[n.left], &b = pool[n.right];
+    std::memcpy(g.c0min, a.box.lo, 12);
+    std::memcpy(g.c0max, a.box.hi, 12);
+    std::memcpy(g.c1min, b.box.lo, 12);
+    std::memcpy(g.c1max, b.box.hi, 12);
+    g.ref0 = r0;
+    g.ref1 = r1;
+    g.axis = n.axis;
+    g.refNode = refIndexOf[t];
+    out->nodes[my] = g;
+    return my;
+  }
+};
+
+}  // namespace
+
+bool buildBvh(const std::vector<PrimBounds>& bounds, const std::vector<uint32_t>& order, int splitMethod,
+              int maxPrimsInNode, BuiltBvh* out, std::string* err) {
+  *out = BuiltBvh();
+  const size_t n = order.size();
+  if (n == 0) { *err = "no primitives"; return false; }
+  if (n >= (1u << 27)) { *err = "too many primitives for the 27-bit leaf offset"; return false; }
+  int maxPrims = std::min(255, maxPrimsInNode);  // bvh_accel.dart:44
+  std::vector<PrimRef> refs(n);
+  for (size_t i = 0; i < n; ++i) {
+    const PrimBounds& b = bounds[order[i]];
+    PrimRef& r = refs[i];
+    std::memcpy(r.lo, b.bmin, 12);
+    std::memcpy(r.hi, b.bmax, 12);
+    // bbox.dart:68: (pMin * 0.5) + (pMax * 0.5), each Point operation rounds to float32
+    for (int a = 0; a < 3; ++a) {
+      float h0 = (float)((double)b.bmin[a] * 0.5), h1 = (float)((double)b.bmax[a] * 0.5);
+      r.cen[a] = (float)((double)h0 + (double)h1);
+    }
+    r.id = order[i];
+  }
+  Arena arena;
+  arena.pool.reserve(2 * n);
+  TreeBuilder tb(refs, splitMethod, maxPrims);
+  int32_t root = tb.build(arena, 0, (uint32_t)n, 0);
+
+  Flattener fl{arena.pool, refs, out};
+  std::vector<int32_t> refIndexOf(arena.pool.size(), -1);
+  out->refNodes.reserve(arena.pool.size());
+  fl.numberRef(root, refIndexOf);
+  out->refOrdered.reserve(n);
+  fl.orderRef(root, refIndexOf);
+  out->leafPrimIds.reserve(n);
+  out->leafCounts.reserve(n);
+  out->nodes.reserve(arena.pool.size() / 2 + 1);
+  out->rootRef = fl.emit(root, 0, refIndexOf);
+  std::memcpy(out->rootMin, arena.pool[root].box.lo, 12);
+  std::memcpy(out->rootMax, arena.pool[root].box.hi, 12);
+  if (out->maxDepth >= 64) {
+    // The reference walks the tree with a fixed 64-entry todo stack (bvh_accel.dart:120).
+    *err = "BVH depth exceeds the reference's 64-entry traversal stack";
+    return false;
+  }
+  return true;
+}
+
+}  // namespace drt

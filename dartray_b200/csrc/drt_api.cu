@@ -1,0 +1,427 @@
+// C ABI of libdartray_gpu.so (include/drt.h).  Host orchestration only: scene staging, BVH build,
+// device residency, launches.  There is deliberately no CPU execution path for any query.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/drt.h"
+#include "bvh_builder.h"
+#include "gpu_types.h"
+#include "trace_kernels.h"
+
+using namespace drt;
+
+static_assert(sizeof(drt_hit) == sizeof(drt_hit_rec), "hit record layout");
+
+namespace {
+thread_local std::string g_createError;
+
+struct HostSphere {
+  float o2w[16], w2o[16];
+  double radius, zmin, zmax, phiMaxDeg;
+};
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+}  // namespace
+
+struct drt_ctx {
+  int device = 0;
+  std::string err;
+  // staged scene (host)
+  std::vector<float> P;
+  std::vector<uint32_t> idx;
+  std::vector<int32_t> matOf, lightOf;
+  std::vector<uint8_t> revOf;
+  std::vector<HostSphere> spheres;
+  std::vector<int32_t> sphMat, sphLight;
+  std::vector<uint8_t> sphRev;
+  std::vector<uint32_t> order;
+  // BVH
+  bool built = false;
+  BuiltBvh bvh;
+  drt_bvh_info info{};
+  DevBuf<GNode> dNodes;
+  DevBuf<GPrim> dPrims;
+  DevBuf<GSphere> dSpheres;
+  DevBuf<DeviceCounters> dCounters;
+  TraceScene ts{};
+  // ray staging for host-buffer calls
+  DevBuf<float4> dRayO, dRayD;
+  DevBuf<drt_hit_rec> dHits;
+  DevBuf<uint8_t> dOcc;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool counting = false;
+  double lastKernelMs = 0.0;
+  uint64_t launches = 0;
+
+  uint32_t ntris() const { return (uint32_t)(idx.size() / 3); }
+  uint32_t nprims() const { return ntris() + (uint32_t)spheres.size(); }
+};
+
+#define CK(ctx, call)                                                                    \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                  \
+      return e__ == cudaErrorMemoryAllocation ? DRT_E_NOMEM : DRT_E_CUDA;                \
+    }                                                                                    \
+  } while (0)
+
+static int fail(drt_ctx* c, int code, const char* msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+// transform.dart:110-129 on a float32 matrix with float64 accumulation (sphere world bounds).
+static void xformPoint(const float* m, const float p[3], float out[3]) {
+  double x = p[0], y = p[1], z = p[2];
+  float ox = (float)((double)m[0] * x + (double)m[1] * y + (double)m[2] * z + (double)m[3]);
+  float oy = (float)((double)m[4] * x + (double)m[5] * y + (double)m[6] * z + (double)m[7]);
+  float oz = (float)((double)m[8] * x + (double)m[9] * y + (double)m[10] * z + (double)m[11]);
+  double w = (double)m[12] * x + (double)m[13] * y + (double)m[14] * z + (double)m[15];
+  if (w != 1.0) { ox = (float)((double)ox / w); oy = (float)((double)oy / w); oz = (float)((double)oz / w); }
+  out[0] = ox; out[1] = oy; out[2] = oz;
+}
+
+static double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+extern "C" {
+
+int drt_version(void) { return DRT_VERSION; }
+
+drt_ctx* drt_create(int device_id) {
+  if (device_id == DRT_DEVICE_NONE) {  // host-only staging context: scene + BVH build/export, no queries
+    drt_ctx* c = new drt_ctx();
+    c->device = DRT_DEVICE_NONE;
+    return c;
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_createError = std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count=0") +
+                    "); libdartray_gpu has no CPU fallback";
+    return nullptr;
+  }
+  if (device_id < 0 || device_id >= count) { g_createError = "device id out of range"; return nullptr; }
+  if ((e = cudaSetDevice(device_id)) != cudaSuccess) { g_createError = cudaGetErrorString(e); return nullptr; }
+  drt_ctx* c = new drt_ctx();
+  c->device = device_id;
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
+      (e = c->dCounters.ensure(1)) != cudaSuccess) {
+    g_createError = cudaGetErrorString(e);
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+
+void drt_destroy(drt_ctx* c) {
+  if (!c) return;
+  if (c->device == DRT_DEVICE_NONE) { delete c; return; }
+  cudaSetDevice(c->device);
+  c->dNodes.release(); c->dPrims.release(); c->dSpheres.release(); c->dCounters.release();
+  c->dRayO.release(); c->dRayD.release(); c->dHits.release(); c->dOcc.release();
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* drt_last_error(const drt_ctx* c) { return c ? c->err.c_str() : g_createError.c_str(); }
+
+int drt_set_triangles(drt_ctx* c, const float* P, uint32_t nverts, const uint32_t* idx, uint32_t ntris,
+                      const int32_t* mat, const int32_t* light, const uint8_t* rev) {
+  if (!c) return DRT_E_INVALID;
+  if ((ntris && (!P || !idx)) || (ntris && !nverts)) return fail(c, DRT_E_INVALID, "null triangle arrays");
+  for (uint64_t i = 0; i < (uint64_t)ntris * 3; ++i)
+    if (idx[i] >= nverts) return fail(c, DRT_E_INVALID, "triangle index out of range");  // triangle_mesh.dart:168-174
+  c->P.assign(P, P + (size_t)nverts * 3);
+  c->idx.assign(idx, idx + (size_t)ntris * 3);
+  c->matOf.assign(ntris, 0);
+  c->lightOf.assign(ntris, -1);
+  c->revOf.assign(ntris, 0);
+  if (mat) c->matOf.assign(mat, mat + ntris);
+  if (light) c->lightOf.assign(light, light + ntris);
+  if (rev) c->revOf.assign(rev, rev + ntris);
+  c->built = false;
+  return DRT_OK;
+}
+
+int drt_set_spheres(drt_ctx* c, uint32_t n, const float* o2w, const float* w2o, const double* prm, const int32_t* mat,
+                    const int32_t* light, const uint8_t* rev) {
+  if (!c) return DRT_E_INVALID;
+  if (n && (!o2w || !w2o || !prm)) return fail(c, DRT_E_INVALID, "null sphere arrays");
+  c->spheres.resize(n);
+  c->sphMat.assign(n, 0);
+  c->sphLight.assign(n, -1);
+  c->sphRev.assign(n, 0);
+  for (uint32_t i = 0; i < n; ++i) {
+    HostSphere& s = c->spheres[i];
+    std::memcpy(s.o2w, o2w + 16 * i, 64);
+    std::memcpy(s.w2o, w2o + 16 * i, 64);
+    s.radius = prm[4 * i]; s.zmin = prm[4 * i + 1]; s.zmax = prm[4 * i + 2]; s.phiMaxDeg = prm[4 * i + 3];
+    if (mat) c->sphMat[i] = mat[i];
+    if (light) c->sphLight[i] = light[i];
+    if (rev) c->sphRev[i] = rev[i];
+  }
+  c->built = false;
+  return DRT_OK;
+}
+
+int drt_set_build_order(drt_ctx* c, const uint32_t* ids, uint32_t n) {
+  if (!c) return DRT_E_INVALID;
+  if (!ids) c->order.clear();
+  else c->order.assign(ids, ids + n);
+  c->built = false;
+  return DRT_OK;
+}
+
+int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
+  if (!c) return DRT_E_INVALID;
+  if (split < 0 || split > 2) return fail(c, DRT_E_INVALID, "split method must be 0 (middle), 1 (equal) or 2 (sah)");
+  if (maxPrims < 1) return fail(c, DRT_E_INVALID, "maxnodeprims must be >= 1");
+  const bool hostOnly = c->device == DRT_DEVICE_NONE;
+  if (!hostOnly) CK(c, cudaSetDevice(c->device));
+  auto t0 = std::chrono::steady_clock::now();
+  const uint32_t nt = c->ntris(), np = c->nprims();
+  c->built = false;
+  c->ts = TraceScene{};
+  c->info = drt_bvh_info{};
+  if (np == 0) {  // bvh_accel.dart:50-53: nodes == null, every query misses
+    c->ts.empty = 1;
+    c->built = true;
+    return DRT_OK;
+  }
+  std::vector<uint32_t> order = c->order;
+  if (order.empty()) {
+    order.resize(np);
+    for (uint32_t i = 0; i < np; ++i) order[i] = i;
+  } else {
+    if (order.size() != np) return fail(c, DRT_E_INVALID, "build order length != primitive count");
+    std::vector<uint8_t> seen(np, 0);
+    for (uint32_t id : order) {
+      if (id >= np || seen[id]) return fail(c, DRT_E_INVALID, "build order is not a permutation of the primitive ids");
+      seen[id] = 1;
+    }
+  }
+  // world bounds: triangle.dart:39-42, sphere.dart:34-37 + shape.dart:38-40
+  std::vector<PrimBounds> bounds(np);
+  for (uint32_t t = 0; t < nt; ++t) {
+    PrimBounds& b = bounds[t];
+    for (int a = 0; a < 3; ++a) {
+      float v0 = c->P[3 * (size_t)c->idx[3 * (size_t)t] + a], v1 = c->P[3 * (size_t)c->idx[3 * (size_t)t + 1] + a],
+            v2 = c->P[3 * (size_t)c->idx[3 * (size_t)t + 2] + a];
+      b.bmin[a] = std::fmin(std::fmin(v0, v1), v2);
+      b.bmax[a] = std::fmax(std::fmax(v0, v1), v2);
+    }
+  }
+  std::vector<GSphere> gs(c->spheres.size());
+  for (size_t i = 0; i < c->spheres.size(); ++i) {
+    const HostSphere& s = c->spheres[i];
+    GSphere& g = gs[i];
+    std::memcpy(g.w2o, s.w2o, 48);
+    std::memcpy(g.w2oRow3, s.w2o + 12, 16);
+    std::memcpy(g.o2w, s.o2w, 48);
+    std::memcpy(g.o2wRow3, s.o2w + 12, 16);
+    g.radius = s.radius;  // sphere.dart:24-32
+    g.zmin = clampd(std::fmin(s.zmin, s.zmax), -s.radius, s.radius);
+    g.zmax = clampd(std::fmax(s.zmin, s.zmax), -s.radius, s.radius);
+    g.thetaMin = std::acos(clampd(g.zmin / s.radius, -1.0, 1.0));
+    g.thetaMax = std::acos(clampd(g.zmax / s.radius, -1.0, 1.0));
+    g.phiMax = (3.141592653589793 / 180.0) * clampd(s.phiMaxDeg, 0.0, 360.0);
+    float lo[3] = {(float)-s.radius, (float)-s.radius, (float)g.zmin}, hi[3] = {(float)s.radius, (float)s.radius, (float)g.zmax};
+    PrimBounds& b = bounds[nt + i];
+    for (int k = 0; k < 8; ++k) {  // transform.dart:163-178
+      float p[3] = {(k & 1) ? hi[0] : lo[0], (k & 2) ? hi[1] : lo[1], (k & 4) ? hi[2] : lo[2]}, q[3];
+      xformPoint(s.o2w, p, q);
+      for (int a = 0; a < 3; ++a) {
+        b.bmin[a] = k == 0 ? q[a] : std::fmin(b.bmin[a], q[a]);
+        b.bmax[a] = k == 0 ? q[a] : std::fmax(b.bmax[a], q[a]);
+      }
+    }
+  }
+  std::string err;
+  if (!buildBvh(bounds, order, split, maxPrims, &c->bvh, &err)) return fail(c, DRT_E_INVALID, err.c_str());
+  const BuiltBvh& B = c->bvh;
+
+  // leaf records
+  std::vector<GPrim> prims(B.leafPrimIds.size());
+  for (size_t i = 0; i < prims.size(); ++i) {
+    uint32_t id = B.leafPrimIds[i];
+    GPrim& g = prims[i];
+    std::memset(&g, 0, sizeof(g));
+    g.primId = (int32_t)id;
+    g.leafCount = (int32_t)B.leafCounts[i];
+    if (id < nt) {
+      const float* a = &c->P[3 * (size_t)c->idx[3 * (size_t)id]];
+      const float* b = &c->P[3 * (size_t)c->idx[3 * (size_t)id + 1]];
+      const float* d = &c->P[3 * (size_t)c->idx[3 * (size_t)id + 2]];
+      std::memcpy(g.p1, a, 12);
+      std::memcpy(g.p2, b, 12);
+      std::memcpy(g.p3, d, 12);
+      g.kindSphere = 0;
+    } else {
+      g.kindSphere = (int32_t)(((id - nt) << 1) | 1u);
+    }
+  }
+  if (hostOnly) {
+    c->info.n_nodes = (uint32_t)B.refNodes.size();
+    c->info.n_prims = np;
+    c->info.n_leaves = B.nLeaves;
+    c->info.max_leaf_prims = B.maxLeafPrims;
+    c->info.max_depth = B.maxDepth;
+    c->info.device_bytes = 0;
+    c->info.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    c->built = true;
+    return DRT_OK;
+  }
+  CK(c, c->dNodes.ensure(std::max<size_t>(1, B.nodes.size())));
+  CK(c, c->dPrims.ensure(prims.size()));
+  CK(c, c->dSpheres.ensure(std::max<size_t>(1, gs.size())));
+  if (!B.nodes.empty())
+    CK(c, cudaMemcpy(c->dNodes.p, B.nodes.data(), B.nodes.size() * sizeof(GNode), cudaMemcpyHostToDevice));
+  CK(c, cudaMemcpy(c->dPrims.p, prims.data(), prims.size() * sizeof(GPrim), cudaMemcpyHostToDevice));
+  if (!gs.empty()) CK(c, cudaMemcpy(c->dSpheres.p, gs.data(), gs.size() * sizeof(GSphere), cudaMemcpyHostToDevice));
+  c->ts.nodes = c->dNodes.p;
+  c->ts.prims = c->dPrims.p;
+  c->ts.spheres = c->dSpheres.p;
+  std::memcpy(c->ts.rootMin, B.rootMin, 12);
+  std::memcpy(c->ts.rootMax, B.rootMax, 12);
+  c->ts.rootRef = B.rootRef;
+  c->ts.empty = 0;
+  c->info.n_nodes = (uint32_t)B.refNodes.size();
+  c->info.n_prims = np;
+  c->info.n_leaves = B.nLeaves;
+  c->info.max_leaf_prims = B.maxLeafPrims;
+  c->info.max_depth = B.maxDepth;
+  c->info.device_bytes = B.nodes.size() * sizeof(GNode) + prims.size() * sizeof(GPrim) + gs.size() * sizeof(GSphere);
+  c->info.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  c->built = true;
+  return DRT_OK;
+}
+
+int drt_bvh_info_get(const drt_ctx* c, drt_bvh_info* out) {
+  if (!c || !out) return DRT_E_INVALID;
+  if (!c->built) return DRT_E_STATE;
+  *out = c->info;
+  return DRT_OK;
+}
+
+int drt_bvh_export(const drt_ctx* c, float* bounds, int32_t* offset, int32_t* nprims, int32_t* axis, uint32_t* ordered) {
+  if (!c) return DRT_E_INVALID;
+  if (!c->built) return DRT_E_STATE;
+  const BuiltBvh& B = c->bvh;
+  for (size_t i = 0; i < B.refNodes.size(); ++i) {
+    const RefNode& n = B.refNodes[i];
+    if (bounds) { std::memcpy(bounds + 6 * i, n.bmin, 12); std::memcpy(bounds + 6 * i + 3, n.bmax, 12); }
+    if (offset) offset[i] = n.offset;
+    if (nprims) nprims[i] = n.nPrimitives;
+    if (axis) axis[i] = n.axis;
+  }
+  if (ordered) std::memcpy(ordered, B.refOrdered.data(), B.refOrdered.size() * sizeof(uint32_t));
+  return DRT_OK;
+}
+
+static const char* kNoDevice = "context has no CUDA device (DRT_DEVICE_NONE): queries need a GPU, there is no CPU fallback";
+
+static int traceDevice(drt_ctx* c, bool any, const void* o, const void* d, uint64_t n, void* out, cudaStream_t st) {
+  if (c->device == DRT_DEVICE_NONE) return fail(c, DRT_E_NODEVICE, kNoDevice);
+  if (!c->built) return fail(c, DRT_E_STATE, "drt_build_bvh must be called before tracing");
+  if (n && (!o || !d || !out)) return fail(c, DRT_E_INVALID, "null ray or output buffer");
+  if (c->counting) CK(c, cudaMemsetAsync(c->dCounters.p, 0, sizeof(DeviceCounters), st));
+  CK(c, launchTrace(c->ts, any, c->counting, o, d, n, out, c->dCounters.p, st));
+  if (n) c->launches++;
+  return DRT_OK;
+}
+
+static int traceHost(drt_ctx* c, bool any, const float* o, const float* d, uint64_t n, void* out) {
+  if (!c) return DRT_E_INVALID;
+  if (c->device == DRT_DEVICE_NONE) return fail(c, DRT_E_NODEVICE, kNoDevice);
+  if (!c->built) return fail(c, DRT_E_STATE, "drt_build_bvh must be called before tracing");
+  if (n == 0) return DRT_OK;
+  if (!o || !d || !out) return fail(c, DRT_E_INVALID, "null ray or output buffer");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, c->dRayO.ensure(n));
+  CK(c, c->dRayD.ensure(n));
+  if (any) CK(c, c->dOcc.ensure(n));
+  else CK(c, c->dHits.ensure(n));
+  cudaStream_t st = c->stream;
+  CK(c, cudaMemcpyAsync(c->dRayO.p, o, n * 16, cudaMemcpyHostToDevice, st));
+  CK(c, cudaMemcpyAsync(c->dRayD.p, d, n * 16, cudaMemcpyHostToDevice, st));
+  CK(c, cudaEventRecord(c->ev0, st));
+  void* dout = any ? (void*)c->dOcc.p : (void*)c->dHits.p;
+  int rc = traceDevice(c, any, c->dRayO.p, c->dRayD.p, n, dout, st);
+  if (rc != DRT_OK) return rc;
+  CK(c, cudaEventRecord(c->ev1, st));
+  CK(c, cudaMemcpyAsync(out, dout, n * (any ? 1 : sizeof(drt_hit_rec)), cudaMemcpyDeviceToHost, st));
+  CK(c, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  CK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->lastKernelMs = ms;
+  return DRT_OK;
+}
+
+int drt_trace_closest(drt_ctx* c, const float* o, const float* d, uint64_t n, drt_hit* hits) {
+  return traceHost(c, false, o, d, n, hits);
+}
+int drt_trace_any(drt_ctx* c, const float* o, const float* d, uint64_t n, uint8_t* occluded) {
+  return traceHost(c, true, o, d, n, occluded);
+}
+int drt_trace_closest_device(drt_ctx* c, const void* o, const void* d, uint64_t n, void* hits, void* stream) {
+  if (!c) return DRT_E_INVALID;
+  return traceDevice(c, false, o, d, n, hits, (cudaStream_t)stream);
+}
+int drt_trace_any_device(drt_ctx* c, const void* o, const void* d, uint64_t n, void* occ, void* stream) {
+  if (!c) return DRT_E_INVALID;
+  return traceDevice(c, true, o, d, n, occ, (cudaStream_t)stream);
+}
+
+int drt_set_counting(drt_ctx* c, int enabled) {
+  if (!c) return DRT_E_INVALID;
+  c->counting = enabled != 0;
+  return DRT_OK;
+}
+
+int drt_get_counters(drt_ctx* c, drt_counters* out) {
+  if (!c || !out) return DRT_E_INVALID;
+  if (c->device == DRT_DEVICE_NONE) return fail(c, DRT_E_NODEVICE, kNoDevice);
+  CK(c, cudaSetDevice(c->device));
+  DeviceCounters h;
+  CK(c, cudaDeviceSynchronize());
+  CK(c, cudaMemcpy(&h, c->dCounters.p, sizeof(h), cudaMemcpyDeviceToHost));
+  out->rays = h.rays;
+  out->nodes_visited = h.nodes_visited;
+  out->prims_tested = h.prims_tested;
+  out->hits = h.hits;
+  return DRT_OK;
+}
+
+double drt_last_kernel_ms(const drt_ctx* c) { return c ? c->lastKernelMs : 0.0; }
+uint64_t drt_kernel_launches(const drt_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

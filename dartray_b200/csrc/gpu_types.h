@@ -1,0 +1,74 @@
+// Device data layout of libdartray_gpu.so (see DESIGN.md "Data layout in HBM").
+#pragma once
+#include <cstdint>
+
+#ifdef __CUDACC__
+#define DRT_HD __host__ __device__
+#else
+#define DRT_HD
+#endif
+
+namespace drt {
+
+// Child reference: >= 0 -> interior node index into GNode[]; < 0 -> leaf, bits = ~ref:
+//   bits & 15  = primitive count (1..14), 15 = count stored in the first record's `leafCount`
+//   bits >> 4  = offset of the leaf's first record in GPrim[]
+static inline DRT_HD bool refIsLeaf(int32_t r) { return r < 0; }
+static inline DRT_HD uint32_t refLeafOffset(int32_t r) { return ((uint32_t)~r) >> 4; }
+static inline DRT_HD uint32_t refLeafCountField(int32_t r) { return ((uint32_t)~r) & 15u; }
+static inline int32_t makeLeafRef(uint32_t offset, uint32_t count) {
+  uint32_t c = count < 15u ? count : 15u;
+  return (int32_t)~((offset << 4) | c);
+}
+
+// One interior node = 64 bytes = four 128-bit loads.  It carries BOTH children's boxes (the
+// reference's _LinearBVHNode, bvh_accel.dart:533-538, carries its own box; moving the boxes up one
+// level lets one fetch decide near/far and is provably the same traversal).
+//   q0 = c0.min.xyz, c0.max.x     q1 = c0.max.yz, c1.min.xy
+//   q2 = c1.min.z, c1.max.xyz     q3 = ref0, ref1, axis, reference node number (for export/debug)
+struct alignas(16) GNode {
+  float c0min[3], c0max[3];
+  float c1min[3], c1max[3];
+  int32_t ref0, ref1;
+  int32_t axis;
+  int32_t refNode;
+};
+static_assert(sizeof(GNode) == 64, "GNode must be 64 bytes");
+
+// One leaf primitive record = 48 bytes = three 128-bit loads, stored in leaf order.
+// Triangle: the three ORIGINAL float32 world-space vertices (triangle.dart:47-50 reads exactly
+// these; edges are formed in f64 on the fly so the arithmetic matches the reference bit for bit).
+//   q0 = p1.xyz, primId     q1 = p2.xyz, leafCount     q2 = p3.xyz, kind|sphereIndex<<1
+struct alignas(16) GPrim {
+  float p1[3];
+  int32_t primId;
+  float p2[3];
+  int32_t leafCount;
+  float p3[3];
+  int32_t kindSphere;  // bit0: 0 = triangle, 1 = sphere; bits 1.. = index into GSphere[]
+};
+static_assert(sizeof(GPrim) == 48, "GPrim must be 48 bytes");
+
+// sphere.dart:24-32: transforms are float32 matrices, the shape parameters are doubles.
+struct alignas(16) GSphere {
+  float w2o[12];  // rows 0..2 of worldToObject (affine)
+  float w2oRow3[4];
+  float o2w[12];
+  float o2wRow3[4];
+  double radius, zmin, zmax, phiMax, thetaMin, thetaMax;
+};
+
+struct TraceScene {
+  const GNode* nodes;
+  const GPrim* prims;
+  const GSphere* spheres;
+  float rootMin[3], rootMax[3];  // box of reference node 0, tested first (bvh_accel.dart:123-125)
+  int32_t rootRef;
+  int32_t empty;  // 1 -> no primitives (bvh_accel.dart:102-104)
+};
+
+struct DeviceCounters {
+  unsigned long long rays, nodes_visited, prims_tested, hits;
+};
+
+}  // namespace drt

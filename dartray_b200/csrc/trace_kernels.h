@@ -1,0 +1,20 @@
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "gpu_types.h"
+
+namespace drt {
+
+struct drt_hit_rec {  // == drt_hit of include/drt.h
+  float t, b1, b2;
+  int32_t prim;
+};
+
+// Launches the closest-hit (any = false) or any-hit (any = true) traversal for n rays whose two
+// float4 arrays live in device memory.  `out` is drt_hit_rec[n] or uint8_t[n].
+cudaError_t launchTrace(const TraceScene& sc, bool any, bool count, const void* rayO, const void* rayD, uint64_t n,
+                        void* out, DeviceCounters* counters, cudaStream_t stream);
+
+}  // namespace drt

@@ -1,0 +1,147 @@
+/* drt.h — C ABI of libdartray_gpu.so, the B200 (sm_100a) ray-tracing core that replaces the
+ * data-parallel hot path of DartRay's SamplerRenderer.
+ *
+ * The reference (brendan-duncan/dartray, 100 % Dart) has NO native boundary.  Its extension
+ * mechanism is the Plugin registry (lib/core/plugin.dart:62-180) and the coarse seam is
+ * Renderer.render(scene) (lib/core/renderer.dart:27-35, called from lib/dartray/dartray.dart:574).
+ * Every entry point below replaces the work that one reference interface does behind that seam and
+ * is what a `dart:ffi` binding in a Dart `GpuSamplerRenderer` would look up.
+ *
+ * Conventions
+ *   - all functions are extern "C", plain pointers and sizes, blocking;
+ *   - return 0 on success, a negative DRT_E_* code on failure; drt_last_error() gives the text
+ *     (reference analogue: LogWarning + null / LogSevere exception, lib/core/log.dart:44-46);
+ *   - the caller owns every input and output buffer; the library copies inputs during the call
+ *     and never retains host pointers;
+ *   - a drt_ctx is bound to ONE CUDA device and may be used from one host thread at a time
+ *     (reference analogue: one isolate with a private scene, lib/dartray_web/render_isolate.dart:31-41);
+ *   - there is NO CPU fallback: creating a context without a usable CUDA device fails.
+ *
+ * Primitive ids: the position in upload order — triangle k of drt_set_triangles is
+ * id k, sphere j of drt_set_spheres is id ntris + j.  Every hit record reports this id.
+ */
+#ifndef DRT_H_
+#define DRT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRT_VERSION 100
+
+enum {
+  DRT_OK = 0,
+  DRT_E_INVALID = -1,   /* bad argument */
+  DRT_E_STATE = -2,     /* call order (e.g. trace before build) */
+  DRT_E_CUDA = -3,      /* CUDA runtime error, text in drt_last_error */
+  DRT_E_NODEVICE = -4,  /* no CUDA device: there is no CPU fallback */
+  DRT_E_NOMEM = -5
+};
+
+/* BVHAccel split methods, lib/accelerators/bvh_accel.dart:37-39 */
+enum { DRT_SPLIT_MIDDLE = 0, DRT_SPLIT_EQUAL_COUNTS = 1, DRT_SPLIT_SAH = 2 };
+
+typedef struct drt_ctx drt_ctx;
+
+/* One closest-hit result: 16 bytes.  t is the reference's f64 tHit rounded to f32; b1/b2 are the
+ * triangle barycentrics of lib/shapes/triangle.dart:77,87 (sphere: u,v of sphere.dart:119-121);
+ * prim is the upload-order primitive id, -1 = miss (then t = +inf, b1 = b2 = 0). */
+typedef struct drt_hit {
+  float t, b1, b2;
+  int32_t prim;
+} drt_hit;
+
+/* Traversal statistics of the last trace call (reference: the Stats counters of
+ * lib/core/stats.dart:541-555 and the probes in bvh_accel.dart:106-135). */
+typedef struct drt_counters {
+  uint64_t rays;
+  uint64_t nodes_visited; /* slab tests, bvh_accel.dart:125/187 */
+  uint64_t prims_tested;  /* primitive tests, bvh_accel.dart:131/193 */
+  uint64_t hits;
+} drt_counters;
+
+typedef struct drt_bvh_info {
+  uint32_t n_nodes;      /* reference _LinearBVHNode count (bvh_accel.dart:82) */
+  uint32_t n_prims;
+  uint32_t n_leaves;
+  uint32_t max_leaf_prims;
+  uint32_t max_depth;
+  uint64_t device_bytes; /* node + primitive records resident in HBM */
+  double build_seconds;
+} drt_bvh_info;
+
+int drt_version(void);
+
+/* Context on CUDA device `device_id`.  Returns NULL when no device is usable (message via
+ * drt_last_error(NULL)).  DRT_DEVICE_NONE creates a host-only staging context that can hold a scene
+ * and run the host side of drt_build_bvh / drt_bvh_export (BVH construction is host code, like the
+ * reference's constructor); every query on it fails with DRT_E_NODEVICE. */
+#define DRT_DEVICE_NONE (-1)
+drt_ctx* drt_create(int device_id);
+void drt_destroy(drt_ctx* ctx);
+const char* drt_last_error(const drt_ctx* ctx);
+
+/* Replaces TriangleMesh storage + refine (lib/shapes/triangle_mesh.dart:24-60,83-89): world-space
+ * float32 positions and uint32 indices.  material_of_tri / light_of_tri (-1 = none) /
+ * reverse_orientation_of_tri may be NULL (0 / -1 / 0). */
+int drt_set_triangles(drt_ctx* ctx, const float* P, uint32_t nverts, const uint32_t* idx, uint32_t ntris,
+                      const int32_t* material_of_tri, const int32_t* light_of_tri,
+                      const uint8_t* reverse_orientation_of_tri);
+
+/* Replaces Sphere construction (lib/shapes/sphere.dart:24-32,314-323).  o2w / w2o: n x 16 row-major
+ * float32 (Matrix4x4, lib/core/matrix4x4.dart:26); params: n x 4 doubles radius, zmin, zmax,
+ * phimax(degrees) exactly as ParamSet hands them to Sphere.Create. */
+int drt_set_spheres(drt_ctx* ctx, uint32_t n, const float* o2w, const float* w2o, const double* radius_zmin_zmax_phimax,
+                    const int32_t* material_of_sphere, const int32_t* light_of_sphere,
+                    const uint8_t* reverse_orientation_of_sphere);
+
+/* Order in which BVHAccel sees the refined primitives (a permutation of primitive ids).  The
+ * reference's Primitive.fullyRefine is LIFO (lib/core/primitive.dart:71-84), so a mesh's triangles
+ * reach the builder in reverse order; the build's partition steps depend on it.  NULL = identity. */
+int drt_set_build_order(drt_ctx* ctx, const uint32_t* prim_ids, uint32_t n);
+
+/* Replaces BVHAccel(p, maxPrims, splitMethod) (lib/accelerators/bvh_accel.dart:41-91, 228-437,
+ * Create :474-482): same tree, same leaf contents and in-leaf order, laid out for the GPU. */
+int drt_build_bvh(drt_ctx* ctx, int split_method, int max_node_prims);
+int drt_bvh_info_get(const drt_ctx* ctx, drt_bvh_info* out);
+
+/* Export the tree in the REFERENCE's linear layout (bvh_accel.dart:419-437, 533-538) for topology
+ * checks: bounds n_nodes x 6 (pMin xyz, pMax xyz), offset, n_primitives, axis per node, and the
+ * reordered primitive list (upload ids).  Any pointer may be NULL. */
+int drt_bvh_export(const drt_ctx* ctx, float* bounds, int32_t* offset, int32_t* n_primitives, int32_t* axis,
+                   uint32_t* ordered_prim_ids);
+
+/* Replaces Scene.intersect -> BVHAccel.intersect (lib/core/scene.dart:51-56,
+ * lib/accelerators/bvh_accel.dart:101-165) with Triangle.intersect (lib/shapes/triangle.dart:44-98)
+ * and Sphere.intersect (lib/shapes/sphere.dart:39-116) for a batch of n rays held in HOST memory.
+ * ray_o_tmin: n x 4 float (origin xyz, minDistance); ray_d_tmax: n x 4 float (direction xyz,
+ * maxDistance; +inf allowed).  hits: n records. */
+int drt_trace_closest(drt_ctx* ctx, const float* ray_o_tmin, const float* ray_d_tmax, uint64_t n, drt_hit* hits);
+
+/* Replaces Scene.intersectP -> BVHAccel.intersectP (bvh_accel.dart:167-226) with
+ * Triangle.intersectP (triangle.dart:162-194) / Sphere.intersectP (sphere.dart:169-241).
+ * occluded: n bytes, 1 = some primitive hit. */
+int drt_trace_any(drt_ctx* ctx, const float* ray_o_tmin, const float* ray_d_tmax, uint64_t n, uint8_t* occluded);
+
+/* Same two queries on buffers already resident in this context's device memory, launched on
+ * `cuda_stream` (a cudaStream_t, NULL = default stream); asynchronous — the caller synchronises. */
+int drt_trace_closest_device(drt_ctx* ctx, const void* d_ray_o_tmin, const void* d_ray_d_tmax, uint64_t n,
+                             void* d_hits, void* cuda_stream);
+int drt_trace_any_device(drt_ctx* ctx, const void* d_ray_o_tmin, const void* d_ray_d_tmax, uint64_t n,
+                         void* d_occluded, void* cuda_stream);
+
+/* When enabled the trace kernels also count slab and primitive tests (slower; off by default). */
+int drt_set_counting(drt_ctx* ctx, int enabled);
+int drt_get_counters(drt_ctx* ctx, drt_counters* out);
+
+/* Device time of the kernels launched by the last host-buffer trace call (CUDA events), ms. */
+double drt_last_kernel_ms(const drt_ctx* ctx);
+/* Number of kernels this context has launched so far. */
+uint64_t drt_kernel_launches(const drt_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRT_H_ */

@@ -1,0 +1,139 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see ref_core.h header).  PARITY UNPINNED.
+//
+// Shapes (Triangle, Sphere) and BVHAccel restated from the reference:
+//   lib/shapes/triangle.dart, lib/shapes/sphere.dart, lib/core/common.dart (Quadratic,
+//   partition, nth_element), lib/accelerators/bvh_accel.dart.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+#include "ref_core.h"
+
+namespace orc {
+
+// lib/shapes/sphere.dart:24-32,314-323 — radius/zmin/zmax/phiMax are Dart doubles.
+struct Sphere {
+  Transform o2w;  // objectToWorld (m) / worldToObject is o2w.mInv kept separately below
+  Transform w2o;
+  double radius, zmin, zmax, phiMax, thetaMin, thetaMax;
+  bool reverseOrientation = false;
+  Sphere() {}
+  Sphere(const float* O2W, const float* W2O, double r, double z0, double z1, double pm, bool ro) {
+    o2w = Transform(O2W, W2O);
+    w2o = Transform(W2O, O2W);
+    radius = r;
+    zmin = clampd(std::fmin(z0, z1), -radius, radius);
+    zmax = clampd(std::fmax(z0, z1), -radius, radius);
+    thetaMin = std::acos(clampd(zmin / radius, -1.0, 1.0));
+    thetaMax = std::acos(clampd(zmax / radius, -1.0, 1.0));
+    phiMax = Radians(clampd(pm, 0.0, 360.0));
+    reverseOrientation = ro;
+  }
+  // sphere.dart:34-37 + lib/core/shape.dart:38-40
+  BBox worldBound() const {
+    BBox ob(Vec(-radius, -radius, zmin), Vec(radius, radius, zmax));
+    return o2w.bbox(ob);
+  }
+};
+
+// Hit record shared by closest-hit queries.  `prim` is the UPLOAD-ORDER id
+// (SURVEY §8b "primitive id convention"): triangles 0..ntris-1, spheres after.
+struct Hit {
+  double t = 0.0;
+  double b1 = 0.0, b2 = 0.0;  // triangle barycentrics / sphere (u, v)
+  int32_t prim = -1;
+  double rayEpsilon = 0.0;
+  Vec phitObj;       // sphere: object-space hit point after the 1e-5*r nudge
+  double phi = 0.0;  // sphere
+};
+
+// lib/core/common.dart:140-167
+static inline bool Quadratic(double A, double B, double C, double* t0, double* t1) {
+  double discrim = B * B - 4.0 * A * C;
+  if (discrim < 0.0) return false;
+  double rootDiscrim = std::sqrt(discrim);
+  double q;
+  if (B < 0.0) q = -0.5 * (B - rootDiscrim);
+  else q = -0.5 * (B + rootDiscrim);
+  *t0 = q / A;
+  *t1 = C / q;
+  if (*t0 > *t1) std::swap(*t0, *t1);
+  return true;
+}
+
+struct Counters {
+  uint64_t nodes_visited = 0;  // every _intersectP call (bvh_accel.dart:125/187)
+  uint64_t prims_tested = 0;   // every primitive test (bvh_accel.dart:131/193)
+  uint64_t rays = 0;
+  void add(const Counters& o) { nodes_visited += o.nodes_visited; prims_tested += o.prims_tested; rays += o.rays; }
+};
+
+struct LinearNode {  // bvh_accel.dart:533-538
+  BBox bounds;
+  int32_t offset = 0;       // primitivesOffset / secondChildOffset
+  int32_t nPrimitives = 0;  // 0 -> interior
+  int32_t axis = 0;
+};
+
+struct Scene {
+  // world-space triangle soup, lib/shapes/triangle_mesh.dart:24-60
+  std::vector<float> P;       // nverts*3
+  std::vector<uint32_t> idx;  // ntris*3
+  std::vector<Sphere> spheres;
+  std::vector<uint32_t> buildOrder;  // refined order handed to BVHAccel (ids in upload numbering)
+
+  // per-primitive attributes (upload numbering)
+  std::vector<int32_t> materialOf;
+  std::vector<int32_t> lightOf;
+  std::vector<uint8_t> reverseOf;
+
+  // BVH (bvh_accel.dart:484-487)
+  int maxPrimsInNode = 4;
+  int splitMethod = 2;
+  std::vector<uint32_t> ordered;  // primitives after the build (ids in upload numbering)
+  std::vector<LinearNode> nodes;
+
+  uint32_t ntris() const { return (uint32_t)(idx.size() / 3); }
+  uint32_t nprims() const { return ntris() + (uint32_t)spheres.size(); }
+
+  void triVerts(uint32_t tri, Vec* p1, Vec* p2, Vec* p3) const {
+    const float* a = &P[3 * (size_t)idx[3 * (size_t)tri + 0]];
+    const float* b = &P[3 * (size_t)idx[3 * (size_t)tri + 1]];
+    const float* c = &P[3 * (size_t)idx[3 * (size_t)tri + 2]];
+    p1->x = a[0]; p1->y = a[1]; p1->z = a[2];
+    p2->x = b[0]; p2->y = b[1]; p2->z = b[2];
+    p3->x = c[0]; p3->y = c[1]; p3->z = c[2];
+  }
+  BBox primBound(uint32_t prim) const {
+    if (prim < ntris()) {  // triangle.dart:39-42
+      Vec p1, p2, p3;
+      triVerts(prim, &p1, &p2, &p3);
+      return UnionPoint(BBox(p1, p2), p3);
+    }
+    return spheres[prim - ntris()].worldBound();
+  }
+
+  // ---- primitive tests -------------------------------------------------
+  bool triIntersect(uint32_t tri, Ray& ray, Hit* hit) const;   // triangle.dart:44-160 (+ geometric_primitive.dart:47-61)
+  bool triIntersectP(uint32_t tri, const Ray& ray) const;      // triangle.dart:162-240
+  bool sphIntersect(const Sphere& s, Ray& r, Hit* hit) const;  // sphere.dart:39-167
+  bool sphIntersectP(const Sphere& s, const Ray& r) const;     // sphere.dart:169-241
+  bool primIntersect(uint32_t prim, Ray& ray, Hit* hit) const {
+    bool h = prim < ntris() ? triIntersect(prim, ray, hit) : sphIntersect(spheres[prim - ntris()], ray, hit);
+    if (h) hit->prim = (int32_t)prim;
+    return h;
+  }
+  bool primIntersectP(uint32_t prim, const Ray& ray) const {
+    return prim < ntris() ? triIntersectP(prim, ray) : sphIntersectP(spheres[prim - ntris()], ray);
+  }
+
+  // ---- BVH ---------------------------------------------------------------
+  void buildBVH(int split, int maxPrims);                       // bvh_accel.dart:41-91
+  bool intersect(Ray& ray, Hit* hit, Counters* c) const;        // bvh_accel.dart:101-165
+  bool intersectP(const Ray& ray, Counters* c) const;           // bvh_accel.dart:167-226
+  // exhaustive loop in upload order (the pattern of aggregate_test_renderer.dart:82-96)
+  bool intersectBrute(Ray& ray, Hit* hit, int* nTies, double* secondT) const;
+};
+
+}  // namespace orc

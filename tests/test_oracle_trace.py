@@ -1,0 +1,192 @@
+"""Pins the CPU oracle for traversal + shapes.  The reference ships no golden vectors
+(test/spectrum_test.dart:14-39 is commented out), so the pins are analytic known answers and the
+accelerated-vs-exhaustive differential check of lib/renderers/aggregate_test_renderer.dart:42-118."""
+import math
+
+import numpy as np
+import pytest
+
+from dartray_b200 import scenes
+from tests.oracle_lib import Oracle
+from tests.util import random_rays, random_soup, translate
+
+INF = np.float32(np.inf)
+
+
+def one_tri():
+    # p1=(0,0), p2=(1,0), p3=(1,1): hit point = (b1 + b2, b2), so x = y is the b1 == 0 edge
+    P = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0]], np.float32)
+    idx = np.array([[0, 1, 2]], np.uint32)
+    o = Oracle()
+    o.set_triangles(P, idx)
+    o.build_bvh()
+    return o
+
+
+def ray(o, d, tmin=0.0, tmax=np.inf):
+    return scenes.pack_rays(np.array([o], np.float32), np.array([d], np.float32), tmin, tmax)
+
+
+def test_triangle_known_answers():
+    o = one_tri()
+    # interior hit: b2 = y, b1 = x - y, t = origin height (triangle.dart:77-95)
+    h = o.trace_closest(*ray((0.75, 0.5, 2.0), (0, 0, -1)))[0]
+    assert h["prim"] == 0 and h["t"] == 2.0 and h["b1"] == 0.25 and h["b2"] == 0.5
+    # inclusive edge: b1 == 0 exactly on the diagonal still hits (triangle.dart:78)
+    h = o.trace_closest(*ray((0.5, 0.5, 1.0), (0, 0, -1)))[0]
+    assert h["prim"] == 0 and h["b1"] == 0.0 and h["b2"] == 0.5
+    # just outside the diagonal
+    assert o.trace_closest(*ray((0.5, 0.5 + 1e-6, 1.0), (0, 0, -1)))[0]["prim"] == -1
+    # NaN semantics of the slab test (bvh_accel.dart:441-471): for an axis-parallel ray whose
+    # origin lies exactly on a box plane, (b - o) * (1/0) = 0 * inf = NaN.  A NaN in the X slab
+    # poisons tmin/tmax (later `tymin > tmin` style updates are false) and the final
+    # `tmin < maxDistance && tmax > minDistance` rejects the node, so the reference MISSES the edge
+    # x == 1 of this triangle for a ray with d.x == 0.  A NaN in the y/z slabs is simply ignored,
+    # so the y == 0 edge (b2 == 0, inclusive) is hit.  The oracle keeps both behaviours.
+    assert o.trace_closest(*ray((1.0, 0.5, 1.0), (0, 0, -1)))[0]["prim"] == -1
+    assert o.trace_closest(*ray((1.0 - 1e-6, 0.5, 1.0), (0, 0, -1)))[0]["prim"] == 0
+    h = o.trace_closest(*ray((0.5, 0.0, 1.0), (0, 0, -1)))[0]
+    assert h["prim"] == 0 and h["b2"] == 0.0
+    # parallel ray: divisor == 0 (triangle.dart:66)
+    assert o.trace_closest(*ray((0.2, 0.1, 1.0), (1, 0, 0)))[0]["prim"] == -1
+    # The triangle's t range is inclusive (triangle.dart:96) but the slab test is strict
+    # (`tmin < maxDistance && tmax > minDistance`, bvh_accel.dart:471): for this FLAT leaf box
+    # tzmin == tzmax == t, so a hit at exactly minDistance or maxDistance is culled by the box.
+    assert o.trace_closest(*ray((0.5, 0.2, 1.0), (0, 0, -1), 0.5, 5.0))[0]["prim"] == 0
+    assert o.trace_closest(*ray((0.5, 0.2, 1.0), (0, 0, -1), 1.0, 5.0))[0]["prim"] == -1
+    assert o.trace_closest(*ray((0.5, 0.2, 1.0), (0, 0, -1), 0.0, 1.0))[0]["prim"] == -1
+    assert o.trace_closest(*ray((0.5, 0.2, 1.0), (0, 0, -1), 1.0000001, 5.0))[0]["prim"] == -1
+    assert o.trace_closest(*ray((0.5, 0.2, 1.0), (0, 0, -1), 0.0, 0.99999))[0]["prim"] == -1
+    # a tilted triangle (plane z = y) has a thick box, so the inclusive ends are observable
+    tilt = Oracle()
+    tilt.set_triangles(np.array([[0, 0, 0], [1, 0, 0], [1, 1, 1]], np.float32), np.array([[0, 1, 2]], np.uint32))
+    tilt.build_bvh()
+    assert tilt.trace_closest(*ray((0.5, 0.25, 1.0), (0, 0, -1)))[0]["t"] == 0.75
+    assert tilt.trace_closest(*ray((0.5, 0.25, 1.0), (0, 0, -1), 0.0, 0.75))[0]["prim"] == 0
+    assert tilt.trace_closest(*ray((0.5, 0.25, 1.0), (0, 0, -1), 0.75, 2.0))[0]["prim"] == 0
+    assert tilt.trace_closest(*ray((0.5, 0.25, 1.0), (0, 0, -1), 0.0, 0.7499999))[0]["prim"] == -1
+    assert tilt.trace_closest(*ray((0.5, 0.25, 1.0), (0, 0, -1), 0.7500001, 2.0))[0]["prim"] == -1
+    assert tilt.trace_any(*ray((0.5, 0.25, 1.0), (0, 0, -1), 0.0, 0.75))[0] == 1
+    # behind the origin
+    assert o.trace_closest(*ray((0.5, 0.2, 1.0), (0, 0, 1)))[0]["prim"] == -1
+    # any-hit agrees
+    assert o.trace_any(*ray((0.75, 0.5, 2.0), (0, 0, -1)))[0] == 1
+    assert o.trace_any(*ray((0.5, 0.5, 1.0), (0, 0, -1)))[0] == 1
+    assert o.trace_any(*ray((0.2, 0.1, 1.0), (1, 0, 0)))[0] == 0
+
+
+def test_equal_t_last_tested_wins():
+    """`t > ray.maxDistance` is the reject test (triangle.dart:96): an equal-t hit tested later
+    replaces the earlier one.  Two coincident triangles -> the brute-force loop ends on prim 1."""
+    P = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0]], np.float32)
+    idx = np.array([[0, 1, 2], [0, 1, 2]], np.uint32)
+    o = Oracle()
+    o.set_triangles(P, idx)
+    o.build_bvh()
+    hb, nties, _ = o.trace_closest_brute(*ray((0.5, 0.2, 1.0), (0, 0, -1)))
+    assert hb[0]["prim"] == 1 and nties[0] == 2
+    # centroid-degenerate range -> one leaf holding both (bvh_accel.dart:265-274), same winner
+    ex = o.bvh_export()
+    assert len(ex["offset"]) == 1 and ex["n_primitives"][0] == 2
+    assert o.trace_closest(*ray((0.5, 0.2, 1.0), (0, 0, -1)))[0]["prim"] == 1
+
+
+def sphere_oracle(radius=1.0, center=(0, 0, 0), zmin=None, zmax=None, phimax=360.0):
+    o = Oracle()
+    o.set_triangles(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32))
+    m, mi = translate(*center)
+    o.set_spheres(m, mi, [[radius, -radius if zmin is None else zmin, radius if zmax is None else zmax, phimax]])
+    o.build_bvh()
+    return o
+
+
+def test_sphere_known_answers():
+    o = sphere_oracle(1.0, (0, 0, 5))
+    h = o.trace_closest(*ray((0, 0, 0), (0, 0, 1)))[0]
+    assert h["prim"] == 0 and h["t"] == 4.0
+    # from inside: t0 < minDistance -> t1 (sphere.dart:86-92)
+    h = o.trace_closest(*ray((0, 0, 5), (0, 0, 1)))[0]
+    assert h["prim"] == 0 and h["t"] == 1.0
+    # grazing miss / tangent
+    assert o.trace_closest(*ray((1.5, 0, 0), (0, 0, 1)))[0]["prim"] == -1
+    # closed form for an oblique ray
+    org, d = np.array([0.3, -0.2, 0.0]), np.array([0.05, 0.1, 1.0])
+    d = (d / np.linalg.norm(d)).astype(np.float32).astype(np.float64)
+    org = org.astype(np.float32).astype(np.float64)
+    oc = org - np.array([0, 0, 5.0])
+    A, B, Cc = d @ d, 2 * (d @ oc), oc @ oc - 1.0
+    t = (-B - math.sqrt(B * B - 4 * A * Cc)) / (2 * A)
+    h = o.trace_closest(*ray(org, d))[0]
+    assert h["prim"] == 0 and abs(h["t"] - t) <= 1e-6 * t
+    assert o.trace_any(*ray(org, d))[0] == 1
+    # tmax clips
+    assert o.trace_closest(*ray((0, 0, 0), (0, 0, 1), 0.0, 3.9))[0]["prim"] == -1
+    assert o.trace_any(*ray((0, 0, 0), (0, 0, 1), 0.0, 3.9))[0] == 0
+
+
+def test_partial_sphere_clipping():
+    # zmax clip: the near cap is cut away, the ray enters through the hole and hits the far side (t1)
+    o = sphere_oracle(1.0, (0, 0, 0), zmin=-1.0, zmax=0.5)
+    h = o.trace_closest(*ray((0, 0.1, 5), (0, 0, -1)))[0]
+    assert h["prim"] == 0 and h["t"] > 5.0
+    # phimax = 180: half sphere y >= 0; a ray at y < 0 misses both roots
+    o = sphere_oracle(1.0, (0, 0, 0), phimax=180.0)
+    assert o.trace_closest(*ray((0.2, -0.5, 5), (0, 0, -1)))[0]["prim"] == -1
+    assert o.trace_closest(*ray((0.2, 0.5, 5), (0, 0, -1)))[0]["prim"] == 0
+
+
+@pytest.mark.parametrize("split", [0, 1, 2])
+def test_bvh_matches_exhaustive(split):
+    """aggregate_test_renderer.dart:82-107: accelerated and exhaustive intersection agree."""
+    P, idx = random_soup(600, seed=split)
+    o = Oracle()
+    o.set_triangles(P, idx)
+    m, mi = translate(0.3, -0.2, 0.1)
+    o.set_spheres(np.stack([m, translate(-0.5, 0.5, 0.2)[0]]), np.stack([mi, translate(-0.5, 0.5, 0.2)[1]]),
+                  [[0.4, -0.4, 0.4, 360.0], [0.3, -0.1, 0.2, 270.0]])
+    o.build_bvh(split, 4)
+    ro, rd = random_rays(3000, seed=10 + split)
+    h = o.trace_closest(ro, rd)
+    hb, nties, _ = o.trace_closest_brute(ro, rd)
+    single = nties <= 1
+    assert (h["prim"][single] == hb["prim"][single]).all()
+    assert (h["t"] == hb["t"]).all()
+    assert (o.trace_any(ro, rd) == o.trace_any_brute(ro, rd)).all()
+    # short rays (shadow-ray style intervals)
+    ro2, rd2 = random_rays(2000, seed=20 + split, tmin=0.5, tmax=2.8)
+    assert (o.trace_closest(ro2, rd2)["t"] == o.trace_closest_brute(ro2, rd2)[0]["t"]).all()
+    assert (o.trace_any(ro2, rd2) == o.trace_any_brute(ro2, rd2)).all()
+
+
+def test_empty_scene_misses():
+    o = Oracle()
+    o.set_triangles(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32))
+    o.build_bvh()
+    ro, rd = random_rays(8, 0)
+    assert (o.trace_closest(ro, rd)["prim"] == -1).all()
+    assert (o.trace_any(ro, rd) == 0).all()
+
+
+def test_sah_tree_shape():
+    """With maxnodeprims 4 the reference still splits every range of <= 4 primitives
+    (bvh_accel.dart:313-316), so leaves hold one primitive unless centroids coincide."""
+    P, idx = scenes.soup(4)
+    o = Oracle()
+    o.set_triangles(P, idx)
+    o.build_bvh(2, 4)
+    ex = o.bvh_export()
+    n = idx.shape[0]
+    leaves = ex["n_primitives"] > 0
+    assert len(ex["offset"]) == 2 * int(leaves.sum()) - 1
+    assert int(ex["n_primitives"].sum()) == n
+    assert sorted(ex["ordered"].tolist()) == list(range(n))
+    assert (ex["n_primitives"][leaves] == 1).mean() > 0.99
+    # flatten: first child at n+1, second child index stored in offset (bvh_accel.dart:419-437)
+    inner = np.nonzero(~leaves)[0]
+    assert (ex["offset"][inner] > inner + 1).all()
+    # parent box is the union of the children's boxes
+    b = ex["bounds"]
+    for i in inner[:200]:
+        c0, c1 = i + 1, ex["offset"][i]
+        assert (b[i, :3] == np.minimum(b[c0, :3], b[c1, :3])).all()
+        assert (b[i, 3:] == np.maximum(b[c0, 3:], b[c1, 3:])).all()

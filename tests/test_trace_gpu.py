@@ -1,0 +1,158 @@
+"""GPU parity: libdartray_gpu's CUDA traversal vs the CPU oracle, through the C ABI.
+Bar (BASELINE.json north_star): closest-hit primitive index bit-exact, t and barycentrics within
+1e-5 relative.  The kernels reproduce the reference arithmetic op for op, so the tests below ask
+for more: float32(t), b1, b2 BIT-IDENTICAL and the any-hit flag identical."""
+import numpy as np
+import pytest
+
+from dartray_b200 import capi, scenes
+from tests.oracle_lib import Oracle
+from tests.util import mesh_refine_order, random_rays, random_soup, translate
+
+pytestmark = pytest.mark.gpu
+
+
+def make_pair(P, idx, spheres=None, order=None, split=2, maxprims=4):
+    o = Oracle()
+    c = capi.Context(0)
+    for x in (o, c):
+        x.set_triangles(P, idx)
+        if spheres is not None:
+            x.set_spheres(*spheres)
+        x.set_build_order(order)
+        x.build_bvh(split, maxprims)
+    return o, c
+
+
+def assert_hits_equal(hg, ho):
+    assert (hg["prim"] == ho["prim"]).all(), f"{(hg['prim'] != ho['prim']).sum()} primitive ids differ"
+    for k in ("t", "b1", "b2"):
+        assert (hg[k].view(np.uint32) == ho[k].view(np.uint32)).all(), k
+
+
+@pytest.mark.parametrize("split", [0, 1, 2])
+def test_random_soup_closest_and_any(drt_lib, split):
+    P, idx = random_soup(5000, seed=split)
+    o, c = make_pair(P, idx, split=split)
+    ro, rd = random_rays(50000, seed=100 + split)
+    assert_hits_equal(c.trace_closest(ro, rd), o.trace_closest(ro, rd, nthreads=8))
+    assert (c.trace_any(ro, rd) == o.trace_any(ro, rd, nthreads=8)).all()
+    # bounded intervals, as shadow rays use them
+    ro, rd = random_rays(50000, seed=200 + split, tmin=0.7, tmax=2.9)
+    assert_hits_equal(c.trace_closest(ro, rd), o.trace_closest(ro, rd, nthreads=8))
+    assert (c.trace_any(ro, rd) == o.trace_any(ro, rd, nthreads=8)).all()
+
+
+def test_mixed_triangles_and_spheres(drt_lib):
+    P, idx = random_soup(800, seed=5)
+    mats = [translate(0.3, 0.1, -0.2), translate(-0.4, 0.2, 0.5), translate(0.0, -0.5, 0.0)]
+    sph = (np.stack([m[0] for m in mats]), np.stack([m[1] for m in mats]),
+           [[0.25, -0.25, 0.25, 360.0], [0.4, -0.1, 0.3, 200.0], [0.3, -0.3, 0.1, 360.0]])
+    o, c = make_pair(P, idx, sph, mesh_refine_order([300, 500], 3))
+    ro, rd = random_rays(40000, seed=6)
+    hg, ho = c.trace_closest(ro, rd), o.trace_closest(ro, rd, nthreads=8)
+    assert (hg["prim"] == ho["prim"]).all()
+    assert (hg["t"].view(np.uint32) == ho["t"].view(np.uint32)).all()
+    sphere_hit = ho["prim"] >= 800
+    assert sphere_hit.sum() > 1000
+    # sphere (u, v) go through atan2/acos: libm vs CUDA may differ in the last ulp of the f64
+    np.testing.assert_allclose(hg["b1"], ho["b1"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(hg["b2"], ho["b2"], rtol=1e-6, atol=1e-7)
+    assert (c.trace_any(ro, rd) == o.trace_any(ro, rd, nthreads=8)).all()
+
+
+def test_known_answer_edge_cases(drt_lib):
+    """Same quirks the oracle test pins: inclusive triangle edges, strict flat-box culling and the
+    NaN behaviour of the slab test for axis-parallel rays (bvh_accel.dart:441-471)."""
+    P = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 0, 2], [1, 0, 2], [1, 1, 3]], np.float32)
+    idx = np.array([[0, 1, 2], [3, 4, 5]], np.uint32)
+    o, c = make_pair(P, idx)
+    cases = [((0.75, 0.5, 1.0), (0, 0, -1), 0, np.inf), ((0.5, 0.5, 1.0), (0, 0, -1), 0, np.inf),
+             ((1.0, 0.5, 1.0), (0, 0, -1), 0, np.inf), ((0.5, 0.0, 1.0), (0, 0, -1), 0, np.inf),
+             ((0.2, 0.1, 1.0), (1, 0, 0), 0, np.inf), ((0.5, 0.2, 1.0), (0, 0, -1), 1.0, 5.0),
+             ((0.5, 0.2, 1.0), (0, 0, -1), 0.0, 1.0), ((0.5, 0.25, 5.0), (0, 0, -1), 0.0, 2.75),
+             ((0.5, 0.25, 5.0), (0, 0, -1), 2.75, 9.0), ((0.5, 0.25, 5.0), (0, 0, -1), 0.0, np.inf),
+             ((0.5, 0.2, -1.0), (0, 0, 1), 0.0, np.inf), ((0.5, 0.2, -1.0), (0, 0, 1), 1.5, np.inf)]
+    ro = np.array([[*c_[0], c_[2]] for c_ in cases], np.float32)
+    rd = np.array([[*c_[1], c_[3]] for c_ in cases], np.float32)
+    assert_hits_equal(c.trace_closest(ro, rd), o.trace_closest(ro, rd))
+    assert (c.trace_any(ro, rd) == o.trace_any(ro, rd)).all()
+
+
+def test_big_leaf_and_equal_t_ties(drt_lib):
+    """Coincident triangles: one 40-primitive leaf; the LAST tested equal-t hit wins (triangle.dart:96)."""
+    tri = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0]], np.float32)
+    P = np.tile(tri, (40, 1))
+    idx = np.arange(120, dtype=np.uint32).reshape(-1, 3)
+    o, c = make_pair(P, idx)
+    ro, rd = scenes.pack_rays(np.array([[0.6, 0.3, 1.0]], np.float32), np.array([[0.01, 0.02, -1.0]], np.float32))
+    hg, ho = c.trace_closest(ro, rd), o.trace_closest(ro, rd)
+    assert ho["prim"][0] == 39
+    assert_hits_equal(hg, ho)
+
+
+def test_empty_scene_and_zero_rays(drt_lib):
+    c = capi.Context(0)
+    c.set_triangles(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32))
+    c.build_bvh()
+    ro, rd = random_rays(100, 1)
+    h = c.trace_closest(ro, rd)
+    assert (h["prim"] == -1).all() and np.isinf(h["t"]).all()
+    assert (c.trace_any(ro, rd) == 0).all()
+    P, idx = random_soup(10, 0)
+    c.set_triangles(P, idx)
+    with pytest.raises(capi.DrtError):
+        c.trace_closest(ro, rd)  # scene changed, BVH not rebuilt
+    c.build_bvh()
+    assert c.trace_closest(ro[:0], rd[:0]).shape[0] == 0
+
+
+def test_counters_match_reference_work(drt_lib):
+    """nodes_visited / prims_tested equal the reference traversal's slab and primitive test counts."""
+    P, idx = scenes.soup(16)
+    o, c = make_pair(P, idx, order=mesh_refine_order([idx.shape[0]]))
+    ro, rd = scenes.incoherent_rays(20000)
+    c.set_counting(True)
+    hg = c.trace_closest(ro, rd)
+    cg = c.counters()
+    ho = o.trace_closest(ro, rd, nthreads=4)
+    co = o.counters()
+    assert_hits_equal(hg, ho)
+    assert cg["rays"] == co["rays"] == 20000
+    assert cg["nodes_visited"] == co["nodes_visited"]
+    assert cg["prims_tested"] == co["prims_tested"]
+    occ = c.trace_any(ro, rd)
+    cg = c.counters()
+    assert (occ == o.trace_any(ro, rd, nthreads=4)).all()
+    co = o.counters()
+    assert cg["nodes_visited"] == co["nodes_visited"] and cg["prims_tested"] == co["prims_tested"]
+    c.set_counting(False)
+
+
+def test_soup_scene_coherent_and_incoherent(drt_lib):
+    """A 127k-triangle slice of the config-2 workload, both ray sets, bit-exact."""
+    P, idx = scenes.soup(64)
+    o, c = make_pair(P, idx)
+    for ro, rd in (scenes.coherent_rays(512, 256), scenes.incoherent_rays(1 << 17)):
+        assert_hits_equal(c.trace_closest(ro, rd), o.trace_closest(ro, rd, nthreads=8))
+        assert (c.trace_any(ro, rd) == o.trace_any(ro, rd, nthreads=8)).all()
+
+
+def test_device_pointer_entry_matches_host_entry(drt_lib):
+    import torch
+    P, idx = scenes.soup(8)
+    c = capi.Context(0)
+    c.set_triangles(P, idx)
+    c.build_bvh()
+    ro, rd = scenes.incoherent_rays(1 << 15)
+    href = c.trace_closest(ro, rd)
+    dro, drd = torch.from_numpy(ro).cuda(), torch.from_numpy(rd).cuda()
+    dh = torch.empty((ro.shape[0], 4), dtype=torch.float32, device="cuda")
+    docc = torch.empty(ro.shape[0], dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    c.trace_closest_device(dro.data_ptr(), drd.data_ptr(), ro.shape[0], dh.data_ptr(), st)
+    c.trace_any_device(dro.data_ptr(), drd.data_ptr(), ro.shape[0], docc.data_ptr(), st)
+    torch.cuda.synchronize()
+    hd = dh.cpu().numpy().view(capi.HIT_DTYPE).reshape(-1)
+    assert (hd["prim"] == href["prim"]).all() and (hd["t"].view(np.uint32) == href["t"].view(np.uint32)).all()
+    assert (docc.cpu().numpy() == c.trace_any(ro, rd)).all()
