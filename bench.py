@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Benchmark of the ray-cast hot path (BASELINE.json configs[1]).
+
+A step = one pass over one batch of synthetic rays on the `soup_1m` scene (1,015,810 triangles,
+SAH BVH, maxnodeprims 4): closest-hit on 8,388,608 coherent primary rays, closest-hit on 8,388,608
+incoherent rays, any-hit (shadow) on the incoherent set.  `value` = rays of all ranks / step time with
+the rays resident in HBM; `e2e` = the same step through the host-buffer C-ABI calls
+(drt_trace_closest / drt_trace_any) from pinned host memory, H2D + kernel + D2H inside the timed
+region.  `--impl reference` times the CPU restatement of the reference path (oracle/) instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mrays/s (closest-hit + shadow)"
+N_SPHERES = 512
+COH_W, COH_H = 4096, 2048
+N_INCOH = 8_388_608
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_workload(rank: int):
+    from dartray_b200 import scenes
+    P, idx = scenes.soup(N_SPHERES)
+    coh = scenes.coherent_rays(COH_W, COH_H)
+    # each rank traces its own incoherent set (weak scaling): PCG32 seeds 2/3 on rank 0 as SURVEY §8d pins
+    inc = scenes.incoherent_rays(N_INCOH, seed_origin=2 + 16 * rank, seed_target=3 + 16 * rank)
+    return P, idx, coh, inc
+
+
+def cpu_sample(coh, inc, n_sample):
+    """Bounded sample of the step for the CPU legs: every k-th ray of each set."""
+    ks = max(1, coh[0].shape[0] // n_sample)
+    ki = max(1, inc[0].shape[0] // n_sample)
+    cs = (np.ascontiguousarray(coh[0][::ks]), np.ascontiguousarray(coh[1][::ks]))
+    is_ = (np.ascontiguousarray(inc[0][::ki]), np.ascontiguousarray(inc[1][::ki]))
+    return cs, is_
+
+
+def run_cpu_step(orc, cs, is_, threads):
+    t0 = time.perf_counter()
+    orc.trace_closest(cs[0], cs[1], nthreads=threads)
+    orc.trace_closest(is_[0], is_[1], nthreads=threads)
+    orc.trace_any(is_[0], is_[1], nthreads=threads)
+    dt = time.perf_counter() - t0
+    return (cs[0].shape[0] + 2 * is_[0].shape[0]), dt
+
+
+def config_dict(n_gpus):
+    return {
+        "workload": "soup_1m ray cast: 1,015,810-triangle procedural mesh, SAH BVH (maxnodeprims 4); per step "
+                    "8,388,608 coherent closest-hit + 8,388,608 incoherent closest-hit + 8,388,608 incoherent "
+                    "any-hit (shadow) rays per GPU",
+        "baseline_config": "BASELINE.json configs[1]",
+        "rays_per_step_per_gpu": COH_W * COH_H + 2 * N_INCOH,
+        "parallelism": f"rays sharded, BVH replicated x{n_gpus}",
+        "l2": "L2 flushed (256 MiB write) between timed steps; ray buffers (268 MB/launch) exceed the 126 MB L2",
+    }
+
+
+def reference_arm(args):
+    """CPU restatement of the reference path (oracle/), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tests.oracle_lib import Oracle
+    threads = os.cpu_count() or 1
+    P, idx, coh, inc = make_workload(0)
+    orc = Oracle()
+    orc.set_triangles(P, idx)
+    orc.build_bvh(2, 4)
+    n_sample = 1 << 18
+    cs, is_ = cpu_sample(coh, inc, n_sample)
+    for _ in range(args.warmup):
+        run_cpu_step(orc, cs, is_, threads)
+    rays = 0
+    t = 0.0
+    for _ in range(args.steps):
+        r, dt = run_cpu_step(orc, cs, is_, threads)
+        rays += r
+        t += dt
+    val = rays / t / 1e6
+    sample = f"every {coh[0].shape[0] // cs[0].shape[0]}-th ray of each set ({cs[0].shape[0]} + 2x{is_[0].shape[0]} rays/step)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample,
+                         "note": "C++ restatement of the DartRay CPU path (oracle/), not the Dart VM: no Dart SDK in the image"},
+        "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from dartray_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: dartray_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    P, idx, coh, inc = make_workload(rank)
+    ctx = capi.Context(local)
+    ctx.set_triangles(P, idx)
+    ctx.build_bvh(capi.SPLIT_SAH, 4)
+    info = ctx.bvh_info()
+
+    n_coh, n_inc = coh[0].shape[0], inc[0].shape[0]
+    d_coh = [torch.from_numpy(a).to(dev) for a in coh]
+    d_inc = [torch.from_numpy(a).to(dev) for a in inc]
+    d_hits = torch.empty((max(n_coh, n_inc), 4), dtype=torch.float32, device=dev)
+    d_occ = torch.empty(n_inc, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def launch(kind):
+        if kind == 0:
+            ctx.trace_closest_device(d_coh[0].data_ptr(), d_coh[1].data_ptr(), n_coh, d_hits.data_ptr(), stream)
+        elif kind == 1:
+            ctx.trace_closest_device(d_inc[0].data_ptr(), d_inc[1].data_ptr(), n_inc, d_hits.data_ptr(), stream)
+        else:
+            ctx.trace_any_device(d_inc[0].data_ptr(), d_inc[1].data_ptr(), n_inc, d_occ.data_ptr(), stream)
+
+    # algorithmic work of the dominant launch (incoherent closest-hit): counted by the kernel's
+    # counting variant (identical to the oracle's counters, tests/test_trace_gpu.py)
+    ctx.set_counting(True)
+    work = []
+    for kind in range(3):
+        launch(kind)
+        torch.cuda.synchronize()
+        work.append(ctx.counters())
+    ctx.set_counting(False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        for kind in range(3):
+            launch(kind)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    clocks = ClockSampler(local)
+    barrier()
+    launches0 = ctx.kernel_launches
+    clocks.start()
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)  # L2 flush, outside the per-step event brackets
+        ev[s][0].record()
+        for kind in range(3):
+            launch(kind)
+            ev[s][kind + 1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks.stop_flag.set()
+    clocks.join()
+    gpu_launches = ctx.kernel_launches - launches0
+    step_ms = [ev[s][0].elapsed_time(ev[s][3]) for s in range(args.steps)]
+    per_kind_ms = [float(np.mean([ev[s][k].elapsed_time(ev[s][k + 1]) for s in range(args.steps)])) for k in range(3)]
+    total_ms = float(sum(step_ms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    rays_per_step = n_coh + 2 * n_inc
+    value = world * rays_per_step * args.steps / (total_ms * 1e-3) / 1e6
+
+    # ---- end to end through the host-buffer C ABI (pinned host memory in, host memory out) ----
+    h_coh = [torch.from_numpy(a).pin_memory() for a in coh]
+    h_inc = [torch.from_numpy(a).pin_memory() for a in inc]
+    h_hits = torch.empty((max(n_coh, n_inc), 4), dtype=torch.float32).pin_memory()
+    h_occ = torch.empty(n_inc, dtype=torch.uint8).pin_memory()
+    hits_np = h_hits.numpy().view(capi.HIT_DTYPE).reshape(-1)
+
+    def e2e_step():
+        ctx.trace_closest(h_coh[0].numpy(), h_coh[1].numpy(), out=hits_np[:n_coh])
+        ctx.trace_closest(h_inc[0].numpy(), h_inc[1].numpy(), out=hits_np[:n_inc])
+        ctx.trace_any(h_inc[0].numpy(), h_inc[1].numpy(), out=h_occ.numpy())
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_val = world * rays_per_step * e2e_steps / float(e2e_t.item()) / 1e6
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk, pk_src = peaks()
+    w = work[1]
+    alg_bytes = 32 * w["nodes_visited"] + 36 * w["prims_tested"] + 48 * w["rays"]
+    achieved = alg_bytes / (per_kind_ms[1] * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(world),
+        "breakdown": {
+            "coherent_closest_mrays": n_coh / per_kind_ms[0] / 1e3, "incoherent_closest_mrays": n_inc / per_kind_ms[1] / 1e3,
+            "incoherent_any_mrays": n_inc / per_kind_ms[2] / 1e3, "ms": per_kind_ms,
+            "wall_s_timed_region": t_wall,
+        },
+        "roofline": {
+            "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+            "traffic": traffic, "kernel": "traceKernel<closest> on the incoherent set",
+            "algorithmic_bytes_per_launch": alg_bytes,
+            "per_ray": {"nodes_visited": w["nodes_visited"] / w["rays"], "prims_tested": w["prims_tested"] / w["rays"],
+                        "bytes": alg_bytes / w["rays"]},
+            "fp_ops_per_launch": 20 * w["nodes_visited"] + 51 * w["prims_tested"],
+            "peak_source": pk_src,
+            "note": "algorithmic bytes = 32*nodes + 36*prims + 48 per ray on the reference BVH (SURVEY 8d); the working "
+                    "set (114 MB) is L2-resident, so this can exceed the HBM copy peak",
+        },
+        "e2e": {"value": e2e_val, "unit": "Mrays/s",
+                "h2d_bytes_per_step": 32 * (n_coh + 2 * n_inc), "d2h_bytes_per_step": 16 * (n_coh + n_inc) + n_inc},
+        "gpu_launches": int(gpu_launches),
+        "clocks": clocks.summary(),
+        "bvh": {"nodes": info["n_nodes"], "device_bytes": info["device_bytes"], "build_seconds": info["build_seconds"]},
+    }
+    if not args.no_cpu_baseline:
+        from tests.oracle_lib import Oracle
+        threads = os.cpu_count() or 1
+        orc = Oracle()
+        orc.set_triangles(P, idx)
+        orc.build_bvh(2, 4)
+        cs, is_ = cpu_sample(coh, inc, 1 << 20)
+        run_cpu_step(orc, (cs[0][:4096], cs[1][:4096]), (is_[0][:4096], is_[1][:4096]), threads)
+        r, dt = run_cpu_step(orc, cs, is_, threads)
+        line["cpu_baseline"] = {
+            "value": r / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+            "sample": f"every {n_coh // cs[0].shape[0]}-th ray of each set ({r} rays, {dt:.1f} s)",
+            "note": "C++ restatement of the DartRay CPU path (oracle/), not the Dart VM: no Dart SDK in the image",
+        }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
