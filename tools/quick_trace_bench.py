@@ -1,5 +1,5 @@
 import sys, time, json
-sys.path.insert(0, '.')
+import os; sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
 import numpy as np, torch
 from dartray_b200 import capi, scenes
 ns = int(sys.argv[1]) if len(sys.argv) > 1 else 512
