@@ -21,7 +21,7 @@ HIT_DTYPE = np.dtype([("t", np.float32), ("b1", np.float32), ("b2", np.float32),
 SYMBOLS = [
     "drt_version", "drt_create", "drt_destroy", "drt_last_error", "drt_set_triangles", "drt_set_spheres",
     "drt_set_build_order", "drt_build_bvh", "drt_bvh_info_get", "drt_bvh_export", "drt_trace_closest",
-    "drt_trace_any", "drt_trace_closest_device", "drt_trace_any_device", "drt_set_counting", "drt_get_counters",
+    "drt_trace_any", "drt_trace_closest_device", "drt_trace_any_device", "drt_set_counting", "drt_get_counters", "drt_set_kernel_variant",
     "drt_last_kernel_ms", "drt_kernel_launches",
 ]
 
@@ -74,6 +74,7 @@ def load():
     L.drt_trace_closest_device.argtypes = [vp, vp, vp, u64, vp, vp]
     L.drt_trace_any_device.argtypes = [vp, vp, vp, u64, vp, vp]
     L.drt_set_counting.argtypes = [vp, i32]
+    L.drt_set_kernel_variant.argtypes = [vp, i32]
     L.drt_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.drt_last_kernel_ms.restype = C.c_double
     L.drt_last_kernel_ms.argtypes = [vp]
@@ -180,6 +181,10 @@ class Context:
 
     def trace_any_device(self, d_ro: int, d_rd: int, n: int, d_occ: int, stream: int = 0):
         self._ck(self.L.drt_trace_any_device(self.h, d_ro, d_rd, n, d_occ, stream))
+
+    def set_kernel_variant(self, variant: int):
+        """0 = FAST (default), 1 = EXACT_WALK (f64 slab test at every node)."""
+        self._ck(self.L.drt_set_kernel_variant(self.h, variant))
 
     def set_counting(self, enabled: bool):
         self._ck(self.L.drt_set_counting(self.h, 1 if enabled else 0))

@@ -67,6 +67,8 @@ struct drt_ctx {
   DevBuf<GPrim> dPrims;
   DevBuf<GSphere> dSpheres;
   DevBuf<DeviceCounters> dCounters;
+  DevBuf<unsigned long long> dNextRay;
+  int numSMs = 148;
   TraceScene ts{};
   // ray staging for host-buffer calls
   DevBuf<float4> dRayO, dRayD;
@@ -75,6 +77,7 @@ struct drt_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool counting = false;
+  bool exactWalk = false;
   double lastKernelMs = 0.0;
   uint64_t launches = 0;
 
@@ -132,7 +135,8 @@ drt_ctx* drt_create(int device_id) {
   c->device = device_id;
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
-      (e = c->dCounters.ensure(1)) != cudaSuccess) {
+      (e = c->dCounters.ensure(1)) != cudaSuccess || (e = c->dNextRay.ensure(1)) != cudaSuccess ||
+      (e = cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, device_id)) != cudaSuccess) {
     g_createError = cudaGetErrorString(e);
     delete c;
     return nullptr;
@@ -144,7 +148,7 @@ void drt_destroy(drt_ctx* c) {
   if (!c) return;
   if (c->device == DRT_DEVICE_NONE) { delete c; return; }
   cudaSetDevice(c->device);
-  c->dNodes.release(); c->dPrims.release(); c->dSpheres.release(); c->dCounters.release();
+  c->dNodes.release(); c->dPrims.release(); c->dSpheres.release(); c->dCounters.release(); c->dNextRay.release();
   c->dRayO.release(); c->dRayD.release(); c->dHits.release(); c->dOcc.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -264,6 +268,8 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
         b.bmax[a] = k == 0 ? q[a] : std::fmax(b.bmax[a], q[a]);
       }
     }
+    std::memcpy(g.wmin, b.bmin, 12);
+    std::memcpy(g.wmax, b.bmax, 12);
   }
   std::string err;
   if (!buildBvh(bounds, order, split, maxPrims, &c->bvh, &err)) return fail(c, DRT_E_INVALID, err.c_str());
@@ -353,8 +359,13 @@ static int traceDevice(drt_ctx* c, bool any, const void* o, const void* d, uint6
   if (c->device == DRT_DEVICE_NONE) return fail(c, DRT_E_NODEVICE, kNoDevice);
   if (!c->built) return fail(c, DRT_E_STATE, "drt_build_bvh must be called before tracing");
   if (n && (!o || !d || !out)) return fail(c, DRT_E_INVALID, "null ray or output buffer");
-  if (c->counting) CK(c, cudaMemsetAsync(c->dCounters.p, 0, sizeof(DeviceCounters), st));
-  CK(c, launchTrace(c->ts, any, c->counting, o, d, n, out, c->dCounters.p, st));
+  if (c->counting || c->exactWalk) {
+    // reference-walk kernel: the slab test in f64 for every node; also the counting variant
+    if (c->counting) CK(c, cudaMemsetAsync(c->dCounters.p, 0, sizeof(DeviceCounters), st));
+    CK(c, launchTrace(c->ts, any, c->counting, o, d, n, out, c->dCounters.p, st));
+  } else {
+    CK(c, launchTraceFast(c->ts, any, o, d, n, out, c->dNextRay.p, c->numSMs, st));
+  }
   if (n) c->launches++;
   return DRT_OK;
 }
@@ -404,6 +415,13 @@ int drt_trace_any_device(drt_ctx* c, const void* o, const void* d, uint64_t n, v
 int drt_set_counting(drt_ctx* c, int enabled) {
   if (!c) return DRT_E_INVALID;
   c->counting = enabled != 0;
+  return DRT_OK;
+}
+
+int drt_set_kernel_variant(drt_ctx* c, int variant) {
+  if (!c) return DRT_E_INVALID;
+  if (variant != DRT_KERNEL_FAST && variant != DRT_KERNEL_EXACT_WALK) return fail(c, DRT_E_INVALID, "unknown kernel variant");
+  c->exactWalk = variant == DRT_KERNEL_EXACT_WALK;
   return DRT_OK;
 }
 

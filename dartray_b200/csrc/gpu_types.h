@@ -56,6 +56,8 @@ struct alignas(16) GSphere {
   float o2w[12];
   float o2wRow3[4];
   double radius, zmin, zmax, phiMax, thetaMin, thetaMax;
+  float wmin[3], wmax[3];  // world bound (sphere.dart:34-37 + shape.dart:38-40), = the leaf box of a 1-sphere leaf
+  float pad_[2];
 };
 
 struct TraceScene {

@@ -1,0 +1,177 @@
+// Device helpers shared by the traversal kernels: the reference's slab test, triangle and sphere
+// tests restated op for op (see trace_kernels.cu header for the arithmetic contract).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <cstdint>
+
+#include "gpu_types.h"
+
+namespace drt {
+
+#define DRT_STACK 64  // bvh_accel.dart:120 — the reference's todo stack has 64 entries
+
+struct RayState {
+  double ox, oy, oz;     // ray.origin (float32 values widened)
+  double dx, dy, dz;     // ray.direction
+  double ix, iy, iz;     // invDir: 1.0/d evaluated in f64, then ROUNDED TO FLOAT32 (bvh_accel.dart:109-111)
+  double mint, maxt;     // ray.minDistance / ray.maxDistance (f64 in the reference, ray.dart:34-36)
+  int negx, negy, negz;  // dirIsNeg (bvh_accel.dart:113-115)
+};
+
+// bvh_accel.dart:439-470 without the final ray-interval comparison: returns whether the three
+// slabs overlap and the [tmin, tmax] the reference would compare against the ray interval.
+static __device__ __forceinline__ bool slabs(const RayState& r, float lox, float loy, float loz, float hix, float hiy,
+                                      float hiz, double* tminOut, double* tmaxOut) {
+  double tmin = ((double)(r.negx ? hix : lox) - r.ox) * r.ix;
+  double tmax = ((double)(r.negx ? lox : hix) - r.ox) * r.ix;
+  double tymin = ((double)(r.negy ? hiy : loy) - r.oy) * r.iy;
+  double tymax = ((double)(r.negy ? loy : hiy) - r.oy) * r.iy;
+  if ((tmin > tymax) || (tymin > tmax)) return false;
+  if (tymin > tmin) tmin = tymin;
+  if (tymax < tmax) tmax = tymax;
+  double tzmin = ((double)(r.negz ? hiz : loz) - r.oz) * r.iz;
+  double tzmax = ((double)(r.negz ? loz : hiz) - r.oz) * r.iz;
+  if ((tmin > tzmax) || (tzmin > tmax)) return false;
+  if (tzmin > tmin) tmin = tzmin;
+  if (tzmax < tmax) tmax = tzmax;
+  *tminOut = tmin;
+  *tmaxOut = tmax;
+  return true;
+}
+
+struct HitState {
+  double t, b1, b2;
+  int prim;
+};
+
+// triangle.dart:52-98, all f64 on the float32 vertices; updates r.maxt like
+// geometric_primitive.dart:59.
+static __device__ __forceinline__ bool triangleClosest(RayState& r, const float4 q0, const float4 q1, const float4 q2,
+                                                HitState* h) {
+  double p1x = q0.x, p1y = q0.y, p1z = q0.z;
+  double e1x = (double)q1.x - p1x, e1y = (double)q1.y - p1y, e1z = (double)q1.z - p1z;
+  double e2x = (double)q2.x - p1x, e2y = (double)q2.y - p1y, e2z = (double)q2.z - p1z;
+  double s1x = (r.dy * e2z) - (r.dz * e2y);
+  double s1y = (r.dz * e2x) - (r.dx * e2z);
+  double s1z = (r.dx * e2y) - (r.dy * e2x);
+  double divisor = (s1x * e1x) + (s1y * e1y) + (s1z * e1z);
+  if (divisor == 0.0) return false;
+  double invDivisor = 1.0 / divisor;
+  double sx = r.ox - p1x, sy = r.oy - p1y, sz = r.oz - p1z;
+  double b1 = (sx * s1x + sy * s1y + sz * s1z) * invDivisor;
+  if (b1 < 0.0 || b1 > 1.0) return false;
+  double s2x = (sy * e1z) - (sz * e1y);
+  double s2y = (sz * e1x) - (sx * e1z);
+  double s2z = (sx * e1y) - (sy * e1x);
+  double b2 = ((r.dx * s2x) + (r.dy * s2y) + (r.dz * s2z)) * invDivisor;
+  if (b2 < 0.0 || b1 + b2 > 1.0) return false;
+  double t = (e2x * s2x + e2y * s2y + e2z * s2z) * invDivisor;
+  if (t < r.mint || t > r.maxt) return false;
+  h->t = t;
+  h->b1 = b1;
+  h->b2 = b2;
+  h->prim = __float_as_int(q0.w);
+  r.maxt = t;
+  return true;
+}
+
+// Rounds an f64 expression to float32 and widens it again: what constructing a Dart
+// Vector/Point (Float32List storage) does to each component.
+static __device__ __forceinline__ double rf(double v) { return (double)__double2float_rn(v); }
+
+// triangle.dart:162-194: e1, e2, s1, s, s2 are Vectors, i.e. float32-rounded.
+static __device__ __forceinline__ bool triangleAny(const RayState& r, const float4 q0, const float4 q1, const float4 q2) {
+  double p1x = q0.x, p1y = q0.y, p1z = q0.z;
+  double e1x = rf((double)q1.x - p1x), e1y = rf((double)q1.y - p1y), e1z = rf((double)q1.z - p1z);
+  double e2x = rf((double)q2.x - p1x), e2y = rf((double)q2.y - p1y), e2z = rf((double)q2.z - p1z);
+  double s1x = rf((r.dy * e2z) - (r.dz * e2y));
+  double s1y = rf((r.dz * e2x) - (r.dx * e2z));
+  double s1z = rf((r.dx * e2y) - (r.dy * e2x));
+  double divisor = s1x * e1x + s1y * e1y + s1z * e1z;
+  if (divisor == 0.0) return false;
+  double invDivisor = 1.0 / divisor;
+  double sx = rf(r.ox - p1x), sy = rf(r.oy - p1y), sz = rf(r.oz - p1z);
+  double b1 = (sx * s1x + sy * s1y + sz * s1z) * invDivisor;
+  if (b1 < 0.0 || b1 > 1.0) return false;
+  double s2x = rf((sy * e1z) - (sz * e1y));
+  double s2y = rf((sz * e1x) - (sx * e1z));
+  double s2z = rf((sx * e1y) - (sy * e1x));
+  double b2 = (r.dx * s2x + r.dy * s2y + r.dz * s2z) * invDivisor;
+  if (b2 < 0.0 || b1 + b2 > 1.0) return false;
+  double t = (e2x * s2x + e2y * s2y + e2z * s2z) * invDivisor;
+  if (t < r.mint || t > r.maxt) return false;
+  return true;
+}
+
+// sphere.dart:39-116 / :169-241.  `shadow` selects intersectP, whose `thit == t1` comparison is
+// between a double and a List and therefore never true (sphere.dart:210).
+static __device__ bool sphereTest(const GSphere& s, const RayState& r, bool shadow, double* thitOut, double* uOut,
+                           double* vOut) {
+  // transform.dart:110-145,180-195: object-space origin/direction are float32 Points/Vectors
+  const float* m = s.w2o;
+  double ox = rf((double)m[0] * r.ox + (double)m[1] * r.oy + (double)m[2] * r.oz + (double)m[3]);
+  double oy = rf((double)m[4] * r.ox + (double)m[5] * r.oy + (double)m[6] * r.oz + (double)m[7]);
+  double oz = rf((double)m[8] * r.ox + (double)m[9] * r.oy + (double)m[10] * r.oz + (double)m[11]);
+  double w = (double)s.w2oRow3[0] * r.ox + (double)s.w2oRow3[1] * r.oy + (double)s.w2oRow3[2] * r.oz +
+             (double)s.w2oRow3[3];
+  if (w != 1.0) { ox = rf(ox / w); oy = rf(oy / w); oz = rf(oz / w); }
+  double dx = rf((double)m[0] * r.dx + (double)m[1] * r.dy + (double)m[2] * r.dz);
+  double dy = rf((double)m[4] * r.dx + (double)m[5] * r.dy + (double)m[6] * r.dz);
+  double dz = rf((double)m[8] * r.dx + (double)m[9] * r.dy + (double)m[10] * r.dz);
+  double A = dx * dx + dy * dy + dz * dz;
+  double B = 2 * (dx * ox + dy * oy + dz * oz);
+  double C = ox * ox + oy * oy + oz * oz - s.radius * s.radius;
+  // common.dart:140-167
+  double discrim = B * B - 4.0 * A * C;
+  if (discrim < 0.0) return false;
+  double rootDiscrim = sqrt(discrim);
+  double q = (B < 0.0) ? -0.5 * (B - rootDiscrim) : -0.5 * (B + rootDiscrim);
+  double t0 = q / A, t1 = C / q;
+  if (t0 > t1) { double tt = t0; t0 = t1; t1 = tt; }
+  if (t0 > r.maxt || t1 < r.mint) return false;
+  double thit = t0;
+  if (thit < r.mint) {
+    thit = t1;
+    if (thit > r.maxt) return false;
+  }
+  // ray.pointAt: origin + (direction * t), two float32 roundings (ray.dart:70-71)
+  double px = rf(ox + rf(dx * thit)), py = rf(oy + rf(dy * thit)), pz = rf(oz + rf(dz * thit));
+  if (px == 0.0 && py == 0.0) px = rf(1.0e-5 * s.radius);
+  double phi = atan2(py, px);
+  if (phi < 0.0) phi += 2.0 * 3.141592653589793;
+  if ((s.zmin > -s.radius && pz < s.zmin) || (s.zmax < s.radius && pz > s.zmax) || phi > s.phiMax) {
+    if (!shadow && thit == t1) return false;
+    if (t1 > r.maxt) return false;
+    thit = t1;
+    px = rf(ox + rf(dx * thit)); py = rf(oy + rf(dy * thit)); pz = rf(oz + rf(dz * thit));
+    if (px == 0.0 && py == 0.0) px = rf(1.0e-5 * s.radius);
+    phi = atan2(py, px);
+    if (phi < 0.0) phi += 2.0 * 3.141592653589793;
+    if ((s.zmin > -s.radius && pz < s.zmin) || (s.zmax < s.radius && pz > s.zmax) || phi > s.phiMax) return false;
+  }
+  *thitOut = thit;
+  if (uOut) {
+    double cz = pz / s.radius;
+    cz = cz < -1.0 ? -1.0 : (cz > 1.0 ? 1.0 : cz);
+    double theta = acos(cz);
+    *uOut = phi / s.phiMax;
+    *vOut = (theta - s.thetaMin) / (s.thetaMax - s.thetaMin);
+  }
+  return true;
+}
+
+static __device__ __forceinline__ void initRay(RayState& r, const float4 o, const float4 d) {
+  r.ox = o.x; r.oy = o.y; r.oz = o.z;
+  r.dx = d.x; r.dy = d.y; r.dz = d.z;
+  r.mint = o.w;
+  r.maxt = d.w;
+  float ixf = __double2float_rn(1.0 / r.dx), iyf = __double2float_rn(1.0 / r.dy), izf = __double2float_rn(1.0 / r.dz);
+  r.ix = ixf; r.iy = iyf; r.iz = izf;
+  r.negx = ixf < 0.f; r.negy = iyf < 0.f; r.negz = izf < 0.f;
+}
+
+static __device__ __forceinline__ float4 ldg4(const void* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+}  // namespace drt

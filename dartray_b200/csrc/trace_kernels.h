@@ -17,4 +17,9 @@ struct drt_hit_rec {  // == drt_hit of include/drt.h
 cudaError_t launchTrace(const TraceScene& sc, bool any, bool count, const void* rayO, const void* rayD, uint64_t n,
                         void* out, DeviceCounters* counters, cudaStream_t stream);
 
+// Production path: persistent warps, while-while traversal, float32-filtered slab test with exact
+// float64 fallback (trace_fast.cu).  `nextRay` is a device counter owned by the context.
+cudaError_t launchTraceFast(const TraceScene& sc, bool any, const void* rayO, const void* rayD, uint64_t n, void* out,
+                            unsigned long long* nextRay, int numSMs, cudaStream_t stream);
+
 }  // namespace drt

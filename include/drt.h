@@ -132,7 +132,15 @@ int drt_trace_closest_device(drt_ctx* ctx, const void* d_ray_o_tmin, const void*
 int drt_trace_any_device(drt_ctx* ctx, const void* d_ray_o_tmin, const void* d_ray_d_tmax, uint64_t n,
                          void* d_occluded, void* cuda_stream);
 
-/* When enabled the trace kernels also count slab and primitive tests (slower; off by default). */
+/* Both kernel variants make every decision with the reference's arithmetic and return identical
+ * results.  FAST (default): persistent warps, float32-filtered slab test with exact float64
+ * fallback.  EXACT_WALK: one thread per ray, float64 slab test at every node — the literal
+ * reference walk, kept as a cross-check and as the counting kernel. */
+enum { DRT_KERNEL_FAST = 0, DRT_KERNEL_EXACT_WALK = 1 };
+int drt_set_kernel_variant(drt_ctx* ctx, int variant);
+
+/* When enabled the trace kernels also count slab and primitive tests (uses the EXACT_WALK kernel;
+ * slower; off by default). */
 int drt_set_counting(drt_ctx* ctx, int enabled);
 int drt_get_counters(drt_ctx* ctx, drt_counters* out);
 

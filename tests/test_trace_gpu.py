@@ -12,9 +12,15 @@ from tests.util import mesh_refine_order, random_rays, random_soup, translate
 pytestmark = pytest.mark.gpu
 
 
-def make_pair(P, idx, spheres=None, order=None, split=2, maxprims=4):
+@pytest.fixture(params=[0, 1], ids=["fast", "exact_walk"])
+def variant(request):
+    return request.param
+
+
+def make_pair(P, idx, spheres=None, order=None, split=2, maxprims=4, variant=0):
     o = Oracle()
     c = capi.Context(0)
+    c.set_kernel_variant(variant)
     for x in (o, c):
         x.set_triangles(P, idx)
         if spheres is not None:
@@ -31,9 +37,9 @@ def assert_hits_equal(hg, ho):
 
 
 @pytest.mark.parametrize("split", [0, 1, 2])
-def test_random_soup_closest_and_any(drt_lib, split):
+def test_random_soup_closest_and_any(drt_lib, split, variant):
     P, idx = random_soup(5000, seed=split)
-    o, c = make_pair(P, idx, split=split)
+    o, c = make_pair(P, idx, split=split, variant=variant)
     ro, rd = random_rays(50000, seed=100 + split)
     assert_hits_equal(c.trace_closest(ro, rd), o.trace_closest(ro, rd, nthreads=8))
     assert (c.trace_any(ro, rd) == o.trace_any(ro, rd, nthreads=8)).all()
@@ -43,12 +49,12 @@ def test_random_soup_closest_and_any(drt_lib, split):
     assert (c.trace_any(ro, rd) == o.trace_any(ro, rd, nthreads=8)).all()
 
 
-def test_mixed_triangles_and_spheres(drt_lib):
+def test_mixed_triangles_and_spheres(drt_lib, variant):
     P, idx = random_soup(800, seed=5)
     mats = [translate(0.3, 0.1, -0.2), translate(-0.4, 0.2, 0.5), translate(0.0, -0.5, 0.0)]
     sph = (np.stack([m[0] for m in mats]), np.stack([m[1] for m in mats]),
            [[0.25, -0.25, 0.25, 360.0], [0.4, -0.1, 0.3, 200.0], [0.3, -0.3, 0.1, 360.0]])
-    o, c = make_pair(P, idx, sph, mesh_refine_order([300, 500], 3))
+    o, c = make_pair(P, idx, sph, mesh_refine_order([300, 500], 3), variant=variant)
     ro, rd = random_rays(40000, seed=6)
     hg, ho = c.trace_closest(ro, rd), o.trace_closest(ro, rd, nthreads=8)
     assert (hg["prim"] == ho["prim"]).all()
@@ -61,12 +67,12 @@ def test_mixed_triangles_and_spheres(drt_lib):
     assert (c.trace_any(ro, rd) == o.trace_any(ro, rd, nthreads=8)).all()
 
 
-def test_known_answer_edge_cases(drt_lib):
+def test_known_answer_edge_cases(drt_lib, variant):
     """Same quirks the oracle test pins: inclusive triangle edges, strict flat-box culling and the
     NaN behaviour of the slab test for axis-parallel rays (bvh_accel.dart:441-471)."""
     P = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 0, 2], [1, 0, 2], [1, 1, 3]], np.float32)
     idx = np.array([[0, 1, 2], [3, 4, 5]], np.uint32)
-    o, c = make_pair(P, idx)
+    o, c = make_pair(P, idx, variant=variant)
     cases = [((0.75, 0.5, 1.0), (0, 0, -1), 0, np.inf), ((0.5, 0.5, 1.0), (0, 0, -1), 0, np.inf),
              ((1.0, 0.5, 1.0), (0, 0, -1), 0, np.inf), ((0.5, 0.0, 1.0), (0, 0, -1), 0, np.inf),
              ((0.2, 0.1, 1.0), (1, 0, 0), 0, np.inf), ((0.5, 0.2, 1.0), (0, 0, -1), 1.0, 5.0),
@@ -79,12 +85,12 @@ def test_known_answer_edge_cases(drt_lib):
     assert (c.trace_any(ro, rd) == o.trace_any(ro, rd)).all()
 
 
-def test_big_leaf_and_equal_t_ties(drt_lib):
+def test_big_leaf_and_equal_t_ties(drt_lib, variant):
     """Coincident triangles: one 40-primitive leaf; the LAST tested equal-t hit wins (triangle.dart:96)."""
     tri = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0]], np.float32)
     P = np.tile(tri, (40, 1))
     idx = np.arange(120, dtype=np.uint32).reshape(-1, 3)
-    o, c = make_pair(P, idx)
+    o, c = make_pair(P, idx, variant=variant)
     ro, rd = scenes.pack_rays(np.array([[0.6, 0.3, 1.0]], np.float32), np.array([[0.01, 0.02, -1.0]], np.float32))
     hg, ho = c.trace_closest(ro, rd), o.trace_closest(ro, rd)
     assert ho["prim"][0] == 39
@@ -129,10 +135,48 @@ def test_counters_match_reference_work(drt_lib):
     c.set_counting(False)
 
 
-def test_soup_scene_coherent_and_incoherent(drt_lib):
+def test_axis_aligned_walls_and_rays(drt_lib, variant):
+    """Cornell-style flat quads: leaf boxes are flat, so after the first triangle of a wall is hit the
+    sibling's box entry distance equals ray.maxDistance up to rounding — the float32 filter cannot
+    decide and the exact float64 path must give the reference's answer.  Also axis-parallel rays
+    (zero direction components: inf / NaN in the slab test)."""
+    q = lambda a, b, c_, d: [a, b, c_, d]
+    quads = [q((-1, -1, 1), (1, -1, 1), (1, 1, 1), (-1, 1, 1)),      # back wall z=1
+             q((-1, -1, -1), (1, -1, -1), (1, -1, 1), (-1, -1, 1)),  # floor y=-1
+             q((-1, 1, -1), (1, 1, -1), (1, 1, 1), (-1, 1, 1)),      # ceiling
+             q((-1, -1, -1), (-1, 1, -1), (-1, 1, 1), (-1, -1, 1)),  # left
+             q((1, -1, -1), (1, 1, -1), (1, 1, 1), (1, -1, 1))]      # right
+    P = np.array([v for qd in quads for v in qd], np.float32)
+    idx = np.array([[4 * k, 4 * k + 1, 4 * k + 2] for k in range(5)] + [[4 * k, 4 * k + 2, 4 * k + 3] for k in range(5)],
+                   np.uint32)
+    o, c = make_pair(P, idx, variant=variant)
+    rng = np.random.default_rng(3)
+    n = 60000
+    org = np.zeros((n, 3), np.float32)
+    org[:, 2] = -3.0
+    d = np.stack([rng.uniform(-0.4, 0.4, n), rng.uniform(-0.4, 0.4, n), np.ones(n)], axis=1)
+    d[:2000, 0] = 0.0          # axis-parallel in x
+    d[2000:4000, :2] = 0.0     # straight down the z axis
+    d[4000:6000, 1] = d[4000:6000, 0]  # exactly on the quad diagonals x == y
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    d[2000:4000] = (0, 0, 1)
+    ro, rd = scenes.pack_rays(org, d)
+    assert_hits_equal(c.trace_closest(ro, rd), o.trace_closest(ro, rd, nthreads=8))
+    assert (c.trace_any(ro, rd) == o.trace_any(ro, rd, nthreads=8)).all()
+    # rays starting ON a wall (secondary-ray style, tmin = 1e-3)
+    org2 = np.stack([rng.uniform(-1, 1, n), np.full(n, -1.0), rng.uniform(-1, 1, n)], axis=1).astype(np.float32)
+    d2 = rng.normal(size=(n, 3))
+    d2[:, 1] = np.abs(d2[:, 1])
+    d2 = (d2 / np.linalg.norm(d2, axis=1, keepdims=True)).astype(np.float32)
+    ro, rd = scenes.pack_rays(org2, d2, 1e-3, np.inf)
+    assert_hits_equal(c.trace_closest(ro, rd), o.trace_closest(ro, rd, nthreads=8))
+    assert (c.trace_any(ro, rd) == o.trace_any(ro, rd, nthreads=8)).all()
+
+
+def test_soup_scene_coherent_and_incoherent(drt_lib, variant):
     """A 127k-triangle slice of the config-2 workload, both ray sets, bit-exact."""
     P, idx = scenes.soup(64)
-    o, c = make_pair(P, idx)
+    o, c = make_pair(P, idx, variant=variant)
     for ro, rd in (scenes.coherent_rays(512, 256), scenes.incoherent_rays(1 << 17)):
         assert_hits_equal(c.trace_closest(ro, rd), o.trace_closest(ro, rd, nthreads=8))
         assert (c.trace_any(ro, rd) == o.trace_any(ro, rd, nthreads=8)).all()
