@@ -27,33 +27,26 @@ namespace drt {
 #define FULL_MASK 0xffffffffu
 #define RAY_CHUNK 256  // rays a warp reserves per atomicAdd on the global ray counter
 
+#ifndef DRT_MIN_BLOCKS
+#define DRT_MIN_BLOCKS 5
+#endif
+#ifndef DRT_LEAF_BATCH
+#define DRT_LEAF_BATCH 16  // lanes holding an untested leaf before the warp runs the exact leaf phase
+#endif
+
+// Hot per-ray state, kept in registers (never address-taken: the exact helpers take it by value).
 struct FastRay {
   float ox, oy, oz;  // ray.origin
-  float dx, dy, dz;  // ray.direction
   float ix, iy, iz;  // invDir: (float)(1.0 / (double)d), bvh_accel.dart:109-111
-  double mint, maxt;
   float mintLo, mintHi, maxtLo, maxtHi;  // float32 brackets of the f64 interval ends
-  bool slow;                             // non-finite origin / invDir: exact path for every box
+  double mint, maxt;
+  unsigned negMask;  // bit a = invDir[a] < 0 (dirIsNeg, bvh_accel.dart:113-115); bit 3 = "slow" ray
 };
 
 struct StackEntry {
   int32_t ref;
   float tmin;  // float32 image of the box entry distance (exact value re-derived when it matters)
 };
-
-static __device__ __forceinline__ void widen(const FastRay& f, RayState& r) {
-  r.ox = f.ox; r.oy = f.oy; r.oz = f.oz;
-  r.dx = f.dx; r.dy = f.dy; r.dz = f.dz;
-  r.ix = f.ix; r.iy = f.iy; r.iz = f.iz;
-  r.mint = f.mint; r.maxt = f.maxt;
-  r.negx = f.ix < 0.f; r.negy = f.iy < 0.f; r.negz = f.iz < 0.f;
-}
-
-static __device__ __forceinline__ void setMaxt(FastRay& f, double t) {
-  f.maxt = t;
-  f.maxtLo = __double2float_rd(t);
-  f.maxtHi = __double2float_ru(t);
-}
 
 #define DRT_EPS 2.384185791015625e-07f  // 2^-22
 #define DRT_TINY 1.0e-37f
@@ -74,23 +67,31 @@ static __device__ __forceinline__ int slabFilter(const FastRay& r, float lox, fl
   return pass ? 1 : (fail ? 0 : 2);
 }
 
-// Exact evaluation of one box (rare).  Returns the reference's decision; *tminOut = f64 tmin.
-static __device__ __noinline__ bool slabExact(const FastRay& f, float lox, float loy, float loz, float hix, float hiy,
-                                              float hiz, double* tminOut) {
+// Exact evaluation of one box (rare), everything passed BY VALUE so the caller's ray state stays in
+// registers.  Returns the reference's decision (bvh_accel.dart:439-472); *tminOut = float32(tmin).
+static __device__ __noinline__ bool slabExact(float ox, float oy, float oz, float ix, float iy, float iz, double mint,
+                                              double maxt, float lox, float loy, float loz, float hix, float hiy,
+                                              float hiz, float* tminOut) {
   RayState r;
-  widen(f, r);
+  r.ox = ox; r.oy = oy; r.oz = oz;
+  r.ix = ix; r.iy = iy; r.iz = iz;
+  r.negx = ix < 0.f; r.negy = iy < 0.f; r.negz = iz < 0.f;
   double tmin, tmax;
   if (!slabs(r, lox, loy, loz, hix, hiy, hiz, &tmin, &tmax)) return false;
-  *tminOut = tmin;
-  return (tmin < r.maxt) && (tmax > r.mint);
+  *tminOut = __double2float_rn(tmin);
+  return (tmin < maxt) && (tmax > mint);
 }
+#define SLAB_EXACT(r, lox, loy, loz, hix, hiy, hiz, tout) \
+  slabExact((r).ox, (r).oy, (r).oz, (r).ix, (r).iy, (r).iz, (r).mint, (r).maxt, lox, loy, loz, hix, hiy, hiz, tout)
 
 // Exact re-test of a popped LEAF whose stored entry distance is too close to maxDistance to call:
 // rebuild the leaf box from its primitives (triangle.dart:39-42 / sphere world bound) and evaluate
-// `tmin < ray.maxDistance` exactly as the reference does when it visits the leaf node.
-static __device__ __noinline__ bool leafStillReachable(const TraceScene& sc, const FastRay& f, int32_t ref) {
+// the slab test exactly as the reference does when it visits the leaf node.
+static __device__ __noinline__ bool leafStillReachable(const GPrim* prims, const GSphere* spheres, float ox, float oy,
+                                                       float oz, float ix, float iy, float iz, double mint, double maxt,
+                                                       int32_t ref) {
   uint32_t off = refLeafOffset(ref), cnt = refLeafCountField(ref);
-  const GPrim* pr = sc.prims + off;
+  const GPrim* pr = prims + off;
   if (cnt == 15u) cnt = (uint32_t)__ldg(&pr->leafCount);
   float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
   for (uint32_t k = 0; k < cnt; ++k) {
@@ -101,37 +102,37 @@ static __device__ __noinline__ bool leafStillReachable(const TraceScene& sc, con
       lo[1] = fminf(lo[1], fminf(a.y, fminf(b.y, c.y))); hi[1] = fmaxf(hi[1], fmaxf(a.y, fmaxf(b.y, c.y)));
       lo[2] = fminf(lo[2], fminf(a.z, fminf(b.z, c.z))); hi[2] = fmaxf(hi[2], fmaxf(a.z, fmaxf(b.z, c.z)));
     } else {
-      const GSphere& s = sc.spheres[kind >> 1];
+      const GSphere& s = spheres[kind >> 1];
       for (int x = 0; x < 3; ++x) { lo[x] = fminf(lo[x], s.wmin[x]); hi[x] = fmaxf(hi[x], s.wmax[x]); }
     }
   }
-  double tmin;
-  return slabExact(f, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], &tmin);
+  float t;
+  return slabExact(ox, oy, oz, ix, iy, iz, mint, maxt, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], &t);
 }
 
 // Pops until an entry survives the reference's pop-time test `tmin < ray.maxDistance`
 // (bvh_accel.dart:139-143,156-159 + :471).  Interior entries inside the undecidable band are
 // entered (their children are culled by the same comparison); leaf entries in the
 // band are re-tested exactly.
-static __device__ __forceinline__ bool popNext(const TraceScene& sc, const FastRay& r, const StackEntry* stack, int& sp,
-                                               int32_t& cur) {
-  while (sp > 0) {
-    --sp;
-    int32_t ref = stack[sp].ref;
-    float t = stack[sp].tmin;
-    float dt = fmaf(DRT_EPS, fabsf(t), DRT_TINY);
-    bool take = (t + dt) < r.maxtLo;
-    if (!take && !((t - dt) >= r.maxtHi)) take = ref >= 0 ? true : leafStillReachable(sc, r, ref);
-    if (take) {
-      cur = ref;
-      return true;
-    }
-  }
-  return false;
-}
+#define POP_NEXT(ok)                                                                                       \
+  do {                                                                                                     \
+    ok = false;                                                                                            \
+    while (sp > 0) {                                                                                       \
+      --sp;                                                                                                \
+      int32_t ref_ = stack[sp].ref;                                                                        \
+      float t_ = stack[sp].tmin;                                                                           \
+      float dt_ = fmaf(DRT_EPS, fabsf(t_), DRT_TINY);                                                      \
+      bool take_ = (t_ + dt_) < r.maxtLo;                                                                  \
+      if (!take_ && !((t_ - dt_) >= r.maxtHi))                                                             \
+        take_ = ref_ >= 0 ? true                                                                           \
+                          : leafStillReachable(sc.prims, sc.spheres, r.ox, r.oy, r.oz, r.ix, r.iy, r.iz,   \
+                                               r.mint, r.maxt, ref_);                                      \
+      if (take_) { cur = ref_; ok = true; break; }                                                         \
+    }                                                                                                      \
+  } while (0)
 
 template <bool ANY>
-__global__ void __launch_bounds__(128, 4) traceFastKernel(TraceScene sc, const float4* __restrict__ rayO,
+__global__ void __launch_bounds__(128, DRT_MIN_BLOCKS) traceFastKernel(TraceScene sc, const float4* __restrict__ rayO,
                                                           const float4* __restrict__ rayD, uint64_t n,
                                                           float4* __restrict__ hits, uint8_t* __restrict__ occluded,
                                                           unsigned long long* __restrict__ nextRay) {
@@ -149,11 +150,13 @@ __global__ void __launch_bounds__(128, 4) traceFastKernel(TraceScene sc, const f
   int hprim = -1;
   bool found = false;
 
-  auto retire = [&]() {
-    alive = false;
-    if (ANY) occluded[rayIdx] = found ? 1 : 0;
-    else hits[rayIdx] = make_float4(found ? __double2float_rn(r.maxt) : CUDART_INF_F, hb1, hb2, __int_as_float(hprim));
-  };
+#define RETIRE()                                                                                             \
+  do {                                                                                                       \
+    alive = false;                                                                                           \
+    if (ANY) occluded[rayIdx] = found ? 1 : 0;                                                               \
+    else hits[rayIdx] = make_float4(found ? __double2float_rn(r.maxt) : CUDART_INF_F, hb1, hb2,              \
+                                    __int_as_float(hprim));                                                  \
+  } while (0)
 
   for (;;) {
     // ---- refill idle lanes from the warp's chunk ----------------------------------------------
@@ -177,26 +180,27 @@ __global__ void __launch_bounds__(128, 4) traceFastKernel(TraceScene sc, const f
         rayIdx = warpNext + rank;
         float4 o = __ldg(rayO + rayIdx), d = __ldg(rayD + rayIdx);
         r.ox = o.x; r.oy = o.y; r.oz = o.z;
-        r.dx = d.x; r.dy = d.y; r.dz = d.z;
         r.ix = __double2float_rn(1.0 / (double)d.x);
         r.iy = __double2float_rn(1.0 / (double)d.y);
         r.iz = __double2float_rn(1.0 / (double)d.z);
         r.mint = o.w;
         r.mintLo = r.mintHi = o.w;
-        setMaxt(r, (double)d.w);
+        r.maxt = d.w;
+        r.maxtLo = r.maxtHi = d.w;
         // any inf/NaN among origin / invDir components -> every box of this ray takes the exact path
-        r.slow = !(fabsf(r.ox) <= 3.0e38f) || !(fabsf(r.oy) <= 3.0e38f) || !(fabsf(r.oz) <= 3.0e38f) ||
-                 !(fabsf(r.ix) <= 3.0e38f) || !(fabsf(r.iy) <= 3.0e38f) || !(fabsf(r.iz) <= 3.0e38f);
+        bool slow = !(fabsf(r.ox) <= 3.0e38f) || !(fabsf(r.oy) <= 3.0e38f) || !(fabsf(r.oz) <= 3.0e38f) ||
+                    !(fabsf(r.ix) <= 3.0e38f) || !(fabsf(r.iy) <= 3.0e38f) || !(fabsf(r.iz) <= 3.0e38f);
+        r.negMask = (r.ix < 0.f ? 1u : 0u) | (r.iy < 0.f ? 2u : 0u) | (r.iz < 0.f ? 4u : 0u) | (slow ? 8u : 0u);
         sp = 0;
         found = false;
         hprim = -1;
         hb1 = hb2 = 0.f;
         alive = true;
         // reference node 0: its own box is tested first (bvh_accel.dart:123-125)
-        double t0 = 0.0;
-        if (sc.empty || !slabExact(r, sc.rootMin[0], sc.rootMin[1], sc.rootMin[2], sc.rootMax[0], sc.rootMax[1],
-                                   sc.rootMax[2], &t0))
-          retire();
+        float t0;
+        if (sc.empty || !SLAB_EXACT(r, sc.rootMin[0], sc.rootMin[1], sc.rootMin[2], sc.rootMax[0], sc.rootMax[1],
+                                    sc.rootMax[2], &t0))
+          RETIRE();
         else
           cur = sc.rootRef;
       }
@@ -204,27 +208,19 @@ __global__ void __launch_bounds__(128, 4) traceFastKernel(TraceScene sc, const f
       if (exhausted && __all_sync(FULL_MASK, !alive)) break;
     }
 
-    // ---- interior phase: walk until this lane holds a leaf (or runs out of nodes) -------------
-    while (alive && cur >= 0) {
+    // ---- one interior step for every lane that holds an interior node ---------------------------
+    if (alive && cur >= 0) {
       const GNode* nd = sc.nodes + cur;
       float4 q0 = ldg4(&nd->c0min[0]), q1 = ldg4(&nd->c0max[1]), q2 = ldg4(&nd->c1min[2]);
       int4 q3 = __ldg(reinterpret_cast<const int4*>(&nd->ref0));
       float tm0 = 0.f, tm1 = 0.f;
-      int c0 = r.slow ? 2 : slabFilter(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tm0);
-      int c1 = r.slow ? 2 : slabFilter(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tm1);
-      if (c0 == 2) {
-        double t = 0.0;
-        c0 = slabExact(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &t) ? 1 : 0;
-        tm0 = __double2float_rn(t);
-      }
-      if (c1 == 2) {
-        double t = 0.0;
-        c1 = slabExact(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &t) ? 1 : 0;
-        tm1 = __double2float_rn(t);
-      }
+      const bool slow = (r.negMask & 8u) != 0;
+      int c0 = slow ? 2 : slabFilter(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tm0);
+      int c1 = slow ? 2 : slabFilter(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tm1);
+      if (c0 == 2) c0 = SLAB_EXACT(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tm0) ? 1 : 0;
+      if (c1 == 2) c1 = SLAB_EXACT(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tm1) ? 1 : 0;
       // near child first: dirIsNeg[axis] ? second : first (bvh_accel.dart:147-153)
-      float iax = q3.z == 0 ? r.ix : (q3.z == 1 ? r.iy : r.iz);
-      bool neg = iax < 0.f;
+      const bool neg = ((r.negMask >> q3.z) & 1u) != 0;
       int32_t nearRef = neg ? q3.y : q3.x, farRef = neg ? q3.x : q3.y;
       int hn = neg ? c1 : c0, hf = neg ? c0 : c1;
       if (hf) {
@@ -232,47 +228,71 @@ __global__ void __launch_bounds__(128, 4) traceFastKernel(TraceScene sc, const f
         stack[sp].tmin = neg ? tm0 : tm1;
         sp++;
       }
-      if (hn) cur = nearRef;
-      else if (!popNext(sc, r, stack, sp, cur)) retire();
+      if (hn) {
+        cur = nearRef;
+      } else {
+        bool ok;
+        POP_NEXT(ok);
+        if (!ok) RETIRE();
+      }
     }
 
-    // ---- leaf phase ------------------------------------------------------------------------------
-    if (alive) {
-      uint32_t off = refLeafOffset(cur), cnt = refLeafCountField(cur);
-      const GPrim* pr = sc.prims + off;
-      if (cnt == 15u) cnt = (uint32_t)__ldg(&pr->leafCount);
-      RayState rs;
-      widen(r, rs);
-      bool stop = false;
-      for (uint32_t k = 0; k < cnt && !stop; ++k) {
-        float4 a = ldg4(&pr[k].p1[0]), b = ldg4(&pr[k].p2[0]), c = ldg4(&pr[k].p3[0]);
-        int kind = __float_as_int(c.w);
-        if ((kind & 1) == 0) {
-          if (ANY) {
-            if (triangleAny(rs, a, b, c)) { found = true; stop = true; }
+    // ---- exact leaf phase, batched: run it when enough lanes wait on a leaf, or nobody can walk ----
+    const bool atLeaf = alive && cur < 0;
+    unsigned waiting = __ballot_sync(FULL_MASK, atLeaf);
+    unsigned walking = __ballot_sync(FULL_MASK, alive && cur >= 0);
+    if (waiting && (__popc(waiting) >= DRT_LEAF_BATCH || walking == 0)) {
+      if (atLeaf) {
+        uint32_t off = refLeafOffset(cur), cnt = refLeafCountField(cur);
+        const GPrim* pr = sc.prims + off;
+        if (cnt == 15u) cnt = (uint32_t)__ldg(&pr->leafCount);
+        float4 o = __ldg(rayO + rayIdx), d = __ldg(rayD + rayIdx);  // direction is only needed here
+        RayState rs;
+        rs.ox = o.x; rs.oy = o.y; rs.oz = o.z;
+        rs.dx = d.x; rs.dy = d.y; rs.dz = d.z;
+        rs.mint = r.mint; rs.maxt = r.maxt;
+        bool stop = false;
+        for (uint32_t k = 0; k < cnt && !stop; ++k) {
+          float4 a = ldg4(&pr[k].p1[0]), b = ldg4(&pr[k].p2[0]), c = ldg4(&pr[k].p3[0]);
+          int kind = __float_as_int(c.w);
+          if ((kind & 1) == 0) {
+            if (ANY) {
+              if (triangleAny(rs, a, b, c)) { found = true; stop = true; }
+            } else {
+              HitState h;
+              if (triangleClosest(rs, a, b, c, &h)) {
+                found = true;
+                hb1 = __double2float_rn(h.b1); hb2 = __double2float_rn(h.b2); hprim = h.prim;
+              }
+            }
           } else {
-            HitState h;
-            if (triangleClosest(rs, a, b, c, &h)) {
+            const GSphere& s = sc.spheres[kind >> 1];
+            double th, u, v;
+            if (ANY) {
+              if (sphereTest(s, rs, true, &th, nullptr, nullptr)) { found = true; stop = true; }
+            } else if (sphereTest(s, rs, false, &th, &u, &v)) {
               found = true;
-              hb1 = __double2float_rn(h.b1); hb2 = __double2float_rn(h.b2); hprim = h.prim;
+              hb1 = __double2float_rn(u); hb2 = __double2float_rn(v); hprim = __float_as_int(a.w);
+              rs.maxt = th;
             }
           }
+        }
+        if (!ANY && rs.maxt != r.maxt) {
+          r.maxt = rs.maxt;
+          r.maxtLo = __double2float_rd(rs.maxt);
+          r.maxtHi = __double2float_ru(rs.maxt);
+        }
+        if (ANY && found) {
+          RETIRE();
         } else {
-          const GSphere& s = sc.spheres[kind >> 1];
-          double th, u, v;
-          if (ANY) {
-            if (sphereTest(s, rs, true, &th, nullptr, nullptr)) { found = true; stop = true; }
-          } else if (sphereTest(s, rs, false, &th, &u, &v)) {
-            found = true;
-            hb1 = __double2float_rn(u); hb2 = __double2float_rn(v); hprim = __float_as_int(a.w);
-            rs.maxt = th;
-          }
+          bool ok;
+          POP_NEXT(ok);
+          if (!ok) RETIRE();
         }
       }
-      if (!ANY && rs.maxt != r.maxt) setMaxt(r, rs.maxt);
-      if ((ANY && found) || !popNext(sc, r, stack, sp, cur)) retire();
     }
   }
+#undef RETIRE
 }
 
 cudaError_t launchTraceFast(const TraceScene& sc, bool any, const void* rayO, const void* rayD, uint64_t n, void* out,
