@@ -254,6 +254,41 @@ struct Flattener {
     orderRef(n.left, refIndexOf);
   }
 
+  // Wide layout: collapse P with its two children (see GNode4).  Must run AFTER emit(): it reuses
+  // the leaf references recorded there so both layouts index the same GPrim[] order.
+  std::vector<int32_t> leafRefOf;  // per pool node: leaf reference (leaves only)
+  int32_t emitWide(int32_t t, const std::vector<int32_t>& refIndexOf) {
+    const TNode& n = pool[t];
+    if (n.left < 0) return leafRefOf[t];
+    int32_t my = (int32_t)out->wide.size();
+    out->wide.emplace_back();
+    GNode4 g;
+    std::memset(&g, 0, sizeof(g));
+    for (int k = 0; k < 4; ++k) {
+      g.ref[k] = DRT_REF_EMPTY;
+      for (int a = 0; a < 3; ++a) { g.box[k][a] = 0.f; g.box[k][3 + a] = 0.f; }
+    }
+    g.axisP = n.axis;
+    g.refNode = refIndexOf[t];
+    const int32_t sides[2] = {n.left, n.right};
+    for (int sIdx = 0; sIdx < 2; ++sIdx) {
+      const TNode& side = pool[sides[sIdx]];
+      int base = 2 * sIdx;
+      int32_t kids[2];
+      int nk;
+      if (side.left < 0) { kids[0] = sides[sIdx]; nk = 1; }
+      else { kids[0] = side.left; kids[1] = side.right; nk = 2; (sIdx == 0 ? g.axisA : g.axisB) = side.axis; }
+      for (int k = 0; k < nk; ++k) {
+        const TNode& c = pool[kids[k]];
+        std::memcpy(&g.box[base + k][0], c.box.lo, 12);
+        std::memcpy(&g.box[base + k][3], c.box.hi, 12);
+        g.ref[base + k] = emitWide(kids[k], refIndexOf);
+      }
+    }
+    out->wide[my] = g;
+    return my;
+  }
+
   // GPU layout: interior nodes in DFS order, leaf records in DFS (left-first) order.
   int32_t emit(int32_t t, uint32_t depth, const std::vector<int32_t>& refIndexOf) {
     const TNode& n = pool[t];
@@ -266,7 +301,8 @@ struct Flattener {
       }
       out->nLeaves++;
       if (n.count > out->maxLeafPrims) out->maxLeafPrims = n.count;
-      return makeLeafRef(off, n.count);
+      leafRefOf[t] = makeLeafRef(off, n.count);
+      return leafRefOf[t];
     }
     int32_t my = (int32_t)out->nodes.size();
     out->nodes.emplace_back();
@@ -294,7 +330,7 @@ bool buildBvh(const std::vector<PrimBounds>& bounds, const std::vector<uint32_t>
   *out = BuiltBvh();
   const size_t n = order.size();
   if (n == 0) { *err = "no primitives"; return false; }
-  if (n >= (1u << 27)) { *err = "too many primitives for the 27-bit leaf offset"; return false; }
+  if (n >= (1u << 26)) { *err = "too many primitives for the 26-bit leaf offset"; return false; }
   int maxPrims = std::min(255, maxPrimsInNode);  // bvh_accel.dart:44
   std::vector<PrimRef> refs(n);
   for (size_t i = 0; i < n; ++i) {
@@ -314,7 +350,8 @@ bool buildBvh(const std::vector<PrimBounds>& bounds, const std::vector<uint32_t>
   TreeBuilder tb(refs, splitMethod, maxPrims);
   int32_t root = tb.build(arena, 0, (uint32_t)n, 0);
 
-  Flattener fl{arena.pool, refs, out};
+  Flattener fl{arena.pool, refs, out, {}};
+  fl.leafRefOf.assign(arena.pool.size(), 0);
   std::vector<int32_t> refIndexOf(arena.pool.size(), -1);
   out->refNodes.reserve(arena.pool.size());
   fl.numberRef(root, refIndexOf);
@@ -324,6 +361,8 @@ bool buildBvh(const std::vector<PrimBounds>& bounds, const std::vector<uint32_t>
   out->leafCounts.reserve(n);
   out->nodes.reserve(arena.pool.size() / 2 + 1);
   out->rootRef = fl.emit(root, 0, refIndexOf);
+  out->wide.reserve(arena.pool.size() / 3 + 1);
+  out->wideRootRef = fl.emitWide(root, refIndexOf);
   std::memcpy(out->rootMin, arena.pool[root].box.lo, 12);
   std::memcpy(out->rootMax, arena.pool[root].box.hi, 12);
   if (out->maxDepth >= 64) {

@@ -64,6 +64,7 @@ struct drt_ctx {
   BuiltBvh bvh;
   drt_bvh_info info{};
   DevBuf<GNode> dNodes;
+  DevBuf<GNode4> dWide;
   DevBuf<GPrim> dPrims;
   DevBuf<GSphere> dSpheres;
   DevBuf<DeviceCounters> dCounters;
@@ -148,7 +149,7 @@ void drt_destroy(drt_ctx* c) {
   if (!c) return;
   if (c->device == DRT_DEVICE_NONE) { delete c; return; }
   cudaSetDevice(c->device);
-  c->dNodes.release(); c->dPrims.release(); c->dSpheres.release(); c->dCounters.release(); c->dNextRay.release();
+  c->dNodes.release(); c->dWide.release(); c->dPrims.release(); c->dSpheres.release(); c->dCounters.release(); c->dNextRay.release();
   c->dRayO.release(); c->dRayD.release(); c->dHits.release(); c->dOcc.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -307,6 +308,9 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
     return DRT_OK;
   }
   CK(c, c->dNodes.ensure(std::max<size_t>(1, B.nodes.size())));
+  CK(c, c->dWide.ensure(std::max<size_t>(1, B.wide.size())));
+  if (!B.wide.empty())
+    CK(c, cudaMemcpy(c->dWide.p, B.wide.data(), B.wide.size() * sizeof(GNode4), cudaMemcpyHostToDevice));
   CK(c, c->dPrims.ensure(prims.size()));
   CK(c, c->dSpheres.ensure(std::max<size_t>(1, gs.size())));
   if (!B.nodes.empty())
@@ -314,6 +318,8 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
   CK(c, cudaMemcpy(c->dPrims.p, prims.data(), prims.size() * sizeof(GPrim), cudaMemcpyHostToDevice));
   if (!gs.empty()) CK(c, cudaMemcpy(c->dSpheres.p, gs.data(), gs.size() * sizeof(GSphere), cudaMemcpyHostToDevice));
   c->ts.nodes = c->dNodes.p;
+  c->ts.wide = c->dWide.p;
+  c->ts.wideRootRef = B.wideRootRef;
   c->ts.prims = c->dPrims.p;
   c->ts.spheres = c->dSpheres.p;
   std::memcpy(c->ts.rootMin, B.rootMin, 12);
@@ -325,7 +331,7 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
   c->info.n_leaves = B.nLeaves;
   c->info.max_leaf_prims = B.maxLeafPrims;
   c->info.max_depth = B.maxDepth;
-  c->info.device_bytes = B.nodes.size() * sizeof(GNode) + prims.size() * sizeof(GPrim) + gs.size() * sizeof(GSphere);
+  c->info.device_bytes = B.wide.size() * sizeof(GNode4) + prims.size() * sizeof(GPrim) + gs.size() * sizeof(GSphere);
   c->info.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   c->built = true;
   return DRT_OK;

@@ -10,15 +10,20 @@
 
 namespace drt {
 
-// Child reference: >= 0 -> interior node index into GNode[]; < 0 -> leaf, bits = ~ref:
-//   bits & 15  = primitive count (1..14), 15 = count stored in the first record's `leafCount`
-//   bits >> 4  = offset of the leaf's first record in GPrim[]
+// Child reference: >= 0 -> interior node index; < 0 -> leaf, bits = ~ref:
+//   bits & 15        = primitive count (1..14), 15 = count stored in the first record's `leafCount`
+//   (bits >> 4) & 1  = "box undecided": the float32 filter could not prove the leaf-box decision, the
+//                      leaf phase must evaluate the reference's slab test exactly before the primitives
+//   bits >> 5        = offset of the leaf's first record in GPrim[]
+#define DRT_REF_EMPTY ((int32_t)0x7fffffff)  // unused slot of a wide node
 static inline DRT_HD bool refIsLeaf(int32_t r) { return r < 0; }
-static inline DRT_HD uint32_t refLeafOffset(int32_t r) { return ((uint32_t)~r) >> 4; }
+static inline DRT_HD uint32_t refLeafOffset(int32_t r) { return ((uint32_t)~r) >> 5; }
 static inline DRT_HD uint32_t refLeafCountField(int32_t r) { return ((uint32_t)~r) & 15u; }
+static inline DRT_HD bool refLeafUndecided(int32_t r) { return (((uint32_t)~r) >> 4) & 1u; }
+static inline DRT_HD int32_t refMarkUndecided(int32_t r) { return r & ~16; }
 static inline int32_t makeLeafRef(uint32_t offset, uint32_t count) {
   uint32_t c = count < 15u ? count : 15u;
-  return (int32_t)~((offset << 4) | c);
+  return (int32_t)~((offset << 5) | c);
 }
 
 // One interior node = 64 bytes = four 128-bit loads.  It carries BOTH children's boxes (the
@@ -34,6 +39,21 @@ struct alignas(16) GNode {
   int32_t refNode;
 };
 static_assert(sizeof(GNode) == 64, "GNode must be 64 bytes");
+
+// Wide node = 128 bytes = eight 128-bit loads: two levels of the reference's binary tree collapsed.
+// For the binary node P with children A (first) and B (second): slots 0,1 hold A's children (or A
+// itself in slot 0 when A is a leaf), slots 2,3 hold B's.  The reference's visiting order is
+// recovered from the three split axes: side = dirIsNeg[axisP] ? B : A first, and inside a side
+// dirIsNeg[axisSide] ? second : first (bvh_accel.dart:147-153).  A's and B's own boxes are not
+// stored: a child box that passes the slab test implies its parent box passes (monotone rounding,
+// DESIGN.md), so skipping them cannot change which leaves are tested.
+struct alignas(16) GNode4 {
+  float box[4][6];   // per slot: min.xyz, max.xyz
+  int32_t ref[4];    // child reference or DRT_REF_EMPTY
+  int32_t axisP, axisA, axisB;
+  int32_t refNode;   // reference node number of P (debug/export)
+};
+static_assert(sizeof(GNode4) == 128, "GNode4 must be 128 bytes");
 
 // One leaf primitive record = 48 bytes = three 128-bit loads, stored in leaf order.
 // Triangle: the three ORIGINAL float32 world-space vertices (triangle.dart:47-50 reads exactly
@@ -61,7 +81,9 @@ struct alignas(16) GSphere {
 };
 
 struct TraceScene {
-  const GNode* nodes;
+  const GNode* nodes;    // binary layout (exact-walk / counting kernel)
+  const GNode4* wide;    // collapsed layout (production kernel)
+  int32_t wideRootRef;
   const GPrim* prims;
   const GSphere* spheres;
   float rootMin[3], rootMax[3];  // box of reference node 0, tested first (bvh_accel.dart:123-125)

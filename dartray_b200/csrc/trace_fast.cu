@@ -1,18 +1,26 @@
-// Production traversal kernels: persistent warps, while-while traversal, float32-FILTERED slab
-// tests with an exact float64 fallback.
+// Production traversal kernels: persistent warps over a two-level-collapsed (4-wide) BVH, float32
+// CONSERVATIVE interior tests, exact leaf decisions, batched exact leaf phase.
 //
-// Every decision the reference makes (bvh_accel.dart:439-472 slab test, :139-159 pop order,
-// triangle.dart:44-98 / :162-194, sphere.dart) is still made with the reference's arithmetic; the
-// float32 filter only answers when its answer provably equals the float64 one:
+// Why this returns exactly what the reference's walk (bvh_accel.dart:101-226) returns:
+//  (1) The reference tests a leaf's primitives iff the leaf's own slab test passes at the moment the
+//      leaf node is visited; every ancestor test is implied: child boxes are contained in parent
+//      boxes (exact float32 min/max unions) and IEEE rounding is monotone, so tmin_parent <=
+//      tmin_child and tmax_parent >= tmax_child for the reference's own f64 expressions, and
+//      maxDistance only shrinks.  Hence visiting a SUPERSET of interior nodes, in the same depth-
+//      first near/far order, cannot change which primitives are tested, in which order, with which
+//      maxDistance — provided each LEAF box decision is the reference's.
+//  (2) Interior boxes are therefore tested in float32 with an outward margin (never a false miss).
+//  (3) A leaf box is decided by the float32 filter only when the margin proves the f64 decision;
+//      otherwise the leaf is marked "undecided" and the leaf phase evaluates the reference's slab
+//      test in f64 (slabs(), trace_device.cuh) on the leaf box rebuilt from its primitives.
+//  (4) Primitive tests are the reference's arithmetic (triangle.dart:44-98 / 162-194, sphere.dart).
 //
 //   reference   t = ((double)b - (double)o) * (double)invDir        (b, o, invDir are float32)
 //   filter      t' = (b - o) * invDir in float32  ->  |t - t'| <= 2^-23 |t'| (+ underflow)
+//   margins     hi(x) = x + 2^-22|x| + tiny,  lo(x) = x - 2^-22|x| - tiny   (monotone in x)
 //
-// With eps = 2^-22 and an absolute floor `tiny`, hi(x) = x + eps|x| + tiny and lo(x) = x - eps|x| - tiny
-// are monotone, so hi(max_i t'_i) >= max_i t_i etc.  A box is accepted/rejected by the filter only if
-// all three reference conditions (max near <= min far, tmin < maxDistance, tmax > minDistance) are
-// decided with that margin; anything else — including NaN/inf from zero direction components and
-// float32 overflow — takes the exact path (slabs() of trace_device.cuh).
+// Rays with a non-finite origin or invDir component (zero direction components) use the exact f64
+// test for every box instead of the filter.
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -26,7 +34,6 @@ namespace drt {
 
 #define FULL_MASK 0xffffffffu
 #define RAY_CHUNK 256  // rays a warp reserves per atomicAdd on the global ray counter
-
 #ifndef DRT_MIN_BLOCKS
 #define DRT_MIN_BLOCKS 5
 #endif
@@ -45,15 +52,15 @@ struct FastRay {
 
 struct StackEntry {
   int32_t ref;
-  float tmin;  // float32 image of the box entry distance (exact value re-derived when it matters)
+  float tmin;  // float32 image of the box entry distance
 };
 
 #define DRT_EPS 2.384185791015625e-07f  // 2^-22
 #define DRT_TINY 1.0e-37f
 
-// 1 = the reference accepts the box, 0 = it rejects it, 2 = not provable in float32.
-static __device__ __forceinline__ int slabFilter(const FastRay& r, float lox, float loy, float loz, float hix,
-                                                 float hiy, float hiz, float* tminOut) {
+// 0 = the reference surely rejects the box, 1 = it surely accepts it, 2 = not provable in float32.
+static __device__ __forceinline__ int slabFilter(const FastRay& r, const float lox, const float loy, const float loz,
+                                                 const float hix, const float hiy, const float hiz, float* tminOut) {
   float t0x = (lox - r.ox) * r.ix, t1x = (hix - r.ox) * r.ix;
   float t0y = (loy - r.oy) * r.iy, t1y = (hiy - r.oy) * r.iy;
   float t0z = (loz - r.oz) * r.iz, t1z = (hiz - r.oz) * r.iz;
@@ -64,11 +71,11 @@ static __device__ __forceinline__ int slabFilter(const FastRay& r, float lox, fl
   bool pass = (tminHi <= tmaxLo) && (tminHi < r.maxtLo) && (tmaxLo > r.mintHi);
   bool fail = (tminLo > tmaxHi) || (tminLo >= r.maxtHi) || (tmaxHi <= r.mintLo);
   *tminOut = tmin;
-  return pass ? 1 : (fail ? 0 : 2);
+  return fail ? 0 : (pass ? 1 : 2);
 }
 
-// Exact evaluation of one box (rare), everything passed BY VALUE so the caller's ray state stays in
-// registers.  Returns the reference's decision (bvh_accel.dart:439-472); *tminOut = float32(tmin).
+// The reference's slab test in f64 (bvh_accel.dart:439-472), arguments BY VALUE so the caller's ray
+// state stays in registers.  *tminOut = float32(tmin).
 static __device__ __noinline__ bool slabExact(float ox, float oy, float oz, float ix, float iy, float iz, double mint,
                                               double maxt, float lox, float loy, float loz, float hix, float hiy,
                                               float hiz, float* tminOut) {
@@ -81,61 +88,43 @@ static __device__ __noinline__ bool slabExact(float ox, float oy, float oz, floa
   *tminOut = __double2float_rn(tmin);
   return (tmin < maxt) && (tmax > mint);
 }
-#define SLAB_EXACT(r, lox, loy, loz, hix, hiy, hiz, tout) \
-  slabExact((r).ox, (r).oy, (r).oz, (r).ix, (r).iy, (r).iz, (r).mint, (r).maxt, lox, loy, loz, hix, hiy, hiz, tout)
 
-// Exact re-test of a popped LEAF whose stored entry distance is too close to maxDistance to call:
-// rebuild the leaf box from its primitives (triangle.dart:39-42 / sphere world bound) and evaluate
-// the slab test exactly as the reference does when it visits the leaf node.
-static __device__ __noinline__ bool leafStillReachable(const GPrim* prims, const GSphere* spheres, float ox, float oy,
-                                                       float oz, float ix, float iy, float iz, double mint, double maxt,
-                                                       int32_t ref) {
-  uint32_t off = refLeafOffset(ref), cnt = refLeafCountField(ref);
-  const GPrim* pr = prims + off;
-  if (cnt == 15u) cnt = (uint32_t)__ldg(&pr->leafCount);
-  float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
-  for (uint32_t k = 0; k < cnt; ++k) {
-    float4 a = ldg4(&pr[k].p1[0]), b = ldg4(&pr[k].p2[0]), c = ldg4(&pr[k].p3[0]);
-    int kind = __float_as_int(c.w);
-    if ((kind & 1) == 0) {
-      lo[0] = fminf(lo[0], fminf(a.x, fminf(b.x, c.x))); hi[0] = fmaxf(hi[0], fmaxf(a.x, fmaxf(b.x, c.x)));
-      lo[1] = fminf(lo[1], fminf(a.y, fminf(b.y, c.y))); hi[1] = fmaxf(hi[1], fmaxf(a.y, fmaxf(b.y, c.y)));
-      lo[2] = fminf(lo[2], fminf(a.z, fminf(b.z, c.z))); hi[2] = fmaxf(hi[2], fmaxf(a.z, fmaxf(b.z, c.z)));
-    } else {
-      const GSphere& s = spheres[kind >> 1];
-      for (int x = 0; x < 3; ++x) { lo[x] = fminf(lo[x], s.wmin[x]); hi[x] = fmaxf(hi[x], s.wmax[x]); }
-    }
-  }
-  float t;
-  return slabExact(ox, oy, oz, ix, iy, iz, mint, maxt, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], &t);
+// One slot of a wide node: conservative for interior children, exact-or-marked for leaf children.
+// Returns whether to visit; may mark a leaf reference "undecided".
+static __device__ __forceinline__ bool testSlot(const FastRay& r, int32_t& ref, const float lox, const float loy,
+                                                const float loz, const float hix, const float hiy, const float hiz,
+                                                float* tmin) {
+  if (ref == DRT_REF_EMPTY) return false;
+  if (r.negMask & 8u)  // slow ray: exact decision for every box
+    return slabExact(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, r.mint, r.maxt, lox, loy, loz, hix, hiy, hiz, tmin);
+  int c = slabFilter(r, lox, loy, loz, hix, hiy, hiz, tmin);
+  if (c == 2 && ref < 0) ref = refMarkUndecided(ref);
+  return c != 0;
 }
 
 // Pops until an entry survives the reference's pop-time test `tmin < ray.maxDistance`
-// (bvh_accel.dart:139-143,156-159 + :471).  Interior entries inside the undecidable band are
-// entered (their children are culled by the same comparison); leaf entries in the
-// band are re-tested exactly.
-#define POP_NEXT(ok)                                                                                       \
-  do {                                                                                                     \
-    ok = false;                                                                                            \
-    while (sp > 0) {                                                                                       \
-      --sp;                                                                                                \
-      int32_t ref_ = stack[sp].ref;                                                                        \
-      float t_ = stack[sp].tmin;                                                                           \
-      float dt_ = fmaf(DRT_EPS, fabsf(t_), DRT_TINY);                                                      \
-      bool take_ = (t_ + dt_) < r.maxtLo;                                                                  \
-      if (!take_ && !((t_ - dt_) >= r.maxtHi))                                                             \
-        take_ = ref_ >= 0 ? true                                                                           \
-                          : leafStillReachable(sc.prims, sc.spheres, r.ox, r.oy, r.oz, r.ix, r.iy, r.iz,   \
-                                               r.mint, r.maxt, ref_);                                      \
-      if (take_) { cur = ref_; ok = true; break; }                                                         \
-    }                                                                                                      \
+// (bvh_accel.dart:139-143,156-159 + :471).  Entries inside the undecidable band are entered:
+// interior ones conservatively, leaf ones marked "undecided" for the exact leaf phase.
+#define POP_NEXT(ok)                                                                \
+  do {                                                                              \
+    ok = false;                                                                     \
+    while (sp > 0) {                                                                \
+      --sp;                                                                         \
+      int32_t ref_ = stack[sp].ref;                                                 \
+      float t_ = stack[sp].tmin;                                                    \
+      float dt_ = fmaf(DRT_EPS, fabsf(t_), DRT_TINY);                               \
+      if ((t_ - dt_) >= r.maxtHi) continue; /* surely culled */                     \
+      if (!((t_ + dt_) < r.maxtLo) && ref_ < 0) ref_ = refMarkUndecided(ref_);      \
+      cur = ref_;                                                                   \
+      ok = true;                                                                    \
+      break;                                                                        \
+    }                                                                               \
   } while (0)
 
 template <bool ANY>
-__global__ void __launch_bounds__(128, DRT_MIN_BLOCKS) traceFastKernel(TraceScene sc, const float4* __restrict__ rayO,
-                                                          const float4* __restrict__ rayD, uint64_t n,
-                                                          float4* __restrict__ hits, uint8_t* __restrict__ occluded,
-                                                          unsigned long long* __restrict__ nextRay) {
+__global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
+    traceFastKernel(TraceScene sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD, uint64_t n,
+                    float4* __restrict__ hits, uint8_t* __restrict__ occluded, unsigned long long* __restrict__ nextRay) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned ltMask = (1u << lane) - 1u;
   unsigned long long warpNext = 0, warpEnd = 0;  // warp-uniform: the chunk of rays this warp owns
@@ -143,7 +132,7 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS) traceFastKernel(TraceScen
   bool alive = false;
   unsigned long long rayIdx = 0;
   FastRay r;
-  StackEntry stack[DRT_STACK];
+  StackEntry stack[100];  // <= 3 pushes per wide level, <= 32 wide levels (binary depth < 64)
   int sp = 0;
   int32_t cur = 0;
   float hb1 = 0.f, hb2 = 0.f;
@@ -187,7 +176,6 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS) traceFastKernel(TraceScen
         r.mintLo = r.mintHi = o.w;
         r.maxt = d.w;
         r.maxtLo = r.maxtHi = d.w;
-        // any inf/NaN among origin / invDir components -> every box of this ray takes the exact path
         bool slow = !(fabsf(r.ox) <= 3.0e38f) || !(fabsf(r.oy) <= 3.0e38f) || !(fabsf(r.oz) <= 3.0e38f) ||
                     !(fabsf(r.ix) <= 3.0e38f) || !(fabsf(r.iy) <= 3.0e38f) || !(fabsf(r.iz) <= 3.0e38f);
         r.negMask = (r.ix < 0.f ? 1u : 0u) | (r.iy < 0.f ? 2u : 0u) | (r.iz < 0.f ? 4u : 0u) | (slow ? 8u : 0u);
@@ -196,41 +184,51 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS) traceFastKernel(TraceScen
         hprim = -1;
         hb1 = hb2 = 0.f;
         alive = true;
-        // reference node 0: its own box is tested first (bvh_accel.dart:123-125)
-        float t0;
-        if (sc.empty || !SLAB_EXACT(r, sc.rootMin[0], sc.rootMin[1], sc.rootMin[2], sc.rootMax[0], sc.rootMax[1],
-                                    sc.rootMax[2], &t0))
+        if (sc.empty) {
           RETIRE();
-        else
-          cur = sc.rootRef;
+        } else {
+          // Reference node 0's own box (bvh_accel.dart:123-125): implied by its children's boxes when
+          // the root is interior; a root LEAF gets its box decided exactly in the leaf phase.
+          cur = sc.wideRootRef;
+          if (cur < 0) cur = refMarkUndecided(cur);
+        }
       }
       warpNext += nDead < avail ? nDead : avail;
       if (exhausted && __all_sync(FULL_MASK, !alive)) break;
     }
 
-    // ---- one interior step for every lane that holds an interior node ---------------------------
+    // ---- one wide-node step for every lane that holds an interior node --------------------------
     if (alive && cur >= 0) {
-      const GNode* nd = sc.nodes + cur;
-      float4 q0 = ldg4(&nd->c0min[0]), q1 = ldg4(&nd->c0max[1]), q2 = ldg4(&nd->c1min[2]);
-      int4 q3 = __ldg(reinterpret_cast<const int4*>(&nd->ref0));
-      float tm0 = 0.f, tm1 = 0.f;
-      const bool slow = (r.negMask & 8u) != 0;
-      int c0 = slow ? 2 : slabFilter(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tm0);
-      int c1 = slow ? 2 : slabFilter(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tm1);
-      if (c0 == 2) c0 = SLAB_EXACT(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tm0) ? 1 : 0;
-      if (c1 == 2) c1 = SLAB_EXACT(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tm1) ? 1 : 0;
-      // near child first: dirIsNeg[axis] ? second : first (bvh_accel.dart:147-153)
-      const bool neg = ((r.negMask >> q3.z) & 1u) != 0;
-      int32_t nearRef = neg ? q3.y : q3.x, farRef = neg ? q3.x : q3.y;
-      int hn = neg ? c1 : c0, hf = neg ? c0 : c1;
-      if (hf) {
-        stack[sp].ref = farRef;
-        stack[sp].tmin = neg ? tm0 : tm1;
-        sp++;
+      const float4* nd = reinterpret_cast<const float4*>(sc.wide + cur);
+      float4 q0 = __ldg(nd + 0), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3), q4 = __ldg(nd + 4),
+             q5 = __ldg(nd + 5);
+      int4 qr = __ldg(reinterpret_cast<const int4*>(nd + 6));
+      int4 qa = __ldg(reinterpret_cast<const int4*>(nd + 7));
+      float t0, t1, t2, t3;
+      int32_t r0 = qr.x, r1 = qr.y, r2 = qr.z, r3 = qr.w;
+      bool p0 = testSlot(r, r0, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &t0);
+      bool p1 = testSlot(r, r1, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &t1);
+      bool p2 = testSlot(r, r2, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, &t2);
+      bool p3 = testSlot(r, r3, q4.z, q4.w, q5.x, q5.y, q5.z, q5.w, &t3);
+      // visiting order of the reference's depth-first walk (bvh_accel.dart:147-153)
+      const bool sA = ((r.negMask >> qa.y) & 1u) != 0, sB = ((r.negMask >> qa.z) & 1u) != 0,
+                 sP = ((r.negMask >> qa.x) & 1u) != 0;
+      if (sA) { int32_t tr = r0; r0 = r1; r1 = tr; float tt = t0; t0 = t1; t1 = tt; bool tp = p0; p0 = p1; p1 = tp; }
+      if (sB) { int32_t tr = r2; r2 = r3; r3 = tr; float tt = t2; t2 = t3; t3 = tt; bool tp = p2; p2 = p3; p3 = tp; }
+      if (sP) {
+        int32_t tr = r0; r0 = r2; r2 = tr; tr = r1; r1 = r3; r3 = tr;
+        float tt = t0; t0 = t2; t2 = tt; tt = t1; t1 = t3; t3 = tt;
+        bool tp = p0; p0 = p2; p2 = tp; tp = p1; p1 = p3; p3 = tp;
       }
-      if (hn) {
-        cur = nearRef;
-      } else {
+      // first passing slot becomes current, the later ones are pushed so that they pop in order
+      if (p3 && (p0 || p1 || p2)) { stack[sp].ref = r3; stack[sp].tmin = t3; sp++; }
+      if (p2 && (p0 || p1)) { stack[sp].ref = r2; stack[sp].tmin = t2; sp++; }
+      if (p1 && p0) { stack[sp].ref = r1; stack[sp].tmin = t1; sp++; }
+      if (p0) cur = r0;
+      else if (p1) cur = r1;
+      else if (p2) cur = r2;
+      else if (p3) cur = r3;
+      else {
         bool ok;
         POP_NEXT(ok);
         if (!ok) RETIRE();
@@ -251,8 +249,31 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS) traceFastKernel(TraceScen
         rs.ox = o.x; rs.oy = o.y; rs.oz = o.z;
         rs.dx = d.x; rs.dy = d.y; rs.dz = d.z;
         rs.mint = r.mint; rs.maxt = r.maxt;
+        bool boxOk = true;
+        if (refLeafUndecided(cur)) {
+          // the reference's own slab test of this leaf node, on the box rebuilt from its primitives
+          // (triangle.dart:39-42 / the sphere's world bound)
+          float lo0 = CUDART_INF_F, lo1 = CUDART_INF_F, lo2 = CUDART_INF_F, hi0 = -CUDART_INF_F, hi1 = -CUDART_INF_F,
+                hi2 = -CUDART_INF_F;
+          for (uint32_t k = 0; k < cnt; ++k) {
+            float4 a = ldg4(&pr[k].p1[0]), b = ldg4(&pr[k].p2[0]), c = ldg4(&pr[k].p3[0]);
+            int kind = __float_as_int(c.w);
+            if ((kind & 1) == 0) {
+              lo0 = fminf(lo0, fminf(a.x, fminf(b.x, c.x))); hi0 = fmaxf(hi0, fmaxf(a.x, fmaxf(b.x, c.x)));
+              lo1 = fminf(lo1, fminf(a.y, fminf(b.y, c.y))); hi1 = fmaxf(hi1, fmaxf(a.y, fmaxf(b.y, c.y)));
+              lo2 = fminf(lo2, fminf(a.z, fminf(b.z, c.z))); hi2 = fmaxf(hi2, fmaxf(a.z, fmaxf(b.z, c.z)));
+            } else {
+              const GSphere& s = sc.spheres[kind >> 1];
+              lo0 = fminf(lo0, s.wmin[0]); hi0 = fmaxf(hi0, s.wmax[0]);
+              lo1 = fminf(lo1, s.wmin[1]); hi1 = fmaxf(hi1, s.wmax[1]);
+              lo2 = fminf(lo2, s.wmin[2]); hi2 = fmaxf(hi2, s.wmax[2]);
+            }
+          }
+          float tt;
+          boxOk = slabExact(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, r.mint, r.maxt, lo0, lo1, lo2, hi0, hi1, hi2, &tt);
+        }
         bool stop = false;
-        for (uint32_t k = 0; k < cnt && !stop; ++k) {
+        for (uint32_t k = 0; boxOk && k < cnt && !stop; ++k) {
           float4 a = ldg4(&pr[k].p1[0]), b = ldg4(&pr[k].p2[0]), c = ldg4(&pr[k].p3[0]);
           int kind = __float_as_int(c.w);
           if ((kind & 1) == 0) {
