@@ -1,0 +1,325 @@
+"""Host-side mirror of the reference objects the render path reads at the C-ABI boundary.
+
+What a Dart `GpuSamplerRenderer` would pull out of the constructed DartRay objects,
+computed here the way the reference computes it so that tests read like the reference's scene setup:
+
+  Transform / Matrix4x4      lib/core/transform.dart:27-349, lib/core/matrix4x4.dart:26 (float32 storage)
+  PerspectiveCamera          lib/cameras/perspective_camera.dart:46-57,134-181 + lib/core/projective_camera.dart:34-53
+  filters                    lib/filters/*.dart (evaluate) -> ImageFilm's 16x16 table (lib/film/image_film.dart:74-82)
+  Primitive.fullyRefine      lib/core/primitive.dart:71-84 (LIFO order) and ShapeSet (lib/core/light/shape_set.dart:26-41)
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+# ---- Matrix4x4 / Transform (float32 storage, float64 arithmetic) ------------------------------------
+
+
+def _m(a):
+    return np.asarray(a, dtype=np.float64).reshape(4, 4).astype(np.float32)
+
+
+def mat_mul(a, b):  # Matrix4x4.Mul, matrix4x4.dart
+    return (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32)
+
+
+def mat_inv(a):
+    return np.linalg.inv(a.astype(np.float64)).astype(np.float32)
+
+
+def translate(x, y, z):  # transform.dart:214-228
+    return _m([[1, 0, 0, x], [0, 1, 0, y], [0, 0, 1, z], [0, 0, 0, 1]])
+
+
+def scale(x, y, z):  # transform.dart:230-243
+    return _m([[x, 0, 0, 0], [0, y, 0, 0], [0, 0, z, 0], [0, 0, 0, 1]])
+
+
+def rotate(angle_deg, axis):  # transform.dart:280-304
+    a = np.asarray(axis, dtype=np.float64)
+    a = (a / np.linalg.norm(a)).astype(np.float32).astype(np.float64)
+    s, c = math.sin(math.radians(angle_deg)), math.cos(math.radians(angle_deg))
+    m = np.zeros((4, 4))
+    m[0] = [a[0] * a[0] + (1 - a[0] * a[0]) * c, a[0] * a[1] * (1 - c) - a[2] * s, a[0] * a[2] * (1 - c) + a[1] * s, 0]
+    m[1] = [a[0] * a[1] * (1 - c) + a[2] * s, a[1] * a[1] + (1 - a[1] * a[1]) * c, a[1] * a[2] * (1 - c) - a[0] * s, 0]
+    m[2] = [a[0] * a[2] * (1 - c) - a[1] * s, a[1] * a[2] * (1 - c) + a[0] * s, a[2] * a[2] + (1 - a[2] * a[2]) * c, 0]
+    m[3] = [0, 0, 0, 1]
+    return _m(m)
+
+
+def look_at(pos, look, up):
+    """Returns cameraToWorld (transform.dart:306-331 builds it as `m`; the CTM is its inverse)."""
+    pos, look, up = (np.asarray(v, dtype=np.float64) for v in (pos, look, up))
+    f32 = lambda v: v.astype(np.float32).astype(np.float64)
+    d = f32((look - pos) / np.linalg.norm(look - pos))
+    upn = f32(up / np.linalg.norm(up))
+    left = np.cross(upn, d)
+    left = f32(f32(left) / np.linalg.norm(f32(left)))
+    new_up = f32(np.cross(d, left))
+    m = np.eye(4)
+    m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = left, new_up, d, pos
+    return _m(m)
+
+
+def perspective(fov, n=1.0e-2, f=1000.0):  # transform.dart:338-349
+    persp = _m([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, f / (f - n), -f * n / (f - n)], [0, 0, 1, 0]])
+    inv_tan = 1.0 / math.tan(math.radians(fov) / 2.0)
+    return mat_mul(scale(inv_tan, inv_tan, 1.0), persp)
+
+
+def transform_points(m, pts):
+    """Transform.transformPoint on float32 points (transform.dart:110-129)."""
+    p = np.asarray(pts, dtype=np.float32).astype(np.float64).reshape(-1, 3)
+    m64 = m.astype(np.float64)
+    out = (p @ m64[:3, :3].T + m64[:3, 3]).astype(np.float32)
+    w = p @ m64[3, :3] + m64[3, 3]
+    ne = w != 1.0
+    if ne.any():
+        out[ne] = (out[ne].astype(np.float64) / w[ne, None]).astype(np.float32)
+    return out
+
+
+# ---- camera / film / sampler / integrator descriptions -------------------------------------------------
+
+
+@dataclass
+class PerspectiveCamera:
+    camera_to_world: np.ndarray
+    fov: float = 60.0
+    lens_radius: float = 0.0
+    focal_distance: float = 1.0e30
+    shutter_open: float = 0.0
+    shutter_close: float = 1.0
+    screen_window: tuple | None = None
+
+    def raster_to_camera(self, xres: int, yres: int) -> np.ndarray:
+        frame = xres / yres  # perspective_camera.dart:150-171
+        sw = self.screen_window
+        if sw is None:
+            sw = (-frame, frame, -1.0, 1.0) if frame > 1.0 else (-1.0, 1.0, -1.0 / frame, 1.0 / frame)
+        screen_to_raster = mat_mul(mat_mul(scale(float(xres), float(yres), 1.0),
+                                           scale(1.0 / (sw[1] - sw[0]), 1.0 / (sw[2] - sw[3]), 1.0)),
+                                   translate(-sw[0], -sw[3], 0.0))  # projective_camera.dart:40-49
+        raster_to_screen = mat_inv(screen_to_raster)
+        return mat_mul(mat_inv(perspective(self.fov)), raster_to_screen)  # :51-52
+
+
+def filter_table(name: str = "box", xwidth: float | None = None, ywidth: float | None = None, **kw) -> tuple:
+    """(xwidth, ywidth, float32[256]) — ImageFilm's precomputed table, image_film.dart:74-82."""
+    defaults = {"box": 0.5, "gaussian": 2.0, "mitchell": 2.0, "triangle": 2.0, "sinc": 4.0}
+    xw = defaults[name] if xwidth is None else xwidth
+    yw = defaults[name] if ywidth is None else ywidth
+    if name == "box":
+        ev = lambda x, y: 1.0  # box_filter.dart:37
+    elif name == "gaussian":  # gaussian_filter.dart:36-47
+        a = kw.get("alpha", 2.0)
+        ex, ey = math.exp(-a * xw * xw), math.exp(-a * yw * yw)
+        ev = lambda x, y: max(0.0, math.exp(-a * x * x) - ex) * max(0.0, math.exp(-a * y * y) - ey)
+    elif name == "mitchell":  # mitchell_filter.dart:41-55
+        b, c = kw.get("B", 1.0 / 3.0), kw.get("C", 1.0 / 3.0)
+
+        def m1(x):
+            x = abs(2.0 * x)
+            if x > 1.0:
+                return ((-b - 6 * c) * x * x * x + (6 * b + 30 * c) * x * x + (-12 * b - 48 * c) * x + (8 * b + 24 * c)) * (1.0 / 6.0)
+            return ((12 - 9 * b - 6 * c) * x * x * x + (-18 + 12 * b + 6 * c) * x * x + (6 - 2 * b)) * (1.0 / 6.0)
+
+        ev = lambda x, y: m1(x * (1.0 / xw)) * m1(y * (1.0 / yw))
+    elif name == "triangle":  # triangle_filter.dart:37
+        ev = lambda x, y: max(0.0, xw - abs(x)) * max(0.0, yw - abs(y))
+    elif name == "sinc":  # lanczos_sinc_filter.dart:39-55
+        tau = kw.get("tau", 3.0)
+
+        def s1(x):
+            x = abs(x)
+            if x < 1e-5:
+                return 1.0
+            if x > 1.0:
+                return 0.0
+            x *= math.pi
+            return (math.sin(x) / x) * (math.sin(x * tau) / (x * tau))
+
+        ev = lambda x, y: s1(x * (1.0 / xw)) * s1(y * (1.0 / yw))
+    else:
+        raise ValueError(name)
+    t = np.empty(256, dtype=np.float32)
+    for y in range(16):
+        fy = (y + 0.5) * yw / 16
+        for x in range(16):
+            fx = (x + 0.5) * xw / 16
+            t[y * 16 + x] = ev(fx, fy)
+    return xw, yw, t
+
+
+@dataclass
+class Film:
+    xres: int
+    yres: int
+    filter: str = "box"
+    xwidth: float | None = None
+    ywidth: float | None = None
+    crop: tuple = (0.0, 1.0, 0.0, 1.0)
+    filter_params: dict = field(default_factory=dict)
+
+    def table(self):
+        return filter_table(self.filter, self.xwidth, self.ywidth, **self.filter_params)
+
+    def extent(self):  # image_film.dart:67-70
+        left = math.ceil(self.xres * self.crop[0])
+        width = max(1, math.ceil(self.xres * self.crop[1]) - left)
+        top = math.ceil(self.yres * self.crop[2])
+        height = max(1, math.ceil(self.yres * self.crop[3]) - top)
+        return left, top, width, height
+
+
+SAMPLER_LD, SAMPLER_STRATIFIED, SAMPLER_RANDOM = 0, 1, 2
+INTEGRATOR_PATH, INTEGRATOR_AO, INTEGRATOR_DIRECT = 0, 1, 2
+RNG_SERIAL, RNG_KEYED = 0, 1
+
+
+@dataclass
+class Sampler:
+    kind: int = SAMPLER_LD
+    spp: int = 4          # lowdiscrepancy / random: pixelsamples
+    xs: int = 2           # stratified: xsamples, ysamples
+    ys: int = 2
+    jitter: bool = True
+    pixel_order: int = 1  # 0 linear, 1 tile (render_options.dart default 'tile')
+    tile_size: int = 32
+    seed: int = 0
+    rng_mode: int = RNG_KEYED
+
+
+@dataclass
+class Integrator:
+    kind: int = INTEGRATOR_DIRECT
+    maxdepth: int = 5
+    strategy: int = 0          # directlighting: 0 all, 1 one
+    ao_nsamples: int = 2048
+    ao_mindist: float = 1.0e-4
+    ao_maxdist: float = math.inf
+
+
+# ---- scene assembly: meshes / spheres / lights in the reference's refine order ---------------------------
+
+
+class SceneBuilder:
+    """Collects shapes in scene-file order and produces the flat arrays of the C ABI."""
+
+    def __init__(self):
+        self.P, self.idx = [], []
+        self.tri_mat, self.tri_light, self.tri_rev = [], [], []
+        self.sph = []  # (o2w, w2o, params, mat, light, rev)
+        self.materials = []  # (kind, kd, sigma)
+        self.lights = []  # dict(kind, L, pos, nsamples, shapes=[("tri"|"sph", local ids...)])
+        self._order = []  # ("mesh", first_tri, ntris) | ("sphere", sphere_index)
+        self._nverts = 0
+
+    def material(self, kd, sigma=0.0) -> int:
+        self.materials.append((0, tuple(float(v) for v in kd), float(sigma)))
+        return len(self.materials) - 1
+
+    def point_light(self, pos, intensity) -> int:
+        self.lights.append(dict(kind=1, L=tuple(intensity), pos=tuple(pos), nsamples=1, shapes=[]))
+        return len(self.lights) - 1
+
+    def _area_light(self, L, nsamples):
+        self.lights.append(dict(kind=0, L=tuple(L), pos=(0, 0, 0), nsamples=nsamples, shapes=[]))
+        return len(self.lights) - 1
+
+    def mesh(self, P, idx, material=0, o2w=None, area_light=None, nsamples=1, reverse=False) -> int:
+        """Shape "trianglemesh": vertices go to world space at construction (triangle_mesh.dart:24-37).
+        `area_light` = emitted radiance: one DiffuseAreaLight per shape (dartray.dart:378-467)."""
+        P = np.asarray(P, dtype=np.float32).reshape(-1, 3)
+        if o2w is not None:
+            P = transform_points(o2w, P)
+        idx = np.asarray(idx, dtype=np.uint32).reshape(-1, 3)
+        first = len(self.tri_mat)
+        light = -1
+        if area_light is not None:
+            light = self._area_light(area_light, nsamples)
+            # ShapeSet refines LIFO (shape_set.dart:26-41): triangles in reverse order
+            self.lights[light]["shapes"] = [("tri", first + k) for k in range(idx.shape[0] - 1, -1, -1)]
+        self.P.append(P)
+        self.idx.append(idx + self._nverts)
+        self._nverts += P.shape[0]
+        n = idx.shape[0]
+        self.tri_mat += [material] * n
+        self.tri_light += [light] * n
+        self.tri_rev += [1 if reverse else 0] * n
+        self._order.append(("mesh", first, n))
+        return first
+
+    def sphere(self, o2w, radius=1.0, zmin=None, zmax=None, phimax=360.0, material=0, area_light=None, nsamples=1,
+               reverse=False) -> int:
+        o2w = np.asarray(o2w, dtype=np.float32).reshape(4, 4)
+        light = -1
+        k = len(self.sph)
+        if area_light is not None:
+            light = self._area_light(area_light, nsamples)
+            self.lights[light]["shapes"] = [("sph", k)]
+        self.sph.append((o2w, mat_inv(o2w), (radius, -radius if zmin is None else zmin, radius if zmax is None else zmax, phimax),
+                         material, light, 1 if reverse else 0))
+        self._order.append(("sphere", k))
+        return k
+
+    def arrays(self) -> dict:
+        ntris = len(self.tri_mat)
+        P = np.concatenate(self.P) if self.P else np.zeros((0, 3), np.float32)
+        idx = np.concatenate(self.idx) if self.idx else np.zeros((0, 3), np.uint32)
+        # refined order handed to BVHAccel: Primitive.fullyRefine is LIFO per primitive (primitive.dart:71-84)
+        order = []
+        for item in self._order:
+            if item[0] == "mesh":
+                order += list(range(item[1] + item[2] - 1, item[1] - 1, -1))
+            else:
+                order.append(ntris + item[1])
+        lights = []
+        for l in self.lights:
+            shapes = [(s[1] if s[0] == "tri" else ntris + s[1]) for s in l["shapes"]]
+            lights.append(dict(kind=l["kind"], L=l["L"], pos=l["pos"], nsamples=l["nsamples"], shapes=shapes))
+        mats = self.materials or [(0, (0.5, 0.5, 0.5), 0.0)]
+        return dict(
+            P=P, idx=idx, tri_mat=np.asarray(self.tri_mat, np.int32), tri_light=np.asarray(self.tri_light, np.int32),
+            tri_rev=np.asarray(self.tri_rev, np.uint8),
+            sph_o2w=np.stack([s[0].reshape(16) for s in self.sph]) if self.sph else np.zeros((0, 16), np.float32),
+            sph_w2o=np.stack([s[1].reshape(16) for s in self.sph]) if self.sph else np.zeros((0, 16), np.float32),
+            sph_params=np.asarray([s[2] for s in self.sph], np.float64).reshape(-1, 4),
+            sph_mat=np.asarray([s[3] for s in self.sph], np.int32), sph_light=np.asarray([s[4] for s in self.sph], np.int32),
+            sph_rev=np.asarray([s[5] for s in self.sph], np.uint8),
+            order=np.asarray(order, np.uint32),
+            mat_kind=np.asarray([m[0] for m in mats], np.int32), mat_kd=np.asarray([m[1] for m in mats], np.float32),
+            mat_sigma=np.asarray([m[2] for m in mats], np.float32),
+            light_kind=np.asarray([l["kind"] for l in lights], np.int32),
+            light_L=np.asarray([l["L"] for l in lights], np.float32).reshape(-1, 3),
+            light_pos=np.asarray([l["pos"] for l in lights], np.float32).reshape(-1, 3),
+            light_nsamples=np.asarray([l["nsamples"] for l in lights], np.int32),
+            light_shape_offsets=np.asarray(np.cumsum([0] + [len(l["shapes"]) for l in lights]), np.uint32),
+            light_shape_prims=np.asarray([p for l in lights for p in l["shapes"]], np.uint32),
+        )
+
+
+def upload_scene(ctx, arrays: dict, split: int = 2, max_node_prims: int = 4):
+    """Drives either dartray_b200.capi.Context or tests.oracle_lib.Oracle (same method names)."""
+    a = arrays
+    ctx.set_triangles(a["P"], a["idx"], a["tri_mat"], a["tri_light"], a["tri_rev"])
+    ctx.set_spheres(a["sph_o2w"], a["sph_w2o"], a["sph_params"], a["sph_mat"], a["sph_light"], a["sph_rev"])
+    ctx.set_build_order(a["order"])
+    ctx.build_bvh(split, max_node_prims)
+    ctx.set_materials(a["mat_kind"], a["mat_kd"], a["mat_sigma"])
+    ctx.set_lights(a["light_kind"], a["light_L"], a["light_pos"], a["light_nsamples"], a["light_shape_offsets"],
+                   a["light_shape_prims"])
+
+
+def configure_render(ctx, camera: PerspectiveCamera, film: Film, sampler: Sampler, integrator: Integrator):
+    ctx.set_camera(camera.raster_to_camera(film.xres, film.yres), camera.camera_to_world, camera.lens_radius,
+                   camera.focal_distance, camera.shutter_open, camera.shutter_close)
+    xw, yw, table = film.table()
+    ctx.set_film(film.xres, film.yres, film.crop, xw, yw, table)
+    ctx.set_sampler(sampler.kind, sampler.xs, sampler.ys, sampler.spp, int(sampler.jitter), sampler.pixel_order,
+                    sampler.tile_size, sampler.seed, sampler.rng_mode)
+    ctx.set_integrator(integrator.kind, integrator.maxdepth, integrator.strategy, integrator.ao_nsamples,
+                       integrator.ao_mindist, integrator.ao_maxdist)

@@ -171,6 +171,62 @@ def incoherent_rays(n: int = 8_388_608, radius: float = 2.5, seed_origin: int = 
     return pack_rays(o32, d.astype(np.float32))
 
 
+def cornell_synth():
+    """the 22 triangles + sphere of web/scenes/cornell-path.pbrt:23-59 (same
+    transforms and Kd values) with the disk light (:15-19) replaced by a 2-triangle quad light,
+    4.24 x 4.24 at y = 9.9 facing -y, L = (36, 36, 36), nsamples 1.  Returns (SceneBuilder, camera)."""
+    from . import host
+
+    sb = host.SceneBuilder()
+    grey = sb.material((0.75, 0.75, 0.75))
+    red = sb.material((0.48, 0.1125, 0.075))
+    green = sb.material((0.1125, 0.375, 0.1125))
+    box = sb.material((0.48, 0.48, 0.48))
+    h = 2.12
+    sb.mesh([[-h, 9.9, -h], [h, 9.9, -h], [h, 9.9, h], [-h, 9.9, h]], [[0, 1, 2], [0, 2, 3]], material=grey,
+            area_light=(36.0, 36.0, 36.0), nsamples=1)
+    quad = [[0, 1, 2], [0, 2, 3]]
+    walls = [
+        (grey, [10, -10, -10, -10, -10, -10, -10, -10, 10, 10, -10, 10]),
+        (grey, [10, 10, -10, 10, 10, 10, -10, 10, 10, -10, 10, -10]),
+        (grey, [10, -10, 10, -10, -10, 10, -10, 10, 10, 10, 10, 10]),
+        (red, [-10, -10, 10, -10, -10, -10, -10, 10, -10, -10, 10, 10]),
+        (green, [10, -10, -10, 10, -10, 10, 10, 10, 10, 10, 10, -10]),
+    ]
+    for m, p in walls:
+        sb.mesh(np.asarray(p, np.float32).reshape(4, 3), quad, material=m)
+    # short box: Translate 4 -7 4, Scale 0.3 0.4 0.3, Rotate 30 0 1 0 (CTM post-multiplies)
+    o2w = host.mat_mul(host.mat_mul(host.translate(4, -7, 4), host.scale(0.3, 0.4, 0.3)), host.rotate(30, (0, 1, 0)))
+    rquad = [[0, 2, 1], [0, 3, 2]]
+    faces = [
+        (rquad, [10, -10, -10, -10, -10, -10, -10, -10, 10, 10, -10, 10]),
+        (rquad, [10, 10, -10, 10, 10, 10, -10, 10, 10, -10, 10, -10]),
+        (rquad, [10, -10, 10, -10, -10, 10, -10, 10, 10, 10, 10, 10]),
+        (rquad, [-10, -10, 10, -10, -10, -10, -10, 10, -10, -10, 10, 10]),
+        (rquad, [10, -10, -10, 10, -10, 10, 10, 10, 10, 10, 10, -10]),
+        (quad, [10, -10, -10, -10, -10, -10, -10, 10, -10, 10, 10, -10]),
+    ]
+    for q, p in faces:
+        sb.mesh(np.asarray(p, np.float32).reshape(4, 3), q, material=box, o2w=o2w)
+    sb.sphere(host.translate(-4, -4, 0), radius=3.0, material=box)
+    cam = host.PerspectiveCamera(host.look_at((0, 0, -35), (0, 0, 0), (0, 1, 0)), fov=35.0)
+    return sb, cam
+
+
+def soup_render_scene(n_spheres: int = 512):
+    """`soup` as a renderable scene (config 3 / 5): grey matte, one quad light above, config-2 camera."""
+    from . import host
+
+    P, idx = soup(n_spheres)
+    sb = host.SceneBuilder()
+    grey = sb.material((0.6, 0.6, 0.6))
+    sb.mesh(P, idx, material=grey)
+    sb.mesh([[-1.5, 2.5, -1.5], [1.5, 2.5, -1.5], [1.5, 2.5, 1.5], [-1.5, 2.5, 1.5]], [[0, 1, 2], [0, 2, 3]], material=grey,
+            area_light=(20.0, 20.0, 20.0), nsamples=1)
+    cam = host.PerspectiveCamera(host.look_at((0, 0, -4), (0, 0, 0), (0, 1, 0)), fov=40.0)
+    return sb, cam
+
+
 def rays_hash(ro: np.ndarray, rd: np.ndarray) -> str:
     h = hashlib.sha256()
     h.update(np.ascontiguousarray(ro).tobytes())

@@ -9,12 +9,14 @@
 #include <string>
 #include <thread>
 
+#include "ref_render.h"
 #include "ref_scene.h"
 
 using namespace orc;
 
 struct orc_ctx {
   Scene scene;
+  RenderScene rs;
   Counters counters;
   std::string err;
   double buildSeconds = 0;
@@ -210,6 +212,116 @@ int orc_get_counters(const orc_ctx* c, uint64_t out[3]) {
   out[0] = c->counters.rays;
   out[1] = c->counters.nodes_visited;
   out[2] = c->counters.prims_tested;
+  return 0;
+}
+
+// ---- renderer (mirrors drt_set_materials ... drt_film_read) -------------------------------------
+int orc_set_materials(orc_ctx* c, uint32_t n, const int32_t* kind, const float* kd, const float* sigma) {
+  c->rs.materials.resize(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    Material& m = c->rs.materials[i];
+    m.kind = kind ? kind[i] : 0;
+    m.kd = Spec(kd[3 * i], kd[3 * i + 1], kd[3 * i + 2]);
+    m.sigma = sigma ? sigma[i] : 0.0;
+  }
+  return 0;
+}
+
+int orc_set_lights(orc_ctx* c, uint32_t n, const int32_t* kind, const float* L, const float* pos, const int32_t* nsamples,
+                   const uint32_t* shape_offsets, const uint32_t* shape_prims) {
+  c->rs.lights.resize(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    Light& l = c->rs.lights[i];
+    l.kind = kind[i];
+    l.L = Spec(L[3 * i], L[3 * i + 1], L[3 * i + 2]);
+    if (pos) { l.pos.x = pos[3 * i]; l.pos.y = pos[3 * i + 1]; l.pos.z = pos[3 * i + 2]; }
+    l.nSamples = nsamples ? nsamples[i] : 1;
+    l.shapes.clear();
+    if (shape_offsets && shape_prims)
+      for (uint32_t k = shape_offsets[i]; k < shape_offsets[i + 1]; ++k) l.shapes.push_back(shape_prims[k]);
+  }
+  return 0;
+}
+
+int orc_set_camera(orc_ctx* c, const float* rasterToCamera, const float* cameraToWorld, double lensRadius,
+                   double focalDistance, double shutterOpen, double shutterClose) {
+  Camera& cam = c->rs.camera;
+  cam.rasterToCamera = Transform(rasterToCamera, rasterToCamera);  // only m is used (point/vector)
+  cam.cameraToWorld = Transform(cameraToWorld, cameraToWorld);
+  cam.lensRadius = lensRadius; cam.focalDistance = focalDistance;
+  cam.shutterOpen = shutterOpen; cam.shutterClose = shutterClose;
+  return 0;
+}
+
+int orc_set_film(orc_ctx* c, int xres, int yres, const double* crop, double xw, double yw, const float* table) {
+  Film& f = c->rs.film;
+  f.xres = xres; f.yres = yres;
+  for (int i = 0; i < 4; ++i) f.crop[i] = crop ? crop[i] : (i & 1 ? 1.0 : 0.0);
+  f.xWidth = xw; f.yWidth = yw;
+  for (int i = 0; i < 256; ++i) f.table[i] = table[i];
+  f.configure();
+  return 0;
+}
+
+int orc_set_sampler(orc_ctx* c, int kind, int xs, int ys, int spp, int jitter, int pixelOrder, int tileSize, uint64_t seed,
+                    int rngMode) {
+  SamplerCfg& s = c->rs.sampler;
+  s.kind = kind; s.xs = xs; s.ys = ys; s.spp = spp; s.jitter = jitter; s.pixelOrder = pixelOrder; s.tileSize = tileSize;
+  s.seed = seed; s.rngMode = rngMode;
+  return 0;
+}
+
+int orc_set_integrator(orc_ctx* c, int kind, int maxDepth, int strategy, int aoSamples, double aoMin, double aoMax) {
+  IntegratorCfg& i = c->rs.integ;
+  i.kind = kind; i.maxDepth = maxDepth; i.strategy = strategy; i.aoSamples = aoSamples; i.aoMinDist = aoMin; i.aoMaxDist = aoMax;
+  return 0;
+}
+
+int orc_render(orc_ctx* c, int taskNum, int taskCount, int nthreads) {
+  c->rs.geom = &c->scene;
+  c->rs.stats = RenderStats();
+  c->rs.render(taskNum, taskCount, nthreads);
+  return 0;
+}
+
+int orc_film_clear(orc_ctx* c) { c->rs.film.configure(); return 0; }
+int orc_film_size(const orc_ctx* c, int out[4]) {
+  out[0] = c->rs.film.left; out[1] = c->rs.film.top; out[2] = c->rs.film.width; out[3] = c->rs.film.height;
+  return 0;
+}
+int orc_film_read(const orc_ctx* c, float* rgb, float* xyz, float* weight) {
+  const Film& f = c->rs.film;
+  if (rgb) f.writeImage(rgb);
+  if (xyz) std::copy(f.Lxyz.begin(), f.Lxyz.end(), xyz);
+  if (weight) std::copy(f.weightSum.begin(), f.weightSum.end(), weight);
+  return 0;
+}
+
+// Sample values of pixel (x, y): per sample imageX-x, imageY-y, lensU, lensV, time, 1D arrays, 2D arrays.
+// Returns floats per sample; *nSamplesOut = samples generated.
+int orc_pixel_samples(orc_ctx* c, int x, int y, float* out, int cap, int* nSamplesOut) {
+  c->rs.geom = &c->scene;
+  std::vector<float> v;
+  int per = c->rs.samplesForPixel(x, y, &v);
+  int n = per ? (int)v.size() / per : 0;
+  if (nSamplesOut) *nSamplesOut = n;
+  for (int i = 0; i < (int)v.size() && i < cap; ++i) out[i] = v[i];
+  return per;
+}
+
+int orc_render_stats(const orc_ctx* c, uint64_t out[5]) {
+  const RenderStats& s = c->rs.stats;
+  out[0] = s.cameraSamples; out[1] = s.closestRays; out[2] = s.shadowRays; out[3] = s.nodesVisited; out[4] = s.primsTested;
+  return 0;
+}
+
+// dart:math Random restatement, for documentation/tests of the serial stream
+int orc_dart_random(int64_t seed, int n, double* floats, uint32_t* uints) {
+  DartRandom r(seed);
+  for (int i = 0; i < n; ++i) {
+    if (floats) floats[i] = r.randomFloat();
+    if (uints) uints[i] = r.randomUint();
+  }
   return 0;
 }
 

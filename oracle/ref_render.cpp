@@ -1,0 +1,1037 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see ref_core.h / ref_render.h headers).  PARITY UNPINNED.
+#include "ref_render.h"
+
+#include <algorithm>
+#include <cassert>
+#include <thread>
+
+namespace orc {
+
+// BSDF flags, lib/core/reflection/bsdf.dart:23-31
+enum { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16, BSDF_ALL = 31 };
+
+static inline double Lerp(double t, double a, double b) { return (1.0 - t) * a + t * b; }  // common.dart:80-81
+
+// ---------------------------------------------------------------------------------------------------
+// montecarlo.dart
+void Distribution1D::init(const std::vector<double>& f) {  // :26-48 (func, cdf are Float32Lists)
+  count = (int)f.size();
+  func.resize(count);
+  for (int i = 0; i < count; ++i) func[i] = f32(f[i]);
+  cdf.assign(count + 1, 0.f);
+  for (int i = 1; i < count + 1; ++i) cdf[i] = f32((double)cdf[i - 1] + (double)func[i - 1] / count);
+  funcInt = cdf[count];
+  if (funcInt == 0.0) {
+    for (int i = 1; i < count + 1; ++i) cdf[i] = f32((double)i / count);
+  } else {
+    for (int i = 1; i < count + 1; ++i) cdf[i] = f32((double)cdf[i] / funcInt);
+  }
+}
+int Distribution1D::sampleDiscrete(double u) const {  // :82-92, upper_bound over cdf[0..count]
+  int ptr = (int)(std::upper_bound(cdf.begin(), cdf.begin() + count + 1, u,
+                                   [](double v, float c) { return v < (double)c; }) - cdf.begin());
+  return std::max(0, ptr - 1);
+}
+
+static inline Vec UniformSampleSphere(double u1, double u2) {  // :113-120
+  double z = 1.0 - 2.0 * u1;
+  double r = std::sqrt(std::fmax(0.0, 1.0 - z * z));
+  double phi = 2.0 * kPi * u2;
+  return Vec(r * std::cos(phi), r * std::sin(phi), z);
+}
+static inline Vec UniformSampleCone2(double u1, double u2, double costhetamax, const Vec& x, const Vec& y, const Vec& z) {
+  double costheta = Lerp(u1, costhetamax, 1.0);  // :135-142
+  double sintheta = std::sqrt(1.0 - costheta * costheta);
+  double phi = u2 * 2.0 * kPi;
+  return x * (std::cos(phi) * sintheta) + y * (std::sin(phi) * sintheta) + z * costheta;
+}
+static inline double UniformConePdf(double cosThetaMax) { return 1.0 / (2.0 * kPi * (1.0 - cosThetaMax)); }
+static void ConcentricSampleDisk(double u1, double u2, double* dx, double* dy) {  // :155-201
+  double r, theta;
+  double sx = 2 * u1 - 1, sy = 2 * u2 - 1;
+  if (sx == 0.0 && sy == 0.0) { *dx = 0.0; *dy = 0.0; return; }
+  if (sx >= -sy) {
+    if (sx > sy) { r = sx; theta = (sy > 0.0) ? sy / r : 8.0 + sy / r; }
+    else { r = sy; theta = 2.0 - sx / r; }
+  } else {
+    if (sx <= sy) { r = -sx; theta = 4.0 - sy / r; }
+    else { r = -sy; theta = 6.0 + sx / r; }
+  }
+  theta *= kPi / 4.0;
+  *dx = r * std::cos(theta);
+  *dy = r * std::sin(theta);
+}
+static inline Vec CosineSampleHemisphere(double u1, double u2) {  // :203-209
+  double dx, dy;
+  ConcentricSampleDisk(u1, u2, &dx, &dy);
+  double z = std::sqrt(std::fmax(0.0, 1.0 - dx * dx - dy * dy));
+  return Vec(dx, dy, z);
+}
+static inline double PowerHeuristic(int nf, double fPdf, int ng, double gPdf) {  // :480-484
+  double f = nf * fPdf, g = ng * gPdf;
+  return (f * f) / (f * f + g * g);
+}
+static inline double Sobol2(uint32_t n, uint32_t scramble) {  // :486-493
+  for (uint32_t v = 1u << 31; n != 0; n >>= 1, v ^= v >> 1)
+    if (n & 0x1) scramble ^= v;
+  return std::fmin(((scramble >> 8) & 0xffffff) / (double)(1 << 24), ONE_MINUS_EPSILON);
+}
+static inline double VanDerCorput(uint32_t n, uint32_t scramble) {  // :495-504
+  n = (n << 16) | (n >> 16);
+  n = ((n & 0x00ff00ff) << 8) | ((n & 0xff00ff00) >> 8);
+  n = ((n & 0x0f0f0f0f) << 4) | ((n & 0xf0f0f0f0) >> 4);
+  n = ((n & 0x33333333) << 2) | ((n & 0xcccccccc) >> 2);
+  n = ((n & 0x55555555) << 1) | ((n & 0xaaaaaaaa) >> 1);
+  n ^= scramble;
+  return std::fmin(((n >> 8) & 0xffffff) / (double)(1 << 24), ONE_MINUS_EPSILON);
+}
+static void Shuffle(float* samples, int offset, int count, int dims, Rng& rng) {  // :294-303
+  for (int i = 0; i < count; ++i) {
+    int other = i + (int)(rng.randomUint() % (uint32_t)(count - i));
+    for (int j = 0; j < dims; ++j) std::swap(samples[offset + dims * i + j], samples[offset + dims * other + j]);
+  }
+}
+static void LDShuffleScrambled1D(int nSamples, int nPixel, float* samples, Rng& rng) {  // :524-536
+  uint32_t scramble = rng.randomUint();
+  for (int i = 0; i < nSamples * nPixel; ++i) samples[i] = f32(VanDerCorput(i, scramble));
+  for (int i = 0; i < nPixel; ++i) Shuffle(samples, i * nSamples, nSamples, 1, rng);
+  Shuffle(samples, 0, nPixel, nSamples, rng);
+}
+static void LDShuffleScrambled2D(int nSamples, int nPixel, float* samples, Rng& rng) {  // :539-551
+  uint32_t s0 = rng.randomUint(), s1 = rng.randomUint();
+  for (int i = 0; i < nSamples * nPixel; ++i) {
+    samples[2 * i] = f32(VanDerCorput(i, s0));
+    samples[2 * i + 1] = f32(Sobol2(i, s1));
+  }
+  for (int i = 0; i < nPixel; ++i) Shuffle(samples, 2 * i * nSamples, nSamples, 2, rng);
+  Shuffle(samples, 0, nPixel, 2 * nSamples, rng);
+}
+static void StratifiedSample1D(float* s, int n, Rng& rng, bool jitter) {  // :270-277
+  double invTot = 1.0 / n;
+  for (int i = 0; i < n; ++i) {
+    double delta = jitter ? rng.randomFloat() : 0.5;
+    s[i] = f32(std::fmin((i + delta) * invTot, ONE_MINUS_EPSILON));
+  }
+}
+static void StratifiedSample2D(float* s, int nx, int ny, Rng& rng, bool jitter) {  // :279-292
+  double dx = 1.0 / nx, dy = 1.0 / ny;
+  int si = 0;
+  for (int y = 0; y < ny; ++y)
+    for (int x = 0; x < nx; ++x) {
+      double jx = jitter ? rng.randomFloat() : 0.5;
+      double jy = jitter ? rng.randomFloat() : 0.5;
+      s[si++] = f32(std::fmin((x + jx) * dx, ONE_MINUS_EPSILON));
+      s[si++] = f32(std::fmin((y + jy) * dy, ONE_MINUS_EPSILON));
+    }
+}
+static void LatinHypercube(float* samples, int nSamples, int nDim, Rng& rng) {  // :305-325
+  double delta = 1.0 / nSamples;
+  for (int i = 0; i < nSamples; ++i)
+    for (int j = 0; j < nDim; ++j) samples[nDim * i + j] = f32(std::fmin((i + rng.randomFloat()) * delta, ONE_MINUS_EPSILON));
+  for (int i = 0; i < nDim; ++i)
+    for (int j = 0; j < nSamples; ++j) {
+      int other = j + (int)(rng.randomUint() % (uint32_t)(nSamples - j));
+      std::swap(samples[nDim * j + i], samples[nDim * other + i]);
+    }
+}
+static inline int RoundUpPow2(int v) {  // common.dart:117-125
+  v--;
+  v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16;
+  return v + 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// film, lib/film/image_film.dart
+void Film::configure() {  // :51-97
+  left = (int)std::ceil(xres * crop[0]);
+  width = std::max(1, (int)std::ceil(xres * crop[1]) - left);
+  top = (int)std::ceil(yres * crop[2]);
+  height = std::max(1, (int)std::ceil(yres * crop[3]) - top);
+  invXWidth = 1.0 / xWidth;  // filter.dart:26-39
+  invYWidth = 1.0 / yWidth;
+  Lxyz.assign((size_t)width * height * 3, 0.f);
+  weightSum.assign((size_t)width * height, 0.f);
+}
+void Film::getSampleExtent(int e[4]) const {  // :247-252
+  e[0] = (int)std::floor(left + 0.5 - xWidth);
+  e[1] = (int)std::ceil(left + 0.5 + width + xWidth);
+  e[2] = (int)std::floor(top + 0.5 - yWidth);
+  e[3] = (int)std::ceil(top + 0.5 + height + yWidth);
+}
+void Film::addSample(double imageX, double imageY, const Spec& L) {  // :99-150
+  double dimageX = imageX - 0.5, dimageY = imageY - 0.5;
+  int x0 = (int)std::ceil(dimageX - xWidth), x1 = (int)std::floor(dimageX + xWidth);
+  int y0 = (int)std::ceil(dimageY - yWidth), y1 = (int)std::floor(dimageY + yWidth);
+  x0 = std::max(x0, left); x1 = std::min(x1, left + width - 1);
+  y0 = std::max(y0, top); y1 = std::min(y1, top + height - 1);
+  if ((x1 - x0) < 0 || (y1 - y0) < 0) return;
+  // L.toXYZ(): XYZColor (float32) via spectrum.dart:293-297
+  double r = L.c[0], g = L.c[1], b = L.c[2];
+  float xyz[3] = {f32(0.412453 * r + 0.357580 * g + 0.180423 * b), f32(0.212671 * r + 0.715160 * g + 0.072169 * b),
+                  f32(0.019334 * r + 0.119193 * g + 0.950227 * b)};
+  for (int y = y0; y <= y1; ++y) {
+    double fy = std::fabs((y - dimageY) * invYWidth * 16);
+    int iy = std::min((int)std::floor(fy), 15);
+    for (int x = x0; x <= x1; ++x) {
+      double fx = std::fabs((x - dimageX) * invXWidth * 16);
+      int ix = std::min((int)std::floor(fx), 15);
+      double filterWt = table[iy * 16 + ix];
+      size_t pi = (size_t)(y - top) * width + (x - left);
+      Lxyz[3 * pi] = f32((double)Lxyz[3 * pi] + filterWt * xyz[0]);
+      Lxyz[3 * pi + 1] = f32((double)Lxyz[3 * pi + 1] + filterWt * xyz[1]);
+      Lxyz[3 * pi + 2] = f32((double)Lxyz[3 * pi + 2] + filterWt * xyz[2]);
+      weightSum[pi] = f32((double)weightSum[pi] + filterWt);
+    }
+  }
+}
+void Film::writeImage(float* rgb) const {  // :268-299 (OutputImage.rgb is a Float32List)
+  for (size_t pi = 0; pi < (size_t)width * height; ++pi) {
+    double x = Lxyz[3 * pi], y = Lxyz[3 * pi + 1], z = Lxyz[3 * pi + 2];
+    double c0 = 3.240479 * x - 1.537150 * y - 0.498535 * z;
+    double c1 = -0.969256 * x + 1.875991 * y + 0.041556 * z;
+    double c2 = 0.055648 * x - 0.204043 * y + 1.057311 * z;
+    double w = weightSum[pi];
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+    if (w != 0.0) {
+      double invWt = 1.0 / w;
+      o0 = f32(std::fmax(0.0, c0 * invWt)); o1 = f32(std::fmax(0.0, c1 * invWt)); o2 = f32(std::fmax(0.0, c2 * invWt));
+    }
+    rgb[3 * pi] = o0; rgb[3 * pi + 1] = o1; rgb[3 * pi + 2] = o2;  // + splatScale * 0
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// shading geometry
+namespace {
+
+struct DG {  // the part of DifferentialGeometry the matte path uses
+  Vec p, nn, dpdu, dpdv;
+};
+
+struct Isect {
+  DG dg;
+  int32_t prim = -1;
+  double rayEpsilon = 0;
+};
+
+struct SampleLayout {
+  std::vector<int> n1D, n2D;
+  int add1D(int n) { n1D.push_back(n); return (int)n1D.size() - 1; }
+  int add2D(int n) { n2D.push_back(n); return (int)n2D.size() - 1; }
+  int floatsPerSample() const {
+    int n = 5;
+    for (int v : n1D) n += v;
+    for (int v : n2D) n += 2 * v;
+    return n;
+  }
+};
+
+struct SampleVals {
+  double imageX = 0, imageY = 0, lensU = 0, lensV = 0, time = 0;
+  std::vector<std::vector<float>> oneD, twoD;
+  void alloc(const SampleLayout& l) {
+    oneD.resize(l.n1D.size());
+    twoD.resize(l.n2D.size());
+    for (size_t i = 0; i < l.n1D.size(); ++i) oneD[i].assign(l.n1D[i], 0.f);
+    for (size_t i = 0; i < l.n2D.size(); ++i) twoD[i].assign(2 * l.n2D[i], 0.f);
+  }
+};
+
+struct SampleOffsets {  // LightSampleOffsets / BSDFSampleOffsets
+  int nSamples = 0, componentOffset = 0, posOffset = 0;
+};
+
+struct U3 {  // LightSample / BSDFSample: two float32 values + one f64 component
+  float u0 = 0, u1 = 0;
+  double comp = 0;
+  static U3 random(Rng& rng) {  // bsdf_sample.dart:38-44, light_sample.dart:45-51
+    U3 s;
+    s.u0 = f32(rng.randomFloat());
+    s.u1 = f32(rng.randomFloat());
+    s.comp = rng.randomFloat();
+    return s;
+  }
+  static U3 fromSample(const SampleVals& sv, const SampleOffsets& o, int n) {
+    U3 s;
+    s.u0 = sv.twoD[o.posOffset][2 * n];
+    s.u1 = sv.twoD[o.posOffset][2 * n + 1];
+    s.comp = sv.oneD[o.componentOffset][n];
+    return s;
+  }
+};
+
+struct Bsdf {  // bsdf.dart:41-255 with at most one diffuse BxDF (matte)
+  Vec p, nn, ng, sn, tn;
+  bool hasBxdf = false;
+  Spec R;
+  bool orenNayar = false;
+  double A = 0, B = 0;
+  Vec worldToLocal(const Vec& v) const { return Vec(Dot(v, sn), Dot(v, tn), Dot(v, nn)); }
+  Vec localToWorld(const Vec& v) const {
+    return Vec((double)sn.x * v.x + (double)tn.x * v.y + (double)nn.x * v.z,
+               (double)sn.y * v.x + (double)tn.y * v.y + (double)nn.y * v.z,
+               (double)sn.z * v.x + (double)tn.z * v.y + (double)nn.z * v.z);
+  }
+  static double CosTheta(const Vec& v) { return v.z; }
+  static double AbsCosTheta(const Vec& v) { return std::fabs((double)v.z); }
+  static double SinTheta2(const Vec& v) { return std::fmax(0.0, 1.0 - CosTheta(v) * CosTheta(v)); }
+  static double SinTheta(const Vec& v) { return std::sqrt(SinTheta2(v)); }
+  static double CosPhi(const Vec& v) { double s = SinTheta(v); return s == 0.0 ? 1.0 : clampd((double)v.x / s, -1.0, 1.0); }
+  static double SinPhi(const Vec& v) { double s = SinTheta(v); return s == 0.0 ? 0.0 : clampd((double)v.y / s, -1.0, 1.0); }
+  Spec bxdfF(const Vec& wo, const Vec& wi) const {
+    if (!orenNayar) return R * INV_PI;  // lambertian.dart:35-37
+    // oren_nayar.dart:33-58
+    double sinthetai = SinTheta(wi), sinthetao = SinTheta(wo);
+    double maxcos = 0.0;
+    if (sinthetai > 1e-4 && sinthetao > 1e-4) {
+      double dcos = CosPhi(wi) * CosPhi(wo) + SinPhi(wi) * SinPhi(wo);
+      maxcos = std::fmax(0.0, dcos);
+    }
+    double sinalpha, tanbeta;
+    if (AbsCosTheta(wi) > AbsCosTheta(wo)) { sinalpha = sinthetao; tanbeta = sinthetai / AbsCosTheta(wi); }
+    else { sinalpha = sinthetai; tanbeta = sinthetao / AbsCosTheta(wo); }
+    return R * (INV_PI * (A + B * maxcos * sinalpha * tanbeta));
+  }
+  static double bxdfPdf(const Vec& wo, const Vec& wi) {  // bxdf.dart:84-88
+    return ((double)wo.z * wi.z > 0.0) ? AbsCosTheta(wi) * INV_PI : 0.0;
+  }
+  static bool matches(int flags) { int type = BSDF_REFLECTION | BSDF_DIFFUSE; return (type & flags) == type; }
+  Spec f(const Vec& woW, const Vec& wiW, int flags) const {  // bsdf.dart:177-198
+    Vec wi = worldToLocal(wiW), wo = worldToLocal(woW);
+    if (Dot(wiW, ng) * Dot(woW, ng) > 0) flags &= ~BSDF_TRANSMISSION;
+    else flags &= ~BSDF_REFLECTION;
+    Spec r(0.0);
+    if (hasBxdf && matches(flags)) r = r + bxdfF(wo, wi);
+    return r;
+  }
+  double pdf(const Vec& woW, const Vec& wiW, int flags) const {  // bsdf.dart:128-146
+    if (!hasBxdf) return 0.0;
+    Vec wo = worldToLocal(woW), wi = worldToLocal(wiW);
+    double p = 0.0;
+    int matching = 0;
+    if (matches(flags)) { ++matching; p += bxdfPdf(wo, wi); }
+    return matching > 0 ? p / matching : 0.0;
+  }
+  Spec sample_f(const Vec& woW, Vec* wiW, const U3& s, double* pdfOut, int flags, int* sampledType) const {  // :53-126
+    int matching = (hasBxdf && matches(flags)) ? 1 : 0;
+    if (matching == 0) { *pdfOut = 0.0; if (sampledType) *sampledType = 0; return Spec(0.0); }
+    Vec wo = worldToLocal(woW);
+    Vec wi = CosineSampleHemisphere(s.u0, s.u1);  // bxdf.dart:37-48
+    if (wo.z < 0.0f) wi.z = f32((double)wi.z * -1.0);
+    *pdfOut = bxdfPdf(wo, wi);
+    if (*pdfOut == 0.0) { if (sampledType) *sampledType = 0; return Spec(0.0); }
+    if (sampledType) *sampledType = BSDF_REFLECTION | BSDF_DIFFUSE;
+    *wiW = localToWorld(wi);
+    Spec r(0.0);
+    if (Dot(*wiW, ng) * Dot(woW, ng) > 0) flags &= ~BSDF_TRANSMISSION;
+    else flags &= ~BSDF_REFLECTION;
+    if (matches(flags)) r = r + bxdfF(wo, wi);
+    return r;
+  }
+};
+
+struct Ctx {
+  RenderScene& rs;
+  const Scene& g;
+  SampleLayout layout;
+  // path integrator offsets (path_integrator.dart:124-131)
+  SampleOffsets lightOff[3], bsdfOff[3], pathOff[3];
+  int lightNumOff[3] = {-1, -1, -1};
+  // direct lighting offsets (direct_lighting_integrator.dart:70-96)
+  std::vector<SampleOffsets> dlLight, dlBsdf;
+  int dlLightNum = -1;
+  RenderStats stats;
+
+  explicit Ctx(RenderScene& r) : rs(r), g(*r.geom) {}
+
+  SampleOffsets lightOffsets(int n) { SampleOffsets o; o.nSamples = n; o.componentOffset = layout.add1D(n); o.posOffset = layout.add2D(n); return o; }
+  SampleOffsets bsdfOffsets(int n) { return lightOffsets(n); }  // componentOffset + dirOffset, same order
+
+  void requestSamples() {
+    const IntegratorCfg& ic = rs.integ;
+    if (ic.kind == 0) {
+      for (int i = 0; i < 3; ++i) {
+        lightOff[i] = lightOffsets(1);
+        lightNumOff[i] = layout.add1D(1);
+        bsdfOff[i] = bsdfOffsets(1);
+        pathOff[i] = bsdfOffsets(1);
+      }
+    } else if (ic.kind == 2) {
+      if (ic.strategy == 0) {
+        for (size_t i = 0; i < rs.lights.size(); ++i) {
+          int n = rs.lights[i].nSamples;
+          if (rs.sampler.kind == 0) n = RoundUpPow2(n);  // sampler.roundSize
+          dlLight.push_back(lightOffsets(n));
+          dlBsdf.push_back(bsdfOffsets(n));
+        }
+        dlLightNum = -1;
+      } else {
+        dlLight.push_back(lightOffsets(1));
+        dlLightNum = layout.add1D(1);
+        dlBsdf.push_back(bsdfOffsets(1));
+      }
+    }
+    // volume integrator "emission" (render_options.dart:24-39 default), emission_integrator.dart:26-29
+    layout.add1D(1);
+    layout.add1D(1);
+  }
+
+  // ---- scene queries with stats ----
+  bool intersect(Ray& ray, Isect* is) {
+    Hit h;
+    Counters c;
+    bool hit = g.intersect(ray, &h, &c);
+    stats.closestRays++;
+    stats.nodesVisited += c.nodes_visited;
+    stats.primsTested += c.prims_tested;
+    if (!hit) return false;
+    fillIsect(ray, h, is);
+    return true;
+  }
+  bool intersectP(const Ray& ray) {
+    Counters c;
+    bool hit = g.intersectP(ray, &c);
+    stats.shadowRays++;
+    stats.nodesVisited += c.nodes_visited;
+    stats.primsTested += c.prims_tested;
+    return hit;
+  }
+
+  // dg.set(...) of triangle.dart:100-154 / sphere.dart:118-160 + differential_geometry.dart:77-99.
+  // `rayAtHit` is the ray the shape test ran on (its maxt already holds tHit for closest-hit queries).
+  void shapeDG(uint32_t prim, const Ray& ray, const Hit& h, DG* dg) const {
+    if (prim < g.ntris()) {
+      Vec p1, p2, p3;
+      g.triVerts(prim, &p1, &p2, &p3);
+      const double uvs[6] = {0.0, 0.0, 1.0, 0.0, 1.0, 1.0};  // triangle.dart:255-262
+      double du1 = uvs[0] - uvs[4], du2 = uvs[2] - uvs[4], dv1 = uvs[1] - uvs[5], dv2 = uvs[3] - uvs[5];
+      Vec dp1 = p1 - p3, dp2 = p2 - p3;
+      double determinant = du1 * dv2 - dv1 * du2;
+      Vec dpdu, dpdv;
+      if (determinant == 0.0) {
+        double e1x = (double)p2.x - p1.x, e1y = (double)p2.y - p1.y, e1z = (double)p2.z - p1.z;
+        double e2x = (double)p3.x - p1.x, e2y = (double)p3.y - p1.y, e2z = (double)p3.z - p1.z;
+        double e3x = (e2y * e1z) - (e2z * e1y), e3y = (e2z * e1x) - (e2x * e1z), e3z = (e2x * e1y) - (e2y * e1x);
+        double len = std::sqrt(e3x * e3x + e3y * e3y + e3z * e3z);
+        CoordinateSystem(Vec(e3x / len, e3y / len, e3z / len), &dpdu, &dpdv);
+      } else {
+        double invdet = 1.0 / determinant;
+        dpdu = (dp1 * dv2 - dp2 * dv1) * invdet;
+        dpdv = (dp1 * -du2 + dp2 * du1) * invdet;
+      }
+      dg->p = ray.at(h.t);
+      dg->dpdu = dpdu;
+      dg->dpdv = dpdv;
+    } else {
+      const Sphere& s = g.spheres[prim - g.ntris()];
+      Vec phit = h.phitObj;
+      double phi = h.phi;
+      double theta = std::acos(clampd((double)phit.z / s.radius, -1.0, 1.0));
+      double zradius = std::sqrt((double)phit.x * phit.x + (double)phit.y * phit.y);
+      double invzradius = 1.0 / zradius;
+      double cosphi = phit.x * invzradius, sinphi = phit.y * invzradius;
+      (void)phi;
+      Vec dpdu(-s.phiMax * phit.y, s.phiMax * phit.x, 0.0);
+      Vec dpdv = Vec(phit.z * cosphi, phit.z * sinphi, -s.radius * std::sin(theta)) * (s.thetaMax - s.thetaMin);
+      dg->p = s.o2w.point(phit);
+      dg->dpdu = s.o2w.vector(dpdu);
+      dg->dpdv = s.o2w.vector(dpdv);
+    }
+    dg->nn = Normalize(Cross(dg->dpdu, dg->dpdv));
+    if (g.reverseOf[prim]) dg->nn = dg->nn * -1.0;  // transformSwapsHandedness is never set (shape.dart:30)
+  }
+  void fillIsect(const Ray& ray, const Hit& h, Isect* is) const {
+    is->prim = h.prim;
+    is->rayEpsilon = h.rayEpsilon;
+    // the shape computed dg.p with the ray it was given; maxt == tHit after a closest-hit query
+    shapeDG((uint32_t)h.prim, ray, h, &is->dg);
+  }
+
+  // Shape.intersect without the GeometricPrimitive side effect (ray.maxDistance unchanged)
+  bool shapeIntersect(uint32_t prim, const Ray& ray, double* thit, DG* dg) const {
+    Ray r = ray;
+    Hit h;
+    if (!g.primIntersect(prim, r, &h)) return false;
+    *thit = h.t;
+    shapeDG(prim, ray, h, dg);
+    return true;
+  }
+
+  // ---- BSDF (intersection.dart:44-50 -> geometric_primitive.dart:71-75 -> matte_material.dart:41-65) ----
+  Bsdf getBSDF(const Isect& is) const {
+    Bsdf b;
+    const DG& dg = is.dg;
+    b.p = dg.p;
+    b.nn = dg.nn;  // dgShading == dg: no per-vertex normals (triangle.dart:273-276), sphere default
+    b.ng = dg.nn;
+    b.sn = Normalize(dg.dpdu);
+    b.tn = Cross(b.nn, b.sn);
+    const Material& m = rs.materials[g.materialOf[is.prim]];
+    Spec r(clampd(m.kd.c[0], 0.0, kInf), clampd(m.kd.c[1], 0.0, kInf), clampd(m.kd.c[2], 0.0, kInf));
+    double sig = clampd(m.sigma, 0.0, 90.0);
+    if (!r.isBlack()) {
+      b.hasBxdf = true;
+      b.R = r;
+      if (sig != 0.0) {  // oren_nayar.dart:24-31
+        b.orenNayar = true;
+        double sigma = Radians(sig), sigma2 = sigma * sigma;
+        b.A = 1.0 - (sigma2 / (2.0 * (sigma2 + 0.33)));
+        b.B = 0.45 * sigma2 / (sigma2 + 0.09);
+      }
+    }
+    return b;
+  }
+
+  // ---- lights ----
+  Spec areaL(const Light& l, const Vec& n, const Vec& w) const { return Dot(n, w) > 0.0 ? l.L : Spec(0.0); }
+  Spec isectLe(const Isect& is, const Vec& wo) const {  // intersection.dart:62-65
+    int li = g.lightOf[is.prim];
+    return li >= 0 ? areaL(rs.lights[li], is.dg.nn, wo) : Spec(0.0);
+  }
+  double shapeArea(uint32_t prim) const {
+    if (prim < g.ntris()) {  // triangle.dart:265-269
+      Vec p1, p2, p3;
+      g.triVerts(prim, &p1, &p2, &p3);
+      return 0.5 * Length(Cross(p2 - p1, p3 - p1));
+    }
+    const Sphere& s = g.spheres[prim - g.ntris()];
+    return s.phiMax * s.radius * (s.zmax - s.zmin);  // sphere.dart:243-245
+  }
+  Vec sphereSample(const Sphere& s, double u1, double u2, Vec* ns) const {  // sphere.dart:247-259
+    Vec p = Vec() + UniformSampleSphere(u1, u2) * s.radius;
+    Vec n = s.o2w.normal(Vec(p.x, p.y, p.z));
+    n = n / Length(n);
+    if (s.reverseOrientation) n = Vec(-(double)n.x, -(double)n.y, -(double)n.z);
+    *ns = n;
+    return s.o2w.point(p);
+  }
+  Vec shapeSample2(uint32_t prim, const Vec& p, double u1, double u2, Vec* ns) const {
+    if (prim < g.ntris()) {  // shape.dart:96-98 -> triangle.dart:366-383
+      double su1 = std::sqrt(u1);
+      double b1 = 1.0 - su1, b2 = u2 * su1;
+      Vec t0, t1, t2;
+      g.triVerts(prim, &t0, &t1, &t2);
+      Vec pt = t0 * b1 + t1 * b2 + t2 * (1.0 - b1 - b2);
+      Vec n = Normalize(Cross(t1 - t0, t2 - t0));
+      if (g.reverseOf[prim]) n = Vec((double)n.x * -1.0, (double)n.y * -1.0, (double)n.z * -1.0);
+      *ns = n;
+      return pt;
+    }
+    const Sphere& s = g.spheres[prim - g.ntris()];  // sphere.dart:261-297
+    Vec Pcenter = s.o2w.point(Vec());
+    Vec wc = Normalize(Pcenter - p);
+    Vec wcX, wcY;
+    CoordinateSystem(wc, &wcX, &wcY);
+    if (DistanceSquared(p, Pcenter) - s.radius * s.radius < 1.0e-4) return sphereSample(s, u1, u2, ns);
+    double sinThetaMax2 = s.radius * s.radius / DistanceSquared(p, Pcenter);
+    double cosThetaMax = std::sqrt(std::fmax(0.0, 1.0 - sinThetaMax2));
+    Ray r(p, UniformSampleCone2(u1, u2, cosThetaMax, wcX, wcY, wc), 1.0e-3);
+    double thit;
+    DG dgs;
+    if (!shapeIntersect(prim, r, &thit, &dgs)) thit = Dot(Pcenter - p, Normalize(r.d));
+    Vec ps = r.at(thit);
+    Vec n = Normalize(ps - Pcenter);
+    if (s.reverseOrientation) n = Vec(-(double)n.x, -(double)n.y, -(double)n.z);
+    *ns = n;
+    return ps;
+  }
+  double shapePdf2(uint32_t prim, const Vec& p, const Vec& wi) const {
+    if (prim >= g.ntris()) {  // sphere.dart:299-311
+      const Sphere& s = g.spheres[prim - g.ntris()];
+      Vec Pcenter = s.o2w.point(Vec());
+      if (!(DistanceSquared(p, Pcenter) - s.radius * s.radius < 1.0e-4)) {
+        double sinThetaMax2 = s.radius * s.radius / DistanceSquared(p, Pcenter);
+        double cosThetaMax = std::sqrt(std::fmax(0.0, 1.0 - sinThetaMax2));
+        return UniformConePdf(cosThetaMax);
+      }
+    }
+    // shape.dart:100-121
+    Ray ray(p, wi, 1.0e-3);
+    ray.depth = -1;
+    double thit;
+    DG dgl;
+    if (!shapeIntersect(prim, ray, &thit, &dgl)) return 0.0;
+    double pdf = DistanceSquared(p, ray.at(thit)) / (AbsDot(dgl.nn, -wi) * shapeArea(prim));
+    if (std::isinf(pdf)) pdf = 0.0;
+    return pdf;
+  }
+  Vec shapeSetSample(const Light& l, const U3& ls, Vec* Ns, const Vec& p) const {  // shape_set.dart:53-79
+    int sn = l.areaDistribution.sampleDiscrete(ls.comp) % (int)l.shapes.size();
+    Vec pt = shapeSample2(l.shapes[sn], p, ls.u0, ls.u1, Ns);
+    Ray r(p, pt - p, 1.0e-3, kInf);
+    double thit = 1.0;
+    bool anyHit = false;
+    DG dg;
+    for (uint32_t sh : l.shapes) anyHit = shapeIntersect(sh, r, &thit, &dg) || anyHit;
+    if (anyHit) *Ns = dg.nn;
+    return r.at(thit);
+  }
+  double shapeSetPdf(const Light& l, const Vec& p, const Vec& wi) const {  // shape_set.dart:81-89
+    double pdf = 0.0;
+    for (size_t i = 0; i < l.shapes.size(); ++i) pdf += l.areas[i] * shapePdf2(l.shapes[i], p, wi);
+    return pdf / l.area;
+  }
+
+  struct Vis { Ray r; };
+  static void setSegment(Vis* v, const Vec& p1, double eps1, const Vec& p2, double eps2, double time) {
+    double dist = Distance(p1, p2);  // visibility_tester.dart:26-29
+    v->r = Ray(p1, (p2 - p1) / dist, eps1, dist * (1.0 - eps2), time);
+  }
+  Spec sampleLAtPoint(const Light& l, const Vec& p, double pEps, const U3& ls, double time, Vec* wi, double* pdf, Vis* vis) const {
+    if (l.kind == 1) {  // point_light.dart:41-47
+      *wi = Normalize(l.pos - p);
+      *pdf = 1.0;
+      setSegment(vis, p, pEps, l.pos, 0.0, time);
+      return l.L / DistanceSquared(l.pos, p);
+    }
+    Vec ns;  // diffuse_area_light.dart:59-70
+    Vec ps = shapeSetSample(l, ls, &ns, p);
+    *wi = Normalize(ps - p);
+    *pdf = shapeSetPdf(l, p, *wi);
+    setSegment(vis, p, pEps, ps, 1.0e-3, time);
+    return areaL(l, ns, -*wi);
+  }
+
+  // integrator.dart:119-185
+  Spec EstimateDirect(const Light& light, int lightIndex, const Vec& p, const Vec& n, const Vec& wo, double rayEpsilon, double time,
+                      const Bsdf& bsdf, const U3& lightSample, const U3& bsdfSample, int flags) {
+    Spec Ld(0.0);
+    Vec wi;
+    double lightPdf = 0.0, bsdfPdf = 0.0;
+    Vis vis;
+    Spec Li = sampleLAtPoint(light, p, rayEpsilon, lightSample, time, &wi, &lightPdf, &vis);
+    const bool delta = light.kind == 1;
+    if (lightPdf > 0.0 && !Li.isBlack()) {
+      Spec f = bsdf.f(wo, wi, flags);
+      if (!f.isBlack() && !intersectP(vis.r)) {
+        // Li *= transmittance == 1
+        Li = Li * Spec(1.0);
+        if (delta) {
+          Ld = Ld + f * Li * (AbsDot(wi, n) / lightPdf);
+        } else {
+          bsdfPdf = bsdf.pdf(wo, wi, flags);
+          double weight = PowerHeuristic(1, lightPdf, 1, bsdfPdf);
+          Ld = Ld + f * Li * ((AbsDot(wi, n) * weight / lightPdf));
+        }
+      }
+    }
+    if (!delta) {
+      int sampledType = 0;
+      Spec f = bsdf.sample_f(wo, &wi, bsdfSample, &bsdfPdf, flags, &sampledType);
+      if (!f.isBlack() && bsdfPdf > 0.0) {
+        double weight = 1.0;
+        if ((sampledType & BSDF_SPECULAR) == 0) {
+          lightPdf = shapeSetPdf(light, p, wi);
+          if (lightPdf == 0.0) return Ld;
+          weight = PowerHeuristic(1, bsdfPdf, 1, lightPdf);
+        }
+        Isect lightIsect;
+        Spec Li2(0.0);
+        Ray ray(p, wi, rayEpsilon, kInf, time);
+        if (intersect(ray, &lightIsect)) {
+          if (g.lightOf[lightIsect.prim] == lightIndex) Li2 = isectLe(lightIsect, -wi);
+        }  // else Li = light.Le(ray) == 0 for area lights
+        if (!Li2.isBlack()) {
+          Li2 = Li2 * Spec(1.0);
+          Ld = Ld + f * Li2 * (AbsDot(wi, n) * weight / bsdfPdf);
+        }
+      }
+    }
+    return Ld;
+  }
+
+  // integrator.dart:79-117
+  Spec UniformSampleOneLight(const Vec& p, const Vec& n, const Vec& wo, double rayEpsilon, double time, const Bsdf& bsdf,
+                             const SampleVals& sample, Rng& rng, int lightNumOffset, const SampleOffsets* lightOff_,
+                             const SampleOffsets* bsdfOff_) {
+    int nLights = (int)rs.lights.size();
+    if (nLights == 0) return Spec(0.0);
+    int lightNum;
+    if (lightNumOffset != -1) lightNum = (int)std::floor(sample.oneD[lightNumOffset][0] * (double)nLights);
+    else lightNum = (int)std::floor(rng.randomFloat() * nLights);
+    lightNum = std::min(lightNum, nLights - 1);
+    U3 ls, bs;
+    if (lightOff_ && bsdfOff_) { ls = U3::fromSample(sample, *lightOff_, 0); bs = U3::fromSample(sample, *bsdfOff_, 0); }
+    else { ls = U3::random(rng); bs = U3::random(rng); }
+    return EstimateDirect(rs.lights[lightNum], lightNum, p, n, wo, rayEpsilon, time, bsdf, ls, bs, BSDF_ALL & ~BSDF_SPECULAR) *
+           (double)nLights;
+  }
+
+  // integrator.dart:39-77
+  Spec UniformSampleAllLights(const Vec& p, const Vec& n, const Vec& wo, double rayEpsilon, double time, const Bsdf& bsdf,
+                              const SampleVals& sample, Rng& rng) {
+    Spec L(0.0);
+    for (size_t i = 0; i < rs.lights.size(); ++i) {
+      int nSamples = dlLight[i].nSamples;
+      Spec Ld(0.0);
+      for (int j = 0; j < nSamples; ++j) {
+        U3 ls = U3::fromSample(sample, dlLight[i], j), bs = U3::fromSample(sample, dlBsdf[i], j);
+        Ld = Ld + EstimateDirect(rs.lights[i], (int)i, p, n, wo, rayEpsilon, time, bsdf, ls, bs, BSDF_ALL & ~BSDF_SPECULAR);
+      }
+      L = L + Ld / (double)nSamples;
+    }
+    (void)rng;
+    return L;
+  }
+
+  // path_integrator.dart:29-122
+  Spec pathLi(const Ray& r, const Isect& isect, const SampleVals& sample, Rng& rng) {
+    Spec pathThroughput(1.0), L(0.0);
+    Ray ray = r;
+    bool specularBounce = false;
+    Isect isectP = isect, localIsect;
+    for (int bounces = 0;; ++bounces) {
+      if (bounces == 0 || specularBounce) L = L + pathThroughput * isectLe(isectP, -ray.d);
+      Bsdf bsdf = getBSDF(isectP);
+      Vec p = bsdf.p, n = bsdf.nn, wo = -ray.d;
+      if (bounces < 3)
+        L = L + pathThroughput * UniformSampleOneLight(p, n, wo, isectP.rayEpsilon, ray.time, bsdf, sample, rng,
+                                                       lightNumOff[bounces], &lightOff[bounces], &bsdfOff[bounces]);
+      else
+        L = L + pathThroughput * UniformSampleOneLight(p, n, wo, isectP.rayEpsilon, ray.time, bsdf, sample, rng, -1, nullptr, nullptr);
+      U3 outgoing = bounces < 3 ? U3::fromSample(sample, pathOff[bounces], 0) : U3::random(rng);
+      Vec wi;
+      double pdf = 0.0;
+      int flags = 0;
+      Spec f = bsdf.sample_f(wo, &wi, outgoing, &pdf, BSDF_ALL, &flags);
+      if (f.isBlack() || pdf == 0.0) break;
+      specularBounce = (flags & BSDF_SPECULAR) != 0;
+      pathThroughput = pathThroughput * (f * AbsDot(wi, n) / pdf);
+      ray = Ray(p, wi, isectP.rayEpsilon, kInf, ray.time, ray.depth + 1);  // RayDifferential.child
+      if (bounces > 3) {
+        double continueProbability = std::fmin(0.5, pathThroughput.luminance());
+        if (rng.randomFloat() > continueProbability) break;
+        pathThroughput = pathThroughput / continueProbability;
+      }
+      if (bounces == rs.integ.maxDepth) break;
+      if (!intersect(ray, &localIsect)) break;  // area lights: Light.Le(ray) == 0
+      // pathThroughput *= transmittance == 1
+      pathThroughput = pathThroughput * Spec(1.0);
+      isectP = localIsect;
+    }
+    return L;
+  }
+
+  // ambient_occlusion_integrator.dart:28-53
+  Spec aoLi(const Ray& ray, const Isect& isect, Rng& rng) {
+    Bsdf bsdf = getBSDF(isect);
+    Vec p = bsdf.p;
+    Vec n = FaceForward(isect.dg.nn, -ray.d);
+    int nSamples = RoundUpPow2(rs.integ.aoSamples);
+    uint32_t s0 = rng.randomUint(), s1 = rng.randomUint();
+    int nClear = 0;
+    for (int i = 0; i < nSamples; ++i) {
+      double u0 = VanDerCorput(i, s0), u1 = Sobol2(i, s1);
+      Vec w = UniformSampleSphere(u0, u1);
+      if (Dot(w, n) < 0.0) w = -w;
+      Ray r(p, w, rs.integ.aoMinDist, rs.integ.aoMaxDist);
+      if (!intersectP(r)) ++nClear;
+    }
+    return Spec((double)nClear / nSamples);
+  }
+
+  // direct_lighting_integrator.dart:30-68
+  Spec directLi(const Ray& ray, const Isect& isect, const SampleVals& sample, Rng& rng) {
+    Spec L(0.0);
+    Bsdf bsdf = getBSDF(isect);
+    Vec wo = -ray.d, p = bsdf.p, n = bsdf.nn;
+    L = L + isectLe(isect, wo);
+    if (!rs.lights.empty()) {
+      if (rs.integ.strategy == 0) L = L + UniformSampleAllLights(p, n, wo, isect.rayEpsilon, ray.time, bsdf, sample, rng);
+      else L = L + UniformSampleOneLight(p, n, wo, isect.rayEpsilon, ray.time, bsdf, sample, rng, dlLightNum, &dlLight[0], &dlBsdf[0]);
+    }
+    if (ray.depth + 1 < rs.integ.maxDepth) {
+      // SpecularReflect / SpecularTransmit (integrator.dart:187-290): a matte BSDF has no specular
+      // component, so both return black — after drawing a BSDFSample.random(rng) each.
+      U3::random(rng);
+      U3::random(rng);
+    }
+    return L;
+  }
+
+  // perspective_camera.dart:93-132 (the differential rays only feed texture filtering: not computed)
+  Ray cameraRay(const SampleVals& s) const {
+    const Camera& c = rs.camera;
+    Vec Pras(s.imageX, s.imageY, 0.0);
+    Vec Pcamera = c.rasterToCamera.point(Pras);
+    Ray ray(Vec(0.0, 0.0, 0.0), Normalize(Pcamera), 0.0, kInf);
+    if (c.lensRadius > 0.0) {
+      double lu, lv;
+      ConcentricSampleDisk(s.lensU, s.lensV, &lu, &lv);
+      lu *= c.lensRadius;
+      lv *= c.lensRadius;
+      double ft = c.focalDistance / ray.d.z;
+      Vec Pfocus = ray.at(ft);
+      ray.o = Vec(lu, lv, 0.0);
+      ray.d = Normalize(Pfocus - ray.o);
+    }
+    ray.time = s.time;
+    Ray w = c.cameraToWorld.ray(ray);
+    w.time = s.time;
+    return w;
+  }
+
+  // sampler_renderer.dart:67-98 + :173-193
+  Spec Li(const SampleVals& s, Rng& rng) {
+    Ray ray = cameraRay(s);
+    stats.cameraSamples++;
+    Isect isect;
+    Spec L(0.0);
+    if (intersect(ray, &isect)) {
+      switch (rs.integ.kind) {
+        case 0: L = pathLi(ray, isect, s, rng); break;
+        case 1: L = aoLi(ray, isect, rng); break;
+        default: L = directLi(ray, isect, s, rng); break;
+      }
+    }  // else sum of lights[i].Le(ray) == 0 for area / point lights
+    // T * Li + Lvi with T = 1, Lvi = 0; then * rayWeight (1.0)
+    L = Spec(1.0) * L + Spec(0.0);
+    L = L * 1.0;
+    if (L.hasNaNs()) L = Spec(0.0);
+    else if (L.luminance() < -1e-5) L = Spec(0.0);
+    else if (std::isinf(L.luminance())) L = Spec(0.0);
+    return L;
+  }
+};
+
+// pixel visitation order, lib/pixel_samplers/*.dart
+std::vector<int32_t> pixelOrder(const SamplerCfg& sc, int x, int y, int width, int height) {
+  std::vector<int32_t> px;
+  px.reserve((size_t)width * height * 2);
+  int right = x + width - 1, bottom = y + height - 1;
+  if (sc.pixelOrder == 0) {  // linear_pixel_sampler.dart:29-40
+    for (int yy = y; yy <= bottom; ++yy)
+      for (int xx = x; xx <= right; ++xx) { px.push_back(xx); px.push_back(yy); }
+    return px;
+  }
+  // tile_pixel_sampler.dart:39-100
+  int ts = sc.tileSize;
+  int nx = width / ts + ((width % ts == 0) ? 0 : 1), ny = height / ts + ((height % ts == 0) ? 0 : 1);
+  std::vector<int32_t> tiles;
+  for (int yi = 0; yi < ny; ++yi)
+    for (int xi = 0; xi < nx; ++xi) { tiles.push_back(xi); tiles.push_back(yi); }
+  int numTiles = (int)tiles.size() / 2;
+  DartRandom rng(5489);  // rng.dart:29
+  for (int ti = 1; ti < numTiles; ++ti) {
+    int lx = ti * 2, rx = (int)(rng.randomUint() % (uint32_t)numTiles) * 2;
+    std::swap(tiles[lx], tiles[rx]);
+    std::swap(tiles[lx + 1], tiles[rx + 1]);
+  }
+  for (int i = 0; i < numTiles; ++i) {
+    int sx = x + tiles[2 * i] * ts, sy = y + tiles[2 * i + 1] * ts;
+    for (int yi = 0; yi < ts; ++yi) {
+      int yy = sy + yi;
+      if (yy > bottom) break;
+      for (int xi = 0; xi < ts; ++xi) {
+        int xx = sx + xi;
+        if (xx > right) break;
+        px.push_back(xx);
+        px.push_back(yy);
+      }
+    }
+  }
+  return px;
+}
+
+// GetSubWindow, common.dart:52-73
+void GetSubWindow(int w, int h, int num, int count, int e[4]) {
+  int nx = count, ny = 1;
+  while ((nx & 0x1) == 0 && 2 * w * ny < h * nx) { nx >>= 1; ny <<= 1; }
+  int xo = num % nx, yo = num / nx;
+  double tx0 = (double)xo / nx, tx1 = (double)(xo + 1) / nx, ty0 = (double)yo / ny, ty1 = (double)(yo + 1) / ny;
+  e[0] = (int)std::floor(Lerp(tx0, 0, w));
+  e[1] = std::min((int)std::floor(Lerp(tx1, 0, w)), w);
+  e[2] = (int)std::floor(Lerp(ty0, 0, h));
+  e[3] = std::min((int)std::floor(Lerp(ty1, 0, h)), h);
+}
+
+// Samples of one pixel visit.  `pass` only matters for the random sampler (one visit per pass).
+// Serial mode draws everything from `serial`; keyed mode derives streams from (seed, x, y).
+int pixelSamples(const SamplerCfg& sc, const SampleLayout& layout, const Camera& cam, int x, int y, int pass, Rng* serial,
+                 std::vector<SampleVals>& out) {
+  const bool keyed = sc.rngMode == 1;
+  if (sc.kind == 0) {  // low_discrepancy_sampler.dart:64-88 + montecarlo.dart:407-473
+    int n = RoundUpPow2(sc.spp);
+    out.resize(n);
+    for (auto& s : out) s.alloc(layout);
+    uint32_t arr = 0;
+    auto stream = [&](KeyedRng& k) -> Rng& {
+      if (!keyed) return *serial;
+      k = KeyedRng(sc.seed, x, y, 0, arr);
+      return k;
+    };
+    KeyedRng k;
+    std::vector<float> img(2 * n), lens(2 * n), tm(n);
+    LDShuffleScrambled2D(1, n, img.data(), stream(k)); arr++;
+    LDShuffleScrambled2D(1, n, lens.data(), stream(k)); arr++;
+    LDShuffleScrambled1D(1, n, tm.data(), stream(k)); arr++;
+    std::vector<std::vector<float>> one(layout.n1D.size()), two(layout.n2D.size());
+    for (size_t i = 0; i < layout.n1D.size(); ++i) {
+      one[i].resize((size_t)layout.n1D[i] * n);
+      LDShuffleScrambled1D(layout.n1D[i], n, one[i].data(), stream(k)); arr++;
+    }
+    for (size_t i = 0; i < layout.n2D.size(); ++i) {
+      two[i].resize((size_t)2 * layout.n2D[i] * n);
+      LDShuffleScrambled2D(layout.n2D[i], n, two[i].data(), stream(k)); arr++;
+    }
+    for (int i = 0; i < n; ++i) {
+      out[i].imageX = x + (double)img[2 * i];
+      out[i].imageY = y + (double)img[2 * i + 1];
+      out[i].time = Lerp(tm[i], cam.shutterOpen, cam.shutterClose);
+      out[i].lensU = lens[2 * i];
+      out[i].lensV = lens[2 * i + 1];
+      for (size_t j = 0; j < layout.n1D.size(); ++j)
+        for (int q = 0; q < layout.n1D[j]; ++q) out[i].oneD[j][q] = one[j][(size_t)layout.n1D[j] * i + q];
+      for (size_t j = 0; j < layout.n2D.size(); ++j)
+        for (int q = 0; q < 2 * layout.n2D[j]; ++q) out[i].twoD[j][q] = two[j][(size_t)2 * layout.n2D[j] * i + q];
+    }
+    return n;
+  }
+  KeyedRng k(sc.seed, x, y, (uint32_t)pass, kStreamPixel);
+  Rng& rng = keyed ? (Rng&)k : *serial;
+  if (sc.kind == 1) {  // stratified_sampler.dart:67-124
+    int n = sc.xs * sc.ys;
+    out.resize(n);
+    for (auto& s : out) s.alloc(layout);
+    std::vector<float> img(2 * n), lens(2 * n), tm(n);
+    StratifiedSample2D(img.data(), sc.xs, sc.ys, rng, sc.jitter != 0);
+    StratifiedSample2D(lens.data(), sc.xs, sc.ys, rng, sc.jitter != 0);
+    StratifiedSample1D(tm.data(), n, rng, sc.jitter != 0);
+    for (int o = 0; o < 2 * n; o += 2) {  // float32 += int
+      img[o] = f32((double)img[o] + x);
+      img[o + 1] = f32((double)img[o + 1] + y);
+    }
+    Shuffle(lens.data(), 0, n, 2, rng);
+    Shuffle(tm.data(), 0, n, 1, rng);
+    for (int i = 0; i < n; ++i) {
+      out[i].imageX = img[2 * i];
+      out[i].imageY = img[2 * i + 1];
+      out[i].lensU = lens[2 * i];
+      out[i].lensV = lens[2 * i + 1];
+      out[i].time = Lerp(tm[i], cam.shutterOpen, cam.shutterClose);
+      for (size_t j = 0; j < layout.n1D.size(); ++j) LatinHypercube(out[i].oneD[j].data(), layout.n1D[j], 1, rng);
+      for (size_t j = 0; j < layout.n2D.size(); ++j) LatinHypercube(out[i].twoD[j].data(), layout.n2D[j], 2, rng);
+    }
+    return n;
+  }
+  // random_sampler.dart:47-88 (FULL_SAMPLING: samplesPerPixel samples per visit)
+  int n = sc.spp;
+  out.resize(n);
+  for (auto& s : out) s.alloc(layout);
+  for (int si = 0; si < n; ++si) {
+    out[si].imageX = rng.randomFloat() + x;
+    out[si].imageY = rng.randomFloat() + y;
+    out[si].lensU = rng.randomFloat();
+    out[si].lensV = rng.randomFloat();
+    out[si].time = Lerp(rng.randomFloat(), cam.shutterOpen, cam.shutterClose);
+    for (size_t i = 0; i < layout.n1D.size(); ++i)
+      for (int j = 0; j < layout.n1D[i]; ++j) out[si].oneD[i][j] = f32(rng.randomFloat());
+    for (size_t i = 0; i < layout.n2D.size(); ++i)
+      for (int j = 0; j < 2 * layout.n2D[i]; ++j) out[si].twoD[i][j] = f32(rng.randomFloat());
+  }
+  return n;
+}
+
+}  // namespace
+
+void RenderScene::finalizeLights() {
+  Ctx c(*this);
+  for (Light& l : lights) {
+    if (l.kind != 0) continue;
+    l.areas.clear();
+    l.area = 0.0;
+    for (uint32_t sh : l.shapes) {  // shape_set.dart:43-50
+      double a = c.shapeArea(sh);
+      l.areas.push_back(a);
+      l.area += a;
+    }
+    l.areaDistribution.init(l.areas);
+  }
+}
+
+int RenderScene::samplesForPixel(int px, int py, std::vector<float>* out) {
+  Ctx c(*this);
+  c.requestSamples();
+  std::vector<SampleVals> sv;
+  DartRandom serial((int64_t)sampler.seed);
+  int n = pixelSamples(sampler, c.layout, camera, px, py, 0, &serial, sv);
+  int per = c.layout.floatsPerSample();
+  out->clear();
+  for (int i = 0; i < n; ++i) {
+    out->push_back((float)(sv[i].imageX - px));
+    out->push_back((float)(sv[i].imageY - py));
+    out->push_back((float)sv[i].lensU);
+    out->push_back((float)sv[i].lensV);
+    out->push_back((float)sv[i].time);
+    for (auto& a : sv[i].oneD) for (float v : a) out->push_back(v);
+    for (auto& a : sv[i].twoD) for (float v : a) out->push_back(v);
+  }
+  return per;
+}
+
+void RenderScene::render(int taskNum, int taskCount, int nthreads) {
+  finalizeLights();
+  int ext[4];
+  film.getSampleExtent(ext);
+  // dartray.dart:1009-1023: the task renders a sub-window of the SAMPLE extent
+  int x = ext[0], y = ext[2], w = ext[1] - ext[0], h = ext[3] - ext[2];
+  if (taskCount > 1) {
+    int e[4];
+    GetSubWindow(w, h, taskNum, taskCount, e);
+    x = ext[0] + e[0]; w = e[1] - e[0];
+    y = ext[2] + e[2]; h = e[3] - e[2];
+  }
+  std::vector<int32_t> px = pixelOrder(sampler, x, y, w, h);
+  const size_t nPix = px.size() / 2;
+  const int passes = sampler.kind == 2 ? sampler.spp : 1;  // random sampler quirk: spp visits of spp samples
+
+  if (sampler.rngMode == 0 || nthreads <= 1) {
+    Ctx c(*this);
+    c.requestSamples();
+    DartRandom serial(taskNum);  // sampler_renderer.dart:137
+    std::vector<SampleVals> sv;
+    for (int pass = 0; pass < passes; ++pass)
+      for (size_t i = 0; i < nPix; ++i) {
+        int n = pixelSamples(sampler, c.layout, camera, px[2 * i], px[2 * i + 1], pass, &serial, sv);
+        std::vector<Spec> Ls(n);
+        for (int s = 0; s < n; ++s) {
+          KeyedRng k(sampler.seed, px[2 * i], px[2 * i + 1], (uint32_t)(pass * n + s), kStreamIntegrator);
+          Rng& rng = sampler.rngMode == 1 ? (Rng&)k : (Rng&)serial;
+          Ls[s] = c.Li(sv[s], rng);
+        }
+        for (int s = 0; s < n; ++s) film.addSample(sv[s].imageX, sv[s].imageY, Ls[s]);
+      }
+    stats = c.stats;
+    return;
+  }
+  // keyed mode, threaded: pixels are independent; film updates are applied in pixel order afterwards
+  struct Contribution { double ix, iy; Spec L; };
+  std::vector<std::vector<Contribution>> perThread(nthreads);
+  std::vector<RenderStats> st(nthreads);
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t)
+    th.emplace_back([&, t] {
+      Ctx c(*this);
+      c.requestSamples();
+      std::vector<SampleVals> sv;
+      size_t b = nPix * t / nthreads, e = nPix * (t + 1) / nthreads;
+      for (int pass = 0; pass < passes; ++pass)
+        for (size_t i = b; i < e; ++i) {
+          int n = pixelSamples(sampler, c.layout, camera, px[2 * i], px[2 * i + 1], pass, nullptr, sv);
+          for (int s = 0; s < n; ++s) {
+            KeyedRng k(sampler.seed, px[2 * i], px[2 * i + 1], (uint32_t)(pass * n + s), kStreamIntegrator);
+            Spec L = c.Li(sv[s], k);
+            perThread[t].push_back({sv[s].imageX, sv[s].imageY, L});
+          }
+        }
+      st[t] = c.stats;
+    });
+  for (auto& t : th) t.join();
+  for (int t = 0; t < nthreads; ++t) {
+    for (const Contribution& c : perThread[t]) film.addSample(c.ix, c.iy, c.L);
+    stats.cameraSamples += st[t].cameraSamples; stats.closestRays += st[t].closestRays; stats.shadowRays += st[t].shadowRays;
+    stats.nodesVisited += st[t].nodesVisited; stats.primsTested += st[t].primsTested;
+  }
+}
+
+}  // namespace orc

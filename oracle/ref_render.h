@@ -1,0 +1,212 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see ref_core.h header).  PARITY UNPINNED.
+//
+// CPU restatement of the rendering half of the DartRay hot path:
+//   RNG                lib/core/rng.dart:27-43 (wraps dart:math Random — Dart SDK, NOT in /root/reference)
+//   pixel samplers     lib/pixel_samplers/{linear,tile}_pixel_sampler.dart
+//   samplers           lib/samplers/{low_discrepancy,stratified,random}_sampler.dart + lib/core/montecarlo.dart
+//   camera             lib/cameras/perspective_camera.dart:93-132
+//   shading geometry   lib/shapes/triangle.dart:100-154, lib/shapes/sphere.dart:118-160,
+//                      lib/core/differential_geometry.dart:77-99
+//   BSDF               lib/core/reflection/{bsdf,bxdf,lambertian,oren_nayar}.dart, lib/materials/matte_material.dart
+//   lights             lib/lights/{diffuse_area,point}_light.dart, lib/core/light/shape_set.dart, lib/core/shape.dart:100-121
+//   integrators        lib/core/integrator.dart:39-185, lib/surface_integrators/{path,ambient_occlusion,direct_lighting}_integrator.dart
+//   renderer           lib/renderers/sampler_renderer.dart:67-98,118-218
+//   film               lib/film/image_film.dart:51-185,247-299
+//
+// Two random-stream modes:
+//   SERIAL — one sequential generator per task shared by sampler and integrators, as the reference
+//            does (sampler_renderer.dart:137).  The generator restates the Dart VM's `Random` from its
+//            published algorithm (sdk/lib/_internal/vm/lib/math_patch.dart + runtime/lib/math.cc;
+//            version unpinned: pubspec.yaml has no SDK constraint) — a documented assumption.
+//   KEYED  — counter-based streams keyed by (pixel, array) for the sampler and (pixel, sample) for the
+//            integrators.  This is the layout the GPU replays; same algorithms, same draw order
+//            inside each stream.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <vector>
+
+#include "ref_scene.h"
+
+namespace orc {
+
+// ---- spectrum: RGBColor, Float32List(3) storage (rgb_color.dart:23-169, spectrum.dart:1145) ----
+struct Spec {
+  float c[3] = {0.f, 0.f, 0.f};
+  Spec() {}
+  explicit Spec(double v) { c[0] = c[1] = c[2] = f32(v); }
+  Spec(double r, double g, double b) { c[0] = f32(r); c[1] = f32(g); c[2] = f32(b); }
+  bool isBlack() const { return !(c[0] != 0.f || c[1] != 0.f || c[2] != 0.f); }
+  bool hasNaNs() const { return std::isnan(c[0]) || std::isnan(c[1]) || std::isnan(c[2]); }
+  double luminance() const { return 0.212671 * c[0] + 0.715160 * c[1] + 0.072169 * c[2]; }  // rgb_color.dart:167-169
+};
+static inline Spec operator+(const Spec& a, const Spec& b) { return Spec((double)a.c[0] + b.c[0], (double)a.c[1] + b.c[1], (double)a.c[2] + b.c[2]); }
+static inline Spec operator*(const Spec& a, const Spec& b) { return Spec((double)a.c[0] * b.c[0], (double)a.c[1] * b.c[1], (double)a.c[2] * b.c[2]); }
+static inline Spec operator*(const Spec& a, double s) { return Spec((double)a.c[0] * s, (double)a.c[1] * s, (double)a.c[2] * s); }
+static inline Spec operator/(const Spec& a, double s) { return Spec((double)a.c[0] / s, (double)a.c[1] / s, (double)a.c[2] / s); }
+
+// ---- random streams -----------------------------------------------------------------------------
+struct Rng {
+  virtual ~Rng() {}
+  virtual uint32_t next32() = 0;  // uniform 32-bit word
+  virtual double randomFloat() = 0;
+  // rng.dart:40-42: Random.nextInt(0xffffffff) -> [0, 2^32 - 2]
+  virtual uint32_t randomUint() = 0;
+};
+
+// Restatement of the Dart VM `Random` (see header comment; unpinned).
+struct DartRandom : Rng {
+  uint32_t lo, hi;
+  static uint64_t mix64(uint64_t n) {
+    n = (~n) + (n << 21);
+    n = n ^ (n >> 24);
+    n = n * 265;
+    n = n ^ (n >> 14);
+    n = n * 21;
+    n = n ^ (n >> 28);
+    n = n + (n << 31);
+    return n;
+  }
+  explicit DartRandom(int64_t seed) {
+    uint64_t s = mix64((uint64_t)seed);
+    if (s == 0) s = 0x5A17;
+    lo = (uint32_t)s;
+    hi = (uint32_t)(s >> 32);
+    for (int i = 0; i < 4; ++i) nextState();
+  }
+  void nextState() {
+    uint64_t st = 0xffffda61ull * lo + hi;
+    lo = (uint32_t)st;
+    hi = (uint32_t)(st >> 32);
+  }
+  uint32_t nextInt(uint64_t max) {
+    if ((max & (~max + 1)) == max) {
+      nextState();
+      return lo & (uint32_t)(max - 1);
+    }
+    uint64_t rnd32, result;
+    do {
+      nextState();
+      rnd32 = lo;
+      result = rnd32 % max;
+    } while ((rnd32 - result + max) > 4294967296ull);
+    return (uint32_t)result;
+  }
+  uint32_t next32() override { nextState(); return lo; }
+  double randomFloat() override {
+    double a = nextInt(1u << 26), b = nextInt(1u << 27);
+    return (a * 134217728.0 + b) / 9007199254740992.0;
+  }
+  uint32_t randomUint() override { return nextInt(0xffffffffull); }
+};
+
+// Counter-based stream (splitmix64 finaliser); the GPU implements exactly this.
+struct KeyedRng : Rng {
+  uint64_t key = 0, ctr = 0;
+  static uint64_t mix(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+  }
+  static uint64_t makeKey(uint64_t seed, int32_t x, int32_t y, uint32_t sampleIdx, uint32_t streamId) {
+    uint64_t k1 = mix(seed ^ ((uint64_t)(uint32_t)x | ((uint64_t)(uint32_t)y << 32)));
+    return mix(k1 ^ ((uint64_t)sampleIdx | ((uint64_t)streamId << 32)) ^ 0xD1B54A32D192ED03ull);
+  }
+  KeyedRng() {}
+  KeyedRng(uint64_t seed, int32_t x, int32_t y, uint32_t sampleIdx, uint32_t streamId)
+      : key(makeKey(seed, x, y, sampleIdx, streamId)), ctr(0) {}
+  uint64_t next64() { ++ctr; return mix(key + ctr * 0x9E3779B97F4A7C15ull); }
+  uint32_t next32() override { return (uint32_t)(next64() >> 32); }
+  double randomFloat() override { return (double)(next64() >> 11) * (1.0 / 9007199254740992.0); }
+  uint32_t randomUint() override { return (uint32_t)(next64() >> 32) % 0xffffffffu; }
+};
+static const uint32_t kStreamPixel = 4095;          // stratified / random sampler: one stream per pixel
+static const uint32_t kStreamIntegrator = 0x80000000u;
+
+// ---- scene description beyond geometry ----------------------------------------------------------------
+struct Material {  // matte_material.dart:41-65 with constant textures
+  int kind = 0;
+  Spec kd = Spec(0.5);
+  double sigma = 0.0;
+};
+
+struct Distribution1D {  // montecarlo.dart:25-98
+  std::vector<float> func, cdf;
+  double funcInt = 0;
+  int count = 0;
+  void init(const std::vector<double>& f);
+  int sampleDiscrete(double u) const;
+};
+
+struct Light {
+  int kind = 0;  // 0 = DiffuseAreaLight, 1 = PointLight
+  Spec L;        // Lemit / intensity
+  Vec pos;       // point light position (world)
+  int nSamples = 1;
+  std::vector<uint32_t> shapes;  // ShapeSet order (shape_set.dart:26-41)
+  std::vector<double> areas;
+  double area = 0;
+  Distribution1D areaDistribution;
+};
+
+struct Camera {  // perspective_camera.dart:46-57 + projective_camera.dart:34-53
+  Transform rasterToCamera, cameraToWorld;
+  double lensRadius = 0, focalDistance = 1e30, shutterOpen = 0, shutterClose = 1;
+};
+
+struct Film {  // image_film.dart:51-97
+  int xres = 0, yres = 0;
+  double crop[4] = {0, 1, 0, 1};
+  double xWidth = 0.5, yWidth = 0.5, invXWidth = 2, invYWidth = 2;
+  float table[256];
+  int left = 0, top = 0, width = 0, height = 0;
+  std::vector<float> Lxyz, weightSum;
+  void configure();
+  void getSampleExtent(int e[4]) const;
+  void addSample(double imageX, double imageY, const Spec& L);  // image_film.dart:99-185
+  void writeImage(float* rgb) const;                            // image_film.dart:268-299
+};
+
+struct SamplerCfg {
+  int kind = 0;  // 0 lowdiscrepancy, 1 stratified, 2 random
+  int xs = 2, ys = 2;
+  int spp = 4;
+  int jitter = 1;
+  int pixelOrder = 1;  // 0 linear, 1 tile
+  int tileSize = 32;
+  uint64_t seed = 0;
+  int rngMode = 1;  // 0 serial (reference), 1 keyed (what the GPU replays)
+};
+
+struct IntegratorCfg {
+  int kind = 0;  // 0 path, 1 ambientocclusion, 2 directlighting
+  int maxDepth = 5;
+  int strategy = 0;  // directlighting: 0 = all, 1 = one
+  int aoSamples = 2048;
+  double aoMinDist = 1e-4, aoMaxDist = kInf;
+};
+
+struct RenderStats {
+  uint64_t cameraSamples = 0, closestRays = 0, shadowRays = 0, nodesVisited = 0, primsTested = 0;
+};
+
+struct RenderScene {
+  Scene* geom = nullptr;
+  std::vector<Material> materials;
+  std::vector<Light> lights;
+  Camera camera;
+  Film film;
+  SamplerCfg sampler;
+  IntegratorCfg integ;
+  RenderStats stats;
+
+  void finalizeLights();
+  // _SamplerRendererTask.run for task taskNum of taskCount (sampler_renderer.dart:118-218 with the
+  // sub-window of dartray.dart:1009-1023); adds into film.
+  void render(int taskNum, int taskCount, int nthreads);
+  // The camera samples only (imageX, imageY, lensU, lensV, time + integrator arrays) of one pixel,
+  // for sampler parity tests.  Returns floats per sample.
+  int samplesForPixel(int px, int py, std::vector<float>* out);
+};
+
+}  // namespace orc

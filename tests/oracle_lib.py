@@ -52,6 +52,20 @@ def lib():
         L.orc_trace_closest_brute.argtypes = [vp, vp, vp, u64, vp, vp, vp, i32]
         L.orc_trace_any_brute.argtypes = [vp, vp, vp, u64, vp, i32]
         L.orc_get_counters.argtypes = [vp, vp]
+        dbl = C.c_double
+        L.orc_set_materials.argtypes = [vp, u32, vp, vp, vp]
+        L.orc_set_lights.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
+        L.orc_set_camera.argtypes = [vp, vp, vp, dbl, dbl, dbl, dbl]
+        L.orc_set_film.argtypes = [vp, i32, i32, vp, dbl, dbl, vp]
+        L.orc_set_sampler.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, u64, i32]
+        L.orc_set_integrator.argtypes = [vp, i32, i32, i32, i32, dbl, dbl]
+        L.orc_render.argtypes = [vp, i32, i32, i32]
+        L.orc_film_clear.argtypes = [vp]
+        L.orc_film_size.argtypes = [vp, vp]
+        L.orc_film_read.argtypes = [vp, vp, vp, vp]
+        L.orc_pixel_samples.argtypes = [vp, i32, i32, vp, i32, vp]
+        L.orc_render_stats.argtypes = [vp, vp]
+        L.orc_dart_random.argtypes = [C.c_int64, i32, vp, vp]
         _lib = L
     return _lib
 
@@ -151,6 +165,59 @@ class Oracle:
         occ = np.empty(n, np.uint8)
         self._ck(self.L.orc_trace_any_brute(self.h, _p(ro), _p(rd), n, _p(occ), nthreads))
         return occ
+
+    # -- renderer (same method names as dartray_b200.capi.Context) --------------------------------
+    def set_materials(self, kind, kd, sigma):
+        kind, kd, sigma = _arr(kind, np.int32), _arr(kd, np.float32).reshape(-1, 3), _arr(sigma, np.float32)
+        self._ck(self.L.orc_set_materials(self.h, kd.shape[0], _p(kind), _p(kd), _p(sigma)))
+
+    def set_lights(self, kind, L, pos, nsamples, shape_offsets, shape_prims):
+        kind, L, pos = _arr(kind, np.int32), _arr(L, np.float32).reshape(-1, 3), _arr(pos, np.float32).reshape(-1, 3)
+        ns, so, sp = _arr(nsamples, np.int32), _arr(shape_offsets, np.uint32), _arr(shape_prims, np.uint32)
+        self._ck(self.L.orc_set_lights(self.h, kind.shape[0], _p(kind), _p(L), _p(pos), _p(ns), _p(so), _p(sp)))
+
+    def set_camera(self, raster_to_camera, camera_to_world, lens_radius=0.0, focal_distance=1e30, shutter_open=0.0,
+                   shutter_close=1.0):
+        r2c, c2w = _arr(raster_to_camera, np.float32).reshape(16), _arr(camera_to_world, np.float32).reshape(16)
+        self._ck(self.L.orc_set_camera(self.h, _p(r2c), _p(c2w), lens_radius, focal_distance, shutter_open, shutter_close))
+
+    def set_film(self, xres, yres, crop, xwidth, ywidth, table):
+        crop, table = _arr(crop, np.float64), _arr(table, np.float32)
+        self._ck(self.L.orc_set_film(self.h, xres, yres, _p(crop), xwidth, ywidth, _p(table)))
+
+    def set_sampler(self, kind, xs, ys, spp, jitter, pixel_order, tile_size, seed, rng_mode):
+        self._ck(self.L.orc_set_sampler(self.h, kind, xs, ys, spp, jitter, pixel_order, tile_size, seed, rng_mode))
+
+    def set_integrator(self, kind, maxdepth, strategy, ao_nsamples, ao_mindist, ao_maxdist):
+        self._ck(self.L.orc_set_integrator(self.h, kind, maxdepth, strategy, ao_nsamples, ao_mindist, ao_maxdist))
+
+    def render(self, task_num=0, task_count=1, nthreads=8):
+        self._ck(self.L.orc_render(self.h, task_num, task_count, nthreads))
+
+    def film_clear(self):
+        self._ck(self.L.orc_film_clear(self.h))
+
+    def film_size(self):
+        out = np.zeros(4, np.int32)
+        self.L.orc_film_size(self.h, _p(out))
+        return tuple(int(v) for v in out)  # left, top, width, height
+
+    def film_read(self):
+        _, _, w, h = self.film_size()
+        rgb, xyz, wt = np.empty((h, w, 3), np.float32), np.empty((h, w, 3), np.float32), np.empty((h, w), np.float32)
+        self._ck(self.L.orc_film_read(self.h, _p(rgb), _p(xyz), _p(wt)))
+        return dict(rgb=rgb, xyz=xyz, weight=wt)
+
+    def pixel_samples(self, x, y, cap=1 << 20):
+        out = np.zeros(cap, np.float32)
+        n = C.c_int(0)
+        per = self.L.orc_pixel_samples(self.h, x, y, _p(out), cap, C.byref(n))
+        return out[:per * n.value].reshape(n.value, per).copy()
+
+    def render_stats(self):
+        out = np.zeros(5, np.uint64)
+        self.L.orc_render_stats(self.h, _p(out))
+        return dict(zip(["camera_samples", "closest_rays", "shadow_rays", "nodes_visited", "prims_tested"], (int(v) for v in out)))
 
     def counters(self):
         out = np.zeros(3, np.uint64)
