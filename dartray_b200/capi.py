@@ -23,6 +23,9 @@ SYMBOLS = [
     "drt_set_build_order", "drt_build_bvh", "drt_bvh_info_get", "drt_bvh_export", "drt_trace_closest",
     "drt_trace_any", "drt_trace_closest_device", "drt_trace_any_device", "drt_set_counting", "drt_get_counters", "drt_set_kernel_variant",
     "drt_last_kernel_ms", "drt_kernel_launches",
+    "drt_set_materials", "drt_set_lights", "drt_set_camera", "drt_set_film", "drt_set_sampler", "drt_set_integrator",
+    "drt_render", "drt_render_shard", "drt_set_batch_slots", "drt_film_clear", "drt_film_size", "drt_film_read",
+    "drt_film_device", "drt_pixel_samples", "drt_render_stats_get",
 ]
 
 
@@ -41,6 +44,11 @@ class BvhInfo(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("nodes_visited", C.c_uint64), ("prims_tested", C.c_uint64),
                 ("hits", C.c_uint64)]
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("camera_samples", C.c_uint64), ("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
+                ("zeroed_samples", C.c_uint64)]
 
 
 _lib = None
@@ -80,6 +88,22 @@ def load():
     L.drt_last_kernel_ms.argtypes = [vp]
     L.drt_kernel_launches.restype = u64
     L.drt_kernel_launches.argtypes = [vp]
+    dbl = C.c_double
+    L.drt_set_materials.argtypes = [vp, u32, vp, vp, vp]
+    L.drt_set_lights.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
+    L.drt_set_camera.argtypes = [vp, vp, vp, dbl, dbl, dbl, dbl]
+    L.drt_set_film.argtypes = [vp, i32, i32, vp, dbl, dbl, vp]
+    L.drt_set_sampler.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, u64]
+    L.drt_set_integrator.argtypes = [vp, i32, i32, i32, i32, dbl, dbl]
+    L.drt_render.argtypes = [vp, i32, i32]
+    L.drt_render_shard.argtypes = [vp, i32, i32]
+    L.drt_set_batch_slots.argtypes = [vp, u64]
+    L.drt_film_clear.argtypes = [vp]
+    L.drt_film_size.argtypes = [vp, vp]
+    L.drt_film_read.argtypes = [vp, vp, vp, vp]
+    L.drt_film_device.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+    L.drt_pixel_samples.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.drt_render_stats_get.argtypes = [vp, C.POINTER(RenderStats)]
     _lib = L
     return L
 
@@ -201,3 +225,71 @@ class Context:
     @property
     def kernel_launches(self) -> int:
         return int(self.L.drt_kernel_launches(self.h))
+
+    # -- renderer: the same method names as the reference-side objects they replace ---------------
+    def set_materials(self, kind, kd, sigma):
+        kind, kd, sigma = _arr(kind, np.int32), _arr(kd, np.float32).reshape(-1, 3), _arr(sigma, np.float32)
+        self._ck(self.L.drt_set_materials(self.h, kd.shape[0], _p(kind), _p(kd), _p(sigma)))
+
+    def set_lights(self, kind, L, pos, nsamples, shape_offsets, shape_prims):
+        kind, L, pos = _arr(kind, np.int32), _arr(L, np.float32).reshape(-1, 3), _arr(pos, np.float32).reshape(-1, 3)
+        ns, so, sp = _arr(nsamples, np.int32), _arr(shape_offsets, np.uint32), _arr(shape_prims, np.uint32)
+        self._ck(self.L.drt_set_lights(self.h, kind.shape[0], _p(kind), _p(L), _p(pos), _p(ns), _p(so), _p(sp)))
+
+    def set_camera(self, raster_to_camera, camera_to_world, lens_radius=0.0, focal_distance=1e30, shutter_open=0.0,
+                   shutter_close=1.0):
+        r2c, c2w = _arr(raster_to_camera, np.float32).reshape(16), _arr(camera_to_world, np.float32).reshape(16)
+        self._ck(self.L.drt_set_camera(self.h, _p(r2c), _p(c2w), lens_radius, focal_distance, shutter_open, shutter_close))
+
+    def set_film(self, xres, yres, crop, xwidth, ywidth, table):
+        crop, table = _arr(crop, np.float64), _arr(table, np.float32)
+        self._ck(self.L.drt_set_film(self.h, xres, yres, _p(crop), xwidth, ywidth, _p(table)))
+
+    def set_sampler(self, kind, xs, ys, spp, jitter, pixel_order, tile_size, seed, rng_mode=1):
+        if rng_mode != 1:
+            raise ValueError("the GPU path replays keyed (counter-based) sample streams only; the reference's single "
+                             "serial RNG stream cannot be evaluated in parallel")
+        self._ck(self.L.drt_set_sampler(self.h, kind, xs, ys, spp, jitter, pixel_order, tile_size, seed))
+
+    def set_integrator(self, kind, maxdepth, strategy, ao_nsamples, ao_mindist, ao_maxdist):
+        self._ck(self.L.drt_set_integrator(self.h, kind, maxdepth, strategy, ao_nsamples, ao_mindist, ao_maxdist))
+
+    def set_batch_slots(self, slots: int):
+        self._ck(self.L.drt_set_batch_slots(self.h, slots))
+
+    def render(self, task_num=0, task_count=1, nthreads=None):
+        self._ck(self.L.drt_render(self.h, task_num, task_count))
+
+    def render_shard(self, shard=0, n_shards=1):
+        self._ck(self.L.drt_render_shard(self.h, shard, n_shards))
+
+    def film_clear(self):
+        self._ck(self.L.drt_film_clear(self.h))
+
+    def film_size(self):
+        out = np.zeros(4, np.int32)
+        self._ck(self.L.drt_film_size(self.h, _p(out)))
+        return tuple(int(v) for v in out)  # left, top, width, height
+
+    def film_read(self):
+        _, _, w, h = self.film_size()
+        rgb, xyz, wt = np.empty((h, w, 3), np.float32), np.empty((h, w, 3), np.float32), np.empty((h, w), np.float32)
+        self._ck(self.L.drt_film_read(self.h, _p(rgb), _p(xyz), _p(wt)))
+        return dict(rgb=rgb, xyz=xyz, weight=wt)
+
+    def film_device(self):
+        """(device pointer, number of float64 elements) of the film accumulators [h, w, (X, Y, Z, weight)]."""
+        ptr, n = C.c_void_p(), C.c_uint64()
+        self._ck(self.L.drt_film_device(self.h, C.byref(ptr), C.byref(n)))
+        return int(ptr.value), int(n.value)
+
+    def pixel_samples(self, x, y, cap=1 << 20):
+        out = np.zeros(cap, np.float32)
+        n, per = C.c_int32(0), C.c_int32(0)
+        self._ck(self.L.drt_pixel_samples(self.h, x, y, _p(out), cap, C.byref(n), C.byref(per)))
+        return out[:per.value * n.value].reshape(n.value, per.value).copy()
+
+    def render_stats(self) -> dict:
+        s = RenderStats()
+        self._ck(self.L.drt_render_stats_get(self.h, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in RenderStats._fields_}

@@ -9,95 +9,10 @@
 #include <string>
 #include <vector>
 
-#include "../../include/drt.h"
-#include "bvh_builder.h"
-#include "gpu_types.h"
-#include "trace_kernels.h"
-
-using namespace drt;
-
-static_assert(sizeof(drt_hit) == sizeof(drt_hit_rec), "hit record layout");
+#include "drt_ctx.h"
 
 namespace {
 thread_local std::string g_createError;
-
-struct HostSphere {
-  float o2w[16], w2o[16];
-  double radius, zmin, zmax, phiMaxDeg;
-};
-
-template <class T>
-struct DevBuf {
-  T* p = nullptr;
-  size_t cap = 0;
-  cudaError_t ensure(size_t n) {
-    if (n <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
-    if (e == cudaSuccess) cap = n;
-    return e;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-};
-}  // namespace
-
-struct drt_ctx {
-  int device = 0;
-  std::string err;
-  // staged scene (host)
-  std::vector<float> P;
-  std::vector<uint32_t> idx;
-  std::vector<int32_t> matOf, lightOf;
-  std::vector<uint8_t> revOf;
-  std::vector<HostSphere> spheres;
-  std::vector<int32_t> sphMat, sphLight;
-  std::vector<uint8_t> sphRev;
-  std::vector<uint32_t> order;
-  // BVH
-  bool built = false;
-  BuiltBvh bvh;
-  drt_bvh_info info{};
-  DevBuf<GNode> dNodes;
-  DevBuf<GNode4> dWide;
-  DevBuf<GPrim> dPrims;
-  DevBuf<GSphere> dSpheres;
-  DevBuf<DeviceCounters> dCounters;
-  DevBuf<unsigned long long> dNextRay;
-  int numSMs = 148;
-  TraceScene ts{};
-  // ray staging for host-buffer calls
-  DevBuf<float4> dRayO, dRayD;
-  DevBuf<drt_hit_rec> dHits;
-  DevBuf<uint8_t> dOcc;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  bool counting = false;
-  bool exactWalk = false;
-  double lastKernelMs = 0.0;
-  uint64_t launches = 0;
-
-  uint32_t ntris() const { return (uint32_t)(idx.size() / 3); }
-  uint32_t nprims() const { return ntris() + (uint32_t)spheres.size(); }
-};
-
-#define CK(ctx, call)                                                                    \
-  do {                                                                                   \
-    cudaError_t e__ = (call);                                                            \
-    if (e__ != cudaSuccess) {                                                            \
-      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                  \
-      return e__ == cudaErrorMemoryAllocation ? DRT_E_NOMEM : DRT_E_CUDA;                \
-    }                                                                                    \
-  } while (0)
-
-static int fail(drt_ctx* c, int code, const char* msg) {
-  if (c) c->err = msg;
-  return code;
 }
 
 // transform.dart:110-129 on a float32 matrix with float64 accumulation (sphere world bounds).
@@ -147,8 +62,9 @@ drt_ctx* drt_create(int device_id) {
 
 void drt_destroy(drt_ctx* c) {
   if (!c) return;
-  if (c->device == DRT_DEVICE_NONE) { delete c; return; }
+  if (c->device == DRT_DEVICE_NONE) { drtRenderStateDestroy(c); delete c; return; }
   cudaSetDevice(c->device);
+  drtRenderStateDestroy(c);
   c->dNodes.release(); c->dWide.release(); c->dPrims.release(); c->dSpheres.release(); c->dCounters.release(); c->dNextRay.release();
   c->dRayO.release(); c->dRayD.release(); c->dHits.release(); c->dOcc.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -215,6 +131,7 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
   auto t0 = std::chrono::steady_clock::now();
   const uint32_t nt = c->ntris(), np = c->nprims();
   c->built = false;
+  c->buildSerial++;
   c->ts = TraceScene{};
   c->info = drt_bvh_info{};
   if (np == 0) {  // bvh_accel.dart:50-53: nodes == null, every query misses
@@ -359,7 +276,6 @@ int drt_bvh_export(const drt_ctx* c, float* bounds, int32_t* offset, int32_t* np
   return DRT_OK;
 }
 
-static const char* kNoDevice = "context has no CUDA device (DRT_DEVICE_NONE): queries need a GPU, there is no CPU fallback";
 
 static int traceDevice(drt_ctx* c, bool any, const void* o, const void* d, uint64_t n, void* out, cudaStream_t st) {
   if (c->device == DRT_DEVICE_NONE) return fail(c, DRT_E_NODEVICE, kNoDevice);

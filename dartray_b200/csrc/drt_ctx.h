@@ -1,0 +1,105 @@
+// Internal: the context object behind the C ABI (include/drt.h), shared by drt_api.cu (scene, BVH,
+// ray queries) and render_api.cu (wavefront renderer).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/drt.h"
+#include "bvh_builder.h"
+#include "gpu_types.h"
+#include "render_types.h"
+#include "trace_kernels.h"
+
+using namespace drt;
+
+static_assert(sizeof(drt_hit) == sizeof(drt_hit_rec), "hit record layout");
+
+struct HostSphere {
+  float o2w[16], w2o[16];
+  double radius, zmin, zmax, phiMaxDeg;
+};
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct drt_ctx {
+  int device = 0;
+  std::string err;
+  // staged scene (host)
+  std::vector<float> P;
+  std::vector<uint32_t> idx;
+  std::vector<int32_t> matOf, lightOf;
+  std::vector<uint8_t> revOf;
+  std::vector<HostSphere> spheres;
+  std::vector<int32_t> sphMat, sphLight;
+  std::vector<uint8_t> sphRev;
+  std::vector<uint32_t> order;
+  // BVH
+  bool built = false;
+  uint64_t buildSerial = 0;  // bumped by every drt_build_bvh
+  BuiltBvh bvh;
+  drt_bvh_info info{};
+  DevBuf<GNode> dNodes;
+  DevBuf<GNode4> dWide;
+  DevBuf<GPrim> dPrims;
+  DevBuf<GSphere> dSpheres;
+  DevBuf<DeviceCounters> dCounters;
+  DevBuf<unsigned long long> dNextRay;
+  int numSMs = 148;
+  TraceScene ts{};
+  // ray staging for host-buffer calls
+  DevBuf<float4> dRayO, dRayD;
+  DevBuf<drt_hit_rec> dHits;
+  DevBuf<uint8_t> dOcc;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool counting = false;
+  bool exactWalk = false;
+  double lastKernelMs = 0.0;
+  uint64_t launches = 0;
+  struct RenderState* render = nullptr;  // render_api.cu
+
+  uint32_t ntris() const { return (uint32_t)(idx.size() / 3); }
+  uint32_t nprims() const { return ntris() + (uint32_t)spheres.size(); }
+};
+
+#define CK(ctx, call)                                                                    \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                  \
+      return e__ == cudaErrorMemoryAllocation ? DRT_E_NOMEM : DRT_E_CUDA;                \
+    }                                                                                    \
+  } while (0)
+
+static inline int fail(drt_ctx* c, int code, const char* msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+
+static const char* const kNoDevice =
+    "context has no CUDA device (DRT_DEVICE_NONE): queries need a GPU, there is no CPU fallback";
+
+// render_api.cu
+void drtRenderStateDestroy(drt_ctx* c);

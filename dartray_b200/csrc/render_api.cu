@@ -1,0 +1,735 @@
+// C ABI, render half (include/drt.h): what _SamplerRendererTask.run does for one task
+// (lib/renderers/sampler_renderer.dart:118-218), as a wavefront pipeline over batches of camera samples.
+// Host orchestration only; every stage is a kernel of render_kernels.cu / trace_fast.cu.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "drt_ctx.h"
+#include "render_kernels.h"
+#include "shade_device.cuh"
+
+namespace {
+
+struct HostLight {
+  int kind = 0;
+  float L[3] = {0, 0, 0}, pos[3] = {0, 0, 0};
+  int nSamples = 1;
+  std::vector<uint32_t> shapes;
+};
+
+struct ByteArena {  // one cudaMalloc per wavefront, carved into aligned arrays
+  char* base = nullptr;
+  size_t size = 0, used = 0;
+  template <class T>
+  T* take(size_t n) {
+    used = (used + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + used) : nullptr;
+    used += n * sizeof(T);
+    return p;
+  }
+};
+
+}  // namespace
+
+struct RenderState {
+  // host-side description
+  std::vector<GMaterial> materials{GMaterial{{0.5f, 0.5f, 0.5f}, 0.f}};
+  std::vector<HostLight> lights;
+  bool haveCamera = false, haveFilm = false;
+  RenderParams rp{};
+  double crop[4] = {0, 1, 0, 1};
+  float table[256];
+  int spp = 4, pixelOrder = 1, tileSize = 32;
+  uint64_t batchSlots = 0;  // 0 = default
+  // device-side scene tables
+  DevBuf<uint32_t> dPrimToRec, dPrimAttr, dLightShapes;
+  DevBuf<GMaterial> dMaterials;
+  DevBuf<GLight> dLights;
+  DevBuf<double> dLightAreas;
+  DevBuf<float> dLightCdf, dTable;
+  DevBuf<DirectOffsets> dDirect;
+  DevBuf<SampleArray> dArrays;
+  DevBuf<double> dFilm;
+  DevBuf<RenderCounters> dCounters;
+  DevBuf<float> dRgb, dXyz, dWeight;
+  size_t filmPixels = 0;
+  bool sceneTablesValid = false;
+  uint64_t buildSerial = 0;
+  // sample layout
+  std::vector<SampleArray> arrays;
+  std::vector<DirectOffsets> direct;
+  int maxVals = 0, maxOthers = 0;
+  // wavefront storage
+  char* wfMem = nullptr;
+  size_t wfBytes = 0;
+  Wavefront wf{};
+  uint32_t shCap = 0;
+  RenderScene rs{};
+  drt_render_stats stats{};
+};
+
+static RenderState* state(drt_ctx* c) {
+  if (!c->render) {
+    c->render = new RenderState();
+    std::memset(c->render->table, 0, sizeof(c->render->table));
+  }
+  return c->render;
+}
+
+void drtRenderStateDestroy(drt_ctx* c) {
+  RenderState* r = c->render;
+  if (!r) return;
+  r->dPrimToRec.release(); r->dPrimAttr.release(); r->dLightShapes.release(); r->dMaterials.release(); r->dLights.release();
+  r->dLightAreas.release(); r->dLightCdf.release(); r->dTable.release(); r->dDirect.release(); r->dArrays.release();
+  r->dFilm.release(); r->dCounters.release(); r->dRgb.release(); r->dXyz.release(); r->dWeight.release();
+  if (r->wfMem) cudaFree(r->wfMem);
+  delete r;
+  c->render = nullptr;
+}
+
+static inline int roundUpPow2(int v) {  // common.dart:117-125
+  v--;
+  v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16;
+  return v + 1;
+}
+
+// ImageFilm constructor (image_film.dart:51-97)
+static void configureFilm(RenderState* r) {
+  RenderParams& p = r->rp;
+  p.left = (int)std::ceil(p.xres * r->crop[0]);
+  p.width = std::max(1, (int)std::ceil(p.xres * r->crop[1]) - p.left);
+  p.top = (int)std::ceil(p.yres * r->crop[2]);
+  p.height = std::max(1, (int)std::ceil(p.yres * r->crop[3]) - p.top);
+  p.invXWidth = 1.0 / p.xWidth;
+  p.invYWidth = 1.0 / p.yWidth;
+}
+
+// Sample layout: what the integrators request (path_integrator.dart:124-131,
+// direct_lighting_integrator.dart:70-96) + the default volume integrator's two 1D samples
+// (emission_integrator.dart:26-29), in the reference's order: 1D arrays first, then 2D.
+static void buildLayout(RenderState* r) {
+  RenderParams& p = r->rp;
+  std::vector<int> n1D, n2D;
+  struct Off { int comp1D, pos2D; };
+  auto offsets = [&](int n) { Off o; n1D.push_back(n); o.comp1D = (int)n1D.size() - 1; n2D.push_back(n); o.pos2D = (int)n2D.size() - 1; return o; };
+  Off pl[3], pb[3], pp[3];
+  int pn[3] = {-1, -1, -1};
+  std::vector<Off> dl, db;
+  std::vector<int> dn;
+  int dlNum = -1;
+  if (p.integKind == 0) {
+    for (int i = 0; i < 3; ++i) {
+      pl[i] = offsets(1);
+      n1D.push_back(1); pn[i] = (int)n1D.size() - 1;
+      pb[i] = offsets(1);
+      pp[i] = offsets(1);
+    }
+  } else if (p.integKind == 2) {
+    if (p.strategy == 0) {
+      for (const HostLight& l : r->lights) {
+        int n = l.nSamples;
+        if (p.samplerKind == 0) n = roundUpPow2(n);  // LowDiscrepancySampler.roundSize
+        dn.push_back(n);
+        dl.push_back(offsets(n));
+        db.push_back(offsets(n));
+      }
+    } else {
+      dn.push_back(1);
+      dl.push_back(offsets(1));
+      n1D.push_back(1); dlNum = (int)n1D.size() - 1;
+      db.push_back(offsets(1));
+    }
+  }
+  n1D.push_back(1);
+  n1D.push_back(1);
+  std::vector<int> v1(n1D.size()), v2(n2D.size());
+  int v = 0;
+  for (size_t i = 0; i < n1D.size(); ++i) { v1[i] = v; v += n1D[i]; }
+  for (size_t i = 0; i < n2D.size(); ++i) { v2[i] = v; v += 2 * n2D[i]; }
+  p.nVals = v;
+  for (int i = 0; i < 3; ++i) {
+    if (p.integKind == 0) {
+      p.pLightComp[i] = v1[pl[i].comp1D]; p.pLightPos[i] = v2[pl[i].pos2D]; p.pLightNum[i] = v1[pn[i]];
+      p.pBsdfComp[i] = v1[pb[i].comp1D]; p.pBsdfPos[i] = v2[pb[i].pos2D];
+      p.pPathComp[i] = v1[pp[i].comp1D]; p.pPathPos[i] = v2[pp[i].pos2D];
+    } else {
+      p.pLightComp[i] = p.pLightPos[i] = p.pLightNum[i] = p.pBsdfComp[i] = p.pBsdfPos[i] = p.pPathComp[i] = p.pPathPos[i] = 0;
+    }
+  }
+  p.dlLightNum = dlNum >= 0 ? v1[dlNum] : 0;
+  r->direct.clear();
+  for (size_t i = 0; i < dl.size(); ++i)
+    r->direct.push_back(DirectOffsets{dn[i], v1[dl[i].comp1D], v2[dl[i].pos2D], v1[db[i].comp1D], v2[db[i].pos2D]});
+  // generation order of the sampler arrays (low_discrepancy_sampler.dart:64-88 -> montecarlo.dart:407-473)
+  r->arrays.clear();
+  uint32_t sid = 0;
+  r->arrays.push_back(SampleArray{2, 1, -1, sid++});
+  r->arrays.push_back(SampleArray{2, 1, -2, sid++});
+  r->arrays.push_back(SampleArray{1, 1, -3, sid++});
+  for (size_t i = 0; i < n1D.size(); ++i) r->arrays.push_back(SampleArray{1, n1D[i], v1[i], sid++});
+  for (size_t i = 0; i < n2D.size(); ++i) r->arrays.push_back(SampleArray{2, n2D[i], v2[i], sid++});
+  r->maxVals = r->maxOthers = 0;
+  for (const SampleArray& a : r->arrays) {
+    r->maxVals = std::max(r->maxVals, a.dims * a.nSamples * p.nPixelSamples);
+    r->maxOthers = std::max(r->maxOthers, a.nSamples * p.nPixelSamples + p.nPixelSamples);
+  }
+}
+
+// Scene tables the shading kernels read: primitive -> leaf record, per-primitive attributes, materials,
+// lights with their ShapeSet areas and area distribution (shape_set.dart:43-50, montecarlo.dart:26-48).
+static int uploadSceneTables(drt_ctx* c, RenderState* r) {
+  const uint32_t nt = c->ntris(), np = c->nprims();
+  std::vector<uint32_t> primToRec(std::max<uint32_t>(np, 1), 0), attr(std::max<uint32_t>(np, 1), 0);
+  for (size_t i = 0; i < c->bvh.leafPrimIds.size(); ++i) primToRec[c->bvh.leafPrimIds[i]] = (uint32_t)i;
+  const int nMat = (int)r->materials.size(), nLights = (int)r->lights.size();
+  for (uint32_t i = 0; i < np; ++i) {
+    int m = i < nt ? c->matOf[i] : c->sphMat[i - nt], l = i < nt ? c->lightOf[i] : c->sphLight[i - nt];
+    int rev = i < nt ? c->revOf[i] : c->sphRev[i - nt];
+    if (m < 0 || m >= nMat) return fail(c, DRT_E_INVALID, "a primitive refers to a material index that drt_set_materials did not define");
+    if (l >= nLights) return fail(c, DRT_E_INVALID, "a primitive refers to a light index that drt_set_lights did not define");
+    if (m > 0xffff || l + 1 > 0x7fff) return fail(c, DRT_E_INVALID, "too many materials (65535) or lights (32766)");
+    attr[i] = (uint32_t)m | ((uint32_t)(l + 1) << 16) | (rev ? 0x80000000u : 0u);
+  }
+  std::vector<GLight> gl(std::max(nLights, 1));
+  std::vector<uint32_t> shapes;
+  std::vector<double> areas;
+  std::vector<float> cdf;
+  for (int i = 0; i < nLights; ++i) {
+    const HostLight& hl = r->lights[i];
+    GLight& g = gl[i];
+    g.kind = hl.kind;
+    std::memcpy(g.L, hl.L, 12);
+    std::memcpy(g.pos, hl.pos, 12);
+    g.nSamples = hl.nSamples;
+    g.shapeOffset = (uint32_t)shapes.size();
+    g.nShapes = (uint32_t)hl.shapes.size();
+    g.cdfOffset = (uint32_t)cdf.size();
+    g.area = 0.0;
+    if (hl.kind == 0 && hl.shapes.empty()) return fail(c, DRT_E_INVALID, "an area light has no shapes");
+    std::vector<double> a;
+    for (uint32_t sh : hl.shapes) {
+      if (sh >= np) return fail(c, DRT_E_INVALID, "light shape id out of range");
+      double area;
+      if (sh < nt) {  // triangle.dart:265-269
+        TriVerts t;
+        const float* p1 = &c->P[3 * (size_t)c->idx[3 * (size_t)sh]];
+        const float* p2 = &c->P[3 * (size_t)c->idx[3 * (size_t)sh + 1]];
+        const float* p3 = &c->P[3 * (size_t)c->idx[3 * (size_t)sh + 2]];
+        t.p1 = V3{p1[0], p1[1], p1[2]}; t.p2 = V3{p2[0], p2[1], p2[2]}; t.p3 = V3{p3[0], p3[1], p3[2]};
+        area = triArea(t);
+      } else {  // sphere.dart:243-245 with the constructor's clamps (sphere.dart:24-32)
+        const HostSphere& s = c->spheres[sh - nt];
+        double zmin = clampD(std::fmin(s.zmin, s.zmax), -s.radius, s.radius), zmax = clampD(std::fmax(s.zmin, s.zmax), -s.radius, s.radius);
+        double phiMax = (DRT_PI / 180.0) * clampD(s.phiMaxDeg, 0.0, 360.0);
+        area = phiMax * s.radius * (zmax - zmin);
+      }
+      a.push_back(area);
+      g.area += area;
+      shapes.push_back(sh);
+      areas.push_back(area);
+    }
+    if (hl.kind == 0) {  // Distribution1D(areas): float32 func and cdf (montecarlo.dart:26-48)
+      const int count = (int)a.size();
+      std::vector<float> func(count), cd(count + 1, 0.f);
+      for (int k = 0; k < count; ++k) func[k] = (float)a[k];
+      for (int k = 1; k < count + 1; ++k) cd[k] = (float)((double)cd[k - 1] + (double)func[k - 1] / count);
+      double funcInt = cd[count];
+      for (int k = 1; k < count + 1; ++k) cd[k] = funcInt == 0.0 ? (float)((double)k / count) : (float)((double)cd[k] / funcInt);
+      cdf.insert(cdf.end(), cd.begin(), cd.end());
+    }
+  }
+  CK(c, r->dPrimToRec.ensure(primToRec.size()));
+  CK(c, r->dPrimAttr.ensure(attr.size()));
+  CK(c, r->dMaterials.ensure(r->materials.size()));
+  CK(c, r->dLights.ensure(gl.size()));
+  CK(c, r->dLightShapes.ensure(std::max<size_t>(1, shapes.size())));
+  CK(c, r->dLightAreas.ensure(std::max<size_t>(1, areas.size())));
+  CK(c, r->dLightCdf.ensure(std::max<size_t>(1, cdf.size())));
+  CK(c, cudaMemcpy(r->dPrimToRec.p, primToRec.data(), primToRec.size() * 4, cudaMemcpyHostToDevice));
+  CK(c, cudaMemcpy(r->dPrimAttr.p, attr.data(), attr.size() * 4, cudaMemcpyHostToDevice));
+  CK(c, cudaMemcpy(r->dMaterials.p, r->materials.data(), r->materials.size() * sizeof(GMaterial), cudaMemcpyHostToDevice));
+  CK(c, cudaMemcpy(r->dLights.p, gl.data(), gl.size() * sizeof(GLight), cudaMemcpyHostToDevice));
+  if (!shapes.empty()) CK(c, cudaMemcpy(r->dLightShapes.p, shapes.data(), shapes.size() * 4, cudaMemcpyHostToDevice));
+  if (!areas.empty()) CK(c, cudaMemcpy(r->dLightAreas.p, areas.data(), areas.size() * 8, cudaMemcpyHostToDevice));
+  if (!cdf.empty()) CK(c, cudaMemcpy(r->dLightCdf.p, cdf.data(), cdf.size() * 4, cudaMemcpyHostToDevice));
+  RenderScene& rs = r->rs;
+  rs.ts = c->ts;
+  rs.ntris = nt;
+  rs.nprims = np;
+  rs.primToRec = r->dPrimToRec.p;
+  rs.primAttr = r->dPrimAttr.p;
+  rs.materials = r->dMaterials.p;
+  rs.lights = r->dLights.p;
+  rs.nLights = nLights;
+  rs.lightShapes = r->dLightShapes.p;
+  rs.lightShapeAreas = r->dLightAreas.p;
+  rs.lightCdf = r->dLightCdf.p;
+  r->sceneTablesValid = true;
+  r->buildSerial = c->buildSerial;
+  return DRT_OK;
+}
+
+static void carve(ByteArena& a, Wavefront& wf, uint32_t cap, uint32_t shCap, int nVals) {
+  wf.cap = cap;
+  wf.pixX = a.take<int32_t>(cap); wf.pixY = a.take<int32_t>(cap); wf.sampleIdx = a.take<uint32_t>(cap);
+  wf.camXY = a.take<double2>(cap); wf.camLens = a.take<double2>(cap); wf.camTime = a.take<float>(cap);
+  wf.vals = a.take<float>((size_t)std::max(nVals, 1) * cap);
+  wf.L = a.take<float>(3 * (size_t)cap); wf.T = a.take<float>(3 * (size_t)cap);
+  wf.pendSh = a.take<float>(3 * (size_t)cap); wf.pendMisF = a.take<float>(3 * (size_t)cap); wf.pendMisScale = a.take<double>(cap);
+  wf.pendT = a.take<float>(3 * (size_t)cap);
+  wf.shIdx = a.take<int32_t>(cap); wf.misIdx = a.take<int32_t>(cap); wf.misLight = a.take<int32_t>(cap);
+  wf.hitP = a.take<float>(3 * (size_t)cap); wf.hitN = a.take<float>(3 * (size_t)cap);
+  wf.aoScramble = a.take<uint32_t>(2 * (size_t)cap); wf.nClear = a.take<int32_t>(cap);
+  wf.Ld = a.take<float>(3 * (size_t)cap);
+  for (int k = 0; k < 2; ++k) {
+    wf.extO[k] = a.take<float4>(cap); wf.extD[k] = a.take<float4>(cap); wf.extRange[k] = a.take<double2>(cap);
+    wf.extSlot[k] = a.take<uint32_t>(cap);
+  }
+  wf.extHit = a.take<float4>(cap); wf.extT = a.take<double>(cap);
+  wf.shO = a.take<float4>(shCap); wf.shD = a.take<float4>(shCap); wf.shRange = a.take<double2>(shCap); wf.shOcc = a.take<uint8_t>(shCap);
+  wf.misO = a.take<float4>(cap); wf.misD = a.take<float4>(cap); wf.misRange = a.take<double2>(cap);
+  wf.misHit = a.take<float4>(cap); wf.misT = a.take<double>(cap);
+  wf.counts = a.take<uint32_t>(Q_COUNT);
+  wf.hitList = a.take<uint32_t>(cap);
+}
+
+static int ensureWavefront(drt_ctx* c, RenderState* r, uint32_t cap, uint32_t shCap) {
+  ByteArena probe;
+  Wavefront tmp{};
+  carve(probe, tmp, cap, shCap, r->rp.nVals);
+  size_t need = probe.used + 256;
+  if (need > r->wfBytes) {
+    if (r->wfMem) cudaFree(r->wfMem);
+    r->wfMem = nullptr;
+    r->wfBytes = 0;
+    CK(c, cudaMalloc((void**)&r->wfMem, need));
+    r->wfBytes = need;
+  }
+  ByteArena a;
+  a.base = r->wfMem;
+  a.size = r->wfBytes;
+  carve(a, r->wf, cap, shCap, r->rp.nVals);
+  r->shCap = shCap;
+  return DRT_OK;
+}
+
+static int ensureFilm(drt_ctx* c, RenderState* r) {
+  const size_t n = (size_t)r->rp.width * r->rp.height;
+  if (n != r->filmPixels || !r->dFilm.p) {
+    CK(c, r->dFilm.ensure(4 * n));
+    CK(c, cudaMemset(r->dFilm.p, 0, 4 * n * sizeof(double)));
+    r->filmPixels = n;
+  }
+  CK(c, r->dTable.ensure(256));
+  CK(c, cudaMemcpy(r->dTable.p, r->table, sizeof(r->table), cudaMemcpyHostToDevice));
+  CK(c, r->dCounters.ensure(1));
+  r->rp.film = r->dFilm.p;
+  r->rp.filterTable = r->dTable.p;
+  return DRT_OK;
+}
+
+// GetSubWindow, common.dart:52-73
+static void getSubWindow(int w, int h, int num, int count, int e[4]) {
+  int nx = count, ny = 1;
+  while ((nx & 0x1) == 0 && 2 * w * ny < h * nx) { nx >>= 1; ny <<= 1; }
+  int xo = num % nx, yo = num / nx;
+  double tx0 = (double)xo / nx, tx1 = (double)(xo + 1) / nx, ty0 = (double)yo / ny, ty1 = (double)(yo + 1) / ny;
+  auto lerp = [](double t, double a, double b) { return (1.0 - t) * a + t * b; };
+  e[0] = (int)std::floor(lerp(tx0, 0, w));
+  e[1] = std::min((int)std::floor(lerp(tx1, 0, w)), w);
+  e[2] = (int)std::floor(lerp(ty0, 0, h));
+  e[3] = std::min((int)std::floor(lerp(ty1, 0, h)), h);
+}
+
+static int prepare(drt_ctx* c, RenderState* r) {
+  if (c->device == DRT_DEVICE_NONE) return fail(c, DRT_E_NODEVICE, kNoDevice);
+  if (!c->built) return fail(c, DRT_E_STATE, "drt_build_bvh must be called before rendering");
+  if (!r->haveCamera || !r->haveFilm) return fail(c, DRT_E_STATE, "drt_set_camera and drt_set_film must be called before rendering");
+  CK(c, cudaSetDevice(c->device));
+  RenderParams& p = r->rp;
+  p.nPixelSamples = p.samplerKind == 0 ? roundUpPow2(r->spp) : (p.samplerKind == 1 ? p.xs * p.ys : r->spp);
+  if (p.nPixelSamples < 1) return fail(c, DRT_E_INVALID, "sampler produces no samples per pixel");
+  buildLayout(r);
+  if (p.integKind == 2 && p.strategy == 0 && r->direct.size() != r->lights.size()) return fail(c, DRT_E_STATE, "light table out of date");
+  if (!r->sceneTablesValid || r->buildSerial != c->buildSerial) {
+    int rc = uploadSceneTables(c, r);
+    if (rc != DRT_OK) return rc;
+  }
+  r->rs.ts = c->ts;
+  CK(c, r->dArrays.ensure(r->arrays.size()));
+  CK(c, cudaMemcpy(r->dArrays.p, r->arrays.data(), r->arrays.size() * sizeof(SampleArray), cudaMemcpyHostToDevice));
+  CK(c, r->dDirect.ensure(std::max<size_t>(1, r->direct.size())));
+  if (!r->direct.empty())
+    CK(c, cudaMemcpy(r->dDirect.p, r->direct.data(), r->direct.size() * sizeof(DirectOffsets), cudaMemcpyHostToDevice));
+  p.direct = r->dDirect.p;
+  int rc = ensureFilm(c, r);
+  if (rc != DRT_OK) return rc;
+  if (p.samplerKind == 0) {
+    size_t smem = 4 * (size_t)(r->maxVals + r->maxOthers) * sizeof(float);
+    if (smem > 200 * 1024) return fail(c, DRT_E_INVALID, "lowdiscrepancy sampler: pixelsamples x light nsamples too large for one warp's shared memory");
+  }
+  return DRT_OK;
+}
+
+static int traceQueue(drt_ctx* c, bool any, const float4* o, const float4* d, const double2* range, const uint32_t* nDev, void* out,
+                      double* tOut, cudaStream_t st) {
+  TraceExtras ex;
+  ex.nDev = nDev;
+  ex.range = range;
+  ex.tOut = tOut;
+  CK(c, launchTraceFast(c->ts, any, o, d, 0, out, c->dNextRay.p, c->numSMs, st, &ex));
+  c->launches++;
+  return DRT_OK;
+}
+
+#define RK(call)                         \
+  do {                                   \
+    int rc__ = (call);                   \
+    if (rc__ != DRT_OK) return rc__;     \
+  } while (0)
+
+// One batch of camera samples through the whole pipeline; everything is enqueued on c->stream.
+static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
+  const RenderParams& p = r->rp;
+  const RenderScene& rs = r->rs;
+  const Wavefront& wf = r->wf;
+  cudaStream_t st = c->stream;
+  const int sms = c->numSMs;
+  const uint32_t nSlots = pb.nPixels * (uint32_t)p.nPixelSamples;
+  RenderCounters* rc = r->dCounters.p;
+  CK(c, launchSampler(p, wf, r->dArrays.p, (int)r->arrays.size(), r->maxVals, r->maxOthers, pb, sms, st));
+  CK(c, launchResetCounts(wf, 0xffu, st));
+  CK(c, launchRaygen(p, wf, pb, st));
+  c->launches += 3;
+  // camera rays: Scene.intersect (sampler_renderer.dart:84)
+  RK(traceQueue(c, false, wf.extO[0], wf.extD[0], wf.extRange[0], wf.counts + Q_EXT0, wf.extHit, wf.extT, st));
+  r->stats.camera_samples += nSlots;
+  r->stats.closest_rays += nSlots;
+  if (p.integKind == 0) {
+    int cur = 0;
+    for (int bounce = 0; bounce <= p.maxDepth; ++bounce) {
+      CK(c, launchResetCounts(wf, (1u << (cur ^ 1)) | (1u << Q_SHADOW) | (1u << Q_MIS), st));
+      CK(c, launchShadePath(p, rs, wf, bounce, cur, rc, sms, st));
+      c->launches += 2;
+      if (rs.nLights > 0) {
+        RK(traceQueue(c, true, wf.shO, wf.shD, wf.shRange, wf.counts + Q_SHADOW, wf.shOcc, nullptr, st));
+        RK(traceQueue(c, false, wf.misO, wf.misD, wf.misRange, wf.counts + Q_MIS, wf.misHit, wf.misT, st));
+        CK(c, launchResolveDirect(p, rs, wf, cur, RESOLVE_PATH, 1, sms, st));
+        c->launches++;
+      }
+      if (bounce == p.maxDepth) break;
+      cur ^= 1;
+      RK(traceQueue(c, false, wf.extO[cur], wf.extD[cur], wf.extRange[cur], wf.counts + cur, wf.extHit, wf.extT, st));
+    }
+  } else if (p.integKind == 1) {
+    CK(c, launchAoSetup(p, rs, wf, sms, st));
+    c->launches++;
+    const int nS = roundUpPow2(p.aoSamples);
+    const uint32_t hitsPerChunk = std::max<uint32_t>(1, r->shCap / (uint32_t)nS);
+    for (uint32_t first = 0; first < nSlots; first += hitsPerChunk) {
+      CK(c, launchAoGen(p, wf, first, hitsPerChunk, sms, st));
+      RK(traceQueue(c, true, wf.shO, wf.shD, wf.shRange, wf.counts + Q_SHADOW, wf.shOcc, nullptr, st));
+      CK(c, launchAoCount(p, wf, first, hitsPerChunk, rc, sms, st));
+      c->launches += 2;
+    }
+  } else {
+    CK(c, launchDirectSetup(p, rs, wf, sms, st));
+    c->launches++;
+    if (rs.nLights > 0) {
+      const bool one = p.strategy != 0;
+      const int nL = one ? 1 : rs.nLights;
+      for (int li = 0; li < nL; ++li) {
+        const int nS = one ? 1 : r->direct[li].nSamples;
+        for (int j = 0; j < nS; ++j) {
+          CK(c, launchResetCounts(wf, (1u << Q_SHADOW) | (1u << Q_MIS), st));
+          CK(c, launchDirectSample(p, rs, wf, one ? -1 : li, j, rc, sms, st));
+          RK(traceQueue(c, true, wf.shO, wf.shD, wf.shRange, wf.counts + Q_SHADOW, wf.shOcc, nullptr, st));
+          RK(traceQueue(c, false, wf.misO, wf.misD, wf.misRange, wf.counts + Q_MIS, wf.misHit, wf.misT, st));
+          int mode = RESOLVE_DIRECT;
+          if (one) mode |= RESOLVE_ONE;
+          else {
+            if (j == 0) mode |= RESOLVE_FIRST_OF_LIGHT;
+            if (j == nS - 1) mode |= RESOLVE_LAST_OF_LIGHT;
+            if (j == nS - 1 && li == nL - 1) mode |= RESOLVE_FINAL;
+          }
+          CK(c, launchResolveDirect(p, rs, wf, 0, mode, nS, sms, st));
+          c->launches += 3;
+        }
+      }
+    }
+  }
+  CK(c, launchFilm(p, wf, nSlots, rc, st));
+  c->launches++;
+  return DRT_OK;
+}
+
+static int renderWindow(drt_ctx* c, int x, int y, int w, int h, uint32_t shard, uint32_t nShards) {
+  RenderState* r = state(c);
+  RK(prepare(c, r));
+  const RenderParams& p = r->rp;
+  if (w <= 0 || h <= 0) return DRT_OK;
+  const uint64_t total = (uint64_t)w * h;
+  const uint32_t blockPixels = 1024;
+  uint64_t mine = total;
+  if (nShards > 1) {  // pixels of the blocks shard, shard + nShards, ...
+    const uint64_t nBlocks = (total + blockPixels - 1) / blockPixels;
+    const uint64_t owned = nBlocks > shard ? (nBlocks - shard + nShards - 1) / nShards : 0;
+    mine = owned * blockPixels;
+    if (owned && (nBlocks - 1) % nShards == shard) mine -= nBlocks * blockPixels - total;
+  }
+  uint64_t slots = r->batchSlots ? r->batchSlots : (1ull << 22);
+  if (const char* e = std::getenv("DRT_BATCH_SLOTS")) slots = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10));
+  uint64_t pixelsPerBatch = std::max<uint64_t>(1, slots / (uint64_t)p.nPixelSamples);
+  pixelsPerBatch = std::min<uint64_t>(pixelsPerBatch, std::max<uint64_t>(mine, 1));
+  const uint64_t cap64 = pixelsPerBatch * (uint64_t)p.nPixelSamples;
+  if (cap64 > 0x7fffffffull) return fail(c, DRT_E_INVALID, "samples per pixel too large for one batch");
+  const uint32_t cap = (uint32_t)cap64;
+  uint32_t shCap = cap;
+  if (p.integKind == 1) {
+    const uint64_t nS = (uint64_t)roundUpPow2(p.aoSamples);
+    shCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(cap, std::max<uint64_t>(nS, 1ull << 24)), (uint64_t)cap * nS);
+    shCap = std::max<uint32_t>(shCap, (uint32_t)nS);
+  }
+  RK(ensureWavefront(c, r, cap, shCap));
+  const int passes = p.samplerKind == 2 ? r->spp : 1;  // random sampler: spp visits of spp samples (random_sampler.dart:47-88)
+  for (int pass = 0; pass < passes; ++pass)
+    for (uint64_t first = 0; first < mine; first += pixelsPerBatch) {
+      PixelBatch pb;
+      pb.x0 = x; pb.y0 = y; pb.w = w;
+      pb.firstPixel = first;
+      pb.nPixels = (uint32_t)std::min<uint64_t>(pixelsPerBatch, mine - first);
+      pb.pass = (uint32_t)pass;
+      pb.shard = shard; pb.nShards = nShards; pb.blockPixels = blockPixels;
+      RK(renderBatch(c, r, pb));
+    }
+  CK(c, cudaStreamSynchronize(c->stream));
+  RenderCounters hc;
+  CK(c, cudaMemcpy(&hc, r->dCounters.p, sizeof(hc), cudaMemcpyDeviceToHost));
+  r->stats.closest_rays += hc.closestRays;
+  r->stats.shadow_rays += hc.shadowRays;
+  r->stats.zeroed_samples += hc.zeroedSamples;
+  CK(c, cudaMemset(r->dCounters.p, 0, sizeof(RenderCounters)));
+  return DRT_OK;
+}
+
+static void sampleExtent(const RenderParams& p, int e[4]) {  // image_film.dart:247-252
+  e[0] = (int)std::floor(p.left + 0.5 - p.xWidth);
+  e[1] = (int)std::ceil(p.left + 0.5 + p.width + p.xWidth);
+  e[2] = (int)std::floor(p.top + 0.5 - p.yWidth);
+  e[3] = (int)std::ceil(p.top + 0.5 + p.height + p.yWidth);
+}
+
+extern "C" {
+
+int drt_set_materials(drt_ctx* c, uint32_t n, const int32_t* kind, const float* kd, const float* sigma) {
+  if (!c) return DRT_E_INVALID;
+  if (n && !kd) return fail(c, DRT_E_INVALID, "null Kd array");
+  RenderState* r = state(c);
+  r->materials.resize(std::max<uint32_t>(n, 1));
+  if (n == 0) r->materials[0] = GMaterial{{0.5f, 0.5f, 0.5f}, 0.f};
+  for (uint32_t i = 0; i < n; ++i) {
+    if (kind && kind[i] != 0) return fail(c, DRT_E_INVALID, "only material kind 0 (matte) is on the GPU path");
+    r->materials[i] = GMaterial{{kd[3 * i], kd[3 * i + 1], kd[3 * i + 2]}, sigma ? sigma[i] : 0.f};
+  }
+  r->sceneTablesValid = false;
+  return DRT_OK;
+}
+
+int drt_set_lights(drt_ctx* c, uint32_t n, const int32_t* kind, const float* L, const float* pos, const int32_t* nsamples,
+                   const uint32_t* shape_offsets, const uint32_t* shape_prims) {
+  if (!c) return DRT_E_INVALID;
+  if (n && (!kind || !L)) return fail(c, DRT_E_INVALID, "null light arrays");
+  RenderState* r = state(c);
+  std::vector<HostLight> ls(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    HostLight& l = ls[i];
+    l.kind = kind[i];
+    if (l.kind != 0 && l.kind != 1) return fail(c, DRT_E_INVALID, "light kind must be 0 (diffuse area) or 1 (point)");
+    std::memcpy(l.L, L + 3 * i, 12);
+    if (pos) std::memcpy(l.pos, pos + 3 * i, 12);
+    l.nSamples = nsamples ? std::max(1, nsamples[i]) : 1;
+    if (shape_offsets && shape_prims)
+      for (uint32_t k = shape_offsets[i]; k < shape_offsets[i + 1]; ++k) l.shapes.push_back(shape_prims[k]);
+  }
+  r->lights.swap(ls);
+  r->sceneTablesValid = false;
+  return DRT_OK;
+}
+
+int drt_set_camera(drt_ctx* c, const float* raster_to_camera, const float* camera_to_world, double lens_radius,
+                   double focal_distance, double shutter_open, double shutter_close) {
+  if (!c) return DRT_E_INVALID;
+  if (!raster_to_camera || !camera_to_world) return fail(c, DRT_E_INVALID, "null camera matrix");
+  RenderState* r = state(c);
+  std::memcpy(r->rp.rasterToCamera, raster_to_camera, 64);
+  std::memcpy(r->rp.cameraToWorld, camera_to_world, 64);
+  r->rp.lensRadius = lens_radius; r->rp.focalDistance = focal_distance;
+  r->rp.shutterOpen = shutter_open; r->rp.shutterClose = shutter_close;
+  r->haveCamera = true;
+  return DRT_OK;
+}
+
+int drt_set_film(drt_ctx* c, int xres, int yres, const double* crop, double xwidth, double ywidth, const float* table) {
+  if (!c) return DRT_E_INVALID;
+  if (xres < 1 || yres < 1 || !(xwidth > 0.0) || !(ywidth > 0.0) || !table) return fail(c, DRT_E_INVALID, "bad film parameters");
+  RenderState* r = state(c);
+  r->rp.xres = xres; r->rp.yres = yres;
+  for (int i = 0; i < 4; ++i) r->crop[i] = crop ? crop[i] : ((i & 1) ? 1.0 : 0.0);
+  r->rp.xWidth = xwidth; r->rp.yWidth = ywidth;
+  std::memcpy(r->table, table, sizeof(r->table));
+  configureFilm(r);
+  r->haveFilm = true;
+  r->filmPixels = 0;  // new film: cleared on the next render / clear
+  return DRT_OK;
+}
+
+int drt_set_sampler(drt_ctx* c, int kind, int xs, int ys, int spp, int jitter, int pixel_order, int tile_size, uint64_t seed) {
+  if (!c) return DRT_E_INVALID;
+  if (kind < 0 || kind > 2) return fail(c, DRT_E_INVALID, "sampler kind must be 0 (lowdiscrepancy), 1 (stratified) or 2 (random)");
+  if (spp < 1 || xs < 1 || ys < 1) return fail(c, DRT_E_INVALID, "sample counts must be >= 1");
+  RenderState* r = state(c);
+  r->rp.samplerKind = kind; r->rp.xs = xs; r->rp.ys = ys; r->rp.jitter = jitter; r->rp.seed = seed;
+  r->spp = spp; r->pixelOrder = pixel_order; r->tileSize = tile_size;
+  return DRT_OK;
+}
+
+int drt_set_integrator(drt_ctx* c, int kind, int maxdepth, int strategy, int ao_nsamples, double ao_mindist, double ao_maxdist) {
+  if (!c) return DRT_E_INVALID;
+  if (kind < 0 || kind > 2) return fail(c, DRT_E_INVALID, "integrator kind must be 0 (path), 1 (ambientocclusion) or 2 (directlighting)");
+  if (kind == 1 && ao_nsamples < 1) return fail(c, DRT_E_INVALID, "ambientocclusion nsamples must be >= 1");
+  RenderState* r = state(c);
+  r->rp.integKind = kind; r->rp.maxDepth = maxdepth; r->rp.strategy = strategy; r->rp.aoSamples = std::max(1, ao_nsamples);
+  r->rp.aoMinDist = ao_mindist; r->rp.aoMaxDist = ao_maxdist;
+  return DRT_OK;
+}
+
+int drt_set_batch_slots(drt_ctx* c, uint64_t slots) {
+  if (!c) return DRT_E_INVALID;
+  state(c)->batchSlots = slots;
+  return DRT_OK;
+}
+
+int drt_render(drt_ctx* c, int task_num, int task_count) {
+  if (!c) return DRT_E_INVALID;
+  if (task_count < 1 || task_num < 0 || task_num >= task_count) return fail(c, DRT_E_INVALID, "bad task_num / task_count");
+  RenderState* r = state(c);
+  if (!r->haveFilm) return fail(c, DRT_E_STATE, "drt_set_film must be called before rendering");
+  int ext[4];
+  sampleExtent(r->rp, ext);
+  int x = ext[0], y = ext[2], w = ext[1] - ext[0], h = ext[3] - ext[2];
+  if (task_count > 1) {  // dartray.dart:1009-1023: the task's sub-window of the SAMPLE extent
+    int e[4];
+    getSubWindow(w, h, task_num, task_count, e);
+    x = ext[0] + e[0]; w = e[1] - e[0];
+    y = ext[2] + e[2]; h = e[3] - e[2];
+  }
+  return renderWindow(c, x, y, w, h, 0, 1);
+}
+
+int drt_render_shard(drt_ctx* c, int shard, int n_shards) {
+  if (!c) return DRT_E_INVALID;
+  if (n_shards < 1 || shard < 0 || shard >= n_shards) return fail(c, DRT_E_INVALID, "bad shard / n_shards");
+  RenderState* r = state(c);
+  if (!r->haveFilm) return fail(c, DRT_E_STATE, "drt_set_film must be called before rendering");
+  int ext[4];
+  sampleExtent(r->rp, ext);
+  return renderWindow(c, ext[0], ext[2], ext[1] - ext[0], ext[3] - ext[2], (uint32_t)shard, (uint32_t)n_shards);
+}
+
+int drt_film_clear(drt_ctx* c) {
+  if (!c) return DRT_E_INVALID;
+  RenderState* r = state(c);
+  if (c->device == DRT_DEVICE_NONE) return fail(c, DRT_E_NODEVICE, kNoDevice);
+  if (!r->haveFilm) return fail(c, DRT_E_STATE, "drt_set_film must be called first");
+  CK(c, cudaSetDevice(c->device));
+  r->filmPixels = 0;
+  int rc = ensureFilm(c, r);
+  r->stats = drt_render_stats{};
+  return rc;
+}
+
+int drt_film_size(const drt_ctx* c, int32_t out[4]) {
+  if (!c || !out || !c->render || !c->render->haveFilm) return DRT_E_STATE;
+  const RenderParams& p = c->render->rp;
+  out[0] = p.left; out[1] = p.top; out[2] = p.width; out[3] = p.height;
+  return DRT_OK;
+}
+
+int drt_film_device(drt_ctx* c, void** d_film, uint64_t* n_doubles) {
+  if (!c || !d_film || !n_doubles) return DRT_E_INVALID;
+  RenderState* r = state(c);
+  if (c->device == DRT_DEVICE_NONE) return fail(c, DRT_E_NODEVICE, kNoDevice);
+  if (!r->haveFilm) return fail(c, DRT_E_STATE, "drt_set_film must be called first");
+  CK(c, cudaSetDevice(c->device));
+  if ((size_t)r->rp.width * r->rp.height != r->filmPixels) RK(ensureFilm(c, r));
+  *d_film = r->dFilm.p;
+  *n_doubles = 4ull * r->filmPixels;
+  return DRT_OK;
+}
+
+int drt_film_read(drt_ctx* c, float* rgb, float* xyz, float* weight) {
+  if (!c) return DRT_E_INVALID;
+  RenderState* r = state(c);
+  if (c->device == DRT_DEVICE_NONE) return fail(c, DRT_E_NODEVICE, kNoDevice);
+  if (!r->haveFilm) return fail(c, DRT_E_STATE, "drt_set_film must be called first");
+  CK(c, cudaSetDevice(c->device));
+  if ((size_t)r->rp.width * r->rp.height != r->filmPixels) RK(ensureFilm(c, r));
+  const size_t n = r->filmPixels;
+  CK(c, r->dRgb.ensure(3 * n));
+  CK(c, r->dXyz.ensure(3 * n));
+  CK(c, r->dWeight.ensure(n));
+  CK(c, cudaDeviceSynchronize());  // the film may have been summed across GPUs on another stream
+  CK(c, launchFilmConvert(r->rp, rgb ? r->dRgb.p : nullptr, xyz ? r->dXyz.p : nullptr, weight ? r->dWeight.p : nullptr, c->stream));
+  c->launches++;
+  if (rgb) CK(c, cudaMemcpyAsync(rgb, r->dRgb.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (xyz) CK(c, cudaMemcpyAsync(xyz, r->dXyz.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (weight) CK(c, cudaMemcpyAsync(weight, r->dWeight.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return DRT_OK;
+}
+
+int drt_pixel_samples(drt_ctx* c, int x, int y, float* out, int cap, int32_t* n_samples, int32_t* floats_per_sample) {
+  if (!c || !out) return DRT_E_INVALID;
+  RenderState* r = state(c);
+  RK(prepare(c, r));
+  const RenderParams& p = r->rp;
+  const uint32_t n = (uint32_t)p.nPixelSamples;
+  RK(ensureWavefront(c, r, n, n));
+  PixelBatch pb{x, y, 1, 0, 1, 0, 0, 1, 1024};
+  CK(c, launchSampler(p, r->wf, r->dArrays.p, (int)r->arrays.size(), r->maxVals, r->maxOthers, pb, c->numSMs, c->stream));
+  c->launches++;
+  std::vector<double2> xy(n), lens(n);
+  std::vector<float> tm(n), vals((size_t)std::max(p.nVals, 1) * n);
+  CK(c, cudaMemcpyAsync(xy.data(), r->wf.camXY, n * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaMemcpyAsync(lens.data(), r->wf.camLens, n * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaMemcpyAsync(tm.data(), r->wf.camTime, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaMemcpyAsync(vals.data(), r->wf.vals, (size_t)p.nVals * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  const int per = 5 + p.nVals;
+  if (n_samples) *n_samples = (int32_t)n;
+  for (uint32_t i = 0; i < n; ++i) {
+    std::vector<float> rec(per);
+    rec[0] = (float)(xy[i].x - x); rec[1] = (float)(xy[i].y - y);
+    rec[2] = (float)lens[i].x; rec[3] = (float)lens[i].y;
+    rec[4] = (float)((1.0 - tm[i]) * p.shutterOpen + tm[i] * p.shutterClose);
+    for (int v = 0; v < p.nVals; ++v) rec[5 + v] = vals[(size_t)v * n + i];
+    for (int k = 0; k < per; ++k)
+      if ((size_t)i * per + k < (size_t)cap) out[(size_t)i * per + k] = rec[k];
+  }
+  if (floats_per_sample) *floats_per_sample = per;
+  return DRT_OK;
+}
+
+int drt_render_stats_get(drt_ctx* c, drt_render_stats* out) {
+  if (!c || !out) return DRT_E_INVALID;
+  *out = state(c)->stats;
+  return DRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,748 @@
+// Wavefront render stages for sm_100a: sampler sequences -> camera rays -> (extend) -> shade ->
+// (shadow / MIS rays) -> resolve -> film.  The traversal itself is trace_fast.cu; everything here is
+// the per-sample arithmetic of the reference, restated per stage:
+//
+//   samplers     lib/samplers/{low_discrepancy,stratified,random}_sampler.dart, lib/core/montecarlo.dart:270-551
+//   camera       lib/cameras/perspective_camera.dart:93-132
+//   path         lib/surface_integrators/path_integrator.dart:29-131
+//   AO           lib/surface_integrators/ambient_occlusion_integrator.dart:28-53
+//   direct       lib/surface_integrators/direct_lighting_integrator.dart:30-96, lib/core/integrator.dart:39-185
+//   renderer     lib/renderers/sampler_renderer.dart:67-98,173-193
+//   film         lib/film/image_film.dart:99-185,268-299
+//
+// Random numbers: counter-based streams keyed by (pixel, array) for the sampler and (pixel, sample)
+// for the integrators (shade_device.cuh); inside a stream the draw order is the reference's.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <cstdint>
+
+#include "render_kernels.h"
+#include "shade_device.cuh"
+
+namespace drt {
+
+#define FULL 0xffffffffu
+
+// Warp-aggregated queue append: one atomicAdd per warp, slots handed out by ballot prefix.
+// Must be reached by all 32 lanes.
+static __device__ __forceinline__ uint32_t warpPush(uint32_t* counter, bool want) {
+  const unsigned m = __ballot_sync(FULL, want);
+  if (m == 0) return 0;
+  const unsigned lane = threadIdx.x & 31u;
+  const int leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(FULL, base, leader);
+  return base + __popc(m & ((1u << lane) - 1u));
+}
+
+static __device__ __forceinline__ Spec ld3(const float* a, uint32_t cap, uint32_t i) { return Spec{a[i], a[cap + i], a[2 * cap + i]}; }
+static __device__ __forceinline__ void st3(float* a, uint32_t cap, uint32_t i, const Spec& s) { a[i] = s.r; a[cap + i] = s.g; a[2 * cap + i] = s.b; }
+static __device__ __forceinline__ V3 ldv3(const float* a, uint32_t cap, uint32_t i) { return V3{a[i], a[cap + i], a[2 * cap + i]}; }
+static __device__ __forceinline__ void stv3(float* a, uint32_t cap, uint32_t i, const V3& s) { a[i] = s.x; a[cap + i] = s.y; a[2 * cap + i] = s.z; }
+
+static __device__ __forceinline__ void pixelOf(const PixelBatch& pb, uint32_t p, int* x, int* y) {
+  uint64_t g = pb.firstPixel + p;
+  if (pb.nShards > 1) g = ((g / pb.blockPixels) * pb.nShards + pb.shard) * pb.blockPixels + (g % pb.blockPixels);
+  *x = pb.x0 + (int)(g % (uint64_t)pb.w);
+  *y = pb.y0 + (int)(g / (uint64_t)pb.w);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Low-discrepancy sampler: one warp per (pixel, array).  LDShuffleScrambled1D/2D
+// (montecarlo.dart:524-551): scrambled (0,2)-sequence values, a Fisher-Yates shuffle inside every
+// block of nSamples and one across the nPixel blocks (Shuffle, montecarlo.dart:294-303).  Values and
+// swap targets are computed by all lanes (the stream is counter-based); the swaps themselves are
+// order-dependent and run on lane 0 in shared memory; the result is written out coalesced.
+__global__ void __launch_bounds__(128) samplerLDKernel(RenderParams rp, Wavefront wf, const SampleArray* __restrict__ arrays,
+                                                       int nArrays, int maxVals, int maxOthers, PixelBatch pb) {
+  extern __shared__ float smem[];
+  const int warpsPerBlock = blockDim.x >> 5, warpInBlock = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* buf = smem + (size_t)warpInBlock * (maxVals + maxOthers);
+  uint32_t* other = reinterpret_cast<uint32_t*>(buf + maxVals);
+  const uint64_t nTasks = (uint64_t)pb.nPixels * nArrays;
+  const uint32_t nP = (uint32_t)rp.nPixelSamples;
+  for (uint64_t task = (uint64_t)blockIdx.x * warpsPerBlock + warpInBlock; task < nTasks; task += (uint64_t)gridDim.x * warpsPerBlock) {
+    const uint32_t p = (uint32_t)(task / nArrays);
+    const SampleArray A = arrays[task % nArrays];
+    int x, y;
+    pixelOf(pb, p, &x, &y);
+    const uint64_t key = streamKey(rp.seed, x, y, 0, A.streamId);
+    const uint32_t nS = (uint32_t)A.nSamples, total = nS * nP, dims = (uint32_t)A.dims;
+    const uint32_t s0 = drawUint(key, 1), s1 = dims == 2 ? drawUint(key, 2) : 0u;
+    const uint64_t base = dims;  // draws consumed by the scrambles
+    for (uint32_t i = lane; i < total; i += 32) {
+      if (dims == 1) buf[i] = (float)VanDerCorput(i, s0);
+      else { buf[2 * i] = (float)VanDerCorput(i, s0); buf[2 * i + 1] = (float)Sobol2(i, s1); }
+    }
+    if (nS > 1)
+      for (uint32_t e = lane; e < total; e += 32) {
+        uint32_t k = e % nS;
+        other[e] = k + drawUint(key, base + e + 1) % (nS - k);
+      }
+    for (uint32_t i = lane; i < nP; i += 32) other[total + i] = i + drawUint(key, base + total + i + 1) % (nP - i);
+    __syncwarp();
+    if (lane == 0) {
+      if (nS > 1)
+        for (uint32_t blk = 0; blk < nP; ++blk)
+          for (uint32_t k = 0; k < nS; ++k) {
+            uint32_t o = other[blk * nS + k];
+            if (o != k)
+              for (uint32_t j = 0; j < dims; ++j) {
+                float a = buf[(blk * nS + k) * dims + j];
+                buf[(blk * nS + k) * dims + j] = buf[(blk * nS + o) * dims + j];
+                buf[(blk * nS + o) * dims + j] = a;
+              }
+          }
+      const uint32_t bs = nS * dims;
+      for (uint32_t i = 0; i < nP; ++i) {
+        uint32_t o = other[total + i];
+        if (o != i)
+          for (uint32_t j = 0; j < bs; ++j) {
+            float a = buf[i * bs + j];
+            buf[i * bs + j] = buf[o * bs + j];
+            buf[o * bs + j] = a;
+          }
+      }
+    }
+    __syncwarp();
+    const uint32_t bs = nS * dims;
+    const uint32_t slot0 = p * nP;
+    if (A.dest >= 0) {
+      for (uint32_t qv = 0; qv < bs; ++qv)
+        for (uint32_t i = lane; i < nP; i += 32) wf.vals[(size_t)(A.dest + qv) * wf.cap + slot0 + i] = buf[i * bs + qv];
+    } else if (A.dest == -1) {  // montecarlo.dart:452-453: imageX = xPos + sample (f64 sum of an int and a float32)
+      for (uint32_t i = lane; i < nP; i += 32) wf.camXY[slot0 + i] = make_double2(x + (double)buf[2 * i], y + (double)buf[2 * i + 1]);
+    } else if (A.dest == -2) {
+      for (uint32_t i = lane; i < nP; i += 32) wf.camLens[slot0 + i] = make_double2((double)buf[2 * i], (double)buf[2 * i + 1]);
+    } else {
+      for (uint32_t i = lane; i < nP; i += 32) wf.camTime[slot0 + i] = buf[i];
+    }
+    __syncwarp();
+  }
+}
+
+// Stratified (stratified_sampler.dart:67-124, montecarlo.dart:270-325) and random
+// (random_sampler.dart:47-88) samplers: one sequential stream per pixel visit -> one thread per pixel.
+__global__ void __launch_bounds__(128) samplerSeqKernel(RenderParams rp, Wavefront wf, const SampleArray* __restrict__ arrays,
+                                                        int nArrays, PixelBatch pb) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pb.nPixels) return;
+  int x, y;
+  pixelOf(pb, p, &x, &y);
+  Stream rng{streamKey(rp.seed, x, y, pb.pass, DRT_STREAM_PIXEL), 0};
+  const uint32_t n = (uint32_t)rp.nPixelSamples, slot0 = p * n, cap = wf.cap;
+  if (rp.samplerKind == 1) {
+    const bool jitter = rp.jitter != 0;
+    const double dx = 1.0 / rp.xs, dy = 1.0 / rp.ys;
+    for (int pass = 0; pass < 2; ++pass) {  // image samples, then lens samples (StratifiedSample2D)
+      uint32_t si = 0;
+      for (int yy = 0; yy < rp.ys; ++yy)
+        for (int xx = 0; xx < rp.xs; ++xx, ++si) {
+          double jx = jitter ? rng.randomFloat() : 0.5;
+          double jy = jitter ? rng.randomFloat() : 0.5;
+          float fx = (float)fmin((xx + jx) * dx, DRT_ONE_MINUS_EPS), fy = (float)fmin((yy + jy) * dy, DRT_ONE_MINUS_EPS);
+          if (pass == 0) {  // stratified_sampler.dart:97-100: shifted to the pixel in float32
+            fx = (float)((double)fx + x);
+            fy = (float)((double)fy + y);
+            wf.camXY[slot0 + si] = make_double2((double)fx, (double)fy);
+          } else {
+            wf.camLens[slot0 + si] = make_double2((double)fx, (double)fy);
+          }
+        }
+    }
+    const double invTot = 1.0 / n;
+    for (uint32_t i = 0; i < n; ++i) {  // StratifiedSample1D(time)
+      double delta = jitter ? rng.randomFloat() : 0.5;
+      wf.camTime[slot0 + i] = (float)fmin((i + delta) * invTot, DRT_ONE_MINUS_EPS);
+    }
+    for (uint32_t i = 0; i < n; ++i) {  // Shuffle(lens, 2 dims)
+      uint32_t o = i + rng.randomUint() % (n - i);
+      double2 a = wf.camLens[slot0 + i];
+      wf.camLens[slot0 + i] = wf.camLens[slot0 + o];
+      wf.camLens[slot0 + o] = a;
+    }
+    for (uint32_t i = 0; i < n; ++i) {  // Shuffle(time)
+      uint32_t o = i + rng.randomUint() % (n - i);
+      float a = wf.camTime[slot0 + i];
+      wf.camTime[slot0 + i] = wf.camTime[slot0 + o];
+      wf.camTime[slot0 + o] = a;
+    }
+    for (uint32_t i = 0; i < n; ++i) {  // LatinHypercube per integrator array, sample by sample
+      for (int a = 3; a < nArrays; ++a) {
+        const SampleArray A = arrays[a];
+        const uint32_t nS = (uint32_t)A.nSamples, nDim = (uint32_t)A.dims;
+        const double delta = 1.0 / nS;
+        float* v = wf.vals + (size_t)A.dest * cap + slot0 + i;  // value q of the array lives at v[q * cap]
+        for (uint32_t s = 0; s < nS; ++s)
+          for (uint32_t j = 0; j < nDim; ++j) v[(size_t)(nDim * s + j) * cap] = (float)fmin((s + rng.randomFloat()) * delta, DRT_ONE_MINUS_EPS);
+        for (uint32_t d = 0; d < nDim; ++d)
+          for (uint32_t j = 0; j < nS; ++j) {
+            uint32_t o = j + rng.randomUint() % (nS - j);
+            float t = v[(size_t)(nDim * j + d) * cap];
+            v[(size_t)(nDim * j + d) * cap] = v[(size_t)(nDim * o + d) * cap];
+            v[(size_t)(nDim * o + d) * cap] = t;
+          }
+      }
+    }
+  } else {
+    for (uint32_t si = 0; si < n; ++si) {
+      double ix = rng.randomFloat() + x, iy = rng.randomFloat() + y;
+      double lu = rng.randomFloat(), lv = rng.randomFloat();
+      wf.camXY[slot0 + si] = make_double2(ix, iy);
+      wf.camLens[slot0 + si] = make_double2(lu, lv);
+      wf.camTime[slot0 + si] = (float)rng.randomFloat();
+      for (int a = 3; a < nArrays; ++a) {
+        const SampleArray A = arrays[a];
+        const uint32_t cnt = (uint32_t)(A.nSamples * A.dims);
+        for (uint32_t q = 0; q < cnt; ++q) wf.vals[(size_t)(A.dest + q) * cap + slot0 + si] = (float)rng.randomFloat();
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Camera rays (perspective_camera.dart:93-132; ray differentials only feed texture filtering and are
+// not generated) + per-slot state reset.  Extension queue 0 = all slots in slot order.
+__global__ void __launch_bounds__(256) raygenKernel(RenderParams rp, Wavefront wf, PixelBatch pb, uint32_t nSlots) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s == 0) wf.counts[Q_EXT0] = nSlots;
+  if (s >= nSlots) return;
+  const uint32_t n = (uint32_t)rp.nPixelSamples, cap = wf.cap;
+  int x, y;
+  pixelOf(pb, s / n, &x, &y);
+  wf.pixX[s] = x;
+  wf.pixY[s] = y;
+  wf.sampleIdx[s] = pb.pass * n + (s % n);
+  const double2 im = wf.camXY[s];
+  V3 Pras = mkv(im.x, im.y, 0.0);
+  V3 Pcamera = XfPoint(rp.rasterToCamera, Pras);
+  V3 o = V3{0.f, 0.f, 0.f}, d = Normalize(Pcamera);
+  if (rp.lensRadius > 0.0) {
+    const double2 ln = wf.camLens[s];
+    double lu, lv;
+    ConcentricSampleDisk(ln.x, ln.y, &lu, &lv);
+    lu *= rp.lensRadius;
+    lv *= rp.lensRadius;
+    double ft = rp.focalDistance / d.z;
+    V3 Pfocus = RayAt(o, d, ft);
+    o = mkv(lu, lv, 0.0);
+    d = Normalize(Pfocus - o);
+  }
+  V3 wo = XfPoint(rp.cameraToWorld, o), wd = XfVector(rp.cameraToWorld, d);
+  wf.extO[0][s] = make_float4(wo.x, wo.y, wo.z, 0.f);
+  wf.extD[0][s] = make_float4(wd.x, wd.y, wd.z, CUDART_INF_F);
+  wf.extRange[0][s] = make_double2(0.0, CUDART_INF);
+  wf.extSlot[0][s] = s;
+  st3(wf.L, cap, s, Spec{0.f, 0.f, 0.f});
+  st3(wf.T, cap, s, Spec{1.f, 1.f, 1.f});
+  wf.shIdx[s] = -1;
+  wf.misIdx[s] = -1;
+}
+
+__global__ void resetCountsKernel(Wavefront wf, unsigned mask) {
+  if (threadIdx.x < Q_COUNT && ((mask >> threadIdx.x) & 1u)) wf.counts[threadIdx.x] = 0;
+}
+
+// Sample-record access helpers (Sample.oneD / twoD, sample.dart:23-79)
+static __device__ __forceinline__ float val(const Wavefront& wf, int v, uint32_t slot) { return wf.vals[(size_t)v * wf.cap + slot]; }
+
+// integrator stream of a slot (sampler_renderer.dart:137 shares one RNG; here keyed per camera sample)
+static __device__ __forceinline__ uint64_t integratorKey(const RenderParams& rp, const Wavefront& wf, uint32_t slot) {
+  return streamKey(rp.seed, wf.pixX[slot], wf.pixY[slot], wf.sampleIdx[slot], DRT_STREAM_INTEGRATOR);
+}
+
+static __device__ __forceinline__ void pushDirectWork(const Wavefront& wf, uint32_t slot, bool valid, const DirectWork& w,
+                                                      const V3& p, double rayEps, int lightNum) {
+  const bool wantSh = valid && w.hasShadow, wantMis = valid && w.hasMis;
+  const uint32_t si = warpPush(&wf.counts[Q_SHADOW], wantSh);
+  const uint32_t mi = warpPush(&wf.counts[Q_MIS], wantMis);
+  const uint32_t cap = wf.cap;
+  if (wantSh) {
+    wf.shO[si] = make_float4(w.shO.x, w.shO.y, w.shO.z, (float)w.shMin);
+    wf.shD[si] = make_float4(w.shD.x, w.shD.y, w.shD.z, (float)w.shMax);
+    wf.shRange[si] = make_double2(w.shMin, w.shMax);
+    st3(wf.pendSh, cap, slot, w.shContribution);
+  }
+  if (wantMis) {
+    wf.misO[mi] = make_float4(p.x, p.y, p.z, (float)rayEps);
+    wf.misD[mi] = make_float4(w.misD.x, w.misD.y, w.misD.z, CUDART_INF_F);
+    wf.misRange[mi] = make_double2(rayEps, CUDART_INF);
+    st3(wf.pendMisF, cap, slot, w.misF);
+    wf.pendMisScale[slot] = w.misScale;
+    wf.misLight[slot] = lightNum;
+  }
+  if (valid) {
+    wf.shIdx[slot] = wantSh ? (int32_t)si : -1;
+    wf.misIdx[slot] = wantMis ? (int32_t)mi : -1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Path integrator, one vertex (path_integrator.dart:44-119 loop body for `bounces` = bounce).
+__global__ void __launch_bounds__(128) shadePathKernel(RenderParams rp, RenderScene rs, Wavefront wf, int bounce, int cur,
+                                                       RenderCounters* rc) {
+  const uint32_t n = wf.counts[cur], cap = wf.cap;
+  const int nxt = cur ^ 1;
+  unsigned long long nShadow = 0, nClosest = 0;
+  for (uint32_t q0 = blockIdx.x * blockDim.x; q0 < n; q0 += gridDim.x * blockDim.x) {
+    const uint32_t q = q0 + threadIdx.x;
+    bool valid = q < n;
+    uint32_t slot = 0;
+    int prim = -1;
+    if (valid) {
+      slot = wf.extSlot[cur][q];
+      prim = __float_as_int(wf.extHit[q].w);
+      wf.shIdx[slot] = -1;
+      wf.misIdx[slot] = -1;
+      valid = prim >= 0;  // miss: the path ends; area/point lights add no Le along escaping rays
+    }
+    DirectWork dw;
+    dw.hasShadow = dw.hasMis = false;
+    bool cont = false;
+    V3 p = V3{0.f, 0.f, 0.f}, wi = V3{0.f, 0.f, 0.f};
+    double rayEps = 0.0;
+    int lightNum = 0;
+    if (valid) {
+      const float4 o4 = wf.extO[cur][q], d4 = wf.extD[cur][q];
+      const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
+      ShapeHit h;
+      hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
+      Spec T = ld3(wf.T, cap, slot);
+      const V3 wo = -d;
+      if (bounce == 0) {  // emitted light at the first vertex (:46-48); matte BSDFs never set specularBounce
+        const int li = primLight(rs, (uint32_t)prim);
+        if (li >= 0) {
+          Spec L = ld3(wf.L, cap, slot);
+          L = L + T * areaL(rs.lights[li], h.nn, wo);
+          st3(wf.L, cap, slot, L);
+        }
+      }
+      const Bsdf bsdf = makeBsdf(rs, (uint32_t)prim, h);
+      p = h.p;
+      rayEps = h.rayEps;
+      const V3 nrm = bsdf.nn;
+      Stream rng{integratorKey(rp, wf, slot), 0};
+      if (bounce > 3) {  // draws already consumed by bounces 3..bounce-1: 10 (or 3 without lights) each, +1 RR from bounce 4 on
+        const uint64_t per = rs.nLights > 0 ? 10 : 3;
+        rng.ctr = (uint64_t)(bounce - 3) * per + (uint64_t)(bounce - 4);
+      }
+      // direct lighting: UniformSampleOneLight (integrator.dart:79-117)
+      if (rs.nLights > 0) {
+        float lu0, lu1, bu0, bu1;
+        double lcomp;
+        if (bounce < 3) {
+          lightNum = (int)floor((double)val(wf, rp.pLightNum[bounce], slot) * (double)rs.nLights);
+          lu0 = val(wf, rp.pLightPos[bounce], slot); lu1 = val(wf, rp.pLightPos[bounce] + 1, slot);
+          lcomp = val(wf, rp.pLightComp[bounce], slot);
+          bu0 = val(wf, rp.pBsdfPos[bounce], slot); bu1 = val(wf, rp.pBsdfPos[bounce] + 1, slot);
+        } else {
+          lightNum = (int)floor(rng.randomFloat() * rs.nLights);
+          lu0 = (float)rng.randomFloat(); lu1 = (float)rng.randomFloat(); lcomp = rng.randomFloat();  // LightSample.random
+          bu0 = (float)rng.randomFloat(); bu1 = (float)rng.randomFloat(); rng.randomFloat();          // BSDFSample.random
+        }
+        lightNum = min(lightNum, rs.nLights - 1);
+        estimateDirectSetup(rs, lightNum, p, nrm, wo, rayEps, bsdf, lu0, lu1, lcomp, bu0, bu1, BSDF_ALL & ~BSDF_SPECULAR, &dw);
+        st3(wf.pendT, cap, slot, T);
+      }
+      // next direction (:63-92)
+      float pu0, pu1;
+      if (bounce < 3) { pu0 = val(wf, rp.pPathPos[bounce], slot); pu1 = val(wf, rp.pPathPos[bounce] + 1, slot); }
+      else { pu0 = (float)rng.randomFloat(); pu1 = (float)rng.randomFloat(); rng.randomFloat(); }
+      double pdf = 0.0;
+      int flags = 0;
+      Spec f = bsdfSampleF(bsdf, wo, &wi, pu0, pu1, &pdf, BSDF_ALL, &flags);
+      if (!(IsBlack(f) || pdf == 0.0)) {
+        T = T * (f * AbsDot(wi, nrm) / pdf);
+        cont = true;
+        if (bounce > 3) {  // Russian roulette (:93-99)
+          double continueProbability = fmin(0.5, Luminance(T));
+          if (rng.randomFloat() > continueProbability) cont = false;
+          else T = T / continueProbability;
+        }
+        if (bounce == rp.maxDepth) cont = false;
+        if (cont) st3(wf.T, cap, slot, T);
+      }
+    }
+    pushDirectWork(wf, slot, valid, dw, p, rayEps, lightNum);
+    const uint32_t ei = warpPush(&wf.counts[nxt], cont);
+    if (cont) {
+      wf.extO[nxt][ei] = make_float4(p.x, p.y, p.z, (float)rayEps);
+      wf.extD[nxt][ei] = make_float4(wi.x, wi.y, wi.z, CUDART_INF_F);
+      wf.extRange[nxt][ei] = make_double2(rayEps, CUDART_INF);
+      wf.extSlot[nxt][ei] = slot;
+    }
+    nShadow += (valid && dw.hasShadow) ? 1 : 0;
+    nClosest += ((valid && dw.hasMis) ? 1 : 0) + (cont ? 1 : 0);
+  }
+  // ray statistics (stats.dart:541-555): one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) {
+    nShadow += __shfl_down_sync(FULL, nShadow, o);
+    nClosest += __shfl_down_sync(FULL, nClosest, o);
+  }
+  if ((threadIdx.x & 31) == 0 && (nShadow | nClosest)) {
+    atomicAdd(&rc->shadowRays, nShadow);
+    atomicAdd(&rc->closestRays, nClosest);
+  }
+}
+
+// Finishes Integrator.EstimateDirect (integrator.dart:119-185) once the shadow and MIS rays of the
+// vertices shaded from extension queue `cur` are traced, and adds the estimate where the integrator
+// adds it.  mode: see RESOLVE_* (render_kernels.h).
+__global__ void __launch_bounds__(128) resolveDirectKernel(RenderParams rp, RenderScene rs, Wavefront wf, int cur, int mode,
+                                                           int nSamplesOfLight) {
+  const uint32_t n = wf.counts[cur], cap = wf.cap;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+    const uint32_t slot = wf.extSlot[cur][q];
+    const int si = wf.shIdx[slot], mi = wf.misIdx[slot];
+    const bool direct = (mode & 1) != 0;
+    if (direct) {
+      if (__float_as_int(wf.extHit[q].w) < 0) continue;  // camera ray missed
+    } else if (si < 0 && mi < 0) {
+      continue;
+    }
+    Spec Ld = mks1(0.0);
+    if (si >= 0 && !wf.shOcc[si]) Ld = Ld + ld3(wf.pendSh, cap, slot);
+    if (mi >= 0) {
+      const int prim = __float_as_int(wf.misHit[mi].w);
+      const int light = wf.misLight[slot];
+      if (prim >= 0 && primLight(rs, (uint32_t)prim) == light) {
+        const float4 o4 = wf.misO[mi], d4 = wf.misD[mi];
+        const V3 o = V3{o4.x, o4.y, o4.z}, wi = V3{d4.x, d4.y, d4.z};
+        ShapeHit h;
+        hitGeometry(rs, (uint32_t)prim, o, wi, wf.misT[mi], &h);
+        Spec Li = areaL(rs.lights[light], h.nn, -wi);  // Intersection.Le, intersection.dart:62-65
+        if (!IsBlack(Li)) {
+          Li = Li * mks1(1.0);
+          Ld = Ld + ld3(wf.pendMisF, cap, slot) * Li * wf.pendMisScale[slot];
+        }
+      }
+    }
+    wf.shIdx[slot] = -1;
+    wf.misIdx[slot] = -1;
+    if (!direct) {  // path: L += pathThroughput * (EstimateDirect * nLights)
+      Spec L = ld3(wf.L, cap, slot);
+      L = L + ld3(wf.pendT, cap, slot) * (Ld * (double)rs.nLights);
+      st3(wf.L, cap, slot, L);
+    } else if (mode & 16) {  // directlighting, strategy one (integrator.dart:79-117)
+      Spec L = ld3(wf.L, cap, slot);
+      L = L + (Ld * (double)rs.nLights);
+      st3(wf.L, cap, slot, L);
+    } else {  // UniformSampleAllLights (integrator.dart:39-77): Ld over the light's samples, L over lights (kept in T)
+      Spec acc = (mode & 2) ? mks1(0.0) : ld3(wf.Ld, cap, slot);
+      acc = acc + Ld;
+      if (mode & 4) {
+        Spec all = ld3(wf.T, cap, slot);
+        all = all + acc / (double)nSamplesOfLight;
+        if (mode & 8) {
+          Spec L = ld3(wf.L, cap, slot);
+          st3(wf.L, cap, slot, L + all);
+        } else {
+          st3(wf.T, cap, slot, all);
+        }
+      } else {
+        st3(wf.Ld, cap, slot, acc);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Ambient occlusion (ambient_occlusion_integrator.dart:28-53)
+__global__ void __launch_bounds__(128) aoSetupKernel(RenderParams rp, RenderScene rs, Wavefront wf) {
+  const uint32_t n = wf.counts[Q_EXT0], cap = wf.cap;
+  for (uint32_t q0 = blockIdx.x * blockDim.x; q0 < n; q0 += gridDim.x * blockDim.x) {
+    const uint32_t q = q0 + threadIdx.x;
+    bool hit = false;
+    uint32_t slot = 0;
+    if (q < n) {
+      slot = wf.extSlot[0][q];
+      const int prim = __float_as_int(wf.extHit[q].w);
+      hit = prim >= 0;
+      if (hit) {
+        const float4 o4 = wf.extO[0][q], d4 = wf.extD[0][q];
+        const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
+        ShapeHit h;
+        hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
+        stv3(wf.hitP, cap, slot, h.p);
+        stv3(wf.hitN, cap, slot, FaceForward(h.nn, -d));
+        Stream rng{integratorKey(rp, wf, slot), 0};
+        wf.aoScramble[slot] = rng.randomUint();
+        wf.aoScramble[cap + slot] = rng.randomUint();
+        wf.nClear[slot] = 0;
+      }
+    }
+    const uint32_t hi = warpPush(&wf.counts[Q_HITS], hit);
+    if (hit) wf.hitList[hi] = slot;
+  }
+}
+
+// AO rays of hits [firstHit, firstHit + maxHits) of the hit list, nSamples each, into the shadow queue
+__global__ void __launch_bounds__(256) aoGenKernel(RenderParams rp, Wavefront wf, uint32_t firstHit, uint32_t maxHits, int nS) {
+  const uint32_t nHits = wf.counts[Q_HITS], cap = wf.cap;
+  const uint32_t hitsHere = nHits > firstHit ? min(nHits - firstHit, maxHits) : 0u;
+  const uint64_t nRays = (uint64_t)hitsHere * nS;
+  if (blockIdx.x == 0 && threadIdx.x == 0) wf.counts[Q_SHADOW] = (uint32_t)nRays;
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nRays; r += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t slot = wf.hitList[firstHit + (uint32_t)(r / nS)];
+    const uint32_t i = (uint32_t)(r % nS);
+    const double u0 = VanDerCorput(i, wf.aoScramble[slot]), u1 = Sobol2(i, wf.aoScramble[cap + slot]);
+    V3 w = UniformSampleSphere(u0, u1);
+    const V3 nrm = ldv3(wf.hitN, cap, slot), p = ldv3(wf.hitP, cap, slot);
+    if (Dot(w, nrm) < 0.0) w = -w;
+    wf.shO[r] = make_float4(p.x, p.y, p.z, (float)rp.aoMinDist);
+    wf.shD[r] = make_float4(w.x, w.y, w.z, (float)rp.aoMaxDist);
+    wf.shRange[r] = make_double2(rp.aoMinDist, rp.aoMaxDist);
+  }
+}
+
+__global__ void __launch_bounds__(256) aoCountKernel(RenderParams rp, Wavefront wf, uint32_t firstHit, uint32_t maxHits, int nS,
+                                                     RenderCounters* rc) {
+  const uint32_t nHits = wf.counts[Q_HITS], cap = wf.cap;
+  const uint32_t hitsHere = nHits > firstHit ? min(nHits - firstHit, maxHits) : 0u;
+  for (uint32_t hI = blockIdx.x * blockDim.x + threadIdx.x; hI < hitsHere; hI += gridDim.x * blockDim.x) {
+    const uint32_t slot = wf.hitList[firstHit + hI];
+    const uint8_t* occ = wf.shOcc + (size_t)hI * nS;
+    int nClear = 0;
+    for (int i = 0; i < nS; ++i) nClear += occ[i] ? 0 : 1;
+    st3(wf.L, cap, slot, mks1((double)nClear / nS));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&rc->shadowRays, (unsigned long long)hitsHere * nS);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Direct lighting (direct_lighting_integrator.dart:30-68): emitted light at the camera hit, then one
+// launch per (light, sample) of UniformSampleAllLights, or one launch of UniformSampleOneLight.
+__global__ void __launch_bounds__(128) directSetupKernel(RenderParams rp, RenderScene rs, Wavefront wf) {
+  const uint32_t n = wf.counts[Q_EXT0], cap = wf.cap;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+    const uint32_t slot = wf.extSlot[0][q];
+    const int prim = __float_as_int(wf.extHit[q].w);
+    st3(wf.T, cap, slot, Spec{0.f, 0.f, 0.f});  // L of UniformSampleAllLights
+    if (prim < 0) continue;
+    const int li = primLight(rs, (uint32_t)prim);
+    if (li < 0) continue;
+    const float4 o4 = wf.extO[0][q], d4 = wf.extD[0][q];
+    const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
+    ShapeHit h;
+    hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
+    st3(wf.L, cap, slot, mks1(0.0) + areaL(rs.lights[li], h.nn, -d));
+  }
+}
+
+__global__ void __launch_bounds__(128) directSampleKernel(RenderParams rp, RenderScene rs, Wavefront wf, int light, int j,
+                                                          RenderCounters* rc) {
+  const uint32_t n = wf.counts[Q_EXT0];
+  unsigned long long nShadow = 0, nClosest = 0;
+  for (uint32_t q0 = blockIdx.x * blockDim.x; q0 < n; q0 += gridDim.x * blockDim.x) {
+    const uint32_t q = q0 + threadIdx.x;
+    bool valid = q < n;
+    uint32_t slot = 0;
+    int prim = -1;
+    if (valid) {
+      slot = wf.extSlot[0][q];
+      prim = __float_as_int(wf.extHit[q].w);
+      valid = prim >= 0;
+    }
+    DirectWork dw;
+    dw.hasShadow = dw.hasMis = false;
+    V3 p = V3{0.f, 0.f, 0.f};
+    double rayEps = 0.0;
+    int lightNum = light;
+    if (valid) {
+      const float4 o4 = wf.extO[0][q], d4 = wf.extD[0][q];
+      const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
+      ShapeHit h;
+      hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
+      const Bsdf bsdf = makeBsdf(rs, (uint32_t)prim, h);
+      p = h.p;
+      rayEps = h.rayEps;
+      DirectOffsets off;
+      if (light < 0) {  // strategy one: light number from the sample record (integrator.dart:92-97)
+        off = rp.direct[0];
+        lightNum = min((int)floor((double)val(wf, rp.dlLightNum, slot) * (double)rs.nLights), rs.nLights - 1);
+      } else {
+        off = rp.direct[light];
+      }
+      const float lu0 = val(wf, off.lightPos + 2 * j, slot), lu1 = val(wf, off.lightPos + 2 * j + 1, slot);
+      const double lcomp = val(wf, off.lightComp + j, slot);
+      const float bu0 = val(wf, off.bsdfPos + 2 * j, slot), bu1 = val(wf, off.bsdfPos + 2 * j + 1, slot);
+      estimateDirectSetup(rs, lightNum, p, bsdf.nn, -d, rayEps, bsdf, lu0, lu1, lcomp, bu0, bu1, BSDF_ALL & ~BSDF_SPECULAR, &dw);
+    }
+    pushDirectWork(wf, slot, valid, dw, p, rayEps, lightNum);
+    nShadow += (valid && dw.hasShadow) ? 1 : 0;
+    nClosest += (valid && dw.hasMis) ? 1 : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    nShadow += __shfl_down_sync(FULL, nShadow, o);
+    nClosest += __shfl_down_sync(FULL, nClosest, o);
+  }
+  if ((threadIdx.x & 31) == 0 && (nShadow | nClosest)) {
+    atomicAdd(&rc->shadowRays, nShadow);
+    atomicAdd(&rc->closestRays, nClosest);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SamplerRenderer's radiance checks (sampler_renderer.dart:181-193) + ImageFilm.addSample
+// (image_film.dart:99-150).  Accumulators are float64 and updated atomically, so the sums do not
+// depend on the order samples arrive in (the reference adds float32 in pixel order).
+__global__ void __launch_bounds__(256) filmKernel(RenderParams rp, Wavefront wf, uint32_t nSlots, RenderCounters* rc) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nSlots) return;
+  Spec L = ld3(wf.L, wf.cap, s);
+  const double lum = Luminance(L);
+  if (isnan(L.r) || isnan(L.g) || isnan(L.b) || lum < -1e-5 || isinf(lum)) {
+    L = Spec{0.f, 0.f, 0.f};
+    atomicAdd(&rc->zeroedSamples, 1ull);
+  }
+  const double2 im = wf.camXY[s];
+  const double dimageX = im.x - 0.5, dimageY = im.y - 0.5;
+  int x0 = (int)ceil(dimageX - rp.xWidth), x1 = (int)floor(dimageX + rp.xWidth);
+  int y0 = (int)ceil(dimageY - rp.yWidth), y1 = (int)floor(dimageY + rp.yWidth);
+  x0 = max(x0, rp.left); x1 = min(x1, rp.left + rp.width - 1);
+  y0 = max(y0, rp.top); y1 = min(y1, rp.top + rp.height - 1);
+  if ((x1 - x0) < 0 || (y1 - y0) < 0) return;
+  const double r = L.r, g = L.g, b = L.b;  // RGBColor.toXYZ -> XYZColor (float32), spectrum.dart:293-297
+  const float X = (float)(0.412453 * r + 0.357580 * g + 0.180423 * b), Y = (float)(0.212671 * r + 0.715160 * g + 0.072169 * b),
+              Z = (float)(0.019334 * r + 0.119193 * g + 0.950227 * b);
+  for (int y = y0; y <= y1; ++y) {
+    const double fy = fabs((y - dimageY) * rp.invYWidth * 16);
+    const int iy = min((int)floor(fy), 15);
+    for (int x = x0; x <= x1; ++x) {
+      const double fx = fabs((x - dimageX) * rp.invXWidth * 16);
+      const int ix = min((int)floor(fx), 15);
+      const double wt = rp.filterTable[iy * 16 + ix];
+      double* px = rp.film + 4 * ((size_t)(y - rp.top) * rp.width + (x - rp.left));
+      atomicAdd(px + 0, wt * X);
+      atomicAdd(px + 1, wt * Y);
+      atomicAdd(px + 2, wt * Z);
+      atomicAdd(px + 3, wt);
+    }
+  }
+}
+
+// ImageFilm.writeImage (image_film.dart:268-299): XYZ -> RGB, divide by the weight sum, clamp at 0
+__global__ void filmConvertKernel(RenderParams rp, float* rgb, float* xyz, float* weight) {
+  const size_t pi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pi >= (size_t)rp.width * rp.height) return;
+  const float X = (float)rp.film[4 * pi], Y = (float)rp.film[4 * pi + 1], Z = (float)rp.film[4 * pi + 2], W = (float)rp.film[4 * pi + 3];
+  if (xyz) { xyz[3 * pi] = X; xyz[3 * pi + 1] = Y; xyz[3 * pi + 2] = Z; }
+  if (weight) weight[pi] = W;
+  if (rgb) {
+    const double x = X, y = Y, z = Z, w = W;
+    const double c0 = 3.240479 * x - 1.537150 * y - 0.498535 * z;
+    const double c1 = -0.969256 * x + 1.875991 * y + 0.041556 * z;
+    const double c2 = 0.055648 * x - 0.204043 * y + 1.057311 * z;
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+    if (w != 0.0) {
+      const double invWt = 1.0 / w;
+      o0 = (float)fmax(0.0, c0 * invWt); o1 = (float)fmax(0.0, c1 * invWt); o2 = (float)fmax(0.0, c2 * invWt);
+    }
+    rgb[3 * pi] = o0; rgb[3 * pi + 1] = o1; rgb[3 * pi + 2] = o2;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+static inline int gridFor(uint64_t n, int block, int numSMs, int perSm) {
+  uint64_t want = (n + block - 1) / block;
+  uint64_t cap = (uint64_t)numSMs * perSm;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+cudaError_t launchSampler(const RenderParams& rp, const Wavefront& wf, const SampleArray* dArrays, int nArrays, int maxVals,
+                          int maxOthers, const PixelBatch& pb, int numSMs, cudaStream_t st) {
+  if (pb.nPixels == 0) return cudaSuccess;
+  if (rp.samplerKind == 0) {
+    const int block = 128;
+    const size_t smem = (size_t)(block / 32) * (maxVals + maxOthers) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(samplerLDKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured = smem;
+    }
+    uint64_t tasks = (uint64_t)pb.nPixels * nArrays;
+    int grid = gridFor(tasks * 32, block, numSMs, 16);
+    samplerLDKernel<<<grid, block, smem, st>>>(rp, wf, dArrays, nArrays, maxVals, maxOthers, pb);
+  } else {
+    samplerSeqKernel<<<(pb.nPixels + 127) / 128, 128, 0, st>>>(rp, wf, dArrays, nArrays, pb);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launchRaygen(const RenderParams& rp, const Wavefront& wf, const PixelBatch& pb, cudaStream_t st) {
+  const uint32_t nSlots = pb.nPixels * (uint32_t)rp.nPixelSamples;
+  if (nSlots == 0) return cudaSuccess;
+  raygenKernel<<<(nSlots + 255) / 256, 256, 0, st>>>(rp, wf, pb, nSlots);
+  return cudaGetLastError();
+}
+
+cudaError_t launchResetCounts(const Wavefront& wf, unsigned mask, cudaStream_t st) {
+  resetCountsKernel<<<1, 32, 0, st>>>(wf, mask);
+  return cudaGetLastError();
+}
+
+cudaError_t launchShadePath(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int bounce, int cur,
+                            RenderCounters* rc, int numSMs, cudaStream_t st) {
+  shadePathKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, bounce, cur, rc);
+  return cudaGetLastError();
+}
+
+cudaError_t launchResolveDirect(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int cur, int mode,
+                                int nSamplesOfLight, int numSMs, cudaStream_t st) {
+  resolveDirectKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, cur, mode, nSamplesOfLight);
+  return cudaGetLastError();
+}
+
+cudaError_t launchAoSetup(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int numSMs, cudaStream_t st) {
+  aoSetupKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf);
+  return cudaGetLastError();
+}
+
+static inline int roundUpPow2(int v) {  // common.dart:117-125
+  v--;
+  v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16;
+  return v + 1;
+}
+
+cudaError_t launchAoGen(const RenderParams& rp, const Wavefront& wf, uint32_t firstHit, uint32_t maxHits, int numSMs,
+                        cudaStream_t st) {
+  const int nS = roundUpPow2(rp.aoSamples);
+  aoGenKernel<<<gridFor((uint64_t)maxHits * nS, 256, numSMs, 8), 256, 0, st>>>(rp, wf, firstHit, maxHits, nS);
+  return cudaGetLastError();
+}
+
+cudaError_t launchAoCount(const RenderParams& rp, const Wavefront& wf, uint32_t firstHit, uint32_t maxHits, RenderCounters* rc,
+                          int numSMs, cudaStream_t st) {
+  const int nS = roundUpPow2(rp.aoSamples);
+  aoCountKernel<<<gridFor(maxHits, 256, numSMs, 8), 256, 0, st>>>(rp, wf, firstHit, maxHits, nS, rc);
+  return cudaGetLastError();
+}
+
+cudaError_t launchDirectSetup(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int numSMs, cudaStream_t st) {
+  directSetupKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf);
+  return cudaGetLastError();
+}
+
+cudaError_t launchDirectSample(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int light, int j,
+                               RenderCounters* rc, int numSMs, cudaStream_t st) {
+  directSampleKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, j, rc);
+  return cudaGetLastError();
+}
+
+cudaError_t launchFilm(const RenderParams& rp, const Wavefront& wf, uint32_t nSlots, RenderCounters* rc, cudaStream_t st) {
+  if (nSlots == 0) return cudaSuccess;
+  filmKernel<<<(nSlots + 255) / 256, 256, 0, st>>>(rp, wf, nSlots, rc);
+  return cudaGetLastError();
+}
+
+cudaError_t launchFilmConvert(const RenderParams& rp, float* rgb, float* xyz, float* weight, cudaStream_t st) {
+  const size_t n = (size_t)rp.width * rp.height;
+  filmConvertKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rp, rgb, xyz, weight);
+  return cudaGetLastError();
+}
+
+}  // namespace drt

@@ -1,0 +1,114 @@
+// Device-side description of what the wavefront renderer reads: materials, lights, camera, film,
+// sampler layout and integrator parameters (see DESIGN.md "Render pipeline").
+#pragma once
+#include <cstdint>
+
+#include "gpu_types.h"
+
+namespace drt {
+
+struct GMaterial {  // matte_material.dart:41-65 with constant textures
+  float kd[3];
+  float sigma;
+};
+
+struct GLight {
+  int32_t kind;  // 0 = DiffuseAreaLight (diffuse_area_light.dart), 1 = PointLight (point_light.dart)
+  float L[3];    // Lemit / intensity
+  float pos[3];
+  int32_t nSamples;
+  uint32_t shapeOffset, nShapes;  // ShapeSet (shape_set.dart:26-50): slice of lightShapes / lightShapeAreas
+  uint32_t cdfOffset;             // slice of lightCdf: nShapes + 1 floats (Distribution1D, montecarlo.dart:25-48)
+  double area;
+};
+
+// Per direct-lighting light: where its LightSampleOffsets / BSDFSampleOffsets live in a sample record
+// (direct_lighting_integrator.dart:70-96); value indices into the integrator part of the record.
+struct DirectOffsets {
+  int32_t nSamples;
+  int32_t lightComp, lightPos, bsdfComp, bsdfPos;
+};
+
+struct RenderScene {
+  TraceScene ts;
+  uint32_t ntris, nprims;
+  const uint32_t* primToRec;  // primitive id -> GPrim record
+  const uint32_t* primAttr;   // bits 0-15 material, 16-30 light + 1, 31 reverseOrientation
+  const GMaterial* materials;
+  const GLight* lights;
+  int32_t nLights;
+  const uint32_t* lightShapes;
+  const double* lightShapeAreas;
+  const float* lightCdf;
+};
+
+struct RenderParams {
+  // camera: perspective_camera.dart:46-57,93-132 + projective_camera.dart:34-53
+  float rasterToCamera[16], cameraToWorld[16];
+  double lensRadius, focalDistance, shutterOpen, shutterClose;
+  // film: image_film.dart:51-97
+  int32_t xres, yres, left, top, width, height;
+  double xWidth, yWidth, invXWidth, invYWidth;
+  const float* filterTable;  // 256 floats
+  double* film;              // width*height x (X, Y, Z, weight)
+  // sampler
+  int32_t samplerKind;  // 0 lowdiscrepancy, 1 stratified, 2 random
+  int32_t xs, ys, jitter;
+  int32_t nPixelSamples;  // samples per pixel visit
+  uint64_t seed;
+  int32_t nVals;  // integrator values per sample (sum n1D + 2 sum n2D)
+  // integrator
+  int32_t integKind;  // 0 path, 1 ambientocclusion, 2 directlighting
+  int32_t maxDepth, strategy, aoSamples;
+  double aoMinDist, aoMaxDist;
+  // path_integrator.dart:124-131: value indices for bounces 0..2
+  int32_t pLightComp[3], pLightPos[3], pLightNum[3], pBsdfComp[3], pBsdfPos[3], pPathComp[3], pPathPos[3];
+  // direct lighting, strategy "one": light number value; per-light offsets in `direct`
+  int32_t dlLightNum;
+  const DirectOffsets* direct;
+};
+
+// One sampler array (montecarlo.dart:524-551 works array by array)
+struct SampleArray {
+  int32_t dims;      // 1 or 2
+  int32_t nSamples;  // values per camera sample
+  int32_t dest;      // >= 0: first value index in the integrator record; -1: image (x,y); -2: lens (u,v); -3: time
+  uint32_t streamId; // position in the reference's generation order (keys the stream)
+};
+
+// Work queues and per-sample state of one batch of camera samples.  `cap` slots.
+struct Wavefront {
+  uint32_t cap;
+  // per slot
+  int32_t* pixX; int32_t* pixY;      // pixel of the slot
+  uint32_t* sampleIdx;               // index of the sample inside its pixel (keys the integrator stream)
+  double2* camXY; double2* camLens;  // imageX, imageY / lensU, lensV
+  float* camTime;                    // time sample in [0,1) (static scenes: carried, not used)
+  float* vals;                       // nVals x cap, value-major
+  float* L;                          // 3 x cap, channel-major: radiance accumulated so far
+  float* T;                          // 3 x cap: path throughput
+  // what the last shaded vertex of a slot waits for (integrator.dart:119-185)
+  float* pendSh;                     // 3 x cap: contribution if the shadow ray is unoccluded
+  float* pendMisF;                   // 3 x cap: f of the BSDF sample
+  double* pendMisScale;
+  float* pendT;                      // 3 x cap: throughput the direct estimate is multiplied by
+  int32_t* shIdx; int32_t* misIdx; int32_t* misLight;
+  // AO / direct-lighting per-slot state
+  float* hitP; float* hitN;          // 3 x cap each
+  uint32_t* aoScramble;              // 2 x cap
+  int32_t* nClear;
+  float* Ld;                         // 3 x cap: per-light accumulator of UniformSampleAllLights
+  // queues: extension rays (double-buffered), shadow rays, MIS rays
+  float4* extO[2]; float4* extD[2]; double2* extRange[2]; uint32_t* extSlot[2];
+  float4* extHit; double* extT;
+  float4* shO; float4* shD; double2* shRange; uint8_t* shOcc;
+  float4* misO; float4* misD; double2* misRange; float4* misHit; double* misT;
+  uint32_t* counts;  // [0],[1] = extension queue sizes, [2] = shadow, [3] = MIS, [4] = hit list size
+  uint32_t* hitList; // slots whose camera ray hit (AO / direct lighting)
+};
+
+struct RenderCounters {  // mirrors the reference's ray counters (stats.dart:541-555)
+  unsigned long long cameraSamples, closestRays, shadowRays, zeroedSamples;
+};
+
+}  // namespace drt

@@ -1,0 +1,636 @@
+// Shading arithmetic of the render path, in the reference's numeric model: Vector/Point/Normal/
+// RGBColor objects STORE float32 and every expression is evaluated in IEEE binary64, rounded to
+// binary32 when an object is built (lib/core/vector.dart:26-74, rgb_color.dart:23-169,
+// spectrum.dart:1145).  The whole library is compiled with -fmad=false, so nothing here contracts.
+//
+// Each function cites the reference code it replaces (paths relative to /root/reference).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <cmath>
+#include <cstdint>
+
+#include "gpu_types.h"
+#include "render_types.h"
+
+namespace drt {
+
+#define DRT_PI 3.141592653589793
+#define DRT_INV_PI 0.31830988618379067154
+#define DRT_ONE_MINUS_EPS 0.9999999403953552  // montecarlo.dart:23
+
+// ---- Vector / Point / Normal (vector.dart:26-218) ---------------------------------------------------
+struct V3 {
+  float x, y, z;
+};
+static DRT_HD inline V3 mkv(double x, double y, double z) { return V3{(float)x, (float)y, (float)z}; }
+static DRT_HD inline V3 operator+(const V3& a, const V3& b) { return mkv((double)a.x + b.x, (double)a.y + b.y, (double)a.z + b.z); }
+static DRT_HD inline V3 operator-(const V3& a, const V3& b) { return mkv((double)a.x - b.x, (double)a.y - b.y, (double)a.z - b.z); }
+static DRT_HD inline V3 operator*(const V3& a, double f) { return mkv((double)a.x * f, (double)a.y * f, (double)a.z * f); }
+static DRT_HD inline V3 operator/(const V3& a, double f) { return mkv((double)a.x / f, (double)a.y / f, (double)a.z / f); }
+static DRT_HD inline V3 operator-(const V3& a) { return V3{-a.x, -a.y, -a.z}; }
+static DRT_HD inline double Dot(const V3& a, const V3& b) { return (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z; }
+static DRT_HD inline double AbsDot(const V3& a, const V3& b) { return fabs(Dot(a, b)); }
+static DRT_HD inline V3 Cross(const V3& a, const V3& b) {
+  double ax = a.x, ay = a.y, az = a.z, bx = b.x, by = b.y, bz = b.z;
+  return mkv((ay * bz) - (az * by), (az * bx) - (ax * bz), (ax * by) - (ay * bx));
+}
+static DRT_HD inline double LengthSquared(const V3& v) { return (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z; }
+static DRT_HD inline double Length(const V3& v) { return sqrt(LengthSquared(v)); }
+static DRT_HD inline V3 Normalize(const V3& v) { return v / Length(v); }
+static DRT_HD inline double DistanceSquared(const V3& a, const V3& b) { return LengthSquared(b - a); }
+static DRT_HD inline double Distance(const V3& a, const V3& b) { return Length(b - a); }
+static DRT_HD inline void CoordinateSystem(const V3& v1, V3* v2, V3* v3) {  // vector.dart:198-214
+  if (fabs((double)v1.x) > fabs((double)v1.y)) {
+    double invLen = 1.0 / sqrt((double)v1.x * v1.x + (double)v1.z * v1.z);
+    *v2 = mkv(-(double)v1.z * invLen, 0.0, (double)v1.x * invLen);
+  } else {
+    double invLen = 1.0 / sqrt((double)v1.y * v1.y + (double)v1.z * v1.z);
+    *v2 = mkv(0.0, (double)v1.z * invLen, -(double)v1.y * invLen);
+  }
+  *v3 = Cross(v1, *v2);
+}
+static DRT_HD inline V3 FaceForward(const V3& n, const V3& v) { return (Dot(n, v) < 0.0) ? -n : n; }
+static DRT_HD inline double clampD(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+static DRT_HD inline double LerpD(double t, double a, double b) { return (1.0 - t) * a + t * b; }  // common.dart:80-81
+
+// ray.dart:70-71: origin + (direction * t), a new float32 object at each step
+static DRT_HD inline V3 RayAt(const V3& o, const V3& d, double t) { return o + (d * t); }
+
+// transform.dart:110-161 on a float32 row-major 4x4
+static DRT_HD inline V3 XfPoint(const float* m, const V3& p) {
+  double x = p.x, y = p.y, z = p.z;
+  V3 out = mkv((double)m[0] * x + (double)m[1] * y + (double)m[2] * z + (double)m[3],
+               (double)m[4] * x + (double)m[5] * y + (double)m[6] * z + (double)m[7],
+               (double)m[8] * x + (double)m[9] * y + (double)m[10] * z + (double)m[11]);
+  double w = (double)m[12] * x + (double)m[13] * y + (double)m[14] * z + (double)m[15];
+  if (w != 1.0) out = mkv((double)out.x / w, (double)out.y / w, (double)out.z / w);
+  return out;
+}
+static DRT_HD inline V3 XfVector(const float* m, const V3& p) {
+  double x = p.x, y = p.y, z = p.z;
+  return mkv((double)m[0] * x + (double)m[1] * y + (double)m[2] * z, (double)m[4] * x + (double)m[5] * y + (double)m[6] * z,
+             (double)m[8] * x + (double)m[9] * y + (double)m[10] * z);
+}
+// normal: transpose of the inverse (transform.dart:147-161); `mInv` is the inverse matrix
+static DRT_HD inline V3 XfNormal(const float* mInv, const V3& p) {
+  double x = p.x, y = p.y, z = p.z;
+  return mkv((double)mInv[0] * x + (double)mInv[4] * y + (double)mInv[8] * z,
+             (double)mInv[1] * x + (double)mInv[5] * y + (double)mInv[9] * z,
+             (double)mInv[2] * x + (double)mInv[6] * y + (double)mInv[10] * z);
+}
+
+// ---- RGBColor (rgb_color.dart:23-169) ---------------------------------------------------------------
+struct Spec {
+  float r, g, b;
+};
+static DRT_HD inline Spec mks(double r, double g, double b) { return Spec{(float)r, (float)g, (float)b}; }
+static DRT_HD inline Spec mks1(double v) { return Spec{(float)v, (float)v, (float)v}; }
+static DRT_HD inline Spec operator+(const Spec& a, const Spec& b) { return mks((double)a.r + b.r, (double)a.g + b.g, (double)a.b + b.b); }
+static DRT_HD inline Spec operator*(const Spec& a, const Spec& b) { return mks((double)a.r * b.r, (double)a.g * b.g, (double)a.b * b.b); }
+static DRT_HD inline Spec operator*(const Spec& a, double s) { return mks((double)a.r * s, (double)a.g * s, (double)a.b * s); }
+static DRT_HD inline Spec operator/(const Spec& a, double s) { return mks((double)a.r / s, (double)a.g / s, (double)a.b / s); }
+static DRT_HD inline bool IsBlack(const Spec& s) { return !(s.r != 0.f || s.g != 0.f || s.b != 0.f); }
+static DRT_HD inline double Luminance(const Spec& s) { return 0.212671 * s.r + 0.715160 * s.g + 0.072169 * s.b; }
+
+// ---- counter-based random streams (the "keyed" layout: one stream per (pixel, array) for the
+// sampler and per (pixel, sample) for the integrators; draw order inside a stream is the
+// reference's, lib/core/rng.dart:27-43) ---------------------------------------------------------------
+static DRT_HD inline uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+static DRT_HD inline uint64_t streamKey(uint64_t seed, int32_t x, int32_t y, uint32_t sampleIdx, uint32_t streamId) {
+  uint64_t k1 = mix64(seed ^ ((uint64_t)(uint32_t)x | ((uint64_t)(uint32_t)y << 32)));
+  return mix64(k1 ^ ((uint64_t)sampleIdx | ((uint64_t)streamId << 32)) ^ 0xD1B54A32D192ED03ull);
+}
+#define DRT_STREAM_PIXEL 4095u
+#define DRT_STREAM_INTEGRATOR 0x80000000u
+// d-th draw of a stream, d = 1, 2, ...
+static DRT_HD inline uint64_t draw64(uint64_t key, uint64_t d) { return mix64(key + d * 0x9E3779B97F4A7C15ull); }
+static DRT_HD inline double drawFloat(uint64_t key, uint64_t d) { return (double)(draw64(key, d) >> 11) * (1.0 / 9007199254740992.0); }
+static DRT_HD inline uint32_t drawUint(uint64_t key, uint64_t d) { return (uint32_t)(draw64(key, d) >> 32) % 0xffffffffu; }
+
+struct Stream {
+  uint64_t key;
+  uint64_t ctr;
+  DRT_HD double randomFloat() { return drawFloat(key, ++ctr); }
+  DRT_HD uint32_t randomUint() { return drawUint(key, ++ctr); }
+};
+
+// ---- montecarlo.dart ----------------------------------------------------------------------------------
+static DRT_HD inline double Sobol2(uint32_t n, uint32_t scramble) {  // :486-493
+  for (uint32_t v = 1u << 31; n != 0; n >>= 1, v ^= v >> 1)
+    if (n & 0x1) scramble ^= v;
+  return fmin(((scramble >> 8) & 0xffffff) / (double)(1 << 24), DRT_ONE_MINUS_EPS);
+}
+static DRT_HD inline double VanDerCorput(uint32_t n, uint32_t scramble) {  // :495-504
+  n = (n << 16) | (n >> 16);
+  n = ((n & 0x00ff00ff) << 8) | ((n & 0xff00ff00) >> 8);
+  n = ((n & 0x0f0f0f0f) << 4) | ((n & 0xf0f0f0f0) >> 4);
+  n = ((n & 0x33333333) << 2) | ((n & 0xcccccccc) >> 2);
+  n = ((n & 0x55555555) << 1) | ((n & 0xaaaaaaaa) >> 1);
+  n ^= scramble;
+  return fmin(((n >> 8) & 0xffffff) / (double)(1 << 24), DRT_ONE_MINUS_EPS);
+}
+static DRT_HD inline V3 UniformSampleSphere(double u1, double u2) {  // :113-120
+  double z = 1.0 - 2.0 * u1;
+  double r = sqrt(fmax(0.0, 1.0 - z * z));
+  double phi = 2.0 * DRT_PI * u2;
+  return mkv(r * cos(phi), r * sin(phi), z);
+}
+static DRT_HD inline void ConcentricSampleDisk(double u1, double u2, double* dx, double* dy) {  // :155-201
+  double r, theta;
+  double sx = 2 * u1 - 1, sy = 2 * u2 - 1;
+  if (sx == 0.0 && sy == 0.0) { *dx = 0.0; *dy = 0.0; return; }
+  if (sx >= -sy) {
+    if (sx > sy) { r = sx; theta = (sy > 0.0) ? sy / r : 8.0 + sy / r; }
+    else { r = sy; theta = 2.0 - sx / r; }
+  } else {
+    if (sx <= sy) { r = -sx; theta = 4.0 - sy / r; }
+    else { r = -sy; theta = 6.0 + sx / r; }
+  }
+  theta *= DRT_PI / 4.0;
+  *dx = r * cos(theta);
+  *dy = r * sin(theta);
+}
+static DRT_HD inline V3 CosineSampleHemisphere(double u1, double u2) {  // :203-209
+  double dx, dy;
+  ConcentricSampleDisk(u1, u2, &dx, &dy);
+  double z = sqrt(fmax(0.0, 1.0 - dx * dx - dy * dy));
+  return mkv(dx, dy, z);
+}
+static DRT_HD inline double PowerHeuristic(int nf, double fPdf, int ng, double gPdf) {  // :480-484
+  double f = nf * fPdf, g = ng * gPdf;
+  return (f * f) / (f * f + g * g);
+}
+static DRT_HD inline V3 UniformSampleCone2(double u1, double u2, double costhetamax, const V3& x, const V3& y, const V3& z) {
+  double costheta = LerpD(u1, costhetamax, 1.0);  // :135-142
+  double sintheta = sqrt(1.0 - costheta * costheta);
+  double phi = u2 * 2.0 * DRT_PI;
+  return x * (cos(phi) * sintheta) + y * (sin(phi) * sintheta) + z * costheta;
+}
+static DRT_HD inline double UniformConePdf(double cosThetaMax) { return 1.0 / (2.0 * DRT_PI * (1.0 - cosThetaMax)); }
+
+// ---- shapes as the shading code sees them ---------------------------------------------------------------
+struct ShapeHit {  // what Shape.intersect leaves behind: tHit, rayEpsilon and the part of dg the matte path reads
+  double t, rayEps;
+  V3 p, nn, dpdu;
+};
+
+struct TriVerts {
+  V3 p1, p2, p3;
+};
+
+static __device__ inline TriVerts loadTri(const RenderScene& rs, uint32_t prim) {
+  const GPrim* g = rs.ts.prims + rs.primToRec[prim];
+  float4 a = __ldg(reinterpret_cast<const float4*>(&g->p1[0])), b = __ldg(reinterpret_cast<const float4*>(&g->p2[0])),
+         c = __ldg(reinterpret_cast<const float4*>(&g->p3[0]));
+  TriVerts t;
+  t.p1 = V3{a.x, a.y, a.z}; t.p2 = V3{b.x, b.y, b.z}; t.p3 = V3{c.x, c.y, c.z};
+  return t;
+}
+
+// triangle.dart:100-154 with the default uvs (0,0),(1,0),(1,1) (:255-262): du1=-1, du2=0, dv1=-1,
+// dv2=-1, determinant 1, so dpdu = (dp1*dv2 - dp2*dv1) * 1 and dpdv = (dp1*-du2 + dp2*du1) * 1.
+static DRT_HD inline void triPartials(const TriVerts& t, V3* dpdu, V3* dpdv) {
+  V3 dp1 = t.p1 - t.p3, dp2 = t.p2 - t.p3;
+  *dpdu = ((dp1 * -1.0) - (dp2 * -1.0)) * 1.0;
+  *dpdv = ((dp1 * -0.0) + (dp2 * -1.0)) * 1.0;
+}
+static DRT_HD inline V3 shapeNormal(const V3& dpdu, const V3& dpdv, bool reverse) {  // differential_geometry.dart:77-99
+  V3 nn = Normalize(Cross(dpdu, dpdv));
+  if (reverse) nn = nn * -1.0;
+  return nn;
+}
+
+// triangle.dart:44-98, f64 throughout
+static DRT_HD inline bool triIntersectT(const TriVerts& tv, const V3& o, const V3& d, double mint, double maxt, double* tOut) {
+  double p1x = tv.p1.x, p1y = tv.p1.y, p1z = tv.p1.z;
+  double e1x = (double)tv.p2.x - p1x, e1y = (double)tv.p2.y - p1y, e1z = (double)tv.p2.z - p1z;
+  double e2x = (double)tv.p3.x - p1x, e2y = (double)tv.p3.y - p1y, e2z = (double)tv.p3.z - p1z;
+  double dx = d.x, dy = d.y, dz = d.z;
+  double s1x = (dy * e2z) - (dz * e2y);
+  double s1y = (dz * e2x) - (dx * e2z);
+  double s1z = (dx * e2y) - (dy * e2x);
+  double divisor = (s1x * e1x) + (s1y * e1y) + (s1z * e1z);
+  if (divisor == 0.0) return false;
+  double invDivisor = 1.0 / divisor;
+  double sx = (double)o.x - p1x, sy = (double)o.y - p1y, sz = (double)o.z - p1z;
+  double b1 = (sx * s1x + sy * s1y + sz * s1z) * invDivisor;
+  if (b1 < 0.0 || b1 > 1.0) return false;
+  double s2x = (sy * e1z) - (sz * e1y);
+  double s2y = (sz * e1x) - (sx * e1z);
+  double s2z = (sx * e1y) - (sy * e1x);
+  double b2 = ((dx * s2x) + (dy * s2y) + (dz * s2z)) * invDivisor;
+  if (b2 < 0.0 || b1 + b2 > 1.0) return false;
+  double t = (e2x * s2x + e2y * s2y + e2z * s2z) * invDivisor;
+  if (t < mint || t > maxt) return false;
+  *tOut = t;
+  return true;
+}
+
+// sphere.dart:39-116: tHit and the object-space hit point (after the 1e-5*r nudge)
+static DRT_HD inline bool sphereIntersectT(const GSphere& s, const V3& o, const V3& d, double mint, double maxt, double* tOut,
+                                           V3* phitOut) {
+  float w2o[16];
+  for (int i = 0; i < 12; ++i) w2o[i] = s.w2o[i];
+  for (int i = 0; i < 4; ++i) w2o[12 + i] = s.w2oRow3[i];
+  V3 ro = XfPoint(w2o, o), rd = XfVector(w2o, d);
+  double dx = rd.x, dy = rd.y, dz = rd.z, ox = ro.x, oy = ro.y, oz = ro.z;
+  double A = dx * dx + dy * dy + dz * dz;
+  double B = 2 * (dx * ox + dy * oy + dz * oz);
+  double C = ox * ox + oy * oy + oz * oz - s.radius * s.radius;
+  double discrim = B * B - 4.0 * A * C;  // common.dart:140-167
+  if (discrim < 0.0) return false;
+  double rootDiscrim = sqrt(discrim);
+  double q = (B < 0.0) ? -0.5 * (B - rootDiscrim) : -0.5 * (B + rootDiscrim);
+  double t0 = q / A, t1 = C / q;
+  if (t0 > t1) { double tt = t0; t0 = t1; t1 = tt; }
+  if (t0 > maxt || t1 < mint) return false;
+  double thit = t0;
+  if (thit < mint) {
+    thit = t1;
+    if (thit > maxt) return false;
+  }
+  V3 phit = RayAt(ro, rd, thit);
+  if (phit.x == 0.0f && phit.y == 0.0f) phit.x = (float)(1.0e-5 * s.radius);
+  double phi = atan2((double)phit.y, (double)phit.x);
+  if (phi < 0.0) phi += 2.0 * DRT_PI;
+  if ((s.zmin > -s.radius && phit.z < s.zmin) || (s.zmax < s.radius && phit.z > s.zmax) || phi > s.phiMax) {
+    if (thit == t1) return false;
+    if (t1 > maxt) return false;
+    thit = t1;
+    phit = RayAt(ro, rd, thit);
+    if (phit.x == 0.0f && phit.y == 0.0f) phit.x = (float)(1.0e-5 * s.radius);
+    phi = atan2((double)phit.y, (double)phit.x);
+    if (phi < 0.0) phi += 2.0 * DRT_PI;
+    if ((s.zmin > -s.radius && phit.z < s.zmin) || (s.zmax < s.radius && phit.z > s.zmax) || phi > s.phiMax) return false;
+  }
+  *tOut = thit;
+  *phitOut = phit;
+  return true;
+}
+
+// sphere.dart:118-160: p, dpdu, dpdv in world space from the object-space hit point
+static DRT_HD inline void spherePartials(const GSphere& s, const V3& phit, V3* p, V3* dpdu, V3* dpdv) {
+  float o2w[16];
+  for (int i = 0; i < 12; ++i) o2w[i] = s.o2w[i];
+  for (int i = 0; i < 4; ++i) o2w[12 + i] = s.o2wRow3[i];
+  double theta = acos(clampD((double)phit.z / s.radius, -1.0, 1.0));
+  double zradius = sqrt((double)phit.x * phit.x + (double)phit.y * phit.y);
+  double invzradius = 1.0 / zradius;
+  double cosphi = phit.x * invzradius, sinphi = phit.y * invzradius;
+  V3 du = mkv(-s.phiMax * phit.y, s.phiMax * phit.x, 0.0);
+  V3 dv = mkv(phit.z * cosphi, phit.z * sinphi, -s.radius * sin(theta)) * (s.thetaMax - s.thetaMin);
+  *p = XfPoint(o2w, phit);
+  *dpdu = XfVector(o2w, du);
+  *dpdv = XfVector(o2w, dv);
+}
+
+static __device__ inline bool primReverse(const RenderScene& rs, uint32_t prim) { return (__ldg(rs.primAttr + prim) >> 31) != 0; }
+static __device__ inline int primLight(const RenderScene& rs, uint32_t prim) { return (int)((__ldg(rs.primAttr + prim) >> 16) & 0x7fffu) - 1; }
+static __device__ inline int primMaterial(const RenderScene& rs, uint32_t prim) { return (int)(__ldg(rs.primAttr + prim) & 0xffffu); }
+
+// Differential geometry of a hit found by the traversal kernels (lib/core/intersection.dart:27-72):
+// the shape is re-evaluated at the known tHit, which reproduces what Shape.intersect stored.
+static __device__ inline void hitGeometry(const RenderScene& rs, uint32_t prim, const V3& o, const V3& d, double t, ShapeHit* h) {
+  h->t = t;
+  V3 dpdv;
+  if (prim < rs.ntris) {
+    TriVerts tv = loadTri(rs, prim);
+    triPartials(tv, &h->dpdu, &dpdv);
+    h->p = RayAt(o, d, t);
+    h->rayEps = 1.0e-3 * t;  // triangle.dart:157
+  } else {
+    const GSphere& s = rs.ts.spheres[prim - rs.ntris];
+    // object-space hit point at tHit: ray.pointAt on the transformed ray (sphere.dart:62-64 / :95-97)
+    float w2o[16];
+    for (int i = 0; i < 12; ++i) w2o[i] = s.w2o[i];
+    for (int i = 0; i < 4; ++i) w2o[12 + i] = s.w2oRow3[i];
+    V3 ro = XfPoint(w2o, o), rd = XfVector(w2o, d);
+    V3 phit = RayAt(ro, rd, t);
+    if (phit.x == 0.0f && phit.y == 0.0f) phit.x = (float)(1.0e-5 * s.radius);
+    spherePartials(s, phit, &h->p, &h->dpdu, &dpdv);
+    h->rayEps = 5.0e-4 * t;  // sphere.dart:164
+  }
+  h->nn = shapeNormal(h->dpdu, dpdv, primReverse(rs, prim));
+}
+
+// Shape.intersect on one shape with an explicit interval (ShapeSet / Shape.pdf2 use it directly,
+// shape_set.dart:65-79, shape.dart:100-121)
+static __device__ inline bool shapeIntersect(const RenderScene& rs, uint32_t prim, const V3& o, const V3& d, double mint,
+                                             double maxt, ShapeHit* h) {
+  V3 dpdv;
+  if (prim < rs.ntris) {
+    TriVerts tv = loadTri(rs, prim);
+    double t;
+    if (!triIntersectT(tv, o, d, mint, maxt, &t)) return false;
+    triPartials(tv, &h->dpdu, &dpdv);
+    h->t = t;
+    h->p = RayAt(o, d, t);
+    h->rayEps = 1.0e-3 * t;
+  } else {
+    const GSphere& s = rs.ts.spheres[prim - rs.ntris];
+    double t;
+    V3 phit;
+    if (!sphereIntersectT(s, o, d, mint, maxt, &t, &phit)) return false;
+    spherePartials(s, phit, &h->p, &h->dpdu, &dpdv);
+    h->t = t;
+    h->rayEps = 5.0e-4 * t;
+  }
+  h->nn = shapeNormal(h->dpdu, dpdv, primReverse(rs, prim));
+  return true;
+}
+
+// ---- BSDF: one diffuse lobe (bsdf.dart:41-255, bxdf.dart:28-91, lambertian.dart:30-48,
+// oren_nayar.dart:24-58, matte_material.dart:41-65) ------------------------------------------------------
+enum { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16, BSDF_ALL = 31 };
+
+struct Bsdf {
+  V3 nn, ng, sn, tn;
+  bool hasBxdf, orenNayar;
+  Spec R;
+  double A, B;
+};
+
+static __device__ inline V3 bsdfToLocal(const Bsdf& b, const V3& v) { return mkv(Dot(v, b.sn), Dot(v, b.tn), Dot(v, b.nn)); }
+static __device__ inline V3 bsdfToWorld(const Bsdf& b, const V3& v) {
+  return mkv((double)b.sn.x * v.x + (double)b.tn.x * v.y + (double)b.nn.x * v.z,
+             (double)b.sn.y * v.x + (double)b.tn.y * v.y + (double)b.nn.y * v.z,
+             (double)b.sn.z * v.x + (double)b.tn.z * v.y + (double)b.nn.z * v.z);
+}
+static __device__ inline double AbsCosTheta(const V3& v) { return fabs((double)v.z); }
+static __device__ inline double SinTheta2(const V3& v) { return fmax(0.0, 1.0 - (double)v.z * v.z); }
+static __device__ inline double SinTheta(const V3& v) { return sqrt(SinTheta2(v)); }
+static __device__ inline double CosPhi(const V3& v) { double s = SinTheta(v); return s == 0.0 ? 1.0 : clampD((double)v.x / s, -1.0, 1.0); }
+static __device__ inline double SinPhi(const V3& v) { double s = SinTheta(v); return s == 0.0 ? 0.0 : clampD((double)v.y / s, -1.0, 1.0); }
+
+static __device__ inline Bsdf makeBsdf(const RenderScene& rs, uint32_t prim, const ShapeHit& h) {
+  Bsdf b;
+  b.nn = h.nn;  // dgShading == dg: meshes without N/S (triangle.dart:273-276), spheres
+  b.ng = h.nn;
+  b.sn = Normalize(h.dpdu);
+  b.tn = Cross(b.nn, b.sn);
+  const GMaterial m = rs.materials[primMaterial(rs, prim)];
+  Spec r = mks(clampD(m.kd[0], 0.0, CUDART_INF), clampD(m.kd[1], 0.0, CUDART_INF), clampD(m.kd[2], 0.0, CUDART_INF));
+  double sig = clampD(m.sigma, 0.0, 90.0);
+  b.hasBxdf = !IsBlack(r);
+  b.orenNayar = false;
+  b.R = r;
+  b.A = b.B = 0.0;
+  if (b.hasBxdf && sig != 0.0) {  // oren_nayar.dart:24-31
+    b.orenNayar = true;
+    double sigma = (DRT_PI / 180.0) * sig, sigma2 = sigma * sigma;
+    b.A = 1.0 - (sigma2 / (2.0 * (sigma2 + 0.33)));
+    b.B = 0.45 * sigma2 / (sigma2 + 0.09);
+  }
+  return b;
+}
+static __device__ inline Spec bxdfF(const Bsdf& b, const V3& wo, const V3& wi) {
+  if (!b.orenNayar) return b.R * DRT_INV_PI;  // lambertian.dart:35-37
+  double sinthetai = SinTheta(wi), sinthetao = SinTheta(wo);  // oren_nayar.dart:33-58
+  double maxcos = 0.0;
+  if (sinthetai > 1e-4 && sinthetao > 1e-4) {
+    double dcos = CosPhi(wi) * CosPhi(wo) + SinPhi(wi) * SinPhi(wo);
+    maxcos = fmax(0.0, dcos);
+  }
+  double sinalpha, tanbeta;
+  if (AbsCosTheta(wi) > AbsCosTheta(wo)) { sinalpha = sinthetao; tanbeta = sinthetai / AbsCosTheta(wi); }
+  else { sinalpha = sinthetai; tanbeta = sinthetao / AbsCosTheta(wo); }
+  return b.R * (DRT_INV_PI * (b.A + b.B * maxcos * sinalpha * tanbeta));
+}
+static __device__ inline double bxdfPdf(const V3& wo, const V3& wi) {  // bxdf.dart:84-88
+  return ((double)wo.z * wi.z > 0.0) ? AbsCosTheta(wi) * DRT_INV_PI : 0.0;
+}
+static __device__ inline bool bxdfMatches(int flags) { const int type = BSDF_REFLECTION | BSDF_DIFFUSE; return (type & flags) == type; }
+static __device__ inline Spec bsdfF(const Bsdf& b, const V3& woW, const V3& wiW, int flags) {  // bsdf.dart:177-198
+  V3 wi = bsdfToLocal(b, wiW), wo = bsdfToLocal(b, woW);
+  if (Dot(wiW, b.ng) * Dot(woW, b.ng) > 0) flags &= ~BSDF_TRANSMISSION;
+  else flags &= ~BSDF_REFLECTION;
+  Spec r = mks1(0.0);
+  if (b.hasBxdf && bxdfMatches(flags)) r = r + bxdfF(b, wo, wi);
+  return r;
+}
+static __device__ inline double bsdfPdf(const Bsdf& b, const V3& woW, const V3& wiW, int flags) {  // bsdf.dart:128-146
+  if (!b.hasBxdf) return 0.0;
+  V3 wo = bsdfToLocal(b, woW), wi = bsdfToLocal(b, wiW);
+  return bxdfMatches(flags) ? bxdfPdf(wo, wi) / 1 : 0.0;
+}
+// bsdf.dart:53-126 with one BxDF; u0/u1 are the float32 direction samples (the component sample picks
+// among matching BxDFs: one candidate, nothing to pick)
+static __device__ inline Spec bsdfSampleF(const Bsdf& b, const V3& woW, V3* wiW, float u0, float u1, double* pdfOut, int flags,
+                                          int* sampledType) {
+  *sampledType = 0;
+  *pdfOut = 0.0;
+  if (!(b.hasBxdf && bxdfMatches(flags))) return mks1(0.0);
+  V3 wo = bsdfToLocal(b, woW);
+  V3 wi = CosineSampleHemisphere(u0, u1);  // bxdf.dart:37-48
+  if (wo.z < 0.0f) wi.z = (float)((double)wi.z * -1.0);
+  *pdfOut = bxdfPdf(wo, wi);
+  if (*pdfOut == 0.0) return mks1(0.0);
+  *sampledType = BSDF_REFLECTION | BSDF_DIFFUSE;
+  *wiW = bsdfToWorld(b, wi);
+  Spec r = mks1(0.0);
+  if (Dot(*wiW, b.ng) * Dot(woW, b.ng) > 0) flags &= ~BSDF_TRANSMISSION;
+  else flags &= ~BSDF_REFLECTION;
+  if (bxdfMatches(flags)) r = r + bxdfF(b, wo, wi);
+  return r;
+}
+
+// ---- lights (diffuse_area_light.dart:44-70, shape_set.dart:43-96, shape.dart:100-121,
+// triangle.dart:265-269,366-383, sphere.dart:243-311, point_light.dart:41-47) --------------------------
+static __device__ inline Spec lightRadiance(const GLight& l) { return Spec{l.L[0], l.L[1], l.L[2]}; }
+static __device__ inline Spec areaL(const GLight& l, const V3& n, const V3& w) { return Dot(n, w) > 0.0 ? lightRadiance(l) : mks1(0.0); }
+
+static DRT_HD inline double triArea(const TriVerts& t) { return 0.5 * Length(Cross(t.p2 - t.p1, t.p3 - t.p1)); }
+
+static __device__ inline V3 sphereCenter(const GSphere& s) {
+  float o2w[16];
+  for (int i = 0; i < 12; ++i) o2w[i] = s.o2w[i];
+  for (int i = 0; i < 4; ++i) o2w[12 + i] = s.o2wRow3[i];
+  return XfPoint(o2w, V3{0.f, 0.f, 0.f});
+}
+
+// Shape.sample(p, u1, u2) -> point on the shape and its normal
+static __device__ inline V3 shapeSample2(const RenderScene& rs, uint32_t prim, const V3& p, double u1, double u2, V3* ns) {
+  if (prim < rs.ntris) {  // shape.dart:96-98 -> triangle.dart:366-383, UniformSampleTriangle montecarlo.dart:215-220
+    double su1 = sqrt(u1);
+    double b1 = 1.0 - su1, b2 = u2 * su1;
+    TriVerts t = loadTri(rs, prim);
+    V3 pt = t.p1 * b1 + t.p2 * b2 + t.p3 * (1.0 - b1 - b2);
+    V3 n = Normalize(Cross(t.p2 - t.p1, t.p3 - t.p1));
+    if (primReverse(rs, prim)) n = mkv((double)n.x * -1.0, (double)n.y * -1.0, (double)n.z * -1.0);
+    *ns = n;
+    return pt;
+  }
+  const GSphere& s = rs.ts.spheres[prim - rs.ntris];  // sphere.dart:261-297
+  const bool rev = primReverse(rs, prim);
+  float o2w[16], w2o[16];
+  for (int i = 0; i < 12; ++i) { o2w[i] = s.o2w[i]; w2o[i] = s.w2o[i]; }
+  for (int i = 0; i < 4; ++i) { o2w[12 + i] = s.o2wRow3[i]; w2o[12 + i] = s.w2oRow3[i]; }
+  V3 Pcenter = XfPoint(o2w, V3{0.f, 0.f, 0.f});
+  V3 wc = Normalize(Pcenter - p);
+  V3 wcX, wcY;
+  CoordinateSystem(wc, &wcX, &wcY);
+  if (DistanceSquared(p, Pcenter) - s.radius * s.radius < 1.0e-4) {  // sphere.dart:247-259
+    V3 ps = V3{0.f, 0.f, 0.f} + UniformSampleSphere(u1, u2) * s.radius;
+    V3 n = XfNormal(w2o, ps);
+    n = n / Length(n);
+    if (rev) n = -n;
+    *ns = n;
+    return XfPoint(o2w, ps);
+  }
+  double sinThetaMax2 = s.radius * s.radius / DistanceSquared(p, Pcenter);
+  double cosThetaMax = sqrt(fmax(0.0, 1.0 - sinThetaMax2));
+  V3 rd = UniformSampleCone2(u1, u2, cosThetaMax, wcX, wcY, wc);
+  double thit;
+  ShapeHit h;
+  if (shapeIntersect(rs, prim, p, rd, 1.0e-3, CUDART_INF, &h)) thit = h.t;
+  else thit = Dot(Pcenter - p, Normalize(rd));
+  V3 ps = RayAt(p, rd, thit);
+  V3 n = Normalize(ps - Pcenter);
+  if (rev) n = -n;
+  *ns = n;
+  return ps;
+}
+
+static __device__ inline double shapePdf2(const RenderScene& rs, uint32_t prim, double area, const V3& p, const V3& wi) {
+  if (prim >= rs.ntris) {  // sphere.dart:299-311
+    const GSphere& s = rs.ts.spheres[prim - rs.ntris];
+    V3 Pcenter = sphereCenter(s);
+    if (!(DistanceSquared(p, Pcenter) - s.radius * s.radius < 1.0e-4)) {
+      double sinThetaMax2 = s.radius * s.radius / DistanceSquared(p, Pcenter);
+      double cosThetaMax = sqrt(fmax(0.0, 1.0 - sinThetaMax2));
+      return UniformConePdf(cosThetaMax);
+    }
+  }
+  ShapeHit h;  // shape.dart:100-121
+  if (!shapeIntersect(rs, prim, p, wi, 1.0e-3, CUDART_INF, &h)) return 0.0;
+  double pdf = DistanceSquared(p, RayAt(p, wi, h.t)) / (AbsDot(h.nn, -wi) * area);
+  if (isinf(pdf)) pdf = 0.0;
+  return pdf;
+}
+
+static __device__ inline double shapeSetPdf(const RenderScene& rs, const GLight& l, const V3& p, const V3& wi) {  // shape_set.dart:81-89
+  double pdf = 0.0;
+  for (uint32_t i = 0; i < l.nShapes; ++i) {
+    double a = rs.lightShapeAreas[l.shapeOffset + i];
+    pdf += a * shapePdf2(rs, rs.lightShapes[l.shapeOffset + i], a, p, wi);
+  }
+  return pdf / l.area;
+}
+
+// Distribution1D.sampleDiscrete (montecarlo.dart:82-92): upper_bound over the float32 cdf
+static __device__ inline int sampleDiscrete(const float* cdf, int count, double u) {
+  int lo = 0, hi = count + 1;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (u < (double)cdf[mid]) hi = mid;
+    else lo = mid + 1;
+  }
+  int r = lo - 1;
+  return r < 0 ? 0 : r;
+}
+
+static __device__ inline V3 shapeSetSample(const RenderScene& rs, const GLight& l, const V3& p, float u0, float u1, double comp,
+                                           V3* Ns) {  // shape_set.dart:53-79
+  int sn = sampleDiscrete(rs.lightCdf + l.cdfOffset, (int)l.nShapes, comp) % (int)l.nShapes;
+  V3 pt = shapeSample2(rs, rs.lightShapes[l.shapeOffset + sn], p, u0, u1, Ns);
+  V3 rd = pt - p;
+  double thit = 1.0;
+  bool anyHit = false;
+  V3 nnLast = *Ns;
+  for (uint32_t i = 0; i < l.nShapes; ++i) {
+    ShapeHit h;
+    if (shapeIntersect(rs, rs.lightShapes[l.shapeOffset + i], p, rd, 1.0e-3, CUDART_INF, &h)) {
+      anyHit = true;
+      thit = h.t;
+      nnLast = h.nn;
+    }
+  }
+  if (anyHit) *Ns = nnLast;
+  return RayAt(p, rd, thit);
+}
+
+// What Integrator.EstimateDirect (integrator.dart:119-185) needs traced before it can finish: the
+// shadow ray of the light sample and the closest-hit ray of the BSDF sample, each with the
+// contribution it carries if the query comes out right.
+struct DirectWork {
+  bool hasShadow, hasMis;
+  V3 shO, shD;
+  double shMin, shMax;
+  Spec shContribution;  // f * Li * (|wi.n| * weight / lightPdf)
+  V3 misD;
+  Spec misF;
+  double misScale;  // |wi.n| * weight / bsdfPdf
+};
+
+static __device__ inline void estimateDirectSetup(const RenderScene& rs, int lightIndex, const V3& p, const V3& n, const V3& wo,
+                                                  double rayEps, const Bsdf& bsdf, float lu0, float lu1, double lcomp, float bu0,
+                                                  float bu1, int flags, DirectWork* w) {
+  const GLight l = rs.lights[lightIndex];
+  w->hasShadow = false;
+  w->hasMis = false;
+  V3 wi;
+  double lightPdf = 0.0, bPdf = 0.0;
+  Spec Li;
+  V3 segTo;
+  double eps2;
+  const bool delta = l.kind == 1;
+  if (delta) {  // point_light.dart:41-47
+    V3 pos = V3{l.pos[0], l.pos[1], l.pos[2]};
+    wi = Normalize(pos - p);
+    lightPdf = 1.0;
+    segTo = pos;
+    eps2 = 0.0;
+    Li = lightRadiance(l) / DistanceSquared(pos, p);
+  } else {  // diffuse_area_light.dart:59-70
+    V3 ns;
+    V3 ps = shapeSetSample(rs, l, p, lu0, lu1, lcomp, &ns);
+    wi = Normalize(ps - p);
+    lightPdf = shapeSetPdf(rs, l, p, wi);
+    segTo = ps;
+    eps2 = 1.0e-3;
+    Li = areaL(l, ns, -wi);
+  }
+  if (lightPdf > 0.0 && !IsBlack(Li)) {
+    Spec f = bsdfF(bsdf, wo, wi, flags);
+    if (!IsBlack(f)) {
+      double dist = Distance(p, segTo);  // visibility_tester.dart:26-29
+      w->hasShadow = true;
+      w->shO = p;
+      w->shD = (segTo - p) / dist;
+      w->shMin = rayEps;
+      w->shMax = dist * (1.0 - eps2);
+      Li = Li * mks1(1.0);  // transmittance
+      if (delta) {
+        w->shContribution = f * Li * (AbsDot(wi, n) / lightPdf);
+      } else {
+        bPdf = bsdfPdf(bsdf, wo, wi, flags);
+        double weight = PowerHeuristic(1, lightPdf, 1, bPdf);
+        w->shContribution = f * Li * ((AbsDot(wi, n) * weight / lightPdf));
+      }
+    }
+  }
+  if (!delta) {
+    int sampledType = 0;
+    Spec f = bsdfSampleF(bsdf, wo, &wi, bu0, bu1, &bPdf, flags, &sampledType);
+    if (!IsBlack(f) && bPdf > 0.0) {
+      double weight = 1.0;
+      if ((sampledType & BSDF_SPECULAR) == 0) {
+        lightPdf = shapeSetPdf(rs, l, p, wi);
+        if (lightPdf == 0.0) return;
+        weight = PowerHeuristic(1, bPdf, 1, lightPdf);
+      }
+      w->hasMis = true;
+      w->misD = wi;
+      w->misF = f;
+      w->misScale = AbsDot(wi, n) * weight / bPdf;
+    }
+  }
+}
+
+}  // namespace drt

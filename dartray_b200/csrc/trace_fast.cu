@@ -124,8 +124,10 @@ static __device__ __forceinline__ bool testSlot(const FastRay& r, int32_t& ref, 
 template <bool ANY>
 __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
     traceFastKernel(TraceScene sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD, uint64_t n,
-                    float4* __restrict__ hits, uint8_t* __restrict__ occluded, unsigned long long* __restrict__ nextRay) {
+                    float4* __restrict__ hits, uint8_t* __restrict__ occluded, unsigned long long* __restrict__ nextRay,
+                    TraceExtras ex) {
   const unsigned lane = threadIdx.x & 31u;
+  if (ex.nDev) n = *ex.nDev;  // wavefront queues: the ray count lives in device memory
   const unsigned ltMask = (1u << lane) - 1u;
   unsigned long long warpNext = 0, warpEnd = 0;  // warp-uniform: the chunk of rays this warp owns
   bool exhausted = false;                        // warp-uniform: the global counter ran past n
@@ -143,8 +145,11 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
   do {                                                                                                       \
     alive = false;                                                                                           \
     if (ANY) occluded[rayIdx] = found ? 1 : 0;                                                               \
-    else hits[rayIdx] = make_float4(found ? __double2float_rn(r.maxt) : CUDART_INF_F, hb1, hb2,              \
-                                    __int_as_float(hprim));                                                  \
+    else {                                                                                                   \
+      hits[rayIdx] = make_float4(found ? __double2float_rn(r.maxt) : CUDART_INF_F, hb1, hb2,                 \
+                                 __int_as_float(hprim));                                                     \
+      if (ex.tOut) ex.tOut[rayIdx] = found ? r.maxt : CUDART_INF;                                            \
+    }                                                                                                        \
   } while (0)
 
   for (;;) {
@@ -172,10 +177,16 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
         r.ix = __double2float_rn(1.0 / (double)d.x);
         r.iy = __double2float_rn(1.0 / (double)d.y);
         r.iz = __double2float_rn(1.0 / (double)d.z);
-        r.mint = o.w;
-        r.mintLo = r.mintHi = o.w;
-        r.maxt = d.w;
-        r.maxtLo = r.maxtHi = d.w;
+        if (ex.range) {  // renderer rays: the reference's f64 minDistance / maxDistance (ray.dart:34-36)
+          double2 mm = __ldg(ex.range + rayIdx);
+          r.mint = mm.x; r.mintLo = __double2float_rd(mm.x); r.mintHi = __double2float_ru(mm.x);
+          r.maxt = mm.y; r.maxtLo = __double2float_rd(mm.y); r.maxtHi = __double2float_ru(mm.y);
+        } else {
+          r.mint = o.w;
+          r.mintLo = r.mintHi = o.w;
+          r.maxt = d.w;
+          r.maxtLo = r.maxtHi = d.w;
+        }
         bool slow = !(fabsf(r.ox) <= 3.0e38f) || !(fabsf(r.oy) <= 3.0e38f) || !(fabsf(r.oz) <= 3.0e38f) ||
                     !(fabsf(r.ix) <= 3.0e38f) || !(fabsf(r.iy) <= 3.0e38f) || !(fabsf(r.iz) <= 3.0e38f);
         r.negMask = (r.ix < 0.f ? 1u : 0u) | (r.iy < 0.f ? 2u : 0u) | (r.iz < 0.f ? 4u : 0u) | (slow ? 8u : 0u);
@@ -317,8 +328,11 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
 }
 
 cudaError_t launchTraceFast(const TraceScene& sc, bool any, const void* rayO, const void* rayD, uint64_t n, void* out,
-                            unsigned long long* nextRay, int numSMs, cudaStream_t stream) {
-  if (n == 0) return cudaSuccess;
+                            unsigned long long* nextRay, int numSMs, cudaStream_t stream, const TraceExtras* extras) {
+  TraceExtras ex{};
+  if (extras) ex = *extras;
+  if (n == 0 && !ex.nDev) return cudaSuccess;
+  if (ex.nDev) n = ~0ull >> 8;  // unknown on the host: launch the full persistent grid
   cudaError_t e = cudaMemsetAsync(nextRay, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
   const int block = 128;
@@ -336,8 +350,8 @@ cudaError_t launchTraceFast(const TraceScene& sc, bool any, const void* rayO, co
   dim3 grid((unsigned)(blocksWanted < persistent ? blocksWanted : persistent));
   const float4* o = static_cast<const float4*>(rayO);
   const float4* d = static_cast<const float4*>(rayD);
-  if (any) traceFastKernel<true><<<grid, block, 0, stream>>>(sc, o, d, n, nullptr, (uint8_t*)out, nextRay);
-  else traceFastKernel<false><<<grid, block, 0, stream>>>(sc, o, d, n, (float4*)out, nullptr, nextRay);
+  if (any) traceFastKernel<true><<<grid, block, 0, stream>>>(sc, o, d, n, nullptr, (uint8_t*)out, nextRay, ex);
+  else traceFastKernel<false><<<grid, block, 0, stream>>>(sc, o, d, n, (float4*)out, nullptr, nextRay, ex);
   return cudaGetLastError();
 }
 

@@ -17,9 +17,17 @@ struct drt_hit_rec {  // == drt_hit of include/drt.h
 cudaError_t launchTrace(const TraceScene& sc, bool any, bool count, const void* rayO, const void* rayD, uint64_t n,
                         void* out, DeviceCounters* counters, cudaStream_t stream);
 
+// Optional inputs/outputs of the production kernel used by the wavefront renderer.
+struct TraceExtras {
+  const uint32_t* nDev = nullptr;  // ray count in device memory (overrides n)
+  const double2* range = nullptr;  // per ray (minDistance, maxDistance) in f64 instead of the float4 .w lanes
+  double* tOut = nullptr;          // closest hit: tHit in f64 (+inf on a miss)
+};
+
 // Production path: persistent warps, while-while traversal, float32-filtered slab test with exact
 // float64 fallback (trace_fast.cu).  `nextRay` is a device counter owned by the context.
 cudaError_t launchTraceFast(const TraceScene& sc, bool any, const void* rayO, const void* rayD, uint64_t n, void* out,
-                            unsigned long long* nextRay, int numSMs, cudaStream_t stream);
+                            unsigned long long* nextRay, int numSMs, cudaStream_t stream,
+                            const TraceExtras* extras = nullptr);
 
 }  // namespace drt

@@ -149,6 +149,92 @@ double drt_last_kernel_ms(const drt_ctx* ctx);
 /* Number of kernels this context has launched so far. */
 uint64_t drt_kernel_launches(const drt_ctx* ctx);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Render path: what Renderer.render(scene) does for a SamplerRenderer (lib/renderers/
+ * sampler_renderer.dart:36-65,118-218) with the objects DartRay.worldEnd built
+ * (lib/dartray/dartray.dart:549-764).  The caller flattens those objects into the arrays below.
+ * ------------------------------------------------------------------------------------------------- */
+
+/* Replaces MatteMaterial (lib/materials/matte_material.dart:41-65) with constant Kd / sigma
+ * textures (lib/core/texture/constant_texture.dart:23-39).  kind: 0 = matte (the only kind on the
+ * path, NULL = all 0); kd_rgb: n x 3; sigma: n (degrees, NULL = 0).  Material index = position. */
+int drt_set_materials(drt_ctx* ctx, uint32_t n, const int32_t* kind, const float* kd_rgb, const float* sigma);
+
+/* Replaces scene.lights: DiffuseAreaLight (kind 0, lib/lights/diffuse_area_light.dart:44-70; L = Lemit
+ * x scale) and PointLight (kind 1, lib/lights/point_light.dart:41-47; L = intensity, pos = world
+ * position).  nsamples: per light (NULL = 1).  The ShapeSet of light i (lib/core/light/
+ * shape_set.dart:26-50) is shape_prims[shape_offsets[i] .. shape_offsets[i+1]) — primitive ids in the
+ * order the reference's refine loop leaves them.  Light index = position; drt_set_triangles /
+ * drt_set_spheres refer to it through light_of_*. */
+int drt_set_lights(drt_ctx* ctx, uint32_t n, const int32_t* kind, const float* L_rgb, const float* pos,
+                   const int32_t* nsamples, const uint32_t* shape_offsets, const uint32_t* shape_prims);
+
+/* Replaces PerspectiveCamera (lib/cameras/perspective_camera.dart:46-57 + lib/core/
+ * projective_camera.dart:34-53): the two float32 row-major matrices the camera holds
+ * (rasterToCamera, cameraToWorld.startTransform) and its lens / shutter scalars. */
+int drt_set_camera(drt_ctx* ctx, const float raster_to_camera[16], const float camera_to_world[16], double lens_radius,
+                   double focal_distance, double shutter_open, double shutter_close);
+
+/* Replaces ImageFilm's constructor (lib/film/image_film.dart:51-97): resolution, crop window
+ * (x0, x1, y0, y1; NULL = 0,1,0,1), filter widths and the 16x16 table of filter.evaluate values
+ * (image_film.dart:74-82) computed by the caller's Filter object.  Resets the film. */
+int drt_set_film(drt_ctx* ctx, int32_t xres, int32_t yres, const double crop[4], double xwidth, double ywidth,
+                 const float filter_table[256]);
+
+/* Replaces the Sampler plugins lowdiscrepancy (kind 0, lib/samplers/low_discrepancy_sampler.dart;
+ * spp rounded up to a power of two), stratified (kind 1, lib/samplers/stratified_sampler.dart; xs x ys
+ * strata, jitter) and random (kind 2, lib/samplers/random_sampler.dart).  pixel_order / tile_size name
+ * the PixelSampler (0 linear, 1 tile: lib/pixel_samplers/*.dart); with per-pixel keyed streams the
+ * visiting order does not change any sample, so they only document the request.  seed keys every
+ * stream (the reference seeds its single RNG with the task number, sampler_renderer.dart:137). */
+int drt_set_sampler(drt_ctx* ctx, int32_t kind, int32_t xs, int32_t ys, int32_t spp, int32_t jitter, int32_t pixel_order,
+                    int32_t tile_size, uint64_t seed);
+
+/* Replaces the SurfaceIntegrator plugins path (kind 0, lib/surface_integrators/path_integrator.dart;
+ * maxdepth), ambientocclusion (kind 1, ambient_occlusion_integrator.dart; nsamples rounded up to a
+ * power of two, mindist, maxdist) and directlighting (kind 2, direct_lighting_integrator.dart;
+ * strategy 0 = all, 1 = one). */
+int drt_set_integrator(drt_ctx* ctx, int32_t kind, int32_t maxdepth, int32_t strategy, int32_t ao_nsamples,
+                       double ao_mindist, double ao_maxdist);
+
+/* Replaces _SamplerRendererTask.run (sampler_renderer.dart:118-218) for task task_num of task_count:
+ * the task's sub-window of the sample extent (lib/dartray/dartray.dart:1009-1023, GetSubWindow
+ * lib/core/common.dart:52-73).  Adds into the context's film; blocking. */
+int drt_render(drt_ctx* ctx, int32_t task_num, int32_t task_count);
+
+/* Same work, split for load balance instead of by sub-window: the sample extent's pixels are cut into
+ * 1024-pixel blocks and shard s renders blocks s, s + n_shards, ...  The union over all shards is
+ * exactly the sample set of drt_render(0, 1). */
+int drt_render_shard(drt_ctx* ctx, int32_t shard, int32_t n_shards);
+
+/* Camera samples in flight per wavefront batch (0 = default 4 Mi). */
+int drt_set_batch_slots(drt_ctx* ctx, uint64_t slots);
+
+int drt_film_clear(drt_ctx* ctx);
+/* left, top, width, height of the film's pixel window (image_film.dart:67-70) */
+int drt_film_size(const drt_ctx* ctx, int32_t out[4]);
+/* Replaces ImageFilm.writeImage (image_film.dart:268-299): rgb = width*height*3 floats (OutputImage.rgb);
+ * xyz (width*height*3) / weight (width*height) are the raw accumulators; any pointer may be NULL. */
+int drt_film_read(drt_ctx* ctx, float* rgb, float* xyz, float* weight);
+/* The film accumulators in device memory: width*height x (X, Y, Z, weight) doubles — what a multi-GPU
+ * caller sums across ranks (NCCL) before drt_film_read. */
+int drt_film_device(drt_ctx* ctx, void** d_film, uint64_t* n_doubles);
+
+/* The camera samples the sampler generates for pixel (x, y) (Sampler.getMoreSamples, lib/core/
+ * sampler.dart:56): per sample imageX - x, imageY - y, lensU, lensV, time, then the integrator's 1D
+ * arrays and 2D arrays in request order.  For parity tests of the sequences. */
+int drt_pixel_samples(drt_ctx* ctx, int32_t x, int32_t y, float* out, int32_t cap, int32_t* n_samples,
+                      int32_t* floats_per_sample);
+
+/* Ray counters of the renders since the last drt_film_clear (lib/core/stats.dart:541-555). */
+typedef struct drt_render_stats {
+  uint64_t camera_samples;
+  uint64_t closest_rays; /* camera + MIS + path-extension rays (Scene.intersect) */
+  uint64_t shadow_rays;  /* Scene.intersectP */
+  uint64_t zeroed_samples; /* NaN / negative / infinite radiance set to black, sampler_renderer.dart:181-193 */
+} drt_render_stats;
+int drt_render_stats_get(drt_ctx* ctx, drt_render_stats* out);
+
 #ifdef __cplusplus
 }
 #endif

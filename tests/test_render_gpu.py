@@ -1,0 +1,209 @@
+"""GPU wavefront renderer (drt_render through the C ABI) against the CPU oracle in keyed-stream mode.
+
+north_star tolerances: replayed sample streams; deterministic integrators (ambient occlusion, direct
+lighting) per pixel within 1e-3 relative; path tracing per-pixel mean within 3 sigma.  Because the GPU
+shading code keeps the reference's arithmetic (float32 storage, float64 expressions), the renders
+agree far more tightly than that; the tests assert the stated tolerance on every pixel and report
+the observed maximum."""
+import math
+
+import numpy as np
+import pytest
+
+from dartray_b200 import capi, host, scenes
+from tests.oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(arrays):
+    g, o = capi.Context(0), Oracle()
+    for c in (g, o):
+        host.upload_scene(c, arrays)
+    return g, o
+
+
+def _cornell():
+    sb, cam = scenes.cornell_synth()
+    return sb.arrays(), cam
+
+
+def _render_both(arrays, cam, film, sampler, integ, task=(0, 1)):
+    g, o = _pair(arrays)
+    for c in (g, o):
+        host.configure_render(c, cam, film, sampler, integ)
+    g.render(*task)
+    o.render(task[0], task[1], 8)
+    return g, o, g.film_read(), o.film_read()
+
+
+def _rel_err(a, b, floor=1e-4):
+    return np.abs(a - b) / np.maximum(np.abs(b), floor)
+
+
+# ---- sampler sequences: bit-exact replay -----------------------------------------------------------------
+@pytest.mark.parametrize("sampler,integ", [
+    (host.Sampler(kind=host.SAMPLER_LD, spp=4), host.Integrator(kind=host.INTEGRATOR_PATH)),
+    (host.Sampler(kind=host.SAMPLER_LD, spp=64, seed=7), host.Integrator(kind=host.INTEGRATOR_PATH)),
+    (host.Sampler(kind=host.SAMPLER_LD, spp=6), host.Integrator(kind=host.INTEGRATOR_DIRECT)),
+    (host.Sampler(kind=host.SAMPLER_LD, spp=8), host.Integrator(kind=host.INTEGRATOR_DIRECT, strategy=1)),
+    (host.Sampler(kind=host.SAMPLER_LD, spp=2), host.Integrator(kind=host.INTEGRATOR_AO)),
+    (host.Sampler(kind=host.SAMPLER_STRATIFIED, xs=3, ys=2), host.Integrator(kind=host.INTEGRATOR_PATH)),
+    (host.Sampler(kind=host.SAMPLER_STRATIFIED, xs=2, ys=2, jitter=False), host.Integrator(kind=host.INTEGRATOR_DIRECT)),
+    (host.Sampler(kind=host.SAMPLER_RANDOM, spp=5), host.Integrator(kind=host.INTEGRATOR_PATH)),
+])
+def test_sampler_sequences_replay_the_oracle_bit_for_bit(sampler, integ):
+    sb, cam = scenes.cornell_synth()
+    # a second light with 4 samples exercises nSamples > 1 arrays of the direct-lighting layout
+    sb.mesh([[-1, 9.8, -1], [1, 9.8, -1], [1, 9.8, 1], [-1, 9.8, 1]], [[0, 1, 2], [0, 2, 3]], area_light=(1, 2, 3), nsamples=3)
+    g, o = _pair(sb.arrays())
+    film = host.Film(32, 24)
+    for c in (g, o):
+        host.configure_render(c, cam, film, sampler, integ)
+    for (x, y) in [(0, 0), (5, 7), (31, 23), (-1, 24)]:
+        sg, so = g.pixel_samples(x, y), o.pixel_samples(x, y)
+        assert sg.shape == so.shape and sg.shape[0] > 0
+        assert np.array_equal(sg.view(np.uint32), so.view(np.uint32)), (x, y, np.argwhere(sg != so)[:4])
+
+
+# ---- deterministic integrators ------------------------------------------------------------------------------
+def test_ambient_occlusion_matches_oracle_per_pixel():
+    arrays, cam = _cornell()
+    g, o, fg, fo = _render_both(arrays, cam, host.Film(96, 72), host.Sampler(kind=host.SAMPLER_LD, spp=2),
+                                host.Integrator(kind=host.INTEGRATOR_AO, ao_nsamples=32))
+    assert np.array_equal(fg["weight"], fo["weight"])
+    err = _rel_err(fg["rgb"], fo["rgb"])
+    print("AO max rel err", err.max(), "pixels differing", int((fg["rgb"] != fo["rgb"]).any(axis=2).sum()))
+    assert err.max() <= 1e-3
+    sg, so = g.render_stats(), o.render_stats()
+    assert sg["camera_samples"] == so["camera_samples"]
+    assert sg["shadow_rays"] == so["shadow_rays"]
+
+
+@pytest.mark.parametrize("strategy", [0, 1])
+def test_direct_lighting_matches_oracle_per_pixel(strategy):
+    sb, cam = scenes.cornell_synth()
+    sb.point_light((0.0, 5.0, -5.0), (40.0, 30.0, 20.0))
+    sb.sphere(host.translate(5, 6, 2), radius=0.8, area_light=(10.0, 10.0, 10.0), nsamples=2)
+    arrays = sb.arrays()
+    g, o, fg, fo = _render_both(arrays, cam, host.Film(80, 60), host.Sampler(kind=host.SAMPLER_LD, spp=4),
+                                host.Integrator(kind=host.INTEGRATOR_DIRECT, strategy=strategy))
+    err = _rel_err(fg["rgb"], fo["rgb"])
+    print("direct max rel err", err.max(), "pixels differing", int((fg["rgb"] != fo["rgb"]).any(axis=2).sum()))
+    assert err.max() <= 1e-3
+    sg, so = g.render_stats(), o.render_stats()
+    assert sg["shadow_rays"] == so["shadow_rays"]
+    assert sg["closest_rays"] == so["closest_rays"]
+
+
+def test_direct_lighting_stratified_sampler_and_oren_nayar():
+    sb, cam = scenes.cornell_synth()
+    rough = sb.material((0.6, 0.5, 0.4), sigma=25.0)
+    sb.mesh([[-3, -9.9, -3], [3, -9.9, -3], [3, -9.9, 3], [-3, -9.9, 3]], [[0, 2, 1], [0, 3, 2]], material=rough)
+    g, o, fg, fo = _render_both(sb.arrays(), cam, host.Film(64, 48), host.Sampler(kind=host.SAMPLER_STRATIFIED, xs=2, ys=2),
+                                host.Integrator(kind=host.INTEGRATOR_DIRECT))
+    assert _rel_err(fg["rgb"], fo["rgb"]).max() <= 1e-3
+
+
+# ---- path tracing ------------------------------------------------------------------------------------------
+def test_path_integrator_matches_oracle():
+    arrays, cam = _cornell()
+    g, o, fg, fo = _render_both(arrays, cam, host.Film(64, 48), host.Sampler(kind=host.SAMPLER_LD, spp=16),
+                                host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=5))
+    # same streams, same arithmetic: the per-pixel means agree far inside 3 sigma of the Monte Carlo noise
+    err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
+    print("path max rel err", err.max(), "pixels differing", int((fg["rgb"] != fo["rgb"]).any(axis=2).sum()))
+    sigma = fo["rgb"].std() / math.sqrt(16)
+    assert np.abs(fg["rgb"] - fo["rgb"]).max() <= 3 * sigma
+    assert abs(fg["rgb"].mean() - fo["rgb"].mean()) <= 5e-3 * fo["rgb"].mean()
+    assert np.quantile(err, 0.999) <= 1e-3
+    sg, so = g.render_stats(), o.render_stats()
+    assert abs(sg["closest_rays"] - so["closest_rays"]) <= 1e-3 * so["closest_rays"]
+    assert abs(sg["shadow_rays"] - so["shadow_rays"]) <= 1e-3 * so["shadow_rays"]
+
+
+def test_path_deep_bounces_use_the_integrator_stream():
+    arrays, cam = _cornell()
+    g, o, fg, fo = _render_both(arrays, cam, host.Film(40, 30), host.Sampler(kind=host.SAMPLER_RANDOM, spp=2),
+                                host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=9))
+    err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
+    assert np.quantile(err, 0.999) <= 1e-3
+    assert abs(fg["rgb"].mean() - fo["rgb"].mean()) <= 5e-3 * fo["rgb"].mean()
+
+
+# ---- film --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flt", ["gaussian", "mitchell", "triangle", "sinc", "box"])
+def test_filters_and_crop_window(flt):
+    arrays, cam = _cornell()
+    film = host.Film(48, 36, filter=flt, crop=(0.25, 0.9, 0.1, 0.8))
+    g, o, fg, fo = _render_both(arrays, cam, film, host.Sampler(kind=host.SAMPLER_LD, spp=4),
+                                host.Integrator(kind=host.INTEGRATOR_DIRECT))
+    assert g.film_size() == o.film_size()
+    assert np.allclose(fg["weight"], fo["weight"], rtol=1e-5, atol=1e-6)
+    assert _rel_err(fg["rgb"], fo["rgb"], floor=1e-3).max() <= 1e-3
+
+
+def test_tasks_and_shards_tile_the_image():
+    arrays, cam = _cornell()
+    film = host.Film(50, 38)
+    sampler, integ = host.Sampler(kind=host.SAMPLER_LD, spp=2), host.Integrator(kind=host.INTEGRATOR_DIRECT)
+    full = capi.Context(0)
+    host.upload_scene(full, arrays)
+    host.configure_render(full, cam, film, sampler, integ)
+    full.render()
+    ref = full.film_read()
+    # reference semantics: task sub-windows of the sample extent (dartray.dart:1009-1023), one film
+    tasks = capi.Context(0)
+    host.upload_scene(tasks, arrays)
+    host.configure_render(tasks, cam, film, sampler, integ)
+    o = Oracle()
+    host.upload_scene(o, arrays)
+    host.configure_render(o, cam, film, sampler, integ)
+    for t in range(3):
+        tasks.render(t, 3)
+        o.render(t, 3, 4)
+    ft = tasks.film_read()
+    assert np.array_equal(ft["weight"], ref["weight"])
+    assert np.allclose(ft["xyz"], ref["xyz"], rtol=1e-6, atol=1e-7)
+    assert _rel_err(ft["rgb"], o.film_read()["rgb"], floor=1e-3).max() <= 1e-3
+    # load-balanced shards: interleaved pixel blocks
+    sh = capi.Context(0)
+    host.upload_scene(sh, arrays)
+    host.configure_render(sh, cam, film, sampler, integ)
+    sh.set_batch_slots(700)  # several batches per shard
+    for s in range(4):
+        sh.render_shard(s, 4)
+    fs = sh.film_read()
+    assert np.array_equal(fs["weight"], ref["weight"])
+    assert np.allclose(fs["xyz"], ref["xyz"], rtol=1e-6, atol=1e-7)
+    assert sh.render_stats()["camera_samples"] == full.render_stats()["camera_samples"]
+
+
+def test_empty_scene_and_no_lights():
+    cam = host.PerspectiveCamera(host.look_at((0, 0, -5), (0, 0, 0), (0, 1, 0)), fov=40.0)
+    sb = host.SceneBuilder()
+    g = capi.Context(0)
+    host.upload_scene(g, sb.arrays())
+    host.configure_render(g, cam, host.Film(16, 12), host.Sampler(spp=1), host.Integrator(kind=host.INTEGRATOR_PATH))
+    g.render()
+    f = g.film_read()
+    assert (f["rgb"] == 0).all() and (f["weight"] == 1).all()
+    # geometry but no lights: black, and the integrator draws differ (UniformSampleOneLight returns early)
+    sb = host.SceneBuilder()
+    sb.sphere(host.translate(0, 0, 0), radius=1.0, material=sb.material((0.5, 0.5, 0.5)))
+    g, o, fg, fo = _render_both(sb.arrays(), cam, host.Film(16, 12), host.Sampler(spp=2),
+                                host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=6))
+    assert (fg["rgb"] == 0).all() and (fo["rgb"] == 0).all()
+    assert g.render_stats()["closest_rays"] == o.render_stats()["closest_rays"]
+
+
+def test_render_errors():
+    g = capi.Context(0)
+    with pytest.raises(capi.DrtError):
+        g.render()  # nothing set
+    with pytest.raises(ValueError):
+        g.set_sampler(0, 1, 1, 4, 1, 1, 32, 0, rng_mode=0)  # serial stream cannot be replayed in parallel
+    with pytest.raises(capi.DrtError):
+        g.set_integrator(5, 5, 0, 1, 0.0, 1.0)
+    with pytest.raises(capi.DrtError):
+        g.set_materials(np.array([3], np.int32), np.ones((1, 3), np.float32), np.zeros(1, np.float32))
