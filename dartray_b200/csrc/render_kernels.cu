@@ -50,40 +50,44 @@ static __device__ __forceinline__ void pixelOf(const PixelBatch& pb, uint32_t p,
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Low-discrepancy sampler: one warp per (pixel, array).  LDShuffleScrambled1D/2D
-// (montecarlo.dart:524-551): scrambled (0,2)-sequence values, a Fisher-Yates shuffle inside every
-// block of nSamples and one across the nPixel blocks (Shuffle, montecarlo.dart:294-303).  Values and
-// swap targets are computed by all lanes (the stream is counter-based); the swaps themselves are
-// order-dependent and run on lane 0 in shared memory; the result is written out coalesced.
+// Low-discrepancy sampler: one group of G lanes (G = 1..32, a power of two chosen from the array
+// size) per (pixel, array).  LDShuffleScrambled1D/2D (montecarlo.dart:524-551): scrambled
+// (0,2)-sequence values, a Fisher-Yates shuffle inside every block of nSamples and one across the
+// nPixel blocks (Shuffle, montecarlo.dart:294-303).  Values and swap targets are computed by all
+// lanes of the group (the stream is counter-based); the swaps themselves are order-dependent and run
+// on the group's first lane in shared memory; the result is written out by the whole group.
 __global__ void __launch_bounds__(128) samplerLDKernel(RenderParams rp, Wavefront wf, const SampleArray* __restrict__ arrays,
-                                                       int nArrays, int maxVals, int maxOthers, PixelBatch pb) {
+                                                       int nArrays, int maxVals, int maxOthers, PixelBatch pb, int G) {
   extern __shared__ float smem[];
-  const int warpsPerBlock = blockDim.x >> 5, warpInBlock = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* buf = smem + (size_t)warpInBlock * (maxVals + maxOthers);
+  const uint32_t groupsPerBlock = blockDim.x / G, grp = threadIdx.x / G, gl = threadIdx.x % G;
+  float* buf = smem + (size_t)grp * ((maxVals + maxOthers) | 1);  // odd stride: groups start in different banks
   uint32_t* other = reinterpret_cast<uint32_t*>(buf + maxVals);
   const uint64_t nTasks = (uint64_t)pb.nPixels * nArrays;
   const uint32_t nP = (uint32_t)rp.nPixelSamples;
-  for (uint64_t task = (uint64_t)blockIdx.x * warpsPerBlock + warpInBlock; task < nTasks; task += (uint64_t)gridDim.x * warpsPerBlock) {
-    const uint32_t p = (uint32_t)(task / nArrays);
-    const SampleArray A = arrays[task % nArrays];
+  for (uint64_t t0 = (uint64_t)blockIdx.x * groupsPerBlock; t0 < nTasks; t0 += (uint64_t)gridDim.x * groupsPerBlock) {
+    const uint64_t task = t0 + grp;
+    const bool valid = task < nTasks;
+    const uint32_t p = valid ? (uint32_t)(task / nArrays) : 0u;
+    const SampleArray A = arrays[valid ? task % nArrays : 0];
     int x, y;
     pixelOf(pb, p, &x, &y);
     const uint64_t key = streamKey(rp.seed, x, y, 0, A.streamId);
-    const uint32_t nS = (uint32_t)A.nSamples, total = nS * nP, dims = (uint32_t)A.dims;
+    const uint32_t nS = (uint32_t)A.nSamples, total = valid ? nS * nP : 0u, dims = (uint32_t)A.dims;
     const uint32_t s0 = drawUint(key, 1), s1 = dims == 2 ? drawUint(key, 2) : 0u;
     const uint64_t base = dims;  // draws consumed by the scrambles
-    for (uint32_t i = lane; i < total; i += 32) {
+    for (uint32_t i = gl; i < total; i += G) {
       if (dims == 1) buf[i] = (float)VanDerCorput(i, s0);
       else { buf[2 * i] = (float)VanDerCorput(i, s0); buf[2 * i + 1] = (float)Sobol2(i, s1); }
     }
     if (nS > 1)
-      for (uint32_t e = lane; e < total; e += 32) {
+      for (uint32_t e = gl; e < total; e += G) {
         uint32_t k = e % nS;
         other[e] = k + drawUint(key, base + e + 1) % (nS - k);
       }
-    for (uint32_t i = lane; i < nP; i += 32) other[total + i] = i + drawUint(key, base + total + i + 1) % (nP - i);
+    if (valid)
+      for (uint32_t i = gl; i < nP; i += G) other[total + i] = i + drawUint(key, base + total + i + 1) % (nP - i);
     __syncwarp();
-    if (lane == 0) {
+    if (gl == 0 && valid) {
       if (nS > 1)
         for (uint32_t blk = 0; blk < nP; ++blk)
           for (uint32_t k = 0; k < nS; ++k) {
@@ -109,15 +113,17 @@ __global__ void __launch_bounds__(128) samplerLDKernel(RenderParams rp, Wavefron
     __syncwarp();
     const uint32_t bs = nS * dims;
     const uint32_t slot0 = p * nP;
-    if (A.dest >= 0) {
-      for (uint32_t qv = 0; qv < bs; ++qv)
-        for (uint32_t i = lane; i < nP; i += 32) wf.vals[(size_t)(A.dest + qv) * wf.cap + slot0 + i] = buf[i * bs + qv];
-    } else if (A.dest == -1) {  // montecarlo.dart:452-453: imageX = xPos + sample (f64 sum of an int and a float32)
-      for (uint32_t i = lane; i < nP; i += 32) wf.camXY[slot0 + i] = make_double2(x + (double)buf[2 * i], y + (double)buf[2 * i + 1]);
-    } else if (A.dest == -2) {
-      for (uint32_t i = lane; i < nP; i += 32) wf.camLens[slot0 + i] = make_double2((double)buf[2 * i], (double)buf[2 * i + 1]);
-    } else {
-      for (uint32_t i = lane; i < nP; i += 32) wf.camTime[slot0 + i] = buf[i];
+    if (valid) {
+      if (A.dest >= 0) {
+        for (uint32_t qv = 0; qv < bs; ++qv)
+          for (uint32_t i = gl; i < nP; i += G) wf.vals[(size_t)(A.dest + qv) * wf.cap + slot0 + i] = buf[i * bs + qv];
+      } else if (A.dest == -1) {  // montecarlo.dart:452-453: imageX = xPos + sample (f64 sum of an int and a float32)
+        for (uint32_t i = gl; i < nP; i += G) wf.camXY[slot0 + i] = make_double2(x + (double)buf[2 * i], y + (double)buf[2 * i + 1]);
+      } else if (A.dest == -2) {
+        for (uint32_t i = gl; i < nP; i += G) wf.camLens[slot0 + i] = make_double2((double)buf[2 * i], (double)buf[2 * i + 1]);
+      } else {
+        for (uint32_t i = gl; i < nP; i += G) wf.camTime[slot0 + i] = buf[i];
+      }
     }
     __syncwarp();
   }
@@ -657,16 +663,17 @@ cudaError_t launchSampler(const RenderParams& rp, const Wavefront& wf, const Sam
   if (pb.nPixels == 0) return cudaSuccess;
   if (rp.samplerKind == 0) {
     const int block = 128;
-    const size_t smem = (size_t)(block / 32) * (maxVals + maxOthers) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    // lanes per (pixel, array) task: about four values per lane, so small pixel-sample counts do not idle a warp
+    int G = 1;
+    while (G < 32 && G * 4 < maxVals) G <<= 1;
+    const size_t smem = (size_t)(block / G) * ((maxVals + maxOthers) | 1) * sizeof(float);
+    if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(samplerLDKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      configured = smem;
     }
     uint64_t tasks = (uint64_t)pb.nPixels * nArrays;
-    int grid = gridFor(tasks * 32, block, numSMs, 16);
-    samplerLDKernel<<<grid, block, smem, st>>>(rp, wf, dArrays, nArrays, maxVals, maxOthers, pb);
+    int grid = gridFor(tasks * G, block, numSMs, 16);
+    samplerLDKernel<<<grid, block, smem, st>>>(rp, wf, dArrays, nArrays, maxVals, maxOthers, pb, G);
   } else {
     samplerSeqKernel<<<(pb.nPixels + 127) / 128, 128, 0, st>>>(rp, wf, dArrays, nArrays, pb);
   }

@@ -1,0 +1,203 @@
+"""Pins the CPU oracle's render half (oracle/ref_render.cpp) with analytic known answers and sequence
+identities (SURVEY §8c "what pins results instead"): the reference ships no golden vectors, so these
+closed forms are what stands between the restatement and a silent mistake."""
+import math
+
+import numpy as np
+import pytest
+
+from dartray_b200 import host, scenes
+from tests.oracle_lib import Oracle, lib
+
+
+def _oracle(sb, cam, film, sampler, integ):
+    o = Oracle()
+    host.upload_scene(o, sb.arrays())
+    host.configure_render(o, cam, film, sampler, integ)
+    return o
+
+
+def _cam(pos=(0, 0, -5), look=(0, 0, 0), fov=40.0):
+    return host.PerspectiveCamera(host.look_at(pos, look, (0, 1, 0)), fov=fov)
+
+
+def _plane(sb, y=0.0, half=50.0, material=0, **kw):
+    # normal +y (triangle normal = normalize(cross(dpdu, dpdv)) with the reference's default uvs)
+    return sb.mesh([[-half, y, -half], [half, y, -half], [half, y, half], [-half, y, half]], [[0, 2, 1], [0, 3, 2]],
+                   material=material, **kw)
+
+
+# ---- sequences (montecarlo.dart:486-551) ----------------------------------------------------------------
+@pytest.mark.parametrize("mode", [host.RNG_KEYED, host.RNG_SERIAL])
+def test_ld_image_samples_form_a_02_net(mode):
+    sb, cam = scenes.cornell_synth()
+    o = _oracle(sb, cam, host.Film(16, 16), host.Sampler(kind=host.SAMPLER_LD, spp=16, rng_mode=mode),
+                host.Integrator(kind=host.INTEGRATOR_PATH))
+    s = o.pixel_samples(3, 5)
+    assert s.shape == (16, 5 + 14 + 18)  # path integrator: 14 one-D + 9 two-D arrays
+    assert (s >= 0).all() and (s < 1).all()
+    xy = s[:, :2].astype(np.float64)
+    for kx in range(5):  # every elementary interval 2^-kx x 2^-(4-kx) holds exactly one of the 16 points
+        ky = 4 - kx
+        cell = np.floor(xy[:, 0] * (1 << kx)).astype(int) * (1 << ky) + np.floor(xy[:, 1] * (1 << ky)).astype(int)
+        assert sorted(cell) == list(range(16)), (kx, ky)
+    # each 1D array is a scrambled van der Corput set: one point per 1/16 stratum
+    for col in range(5, 5 + 14):
+        assert sorted(np.floor(s[:, col] * 16).astype(int)) == list(range(16))
+
+
+def test_ld_rounds_pixel_samples_up_to_a_power_of_two():
+    sb, cam = scenes.cornell_synth()
+    o = _oracle(sb, cam, host.Film(8, 8), host.Sampler(kind=host.SAMPLER_LD, spp=5), host.Integrator(kind=host.INTEGRATOR_AO))
+    assert o.pixel_samples(0, 0).shape == (8, 5 + 2)  # AO requests nothing; the emission volume integrator asks for 2
+
+
+def test_stratified_samples_land_in_their_strata():
+    sb, cam = scenes.cornell_synth()
+    o = _oracle(sb, cam, host.Film(8, 8), host.Sampler(kind=host.SAMPLER_STRATIFIED, xs=4, ys=3),
+                host.Integrator(kind=host.INTEGRATOR_DIRECT))
+    s = o.pixel_samples(2, 1)
+    assert s.shape[0] == 12
+    ix, iy = np.floor(s[:, 0] * 4).astype(int), np.floor(s[:, 1] * 3).astype(int)
+    assert sorted(iy * 4 + ix) == list(range(12))  # image samples stay in stratum order (x fastest)
+    assert list(iy * 4 + ix) == list(range(12))
+    lens = np.floor(s[:, 2] * 4).astype(int) + 4 * np.floor(s[:, 3] * 3).astype(int)
+    assert sorted(lens) == list(range(12))         # lens samples are stratified then shuffled
+    assert sorted(np.floor(s[:, 4] * 12).astype(int)) == list(range(12))
+    assert s.max() <= np.float32(0.9999999403953552)  # ONE_MINUS_EPSILON clamp, montecarlo.dart:23
+    nj = _oracle(sb, cam, host.Film(8, 8), host.Sampler(kind=host.SAMPLER_STRATIFIED, xs=2, ys=2, jitter=False),
+                 host.Integrator(kind=host.INTEGRATOR_AO)).pixel_samples(0, 0)
+    assert np.allclose(np.sort(nj[:, 0]), [0.25, 0.25, 0.75, 0.75])
+
+
+def test_dart_random_restatement_is_deterministic_and_in_range():
+    L = lib()
+    f1, u1 = np.zeros(64), np.zeros(64, np.uint32)
+    f2, u2 = np.zeros(64), np.zeros(64, np.uint32)
+    L.orc_dart_random(5489, 64, f1.ctypes.data, u1.ctypes.data)
+    L.orc_dart_random(5489, 64, f2.ctypes.data, u2.ctypes.data)
+    assert np.array_equal(f1, f2) and np.array_equal(u1, u2)
+    assert (f1 >= 0).all() and (f1 < 1).all() and (u1 < 0xffffffff).all()
+    L.orc_dart_random(5490, 64, f2.ctypes.data, u2.ctypes.data)
+    assert not np.array_equal(f1, f2)
+    assert len(set(u1.tolist())) > 60
+
+
+# ---- integrators: closed forms ------------------------------------------------------------------------------
+def test_ambient_occlusion_open_plane_is_one_and_closed_box_is_zero():
+    sb = host.SceneBuilder()
+    _plane(sb, y=0.0)
+    cam = _cam(pos=(0, 3, -6), look=(0, 0, 0))
+    o = _oracle(sb, cam, host.Film(16, 12), host.Sampler(kind=host.SAMPLER_STRATIFIED, xs=1, ys=1, jitter=False),
+                host.Integrator(kind=host.INTEGRATOR_AO, ao_nsamples=32))
+    o.render()
+    f = o.film_read()
+    hit = f["rgb"][8:, :, 0]  # lower half of the image looks at the plane
+    assert np.allclose(hit, 1.0, rtol=0, atol=2e-6)  # RGB -> XYZ -> RGB through the film is not an exact identity
+    # inside a closed sphere every hemisphere ray is blocked
+    sb = host.SceneBuilder()
+    sb.sphere(host.translate(0, 0, 0), radius=4.0)
+    o = _oracle(sb, _cam(pos=(0, 0, -1)), host.Film(8, 8), host.Sampler(kind=host.SAMPLER_LD, spp=1),
+                host.Integrator(kind=host.INTEGRATOR_AO, ao_nsamples=16))
+    o.render()
+    assert (o.film_read()["rgb"] == 0.0).all()
+    assert o.render_stats()["shadow_rays"] == 81 * 16  # 9 x 9 sample extent, every camera ray hits
+
+
+def test_direct_lighting_point_light_on_a_matte_plane_closed_form():
+    kd, inten, h = 0.6, 50.0, 4.0
+    sb = host.SceneBuilder()
+    _plane(sb, y=0.0, material=sb.material((kd, kd, kd)))
+    sb.point_light((0.0, h, 0.0), (inten, inten, inten))
+    cam = _cam(pos=(0, 6, -8), look=(0, 0, 0), fov=30.0)
+    film = host.Film(33, 33)
+    o = _oracle(sb, cam, film, host.Sampler(kind=host.SAMPLER_STRATIFIED, xs=1, ys=1, jitter=False),
+                host.Integrator(kind=host.INTEGRATOR_DIRECT))
+    o.render()
+    rgb = o.film_read()["rgb"]
+    # the centre pixel looks at the origin: L = Kd/pi * I / h^2 * cos(0)
+    assert rgb[16, 16, 0] == pytest.approx(kd / math.pi * inten / (h * h), rel=2e-3)
+    # everywhere on the plane: L(x) = Kd/pi * I * h / (h^2 + r^2)^(3/2); check the image's maximum is at the centre
+    assert np.unravel_index(np.argmax(rgb[:, :, 0]), rgb.shape[:2]) == (16, 16)
+
+
+def test_direct_lighting_quad_light_matches_form_factor():
+    # unoccluded matte point under a parallel square light: L = Kd/pi * Le * integral(cos cos / r^2 dA)
+    kd, Le, h, a = 0.5, 10.0, 2.0, 1.0
+    sb = host.SceneBuilder()
+    _plane(sb, y=0.0, material=sb.material((kd, kd, kd)))
+    sb.mesh([[-a, h, -a], [a, h, -a], [a, h, a], [-a, h, a]], [[0, 1, 2], [0, 2, 3]], area_light=(Le, Le, Le), nsamples=16)
+    cam = _cam(pos=(0.2, 1.5, -0.2), look=(0, 0, 0), fov=1.0)  # narrow, steep view of the origin from under the light
+    o = _oracle(sb, cam, host.Film(4, 4), host.Sampler(kind=host.SAMPLER_LD, spp=64), host.Integrator(kind=host.INTEGRATOR_DIRECT))
+    o.render()
+    xs = (np.arange(400) + 0.5) / 400 * 2 * a - a
+    X, Z = np.meshgrid(xs, xs)
+    r2 = X * X + Z * Z + h * h
+    E = Le * np.sum((h * h) / (r2 * r2)) * (2 * a / 400) ** 2
+    assert o.film_read()["rgb"].mean() == pytest.approx(kd / math.pi * E, rel=1e-2)
+
+
+@pytest.mark.parametrize("rho,Le,maxdepth", [(0.5, 1.0, 5), (0.8, 2.0, 3)])
+def test_path_white_furnace(rho, Le, maxdepth):
+    # closed emissive matte sphere seen from inside: L = Le * sum_{k=0}^{maxdepth+1} rho^k
+    # (emission at the first vertex + one direct-lighting estimate per vertex, path_integrator.dart:44-119)
+    sb = host.SceneBuilder()
+    sb.sphere(host.translate(0, 0, 0), radius=5.0, material=sb.material((rho, rho, rho)), area_light=(Le, Le, Le), reverse=True)
+    o = _oracle(sb, _cam(pos=(0, 0, -1), fov=60.0), host.Film(24, 24), host.Sampler(kind=host.SAMPLER_LD, spp=32),
+                host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=maxdepth))
+    o.render()
+    expect = Le * sum(rho ** k for k in range(maxdepth + 2))
+    assert o.film_read()["rgb"].mean() == pytest.approx(expect, rel=3e-3)
+
+
+# ---- film (image_film.dart:99-185,247-299) -----------------------------------------------------------------
+def test_box_filter_weight_equals_sample_count_and_sample_extent():
+    sb, cam = scenes.cornell_synth()
+    o = _oracle(sb, cam, host.Film(20, 14), host.Sampler(kind=host.SAMPLER_LD, spp=4), host.Integrator(kind=host.INTEGRATOR_DIRECT))
+    o.render()
+    f = o.film_read()
+    assert (f["weight"] == 4.0).all()
+    assert o.render_stats()["camera_samples"] == 21 * 15 * 4  # sample extent is one pixel wider and taller
+    o2 = _oracle(sb, cam, host.Film(20, 14, filter="gaussian"), host.Sampler(kind=host.SAMPLER_LD, spp=4),
+                 host.Integrator(kind=host.INTEGRATOR_DIRECT))
+    o2.render()
+    assert o2.render_stats()["camera_samples"] == 25 * 19 * 4  # width-2 filter: floor(.5-2) .. ceil(.5+w+2)
+    g = o2.film_read()
+    assert g["rgb"].shape == (14, 20, 3) and np.isfinite(g["rgb"]).all()
+    assert abs(g["rgb"].mean() - f["rgb"].mean()) < 0.1 * f["rgb"].mean()  # blur at a 20 x 14 image border
+
+
+def test_filter_tables_match_their_closed_forms():
+    for name, centre in (("box", 1.0), ("triangle", (2 - 1 / 16) ** 2), ("gaussian", None), ("mitchell", None), ("sinc", None)):
+        xw, yw, t = host.filter_table(name)
+        assert t.shape == (256,) and np.isfinite(t).all()
+        assert np.allclose(t.reshape(16, 16), t.reshape(16, 16).T)  # separable and symmetric in x/y
+        if centre is not None:
+            assert t[0] == pytest.approx(centre, rel=1e-6)
+    assert host.filter_table("gaussian")[2][255] >= 0.0
+
+
+def test_tasks_cover_the_sample_extent_once():
+    sb, cam = scenes.cornell_synth()
+    film, sampler, integ = host.Film(30, 22), host.Sampler(kind=host.SAMPLER_LD, spp=2), host.Integrator(kind=host.INTEGRATOR_DIRECT)
+    whole = _oracle(sb, cam, film, sampler, integ)
+    whole.render()
+    parts = _oracle(sb, cam, film, sampler, integ)
+    for t in range(4):
+        parts.render(t, 4, 2)
+    a, b = whole.film_read(), parts.film_read()
+    assert np.array_equal(a["weight"], b["weight"])
+    assert np.allclose(a["xyz"], b["xyz"], rtol=1e-5, atol=1e-6)
+
+
+def test_keyed_and_serial_streams_agree_statistically():
+    # The GPU replays KEYED streams; the reference runs one SERIAL stream.  Same estimator, different
+    # random numbers: image means agree within Monte Carlo noise.
+    sb, cam = scenes.cornell_synth()
+    means = []
+    for mode in (host.RNG_KEYED, host.RNG_SERIAL):
+        o = _oracle(sb, cam, host.Film(48, 36), host.Sampler(kind=host.SAMPLER_LD, spp=16, rng_mode=mode),
+                    host.Integrator(kind=host.INTEGRATOR_PATH))
+        o.render(0, 1, 8)
+        means.append(o.film_read()["rgb"].mean(axis=(0, 1)))
+    assert np.allclose(means[0], means[1], rtol=0.02)
