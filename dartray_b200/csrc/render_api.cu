@@ -371,7 +371,7 @@ static int prepare(drt_ctx* c, RenderState* r) {
   int rc = ensureFilm(c, r);
   if (rc != DRT_OK) return rc;
   if (p.samplerKind == 0) {
-    size_t smem = 4 * (size_t)(r->maxVals + r->maxOthers) * sizeof(float);  // G = 32: four tasks per block
+    size_t smem = 4 * (size_t)(r->maxVals | 1) * sizeof(float);  // G = 32: four tasks per block
     if (smem > 200 * 1024) return fail(c, DRT_E_INVALID, "lowdiscrepancy sampler: pixelsamples x light nsamples too large for one warp's shared memory");
   }
   return DRT_OK;

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include <algorithm>
 #include <cstdint>
 
 #include "render_kernels.h"
@@ -50,18 +51,17 @@ static __device__ __forceinline__ void pixelOf(const PixelBatch& pb, uint32_t p,
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Low-discrepancy sampler: one group of G lanes (G = 1..32, a power of two chosen from the array
-// size) per (pixel, array).  LDShuffleScrambled1D/2D (montecarlo.dart:524-551): scrambled
-// (0,2)-sequence values, a Fisher-Yates shuffle inside every block of nSamples and one across the
-// nPixel blocks (Shuffle, montecarlo.dart:294-303).  Values and swap targets are computed by all
-// lanes of the group (the stream is counter-based); the swaps themselves are order-dependent and run
-// on the group's first lane in shared memory; the result is written out by the whole group.
+// Low-discrepancy sampler: one group of G lanes (G = 1..32, a power of two chosen so that a block's
+// arrays fit in shared memory) per (pixel, array).  LDShuffleScrambled1D/2D (montecarlo.dart:524-551):
+// scrambled (0,2)-sequence values, a Fisher-Yates shuffle inside every block of nSamples and one
+// across the nPixel blocks (Shuffle, montecarlo.dart:294-303).  Values are computed and written out by
+// all lanes of the group; the swaps are order-dependent and run on the group's first lane in shared
+// memory (the stream is counter-based, so every swap target is drawn in place).
 __global__ void __launch_bounds__(128) samplerLDKernel(RenderParams rp, Wavefront wf, const SampleArray* __restrict__ arrays,
-                                                       int nArrays, int maxVals, int maxOthers, PixelBatch pb, int G) {
+                                                       int nArrays, int maxVals, PixelBatch pb, int G) {
   extern __shared__ float smem[];
   const uint32_t groupsPerBlock = blockDim.x / G, grp = threadIdx.x / G, gl = threadIdx.x % G;
-  float* buf = smem + (size_t)grp * ((maxVals + maxOthers) | 1);  // odd stride: groups start in different banks
-  uint32_t* other = reinterpret_cast<uint32_t*>(buf + maxVals);
+  float* buf = smem + (size_t)grp * (maxVals | 1);  // odd stride: groups start in different banks
   const uint64_t nTasks = (uint64_t)pb.nPixels * nArrays;
   const uint32_t nP = (uint32_t)rp.nPixelSamples;
   for (uint64_t t0 = (uint64_t)blockIdx.x * groupsPerBlock; t0 < nTasks; t0 += (uint64_t)gridDim.x * groupsPerBlock) {
@@ -79,29 +79,23 @@ __global__ void __launch_bounds__(128) samplerLDKernel(RenderParams rp, Wavefron
       if (dims == 1) buf[i] = (float)VanDerCorput(i, s0);
       else { buf[2 * i] = (float)VanDerCorput(i, s0); buf[2 * i + 1] = (float)Sobol2(i, s1); }
     }
-    if (nS > 1)
-      for (uint32_t e = gl; e < total; e += G) {
-        uint32_t k = e % nS;
-        other[e] = k + drawUint(key, base + e + 1) % (nS - k);
-      }
-    if (valid)
-      for (uint32_t i = gl; i < nP; i += G) other[total + i] = i + drawUint(key, base + total + i + 1) % (nP - i);
     __syncwarp();
     if (gl == 0 && valid) {
       if (nS > 1)
         for (uint32_t blk = 0; blk < nP; ++blk)
           for (uint32_t k = 0; k < nS; ++k) {
-            uint32_t o = other[blk * nS + k];
+            const uint32_t e = blk * nS + k;
+            const uint32_t o = k + drawUint(key, base + e + 1) % (nS - k);
             if (o != k)
               for (uint32_t j = 0; j < dims; ++j) {
-                float a = buf[(blk * nS + k) * dims + j];
-                buf[(blk * nS + k) * dims + j] = buf[(blk * nS + o) * dims + j];
+                float a = buf[e * dims + j];
+                buf[e * dims + j] = buf[(blk * nS + o) * dims + j];
                 buf[(blk * nS + o) * dims + j] = a;
               }
           }
       const uint32_t bs = nS * dims;
       for (uint32_t i = 0; i < nP; ++i) {
-        uint32_t o = other[total + i];
+        const uint32_t o = i + drawUint(key, base + nS * nP + i + 1) % (nP - i);
         if (o != i)
           for (uint32_t j = 0; j < bs; ++j) {
             float a = buf[i * bs + j];
@@ -287,7 +281,10 @@ static __device__ __forceinline__ void pushDirectWork(const Wavefront& wf, uint3
 
 // ---------------------------------------------------------------------------------------------------
 // Path integrator, one vertex (path_integrator.dart:44-119 loop body for `bounces` = bounce).
-__global__ void __launch_bounds__(128) shadePathKernel(RenderParams rp, RenderScene rs, Wavefront wf, int bounce, int cur,
+#ifndef DRT_SHADE_MIN_BLOCKS
+#define DRT_SHADE_MIN_BLOCKS 4  // 128 registers: 16 warps/SM; 321 vs 277 Msamples/s at 2 (tools/shade_sweep.sh)
+#endif
+__global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(RenderParams rp, RenderScene rs, Wavefront wf, int bounce, int cur,
                                                        RenderCounters* rc) {
   const uint32_t n = wf.counts[cur], cap = wf.cap;
   const int nxt = cur ^ 1;
@@ -663,17 +660,20 @@ cudaError_t launchSampler(const RenderParams& rp, const Wavefront& wf, const Sam
   if (pb.nPixels == 0) return cudaSuccess;
   if (rp.samplerKind == 0) {
     const int block = 128;
-    // lanes per (pixel, array) task: about four values per lane, so small pixel-sample counts do not idle a warp
+    // lanes per (pixel, array) task: as few as shared memory allows (48 KB of arrays per block), because the
+    // order-dependent shuffle runs on one lane per task
+    const size_t taskBytes = (size_t)(maxVals | 1) * sizeof(float);
+    int tasksPerBlock = (int)std::min<size_t>(block, std::max<size_t>(4, (48 * 1024) / taskBytes));
     int G = 1;
-    while (G < 32 && G * 4 < maxVals) G <<= 1;
-    const size_t smem = (size_t)(block / G) * ((maxVals + maxOthers) | 1) * sizeof(float);
+    while (block / G > tasksPerBlock) G <<= 1;
+    const size_t smem = (size_t)(block / G) * taskBytes;
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(samplerLDKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
     }
     uint64_t tasks = (uint64_t)pb.nPixels * nArrays;
     int grid = gridFor(tasks * G, block, numSMs, 16);
-    samplerLDKernel<<<grid, block, smem, st>>>(rp, wf, dArrays, nArrays, maxVals, maxOthers, pb, G);
+    samplerLDKernel<<<grid, block, smem, st>>>(rp, wf, dArrays, nArrays, maxVals, pb, G);
   } else {
     samplerSeqKernel<<<(pb.nPixels + 127) / 128, 128, 0, st>>>(rp, wf, dArrays, nArrays, pb);
   }

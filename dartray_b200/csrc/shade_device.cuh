@@ -321,7 +321,10 @@ static __device__ inline void hitGeometry(const RenderScene& rs, uint32_t prim, 
 
 // Shape.intersect on one shape with an explicit interval (ShapeSet / Shape.pdf2 use it directly,
 // shape_set.dart:65-79, shape.dart:100-121)
-static __device__ inline bool shapeIntersect(const RenderScene& rs, uint32_t prim, const V3& o, const V3& d, double mint,
+#ifndef DRT_SHAPE_INLINE
+#define DRT_SHAPE_INLINE inline  // measured on B200 (tools/shade_sweep.sh): inlined + 4 CTAs/SM is fastest
+#endif
+static __device__ DRT_SHAPE_INLINE bool shapeIntersect(const RenderScene& rs, uint32_t prim, const V3& o, const V3& d, double mint,
                                              double maxt, ShapeHit* h) {
   V3 dpdv;
   if (prim < rs.ntris) {
