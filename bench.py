@@ -106,6 +106,86 @@ def config_dict(n_gpus):
     }
 
 
+# ---- render legs (BASELINE.json configs[2] and configs[3]) ------------------------------------------------
+RENDER_RES = (1920, 1080)
+AO_RAYS = 64
+PATH_SPP = 256
+
+
+def render_configs():
+    from dartray_b200 import host
+    ao = (host.Sampler(kind=host.SAMPLER_STRATIFIED, xs=1, ys=1, jitter=False),
+          host.Integrator(kind=host.INTEGRATOR_AO, ao_nsamples=AO_RAYS))
+    path = (host.Sampler(kind=host.SAMPLER_LD, spp=PATH_SPP), host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=5))
+    return ao, path
+
+
+def render_legs(ctx_soup, rank, world, barrier):
+    """configs[2]: ambient occlusion on soup_1m; configs[3]: cornell_synth path tracing, 256 spp.  Pixels are
+    sharded over the ranks (interleaved 1024-pixel blocks), the films summed with NCCL; timed as the blocking
+    C-ABI call (wall clock between barriers, max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    from dartray_b200 import capi, distributed, host, scenes
+
+    dev = torch.device("cuda", ctx_soup.device)
+    out = {}
+    (ao_s, ao_i), (pt_s, pt_i) = render_configs()
+    cam_soup = host.PerspectiveCamera(host.look_at((0, 0, -4), (0, 0, 0), (0, 1, 0)), fov=40.0)
+    sb, cam_cornell = scenes.cornell_synth()
+    ctx_c = capi.Context(ctx_soup.device)
+    host.upload_scene(ctx_c, sb.arrays())
+    legs = [("ao", ctx_soup, cam_soup, ao_s, ao_i), ("path", ctx_c, cam_cornell, pt_s, pt_i)]
+    for name, ctx, cam, smp, integ in legs:
+        film = host.Film(*RENDER_RES)
+        warm = host.Sampler(kind=smp.kind, spp=min(smp.spp, 16), xs=smp.xs, ys=smp.ys, jitter=smp.jitter)
+        host.configure_render(ctx, cam, film, warm, integ)
+        distributed.render_sharded(ctx, rank, world)  # warm-up: allocations, first launches, NCCL channel
+        host.configure_render(ctx, cam, film, smp, integ)
+        ctx.film_clear()
+        l0 = ctx.kernel_launches
+        barrier()
+        t0 = time.perf_counter()
+        distributed.render_sharded(ctx, rank, world)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        st = ctx.render_stats()
+        cnt = torch.tensor([st["camera_samples"], st["closest_rays"], st["shadow_rays"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        sec = float(dt.item())
+        samples, closest, shadow = (float(v) for v in cnt.tolist())
+        rgb = ctx.film_read()["rgb"]
+        out[name] = {"seconds": sec, "camera_samples": int(samples), "samples_per_s": samples / sec,
+                     "mrays_per_s": (closest + shadow) / sec / 1e6, "closest_rays": int(closest), "shadow_rays": int(shadow),
+                     "launches_rank0": int(ctx.kernel_launches - l0), "mean_rgb": [float(v) for v in rgb.mean(axis=(0, 1))]}
+    out["ao"]["config"] = (f"BASELINE.json configs[2]: soup_1m, {RENDER_RES[0]}x{RENDER_RES[1]}, 1 camera sample/pixel at the "
+                           f"pixel centre, {AO_RAYS} AO rays per hit")
+    out["path"]["config"] = (f"BASELINE.json configs[3]: cornell_synth, {RENDER_RES[0]}x{RENDER_RES[1]}, lowdiscrepancy "
+                             f"{PATH_SPP} spp, path maxdepth 5, box filter; pixel blocks sharded over {world} GPU(s), film "
+                             "summed with NCCL")
+    out["timing"] = "wall clock of the blocking drt_render_shard + film all-reduce, between barriers, max over ranks"
+    return out
+
+
+def cpu_render_sample(threads):
+    """The oracle on a bounded sample of configs[3]: a 240x135 film of the same camera at 16 spp."""
+    from dartray_b200 import host, scenes
+    from tests.oracle_lib import Oracle
+    sb, cam = scenes.cornell_synth()
+    o = Oracle()
+    host.upload_scene(o, sb.arrays())
+    host.configure_render(o, cam, host.Film(240, 135), host.Sampler(kind=host.SAMPLER_LD, spp=16),
+                          host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=5))
+    t0 = time.perf_counter()
+    o.render(0, 1, threads)
+    dt = time.perf_counter() - t0
+    st = o.render_stats()
+    return {"path_samples_per_s": st["camera_samples"] / dt, "path_mrays_per_s": (st["closest_rays"] + st["shadow_rays"]) / dt / 1e6,
+            "sample": f"cornell_synth 240x135, 16 spp, maxdepth 5 ({st['camera_samples']} camera samples, {dt:.1f} s)"}
+
+
 def reference_arm(args):
     """CPU restatement of the reference path (oracle/), all host threads, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -134,7 +214,8 @@ def reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus),
         "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample,
-                         "note": "C++ restatement of the DartRay CPU path (oracle/), not the Dart VM: no Dart SDK in the image"},
+                         "note": "C++ restatement of the DartRay CPU path (oracle/), not the Dart VM: no Dart SDK in the image",
+                         "render": cpu_render_sample(threads)},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -147,6 +228,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-render", action="store_true", help="skip the configs[2]/[3] render legs")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -162,6 +244,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: dartray_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -257,6 +340,8 @@ def main():
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_val = world * rays_per_step * e2e_steps / float(e2e_t.item()) / 1e6
 
+    render = None if args.no_render else render_legs(ctx, rank, world, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -296,6 +381,8 @@ def main():
         "clocks": clocks.summary(),
         "bvh": {"nodes": info["n_nodes"], "device_bytes": info["device_bytes"], "build_seconds": info["build_seconds"]},
     }
+    if render is not None:
+        line["render"] = render
     if not args.no_cpu_baseline:
         from tests.oracle_lib import Oracle
         threads = os.cpu_count() or 1
@@ -310,6 +397,8 @@ def main():
             "sample": f"every {n_coh // cs[0].shape[0]}-th ray of each set ({r} rays, {dt:.1f} s)",
             "note": "C++ restatement of the DartRay CPU path (oracle/), not the Dart VM: no Dart SDK in the image",
         }
+        if render is not None:
+            line["cpu_baseline"]["render"] = cpu_render_sample(threads)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
