@@ -266,7 +266,7 @@ struct Flattener {
     std::memset(&g, 0, sizeof(g));
     for (int k = 0; k < 4; ++k) {
       g.ref[k] = DRT_REF_EMPTY;
-      for (int a = 0; a < 3; ++a) { g.box[k][a] = 0.f; g.box[k][3 + a] = 0.f; }
+      for (int a = 0; a < 6; ++a) g.box[k][a] = 0.f;
     }
     g.axisP = n.axis;
     g.refNode = refIndexOf[t];
@@ -280,8 +280,10 @@ struct Flattener {
       else { kids[0] = side.left; kids[1] = side.right; nk = 2; (sIdx == 0 ? g.axisA : g.axisB) = side.axis; }
       for (int k = 0; k < nk; ++k) {
         const TNode& c = pool[kids[k]];
-        std::memcpy(&g.box[base + k][0], c.box.lo, 12);
-        std::memcpy(&g.box[base + k][3], c.box.hi, 12);
+        for (int a = 0; a < 3; ++a) {  // (lo, hi) pairs per axis: one packed f32x2 operand each
+          g.box[base + k][2 * a] = c.box.lo[a];
+          g.box[base + k][2 * a + 1] = c.box.hi[a];
+        }
         g.ref[base + k] = emitWide(kids[k], refIndexOf);
       }
     }

@@ -48,7 +48,7 @@ static_assert(sizeof(GNode) == 64, "GNode must be 64 bytes");
 // stored: a child box that passes the slab test implies its parent box passes (monotone rounding,
 // DESIGN.md), so skipping them cannot change which leaves are tested.
 struct alignas(16) GNode4 {
-  float box[4][6];   // per slot: min.xyz, max.xyz
+  float box[4][6];   // per slot: (min.x, max.x), (min.y, max.y), (min.z, max.z) — each pair is one f32x2 operand
   int32_t ref[4];    // child reference or DRT_REF_EMPTY
   int32_t axisP, axisA, axisB;
   int32_t refNode;   // reference node number of P (debug/export)

@@ -37,14 +37,18 @@ namespace drt {
 #ifndef DRT_MIN_BLOCKS
 #define DRT_MIN_BLOCKS 5
 #endif
+#ifndef DRT_SMEM_STACK
+#define DRT_SMEM_STACK 24  // stack entries per thread kept in shared memory (24 KB per 128-thread CTA)
+#endif
 #ifndef DRT_LEAF_BATCH
 #define DRT_LEAF_BATCH 16  // lanes holding an untested leaf before the warp runs the exact leaf phase
 #endif
 
 // Hot per-ray state, kept in registers (never address-taken: the exact helpers take it by value).
 struct FastRay {
-  float ox, oy, oz;  // ray.origin
-  float ix, iy, iz;  // invDir: (float)(1.0 / (double)d), bvh_accel.dart:109-111
+  // ray.origin and invDir = (float)(1.0 / (double)d) (bvh_accel.dart:109-111), each value duplicated into both
+  // halves of an f32x2 operand
+  unsigned long long ox2, oy2, oz2, ix2, iy2, iz2;
   float mintLo, mintHi, maxtLo, maxtHi;  // float32 brackets of the f64 interval ends
   double mint, maxt;
   unsigned negMask;  // bit a = invDir[a] < 0 (dirIsNeg, bvh_accel.dart:113-115); bit 3 = "slow" ray
@@ -58,12 +62,35 @@ struct StackEntry {
 #define DRT_EPS 2.384185791015625e-07f  // 2^-22
 #define DRT_TINY 1.0e-37f
 
-// 0 = the reference surely rejects the box, 1 = it surely accepts it, 2 = not provable in float32.
-static __device__ __forceinline__ int slabFilter(const FastRay& r, const float lox, const float loy, const float loz,
-                                                 const float hix, const float hiy, const float hiz, float* tminOut) {
-  float t0x = (lox - r.ox) * r.ix, t1x = (hix - r.ox) * r.ix;
-  float t0y = (loy - r.oy) * r.iy, t1y = (hiy - r.oy) * r.iy;
-  float t0z = (loz - r.oz) * r.iz, t1z = (hiz - r.oz) * r.iz;
+// Blackwell packed float32 arithmetic (FADD2 / FMUL2): both lanes are IEEE round-to-nearest, i.e. the
+// same values two scalar instructions give.
+static __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+static __device__ __forceinline__ void ldg256(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+static __device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
+static __device__ __forceinline__ void slabPair(unsigned long long box, unsigned long long o2, unsigned long long i2, float* t0,
+                                                float* t1) {
+  unsigned long long d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(box), "l"(o2));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(d), "l"(i2));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(*t0), "=f"(*t1) : "l"(d));
+}
+
+// Float32 image of the reference's slab test on one box given as three (lo, hi) pairs.
+// Returns 0 = the reference surely rejects the box, 1 = it surely accepts it, 2 = not provable in float32.
+static __device__ __forceinline__ int slabFilter(const FastRay& r, unsigned long long bx, unsigned long long by,
+                                                 unsigned long long bz, float* tminOut) {
+  float t0x, t1x, t0y, t1y, t0z, t1z;
+  slabPair(bx, r.ox2, r.ix2, &t0x, &t1x);
+  slabPair(by, r.oy2, r.iy2, &t0y, &t1y);
+  slabPair(bz, r.oz2, r.iz2, &t0z, &t1z);
   float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
   float tmax = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
   float dmin = fmaf(DRT_EPS, fabsf(tmin), DRT_TINY), dmax = fmaf(DRT_EPS, fabsf(tmax), DRT_TINY);
@@ -90,16 +117,17 @@ static __device__ __noinline__ bool slabExact(float ox, float oy, float oz, floa
 }
 
 // One slot of a wide node: conservative for interior children, exact-or-marked for leaf children.
-// Returns whether to visit; may mark a leaf reference "undecided".
-static __device__ __forceinline__ bool testSlot(const FastRay& r, int32_t& ref, const float lox, const float loy,
-                                                const float loz, const float hix, const float hiy, const float hiz,
-                                                float* tmin) {
-  if (ref == DRT_REF_EMPTY) return false;
-  if (r.negMask & 8u)  // slow ray: exact decision for every box
-    return slabExact(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, r.mint, r.maxt, lox, loy, loz, hix, hiy, hiz, tmin);
-  int c = slabFilter(r, lox, loy, loz, hix, hiy, hiz, tmin);
-  if (c == 2 && ref < 0) ref = refMarkUndecided(ref);
-  return c != 0;
+// Returns the reference to visit (a leaf reference possibly marked "undecided") or DRT_REF_EMPTY.
+static __device__ __forceinline__ int32_t testSlot(const FastRay& r, int32_t ref, const float2 bx, const float2 by,
+                                                   const float2 bz, float* tmin) {
+  if (r.negMask & 8u) {  // slow ray (warp-divergent, rare): exact decision for every box
+    if (ref == DRT_REF_EMPTY) return ref;
+    return slabExact(lo32(r.ox2), lo32(r.oy2), lo32(r.oz2), lo32(r.ix2), lo32(r.iy2), lo32(r.iz2), r.mint, r.maxt, bx.x, by.x, bz.x, bx.y, by.y, bz.y, tmin) ? ref
+                                                                                                                  : DRT_REF_EMPTY;
+  }
+  int c = slabFilter(r, pack2(bx.x, bx.y), pack2(by.x, by.y), pack2(bz.x, bz.y), tmin);
+  int32_t marked = (c == 2 && ref < 0) ? refMarkUndecided(ref) : ref;  // an EMPTY slot is positive: never marked
+  return c != 0 ? marked : DRT_REF_EMPTY;
 }
 
 // Pops until an entry survives the reference's pop-time test `tmin < ray.maxDistance`
@@ -110,8 +138,9 @@ static __device__ __forceinline__ bool testSlot(const FastRay& r, int32_t& ref, 
     ok = false;                                                                     \
     while (sp > 0) {                                                                \
       --sp;                                                                         \
-      int32_t ref_ = stack[sp].ref;                                                 \
-      float t_ = stack[sp].tmin;                                                    \
+      const uint2 e_ = STACK_LOAD(sp);                                              \
+      int32_t ref_ = (int32_t)e_.x;                                                 \
+      float t_ = __uint_as_float(e_.y);                                             \
       float dt_ = fmaf(DRT_EPS, fabsf(t_), DRT_TINY);                               \
       if ((t_ - dt_) >= r.maxtHi) continue; /* surely culled */                     \
       if (!((t_ + dt_) < r.maxtLo) && ref_ < 0) ref_ = refMarkUndecided(ref_);      \
@@ -123,18 +152,29 @@ static __device__ __forceinline__ bool testSlot(const FastRay& r, int32_t& ref, 
 
 template <bool ANY>
 __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
-    traceFastKernel(TraceScene sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD, uint64_t n,
-                    float4* __restrict__ hits, uint8_t* __restrict__ occluded, unsigned long long* __restrict__ nextRay,
+    traceFastKernel(TraceScene sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD, uint32_t n,
+                    float4* __restrict__ hits, uint8_t* __restrict__ occluded, unsigned int* __restrict__ nextRay,
                     TraceExtras ex) {
   const unsigned lane = threadIdx.x & 31u;
   if (ex.nDev) n = *ex.nDev;  // wavefront queues: the ray count lives in device memory
   const unsigned ltMask = (1u << lane) - 1u;
-  unsigned long long warpNext = 0, warpEnd = 0;  // warp-uniform: the chunk of rays this warp owns
+  uint32_t warpNext = 0, warpEnd = 0;  // warp-uniform: the chunk of rays this warp owns (launches hold < 2^31 rays)
   bool exhausted = false;                        // warp-uniform: the global counter ran past n
   bool alive = false;
-  unsigned long long rayIdx = 0;
+  uint32_t rayIdx = 0;
   FastRay r;
-  StackEntry stack[100];  // <= 3 pushes per wide level, <= 32 wide levels (binary depth < 64)
+  // Traversal stack: the first DRT_SMEM_STACK entries of every thread live in shared memory, laid out
+  // [entry][thread] so that a warp's accesses are bank-conflict free whatever the lanes' depths; deeper
+  // entries (rare) overflow to local memory.  <= 3 pushes per wide level, <= 32 wide levels.
+  extern __shared__ uint2 smStack[];
+  uint2 deepStack[104 - DRT_SMEM_STACK];
+#define STACK_STORE(i, refv, tv)                                                                   \
+  do {                                                                                             \
+    const uint2 e__ = make_uint2((unsigned)(refv), __float_as_uint(tv));                           \
+    if ((i) < DRT_SMEM_STACK) smStack[(i) * 128 + threadIdx.x] = e__;                              \
+    else deepStack[(i) - DRT_SMEM_STACK] = e__;                                                    \
+  } while (0)
+#define STACK_LOAD(i) ((i) < DRT_SMEM_STACK ? smStack[(i) * 128 + threadIdx.x] : deepStack[(i) - DRT_SMEM_STACK])
   int sp = 0;
   int32_t cur = 0;
   float hb1 = 0.f, hb2 = 0.f;
@@ -157,8 +197,8 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
     unsigned dead = __ballot_sync(FULL_MASK, !alive);
     if (dead) {
       if (warpNext == warpEnd && !exhausted) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(nextRay, (unsigned long long)RAY_CHUNK);
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(nextRay, (unsigned)RAY_CHUNK);
         base = __shfl_sync(FULL_MASK, base, 0);
         if (base >= n) {
           exhausted = true;
@@ -173,10 +213,10 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
       if (!alive && rank < avail) {
         rayIdx = warpNext + rank;
         float4 o = __ldg(rayO + rayIdx), d = __ldg(rayD + rayIdx);
-        r.ox = o.x; r.oy = o.y; r.oz = o.z;
-        r.ix = __double2float_rn(1.0 / (double)d.x);
-        r.iy = __double2float_rn(1.0 / (double)d.y);
-        r.iz = __double2float_rn(1.0 / (double)d.z);
+        const float ix = __double2float_rn(1.0 / (double)d.x), iy = __double2float_rn(1.0 / (double)d.y),
+                    iz = __double2float_rn(1.0 / (double)d.z);
+        r.ox2 = pack2(o.x, o.x); r.oy2 = pack2(o.y, o.y); r.oz2 = pack2(o.z, o.z);
+        r.ix2 = pack2(ix, ix); r.iy2 = pack2(iy, iy); r.iz2 = pack2(iz, iz);
         if (ex.range) {  // renderer rays: the reference's f64 minDistance / maxDistance (ray.dart:34-36)
           double2 mm = __ldg(ex.range + rayIdx);
           r.mint = mm.x; r.mintLo = __double2float_rd(mm.x); r.mintHi = __double2float_ru(mm.x);
@@ -187,9 +227,9 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
           r.maxt = d.w;
           r.maxtLo = r.maxtHi = d.w;
         }
-        bool slow = !(fabsf(r.ox) <= 3.0e38f) || !(fabsf(r.oy) <= 3.0e38f) || !(fabsf(r.oz) <= 3.0e38f) ||
-                    !(fabsf(r.ix) <= 3.0e38f) || !(fabsf(r.iy) <= 3.0e38f) || !(fabsf(r.iz) <= 3.0e38f);
-        r.negMask = (r.ix < 0.f ? 1u : 0u) | (r.iy < 0.f ? 2u : 0u) | (r.iz < 0.f ? 4u : 0u) | (slow ? 8u : 0u);
+        bool slow = !(fabsf(o.x) <= 3.0e38f) || !(fabsf(o.y) <= 3.0e38f) || !(fabsf(o.z) <= 3.0e38f) ||
+                    !(fabsf(ix) <= 3.0e38f) || !(fabsf(iy) <= 3.0e38f) || !(fabsf(iz) <= 3.0e38f);
+        r.negMask = (ix < 0.f ? 1u : 0u) | (iy < 0.f ? 2u : 0u) | (iz < 0.f ? 4u : 0u) | (slow ? 8u : 0u);
         sp = 0;
         found = false;
         hprim = -1;
@@ -209,41 +249,42 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
     }
 
     // ---- one wide-node step for every lane that holds an interior node --------------------------
+    bool needPop = false;
     if (alive && cur >= 0) {
-      const float4* nd = reinterpret_cast<const float4*>(sc.wide + cur);
-      float4 q0 = __ldg(nd + 0), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3), q4 = __ldg(nd + 4),
-             q5 = __ldg(nd + 5);
-      int4 qr = __ldg(reinterpret_cast<const int4*>(nd + 6));
-      int4 qa = __ldg(reinterpret_cast<const int4*>(nd + 7));
+      // the 128-byte node in four 256-bit loads (LDG.E.256, sm_100): half the L1 requests of 128-bit loads
+      const GNode4* nd = sc.wide + cur;
+      float4 q0, q1, q2, q3, q4, q5;
+      int4 qr, qa;
+      ldg256(reinterpret_cast<const float*>(nd), q0, q1);
+      ldg256(reinterpret_cast<const float*>(nd) + 8, q2, q3);
+      ldg256(reinterpret_cast<const float*>(nd) + 16, q4, q5);
+      {
+        float4 fr, fa;
+        ldg256(reinterpret_cast<const float*>(nd) + 24, fr, fa);
+        qr = make_int4(__float_as_int(fr.x), __float_as_int(fr.y), __float_as_int(fr.z), __float_as_int(fr.w));
+        qa = make_int4(__float_as_int(fa.x), __float_as_int(fa.y), __float_as_int(fa.z), __float_as_int(fa.w));
+      }
       float t0, t1, t2, t3;
-      int32_t r0 = qr.x, r1 = qr.y, r2 = qr.z, r3 = qr.w;
-      bool p0 = testSlot(r, r0, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &t0);
-      bool p1 = testSlot(r, r1, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &t1);
-      bool p2 = testSlot(r, r2, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, &t2);
-      bool p3 = testSlot(r, r3, q4.z, q4.w, q5.x, q5.y, q5.z, q5.w, &t3);
-      // visiting order of the reference's depth-first walk (bvh_accel.dart:147-153)
+      // slot k: (lo.x, hi.x) (lo.y, hi.y) (lo.z, hi.z), six consecutive floats
+      int32_t r0 = testSlot(r, qr.x, make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y), &t0);
+      int32_t r1 = testSlot(r, qr.y, make_float2(q1.z, q1.w), make_float2(q2.x, q2.y), make_float2(q2.z, q2.w), &t1);
+      int32_t r2 = testSlot(r, qr.z, make_float2(q3.x, q3.y), make_float2(q3.z, q3.w), make_float2(q4.x, q4.y), &t2);
+      int32_t r3 = testSlot(r, qr.w, make_float2(q4.z, q4.w), make_float2(q5.x, q5.y), make_float2(q5.z, q5.w), &t3);
+      // visiting order of the reference's depth-first walk (bvh_accel.dart:147-153), branch-free
       const bool sA = ((r.negMask >> qa.y) & 1u) != 0, sB = ((r.negMask >> qa.z) & 1u) != 0,
                  sP = ((r.negMask >> qa.x) & 1u) != 0;
-      if (sA) { int32_t tr = r0; r0 = r1; r1 = tr; float tt = t0; t0 = t1; t1 = tt; bool tp = p0; p0 = p1; p1 = tp; }
-      if (sB) { int32_t tr = r2; r2 = r3; r3 = tr; float tt = t2; t2 = t3; t3 = tt; bool tp = p2; p2 = p3; p3 = tp; }
-      if (sP) {
-        int32_t tr = r0; r0 = r2; r2 = tr; tr = r1; r1 = r3; r3 = tr;
-        float tt = t0; t0 = t2; t2 = tt; tt = t1; t1 = t3; t3 = tt;
-        bool tp = p0; p0 = p2; p2 = tp; tp = p1; p1 = p3; p3 = tp;
-      }
-      // first passing slot becomes current, the later ones are pushed so that they pop in order
-      if (p3 && (p0 || p1 || p2)) { stack[sp].ref = r3; stack[sp].tmin = t3; sp++; }
-      if (p2 && (p0 || p1)) { stack[sp].ref = r2; stack[sp].tmin = t2; sp++; }
-      if (p1 && p0) { stack[sp].ref = r1; stack[sp].tmin = t1; sp++; }
-      if (p0) cur = r0;
-      else if (p1) cur = r1;
-      else if (p2) cur = r2;
-      else if (p3) cur = r3;
-      else {
-        bool ok;
-        POP_NEXT(ok);
-        if (!ok) RETIRE();
-      }
+      const int32_t a0 = sA ? r1 : r0, a1 = sA ? r0 : r1, b0 = sB ? r3 : r2, b1 = sB ? r2 : r3;
+      const float ta0 = sA ? t1 : t0, ta1 = sA ? t0 : t1, tb0 = sB ? t3 : t2, tb1 = sB ? t2 : t3;
+      const int32_t s0 = sP ? b0 : a0, s1 = sP ? b1 : a1, s2 = sP ? a0 : b0, s3 = sP ? a1 : b1;
+      const float u1 = sP ? tb1 : ta1, u2 = sP ? ta0 : tb0, u3 = sP ? ta1 : tb1;
+      const bool v0 = s0 != DRT_REF_EMPTY, v1 = s1 != DRT_REF_EMPTY, v2 = s2 != DRT_REF_EMPTY, v3 = s3 != DRT_REF_EMPTY;
+      // the first passing slot becomes current; the later ones are pushed so that they pop in order.
+      // Stores are unconditional, the stack pointer moves only for real pushes.
+      STACK_STORE(sp, s3, u3); sp += (v3 && (v0 || v1 || v2)) ? 1 : 0;
+      STACK_STORE(sp, s2, u2); sp += (v2 && (v0 || v1)) ? 1 : 0;
+      STACK_STORE(sp, s1, u1); sp += (v1 && v0) ? 1 : 0;
+      cur = v0 ? s0 : (v1 ? s1 : (v2 ? s2 : s3));
+      needPop = !(v0 || v1 || v2 || v3);
     }
 
     // ---- exact leaf phase, batched: run it when enough lanes wait on a leaf, or nobody can walk ----
@@ -281,7 +322,7 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
             }
           }
           float tt;
-          boxOk = slabExact(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, r.mint, r.maxt, lo0, lo1, lo2, hi0, hi1, hi2, &tt);
+          boxOk = slabExact(lo32(r.ox2), lo32(r.oy2), lo32(r.oz2), lo32(r.ix2), lo32(r.iy2), lo32(r.iz2), r.mint, r.maxt, lo0, lo1, lo2, hi0, hi1, hi2, &tt);
         }
         bool stop = false;
         for (uint32_t k = 0; boxOk && k < cnt && !stop; ++k) {
@@ -314,45 +355,63 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
           r.maxtLo = __double2float_rd(rs.maxt);
           r.maxtHi = __double2float_ru(rs.maxt);
         }
-        if (ANY && found) {
-          RETIRE();
-        } else {
-          bool ok;
-          POP_NEXT(ok);
-          if (!ok) RETIRE();
-        }
+        if (ANY && found) RETIRE();
+        else needPop = true;
       }
+    }
+
+    // ---- next stack entry for every lane that finished a node without a child or a leaf ----------
+    if (alive && needPop) {
+      bool ok;
+      POP_NEXT(ok);
+      if (!ok) RETIRE();
     }
   }
 #undef RETIRE
+}
+
+static cudaError_t launchOne(const TraceScene& sc, bool any, const float4* o, const float4* d, uint32_t n, bool nUnknown, void* out,
+                             unsigned long long* nextRay, int numSMs, cudaStream_t stream, const TraceExtras& ex) {
+  cudaError_t e = cudaMemsetAsync(nextRay, 0, sizeof(unsigned long long), stream);
+  if (e != cudaSuccess) return e;
+  const int block = 128;
+  const size_t smem = (size_t)DRT_SMEM_STACK * block * sizeof(uint2);
+  static int perSm[2] = {0, 0};
+  if (!perSm[any ? 1 : 0]) {
+    int b = 0;
+    e = any ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, traceFastKernel<true>, block, smem)
+            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, traceFastKernel<false>, block, smem);
+    if (e != cudaSuccess) return e;
+    perSm[any ? 1 : 0] = b > 0 ? b : 1;
+  }
+  uint64_t want = nUnknown ? ~0ull >> 8 : ((uint64_t)n + RAY_CHUNK - 1) / RAY_CHUNK;  // one warp per chunk is enough
+  uint64_t blocksWanted = (want + 3) / 4;
+  uint64_t persistent = (uint64_t)numSMs * perSm[any ? 1 : 0];  // one resident wave: persistent warps
+  dim3 grid((unsigned)(blocksWanted < persistent ? blocksWanted : persistent));
+  unsigned int* ctr = reinterpret_cast<unsigned int*>(nextRay);
+  if (any) traceFastKernel<true><<<grid, block, smem, stream>>>(sc, o, d, n, nullptr, (uint8_t*)out, ctr, ex);
+  else traceFastKernel<false><<<grid, block, smem, stream>>>(sc, o, d, n, (float4*)out, nullptr, ctr, ex);
+  return cudaGetLastError();
 }
 
 cudaError_t launchTraceFast(const TraceScene& sc, bool any, const void* rayO, const void* rayD, uint64_t n, void* out,
                             unsigned long long* nextRay, int numSMs, cudaStream_t stream, const TraceExtras* extras) {
   TraceExtras ex{};
   if (extras) ex = *extras;
-  if (n == 0 && !ex.nDev) return cudaSuccess;
-  if (ex.nDev) n = ~0ull >> 8;  // unknown on the host: launch the full persistent grid
-  cudaError_t e = cudaMemsetAsync(nextRay, 0, sizeof(unsigned long long), stream);
-  if (e != cudaSuccess) return e;
-  const int block = 128;
-  static int perSm[2] = {0, 0};
-  if (!perSm[any ? 1 : 0]) {
-    int b = 0;
-    e = any ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, traceFastKernel<true>, block, 0)
-            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, traceFastKernel<false>, block, 0);
-    if (e != cudaSuccess) return e;
-    perSm[any ? 1 : 0] = b > 0 ? b : 1;
-  }
-  uint64_t want = (n + RAY_CHUNK - 1) / RAY_CHUNK;  // one warp per chunk is enough
-  uint64_t blocksWanted = (want + 3) / 4;
-  uint64_t persistent = (uint64_t)numSMs * perSm[any ? 1 : 0];  // one resident wave: persistent warps
-  dim3 grid((unsigned)(blocksWanted < persistent ? blocksWanted : persistent));
   const float4* o = static_cast<const float4*>(rayO);
   const float4* d = static_cast<const float4*>(rayD);
-  if (any) traceFastKernel<true><<<grid, block, 0, stream>>>(sc, o, d, n, nullptr, (uint8_t*)out, nextRay, ex);
-  else traceFastKernel<false><<<grid, block, 0, stream>>>(sc, o, d, n, (float4*)out, nullptr, nextRay, ex);
-  return cudaGetLastError();
+  if (ex.nDev) return launchOne(sc, any, o, d, 0, true, out, nextRay, numSMs, stream, ex);  // count lives on the device (< 2^31)
+  const uint64_t kMax = 1ull << 30;  // rays per launch: 32-bit ray indices inside the kernel
+  for (uint64_t first = 0; first < n; first += kMax) {
+    const uint32_t m = (uint32_t)(n - first < kMax ? n - first : kMax);
+    TraceExtras e2 = ex;
+    if (e2.range) e2.range += first;
+    if (e2.tOut) e2.tOut += first;
+    void* o2 = any ? (void*)((uint8_t*)out + first) : (void*)((float4*)out + first);
+    cudaError_t e = launchOne(sc, any, o + first, d + first, m, false, o2, nextRay, numSMs, stream, e2);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 }  // namespace drt
