@@ -33,7 +33,9 @@
 namespace drt {
 
 #define FULL_MASK 0xffffffffu
-#define RAY_CHUNK 256  // rays a warp reserves per atomicAdd on the global ray counter
+#ifndef RAY_CHUNK
+#define RAY_CHUNK 64  // measured on B200: 64 beats 128 / 256 (shorter tail, tools/variant_sweep.sh)
+#endif  // rays a warp reserves per atomicAdd on the global ray counter
 #ifndef DRT_MIN_BLOCKS
 #define DRT_MIN_BLOCKS 5
 #endif
@@ -167,6 +169,7 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
   // [entry][thread] so that a warp's accesses are bank-conflict free whatever the lanes' depths; deeper
   // entries (rare) overflow to local memory.  <= 3 pushes per wide level, <= 32 wide levels.
   extern __shared__ uint2 smStack[];
+  float* smDir = reinterpret_cast<float*>(smStack + DRT_SMEM_STACK * 128);  // [3][128]: ray.direction, read by the leaf phase
   uint2 deepStack[104 - DRT_SMEM_STACK];
 #define STACK_STORE(i, refv, tv)                                                                   \
   do {                                                                                             \
@@ -205,6 +208,18 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
         } else {
           warpNext = base;
           warpEnd = (base + RAY_CHUNK) < n ? (base + RAY_CHUNK) : n;
+#ifndef DRT_NO_RAY_PREFETCH
+          // the chunk's ray records (2 x 16 B per ray) are streamed from HBM: start them towards L1 now so
+          // that the lane-by-lane refills below do not each wait for DRAM
+          {
+            const uint32_t linesPerArray = (RAY_CHUNK * 16 + 127) / 128;
+            if (lane < 2 * linesPerArray) {
+              const float4* basePtr = (lane < linesPerArray ? rayO : rayD) + base;
+              const char* pf = reinterpret_cast<const char*>(basePtr) + 128 * (lane % linesPerArray);
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+            }
+          }
+#endif
         }
       }
       unsigned avail = (unsigned)(warpEnd - warpNext);
@@ -215,6 +230,7 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
         float4 o = __ldg(rayO + rayIdx), d = __ldg(rayD + rayIdx);
         const float ix = __double2float_rn(1.0 / (double)d.x), iy = __double2float_rn(1.0 / (double)d.y),
                     iz = __double2float_rn(1.0 / (double)d.z);
+        smDir[threadIdx.x] = d.x; smDir[128 + threadIdx.x] = d.y; smDir[256 + threadIdx.x] = d.z;
         r.ox2 = pack2(o.x, o.x); r.oy2 = pack2(o.y, o.y); r.oz2 = pack2(o.z, o.z);
         r.ix2 = pack2(ix, ix); r.iy2 = pack2(iy, iy); r.iz2 = pack2(iz, iz);
         if (ex.range) {  // renderer rays: the reference's f64 minDistance / maxDistance (ray.dart:34-36)
@@ -296,10 +312,9 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
         uint32_t off = refLeafOffset(cur), cnt = refLeafCountField(cur);
         const GPrim* pr = sc.prims + off;
         if (cnt == 15u) cnt = (uint32_t)__ldg(&pr->leafCount);
-        float4 o = __ldg(rayO + rayIdx), d = __ldg(rayD + rayIdx);  // direction is only needed here
-        RayState rs;
-        rs.ox = o.x; rs.oy = o.y; rs.oz = o.z;
-        rs.dx = d.x; rs.dy = d.y; rs.dz = d.z;
+        RayState rs;  // origin from the packed registers, direction from shared memory (only needed here)
+        rs.ox = lo32(r.ox2); rs.oy = lo32(r.oy2); rs.oz = lo32(r.oz2);
+        rs.dx = smDir[threadIdx.x]; rs.dy = smDir[128 + threadIdx.x]; rs.dz = smDir[256 + threadIdx.x];
         rs.mint = r.mint; rs.maxt = r.maxt;
         bool boxOk = true;
         if (refLeafUndecided(cur)) {
@@ -375,7 +390,7 @@ static cudaError_t launchOne(const TraceScene& sc, bool any, const float4* o, co
   cudaError_t e = cudaMemsetAsync(nextRay, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
   const int block = 128;
-  const size_t smem = (size_t)DRT_SMEM_STACK * block * sizeof(uint2);
+  const size_t smem = (size_t)DRT_SMEM_STACK * block * sizeof(uint2) + 3 * block * sizeof(float);
   static int perSm[2] = {0, 0};
   if (!perSm[any ? 1 : 0]) {
     int b = 0;
