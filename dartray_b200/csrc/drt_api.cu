@@ -51,10 +51,17 @@ drt_ctx* drt_create(int device_id) {
   c->device = device_id;
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
-      (e = c->dCounters.ensure(1)) != cudaSuccess || (e = c->dNextRay.ensure(1)) != cudaSuccess ||
+      (e = c->dCounters.ensure(1)) != cudaSuccess || (e = c->dNextRay.ensure(1 + drt_ctx::kPipe)) != cudaSuccess ||
       (e = cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, device_id)) != cudaSuccess) {
     g_createError = cudaGetErrorString(e);
     delete c;
+    return nullptr;
+  }
+  for (int i = 0; i < drt_ctx::kPipe && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking);
+  for (int i = 0; i < 2 * drt_ctx::kMaxChunks && e == cudaSuccess; ++i) e = cudaEventCreate(&c->chunkEv[i]);
+  if (e != cudaSuccess) {
+    g_createError = cudaGetErrorString(e);
+    drt_destroy(c);
     return nullptr;
   }
   return c;
@@ -70,6 +77,8 @@ void drt_destroy(drt_ctx* c) {
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
+  for (int i = 0; i < drt_ctx::kPipe; ++i) if (c->pipe[i]) cudaStreamDestroy(c->pipe[i]);
+  for (int i = 0; i < 2 * drt_ctx::kMaxChunks; ++i) if (c->chunkEv[i]) cudaEventDestroy(c->chunkEv[i]);
   delete c;
 }
 
@@ -277,7 +286,8 @@ int drt_bvh_export(const drt_ctx* c, float* bounds, int32_t* offset, int32_t* np
 }
 
 
-static int traceDevice(drt_ctx* c, bool any, const void* o, const void* d, uint64_t n, void* out, cudaStream_t st) {
+static int traceDevice(drt_ctx* c, bool any, const void* o, const void* d, uint64_t n, void* out, cudaStream_t st,
+                       int counterSlot = 0) {
   if (c->device == DRT_DEVICE_NONE) return fail(c, DRT_E_NODEVICE, kNoDevice);
   if (!c->built) return fail(c, DRT_E_STATE, "drt_build_bvh must be called before tracing");
   if (n && (!o || !d || !out)) return fail(c, DRT_E_INVALID, "null ray or output buffer");
@@ -286,7 +296,7 @@ static int traceDevice(drt_ctx* c, bool any, const void* o, const void* d, uint6
     if (c->counting) CK(c, cudaMemsetAsync(c->dCounters.p, 0, sizeof(DeviceCounters), st));
     CK(c, launchTrace(c->ts, any, c->counting, o, d, n, out, c->dCounters.p, st));
   } else {
-    CK(c, launchTraceFast(c->ts, any, o, d, n, out, c->dNextRay.p, c->numSMs, st));
+    CK(c, launchTraceFast(c->ts, any, o, d, n, out, c->dNextRay.p + counterSlot, c->numSMs, st));
   }
   if (n) c->launches++;
   return DRT_OK;
@@ -303,19 +313,34 @@ static int traceHost(drt_ctx* c, bool any, const float* o, const float* d, uint6
   CK(c, c->dRayD.ensure(n));
   if (any) CK(c, c->dOcc.ensure(n));
   else CK(c, c->dHits.ensure(n));
-  cudaStream_t st = c->stream;
-  CK(c, cudaMemcpyAsync(c->dRayO.p, o, n * 16, cudaMemcpyHostToDevice, st));
-  CK(c, cudaMemcpyAsync(c->dRayD.p, d, n * 16, cudaMemcpyHostToDevice, st));
-  CK(c, cudaEventRecord(c->ev0, st));
   void* dout = any ? (void*)c->dOcc.p : (void*)c->dHits.p;
-  int rc = traceDevice(c, any, c->dRayO.p, c->dRayD.p, n, dout, st);
-  if (rc != DRT_OK) return rc;
-  CK(c, cudaEventRecord(c->ev1, st));
-  CK(c, cudaMemcpyAsync(out, dout, n * (any ? 1 : sizeof(drt_hit_rec)), cudaMemcpyDeviceToHost, st));
-  CK(c, cudaStreamSynchronize(st));
-  float ms = 0.f;
-  CK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-  c->lastKernelMs = ms;
+  const size_t outSize = any ? 1 : sizeof(drt_hit_rec);
+  // Chunks of >= 1 Mi rays, at most kMaxChunks, round-robin over the pipeline streams: with pinned host buffers
+  // the upload of the next chunk and the download of the previous one overlap the traversal of this one.
+  uint64_t chunk = 1ull << 20;
+  if ((n + chunk - 1) / chunk > (uint64_t)drt_ctx::kMaxChunks) chunk = (n + drt_ctx::kMaxChunks - 1) / drt_ctx::kMaxChunks;
+  if (c->counting || c->exactWalk) chunk = n;  // one launch: the counters describe the whole batch
+  int nChunks = 0;
+  for (uint64_t first = 0; first < n; first += chunk, ++nChunks) {
+    const uint64_t m = n - first < chunk ? n - first : chunk;
+    const int slot = nChunks % drt_ctx::kPipe;
+    cudaStream_t st = c->pipe[slot];
+    CK(c, cudaMemcpyAsync(c->dRayO.p + first, o + 4 * first, m * 16, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(c->dRayD.p + first, d + 4 * first, m * 16, cudaMemcpyHostToDevice, st));
+    CK(c, cudaEventRecord(c->chunkEv[2 * nChunks], st));
+    int rc = traceDevice(c, any, c->dRayO.p + first, c->dRayD.p + first, m, (char*)dout + first * outSize, st, 1 + slot);
+    if (rc != DRT_OK) return rc;
+    CK(c, cudaEventRecord(c->chunkEv[2 * nChunks + 1], st));
+    CK(c, cudaMemcpyAsync((char*)out + first * outSize, (char*)dout + first * outSize, m * outSize, cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < drt_ctx::kPipe; ++i) CK(c, cudaStreamSynchronize(c->pipe[i]));
+  double ms = 0.0;
+  for (int k = 0; k < nChunks; ++k) {
+    float t = 0.f;
+    CK(c, cudaEventElapsedTime(&t, c->chunkEv[2 * k], c->chunkEv[2 * k + 1]));
+    ms += t;
+  }
+  c->lastKernelMs = ms;  // sum of the chunks' launch-to-finish spans (they overlap copies of their neighbours)
   return DRT_OK;
 }
 
