@@ -103,7 +103,8 @@ static DRT_HD inline uint64_t mix64(uint64_t z) {
   return z ^ (z >> 31);
 }
 static DRT_HD inline uint64_t streamKey(uint64_t seed, int32_t x, int32_t y, uint32_t sampleIdx, uint32_t streamId) {
-  uint64_t k1 = mix64(seed ^ ((uint64_t)(uint32_t)x | ((uint64_t)(uint32_t)y << 32)));
+  // the seed is hashed before it meets the pixel, so that seeds s and s^1 do not merely swap neighbouring pixels' streams
+  uint64_t k1 = mix64(mix64(seed + 0x9E3779B97F4A7C15ull) ^ ((uint64_t)(uint32_t)x | ((uint64_t)(uint32_t)y << 32)));
   return mix64(k1 ^ ((uint64_t)sampleIdx | ((uint64_t)streamId << 32)) ^ 0xD1B54A32D192ED03ull);
 }
 #define DRT_STREAM_PIXEL 4095u

@@ -109,7 +109,8 @@ struct KeyedRng : Rng {
     return z ^ (z >> 31);
   }
   static uint64_t makeKey(uint64_t seed, int32_t x, int32_t y, uint32_t sampleIdx, uint32_t streamId) {
-    uint64_t k1 = mix(seed ^ ((uint64_t)(uint32_t)x | ((uint64_t)(uint32_t)y << 32)));
+    // the seed is hashed before it meets the pixel, so that seeds s and s^1 do not merely swap neighbouring pixels' streams
+    uint64_t k1 = mix(mix(seed + 0x9E3779B97F4A7C15ull) ^ ((uint64_t)(uint32_t)x | ((uint64_t)(uint32_t)y << 32)));
     return mix(k1 ^ ((uint64_t)sampleIdx | ((uint64_t)streamId << 32)) ^ 0xD1B54A32D192ED03ull);
   }
   KeyedRng() {}
