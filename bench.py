@@ -244,10 +244,20 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: dartray_b200 has no CPU fallback")
     torch.cuda.set_device(local)
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    if world > 1:
+        # stdout carries exactly one JSON line: NCCL prints its version banner to stdout when the communicator is
+        # created, so create it (first collective) with fd 1 pointing at stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
 
     P, idx, coh, inc = make_workload(rank)
     ctx = capi.Context(local)
