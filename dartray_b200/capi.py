@@ -19,7 +19,7 @@ HIT_DTYPE = np.dtype([("t", np.float32), ("b1", np.float32), ("b2", np.float32),
 
 # every symbol include/drt.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
-    "drt_version", "drt_create", "drt_destroy", "drt_last_error", "drt_set_triangles", "drt_set_spheres",
+    "drt_version", "drt_create", "drt_destroy", "drt_last_error", "drt_set_triangles", "drt_set_spheres", "drt_set_disks",
     "drt_set_build_order", "drt_build_bvh", "drt_bvh_info_get", "drt_bvh_export", "drt_trace_closest",
     "drt_trace_any", "drt_trace_closest_device", "drt_trace_any_device", "drt_set_counting", "drt_get_counters", "drt_set_kernel_variant",
     "drt_last_kernel_ms", "drt_kernel_launches",
@@ -73,6 +73,7 @@ def load():
     L.drt_last_error.argtypes = [vp]
     L.drt_set_triangles.argtypes = [vp, vp, u32, vp, u32, vp, vp, vp]
     L.drt_set_spheres.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
+    L.drt_set_disks.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
     L.drt_set_build_order.argtypes = [vp, vp, u32]
     L.drt_build_bvh.argtypes = [vp, i32, i32]
     L.drt_bvh_info_get.argtypes = [vp, C.POINTER(BvhInfo)]
@@ -157,6 +158,14 @@ class Context:
         params = _arr(params, np.float64).reshape(-1, 4)
         m, l, r = _arr(material, np.int32), _arr(light, np.int32), _arr(reverse, np.uint8)
         self._ck(self.L.drt_set_spheres(self.h, o2w.shape[0], _p(o2w), _p(w2o), _p(params), _p(m), _p(l), _p(r)))
+
+    def set_disks(self, o2w, w2o, params, material=None, light=None, reverse=None):
+        """params: n x 4 (height, radius, innerradius, phimax degrees); call after set_spheres."""
+        o2w = _arr(o2w, np.float32).reshape(-1, 16)
+        w2o = _arr(w2o, np.float32).reshape(-1, 16)
+        params = _arr(params, np.float64).reshape(-1, 4)
+        m, l, r = _arr(material, np.int32), _arr(light, np.int32), _arr(reverse, np.uint8)
+        self._ck(self.L.drt_set_disks(self.h, o2w.shape[0], _p(o2w), _p(w2o), _p(params), _p(m), _p(l), _p(r)))
 
     def set_build_order(self, order):
         if order is None:

@@ -115,9 +115,30 @@ int drt_set_spheres(drt_ctx* c, uint32_t n, const float* o2w, const float* w2o, 
     std::memcpy(s.o2w, o2w + 16 * i, 64);
     std::memcpy(s.w2o, w2o + 16 * i, 64);
     s.radius = prm[4 * i]; s.zmin = prm[4 * i + 1]; s.zmax = prm[4 * i + 2]; s.phiMaxDeg = prm[4 * i + 3];
+    s.shape = 0; s.height = 0.0; s.innerRadius = 0.0;
     if (mat) c->sphMat[i] = mat[i];
     if (light) c->sphLight[i] = light[i];
     if (rev) c->sphRev[i] = rev[i];
+  }
+  c->built = false;
+  return DRT_OK;
+}
+
+int drt_set_disks(drt_ctx* c, uint32_t n, const float* o2w, const float* w2o, const double* prm, const int32_t* mat,
+                  const int32_t* light, const uint8_t* rev) {
+  if (!c) return DRT_E_INVALID;
+  if (n && (!o2w || !w2o || !prm)) return fail(c, DRT_E_INVALID, "null disk arrays");
+  for (uint32_t i = 0; i < n; ++i) {  // appended to the quadric range, after the spheres
+    HostSphere s;
+    std::memcpy(s.o2w, o2w + 16 * i, 64);
+    std::memcpy(s.w2o, w2o + 16 * i, 64);
+    s.shape = 1;
+    s.height = prm[4 * i]; s.radius = prm[4 * i + 1]; s.innerRadius = prm[4 * i + 2]; s.phiMaxDeg = prm[4 * i + 3];
+    s.zmin = s.zmax = s.height;
+    c->spheres.push_back(s);
+    c->sphMat.push_back(mat ? mat[i] : 0);
+    c->sphLight.push_back(light ? light[i] : -1);
+    c->sphRev.push_back(rev ? rev[i] : 0);
   }
   c->built = false;
   return DRT_OK;
@@ -180,11 +201,20 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
     std::memcpy(g.o2w, s.o2w, 48);
     std::memcpy(g.o2wRow3, s.o2w + 12, 16);
     g.radius = s.radius;  // sphere.dart:24-32
-    g.zmin = clampd(std::fmin(s.zmin, s.zmax), -s.radius, s.radius);
-    g.zmax = clampd(std::fmax(s.zmin, s.zmax), -s.radius, s.radius);
-    g.thetaMin = std::acos(clampd(g.zmin / s.radius, -1.0, 1.0));
-    g.thetaMax = std::acos(clampd(g.zmax / s.radius, -1.0, 1.0));
+    g.shape = s.shape;
+    g.pad_ = 0.f;
+    g.height = s.height;
+    g.innerRadius = s.innerRadius;
     g.phiMax = (3.141592653589793 / 180.0) * clampd(s.phiMaxDeg, 0.0, 360.0);
+    if (s.shape == 1) {  // disk.dart:24-35: object bound (-r, -r, h) .. (r, r, h)
+      g.zmin = g.zmax = s.height;
+      g.thetaMin = g.thetaMax = 0.0;
+    } else {
+      g.zmin = clampd(std::fmin(s.zmin, s.zmax), -s.radius, s.radius);
+      g.zmax = clampd(std::fmax(s.zmin, s.zmax), -s.radius, s.radius);
+      g.thetaMin = std::acos(clampd(g.zmin / s.radius, -1.0, 1.0));
+      g.thetaMax = std::acos(clampd(g.zmax / s.radius, -1.0, 1.0));
+    }
     float lo[3] = {(float)-s.radius, (float)-s.radius, (float)g.zmin}, hi[3] = {(float)s.radius, (float)s.radius, (float)g.zmax};
     PrimBounds& b = bounds[nt + i];
     for (int k = 0; k < 8; ++k) {  // transform.dart:163-178

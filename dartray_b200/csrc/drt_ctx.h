@@ -17,9 +17,11 @@ using namespace drt;
 
 static_assert(sizeof(drt_hit) == sizeof(drt_hit_rec), "hit record layout");
 
-struct HostSphere {
+struct HostSphere {  // a quadric: sphere (shape 0) or disk (shape 1: height, radius, innerRadius, phiMaxDeg)
   float o2w[16], w2o[16];
   double radius, zmin, zmax, phiMaxDeg;
+  int shape = 0;
+  double height = 0.0, innerRadius = 0.0;
 };
 
 template <class T>

@@ -69,7 +69,8 @@ struct alignas(16) GPrim {
 };
 static_assert(sizeof(GPrim) == 48, "GPrim must be 48 bytes");
 
-// sphere.dart:24-32: transforms are float32 matrices, the shape parameters are doubles.
+// sphere.dart:24-32: transforms are float32 matrices, the shape parameters are doubles.  The record also carries
+// the path's other quadric, Disk (disk.dart:24-31): shape == 1 with height / radius / innerRadius / phiMax.
 struct alignas(16) GSphere {
   float w2o[12];  // rows 0..2 of worldToObject (affine)
   float w2oRow3[4];
@@ -77,7 +78,9 @@ struct alignas(16) GSphere {
   float o2wRow3[4];
   double radius, zmin, zmax, phiMax, thetaMin, thetaMax;
   float wmin[3], wmax[3];  // world bound (sphere.dart:34-37 + shape.dart:38-40), = the leaf box of a 1-sphere leaf
-  float pad_[2];
+  int32_t shape;           // 0 sphere, 1 disk
+  float pad_;
+  double height, innerRadius;  // disk only
 };
 
 struct TraceScene {

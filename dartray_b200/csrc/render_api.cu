@@ -225,6 +225,15 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
         area = triArea(t);
       } else {  // sphere.dart:243-245 with the constructor's clamps (sphere.dart:24-32)
         const HostSphere& s = c->spheres[sh - nt];
+        if (s.shape == 1) {  // disk.dart:142-145
+          double phiMaxD = (DRT_PI / 180.0) * clampD(s.phiMaxDeg, 0.0, 360.0);
+          area = phiMaxD * 0.5 * (s.radius * s.radius - s.innerRadius * s.innerRadius);
+          a.push_back(area);
+          g.area += area;
+          shapes.push_back(sh);
+          areas.push_back(area);
+          continue;
+        }
         double zmin = clampD(std::fmin(s.zmin, s.zmax), -s.radius, s.radius), zmax = clampD(std::fmax(s.zmin, s.zmax), -s.radius, s.radius);
         double phiMax = (DRT_PI / 180.0) * clampD(s.phiMaxDeg, 0.0, 360.0);
         area = phiMax * s.radius * (zmax - zmin);

@@ -275,6 +275,44 @@ static DRT_HD inline bool sphereIntersectT(const GSphere& s, const V3& o, const 
   return true;
 }
 
+// disk.dart:39-67: tHit and the object-space hit point
+static DRT_HD inline bool diskIntersectT(const GSphere& s, const V3& o, const V3& d, double mint, double maxt, double* tOut,
+                                         V3* phitOut) {
+  float w2o[16];
+  for (int i = 0; i < 12; ++i) w2o[i] = s.w2o[i];
+  for (int i = 0; i < 4; ++i) w2o[12 + i] = s.w2oRow3[i];
+  V3 ro = XfPoint(w2o, o), rd = XfVector(w2o, d);
+  if (fabs((double)rd.z) < 1.0e-7) return false;
+  double thit = (s.height - ro.z) / rd.z;
+  if (thit < mint || thit > maxt) return false;
+  V3 phit = RayAt(ro, rd, thit);
+  double dist2 = (double)phit.x * phit.x + (double)phit.y * phit.y;
+  if (dist2 > s.radius * s.radius || dist2 < s.innerRadius * s.innerRadius) return false;
+  double phi = atan2((double)phit.y, (double)phit.x);
+  if (phi < 0) phi += 2.0 * DRT_PI;
+  if (phi > s.phiMax) return false;
+  *tOut = thit;
+  *phitOut = phit;
+  return true;
+}
+
+// disk.dart:69-97: p, dpdu, dpdv in world space from the object-space hit point
+static DRT_HD inline void diskPartials(const GSphere& s, const V3& phit, V3* p, V3* dpdu, V3* dpdv) {
+  float o2w[16];
+  for (int i = 0; i < 12; ++i) o2w[i] = s.o2w[i];
+  for (int i = 0; i < 4; ++i) o2w[12 + i] = s.o2wRow3[i];
+  double dist2 = (double)phit.x * phit.x + (double)phit.y * phit.y;
+  double oneMinusV = (sqrt(dist2) - s.innerRadius) / (s.radius - s.innerRadius);
+  double invOneMinusV = (oneMinusV > 0.0) ? (1.0 / oneMinusV) : 0.0;
+  V3 du = mkv(-s.phiMax * phit.y, s.phiMax * phit.x, 0.0);
+  V3 dv = mkv(-(double)phit.x * invOneMinusV, -(double)phit.y * invOneMinusV, 0.0);
+  du = du * (s.phiMax * 0.15915494309189533577);  // INV_TWOPI, common.dart:24
+  dv = dv * ((s.radius - s.innerRadius) / s.radius);
+  *p = XfPoint(o2w, phit);
+  *dpdu = XfVector(o2w, du);
+  *dpdv = XfVector(o2w, dv);
+}
+
 // sphere.dart:118-160: p, dpdu, dpdv in world space from the object-space hit point
 static DRT_HD inline void spherePartials(const GSphere& s, const V3& phit, V3* p, V3* dpdu, V3* dpdv) {
   float o2w[16];
@@ -313,9 +351,13 @@ static __device__ inline void hitGeometry(const RenderScene& rs, uint32_t prim, 
     for (int i = 0; i < 4; ++i) w2o[12 + i] = s.w2oRow3[i];
     V3 ro = XfPoint(w2o, o), rd = XfVector(w2o, d);
     V3 phit = RayAt(ro, rd, t);
-    if (phit.x == 0.0f && phit.y == 0.0f) phit.x = (float)(1.0e-5 * s.radius);
-    spherePartials(s, phit, &h->p, &h->dpdu, &dpdv);
-    h->rayEps = 5.0e-4 * t;  // sphere.dart:164
+    if (s.shape == 1) {
+      diskPartials(s, phit, &h->p, &h->dpdu, &dpdv);
+    } else {
+      if (phit.x == 0.0f && phit.y == 0.0f) phit.x = (float)(1.0e-5 * s.radius);
+      spherePartials(s, phit, &h->p, &h->dpdu, &dpdv);
+    }
+    h->rayEps = 5.0e-4 * t;  // sphere.dart:164, disk.dart:100
   }
   h->nn = shapeNormal(h->dpdu, dpdv, primReverse(rs, prim));
 }
@@ -340,8 +382,13 @@ static __device__ DRT_SHAPE_INLINE bool shapeIntersect(const RenderScene& rs, ui
     const GSphere& s = rs.ts.spheres[prim - rs.ntris];
     double t;
     V3 phit;
-    if (!sphereIntersectT(s, o, d, mint, maxt, &t, &phit)) return false;
-    spherePartials(s, phit, &h->p, &h->dpdu, &dpdv);
+    if (s.shape == 1) {
+      if (!diskIntersectT(s, o, d, mint, maxt, &t, &phit)) return false;
+      diskPartials(s, phit, &h->p, &h->dpdu, &dpdv);
+    } else {
+      if (!sphereIntersectT(s, o, d, mint, maxt, &t, &phit)) return false;
+      spherePartials(s, phit, &h->p, &h->dpdu, &dpdv);
+    }
     h->t = t;
     h->rayEps = 5.0e-4 * t;
   }
@@ -470,11 +517,22 @@ static __device__ inline V3 shapeSample2(const RenderScene& rs, uint32_t prim, c
     *ns = n;
     return pt;
   }
-  const GSphere& s = rs.ts.spheres[prim - rs.ntris];  // sphere.dart:261-297
+  const GSphere& s = rs.ts.spheres[prim - rs.ntris];
   const bool rev = primReverse(rs, prim);
   float o2w[16], w2o[16];
   for (int i = 0; i < 12; ++i) { o2w[i] = s.o2w[i]; w2o[i] = s.w2o[i]; }
   for (int i = 0; i < 4; ++i) { o2w[12 + i] = s.o2wRow3[i]; w2o[12 + i] = s.w2oRow3[i]; }
+  if (s.shape == 1) {  // shape.dart:96-98 -> disk.dart:147-159
+    double t0, t1;
+    ConcentricSampleDisk(u1, u2, &t0, &t1);
+    V3 pd = mkv(t0 * s.radius, t1 * s.radius, s.height);
+    V3 n = XfNormal(w2o, V3{0.f, 0.f, 1.f});
+    n = n / Length(n);
+    if (rev) n = n * -1.0;
+    *ns = n;
+    return XfPoint(o2w, pd);
+  }
+  // sphere.dart:261-297
   V3 Pcenter = XfPoint(o2w, V3{0.f, 0.f, 0.f});
   V3 wc = Normalize(Pcenter - p);
   V3 wcX, wcY;
@@ -502,7 +560,7 @@ static __device__ inline V3 shapeSample2(const RenderScene& rs, uint32_t prim, c
 }
 
 static __device__ inline double shapePdf2(const RenderScene& rs, uint32_t prim, double area, const V3& p, const V3& wi) {
-  if (prim >= rs.ntris) {  // sphere.dart:299-311
+  if (prim >= rs.ntris && rs.ts.spheres[prim - rs.ntris].shape == 0) {  // sphere.dart:299-311
     const GSphere& s = rs.ts.spheres[prim - rs.ntris];
     V3 Pcenter = sphereCenter(s);
     if (!(DistanceSquared(p, Pcenter) - s.radius * s.radius < 1.0e-4)) {

@@ -111,6 +111,32 @@ static __device__ bool sphereTest(const GSphere& s, const RayState& r, bool shad
                            double* vOut) {
   // transform.dart:110-145,180-195: object-space origin/direction are float32 Points/Vectors
   const float* m = s.w2o;
+  if (s.shape == 1) {  // Disk.intersect / intersectP, lib/shapes/disk.dart:39-75 / :107-140 (same decisions)
+    double ox = rf((double)m[0] * r.ox + (double)m[1] * r.oy + (double)m[2] * r.oz + (double)m[3]);
+    double oy = rf((double)m[4] * r.ox + (double)m[5] * r.oy + (double)m[6] * r.oz + (double)m[7]);
+    double oz = rf((double)m[8] * r.ox + (double)m[9] * r.oy + (double)m[10] * r.oz + (double)m[11]);
+    double w = (double)s.w2oRow3[0] * r.ox + (double)s.w2oRow3[1] * r.oy + (double)s.w2oRow3[2] * r.oz + (double)s.w2oRow3[3];
+    if (w != 1.0) { ox = rf(ox / w); oy = rf(oy / w); oz = rf(oz / w); }
+    double dx = rf((double)m[0] * r.dx + (double)m[1] * r.dy + (double)m[2] * r.dz);
+    double dy = rf((double)m[4] * r.dx + (double)m[5] * r.dy + (double)m[6] * r.dz);
+    double dz = rf((double)m[8] * r.dx + (double)m[9] * r.dy + (double)m[10] * r.dz);
+    if (fabs(dz) < 1.0e-7) return false;
+    double thit = (s.height - oz) / dz;
+    if (thit < r.mint || thit > r.maxt) return false;
+    double px = rf(ox + rf(dx * thit)), py = rf(oy + rf(dy * thit));
+    double dist2 = px * px + py * py;
+    if (dist2 > s.radius * s.radius || dist2 < s.innerRadius * s.innerRadius) return false;
+    double phi = atan2(py, px);
+    if (phi < 0) phi += 2.0 * 3.141592653589793;
+    if (phi > s.phiMax) return false;
+    *thitOut = thit;
+    if (uOut) {
+      double oneMinusV = (sqrt(dist2) - s.innerRadius) / (s.radius - s.innerRadius);
+      *uOut = phi / s.phiMax;
+      *vOut = 1.0 - oneMinusV;
+    }
+    return true;
+  }
   double ox = rf((double)m[0] * r.ox + (double)m[1] * r.oy + (double)m[2] * r.oz + (double)m[3]);
   double oy = rf((double)m[4] * r.ox + (double)m[5] * r.oy + (double)m[6] * r.oz + (double)m[7]);
   double oz = rf((double)m[8] * r.ox + (double)m[9] * r.oy + (double)m[10] * r.oz + (double)m[11]);

@@ -213,6 +213,7 @@ class SceneBuilder:
         self.P, self.idx = [], []
         self.tri_mat, self.tri_light, self.tri_rev = [], [], []
         self.sph = []  # (o2w, w2o, params, mat, light, rev)
+        self.dsk = []  # (o2w, w2o, (height, radius, innerradius, phimax), mat, light, rev)
         self.materials = []  # (kind, kd, sigma)
         self.lights = []  # dict(kind, L, pos, nsamples, shapes=[("tri"|"sph", local ids...)])
         self._order = []  # ("mesh", first_tri, ntris) | ("sphere", sphere_index)
@@ -266,8 +267,22 @@ class SceneBuilder:
         self._order.append(("sphere", k))
         return k
 
+    def disk(self, o2w, height=0.0, radius=1.0, innerradius=0.0, phimax=360.0, material=0, area_light=None, nsamples=1,
+             reverse=False) -> int:
+        """Shape "disk" (lib/shapes/disk.dart:157-166)."""
+        o2w = np.asarray(o2w, dtype=np.float32).reshape(4, 4)
+        light = -1
+        k = len(self.dsk)
+        if area_light is not None:
+            light = self._area_light(area_light, nsamples)
+            self.lights[light]["shapes"] = [("dsk", k)]
+        self.dsk.append((o2w, mat_inv(o2w), (height, radius, innerradius, phimax), material, light, 1 if reverse else 0))
+        self._order.append(("disk", k))
+        return k
+
     def arrays(self) -> dict:
         ntris = len(self.tri_mat)
+        nsph = len(self.sph)
         P = np.concatenate(self.P) if self.P else np.zeros((0, 3), np.float32)
         idx = np.concatenate(self.idx) if self.idx else np.zeros((0, 3), np.uint32)
         # refined order handed to BVHAccel: Primitive.fullyRefine is LIFO per primitive (primitive.dart:71-84)
@@ -275,11 +290,14 @@ class SceneBuilder:
         for item in self._order:
             if item[0] == "mesh":
                 order += list(range(item[1] + item[2] - 1, item[1] - 1, -1))
-            else:
+            elif item[0] == "sphere":
                 order.append(ntris + item[1])
+            else:
+                order.append(ntris + nsph + item[1])
         lights = []
+        base = {"tri": 0, "sph": ntris, "dsk": ntris + nsph}
         for l in self.lights:
-            shapes = [(s[1] if s[0] == "tri" else ntris + s[1]) for s in l["shapes"]]
+            shapes = [base[s[0]] + s[1] for s in l["shapes"]]
             lights.append(dict(kind=l["kind"], L=l["L"], pos=l["pos"], nsamples=l["nsamples"], shapes=shapes))
         mats = self.materials or [(0, (0.5, 0.5, 0.5), 0.0)]
         return dict(
@@ -290,6 +308,11 @@ class SceneBuilder:
             sph_params=np.asarray([s[2] for s in self.sph], np.float64).reshape(-1, 4),
             sph_mat=np.asarray([s[3] for s in self.sph], np.int32), sph_light=np.asarray([s[4] for s in self.sph], np.int32),
             sph_rev=np.asarray([s[5] for s in self.sph], np.uint8),
+            dsk_o2w=np.stack([s[0].reshape(16) for s in self.dsk]) if self.dsk else np.zeros((0, 16), np.float32),
+            dsk_w2o=np.stack([s[1].reshape(16) for s in self.dsk]) if self.dsk else np.zeros((0, 16), np.float32),
+            dsk_params=np.asarray([s[2] for s in self.dsk], np.float64).reshape(-1, 4),
+            dsk_mat=np.asarray([s[3] for s in self.dsk], np.int32), dsk_light=np.asarray([s[4] for s in self.dsk], np.int32),
+            dsk_rev=np.asarray([s[5] for s in self.dsk], np.uint8),
             order=np.asarray(order, np.uint32),
             mat_kind=np.asarray([m[0] for m in mats], np.int32), mat_kd=np.asarray([m[1] for m in mats], np.float32),
             mat_sigma=np.asarray([m[2] for m in mats], np.float32),
@@ -307,6 +330,8 @@ def upload_scene(ctx, arrays: dict, split: int = 2, max_node_prims: int = 4):
     a = arrays
     ctx.set_triangles(a["P"], a["idx"], a["tri_mat"], a["tri_light"], a["tri_rev"])
     ctx.set_spheres(a["sph_o2w"], a["sph_w2o"], a["sph_params"], a["sph_mat"], a["sph_light"], a["sph_rev"])
+    if a["dsk_params"].shape[0]:
+        ctx.set_disks(a["dsk_o2w"], a["dsk_w2o"], a["dsk_params"], a["dsk_mat"], a["dsk_light"], a["dsk_rev"])
     ctx.set_build_order(a["order"])
     ctx.build_bvh(split, max_node_prims)
     ctx.set_materials(a["mat_kind"], a["mat_kd"], a["mat_sigma"])

@@ -213,6 +213,47 @@ def cornell_synth():
     return sb, cam
 
 
+def cornell_path():
+    """web/scenes/cornell-path.pbrt:1-61 as shipped: disk area light (radius 3 at y = 9.9, rotated 90 degrees about x,
+    L = 36, nsamples 1, default matte Kd 0.5), five walls, the short box, the sphere.  Returns (SceneBuilder, camera);
+    the file's film is 320x240 with lowdiscrepancy 16 spp, BASELINE.json configs[0] overrides it to 256x256, 4 spp."""
+    from . import host
+
+    sb = host.SceneBuilder()
+    default = sb.material((0.5, 0.5, 0.5))  # matte_material.dart Create: Kd default 0.5
+    grey = sb.material((0.75, 0.75, 0.75))
+    red = sb.material((0.48, 0.1125, 0.075))
+    green = sb.material((0.1125, 0.375, 0.1125))
+    box = sb.material((0.48, 0.48, 0.48))
+    sb.disk(host.mat_mul(host.translate(0, 9.9, 0), host.rotate(90, (1, 0, 0))), radius=3.0, material=default,
+            area_light=(36.0, 36.0, 36.0), nsamples=1)
+    quad = [[0, 1, 2], [0, 2, 3]]
+    walls = [
+        (grey, [10, -10, -10, -10, -10, -10, -10, -10, 10, 10, -10, 10]),
+        (grey, [10, 10, -10, 10, 10, 10, -10, 10, 10, -10, 10, -10]),
+        (grey, [10, -10, 10, -10, -10, 10, -10, 10, 10, 10, 10, 10]),
+        (red, [-10, -10, 10, -10, -10, -10, -10, 10, -10, -10, 10, 10]),
+        (green, [10, -10, -10, 10, -10, 10, 10, 10, 10, 10, 10, -10]),
+    ]
+    for m, p in walls:
+        sb.mesh(np.asarray(p, np.float32).reshape(4, 3), quad, material=m)
+    o2w = host.mat_mul(host.mat_mul(host.translate(4, -7, 4), host.scale(0.3, 0.4, 0.3)), host.rotate(30, (0, 1, 0)))
+    rquad = [[0, 2, 1], [0, 3, 2]]
+    faces = [
+        (rquad, [10, -10, -10, -10, -10, -10, -10, -10, 10, 10, -10, 10]),
+        (rquad, [10, 10, -10, 10, 10, 10, -10, 10, 10, -10, 10, -10]),
+        (rquad, [10, -10, 10, -10, -10, 10, -10, 10, 10, 10, 10, 10]),
+        (rquad, [-10, -10, 10, -10, -10, -10, -10, 10, -10, -10, 10, 10]),
+        (rquad, [10, -10, -10, 10, -10, 10, 10, 10, 10, 10, 10, -10]),
+        (quad, [10, -10, -10, -10, -10, -10, -10, 10, -10, 10, 10, -10]),
+    ]
+    for q, p in faces:
+        sb.mesh(np.asarray(p, np.float32).reshape(4, 3), q, material=box, o2w=o2w)
+    sb.sphere(host.translate(-4, -4, 0), radius=3.0, material=box)
+    cam = host.PerspectiveCamera(host.look_at((0, 0, -35), (0, 0, 0), (0, 1, 0)), fov=35.0)
+    return sb, cam
+
+
 def soup_render_scene(n_spheres: int = 512):
     """`soup` as a renderable scene (config 3 / 5): grey matte, one quad light above, config-2 camera."""
     from . import host

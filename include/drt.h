@@ -18,7 +18,8 @@
  *   - there is NO CPU fallback: creating a context without a usable CUDA device fails.
  *
  * Primitive ids: the position in upload order — triangle k of drt_set_triangles is
- * id k, sphere j of drt_set_spheres is id ntris + j.  Every hit record reports this id.
+ * id k, sphere j of drt_set_spheres is id ntris + j, disk j of drt_set_disks is id ntris + nspheres + j.  Every hit
+ * record reports this id.
  */
 #ifndef DRT_H_
 #define DRT_H_
@@ -96,6 +97,12 @@ int drt_set_triangles(drt_ctx* ctx, const float* P, uint32_t nverts, const uint3
 int drt_set_spheres(drt_ctx* ctx, uint32_t n, const float* o2w, const float* w2o, const double* radius_zmin_zmax_phimax,
                     const int32_t* material_of_sphere, const int32_t* light_of_sphere,
                     const uint8_t* reverse_orientation_of_sphere);
+
+/* Replaces Disk construction (lib/shapes/disk.dart:24-31,157-166).  Disks join the spheres in one quadric id
+ * range: disk j is primitive ntris + nspheres + j, so call this AFTER drt_set_spheres (which resets the range).
+ * params: n x 4 doubles height, radius, innerradius, phimax(degrees) as ParamSet hands them to Disk.Create. */
+int drt_set_disks(drt_ctx* ctx, uint32_t n, const float* o2w, const float* w2o, const double* height_radius_inner_phimax,
+                  const int32_t* material_of_disk, const int32_t* light_of_disk, const uint8_t* reverse_orientation_of_disk);
 
 /* Order in which BVHAccel sees the refined primitives (a permutation of primitive ids).  The
  * reference's Primitive.fullyRefine is LIFO (lib/core/primitive.dart:71-84), so a mesh's triangles

@@ -84,6 +84,25 @@ int orc_set_spheres(orc_ctx* c, uint32_t n, const float* o2w, const float* w2o, 
   return 0;
 }
 
+// Disks (lib/shapes/disk.dart) share the quadric id range: they are appended after the spheres, so call this after
+// orc_set_spheres (which resets the range).  prm: n x 4 doubles height, radius, innerradius, phimax(degrees).
+int orc_set_disks(orc_ctx* c, uint32_t n, const float* o2w, const float* w2o, const double* prm, const int32_t* mat,
+                  const int32_t* light, const uint8_t* rev) {
+  Scene& s = c->scene;
+  uint32_t base = s.nprims();
+  s.materialOf.resize(base + n, 0);
+  s.lightOf.resize(base + n, -1);
+  s.reverseOf.resize(base + n, 0);
+  for (uint32_t i = 0; i < n; ++i) {
+    s.spheres.push_back(Sphere::makeDisk(o2w + 16 * i, w2o + 16 * i, prm[4 * i], prm[4 * i + 1], prm[4 * i + 2], prm[4 * i + 3],
+                                         rev ? rev[i] != 0 : false));
+    s.materialOf[base + i] = mat ? mat[i] : 0;
+    s.lightOf[base + i] = light ? light[i] : -1;
+    s.reverseOf[base + i] = rev ? rev[i] : 0;
+  }
+  return 0;
+}
+
 int orc_set_build_order(orc_ctx* c, const uint32_t* ids, uint32_t n) {
   if (!ids) { c->scene.buildOrder.clear(); return 0; }
   c->scene.buildOrder.assign(ids, ids + n);

@@ -422,6 +422,19 @@ struct Ctx {
       dg->p = ray.at(h.t);
       dg->dpdu = dpdu;
       dg->dpdv = dpdv;
+    } else if (g.spheres[prim - g.ntris()].shape == 1) {  // disk.dart:69-97
+      const Sphere& s = g.spheres[prim - g.ntris()];
+      Vec phit = h.phitObj;
+      double dist2 = (double)phit.x * phit.x + (double)phit.y * phit.y;
+      double oneMinusV = (std::sqrt(dist2) - s.innerRadius) / (s.radius - s.innerRadius);
+      double invOneMinusV = (oneMinusV > 0.0) ? (1.0 / oneMinusV) : 0.0;
+      Vec dpdu(-s.phiMax * phit.y, s.phiMax * phit.x, 0.0);
+      Vec dpdv(-(double)phit.x * invOneMinusV, -(double)phit.y * invOneMinusV, 0.0);
+      dpdu = dpdu * (s.phiMax * INV_TWOPI);
+      dpdv = dpdv * ((s.radius - s.innerRadius) / s.radius);
+      dg->p = s.o2w.point(phit);
+      dg->dpdu = s.o2w.vector(dpdu);
+      dg->dpdv = s.o2w.vector(dpdv);
     } else {
       const Sphere& s = g.spheres[prim - g.ntris()];
       Vec phit = h.phitObj;
@@ -495,6 +508,7 @@ struct Ctx {
       return 0.5 * Length(Cross(p2 - p1, p3 - p1));
     }
     const Sphere& s = g.spheres[prim - g.ntris()];
+    if (s.shape == 1) return s.phiMax * 0.5 * (s.radius * s.radius - s.innerRadius * s.innerRadius);  // disk.dart:142-145
     return s.phiMax * s.radius * (s.zmax - s.zmin);  // sphere.dart:243-245
   }
   Vec sphereSample(const Sphere& s, double u1, double u2, Vec* ns) const {  // sphere.dart:247-259
@@ -517,7 +531,18 @@ struct Ctx {
       *ns = n;
       return pt;
     }
-    const Sphere& s = g.spheres[prim - g.ntris()];  // sphere.dart:261-297
+    const Sphere& s = g.spheres[prim - g.ntris()];
+    if (s.shape == 1) {  // shape.dart:96-98 -> disk.dart:147-159
+      double t0, t1;
+      ConcentricSampleDisk(u1, u2, &t0, &t1);
+      Vec pd(t0 * s.radius, t1 * s.radius, s.height);
+      Vec n = s.o2w.normal(Vec(0.0, 0.0, 1.0));
+      n = n / Length(n);
+      if (s.reverseOrientation) n = n * -1.0;
+      *ns = n;
+      return s.o2w.point(pd);
+    }
+    // sphere.dart:261-297
     Vec Pcenter = s.o2w.point(Vec());
     Vec wc = Normalize(Pcenter - p);
     Vec wcX, wcY;
@@ -536,7 +561,7 @@ struct Ctx {
     return ps;
   }
   double shapePdf2(uint32_t prim, const Vec& p, const Vec& wi) const {
-    if (prim >= g.ntris()) {  // sphere.dart:299-311
+    if (prim >= g.ntris() && g.spheres[prim - g.ntris()].shape == 0) {  // sphere.dart:299-311
       const Sphere& s = g.spheres[prim - g.ntris()];
       Vec Pcenter = s.o2w.point(Vec());
       if (!(DistanceSquared(p, Pcenter) - s.radius * s.radius < 1.0e-4)) {

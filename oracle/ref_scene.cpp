@@ -99,9 +99,40 @@ static bool sphereCore(const Sphere& s, const Ray& r, bool shadowVariant, double
   return true;
 }
 
+// lib/shapes/disk.dart:39-67 (intersect) == :107-140 (intersectP) up to the hit decision
+static bool diskCore(const Sphere& s, const Ray& r, double* thitOut, Vec* phitOut, double* phiOut) {
+  Ray ray = s.w2o.ray(r);
+  if (std::fabs((double)ray.d.z) < 1.0e-7) return false;
+  double thit = (s.height - ray.o.z) / ray.d.z;
+  if (thit < ray.mint || thit > ray.maxt) return false;
+  Vec phit = ray.at(thit);
+  double dist2 = (double)phit.x * phit.x + (double)phit.y * phit.y;
+  if (dist2 > s.radius * s.radius || dist2 < s.innerRadius * s.innerRadius) return false;
+  double phi = std::atan2((double)phit.y, (double)phit.x);
+  if (phi < 0) phi += 2.0 * kPi;
+  if (phi > s.phiMax) return false;
+  *thitOut = thit;
+  *phitOut = phit;
+  *phiOut = phi;
+  return true;
+}
+
 bool Scene::sphIntersect(const Sphere& s, Ray& r, Hit* hit) const {
   double thit, phi;
   Vec phit;
+  if (s.shape == 1) {
+    if (!diskCore(s, r, &thit, &phit, &phi)) return false;
+    hit->t = thit;
+    hit->phitObj = phit;
+    hit->phi = phi;
+    double dist2 = (double)phit.x * phit.x + (double)phit.y * phit.y;  // disk.dart:69-75 parametric (u, v)
+    double oneMinusV = (std::sqrt(dist2) - s.innerRadius) / (s.radius - s.innerRadius);
+    hit->b1 = phi / s.phiMax;
+    hit->b2 = 1.0 - oneMinusV;
+    hit->rayEpsilon = 5.0e-4 * thit;  // disk.dart:100
+    r.maxt = thit;
+    return true;
+  }
   if (!sphereCore(s, r, false, &thit, &phit, &phi)) return false;
   hit->t = thit;
   hit->phitObj = phit;
@@ -118,6 +149,7 @@ bool Scene::sphIntersect(const Sphere& s, Ray& r, Hit* hit) const {
 bool Scene::sphIntersectP(const Sphere& s, const Ray& r) const {
   double thit, phi;
   Vec phit;
+  if (s.shape == 1) return diskCore(s, r, &thit, &phit, &phi);
   return sphereCore(s, r, true, &thit, &phit, &phi);
 }
 

@@ -13,12 +13,30 @@
 namespace orc {
 
 // lib/shapes/sphere.dart:24-32,314-323 — radius/zmin/zmax/phiMax are Dart doubles.
+// The same record also carries the other quadric on the path, Disk (lib/shapes/disk.dart:24-31,157-166):
+// shape == 1, with height / radius / innerRadius / phiMax.  Quadrics share one id range after the triangles.
 struct Sphere {
   Transform o2w;  // objectToWorld (m) / worldToObject is o2w.mInv kept separately below
   Transform w2o;
   double radius, zmin, zmax, phiMax, thetaMin, thetaMax;
   bool reverseOrientation = false;
+  int shape = 0;  // 0 sphere, 1 disk
+  double height = 0.0, innerRadius = 0.0;
   Sphere() {}
+  static Sphere makeDisk(const float* O2W, const float* W2O, double h, double r, double ri, double pm, bool ro) {
+    Sphere d;
+    d.o2w = Transform(O2W, W2O);
+    d.w2o = Transform(W2O, O2W);
+    d.shape = 1;
+    d.height = h;
+    d.radius = r;
+    d.innerRadius = ri;
+    d.phiMax = Radians(clampd(pm, 0.0, 360.0));  // disk.dart:28
+    d.zmin = d.zmax = h;
+    d.thetaMin = d.thetaMax = 0.0;
+    d.reverseOrientation = ro;
+    return d;
+  }
   Sphere(const float* O2W, const float* W2O, double r, double z0, double z1, double pm, bool ro) {
     o2w = Transform(O2W, W2O);
     w2o = Transform(W2O, O2W);
@@ -32,6 +50,7 @@ struct Sphere {
   }
   // sphere.dart:34-37 + lib/core/shape.dart:38-40
   BBox worldBound() const {
+    if (shape == 1) return o2w.bbox(BBox(Vec(-radius, -radius, height), Vec(radius, radius, height)));  // disk.dart:32-35
     BBox ob(Vec(-radius, -radius, zmin), Vec(radius, radius, zmax));
     return o2w.bbox(ob);
   }

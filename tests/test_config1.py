@@ -1,10 +1,10 @@
 """BASELINE.json configs[0] / SURVEY §8d config 1: the Cornell scene of web/scenes/cornell-path.pbrt at 256x256,
 path integrator, lowdiscrepancy 4 spp, box filter, tile pixel order, task 0 of 1.
 
-Variant used: `cornell_synth` — the 22 triangles + sphere of cornell-path.pbrt:23-59 with the DISK area light
-(:15-19, `Shape "disk"` is row f2 of SURVEY §8f, not on the GPU path yet) replaced by an inscribed 2-triangle quad
-light.  The reference itself cannot be run (no Dart VM in the image): the anchor is the CPU oracle in the
-reference's SERIAL stream mode; the GPU replays the KEYED streams."""
+Two variants: `cornell_path` — the scene as shipped, with its DISK area light (cornell-path.pbrt:15-19; `Shape
+"disk"`, SURVEY §8f f2, is on the GPU path) — and `cornell_synth`, the same geometry with the disk replaced by a
+2-triangle quad light (the config-4 benchmark scene).  The reference itself cannot be run (no Dart VM in the image):
+the anchor is the CPU oracle in the reference's SERIAL stream mode; the GPU replays the KEYED streams."""
 import numpy as np
 import pytest
 
@@ -39,6 +39,25 @@ def test_config1_keyed_streams_match_the_serial_reference_stream_statistically()
     # per pixel: within 3 sigma of the Monte Carlo noise (sigma estimated from the two independent keyed renders)
     sigma = np.abs(keyed - keyed2).mean() / 1.128 + 1e-6  # E|a-b| = 1.128 sigma for two normal draws
     assert (np.abs(keyed - serial) <= 3 * sigma * np.sqrt(2)).mean() > 0.9
+
+
+@pytest.mark.gpu
+def test_config1_real_scene_with_disk_light_gpu_matches_oracle():
+    """web/scenes/cornell-path.pbrt as shipped (disk area light), film / sampler overridden as configs[0] says."""
+    sb, cam = scenes.cornell_path()
+    arrays = sb.arrays()
+    g, o = capi.Context(0), Oracle()
+    for c in (g, o):
+        host.upload_scene(c, arrays)
+        host.configure_render(c, cam, FILM, host.Sampler(kind=host.SAMPLER_LD, spp=4, pixel_order=1), INTEG)
+    g.render(0, 1)
+    o.render(0, 1, 8)
+    rgb, ref = g.film_read()["rgb"], o.film_read()["rgb"]
+    err = np.abs(rgb - ref) / np.maximum(np.abs(ref), 1e-3)
+    assert abs(rgb.mean() - ref.mean()) <= 1e-4 * ref.mean()
+    assert np.quantile(err, 0.9999) <= 1e-3
+    sg, so = g.render_stats(), o.render_stats()
+    assert abs(sg["shadow_rays"] - so["shadow_rays"]) <= 1e-4 * so["shadow_rays"]
 
 
 @pytest.mark.gpu

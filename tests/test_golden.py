@@ -31,8 +31,8 @@ def _check_trace(ctx, g, exact_t64=None):
     assert np.array_equal(b["bounds"], g["bvh_bounds"])
 
 
-def _render(ctx, name):
-    sb, cam = scenes.cornell_synth()
+def _render(ctx, name, scene=scenes.cornell_synth):
+    sb, cam = scene()
     host.upload_scene(ctx, sb.arrays())
     sampler, integ = RENDERS[name]
     host.configure_render(ctx, cam, host.Film(*FILM), sampler, integ)
@@ -55,6 +55,24 @@ def test_oracle_reproduces_render_golden(name):
     assert np.array_equal(o.pixel_samples(5, 7), g[name + "_samples_px_5_7"])
     st = o.render_stats()
     assert [st["camera_samples"], st["closest_rays"], st["shadow_rays"]] == g[name + "_rays"].tolist()
+
+
+def test_oracle_reproduces_cornell_path_golden():
+    g = np.load(os.path.join(GOLD, "render_cornell_path.npz"))
+    o = _render(Oracle(), "path", scenes.cornell_path)
+    assert np.array_equal(o.film_read()["rgb"], g["path_rgb"])
+    st = o.render_stats()
+    assert [st["camera_samples"], st["closest_rays"], st["shadow_rays"]] == g["path_rays"].tolist()
+
+
+@pytest.mark.gpu
+def test_gpu_matches_cornell_path_golden():
+    g = np.load(os.path.join(GOLD, "render_cornell_path.npz"))
+    c = _render(capi.Context(0), "path", scenes.cornell_path)
+    f = c.film_read()
+    assert np.array_equal(f["weight"], g["path_weight"])
+    err = np.abs(f["rgb"] - g["path_rgb"]) / np.maximum(np.abs(g["path_rgb"]), 1e-3)
+    assert err.max() <= 1e-3
 
 
 def test_host_bvh_builder_reproduces_golden_topology(drt_lib):

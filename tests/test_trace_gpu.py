@@ -5,7 +5,7 @@ for more: float32(t), b1, b2 BIT-IDENTICAL and the any-hit flag identical."""
 import numpy as np
 import pytest
 
-from dartray_b200 import capi, scenes
+from dartray_b200 import capi, host, scenes
 from tests.oracle_lib import Oracle
 from tests.util import mesh_refine_order, random_rays, random_soup, translate
 
@@ -17,7 +17,7 @@ def variant(request):
     return request.param
 
 
-def make_pair(P, idx, spheres=None, order=None, split=2, maxprims=4, variant=0):
+def make_pair(P, idx, spheres=None, order=None, split=2, maxprims=4, variant=0, disks=None):
     o = Oracle()
     c = capi.Context(0)
     c.set_kernel_variant(variant)
@@ -25,6 +25,8 @@ def make_pair(P, idx, spheres=None, order=None, split=2, maxprims=4, variant=0):
         x.set_triangles(P, idx)
         if spheres is not None:
             x.set_spheres(*spheres)
+        if disks is not None:
+            x.set_disks(*disks)
         x.set_build_order(order)
         x.build_bvh(split, maxprims)
     return o, c
@@ -65,6 +67,29 @@ def test_mixed_triangles_and_spheres(drt_lib, variant):
     np.testing.assert_allclose(hg["b1"], ho["b1"], rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(hg["b2"], ho["b2"], rtol=1e-6, atol=1e-7)
     assert (c.trace_any(ro, rd) == o.trace_any(ro, rd, nthreads=8)).all()
+
+
+def test_disks_with_triangles_and_spheres(drt_lib, variant):
+    """Disk (lib/shapes/disk.dart): quadric ids continue after the spheres."""
+    P, idx = random_soup(600, seed=9)
+    mats = [translate(0.3, 0.1, -0.2), translate(-0.4, 0.2, 0.5)]
+    sph = (np.stack([m[0] for m in mats]), np.stack([m[1] for m in mats]), [[0.25, -0.25, 0.25, 360.0], [0.3, -0.1, 0.2, 300.0]])
+    rot = host.rotate(35.0, (1.0, 0.3, 0.2))
+    dm = [host.mat_mul(host.translate(0.1, -0.3, 0.2), rot), host.translate(-0.5, 0.5, -0.4), host.mat_mul(host.translate(0.6, 0.6, 0.1), host.rotate(80, (0, 1, 0)))]
+    dsk = (np.stack([m.reshape(16) for m in dm]), np.stack([host.mat_inv(m).reshape(16) for m in dm]),
+           [[0.0, 0.6, 0.0, 360.0], [0.1, 0.5, 0.2, 360.0], [-0.05, 0.45, 0.0, 250.0]])
+    o, c = make_pair(P, idx, sph, None, variant=variant, disks=dsk)
+    for tmin, tmax in ((0.0, np.inf), (0.5, 2.8)):
+        ro, rd = random_rays(60000, seed=10, tmin=tmin, tmax=tmax)
+        hg, ho = c.trace_closest(ro, rd), o.trace_closest(ro, rd, nthreads=8)
+        assert (hg["prim"] == ho["prim"]).all()
+        assert (hg["t"].view(np.uint32) == ho["t"].view(np.uint32)).all()
+        assert (ho["prim"] >= 602).sum() > 1500  # the disks are hit
+        np.testing.assert_allclose(hg["b1"], ho["b1"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(hg["b2"], ho["b2"], rtol=1e-6, atol=1e-7)
+        assert (c.trace_any(ro, rd) == o.trace_any(ro, rd, nthreads=8)).all()
+    for k in ("offset", "n_primitives", "axis", "ordered", "bounds"):
+        assert np.array_equal(c.bvh_export()[k], o.bvh_export()[k]), k
 
 
 def test_known_answer_edge_cases(drt_lib, variant):

@@ -67,6 +67,17 @@ def render_vectors():
         st = o.render_stats()
         out[f"{name}_rays"] = np.array([st["camera_samples"], st["closest_rays"], st["shadow_rays"]], np.int64)
     np.savez_compressed(os.path.join(OUT, "render_cornell_synth.npz"), **out)
+    # the shipped scene itself (disk area light), web/scenes/cornell-path.pbrt
+    sb, cam = scenes.cornell_path()
+    o = Oracle()
+    host.upload_scene(o, sb.arrays())
+    sampler, integ = RENDERS["path"]
+    host.configure_render(o, cam, host.Film(*FILM), sampler, integ)
+    o.render(0, 1, 1)
+    f = o.film_read()
+    st = o.render_stats()
+    np.savez_compressed(os.path.join(OUT, "render_cornell_path.npz"), path_rgb=f["rgb"], path_weight=f["weight"],
+                        path_rays=np.array([st["camera_samples"], st["closest_rays"], st["shadow_rays"]], np.int64))
 
 
 if __name__ == "__main__":
