@@ -48,10 +48,10 @@ struct RenderState {
   int spp = 4, pixelOrder = 1, tileSize = 32;
   uint64_t batchSlots = 0;  // 0 = default
   // device-side scene tables
-  DevBuf<uint32_t> dPrimToRec, dPrimAttr, dLightShapes;
+  DevBuf<uint32_t> dPrimToRec, dPrimAttr;
+  DevBuf<GLightShape> dLightShapes;
   DevBuf<GMaterial> dMaterials;
   DevBuf<GLight> dLights;
-  DevBuf<double> dLightAreas;
   DevBuf<float> dLightCdf, dTable;
   DevBuf<DirectOffsets> dDirect;
   DevBuf<SampleArray> dArrays;
@@ -86,7 +86,7 @@ void drtRenderStateDestroy(drt_ctx* c) {
   RenderState* r = c->render;
   if (!r) return;
   r->dPrimToRec.release(); r->dPrimAttr.release(); r->dLightShapes.release(); r->dMaterials.release(); r->dLights.release();
-  r->dLightAreas.release(); r->dLightCdf.release(); r->dTable.release(); r->dDirect.release(); r->dArrays.release();
+  r->dLightCdf.release(); r->dTable.release(); r->dDirect.release(); r->dArrays.release();
   r->dFilm.release(); r->dCounters.release(); r->dRgb.release(); r->dXyz.release(); r->dWeight.release();
   if (r->wfMem) cudaFree(r->wfMem);
   delete r;
@@ -197,9 +197,31 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
     attr[i] = (uint32_t)m | ((uint32_t)(l + 1) << 16) | (rev ? 0x80000000u : 0u);
   }
   std::vector<GLight> gl(std::max(nLights, 1));
-  std::vector<uint32_t> shapes;
-  std::vector<double> areas;
+  std::vector<GLightShape> shapes;
   std::vector<float> cdf;
+  auto pushShape = [&](uint32_t sh, double area) {
+    GLightShape ls;
+    std::memset(&ls, 0, sizeof(ls));
+    ls.prim = sh;
+    ls.area = area;
+    if (sh < nt) {
+      TriVerts t;
+      const float* p1 = &c->P[3 * (size_t)c->idx[3 * (size_t)sh]];
+      const float* p2 = &c->P[3 * (size_t)c->idx[3 * (size_t)sh + 1]];
+      const float* p3 = &c->P[3 * (size_t)c->idx[3 * (size_t)sh + 2]];
+      t.p1 = V3{p1[0], p1[1], p1[2]}; t.p2 = V3{p2[0], p2[1], p2[2]}; t.p3 = V3{p3[0], p3[1], p3[2]};
+      std::memcpy(ls.p1, p1, 12); std::memcpy(ls.p2, p2, 12); std::memcpy(ls.p3, p3, 12);
+      const bool rev = c->revOf[sh] != 0;
+      V3 dpdu, dpdv;
+      triPartials(t, &dpdu, &dpdv);
+      V3 nn = shapeNormal(dpdu, dpdv, rev);  // the dg.nn Triangle.intersect leaves behind
+      V3 ns = Normalize(Cross(t.p2 - t.p1, t.p3 - t.p1));  // triangle.dart:374-381
+      if (rev) ns = mkv((double)ns.x * -1.0, (double)ns.y * -1.0, (double)ns.z * -1.0);
+      ls.nn[0] = nn.x; ls.nn[1] = nn.y; ls.nn[2] = nn.z;
+      ls.ns[0] = ns.x; ls.ns[1] = ns.y; ls.ns[2] = ns.z;
+    }
+    shapes.push_back(ls);
+  };
   for (int i = 0; i < nLights; ++i) {
     const HostLight& hl = r->lights[i];
     GLight& g = gl[i];
@@ -230,8 +252,7 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
           area = phiMaxD * 0.5 * (s.radius * s.radius - s.innerRadius * s.innerRadius);
           a.push_back(area);
           g.area += area;
-          shapes.push_back(sh);
-          areas.push_back(area);
+          pushShape(sh, area);
           continue;
         }
         double zmin = clampD(std::fmin(s.zmin, s.zmax), -s.radius, s.radius), zmax = clampD(std::fmax(s.zmin, s.zmax), -s.radius, s.radius);
@@ -240,8 +261,7 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
       }
       a.push_back(area);
       g.area += area;
-      shapes.push_back(sh);
-      areas.push_back(area);
+      pushShape(sh, area);
     }
     if (hl.kind == 0) {  // Distribution1D(areas): float32 func and cdf (montecarlo.dart:26-48)
       const int count = (int)a.size();
@@ -258,14 +278,12 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
   CK(c, r->dMaterials.ensure(r->materials.size()));
   CK(c, r->dLights.ensure(gl.size()));
   CK(c, r->dLightShapes.ensure(std::max<size_t>(1, shapes.size())));
-  CK(c, r->dLightAreas.ensure(std::max<size_t>(1, areas.size())));
   CK(c, r->dLightCdf.ensure(std::max<size_t>(1, cdf.size())));
   CK(c, cudaMemcpy(r->dPrimToRec.p, primToRec.data(), primToRec.size() * 4, cudaMemcpyHostToDevice));
   CK(c, cudaMemcpy(r->dPrimAttr.p, attr.data(), attr.size() * 4, cudaMemcpyHostToDevice));
   CK(c, cudaMemcpy(r->dMaterials.p, r->materials.data(), r->materials.size() * sizeof(GMaterial), cudaMemcpyHostToDevice));
   CK(c, cudaMemcpy(r->dLights.p, gl.data(), gl.size() * sizeof(GLight), cudaMemcpyHostToDevice));
-  if (!shapes.empty()) CK(c, cudaMemcpy(r->dLightShapes.p, shapes.data(), shapes.size() * 4, cudaMemcpyHostToDevice));
-  if (!areas.empty()) CK(c, cudaMemcpy(r->dLightAreas.p, areas.data(), areas.size() * 8, cudaMemcpyHostToDevice));
+  if (!shapes.empty()) CK(c, cudaMemcpy(r->dLightShapes.p, shapes.data(), shapes.size() * sizeof(GLightShape), cudaMemcpyHostToDevice));
   if (!cdf.empty()) CK(c, cudaMemcpy(r->dLightCdf.p, cdf.data(), cdf.size() * 4, cudaMemcpyHostToDevice));
   RenderScene& rs = r->rs;
   rs.ts = c->ts;
@@ -277,7 +295,6 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
   rs.lights = r->dLights.p;
   rs.nLights = nLights;
   rs.lightShapes = r->dLightShapes.p;
-  rs.lightShapeAreas = r->dLightAreas.p;
   rs.lightCdf = r->dLightCdf.p;
   r->sceneTablesValid = true;
   r->buildSerial = c->buildSerial;

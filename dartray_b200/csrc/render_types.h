@@ -29,6 +29,17 @@ struct DirectOffsets {
   int32_t lightComp, lightPos, bsdfComp, bsdfPos;
 };
 
+// One shape of a light's ShapeSet with everything the light-sampling code needs resident in one record.  For a
+// triangle the two normals are constants of the shape (triangle.dart:100-154 with the default uvs; :366-383), so
+// they are computed once on the host with the same arithmetic instead of at every hit.
+struct GLightShape {
+  float p1[3], p2[3], p3[3];  // triangle vertices (unused for quadrics)
+  float nn[3];                // dg.nn of any hit: normalize(cross(dpdu, dpdv)), flipped by reverseOrientation
+  float ns[3];                // Triangle.sample's normal: normalize(cross(p2 - p1, p3 - p1)), flipped likewise
+  uint32_t prim;              // primitive id (>= ntris: sphere / disk, evaluated by the general shape code)
+  double area;
+};
+
 struct RenderScene {
   TraceScene ts;
   uint32_t ntris, nprims;
@@ -37,8 +48,7 @@ struct RenderScene {
   const GMaterial* materials;
   const GLight* lights;
   int32_t nLights;
-  const uint32_t* lightShapes;
-  const double* lightShapeAreas;
+  const GLightShape* lightShapes;
   const float* lightCdf;
 };
 

@@ -505,16 +505,32 @@ static __device__ inline V3 sphereCenter(const GSphere& s) {
   return XfPoint(o2w, V3{0.f, 0.f, 0.f});
 }
 
+// Shape.intersect on one shape of a ShapeSet: tHit and dg.nn (all the light code reads).
+static __device__ inline bool lightShapeIntersect(const RenderScene& rs, const GLightShape& ls, const V3& o, const V3& d,
+                                                  double mint, double maxt, double* tOut, V3* nnOut) {
+  if (ls.prim < rs.ntris) {
+    TriVerts tv;
+    tv.p1 = V3{ls.p1[0], ls.p1[1], ls.p1[2]}; tv.p2 = V3{ls.p2[0], ls.p2[1], ls.p2[2]}; tv.p3 = V3{ls.p3[0], ls.p3[1], ls.p3[2]};
+    if (!triIntersectT(tv, o, d, mint, maxt, tOut)) return false;
+    *nnOut = V3{ls.nn[0], ls.nn[1], ls.nn[2]};
+    return true;
+  }
+  ShapeHit h;
+  if (!shapeIntersect(rs, ls.prim, o, d, mint, maxt, &h)) return false;
+  *tOut = h.t;
+  *nnOut = h.nn;
+  return true;
+}
+
 // Shape.sample(p, u1, u2) -> point on the shape and its normal
-static __device__ inline V3 shapeSample2(const RenderScene& rs, uint32_t prim, const V3& p, double u1, double u2, V3* ns) {
+static __device__ inline V3 shapeSample2(const RenderScene& rs, const GLightShape& ls, const V3& p, double u1, double u2, V3* ns) {
+  const uint32_t prim = ls.prim;
   if (prim < rs.ntris) {  // shape.dart:96-98 -> triangle.dart:366-383, UniformSampleTriangle montecarlo.dart:215-220
     double su1 = sqrt(u1);
     double b1 = 1.0 - su1, b2 = u2 * su1;
-    TriVerts t = loadTri(rs, prim);
-    V3 pt = t.p1 * b1 + t.p2 * b2 + t.p3 * (1.0 - b1 - b2);
-    V3 n = Normalize(Cross(t.p2 - t.p1, t.p3 - t.p1));
-    if (primReverse(rs, prim)) n = mkv((double)n.x * -1.0, (double)n.y * -1.0, (double)n.z * -1.0);
-    *ns = n;
+    V3 p1 = V3{ls.p1[0], ls.p1[1], ls.p1[2]}, p2 = V3{ls.p2[0], ls.p2[1], ls.p2[2]}, p3 = V3{ls.p3[0], ls.p3[1], ls.p3[2]};
+    V3 pt = p1 * b1 + p2 * b2 + p3 * (1.0 - b1 - b2);
+    *ns = V3{ls.ns[0], ls.ns[1], ls.ns[2]};
     return pt;
   }
   const GSphere& s = rs.ts.spheres[prim - rs.ntris];
@@ -559,7 +575,8 @@ static __device__ inline V3 shapeSample2(const RenderScene& rs, uint32_t prim, c
   return ps;
 }
 
-static __device__ inline double shapePdf2(const RenderScene& rs, uint32_t prim, double area, const V3& p, const V3& wi) {
+static __device__ inline double shapePdf2(const RenderScene& rs, const GLightShape& ls, const V3& p, const V3& wi) {
+  const uint32_t prim = ls.prim;
   if (prim >= rs.ntris && rs.ts.spheres[prim - rs.ntris].shape == 0) {  // sphere.dart:299-311
     const GSphere& s = rs.ts.spheres[prim - rs.ntris];
     V3 Pcenter = sphereCenter(s);
@@ -569,9 +586,10 @@ static __device__ inline double shapePdf2(const RenderScene& rs, uint32_t prim, 
       return UniformConePdf(cosThetaMax);
     }
   }
-  ShapeHit h;  // shape.dart:100-121
-  if (!shapeIntersect(rs, prim, p, wi, 1.0e-3, CUDART_INF, &h)) return 0.0;
-  double pdf = DistanceSquared(p, RayAt(p, wi, h.t)) / (AbsDot(h.nn, -wi) * area);
+  double t;  // shape.dart:100-121
+  V3 nn;
+  if (!lightShapeIntersect(rs, ls, p, wi, 1.0e-3, CUDART_INF, &t, &nn)) return 0.0;
+  double pdf = DistanceSquared(p, RayAt(p, wi, t)) / (AbsDot(nn, -wi) * ls.area);
   if (isinf(pdf)) pdf = 0.0;
   return pdf;
 }
@@ -579,8 +597,8 @@ static __device__ inline double shapePdf2(const RenderScene& rs, uint32_t prim, 
 static __device__ inline double shapeSetPdf(const RenderScene& rs, const GLight& l, const V3& p, const V3& wi) {  // shape_set.dart:81-89
   double pdf = 0.0;
   for (uint32_t i = 0; i < l.nShapes; ++i) {
-    double a = rs.lightShapeAreas[l.shapeOffset + i];
-    pdf += a * shapePdf2(rs, rs.lightShapes[l.shapeOffset + i], a, p, wi);
+    const GLightShape& ls = rs.lightShapes[l.shapeOffset + i];
+    pdf += ls.area * shapePdf2(rs, ls, p, wi);
   }
   return pdf / l.area;
 }
@@ -606,11 +624,12 @@ static __device__ inline V3 shapeSetSample(const RenderScene& rs, const GLight& 
   bool anyHit = false;
   V3 nnLast = *Ns;
   for (uint32_t i = 0; i < l.nShapes; ++i) {
-    ShapeHit h;
-    if (shapeIntersect(rs, rs.lightShapes[l.shapeOffset + i], p, rd, 1.0e-3, CUDART_INF, &h)) {
+    double t;
+    V3 nn;
+    if (lightShapeIntersect(rs, rs.lightShapes[l.shapeOffset + i], p, rd, 1.0e-3, CUDART_INF, &t, &nn)) {
       anyHit = true;
-      thit = h.t;
-      nnLast = h.nn;
+      thit = t;
+      nnLast = nn;
     }
   }
   if (anyHit) *Ns = nnLast;

@@ -131,6 +131,23 @@ def test_path_deep_bounces_use_the_integrator_stream():
     assert abs(fg["rgb"].mean() - fo["rgb"].mean()) <= 5e-3 * fo["rgb"].mean()
 
 
+def test_thin_lens_camera_and_random_sampler():
+    """perspective_camera.dart:104-119: lensRadius > 0 moves the ray origin on the lens (ConcentricSampleDisk)."""
+    sb, cam = scenes.cornell_synth()
+    cam.lens_radius, cam.focal_distance = 0.8, 33.0
+    for sampler in (host.Sampler(kind=host.SAMPLER_LD, spp=8), host.Sampler(kind=host.SAMPLER_RANDOM, spp=3),
+                    host.Sampler(kind=host.SAMPLER_STRATIFIED, xs=2, ys=2)):
+        g, o, fg, fo = _render_both(sb.arrays(), cam, host.Film(48, 36), sampler, host.Integrator(kind=host.INTEGRATOR_DIRECT))
+        assert np.array_equal(fg["weight"], fo["weight"])
+        assert _rel_err(fg["rgb"], fo["rgb"], floor=1e-3).max() <= 1e-3
+    sharp = host.PerspectiveCamera(cam.camera_to_world, fov=cam.fov)
+    g2 = capi.Context(0)
+    host.upload_scene(g2, sb.arrays())
+    host.configure_render(g2, sharp, host.Film(48, 36), host.Sampler(kind=host.SAMPLER_LD, spp=8), host.Integrator(kind=host.INTEGRATOR_DIRECT))
+    g2.render()
+    assert np.abs(g2.film_read()["rgb"] - fg["rgb"]).max() > 1e-3  # the lens does change the image
+
+
 # ---- film --------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("flt", ["gaussian", "mitchell", "triangle", "sinc", "box"])
 def test_filters_and_crop_window(flt):
