@@ -270,14 +270,29 @@ struct Flattener {
     }
     g.axisP = n.axis;
     g.refNode = refIndexOf[t];
-    const int32_t sides[2] = {n.left, n.right};
+    // Slot order = any-hit visiting order (that kernel walks the slots as stored: its answer does not depend on
+    // the order): the larger box first, inside each side and between the sides.  A swap is recorded in bit 2 of
+    // the axis field, which the closest-hit kernel XORs into dirIsNeg[axis] to recover the reference's order.
+    int32_t sides[2] = {n.left, n.right};
+    if (pool[sides[1]].box.area() > pool[sides[0]].box.area()) {
+      std::swap(sides[0], sides[1]);
+      g.axisP |= 4;
+    }
     for (int sIdx = 0; sIdx < 2; ++sIdx) {
       const TNode& side = pool[sides[sIdx]];
       int base = 2 * sIdx;
       int32_t kids[2];
       int nk;
       if (side.left < 0) { kids[0] = sides[sIdx]; nk = 1; }
-      else { kids[0] = side.left; kids[1] = side.right; nk = 2; (sIdx == 0 ? g.axisA : g.axisB) = side.axis; }
+      else {
+        kids[0] = side.left; kids[1] = side.right; nk = 2;
+        int32_t ax = side.axis;
+        if (pool[kids[1]].box.area() > pool[kids[0]].box.area()) {
+          std::swap(kids[0], kids[1]);
+          ax |= 4;
+        }
+        (sIdx == 0 ? g.axisA : g.axisB) = ax;
+      }
       for (int k = 0; k < nk; ++k) {
         const TNode& c = pool[kids[k]];
         for (int a = 0; a < 3; ++a) {  // (lo, hi) pairs per axis: one packed f32x2 operand each

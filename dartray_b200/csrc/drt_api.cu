@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 
 #include <chrono>
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -347,7 +349,8 @@ static int traceHost(drt_ctx* c, bool any, const float* o, const float* d, uint6
   const size_t outSize = any ? 1 : sizeof(drt_hit_rec);
   // Chunks of >= 1 Mi rays, at most kMaxChunks, round-robin over the pipeline streams: with pinned host buffers
   // the upload of the next chunk and the download of the previous one overlap the traversal of this one.
-  uint64_t chunk = 1ull << 20;
+  uint64_t chunk = 1ull << 20;  // measured (tools/e2e_sweep.py): 1 Mi beats 128 Ki .. 512 Ki (small launches underfill the GPU) and 2 Mi
+  if (const char* e = std::getenv("DRT_E2E_CHUNK")) chunk = std::max<uint64_t>(1024, std::strtoull(e, nullptr, 10));
   if ((n + chunk - 1) / chunk > (uint64_t)drt_ctx::kMaxChunks) chunk = (n + drt_ctx::kMaxChunks - 1) / drt_ctx::kMaxChunks;
   if (c->counting || c->exactWalk) chunk = n;  // one launch: the counters describe the whole batch
   int nChunks = 0;

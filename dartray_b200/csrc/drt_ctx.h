@@ -76,7 +76,7 @@ struct drt_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // host-buffer queries are pipelined over three streams: H2D of chunk k+1, kernel k, D2H of chunk k-1 overlap
-  static const int kPipe = 3, kMaxChunks = 32;
+  static const int kPipe = 3, kMaxChunks = 64;
   cudaStream_t pipe[kPipe] = {nullptr, nullptr, nullptr};
   cudaEvent_t chunkEv[2 * kMaxChunks] = {};
   bool counting = false;

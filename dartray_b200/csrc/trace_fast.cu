@@ -287,8 +287,12 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
       int32_t r2 = testSlot(r, qr.z, make_float2(q3.x, q3.y), make_float2(q3.z, q3.w), make_float2(q4.x, q4.y), &t2);
       int32_t r3 = testSlot(r, qr.w, make_float2(q4.z, q4.w), make_float2(q5.x, q5.y), make_float2(q5.z, q5.w), &t3);
       // visiting order of the reference's depth-first walk (bvh_accel.dart:147-153), branch-free
-      const bool sA = ((r.negMask >> qa.y) & 1u) != 0, sB = ((r.negMask >> qa.z) & 1u) != 0,
-                 sP = ((r.negMask >> qa.x) & 1u) != 0;
+      // closest hit: bit a of negMask = dirIsNeg[a]; bit 2 of an axis field = "the builder swapped this pair".
+      // any hit: the answer is the OR over all leaves whose box test passes, whatever the visiting order, so the
+      // slots are walked as stored (the builder put the larger boxes first).
+      const bool sA = !ANY && (((r.negMask >> (qa.y & 3)) ^ (unsigned)(qa.y >> 2)) & 1u) != 0,
+                 sB = !ANY && (((r.negMask >> (qa.z & 3)) ^ (unsigned)(qa.z >> 2)) & 1u) != 0,
+                 sP = !ANY && (((r.negMask >> (qa.x & 3)) ^ (unsigned)(qa.x >> 2)) & 1u) != 0;
       const int32_t a0 = sA ? r1 : r0, a1 = sA ? r0 : r1, b0 = sB ? r3 : r2, b1 = sB ? r2 : r3;
       const float ta0 = sA ? t1 : t0, ta1 = sA ? t0 : t1, tb0 = sB ? t3 : t2, tb1 = sB ? t2 : t3;
       const int32_t s0 = sP ? b0 : a0, s1 = sP ? b1 : a1, s2 = sP ? a0 : b0, s3 = sP ? a1 : b1;
