@@ -269,7 +269,7 @@ struct Flattener {
       for (int a = 0; a < 6; ++a) g.box[k][a] = 0.f;
     }
     g.axisP = n.axis;
-    g.refNode = refIndexOf[t];
+    (void)refIndexOf;
     // Slot order = any-hit visiting order (that kernel walks the slots as stored: its answer does not depend on
     // the order): the larger box first, inside each side and between the sides.  A swap is recorded in bit 2 of
     // the axis field, which the closest-hit kernel XORs into dirIsNeg[axis] to recover the reference's order.
@@ -302,6 +302,14 @@ struct Flattener {
         g.ref[base + k] = emitWide(kids[k], refIndexOf);
       }
     }
+    // visiting decisions of the closest-hit walk for each of the 8 dirIsNeg octants, 3 bits each:
+    // bit 0 = slots 2,3 before 0,1; bit 1 = slot 1 before 0; bit 2 = slot 3 before 2
+    uint32_t lut = 0;
+    for (uint32_t o = 0; o < 8; ++o) {
+      auto dec = [&](int32_t ax) { return ((o >> (ax & 3)) ^ (uint32_t)(ax >> 2)) & 1u; };
+      lut |= (dec(g.axisP) | (dec(g.axisA) << 1) | (dec(g.axisB) << 2)) << (3 * o);
+    }
+    g.orderLut = (int32_t)lut;
     out->wide[my] = g;
     return my;
   }

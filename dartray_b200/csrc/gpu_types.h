@@ -51,7 +51,7 @@ struct alignas(16) GNode4 {
   float box[4][6];   // per slot: (min.x, max.x), (min.y, max.y), (min.z, max.z) — each pair is one f32x2 operand
   int32_t ref[4];    // child reference or DRT_REF_EMPTY
   int32_t axisP, axisA, axisB;  // bits 0-1: split axis; bit 2: the pair is stored swapped (larger box first)
-  int32_t refNode;   // reference node number of P (debug/export)
+  int32_t orderLut;  // closest-hit visiting decisions per dirIsNeg octant, 3 bits each (see bvh_builder.cpp)
 };
 static_assert(sizeof(GNode4) == 128, "GNode4 must be 128 bytes");
 

@@ -53,7 +53,7 @@ struct FastRay {
   unsigned long long ox2, oy2, oz2, ix2, iy2, iz2;
   float mintLo, mintHi, maxtLo, maxtHi;  // float32 brackets of the f64 interval ends
   double mint, maxt;
-  unsigned negMask;  // bit a = invDir[a] < 0 (dirIsNeg, bvh_accel.dart:113-115); bit 3 = "slow" ray
+  unsigned negMask;  // bit a = invDir[a] < 0 (dirIsNeg, bvh_accel.dart:113-115); bit 3 = "slow" ray; bits 8.. = 3 * octant
 };
 
 struct StackEntry {
@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
         bool slow = !(fabsf(o.x) <= 3.0e38f) || !(fabsf(o.y) <= 3.0e38f) || !(fabsf(o.z) <= 3.0e38f) ||
                     !(fabsf(ix) <= 3.0e38f) || !(fabsf(iy) <= 3.0e38f) || !(fabsf(iz) <= 3.0e38f);
         r.negMask = (ix < 0.f ? 1u : 0u) | (iy < 0.f ? 2u : 0u) | (iz < 0.f ? 4u : 0u) | (slow ? 8u : 0u);
+        r.negMask |= (3u * (r.negMask & 7u)) << 8;  // bits 8..: shift of this ray's octant in a node's orderLut
         sp = 0;
         found = false;
         hprim = -1;
@@ -287,12 +288,11 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
       int32_t r2 = testSlot(r, qr.z, make_float2(q3.x, q3.y), make_float2(q3.z, q3.w), make_float2(q4.x, q4.y), &t2);
       int32_t r3 = testSlot(r, qr.w, make_float2(q4.z, q4.w), make_float2(q5.x, q5.y), make_float2(q5.z, q5.w), &t3);
       // visiting order of the reference's depth-first walk (bvh_accel.dart:147-153), branch-free
-      // closest hit: bit a of negMask = dirIsNeg[a]; bit 2 of an axis field = "the builder swapped this pair".
+      // closest hit: the node carries its three near/far decisions for each dirIsNeg octant (orderLut).
       // any hit: the answer is the OR over all leaves whose box test passes, whatever the visiting order, so the
       // slots are walked as stored (the builder put the larger boxes first).
-      const bool sA = !ANY && (((r.negMask >> (qa.y & 3)) ^ (unsigned)(qa.y >> 2)) & 1u) != 0,
-                 sB = !ANY && (((r.negMask >> (qa.z & 3)) ^ (unsigned)(qa.z >> 2)) & 1u) != 0,
-                 sP = !ANY && (((r.negMask >> (qa.x & 3)) ^ (unsigned)(qa.x >> 2)) & 1u) != 0;
+      const unsigned dec = ANY ? 0u : ((unsigned)qa.w >> (r.negMask >> 8));  // the node's decisions for this ray's octant
+      const bool sP = (dec & 1u) != 0, sA = (dec & 2u) != 0, sB = (dec & 4u) != 0;
       const int32_t a0 = sA ? r1 : r0, a1 = sA ? r0 : r1, b0 = sB ? r3 : r2, b1 = sB ? r2 : r3;
       const float ta0 = sA ? t1 : t0, ta1 = sA ? t0 : t1, tb0 = sB ? t3 : t2, tb1 = sB ? t2 : t3;
       const int32_t s0 = sP ? b0 : a0, s1 = sP ? b1 : a1, s2 = sP ? a0 : b0, s3 = sP ? a1 : b1;
