@@ -23,7 +23,7 @@ SYMBOLS = [
     "drt_set_build_order", "drt_build_bvh", "drt_bvh_info_get", "drt_bvh_export", "drt_trace_closest",
     "drt_trace_any", "drt_trace_closest_device", "drt_trace_any_device", "drt_set_counting", "drt_get_counters", "drt_set_kernel_variant",
     "drt_last_kernel_ms", "drt_kernel_launches",
-    "drt_set_materials", "drt_set_lights", "drt_set_camera", "drt_set_film", "drt_set_sampler", "drt_set_integrator",
+    "drt_set_materials", "drt_set_lights", "drt_set_camera", "drt_set_camera_kind", "drt_set_film", "drt_set_sampler", "drt_set_integrator",
     "drt_render", "drt_render_shard", "drt_set_batch_slots", "drt_film_clear", "drt_film_size", "drt_film_read",
     "drt_film_device", "drt_pixel_samples", "drt_render_stats_get",
 ]
@@ -93,6 +93,7 @@ def load():
     L.drt_set_materials.argtypes = [vp, u32, vp, vp, vp]
     L.drt_set_lights.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
     L.drt_set_camera.argtypes = [vp, vp, vp, dbl, dbl, dbl, dbl]
+    L.drt_set_camera_kind.argtypes = [vp, i32]
     L.drt_set_film.argtypes = [vp, i32, i32, vp, dbl, dbl, vp]
     L.drt_set_sampler.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, u64]
     L.drt_set_integrator.argtypes = [vp, i32, i32, i32, i32, dbl, dbl]
@@ -249,6 +250,9 @@ class Context:
                    shutter_close=1.0):
         r2c, c2w = _arr(raster_to_camera, np.float32).reshape(16), _arr(camera_to_world, np.float32).reshape(16)
         self._ck(self.L.drt_set_camera(self.h, _p(r2c), _p(c2w), lens_radius, focal_distance, shutter_open, shutter_close))
+
+    def set_camera_kind(self, kind):
+        self._ck(self.L.drt_set_camera_kind(self.h, kind))
 
     def set_film(self, xres, yres, crop, xwidth, ywidth, table):
         crop, table = _arr(crop, np.float64), _arr(table, np.float32)

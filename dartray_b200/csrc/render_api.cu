@@ -601,6 +601,13 @@ int drt_set_camera(drt_ctx* c, const float* raster_to_camera, const float* camer
   return DRT_OK;
 }
 
+int drt_set_camera_kind(drt_ctx* c, int kind) {
+  if (!c) return DRT_E_INVALID;
+  if (kind < 0 || kind > 2) return fail(c, DRT_E_INVALID, "camera kind must be 0 (perspective), 1 (orthographic) or 2 (environment)");
+  state(c)->rp.cameraKind = kind;
+  return DRT_OK;
+}
+
 int drt_set_film(drt_ctx* c, int xres, int yres, const double* crop, double xwidth, double ywidth, const float* table) {
   if (!c) return DRT_E_INVALID;
   if (xres < 1 || yres < 1 || !(xwidth > 0.0) || !(ywidth > 0.0) || !table) return fail(c, DRT_E_INVALID, "bad film parameters");

@@ -216,10 +216,17 @@ __global__ void __launch_bounds__(256) raygenKernel(RenderParams rp, Wavefront w
   wf.pixY[s] = y;
   wf.sampleIdx[s] = pb.pass * n + (s % n);
   const double2 im = wf.camXY[s];
-  V3 Pras = mkv(im.x, im.y, 0.0);
-  V3 Pcamera = XfPoint(rp.rasterToCamera, Pras);
-  V3 o = V3{0.f, 0.f, 0.f}, d = Normalize(Pcamera);
-  if (rp.lensRadius > 0.0) {
+  V3 o = V3{0.f, 0.f, 0.f}, d;
+  if (rp.cameraKind == 2) {  // environment_camera.dart:42-52
+    const double theta = DRT_PI * im.y / rp.yres, phi = 2 * DRT_PI * im.x / rp.xres;
+    d = mkv(sin(theta) * cos(phi), cos(theta), sin(theta) * sin(phi));
+  } else {
+    V3 Pras = mkv(im.x, im.y, 0.0);
+    V3 Pcamera = XfPoint(rp.rasterToCamera, Pras);
+    if (rp.cameraKind == 1) { o = Pcamera; d = V3{0.f, 0.f, 1.f}; }  // orthographic_camera.dart:52-58
+    else d = Normalize(Pcamera);
+  }
+  if (rp.cameraKind != 2 && rp.lensRadius > 0.0) {
     const double2 ln = wf.camLens[s];
     double lu, lv;
     ConcentricSampleDisk(ln.x, ln.y, &lu, &lv);

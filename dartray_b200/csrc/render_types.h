@@ -56,6 +56,7 @@ struct RenderParams {
   // camera: perspective_camera.dart:46-57,93-132 + projective_camera.dart:34-53
   float rasterToCamera[16], cameraToWorld[16];
   double lensRadius, focalDistance, shutterOpen, shutterClose;
+  int32_t cameraKind;  // 0 perspective, 1 orthographic (orthographic_camera.dart:52-80), 2 environment (environment_camera.dart:42-52)
   // film: image_film.dart:51-97
   int32_t xres, yres, left, top, width, height;
   double xWidth, yWidth, invXWidth, invYWidth;

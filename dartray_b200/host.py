@@ -107,6 +107,35 @@ class PerspectiveCamera:
         return mat_mul(mat_inv(perspective(self.fov)), raster_to_screen)  # :51-52
 
 
+def orthographic(znear=0.0, zfar=1.0):  # transform.dart:333-336
+    return mat_mul(scale(1.0, 1.0, 1.0 / (zfar - znear)), translate(0.0, 0.0, -znear))
+
+
+@dataclass
+class OrthographicCamera(PerspectiveCamera):
+    """Camera "orthographic" (lib/cameras/orthographic_camera.dart:38-50): Transform.Orthographic(0, 1) projection."""
+    kind = 1
+
+    def raster_to_camera(self, xres: int, yres: int) -> np.ndarray:
+        frame = xres / yres
+        sw = self.screen_window
+        if sw is None:
+            sw = (-frame, frame, -1.0, 1.0) if frame > 1.0 else (-1.0, 1.0, -1.0 / frame, 1.0 / frame)
+        screen_to_raster = mat_mul(mat_mul(scale(float(xres), float(yres), 1.0),
+                                           scale(1.0 / (sw[1] - sw[0]), 1.0 / (sw[2] - sw[3]), 1.0)),
+                                   translate(-sw[0], -sw[3], 0.0))
+        return mat_mul(mat_inv(orthographic(0.0, 1.0)), mat_inv(screen_to_raster))
+
+
+@dataclass
+class EnvironmentCamera(PerspectiveCamera):
+    """Camera "environment" (lib/cameras/environment_camera.dart:37-52): no projection matrix, no lens."""
+    kind = 2
+
+    def raster_to_camera(self, xres: int, yres: int) -> np.ndarray:
+        return np.eye(4, dtype=np.float32)
+
+
 def filter_table(name: str = "box", xwidth: float | None = None, ywidth: float | None = None, **kw) -> tuple:
     """(xwidth, ywidth, float32[256]) — ImageFilm's precomputed table, image_film.dart:74-82."""
     defaults = {"box": 0.5, "gaussian": 2.0, "mitchell": 2.0, "triangle": 2.0, "sinc": 4.0}
@@ -342,6 +371,7 @@ def upload_scene(ctx, arrays: dict, split: int = 2, max_node_prims: int = 4):
 def configure_render(ctx, camera: PerspectiveCamera, film: Film, sampler: Sampler, integrator: Integrator):
     ctx.set_camera(camera.raster_to_camera(film.xres, film.yres), camera.camera_to_world, camera.lens_radius,
                    camera.focal_distance, camera.shutter_open, camera.shutter_close)
+    ctx.set_camera_kind(getattr(camera, "kind", 0))
     xw, yw, table = film.table()
     ctx.set_film(film.xres, film.yres, film.crop, xw, yw, table)
     ctx.set_sampler(sampler.kind, sampler.xs, sampler.ys, sampler.spp, int(sampler.jitter), sampler.pixel_order,

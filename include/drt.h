@@ -182,6 +182,12 @@ int drt_set_lights(drt_ctx* ctx, uint32_t n, const int32_t* kind, const float* L
 int drt_set_camera(drt_ctx* ctx, const float raster_to_camera[16], const float camera_to_world[16], double lens_radius,
                    double focal_distance, double shutter_open, double shutter_close);
 
+/* Which Camera plugin the matrices of drt_set_camera belong to: 0 = perspective (default), 1 = orthographic
+ * (lib/cameras/orthographic_camera.dart:52-80: origin = rasterToCamera(Pras), direction +z; same lens model),
+ * 2 = environment (lib/cameras/environment_camera.dart:42-52: direction from (theta, phi) of the raster
+ * position; raster_to_camera is ignored). */
+int drt_set_camera_kind(drt_ctx* ctx, int32_t kind);
+
 /* Replaces ImageFilm's constructor (lib/film/image_film.dart:51-97): resolution, crop window
  * (x0, x1, y0, y1; NULL = 0,1,0,1), filter widths and the 16x16 table of filter.evaluate values
  * (image_film.dart:74-82) computed by the caller's Filter object.  Resets the film. */

@@ -272,6 +272,8 @@ int orc_set_camera(orc_ctx* c, const float* rasterToCamera, const float* cameraT
   return 0;
 }
 
+int orc_set_camera_kind(orc_ctx* c, int kind) { c->rs.camera.kind = kind; return 0; }
+
 int orc_set_film(orc_ctx* c, int xres, int yres, const double* crop, double xw, double yw, const float* table) {
   Film& f = c->rs.film;
   f.xres = xres; f.yres = yres;

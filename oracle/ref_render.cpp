@@ -777,9 +777,19 @@ struct Ctx {
   // perspective_camera.dart:93-132 (the differential rays only feed texture filtering: not computed)
   Ray cameraRay(const SampleVals& s) const {
     const Camera& c = rs.camera;
+    if (c.kind == 2) {  // environment_camera.dart:42-52
+      double theta = kPi * s.imageY / rs.film.yres;
+      double phi = 2 * kPi * s.imageX / rs.film.xres;
+      Ray er(Vec(), Vec(std::sin(theta) * std::cos(phi), std::cos(theta), std::sin(theta) * std::sin(phi)), 0.0, kInf);
+      er.time = s.time;
+      Ray ew = c.cameraToWorld.ray(er);
+      ew.time = s.time;
+      return ew;
+    }
     Vec Pras(s.imageX, s.imageY, 0.0);
     Vec Pcamera = c.rasterToCamera.point(Pras);
     Ray ray(Vec(0.0, 0.0, 0.0), Normalize(Pcamera), 0.0, kInf);
+    if (c.kind == 1) ray = Ray(Pcamera, Vec(0.0, 0.0, 1.0), 0.0, kInf);  // orthographic_camera.dart:52-58
     if (c.lensRadius > 0.0) {
       double lu, lv;
       ConcentricSampleDisk(s.lensU, s.lensV, &lu, &lv);

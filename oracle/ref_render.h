@@ -153,6 +153,7 @@ struct Light {
 struct Camera {  // perspective_camera.dart:46-57 + projective_camera.dart:34-53
   Transform rasterToCamera, cameraToWorld;
   double lensRadius = 0, focalDistance = 1e30, shutterOpen = 0, shutterClose = 1;
+  int kind = 0;  // 0 perspective, 1 orthographic (orthographic_camera.dart:52-80), 2 environment (environment_camera.dart:42-52)
 };
 
 struct Film {  // image_film.dart:51-97

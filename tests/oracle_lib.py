@@ -57,6 +57,7 @@ def lib():
         L.orc_set_materials.argtypes = [vp, u32, vp, vp, vp]
         L.orc_set_lights.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
         L.orc_set_camera.argtypes = [vp, vp, vp, dbl, dbl, dbl, dbl]
+        L.orc_set_camera_kind.argtypes = [vp, i32]
         L.orc_set_film.argtypes = [vp, i32, i32, vp, dbl, dbl, vp]
         L.orc_set_sampler.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, u64, i32]
         L.orc_set_integrator.argtypes = [vp, i32, i32, i32, i32, dbl, dbl]
@@ -188,6 +189,9 @@ class Oracle:
                    shutter_close=1.0):
         r2c, c2w = _arr(raster_to_camera, np.float32).reshape(16), _arr(camera_to_world, np.float32).reshape(16)
         self._ck(self.L.orc_set_camera(self.h, _p(r2c), _p(c2w), lens_radius, focal_distance, shutter_open, shutter_close))
+
+    def set_camera_kind(self, kind):
+        self._ck(self.L.orc_set_camera_kind(self.h, kind))
 
     def set_film(self, xres, yres, crop, xwidth, ywidth, table):
         crop, table = _arr(crop, np.float64), _arr(table, np.float32)

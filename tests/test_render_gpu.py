@@ -148,6 +148,24 @@ def test_thin_lens_camera_and_random_sampler():
     assert np.abs(g2.film_read()["rgb"] - fg["rgb"]).max() > 1e-3  # the lens does change the image
 
 
+def test_orthographic_and_environment_cameras():
+    """lib/cameras/orthographic_camera.dart:52-80 and environment_camera.dart:42-52."""
+    sb, pcam = scenes.cornell_synth()
+    integ = host.Integrator(kind=host.INTEGRATOR_DIRECT)
+    ortho = host.OrthographicCamera(pcam.camera_to_world, screen_window=(-10.0, 10.0, -7.5, 7.5), lens_radius=0.3, focal_distance=30.0)
+    env = host.EnvironmentCamera(host.look_at((0, 0, 0), (0, 0, 1), (0, 1, 0)))
+    images = []
+    for cam in (ortho, env):
+        g, o, fg, fo = _render_both(sb.arrays(), cam, host.Film(64, 48), host.Sampler(kind=host.SAMPLER_LD, spp=4), integ)
+        assert fo["rgb"].mean() > 0.05
+        assert _rel_err(fg["rgb"], fo["rgb"], floor=1e-3).max() <= 1e-3
+        assert g.render_stats()["closest_rays"] == o.render_stats()["closest_rays"]
+        images.append(fg["rgb"])
+    assert np.abs(images[0] - images[1]).max() > 0.05
+    with pytest.raises(capi.DrtError):
+        capi.Context(0).set_camera_kind(7)
+
+
 # ---- film --------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("flt", ["gaussian", "mitchell", "triangle", "sinc", "box"])
 def test_filters_and_crop_window(flt):
