@@ -76,6 +76,16 @@ static __device__ __forceinline__ void ldg256(const float* p, float4& a, float4&
                : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                : "l"(p));
 }
+// Traversal-stack accesses with explicit 32-bit shared-space addresses: the generic-pointer forms cost an S2R + address
+// arithmetic per access (the compiler has to pick between the shared window and local memory).
+static __device__ __forceinline__ void sts64(unsigned addr, int32_t ref, float t) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(ref), "r"(__float_as_uint(t)) : "memory");
+}
+static __device__ __forceinline__ uint2 lds64(unsigned addr) {
+  uint2 e;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(addr) : "memory");
+  return e;
+}
 static __device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
 static __device__ __forceinline__ void slabPair(unsigned long long box, unsigned long long o2, unsigned long long i2, float* t0,
                                                 float* t1) {
@@ -124,8 +134,11 @@ static __device__ __forceinline__ int32_t testSlot(const FastRay& r, int32_t ref
                                                    const float2 bz, float* tmin) {
   if (r.negMask & 8u) {  // slow ray (warp-divergent, rare): exact decision for every box
     if (ref == DRT_REF_EMPTY) return ref;
-    return slabExact(lo32(r.ox2), lo32(r.oy2), lo32(r.oz2), lo32(r.ix2), lo32(r.iy2), lo32(r.iz2), r.mint, r.maxt, bx.x, by.x, bz.x, bx.y, by.y, bz.y, tmin) ? ref
-                                                                                                                  : DRT_REF_EMPTY;
+    float te = 0.f;  // only this temporary is address-taken: the caller's t0..t3 stay in registers
+    const bool ok = slabExact(lo32(r.ox2), lo32(r.oy2), lo32(r.oz2), lo32(r.ix2), lo32(r.iy2), lo32(r.iz2), r.mint, r.maxt, bx.x, by.x,
+                              bz.x, bx.y, by.y, bz.y, &te);
+    *tmin = te;
+    return ok ? ref : DRT_REF_EMPTY;
   }
   int c = slabFilter(r, pack2(bx.x, bx.y), pack2(by.x, by.y), pack2(bz.x, bz.y), tmin);
   int32_t marked = (c == 2 && ref < 0) ? refMarkUndecided(ref) : ref;  // an EMPTY slot is positive: never marked
@@ -140,7 +153,7 @@ static __device__ __forceinline__ int32_t testSlot(const FastRay& r, int32_t ref
     ok = false;                                                                     \
     while (sp > 0) {                                                                \
       --sp;                                                                         \
-      const uint2 e_ = STACK_LOAD(sp);                                              \
+      const uint2 e_ = sp < DRT_SMEM_STACK ? lds64(smBase + (unsigned)sp * 1024u) : deepStack[sp - DRT_SMEM_STACK]; \
       int32_t ref_ = (int32_t)e_.x;                                                 \
       float t_ = __uint_as_float(e_.y);                                             \
       float dt_ = fmaf(DRT_EPS, fabsf(t_), DRT_TINY);                               \
@@ -178,6 +191,7 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
     else deepStack[(i) - DRT_SMEM_STACK] = e__;                                                    \
   } while (0)
 #define STACK_LOAD(i) ((i) < DRT_SMEM_STACK ? smStack[(i) * 128 + threadIdx.x] : deepStack[(i) - DRT_SMEM_STACK])
+  const unsigned smBase = (unsigned)__cvta_generic_to_shared(smStack) + threadIdx.x * 8u;  // entry i of this thread: + i * 1024
   int sp = 0;
   int32_t cur = 0;
   float hb1 = 0.f, hb2 = 0.f;
@@ -228,8 +242,10 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
       if (!alive && rank < avail) {
         rayIdx = warpNext + rank;
         float4 o = __ldg(rayO + rayIdx), d = __ldg(rayD + rayIdx);
-        const float ix = __double2float_rn(1.0 / (double)d.x), iy = __double2float_rn(1.0 / (double)d.y),
-                    iz = __double2float_rn(1.0 / (double)d.z);
+        // invDir = (float)(1.0 / (double)d) (bvh_accel.dart:109-111).  The correctly rounded float32 quotient is the same
+        // value: rounding a quotient to 53 bits and then to 24 cannot differ from rounding it to 24 directly
+        // (53 >= 2 * 24 + 2), subnormal and infinite results included.
+        const float ix = __fdiv_rn(1.0f, d.x), iy = __fdiv_rn(1.0f, d.y), iz = __fdiv_rn(1.0f, d.z);
         smDir[threadIdx.x] = d.x; smDir[128 + threadIdx.x] = d.y; smDir[256 + threadIdx.x] = d.z;
         r.ox2 = pack2(o.x, o.x); r.oy2 = pack2(o.y, o.y); r.oz2 = pack2(o.z, o.z);
         r.ix2 = pack2(ix, ix); r.iy2 = pack2(iy, iy); r.iz2 = pack2(iz, iz);
@@ -300,9 +316,18 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
       const bool v0 = s0 != DRT_REF_EMPTY, v1 = s1 != DRT_REF_EMPTY, v2 = s2 != DRT_REF_EMPTY, v3 = s3 != DRT_REF_EMPTY;
       // the first passing slot becomes current; the later ones are pushed so that they pop in order.
       // Stores are unconditional, the stack pointer moves only for real pushes.
-      STACK_STORE(sp, s3, u3); sp += (v3 && (v0 || v1 || v2)) ? 1 : 0;
-      STACK_STORE(sp, s2, u2); sp += (v2 && (v0 || v1)) ? 1 : 0;
-      STACK_STORE(sp, s1, u1); sp += (v1 && v0) ? 1 : 0;
+      const int p3 = (v3 && (v0 || v1 || v2)) ? 1 : 0, p2 = (v2 && (v0 || v1)) ? 1 : 0, p1 = (v1 && v0) ? 1 : 0;
+      if (sp <= DRT_SMEM_STACK - 3) {  // all three stores land in shared memory (the common case)
+        unsigned a = smBase + (unsigned)sp * 1024u;
+        sts64(a, s3, u3); a += p3 ? 1024u : 0u;
+        sts64(a, s2, u2); a += p2 ? 1024u : 0u;
+        sts64(a, s1, u1);
+        sp += p3 + p2 + p1;
+      } else {
+        STACK_STORE(sp, s3, u3); sp += p3;
+        STACK_STORE(sp, s2, u2); sp += p2;
+        STACK_STORE(sp, s1, u1); sp += p1;
+      }
       cur = v0 ? s0 : (v1 ? s1 : (v2 ? s2 : s3));
       needPop = !(v0 || v1 || v2 || v3);
     }
