@@ -191,7 +191,11 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
     else deepStack[(i) - DRT_SMEM_STACK] = e__;                                                    \
   } while (0)
 #define STACK_LOAD(i) ((i) < DRT_SMEM_STACK ? smStack[(i) * 128 + threadIdx.x] : deepStack[(i) - DRT_SMEM_STACK])
-  const unsigned smBase = (unsigned)__cvta_generic_to_shared(smStack) + threadIdx.x * 8u;  // entry i of this thread: + i * 1024
+  // entry i of this thread: smBase + i * 1024.  Computed by a volatile asm so that the compiler keeps it in a register
+  // instead of rematerialising it (S2R SR_CgaCtaId + LEA) at every stack access.
+  unsigned smBase;
+  asm volatile("{ .reg .u64 t64; cvta.to.shared.u64 t64, %1; cvt.u32.u64 %0, t64; }" : "=r"(smBase) : "l"(smStack));
+  smBase += threadIdx.x * 8u;
   int sp = 0;
   int32_t cur = 0;
   float hb1 = 0.f, hb2 = 0.f;
