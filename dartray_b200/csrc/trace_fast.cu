@@ -155,6 +155,11 @@ static __device__ __forceinline__ int32_t testSlot(const FastRay& r, int32_t ref
       --sp;                                                                         \
       const uint2 e_ = sp < DRT_SMEM_STACK ? lds64(smBase + (unsigned)sp * 1024u) : deepStack[sp - DRT_SMEM_STACK]; \
       int32_t ref_ = (int32_t)e_.x;                                                 \
+      if (ANY) { /* maxDistance never shrinks: neither culled nor re-marked */      \
+        cur = ref_;                                                                 \
+        ok = true;                                                                  \
+        break;                                                                      \
+      }                                                                             \
       float t_ = __uint_as_float(e_.y);                                             \
       float dt_ = fmaf(DRT_EPS, fabsf(t_), DRT_TINY);                               \
       if ((t_ - dt_) >= r.maxtHi) continue; /* surely culled */                     \
