@@ -23,7 +23,7 @@ SYMBOLS = [
     "drt_set_build_order", "drt_build_bvh", "drt_bvh_info_get", "drt_bvh_export", "drt_trace_closest",
     "drt_trace_any", "drt_trace_closest_device", "drt_trace_any_device", "drt_set_counting", "drt_get_counters", "drt_set_kernel_variant",
     "drt_last_kernel_ms", "drt_kernel_launches",
-    "drt_set_materials", "drt_set_lights", "drt_set_camera", "drt_set_camera_kind", "drt_set_film", "drt_set_sampler", "drt_set_integrator",
+    "drt_set_materials", "drt_set_material_lobes", "drt_set_lights", "drt_set_camera", "drt_set_camera_kind", "drt_set_film", "drt_set_sampler", "drt_set_integrator",
     "drt_render", "drt_render_shard", "drt_set_batch_slots", "drt_film_clear", "drt_film_size", "drt_film_read",
     "drt_film_device", "drt_pixel_samples", "drt_render_stats_get",
 ]
@@ -91,6 +91,7 @@ def load():
     L.drt_kernel_launches.argtypes = [vp]
     dbl = C.c_double
     L.drt_set_materials.argtypes = [vp, u32, vp, vp, vp]
+    L.drt_set_material_lobes.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp]
     L.drt_set_lights.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
     L.drt_set_camera.argtypes = [vp, vp, vp, dbl, dbl, dbl, dbl]
     L.drt_set_camera_kind.argtypes = [vp, i32]
@@ -240,6 +241,14 @@ class Context:
     def set_materials(self, kind, kd, sigma):
         kind, kd, sigma = _arr(kind, np.int32), _arr(kd, np.float32).reshape(-1, 3), _arr(sigma, np.float32)
         self._ck(self.L.drt_set_materials(self.h, kd.shape[0], _p(kind), _p(kd), _p(sigma)))
+
+    def set_material_lobes(self, offsets, kind, rgb, fresnel, eta, k, scalars):
+        """Materials as ordered BxDF lists (host.matte_lobes / mirror_lobes / glass_lobes / plastic_lobes / ...)."""
+        offsets, kind, fresnel = _arr(offsets, np.uint32), _arr(kind, np.int32), _arr(fresnel, np.int32)
+        rgb, eta, k = (_arr(v, np.float32).reshape(-1, 3) for v in (rgb, eta, k))
+        scalars = _arr(scalars, np.float64).reshape(-1, 3)
+        self._ck(self.L.drt_set_material_lobes(self.h, offsets.shape[0] - 1, _p(offsets), _p(kind), _p(rgb), _p(fresnel), _p(eta),
+                                                _p(k), _p(scalars)))
 
     def set_lights(self, kind, L, pos, nsamples, shape_offsets, shape_prims):
         kind, L, pos = _arr(kind, np.int32), _arr(L, np.float32).reshape(-1, 3), _arr(pos, np.float32).reshape(-1, 3)

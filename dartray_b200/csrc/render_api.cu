@@ -40,6 +40,10 @@ struct ByteArena {  // one cudaMalloc per wavefront, carved into aligned arrays
 struct RenderState {
   // host-side description
   std::vector<GMaterial> materials{GMaterial{{0.5f, 0.5f, 0.5f}, 0.f}};
+  // general materials (drt_set_material_lobes): BxDF lists; empty when every material is matte
+  bool general = false, hasSpecular = false;
+  std::vector<uint2> matLobes;
+  std::vector<GLobe> lobes;
   std::vector<HostLight> lights;
   bool haveCamera = false, haveFilm = false;
   RenderParams rp{};
@@ -51,6 +55,8 @@ struct RenderState {
   DevBuf<uint32_t> dPrimToRec, dPrimAttr;
   DevBuf<GLightShape> dLightShapes;
   DevBuf<GMaterial> dMaterials;
+  DevBuf<uint2> dMatLobes;
+  DevBuf<GLobe> dLobes;
   DevBuf<GLight> dLights;
   DevBuf<float> dLightCdf, dTable;
   DevBuf<DirectOffsets> dDirect;
@@ -282,6 +288,10 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
   CK(c, cudaMemcpy(r->dPrimToRec.p, primToRec.data(), primToRec.size() * 4, cudaMemcpyHostToDevice));
   CK(c, cudaMemcpy(r->dPrimAttr.p, attr.data(), attr.size() * 4, cudaMemcpyHostToDevice));
   CK(c, cudaMemcpy(r->dMaterials.p, r->materials.data(), r->materials.size() * sizeof(GMaterial), cudaMemcpyHostToDevice));
+  CK(c, r->dMatLobes.ensure(std::max<size_t>(1, r->matLobes.size())));
+  CK(c, r->dLobes.ensure(std::max<size_t>(1, r->lobes.size())));
+  if (!r->matLobes.empty()) CK(c, cudaMemcpy(r->dMatLobes.p, r->matLobes.data(), r->matLobes.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+  if (!r->lobes.empty()) CK(c, cudaMemcpy(r->dLobes.p, r->lobes.data(), r->lobes.size() * sizeof(GLobe), cudaMemcpyHostToDevice));
   CK(c, cudaMemcpy(r->dLights.p, gl.data(), gl.size() * sizeof(GLight), cudaMemcpyHostToDevice));
   if (!shapes.empty()) CK(c, cudaMemcpy(r->dLightShapes.p, shapes.data(), shapes.size() * sizeof(GLightShape), cudaMemcpyHostToDevice));
   if (!cdf.empty()) CK(c, cudaMemcpy(r->dLightCdf.p, cdf.data(), cdf.size() * 4, cudaMemcpyHostToDevice));
@@ -292,6 +302,9 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
   rs.primToRec = r->dPrimToRec.p;
   rs.primAttr = r->dPrimAttr.p;
   rs.materials = r->dMaterials.p;
+  rs.general = r->general ? 1 : 0;
+  rs.matLobes = r->dMatLobes.p;
+  rs.lobes = r->dLobes.p;
   rs.lights = r->dLights.p;
   rs.nLights = nLights;
   rs.lightShapes = r->dLightShapes.p;
@@ -310,6 +323,7 @@ static void carve(ByteArena& a, Wavefront& wf, uint32_t cap, uint32_t shCap, int
   wf.pendSh = a.take<float>(3 * (size_t)cap); wf.pendMisF = a.take<float>(3 * (size_t)cap); wf.pendMisScale = a.take<double>(cap);
   wf.pendT = a.take<float>(3 * (size_t)cap);
   wf.shIdx = a.take<int32_t>(cap); wf.misIdx = a.take<int32_t>(cap); wf.misLight = a.take<int32_t>(cap);
+  wf.specBounce = a.take<uint8_t>(cap);
   wf.hitP = a.take<float>(3 * (size_t)cap); wf.hitN = a.take<float>(3 * (size_t)cap);
   wf.aoScramble = a.take<uint32_t>(2 * (size_t)cap); wf.nClear = a.take<int32_t>(cap);
   wf.Ld = a.take<float>(3 * (size_t)cap);
@@ -354,7 +368,10 @@ static int ensureFilm(drt_ctx* c, RenderState* r) {
   }
   CK(c, r->dTable.ensure(256));
   CK(c, cudaMemcpy(r->dTable.p, r->table, sizeof(r->table), cudaMemcpyHostToDevice));
-  CK(c, r->dCounters.ensure(1));
+  if (!r->dCounters.p) {  // cudaMalloc does not clear: a fresh context must not inherit a freed buffer's bytes as ray counts
+    CK(c, r->dCounters.ensure(1));
+    CK(c, cudaMemset(r->dCounters.p, 0, sizeof(RenderCounters)));
+  }
   r->rp.film = r->dFilm.p;
   r->rp.filterTable = r->dTable.p;
   return DRT_OK;
@@ -499,6 +516,10 @@ static int renderWindow(drt_ctx* c, int x, int y, int w, int h, uint32_t shard, 
   RenderState* r = state(c);
   RK(prepare(c, r));
   const RenderParams& p = r->rp;
+  if (p.integKind == 2 && r->hasSpecular && p.maxDepth > 1)
+    return fail(c, DRT_E_UNSUPPORTED,
+                "directlighting with specular BxDFs needs the SpecularReflect / SpecularTransmit recursion "
+                "(integrator.dart:187-290), which is not on the GPU path yet: use the path integrator or maxdepth 1");
   if (w <= 0 || h <= 0) return DRT_OK;
   const uint64_t total = (uint64_t)w * h;
   const uint32_t blockPixels = 1024;
@@ -563,6 +584,51 @@ int drt_set_materials(drt_ctx* c, uint32_t n, const int32_t* kind, const float* 
     if (kind && kind[i] != 0) return fail(c, DRT_E_INVALID, "only material kind 0 (matte) is on the GPU path");
     r->materials[i] = GMaterial{{kd[3 * i], kd[3 * i + 1], kd[3 * i + 2]}, sigma ? sigma[i] : 0.f};
   }
+  r->general = r->hasSpecular = false;
+  r->matLobes.clear();
+  r->lobes.clear();
+  r->sceneTablesValid = false;
+  return DRT_OK;
+}
+
+int drt_set_material_lobes(drt_ctx* c, uint32_t n, const uint32_t* lobe_offsets, const int32_t* lobe_kind, const float* lobe_rgb,
+                           const int32_t* fresnel_kind, const float* fresnel_eta, const float* fresnel_k,
+                           const double* lobe_scalars) {
+  if (!c) return DRT_E_INVALID;
+  if (n == 0 || !lobe_offsets) return fail(c, DRT_E_INVALID, "drt_set_material_lobes needs at least one material and its offsets");
+  const uint32_t nl = lobe_offsets[n];
+  if (nl && (!lobe_kind || !lobe_rgb || !lobe_scalars)) return fail(c, DRT_E_INVALID, "null lobe arrays");
+  RenderState* r = state(c);
+  std::vector<uint2> ml(n);
+  std::vector<GLobe> ls(nl);
+  bool spec = false;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (lobe_offsets[i + 1] < lobe_offsets[i] || lobe_offsets[i + 1] - lobe_offsets[i] > 8)
+      return fail(c, DRT_E_INVALID, "a BSDF holds at most 8 BxDFs (bsdf.dart:253) and the offsets must not decrease");
+    ml[i] = make_uint2(lobe_offsets[i], lobe_offsets[i + 1] - lobe_offsets[i]);
+  }
+  for (uint32_t j = 0; j < nl; ++j) {
+    GLobe& l = ls[j];
+    l.kind = lobe_kind[j];
+    l.fresnel = fresnel_kind ? fresnel_kind[j] : 0;
+    if (l.kind < 0 || l.kind > 4 || l.fresnel < 0 || l.fresnel > 2) return fail(c, DRT_E_INVALID, "unknown BxDF or Fresnel kind");
+    if (l.fresnel == 2 && (!fresnel_eta || !fresnel_k)) return fail(c, DRT_E_INVALID, "FresnelConductor needs eta and k");
+    for (int k = 0; k < 3; ++k) {
+      l.rgb[k] = lobe_rgb[3 * j + k];
+      l.eta[k] = fresnel_eta ? fresnel_eta[3 * j + k] : 0.f;
+      l.k[k] = fresnel_k ? fresnel_k[3 * j + k] : 0.f;
+    }
+    l.pad_ = 0.f;
+    l.param = lobe_scalars[3 * j];
+    l.ei = lobe_scalars[3 * j + 1];
+    l.et = lobe_scalars[3 * j + 2];
+    spec = spec || l.kind >= 3;
+  }
+  r->materials.assign(n, GMaterial{{0.f, 0.f, 0.f}, 0.f});  // the single-lobe table is not read when `general` is set
+  r->matLobes.swap(ml);
+  r->lobes.swap(ls);
+  r->general = true;
+  r->hasSpecular = spec;
   r->sceneTablesValid = false;
   return DRT_OK;
 }

@@ -291,6 +291,8 @@ static __device__ __forceinline__ void pushDirectWork(const Wavefront& wf, uint3
 #ifndef DRT_SHADE_MIN_BLOCKS
 #define DRT_SHADE_MIN_BLOCKS 4  // 128 registers: 16 warps/SM; 321 vs 277 Msamples/s at 2 (tools/shade_sweep.sh)
 #endif
+// GENERAL = false: every material is matte (one diffuse BxDF, never a specular bounce); true: BxDF lists.
+template <bool GENERAL>
 __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(RenderParams rp, RenderScene rs, Wavefront wf, int bounce, int cur,
                                                        RenderCounters* rc) {
   const uint32_t n = wf.counts[cur], cap = wf.cap;
@@ -321,7 +323,8 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(Ren
       hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
       Spec T = ld3(wf.T, cap, slot);
       const V3 wo = -d;
-      if (bounce == 0) {  // emitted light at the first vertex (:46-48); matte BSDFs never set specularBounce
+      // emitted light at the first vertex or after a specular bounce (:46-48); matte BSDFs never set specularBounce
+      if (bounce == 0 || (GENERAL && wf.specBounce[slot])) {
         const int li = primLight(rs, (uint32_t)prim);
         if (li >= 0) {
           Spec L = ld3(wf.L, cap, slot);
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(Ren
           st3(wf.L, cap, slot, L);
         }
       }
-      const Bsdf bsdf = makeBsdf(rs, (uint32_t)prim, h);
+      const typename BsdfOf<GENERAL>::type bsdf = makeBsdfT<GENERAL>(rs, (uint32_t)prim, h);
       p = h.p;
       rayEps = h.rayEps;
       const V3 nrm = bsdf.nn;
@@ -341,29 +344,36 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(Ren
       // direct lighting: UniformSampleOneLight (integrator.dart:79-117)
       if (rs.nLights > 0) {
         float lu0, lu1, bu0, bu1;
-        double lcomp;
+        double lcomp, bcomp;
         if (bounce < 3) {
           lightNum = (int)floor((double)val(wf, rp.pLightNum[bounce], slot) * (double)rs.nLights);
           lu0 = val(wf, rp.pLightPos[bounce], slot); lu1 = val(wf, rp.pLightPos[bounce] + 1, slot);
           lcomp = val(wf, rp.pLightComp[bounce], slot);
           bu0 = val(wf, rp.pBsdfPos[bounce], slot); bu1 = val(wf, rp.pBsdfPos[bounce] + 1, slot);
+          bcomp = GENERAL ? (double)val(wf, rp.pBsdfComp[bounce], slot) : 0.0;
         } else {
           lightNum = (int)floor(rng.randomFloat() * rs.nLights);
           lu0 = (float)rng.randomFloat(); lu1 = (float)rng.randomFloat(); lcomp = rng.randomFloat();  // LightSample.random
-          bu0 = (float)rng.randomFloat(); bu1 = (float)rng.randomFloat(); rng.randomFloat();          // BSDFSample.random
+          bu0 = (float)rng.randomFloat(); bu1 = (float)rng.randomFloat(); bcomp = rng.randomFloat();  // BSDFSample.random
         }
         lightNum = min(lightNum, rs.nLights - 1);
-        estimateDirectSetup(rs, lightNum, p, nrm, wo, rayEps, bsdf, lu0, lu1, lcomp, bu0, bu1, BSDF_ALL & ~BSDF_SPECULAR, &dw);
+        estimateDirectSetup(rs, lightNum, p, nrm, wo, rayEps, bsdf, lu0, lu1, lcomp, bu0, bu1, bcomp, BSDF_ALL & ~BSDF_SPECULAR, &dw);
         st3(wf.pendT, cap, slot, T);
       }
       // next direction (:63-92)
       float pu0, pu1;
-      if (bounce < 3) { pu0 = val(wf, rp.pPathPos[bounce], slot); pu1 = val(wf, rp.pPathPos[bounce] + 1, slot); }
-      else { pu0 = (float)rng.randomFloat(); pu1 = (float)rng.randomFloat(); rng.randomFloat(); }
+      double pcomp;
+      if (bounce < 3) {
+        pu0 = val(wf, rp.pPathPos[bounce], slot); pu1 = val(wf, rp.pPathPos[bounce] + 1, slot);
+        pcomp = GENERAL ? (double)val(wf, rp.pPathComp[bounce], slot) : 0.0;
+      } else {
+        pu0 = (float)rng.randomFloat(); pu1 = (float)rng.randomFloat(); pcomp = rng.randomFloat();
+      }
       double pdf = 0.0;
       int flags = 0;
-      Spec f = bsdfSampleF(bsdf, wo, &wi, pu0, pu1, &pdf, BSDF_ALL, &flags);
+      Spec f = bsdfSampleF(bsdf, wo, &wi, pu0, pu1, pcomp, &pdf, BSDF_ALL, &flags);
       if (!(IsBlack(f) || pdf == 0.0)) {
+        if (GENERAL) wf.specBounce[slot] = (flags & BSDF_SPECULAR) != 0 ? 1 : 0;
         T = T * (f * AbsDot(wi, nrm) / pdf);
         cont = true;
         if (bounce > 3) {  // Russian roulette (:93-99)
@@ -541,6 +551,7 @@ __global__ void __launch_bounds__(128) directSetupKernel(RenderParams rp, Render
   }
 }
 
+template <bool GENERAL>
 __global__ void __launch_bounds__(128) directSampleKernel(RenderParams rp, RenderScene rs, Wavefront wf, int light, int j,
                                                           RenderCounters* rc) {
   const uint32_t n = wf.counts[Q_EXT0];
@@ -565,7 +576,7 @@ __global__ void __launch_bounds__(128) directSampleKernel(RenderParams rp, Rende
       const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
       ShapeHit h;
       hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
-      const Bsdf bsdf = makeBsdf(rs, (uint32_t)prim, h);
+      const typename BsdfOf<GENERAL>::type bsdf = makeBsdfT<GENERAL>(rs, (uint32_t)prim, h);
       p = h.p;
       rayEps = h.rayEps;
       DirectOffsets off;
@@ -578,7 +589,8 @@ __global__ void __launch_bounds__(128) directSampleKernel(RenderParams rp, Rende
       const float lu0 = val(wf, off.lightPos + 2 * j, slot), lu1 = val(wf, off.lightPos + 2 * j + 1, slot);
       const double lcomp = val(wf, off.lightComp + j, slot);
       const float bu0 = val(wf, off.bsdfPos + 2 * j, slot), bu1 = val(wf, off.bsdfPos + 2 * j + 1, slot);
-      estimateDirectSetup(rs, lightNum, p, bsdf.nn, -d, rayEps, bsdf, lu0, lu1, lcomp, bu0, bu1, BSDF_ALL & ~BSDF_SPECULAR, &dw);
+      const double bcomp = GENERAL ? (double)val(wf, off.bsdfComp + j, slot) : 0.0;
+      estimateDirectSetup(rs, lightNum, p, bsdf.nn, -d, rayEps, bsdf, lu0, lu1, lcomp, bu0, bu1, bcomp, BSDF_ALL & ~BSDF_SPECULAR, &dw);
     }
     pushDirectWork(wf, slot, valid, dw, p, rayEps, lightNum);
     nShadow += (valid && dw.hasShadow) ? 1 : 0;
@@ -701,7 +713,8 @@ cudaError_t launchResetCounts(const Wavefront& wf, unsigned mask, cudaStream_t s
 
 cudaError_t launchShadePath(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int bounce, int cur,
                             RenderCounters* rc, int numSMs, cudaStream_t st) {
-  shadePathKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, bounce, cur, rc);
+  if (rs.general) shadePathKernel<true><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, bounce, cur, rc);
+  else shadePathKernel<false><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, bounce, cur, rc);
   return cudaGetLastError();
 }
 
@@ -743,7 +756,8 @@ cudaError_t launchDirectSetup(const RenderParams& rp, const RenderScene& rs, con
 
 cudaError_t launchDirectSample(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int light, int j,
                                RenderCounters* rc, int numSMs, cudaStream_t st) {
-  directSampleKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, j, rc);
+  if (rs.general) directSampleKernel<true><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, j, rc);
+  else directSampleKernel<false><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, j, rc);
   return cudaGetLastError();
 }
 

@@ -12,6 +12,20 @@ struct GMaterial {  // matte_material.dart:41-65 with constant textures
   float sigma;
 };
 
+// One BxDF of a material's BSDF (drt_set_material_lobes; lib/core/reflection/*.dart with constant textures):
+// kind 0 Lambertian, 1 OrenNayar (param = sigma in degrees), 2 Microfacet with a Blinn distribution (param = exponent),
+// 3 SpecularReflection, 4 SpecularTransmission (ei, et); fresnel 0 FresnelNoOp, 1 FresnelDielectric(ei, et),
+// 2 FresnelConductor(eta, k).
+struct GLobe {
+  int32_t kind, fresnel;
+  float rgb[3];
+  float eta[3];
+  float k[3];
+  float pad_;
+  double param, ei, et;
+};
+static_assert(sizeof(GLobe) == 72, "GLobe layout");
+
 struct GLight {
   int32_t kind;  // 0 = DiffuseAreaLight (diffuse_area_light.dart), 1 = PointLight (point_light.dart)
   float L[3];    // Lemit / intensity
@@ -46,6 +60,10 @@ struct RenderScene {
   const uint32_t* primToRec;  // primitive id -> GPrim record
   const uint32_t* primAttr;   // bits 0-15 material, 16-30 light + 1, 31 reverseOrientation
   const GMaterial* materials;
+  // general materials (any BxDF list): material m owns lobes [matLobes[m].x, matLobes[m].x + matLobes[m].y)
+  int32_t general;  // 0: every material is matte and the shading kernels take the single-lobe path
+  const uint2* matLobes;
+  const GLobe* lobes;
   const GLight* lights;
   int32_t nLights;
   const GLightShape* lightShapes;
@@ -104,6 +122,7 @@ struct Wavefront {
   double* pendMisScale;
   float* pendT;                      // 3 x cap: throughput the direct estimate is multiplied by
   int32_t* shIdx; int32_t* misIdx; int32_t* misLight;
+  uint8_t* specBounce;               // path integrator: the last sampled BxDF was specular (path_integrator.dart:85)
   // AO / direct-lighting per-slot state
   float* hitP; float* hitN;          // 3 x cap each
   uint32_t* aoScramble;              // 2 x cap

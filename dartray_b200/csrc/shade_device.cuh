@@ -18,6 +18,7 @@ namespace drt {
 
 #define DRT_PI 3.141592653589793
 #define DRT_INV_PI 0.31830988618379067154
+#define DRT_INV_TWOPI 0.15915494309189533577
 #define DRT_ONE_MINUS_EPS 0.9999999403953552  // montecarlo.dart:23
 
 // ---- Vector / Point / Normal (vector.dart:26-218) ---------------------------------------------------
@@ -491,6 +492,235 @@ static __device__ inline Spec bsdfSampleF(const Bsdf& b, const V3& woW, V3* wiW,
   return r;
 }
 
+// The single-lobe BSDF ignores the component sample (one candidate, nothing to pick)
+static __device__ inline Spec bsdfSampleF(const Bsdf& b, const V3& woW, V3* wiW, float u0, float u1, double comp, double* pdfOut,
+                                          int flags, int* sampledType) {
+  (void)comp;
+  return bsdfSampleF(b, woW, wiW, u0, u1, pdfOut, flags, sampledType);
+}
+
+// ---- general BSDF: an ordered list of BxDFs per material (bsdf.dart:41-255; lambertian / oren_nayar / microfacet +
+// blinn / specular_reflection / specular_transmission / fresnel_*.dart).  Used when drt_set_material_lobes defined
+// the materials; scenes with matte materials only keep the single-lobe code above.
+struct BsdfG {
+  V3 nn, ng, sn, tn;
+  int n;
+  const GLobe* lobes;
+};
+static __device__ inline V3 bsdfToLocal(const BsdfG& b, const V3& v) { return mkv(Dot(v, b.sn), Dot(v, b.tn), Dot(v, b.nn)); }
+static __device__ inline V3 bsdfToWorld(const BsdfG& b, const V3& v) {
+  return mkv((double)b.sn.x * v.x + (double)b.tn.x * v.y + (double)b.nn.x * v.z,
+             (double)b.sn.y * v.x + (double)b.tn.y * v.y + (double)b.nn.y * v.z,
+             (double)b.sn.z * v.x + (double)b.tn.z * v.y + (double)b.nn.z * v.z);
+}
+static __device__ inline BsdfG makeBsdfG(const RenderScene& rs, uint32_t prim, const ShapeHit& h) {
+  BsdfG b;
+  b.nn = h.nn;
+  b.ng = h.nn;
+  b.sn = Normalize(h.dpdu);
+  b.tn = Cross(b.nn, b.sn);
+  const uint2 ml = __ldg(rs.matLobes + primMaterial(rs, prim));
+  b.lobes = rs.lobes + ml.x;
+  b.n = (int)ml.y;
+  return b;
+}
+// dart:math min / max: NaN when either argument is NaN
+static __device__ inline double dartMin(double a, double b) { return (isnan(a) || isnan(b)) ? CUDART_NAN : (a < b ? a : b); }
+static __device__ inline double dartMax(double a, double b) { return (isnan(a) || isnan(b)) ? CUDART_NAN : (a > b ? a : b); }
+static __device__ inline Spec operator-(const Spec& a, const Spec& b) { return mks((double)a.r - b.r, (double)a.g - b.g, (double)a.b - b.b); }
+static __device__ inline Spec operator/(const Spec& a, const Spec& b) { return mks((double)a.r / b.r, (double)a.g / b.g, (double)a.b / b.b); }
+static __device__ inline bool SameHemisphere(const V3& w, const V3& wp) { return (double)w.z * wp.z > 0.0; }  // vector.dart:194-196
+
+static __device__ inline int lobeType(int kind) {
+  return kind <= 1 ? (BSDF_REFLECTION | BSDF_DIFFUSE)
+                   : (kind == 2 ? (BSDF_REFLECTION | BSDF_GLOSSY)
+                                : (kind == 3 ? (BSDF_REFLECTION | BSDF_SPECULAR) : (BSDF_TRANSMISSION | BSDF_SPECULAR)));
+}
+static __device__ inline bool lobeMatches(const GLobe& l, int flags) { const int t = lobeType(l.kind); return (t & flags) == t; }
+
+static __device__ inline Spec fresnelDielectric(double cosi, double eta_i, double eta_t) {  // fresnel_dielectric.dart:24-56
+  if (!isnan(cosi)) cosi = clampD(cosi, -1.0, 1.0);
+  const bool entering = cosi > 0.0;
+  double ei = eta_i, et = eta_t;
+  if (!entering) { const double t = ei; ei = et; et = t; }
+  const double sint = ei / et * sqrt(dartMax(0.0, 1.0 - cosi * cosi));
+  if (sint >= 1.0) return mks1(1.0);
+  const double cost = sqrt(dartMax(0.0, 1.0 - sint * sint));
+  cosi = fabs(cosi);
+  const double Rparl = ((et * cosi) - (ei * cost)) / ((et * cosi) + (ei * cost));
+  const double Rperp = ((ei * cosi) - (et * cost)) / ((ei * cosi) + (et * cost));
+  return mks1((Rparl * Rparl + Rperp * Rperp) / 2.0);
+}
+static __device__ inline Spec lobeFresnel(const GLobe& l, double cosi) {
+  if (l.fresnel == 0) return mks1(1.0);  // fresnel_no_op.dart
+  if (l.fresnel == 1) return fresnelDielectric(cosi, l.ei, l.et);
+  cosi = fabs(cosi);  // fresnel_conductor.dart:24-49
+  const Spec ONE = mks1(1.0), cosSqr = mks1(cosi * cosi);
+  const Spec eta = Spec{l.eta[0], l.eta[1], l.eta[2]}, k = Spec{l.k[0], l.k[1], l.k[2]};
+  const Spec tmp = (eta * eta + k * k) * (cosi * cosi);
+  Spec r1 = (tmp - (eta * (2.0 * cosi)) + ONE);
+  Spec r2 = (tmp + (eta * (2.0 * cosi)) + ONE);
+  const Spec Rparl2 = r1 / r2;
+  const Spec tmp_f = eta * eta + k * k;
+  r1 = (tmp_f - (eta * (2.0 * cosi)) + cosSqr);
+  r2 = (tmp_f + (eta * (2.0 * cosi)) + cosSqr);
+  const Spec Rperp2 = r1 / r2;
+  return (Rparl2 + Rperp2) / 2.0;
+}
+static __device__ inline double blinnPdfOf(double exponent, double costheta, double woDotWh) {  // blinn.dart:50-56,62-68
+  double pdf = ((exponent + 1.0) * pow(costheta, exponent)) / (2.0 * DRT_PI * 4.0 * woDotWh);
+  if (woDotWh <= 0.0) pdf = 0.0;
+  return pdf;
+}
+static __device__ inline Spec lobeF(const GLobe& l, const V3& wo, const V3& wi) {
+  const Spec R = Spec{l.rgb[0], l.rgb[1], l.rgb[2]};
+  if (l.kind == 0) return R * DRT_INV_PI;  // lambertian.dart:35-37
+  if (l.kind == 1) {                       // oren_nayar.dart:24-58
+    const double sigma = (DRT_PI / 180.0) * l.param, sigma2 = sigma * sigma;
+    const double A = 1.0 - (sigma2 / (2.0 * (sigma2 + 0.33))), B = 0.45 * sigma2 / (sigma2 + 0.09);
+    const double sinthetai = SinTheta(wi), sinthetao = SinTheta(wo);
+    double maxcos = 0.0;
+    if (sinthetai > 1e-4 && sinthetao > 1e-4) {
+      const double dcos = CosPhi(wi) * CosPhi(wo) + SinPhi(wi) * SinPhi(wo);
+      maxcos = fmax(0.0, dcos);
+    }
+    double sinalpha, tanbeta;
+    if (AbsCosTheta(wi) > AbsCosTheta(wo)) { sinalpha = sinthetao; tanbeta = sinthetai / AbsCosTheta(wi); }
+    else { sinalpha = sinthetai; tanbeta = sinthetao / AbsCosTheta(wo); }
+    return R * (DRT_INV_PI * (A + B * maxcos * sinalpha * tanbeta));
+  }
+  if (l.kind == 2) {  // microfacet.dart:28-57, blinn.dart:31-34
+    const double cosThetaO = AbsCosTheta(wo), cosThetaI = AbsCosTheta(wi);
+    if (cosThetaI == 0.0 || cosThetaO == 0.0) return mks1(0.0);
+    V3 wh = wi + wo;
+    if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return mks1(0.0);
+    wh = Normalize(wh);
+    const double cosThetaH = Dot(wi, wh);
+    const Spec F = lobeFresnel(l, cosThetaH);
+    const double NdotWh = AbsCosTheta(wh), WOdotWh = AbsDot(wo, wh);
+    const double G = dartMin(1.0, dartMin((2.0 * NdotWh * cosThetaO / WOdotWh), (2.0 * NdotWh * cosThetaI / WOdotWh)));
+    const double D = (l.param + 2.0) * DRT_INV_TWOPI * pow(NdotWh, l.param);
+    return R * (D * G) * F / (4.0 * cosThetaI * cosThetaO);
+  }
+  return mks1(0.0);  // specular BxDFs: f == 0
+}
+static __device__ inline double lobePdf(const GLobe& l, const V3& wo, const V3& wi) {
+  if (l.kind <= 1) return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * DRT_INV_PI : 0.0;  // bxdf.dart:84-88
+  if (l.kind == 2) {                                                                     // microfacet.dart:68-73
+    if (!SameHemisphere(wo, wi)) return 0.0;
+    const V3 wh = Normalize(wo + wi);
+    return blinnPdfOf(l.param, AbsCosTheta(wh), Dot(wo, wh));
+  }
+  return 0.0;
+}
+// *pdfOut is left untouched when the BxDF returns without setting it (specular_transmission.dart:52-54)
+static __device__ inline Spec lobeSampleF(const GLobe& l, const V3& wo, V3* wi, double u1, double u2, double* pdfOut) {
+  if (l.kind <= 1) {  // bxdf.dart:37-48
+    *wi = CosineSampleHemisphere(u1, u2);
+    if (wo.z < 0.0f) wi->z = (float)((double)wi->z * -1.0);
+    *pdfOut = lobePdf(l, wo, *wi);
+    return lobeF(l, wo, *wi);
+  }
+  if (l.kind == 2) {  // microfacet.dart:59-66 + blinn.dart:36-60
+    const double exponent = l.param;
+    const double costheta = pow(u1, 1.0 / (exponent + 1.0));
+    const double sintheta = sqrt(dartMax(0.0, 1.0 - costheta * costheta));
+    const double phi = u2 * 2.0 * DRT_PI;
+    V3 wh = mkv(sintheta * cos(phi), sintheta * sin(phi), costheta);
+    if (!SameHemisphere(wo, wh)) wh = -wh;
+    *wi = -wo + wh * 2.0 * Dot(wo, wh);
+    *pdfOut = blinnPdfOf(exponent, costheta, Dot(wo, wh));
+    if (!SameHemisphere(wo, *wi)) return mks1(0.0);
+    return lobeF(l, wo, *wi);
+  }
+  const Spec R = Spec{l.rgb[0], l.rgb[1], l.rgb[2]};
+  if (l.kind == 3) {  // specular_reflection.dart:34-41
+    *wi = V3{-wo.x, -wo.y, wo.z};
+    *pdfOut = 1.0;
+    return (lobeFresnel(l, (double)wo.z) * R) / AbsCosTheta(*wi);
+  }
+  // specular_transmission.dart:37-66
+  const bool entering = (double)wo.z > 0.0;
+  double ei = l.ei, et = l.et;
+  if (!entering) { const double t = ei; ei = et; et = t; }
+  const double sini2 = SinTheta2(wo);
+  const double eta = ei / et;
+  const double sint2 = eta * eta * sini2;
+  if (sint2 >= 1.0) return mks1(0.0);
+  double cost = sqrt(dartMax(0.0, 1.0 - sint2));
+  if (entering) cost = -cost;
+  *wi = mkv(eta * -(double)wo.x, eta * -(double)wo.y, cost);
+  *pdfOut = 1.0;
+  const Spec F = fresnelDielectric((double)wo.z, l.ei, l.et);
+  return ((mks1(1.0) - F) * R) / AbsCosTheta(*wi);
+}
+
+static __device__ inline Spec bsdfF(const BsdfG& b, const V3& woW, const V3& wiW, int flags) {  // bsdf.dart:177-198
+  const V3 wi = bsdfToLocal(b, wiW), wo = bsdfToLocal(b, woW);
+  if (Dot(wiW, b.ng) * Dot(woW, b.ng) > 0) flags &= ~BSDF_TRANSMISSION;
+  else flags &= ~BSDF_REFLECTION;
+  Spec r = mks1(0.0);
+  for (int i = 0; i < b.n; ++i) {
+    const GLobe l = b.lobes[i];
+    if (lobeMatches(l, flags)) r = r + lobeF(l, wo, wi);
+  }
+  return r;
+}
+static __device__ inline double bsdfPdf(const BsdfG& b, const V3& woW, const V3& wiW, int flags) {  // bsdf.dart:128-146
+  if (b.n == 0) return 0.0;
+  const V3 wo = bsdfToLocal(b, woW), wi = bsdfToLocal(b, wiW);
+  double p = 0.0;
+  int matching = 0;
+  for (int i = 0; i < b.n; ++i) {
+    const GLobe l = b.lobes[i];
+    if (lobeMatches(l, flags)) { ++matching; p += lobePdf(l, wo, wi); }
+  }
+  return matching > 0 ? p / matching : 0.0;
+}
+static __device__ inline Spec bsdfSampleF(const BsdfG& b, const V3& woW, V3* wiW, float u0, float u1, double comp, double* pdfOut,
+                                          int flags, int* sampledType) {  // bsdf.dart:53-126
+  *sampledType = 0;
+  *pdfOut = 0.0;
+  int matching = 0;
+  for (int i = 0; i < b.n; ++i) matching += lobeMatches(b.lobes[i], flags) ? 1 : 0;
+  if (matching == 0) return mks1(0.0);
+  const int which = min((int)floor(comp * matching), matching - 1);
+  int chosen = 0, count = which;
+  for (int i = 0; i < b.n; ++i)
+    if (lobeMatches(b.lobes[i], flags) && count-- == 0) { chosen = i; break; }
+  const GLobe lc = b.lobes[chosen];
+  const int type = lobeType(lc.kind);
+  const V3 wo = bsdfToLocal(b, woW);
+  V3 wi = V3{0.f, 0.f, 0.f};
+  Spec f = lobeSampleF(lc, wo, &wi, (double)u0, (double)u1, pdfOut);
+  if (*pdfOut == 0.0) return mks1(0.0);
+  *sampledType = type;
+  *wiW = bsdfToWorld(b, wi);
+  if (!((type & BSDF_SPECULAR) != 0) && matching > 1)
+    for (int i = 0; i < b.n; ++i) {
+      const GLobe l = b.lobes[i];
+      if (i != chosen && lobeMatches(l, flags)) *pdfOut += lobePdf(l, wo, wi);
+    }
+  if (matching > 1) *pdfOut /= matching;
+  if ((type & BSDF_SPECULAR) == 0) {
+    f = mks1(0.0);
+    if (Dot(*wiW, b.ng) * Dot(woW, b.ng) > 0) flags &= ~BSDF_TRANSMISSION;
+    else flags &= ~BSDF_REFLECTION;
+    for (int i = 0; i < b.n; ++i) {
+      const GLobe l = b.lobes[i];
+      if (lobeMatches(l, flags)) f = f + lobeF(l, wo, wi);
+    }
+  }
+  return f;
+}
+
+template <bool GENERAL> struct BsdfOf { typedef Bsdf type; };
+template <> struct BsdfOf<true> { typedef BsdfG type; };
+template <bool GENERAL>
+static __device__ inline typename BsdfOf<GENERAL>::type makeBsdfT(const RenderScene& rs, uint32_t prim, const ShapeHit& h);
+template <> __device__ inline Bsdf makeBsdfT<false>(const RenderScene& rs, uint32_t prim, const ShapeHit& h) { return makeBsdf(rs, prim, h); }
+template <> __device__ inline BsdfG makeBsdfT<true>(const RenderScene& rs, uint32_t prim, const ShapeHit& h) { return makeBsdfG(rs, prim, h); }
+
 // ---- lights (diffuse_area_light.dart:44-70, shape_set.dart:43-96, shape.dart:100-121,
 // triangle.dart:265-269,366-383, sphere.dart:243-311, point_light.dart:41-47) --------------------------
 static __device__ inline Spec lightRadiance(const GLight& l) { return Spec{l.L[0], l.L[1], l.L[2]}; }
@@ -649,9 +879,10 @@ struct DirectWork {
   double misScale;  // |wi.n| * weight / bsdfPdf
 };
 
+template <typename BSDF>
 static __device__ inline void estimateDirectSetup(const RenderScene& rs, int lightIndex, const V3& p, const V3& n, const V3& wo,
-                                                  double rayEps, const Bsdf& bsdf, float lu0, float lu1, double lcomp, float bu0,
-                                                  float bu1, int flags, DirectWork* w) {
+                                                  double rayEps, const BSDF& bsdf, float lu0, float lu1, double lcomp, float bu0,
+                                                  float bu1, double bcomp, int flags, DirectWork* w) {
   const GLight l = rs.lights[lightIndex];
   w->hasShadow = false;
   w->hasMis = false;
@@ -698,7 +929,7 @@ static __device__ inline void estimateDirectSetup(const RenderScene& rs, int lig
   }
   if (!delta) {
     int sampledType = 0;
-    Spec f = bsdfSampleF(bsdf, wo, &wi, bu0, bu1, &bPdf, flags, &sampledType);
+    Spec f = bsdfSampleF(bsdf, wo, &wi, bu0, bu1, bcomp, &bPdf, flags, &sampledType);
     if (!IsBlack(f) && bPdf > 0.0) {
       double weight = 1.0;
       if ((sampledType & BSDF_SPECULAR) == 0) {

@@ -235,6 +235,95 @@ class Integrator:
 # ---- scene assembly: meshes / spheres / lights in the reference's refine order ---------------------------
 
 
+# ---- materials as ordered BxDF lists (drt_set_material_lobes) ----------------------------------------------------
+# The Dart shim does the same flattening when it walks GeometricPrimitive.material: every Material.getBSDF below only
+# evaluates constant textures, so the BxDF list of a material is a constant of the scene.  Spectrum arithmetic is
+# float32 storage / float64 expressions like RGBColor (rgb_color.dart:142-169).
+LOBE_LAMBERTIAN, LOBE_OREN_NAYAR, LOBE_MICROFACET_BLINN, LOBE_SPECULAR_REFLECTION, LOBE_SPECULAR_TRANSMISSION = range(5)
+FRESNEL_NOOP, FRESNEL_DIELECTRIC, FRESNEL_CONDUCTOR = range(3)
+
+
+def _spec(v) -> np.ndarray:
+    return np.broadcast_to(np.asarray(v, np.float64), (3,)).astype(np.float32)
+
+
+def _clamp(s) -> np.ndarray:  # Spectrum.clamp (spectrum.dart:263-269)
+    return np.clip(_spec(s).astype(np.float64), 0.0, np.inf).astype(np.float32)
+
+
+def _mul(a, b) -> np.ndarray:
+    return (a.astype(np.float64) * np.asarray(b, np.float64)).astype(np.float32)
+
+
+def _black(s) -> bool:
+    return not bool(np.any(s != 0))
+
+
+def _lobe(kind, rgb, fresnel=FRESNEL_NOOP, eta=(0, 0, 0), k=(0, 0, 0), param=0.0, ei=1.0, et=1.0) -> dict:
+    return dict(kind=int(kind), rgb=_spec(rgb), fresnel=int(fresnel), eta=_spec(eta), k=_spec(k), param=float(param),
+                ei=float(ei), et=float(et))
+
+
+def _blinn_exponent(roughness: float) -> float:  # 1 / roughness, then blinn.dart:24-28
+    with np.errstate(divide="ignore"):
+        e = float(np.float64(1.0) / np.float64(roughness))
+    return 10000.0 if (e > 10000.0 or math.isnan(e)) else e
+
+
+def matte_lobes(kd=0.5, sigma=0.0) -> list:  # matte_material.dart:41-65
+    r, sig = _clamp(kd), min(max(float(sigma), 0.0), 90.0)
+    if _black(r):
+        return []
+    return [_lobe(LOBE_LAMBERTIAN, r)] if sig == 0.0 else [_lobe(LOBE_OREN_NAYAR, r, param=sig)]
+
+
+def mirror_lobes(kr=0.9) -> list:  # mirror_material.dart:26-43
+    r = _clamp(kr)
+    return [] if _black(r) else [_lobe(LOBE_SPECULAR_REFLECTION, r, FRESNEL_NOOP)]
+
+
+def glass_lobes(kr=1.0, kt=1.0, index=1.5) -> list:  # glass_material.dart:26-52
+    out, r, t = [], _clamp(kr), _clamp(kt)
+    if not _black(r):
+        out.append(_lobe(LOBE_SPECULAR_REFLECTION, r, FRESNEL_DIELECTRIC, ei=1.0, et=index))
+    if not _black(t):
+        out.append(_lobe(LOBE_SPECULAR_TRANSMISSION, t, FRESNEL_DIELECTRIC, ei=1.0, et=index))
+    return out
+
+
+def plastic_lobes(kd=0.25, ks=0.25, roughness=0.1) -> list:  # plastic_material.dart:26-53
+    out, d, sp = [], _clamp(kd), _clamp(ks)
+    if not _black(d):
+        out.append(_lobe(LOBE_LAMBERTIAN, d))
+    if not _black(sp):
+        out.append(_lobe(LOBE_MICROFACET_BLINN, sp, FRESNEL_DIELECTRIC, param=_blinn_exponent(roughness), ei=1.5, et=1.0))
+    return out
+
+
+def metal_lobes(eta, k, roughness=0.01) -> list:  # metal_material.dart:26-46 (eta / k given as RGB)
+    return [_lobe(LOBE_MICROFACET_BLINN, 1.0, FRESNEL_CONDUCTOR, eta=eta, k=k, param=_blinn_exponent(roughness))]
+
+
+def uber_lobes(kd=0.25, ks=0.25, kr=0.0, kt=0.0, roughness=0.1, index=1.5, opacity=1.0) -> list:  # uber_material.dart:27-75
+    out, op = [], _clamp(opacity)
+    if not bool(np.all(op == 1.0)):
+        t = ((-op.astype(np.float64)).astype(np.float32).astype(np.float64) + 1.0).astype(np.float32)
+        out.append(_lobe(LOBE_SPECULAR_TRANSMISSION, t, FRESNEL_DIELECTRIC, ei=1.0, et=1.0))
+    d = _mul(op, _clamp(kd))
+    if not _black(d):
+        out.append(_lobe(LOBE_LAMBERTIAN, d))
+    sp = _mul(op, _clamp(ks))
+    if not _black(sp):
+        out.append(_lobe(LOBE_MICROFACET_BLINN, sp, FRESNEL_DIELECTRIC, param=_blinn_exponent(roughness), ei=index, et=1.0))
+    r = _mul(op, _clamp(kr))
+    if not _black(r):
+        out.append(_lobe(LOBE_SPECULAR_REFLECTION, r, FRESNEL_DIELECTRIC, ei=index, et=1.0))
+    t = _mul(op, _clamp(kt))
+    if not _black(t):
+        out.append(_lobe(LOBE_SPECULAR_TRANSMISSION, t, FRESNEL_DIELECTRIC, ei=index, et=1.0))
+    return out
+
+
 class SceneBuilder:
     """Collects shapes in scene-file order and produces the flat arrays of the C ABI."""
 
@@ -250,6 +339,11 @@ class SceneBuilder:
 
     def material(self, kd, sigma=0.0) -> int:
         self.materials.append((0, tuple(float(v) for v in kd), float(sigma)))
+        return len(self.materials) - 1
+
+    def material_lobes(self, lobes: list) -> int:
+        """A material given as its ordered BxDF list (mirror_lobes, glass_lobes, plastic_lobes, metal_lobes, uber_lobes ...)."""
+        self.materials.append(("lobes", list(lobes)))
         return len(self.materials) - 1
 
     def point_light(self, pos, intensity) -> int:
@@ -329,6 +423,11 @@ class SceneBuilder:
             shapes = [base[s[0]] + s[1] for s in l["shapes"]]
             lights.append(dict(kind=l["kind"], L=l["L"], pos=l["pos"], nsamples=l["nsamples"], shapes=shapes))
         mats = self.materials or [(0, (0.5, 0.5, 0.5), 0.0)]
+        general = any(m[0] == "lobes" for m in mats)
+        lobe_lists = [m[1] if m[0] == "lobes" else matte_lobes(m[1], m[2]) for m in mats]
+        lobes = [l for ll in lobe_lists for l in ll]
+        if general:  # the matte-only entry point cannot carry these: upload_scene uses drt_set_material_lobes instead
+            mats = [(0, (0.0, 0.0, 0.0), 0.0) for _ in mats]
         return dict(
             P=P, idx=idx, tri_mat=np.asarray(self.tri_mat, np.int32), tri_light=np.asarray(self.tri_light, np.int32),
             tri_rev=np.asarray(self.tri_rev, np.uint8),
@@ -345,6 +444,14 @@ class SceneBuilder:
             order=np.asarray(order, np.uint32),
             mat_kind=np.asarray([m[0] for m in mats], np.int32), mat_kd=np.asarray([m[1] for m in mats], np.float32),
             mat_sigma=np.asarray([m[2] for m in mats], np.float32),
+            mat_general=general,
+            mat_lobe_offsets=np.asarray(np.cumsum([0] + [len(ll) for ll in lobe_lists]), np.uint32),
+            lobe_kind=np.asarray([l["kind"] for l in lobes], np.int32),
+            lobe_rgb=np.asarray([l["rgb"] for l in lobes], np.float32).reshape(-1, 3),
+            lobe_fresnel=np.asarray([l["fresnel"] for l in lobes], np.int32),
+            lobe_eta=np.asarray([l["eta"] for l in lobes], np.float32).reshape(-1, 3),
+            lobe_k=np.asarray([l["k"] for l in lobes], np.float32).reshape(-1, 3),
+            lobe_scalars=np.asarray([(l["param"], l["ei"], l["et"]) for l in lobes], np.float64).reshape(-1, 3),
             light_kind=np.asarray([l["kind"] for l in lights], np.int32),
             light_L=np.asarray([l["L"] for l in lights], np.float32).reshape(-1, 3),
             light_pos=np.asarray([l["pos"] for l in lights], np.float32).reshape(-1, 3),
@@ -363,7 +470,11 @@ def upload_scene(ctx, arrays: dict, split: int = 2, max_node_prims: int = 4):
         ctx.set_disks(a["dsk_o2w"], a["dsk_w2o"], a["dsk_params"], a["dsk_mat"], a["dsk_light"], a["dsk_rev"])
     ctx.set_build_order(a["order"])
     ctx.build_bvh(split, max_node_prims)
-    ctx.set_materials(a["mat_kind"], a["mat_kd"], a["mat_sigma"])
+    if a.get("mat_general"):
+        ctx.set_material_lobes(a["mat_lobe_offsets"], a["lobe_kind"], a["lobe_rgb"], a["lobe_fresnel"], a["lobe_eta"], a["lobe_k"],
+                               a["lobe_scalars"])
+    else:
+        ctx.set_materials(a["mat_kind"], a["mat_kd"], a["mat_sigma"])
     ctx.set_lights(a["light_kind"], a["light_L"], a["light_pos"], a["light_nsamples"], a["light_shape_offsets"],
                    a["light_shape_prims"])
 

@@ -171,17 +171,25 @@ def incoherent_rays(n: int = 8_388_608, radius: float = 2.5, seed_origin: int = 
     return pack_rays(o32, d.astype(np.float32))
 
 
-def cornell_synth():
+def cornell_synth(overrides: dict | None = None):
     """the 22 triangles + sphere of web/scenes/cornell-path.pbrt:23-59 (same
     transforms and Kd values) with the disk light (:15-19) replaced by a 2-triangle quad light,
-    4.24 x 4.24 at y = 9.9 facing -y, L = (36, 36, 36), nsamples 1.  Returns (SceneBuilder, camera)."""
+    4.24 x 4.24 at y = 9.9 facing -y, L = (36, 36, 36), nsamples 1.  Returns (SceneBuilder, camera).
+    `overrides` maps "grey" / "red" / "green" / "box" / "sphere" to BxDF lists (host.mirror_lobes(...), ...) for the
+    material tests; None keeps the file's matte materials."""
     from . import host
 
     sb = host.SceneBuilder()
-    grey = sb.material((0.75, 0.75, 0.75))
-    red = sb.material((0.48, 0.1125, 0.075))
-    green = sb.material((0.1125, 0.375, 0.1125))
-    box = sb.material((0.48, 0.48, 0.48))
+    ov = overrides or {}
+
+    def mat(name, kd):
+        return sb.material_lobes(ov[name]) if name in ov else sb.material(kd)
+
+    grey = mat("grey", (0.75, 0.75, 0.75))
+    red = mat("red", (0.48, 0.1125, 0.075))
+    green = mat("green", (0.1125, 0.375, 0.1125))
+    box = mat("box", (0.48, 0.48, 0.48))
+    ball = mat("sphere", (0.48, 0.48, 0.48)) if "sphere" in ov else box
     h = 2.12
     sb.mesh([[-h, 9.9, -h], [h, 9.9, -h], [h, 9.9, h], [-h, 9.9, h]], [[0, 1, 2], [0, 2, 3]], material=grey,
             area_light=(36.0, 36.0, 36.0), nsamples=1)
@@ -208,7 +216,7 @@ def cornell_synth():
     ]
     for q, p in faces:
         sb.mesh(np.asarray(p, np.float32).reshape(4, 3), q, material=box, o2w=o2w)
-    sb.sphere(host.translate(-4, -4, 0), radius=3.0, material=box)
+    sb.sphere(host.translate(-4, -4, 0), radius=3.0, material=ball)
     cam = host.PerspectiveCamera(host.look_at((0, 0, -35), (0, 0, 0), (0, 1, 0)), fov=35.0)
     return sb, cam
 

@@ -38,7 +38,8 @@ enum {
   DRT_E_STATE = -2,     /* call order (e.g. trace before build) */
   DRT_E_CUDA = -3,      /* CUDA runtime error, text in drt_last_error */
   DRT_E_NODEVICE = -4,  /* no CUDA device: there is no CPU fallback */
-  DRT_E_NOMEM = -5
+  DRT_E_NOMEM = -5,
+  DRT_E_UNSUPPORTED = -6 /* a reference feature that is not on the GPU path: the caller keeps the Dart renderer for it */
 };
 
 /* BVHAccel split methods, lib/accelerators/bvh_accel.dart:37-39 */
@@ -166,6 +167,25 @@ uint64_t drt_kernel_launches(const drt_ctx* ctx);
  * textures (lib/core/texture/constant_texture.dart:23-39).  kind: 0 = matte (the only kind on the
  * path, NULL = all 0); kd_rgb: n x 3; sigma: n (degrees, NULL = 0).  Material index = position. */
 int drt_set_materials(drt_ctx* ctx, uint32_t n, const int32_t* kind, const float* kd_rgb, const float* sigma);
+
+/* Materials as ordered BxDF lists: what Material.getBSDF builds with constant textures, for the materials whose
+ * getBSDF only adds these BxDFs: matte (lib/materials/matte_material.dart:41-65), mirror
+ * (mirror_material.dart:26-43), glass (glass_material.dart:26-52), plastic (plastic_material.dart:26-53), metal
+ * (metal_material.dart:26-46), uber (uber_material.dart:27-75).  Material i owns lobes [lobe_offsets[i],
+ * lobe_offsets[i + 1]) in the order of its bsdf.add calls (BSDF.sample_f picks by position, bsdf.dart:68-79; at most 8,
+ * bsdf.dart:253).  Per lobe:
+ *   lobe_kind     0 Lambertian (lambertian.dart), 1 OrenNayar (oren_nayar.dart), 2 Microfacet with a Blinn distribution
+ *                 (microfacet.dart, blinn.dart), 3 SpecularReflection, 4 SpecularTransmission
+ *   lobe_rgb      R / T of the BxDF, already clamped and multiplied as the material does (n_lobes x 3)
+ *   fresnel_kind  0 FresnelNoOp, 1 FresnelDielectric(ei, et), 2 FresnelConductor(eta, k) (fresnel_*.dart); NULL = all 0
+ *   fresnel_eta, fresnel_k   conductor spectra as RGB (n_lobes x 3; NULL when no lobe uses a conductor)
+ *   lobe_scalars  n_lobes x 3 doubles: {Blinn exponent after blinn.dart:24-28 | OrenNayar sigma in degrees, ei, et}
+ * The path and ambient-occlusion integrators take every combination; directlighting returns DRT_E_UNSUPPORTED from
+ * drt_render when a specular BxDF is present and maxdepth > 1 (its SpecularReflect / SpecularTransmit recursion,
+ * lib/core/integrator.dart:187-290, is not on the GPU path yet).  Replaces a previous drt_set_materials and vice versa. */
+int drt_set_material_lobes(drt_ctx* ctx, uint32_t n, const uint32_t* lobe_offsets, const int32_t* lobe_kind, const float* lobe_rgb,
+                           const int32_t* fresnel_kind, const float* fresnel_eta, const float* fresnel_k,
+                           const double* lobe_scalars);
 
 /* Replaces scene.lights: DiffuseAreaLight (kind 0, lib/lights/diffuse_area_light.dart:44-70; L = Lemit
  * x scale) and PointLight (kind 1, lib/lights/point_light.dart:41-47; L = intensity, pos = world

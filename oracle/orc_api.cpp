@@ -238,10 +238,30 @@ int orc_get_counters(const orc_ctx* c, uint64_t out[3]) {
 int orc_set_materials(orc_ctx* c, uint32_t n, const int32_t* kind, const float* kd, const float* sigma) {
   c->rs.materials.resize(n);
   for (uint32_t i = 0; i < n; ++i) {
-    Material& m = c->rs.materials[i];
-    m.kind = kind ? kind[i] : 0;
-    m.kd = Spec(kd[3 * i], kd[3 * i + 1], kd[3 * i + 2]);
-    m.sigma = sigma ? sigma[i] : 0.0;
+    if (kind && kind[i] != 0) return -1;
+    c->rs.materials[i] = Material::matte(Spec(kd[3 * i], kd[3 * i + 1], kd[3 * i + 2]), sigma ? sigma[i] : 0.0);
+  }
+  return 0;
+}
+
+// mirrors drt_set_material_lobes (include/drt.h): material i owns lobes [offsets[i], offsets[i + 1])
+int orc_set_material_lobes(orc_ctx* c, uint32_t n, const uint32_t* offsets, const int32_t* kind, const float* rgb,
+                           const int32_t* fresnel, const float* eta, const float* k, const double* scalars) {
+  c->rs.materials.assign(n, Material());
+  for (uint32_t i = 0; i < n; ++i) {
+    if (offsets[i + 1] - offsets[i] > 8) return -1;
+    for (uint32_t j = offsets[i]; j < offsets[i + 1]; ++j) {
+      Lobe l;
+      l.kind = kind[j];
+      l.R = Spec(rgb[3 * j], rgb[3 * j + 1], rgb[3 * j + 2]);
+      l.fresnel = fresnel ? fresnel[j] : 0;
+      if (eta) l.eta = Spec(eta[3 * j], eta[3 * j + 1], eta[3 * j + 2]);
+      if (k) l.k = Spec(k[3 * j], k[3 * j + 1], k[3 * j + 2]);
+      l.param = scalars[3 * j];
+      l.ei = scalars[3 * j + 1];
+      l.et = scalars[3 * j + 2];
+      c->rs.materials[i].lobes.push_back(l);
+    }
   }
   return 0;
 }

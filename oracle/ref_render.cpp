@@ -140,6 +140,21 @@ static inline int RoundUpPow2(int v) {  // common.dart:117-125
   return v + 1;
 }
 
+// matte_material.dart:41-65 with constant textures
+Material Material::matte(const Spec& kd, double sigma) {
+  Material m;
+  Spec r(clampd(kd.c[0], 0.0, kInf), clampd(kd.c[1], 0.0, kInf), clampd(kd.c[2], 0.0, kInf));
+  double sig = clampd(sigma, 0.0, 90.0);
+  if (!r.isBlack()) {
+    Lobe l;
+    l.R = r;
+    if (sig == 0.0) l.kind = 0;
+    else { l.kind = 1; l.param = sig; }
+    m.lobes.push_back(l);
+  }
+  return m;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // film, lib/film/image_film.dart
 void Film::configure() {  // :51-97
@@ -260,73 +275,238 @@ struct U3 {  // LightSample / BSDFSample: two float32 values + one f64 component
   }
 };
 
-struct Bsdf {  // bsdf.dart:41-255 with at most one diffuse BxDF (matte)
-  Vec p, nn, ng, sn, tn;
-  bool hasBxdf = false;
-  Spec R;
-  bool orenNayar = false;
-  double A = 0, B = 0;
-  Vec worldToLocal(const Vec& v) const { return Vec(Dot(v, sn), Dot(v, tn), Dot(v, nn)); }
-  Vec localToWorld(const Vec& v) const {
-    return Vec((double)sn.x * v.x + (double)tn.x * v.y + (double)nn.x * v.z,
-               (double)sn.y * v.x + (double)tn.y * v.y + (double)nn.y * v.z,
-               (double)sn.z * v.x + (double)tn.z * v.y + (double)nn.z * v.z);
-  }
+// dart:math min / max return NaN when either argument is NaN
+static inline double dmin(double a, double b) { return (std::isnan(a) || std::isnan(b)) ? std::nan("") : (a < b ? a : b); }
+static inline double dmax(double a, double b) { return (std::isnan(a) || std::isnan(b)) ? std::nan("") : (a > b ? a : b); }
+
+// One BxDF with its per-hit constants (lib/core/reflection/*.dart).  Local frame: z = shading normal.
+struct LobeEval {
+  Lobe l;
+  int type = 0;
+  double A = 0, B = 0;  // OrenNayar (oren_nayar.dart:24-31)
+
   static double CosTheta(const Vec& v) { return v.z; }
   static double AbsCosTheta(const Vec& v) { return std::fabs((double)v.z); }
   static double SinTheta2(const Vec& v) { return std::fmax(0.0, 1.0 - CosTheta(v) * CosTheta(v)); }
   static double SinTheta(const Vec& v) { return std::sqrt(SinTheta2(v)); }
   static double CosPhi(const Vec& v) { double s = SinTheta(v); return s == 0.0 ? 1.0 : clampd((double)v.x / s, -1.0, 1.0); }
   static double SinPhi(const Vec& v) { double s = SinTheta(v); return s == 0.0 ? 0.0 : clampd((double)v.y / s, -1.0, 1.0); }
-  Spec bxdfF(const Vec& wo, const Vec& wi) const {
-    if (!orenNayar) return R * INV_PI;  // lambertian.dart:35-37
-    // oren_nayar.dart:33-58
-    double sinthetai = SinTheta(wi), sinthetao = SinTheta(wo);
-    double maxcos = 0.0;
-    if (sinthetai > 1e-4 && sinthetao > 1e-4) {
-      double dcos = CosPhi(wi) * CosPhi(wo) + SinPhi(wi) * SinPhi(wo);
-      maxcos = std::fmax(0.0, dcos);
+  static bool SameHemisphere(const Vec& w, const Vec& wp) { return (double)w.z * wp.z > 0.0; }  // vector.dart:194-196
+
+  void init(const Lobe& lobe) {
+    l = lobe;
+    switch (l.kind) {
+      case 0: type = BSDF_REFLECTION | BSDF_DIFFUSE; break;
+      case 1: {
+        type = BSDF_REFLECTION | BSDF_DIFFUSE;
+        double sigma = Radians(l.param), sigma2 = sigma * sigma;
+        A = 1.0 - (sigma2 / (2.0 * (sigma2 + 0.33)));
+        B = 0.45 * sigma2 / (sigma2 + 0.09);
+        break;
+      }
+      case 2: type = BSDF_REFLECTION | BSDF_GLOSSY; break;
+      case 3: type = BSDF_REFLECTION | BSDF_SPECULAR; break;
+      default: type = BSDF_TRANSMISSION | BSDF_SPECULAR; break;
     }
-    double sinalpha, tanbeta;
-    if (AbsCosTheta(wi) > AbsCosTheta(wo)) { sinalpha = sinthetao; tanbeta = sinthetai / AbsCosTheta(wi); }
-    else { sinalpha = sinthetai; tanbeta = sinthetao / AbsCosTheta(wo); }
-    return R * (INV_PI * (A + B * maxcos * sinalpha * tanbeta));
   }
-  static double bxdfPdf(const Vec& wo, const Vec& wi) {  // bxdf.dart:84-88
-    return ((double)wo.z * wi.z > 0.0) ? AbsCosTheta(wi) * INV_PI : 0.0;
+  bool matches(int flags) const { return (type & flags) == type; }  // bxdf.dart:31-33
+
+  // fresnel_dielectric.dart:24-56, fresnel_conductor.dart:24-49, fresnel_no_op.dart
+  static Spec dielectric(double cosi, double eta_i, double eta_t) {
+    cosi = std::isnan(cosi) ? cosi : clampd(cosi, -1.0, 1.0);
+    bool entering = cosi > 0.0;
+    double ei = eta_i, et = eta_t;
+    if (!entering) std::swap(ei, et);
+    double sint = ei / et * std::sqrt(dmax(0.0, 1.0 - cosi * cosi));
+    if (sint >= 1.0) return Spec(1.0);
+    double cost = std::sqrt(dmax(0.0, 1.0 - sint * sint));
+    cosi = std::fabs(cosi);
+    double Rparl = ((et * cosi) - (ei * cost)) / ((et * cosi) + (ei * cost));
+    double Rperp = ((ei * cosi) - (et * cost)) / ((ei * cosi) + (et * cost));
+    return Spec((Rparl * Rparl + Rperp * Rperp) / 2.0);
   }
-  static bool matches(int flags) { int type = BSDF_REFLECTION | BSDF_DIFFUSE; return (type & flags) == type; }
+  Spec fresnel(double cosi) const {
+    if (l.fresnel == 0) return Spec(1.0);
+    if (l.fresnel == 1) return dielectric(cosi, l.ei, l.et);
+    cosi = std::fabs(cosi);
+    const Spec ONE(1.0), cosSqr(cosi * cosi);
+    const Spec& eta = l.eta;
+    const Spec& k = l.k;
+    Spec tmp = (eta * eta + k * k) * (cosi * cosi);
+    Spec r1 = (tmp - (eta * (2.0 * cosi)) + ONE);
+    Spec r2 = (tmp + (eta * (2.0 * cosi)) + ONE);
+    Spec Rparl2 = r1 / r2;
+    Spec tmp_f = eta * eta + k * k;
+    r1 = (tmp_f - (eta * (2.0 * cosi)) + cosSqr);
+    r2 = (tmp_f + (eta * (2.0 * cosi)) + cosSqr);
+    Spec Rperp2 = r1 / r2;
+    return (Rparl2 + Rperp2) / 2.0;
+  }
+
+  // blinn.dart:31-71
+  double blinnD(const Vec& wh) const {
+    double costhetah = AbsCosTheta(wh);
+    return (l.param + 2.0) * INV_TWOPI * std::pow(costhetah, l.param);
+  }
+  double blinnSample(const Vec& wo, Vec* wi, double u1, double u2) const {
+    const double exponent = l.param;
+    double costheta = std::pow(u1, 1.0 / (exponent + 1.0));
+    double sintheta = std::sqrt(dmax(0.0, 1.0 - costheta * costheta));
+    double phi = u2 * 2.0 * kPi;
+    Vec wh(sintheta * std::cos(phi), sintheta * std::sin(phi), costheta);  // vector.dart:172-176
+    if (!SameHemisphere(wo, wh)) wh = -wh;
+    *wi = -wo + wh * 2.0 * Dot(wo, wh);
+    double pdf = ((exponent + 1.0) * std::pow(costheta, exponent)) / (2.0 * kPi * 4.0 * Dot(wo, wh));
+    if (Dot(wo, wh) <= 0.0) pdf = 0.0;
+    return pdf;
+  }
+  double blinnPdf(const Vec& wo, const Vec& wi) const {
+    const double exponent = l.param;
+    Vec wh = Normalize(wo + wi);
+    double costheta = AbsCosTheta(wh);
+    double pdf = ((exponent + 1.0) * std::pow(costheta, exponent)) / (2.0 * kPi * 4.0 * Dot(wo, wh));
+    if (Dot(wo, wh) <= 0.0) pdf = 0.0;
+    return pdf;
+  }
+
+  Spec f(const Vec& wo, const Vec& wi) const {
+    switch (l.kind) {
+      case 0: return l.R * INV_PI;  // lambertian.dart:35-37
+      case 1: {                     // oren_nayar.dart:33-58
+        double sinthetai = SinTheta(wi), sinthetao = SinTheta(wo);
+        double maxcos = 0.0;
+        if (sinthetai > 1e-4 && sinthetao > 1e-4) {
+          double dcos = CosPhi(wi) * CosPhi(wo) + SinPhi(wi) * SinPhi(wo);
+          maxcos = std::fmax(0.0, dcos);
+        }
+        double sinalpha, tanbeta;
+        if (AbsCosTheta(wi) > AbsCosTheta(wo)) { sinalpha = sinthetao; tanbeta = sinthetai / AbsCosTheta(wi); }
+        else { sinalpha = sinthetai; tanbeta = sinthetao / AbsCosTheta(wo); }
+        return l.R * (INV_PI * (A + B * maxcos * sinalpha * tanbeta));
+      }
+      case 2: {  // microfacet.dart:28-57
+        double cosThetaO = AbsCosTheta(wo), cosThetaI = AbsCosTheta(wi);
+        if (cosThetaI == 0.0 || cosThetaO == 0.0) return Spec(0.0);
+        Vec wh = wi + wo;
+        if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return Spec(0.0);
+        wh = Normalize(wh);
+        double cosThetaH = Dot(wi, wh);
+        Spec F = fresnel(cosThetaH);
+        double NdotWh = AbsCosTheta(wh), NdotWo = AbsCosTheta(wo), NdotWi = AbsCosTheta(wi), WOdotWh = AbsDot(wo, wh);
+        double G = dmin(1.0, dmin((2.0 * NdotWh * NdotWo / WOdotWh), (2.0 * NdotWh * NdotWi / WOdotWh)));
+        return l.R * (blinnD(wh) * G) * F / (4.0 * cosThetaI * cosThetaO);
+      }
+      default: return Spec(0.0);  // specular_reflection.dart:30-32, specular_transmission.dart:33-35
+    }
+  }
+  double pdf(const Vec& wo, const Vec& wi) const {
+    switch (l.kind) {
+      case 0:
+      case 1: return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * INV_PI : 0.0;  // bxdf.dart:84-88
+      case 2: return SameHemisphere(wo, wi) ? blinnPdf(wo, wi) : 0.0;          // microfacet.dart:68-73
+      default: return 0.0;
+    }
+  }
+  // pdf is untouched when a BxDF returns without setting it (specular_transmission.dart:52-54)
+  Spec sample_f(const Vec& wo, Vec* wi, double u1, double u2, double* pdfOut) const {
+    switch (l.kind) {
+      case 0:
+      case 1: {  // bxdf.dart:37-48
+        *wi = CosineSampleHemisphere(u1, u2);
+        if (wo.z < 0.0f) wi->z = f32((double)wi->z * -1.0);
+        *pdfOut = pdf(wo, *wi);
+        return f(wo, *wi);
+      }
+      case 2: {  // microfacet.dart:59-66
+        *pdfOut = blinnSample(wo, wi, u1, u2);
+        if (!SameHemisphere(wo, *wi)) return Spec(0.0);
+        return f(wo, *wi);
+      }
+      case 3: {  // specular_reflection.dart:34-41
+        *wi = Vec(-(double)wo.x, -(double)wo.y, wo.z);
+        *pdfOut = 1.0;
+        return (fresnel(CosTheta(wo)) * l.R) / AbsCosTheta(*wi);
+      }
+      default: {  // specular_transmission.dart:37-66
+        bool entering = CosTheta(wo) > 0.0;
+        double ei = l.ei, et = l.et;
+        if (!entering) std::swap(ei, et);
+        double sini2 = SinTheta2(wo);
+        double eta = ei / et;
+        double sint2 = eta * eta * sini2;
+        if (sint2 >= 1.0) return Spec(0.0);
+        double cost = std::sqrt(dmax(0.0, 1.0 - sint2));
+        if (entering) cost = -cost;
+        double sintOverSini = eta;
+        *wi = Vec(sintOverSini * -(double)wo.x, sintOverSini * -(double)wo.y, cost);
+        *pdfOut = 1.0;
+        Spec F = dielectric(CosTheta(wo), l.ei, l.et);
+        return ((Spec(1.0) - F) * l.R) / AbsCosTheta(*wi);
+      }
+    }
+  }
+};
+
+struct Bsdf {  // bsdf.dart:41-255
+  Vec p, nn, ng, sn, tn;
+  int nBxDFs = 0;
+  LobeEval bxdfs[8];
+  Vec worldToLocal(const Vec& v) const { return Vec(Dot(v, sn), Dot(v, tn), Dot(v, nn)); }
+  Vec localToWorld(const Vec& v) const {
+    return Vec((double)sn.x * v.x + (double)tn.x * v.y + (double)nn.x * v.z,
+               (double)sn.y * v.x + (double)tn.y * v.y + (double)nn.y * v.z,
+               (double)sn.z * v.x + (double)tn.z * v.y + (double)nn.z * v.z);
+  }
+  int numComponents(int flags) const {
+    int n = 0;
+    for (int i = 0; i < nBxDFs; ++i) n += bxdfs[i].matches(flags) ? 1 : 0;
+    return n;
+  }
   Spec f(const Vec& woW, const Vec& wiW, int flags) const {  // bsdf.dart:177-198
     Vec wi = worldToLocal(wiW), wo = worldToLocal(woW);
     if (Dot(wiW, ng) * Dot(woW, ng) > 0) flags &= ~BSDF_TRANSMISSION;
     else flags &= ~BSDF_REFLECTION;
     Spec r(0.0);
-    if (hasBxdf && matches(flags)) r = r + bxdfF(wo, wi);
+    for (int i = 0; i < nBxDFs; ++i)
+      if (bxdfs[i].matches(flags)) r = r + bxdfs[i].f(wo, wi);
     return r;
   }
   double pdf(const Vec& woW, const Vec& wiW, int flags) const {  // bsdf.dart:128-146
-    if (!hasBxdf) return 0.0;
+    if (nBxDFs == 0) return 0.0;
     Vec wo = worldToLocal(woW), wi = worldToLocal(wiW);
     double p = 0.0;
     int matching = 0;
-    if (matches(flags)) { ++matching; p += bxdfPdf(wo, wi); }
+    for (int i = 0; i < nBxDFs; ++i)
+      if (bxdfs[i].matches(flags)) { ++matching; p += bxdfs[i].pdf(wo, wi); }
     return matching > 0 ? p / matching : 0.0;
   }
   Spec sample_f(const Vec& woW, Vec* wiW, const U3& s, double* pdfOut, int flags, int* sampledType) const {  // :53-126
-    int matching = (hasBxdf && matches(flags)) ? 1 : 0;
+    int matching = numComponents(flags);
     if (matching == 0) { *pdfOut = 0.0; if (sampledType) *sampledType = 0; return Spec(0.0); }
+    int which = std::min((int)std::floor(s.comp * matching), matching - 1);
+    const LobeEval* bxdf = nullptr;
+    int count = which;
+    for (int i = 0; i < nBxDFs; ++i)
+      if (bxdfs[i].matches(flags) && count-- == 0) { bxdf = &bxdfs[i]; break; }
     Vec wo = worldToLocal(woW);
-    Vec wi = CosineSampleHemisphere(s.u0, s.u1);  // bxdf.dart:37-48
-    if (wo.z < 0.0f) wi.z = f32((double)wi.z * -1.0);
-    *pdfOut = bxdfPdf(wo, wi);
+    Vec wi;
+    *pdfOut = 0.0;
+    Spec f = bxdf->sample_f(wo, &wi, s.u0, s.u1, pdfOut);
     if (*pdfOut == 0.0) { if (sampledType) *sampledType = 0; return Spec(0.0); }
-    if (sampledType) *sampledType = BSDF_REFLECTION | BSDF_DIFFUSE;
+    if (sampledType) *sampledType = bxdf->type;
     *wiW = localToWorld(wi);
-    Spec r(0.0);
-    if (Dot(*wiW, ng) * Dot(woW, ng) > 0) flags &= ~BSDF_TRANSMISSION;
-    else flags &= ~BSDF_REFLECTION;
-    if (matches(flags)) r = r + bxdfF(wo, wi);
-    return r;
+    if (!((bxdf->type & BSDF_SPECULAR) != 0) && matching > 1)
+      for (int i = 0; i < nBxDFs; ++i)
+        if (&bxdfs[i] != bxdf && bxdfs[i].matches(flags)) *pdfOut += bxdfs[i].pdf(wo, wi);
+    if (matching > 1) *pdfOut /= matching;
+    if ((bxdf->type & BSDF_SPECULAR) == 0) {
+      f = Spec(0.0);
+      if (Dot(*wiW, ng) * Dot(woW, ng) > 0) flags &= ~BSDF_TRANSMISSION;
+      else flags &= ~BSDF_REFLECTION;
+      for (int i = 0; i < nBxDFs; ++i)
+        if (bxdfs[i].matches(flags)) f = f + bxdfs[i].f(wo, wi);
+    }
+    return f;
   }
 };
 
@@ -480,18 +660,7 @@ struct Ctx {
     b.sn = Normalize(dg.dpdu);
     b.tn = Cross(b.nn, b.sn);
     const Material& m = rs.materials[g.materialOf[is.prim]];
-    Spec r(clampd(m.kd.c[0], 0.0, kInf), clampd(m.kd.c[1], 0.0, kInf), clampd(m.kd.c[2], 0.0, kInf));
-    double sig = clampd(m.sigma, 0.0, 90.0);
-    if (!r.isBlack()) {
-      b.hasBxdf = true;
-      b.R = r;
-      if (sig != 0.0) {  // oren_nayar.dart:24-31
-        b.orenNayar = true;
-        double sigma = Radians(sig), sigma2 = sigma * sigma;
-        b.A = 1.0 - (sigma2 / (2.0 * (sigma2 + 0.33)));
-        b.B = 0.45 * sigma2 / (sigma2 + 0.09);
-      }
-    }
+    for (const Lobe& l : m.lobes) b.bxdfs[b.nBxDFs++].init(l);
     return b;
   }
 
@@ -766,10 +935,25 @@ struct Ctx {
       else L = L + UniformSampleOneLight(p, n, wo, isect.rayEpsilon, ray.time, bsdf, sample, rng, dlLightNum, &dlLight[0], &dlBsdf[0]);
     }
     if (ray.depth + 1 < rs.integ.maxDepth) {
-      // SpecularReflect / SpecularTransmit (integrator.dart:187-290): a matte BSDF has no specular
-      // component, so both return black — after drawing a BSDFSample.random(rng) each.
-      U3::random(rng);
-      U3::random(rng);
+      L = L + specularBranch(ray, bsdf, isect, sample, rng, BSDF_REFLECTION | BSDF_SPECULAR);
+      L = L + specularBranch(ray, bsdf, isect, sample, rng, BSDF_TRANSMISSION | BSDF_SPECULAR);
+    }
+    return L;
+  }
+
+  // Integrator.SpecularReflect / SpecularTransmit (integrator.dart:187-290) without the ray differentials (they only
+  // feed texture filtering): one BSDFSample.random(rng) is drawn whether or not the BSDF has such a component.
+  Spec specularBranch(const Ray& ray, const Bsdf& bsdf, const Isect& isect, const SampleVals& sample, Rng& rng, int flags) {
+    Vec wo = -ray.d, wi;
+    double pdf = 0.0;
+    Vec p = bsdf.p, n = bsdf.nn;
+    U3 u = U3::random(rng);
+    Spec f = bsdf.sample_f(wo, &wi, u, &pdf, flags, nullptr);
+    Spec L(0.0);
+    if (pdf > 0.0 && !f.isBlack() && AbsDot(wi, n) != 0.0) {
+      Ray rd(p, wi, isect.rayEpsilon, kInf, ray.time, ray.depth + 1);  // RayDifferential.child
+      Spec Li = LiRay(rd, sample, rng);
+      L = f * Li * (AbsDot(wi, n) / pdf);
     }
     return L;
   }
@@ -806,10 +990,9 @@ struct Ctx {
     return w;
   }
 
-  // sampler_renderer.dart:67-98 + :173-193
-  Spec Li(const SampleVals& s, Rng& rng) {
-    Ray ray = cameraRay(s);
-    stats.cameraSamples++;
+  // SamplerRenderer.Li (sampler_renderer.dart:67-98): also what the specular recursion calls
+  Spec LiRay(const Ray& rayIn, const SampleVals& s, Rng& rng) {
+    Ray ray = rayIn;  // Scene.intersect shrinks ray.maxDistance to the hit (geometric_primitive.dart:47-61)
     Isect isect;
     Spec L(0.0);
     if (intersect(ray, &isect)) {
@@ -819,9 +1002,16 @@ struct Ctx {
         default: L = directLi(ray, isect, s, rng); break;
       }
     }  // else sum of lights[i].Le(ray) == 0 for area / point lights
-    // T * Li + Lvi with T = 1, Lvi = 0; then * rayWeight (1.0)
-    L = Spec(1.0) * L + Spec(0.0);
-    L = L * 1.0;
+    // T * Li + Lvi with T = 1, Lvi = 0
+    return Spec(1.0) * L + Spec(0.0);
+  }
+
+  // sampler_renderer.dart:173-193
+  Spec Li(const SampleVals& s, Rng& rng) {
+    Ray ray = cameraRay(s);
+    stats.cameraSamples++;
+    Spec L = LiRay(ray, s, rng);
+    L = L * 1.0;  // rayWeight
     if (L.hasNaNs()) L = Spec(0.0);
     else if (L.luminance() < -1e-5) L = Spec(0.0);
     else if (std::isinf(L.luminance())) L = Spec(0.0);

@@ -43,6 +43,8 @@ struct Spec {
 static inline Spec operator+(const Spec& a, const Spec& b) { return Spec((double)a.c[0] + b.c[0], (double)a.c[1] + b.c[1], (double)a.c[2] + b.c[2]); }
 static inline Spec operator*(const Spec& a, const Spec& b) { return Spec((double)a.c[0] * b.c[0], (double)a.c[1] * b.c[1], (double)a.c[2] * b.c[2]); }
 static inline Spec operator*(const Spec& a, double s) { return Spec((double)a.c[0] * s, (double)a.c[1] * s, (double)a.c[2] * s); }
+static inline Spec operator-(const Spec& a, const Spec& b) { return Spec((double)a.c[0] - b.c[0], (double)a.c[1] - b.c[1], (double)a.c[2] - b.c[2]); }
+static inline Spec operator/(const Spec& a, const Spec& b) { return Spec((double)a.c[0] / b.c[0], (double)a.c[1] / b.c[1], (double)a.c[2] / b.c[2]); }
 static inline Spec operator/(const Spec& a, double s) { return Spec((double)a.c[0] / s, (double)a.c[1] / s, (double)a.c[2] / s); }
 
 // ---- random streams -----------------------------------------------------------------------------
@@ -125,10 +127,28 @@ static const uint32_t kStreamPixel = 4095;          // stratified / random sampl
 static const uint32_t kStreamIntegrator = 0x80000000u;
 
 // ---- scene description beyond geometry ----------------------------------------------------------------
-struct Material {  // matte_material.dart:41-65 with constant textures
-  int kind = 0;
-  Spec kd = Spec(0.5);
-  double sigma = 0.0;
+// One BxDF of a material's BSDF with constant textures.  The materials of lib/materials/*.dart decompose into
+// ordered lists of these (the order is the order of their bsdf.add calls, which BSDF.sample_f's component choice
+// depends on, bsdf.dart:68-79):
+//   matte    matte_material.dart:41-65      Lambertian | OrenNayar
+//   mirror   mirror_material.dart:26-43     SpecularReflection(Kr, FresnelNoOp)
+//   glass    glass_material.dart:26-52      SpecularReflection(Kr, FresnelDielectric(1, ior)) + SpecularTransmission(Kt, 1, ior)
+//   plastic  plastic_material.dart:26-53    Lambertian(Kd) + Microfacet(Ks, FresnelDielectric(1.5, 1), Blinn(1/roughness))
+//   metal    metal_material.dart:26-46      Microfacet(1, FresnelConductor(eta, k), Blinn(1/roughness))
+//   uber     uber_material.dart:27-75       SpecularTransmission(1-op, 1, 1) + Lambertian + Microfacet + SpecularReflection + SpecularTransmission
+struct Lobe {
+  int kind = 0;     // 0 Lambertian, 1 OrenNayar, 2 Microfacet(Blinn), 3 SpecularReflection, 4 SpecularTransmission
+  Spec R;           // R / T of the BxDF (already clamped by the material)
+  int fresnel = 0;  // 0 FresnelNoOp, 1 FresnelDielectric(ei, et), 2 FresnelConductor(eta, k)
+  Spec eta, k;      // conductor
+  double ei = 1.0, et = 1.0;  // FresnelDielectric / SpecularTransmission indices
+  double param = 0.0;         // Blinn exponent (blinn.dart:24-28: clamped to 10000) | OrenNayar sigma in degrees
+};
+
+struct Material {
+  std::vector<Lobe> lobes;  // <= 8 (bsdf.dart:253)
+  // matte_material.dart:41-65 with constant Kd / sigma
+  static Material matte(const Spec& kd, double sigma);
 };
 
 struct Distribution1D {  // montecarlo.dart:25-98

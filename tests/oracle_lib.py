@@ -55,6 +55,7 @@ def lib():
         L.orc_get_counters.argtypes = [vp, vp]
         dbl = C.c_double
         L.orc_set_materials.argtypes = [vp, u32, vp, vp, vp]
+        L.orc_set_material_lobes.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp]
         L.orc_set_lights.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
         L.orc_set_camera.argtypes = [vp, vp, vp, dbl, dbl, dbl, dbl]
         L.orc_set_camera_kind.argtypes = [vp, i32]
@@ -179,6 +180,14 @@ class Oracle:
     def set_materials(self, kind, kd, sigma):
         kind, kd, sigma = _arr(kind, np.int32), _arr(kd, np.float32).reshape(-1, 3), _arr(sigma, np.float32)
         self._ck(self.L.orc_set_materials(self.h, kd.shape[0], _p(kind), _p(kd), _p(sigma)))
+
+    def set_material_lobes(self, offsets, kind, rgb, fresnel, eta, k, scalars):
+        """Materials as ordered BxDF lists (host.matte_lobes / mirror_lobes / glass_lobes / plastic_lobes / ...)."""
+        offsets, kind, fresnel = _arr(offsets, np.uint32), _arr(kind, np.int32), _arr(fresnel, np.int32)
+        rgb, eta, k = (_arr(v, np.float32).reshape(-1, 3) for v in (rgb, eta, k))
+        scalars = _arr(scalars, np.float64).reshape(-1, 3)
+        self._ck(self.L.orc_set_material_lobes(self.h, offsets.shape[0] - 1, _p(offsets), _p(kind), _p(rgb), _p(fresnel), _p(eta),
+                                                _p(k), _p(scalars)))
 
     def set_lights(self, kind, L, pos, nsamples, shape_offsets, shape_prims):
         kind, L, pos = _arr(kind, np.int32), _arr(L, np.float32).reshape(-1, 3), _arr(pos, np.float32).reshape(-1, 3)

@@ -131,6 +131,92 @@ def test_path_deep_bounces_use_the_integrator_stream():
     assert abs(fg["rgb"].mean() - fo["rgb"].mean()) <= 5e-3 * fo["rgb"].mean()
 
 
+# ---- materials beyond matte: BxDF lists through drt_set_material_lobes -------------------------------
+def _material_cornell(which):
+    ov = {
+        "specular": {"sphere": host.glass_lobes(1.0, 1.0, 1.5), "box": host.mirror_lobes((0.9, 0.85, 0.7))},
+        "glossy": {"grey": host.plastic_lobes((0.6, 0.6, 0.55), 0.3, 0.08), "sphere": host.metal_lobes((0.2, 0.92, 1.1), (3.9, 2.45, 2.14), 0.05),
+                   "box": host.matte_lobes((0.5, 0.4, 0.3), 25.0)},
+        "uber": {"sphere": host.uber_lobes(kd=(0.3, 0.2, 0.2), ks=0.3, kr=0.2, kt=0.25, roughness=0.15, index=1.33, opacity=(0.8, 0.7, 0.9)),
+                 "box": host.uber_lobes(kd=0.4, ks=0.2, roughness=0.3), "red": host.plastic_lobes((0.48, 0.1, 0.07), 0.2, 0.3)},
+    }[which]
+    sb, cam = scenes.cornell_synth(ov)
+    return sb.arrays(), cam
+
+
+@pytest.mark.parametrize("which", ["specular", "glossy", "uber"])
+def test_path_integrator_with_bxdf_lists_matches_oracle(which):
+    arrays, cam = _material_cornell(which)
+    spp = 16
+    g, o, fg, fo = _render_both(arrays, cam, host.Film(64, 48), host.Sampler(kind=host.SAMPLER_LD, spp=spp),
+                                host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=7))
+    err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
+    print(which, "max rel err", err.max(), "q999", np.quantile(err, 0.999), "pixels differing", int((fg["rgb"] != fo["rgb"]).any(axis=2).sum()))
+    assert np.isfinite(fg["rgb"]).all()
+    # north_star: per-pixel mean within 3 sigma of the Monte Carlo noise; replayed streams do far better
+    sigma = fo["rgb"].std() / math.sqrt(spp)
+    assert np.quantile(np.abs(fg["rgb"] - fo["rgb"]), 0.999) <= 3 * sigma
+    assert abs(fg["rgb"].mean() - fo["rgb"].mean()) <= 5e-3 * fo["rgb"].mean()
+    # libm pow / sin / cos differ from CUDA's in the last ulp and a specular path can amplify that: allow 1 % of the pixels
+    assert np.quantile(err, 0.99) <= 1e-3
+    sg, so = g.render_stats(), o.render_stats()
+    assert abs(sg["closest_rays"] - so["closest_rays"]) <= 2e-3 * so["closest_rays"]
+    assert abs(sg["shadow_rays"] - so["shadow_rays"]) <= 2e-3 * so["shadow_rays"]
+    # and the materials do change the picture
+    plain = capi.Context(0)
+    sb0, _ = scenes.cornell_synth()
+    host.upload_scene(plain, sb0.arrays())
+    host.configure_render(plain, cam, host.Film(64, 48), host.Sampler(kind=host.SAMPLER_LD, spp=spp), host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=7))
+    plain.render()
+    assert np.abs(plain.film_read()["rgb"] - fg["rgb"]).mean() > 1e-2
+
+
+def test_direct_lighting_with_glossy_bxdf_lists_matches_oracle_per_pixel():
+    arrays, cam = _material_cornell("glossy")
+    for strategy in (0, 1):
+        g, o, fg, fo = _render_both(arrays, cam, host.Film(64, 48), host.Sampler(kind=host.SAMPLER_LD, spp=4),
+                                    host.Integrator(kind=host.INTEGRATOR_DIRECT, strategy=strategy, maxdepth=5))
+        err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
+        print("direct glossy strategy", strategy, "max rel err", err.max())
+        assert err.max() <= 1e-3  # north_star: deterministic integrators per pixel within 1e-3 relative
+
+
+def test_bxdf_lists_of_plain_matte_equal_the_matte_entry_point():
+    """drt_set_material_lobes with one Lambertian / OrenNayar lobe per material takes the general kernels and must
+    reproduce drt_set_materials bit for bit."""
+    sb, cam = scenes.cornell_synth()
+    sb.materials[3] = (0, (0.48, 0.48, 0.48), 20.0)  # OrenNayar on the box
+    a = sb.arrays()
+    film, smp, integ = host.Film(48, 36), host.Sampler(kind=host.SAMPLER_LD, spp=8), host.Integrator(kind=host.INTEGRATOR_PATH)
+    g1, g2 = capi.Context(0), capi.Context(0)
+    host.upload_scene(g1, a)
+    b = dict(a)
+    b["mat_general"] = True
+    host.upload_scene(g2, b)
+    for g in (g1, g2):
+        host.configure_render(g, cam, film, smp, integ)
+        g.render()
+    assert np.array_equal(g1.film_read()["rgb"], g2.film_read()["rgb"])
+
+
+def test_directlighting_specular_recursion_is_reported_unsupported():
+    arrays, cam = _material_cornell("specular")
+    g = capi.Context(0)
+    host.upload_scene(g, arrays)
+    host.configure_render(g, cam, host.Film(16, 12), host.Sampler(kind=host.SAMPLER_LD, spp=2), host.Integrator(kind=host.INTEGRATOR_DIRECT, maxdepth=5))
+    with pytest.raises(capi.DrtError) as e:
+        g.render()
+    assert e.value.code == -6 and "SpecularReflect" in str(e.value)
+    # maxdepth 1 cuts the recursion in the reference too (direct_lighting_integrator.dart:56): that renders
+    o = Oracle()
+    host.upload_scene(o, arrays)
+    for c in (g, o):
+        host.configure_render(c, cam, host.Film(16, 12), host.Sampler(kind=host.SAMPLER_LD, spp=2), host.Integrator(kind=host.INTEGRATOR_DIRECT, maxdepth=1))
+    g.render()
+    o.render(0, 1, 2)
+    assert _rel_err(g.film_read()["rgb"], o.film_read()["rgb"], floor=1e-3).max() <= 1e-3
+
+
 def test_thin_lens_camera_and_random_sampler():
     """perspective_camera.dart:104-119: lensRadius > 0 moves the ray origin on the lens (ConcentricSampleDisk)."""
     sb, cam = scenes.cornell_synth()
