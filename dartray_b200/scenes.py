@@ -221,6 +221,20 @@ def cornell_synth(overrides: dict | None = None):
     return sb, cam
 
 
+def cornell_materials():
+    """cornell_synth with one material of each family the BxDF-list path covers: plastic back wall
+    and ceiling, glass sphere, mirror-ish uber box, metal floor stays matte grey, OrenNayar red wall."""
+    from . import host
+
+    return cornell_synth({
+        "grey": host.plastic_lobes((0.6, 0.6, 0.55), 0.3, 0.08),
+        "red": host.matte_lobes((0.48, 0.1125, 0.075), 30.0),
+        "green": host.metal_lobes((0.2, 0.92, 1.1), (3.9, 2.45, 2.14), 0.1),
+        "box": host.uber_lobes(kd=(0.3, 0.2, 0.2), ks=0.3, kr=0.3, kt=0.0, roughness=0.15, index=1.33, opacity=(0.9, 0.8, 0.9)),
+        "sphere": host.glass_lobes(1.0, 1.0, 1.5),
+    })
+
+
 def cornell_path():
     """web/scenes/cornell-path.pbrt:1-61 as shipped: disk area light (radius 3 at y = 9.9, rotated 90 degrees about x,
     L = 36, nsamples 1, default matte Kd 0.5), five walls, the short box, the sphere.  Returns (SceneBuilder, camera);

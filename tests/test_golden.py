@@ -65,6 +65,24 @@ def test_oracle_reproduces_cornell_path_golden():
     assert [st["camera_samples"], st["closest_rays"], st["shadow_rays"]] == g["path_rays"].tolist()
 
 
+def test_oracle_reproduces_cornell_materials_golden():
+    g = np.load(os.path.join(GOLD, "render_cornell_materials.npz"))
+    o = _render(Oracle(), "path", scenes.cornell_materials)
+    assert np.allclose(o.film_read()["rgb"], g["path_rgb"], rtol=1e-6, atol=1e-7)  # libm pow / sin / cos in the glossy lobes
+    st = o.render_stats()
+    assert [st["camera_samples"], st["closest_rays"], st["shadow_rays"]] == g["path_rays"].tolist()
+
+
+@pytest.mark.gpu
+def test_gpu_matches_cornell_materials_golden():
+    g = np.load(os.path.join(GOLD, "render_cornell_materials.npz"))
+    c = _render(capi.Context(0), "path", scenes.cornell_materials)
+    f = c.film_read()
+    assert np.array_equal(f["weight"], g["path_weight"])
+    err = np.abs(f["rgb"] - g["path_rgb"]) / np.maximum(np.abs(g["path_rgb"]), 1e-3)
+    assert np.quantile(err, 0.99) <= 1e-3 and abs(f["rgb"].mean() - g["path_rgb"].mean()) <= 5e-3 * g["path_rgb"].mean()
+
+
 @pytest.mark.gpu
 def test_gpu_matches_cornell_path_golden():
     g = np.load(os.path.join(GOLD, "render_cornell_path.npz"))

@@ -80,9 +80,23 @@ def render_vectors():
                         path_rays=np.array([st["camera_samples"], st["closest_rays"], st["shadow_rays"]], np.int64))
 
 
+def material_vectors():
+    sb, cam = scenes.cornell_materials()
+    o = Oracle()
+    host.upload_scene(o, sb.arrays())
+    sampler, integ = RENDERS["path"]
+    host.configure_render(o, cam, host.Film(*FILM), sampler, integ)
+    o.render(0, 1, 1)
+    f = o.film_read()
+    st = o.render_stats()
+    np.savez_compressed(os.path.join(OUT, "render_cornell_materials.npz"), path_rgb=f["rgb"], path_weight=f["weight"],
+                        path_rays=np.array([st["camera_samples"], st["closest_rays"], st["shadow_rays"]], np.int64))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     trace_vectors()
     render_vectors()
+    material_vectors()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
