@@ -181,7 +181,9 @@ static void buildLayout(RenderState* r) {
   for (size_t i = 0; i < n1D.size(); ++i) r->arrays.push_back(SampleArray{1, n1D[i], v1[i], sid++});
   for (size_t i = 0; i < n2D.size(); ++i) r->arrays.push_back(SampleArray{2, n2D[i], v2[i], sid++});
   r->maxVals = r->maxOthers = 0;
+  p.ldAllSingle = 1;
   for (const SampleArray& a : r->arrays) {
+    if (a.nSamples != 1) p.ldAllSingle = 0;
     r->maxVals = std::max(r->maxVals, a.dims * a.nSamples * p.nPixelSamples);
     r->maxOthers = std::max(r->maxOthers, a.nSamples * p.nPixelSamples + p.nPixelSamples);
   }

@@ -105,18 +105,99 @@ __global__ void __launch_bounds__(128) samplerLDKernel(RenderParams rp, Wavefron
       }
     }
     __syncwarp();
+    // Write-out by the whole warp, one group after the other: consecutive lanes store consecutive samples of one value
+    // row (full 128-byte lines) instead of every group scattering 4-byte stores over its own rows.
     const uint32_t bs = nS * dims;
     const uint32_t slot0 = p * nP;
-    if (valid) {
-      if (A.dest >= 0) {
-        for (uint32_t qv = 0; qv < bs; ++qv)
-          for (uint32_t i = gl; i < nP; i += G) wf.vals[(size_t)(A.dest + qv) * wf.cap + slot0 + i] = buf[i * bs + qv];
-      } else if (A.dest == -1) {  // montecarlo.dart:452-453: imageX = xPos + sample (f64 sum of an int and a float32)
-        for (uint32_t i = gl; i < nP; i += G) wf.camXY[slot0 + i] = make_double2(x + (double)buf[2 * i], y + (double)buf[2 * i + 1]);
-      } else if (A.dest == -2) {
-        for (uint32_t i = gl; i < nP; i += G) wf.camLens[slot0 + i] = make_double2((double)buf[2 * i], (double)buf[2 * i + 1]);
+    const uint32_t lane = threadIdx.x & 31u, groupsPerWarp = 32u / (uint32_t)G;
+    for (uint32_t gi = 0; gi < groupsPerWarp; ++gi) {
+      const int src = (int)(gi * (uint32_t)G);
+      const bool v_ = __shfl_sync(FULL, valid ? 1 : 0, src) != 0;
+      const int dest_ = __shfl_sync(FULL, A.dest, src);
+      const uint32_t slot0_ = __shfl_sync(FULL, slot0, src), bs_ = __shfl_sync(FULL, bs, src);
+      const int x_ = __shfl_sync(FULL, x, src), y_ = __shfl_sync(FULL, y, src);
+      if (!v_) continue;
+      const float* b_ = smem + (size_t)((threadIdx.x >> 5) * groupsPerWarp + gi) * (maxVals | 1);
+      if (dest_ >= 0) {
+        for (uint32_t qv = 0; qv < bs_; ++qv)
+          for (uint32_t i = lane; i < nP; i += 32u) wf.vals[(size_t)(dest_ + qv) * wf.cap + slot0_ + i] = b_[i * bs_ + qv];
+      } else if (dest_ == -1) {  // montecarlo.dart:452-453: imageX = xPos + sample (f64 sum of an int and a float32)
+        for (uint32_t i = lane; i < nP; i += 32u) wf.camXY[slot0_ + i] = make_double2(x_ + (double)b_[2 * i], y_ + (double)b_[2 * i + 1]);
+      } else if (dest_ == -2) {
+        for (uint32_t i = lane; i < nP; i += 32u) wf.camLens[slot0_ + i] = make_double2((double)b_[2 * i], (double)b_[2 * i + 1]);
       } else {
-        for (uint32_t i = gl; i < nP; i += G) wf.camTime[slot0 + i] = buf[i];
+        for (uint32_t i = lane; i < nP; i += 32u) wf.camTime[slot0_ + i] = b_[i];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// The same sampler when every array holds ONE value per camera sample (path integrator, ambient occlusion): then
+// LDShuffleScrambled1D/2D reduces to the shuffle across the nPixel samples, and because the i-th value of the
+// (0,2)-sequence is a pure function of i, it is enough to shuffle INDICES: all lanes draw the swap targets (the stream
+// is counter-based), one lane per group applies the swaps to a 16-bit permutation in shared memory (the only
+// order-dependent part: four shared-memory accesses per step), then the whole warp evaluates VanDerCorput / Sobol2 at
+// the permuted indices and stores full lines.  Shared memory per task: 4 bytes per pixel sample.
+__global__ void __launch_bounds__(128) samplerLDPermKernel(RenderParams rp, Wavefront wf, const SampleArray* __restrict__ arrays,
+                                                           int nArrays, PixelBatch pb, int G, int strideWords) {
+  extern __shared__ float smem[];
+  const uint32_t groupsPerBlock = blockDim.x / G, grp = threadIdx.x / G, gl = threadIdx.x % G;
+  const uint32_t nP = (uint32_t)rp.nPixelSamples;
+  uint16_t* tgt = reinterpret_cast<uint16_t*>(smem + (size_t)grp * strideWords);
+  uint16_t* perm = tgt + nP;
+  const uint64_t nTasks = (uint64_t)pb.nPixels * nArrays;
+  const uint32_t lane = threadIdx.x & 31u, groupsPerWarp = 32u / (uint32_t)G;
+  for (uint64_t t0 = (uint64_t)blockIdx.x * groupsPerBlock; t0 < nTasks; t0 += (uint64_t)gridDim.x * groupsPerBlock) {
+    const uint64_t task = t0 + grp;
+    const bool valid = task < nTasks;
+    const uint32_t p = valid ? (uint32_t)(task / nArrays) : 0u;
+    const SampleArray A = arrays[valid ? task % nArrays : 0];
+    int x, y;
+    pixelOf(pb, p, &x, &y);
+    const uint64_t key = streamKey(rp.seed, x, y, 0, A.streamId);
+    const uint32_t dims = (uint32_t)A.dims;
+    const uint32_t s0 = drawUint(key, 1), s1 = dims == 2 ? drawUint(key, 2) : 0u;
+    // draws: dims scrambles, nP (unused: blocks of one sample are not shuffled, montecarlo.dart:528-530), then the nP swaps
+    const uint64_t base = (uint64_t)dims + nP;
+    if (valid)
+      for (uint32_t i = gl; i < nP; i += G) {
+        tgt[i] = (uint16_t)(i + drawUint(key, base + i + 1) % (nP - i));
+        perm[i] = (uint16_t)i;
+      }
+    __syncwarp();
+    if (gl == 0 && valid)
+      for (uint32_t i = 0; i < nP; ++i) {  // Shuffle (montecarlo.dart:294-303) on the indices
+        const uint32_t o = tgt[i];
+        const uint16_t a = perm[i];
+        perm[i] = perm[o];
+        perm[o] = a;
+      }
+    __syncwarp();
+    const uint32_t slot0 = p * nP;
+    for (uint32_t gi = 0; gi < groupsPerWarp; ++gi) {
+      const int src = (int)(gi * (uint32_t)G);
+      const bool v_ = __shfl_sync(FULL, valid ? 1 : 0, src) != 0;
+      const int dest_ = __shfl_sync(FULL, A.dest, src);
+      const uint32_t slot0_ = __shfl_sync(FULL, slot0, src), dims_ = __shfl_sync(FULL, dims, src);
+      const uint32_t s0_ = __shfl_sync(FULL, s0, src), s1_ = __shfl_sync(FULL, s1, src);
+      const int x_ = __shfl_sync(FULL, x, src), y_ = __shfl_sync(FULL, y, src);
+      if (!v_) continue;
+      const uint16_t* pm = reinterpret_cast<const uint16_t*>(smem + (size_t)((threadIdx.x >> 5) * groupsPerWarp + gi) * strideWords) + nP;
+      for (uint32_t i = lane; i < nP; i += 32u) {
+        const uint32_t e = pm[i];
+        const float v0 = (float)VanDerCorput(e, s0_);
+        const float v1 = dims_ == 2 ? (float)Sobol2(e, s1_) : 0.f;
+        if (dest_ >= 0) {
+          wf.vals[(size_t)dest_ * wf.cap + slot0_ + i] = v0;
+          if (dims_ == 2) wf.vals[(size_t)(dest_ + 1) * wf.cap + slot0_ + i] = v1;
+        } else if (dest_ == -1) {  // montecarlo.dart:452-453: imageX = xPos + sample (f64 sum of an int and a float32)
+          wf.camXY[slot0_ + i] = make_double2(x_ + (double)v0, y_ + (double)v1);
+        } else if (dest_ == -2) {
+          wf.camLens[slot0_ + i] = make_double2((double)v0, (double)v1);
+        } else {
+          wf.camTime[slot0_ + i] = v0;
+        }
       }
     }
     __syncwarp();
@@ -677,7 +758,18 @@ static inline int gridFor(uint64_t n, int block, int numSMs, int perSm) {
 cudaError_t launchSampler(const RenderParams& rp, const Wavefront& wf, const SampleArray* dArrays, int nArrays, int maxVals,
                           int maxOthers, const PixelBatch& pb, int numSMs, cudaStream_t st) {
   if (pb.nPixels == 0) return cudaSuccess;
-  if (rp.samplerKind == 0) {
+  if (rp.samplerKind == 0 && rp.ldAllSingle && rp.nPixelSamples <= 2048) {
+    const int block = 128;
+    const int strideWords = rp.nPixelSamples | 1;  // two 16-bit arrays of nPixelSamples entries; odd word stride
+    const size_t taskBytes = (size_t)strideWords * sizeof(float);
+    int tasksPerBlock = (int)std::min<size_t>(block, std::max<size_t>(4, (48 * 1024) / taskBytes));
+    int G = 1;
+    while (block / G > tasksPerBlock) G <<= 1;
+    const size_t smem = (size_t)(block / G) * taskBytes;
+    uint64_t tasks = (uint64_t)pb.nPixels * nArrays;
+    int grid = gridFor(tasks * G, block, numSMs, 16);
+    samplerLDPermKernel<<<grid, block, smem, st>>>(rp, wf, dArrays, nArrays, pb, G, strideWords);
+  } else if (rp.samplerKind == 0) {
     const int block = 128;
     // lanes per (pixel, array) task: as few as shared memory allows (48 KB of arrays per block), because the
     // order-dependent shuffle runs on one lane per task

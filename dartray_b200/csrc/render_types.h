@@ -86,6 +86,7 @@ struct RenderParams {
   int32_t nPixelSamples;  // samples per pixel visit
   uint64_t seed;
   int32_t nVals;  // integrator values per sample (sum n1D + 2 sum n2D)
+  int32_t ldAllSingle;  // lowdiscrepancy: every array holds one value per camera sample (path / AO): index-shuffle fast path
   // integrator
   int32_t integKind;  // 0 path, 1 ambientocclusion, 2 directlighting
   int32_t maxDepth, strategy, aoSamples;
