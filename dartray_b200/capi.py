@@ -23,7 +23,7 @@ SYMBOLS = [
     "drt_set_build_order", "drt_build_bvh", "drt_bvh_info_get", "drt_bvh_export", "drt_trace_closest",
     "drt_trace_any", "drt_trace_closest_device", "drt_trace_any_device", "drt_set_counting", "drt_get_counters", "drt_set_kernel_variant",
     "drt_last_kernel_ms", "drt_kernel_launches",
-    "drt_set_materials", "drt_set_material_lobes", "drt_set_lights", "drt_set_camera", "drt_set_camera_kind", "drt_set_film", "drt_set_sampler", "drt_set_integrator",
+    "drt_set_materials", "drt_set_material_lobes", "drt_set_lights", "drt_set_spot_params", "drt_set_camera", "drt_set_camera_kind", "drt_set_film", "drt_set_sampler", "drt_set_integrator",
     "drt_render", "drt_render_shard", "drt_set_batch_slots", "drt_film_clear", "drt_film_size", "drt_film_read",
     "drt_film_device", "drt_pixel_samples", "drt_render_stats_get",
 ]
@@ -92,6 +92,7 @@ def load():
     dbl = C.c_double
     L.drt_set_materials.argtypes = [vp, u32, vp, vp, vp]
     L.drt_set_material_lobes.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp]
+    L.drt_set_spot_params.argtypes = [vp, u32, vp, vp]
     L.drt_set_lights.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
     L.drt_set_camera.argtypes = [vp, vp, vp, dbl, dbl, dbl, dbl]
     L.drt_set_camera_kind.argtypes = [vp, i32]
@@ -254,6 +255,11 @@ class Context:
         kind, L, pos = _arr(kind, np.int32), _arr(L, np.float32).reshape(-1, 3), _arr(pos, np.float32).reshape(-1, 3)
         ns, so, sp = _arr(nsamples, np.int32), _arr(shape_offsets, np.uint32), _arr(shape_prims, np.uint32)
         self._ck(self.L.drt_set_lights(self.h, kind.shape[0], _p(kind), _p(L), _p(pos), _p(ns), _p(so), _p(sp)))
+
+    def set_spot_params(self, world_to_light, cosines):
+        """worldToLight (n x 16) and (cosTotalWidth, cosFalloffStart) (n x 2) of the spot lights of the last set_lights."""
+        w, cs = _arr(world_to_light, np.float32).reshape(-1, 16), _arr(cosines, np.float64).reshape(-1, 2)
+        self._ck(self.L.drt_set_spot_params(self.h, w.shape[0], _p(w), _p(cs)))
 
     def set_camera(self, raster_to_camera, camera_to_world, lens_radius=0.0, focal_distance=1e30, shutter_open=0.0,
                    shutter_close=1.0):

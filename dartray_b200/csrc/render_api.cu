@@ -21,6 +21,9 @@ struct HostLight {
   float L[3] = {0, 0, 0}, pos[3] = {0, 0, 0};
   int nSamples = 1;
   std::vector<uint32_t> shapes;
+  float w2l[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};  // spot lights (drt_set_spot_params)
+  double cosTotalWidth = 0, cosFalloffStart = 0;
+  bool haveSpot = false;
 };
 
 struct ByteArena {  // one cudaMalloc per wavefront, carved into aligned arrays
@@ -234,6 +237,10 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
     const HostLight& hl = r->lights[i];
     GLight& g = gl[i];
     g.kind = hl.kind;
+    if (hl.kind == 3 && !hl.haveSpot) return fail(c, DRT_E_STATE, "a spot light (kind 3) needs drt_set_spot_params after drt_set_lights");
+    std::memcpy(g.w2l, hl.w2l, sizeof(g.w2l));
+    g.cosTotalWidth = hl.cosTotalWidth;
+    g.cosFalloffStart = hl.cosFalloffStart;
     std::memcpy(g.L, hl.L, 12);
     std::memcpy(g.pos, hl.pos, 12);
     g.nSamples = hl.nSamples;
@@ -644,7 +651,8 @@ int drt_set_lights(drt_ctx* c, uint32_t n, const int32_t* kind, const float* L, 
   for (uint32_t i = 0; i < n; ++i) {
     HostLight& l = ls[i];
     l.kind = kind[i];
-    if (l.kind != 0 && l.kind != 1) return fail(c, DRT_E_INVALID, "light kind must be 0 (diffuse area) or 1 (point)");
+    if (l.kind < 0 || l.kind > 3) return fail(c, DRT_E_INVALID, "light kind must be 0 (diffuse area), 1 (point), 2 (distant) or 3 (spot)");
+    if (l.kind != 0 && !pos) return fail(c, DRT_E_INVALID, "point / distant / spot lights need the pos array");
     std::memcpy(l.L, L + 3 * i, 12);
     if (pos) std::memcpy(l.pos, pos + 3 * i, 12);
     l.nSamples = nsamples ? std::max(1, nsamples[i]) : 1;
@@ -652,6 +660,24 @@ int drt_set_lights(drt_ctx* c, uint32_t n, const int32_t* kind, const float* L, 
       for (uint32_t k = shape_offsets[i]; k < shape_offsets[i + 1]; ++k) l.shapes.push_back(shape_prims[k]);
   }
   r->lights.swap(ls);
+  r->sceneTablesValid = false;
+  return DRT_OK;
+}
+
+int drt_set_spot_params(drt_ctx* c, uint32_t n, const float* world_to_light, const double* cos_total_falloff) {
+  if (!c) return DRT_E_INVALID;
+  RenderState* r = state(c);
+  if (n != r->lights.size()) return fail(c, DRT_E_STATE, "drt_set_spot_params: n must equal the light count of the last drt_set_lights");
+  if (n && (!world_to_light || !cos_total_falloff)) return fail(c, DRT_E_INVALID, "null spot-light arrays");
+  for (uint32_t i = 0; i < n; ++i) {
+    HostLight& l = r->lights[i];
+    const float* m = world_to_light + 16 * i;
+    for (int row = 0; row < 3; ++row)
+      for (int col = 0; col < 3; ++col) l.w2l[3 * row + col] = m[4 * row + col];
+    l.cosTotalWidth = cos_total_falloff[2 * i];
+    l.cosFalloffStart = cos_total_falloff[2 * i + 1];
+    l.haveSpot = true;
+  }
   r->sceneTablesValid = false;
   return DRT_OK;
 }

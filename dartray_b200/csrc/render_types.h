@@ -27,9 +27,12 @@ struct GLobe {
 static_assert(sizeof(GLobe) == 72, "GLobe layout");
 
 struct GLight {
-  int32_t kind;  // 0 = DiffuseAreaLight (diffuse_area_light.dart), 1 = PointLight (point_light.dart)
-  float L[3];    // Lemit / intensity
+  int32_t kind;  // 0 = DiffuseAreaLight (diffuse_area_light.dart), 1 = PointLight (point_light.dart),
+                 // 2 = DistantLight (distant_light.dart; pos = lightDir), 3 = SpotLight (spot_light.dart)
+  float L[3];    // Lemit / intensity / radiance
   float pos[3];
+  float w2l[9];  // spot: rows of worldToLight's upper 3x3 (Transform.transformVector, transform.dart:139-146)
+  double cosTotalWidth, cosFalloffStart;
   int32_t nSamples;
   uint32_t shapeOffset, nShapes;  // ShapeSet (shape_set.dart:26-50): slice of lightShapes / lightShapeAreas
   uint32_t cdfOffset;             // slice of lightCdf: nShapes + 1 floats (Distribution1D, montecarlo.dart:25-48)

@@ -891,14 +891,37 @@ static __device__ inline void estimateDirectSetup(const RenderScene& rs, int lig
   Spec Li;
   V3 segTo;
   double eps2;
-  const bool delta = l.kind == 1;
-  if (delta) {  // point_light.dart:41-47
+  const bool delta = l.kind != 0;  // isDeltaLight: point, distant, spot
+  const bool distant = l.kind == 2;
+  if (distant) {  // distant_light.dart:41-48: the shadow ray runs to infinity (visibility_tester.dart:31-33)
+    wi = V3{l.pos[0], l.pos[1], l.pos[2]};
+    lightPdf = 1.0;
+    segTo = p;
+    eps2 = 0.0;
+    Li = lightRadiance(l);
+  } else if (delta) {  // point_light.dart:41-47, spot_light.dart:36-70
     V3 pos = V3{l.pos[0], l.pos[1], l.pos[2]};
     wi = Normalize(pos - p);
     lightPdf = 1.0;
     segTo = pos;
     eps2 = 0.0;
-    Li = lightRadiance(l) / DistanceSquared(pos, p);
+    if (l.kind == 1) {
+      Li = lightRadiance(l) / DistanceSquared(pos, p);
+    } else {
+      const V3 w = -wi;
+      const V3 wl = Normalize(mkv((double)l.w2l[0] * w.x + (double)l.w2l[1] * w.y + (double)l.w2l[2] * w.z,
+                                  (double)l.w2l[3] * w.x + (double)l.w2l[4] * w.y + (double)l.w2l[5] * w.z,
+                                  (double)l.w2l[6] * w.x + (double)l.w2l[7] * w.y + (double)l.w2l[8] * w.z));
+      const double costheta = wl.z;
+      double falloff;
+      if (costheta < l.cosTotalWidth) falloff = 0.0;
+      else if (costheta > l.cosFalloffStart) falloff = 1.0;
+      else {
+        const double dl = (costheta - l.cosTotalWidth) / (l.cosFalloffStart - l.cosTotalWidth);
+        falloff = dl * dl * dl * dl;
+      }
+      Li = lightRadiance(l) * falloff / DistanceSquared(pos, p);
+    }
   } else {  // diffuse_area_light.dart:59-70
     V3 ns;
     V3 ps = shapeSetSample(rs, l, p, lu0, lu1, lcomp, &ns);
@@ -911,12 +934,17 @@ static __device__ inline void estimateDirectSetup(const RenderScene& rs, int lig
   if (lightPdf > 0.0 && !IsBlack(Li)) {
     Spec f = bsdfF(bsdf, wo, wi, flags);
     if (!IsBlack(f)) {
-      double dist = Distance(p, segTo);  // visibility_tester.dart:26-29
       w->hasShadow = true;
       w->shO = p;
-      w->shD = (segTo - p) / dist;
       w->shMin = rayEps;
-      w->shMax = dist * (1.0 - eps2);
+      if (distant) {
+        w->shD = wi;
+        w->shMax = CUDART_INF;
+      } else {
+        double dist = Distance(p, segTo);  // visibility_tester.dart:26-29
+        w->shD = (segTo - p) / dist;
+        w->shMax = dist * (1.0 - eps2);
+      }
       Li = Li * mks1(1.0);  // transmittance
       if (delta) {
         w->shContribution = f * Li * (AbsDot(wi, n) / lightPdf);

@@ -350,6 +350,36 @@ class SceneBuilder:
         self.lights.append(dict(kind=1, L=tuple(intensity), pos=tuple(pos), nsamples=1, shapes=[]))
         return len(self.lights) - 1
 
+    def distant_light(self, frm, to, L) -> int:
+        """DistantLight.Create (distant_light.dart:83-91) with an identity light-to-world: lightDir = normalize(from - to)."""
+        d = (np.asarray(frm, np.float32).astype(np.float64) - np.asarray(to, np.float32).astype(np.float64)).astype(np.float32)
+        d = (d.astype(np.float64) / math.sqrt(float((d.astype(np.float64) ** 2).sum()))).astype(np.float32)
+        self.lights.append(dict(kind=2, L=tuple(L), pos=tuple(float(v) for v in d), nsamples=1, shapes=[]))
+        return len(self.lights) - 1
+
+    def spot_light(self, frm, to, I, coneangle=30.0, conedelta=5.0) -> int:
+        """SpotLight.Create (spot_light.dart:88-118) with an identity CTM: light2world = Translate(from) * Inverse(dirToZ)."""
+        frm64, to64 = np.asarray(frm, np.float64), np.asarray(to, np.float64)
+        d = to64 - frm64
+        d = (d / np.linalg.norm(d)).astype(np.float32).astype(np.float64)
+        # Vector.CoordinateSystem (vector.dart:198-214)
+        if abs(d[0]) > abs(d[1]):
+            inv = 1.0 / math.sqrt(d[0] * d[0] + d[2] * d[2])
+            du = np.array([-d[2] * inv, 0.0, d[0] * inv])
+        else:
+            inv = 1.0 / math.sqrt(d[1] * d[1] + d[2] * d[2])
+            du = np.array([0.0, d[2] * inv, -d[1] * inv])
+        du = du.astype(np.float32).astype(np.float64)
+        dv = np.cross(d, du).astype(np.float32).astype(np.float64)
+        dir_to_z = np.eye(4, dtype=np.float32)
+        dir_to_z[0, :3], dir_to_z[1, :3], dir_to_z[2, :3] = du, dv, d
+        l2w = mat_mul(translate(*[float(v) for v in np.asarray(frm, np.float32)]), mat_inv(dir_to_z))
+        w2l = mat_inv(l2w)
+        pos = transform_points(l2w, np.zeros((1, 3), np.float32))[0]
+        self.lights.append(dict(kind=3, L=tuple(I), pos=tuple(float(v) for v in pos), nsamples=1, shapes=[],
+                                w2l=_m(w2l).reshape(16), cos=(math.cos(math.radians(coneangle)), math.cos(math.radians(coneangle - conedelta)))))
+        return len(self.lights) - 1
+
     def _area_light(self, L, nsamples):
         self.lights.append(dict(kind=0, L=tuple(L), pos=(0, 0, 0), nsamples=nsamples, shapes=[]))
         return len(self.lights) - 1
@@ -421,7 +451,8 @@ class SceneBuilder:
         base = {"tri": 0, "sph": ntris, "dsk": ntris + nsph}
         for l in self.lights:
             shapes = [base[s[0]] + s[1] for s in l["shapes"]]
-            lights.append(dict(kind=l["kind"], L=l["L"], pos=l["pos"], nsamples=l["nsamples"], shapes=shapes))
+            lights.append(dict(kind=l["kind"], L=l["L"], pos=l["pos"], nsamples=l["nsamples"], shapes=shapes,
+                               w2l=l.get("w2l", np.eye(4, dtype=np.float32).reshape(16)), cos=l.get("cos", (0.0, 0.0))))
         mats = self.materials or [(0, (0.5, 0.5, 0.5), 0.0)]
         general = any(m[0] == "lobes" for m in mats)
         lobe_lists = [m[1] if m[0] == "lobes" else matte_lobes(m[1], m[2]) for m in mats]
@@ -456,6 +487,9 @@ class SceneBuilder:
             light_L=np.asarray([l["L"] for l in lights], np.float32).reshape(-1, 3),
             light_pos=np.asarray([l["pos"] for l in lights], np.float32).reshape(-1, 3),
             light_nsamples=np.asarray([l["nsamples"] for l in lights], np.int32),
+            light_w2l=np.asarray([l["w2l"] for l in lights], np.float32).reshape(-1, 16),
+            light_cos=np.asarray([l["cos"] for l in lights], np.float64).reshape(-1, 2),
+            light_has_spot=any(l["kind"] == 3 for l in lights),
             light_shape_offsets=np.asarray(np.cumsum([0] + [len(l["shapes"]) for l in lights]), np.uint32),
             light_shape_prims=np.asarray([p for l in lights for p in l["shapes"]], np.uint32),
         )
@@ -477,6 +511,8 @@ def upload_scene(ctx, arrays: dict, split: int = 2, max_node_prims: int = 4):
         ctx.set_materials(a["mat_kind"], a["mat_kd"], a["mat_sigma"])
     ctx.set_lights(a["light_kind"], a["light_L"], a["light_pos"], a["light_nsamples"], a["light_shape_offsets"],
                    a["light_shape_prims"])
+    if a.get("light_has_spot"):
+        ctx.set_spot_params(a["light_w2l"], a["light_cos"])
 
 
 def configure_render(ctx, camera: PerspectiveCamera, film: Film, sampler: Sampler, integrator: Integrator):

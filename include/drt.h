@@ -189,12 +189,20 @@ int drt_set_material_lobes(drt_ctx* ctx, uint32_t n, const uint32_t* lobe_offset
 
 /* Replaces scene.lights: DiffuseAreaLight (kind 0, lib/lights/diffuse_area_light.dart:44-70; L = Lemit
  * x scale) and PointLight (kind 1, lib/lights/point_light.dart:41-47; L = intensity, pos = world
- * position).  nsamples: per light (NULL = 1).  The ShapeSet of light i (lib/core/light/
+ * position); kinds 2 / 3: see drt_set_spot_params below.  nsamples: per light (NULL = 1).  The ShapeSet of light i (lib/core/light/
  * shape_set.dart:26-50) is shape_prims[shape_offsets[i] .. shape_offsets[i+1]) — primitive ids in the
  * order the reference's refine loop leaves them.  Light index = position; drt_set_triangles /
  * drt_set_spheres refer to it through light_of_*. */
 int drt_set_lights(drt_ctx* ctx, uint32_t n, const int32_t* kind, const float* L_rgb, const float* pos,
                    const int32_t* nsamples, const uint32_t* shape_offsets, const uint32_t* shape_prims);
+
+/* The other delta lights of scene.lights go through the same call: DistantLight (kind 2,
+ * lib/lights/distant_light.dart:24-48; L = radiance x scale, pos = lightDir = normalize(lightToWorld(from - to)), the
+ * float32 Vector the light holds) and SpotLight (kind 3, lib/lights/spot_light.dart:24-70; L = intensity x scale,
+ * pos = lightPos).  Spot lights additionally need, after drt_set_lights, their worldToLight matrix (n x 16 float32,
+ * row-major; rows of other lights are ignored) and {cosTotalWidth, cosFalloffStart} (n x 2 doubles,
+ * spot_light.dart:29-30). */
+int drt_set_spot_params(drt_ctx* ctx, uint32_t n, const float* world_to_light, const double* cos_total_falloff);
 
 /* Replaces PerspectiveCamera (lib/cameras/perspective_camera.dart:46-57 + lib/core/
  * projective_camera.dart:34-53): the two float32 row-major matrices the camera holds

@@ -282,6 +282,18 @@ int orc_set_lights(orc_ctx* c, uint32_t n, const int32_t* kind, const float* L, 
   return 0;
 }
 
+// mirrors drt_set_spot_params: worldToLight matrices and the two cosines of the spot lights set by orc_set_lights
+int orc_set_spot_params(orc_ctx* c, uint32_t n, const float* w2l, const double* cosines) {
+  if (n != c->rs.lights.size()) return -1;
+  for (uint32_t i = 0; i < n; ++i) {
+    Light& l = c->rs.lights[i];
+    l.worldToLight = Transform(w2l + 16 * i, w2l + 16 * i);  // only m is used (vector)
+    l.cosTotalWidth = cosines[2 * i];
+    l.cosFalloffStart = cosines[2 * i + 1];
+  }
+  return 0;
+}
+
 int orc_set_camera(orc_ctx* c, const float* rasterToCamera, const float* cameraToWorld, double lensRadius,
                    double focalDistance, double shutterOpen, double shutterClose) {
   Camera& cam = c->rs.camera;

@@ -778,6 +778,26 @@ struct Ctx {
       setSegment(vis, p, pEps, l.pos, 0.0, time);
       return l.L / DistanceSquared(l.pos, p);
     }
+    if (l.kind == 2) {  // distant_light.dart:41-48
+      *wi = l.pos;
+      *pdf = 1.0;
+      vis->r = Ray(p, *wi, pEps, kInf, time);  // visibility_tester.dart:31-33
+      return l.L;
+    }
+    if (l.kind == 3) {  // spot_light.dart:62-70 with falloff (:36-53)
+      *wi = Normalize(l.pos - p);
+      *pdf = 1.0;
+      setSegment(vis, p, pEps, l.pos, 0.0, time);
+      Vec wl = Normalize(l.worldToLight.vector(-*wi));
+      double costheta = wl.z, falloff;
+      if (costheta < l.cosTotalWidth) falloff = 0.0;
+      else if (costheta > l.cosFalloffStart) falloff = 1.0;
+      else {
+        double delta = (costheta - l.cosTotalWidth) / (l.cosFalloffStart - l.cosTotalWidth);
+        falloff = delta * delta * delta * delta;
+      }
+      return l.L * falloff / DistanceSquared(l.pos, p);
+    }
     Vec ns;  // diffuse_area_light.dart:59-70
     Vec ps = shapeSetSample(l, ls, &ns, p);
     *wi = Normalize(ps - p);
@@ -794,7 +814,7 @@ struct Ctx {
     double lightPdf = 0.0, bsdfPdf = 0.0;
     Vis vis;
     Spec Li = sampleLAtPoint(light, p, rayEpsilon, lightSample, time, &wi, &lightPdf, &vis);
-    const bool delta = light.kind == 1;
+    const bool delta = light.kind != 0;  // isDeltaLight: point, distant, spot
     if (lightPdf > 0.0 && !Li.isBlack()) {
       Spec f = bsdf.f(wo, wi, flags);
       if (!f.isBlack() && !intersectP(vis.r)) {

@@ -160,9 +160,11 @@ struct Distribution1D {  // montecarlo.dart:25-98
 };
 
 struct Light {
-  int kind = 0;  // 0 = DiffuseAreaLight, 1 = PointLight
-  Spec L;        // Lemit / intensity
-  Vec pos;       // point light position (world)
+  int kind = 0;  // 0 = DiffuseAreaLight, 1 = PointLight, 2 = DistantLight, 3 = SpotLight
+  Spec L;        // Lemit / intensity / radiance
+  Vec pos;       // point / spot light position (world); distant light: lightDir (distant_light.dart:26)
+  Transform worldToLight;                            // spot light (spot_light.dart:38-53)
+  double cosTotalWidth = 0, cosFalloffStart = 0;     // spot light (spot_light.dart:29-30)
   int nSamples = 1;
   std::vector<uint32_t> shapes;  // ShapeSet order (shape_set.dart:26-41)
   std::vector<double> areas;

@@ -56,6 +56,7 @@ def lib():
         dbl = C.c_double
         L.orc_set_materials.argtypes = [vp, u32, vp, vp, vp]
         L.orc_set_material_lobes.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp]
+        L.orc_set_spot_params.argtypes = [vp, u32, vp, vp]
         L.orc_set_lights.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
         L.orc_set_camera.argtypes = [vp, vp, vp, dbl, dbl, dbl, dbl]
         L.orc_set_camera_kind.argtypes = [vp, i32]
@@ -193,6 +194,11 @@ class Oracle:
         kind, L, pos = _arr(kind, np.int32), _arr(L, np.float32).reshape(-1, 3), _arr(pos, np.float32).reshape(-1, 3)
         ns, so, sp = _arr(nsamples, np.int32), _arr(shape_offsets, np.uint32), _arr(shape_prims, np.uint32)
         self._ck(self.L.orc_set_lights(self.h, kind.shape[0], _p(kind), _p(L), _p(pos), _p(ns), _p(so), _p(sp)))
+
+    def set_spot_params(self, world_to_light, cosines):
+        """worldToLight (n x 16) and (cosTotalWidth, cosFalloffStart) (n x 2) of the spot lights of the last set_lights."""
+        w, cs = _arr(world_to_light, np.float32).reshape(-1, 16), _arr(cosines, np.float64).reshape(-1, 2)
+        self._ck(self.L.orc_set_spot_params(self.h, w.shape[0], _p(w), _p(cs)))
 
     def set_camera(self, raster_to_camera, camera_to_world, lens_radius=0.0, focal_distance=1e30, shutter_open=0.0,
                    shutter_close=1.0):

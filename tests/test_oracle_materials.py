@@ -205,3 +205,38 @@ def test_directlighting_sees_a_lit_matte_wall_through_a_mirror():
     o1 = _oracle(sb, cam, film, smp, host.Integrator(kind=host.INTEGRATOR_DIRECT, maxdepth=1))
     o1.render(0, 1, 1)
     assert np.all(_centre(o1, film) == 0)
+
+
+# ---- the other delta lights (distant_light.dart:41-48, spot_light.dart:36-70) ---------------------------------------
+def test_distant_and_spot_lights_match_their_closed_forms():
+    kd = 0.5
+    cam = host.PerspectiveCamera(host.look_at((0, 10, 0), (0, 0, 0), (0, 0, 1)), fov=1.0)  # looks straight down at the origin
+    film = host.Film(1, 1)
+    smp = host.Sampler(kind=host.SAMPLER_STRATIFIED, xs=1, ys=1, jitter=False)
+    integ = host.Integrator(kind=host.INTEGRATOR_DIRECT, maxdepth=1)
+    # distant light arriving 60 degrees off the normal: L * kd/pi * cos(60)
+    sb = host.SceneBuilder()
+    _floor(sb, 0.0, material=sb.material((kd, kd, kd)))
+    sb.distant_light((0.0, 1.0, math.sqrt(3.0)), (0, 0, 0), (3.0, 2.0, 1.0))
+    o = _oracle(sb, cam, film, smp, integ)
+    o.render(0, 1, 1)
+    assert np.allclose(_centre(o, film), np.array([3.0, 2.0, 1.0]) * kd / math.pi * 0.5, rtol=2e-5)
+    # an occluder anywhere along the infinite shadow ray blocks it (visibility_tester.dart:31-33)
+    _quad(sb, [[-50, 40, 30], [50, 40, 30], [50, 40, 110], [-50, 40, 110]])
+    o = _oracle(sb, cam, film, smp, integ)
+    o.render(0, 1, 1)
+    assert np.all(_centre(o, film) == 0)
+    # spot light above the origin pointing down: full intensity inside the falloff start, smooth step between, zero outside
+    I, h = 8.0, 4.0
+    for off, cone, delta in ((0.0, 30.0, 5.0), (2.0, 30.0, 5.0), (4.0, 30.0, 5.0)):
+        sb = host.SceneBuilder()
+        _floor(sb, 0.0, material=sb.material((kd, kd, kd)))
+        sb.spot_light((off, h, 0.0), (off, 0.0, 0.0), (I, I, I), cone, delta)
+        o = _oracle(sb, cam, film, smp, integ)
+        o.render(0, 1, 1)
+        d2 = off * off + h * h
+        cos_l = h / math.sqrt(d2)  # angle at the light between its axis and the direction to the origin
+        ct, cf = math.cos(math.radians(cone)), math.cos(math.radians(cone - delta))
+        fall = 0.0 if cos_l < ct else (1.0 if cos_l > cf else ((cos_l - ct) / (cf - ct)) ** 4)
+        expect = I * fall / d2 * kd / math.pi * cos_l  # surface cosine equals cos_l here (floor normal parallel to the axis)
+        assert np.allclose(_centre(o, film), expect, rtol=1e-4, atol=1e-9), (off, _centre(o, film), expect)

@@ -217,6 +217,27 @@ def test_directlighting_specular_recursion_is_reported_unsupported():
     assert _rel_err(g.film_read()["rgb"], o.film_read()["rgb"], floor=1e-3).max() <= 1e-3
 
 
+def test_distant_and_spot_lights_match_oracle_per_pixel():
+    """lib/lights/distant_light.dart:41-48 and spot_light.dart:36-70 through drt_set_lights kinds 2 / 3 + drt_set_spot_params."""
+    sb, cam = scenes.cornell_synth()
+    sb.distant_light((3.0, 6.0, -10.0), (0, 0, 0), (2.0, 1.5, 1.0))
+    sb.spot_light((-6.0, 8.0, -8.0), (2.0, -8.0, 2.0), (300.0, 300.0, 400.0), 25.0, 8.0)
+    arrays = sb.arrays()
+    for integ in (host.Integrator(kind=host.INTEGRATOR_DIRECT), host.Integrator(kind=host.INTEGRATOR_DIRECT, strategy=1),
+                  host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=4)):
+        g, o, fg, fo = _render_both(arrays, cam, host.Film(64, 48), host.Sampler(kind=host.SAMPLER_LD, spp=4), integ)
+        err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
+        print("delta lights, integrator", integ.kind, "max rel err", err.max())
+        assert err.max() <= 1e-3
+    # the spot's cone edge is in the picture: some pixels lit by it, some not
+    base, _ = scenes.cornell_synth()
+    g0 = capi.Context(0)
+    host.upload_scene(g0, base.arrays())
+    host.configure_render(g0, cam, host.Film(64, 48), host.Sampler(kind=host.SAMPLER_LD, spp=4), host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=4))
+    g0.render()
+    assert np.abs(g0.film_read()["rgb"] - fg["rgb"]).max() > 0.05
+
+
 def test_thin_lens_camera_and_random_sampler():
     """perspective_camera.dart:104-119: lensRadius > 0 moves the ray origin on the lens (ConcentricSampleDisk)."""
     sb, cam = scenes.cornell_synth()
