@@ -42,6 +42,9 @@ namespace drt {
 #ifndef DRT_SMEM_STACK
 #define DRT_SMEM_STACK 24  // stack entries per thread kept in shared memory (24 KB per 128-thread CTA)
 #endif
+#ifndef DRT_REFILL_MIN
+#define DRT_REFILL_MIN 4  // idle lanes before a warp refills from its chunk: 4 beats 1 / 8 / 12 (tools/variant_sweep.sh, +2 %)
+#endif
 #ifndef DRT_LEAF_BATCH
 #define DRT_LEAF_BATCH 16  // lanes holding an untested leaf before the warp runs the exact leaf phase
 #endif
@@ -221,7 +224,8 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
   for (;;) {
     // ---- refill idle lanes from the warp's chunk ----------------------------------------------
     unsigned dead = __ballot_sync(FULL_MASK, !alive);
-    if (dead) {
+    // ray set-up runs at a handful of lanes: wait until DRT_REFILL_MIN lanes are idle (or nothing is left to wait for)
+    if (dead && (__popc(dead) >= DRT_REFILL_MIN || dead == FULL_MASK || (exhausted && warpNext == warpEnd))) {
       if (warpNext == warpEnd && !exhausted) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(nextRay, (unsigned)RAY_CHUNK);
@@ -253,8 +257,8 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
         float4 o = __ldg(rayO + rayIdx), d = __ldg(rayD + rayIdx);
         // invDir = (float)(1.0 / (double)d) (bvh_accel.dart:109-111).  The correctly rounded float32 quotient is the same
         // value: rounding a quotient to 53 bits and then to 24 cannot differ from rounding it to 24 directly
-        // (53 >= 2 * 24 + 2), subnormal and infinite results included.
-        const float ix = __fdiv_rn(1.0f, d.x), iy = __fdiv_rn(1.0f, d.y), iz = __fdiv_rn(1.0f, d.z);
+        // (53 >= 2 * 24 + 2), subnormal and infinite results included.  rcp.rn.f32 is that quotient.
+        const float ix = __frcp_rn(d.x), iy = __frcp_rn(d.y), iz = __frcp_rn(d.z);
         smDir[threadIdx.x] = d.x; smDir[128 + threadIdx.x] = d.y; smDir[256 + threadIdx.x] = d.z;
         r.ox2 = pack2(o.x, o.x); r.oy2 = pack2(o.y, o.y); r.oz2 = pack2(o.z, o.z);
         r.ix2 = pack2(ix, ix); r.iy2 = pack2(iy, iy); r.iz2 = pack2(iz, iz);
