@@ -1,0 +1,143 @@
+// @dart=2.9
+// dart:ffi binding of libdartray_gpu.so (include/drt.h).  One typedef pair per C entry point; the
+// signatures are the header's, argument for argument.  REVIEWED, NOT RUN: the build image has no Dart
+// SDK (SURVEY.md section 8c); dartray_b200/capi.py binds the same symbol table with ctypes and is the
+// tested twin (tests/test_abi.py checks every symbol declared in include/drt.h is exported).
+library dartray_gpu_ffi;
+
+import 'dart:ffi';
+import 'package:ffi/ffi.dart';
+
+class DrtHit extends Struct { // drt_hit
+  @Float() double t;
+  @Float() double b1;
+  @Float() double b2;
+  @Int32() int prim;
+}
+
+class DrtRenderStats extends Struct { // drt_render_stats
+  @Uint64() int cameraSamples;
+  @Uint64() int closestRays;
+  @Uint64() int shadowRays;
+  @Uint64() int zeroedSamples;
+}
+
+typedef _Ctx = Pointer<Void>;
+typedef _PF = Pointer<Float>;
+typedef _PD = Pointer<Double>;
+typedef _PI = Pointer<Int32>;
+typedef _PU = Pointer<Uint32>;
+typedef _PB = Pointer<Uint8>;
+
+typedef _CreateC = _Ctx Function(Int32);
+typedef _CreateD = _Ctx Function(int);
+typedef _DestroyC = Void Function(_Ctx);
+typedef _DestroyD = void Function(_Ctx);
+typedef _LastErrorC = Pointer<Utf8> Function(_Ctx);
+typedef _SetTrianglesC = Int32 Function(_Ctx, _PF, Uint32, _PU, Uint32, _PI, _PI, _PB);
+typedef _SetTrianglesD = int Function(_Ctx, _PF, int, _PU, int, _PI, _PI, _PB);
+typedef _SetQuadricsC = Int32 Function(_Ctx, Uint32, _PF, _PF, _PD, _PI, _PI, _PB);
+typedef _SetQuadricsD = int Function(_Ctx, int, _PF, _PF, _PD, _PI, _PI, _PB);
+typedef _SetOrderC = Int32 Function(_Ctx, _PU, Uint32);
+typedef _SetOrderD = int Function(_Ctx, _PU, int);
+typedef _BuildC = Int32 Function(_Ctx, Int32, Int32);
+typedef _BuildD = int Function(_Ctx, int, int);
+typedef _SetMaterialsC = Int32 Function(_Ctx, Uint32, _PI, _PF, _PF);
+typedef _SetMaterialsD = int Function(_Ctx, int, _PI, _PF, _PF);
+typedef _SetLobesC = Int32 Function(_Ctx, Uint32, _PU, _PI, _PF, _PI, _PF, _PF, _PD);
+typedef _SetLobesD = int Function(_Ctx, int, _PU, _PI, _PF, _PI, _PF, _PF, _PD);
+typedef _SetLightsC = Int32 Function(_Ctx, Uint32, _PI, _PF, _PF, _PI, _PU, _PU);
+typedef _SetLightsD = int Function(_Ctx, int, _PI, _PF, _PF, _PI, _PU, _PU);
+typedef _SetSpotC = Int32 Function(_Ctx, Uint32, _PF, _PD);
+typedef _SetSpotD = int Function(_Ctx, int, _PF, _PD);
+typedef _SetCameraC = Int32 Function(_Ctx, _PF, _PF, Double, Double, Double, Double);
+typedef _SetCameraD = int Function(_Ctx, _PF, _PF, double, double, double, double);
+typedef _SetIntC = Int32 Function(_Ctx, Int32);
+typedef _SetIntD = int Function(_Ctx, int);
+typedef _SetFilmC = Int32 Function(_Ctx, Int32, Int32, _PD, Double, Double, _PF);
+typedef _SetFilmD = int Function(_Ctx, int, int, _PD, double, double, _PF);
+typedef _SetSamplerC = Int32 Function(_Ctx, Int32, Int32, Int32, Int32, Int32, Int32, Int32, Uint64);
+typedef _SetSamplerD = int Function(_Ctx, int, int, int, int, int, int, int, int);
+typedef _SetIntegratorC = Int32 Function(_Ctx, Int32, Int32, Int32, Int32, Double, Double);
+typedef _SetIntegratorD = int Function(_Ctx, int, int, int, int, double, double);
+typedef _RenderC = Int32 Function(_Ctx, Int32, Int32);
+typedef _RenderD = int Function(_Ctx, int, int);
+typedef _FilmReadC = Int32 Function(_Ctx, _PF, _PF, _PF);
+typedef _FilmReadD = int Function(_Ctx, _PF, _PF, _PF);
+typedef _FilmSizeC = Int32 Function(_Ctx, _PI);
+typedef _FilmSizeD = int Function(_Ctx, _PI);
+typedef _StatsC = Int32 Function(_Ctx, Pointer<DrtRenderStats>);
+typedef _StatsD = int Function(_Ctx, Pointer<DrtRenderStats>);
+typedef _TraceC = Int32 Function(_Ctx, _PF, _PF, Uint64, Pointer<DrtHit>);
+typedef _TraceD = int Function(_Ctx, _PF, _PF, int, Pointer<DrtHit>);
+typedef _TraceAnyC = Int32 Function(_Ctx, _PF, _PF, Uint64, _PB);
+typedef _TraceAnyD = int Function(_Ctx, _PF, _PF, int, _PB);
+
+class DrtError implements Exception {
+  final int code;
+  final String message;
+  DrtError(this.code, this.message);
+  String toString() => 'libdartray_gpu error $code: $message';
+}
+
+/// Thin wrapper: one method per C entry point, `check` turns a negative return code into a [DrtError]
+/// carrying drt_last_error (the shim maps it to LogSevere, lib/core/log.dart:44-46).
+class Drt {
+  final DynamicLibrary lib;
+  _Ctx ctx;
+
+  Drt([String path = 'libdartray_gpu.so']) : lib = DynamicLibrary.open(path);
+
+  void create([int device = 0]) {
+    ctx = lib.lookupFunction<_CreateC, _CreateD>('drt_create')(device);
+    if (ctx == nullptr) {
+      throw new DrtError(-4, 'drt_create failed: no CUDA device (there is no CPU fallback)');
+    }
+  }
+
+  void destroy() {
+    if (ctx != null && ctx != nullptr) {
+      lib.lookupFunction<_DestroyC, _DestroyD>('drt_destroy')(ctx);
+    }
+    ctx = nullptr;
+  }
+
+  String lastError() => lib.lookupFunction<_LastErrorC, _LastErrorC>('drt_last_error')(ctx).toDartString();
+
+  void check(int rc) {
+    if (rc < 0) {
+      throw new DrtError(rc, lastError());
+    }
+  }
+
+  void setTriangles(_PF p, int nverts, _PU idx, int ntris, _PI mat, _PI light, _PB rev) =>
+      check(lib.lookupFunction<_SetTrianglesC, _SetTrianglesD>('drt_set_triangles')(ctx, p, nverts, idx, ntris, mat, light, rev));
+  void setSpheres(int n, _PF o2w, _PF w2o, _PD params, _PI mat, _PI light, _PB rev) =>
+      check(lib.lookupFunction<_SetQuadricsC, _SetQuadricsD>('drt_set_spheres')(ctx, n, o2w, w2o, params, mat, light, rev));
+  void setDisks(int n, _PF o2w, _PF w2o, _PD params, _PI mat, _PI light, _PB rev) =>
+      check(lib.lookupFunction<_SetQuadricsC, _SetQuadricsD>('drt_set_disks')(ctx, n, o2w, w2o, params, mat, light, rev));
+  void setBuildOrder(_PU order, int n) => check(lib.lookupFunction<_SetOrderC, _SetOrderD>('drt_set_build_order')(ctx, order, n));
+  void buildBvh(int split, int maxNodePrims) => check(lib.lookupFunction<_BuildC, _BuildD>('drt_build_bvh')(ctx, split, maxNodePrims));
+  void setMaterials(int n, _PI kind, _PF kd, _PF sigma) =>
+      check(lib.lookupFunction<_SetMaterialsC, _SetMaterialsD>('drt_set_materials')(ctx, n, kind, kd, sigma));
+  void setMaterialLobes(int n, _PU offsets, _PI kind, _PF rgb, _PI fresnel, _PF eta, _PF k, _PD scalars) =>
+      check(lib.lookupFunction<_SetLobesC, _SetLobesD>('drt_set_material_lobes')(ctx, n, offsets, kind, rgb, fresnel, eta, k, scalars));
+  void setLights(int n, _PI kind, _PF L, _PF pos, _PI nsamples, _PU shapeOffsets, _PU shapePrims) =>
+      check(lib.lookupFunction<_SetLightsC, _SetLightsD>('drt_set_lights')(ctx, n, kind, L, pos, nsamples, shapeOffsets, shapePrims));
+  void setSpotParams(int n, _PF w2l, _PD cosines) => check(lib.lookupFunction<_SetSpotC, _SetSpotD>('drt_set_spot_params')(ctx, n, w2l, cosines));
+  void setCamera(_PF rasterToCamera, _PF cameraToWorld, double lensRadius, double focalDistance, double open, double close) =>
+      check(lib.lookupFunction<_SetCameraC, _SetCameraD>('drt_set_camera')(ctx, rasterToCamera, cameraToWorld, lensRadius, focalDistance, open, close));
+  void setCameraKind(int kind) => check(lib.lookupFunction<_SetIntC, _SetIntD>('drt_set_camera_kind')(ctx, kind));
+  void setFilm(int xres, int yres, _PD crop, double xw, double yw, _PF table) =>
+      check(lib.lookupFunction<_SetFilmC, _SetFilmD>('drt_set_film')(ctx, xres, yres, crop, xw, yw, table));
+  void setSampler(int kind, int xs, int ys, int spp, int jitter, int pixelOrder, int tileSize, int seed) =>
+      check(lib.lookupFunction<_SetSamplerC, _SetSamplerD>('drt_set_sampler')(ctx, kind, xs, ys, spp, jitter, pixelOrder, tileSize, seed));
+  void setIntegrator(int kind, int maxDepth, int strategy, int aoSamples, double aoMin, double aoMax) =>
+      check(lib.lookupFunction<_SetIntegratorC, _SetIntegratorD>('drt_set_integrator')(ctx, kind, maxDepth, strategy, aoSamples, aoMin, aoMax));
+  void render(int taskNum, int taskCount) => check(lib.lookupFunction<_RenderC, _RenderD>('drt_render')(ctx, taskNum, taskCount));
+  void filmSize(_PI out4) => check(lib.lookupFunction<_FilmSizeC, _FilmSizeD>('drt_film_size')(ctx, out4));
+  void filmRead(_PF rgb, _PF xyz, _PF weight) => check(lib.lookupFunction<_FilmReadC, _FilmReadD>('drt_film_read')(ctx, rgb, xyz, weight));
+  void renderStats(Pointer<DrtRenderStats> out) => check(lib.lookupFunction<_StatsC, _StatsD>('drt_render_stats_get')(ctx, out));
+  void traceClosest(_PF o, _PF d, int n, Pointer<DrtHit> hits) => check(lib.lookupFunction<_TraceC, _TraceD>('drt_trace_closest')(ctx, o, d, n, hits));
+  void traceAny(_PF o, _PF d, int n, _PB occluded) => check(lib.lookupFunction<_TraceAnyC, _TraceAnyD>('drt_trace_any')(ctx, o, d, n, occluded));
+}

@@ -1,0 +1,475 @@
+// @dart=2.9
+// GpuSamplerRenderer: the Renderer (lib/core/renderer.dart:27-35) that replaces SamplerRenderer
+// (lib/renderers/sampler_renderer.dart) when libdartray_gpu.so can take the scene.  It walks the objects
+// DartRay.worldEnd has already constructed, flattens them into typed arrays and makes ONE coarse call
+// sequence through dart:ffi (include/drt.h).  Scene parsing, plugin names and the CLI are untouched.
+//
+// REVIEWED, NOT RUN: no Dart SDK exists in the build image (SURVEY.md section 8c).  The Python twin of this
+// file — dartray_b200/host.py (SceneBuilder.arrays, upload_scene, configure_render, *_lobes) — performs the
+// same flattening against the same ABI and is what tests/ exercise.
+library dartray_gpu;
+
+import 'dart:async';
+import 'dart:ffi';
+import 'dart:math' as Math;
+import 'dart:typed_data';
+import 'package:ffi/ffi.dart';
+import 'package:dartray/dartray_core.dart';
+import 'drt_ffi.dart';
+
+/// Thrown by the flattener when the scene uses something the GPU path does not cover; the caller then
+/// keeps the stock SamplerRenderer (see `makeRenderer` at the bottom).
+class GpuUnsupported implements Exception {
+  final String what;
+  GpuUnsupported(this.what);
+  String toString() => 'not on the GPU path: $what';
+}
+
+const int _LAMBERTIAN = 0, _OREN_NAYAR = 1, _MICROFACET_BLINN = 2, _SPEC_REFLECTION = 3, _SPEC_TRANSMISSION = 4;
+const int _FRESNEL_NOOP = 0, _FRESNEL_DIELECTRIC = 1, _FRESNEL_CONDUCTOR = 2;
+
+class _Lobe {
+  int kind, fresnel = _FRESNEL_NOOP;
+  Spectrum rgb, eta, k;
+  double param = 0.0, ei = 1.0, et = 1.0;
+  _Lobe(this.kind, this.rgb, {this.fresnel: _FRESNEL_NOOP, this.eta, this.k, this.param: 0.0, this.ei: 1.0, this.et: 1.0});
+}
+
+class _Arena {
+  final List<Pointer> _owned = [];
+  Pointer<Float> floats(List<double> v) {
+    final p = calloc<Float>(Math.max(v.length, 1));
+    p.asTypedList(v.length).setAll(0, v);
+    _owned.add(p);
+    return p;
+  }
+  Pointer<Double> doubles(List<double> v) {
+    final p = calloc<Double>(Math.max(v.length, 1));
+    p.asTypedList(v.length).setAll(0, v);
+    _owned.add(p);
+    return p;
+  }
+  Pointer<Int32> ints(List<int> v) {
+    final p = calloc<Int32>(Math.max(v.length, 1));
+    p.asTypedList(v.length).setAll(0, v);
+    _owned.add(p);
+    return p;
+  }
+  Pointer<Uint32> uints(List<int> v) {
+    final p = calloc<Uint32>(Math.max(v.length, 1));
+    p.asTypedList(v.length).setAll(0, v);
+    _owned.add(p);
+    return p;
+  }
+  Pointer<Uint8> bytes(List<int> v) {
+    final p = calloc<Uint8>(Math.max(v.length, 1));
+    p.asTypedList(v.length).setAll(0, v);
+    _owned.add(p);
+    return p;
+  }
+  void free() {
+    for (final p in _owned) {
+      calloc.free(p);
+    }
+    _owned.clear();
+  }
+}
+
+class GpuSamplerRenderer extends Renderer {
+  final Sampler sampler;
+  final Camera camera;
+  final SurfaceIntegrator surfaceIntegrator;
+  final int taskNum, taskCount;
+  final String libraryPath;
+
+  GpuSamplerRenderer(this.sampler, this.camera, this.surfaceIntegrator, this.taskNum, this.taskCount,
+                     {this.libraryPath: 'libdartray_gpu.so'});
+
+  // The per-ray entry points of the interface are not used on the GPU path (the whole loop of
+  // sampler_renderer.dart:118-218 runs inside drt_render).
+  Spectrum Li(Scene scene, RayDifferential ray, Sample sample, RNG rng, [Intersection isect, Spectrum T]) =>
+      throw new UnsupportedError('GpuSamplerRenderer renders whole tasks; Li is not called per ray');
+  Spectrum transmittance(Scene scene, RayDifferential ray, Sample sample, RNG rng) => new Spectrum(1.0);
+
+  // ---- materials: Material.getBSDF with constant textures, as ordered BxDF lists ------------------------
+  static Spectrum _const(Texture t, String what) {
+    if (t is ConstantTexture) {
+      return t.value is Spectrum ? new Spectrum.from(t.value) : new Spectrum(t.value.toDouble());
+    }
+    throw new GpuUnsupported('$what is not a constant texture');
+  }
+  static double _constF(Texture t, String what) {
+    if (t is ConstantTexture) {
+      return t.value.toDouble();
+    }
+    throw new GpuUnsupported('$what is not a constant texture');
+  }
+  static double _blinn(double roughness) {  // 1 / roughness, then blinn.dart:24-28
+    double e = 1.0 / roughness;
+    return (e > 10000.0 || e.isNaN) ? 10000.0 : e;
+  }
+
+  static List<_Lobe> _lobes(Material m) {
+    final out = <_Lobe>[];
+    void noBump(Texture b) {
+      if (b != null) {
+        throw new GpuUnsupported('bump maps');
+      }
+    }
+    if (m is MatteMaterial) {  // matte_material.dart:41-65
+      noBump(m.bumpMap);
+      Spectrum r = _const(m.Kd, 'matte Kd').clamp();
+      double sig = _constF(m.sigma, 'matte sigma').clamp(0.0, 90.0);
+      if (!r.isBlack()) {
+        out.add(sig == 0.0 ? new _Lobe(_LAMBERTIAN, r) : new _Lobe(_OREN_NAYAR, r, param: sig));
+      }
+    } else if (m is MirrorMaterial) {  // mirror_material.dart:26-43
+      noBump(m.bumpMap);
+      Spectrum r = _const(m.Kr, 'mirror Kr').clamp();
+      if (!r.isBlack()) {
+        out.add(new _Lobe(_SPEC_REFLECTION, r));
+      }
+    } else if (m is GlassMaterial) {  // glass_material.dart:26-52
+      noBump(m.bumpMap);
+      double ior = _constF(m.index, 'glass index');
+      Spectrum r = _const(m.Kr, 'glass Kr').clamp(), t = _const(m.Kt, 'glass Kt').clamp();
+      if (!r.isBlack()) {
+        out.add(new _Lobe(_SPEC_REFLECTION, r, fresnel: _FRESNEL_DIELECTRIC, ei: 1.0, et: ior));
+      }
+      if (!t.isBlack()) {
+        out.add(new _Lobe(_SPEC_TRANSMISSION, t, fresnel: _FRESNEL_DIELECTRIC, ei: 1.0, et: ior));
+      }
+    } else if (m is PlasticMaterial) {  // plastic_material.dart:26-53
+      noBump(m.bumpMap);
+      Spectrum kd = _const(m.Kd, 'plastic Kd').clamp(), ks = _const(m.Ks, 'plastic Ks').clamp();
+      if (!kd.isBlack()) {
+        out.add(new _Lobe(_LAMBERTIAN, kd));
+      }
+      if (!ks.isBlack()) {
+        out.add(new _Lobe(_MICROFACET_BLINN, ks, fresnel: _FRESNEL_DIELECTRIC, ei: 1.5, et: 1.0,
+                          param: _blinn(_constF(m.roughness, 'plastic roughness'))));
+      }
+    } else if (m is MetalMaterial) {  // metal_material.dart:26-46
+      noBump(m.bumpMap);
+      out.add(new _Lobe(_MICROFACET_BLINN, new Spectrum(1.0), fresnel: _FRESNEL_CONDUCTOR,
+                        eta: _const(m.eta, 'metal eta'), k: _const(m.k, 'metal k'),
+                        param: _blinn(_constF(m.roughness, 'metal roughness'))));
+    } else if (m is UberMaterial) {  // uber_material.dart:27-75
+      noBump(m.bumpMap);
+      Spectrum op = _const(m.opacity, 'uber opacity').clamp();
+      if (!op.isValue(1.0)) {
+        out.add(new _Lobe(_SPEC_TRANSMISSION, -op + Spectrum.ONE, fresnel: _FRESNEL_DIELECTRIC, ei: 1.0, et: 1.0));
+      }
+      double e = _constF(m.eta, 'uber index');
+      Spectrum kd = op * _const(m.Kd, 'uber Kd').clamp();
+      if (!kd.isBlack()) {
+        out.add(new _Lobe(_LAMBERTIAN, kd));
+      }
+      Spectrum ks = op * _const(m.Ks, 'uber Ks').clamp();
+      if (!ks.isBlack()) {
+        out.add(new _Lobe(_MICROFACET_BLINN, ks, fresnel: _FRESNEL_DIELECTRIC, ei: e, et: 1.0,
+                          param: _blinn(_constF(m.roughness, 'uber roughness'))));
+      }
+      Spectrum kr = op * _const(m.Kr, 'uber Kr').clamp();
+      if (!kr.isBlack()) {
+        out.add(new _Lobe(_SPEC_REFLECTION, kr, fresnel: _FRESNEL_DIELECTRIC, ei: e, et: 1.0));
+      }
+      Spectrum kt = op * _const(m.Kt, 'uber Kt').clamp();
+      if (!kt.isBlack()) {
+        out.add(new _Lobe(_SPEC_TRANSMISSION, kt, fresnel: _FRESNEL_DIELECTRIC, ei: e, et: 1.0));
+      }
+    } else {
+      throw new GpuUnsupported('material ${m.runtimeType}');
+    }
+    return out;
+  }
+
+  static List<double> _rgb(Spectrum s) {
+    if (s == null) {
+      return [0.0, 0.0, 0.0];
+    }
+    final c = s.toRGB();
+    return [c.c[0], c.c[1], c.c[2]];
+  }
+
+  // ---- the render call ------------------------------------------------------------------------------
+  Future<OutputImage> render(Scene scene) {
+    final a = new _Arena();
+    final drt = new Drt(libraryPath);
+    try {
+      drt.create(0);
+      _uploadScene(drt, a, scene);
+      _configure(drt, a);
+      drt.render(taskNum, taskCount);  // blocking: replaces _SamplerRendererTask.run
+      final size = calloc<Int32>(4);
+      drt.filmSize(size);
+      final int left = size[0], top = size[1], w = size[2], h = size[3];
+      calloc.free(size);
+      final rgb = calloc<Float>(w * h * 3);
+      drt.filmRead(rgb, nullptr, nullptr);  // replaces ImageFilm.writeImage (image_film.dart:268-299)
+      final film = camera.film;
+      final out = new OutputImage(left, top, w, h, film.xResolution, film.yResolution,
+                                  new Float32List.fromList(rgb.asTypedList(w * h * 3)));
+      calloc.free(rgb);
+      return new Future.value(out);
+    } finally {
+      drt.destroy();
+      a.free();
+    }
+  }
+
+  void _uploadScene(Drt drt, _Arena a, Scene scene) {
+    if (scene.volumeRegion != null) {
+      throw new GpuUnsupported('participating media');
+    }
+    if (scene.aggregate is! BVHAccel) {
+      throw new GpuUnsupported('accelerator ${scene.aggregate.runtimeType} (only bvh)');
+    }
+    final BVHAccel bvh = scene.aggregate;
+    // primitives arrive in the order BVHAccel's constructor refined them (bvh_accel.dart:46-52): that IS the build
+    // order; ids are assigned per kind in upload order: triangles, then spheres, then disks.
+    final tris = <GeometricPrimitive>[], sphs = <GeometricPrimitive>[], dsks = <GeometricPrimitive>[];
+    for (final Primitive p in bvh.primitives) {
+      if (p is! GeometricPrimitive) {
+        throw new GpuUnsupported('primitive ${p.runtimeType} (instancing / motion blur)');
+      }
+      final GeometricPrimitive g = p;
+      if (g.shape is Triangle) {
+        tris.add(g);
+      } else if (g.shape is Sphere) {
+        sphs.add(g);
+      } else if (g.shape is Disk) {
+        dsks.add(g);
+      } else {
+        throw new GpuUnsupported('shape ${g.shape.runtimeType}');
+      }
+    }
+    final ids = new Map<GeometricPrimitive, int>.identity();
+    for (int i = 0; i < tris.length; ++i) ids[tris[i]] = i;
+    for (int i = 0; i < sphs.length; ++i) ids[sphs[i]] = tris.length + i;
+    for (int i = 0; i < dsks.length; ++i) ids[dsks[i]] = tris.length + sphs.length + i;
+
+    // materials and area lights by identity
+    final materials = <Material>[], lights = scene.lights;
+    final matIndex = new Map<Material, int>.identity(), lightIndex = new Map<Light, int>.identity();
+    for (int i = 0; i < lights.length; ++i) lightIndex[lights[i]] = i;
+    int matOf(GeometricPrimitive g) => matIndex.putIfAbsent(g.material, () {
+      materials.add(g.material);
+      return materials.length - 1;
+    });
+    int lightOf(GeometricPrimitive g) => g.areaLight == null ? -1 : lightIndex[g.areaLight];
+
+    // triangles: three world-space float32 vertices each (TriangleMesh.point, triangle_mesh.dart:39-42); no sharing
+    final P = <double>[], idx = <int>[], tm = <int>[], tl = <int>[], tr = <int>[];
+    final triKey = new Map<TriangleMesh, Map<int, int>>.identity();
+    for (int i = 0; i < tris.length; ++i) {
+      final Triangle t = tris[i].shape;
+      if (t.mesh.n != null || t.mesh.s != null || t.mesh.uvs != null || t.mesh.alphaTexture != null) {
+        throw new GpuUnsupported('triangle meshes with normals, tangents, uvs or alpha textures');
+      }
+      for (int k = 0; k < 3; ++k) {
+        final Point p = t.mesh.point(t.mesh.vertexIndex[3 * t.index + k]);
+        P..add(p.x)..add(p.y)..add(p.z);
+        idx.add(3 * i + k);
+      }
+      tm.add(matOf(tris[i]));
+      tl.add(lightOf(tris[i]));
+      tr.add(t.reverseOrientation ? 1 : 0);
+      triKey.putIfAbsent(t.mesh, () => <int, int>{})[t.index] = i;
+    }
+    drt.setTriangles(a.floats(P), P.length ~/ 3, a.uints(idx), tris.length, a.ints(tm), a.ints(tl), a.bytes(tr));
+
+    void quadrics(List<GeometricPrimitive> prims, bool disk) {
+      if (prims.isEmpty) {
+        return;
+      }
+      final o2w = <double>[], w2o = <double>[], prm = <double>[], qm = <int>[], ql = <int>[], qr = <int>[];
+      for (final g in prims) {
+        o2w.addAll(g.shape.objectToWorld.m.data);
+        w2o.addAll(g.shape.worldToObject.m.data);
+        if (disk) {
+          final Disk d = g.shape;  // the PARAMETERS of disk.dart:157-166: phiMax is stored in radians there
+          prm..add(d.height)..add(d.radius)..add(d.innerRadius)..add(Degrees(d.phiMax));
+        } else {
+          final Sphere s = g.shape;  // sphere.dart:24-32 stores clamped zmin / zmax and phiMax in radians
+          prm..add(s.radius)..add(s.zmin)..add(s.zmax)..add(Degrees(s.phiMax));
+        }
+        qm.add(matOf(g));
+        ql.add(lightOf(g));
+        qr.add(g.shape.reverseOrientation ? 1 : 0);
+      }
+      if (disk) {
+        drt.setDisks(prims.length, a.floats(o2w), a.floats(w2o), a.doubles(prm), a.ints(qm), a.ints(ql), a.bytes(qr));
+      } else {
+        drt.setSpheres(prims.length, a.floats(o2w), a.floats(w2o), a.doubles(prm), a.ints(qm), a.ints(ql), a.bytes(qr));
+      }
+    }
+    quadrics(sphs, false);
+    quadrics(dsks, true);
+
+    final order = <int>[];
+    for (final Primitive p in bvh.primitives) order.add(ids[p]);
+    drt.setBuildOrder(a.uints(order), order.length);
+    drt.buildBvh(bvh.splitMethod, bvh.maxPrimsInNode);
+
+    // materials
+    final lobeLists = materials.map(_lobes).toList();
+    final offsets = <int>[0], kind = <int>[], fres = <int>[], rgb = <double>[], eta = <double>[], kk = <double>[], scal = <double>[];
+    for (final ll in lobeLists) {
+      for (final l in ll) {
+        kind.add(l.kind);
+        fres.add(l.fresnel);
+        rgb.addAll(_rgb(l.rgb));
+        eta.addAll(_rgb(l.eta));
+        kk.addAll(_rgb(l.k));
+        scal..add(l.param)..add(l.ei)..add(l.et);
+      }
+      offsets.add(kind.length);
+    }
+    if (materials.isNotEmpty) {
+      drt.setMaterialLobes(materials.length, a.uints(offsets), a.ints(kind), a.floats(rgb), a.ints(fres), a.floats(eta),
+                           a.floats(kk), a.doubles(scal));
+    }
+
+    // lights
+    final lk = <int>[], lL = <double>[], lpos = <double>[], lns = <int>[], so = <int>[0], sp = <int>[];
+    final w2l = <double>[], cosines = <double>[];
+    bool anySpot = false;
+    for (final Light l in lights) {
+      lns.add(l.nSamples);
+      w2l.addAll(l.worldToLight.m.data);
+      if (l is DiffuseAreaLight) {
+        lk.add(0);
+        lL.addAll(_rgb(l.Lemit));
+        lpos.addAll([0.0, 0.0, 0.0]);
+        cosines.addAll([0.0, 0.0]);
+        for (final Shape s in l.shapeSet.shapes) {  // shape_set.dart:26-41: its own refinement of the light's shape
+          if (s is Triangle) {
+            sp.add(triKey[s.mesh][s.index]);
+          } else {
+            final g = (sphs + dsks).firstWhere((q) => identical(q.shape, s));
+            sp.add(ids[g]);
+          }
+        }
+      } else if (l is PointLight) {
+        lk.add(1);
+        lL.addAll(_rgb(l.intensity));
+        lpos..add(l.lightPos.x)..add(l.lightPos.y)..add(l.lightPos.z);
+        cosines.addAll([0.0, 0.0]);
+      } else if (l is DistantLight) {
+        lk.add(2);
+        lL.addAll(_rgb(l.L));
+        lpos..add(l.lightDir.x)..add(l.lightDir.y)..add(l.lightDir.z);
+        cosines.addAll([0.0, 0.0]);
+      } else if (l is SpotLight) {
+        lk.add(3);
+        anySpot = true;
+        lL.addAll(_rgb(l.intensity));
+        lpos..add(l.lightPos.x)..add(l.lightPos.y)..add(l.lightPos.z);
+        cosines..add(l.cosTotalWidth)..add(l.cosFalloffStart);
+      } else {
+        throw new GpuUnsupported('light ${l.runtimeType}');
+      }
+      so.add(sp.length);
+    }
+    drt.setLights(lights.length, a.ints(lk), a.floats(lL), a.floats(lpos), a.ints(lns), a.uints(so), a.uints(sp));
+    if (anySpot) {
+      drt.setSpotParams(lights.length, a.floats(w2l), a.doubles(cosines));
+    }
+  }
+
+  void _configure(Drt drt, _Arena a) {
+    // camera (perspective_camera.dart:46-57, orthographic_camera.dart, environment_camera.dart)
+    if (camera.cameraToWorld.actuallyAnimated) {
+      throw new GpuUnsupported('animated cameras');
+    }
+    final c2w = camera.cameraToWorld.startTransform.m.data;
+    if (camera is ProjectiveCamera) {
+      final ProjectiveCamera pc = camera;
+      drt.setCamera(a.floats(pc.rasterToCamera.m.data), a.floats(c2w), pc.lensRadius, pc.focalDistance,
+                    camera.shutterOpen, camera.shutterClose);
+      drt.setCameraKind(camera is OrthographicCamera ? 1 : 0);
+    } else if (camera is EnvironmentCamera) {
+      drt.setCamera(a.floats(new Matrix4x4().data), a.floats(c2w), 0.0, 1.0e30, camera.shutterOpen, camera.shutterClose);
+      drt.setCameraKind(2);
+    } else {
+      throw new GpuUnsupported('camera ${camera.runtimeType}');
+    }
+
+    // film: the 16 x 16 filter table ImageFilm builds (image_film.dart:74-82), recomputed through the public Filter API
+    if (camera.film is! ImageFilm) {
+      throw new GpuUnsupported('film ${camera.film.runtimeType}');
+    }
+    final ImageFilm film = camera.film;
+    final Filter f = film.filter;
+    final table = <double>[];
+    for (int y = 0; y < 16; ++y) {
+      final double fy = (y + 0.5) * f.yWidth / 16;
+      for (int x = 0; x < 16; ++x) {
+        final double fx = (x + 0.5) * f.xWidth / 16;
+        table.add(f.evaluate(fx, fy));
+      }
+    }
+    drt.setFilm(film.xResolution, film.yResolution, a.doubles(film.cropWindow), f.xWidth, f.yWidth, a.floats(table));
+
+    // sampler: seed = task number (sampler_renderer.dart:137)
+    int order(PixelSampler p) => p is LinearPixelSampler ? 0 : 1;
+    if (sampler is LowDiscrepancySampler) {
+      final LowDiscrepancySampler s = sampler;
+      drt.setSampler(0, 1, 1, s.nPixelSamples, 1, order(s.pixels), 32, taskNum);
+    } else if (sampler is StratifiedSampler) {
+      final StratifiedSampler s = sampler;
+      drt.setSampler(1, s.xPixelSamples, s.yPixelSamples, s.xPixelSamples * s.yPixelSamples, s.jitterSamples ? 1 : 0,
+                     order(s.pixels), 32, taskNum);
+    } else if (sampler is RandomSampler) {
+      final RandomSampler s = sampler;
+      drt.setSampler(2, 1, 1, s.samplesPerPixel, 1, order(s.pixels), 32, taskNum);
+    } else {
+      throw new GpuUnsupported('sampler ${sampler.runtimeType}');
+    }
+
+    // surface integrator
+    if (surfaceIntegrator is PathIntegrator) {
+      final PathIntegrator p = surfaceIntegrator;
+      drt.setIntegrator(0, p.maxDepth, 0, 1, 0.0, double.infinity);
+    } else if (surfaceIntegrator is AmbientOcclusionIntegrator) {
+      final AmbientOcclusionIntegrator ao = surfaceIntegrator;
+      drt.setIntegrator(1, 0, 0, ao.nSamples, ao.minDist, ao.maxDist);
+    } else if (surfaceIntegrator is DirectLightingIntegrator) {
+      final DirectLightingIntegrator d = surfaceIntegrator;
+      drt.setIntegrator(2, d.maxDepth, d.strategy, 1, 0.0, double.infinity);
+    } else {
+      throw new GpuUnsupported('surface integrator ${surfaceIntegrator.runtimeType}');
+    }
+  }
+}
+
+/// What DartRay._makeRenderer's else-branch (lib/dartray/dartray.dart:756-761) calls instead of constructing a
+/// SamplerRenderer directly: the GPU renderer wrapped so that a scene it cannot take (GpuUnsupported) or a
+/// DRT_E_UNSUPPORTED / missing library falls back to the stock Dart renderer with a warning.
+class GpuOrDartRenderer extends Renderer {
+  final GpuSamplerRenderer gpu;
+  final SamplerRenderer dart;
+  GpuOrDartRenderer(this.gpu, this.dart);
+
+  Future<OutputImage> render(Scene scene) {
+    try {
+      return gpu.render(scene);
+    } on GpuUnsupported catch (e) {
+      LogWarning('GPU renderer: $e; rendering with the Dart SamplerRenderer');
+    } on DrtError catch (e) {
+      if (e.code != -6) {  // DRT_E_UNSUPPORTED falls back, anything else is a real error (log.dart:44-46)
+        LogSevere(e.toString());
+      }
+      LogWarning('GPU renderer: ${e.message}; rendering with the Dart SamplerRenderer');
+    } on ArgumentError catch (e) {  // DynamicLibrary.open failed
+      LogWarning('GPU renderer: libdartray_gpu.so not loadable ($e); rendering with the Dart SamplerRenderer');
+    }
+    return dart.render(scene);
+  }
+
+  Spectrum Li(Scene scene, RayDifferential ray, Sample sample, RNG rng, [Intersection isect, Spectrum T]) =>
+      dart.Li(scene, ray, sample, rng, isect, T);
+  Spectrum transmittance(Scene scene, RayDifferential ray, Sample sample, RNG rng) =>
+      dart.transmittance(scene, ray, sample, rng);
+}
