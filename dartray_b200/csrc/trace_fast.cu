@@ -131,21 +131,26 @@ static __device__ __noinline__ bool slabExact(float ox, float oy, float oz, floa
   return (tmin < maxt) && (tmax > mint);
 }
 
-// One slot of a wide node: conservative for interior children, exact-or-marked for leaf children.
+// One slot of a wide node for a regular ray: conservative for interior children, exact-or-marked for leaf children.
 // Returns the reference to visit (a leaf reference possibly marked "undecided") or DRT_REF_EMPTY.
 static __device__ __forceinline__ int32_t testSlot(const FastRay& r, int32_t ref, const float2 bx, const float2 by,
                                                    const float2 bz, float* tmin) {
-  if (r.negMask & 8u) {  // slow ray (warp-divergent, rare): exact decision for every box
-    if (ref == DRT_REF_EMPTY) return ref;
-    float te = 0.f;  // only this temporary is address-taken: the caller's t0..t3 stay in registers
-    const bool ok = slabExact(lo32(r.ox2), lo32(r.oy2), lo32(r.oz2), lo32(r.ix2), lo32(r.iy2), lo32(r.iz2), r.mint, r.maxt, bx.x, by.x,
-                              bz.x, bx.y, by.y, bz.y, &te);
-    *tmin = te;
-    return ok ? ref : DRT_REF_EMPTY;
-  }
   int c = slabFilter(r, pack2(bx.x, bx.y), pack2(by.x, by.y), pack2(bz.x, bz.y), tmin);
   int32_t marked = (c == 2 && ref < 0) ? refMarkUndecided(ref) : ref;  // an EMPTY slot is positive: never marked
   return c != 0 ? marked : DRT_REF_EMPTY;
+}
+
+// The same slot for a "slow" ray (non-finite origin or invDir component; warp-divergent, rare): the reference's own
+// f64 decision for every box.
+static __device__ __forceinline__ int32_t testSlotExact(const FastRay& r, int32_t ref, const float2 bx, const float2 by,
+                                                        const float2 bz, float* tmin) {
+  *tmin = 0.f;
+  if (ref == DRT_REF_EMPTY) return ref;
+  float te = 0.f;  // only this temporary is address-taken: the caller's t0..t3 stay in registers
+  const bool ok = slabExact(lo32(r.ox2), lo32(r.oy2), lo32(r.oz2), lo32(r.ix2), lo32(r.iy2), lo32(r.iz2), r.mint, r.maxt, bx.x, by.x,
+                            bz.x, bx.y, by.y, bz.y, &te);
+  *tmin = te;
+  return ok ? ref : DRT_REF_EMPTY;
 }
 
 // Pops until an entry survives the reference's pop-time test `tmin < ray.maxDistance`
@@ -312,10 +317,18 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
       }
       float t0, t1, t2, t3;
       // slot k: (lo.x, hi.x) (lo.y, hi.y) (lo.z, hi.z), six consecutive floats
-      int32_t r0 = testSlot(r, qr.x, make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y), &t0);
-      int32_t r1 = testSlot(r, qr.y, make_float2(q1.z, q1.w), make_float2(q2.x, q2.y), make_float2(q2.z, q2.w), &t1);
-      int32_t r2 = testSlot(r, qr.z, make_float2(q3.x, q3.y), make_float2(q3.z, q3.w), make_float2(q4.x, q4.y), &t2);
-      int32_t r3 = testSlot(r, qr.w, make_float2(q4.z, q4.w), make_float2(q5.x, q5.y), make_float2(q5.z, q5.w), &t3);
+      int32_t r0, r1, r2, r3;
+      if (!(r.negMask & 8u)) {
+        r0 = testSlot(r, qr.x, make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y), &t0);
+        r1 = testSlot(r, qr.y, make_float2(q1.z, q1.w), make_float2(q2.x, q2.y), make_float2(q2.z, q2.w), &t1);
+        r2 = testSlot(r, qr.z, make_float2(q3.x, q3.y), make_float2(q3.z, q3.w), make_float2(q4.x, q4.y), &t2);
+        r3 = testSlot(r, qr.w, make_float2(q4.z, q4.w), make_float2(q5.x, q5.y), make_float2(q5.z, q5.w), &t3);
+      } else {
+        r0 = testSlotExact(r, qr.x, make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y), &t0);
+        r1 = testSlotExact(r, qr.y, make_float2(q1.z, q1.w), make_float2(q2.x, q2.y), make_float2(q2.z, q2.w), &t1);
+        r2 = testSlotExact(r, qr.z, make_float2(q3.x, q3.y), make_float2(q3.z, q3.w), make_float2(q4.x, q4.y), &t2);
+        r3 = testSlotExact(r, qr.w, make_float2(q4.z, q4.w), make_float2(q5.x, q5.y), make_float2(q5.z, q5.w), &t3);
+      }
       // visiting order of the reference's depth-first walk (bvh_accel.dart:147-153), branch-free
       // closest hit: the node carries its three near/far decisions for each dirIsNeg octant (orderLut).
       // any hit: the answer is the OR over all leaves whose box test passes, whatever the visiting order, so the
