@@ -51,6 +51,11 @@ def _rel_err(a, b, floor=1e-4):
     (host.Sampler(kind=host.SAMPLER_STRATIFIED, xs=3, ys=2), host.Integrator(kind=host.INTEGRATOR_PATH)),
     (host.Sampler(kind=host.SAMPLER_STRATIFIED, xs=2, ys=2, jitter=False), host.Integrator(kind=host.INTEGRATOR_DIRECT)),
     (host.Sampler(kind=host.SAMPLER_RANDOM, spp=5), host.Integrator(kind=host.INTEGRATOR_PATH)),
+    # index-shuffle fast path edge cases (one / two samples per pixel) and its fallback above 2048 samples per pixel
+    (host.Sampler(kind=host.SAMPLER_LD, spp=1), host.Integrator(kind=host.INTEGRATOR_PATH)),
+    (host.Sampler(kind=host.SAMPLER_LD, spp=2), host.Integrator(kind=host.INTEGRATOR_AO)),
+    (host.Sampler(kind=host.SAMPLER_LD, spp=1024, seed=11), host.Integrator(kind=host.INTEGRATOR_PATH)),
+    (host.Sampler(kind=host.SAMPLER_LD, spp=4096, seed=5), host.Integrator(kind=host.INTEGRATOR_PATH)),
 ])
 def test_sampler_sequences_replay_the_oracle_bit_for_bit(sampler, integ):
     sb, cam = scenes.cornell_synth()
