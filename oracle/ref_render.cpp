@@ -659,7 +659,9 @@ struct Ctx {
     b.ng = dg.nn;
     b.sn = Normalize(dg.dpdu);
     b.tn = Cross(b.nn, b.sn);
-    const Material& m = rs.materials[g.materialOf[is.prim]];
+    // no material table: every primitive is the default matte, Kd = 0.5 (matte_material.dart:67-72), as in drt_create
+    static const Material kDefault = Material::matte(Spec(0.5), 0.0);
+    const Material& m = rs.materials.empty() ? kDefault : rs.materials[g.materialOf[is.prim]];
     for (const Lobe& l : m.lobes) b.bxdfs[b.nBxDFs++].init(l);
     return b;
   }
