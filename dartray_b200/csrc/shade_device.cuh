@@ -397,6 +397,14 @@ static __device__ DRT_SHAPE_INLINE bool shapeIntersect(const RenderScene& rs, ui
   return true;
 }
 
+// Out-of-line copy for the light-sampling code, where the general shape test only runs for sphere / disk light shapes
+// (triangle light shapes are tested from their resident GLightShape record): inlining it at every call site of
+// shapeSetSample / shapeSetPdf made shadePathKernel 15,152 instructions (242 KB), far beyond the instruction caches.
+static __device__ __noinline__ bool shapeIntersectCold(const RenderScene& rs, uint32_t prim, V3 o, V3 d, double mint, double maxt,
+                                                       ShapeHit* h) {
+  return shapeIntersect(rs, prim, o, d, mint, maxt, h);
+}
+
 // ---- BSDF: one diffuse lobe (bsdf.dart:41-255, bxdf.dart:28-91, lambertian.dart:30-48,
 // oren_nayar.dart:24-58, matte_material.dart:41-65) ------------------------------------------------------
 enum { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16, BSDF_ALL = 31 };
@@ -746,7 +754,7 @@ static __device__ inline bool lightShapeIntersect(const RenderScene& rs, const G
     return true;
   }
   ShapeHit h;
-  if (!shapeIntersect(rs, ls.prim, o, d, mint, maxt, &h)) return false;
+  if (!shapeIntersectCold(rs, ls.prim, o, d, mint, maxt, &h)) return false;
   *tOut = h.t;
   *nnOut = h.nn;
   return true;
@@ -796,7 +804,7 @@ static __device__ inline V3 shapeSample2(const RenderScene& rs, const GLightShap
   V3 rd = UniformSampleCone2(u1, u2, cosThetaMax, wcX, wcY, wc);
   double thit;
   ShapeHit h;
-  if (shapeIntersect(rs, prim, p, rd, 1.0e-3, CUDART_INF, &h)) thit = h.t;
+  if (shapeIntersectCold(rs, prim, p, rd, 1.0e-3, CUDART_INF, &h)) thit = h.t;
   else thit = Dot(Pcenter - p, Normalize(rd));
   V3 ps = RayAt(p, rd, thit);
   V3 n = Normalize(ps - Pcenter);
