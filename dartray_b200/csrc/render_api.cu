@@ -323,7 +323,9 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
   return DRT_OK;
 }
 
-static void carve(ByteArena& a, Wavefront& wf, uint32_t cap, uint32_t shCap, int nVals) {
+static const int kMaxChainLevels = 16;  // specular recursion depth the chain evaluation covers (maxdepth <= 17)
+
+static void carve(ByteArena& a, Wavefront& wf, uint32_t cap, uint32_t shCap, int nVals, bool chains) {
   wf.cap = cap;
   wf.pixX = a.take<int32_t>(cap); wf.pixY = a.take<int32_t>(cap); wf.sampleIdx = a.take<uint32_t>(cap);
   wf.camXY = a.take<double2>(cap); wf.camLens = a.take<double2>(cap); wf.camTime = a.take<float>(cap);
@@ -346,12 +348,22 @@ static void carve(ByteArena& a, Wavefront& wf, uint32_t cap, uint32_t shCap, int
   wf.misHit = a.take<float4>(cap); wf.misT = a.take<double>(cap);
   wf.counts = a.take<uint32_t>(Q_COUNT);
   wf.hitList = a.take<uint32_t>(cap);
+  if (chains) {  // directlighting with specular BxDFs: counters per recursion level + a copy of the camera-ray queue
+    wf.specCtr = a.take<uint32_t>(cap);
+    wf.specCtrAt = a.take<uint32_t>((size_t)kMaxChainLevels * cap);
+    wf.bakO = a.take<float4>(cap); wf.bakD = a.take<float4>(cap); wf.bakRange = a.take<double2>(cap);
+    wf.bakSlot = a.take<uint32_t>(cap); wf.bakHit = a.take<float4>(cap); wf.bakT = a.take<double>(cap);
+  } else {
+    wf.specCtr = wf.specCtrAt = nullptr;
+    wf.bakO = wf.bakD = nullptr; wf.bakRange = nullptr; wf.bakSlot = nullptr; wf.bakHit = nullptr; wf.bakT = nullptr;
+  }
 }
 
 static int ensureWavefront(drt_ctx* c, RenderState* r, uint32_t cap, uint32_t shCap) {
+  const bool chains = r->rp.integKind == 2 && r->hasSpecular && r->rp.maxDepth > 1;
   ByteArena probe;
   Wavefront tmp{};
-  carve(probe, tmp, cap, shCap, r->rp.nVals);
+  carve(probe, tmp, cap, shCap, r->rp.nVals, chains);
   size_t need = probe.used + 256;
   if (need > r->wfBytes) {
     if (r->wfMem) cudaFree(r->wfMem);
@@ -363,7 +375,7 @@ static int ensureWavefront(drt_ctx* c, RenderState* r, uint32_t cap, uint32_t sh
   ByteArena a;
   a.base = r->wfMem;
   a.size = r->wfBytes;
-  carve(a, r->wf, cap, shCap, r->rp.nVals);
+  carve(a, r->wf, cap, shCap, r->rp.nVals, chains);
   r->shCap = shCap;
   return DRT_OK;
 }
@@ -446,6 +458,114 @@ static int traceQueue(drt_ctx* c, bool any, const float4* o, const float4* d, co
     if (rc__ != DRT_OK) return rc__;     \
   } while (0)
 
+// DirectLightingIntegrator.Li without its recursion (direct_lighting_integrator.dart:30-55) on the vertices of extension
+// queue `cur`: emitted light, then UniformSampleAllLights / UniformSampleOneLight, one launch group per (light, sample).
+// `weighted`: the vertices are the ends of a specular chain; their radiance is added with the chain weight.
+static int directStage(drt_ctx* c, RenderState* r, int cur, bool weighted) {
+  const RenderParams& p = r->rp;
+  const RenderScene& rs = r->rs;
+  const Wavefront& wf = r->wf;
+  cudaStream_t st = c->stream;
+  const int sms = c->numSMs;
+  RenderCounters* rc = r->dCounters.p;
+  CK(c, launchDirectSetup(p, rs, wf, cur, weighted ? 1 : 0, sms, st));
+  c->launches++;
+  if (rs.nLights <= 0) return DRT_OK;
+  const bool one = p.strategy != 0;
+  const int nL = one ? 1 : rs.nLights;
+  for (int li = 0; li < nL; ++li) {
+    const int nS = one ? 1 : r->direct[li].nSamples;
+    for (int j = 0; j < nS; ++j) {
+      CK(c, launchResetCounts(wf, (1u << Q_SHADOW) | (1u << Q_MIS), st));
+      CK(c, launchDirectSample(p, rs, wf, one ? -1 : li, j, cur, rc, sms, st));
+      RK(traceQueue(c, true, wf.shO, wf.shD, wf.shRange, wf.counts + Q_SHADOW, wf.shOcc, nullptr, st));
+      RK(traceQueue(c, false, wf.misO, wf.misD, wf.misRange, wf.counts + Q_MIS, wf.misHit, wf.misT, st));
+      int mode = RESOLVE_DIRECT | (weighted ? RESOLVE_WEIGHTED : 0);
+      if (one) mode |= RESOLVE_ONE;
+      else {
+        if (j == 0) mode |= RESOLVE_FIRST_OF_LIGHT;
+        if (j == nS - 1) mode |= RESOLVE_LAST_OF_LIGHT;
+        if (j == nS - 1 && li == nL - 1) mode |= RESOLVE_FINAL;
+      }
+      CK(c, launchResolveDirect(p, rs, wf, cur, mode, nS, sms, st));
+      c->launches += 3;
+    }
+  }
+  return DRT_OK;
+}
+
+// The specular recursion of DirectLightingIntegrator.Li (direct_lighting_integrator.dart:56-64 -> Integrator.
+// SpecularReflect / SpecularTransmit, integrator.dart:187-290 -> renderer.Li) evaluated chain by chain.  Radiance is
+// linear in the chain weights, so L = sum over chains (one reflect / transmit choice per level) of weight x
+// (Le + direct lighting at the chain's last vertex).  Chains are visited in the recursion's own depth-first order
+// (reflect before transmit), each re-walking its prefix from the saved camera-ray queue; the LAST step of a chain is a
+// call the recursion makes at that moment, so the per-slot stream counters advance exactly as the reference's shared
+// RNG does (one BSDFSample.random per call, valid component or not).  A prefix nobody survives prunes its subtree.
+static int specularChains(drt_ctx* c, RenderState* r) {
+  const RenderParams& p = r->rp;
+  const RenderScene& rs = r->rs;
+  const Wavefront& wf = r->wf;
+  cudaStream_t st = c->stream;
+  const int sms = c->numSMs;
+  RenderCounters* rc = r->dCounters.p;
+  const size_t cap = wf.cap;
+  const int maxLevel = std::min(p.maxDepth - 1, kMaxChainLevels - 1);  // a vertex at depth d recurses iff d + 1 < maxDepth
+  if (maxLevel < 1) return DRT_OK;
+  // save the camera-ray queue (buffer 0 and the hit results of its trace)
+  CK(c, cudaMemcpyAsync(wf.bakO, wf.extO[0], cap * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+  CK(c, cudaMemcpyAsync(wf.bakD, wf.extD[0], cap * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+  CK(c, cudaMemcpyAsync(wf.bakRange, wf.extRange[0], cap * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+  CK(c, cudaMemcpyAsync(wf.bakSlot, wf.extSlot[0], cap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  CK(c, cudaMemcpyAsync(wf.bakHit, wf.extHit, cap * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+  CK(c, cudaMemcpyAsync(wf.bakT, wf.extT, cap * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CK(c, cudaMemsetAsync(wf.specCtr, 0, cap * sizeof(uint32_t), st));
+  uint32_t n0 = 0;
+  CK(c, cudaMemcpyAsync(&n0, wf.counts + Q_EXT0, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CK(c, cudaStreamSynchronize(st));
+  if (n0 == 0) return DRT_OK;
+  const int kFlags[2] = {1 | 16, 2 | 16};  // BSDF_REFLECTION | BSDF_SPECULAR, BSDF_TRANSMISSION | BSDF_SPECULAR
+  std::vector<int> chain;  // branch choice per level
+  // explicit depth-first walk: `next[level]` = the next branch to try below the current prefix of that length
+  std::vector<int> next(1, 0);
+  while (!next.empty()) {
+    const int len = (int)next.size() - 1;  // current prefix length
+    if (next.back() >= 2) {                // both branches of this prefix done
+      next.pop_back();
+      if (!chain.empty()) chain.pop_back();
+      continue;
+    }
+    const int b = next.back()++;
+    chain.push_back(b);
+    // re-walk the chain from the camera-ray queue
+    CK(c, cudaMemcpyAsync(wf.extO[0], wf.bakO, n0 * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    CK(c, cudaMemcpyAsync(wf.extD[0], wf.bakD, n0 * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    CK(c, cudaMemcpyAsync(wf.extRange[0], wf.bakRange, n0 * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+    CK(c, cudaMemcpyAsync(wf.extSlot[0], wf.bakSlot, n0 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    CK(c, cudaMemcpyAsync(wf.extHit, wf.bakHit, n0 * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    CK(c, cudaMemcpyAsync(wf.extT, wf.bakT, n0 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CK(c, cudaMemcpyAsync(wf.counts + Q_EXT0, &n0, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    int cur = 0;
+    for (int k = 1; k <= len + 1; ++k) {
+      CK(c, launchResetCounts(wf, 1u << (cur ^ 1), st));
+      CK(c, launchSpecularStep(p, rs, wf, cur, kFlags[chain[k - 1]], k, k == len + 1 ? 1 : 0, rc, sms, st));
+      c->launches += 2;
+      cur ^= 1;
+      RK(traceQueue(c, false, wf.extO[cur], wf.extD[cur], wf.extRange[cur], wf.counts + cur, wf.extHit, wf.extT, st));
+    }
+    uint32_t live = 0;
+    CK(c, cudaMemcpyAsync(&live, wf.counts + cur, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    if (live == 0) {  // nobody took this branch: no vertex, no deeper calls
+      chain.pop_back();
+      continue;
+    }
+    RK(directStage(c, r, cur, true));
+    if (len + 1 < maxLevel) next.push_back(0);  // the new vertices recurse themselves
+    else chain.pop_back();
+  }
+  return DRT_OK;
+}
+
 // One batch of camera samples through the whole pipeline; everything is enqueued on c->stream.
 static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
   const RenderParams& p = r->rp;
@@ -491,30 +611,8 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
       c->launches += 2;
     }
   } else {
-    CK(c, launchDirectSetup(p, rs, wf, sms, st));
-    c->launches++;
-    if (rs.nLights > 0) {
-      const bool one = p.strategy != 0;
-      const int nL = one ? 1 : rs.nLights;
-      for (int li = 0; li < nL; ++li) {
-        const int nS = one ? 1 : r->direct[li].nSamples;
-        for (int j = 0; j < nS; ++j) {
-          CK(c, launchResetCounts(wf, (1u << Q_SHADOW) | (1u << Q_MIS), st));
-          CK(c, launchDirectSample(p, rs, wf, one ? -1 : li, j, rc, sms, st));
-          RK(traceQueue(c, true, wf.shO, wf.shD, wf.shRange, wf.counts + Q_SHADOW, wf.shOcc, nullptr, st));
-          RK(traceQueue(c, false, wf.misO, wf.misD, wf.misRange, wf.counts + Q_MIS, wf.misHit, wf.misT, st));
-          int mode = RESOLVE_DIRECT;
-          if (one) mode |= RESOLVE_ONE;
-          else {
-            if (j == 0) mode |= RESOLVE_FIRST_OF_LIGHT;
-            if (j == nS - 1) mode |= RESOLVE_LAST_OF_LIGHT;
-            if (j == nS - 1 && li == nL - 1) mode |= RESOLVE_FINAL;
-          }
-          CK(c, launchResolveDirect(p, rs, wf, 0, mode, nS, sms, st));
-          c->launches += 3;
-        }
-      }
-    }
+    RK(directStage(c, r, 0, false));
+    if (wf.specCtr) RK(specularChains(c, r));
   }
   CK(c, launchFilm(p, wf, nSlots, rc, st));
   c->launches++;
@@ -525,10 +623,8 @@ static int renderWindow(drt_ctx* c, int x, int y, int w, int h, uint32_t shard, 
   RenderState* r = state(c);
   RK(prepare(c, r));
   const RenderParams& p = r->rp;
-  if (p.integKind == 2 && r->hasSpecular && p.maxDepth > 1)
-    return fail(c, DRT_E_UNSUPPORTED,
-                "directlighting with specular BxDFs needs the SpecularReflect / SpecularTransmit recursion "
-                "(integrator.dart:187-290), which is not on the GPU path yet: use the path integrator or maxdepth 1");
+  if (p.integKind == 2 && r->hasSpecular && p.maxDepth - 1 > kMaxChainLevels - 1)
+    return fail(c, DRT_E_UNSUPPORTED, "directlighting with specular BxDFs: maxdepth above 16 is not on the GPU path");
   if (w <= 0 || h <= 0) return DRT_OK;
   const uint64_t total = (uint64_t)w * h;
   const uint32_t blockPixels = 1024;

@@ -528,7 +528,8 @@ __global__ void __launch_bounds__(128) resolveDirectKernel(RenderParams rp, Rend
       st3(wf.L, cap, slot, L);
     } else if (mode & 16) {  // directlighting, strategy one (integrator.dart:79-117)
       Spec L = ld3(wf.L, cap, slot);
-      L = L + (Ld * (double)rs.nLights);
+      const Spec est = Ld * (double)rs.nLights;
+      L = L + ((mode & 32) ? ld3(wf.pendT, cap, slot) * est : est);
       st3(wf.L, cap, slot, L);
     } else {  // UniformSampleAllLights (integrator.dart:39-77): Ld over the light's samples, L over lights (kept in T)
       Spec acc = (mode & 2) ? mks1(0.0) : ld3(wf.Ld, cap, slot);
@@ -538,7 +539,7 @@ __global__ void __launch_bounds__(128) resolveDirectKernel(RenderParams rp, Rend
         all = all + acc / (double)nSamplesOfLight;
         if (mode & 8) {
           Spec L = ld3(wf.L, cap, slot);
-          st3(wf.L, cap, slot, L + all);
+          st3(wf.L, cap, slot, L + ((mode & 32) ? ld3(wf.pendT, cap, slot) * all : all));
         } else {
           st3(wf.T, cap, slot, all);
         }
@@ -615,27 +616,93 @@ __global__ void __launch_bounds__(256) aoCountKernel(RenderParams rp, Wavefront 
 // ---------------------------------------------------------------------------------------------------
 // Direct lighting (direct_lighting_integrator.dart:30-68): emitted light at the camera hit, then one
 // launch per (light, sample) of UniformSampleAllLights, or one launch of UniformSampleOneLight.
-__global__ void __launch_bounds__(128) directSetupKernel(RenderParams rp, RenderScene rs, Wavefront wf) {
-  const uint32_t n = wf.counts[Q_EXT0], cap = wf.cap;
+// `cur`: the extension queue holding the vertices; `weighted`: the vertices are those of a specular chain
+// (integrator.dart:187-290) and contribute with the chain's weight (kept in pendT), added to what L already holds.
+__global__ void __launch_bounds__(128) directSetupKernel(RenderParams rp, RenderScene rs, Wavefront wf, int cur, int weighted) {
+  const uint32_t n = wf.counts[cur], cap = wf.cap;
   for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
-    const uint32_t slot = wf.extSlot[0][q];
+    const uint32_t slot = wf.extSlot[cur][q];
     const int prim = __float_as_int(wf.extHit[q].w);
     st3(wf.T, cap, slot, Spec{0.f, 0.f, 0.f});  // L of UniformSampleAllLights
     if (prim < 0) continue;
     const int li = primLight(rs, (uint32_t)prim);
     if (li < 0) continue;
-    const float4 o4 = wf.extO[0][q], d4 = wf.extD[0][q];
+    const float4 o4 = wf.extO[cur][q], d4 = wf.extD[cur][q];
     const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
     ShapeHit h;
     hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
-    st3(wf.L, cap, slot, mks1(0.0) + areaL(rs.lights[li], h.nn, -d));
+    const Spec Le = mks1(0.0) + areaL(rs.lights[li], h.nn, -d);
+    if (!weighted) st3(wf.L, cap, slot, Le);
+    else st3(wf.L, cap, slot, ld3(wf.L, cap, slot) + ld3(wf.pendT, cap, slot) * Le);
   }
 }
 
+// One SpecularReflect / SpecularTransmit call (integrator.dart:187-290) for every vertex of queue `cur`: draws the
+// BSDFSample.random of the call from the slot's integrator stream, samples the BSDF with `flags`, and, where the
+// reference recurses, appends the child ray to the other queue and multiplies the chain weight (pendT) by
+// f * |wi.n| / pdf.  `level` = 1 for the call at the camera vertex; `isNew`: this call has not been made before for
+// this prefix (chains re-walk their prefixes with the counters recorded the first time).
+__global__ void __launch_bounds__(128) specularStepKernel(RenderParams rp, RenderScene rs, Wavefront wf, int cur, int flags, int level,
+                                                          int isNew, RenderCounters* rc) {
+  const uint32_t n = wf.counts[cur], cap = wf.cap;
+  const int nxt = cur ^ 1;
+  unsigned long long nClosest = 0;
+  for (uint32_t q0 = blockIdx.x * blockDim.x; q0 < n; q0 += gridDim.x * blockDim.x) {
+    const uint32_t q = q0 + threadIdx.x;
+    bool cont = false;
+    uint32_t slot = 0;
+    V3 p = V3{0.f, 0.f, 0.f}, wi = V3{0.f, 0.f, 0.f};
+    double rayEps = 0.0;
+    if (q < n) {
+      slot = wf.extSlot[cur][q];
+      const int prim = __float_as_int(wf.extHit[q].w);
+      if (prim >= 0) {
+        uint32_t base;
+        if (isNew) {
+          base = wf.specCtr[slot];
+          wf.specCtrAt[(size_t)level * cap + slot] = base;
+          wf.specCtr[slot] = base + 3;
+        } else {
+          base = wf.specCtrAt[(size_t)level * cap + slot];
+        }
+        Stream rng{integratorKey(rp, wf, slot), base};
+        const float u0 = (float)rng.randomFloat(), u1 = (float)rng.randomFloat();
+        const double comp = rng.randomFloat();
+        const float4 o4 = wf.extO[cur][q], d4 = wf.extD[cur][q];
+        const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
+        ShapeHit h;
+        hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
+        const BsdfG bsdf = makeBsdfG(rs, (uint32_t)prim, h);
+        double pdf = 0.0;
+        int type = 0;
+        const Spec f = bsdfSampleF(bsdf, -d, &wi, u0, u1, comp, &pdf, flags, &type);
+        const double an = AbsDot(wi, bsdf.nn);
+        if (pdf > 0.0 && !IsBlack(f) && an != 0.0) {
+          cont = true;
+          p = h.p;
+          rayEps = h.rayEps;
+          const Spec w = f * (an / pdf);
+          st3(wf.pendT, cap, slot, level == 1 ? w : ld3(wf.pendT, cap, slot) * w);
+        }
+      }
+    }
+    const uint32_t ei = warpPush(&wf.counts[nxt], cont);
+    if (cont) {
+      wf.extO[nxt][ei] = make_float4(p.x, p.y, p.z, (float)rayEps);
+      wf.extD[nxt][ei] = make_float4(wi.x, wi.y, wi.z, CUDART_INF_F);
+      wf.extRange[nxt][ei] = make_double2(rayEps, CUDART_INF);
+      wf.extSlot[nxt][ei] = slot;
+    }
+    nClosest += (cont && isNew) ? 1 : 0;  // re-walked prefix rays are an artefact of the chain evaluation, not reference rays
+  }
+  for (int o = 16; o > 0; o >>= 1) nClosest += __shfl_down_sync(FULL, nClosest, o);
+  if ((threadIdx.x & 31) == 0 && nClosest) atomicAdd(&rc->closestRays, nClosest);
+}
+
 template <bool GENERAL>
-__global__ void __launch_bounds__(128) directSampleKernel(RenderParams rp, RenderScene rs, Wavefront wf, int light, int j,
+__global__ void __launch_bounds__(128) directSampleKernel(RenderParams rp, RenderScene rs, Wavefront wf, int light, int j, int cur,
                                                           RenderCounters* rc) {
-  const uint32_t n = wf.counts[Q_EXT0];
+  const uint32_t n = wf.counts[cur];
   unsigned long long nShadow = 0, nClosest = 0;
   for (uint32_t q0 = blockIdx.x * blockDim.x; q0 < n; q0 += gridDim.x * blockDim.x) {
     const uint32_t q = q0 + threadIdx.x;
@@ -643,7 +710,7 @@ __global__ void __launch_bounds__(128) directSampleKernel(RenderParams rp, Rende
     uint32_t slot = 0;
     int prim = -1;
     if (valid) {
-      slot = wf.extSlot[0][q];
+      slot = wf.extSlot[cur][q];
       prim = __float_as_int(wf.extHit[q].w);
       valid = prim >= 0;
     }
@@ -653,7 +720,7 @@ __global__ void __launch_bounds__(128) directSampleKernel(RenderParams rp, Rende
     double rayEps = 0.0;
     int lightNum = light;
     if (valid) {
-      const float4 o4 = wf.extO[0][q], d4 = wf.extD[0][q];
+      const float4 o4 = wf.extO[cur][q], d4 = wf.extD[cur][q];
       const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
       ShapeHit h;
       hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
@@ -841,15 +908,22 @@ cudaError_t launchAoCount(const RenderParams& rp, const Wavefront& wf, uint32_t 
   return cudaGetLastError();
 }
 
-cudaError_t launchDirectSetup(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int numSMs, cudaStream_t st) {
-  directSetupKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf);
+cudaError_t launchDirectSetup(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int cur, int weighted, int numSMs,
+                              cudaStream_t st) {
+  directSetupKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, cur, weighted);
   return cudaGetLastError();
 }
 
-cudaError_t launchDirectSample(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int light, int j,
+cudaError_t launchDirectSample(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int light, int j, int cur,
                                RenderCounters* rc, int numSMs, cudaStream_t st) {
-  if (rs.general) directSampleKernel<true><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, j, rc);
-  else directSampleKernel<false><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, j, rc);
+  if (rs.general) directSampleKernel<true><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, j, cur, rc);
+  else directSampleKernel<false><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, j, cur, rc);
+  return cudaGetLastError();
+}
+
+cudaError_t launchSpecularStep(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int cur, int flags, int level,
+                               int isNew, RenderCounters* rc, int numSMs, cudaStream_t st) {
+  specularStepKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, cur, flags, level, isNew, rc);
   return cudaGetLastError();
 }
 

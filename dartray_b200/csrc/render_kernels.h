@@ -39,15 +39,22 @@ cudaError_t launchAoGen(const RenderParams& rp, const Wavefront& wf, uint32_t fi
 cudaError_t launchAoCount(const RenderParams& rp, const Wavefront& wf, uint32_t firstHit, uint32_t maxHits, RenderCounters* rc,
                           int numSMs, cudaStream_t st);
 // direct lighting
-cudaError_t launchDirectSetup(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int numSMs, cudaStream_t st);
-cudaError_t launchDirectSample(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int light, int j,
+cudaError_t launchDirectSetup(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int cur, int weighted, int numSMs,
+                              cudaStream_t st);
+cudaError_t launchDirectSample(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int light, int j, int cur,
                                RenderCounters* rc, int numSMs, cudaStream_t st);
+// one SpecularReflect / SpecularTransmit call per vertex of queue `cur` (flags: BSDF_REFLECTION | BSDF_SPECULAR = 17 or
+// BSDF_TRANSMISSION | BSDF_SPECULAR = 18); children go to queue cur ^ 1
+cudaError_t launchSpecularStep(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int cur, int flags, int level,
+                               int isNew, RenderCounters* rc, int numSMs, cudaStream_t st);
 // film
 cudaError_t launchFilm(const RenderParams& rp, const Wavefront& wf, uint32_t nSlots, RenderCounters* rc, cudaStream_t st);
 cudaError_t launchFilmConvert(const RenderParams& rp, float* rgb, float* xyz, float* weight, cudaStream_t st);
 
 // resolve mode bits: 1 = direct-lighting integrator (0 = path), 2 = first sample of a light, 4 = last sample of a
-// light, 8 = last light (add the sum to L), 16 = strategy "one"
-enum { RESOLVE_PATH = 0, RESOLVE_DIRECT = 1, RESOLVE_FIRST_OF_LIGHT = 2, RESOLVE_LAST_OF_LIGHT = 4, RESOLVE_FINAL = 8, RESOLVE_ONE = 16 };
+// light, 8 = last light (add the sum to L), 16 = strategy "one", 32 = the vertices belong to a specular chain: weight the
+// sum by the chain weight (pendT)
+enum { RESOLVE_PATH = 0, RESOLVE_DIRECT = 1, RESOLVE_FIRST_OF_LIGHT = 2, RESOLVE_LAST_OF_LIGHT = 4, RESOLVE_FINAL = 8, RESOLVE_ONE = 16,
+       RESOLVE_WEIGHTED = 32 };
 
 }  // namespace drt

@@ -127,6 +127,11 @@ struct Wavefront {
   float* pendT;                      // 3 x cap: throughput the direct estimate is multiplied by
   int32_t* shIdx; int32_t* misIdx; int32_t* misLight;
   uint8_t* specBounce;               // path integrator: the last sampled BxDF was specular (path_integrator.dart:85)
+  // directlighting with specular BxDFs (integrator.dart:187-290): the recursion is evaluated chain by chain (one
+  // reflect / transmit choice per level), see renderBatch.  All null unless the scene needs it.
+  uint32_t* specCtr;                 // per slot: draws of the integrator stream consumed so far (BSDFSample.random per branch call)
+  uint32_t* specCtrAt;               // [level][slot]: the counter the branch call of that level used (chains re-walk their prefix)
+  float4* bakO; float4* bakD; double2* bakRange; uint32_t* bakSlot; float4* bakHit; double* bakT;  // the camera-ray queue
   // AO / direct-lighting per-slot state
   float* hitP; float* hitN;          // 3 x cap each
   uint32_t* aoScramble;              // 2 x cap

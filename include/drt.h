@@ -180,9 +180,9 @@ int drt_set_materials(drt_ctx* ctx, uint32_t n, const int32_t* kind, const float
  *   fresnel_kind  0 FresnelNoOp, 1 FresnelDielectric(ei, et), 2 FresnelConductor(eta, k) (fresnel_*.dart); NULL = all 0
  *   fresnel_eta, fresnel_k   conductor spectra as RGB (n_lobes x 3; NULL when no lobe uses a conductor)
  *   lobe_scalars  n_lobes x 3 doubles: {Blinn exponent after blinn.dart:24-28 | OrenNayar sigma in degrees, ei, et}
- * The path and ambient-occlusion integrators take every combination; directlighting returns DRT_E_UNSUPPORTED from
- * drt_render when a specular BxDF is present and maxdepth > 1 (its SpecularReflect / SpecularTransmit recursion,
- * lib/core/integrator.dart:187-290, is not on the GPU path yet).  Replaces a previous drt_set_materials and vice versa. */
+ * Every integrator takes every combination; directlighting evaluates its SpecularReflect / SpecularTransmit recursion
+ * (lib/core/integrator.dart:187-290) chain by chain up to maxdepth 17 (DRT_E_UNSUPPORTED beyond).  Replaces a previous
+ * drt_set_materials and vice versa. */
 int drt_set_material_lobes(drt_ctx* ctx, uint32_t n, const uint32_t* lobe_offsets, const int32_t* lobe_kind, const float* lobe_rgb,
                            const int32_t* fresnel_kind, const float* fresnel_eta, const float* fresnel_k,
                            const double* lobe_scalars);
