@@ -438,6 +438,9 @@ class GpuSamplerRenderer extends Renderer {
     } else if (surfaceIntegrator is DirectLightingIntegrator) {
       final DirectLightingIntegrator d = surfaceIntegrator;
       drt.setIntegrator(2, d.maxDepth, d.strategy, 1, 0.0, double.infinity);
+    } else if (surfaceIntegrator is WhittedIntegrator) {
+      final WhittedIntegrator w = surfaceIntegrator;
+      drt.setIntegrator(3, w.maxDepth, 0, 1, 0.0, double.infinity);
     } else {
       throw new GpuUnsupported('surface integrator ${surfaceIntegrator.runtimeType}');
     }

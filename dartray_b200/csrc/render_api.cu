@@ -360,7 +360,8 @@ static void carve(ByteArena& a, Wavefront& wf, uint32_t cap, uint32_t shCap, int
 }
 
 static int ensureWavefront(drt_ctx* c, RenderState* r, uint32_t cap, uint32_t shCap) {
-  const bool chains = r->rp.integKind == 2 && r->hasSpecular && r->rp.maxDepth > 1;
+  // the whitted integrator draws its light samples from the per-slot stream counter even without specular BxDFs
+  const bool chains = (r->rp.integKind == 2 && r->hasSpecular && r->rp.maxDepth > 1) || r->rp.integKind == 3;
   ByteArena probe;
   Wavefront tmp{};
   carve(probe, tmp, cap, shCap, r->rp.nVals, chains);
@@ -501,6 +502,30 @@ static int directStage(drt_ctx* c, RenderState* r, int cur, bool weighted) {
 // (reflect before transmit), each re-walking its prefix from the saved camera-ray queue; the LAST step of a chain is a
 // call the recursion makes at that moment, so the per-slot stream counters advance exactly as the reference's shared
 // RNG does (one BSDFSample.random per call, valid component or not).  A prefix nobody survives prunes its subtree.
+// WhittedIntegrator.Li without its recursion (whitted_integrator.dart:26-63) on the vertices of queue `cur`.
+static int whittedStage(drt_ctx* c, RenderState* r, int cur, bool weighted) {
+  const RenderParams& p = r->rp;
+  const RenderScene& rs = r->rs;
+  const Wavefront& wf = r->wf;
+  cudaStream_t st = c->stream;
+  const int sms = c->numSMs;
+  RenderCounters* rc = r->dCounters.p;
+  CK(c, launchWhittedSetup(p, rs, wf, cur, weighted ? 1 : 0, sms, st));
+  c->launches++;
+  for (int li = 0; li < rs.nLights; ++li) {
+    CK(c, launchResetCounts(wf, (1u << Q_SHADOW) | (1u << Q_MIS), st));
+    CK(c, launchWhittedSample(p, rs, wf, li, cur, rc, sms, st));
+    RK(traceQueue(c, true, wf.shO, wf.shD, wf.shRange, wf.counts + Q_SHADOW, wf.shOcc, nullptr, st));
+    CK(c, launchResolveDirect(p, rs, wf, cur, RESOLVE_DIRECT | RESOLVE_WHITTED | (weighted ? RESOLVE_WEIGHTED : 0), 1, sms, st));
+    c->launches += 3;
+  }
+  return DRT_OK;
+}
+
+static int integratorStage(drt_ctx* c, RenderState* r, int cur, bool weighted) {
+  return r->rp.integKind == 3 ? whittedStage(c, r, cur, weighted) : directStage(c, r, cur, weighted);
+}
+
 static int specularChains(drt_ctx* c, RenderState* r) {
   const RenderParams& p = r->rp;
   const RenderScene& rs = r->rs;
@@ -518,7 +543,6 @@ static int specularChains(drt_ctx* c, RenderState* r) {
   CK(c, cudaMemcpyAsync(wf.bakSlot, wf.extSlot[0], cap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
   CK(c, cudaMemcpyAsync(wf.bakHit, wf.extHit, cap * sizeof(float4), cudaMemcpyDeviceToDevice, st));
   CK(c, cudaMemcpyAsync(wf.bakT, wf.extT, cap * sizeof(double), cudaMemcpyDeviceToDevice, st));
-  CK(c, cudaMemsetAsync(wf.specCtr, 0, cap * sizeof(uint32_t), st));
   uint32_t n0 = 0;
   CK(c, cudaMemcpyAsync(&n0, wf.counts + Q_EXT0, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   CK(c, cudaStreamSynchronize(st));
@@ -559,7 +583,7 @@ static int specularChains(drt_ctx* c, RenderState* r) {
       chain.pop_back();
       continue;
     }
-    RK(directStage(c, r, cur, true));
+    RK(integratorStage(c, r, cur, true));
     if (len + 1 < maxLevel) next.push_back(0);  // the new vertices recurse themselves
     else chain.pop_back();
   }
@@ -610,9 +634,10 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
       CK(c, launchAoCount(p, wf, first, hitsPerChunk, rc, sms, st));
       c->launches += 2;
     }
-  } else {
-    RK(directStage(c, r, 0, false));
-    if (wf.specCtr) RK(specularChains(c, r));
+  } else {  // directlighting / whitted: the integrator at the camera vertices, then its specular recursion
+    if (wf.specCtr) CK(c, cudaMemsetAsync(wf.specCtr, 0, (size_t)wf.cap * sizeof(uint32_t), st));
+    RK(integratorStage(c, r, 0, false));
+    if (wf.specCtr && r->hasSpecular) RK(specularChains(c, r));
   }
   CK(c, launchFilm(p, wf, nSlots, rc, st));
   c->launches++;
@@ -623,8 +648,8 @@ static int renderWindow(drt_ctx* c, int x, int y, int w, int h, uint32_t shard, 
   RenderState* r = state(c);
   RK(prepare(c, r));
   const RenderParams& p = r->rp;
-  if (p.integKind == 2 && r->hasSpecular && p.maxDepth - 1 > kMaxChainLevels - 1)
-    return fail(c, DRT_E_UNSUPPORTED, "directlighting with specular BxDFs: maxdepth above 16 is not on the GPU path");
+  if (p.integKind >= 2 && r->hasSpecular && p.maxDepth - 1 > kMaxChainLevels - 1)
+    return fail(c, DRT_E_UNSUPPORTED, "directlighting / whitted with specular BxDFs: maxdepth above 16 is not on the GPU path");
   if (w <= 0 || h <= 0) return DRT_OK;
   const uint64_t total = (uint64_t)w * h;
   const uint32_t blockPixels = 1024;
@@ -824,7 +849,8 @@ int drt_set_sampler(drt_ctx* c, int kind, int xs, int ys, int spp, int jitter, i
 
 int drt_set_integrator(drt_ctx* c, int kind, int maxdepth, int strategy, int ao_nsamples, double ao_mindist, double ao_maxdist) {
   if (!c) return DRT_E_INVALID;
-  if (kind < 0 || kind > 2) return fail(c, DRT_E_INVALID, "integrator kind must be 0 (path), 1 (ambientocclusion) or 2 (directlighting)");
+  if (kind < 0 || kind > 3)
+    return fail(c, DRT_E_INVALID, "integrator kind must be 0 (path), 1 (ambientocclusion), 2 (directlighting) or 3 (whitted)");
   if (kind == 1 && ao_nsamples < 1) return fail(c, DRT_E_INVALID, "ambientocclusion nsamples must be >= 1");
   RenderState* r = state(c);
   r->rp.integKind = kind; r->rp.maxDepth = maxdepth; r->rp.strategy = strategy; r->rp.aoSamples = std::max(1, ao_nsamples);

@@ -526,9 +526,9 @@ __global__ void __launch_bounds__(128) resolveDirectKernel(RenderParams rp, Rend
       Spec L = ld3(wf.L, cap, slot);
       L = L + ld3(wf.pendT, cap, slot) * (Ld * (double)rs.nLights);
       st3(wf.L, cap, slot, L);
-    } else if (mode & 16) {  // directlighting, strategy one (integrator.dart:79-117)
+    } else if (mode & (16 | 64)) {  // directlighting, strategy one (integrator.dart:79-117); whitted: the sample as it is
       Spec L = ld3(wf.L, cap, slot);
-      const Spec est = Ld * (double)rs.nLights;
+      const Spec est = (mode & 64) ? Ld : Ld * (double)rs.nLights;
       L = L + ((mode & 32) ? ld3(wf.pendT, cap, slot) * est : est);
       st3(wf.L, cap, slot, L);
     } else {  // UniformSampleAllLights (integrator.dart:39-77): Ld over the light's samples, L over lights (kept in T)
@@ -635,6 +635,68 @@ __global__ void __launch_bounds__(128) directSetupKernel(RenderParams rp, Render
     if (!weighted) st3(wf.L, cap, slot, Le);
     else st3(wf.L, cap, slot, ld3(wf.L, cap, slot) + ld3(wf.pendT, cap, slot) * Le);
   }
+}
+
+// Whitted integrator (whitted_integrator.dart:26-78) on the vertices of queue `cur`: emitted light and the stream
+// position of the vertex's light samples (one LightSample.random(rng) per light, drawn before the specular branch calls)
+__global__ void __launch_bounds__(128) whittedSetupKernel(RenderParams rp, RenderScene rs, Wavefront wf, int cur, int weighted) {
+  const uint32_t n = wf.counts[cur], cap = wf.cap;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+    const uint32_t slot = wf.extSlot[cur][q];
+    const int prim = __float_as_int(wf.extHit[q].w);
+    if (prim < 0) continue;
+    const uint32_t base = wf.specCtr[slot];
+    wf.aoScramble[slot] = base;  // free in this integrator: the counter the vertex's first light sample starts from
+    wf.specCtr[slot] = base + 3u * (uint32_t)rs.nLights;
+    const int li = primLight(rs, (uint32_t)prim);
+    if (li < 0) continue;
+    const float4 o4 = wf.extO[cur][q], d4 = wf.extD[cur][q];
+    const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
+    ShapeHit h;
+    hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
+    const Spec Le = mks1(0.0) + areaL(rs.lights[li], h.nn, -d);
+    if (!weighted) st3(wf.L, cap, slot, Le);
+    else st3(wf.L, cap, slot, ld3(wf.L, cap, slot) + ld3(wf.pendT, cap, slot) * Le);
+  }
+}
+
+template <bool GENERAL>
+__global__ void __launch_bounds__(128) whittedSampleKernel(RenderParams rp, RenderScene rs, Wavefront wf, int light, int cur,
+                                                           RenderCounters* rc) {
+  const uint32_t n = wf.counts[cur];
+  unsigned long long nShadow = 0;
+  for (uint32_t q0 = blockIdx.x * blockDim.x; q0 < n; q0 += gridDim.x * blockDim.x) {
+    const uint32_t q = q0 + threadIdx.x;
+    bool valid = q < n;
+    uint32_t slot = 0;
+    int prim = -1;
+    if (valid) {
+      slot = wf.extSlot[cur][q];
+      prim = __float_as_int(wf.extHit[q].w);
+      valid = prim >= 0;
+    }
+    DirectWork dw;
+    dw.hasShadow = dw.hasMis = false;
+    V3 p = V3{0.f, 0.f, 0.f};
+    double rayEps = 0.0;
+    if (valid) {
+      const float4 o4 = wf.extO[cur][q], d4 = wf.extD[cur][q];
+      const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
+      ShapeHit h;
+      hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
+      const typename BsdfOf<GENERAL>::type bsdf = makeBsdfT<GENERAL>(rs, (uint32_t)prim, h);
+      p = h.p;
+      rayEps = h.rayEps;
+      Stream rng{integratorKey(rp, wf, slot), (uint64_t)wf.aoScramble[slot] + 3ull * (uint64_t)light};
+      const float lu0 = (float)rng.randomFloat(), lu1 = (float)rng.randomFloat();  // LightSample.random (light_sample.dart:45-51)
+      const double lcomp = rng.randomFloat();
+      whittedLightSetup(rs, light, p, bsdf.nn, -d, rayEps, bsdf, lu0, lu1, lcomp, &dw);
+    }
+    pushDirectWork(wf, slot, valid, dw, p, rayEps, light);
+    nShadow += (valid && dw.hasShadow) ? 1 : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) nShadow += __shfl_down_sync(FULL, nShadow, o);
+  if ((threadIdx.x & 31) == 0 && nShadow) atomicAdd(&rc->shadowRays, nShadow);
 }
 
 // One SpecularReflect / SpecularTransmit call (integrator.dart:187-290) for every vertex of queue `cur`: draws the
@@ -918,6 +980,19 @@ cudaError_t launchDirectSample(const RenderParams& rp, const RenderScene& rs, co
                                RenderCounters* rc, int numSMs, cudaStream_t st) {
   if (rs.general) directSampleKernel<true><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, j, cur, rc);
   else directSampleKernel<false><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, j, cur, rc);
+  return cudaGetLastError();
+}
+
+cudaError_t launchWhittedSetup(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int cur, int weighted, int numSMs,
+                               cudaStream_t st) {
+  whittedSetupKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, cur, weighted);
+  return cudaGetLastError();
+}
+
+cudaError_t launchWhittedSample(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int light, int cur,
+                                RenderCounters* rc, int numSMs, cudaStream_t st) {
+  if (rs.general) whittedSampleKernel<true><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, cur, rc);
+  else whittedSampleKernel<false><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, cur, rc);
   return cudaGetLastError();
 }
 

@@ -43,6 +43,11 @@ cudaError_t launchDirectSetup(const RenderParams& rp, const RenderScene& rs, con
                               cudaStream_t st);
 cudaError_t launchDirectSample(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int light, int j, int cur,
                                RenderCounters* rc, int numSMs, cudaStream_t st);
+// whitted integrator (whitted_integrator.dart:26-78): emitted light + stream positions, then one launch per light
+cudaError_t launchWhittedSetup(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int cur, int weighted, int numSMs,
+                               cudaStream_t st);
+cudaError_t launchWhittedSample(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int light, int cur,
+                                RenderCounters* rc, int numSMs, cudaStream_t st);
 // one SpecularReflect / SpecularTransmit call per vertex of queue `cur` (flags: BSDF_REFLECTION | BSDF_SPECULAR = 17 or
 // BSDF_TRANSMISSION | BSDF_SPECULAR = 18); children go to queue cur ^ 1
 cudaError_t launchSpecularStep(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int cur, int flags, int level,
@@ -55,6 +60,6 @@ cudaError_t launchFilmConvert(const RenderParams& rp, float* rgb, float* xyz, fl
 // light, 8 = last light (add the sum to L), 16 = strategy "one", 32 = the vertices belong to a specular chain: weight the
 // sum by the chain weight (pendT)
 enum { RESOLVE_PATH = 0, RESOLVE_DIRECT = 1, RESOLVE_FIRST_OF_LIGHT = 2, RESOLVE_LAST_OF_LIGHT = 4, RESOLVE_FINAL = 8, RESOLVE_ONE = 16,
-       RESOLVE_WEIGHTED = 32 };
+       RESOLVE_WEIGHTED = 32, RESOLVE_WHITTED = 64 /* one unweighted light sample: add it as it is */ };
 
 }  // namespace drt

@@ -981,4 +981,66 @@ static __device__ inline void estimateDirectSetup(const RenderScene& rs, int lig
   }
 }
 
+// WhittedIntegrator.Li's light loop body (whitted_integrator.dart:46-63): one light sample, every BxDF, no multiple
+// importance sampling.  Fills the shadow-ray part of DirectWork.
+template <typename BSDF>
+static __device__ inline void whittedLightSetup(const RenderScene& rs, int lightIndex, const V3& p, const V3& n, const V3& wo,
+                                                double rayEps, const BSDF& bsdf, float lu0, float lu1, double lcomp, DirectWork* w) {
+  const GLight l = rs.lights[lightIndex];
+  w->hasShadow = false;
+  w->hasMis = false;
+  V3 wi, segTo = p;
+  double lightPdf = 1.0, eps2 = 0.0;
+  Spec Li;
+  const bool distant = l.kind == 2;
+  if (distant) {  // distant_light.dart:41-48
+    wi = V3{l.pos[0], l.pos[1], l.pos[2]};
+    Li = lightRadiance(l);
+  } else if (l.kind != 0) {  // point_light.dart:41-47, spot_light.dart:36-70
+    const V3 pos = V3{l.pos[0], l.pos[1], l.pos[2]};
+    wi = Normalize(pos - p);
+    segTo = pos;
+    if (l.kind == 1) {
+      Li = lightRadiance(l) / DistanceSquared(pos, p);
+    } else {
+      const V3 wn = -wi;
+      const V3 wl = Normalize(mkv((double)l.w2l[0] * wn.x + (double)l.w2l[1] * wn.y + (double)l.w2l[2] * wn.z,
+                                  (double)l.w2l[3] * wn.x + (double)l.w2l[4] * wn.y + (double)l.w2l[5] * wn.z,
+                                  (double)l.w2l[6] * wn.x + (double)l.w2l[7] * wn.y + (double)l.w2l[8] * wn.z));
+      const double costheta = wl.z;
+      double falloff;
+      if (costheta < l.cosTotalWidth) falloff = 0.0;
+      else if (costheta > l.cosFalloffStart) falloff = 1.0;
+      else {
+        const double dl = (costheta - l.cosTotalWidth) / (l.cosFalloffStart - l.cosTotalWidth);
+        falloff = dl * dl * dl * dl;
+      }
+      Li = lightRadiance(l) * falloff / DistanceSquared(pos, p);
+    }
+  } else {  // diffuse_area_light.dart:59-70
+    V3 ns;
+    const V3 ps = shapeSetSample(rs, l, p, lu0, lu1, lcomp, &ns);
+    wi = Normalize(ps - p);
+    lightPdf = shapeSetPdf(rs, l, p, wi);
+    segTo = ps;
+    eps2 = 1.0e-3;
+    Li = areaL(l, ns, -wi);
+  }
+  if (IsBlack(Li) || lightPdf == 0.0) return;
+  const Spec f = bsdfF(bsdf, wo, wi, BSDF_ALL);
+  if (IsBlack(f)) return;
+  w->hasShadow = true;
+  w->shO = p;
+  w->shMin = rayEps;
+  if (distant) {
+    w->shD = wi;
+    w->shMax = CUDART_INF;
+  } else {
+    const double dist = Distance(p, segTo);  // visibility_tester.dart:26-29
+    w->shD = (segTo - p) / dist;
+    w->shMax = dist * (1.0 - eps2);
+  }
+  w->shContribution = f * Li * AbsDot(wi, n) * mks1(1.0) / lightPdf;  // :59-61, transmittance == 1
+}
+
 }  // namespace drt

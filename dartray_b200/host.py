@@ -205,7 +205,7 @@ class Film:
 
 
 SAMPLER_LD, SAMPLER_STRATIFIED, SAMPLER_RANDOM = 0, 1, 2
-INTEGRATOR_PATH, INTEGRATOR_AO, INTEGRATOR_DIRECT = 0, 1, 2
+INTEGRATOR_PATH, INTEGRATOR_AO, INTEGRATOR_DIRECT, INTEGRATOR_WHITTED = 0, 1, 2, 3
 RNG_SERIAL, RNG_KEYED = 0, 1
 
 

@@ -234,7 +234,8 @@ int drt_set_sampler(drt_ctx* ctx, int32_t kind, int32_t xs, int32_t ys, int32_t 
 /* Replaces the SurfaceIntegrator plugins path (kind 0, lib/surface_integrators/path_integrator.dart;
  * maxdepth), ambientocclusion (kind 1, ambient_occlusion_integrator.dart; nsamples rounded up to a
  * power of two, mindist, maxdist) and directlighting (kind 2, direct_lighting_integrator.dart;
- * strategy 0 = all, 1 = one). */
+ * strategy 0 = all, 1 = one) and whitted (kind 3, whitted_integrator.dart; maxdepth).  directlighting and whitted
+ * evaluate their SpecularReflect / SpecularTransmit recursion (lib/core/integrator.dart:187-290) up to maxdepth 17. */
 int drt_set_integrator(drt_ctx* ctx, int32_t kind, int32_t maxdepth, int32_t strategy, int32_t ao_nsamples,
                        double ao_mindist, double ao_maxdist);
 

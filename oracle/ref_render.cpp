@@ -963,6 +963,29 @@ struct Ctx {
     return L;
   }
 
+  // whitted_integrator.dart:26-78: emitted light, one LightSample.random(rng) per light (no multiple importance
+  // sampling, every BxDF), then the specular recursion
+  Spec whittedLi(const Ray& ray, const Isect& isect, const SampleVals& sample, Rng& rng) {
+    Spec L(0.0);
+    Bsdf bsdf = getBSDF(isect);
+    Vec p = bsdf.p, n = bsdf.nn, wo = -ray.d;
+    L = L + isectLe(isect, wo);
+    for (size_t i = 0; i < rs.lights.size(); ++i) {
+      Vec wi;
+      double pdf = 0.0;
+      Vis vis;
+      Spec Li = sampleLAtPoint(rs.lights[i], p, isect.rayEpsilon, U3::random(rng), ray.time, &wi, &pdf, &vis);
+      if (Li.isBlack() || pdf == 0.0) continue;
+      Spec f = bsdf.f(wo, wi, BSDF_ALL);
+      if (!f.isBlack() && !intersectP(vis.r)) L = L + f * Li * AbsDot(wi, n) * Spec(1.0) / pdf;
+    }
+    if (ray.depth + 1 < rs.integ.maxDepth) {
+      L = L + specularBranch(ray, bsdf, isect, sample, rng, BSDF_REFLECTION | BSDF_SPECULAR);
+      L = L + specularBranch(ray, bsdf, isect, sample, rng, BSDF_TRANSMISSION | BSDF_SPECULAR);
+    }
+    return L;
+  }
+
   // Integrator.SpecularReflect / SpecularTransmit (integrator.dart:187-290) without the ray differentials (they only
   // feed texture filtering): one BSDFSample.random(rng) is drawn whether or not the BSDF has such a component.
   Spec specularBranch(const Ray& ray, const Bsdf& bsdf, const Isect& isect, const SampleVals& sample, Rng& rng, int flags) {
@@ -1021,6 +1044,7 @@ struct Ctx {
       switch (rs.integ.kind) {
         case 0: L = pathLi(ray, isect, s, rng); break;
         case 1: L = aoLi(ray, isect, rng); break;
+        case 3: L = whittedLi(ray, isect, s, rng); break;
         default: L = directLi(ray, isect, s, rng); break;
       }
     }  // else sum of lights[i].Le(ray) == 0 for area / point lights

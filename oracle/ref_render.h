@@ -203,7 +203,7 @@ struct SamplerCfg {
 };
 
 struct IntegratorCfg {
-  int kind = 0;  // 0 path, 1 ambientocclusion, 2 directlighting
+  int kind = 0;  // 0 path, 1 ambientocclusion, 2 directlighting, 3 whitted
   int maxDepth = 5;
   int strategy = 0;  // directlighting: 0 = all, 1 = one
   int aoSamples = 2048;

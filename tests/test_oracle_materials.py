@@ -240,3 +240,33 @@ def test_distant_and_spot_lights_match_their_closed_forms():
         fall = 0.0 if cos_l < ct else (1.0 if cos_l > cf else ((cos_l - ct) / (cf - ct)) ** 4)
         expect = I * fall / d2 * kd / math.pi * cos_l  # surface cosine equals cos_l here (floor normal parallel to the axis)
         assert np.allclose(_centre(o, film), expect, rtol=1e-4, atol=1e-9), (off, _centre(o, film), expect)
+
+
+# ---- whitted integrator (whitted_integrator.dart:26-78) ----------------------------------------------------------------
+def test_whitted_point_light_and_mirror_recursion_match_closed_forms():
+    kd, I = 0.6, 20.0
+    smp = host.Sampler(kind=host.SAMPLER_STRATIFIED, xs=1, ys=1, jitter=False)
+    film = host.Film(1, 1)
+    # matte floor under a point light, seen straight down: L = kd/pi * I/h^2 (one light sample, no MIS)
+    sb = host.SceneBuilder()
+    _floor(sb, 0.0, material=sb.material((kd, kd, kd)))
+    sb.point_light((0, 3, 0), (I, I, I))
+    cam = host.PerspectiveCamera(host.look_at((0, 10, 0), (0, 0, 0), (0, 0, 1)), fov=1.0)
+    o = _oracle(sb, cam, film, smp, host.Integrator(kind=host.INTEGRATOR_WHITTED, maxdepth=5))
+    o.render(0, 1, 1)
+    assert np.allclose(_centre(o, film), kd / math.pi * I / 9.0, rtol=2e-5)
+    # the same lit wall seen through a mirror (the scene of test_directlighting_sees_a_lit_matte_wall_through_a_mirror)
+    sb = host.SceneBuilder()
+    _floor(sb, 0.0, half=4.0, material=sb.material_lobes(host.mirror_lobes(0.8)))
+    _quad(sb, [[-30, -30, 5], [30, -30, 5], [30, 30, 5], [-30, 30, 5]], material=sb.material_lobes(host.matte_lobes(kd)))
+    sb.point_light((0, 3, 2), (I, I, I))
+    cam = host.PerspectiveCamera(host.look_at((0, 3, -3), (0, 0, 0), (0, 1, 0)), fov=1.0)
+    o = _oracle(sb, cam, film, smp, host.Integrator(kind=host.INTEGRATOR_WHITTED, maxdepth=5))
+    o.render(0, 1, 1)
+    to_l = np.array([0.0, 3.0, 2.0]) - np.array([0.0, 5.0, 5.0])
+    d2 = float(to_l @ to_l)
+    expect = 0.8 * (kd / math.pi) * I / d2 * abs(to_l[2]) / math.sqrt(d2)
+    assert np.allclose(_centre(o, film), expect, rtol=1e-4), (_centre(o, film), expect)
+    o1 = _oracle(sb, cam, film, smp, host.Integrator(kind=host.INTEGRATOR_WHITTED, maxdepth=1))
+    o1.render(0, 1, 1)
+    assert np.all(_centre(o1, film) == 0)

@@ -226,6 +226,29 @@ def test_directlighting_specular_recursion_matches_oracle(which, maxdepth, strat
         assert np.abs(g1.film_read()["rgb"] - fg["rgb"]).mean() > 1e-3
 
 
+@pytest.mark.parametrize("which,maxdepth", [("specular", 5), ("glossy", 5), ("uber", 4), ("specular", 1), (None, 3)])
+def test_whitted_integrator_matches_oracle(which, maxdepth):
+    """WhittedIntegrator.Li (whitted_integrator.dart:26-78): one LightSample.random(rng) per light at every vertex — so an
+    area light's sample position depends on how many draws the recursion has consumed before the vertex is reached."""
+    if which is None:
+        sb, cam = scenes.cornell_synth()
+    else:
+        sb, cam = scenes.cornell_synth({
+            "specular": {"sphere": host.glass_lobes(1.0, 1.0, 1.5), "box": host.mirror_lobes((0.9, 0.85, 0.7))},
+            "glossy": {"grey": host.plastic_lobes((0.6, 0.6, 0.55), 0.3, 0.08), "sphere": host.metal_lobes((0.2, 0.92, 1.1), (3.9, 2.45, 2.14), 0.05)},
+            "uber": {"sphere": host.uber_lobes(kd=(0.3, 0.2, 0.2), ks=0.3, kr=0.2, kt=0.25, roughness=0.15, index=1.33, opacity=(0.8, 0.7, 0.9))},
+        }[which])
+    sb.point_light((0.0, 5.0, -5.0), (40.0, 30.0, 20.0))
+    sb.spot_light((-6.0, 8.0, -8.0), (2.0, -8.0, 2.0), (300.0, 300.0, 400.0), 25.0, 8.0)
+    g, o, fg, fo = _render_both(sb.arrays(), cam, host.Film(64, 48), host.Sampler(kind=host.SAMPLER_LD, spp=4),
+                                host.Integrator(kind=host.INTEGRATOR_WHITTED, maxdepth=maxdepth))
+    err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
+    print("whitted", which, maxdepth, "max rel err", err.max())
+    assert err.max() <= 1e-3 and fo["rgb"].mean() > 0.05
+    sg, so = g.render_stats(), o.render_stats()
+    assert sg["closest_rays"] == so["closest_rays"] and abs(sg["shadow_rays"] - so["shadow_rays"]) <= 2
+
+
 def test_distant_and_spot_lights_match_oracle_per_pixel():
     """lib/lights/distant_light.dart:41-48 and spot_light.dart:36-70 through drt_set_lights kinds 2 / 3 + drt_set_spot_params."""
     sb, cam = scenes.cornell_synth()
