@@ -36,6 +36,23 @@ def peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def other_bounds(alg_bytes, fp_ops, ms):
+    """SURVEY 8d asks for both candidate rooflines: the same algorithmic work against the L2 read bandwidth at the BVH's
+    working-set size and against the FP32 FMA rate, both measured on this pool's B200 by tools/microbench.cu
+    (profiles/r01_microbench.json).  The HBM figure above is the one the contract's `peak` names."""
+    try:
+        mb = json.load(open(os.path.join(ROOT, "profiles", "r01_microbench.json")))
+    except Exception:
+        return None
+    l2 = mb["l2_read_gb_per_s"]["114MB"]
+    fp = 2.0 * mb["fp32_fma_per_s"]
+    t = ms * 1e-3
+    return {"l2": {"achieved": alg_bytes / t / 1e9, "peak": l2, "unit": "GB/s", "frac": alg_bytes / t / 1e9 / l2,
+                   "note": "L2 read bandwidth over a 114 MB working set (the soup_1m BVH)"},
+            "fp32": {"achieved": fp_ops / t / 1e12, "peak": fp / 1e12, "unit": "TFLOP/s", "frac": fp_ops / t / fp,
+                     "note": "20 x nodes + 51 x prims reference operations per ray (SURVEY 8d) against the FP32 FMA rate"}}
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks / clock-event (throttle) reasons while the timed region runs: NVML polled every 2 ms (the same
     counters `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` prints; spawning nvidia-smi takes
@@ -413,6 +430,7 @@ def main():
             "per_ray": {"nodes_visited": w["nodes_visited"] / w["rays"], "prims_tested": w["prims_tested"] / w["rays"],
                         "bytes": alg_bytes / w["rays"]},
             "fp_ops_per_launch": 20 * w["nodes_visited"] + 51 * w["prims_tested"],
+            "other_bounds": other_bounds(alg_bytes, 20 * w["nodes_visited"] + 51 * w["prims_tested"], per_kind_ms[1]),
             "peak_source": pk_src,
             "note": "algorithmic bytes = 32*nodes + 36*prims + 48 per ray on the reference BVH (SURVEY 8d); the working "
                     "set (114 MB) is L2-resident, so this can exceed the HBM copy peak",
