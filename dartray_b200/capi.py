@@ -19,7 +19,7 @@ HIT_DTYPE = np.dtype([("t", np.float32), ("b1", np.float32), ("b2", np.float32),
 
 # every symbol include/drt.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
-    "drt_version", "drt_create", "drt_destroy", "drt_last_error", "drt_set_triangles", "drt_set_spheres", "drt_set_disks",
+    "drt_version", "drt_create", "drt_destroy", "drt_last_error", "drt_set_triangles", "drt_set_spheres", "drt_set_disks", "drt_set_quadrics",
     "drt_set_build_order", "drt_build_bvh", "drt_bvh_info_get", "drt_bvh_export", "drt_trace_closest",
     "drt_trace_any", "drt_trace_closest_device", "drt_trace_any_device", "drt_set_counting", "drt_get_counters", "drt_set_kernel_variant",
     "drt_last_kernel_ms", "drt_kernel_launches",
@@ -74,6 +74,7 @@ def load():
     L.drt_set_triangles.argtypes = [vp, vp, u32, vp, u32, vp, vp, vp]
     L.drt_set_spheres.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
     L.drt_set_disks.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
+    L.drt_set_quadrics.argtypes = [vp, i32, u32, vp, vp, vp, vp, vp, vp]
     L.drt_set_build_order.argtypes = [vp, vp, u32]
     L.drt_build_bvh.argtypes = [vp, i32, i32]
     L.drt_bvh_info_get.argtypes = [vp, C.POINTER(BvhInfo)]
@@ -169,6 +170,15 @@ class Context:
         params = _arr(params, np.float64).reshape(-1, 4)
         m, l, r = _arr(material, np.int32), _arr(light, np.int32), _arr(reverse, np.uint8)
         self._ck(self.L.drt_set_disks(self.h, o2w.shape[0], _p(o2w), _p(w2o), _p(params), _p(m), _p(l), _p(r)))
+
+    def set_quadrics(self, kind, o2w, w2o, params, material=None, light=None, reverse=None):
+        """kind 2 cylinder / 3 cone / 4 paraboloid / 5 hyperboloid; params: n x 8 doubles (include/drt.h); appended to the
+        quadric id range in call order, after set_spheres / set_disks."""
+        o2w = _arr(o2w, np.float32).reshape(-1, 16)
+        w2o = _arr(w2o, np.float32).reshape(-1, 16)
+        params = _arr(params, np.float64).reshape(-1, 8)
+        m, l, r = _arr(material, np.int32), _arr(light, np.int32), _arr(reverse, np.uint8)
+        self._ck(self.L.drt_set_quadrics(self.h, int(kind), o2w.shape[0], _p(o2w), _p(w2o), _p(params), _p(m), _p(l), _p(r)))
 
     def set_build_order(self, order):
         if order is None:

@@ -146,12 +146,84 @@ int drt_set_disks(drt_ctx* c, uint32_t n, const float* o2w, const float* w2o, co
   return DRT_OK;
 }
 
+int drt_set_quadrics(drt_ctx* c, int kind, uint32_t n, const float* o2w, const float* w2o, const double* prm, const int32_t* mat,
+                     const int32_t* light, const uint8_t* rev) {
+  if (!c) return DRT_E_INVALID;
+  if (kind < DRT_QUADRIC_CYLINDER || kind > DRT_QUADRIC_HYPERBOLOID) return fail(c, DRT_E_INVALID, "unknown quadric kind");
+  if (n && (!o2w || !w2o || !prm)) return fail(c, DRT_E_INVALID, "null quadric arrays");
+  for (uint32_t i = 0; i < n; ++i) {  // appended to the quadric range in call order
+    HostSphere s;
+    std::memcpy(s.o2w, o2w + 16 * i, 64);
+    std::memcpy(s.w2o, w2o + 16 * i, 64);
+    s.shape = kind;
+    std::memcpy(s.prm, prm + 8 * i, sizeof(s.prm));
+    c->spheres.push_back(s);
+    c->sphMat.push_back(mat ? mat[i] : 0);
+    c->sphLight.push_back(light ? light[i] : -1);
+    c->sphRev.push_back(rev ? rev[i] : 0);
+  }
+  c->built = false;
+  return DRT_OK;
+}
+
 int drt_set_build_order(drt_ctx* c, const uint32_t* ids, uint32_t n) {
   if (!c) return DRT_E_INVALID;
   if (!ids) c->order.clear();
   else c->order.assign(ids, ids + n);
   c->built = false;
   return DRT_OK;
+}
+
+// Constructors of the remaining quadrics: cylinder.dart:24-31, cone.dart:23-27, paraboloid.dart:23-29,
+// hyperboloid.dart:23-49 (Points are float32, the expressions f64).  The object bound of each is
+// (-radius, -radius, zmin) .. (radius, radius, zmax) with the record's radius / zmin / zmax (cone: 0 .. height;
+// hyperboloid: rmax).
+static void quadricSetup(const HostSphere& s, GSphere* gp) {
+  GSphere& g = *gp;
+  const double* prm = s.prm;
+  double pm = 360.0;
+  g.thetaMin = g.thetaMax = 0.0;
+  g.height = 0.0;
+  g.innerRadius = 0.0;
+  if (s.shape == DRT_QUADRIC_CYLINDER || s.shape == DRT_QUADRIC_PARABOLOID) {
+    g.radius = prm[0];
+    g.zmin = std::fmin(prm[1], prm[2]);
+    g.zmax = std::fmax(prm[1], prm[2]);
+    pm = prm[3];
+  } else if (s.shape == DRT_QUADRIC_CONE) {
+    g.height = prm[0];
+    g.radius = prm[1];
+    g.zmin = 0.0;
+    g.zmax = g.height;
+    pm = prm[2];
+  } else {
+    float p1[3] = {(float)prm[0], (float)prm[1], (float)prm[2]}, p2[3] = {(float)prm[3], (float)prm[4], (float)prm[5]};
+    pm = prm[6];
+    double radius1 = std::sqrt((double)p1[0] * p1[0] + (double)p1[1] * p1[1]);
+    double radius2 = std::sqrt((double)p2[0] * p2[0] + (double)p2[1] * p2[1]);
+    g.radius = std::fmax(radius1, radius2);
+    g.zmin = std::fmin((double)p1[2], (double)p2[2]);
+    g.zmax = std::fmax((double)p1[2], (double)p2[2]);
+    if (p2[2] == 0.0f)
+      for (int k = 0; k < 3; ++k) std::swap(p1[k], p2[k]);
+    float pp[3] = {p1[0], p1[1], p1[2]};
+    double a, cc;
+    do {
+      for (int k = 0; k < 3; ++k) {
+        float dk = (float)((double)p2[k] - (double)p1[k]);  // Vector p2 - p1
+        float d2 = (float)((double)dk * 2.0);               // * 2.0
+        pp[k] = (float)((double)pp[k] + (double)d2);        // Point + Vector
+      }
+      double xy1 = (double)pp[0] * pp[0] + (double)pp[1] * pp[1];
+      double xy2 = (double)p2[0] * p2[0] + (double)p2[1] * p2[1];
+      a = (1.0 / xy1 - ((double)pp[2] * pp[2]) / (xy1 * p2[2] * p2[2])) / (1.0 - (xy2 * pp[2] * pp[2]) / (xy1 * p2[2] * p2[2]));
+      cc = (a * xy2 - 1.0) / ((double)p2[2] * p2[2]);
+    } while (std::isinf(a) || std::isnan(a));
+    for (int k = 0; k < 3; ++k) { g.hp1[k] = p1[k]; g.hp2[k] = p2[k]; }
+    g.ha = a;
+    g.hc = cc;
+  }
+  g.phiMax = (3.141592653589793 / 180.0) * clampd(pm, 0.0, 360.0);
 }
 
 int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
@@ -208,16 +280,20 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
     g.height = s.height;
     g.innerRadius = s.innerRadius;
     g.phiMax = (3.141592653589793 / 180.0) * clampd(s.phiMaxDeg, 0.0, 360.0);
+    g.ha = g.hc = 0.0;
+    for (int k = 0; k < 3; ++k) g.hp1[k] = g.hp2[k] = 0.f;
     if (s.shape == 1) {  // disk.dart:24-35: object bound (-r, -r, h) .. (r, r, h)
       g.zmin = g.zmax = s.height;
       g.thetaMin = g.thetaMax = 0.0;
+    } else if (s.shape >= 2) {
+      quadricSetup(s, &g);
     } else {
       g.zmin = clampd(std::fmin(s.zmin, s.zmax), -s.radius, s.radius);
       g.zmax = clampd(std::fmax(s.zmin, s.zmax), -s.radius, s.radius);
       g.thetaMin = std::acos(clampd(g.zmin / s.radius, -1.0, 1.0));
       g.thetaMax = std::acos(clampd(g.zmax / s.radius, -1.0, 1.0));
     }
-    float lo[3] = {(float)-s.radius, (float)-s.radius, (float)g.zmin}, hi[3] = {(float)s.radius, (float)s.radius, (float)g.zmax};
+    float lo[3] = {(float)-g.radius, (float)-g.radius, (float)g.zmin}, hi[3] = {(float)g.radius, (float)g.radius, (float)g.zmax};
     PrimBounds& b = bounds[nt + i];
     for (int k = 0; k < 8; ++k) {  // transform.dart:163-178
       float p[3] = {(k & 1) ? hi[0] : lo[0], (k & 2) ? hi[1] : lo[1], (k & 4) ? hi[2] : lo[2]}, q[3];

@@ -17,11 +17,14 @@ using namespace drt;
 
 static_assert(sizeof(drt_hit) == sizeof(drt_hit_rec), "hit record layout");
 
-struct HostSphere {  // a quadric: sphere (shape 0) or disk (shape 1: height, radius, innerRadius, phiMaxDeg)
+// a quadric: sphere (shape 0), disk (1: height, radius, innerRadius, phiMaxDeg), cylinder (2), cone (3: height, radius),
+// paraboloid (4), hyperboloid (5: prm = p1, p2 as given)
+struct HostSphere {
   float o2w[16], w2o[16];
-  double radius, zmin, zmax, phiMaxDeg;
+  double radius = 0.0, zmin = 0.0, zmax = 0.0, phiMaxDeg = 360.0;
   int shape = 0;
   double height = 0.0, innerRadius = 0.0;
+  double prm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 template <class T>

@@ -78,9 +78,11 @@ struct alignas(16) GSphere {
   float o2wRow3[4];
   double radius, zmin, zmax, phiMax, thetaMin, thetaMax;
   float wmin[3], wmax[3];  // world bound (sphere.dart:34-37 + shape.dart:38-40), = the leaf box of a 1-sphere leaf
-  int32_t shape;           // 0 sphere, 1 disk
+  int32_t shape;           // 0 sphere, 1 disk, 2 cylinder, 3 cone, 4 paraboloid, 5 hyperboloid
   float pad_;
-  double height, innerRadius;  // disk only
+  double height, innerRadius;  // disk (both), cone (height)
+  float hp1[3], hp2[3];        // hyperboloid.dart:24: the two Points after the constructor's swap (:36-39)
+  double ha, hc;               // hyperboloid.dart:40-48 implicit coefficients; `radius` holds rmax
 };
 
 struct TraceScene {

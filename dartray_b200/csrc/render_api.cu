@@ -262,6 +262,17 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
         area = triArea(t);
       } else {  // sphere.dart:243-245 with the constructor's clamps (sphere.dart:24-32)
         const HostSphere& s = c->spheres[sh - nt];
+        if (s.shape == DRT_QUADRIC_CYLINDER) {  // cylinder.dart:226-228 with the constructor's min / max / clamp (:24-31)
+          double zmin = std::fmin(s.prm[1], s.prm[2]), zmax = std::fmax(s.prm[1], s.prm[2]);
+          double phiMaxC = (DRT_PI / 180.0) * clampD(s.prm[3], 0.0, 360.0);
+          area = (zmax - zmin) * phiMaxC * s.prm[0];
+          a.push_back(area);
+          g.area += area;
+          pushShape(sh, area);
+          continue;
+        }
+        if (s.shape > DRT_QUADRIC_CYLINDER)  // shape.dart:83-86: Shape.sample is unimplemented for cone / paraboloid / hyperboloid
+          return fail(c, DRT_E_INVALID, "cone / paraboloid / hyperboloid shapes cannot be area lights (no Shape.sample in the reference)");
         if (s.shape == 1) {  // disk.dart:142-145
           double phiMaxD = (DRT_PI / 180.0) * clampD(s.phiMaxDeg, 0.0, 360.0);
           area = phiMaxD * 0.5 * (s.radius * s.radius - s.innerRadius * s.innerRadius);

@@ -276,6 +276,132 @@ static DRT_HD inline bool sphereIntersectT(const GSphere& s, const V3& o, const 
   return true;
 }
 
+// cylinder.dart:39-104, cone.dart:35-98, paraboloid.dart:37-100, hyperboloid.dart:57-122: tHit, the object-space hit
+// point and phi (see quadricTest in trace_device.cuh for the decision sequence the four files share)
+static DRT_HD inline double quadricPhiV(const GSphere& s, const V3& phit) {
+  double ay = phit.y, ax = phit.x;
+  if (s.shape == 5) {  // hyperboloid.dart:96-103
+    V3 hp1 = V3{s.hp1[0], s.hp1[1], s.hp1[2]}, hp2 = V3{s.hp2[0], s.hp2[1], s.hp2[2]};
+    double v = ((double)phit.z - hp1.z) / ((double)hp2.z - hp1.z);
+    V3 pr = (hp1 * (1.0 - v)) + (hp2 * v);
+    ay = (double)pr.x * phit.y - (double)phit.x * pr.y;
+    ax = (double)phit.x * pr.x + (double)phit.y * pr.y;
+  }
+  double phi = atan2(ay, ax);
+  if (phi < 0.0) phi += 2.0 * DRT_PI;
+  return phi;
+}
+static DRT_HD inline bool quadricIntersectT(const GSphere& s, const V3& o, const V3& d, double mint, double maxt, double* tOut,
+                                            V3* phitOut) {
+  float w2o[16];
+  for (int i = 0; i < 12; ++i) w2o[i] = s.w2o[i];
+  for (int i = 0; i < 4; ++i) w2o[12 + i] = s.w2oRow3[i];
+  V3 ro = XfPoint(w2o, o), rd = XfVector(w2o, d);
+  double dx = rd.x, dy = rd.y, dz = rd.z, ox = ro.x, oy = ro.y, oz = ro.z;
+  double A, B, C, zlo = s.zmin, zhi = s.zmax;
+  if (s.shape == 2) {
+    A = dx * dx + dy * dy;
+    B = 2.0 * (dx * ox + dy * oy);
+    C = ox * ox + oy * oy - s.radius * s.radius;
+  } else if (s.shape == 3) {
+    double k = s.radius / s.height;
+    k = k * k;
+    A = dx * dx + dy * dy - k * dz * dz;
+    B = 2.0 * (dx * ox + dy * oy - k * dz * (oz - s.height));
+    C = ox * ox + oy * oy - k * (oz - s.height) * (oz - s.height);
+    zlo = 0.0;
+    zhi = s.height;
+  } else if (s.shape == 4) {
+    double k = s.zmax / (s.radius * s.radius);
+    A = k * (dx * dx + dy * dy);
+    B = 2 * k * (dx * ox + dy * oy) - dz;
+    C = k * (ox * ox + oy * oy) - oz;
+  } else {
+    double a = s.ha, c = s.hc;
+    A = a * dx * dx + a * dy * dy - c * dz * dz;
+    B = 2.0 * (a * dx * ox + a * dy * oy - c * dz * oz);
+    C = a * ox * ox + a * oy * oy - c * oz * oz - 1;
+  }
+  double discrim = B * B - 4.0 * A * C;  // common.dart:140-167
+  if (discrim < 0.0) return false;
+  double rootDiscrim = sqrt(discrim);
+  double q = (B < 0.0) ? -0.5 * (B - rootDiscrim) : -0.5 * (B + rootDiscrim);
+  double t0 = q / A, t1 = C / q;
+  if (t0 > t1) { double tt = t0; t0 = t1; t1 = tt; }
+  if (t0 > maxt || t1 < mint) return false;
+  double thit = t0;
+  if (t0 < mint) {
+    thit = t1;
+    if (thit > maxt) return false;
+  }
+  V3 phit = RayAt(ro, rd, thit);
+  double phi = quadricPhiV(s, phit);
+  if (phit.z < zlo || phit.z > zhi || phi > s.phiMax) {
+    if (thit == t1) return false;
+    thit = t1;
+    if (t1 > maxt) return false;
+    phit = RayAt(ro, rd, thit);
+    phi = quadricPhiV(s, phit);
+    if (phit.z < zlo || phit.z > zhi || phi > s.phiMax) return false;
+  }
+  *tOut = thit;
+  *phitOut = phit;
+  return true;
+}
+
+// cylinder.dart:111-112, cone.dart:101-107, paraboloid.dart:107-109, hyperboloid.dart:125-133: p, dpdu, dpdv in world space
+static DRT_HD inline void quadricPartials(const GSphere& s, const V3& phit, V3* p, V3* dpdu, V3* dpdv) {
+  float o2w[16];
+  for (int i = 0; i < 12; ++i) o2w[i] = s.o2w[i];
+  for (int i = 0; i < 4; ++i) o2w[12 + i] = s.o2wRow3[i];
+  V3 du = mkv(-s.phiMax * phit.y, s.phiMax * phit.x, 0.0);
+  V3 dv;
+  if (s.shape == 2) {
+    dv = mkv(0.0, 0.0, s.zmax - s.zmin);
+  } else if (s.shape == 3) {
+    double v = (double)phit.z / s.height;
+    dv = mkv(-(double)phit.x / (1.0 - v), -(double)phit.y / (1.0 - v), s.height);
+  } else if (s.shape == 4) {
+    dv = mkv((double)phit.x / (2.0 * phit.z), (double)phit.y / (2.0 * phit.z), 1.0) * (s.zmax - s.zmin);
+  } else {
+    double phi = quadricPhiV(s, phit);
+    double cosphi = cos(phi), sinphi = sin(phi);
+    double ex = (double)s.hp2[0] - (double)s.hp1[0], ey = (double)s.hp2[1] - (double)s.hp1[1];
+    dv = mkv(ex * cosphi - ey * sinphi, ex * sinphi + ey * cosphi, (double)s.hp2[2] - (double)s.hp1[2]);
+  }
+  *p = XfPoint(o2w, phit);
+  *dpdu = XfVector(o2w, du);
+  *dpdv = XfVector(o2w, dv);
+}
+
+#ifdef __CUDACC__
+// Out-of-line entry points: the rare quadrics must not grow the shading kernels (instruction-cache bound).
+static __device__ __noinline__ void quadricPartialsCold(const GSphere& s, V3 phit, V3* p, V3* dpdu, V3* dpdv) {
+  quadricPartials(s, phit, p, dpdu, dpdv);
+}
+static __device__ __noinline__ bool quadricIntersectCold(const GSphere& s, V3 o, V3 d, double mint, double maxt, double* tOut, V3* p,
+                                                         V3* dpdu, V3* dpdv) {
+  V3 phit;
+  if (!quadricIntersectT(s, o, d, mint, maxt, tOut, &phit)) return false;
+  quadricPartials(s, phit, p, dpdu, dpdv);
+  return true;
+}
+// shape.dart:96-98 -> cylinder.dart:230-240
+static __device__ __noinline__ V3 cylinderSampleCold(const GSphere& s, bool rev, double u1, double u2, V3* ns) {
+  float o2w[16], w2o[16];
+  for (int i = 0; i < 12; ++i) { o2w[i] = s.o2w[i]; w2o[i] = s.w2o[i]; }
+  for (int i = 0; i < 4; ++i) { o2w[12 + i] = s.o2wRow3[i]; w2o[12 + i] = s.w2oRow3[i]; }
+  double z = s.zmin * (1.0 - u1) + s.zmax * u1;  // Lerp, common.dart:80-81
+  double t = u2 * s.phiMax;
+  V3 pc = mkv(s.radius * cos(t), s.radius * sin(t), z);
+  V3 n = XfNormal(w2o, V3{pc.x, pc.y, 0.f});
+  n = n / Length(n);
+  if (rev) n = n * -1.0;
+  *ns = n;
+  return XfPoint(o2w, pc);
+}
+#endif
+
 // disk.dart:39-67: tHit and the object-space hit point
 static DRT_HD inline bool diskIntersectT(const GSphere& s, const V3& o, const V3& d, double mint, double maxt, double* tOut,
                                          V3* phitOut) {
@@ -352,7 +478,9 @@ static __device__ inline void hitGeometry(const RenderScene& rs, uint32_t prim, 
     for (int i = 0; i < 4; ++i) w2o[12 + i] = s.w2oRow3[i];
     V3 ro = XfPoint(w2o, o), rd = XfVector(w2o, d);
     V3 phit = RayAt(ro, rd, t);
-    if (s.shape == 1) {
+    if (s.shape >= 2) {
+      quadricPartialsCold(s, phit, &h->p, &h->dpdu, &dpdv);
+    } else if (s.shape == 1) {
       diskPartials(s, phit, &h->p, &h->dpdu, &dpdv);
     } else {
       if (phit.x == 0.0f && phit.y == 0.0f) phit.x = (float)(1.0e-5 * s.radius);
@@ -383,7 +511,9 @@ static __device__ DRT_SHAPE_INLINE bool shapeIntersect(const RenderScene& rs, ui
     const GSphere& s = rs.ts.spheres[prim - rs.ntris];
     double t;
     V3 phit;
-    if (s.shape == 1) {
+    if (s.shape >= 2) {
+      if (!quadricIntersectCold(s, o, d, mint, maxt, &t, &h->p, &h->dpdu, &dpdv)) return false;
+    } else if (s.shape == 1) {
       if (!diskIntersectT(s, o, d, mint, maxt, &t, &phit)) return false;
       diskPartials(s, phit, &h->p, &h->dpdu, &dpdv);
     } else {
@@ -786,6 +916,7 @@ static __device__ inline V3 shapeSample2(const RenderScene& rs, const GLightShap
     *ns = n;
     return XfPoint(o2w, pd);
   }
+  if (s.shape == 2) return cylinderSampleCold(s, rev, u1, u2, ns);
   // sphere.dart:261-297
   V3 Pcenter = XfPoint(o2w, V3{0.f, 0.f, 0.f});
   V3 wc = Normalize(Pcenter - p);

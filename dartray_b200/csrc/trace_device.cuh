@@ -105,11 +105,97 @@ static __device__ __forceinline__ bool triangleAny(const RayState& r, const floa
   return true;
 }
 
+// Cylinder / Cone / Paraboloid / Hyperboloid intersect == intersectP up to the hit decision (cylinder.dart:39-104 /
+// :153-221, cone.dart:35-98 / :155-214, paraboloid.dart:37-100 / :158-217, hyperboloid.dart:57-122 / :178-244): one
+// decision sequence, different coefficients, z range and phi.  Kept out of line: these shapes are rare next to
+// triangles and must not grow the leaf phase of the traversal kernels.
+static __device__ __forceinline__ double quadricPhi(const GSphere& s, double px, double py, double pz, double* vOut) {
+  double ax = px, ay = py;
+  if (s.shape == 5) {  // hyperboloid.dart:96-103: pr = p1 * (1 - v) + p2 * v in float32 Points
+    double v = (pz - (double)s.hp1[2]) / ((double)s.hp2[2] - (double)s.hp1[2]);
+    double prx = rf(rf((double)s.hp1[0] * (1.0 - v)) + rf((double)s.hp2[0] * v));
+    double pry = rf(rf((double)s.hp1[1] * (1.0 - v)) + rf((double)s.hp2[1] * v));
+    ay = prx * py - px * pry;
+    ax = px * prx + py * pry;
+    *vOut = v;
+  }
+  double phi = atan2(ay, ax);
+  if (phi < 0.0) phi += 2.0 * 3.141592653589793;
+  return phi;
+}
+static __device__ __noinline__ bool quadricTest(const GSphere& s, const RayState& r, double* thitOut, double* uOut, double* vOut) {
+  const float* m = s.w2o;
+  double ox = rf((double)m[0] * r.ox + (double)m[1] * r.oy + (double)m[2] * r.oz + (double)m[3]);
+  double oy = rf((double)m[4] * r.ox + (double)m[5] * r.oy + (double)m[6] * r.oz + (double)m[7]);
+  double oz = rf((double)m[8] * r.ox + (double)m[9] * r.oy + (double)m[10] * r.oz + (double)m[11]);
+  double w = (double)s.w2oRow3[0] * r.ox + (double)s.w2oRow3[1] * r.oy + (double)s.w2oRow3[2] * r.oz + (double)s.w2oRow3[3];
+  if (w != 1.0) { ox = rf(ox / w); oy = rf(oy / w); oz = rf(oz / w); }
+  double dx = rf((double)m[0] * r.dx + (double)m[1] * r.dy + (double)m[2] * r.dz);
+  double dy = rf((double)m[4] * r.dx + (double)m[5] * r.dy + (double)m[6] * r.dz);
+  double dz = rf((double)m[8] * r.dx + (double)m[9] * r.dy + (double)m[10] * r.dz);
+  double A, B, C, zlo = s.zmin, zhi = s.zmax;
+  if (s.shape == 2) {
+    A = dx * dx + dy * dy;
+    B = 2.0 * (dx * ox + dy * oy);
+    C = ox * ox + oy * oy - s.radius * s.radius;
+  } else if (s.shape == 3) {
+    double k = s.radius / s.height;
+    k = k * k;
+    A = dx * dx + dy * dy - k * dz * dz;
+    B = 2.0 * (dx * ox + dy * oy - k * dz * (oz - s.height));
+    C = ox * ox + oy * oy - k * (oz - s.height) * (oz - s.height);
+    zlo = 0.0;
+    zhi = s.height;
+  } else if (s.shape == 4) {
+    double k = s.zmax / (s.radius * s.radius);
+    A = k * (dx * dx + dy * dy);
+    B = 2 * k * (dx * ox + dy * oy) - dz;
+    C = k * (ox * ox + oy * oy) - oz;
+  } else {
+    double a = s.ha, c = s.hc;
+    A = a * dx * dx + a * dy * dy - c * dz * dz;
+    B = 2.0 * (a * dx * ox + a * dy * oy - c * dz * oz);
+    C = a * ox * ox + a * oy * oy - c * oz * oz - 1;
+  }
+  double discrim = B * B - 4.0 * A * C;  // common.dart:140-167
+  if (discrim < 0.0) return false;
+  double rootDiscrim = sqrt(discrim);
+  double q = (B < 0.0) ? -0.5 * (B - rootDiscrim) : -0.5 * (B + rootDiscrim);
+  double t0 = q / A, t1 = C / q;
+  if (t0 > t1) { double tt = t0; t0 = t1; t1 = tt; }
+  if (t0 > r.maxt || t1 < r.mint) return false;
+  double thit = t0;
+  if (t0 < r.mint) {
+    thit = t1;
+    if (thit > r.maxt) return false;
+  }
+  double px = rf(ox + rf(dx * thit)), py = rf(oy + rf(dy * thit)), pz = rf(oz + rf(dz * thit));
+  double v = 0.0;
+  double phi = quadricPhi(s, px, py, pz, &v);
+  if (pz < zlo || pz > zhi || phi > s.phiMax) {
+    if (thit == t1) return false;
+    thit = t1;
+    if (t1 > r.maxt) return false;
+    px = rf(ox + rf(dx * thit)); py = rf(oy + rf(dy * thit)); pz = rf(oz + rf(dz * thit));
+    phi = quadricPhi(s, px, py, pz, &v);
+    if (pz < zlo || pz > zhi || phi > s.phiMax) return false;
+  }
+  *thitOut = thit;
+  if (uOut) {
+    if (s.shape == 2 || s.shape == 4) v = (pz - s.zmin) / (s.zmax - s.zmin);
+    else if (s.shape == 3) v = pz / s.height;
+    *uOut = phi / s.phiMax;
+    *vOut = v;
+  }
+  return true;
+}
+
 // sphere.dart:39-116 / :169-241.  `shadow` selects intersectP, whose `thit == t1` comparison is
 // between a double and a List and therefore never true (sphere.dart:210).
 static __device__ bool sphereTest(const GSphere& s, const RayState& r, bool shadow, double* thitOut, double* uOut,
                            double* vOut) {
   // transform.dart:110-145,180-195: object-space origin/direction are float32 Points/Vectors
+  if (s.shape >= 2) return quadricTest(s, r, thitOut, uOut, vOut);
   const float* m = s.w2o;
   if (s.shape == 1) {  // Disk.intersect / intersectP, lib/shapes/disk.dart:39-75 / :107-140 (same decisions)
     double ox = rf((double)m[0] * r.ox + (double)m[1] * r.oy + (double)m[2] * r.oz + (double)m[3]);

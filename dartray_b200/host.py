@@ -15,6 +15,9 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
+# quadric kinds of drt_set_quadrics (include/drt.h); sphere = 0 and disk = 1 have their own entry points
+QUADRIC_CYLINDER, QUADRIC_CONE, QUADRIC_PARABOLOID, QUADRIC_HYPERBOLOID = 2, 3, 4, 5
+
 # ---- Matrix4x4 / Transform (float32 storage, float64 arithmetic) ------------------------------------
 
 
@@ -332,6 +335,7 @@ class SceneBuilder:
         self.tri_mat, self.tri_light, self.tri_rev = [], [], []
         self.sph = []  # (o2w, w2o, params, mat, light, rev)
         self.dsk = []  # (o2w, w2o, (height, radius, innerradius, phimax), mat, light, rev)
+        self.quad = []  # (kind 2..5, o2w, w2o, 8 params, mat, light, rev): cylinder / cone / paraboloid / hyperboloid
         self.materials = []  # (kind, kd, sigma)
         self.lights = []  # dict(kind, L, pos, nsamples, shapes=[("tri"|"sph", local ids...)])
         self._order = []  # ("mesh", first_tri, ntris) | ("sphere", sphere_index)
@@ -433,9 +437,41 @@ class SceneBuilder:
         self._order.append(("disk", k))
         return k
 
+    def _quadric(self, kind, o2w, params, material, area_light, nsamples, reverse) -> int:
+        o2w = np.asarray(o2w, dtype=np.float32).reshape(4, 4)
+        light = -1
+        k = len(self.quad)
+        if area_light is not None:
+            if kind != QUADRIC_CYLINDER:  # Shape.sample is unimplemented for them (lib/core/shape.dart:83-86)
+                raise ValueError("only the cylinder among these quadrics can be an area light (it alone has sample())")
+            light = self._area_light(area_light, nsamples)
+            self.lights[light]["shapes"] = [("quad", k)]
+        prm = tuple(params) + (0.0,) * (8 - len(params))
+        self.quad.append((kind, o2w, mat_inv(o2w), prm, material, light, 1 if reverse else 0))
+        self._order.append(("quad", k))
+        return k
+
+    def cylinder(self, o2w, radius=1.0, zmin=-1.0, zmax=1.0, phimax=360.0, material=0, area_light=None, nsamples=1,
+                 reverse=False) -> int:
+        """Shape "cylinder" (lib/shapes/cylinder.dart:239-247)."""
+        return self._quadric(QUADRIC_CYLINDER, o2w, (radius, zmin, zmax, phimax), material, area_light, nsamples, reverse)
+
+    def cone(self, o2w, radius=1.0, height=1.0, phimax=360.0, material=0, reverse=False) -> int:
+        """Shape "cone" (lib/shapes/cone.dart:216-222)."""
+        return self._quadric(QUADRIC_CONE, o2w, (height, radius, phimax), material, None, 1, reverse)
+
+    def paraboloid(self, o2w, radius=1.0, zmin=0.0, zmax=1.0, phimax=360.0, material=0, reverse=False) -> int:
+        """Shape "paraboloid" (lib/shapes/paraboloid.dart:220-228)."""
+        return self._quadric(QUADRIC_PARABOLOID, o2w, (radius, zmin, zmax, phimax), material, None, 1, reverse)
+
+    def hyperboloid(self, o2w, p1=(0.0, 0.0, 0.0), p2=(1.0, 1.0, 1.0), phimax=360.0, material=0, reverse=False) -> int:
+        """Shape "hyperboloid" (lib/shapes/hyperboloid.dart:263-268)."""
+        return self._quadric(QUADRIC_HYPERBOLOID, o2w, tuple(p1) + tuple(p2) + (phimax,), material, None, 1, reverse)
+
     def arrays(self) -> dict:
         ntris = len(self.tri_mat)
         nsph = len(self.sph)
+        ndsk = len(self.dsk)
         P = np.concatenate(self.P) if self.P else np.zeros((0, 3), np.float32)
         idx = np.concatenate(self.idx) if self.idx else np.zeros((0, 3), np.uint32)
         # refined order handed to BVHAccel: Primitive.fullyRefine is LIFO per primitive (primitive.dart:71-84)
@@ -445,10 +481,12 @@ class SceneBuilder:
                 order += list(range(item[1] + item[2] - 1, item[1] - 1, -1))
             elif item[0] == "sphere":
                 order.append(ntris + item[1])
-            else:
+            elif item[0] == "disk":
                 order.append(ntris + nsph + item[1])
+            else:
+                order.append(ntris + nsph + ndsk + item[1])
         lights = []
-        base = {"tri": 0, "sph": ntris, "dsk": ntris + nsph}
+        base = {"tri": 0, "sph": ntris, "dsk": ntris + nsph, "quad": ntris + nsph + ndsk}
         for l in self.lights:
             shapes = [base[s[0]] + s[1] for s in l["shapes"]]
             lights.append(dict(kind=l["kind"], L=l["L"], pos=l["pos"], nsamples=l["nsamples"], shapes=shapes,
@@ -472,6 +510,12 @@ class SceneBuilder:
             dsk_params=np.asarray([s[2] for s in self.dsk], np.float64).reshape(-1, 4),
             dsk_mat=np.asarray([s[3] for s in self.dsk], np.int32), dsk_light=np.asarray([s[4] for s in self.dsk], np.int32),
             dsk_rev=np.asarray([s[5] for s in self.dsk], np.uint8),
+            quad_kind=np.asarray([q[0] for q in self.quad], np.int32),
+            quad_o2w=np.stack([q[1].reshape(16) for q in self.quad]) if self.quad else np.zeros((0, 16), np.float32),
+            quad_w2o=np.stack([q[2].reshape(16) for q in self.quad]) if self.quad else np.zeros((0, 16), np.float32),
+            quad_params=np.asarray([q[3] for q in self.quad], np.float64).reshape(-1, 8),
+            quad_mat=np.asarray([q[4] for q in self.quad], np.int32), quad_light=np.asarray([q[5] for q in self.quad], np.int32),
+            quad_rev=np.asarray([q[6] for q in self.quad], np.uint8),
             order=np.asarray(order, np.uint32),
             mat_kind=np.asarray([m[0] for m in mats], np.int32), mat_kd=np.asarray([m[1] for m in mats], np.float32),
             mat_sigma=np.asarray([m[2] for m in mats], np.float32),
@@ -502,6 +546,15 @@ def upload_scene(ctx, arrays: dict, split: int = 2, max_node_prims: int = 4):
     ctx.set_spheres(a["sph_o2w"], a["sph_w2o"], a["sph_params"], a["sph_mat"], a["sph_light"], a["sph_rev"])
     if a["dsk_params"].shape[0]:
         ctx.set_disks(a["dsk_o2w"], a["dsk_w2o"], a["dsk_params"], a["dsk_mat"], a["dsk_light"], a["dsk_rev"])
+    qk = a.get("quad_kind", np.zeros(0, np.int32))
+    i = 0
+    while i < qk.shape[0]:  # one call per run of equal kinds keeps the ids in append order
+        j = i
+        while j < qk.shape[0] and qk[j] == qk[i]:
+            j += 1
+        ctx.set_quadrics(int(qk[i]), a["quad_o2w"][i:j], a["quad_w2o"][i:j], a["quad_params"][i:j], a["quad_mat"][i:j],
+                         a["quad_light"][i:j], a["quad_rev"][i:j])
+        i = j
     ctx.set_build_order(a["order"])
     ctx.build_bvh(split, max_node_prims)
     if a.get("mat_general"):

@@ -105,6 +105,24 @@ int drt_set_spheres(drt_ctx* ctx, uint32_t n, const float* o2w, const float* w2o
 int drt_set_disks(drt_ctx* ctx, uint32_t n, const float* o2w, const float* w2o, const double* height_radius_inner_phimax,
                   const int32_t* material_of_disk, const int32_t* light_of_disk, const uint8_t* reverse_orientation_of_disk);
 
+/* Replaces Cylinder / Cone / Paraboloid / Hyperboloid construction (lib/shapes/cylinder.dart:24-31,239-247,
+ * cone.dart:23-27,216-222, paraboloid.dart:23-29,220-228, hyperboloid.dart:23-49,263-268).  They are appended to the
+ * same quadric id range in call order (after drt_set_spheres / drt_set_disks).  params: n x 8 doubles, the ParamSet
+ * values in the order of each Create():
+ *   kind 2 cylinder    radius, zmin, zmax, phimax(degrees)
+ *   kind 3 cone        height, radius, phimax
+ *   kind 4 paraboloid  radius, zmin, zmax, phimax
+ *   kind 5 hyperboloid p1.x, p1.y, p1.z, p2.x, p2.y, p2.z, phimax
+ * Of these only the cylinder implements Shape.sample (cylinder.dart:230-240), so only it may be an area light's shape;
+ * drt_set_lights rejects the others (the reference logs 'Unimplemented Shape.sample' and returns garbage). */
+#define DRT_QUADRIC_CYLINDER 2
+#define DRT_QUADRIC_CONE 3
+#define DRT_QUADRIC_PARABOLOID 4
+#define DRT_QUADRIC_HYPERBOLOID 5
+int drt_set_quadrics(drt_ctx* ctx, int kind, uint32_t n, const float* o2w, const float* w2o, const double* params8,
+                     const int32_t* material_of_quadric, const int32_t* light_of_quadric,
+                     const uint8_t* reverse_orientation_of_quadric);
+
 /* Order in which BVHAccel sees the refined primitives (a permutation of primitive ids).  The
  * reference's Primitive.fullyRefine is LIFO (lib/core/primitive.dart:71-84), so a mesh's triangles
  * reach the builder in reverse order; the build's partition steps depend on it.  NULL = identity. */

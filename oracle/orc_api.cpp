@@ -103,6 +103,25 @@ int orc_set_disks(orc_ctx* c, uint32_t n, const float* o2w, const float* w2o, co
   return 0;
 }
 
+// Cylinders / cones / paraboloids / hyperboloids (kind 2..5) join the same quadric id range, appended in call order.
+// prm: n x 8 doubles, see Sphere::makeQuadric.
+int orc_set_quadrics(orc_ctx* c, int kind, uint32_t n, const float* o2w, const float* w2o, const double* prm, const int32_t* mat,
+                     const int32_t* light, const uint8_t* rev) {
+  if (kind < 2 || kind > 5) return -1;
+  Scene& s = c->scene;
+  uint32_t base = s.nprims();
+  s.materialOf.resize(base + n, 0);
+  s.lightOf.resize(base + n, -1);
+  s.reverseOf.resize(base + n, 0);
+  for (uint32_t i = 0; i < n; ++i) {
+    s.spheres.push_back(Sphere::makeQuadric(kind, o2w + 16 * i, w2o + 16 * i, prm + 8 * i, rev ? rev[i] != 0 : false));
+    s.materialOf[base + i] = mat ? mat[i] : 0;
+    s.lightOf[base + i] = light ? light[i] : -1;
+    s.reverseOf[base + i] = rev ? rev[i] : 0;
+  }
+  return 0;
+}
+
 int orc_set_build_order(orc_ctx* c, const uint32_t* ids, uint32_t n) {
   if (!ids) { c->scene.buildOrder.clear(); return 0; }
   c->scene.buildOrder.assign(ids, ids + n);

@@ -602,6 +602,26 @@ struct Ctx {
       dg->p = ray.at(h.t);
       dg->dpdu = dpdu;
       dg->dpdv = dpdv;
+    } else if (g.spheres[prim - g.ntris()].shape >= 2) {
+      const Sphere& s = g.spheres[prim - g.ntris()];
+      Vec phit = h.phitObj;
+      Vec dpdu(-s.phiMax * phit.y, s.phiMax * phit.x, 0.0);  // the same expression in all four files
+      Vec dpdv;
+      if (s.shape == 2) {  // cylinder.dart:111-112
+        dpdv = Vec(0.0, 0.0, s.zmax - s.zmin);
+      } else if (s.shape == 3) {  // cone.dart:101-107
+        double v = (double)phit.z / s.height;
+        dpdv = Vec(-(double)phit.x / (1.0 - v), -(double)phit.y / (1.0 - v), s.height);
+      } else if (s.shape == 4) {  // paraboloid.dart:107-109
+        dpdv = Vec((double)phit.x / (2.0 * phit.z), (double)phit.y / (2.0 * phit.z), 1.0) * (s.zmax - s.zmin);
+      } else {  // hyperboloid.dart:128-133
+        double cosphi = std::cos(h.phi), sinphi = std::sin(h.phi);
+        dpdv = Vec(((double)s.hp2.x - s.hp1.x) * cosphi - ((double)s.hp2.y - s.hp1.y) * sinphi,
+                   ((double)s.hp2.x - s.hp1.x) * sinphi + ((double)s.hp2.y - s.hp1.y) * cosphi, (double)s.hp2.z - s.hp1.z);
+      }
+      dg->p = s.o2w.point(phit);
+      dg->dpdu = s.o2w.vector(dpdu);
+      dg->dpdv = s.o2w.vector(dpdv);
     } else if (g.spheres[prim - g.ntris()].shape == 1) {  // disk.dart:69-97
       const Sphere& s = g.spheres[prim - g.ntris()];
       Vec phit = h.phitObj;
@@ -680,6 +700,20 @@ struct Ctx {
     }
     const Sphere& s = g.spheres[prim - g.ntris()];
     if (s.shape == 1) return s.phiMax * 0.5 * (s.radius * s.radius - s.innerRadius * s.innerRadius);  // disk.dart:142-145
+    if (s.shape == 2) return (s.zmax - s.zmin) * s.phiMax * s.radius;                                // cylinder.dart:226-228
+    if (s.shape == 3) return s.radius * std::sqrt((s.height * s.height) + (s.radius * s.radius)) * s.phiMax / 2.0;  // cone.dart:211-214
+    if (s.shape == 4) return s.phiMax / 12.0 * (std::pow(1 + 4 * s.zmin, 1.5) - std::pow(1 + 4 * s.zmax, 1.5));  // paraboloid.dart:215-218 (as written)
+    if (s.shape == 5) {  // hyperboloid.dart:246-261
+      double p1x = s.hp1.x, p1y = s.hp1.y, p1z = s.hp1.z, p2x = s.hp2.x, p2y = s.hp2.y, p2z = s.hp2.z;
+      auto SQR = [](double a) { return a * a; };
+      auto QUAD = [](double a) { return a * a * a * a; };
+      return s.phiMax / 6.0 *
+             (2.0 * QUAD(p1x) - 2.0 * p1x * p1x * p1x * p2x + 2.0 * QUAD(p2x) +
+              2.0 * (p1y * p1y + p1y * p2y + p2y * p2y) * (SQR(p1y - p2y) + SQR(p1z - p2z)) +
+              p2x * p2x * (5.0 * p1y * p1y + 2.0 * p1y * p2y - 4.0 * p2y * p2y + 2.0 * SQR(p1z - p2z)) +
+              p1x * p1x * (-4.0 * p1y * p1y + 2.0 * p1y * p2y + 5.0 * p2y * p2y + 2.0 * SQR(p1z - p2z)) -
+              2.0 * p1x * p2x * (p2x * p2x - p1y * p1y + 5.0 * p1y * p2y - p2y * p2y - p1z * p1z + 2.0 * p1z * p2z - p2z * p2z));
+    }
     return s.phiMax * s.radius * (s.zmax - s.zmin);  // sphere.dart:243-245
   }
   Vec sphereSample(const Sphere& s, double u1, double u2, Vec* ns) const {  // sphere.dart:247-259
@@ -712,6 +746,16 @@ struct Ctx {
       if (s.reverseOrientation) n = n * -1.0;
       *ns = n;
       return s.o2w.point(pd);
+    }
+    if (s.shape == 2) {  // shape.dart:96-98 -> cylinder.dart:230-240 (the only other quadric with a sample())
+      double z = s.zmin * (1.0 - u1) + s.zmax * u1;  // Lerp, common.dart:80-81
+      double t = u2 * s.phiMax;
+      Vec pc(s.radius * std::cos(t), s.radius * std::sin(t), z);
+      Vec n = s.o2w.normal(Vec(pc.x, pc.y, 0.0));
+      n = n / Length(n);
+      if (s.reverseOrientation) n = n * -1.0;
+      *ns = n;
+      return s.o2w.point(pc);
     }
     // sphere.dart:261-297
     Vec Pcenter = s.o2w.point(Vec());

@@ -117,9 +117,92 @@ static bool diskCore(const Sphere& s, const Ray& r, double* thitOut, Vec* phitOu
   return true;
 }
 
+// cylinder.dart:39-104 / :153-221, cone.dart:35-98 / :155-214, paraboloid.dart:37-100 / :158-217,
+// hyperboloid.dart:57-122 / :178-244: the four quadrics share one decision sequence (quadratic, nearer root in
+// range, clip by z and phi, retry at the farther root) and differ in the coefficients, the z range and phi.
+static inline double quadricPhi(const Sphere& s, const Vec& phit, double* vOut) {
+  if (s.shape == 5) {  // hyperboloid.dart:96-103
+    double v = ((double)phit.z - s.hp1.z) / ((double)s.hp2.z - s.hp1.z);
+    Vec pr = (s.hp1 * (1.0 - v)) + (s.hp2 * v);
+    double phi = std::atan2((double)pr.x * phit.y - (double)phit.x * pr.y, (double)phit.x * pr.x + (double)phit.y * pr.y);
+    if (phi < 0.0) phi += 2.0 * kPi;
+    *vOut = v;
+    return phi;
+  }
+  double phi = std::atan2((double)phit.y, (double)phit.x);
+  if (phi < 0.0) phi += 2.0 * kPi;
+  return phi;
+}
+static bool quadricCore(const Sphere& s, const Ray& r, double* thitOut, Vec* phitOut, double* phiOut, double* vOut) {
+  Ray ray = s.w2o.ray(r);
+  double dx = ray.d.x, dy = ray.d.y, dz = ray.d.z, ox = ray.o.x, oy = ray.o.y, oz = ray.o.z;
+  double A, B, C, zlo = s.zmin, zhi = s.zmax;
+  if (s.shape == 2) {  // cylinder.dart:46-52
+    A = dx * dx + dy * dy;
+    B = 2.0 * (dx * ox + dy * oy);
+    C = ox * ox + oy * oy - s.radius * s.radius;
+  } else if (s.shape == 3) {  // cone.dart:42-51
+    double k = s.radius / s.height;
+    k = k * k;
+    A = dx * dx + dy * dy - k * dz * dz;
+    B = 2.0 * (dx * ox + dy * oy - k * dz * (oz - s.height));
+    C = ox * ox + oy * oy - k * (oz - s.height) * (oz - s.height);
+    zlo = 0.0;
+    zhi = s.height;
+  } else if (s.shape == 4) {  // paraboloid.dart:44-50
+    double k = s.zmax / (s.radius * s.radius);
+    A = k * (dx * dx + dy * dy);
+    B = 2 * k * (dx * ox + dy * oy) - dz;
+    C = k * (ox * ox + oy * oy) - oz;
+  } else {  // hyperboloid.dart:64-72
+    double a = s.ha, c = s.hc;
+    A = a * dx * dx + a * dy * dy - c * dz * dz;
+    B = 2.0 * (a * dx * ox + a * dy * oy - c * dz * oz);
+    C = a * ox * ox + a * oy * oy - c * oz * oz - 1;
+  }
+  double t0, t1;
+  if (!Quadratic(A, B, C, &t0, &t1)) return false;
+  if (t0 > ray.maxt || t1 < ray.mint) return false;
+  double thit = t0;
+  if (t0 < ray.mint) {
+    thit = t1;
+    if (thit > ray.maxt) return false;
+  }
+  Vec phit = ray.at(thit);
+  double v = 0.0;
+  double phi = quadricPhi(s, phit, &v);
+  if (phit.z < zlo || phit.z > zhi || phi > s.phiMax) {
+    if (thit == t1) return false;
+    thit = t1;
+    if (t1 > ray.maxt) return false;
+    phit = ray.at(thit);
+    phi = quadricPhi(s, phit, &v);
+    if (phit.z < zlo || phit.z > zhi || phi > s.phiMax) return false;
+  }
+  if (s.shape == 2 || s.shape == 4) v = ((double)phit.z - s.zmin) / (s.zmax - s.zmin);  // cylinder.dart:108, paraboloid.dart:104
+  else if (s.shape == 3) v = (double)phit.z / s.height;                                   // cone.dart:102
+  *thitOut = thit;
+  *phitOut = phit;
+  *phiOut = phi;
+  *vOut = v;
+  return true;
+}
+
 bool Scene::sphIntersect(const Sphere& s, Ray& r, Hit* hit) const {
   double thit, phi;
   Vec phit;
+  if (s.shape >= 2) {
+    double v;
+    if (!quadricCore(s, r, &thit, &phit, &phi, &v)) return false;
+    hit->t = thit;
+    hit->phitObj = phit;
+    hit->phi = phi;
+    hit->b1 = phi / s.phiMax;
+    hit->b2 = v;
+    hit->rayEpsilon = 5.0e-4 * thit;  // cylinder.dart:147, cone.dart:149, paraboloid.dart:152, hyperboloid.dart:172
+    r.maxt = thit;
+    return true;
+  }
   if (s.shape == 1) {
     if (!diskCore(s, r, &thit, &phit, &phi)) return false;
     hit->t = thit;
@@ -150,6 +233,10 @@ bool Scene::sphIntersectP(const Sphere& s, const Ray& r) const {
   double thit, phi;
   Vec phit;
   if (s.shape == 1) return diskCore(s, r, &thit, &phit, &phi);
+  if (s.shape >= 2) {
+    double v;
+    return quadricCore(s, r, &thit, &phit, &phi, &v);
+  }
   return sphereCore(s, r, true, &thit, &phit, &phi);
 }
 

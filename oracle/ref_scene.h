@@ -20,9 +20,61 @@ struct Sphere {
   Transform w2o;
   double radius, zmin, zmax, phiMax, thetaMin, thetaMax;
   bool reverseOrientation = false;
-  int shape = 0;  // 0 sphere, 1 disk
+  int shape = 0;  // 0 sphere, 1 disk, 2 cylinder, 3 cone, 4 paraboloid, 5 hyperboloid
   double height = 0.0, innerRadius = 0.0;
+  Vec hp1, hp2;               // hyperboloid.dart:24 (Points, float32)
+  double ha = 0.0, hc = 0.0;  // hyperboloid.dart:36-49 implicit coefficients
   Sphere() {}
+  // The remaining quadrics.  prm: the ParamSet values in the order of each Create():
+  //   2 cylinder   radius, zmin, zmax, phimax            (cylinder.dart:24-31,239-247)
+  //   3 cone       height, radius, phimax                (cone.dart:23-27,216-222)
+  //   4 paraboloid radius, zmin, zmax, phimax            (paraboloid.dart:23-29,220-228)
+  //   5 hyperboloid p1.xyz, p2.xyz, phimax               (hyperboloid.dart:23-49,263-268)
+  static Sphere makeQuadric(int kind, const float* O2W, const float* W2O, const double* prm, bool ro) {
+    Sphere q;
+    q.o2w = Transform(O2W, W2O);
+    q.w2o = Transform(W2O, O2W);
+    q.shape = kind;
+    q.reverseOrientation = ro;
+    q.thetaMin = q.thetaMax = 0.0;
+    double pm = 360.0;
+    if (kind == 2 || kind == 4) {
+      q.radius = prm[0];
+      q.zmin = std::fmin(prm[1], prm[2]);
+      q.zmax = std::fmax(prm[1], prm[2]);
+      pm = prm[3];
+    } else if (kind == 3) {
+      q.height = prm[0];
+      q.radius = prm[1];
+      q.zmin = 0.0;
+      q.zmax = q.height;
+      pm = prm[2];
+    } else {
+      Vec p1(prm[0], prm[1], prm[2]), p2(prm[3], prm[4], prm[5]);
+      pm = prm[6];
+      double radius1 = std::sqrt((double)p1.x * p1.x + (double)p1.y * p1.y);
+      double radius2 = std::sqrt((double)p2.x * p2.x + (double)p2.y * p2.y);
+      q.radius = std::fmax(radius1, radius2);  // rmax
+      q.zmin = std::fmin((double)p1.z, (double)p2.z);
+      q.zmax = std::fmax((double)p1.z, (double)p2.z);
+      if (p2.z == 0.0f) std::swap(p1, p2);
+      Vec pp = p1;
+      double a, c;
+      do {  // hyperboloid.dart:40-48
+        pp = pp + ((p2 - p1) * 2.0);
+        double xy1 = (double)pp.x * pp.x + (double)pp.y * pp.y;
+        double xy2 = (double)p2.x * p2.x + (double)p2.y * p2.y;
+        a = (1.0 / xy1 - ((double)pp.z * pp.z) / (xy1 * p2.z * p2.z)) / (1.0 - (xy2 * pp.z * pp.z) / (xy1 * p2.z * p2.z));
+        c = (a * xy2 - 1.0) / ((double)p2.z * p2.z);
+      } while (std::isinf(a) || std::isnan(a));
+      q.hp1 = p1;
+      q.hp2 = p2;
+      q.ha = a;
+      q.hc = c;
+    }
+    q.phiMax = Radians(clampd(pm, 0.0, 360.0));
+    return q;
+  }
   static Sphere makeDisk(const float* O2W, const float* W2O, double h, double r, double ri, double pm, bool ro) {
     Sphere d;
     d.o2w = Transform(O2W, W2O);
@@ -51,6 +103,7 @@ struct Sphere {
   // sphere.dart:34-37 + lib/core/shape.dart:38-40
   BBox worldBound() const {
     if (shape == 1) return o2w.bbox(BBox(Vec(-radius, -radius, height), Vec(radius, radius, height)));  // disk.dart:32-35
+    // shape >= 2: cylinder.dart:33-37, cone.dart:29-33 (z in [0, height]), paraboloid.dart:31-35, hyperboloid.dart:51-55 (rmax)
     BBox ob(Vec(-radius, -radius, zmin), Vec(radius, radius, zmax));
     return o2w.bbox(ob);
   }

@@ -39,6 +39,7 @@ def lib():
         L.orc_set_triangles.argtypes = [vp, vp, u32, vp, u32, vp, vp, vp]
         L.orc_set_spheres.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
         L.orc_set_disks.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
+        L.orc_set_quadrics.argtypes = [vp, i32, u32, vp, vp, vp, vp, vp, vp]
         L.orc_set_build_order.argtypes = [vp, vp, u32]
         L.orc_build_bvh.argtypes = [vp, i32, i32]
         L.orc_build_seconds.restype = C.c_double
@@ -120,6 +121,13 @@ class Oracle:
         params = _arr(params, np.float64).reshape(-1, 4)
         m, l, r = _arr(material, np.int32), _arr(light, np.int32), _arr(reverse, np.uint8)
         self._ck(self.L.orc_set_disks(self.h, o2w.shape[0], _p(o2w), _p(w2o), _p(params), _p(m), _p(l), _p(r)))
+
+    def set_quadrics(self, kind, o2w, w2o, params, material=None, light=None, reverse=None):
+        o2w = _arr(o2w, np.float32).reshape(-1, 16)
+        w2o = _arr(w2o, np.float32).reshape(-1, 16)
+        params = _arr(params, np.float64).reshape(-1, 8)
+        m, l, r = _arr(material, np.int32), _arr(light, np.int32), _arr(reverse, np.uint8)
+        self._ck(self.L.orc_set_quadrics(self.h, int(kind), o2w.shape[0], _p(o2w), _p(w2o), _p(params), _p(m), _p(l), _p(r)))
 
     def set_build_order(self, order):
         if order is None:

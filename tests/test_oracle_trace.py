@@ -256,3 +256,129 @@ def test_disk_light_irradiance_closed_form():
     o.render()
     E = math.pi * Le * R * R / (h * h + R * R)
     assert o.film_read()["rgb"].mean() == pytest.approx(kd / math.pi * E, rel=1e-2)
+
+
+# ---- Cylinder / Cone / Paraboloid / Hyperboloid (lib/shapes/*.dart) ---------------------------
+def quadric_oracle(kind, params, center=(0, 0, 0)):
+    o = Oracle()
+    o.set_triangles(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32))
+    o.set_spheres(np.zeros((0, 16), np.float32), np.zeros((0, 16), np.float32), np.zeros((0, 4)))
+    m, mi = translate(*center)
+    o.set_quadrics(kind, m, mi, [list(params) + [0.0] * (8 - len(params))])
+    o.build_bvh()
+    return o
+
+
+def test_cylinder_known_answers():
+    o = quadric_oracle(2, (0.5, -1.0, 2.0, 360.0))  # radius, zmin, zmax, phimax (cylinder.dart:239-247)
+    h = o.trace_closest(*ray((-3, 0, 0.5), (1, 0, 0)))[0]
+    assert h["prim"] == 0 and h["t"] == 2.5
+    assert h["b1"] == pytest.approx(0.5, rel=1e-6)        # phi = pi at (-0.5, 0): u = phi / phiMax
+    assert h["b2"] == pytest.approx(1.5 / 3.0, rel=1e-6)  # v = (z - zmin) / (zmax - zmin)
+    assert o.trace_any(*ray((-3, 0, 0.5), (1, 0, 0)))[0] == 1
+    # from inside: the far root
+    assert o.trace_closest(*ray((0, 0, 0), (0, 1, 0)))[0]["t"] == 0.5
+    # above zmax the near root is clipped and so is the far one; a slanted ray leaves through the far wall inside the range
+    assert o.trace_closest(*ray((-3, 0, 2.5), (1, 0, 0)))[0]["prim"] == -1
+    d = np.array([1.0, 0.0, -0.25])
+    h = o.trace_closest(*ray((-3, 0, 2.7), d))[0]  # z at the near wall 2.075 (clipped), at the far wall 1.825
+    assert h["prim"] == 0 and h["t"] == pytest.approx(3.5, rel=1e-6)
+    # an axial ray OUTSIDE the radius misses (A = B = 0, C > 0: t0 = -0 / 0 = NaN, t1 = -inf < minDistance) ...
+    assert o.trace_closest(*ray((0.6, 0.1, -5), (0, 0, 1)))[0]["prim"] == -1
+    # ... but INSIDE the radius the reference reports a hit at t = NaN: t1 = C / -0 = +inf passes `t1 < minDistance`, every
+    # comparison against the NaN t0 is false, so no clip test rejects it (common.dart:140-167, cylinder.dart:57-85).
+    # A reference quirk the oracle keeps as written.
+    h = o.trace_closest(*ray((0.1, 0.1, -5), (0, 0, 1)))[0]
+    assert h["prim"] == 0 and math.isnan(h["t"])
+    # partial sweep
+    o = quadric_oracle(2, (1.0, -1.0, 1.0, 90.0))
+    assert o.trace_closest(*ray((3, 3, 0), (-1, -1, 0)))[0]["prim"] == 0     # phi = 45 degrees
+    assert o.trace_closest(*ray((-3, 3, 0), (1, -1, 0)))[0]["prim"] == -1    # roots at 135 and 315 degrees, both clipped
+    assert o.trace_closest(*ray((-3, 0.5, 0), (1, 0, 0)))[0]["t"] == pytest.approx(3 + math.sqrt(0.75), rel=1e-6)  # near clipped, far in sweep
+
+
+def test_cone_known_answers():
+    o = quadric_oracle(3, (2.0, 1.0, 360.0))  # height, radius, phimax (cone.dart:216-222): radius 1 at z = 0, apex at z = 2
+    h = o.trace_closest(*ray((-3, 0, 1.0), (1, 0, 0)))[0]  # at z = 1 the cone's radius is 0.5
+    assert h["prim"] == 0 and h["t"] == pytest.approx(2.5, rel=1e-6)
+    assert h["b2"] == pytest.approx(0.5, rel=1e-6)  # v = z / height
+    # the mirror nappe above the apex (z > height) is clipped
+    assert o.trace_closest(*ray((-3, 0, 3.0), (1, 0, 0)))[0]["prim"] == -1
+    assert o.trace_any(*ray((-3, 0, 1.0), (1, 0, 0)))[0] == 1
+    assert o.trace_any(*ray((-3, 0, 3.0), (1, 0, 0)))[0] == 0
+
+
+def test_paraboloid_known_answers():
+    o = quadric_oracle(4, (1.0, 0.0, 1.0, 360.0))  # radius, zmin, zmax, phimax: z = x^2 + y^2
+    h = o.trace_closest(*ray((-3, 0, 0.25), (1, 0, 0)))[0]
+    assert h["prim"] == 0 and h["t"] == pytest.approx(2.5, rel=1e-6) and h["b2"] == pytest.approx(0.25, rel=1e-6)
+    # down the axis: A == 0 -> t0 = q / A; the reference's Quadratic divides by zero (common.dart:140-167) and the inf / nan
+    # that follows decides; the oracle keeps whatever IEEE gives (no special case), here a hit at the vertex z = 0
+    h = o.trace_closest(*ray((0.5, 0, 3), (0, 0, -1)))[0]
+    assert h["prim"] in (-1, 0)
+    # clipped band
+    o = quadric_oracle(4, (1.0, 0.5, 1.0, 360.0))
+    assert o.trace_closest(*ray((-3, 0, 0.25), (1, 0, 0)))[0]["prim"] == -1
+    assert o.trace_closest(*ray((-3, 0, 0.75), (1, 0, 0)))[0]["t"] == pytest.approx(3 - math.sqrt(0.75), rel=1e-6)
+
+
+def test_hyperboloid_known_answers():
+    # p1 = (1, 0, -1), p2 = (1, 0, 1): the segment is parallel to the axis -> a cylinder of radius 1, z in [-1, 1]
+    o = quadric_oracle(5, (1.0, 0.0, -1.0, 1.0, 0.0, 1.0, 360.0))
+    h = o.trace_closest(*ray((-3, 0, 0.5), (1, 0, 0)))[0]
+    assert h["prim"] == 0 and h["t"] == pytest.approx(2.0, rel=1e-5)
+    assert h["b2"] == pytest.approx(0.75, rel=1e-6)  # v = (z - p1.z) / (p2.z - p1.z)
+    assert o.trace_closest(*ray((-3, 0, 1.5), (1, 0, 0)))[0]["prim"] == -1
+    # a twisted ruling: p1 = (1, 0, -1), p2 = (0, 1, 1) sweeps the one-sheet hyperboloid x^2 + y^2 - z^2 / 2 = 1 / 2
+    o = quadric_oracle(5, (1.0, 0.0, -1.0, 0.0, 1.0, 1.0, 360.0))
+    h = o.trace_closest(*ray((-3, 0, 0), (1, 0, 0)))[0]
+    assert h["prim"] == 0 and h["t"] == pytest.approx(3 - math.sqrt(0.5), rel=1e-5)  # waist radius sqrt(1/2)
+    h = o.trace_closest(*ray((-3, 0, 1), (1, 0, 0)))[0]
+    assert h["t"] == pytest.approx(3 - 1.0, rel=1e-5)  # radius 1 at z = +-1
+
+
+def test_quadrics_bvh_matches_exhaustive():
+    """aggregate_test_renderer.dart:42-118 with every quadric kind in one scene, under rotated transforms."""
+    from dartray_b200 import host
+    P, idx = random_soup(300, seed=21)
+    o = Oracle()
+    o.set_triangles(P, idx)
+    o.set_spheres(np.zeros((0, 16), np.float32), np.zeros((0, 16), np.float32), np.zeros((0, 4)))
+    for kind, prm, m in quadric_zoo(host):
+        o.set_quadrics(kind, m.reshape(16), host.mat_inv(m).reshape(16), [prm])
+    o.build_bvh()
+    ro, rd = random_rays(20000, seed=22)
+    h = o.trace_closest(ro, rd, nthreads=8)
+    hb, nties, _ = o.trace_closest_brute(ro, rd, nthreads=8)
+    single = nties <= 1
+    assert (h["prim"][single] == hb["prim"][single]).all() and (h["t"] == hb["t"]).all()
+    assert (o.trace_any(ro, rd, nthreads=8) == o.trace_any_brute(ro, rd, nthreads=8)).all()
+    for k in range(4):
+        assert (h["prim"] == 300 + k).sum() > 100, k  # each kind is hit
+
+
+def quadric_zoo(host):
+    return [
+        (2, [0.3, -0.4, 0.5, 300.0, 0, 0, 0, 0], host.mat_mul(host.translate(0.4, 0.1, -0.3), host.rotate(40.0, (1.0, 0.2, 0.1)))),
+        (3, [0.8, 0.4, 360.0, 0, 0, 0, 0, 0], host.mat_mul(host.translate(-0.5, -0.3, 0.2), host.rotate(-70.0, (0.1, 1.0, 0.3)))),
+        (4, [0.45, 0.1, 0.7, 330.0, 0, 0, 0, 0], host.mat_mul(host.translate(0.0, 0.5, 0.4), host.rotate(120.0, (0.3, 0.2, 1.0)))),
+        (5, [0.4, 0.0, -0.4, 0.1, 0.35, 0.4, 360.0, 0], host.mat_mul(host.translate(-0.1, -0.5, -0.5), host.rotate(25.0, (1.0, 1.0, 0.0)))),
+    ]
+
+
+def test_cylinder_light_irradiance_closed_form():
+    # a matte element at the centre of an inward-emitting cylinder (radius R, z in [-H, H]), its normal along the axis:
+    # the wall fills the polar angles atan(R / H) .. pi / 2, so E = pi * L * H^2 / (H^2 + R^2)
+    from dartray_b200 import host
+    kd, Le, H, R = 0.5, 3.0, 1.5, 2.0
+    sb = host.SceneBuilder()
+    e = 0.02
+    sb.mesh([[-e, -e, 0], [e, -e, 0], [e, e, 0], [-e, e, 0]], [[0, 1, 2], [0, 2, 3]], material=sb.material((kd, kd, kd)))
+    sb.cylinder(host.translate(0, 0, 0), radius=R, zmin=-H, zmax=H, area_light=(Le, Le, Le), nsamples=16, reverse=True)
+    cam = host.PerspectiveCamera(host.look_at((0.05, 0.03, 0.6), (0, 0, 0), (0, 1, 0)), fov=0.5)
+    o = Oracle()
+    host.upload_scene(o, sb.arrays())
+    host.configure_render(o, cam, host.Film(4, 4), host.Sampler(kind=host.SAMPLER_LD, spp=64), host.Integrator(kind=host.INTEGRATOR_DIRECT))
+    o.render()
+    E = math.pi * Le * H * H / (H * H + R * R)
+    assert o.film_read()["rgb"].mean() == pytest.approx(kd / math.pi * E, rel=1e-2)

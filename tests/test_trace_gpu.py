@@ -92,6 +92,52 @@ def test_disks_with_triangles_and_spheres(drt_lib, variant):
         assert np.array_equal(c.bvh_export()[k], o.bvh_export()[k]), k
 
 
+def test_cylinders_cones_paraboloids_hyperboloids(drt_lib, variant):
+    """cylinder.dart / cone.dart / paraboloid.dart / hyperboloid.dart: kinds 2..5 of drt_set_quadrics, ids after the disks."""
+    from tests.test_oracle_trace import quadric_zoo
+    P, idx = random_soup(500, seed=31)
+    mats = [translate(0.3, 0.6, -0.2)]
+    sph = (np.stack([m[0] for m in mats]), np.stack([m[1] for m in mats]), [[0.2, -0.2, 0.2, 360.0]])
+    dm = [host.mat_mul(host.translate(0.6, -0.6, 0.1), host.rotate(80, (0, 1, 0)))]
+    dsk = (np.stack([m.reshape(16) for m in dm]), np.stack([host.mat_inv(m).reshape(16) for m in dm]), [[0.0, 0.3, 0.0, 360.0]])
+    o, c = Oracle(), capi.Context(0)
+    c.set_kernel_variant(variant)
+    for x in (o, c):
+        x.set_triangles(P, idx)
+        x.set_spheres(*sph)
+        x.set_disks(*dsk)
+        for kind, prm, m in quadric_zoo(host):
+            x.set_quadrics(kind, m.reshape(16), host.mat_inv(m).reshape(16), [prm])
+        x.build_bvh(2, 4)
+    for tmin, tmax in ((0.0, np.inf), (0.5, 2.9)):
+        ro, rd = random_rays(80000, seed=32, tmin=tmin, tmax=tmax)
+        hg, ho = c.trace_closest(ro, rd), o.trace_closest(ro, rd, nthreads=8)
+        assert (hg["prim"] == ho["prim"]).all()
+        assert (hg["t"].view(np.uint32) == ho["t"].view(np.uint32)).all()
+        for k in range(4):
+            assert (ho["prim"] == 502 + k).sum() > 300, k  # every kind is hit
+        np.testing.assert_allclose(hg["b1"], ho["b1"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(hg["b2"], ho["b2"], rtol=1e-6, atol=1e-7)
+        assert (c.trace_any(ro, rd) == o.trace_any(ro, rd, nthreads=8)).all()
+    for k in ("offset", "n_primitives", "axis", "ordered", "bounds"):
+        assert np.array_equal(c.bvh_export()[k], o.bvh_export()[k]), k
+    # the reference's NaN hit for an axial ray inside a cylinder (tests/test_oracle_trace.py::test_cylinder_known_answers)
+    o2, c2 = Oracle(), capi.Context(0)
+    c2.set_kernel_variant(variant)
+    eye = np.eye(4, dtype=np.float32).reshape(16)
+    for x in (o2, c2):
+        x.set_triangles(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32))
+        x.set_spheres(np.zeros((0, 16), np.float32), np.zeros((0, 16), np.float32), np.zeros((0, 4)))
+        x.set_quadrics(2, eye, eye, [[0.5, -1.0, 2.0, 360.0, 0, 0, 0, 0]])
+        x.build_bvh(2, 4)
+    ro, rd = scenes.pack_rays(np.array([[0.1, 0.1, -5], [0.6, 0.1, -5], [-3, 0, 0.5]], np.float32),
+                              np.array([[0, 0, 1], [0, 0, 1], [1, 0, 0]], np.float32), 0.0, np.inf)
+    hg, ho = c2.trace_closest(ro, rd), o2.trace_closest(ro, rd)
+    assert (hg["prim"] == ho["prim"]).all() and list(ho["prim"]) == [0, -1, 0]
+    assert np.isnan(hg["t"][0]) and np.isnan(ho["t"][0]) and hg["t"][2] == ho["t"][2] == 2.5
+    assert (c2.trace_any(ro, rd) == o2.trace_any(ro, rd)).all()
+
+
 def test_known_answer_edge_cases(drt_lib, variant):
     """Same quirks the oracle test pins: inclusive triangle edges, strict flat-box culling and the
     NaN behaviour of the slab test for axis-parallel rays (bvh_accel.dart:441-471)."""
