@@ -19,7 +19,7 @@ HIT_DTYPE = np.dtype([("t", np.float32), ("b1", np.float32), ("b2", np.float32),
 
 # every symbol include/drt.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
-    "drt_version", "drt_create", "drt_destroy", "drt_last_error", "drt_set_triangles", "drt_set_spheres", "drt_set_disks", "drt_set_quadrics",
+    "drt_version", "drt_create", "drt_destroy", "drt_last_error", "drt_set_triangles", "drt_set_spheres", "drt_set_disks", "drt_set_quadrics", "drt_set_mesh_shading",
     "drt_set_build_order", "drt_build_bvh", "drt_bvh_info_get", "drt_bvh_export", "drt_trace_closest",
     "drt_trace_any", "drt_trace_closest_device", "drt_trace_any_device", "drt_set_counting", "drt_get_counters", "drt_set_kernel_variant",
     "drt_last_kernel_ms", "drt_kernel_launches",
@@ -75,6 +75,7 @@ def load():
     L.drt_set_spheres.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
     L.drt_set_disks.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
     L.drt_set_quadrics.argtypes = [vp, i32, u32, vp, vp, vp, vp, vp, vp]
+    L.drt_set_mesh_shading.argtypes = [vp, vp, vp, vp, vp, u32, vp, vp, vp]
     L.drt_set_build_order.argtypes = [vp, vp, u32]
     L.drt_build_bvh.argtypes = [vp, i32, i32]
     L.drt_bvh_info_get.argtypes = [vp, C.POINTER(BvhInfo)]
@@ -179,6 +180,14 @@ class Context:
         params = _arr(params, np.float64).reshape(-1, 8)
         m, l, r = _arr(material, np.int32), _arr(light, np.int32), _arr(reverse, np.uint8)
         self._ck(self.L.drt_set_quadrics(self.h, int(kind), o2w.shape[0], _p(o2w), _p(w2o), _p(params), _p(m), _p(l), _p(r)))
+
+    def set_mesh_shading(self, N, S, uv, mesh_of_tri, o2w, w2o, flags):
+        """Per-vertex N / S (object space) / uv (any may be None), mesh index per triangle, per-mesh transforms and flags
+        (bit 0 N, 1 S, 2 uv): what Triangle.getShadingGeometry reads (include/drt.h)."""
+        N, S, uv = _arr(N, np.float32), _arr(S, np.float32), _arr(uv, np.float32)
+        mot, flags = _arr(mesh_of_tri, np.uint32), _arr(flags, np.uint8)
+        o2w, w2o = _arr(o2w, np.float32).reshape(-1, 16), _arr(w2o, np.float32).reshape(-1, 16)
+        self._ck(self.L.drt_set_mesh_shading(self.h, _p(N), _p(S), _p(uv), _p(mot), o2w.shape[0], _p(o2w), _p(w2o), _p(flags)))
 
     def set_build_order(self, order):
         if order is None:

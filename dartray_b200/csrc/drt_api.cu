@@ -94,6 +94,8 @@ int drt_set_triangles(drt_ctx* c, const float* P, uint32_t nverts, const uint32_
     if (idx[i] >= nverts) return fail(c, DRT_E_INVALID, "triangle index out of range");  // triangle_mesh.dart:168-174
   c->P.assign(P, P + (size_t)nverts * 3);
   c->idx.assign(idx, idx + (size_t)ntris * 3);
+  c->vertN.clear(); c->vertS.clear(); c->vertUV.clear(); c->meshOfTri.clear();
+  c->meshO2W.clear(); c->meshW2O.clear(); c->meshFlags.clear();
   c->matOf.assign(ntris, 0);
   c->lightOf.assign(ntris, -1);
   c->revOf.assign(ntris, 0);
@@ -101,6 +103,29 @@ int drt_set_triangles(drt_ctx* c, const float* P, uint32_t nverts, const uint32_
   if (light) c->lightOf.assign(light, light + ntris);
   if (rev) c->revOf.assign(rev, rev + ntris);
   c->built = false;
+  return DRT_OK;
+}
+
+int drt_set_mesh_shading(drt_ctx* c, const float* N, const float* S, const float* uv, const uint32_t* meshOfTri, uint32_t nmeshes,
+                         const float* o2w, const float* w2o, const uint8_t* flags) {
+  if (!c) return DRT_E_INVALID;
+  c->vertN.clear(); c->vertS.clear(); c->vertUV.clear(); c->meshOfTri.clear();
+  c->meshO2W.clear(); c->meshW2O.clear(); c->meshFlags.clear();
+  c->buildSerial++;  // the render tables depend on it
+  if (nmeshes == 0) return DRT_OK;
+  if (!meshOfTri || !o2w || !w2o || !flags) return fail(c, DRT_E_INVALID, "null mesh arrays");
+  const size_t nv = c->P.size() / 3, nt = c->ntris();
+  for (size_t t = 0; t < nt; ++t)
+    if (meshOfTri[t] >= nmeshes) return fail(c, DRT_E_INVALID, "mesh index out of range");
+  if (N) c->vertN.assign(N, N + 3 * nv);
+  if (S) c->vertS.assign(S, S + 3 * nv);
+  if (uv) c->vertUV.assign(uv, uv + 2 * nv);
+  c->meshOfTri.assign(meshOfTri, meshOfTri + nt);
+  c->meshO2W.assign(o2w, o2w + 16 * (size_t)nmeshes);
+  c->meshW2O.assign(w2o, w2o + 16 * (size_t)nmeshes);
+  c->meshFlags.resize(nmeshes);
+  for (uint32_t m = 0; m < nmeshes; ++m)
+    c->meshFlags[m] = (uint8_t)(((flags[m] & 1) && N ? 1 : 0) | ((flags[m] & 2) && S ? 2 : 0) | ((flags[m] & 4) && uv ? 4 : 0));
   return DRT_OK;
 }
 
@@ -360,6 +385,8 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
   std::memcpy(c->ts.rootMax, B.rootMax, 12);
   c->ts.rootRef = B.rootRef;
   c->ts.empty = 0;
+  c->ts.quadMode = 0;
+  for (const HostSphere& hs : c->spheres) c->ts.quadMode = std::max(c->ts.quadMode, hs.shape >= 2 ? 2 : 1);
   c->info.n_nodes = (uint32_t)B.refNodes.size();
   c->info.n_prims = np;
   c->info.n_leaves = B.nLeaves;

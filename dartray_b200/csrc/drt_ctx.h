@@ -86,6 +86,12 @@ struct drt_ctx {
   bool exactWalk = false;
   double lastKernelMs = 0.0;
   uint64_t launches = 0;
+  // drt_set_mesh_shading: per-vertex N / S (object space) / uv, mesh of each triangle, per-mesh transforms + flags
+  std::vector<float> vertN, vertS, vertUV;
+  std::vector<uint32_t> meshOfTri;
+  std::vector<float> meshO2W, meshW2O;  // nmeshes x 16
+  std::vector<uint8_t> meshFlags;
+
   struct RenderState* render = nullptr;  // render_api.cu
 
   uint32_t ntris() const { return (uint32_t)(idx.size() / 3); }

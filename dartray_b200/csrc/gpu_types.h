@@ -94,6 +94,7 @@ struct TraceScene {
   float rootMin[3], rootMax[3];  // box of reference node 0, tested first (bvh_accel.dart:123-125)
   int32_t rootRef;
   int32_t empty;  // 1 -> no primitives (bvh_accel.dart:102-104)
+  int32_t quadMode;  // which leaf code the scene needs: 0 triangles only, 1 + spheres / disks, 2 + the other quadrics
 };
 
 struct DeviceCounters {

@@ -40,6 +40,10 @@ struct ByteArena {  // one cudaMalloc per wavefront, carved into aligned arrays
 
 }  // namespace
 
+// Stage launchers: the `extra` build of render_kernels.cu when the scene carries mesh attributes or the rarer quadrics
+// (RenderScene::extra), the `plain` build otherwise (render_kernels.h).
+#define STAGE(fn) (r->rs.extra ? drt::extra::fn : drt::plain::fn)
+
 struct RenderState {
   // host-side description
   std::vector<GMaterial> materials{GMaterial{{0.5f, 0.5f, 0.5f}, 0.f}};
@@ -62,6 +66,9 @@ struct RenderState {
   DevBuf<GLobe> dLobes;
   DevBuf<GLight> dLights;
   DevBuf<float> dLightCdf, dTable;
+  DevBuf<uint32_t> dMeshOfTri, dTriIdx;
+  DevBuf<GMesh> dMeshes;
+  DevBuf<float> dVertN, dVertS, dVertUV;
   DevBuf<DirectOffsets> dDirect;
   DevBuf<SampleArray> dArrays;
   DevBuf<double> dFilm;
@@ -96,6 +103,7 @@ void drtRenderStateDestroy(drt_ctx* c) {
   if (!r) return;
   r->dPrimToRec.release(); r->dPrimAttr.release(); r->dLightShapes.release(); r->dMaterials.release(); r->dLights.release();
   r->dLightCdf.release(); r->dTable.release(); r->dDirect.release(); r->dArrays.release();
+  r->dMeshOfTri.release(); r->dTriIdx.release(); r->dMeshes.release(); r->dVertN.release(); r->dVertS.release(); r->dVertUV.release();
   r->dFilm.release(); r->dCounters.release(); r->dRgb.release(); r->dXyz.release(); r->dWeight.release();
   if (r->wfMem) cudaFree(r->wfMem);
   delete r;
@@ -224,7 +232,13 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
       std::memcpy(ls.p1, p1, 12); std::memcpy(ls.p2, p2, 12); std::memcpy(ls.p3, p3, 12);
       const bool rev = c->revOf[sh] != 0;
       V3 dpdu, dpdv;
-      triPartials(t, &dpdu, &dpdv);
+      double uv[6] = {0.0, 0.0, 1.0, 0.0, 1.0, 1.0};
+      if (!c->meshOfTri.empty() && (c->meshFlags[c->meshOfTri[sh]] & 4))  // triangle.dart:246-254: the mesh's own uvs
+        for (int k = 0; k < 3; ++k) {
+          uv[2 * k] = c->vertUV[2 * (size_t)c->idx[3 * (size_t)sh + k]];
+          uv[2 * k + 1] = c->vertUV[2 * (size_t)c->idx[3 * (size_t)sh + k] + 1];
+        }
+      triPartialsUV(t, uv, &dpdu, &dpdv);
       V3 nn = shapeNormal(dpdu, dpdv, rev);  // the dg.nn Triangle.intersect leaves behind
       V3 ns = Normalize(Cross(t.p2 - t.p1, t.p3 - t.p1));  // triangle.dart:374-381
       if (rev) ns = mkv((double)ns.x * -1.0, (double)ns.y * -1.0, (double)ns.z * -1.0);
@@ -316,7 +330,44 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
   if (!shapes.empty()) CK(c, cudaMemcpy(r->dLightShapes.p, shapes.data(), shapes.size() * sizeof(GLightShape), cudaMemcpyHostToDevice));
   if (!cdf.empty()) CK(c, cudaMemcpy(r->dLightCdf.p, cdf.data(), cdf.size() * 4, cudaMemcpyHostToDevice));
   RenderScene& rs = r->rs;
+  rs.meshOfTri = nullptr; rs.triIdx = nullptr; rs.meshes = nullptr; rs.vertN = rs.vertS = rs.vertUV = nullptr;
+  if (!c->meshOfTri.empty() && nt > 0) {  // drt_set_mesh_shading
+    const size_t nm = c->meshFlags.size();
+    std::vector<GMesh> gm(nm);
+    for (size_t m = 0; m < nm; ++m) {
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+          gm[m].o2w[3 * a + b] = c->meshO2W[16 * m + 4 * a + b];
+          gm[m].w2o[3 * a + b] = c->meshW2O[16 * m + 4 * a + b];
+        }
+      gm[m].flags = c->meshFlags[m];
+      gm[m].pad_ = 0.f;
+    }
+    CK(c, r->dMeshOfTri.ensure(nt));
+    CK(c, r->dTriIdx.ensure(3 * (size_t)nt));
+    CK(c, r->dMeshes.ensure(nm));
+    CK(c, cudaMemcpy(r->dMeshOfTri.p, c->meshOfTri.data(), (size_t)nt * 4, cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpy(r->dTriIdx.p, c->idx.data(), 3 * (size_t)nt * 4, cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpy(r->dMeshes.p, gm.data(), nm * sizeof(GMesh), cudaMemcpyHostToDevice));
+    rs.meshOfTri = r->dMeshOfTri.p; rs.triIdx = r->dTriIdx.p; rs.meshes = r->dMeshes.p;
+    if (!c->vertN.empty()) {
+      CK(c, r->dVertN.ensure(c->vertN.size()));
+      CK(c, cudaMemcpy(r->dVertN.p, c->vertN.data(), c->vertN.size() * 4, cudaMemcpyHostToDevice));
+      rs.vertN = r->dVertN.p;
+    }
+    if (!c->vertS.empty()) {
+      CK(c, r->dVertS.ensure(c->vertS.size()));
+      CK(c, cudaMemcpy(r->dVertS.p, c->vertS.data(), c->vertS.size() * 4, cudaMemcpyHostToDevice));
+      rs.vertS = r->dVertS.p;
+    }
+    if (!c->vertUV.empty()) {
+      CK(c, r->dVertUV.ensure(c->vertUV.size()));
+      CK(c, cudaMemcpy(r->dVertUV.p, c->vertUV.data(), c->vertUV.size() * 4, cudaMemcpyHostToDevice));
+      rs.vertUV = r->dVertUV.p;
+    }
+  }
   rs.ts = c->ts;
+  rs.extra = (rs.meshOfTri != nullptr || c->ts.quadMode == 2) ? 1 : 0;
   rs.ntris = nt;
   rs.nprims = np;
   rs.primToRec = r->dPrimToRec.p;
@@ -480,7 +531,7 @@ static int directStage(drt_ctx* c, RenderState* r, int cur, bool weighted) {
   cudaStream_t st = c->stream;
   const int sms = c->numSMs;
   RenderCounters* rc = r->dCounters.p;
-  CK(c, launchDirectSetup(p, rs, wf, cur, weighted ? 1 : 0, sms, st));
+  CK(c, STAGE(launchDirectSetup)(p, rs, wf, cur, weighted ? 1 : 0, sms, st));
   c->launches++;
   if (rs.nLights <= 0) return DRT_OK;
   const bool one = p.strategy != 0;
@@ -488,8 +539,8 @@ static int directStage(drt_ctx* c, RenderState* r, int cur, bool weighted) {
   for (int li = 0; li < nL; ++li) {
     const int nS = one ? 1 : r->direct[li].nSamples;
     for (int j = 0; j < nS; ++j) {
-      CK(c, launchResetCounts(wf, (1u << Q_SHADOW) | (1u << Q_MIS), st));
-      CK(c, launchDirectSample(p, rs, wf, one ? -1 : li, j, cur, rc, sms, st));
+      CK(c, STAGE(launchResetCounts)(wf, (1u << Q_SHADOW) | (1u << Q_MIS), st));
+      CK(c, STAGE(launchDirectSample)(p, rs, wf, one ? -1 : li, j, cur, rc, sms, st));
       RK(traceQueue(c, true, wf.shO, wf.shD, wf.shRange, wf.counts + Q_SHADOW, wf.shOcc, nullptr, st));
       RK(traceQueue(c, false, wf.misO, wf.misD, wf.misRange, wf.counts + Q_MIS, wf.misHit, wf.misT, st));
       int mode = RESOLVE_DIRECT | (weighted ? RESOLVE_WEIGHTED : 0);
@@ -499,7 +550,7 @@ static int directStage(drt_ctx* c, RenderState* r, int cur, bool weighted) {
         if (j == nS - 1) mode |= RESOLVE_LAST_OF_LIGHT;
         if (j == nS - 1 && li == nL - 1) mode |= RESOLVE_FINAL;
       }
-      CK(c, launchResolveDirect(p, rs, wf, cur, mode, nS, sms, st));
+      CK(c, STAGE(launchResolveDirect)(p, rs, wf, cur, mode, nS, sms, st));
       c->launches += 3;
     }
   }
@@ -521,13 +572,13 @@ static int whittedStage(drt_ctx* c, RenderState* r, int cur, bool weighted) {
   cudaStream_t st = c->stream;
   const int sms = c->numSMs;
   RenderCounters* rc = r->dCounters.p;
-  CK(c, launchWhittedSetup(p, rs, wf, cur, weighted ? 1 : 0, sms, st));
+  CK(c, STAGE(launchWhittedSetup)(p, rs, wf, cur, weighted ? 1 : 0, sms, st));
   c->launches++;
   for (int li = 0; li < rs.nLights; ++li) {
-    CK(c, launchResetCounts(wf, (1u << Q_SHADOW) | (1u << Q_MIS), st));
-    CK(c, launchWhittedSample(p, rs, wf, li, cur, rc, sms, st));
+    CK(c, STAGE(launchResetCounts)(wf, (1u << Q_SHADOW) | (1u << Q_MIS), st));
+    CK(c, STAGE(launchWhittedSample)(p, rs, wf, li, cur, rc, sms, st));
     RK(traceQueue(c, true, wf.shO, wf.shD, wf.shRange, wf.counts + Q_SHADOW, wf.shOcc, nullptr, st));
-    CK(c, launchResolveDirect(p, rs, wf, cur, RESOLVE_DIRECT | RESOLVE_WHITTED | (weighted ? RESOLVE_WEIGHTED : 0), 1, sms, st));
+    CK(c, STAGE(launchResolveDirect)(p, rs, wf, cur, RESOLVE_DIRECT | RESOLVE_WHITTED | (weighted ? RESOLVE_WEIGHTED : 0), 1, sms, st));
     c->launches += 3;
   }
   return DRT_OK;
@@ -581,8 +632,8 @@ static int specularChains(drt_ctx* c, RenderState* r) {
     CK(c, cudaMemcpyAsync(wf.counts + Q_EXT0, &n0, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     int cur = 0;
     for (int k = 1; k <= len + 1; ++k) {
-      CK(c, launchResetCounts(wf, 1u << (cur ^ 1), st));
-      CK(c, launchSpecularStep(p, rs, wf, cur, kFlags[chain[k - 1]], k, k == len + 1 ? 1 : 0, rc, sms, st));
+      CK(c, STAGE(launchResetCounts)(wf, 1u << (cur ^ 1), st));
+      CK(c, STAGE(launchSpecularStep)(p, rs, wf, cur, kFlags[chain[k - 1]], k, k == len + 1 ? 1 : 0, rc, sms, st));
       c->launches += 2;
       cur ^= 1;
       RK(traceQueue(c, false, wf.extO[cur], wf.extD[cur], wf.extRange[cur], wf.counts + cur, wf.extHit, wf.extT, st));
@@ -610,9 +661,9 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
   const int sms = c->numSMs;
   const uint32_t nSlots = pb.nPixels * (uint32_t)p.nPixelSamples;
   RenderCounters* rc = r->dCounters.p;
-  CK(c, launchSampler(p, wf, r->dArrays.p, (int)r->arrays.size(), r->maxVals, r->maxOthers, pb, sms, st));
-  CK(c, launchResetCounts(wf, 0xffu, st));
-  CK(c, launchRaygen(p, wf, pb, st));
+  CK(c, STAGE(launchSampler)(p, wf, r->dArrays.p, (int)r->arrays.size(), r->maxVals, r->maxOthers, pb, sms, st));
+  CK(c, STAGE(launchResetCounts)(wf, 0xffu, st));
+  CK(c, STAGE(launchRaygen)(p, wf, pb, st));
   c->launches += 3;
   // camera rays: Scene.intersect (sampler_renderer.dart:84)
   RK(traceQueue(c, false, wf.extO[0], wf.extD[0], wf.extRange[0], wf.counts + Q_EXT0, wf.extHit, wf.extT, st));
@@ -621,13 +672,13 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
   if (p.integKind == 0) {
     int cur = 0;
     for (int bounce = 0; bounce <= p.maxDepth; ++bounce) {
-      CK(c, launchResetCounts(wf, (1u << (cur ^ 1)) | (1u << Q_SHADOW) | (1u << Q_MIS), st));
-      CK(c, launchShadePath(p, rs, wf, bounce, cur, rc, sms, st));
+      CK(c, STAGE(launchResetCounts)(wf, (1u << (cur ^ 1)) | (1u << Q_SHADOW) | (1u << Q_MIS), st));
+      CK(c, STAGE(launchShadePath)(p, rs, wf, bounce, cur, rc, sms, st));
       c->launches += 2;
       if (rs.nLights > 0) {
         RK(traceQueue(c, true, wf.shO, wf.shD, wf.shRange, wf.counts + Q_SHADOW, wf.shOcc, nullptr, st));
         RK(traceQueue(c, false, wf.misO, wf.misD, wf.misRange, wf.counts + Q_MIS, wf.misHit, wf.misT, st));
-        CK(c, launchResolveDirect(p, rs, wf, cur, RESOLVE_PATH, 1, sms, st));
+        CK(c, STAGE(launchResolveDirect)(p, rs, wf, cur, RESOLVE_PATH, 1, sms, st));
         c->launches++;
       }
       if (bounce == p.maxDepth) break;
@@ -635,14 +686,14 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
       RK(traceQueue(c, false, wf.extO[cur], wf.extD[cur], wf.extRange[cur], wf.counts + cur, wf.extHit, wf.extT, st));
     }
   } else if (p.integKind == 1) {
-    CK(c, launchAoSetup(p, rs, wf, sms, st));
+    CK(c, STAGE(launchAoSetup)(p, rs, wf, sms, st));
     c->launches++;
     const int nS = roundUpPow2(p.aoSamples);
     const uint32_t hitsPerChunk = std::max<uint32_t>(1, r->shCap / (uint32_t)nS);
     for (uint32_t first = 0; first < nSlots; first += hitsPerChunk) {
-      CK(c, launchAoGen(p, wf, first, hitsPerChunk, sms, st));
+      CK(c, STAGE(launchAoGen)(p, wf, first, hitsPerChunk, sms, st));
       RK(traceQueue(c, true, wf.shO, wf.shD, wf.shRange, wf.counts + Q_SHADOW, wf.shOcc, nullptr, st));
-      CK(c, launchAoCount(p, wf, first, hitsPerChunk, rc, sms, st));
+      CK(c, STAGE(launchAoCount)(p, wf, first, hitsPerChunk, rc, sms, st));
       c->launches += 2;
     }
   } else {  // directlighting / whitted: the integrator at the camera vertices, then its specular recursion
@@ -650,7 +701,7 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
     RK(integratorStage(c, r, 0, false));
     if (wf.specCtr && r->hasSpecular) RK(specularChains(c, r));
   }
-  CK(c, launchFilm(p, wf, nSlots, rc, st));
+  CK(c, STAGE(launchFilm)(p, wf, nSlots, rc, st));
   c->launches++;
   return DRT_OK;
 }
@@ -945,7 +996,7 @@ int drt_film_read(drt_ctx* c, float* rgb, float* xyz, float* weight) {
   CK(c, r->dXyz.ensure(3 * n));
   CK(c, r->dWeight.ensure(n));
   CK(c, cudaDeviceSynchronize());  // the film may have been summed across GPUs on another stream
-  CK(c, launchFilmConvert(r->rp, rgb ? r->dRgb.p : nullptr, xyz ? r->dXyz.p : nullptr, weight ? r->dWeight.p : nullptr, c->stream));
+  CK(c, STAGE(launchFilmConvert)(r->rp, rgb ? r->dRgb.p : nullptr, xyz ? r->dXyz.p : nullptr, weight ? r->dWeight.p : nullptr, c->stream));
   c->launches++;
   if (rgb) CK(c, cudaMemcpyAsync(rgb, r->dRgb.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   if (xyz) CK(c, cudaMemcpyAsync(xyz, r->dXyz.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -962,7 +1013,7 @@ int drt_pixel_samples(drt_ctx* c, int x, int y, float* out, int cap, int32_t* n_
   const uint32_t n = (uint32_t)p.nPixelSamples;
   RK(ensureWavefront(c, r, n, n));
   PixelBatch pb{x, y, 1, 0, 1, 0, 0, 1, 1024};
-  CK(c, launchSampler(p, r->wf, r->dArrays.p, (int)r->arrays.size(), r->maxVals, r->maxOthers, pb, c->numSMs, c->stream));
+  CK(c, STAGE(launchSampler)(p, r->wf, r->dArrays.p, (int)r->arrays.size(), r->maxVals, r->maxOthers, pb, c->numSMs, c->stream));
   c->launches++;
   std::vector<double2> xy(n), lens(n);
   std::vector<float> tm(n), vals((size_t)std::max(p.nVals, 1) * n);

@@ -21,7 +21,12 @@
 #include "render_kernels.h"
 #include "shade_device.cuh"
 
+#ifndef DRT_RK_NS
+#define DRT_RK_NS extra  // this file as it stands; render_kernels_plain.cu includes it again with DRT_EXTRA = 0 / plain
+#endif
+
 namespace drt {
+namespace DRT_RK_NS {
 
 #define FULL 0xffffffffu
 
@@ -373,7 +378,8 @@ static __device__ __forceinline__ void pushDirectWork(const Wavefront& wf, uint3
 #define DRT_SHADE_MIN_BLOCKS 4  // 128 registers: 16 warps/SM; 321 vs 277 Msamples/s at 2 (tools/shade_sweep.sh)
 #endif
 // GENERAL = false: every material is matte (one diffuse BxDF, never a specular bounce); true: BxDF lists.
-template <bool GENERAL>
+// EXTRA: see hitGeometry (shade_device.cuh).
+template <bool GENERAL, bool EXTRA>
 __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(RenderParams rp, RenderScene rs, Wavefront wf, int bounce, int cur,
                                                        RenderCounters* rc) {
   const uint32_t n = wf.counts[cur], cap = wf.cap;
@@ -401,7 +407,7 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(Ren
       const float4 o4 = wf.extO[cur][q], d4 = wf.extD[cur][q];
       const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
       ShapeHit h;
-      hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
+      hitGeometry<EXTRA>(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
       Spec T = ld3(wf.T, cap, slot);
       const V3 wo = -d;
       // emitted light at the first vertex or after a specular bounce (:46-48); matte BSDFs never set specularBounce
@@ -413,7 +419,7 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(Ren
           st3(wf.L, cap, slot, L);
         }
       }
-      const typename BsdfOf<GENERAL>::type bsdf = makeBsdfT<GENERAL>(rs, (uint32_t)prim, h);
+      const typename BsdfOf<GENERAL>::type bsdf = makeBsdfT<GENERAL, EXTRA>(rs, (uint32_t)prim, h, o, d);
       p = h.p;
       rayEps = h.rayEps;
       const V3 nrm = bsdf.nn;
@@ -491,6 +497,7 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(Ren
 // Finishes Integrator.EstimateDirect (integrator.dart:119-185) once the shadow and MIS rays of the
 // vertices shaded from extension queue `cur` are traced, and adds the estimate where the integrator
 // adds it.  mode: see RESOLVE_* (render_kernels.h).
+template <bool EXTRA>
 __global__ void __launch_bounds__(128) resolveDirectKernel(RenderParams rp, RenderScene rs, Wavefront wf, int cur, int mode,
                                                            int nSamplesOfLight) {
   const uint32_t n = wf.counts[cur], cap = wf.cap;
@@ -512,7 +519,7 @@ __global__ void __launch_bounds__(128) resolveDirectKernel(RenderParams rp, Rend
         const float4 o4 = wf.misO[mi], d4 = wf.misD[mi];
         const V3 o = V3{o4.x, o4.y, o4.z}, wi = V3{d4.x, d4.y, d4.z};
         ShapeHit h;
-        hitGeometry(rs, (uint32_t)prim, o, wi, wf.misT[mi], &h);
+        hitGeometry<EXTRA>(rs, (uint32_t)prim, o, wi, wf.misT[mi], &h);
         Spec Li = areaL(rs.lights[light], h.nn, -wi);  // Intersection.Le, intersection.dart:62-65
         if (!IsBlack(Li)) {
           Li = Li * mks1(1.0);
@@ -684,7 +691,7 @@ __global__ void __launch_bounds__(128) whittedSampleKernel(RenderParams rp, Rend
       const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
       ShapeHit h;
       hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
-      const typename BsdfOf<GENERAL>::type bsdf = makeBsdfT<GENERAL>(rs, (uint32_t)prim, h);
+      const typename BsdfOf<GENERAL>::type bsdf = makeBsdfT<GENERAL>(rs, (uint32_t)prim, h, o, d);
       p = h.p;
       rayEps = h.rayEps;
       Stream rng{integratorKey(rp, wf, slot), (uint64_t)wf.aoScramble[slot] + 3ull * (uint64_t)light};
@@ -734,7 +741,7 @@ __global__ void __launch_bounds__(128) specularStepKernel(RenderParams rp, Rende
         const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
         ShapeHit h;
         hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
-        const BsdfG bsdf = makeBsdfG(rs, (uint32_t)prim, h);
+        const BsdfG bsdf = makeBsdfG(rs, (uint32_t)prim, h, o, d);
         double pdf = 0.0;
         int type = 0;
         const Spec f = bsdfSampleF(bsdf, -d, &wi, u0, u1, comp, &pdf, flags, &type);
@@ -786,7 +793,7 @@ __global__ void __launch_bounds__(128) directSampleKernel(RenderParams rp, Rende
       const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
       ShapeHit h;
       hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
-      const typename BsdfOf<GENERAL>::type bsdf = makeBsdfT<GENERAL>(rs, (uint32_t)prim, h);
+      const typename BsdfOf<GENERAL>::type bsdf = makeBsdfT<GENERAL>(rs, (uint32_t)prim, h, o, d);
       p = h.p;
       rayEps = h.rayEps;
       DirectOffsets off;
@@ -934,14 +941,15 @@ cudaError_t launchResetCounts(const Wavefront& wf, unsigned mask, cudaStream_t s
 
 cudaError_t launchShadePath(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int bounce, int cur,
                             RenderCounters* rc, int numSMs, cudaStream_t st) {
-  if (rs.general) shadePathKernel<true><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, bounce, cur, rc);
-  else shadePathKernel<false><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, bounce, cur, rc);
+  const int grid = gridFor(wf.cap, 128, numSMs, 8);
+  if (rs.general) shadePathKernel<true, DRT_EXTRA != 0><<<grid, 128, 0, st>>>(rp, rs, wf, bounce, cur, rc);
+  else shadePathKernel<false, DRT_EXTRA != 0><<<grid, 128, 0, st>>>(rp, rs, wf, bounce, cur, rc);
   return cudaGetLastError();
 }
 
 cudaError_t launchResolveDirect(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int cur, int mode,
                                 int nSamplesOfLight, int numSMs, cudaStream_t st) {
-  resolveDirectKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, cur, mode, nSamplesOfLight);
+  resolveDirectKernel<DRT_EXTRA != 0><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, cur, mode, nSamplesOfLight);
   return cudaGetLastError();
 }
 
@@ -1014,4 +1022,5 @@ cudaError_t launchFilmConvert(const RenderParams& rp, float* rgb, float* xyz, fl
   return cudaGetLastError();
 }
 
+}  // namespace DRT_RK_NS
 }  // namespace drt

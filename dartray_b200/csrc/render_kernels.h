@@ -23,38 +23,15 @@ struct PixelBatch {
 
 enum { Q_EXT0 = 0, Q_EXT1 = 1, Q_SHADOW = 2, Q_MIS = 3, Q_HITS = 4, Q_COUNT = 8 };
 
-cudaError_t launchSampler(const RenderParams& rp, const Wavefront& wf, const SampleArray* dArrays, int nArrays, int maxVals,
-                          int maxOthers, const PixelBatch& pb, int numSMs, cudaStream_t st);
-cudaError_t launchRaygen(const RenderParams& rp, const Wavefront& wf, const PixelBatch& pb, cudaStream_t st);
-cudaError_t launchResetCounts(const Wavefront& wf, unsigned mask, cudaStream_t st);
-// path integrator
-cudaError_t launchShadePath(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int bounce, int cur,
-                            RenderCounters* rc, int numSMs, cudaStream_t st);
-cudaError_t launchResolveDirect(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int cur, int mode,
-                                int nSamplesOfLight, int numSMs, cudaStream_t st);
-// ambient occlusion
-cudaError_t launchAoSetup(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int numSMs, cudaStream_t st);
-cudaError_t launchAoGen(const RenderParams& rp, const Wavefront& wf, uint32_t firstHit, uint32_t maxHits, int numSMs,
-                        cudaStream_t st);
-cudaError_t launchAoCount(const RenderParams& rp, const Wavefront& wf, uint32_t firstHit, uint32_t maxHits, RenderCounters* rc,
-                          int numSMs, cudaStream_t st);
-// direct lighting
-cudaError_t launchDirectSetup(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int cur, int weighted, int numSMs,
-                              cudaStream_t st);
-cudaError_t launchDirectSample(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int light, int j, int cur,
-                               RenderCounters* rc, int numSMs, cudaStream_t st);
-// whitted integrator (whitted_integrator.dart:26-78): emitted light + stream positions, then one launch per light
-cudaError_t launchWhittedSetup(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int cur, int weighted, int numSMs,
-                               cudaStream_t st);
-cudaError_t launchWhittedSample(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int light, int cur,
-                                RenderCounters* rc, int numSMs, cudaStream_t st);
-// one SpecularReflect / SpecularTransmit call per vertex of queue `cur` (flags: BSDF_REFLECTION | BSDF_SPECULAR = 17 or
-// BSDF_TRANSMISSION | BSDF_SPECULAR = 18); children go to queue cur ^ 1
-cudaError_t launchSpecularStep(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int cur, int flags, int level,
-                               int isNew, RenderCounters* rc, int numSMs, cudaStream_t st);
-// film
-cudaError_t launchFilm(const RenderParams& rp, const Wavefront& wf, uint32_t nSlots, RenderCounters* rc, cudaStream_t st);
-cudaError_t launchFilmConvert(const RenderParams& rp, float* rgb, float* xyz, float* weight, cudaStream_t st);
+// render_kernels.cu is compiled twice (shade_device.cuh, DRT_EXTRA): `plain` without per-vertex mesh attributes and the
+// cylinder / cone / paraboloid / hyperboloid shapes — the kernels the benchmark scenes run, byte for byte what they were
+// before those features existed — and `extra` with them.  render_api.cu picks by RenderScene::extra.
+namespace plain {
+#include "render_launchers.inc"
+}
+namespace extra {
+#include "render_launchers.inc"
+}
 
 // resolve mode bits: 1 = direct-lighting integrator (0 = path), 2 = first sample of a light, 4 = last sample of a
 // light, 8 = last light (add the sum to L), 16 = strategy "one", 32 = the vertices belong to a specular chain: weight the

@@ -57,6 +57,14 @@ struct GLightShape {
   double area;
 };
 
+// One TriangleMesh of drt_set_mesh_shading: the upper 3x3 of objectToWorld (Transform.transformVector) and of
+// worldToObject (Transform.transformNormal multiplies by its transpose, transform.dart:147-161), and the attribute flags.
+struct GMesh {
+  float o2w[9], w2o[9];
+  uint32_t flags;  // bit 0 N, 1 S, 2 uv
+  float pad_;
+};
+
 struct RenderScene {
   TraceScene ts;
   uint32_t ntris, nprims;
@@ -71,6 +79,12 @@ struct RenderScene {
   int32_t nLights;
   const GLightShape* lightShapes;
   const float* lightCdf;
+  // per-vertex shading attributes (null when no mesh carries any: triangle.dart:273-276 copies dg)
+  const uint32_t* meshOfTri;  // ntris
+  const uint32_t* triIdx;     // ntris x 3 vertex indices
+  const GMesh* meshes;
+  const float* vertN; const float* vertS; const float* vertUV;
+  int32_t extra;  // 1: mesh attributes or quadrics of shape >= 2 are present (selects the kernels compiled with EXTRA)
 };
 
 struct RenderParams {

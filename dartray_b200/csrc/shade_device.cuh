@@ -16,6 +16,12 @@
 
 namespace drt {
 
+// DRT_EXTRA = 0 compiles the shading code WITHOUT per-vertex mesh attributes and the cylinder / cone / paraboloid /
+// hyperboloid shapes: render_kernels.cu is built twice (plain / extra, see render_kernels_extra.cu) and the launchers pick
+// by RenderScene::extra, so the kernels the benchmark scenes run carry no trace of the rare features.
+#ifndef DRT_EXTRA
+#define DRT_EXTRA 1
+#endif
 #define DRT_PI 3.141592653589793
 #define DRT_INV_PI 0.31830988618379067154
 #define DRT_INV_TWOPI 0.15915494309189533577
@@ -201,6 +207,23 @@ static DRT_HD inline void triPartials(const TriVerts& t, V3* dpdu, V3* dpdv) {
   V3 dp1 = t.p1 - t.p3, dp2 = t.p2 - t.p3;
   *dpdu = ((dp1 * -1.0) - (dp2 * -1.0)) * 1.0;
   *dpdv = ((dp1 * -0.0) + (dp2 * -1.0)) * 1.0;
+}
+// triangle.dart:104-131 with the mesh's own uvs (getUVs, :246-254)
+static DRT_HD inline void triPartialsUV(const TriVerts& t, const double uv[6], V3* dpdu, V3* dpdv) {
+  double du1 = uv[0] - uv[4], du2 = uv[2] - uv[4], dv1 = uv[1] - uv[5], dv2 = uv[3] - uv[5];
+  V3 dp1 = t.p1 - t.p3, dp2 = t.p2 - t.p3;
+  double determinant = du1 * dv2 - dv1 * du2;
+  if (determinant == 0.0) {
+    double e1x = (double)t.p2.x - t.p1.x, e1y = (double)t.p2.y - t.p1.y, e1z = (double)t.p2.z - t.p1.z;
+    double e2x = (double)t.p3.x - t.p1.x, e2y = (double)t.p3.y - t.p1.y, e2z = (double)t.p3.z - t.p1.z;
+    double e3x = (e2y * e1z) - (e2z * e1y), e3y = (e2z * e1x) - (e2x * e1z), e3z = (e2x * e1y) - (e2y * e1x);
+    double len = sqrt(e3x * e3x + e3y * e3y + e3z * e3z);
+    CoordinateSystem(mkv(e3x / len, e3y / len, e3z / len), dpdu, dpdv);
+  } else {
+    double invdet = 1.0 / determinant;
+    *dpdu = ((dp1 * dv2) - (dp2 * dv1)) * invdet;
+    *dpdv = ((dp1 * -du2) + (dp2 * du1)) * invdet;
+  }
 }
 static DRT_HD inline V3 shapeNormal(const V3& dpdu, const V3& dpdv, bool reverse) {  // differential_geometry.dart:77-99
   V3 nn = Normalize(Cross(dpdu, dpdv));
@@ -460,16 +483,124 @@ static __device__ inline bool primReverse(const RenderScene& rs, uint32_t prim) 
 static __device__ inline int primLight(const RenderScene& rs, uint32_t prim) { return (int)((__ldg(rs.primAttr + prim) >> 16) & 0x7fffu) - 1; }
 static __device__ inline int primMaterial(const RenderScene& rs, uint32_t prim) { return (int)(__ldg(rs.primAttr + prim) & 0xffffu); }
 
+// A triangle of a mesh that carries uv / N / S (drt_set_mesh_shading).  Two out-of-line pieces — meshes without attributes
+// (the benchmark scenes) never come here, and no address of the caller's ShapeHit escapes into them:
+//   triMeshDgCold       dg.dpdu / dg.nn from the mesh's own uvs (triangle.dart:104-131, getUVs :246-254)
+//   triMeshShadingCold  Triangle.getShadingGeometry (:271-364): dgShading.nn and dgShading.dpdu.  The barycentrics are
+//                       re-derived from the ray with the expressions of Triangle.intersect (:52-95), i.e. the values the
+//                       reference holds at this point.
+struct MeshGeom {
+  V3 a, b;
+};
+static __device__ inline void meshTriUVs(const RenderScene& rs, const GMesh& mesh, uint32_t i0, uint32_t i1, uint32_t i2, double uv[6]) {
+  uv[0] = 0.0; uv[1] = 0.0; uv[2] = 1.0; uv[3] = 0.0; uv[4] = 1.0; uv[5] = 1.0;
+  if (mesh.flags & 4u) {
+    uv[0] = rs.vertUV[2 * (size_t)i0]; uv[1] = rs.vertUV[2 * (size_t)i0 + 1];
+    uv[2] = rs.vertUV[2 * (size_t)i1]; uv[3] = rs.vertUV[2 * (size_t)i1 + 1];
+    uv[4] = rs.vertUV[2 * (size_t)i2]; uv[5] = rs.vertUV[2 * (size_t)i2 + 1];
+  }
+}
+static __device__ __noinline__ void triMeshDgCold(const RenderScene& rs, uint32_t prim, bool rev, MeshGeom* out) {
+  const GMesh& mesh = rs.meshes[__ldg(rs.meshOfTri + prim)];
+  const uint32_t i0 = __ldg(rs.triIdx + 3 * (size_t)prim), i1 = __ldg(rs.triIdx + 3 * (size_t)prim + 1),
+                 i2 = __ldg(rs.triIdx + 3 * (size_t)prim + 2);
+  const TriVerts tv = loadTri(rs, prim);
+  double uv[6];
+  meshTriUVs(rs, mesh, i0, i1, i2, uv);
+  V3 dpdu, dpdv;
+  triPartialsUV(tv, uv, &dpdu, &dpdv);
+  out->a = dpdu;
+  out->b = shapeNormal(dpdu, dpdv, rev);
+}
+static __device__ __noinline__ void triMeshShadingCold(const RenderScene& rs, uint32_t prim, V3 o, V3 d, bool rev, V3 nn, V3 dpdu,
+                                                       MeshGeom* out) {
+  out->a = nn;    // dgShading.nn
+  out->b = dpdu;  // dgShading.dpdu
+  const GMesh& mesh = rs.meshes[__ldg(rs.meshOfTri + prim)];
+  if (!(mesh.flags & 3u)) return;  // triangle.dart:273-276
+  const uint32_t i0 = __ldg(rs.triIdx + 3 * (size_t)prim), i1 = __ldg(rs.triIdx + 3 * (size_t)prim + 1),
+                 i2 = __ldg(rs.triIdx + 3 * (size_t)prim + 2);
+  const TriVerts tv = loadTri(rs, prim);
+  double uv[6];
+  meshTriUVs(rs, mesh, i0, i1, i2, uv);
+  // b1, b2 of Triangle.intersect (:52-95)
+  double p1x = tv.p1.x, p1y = tv.p1.y, p1z = tv.p1.z;
+  double e1x = (double)tv.p2.x - p1x, e1y = (double)tv.p2.y - p1y, e1z = (double)tv.p2.z - p1z;
+  double e2x = (double)tv.p3.x - p1x, e2y = (double)tv.p3.y - p1y, e2z = (double)tv.p3.z - p1z;
+  double dx = d.x, dy = d.y, dz = d.z;
+  double s1x = (dy * e2z) - (dz * e2y), s1y = (dz * e2x) - (dx * e2z), s1z = (dx * e2y) - (dy * e2x);
+  double invDivisor = 1.0 / ((s1x * e1x) + (s1y * e1y) + (s1z * e1z));
+  double sx = (double)o.x - p1x, sy = (double)o.y - p1y, sz = (double)o.z - p1z;
+  double b1 = (sx * s1x + sy * s1y + sz * s1z) * invDivisor;
+  double s2x = (sy * e1z) - (sz * e1y), s2y = (sz * e1x) - (sx * e1z), s2z = (sx * e1y) - (sy * e1x);
+  double b2 = ((dx * s2x) + (dy * s2y) + (dz * s2z)) * invDivisor;
+  double b0 = 1.0 - b1 - b2;
+  double tu = b0 * uv[0] + b1 * uv[2] + b2 * uv[4], tv_ = b0 * uv[1] + b1 * uv[3] + b2 * uv[5];
+  // getShadingGeometry: barycentrics back from (u, v) by SolveLinearSystem2x2 (common.dart:170-185)
+  double A0 = uv[2] - uv[0], A1 = uv[4] - uv[0], A2 = uv[3] - uv[1], A3 = uv[5] - uv[1];
+  double C0 = tu - uv[0], C1 = tv_ - uv[1];
+  double det = A0 * A3 - A1 * A2, bx, by = 0.0, bz = 0.0;
+  bool ok = !(fabs(det) < 1.0e-10);
+  if (ok) {
+    by = (A3 * C0 - A1 * C1) / det;
+    bz = (A0 * C1 - A2 * C0) / det;
+    if (isnan(by) || isnan(bz)) ok = false;
+  }
+  if (!ok) bx = by = bz = 1.0 / 3.0;
+  else bx = 1.0 - by - bz;
+  V3 ns, ss, ts;
+  if (mesh.flags & 1u) {
+    const float* n = rs.vertN;
+    V3 n0 = V3{n[3 * (size_t)i0], n[3 * (size_t)i0 + 1], n[3 * (size_t)i0 + 2]}, n1 = V3{n[3 * (size_t)i1], n[3 * (size_t)i1 + 1], n[3 * (size_t)i1 + 2]},
+       n2 = V3{n[3 * (size_t)i2], n[3 * (size_t)i2 + 1], n[3 * (size_t)i2 + 2]};
+    V3 ni = ((n0 * bx) + (n1 * by)) + (n2 * bz);
+    const float* w = mesh.w2o;  // transformNormal: transpose of the inverse (transform.dart:147-161)
+    ns = Normalize(mkv((double)w[0] * ni.x + (double)w[3] * ni.y + (double)w[6] * ni.z, (double)w[1] * ni.x + (double)w[4] * ni.y + (double)w[7] * ni.z,
+                       (double)w[2] * ni.x + (double)w[5] * ni.y + (double)w[8] * ni.z));
+  } else {
+    ns = nn;
+  }
+  if (mesh.flags & 2u) {
+    const float* sv = rs.vertS;
+    V3 s0 = V3{sv[3 * (size_t)i0], sv[3 * (size_t)i0 + 1], sv[3 * (size_t)i0 + 2]}, s1 = V3{sv[3 * (size_t)i1], sv[3 * (size_t)i1 + 1], sv[3 * (size_t)i1 + 2]},
+       s2 = V3{sv[3 * (size_t)i2], sv[3 * (size_t)i2 + 1], sv[3 * (size_t)i2 + 2]};
+    V3 si = ((s0 * bx) + (s1 * by)) + (s2 * bz);
+    const float* m = mesh.o2w;
+    ss = Normalize(mkv((double)m[0] * si.x + (double)m[1] * si.y + (double)m[2] * si.z, (double)m[3] * si.x + (double)m[4] * si.y + (double)m[5] * si.z,
+                       (double)m[6] * si.x + (double)m[7] * si.y + (double)m[8] * si.z));
+  } else {
+    ss = Normalize(dpdu);
+  }
+  ts = Cross(ss, ns);
+  if (LengthSquared(ts) > 0.0) {
+    ts = Normalize(ts);
+    ss = Cross(ts, ns);
+  } else {
+    CoordinateSystem(ns, &ss, &ts);
+  }
+  out->a = shapeNormal(ss, ts, rev);  // dgShading.set(dg.p, ss, ts, ...): differential_geometry.dart:77-99
+  out->b = ss;
+}
+
 // Differential geometry of a hit found by the traversal kernels (lib/core/intersection.dart:27-72):
 // the shape is re-evaluated at the known tHit, which reproduces what Shape.intersect stored.
+// EXTRA = false: the scene has neither per-vertex mesh attributes nor cylinder / cone / paraboloid / hyperboloid shapes
+// (RenderScene::extra == 0); their out-of-line calls are compiled out of the kernels config 3 / 4 run.
+template <bool EXTRA = (DRT_EXTRA != 0)>
 static __device__ inline void hitGeometry(const RenderScene& rs, uint32_t prim, const V3& o, const V3& d, double t, ShapeHit* h) {
   h->t = t;
   V3 dpdv;
   if (prim < rs.ntris) {
     TriVerts tv = loadTri(rs, prim);
-    triPartials(tv, &h->dpdu, &dpdv);
     h->p = RayAt(o, d, t);
     h->rayEps = 1.0e-3 * t;  // triangle.dart:157
+    if (EXTRA && rs.meshOfTri) {  // through a temporary: the address of *h must not escape into an out-of-line call
+      MeshGeom mg;
+      triMeshDgCold(rs, prim, primReverse(rs, prim), &mg);
+      h->dpdu = mg.a; h->nn = mg.b;
+      return;
+    }
+    triPartials(tv, &h->dpdu, &dpdv);
   } else {
     const GSphere& s = rs.ts.spheres[prim - rs.ntris];
     // object-space hit point at tHit: ray.pointAt on the transformed ray (sphere.dart:62-64 / :95-97)
@@ -478,8 +609,10 @@ static __device__ inline void hitGeometry(const RenderScene& rs, uint32_t prim, 
     for (int i = 0; i < 4; ++i) w2o[12 + i] = s.w2oRow3[i];
     V3 ro = XfPoint(w2o, o), rd = XfVector(w2o, d);
     V3 phit = RayAt(ro, rd, t);
-    if (s.shape >= 2) {
-      quadricPartialsCold(s, phit, &h->p, &h->dpdu, &dpdv);
+    if (EXTRA && s.shape >= 2) {  // results through temporaries: the address of *h must not escape into an out-of-line call
+      V3 qp, qu, qv;
+      quadricPartialsCold(s, phit, &qp, &qu, &qv);
+      h->p = qp; h->dpdu = qu; dpdv = qv;
     } else if (s.shape == 1) {
       diskPartials(s, phit, &h->p, &h->dpdu, &dpdv);
     } else {
@@ -503,16 +636,25 @@ static __device__ DRT_SHAPE_INLINE bool shapeIntersect(const RenderScene& rs, ui
     TriVerts tv = loadTri(rs, prim);
     double t;
     if (!triIntersectT(tv, o, d, mint, maxt, &t)) return false;
-    triPartials(tv, &h->dpdu, &dpdv);
     h->t = t;
     h->p = RayAt(o, d, t);
     h->rayEps = 1.0e-3 * t;
+    if (DRT_EXTRA && rs.meshOfTri) {
+      MeshGeom mg;
+      triMeshDgCold(rs, prim, primReverse(rs, prim), &mg);
+      h->dpdu = mg.a; h->nn = mg.b;
+      return true;
+    }
+    triPartials(tv, &h->dpdu, &dpdv);
   } else {
     const GSphere& s = rs.ts.spheres[prim - rs.ntris];
     double t;
     V3 phit;
-    if (s.shape >= 2) {
-      if (!quadricIntersectCold(s, o, d, mint, maxt, &t, &h->p, &h->dpdu, &dpdv)) return false;
+    if (DRT_EXTRA && s.shape >= 2) {
+      V3 qp, qu, qv;
+      double qt;
+      if (!quadricIntersectCold(s, o, d, mint, maxt, &qt, &qp, &qu, &qv)) return false;
+      t = qt; h->p = qp; h->dpdu = qu; dpdv = qv;
     } else if (s.shape == 1) {
       if (!diskIntersectT(s, o, d, mint, maxt, &t, &phit)) return false;
       diskPartials(s, phit, &h->p, &h->dpdu, &dpdv);
@@ -558,11 +700,27 @@ static __device__ inline double SinTheta(const V3& v) { return sqrt(SinTheta2(v)
 static __device__ inline double CosPhi(const V3& v) { double s = SinTheta(v); return s == 0.0 ? 1.0 : clampD((double)v.x / s, -1.0, 1.0); }
 static __device__ inline double SinPhi(const V3& v) { double s = SinTheta(v); return s == 0.0 ? 0.0 : clampD((double)v.y / s, -1.0, 1.0); }
 
-static __device__ inline Bsdf makeBsdf(const RenderScene& rs, uint32_t prim, const ShapeHit& h) {
+// dgShading.nn / dgShading.dpdu of the hit: dg's own for meshes without N / S (triangle.dart:273-276) and quadrics
+// (shape.dart:73-77).  o, d: the ray that found the hit.
+template <bool EXTRA>
+static __device__ inline void shadingFrame(const RenderScene& rs, uint32_t prim, const ShapeHit& h, const V3& o, const V3& d, V3* nsh,
+                                           V3* ssh) {
+  *nsh = h.nn;
+  *ssh = h.dpdu;
+  if (EXTRA && rs.meshOfTri && prim < rs.ntris) {
+    MeshGeom mg;
+    triMeshShadingCold(rs, prim, o, d, primReverse(rs, prim), h.nn, h.dpdu, &mg);
+    *nsh = mg.a;
+    *ssh = mg.b;
+  }
+}
+template <bool EXTRA = (DRT_EXTRA != 0)>
+static __device__ inline Bsdf makeBsdf(const RenderScene& rs, uint32_t prim, const ShapeHit& h, const V3& o, const V3& d) {
   Bsdf b;
-  b.nn = h.nn;  // dgShading == dg: meshes without N/S (triangle.dart:273-276), spheres
+  V3 ssh;
+  shadingFrame<EXTRA>(rs, prim, h, o, d, &b.nn, &ssh);
   b.ng = h.nn;
-  b.sn = Normalize(h.dpdu);
+  b.sn = Normalize(ssh);
   b.tn = Cross(b.nn, b.sn);
   const GMaterial m = rs.materials[primMaterial(rs, prim)];
   Spec r = mks(clampD(m.kd[0], 0.0, CUDART_INF), clampD(m.kd[1], 0.0, CUDART_INF), clampD(m.kd[2], 0.0, CUDART_INF));
@@ -651,11 +809,13 @@ static __device__ inline V3 bsdfToWorld(const BsdfG& b, const V3& v) {
              (double)b.sn.y * v.x + (double)b.tn.y * v.y + (double)b.nn.y * v.z,
              (double)b.sn.z * v.x + (double)b.tn.z * v.y + (double)b.nn.z * v.z);
 }
-static __device__ inline BsdfG makeBsdfG(const RenderScene& rs, uint32_t prim, const ShapeHit& h) {
+template <bool EXTRA = (DRT_EXTRA != 0)>
+static __device__ inline BsdfG makeBsdfG(const RenderScene& rs, uint32_t prim, const ShapeHit& h, const V3& o, const V3& d) {
   BsdfG b;
-  b.nn = h.nn;
+  V3 ssh;
+  shadingFrame<EXTRA>(rs, prim, h, o, d, &b.nn, &ssh);
   b.ng = h.nn;
-  b.sn = Normalize(h.dpdu);
+  b.sn = Normalize(ssh);
   b.tn = Cross(b.nn, b.sn);
   const uint2 ml = __ldg(rs.matLobes + primMaterial(rs, prim));
   b.lobes = rs.lobes + ml.x;
@@ -854,10 +1014,25 @@ static __device__ inline Spec bsdfSampleF(const BsdfG& b, const V3& woW, V3* wiW
 
 template <bool GENERAL> struct BsdfOf { typedef Bsdf type; };
 template <> struct BsdfOf<true> { typedef BsdfG type; };
-template <bool GENERAL>
-static __device__ inline typename BsdfOf<GENERAL>::type makeBsdfT(const RenderScene& rs, uint32_t prim, const ShapeHit& h);
-template <> __device__ inline Bsdf makeBsdfT<false>(const RenderScene& rs, uint32_t prim, const ShapeHit& h) { return makeBsdf(rs, prim, h); }
-template <> __device__ inline BsdfG makeBsdfT<true>(const RenderScene& rs, uint32_t prim, const ShapeHit& h) { return makeBsdfG(rs, prim, h); }
+template <bool GENERAL, bool EXTRA>
+struct MakeBsdf;
+template <bool EXTRA>
+struct MakeBsdf<false, EXTRA> {
+  static __device__ inline Bsdf make(const RenderScene& rs, uint32_t prim, const ShapeHit& h, const V3& o, const V3& d) {
+    return makeBsdf<EXTRA>(rs, prim, h, o, d);
+  }
+};
+template <bool EXTRA>
+struct MakeBsdf<true, EXTRA> {
+  static __device__ inline BsdfG make(const RenderScene& rs, uint32_t prim, const ShapeHit& h, const V3& o, const V3& d) {
+    return makeBsdfG<EXTRA>(rs, prim, h, o, d);
+  }
+};
+template <bool GENERAL, bool EXTRA = (DRT_EXTRA != 0)>
+static __device__ inline typename BsdfOf<GENERAL>::type makeBsdfT(const RenderScene& rs, uint32_t prim, const ShapeHit& h, const V3& o,
+                                                                  const V3& d) {
+  return MakeBsdf<GENERAL, EXTRA>::make(rs, prim, h, o, d);
+}
 
 // ---- lights (diffuse_area_light.dart:44-70, shape_set.dart:43-96, shape.dart:100-121,
 // triangle.dart:265-269,366-383, sphere.dart:243-311, point_light.dart:41-47) --------------------------
@@ -891,6 +1066,8 @@ static __device__ inline bool lightShapeIntersect(const RenderScene& rs, const G
 }
 
 // Shape.sample(p, u1, u2) -> point on the shape and its normal
+static __device__ __noinline__ void quadricSample2Cold(const RenderScene& rs, uint32_t prim, V3 p, double u1, double u2, V3* ptOut, V3* ns);
+static __device__ inline V3 quadricSample2(const RenderScene& rs, uint32_t prim, const V3& p, double u1, double u2, V3* ns);
 static __device__ inline V3 shapeSample2(const RenderScene& rs, const GLightShape& ls, const V3& p, double u1, double u2, V3* ns) {
   const uint32_t prim = ls.prim;
   if (prim < rs.ntris) {  // shape.dart:96-98 -> triangle.dart:366-383, UniformSampleTriangle montecarlo.dart:215-220
@@ -901,6 +1078,18 @@ static __device__ inline V3 shapeSample2(const RenderScene& rs, const GLightShap
     *ns = V3{ls.ns[0], ls.ns[1], ls.ns[2]};
     return pt;
   }
+  // sphere / disk / cylinder light shapes: out of line, like their intersection test (shapeIntersectCold), so that the
+  // kernels of a triangle-light scene (config 4) do not carry them; results through temporaries
+#ifdef DRT_QSAMPLE_INLINE
+  return quadricSample2(rs, prim, p, u1, u2, ns);
+#else
+  V3 pt, nq;
+  quadricSample2Cold(rs, prim, p, u1, u2, &pt, &nq);
+  *ns = nq;
+  return pt;
+#endif
+}
+static __device__ inline V3 quadricSample2(const RenderScene& rs, uint32_t prim, const V3& p, double u1, double u2, V3* ns) {
   const GSphere& s = rs.ts.spheres[prim - rs.ntris];
   const bool rev = primReverse(rs, prim);
   float o2w[16], w2o[16];
@@ -916,7 +1105,7 @@ static __device__ inline V3 shapeSample2(const RenderScene& rs, const GLightShap
     *ns = n;
     return XfPoint(o2w, pd);
   }
-  if (s.shape == 2) return cylinderSampleCold(s, rev, u1, u2, ns);
+  if (DRT_EXTRA && s.shape == 2) return cylinderSampleCold(s, rev, u1, u2, ns);
   // sphere.dart:261-297
   V3 Pcenter = XfPoint(o2w, V3{0.f, 0.f, 0.f});
   V3 wc = Normalize(Pcenter - p);
@@ -942,6 +1131,10 @@ static __device__ inline V3 shapeSample2(const RenderScene& rs, const GLightShap
   if (rev) n = -n;
   *ns = n;
   return ps;
+}
+
+static __device__ __noinline__ void quadricSample2Cold(const RenderScene& rs, uint32_t prim, V3 p, double u1, double u2, V3* ptOut, V3* ns) {
+  *ptOut = quadricSample2(rs, prim, p, u1, u2, ns);
 }
 
 static __device__ inline double shapePdf2(const RenderScene& rs, const GLightShape& ls, const V3& p, const V3& wi) {

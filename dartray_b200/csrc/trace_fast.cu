@@ -178,7 +178,8 @@ static __device__ __forceinline__ int32_t testSlotExact(const FastRay& r, int32_
     }                                                                               \
   } while (0)
 
-template <bool ANY>
+// QUAD: the leaf code the scene needs (TraceScene::quadMode): 0 triangles only, 1 + spheres / disks, 2 + the remaining quadrics.
+template <bool ANY, int QUAD>
 __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
     traceFastKernel(TraceScene sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD, uint32_t n,
                     float4* __restrict__ hits, uint8_t* __restrict__ occluded, unsigned int* __restrict__ nextRay,
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
         for (uint32_t k = 0; boxOk && k < cnt && !stop; ++k) {
           float4 a = ldg4(&pr[k].p1[0]), b = ldg4(&pr[k].p2[0]), c = ldg4(&pr[k].p3[0]);
           int kind = __float_as_int(c.w);
-          if ((kind & 1) == 0) {
+          if (QUAD == 0 || (kind & 1) == 0) {
             if (ANY) {
               if (triangleAny(rs, a, b, c)) { found = true; stop = true; }
             } else {
@@ -412,8 +413,8 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
             const GSphere& s = sc.spheres[kind >> 1];
             double th, u, v;
             if (ANY) {
-              if (sphereTest(s, rs, true, &th, nullptr, nullptr)) { found = true; stop = true; }
-            } else if (sphereTest(s, rs, false, &th, &u, &v)) {
+              if (sphereTest<QUAD == 2>(s, rs, true, &th, nullptr, nullptr)) { found = true; stop = true; }
+            } else if (sphereTest<QUAD == 2>(s, rs, false, &th, &u, &v)) {
               found = true;
               hb1 = __double2float_rn(u); hb2 = __double2float_rn(v); hprim = __float_as_int(a.w);
               rs.maxt = th;
@@ -446,21 +447,25 @@ static cudaError_t launchOne(const TraceScene& sc, bool any, const float4* o, co
   if (e != cudaSuccess) return e;
   const int block = 128;
   const size_t smem = (size_t)DRT_SMEM_STACK * block * sizeof(uint2) + 3 * block * sizeof(float);
-  static int perSm[2] = {0, 0};
-  if (!perSm[any ? 1 : 0]) {
+  typedef void (*KernelFn)(TraceScene, const float4*, const float4*, uint32_t, float4*, uint8_t*, unsigned int*, TraceExtras);
+  static const KernelFn kKernels[6] = {traceFastKernel<false, 0>, traceFastKernel<false, 1>, traceFastKernel<false, 2>,
+                                       traceFastKernel<true, 0>,  traceFastKernel<true, 1>,  traceFastKernel<true, 2>};
+  const int variant = (any ? 3 : 0) + (sc.quadMode < 0 ? 0 : (sc.quadMode > 2 ? 2 : sc.quadMode));
+  const KernelFn kernel = kKernels[variant];
+  static int perSm[6] = {0, 0, 0, 0, 0, 0};
+  if (!perSm[variant]) {
     int b = 0;
-    e = any ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, traceFastKernel<true>, block, smem)
-            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, traceFastKernel<false>, block, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, block, smem);
     if (e != cudaSuccess) return e;
-    perSm[any ? 1 : 0] = b > 0 ? b : 1;
+    perSm[variant] = b > 0 ? b : 1;
   }
   uint64_t want = nUnknown ? ~0ull >> 8 : ((uint64_t)n + RAY_CHUNK - 1) / RAY_CHUNK;  // one warp per chunk is enough
   uint64_t blocksWanted = (want + 3) / 4;
-  uint64_t persistent = (uint64_t)numSMs * perSm[any ? 1 : 0];  // one resident wave: persistent warps
+  uint64_t persistent = (uint64_t)numSMs * perSm[variant];  // one resident wave: persistent warps
   dim3 grid((unsigned)(blocksWanted < persistent ? blocksWanted : persistent));
   unsigned int* ctr = reinterpret_cast<unsigned int*>(nextRay);
-  if (any) traceFastKernel<true><<<grid, block, smem, stream>>>(sc, o, d, n, nullptr, (uint8_t*)out, ctr, ex);
-  else traceFastKernel<false><<<grid, block, smem, stream>>>(sc, o, d, n, (float4*)out, nullptr, ctr, ex);
+  if (any) kernel<<<grid, block, smem, stream>>>(sc, o, d, n, nullptr, (uint8_t*)out, ctr, ex);
+  else kernel<<<grid, block, smem, stream>>>(sc, o, d, n, (float4*)out, nullptr, ctr, ex);
   return cudaGetLastError();
 }
 

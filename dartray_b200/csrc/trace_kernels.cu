@@ -98,8 +98,8 @@ __global__ void __launch_bounds__(128) traceKernel(TraceScene sc, const float4* 
             const GSphere& s = sc.spheres[kind >> 1];
             double th, u, v;
             if (ANY) {
-              if (sphereTest(s, r, true, &th, nullptr, nullptr)) { found = true; break; }
-            } else if (sphereTest(s, r, false, &th, &u, &v)) {
+              if (sphereTest<true>(s, r, true, &th, nullptr, nullptr)) { found = true; break; }
+            } else if (sphereTest<true>(s, r, false, &th, &u, &v)) {
               hit.t = th; hit.b1 = u; hit.b2 = v; hit.prim = __float_as_int(a.w);
               r.maxt = th;
               found = true;

@@ -335,6 +335,7 @@ class SceneBuilder:
         self.tri_mat, self.tri_light, self.tri_rev = [], [], []
         self.sph = []  # (o2w, w2o, params, mat, light, rev)
         self.dsk = []  # (o2w, w2o, (height, radius, innerradius, phimax), mat, light, rev)
+        self.mesh_info, self.vertN, self.vertS, self.vertUV, self.tri_mesh = [], [], [], [], []  # per-vertex shading attributes
         self.quad = []  # (kind 2..5, o2w, w2o, 8 params, mat, light, rev): cylinder / cone / paraboloid / hyperboloid
         self.materials = []  # (kind, kd, sigma)
         self.lights = []  # dict(kind, L, pos, nsamples, shapes=[("tri"|"sph", local ids...)])
@@ -388,10 +389,20 @@ class SceneBuilder:
         self.lights.append(dict(kind=0, L=tuple(L), pos=(0, 0, 0), nsamples=nsamples, shapes=[]))
         return len(self.lights) - 1
 
-    def mesh(self, P, idx, material=0, o2w=None, area_light=None, nsamples=1, reverse=False) -> int:
+    def mesh(self, P, idx, material=0, o2w=None, area_light=None, nsamples=1, reverse=False, N=None, S=None, uv=None) -> int:
         """Shape "trianglemesh": vertices go to world space at construction (triangle_mesh.dart:24-37).
-        `area_light` = emitted radiance: one DiffuseAreaLight per shape (dartray.dart:378-467)."""
+        `area_light` = emitted radiance: one DiffuseAreaLight per shape (dartray.dart:378-467).
+        N / S / uv: the per-vertex "normal N" / "vector S" / "float uv" parameters (triangle_mesh.dart:88-140), kept in object
+        space as the reference keeps them; Triangle.getShadingGeometry transforms them per hit (triangle.dart:271-364)."""
         P = np.asarray(P, dtype=np.float32).reshape(-1, 3)
+        nv = P.shape[0]
+        m2w = np.eye(4, dtype=np.float32) if o2w is None else np.asarray(o2w, dtype=np.float32).reshape(4, 4)
+        flags = (1 if N is not None else 0) | (2 if S is not None else 0) | (4 if uv is not None else 0)
+        self.mesh_info.append((m2w, mat_inv(m2w), flags))
+        self.vertN.append(np.zeros((nv, 3), np.float32) if N is None else np.asarray(N, np.float32).reshape(nv, 3))
+        self.vertS.append(np.zeros((nv, 3), np.float32) if S is None else np.asarray(S, np.float32).reshape(nv, 3))
+        self.vertUV.append(np.zeros((nv, 2), np.float32) if uv is None else np.asarray(uv, np.float32).reshape(nv, 2))
+        self.tri_mesh += [len(self.mesh_info) - 1] * np.asarray(idx).reshape(-1, 3).shape[0]
         if o2w is not None:
             P = transform_points(o2w, P)
         idx = np.asarray(idx, dtype=np.uint32).reshape(-1, 3)
@@ -510,6 +521,14 @@ class SceneBuilder:
             dsk_params=np.asarray([s[2] for s in self.dsk], np.float64).reshape(-1, 4),
             dsk_mat=np.asarray([s[3] for s in self.dsk], np.int32), dsk_light=np.asarray([s[4] for s in self.dsk], np.int32),
             dsk_rev=np.asarray([s[5] for s in self.dsk], np.uint8),
+            mesh_shading=any(m[2] for m in self.mesh_info),
+            mesh_of_tri=np.asarray(self.tri_mesh, np.uint32),
+            mesh_o2w=np.stack([m[0].reshape(16) for m in self.mesh_info]) if self.mesh_info else np.zeros((0, 16), np.float32),
+            mesh_w2o=np.stack([m[1].reshape(16) for m in self.mesh_info]) if self.mesh_info else np.zeros((0, 16), np.float32),
+            mesh_flags=np.asarray([m[2] for m in self.mesh_info], np.uint8),
+            vert_N=np.concatenate(self.vertN) if self.vertN else np.zeros((0, 3), np.float32),
+            vert_S=np.concatenate(self.vertS) if self.vertS else np.zeros((0, 3), np.float32),
+            vert_uv=np.concatenate(self.vertUV) if self.vertUV else np.zeros((0, 2), np.float32),
             quad_kind=np.asarray([q[0] for q in self.quad], np.int32),
             quad_o2w=np.stack([q[1].reshape(16) for q in self.quad]) if self.quad else np.zeros((0, 16), np.float32),
             quad_w2o=np.stack([q[2].reshape(16) for q in self.quad]) if self.quad else np.zeros((0, 16), np.float32),
@@ -543,6 +562,10 @@ def upload_scene(ctx, arrays: dict, split: int = 2, max_node_prims: int = 4):
     """Drives either dartray_b200.capi.Context or tests.oracle_lib.Oracle (same method names)."""
     a = arrays
     ctx.set_triangles(a["P"], a["idx"], a["tri_mat"], a["tri_light"], a["tri_rev"])
+    if a.get("mesh_shading"):
+        fl = a["mesh_flags"]
+        ctx.set_mesh_shading(a["vert_N"] if (fl & 1).any() else None, a["vert_S"] if (fl & 2).any() else None,
+                             a["vert_uv"] if (fl & 4).any() else None, a["mesh_of_tri"], a["mesh_o2w"], a["mesh_w2o"], fl)
     ctx.set_spheres(a["sph_o2w"], a["sph_w2o"], a["sph_params"], a["sph_mat"], a["sph_light"], a["sph_rev"])
     if a["dsk_params"].shape[0]:
         ctx.set_disks(a["dsk_o2w"], a["dsk_w2o"], a["dsk_params"], a["dsk_mat"], a["dsk_light"], a["dsk_rev"])

@@ -92,6 +92,16 @@ int drt_set_triangles(drt_ctx* ctx, const float* P, uint32_t nverts, const uint3
                       const int32_t* material_of_tri, const int32_t* light_of_tri,
                       const uint8_t* reverse_orientation_of_tri);
 
+/* Per-vertex shading attributes of the TriangleMeshes the soup was merged from: what Triangle.getUVs and
+ * Triangle.getShadingGeometry read (lib/shapes/triangle.dart:246-262, 271-364; storage lib/shapes/triangle_mesh.dart:24-28).
+ * N / S: nverts x 3 float32 in OBJECT space as the scene file gives them (the reference transforms them per hit with the
+ * mesh's objectToWorld); uv: nverts x 2 float32.  Any of the three may be NULL.  mesh_of_tri: ntris mesh indices;
+ * o2w / w2o: nmeshes x 16 row-major float32; mesh_flags bit 0 / 1 / 2: the mesh has N / S / uv (vertices of a mesh without
+ * an attribute may hold anything in that array).  Call after drt_set_triangles (which clears it); nmeshes == 0 clears.
+ * With uv present the triangle's dpdu / dpdv — and through them dg.nn — follow the file's parameterisation. */
+int drt_set_mesh_shading(drt_ctx* ctx, const float* N, const float* S, const float* uv, const uint32_t* mesh_of_tri,
+                         uint32_t nmeshes, const float* o2w, const float* w2o, const uint8_t* mesh_flags);
+
 /* Replaces Sphere construction (lib/shapes/sphere.dart:24-32,314-323).  o2w / w2o: n x 16 row-major
  * float32 (Matrix4x4, lib/core/matrix4x4.dart:26); params: n x 4 doubles radius, zmin, zmax,
  * phimax(degrees) exactly as ParamSet hands them to Sphere.Create. */

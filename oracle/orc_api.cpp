@@ -54,6 +54,7 @@ int orc_set_triangles(orc_ctx* c, const float* P, uint32_t nverts, const uint32_
     if (idx[i] >= nverts) { c->err = "triangle index out of range"; return -1; }
   s.P.assign(P, P + (size_t)nverts * 3);
   s.idx.assign(idx, idx + (size_t)ntris * 3);
+  s.vertN.clear(); s.vertS.clear(); s.vertUV.clear(); s.meshOfTri.clear(); s.meshes.clear();
   size_t np = s.nprims();
   s.materialOf.resize(np, 0);
   s.lightOf.resize(np, -1);
@@ -62,6 +63,31 @@ int orc_set_triangles(orc_ctx* c, const float* P, uint32_t nverts, const uint32_
     s.materialOf[i] = mat ? mat[i] : 0;
     s.lightOf[i] = light ? light[i] : -1;
     s.reverseOf[i] = rev ? rev[i] : 0;
+  }
+  return 0;
+}
+
+// Per-vertex shading attributes (triangle_mesh.dart:24-28, triangle.dart:246-262,271-364): N / S in object space and uv,
+// each nverts long or NULL; mesh_of_tri names the mesh (objectToWorld + which attributes it has: bit 0 N, 1 S, 2 uv).
+int orc_set_mesh_shading(orc_ctx* c, const float* N, const float* S, const float* uv, const uint32_t* meshOfTri, uint32_t nmeshes,
+                         const float* o2w, const float* w2o, const uint8_t* flags) {
+  Scene& s = c->scene;
+  s.vertN.clear(); s.vertS.clear(); s.vertUV.clear(); s.meshOfTri.clear(); s.meshes.clear();
+  if (nmeshes == 0 || !meshOfTri) return 0;
+  size_t nv = s.P.size() / 3;
+  if (N) s.vertN.assign(N, N + 3 * nv);
+  if (S) s.vertS.assign(S, S + 3 * nv);
+  if (uv) s.vertUV.assign(uv, uv + 2 * nv);
+  s.meshOfTri.assign(meshOfTri, meshOfTri + s.ntris());
+  for (uint32_t t = 0; t < s.ntris(); ++t)
+    if (meshOfTri[t] >= nmeshes) { c->err = "mesh index out of range"; return -1; }
+  for (uint32_t m = 0; m < nmeshes; ++m) {
+    Scene::MeshInfo mi;
+    mi.o2w = Transform(o2w + 16 * m, w2o + 16 * m);
+    mi.hasN = (flags[m] & 1) && N;
+    mi.hasS = (flags[m] & 2) && S;
+    mi.hasUV = (flags[m] & 4) && uv;
+    s.meshes.push_back(mi);
   }
   return 0;
 }

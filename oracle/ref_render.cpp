@@ -221,6 +221,7 @@ namespace {
 
 struct DG {  // the part of DifferentialGeometry the matte path uses
   Vec p, nn, dpdu, dpdv;
+  double u = 0.0, v = 0.0;  // triangles: the interpolated (tu, tv) of triangle.dart:134-136 (getShadingGeometry reads them)
 };
 
 struct Isect {
@@ -583,7 +584,13 @@ struct Ctx {
     if (prim < g.ntris()) {
       Vec p1, p2, p3;
       g.triVerts(prim, &p1, &p2, &p3);
-      const double uvs[6] = {0.0, 0.0, 1.0, 0.0, 1.0, 1.0};  // triangle.dart:255-262
+      double uvs[6];  // triangle.dart:105 getUVs: the mesh's uvs or (0,0),(1,0),(1,1) (:246-262)
+      g.triUVs(prim, uvs);
+      {  // triangle.dart:133-136
+        double b0 = 1.0 - h.b1 - h.b2;
+        dg->u = b0 * uvs[0] + h.b1 * uvs[2] + h.b2 * uvs[4];
+        dg->v = b0 * uvs[1] + h.b1 * uvs[3] + h.b2 * uvs[5];
+      }
       double du1 = uvs[0] - uvs[4], du2 = uvs[2] - uvs[4], dv1 = uvs[1] - uvs[5], dv2 = uvs[3] - uvs[5];
       Vec dp1 = p1 - p3, dp2 = p2 - p3;
       double determinant = du1 * dv2 - dv1 * du2;
@@ -675,9 +682,48 @@ struct Ctx {
     Bsdf b;
     const DG& dg = is.dg;
     b.p = dg.p;
-    b.nn = dg.nn;  // dgShading == dg: no per-vertex normals (triangle.dart:273-276), sphere default
+    b.nn = dg.nn;  // dgShading == dg: no per-vertex normals (triangle.dart:273-276), quadrics (shape.dart:73-77)
     b.ng = dg.nn;
-    b.sn = Normalize(dg.dpdu);
+    Vec ss = dg.dpdu;
+    const Scene::MeshInfo* mesh = (uint32_t)is.prim < g.ntris() ? g.meshOf((uint32_t)is.prim) : nullptr;
+    if (mesh && (mesh->hasN || mesh->hasS)) {  // Triangle.getShadingGeometry, triangle.dart:271-364
+      const uint32_t tri = (uint32_t)is.prim;
+      double uv[6];
+      g.triUVs(tri, uv);
+      double A0 = uv[2] - uv[0], A1 = uv[4] - uv[0], A2 = uv[3] - uv[1], A3 = uv[5] - uv[1];
+      double C0 = dg.u - uv[0], C1 = dg.v - uv[1];
+      double bx, by, bz;
+      double det = A0 * A3 - A1 * A2;  // SolveLinearSystem2x2, common.dart:170-185
+      bool ok = !(std::fabs(det) < 1.0e-10);
+      if (ok) {
+        by = (A3 * C0 - A1 * C1) / det;
+        bz = (A0 * C1 - A2 * C0) / det;
+        if (std::isnan(by) || std::isnan(bz)) ok = false;
+      }
+      if (!ok) bx = by = bz = 1.0 / 3.0;
+      else bx = 1.0 - by - bz;
+      auto vert = [&](const std::vector<float>& a, int k) {
+        const float* q = &a[3 * (size_t)g.idx[3 * (size_t)tri + k]];
+        return Vec(q[0], q[1], q[2]);
+      };
+      Vec ns, ts;
+      if (mesh->hasN) ns = Normalize(mesh->o2w.normal(((vert(g.vertN, 0) * bx) + (vert(g.vertN, 1) * by)) + (vert(g.vertN, 2) * bz)));
+      else ns = dg.nn;
+      if (mesh->hasS) ss = Normalize(mesh->o2w.vector(((vert(g.vertS, 0) * bx) + (vert(g.vertS, 1) * by)) + (vert(g.vertS, 2) * bz)));
+      else ss = Normalize(dg.dpdu);
+      ts = Cross(ss, ns);
+      if (LengthSquared(ts) > 0.0) {
+        ts = Normalize(ts);
+        ss = Cross(ts, ns);
+      } else {
+        CoordinateSystem(ns, &ss, &ts);
+      }
+      // dgShading.set(dg.p, ss, ts, ...): nn = normalize(cross(dpdu, dpdv)), flipped by reverseOrientation
+      // (differential_geometry.dart:77-99)
+      b.nn = Normalize(Cross(ss, ts));
+      if (g.reverseOf[is.prim]) b.nn = b.nn * -1.0;
+    }
+    b.sn = Normalize(ss);
     b.tn = Cross(b.nn, b.sn);
     // no material table: every primitive is the default matte, Kd = 0.5 (matte_material.dart:67-72), as in drt_create
     static const Material kDefault = Material::matte(Spec(0.5), 0.0);

@@ -155,6 +155,29 @@ struct Scene {
   std::vector<Sphere> spheres;
   std::vector<uint32_t> buildOrder;  // refined order handed to BVHAccel (ids in upload numbering)
 
+  // per-vertex shading attributes of the meshes the soup was merged from (triangle_mesh.dart:24-28: n, s, uvs are kept
+  // as given, i.e. in OBJECT space; triangle.dart:271-364 transforms them with the mesh's objectToWorld)
+  struct MeshInfo {
+    Transform o2w;
+    bool hasN = false, hasS = false, hasUV = false;
+  };
+  std::vector<float> vertN, vertS, vertUV;  // nverts*3, nverts*3, nverts*2 (empty when no mesh has them)
+  std::vector<uint32_t> meshOfTri;          // ntris (empty: no mesh carries attributes)
+  std::vector<MeshInfo> meshes;
+  const MeshInfo* meshOf(uint32_t tri) const { return meshOfTri.empty() ? nullptr : &meshes[meshOfTri[tri]]; }
+  // triangle.dart:246-262 getUVs
+  void triUVs(uint32_t tri, double uv[6]) const {
+    const MeshInfo* m = meshOf(tri);
+    if (m && m->hasUV) {
+      for (int k = 0; k < 3; ++k) {
+        uv[2 * k] = vertUV[2 * (size_t)idx[3 * (size_t)tri + k]];
+        uv[2 * k + 1] = vertUV[2 * (size_t)idx[3 * (size_t)tri + k] + 1];
+      }
+    } else {
+      uv[0] = 0.0; uv[1] = 0.0; uv[2] = 1.0; uv[3] = 0.0; uv[4] = 1.0; uv[5] = 1.0;
+    }
+  }
+
   // per-primitive attributes (upload numbering)
   std::vector<int32_t> materialOf;
   std::vector<int32_t> lightOf;

@@ -40,6 +40,7 @@ def lib():
         L.orc_set_spheres.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
         L.orc_set_disks.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
         L.orc_set_quadrics.argtypes = [vp, i32, u32, vp, vp, vp, vp, vp, vp]
+        L.orc_set_mesh_shading.argtypes = [vp, vp, vp, vp, vp, u32, vp, vp, vp]
         L.orc_set_build_order.argtypes = [vp, vp, u32]
         L.orc_build_bvh.argtypes = [vp, i32, i32]
         L.orc_build_seconds.restype = C.c_double
@@ -128,6 +129,12 @@ class Oracle:
         params = _arr(params, np.float64).reshape(-1, 8)
         m, l, r = _arr(material, np.int32), _arr(light, np.int32), _arr(reverse, np.uint8)
         self._ck(self.L.orc_set_quadrics(self.h, int(kind), o2w.shape[0], _p(o2w), _p(w2o), _p(params), _p(m), _p(l), _p(r)))
+
+    def set_mesh_shading(self, N, S, uv, mesh_of_tri, o2w, w2o, flags):
+        N, S, uv = _arr(N, np.float32), _arr(S, np.float32), _arr(uv, np.float32)
+        mot, flags = _arr(mesh_of_tri, np.uint32), _arr(flags, np.uint8)
+        o2w, w2o = _arr(o2w, np.float32).reshape(-1, 16), _arr(w2o, np.float32).reshape(-1, 16)
+        self._ck(self.L.orc_set_mesh_shading(self.h, _p(N), _p(S), _p(uv), _p(mot), o2w.shape[0], _p(o2w), _p(w2o), _p(flags)))
 
     def set_build_order(self, order):
         if order is None:

@@ -201,3 +201,51 @@ def test_keyed_and_serial_streams_agree_statistically():
         o.render(0, 1, 8)
         means.append(o.film_read()["rgb"].mean(axis=(0, 1)))
     assert np.allclose(means[0], means[1], rtol=0.02)
+
+
+# ---- per-vertex shading attributes: Triangle.getShadingGeometry (triangle.dart:271-364) -------------------------------
+def _lit_quad(N=None, uv=None, S=None, reverse=False, idx=((0, 2, 1), (0, 3, 2))):
+    """A matte quad in the plane y = 0 under a point light straight above the point the camera looks at."""
+    kd, I, hgt = 0.6, 50.0, 5.0
+    sb = host.SceneBuilder()
+    sb.mesh([[-4, 0, -4], [4, 0, -4], [4, 0, 4], [-4, 0, 4]], idx, material=sb.material((kd, kd, kd)), N=N, uv=uv, S=S, reverse=reverse)
+    sb.point_light((0.0, hgt, 0.0), (I, I, I))
+    cam = host.PerspectiveCamera(host.look_at((0.3, 2.0, -0.2), (0, 0, 0), (0, 1, 0)), fov=0.2)
+    o = _oracle(sb, cam, host.Film(2, 2), host.Sampler(kind=host.SAMPLER_STRATIFIED, xs=1, ys=1, jitter=False),
+                host.Integrator(kind=host.INTEGRATOR_DIRECT))
+    o.render()
+    return o.film_read()["rgb"].mean(), kd / math.pi * I / (hgt * hgt)
+
+
+def test_vertex_normals_tilt_the_shading_normal_closed_form():
+    flat, base = _lit_quad()
+    assert flat == pytest.approx(base, rel=1e-4)  # |cos| = 1 with the geometric normal
+    t = 1.0 / math.sqrt(2.0)
+    tilted, _ = _lit_quad(N=[[t, t, 0]] * 4)
+    assert tilted == pytest.approx(base * t, rel=1e-4)  # L = f * Li * |wi . ns| with ns = normalize(1, 1, 0)
+    # unnormalised N are normalised after the transform (triangle.dart:301-303); S alone leaves ns = dg.nn (:304-306)
+    assert _lit_quad(N=[[3, 3, 0]] * 4)[0] == pytest.approx(tilted, rel=1e-6)
+    assert _lit_quad(S=[[1, 0, 0]] * 4)[0] == pytest.approx(base, rel=1e-4)
+    # interpolation: N = +y at x = -4 and normalize(1, 1, 0) at x = +4 -> at x = 0 the blend (t/2, (1 + t)/2, 0), normalised
+    mixed, _ = _lit_quad(N=[[0, 1, 0], [t, t, 0], [t, t, 0], [0, 1, 0]])
+    nx, ny = t / 2, (1 + t) / 2
+    assert mixed == pytest.approx(base * ny / math.hypot(nx, ny), rel=2e-3)
+
+
+def test_uv_orientation_decides_the_side_an_area_light_emits_to():
+    # dg.nn = normalize(cross(dpdu, dpdv)) follows the mesh's uvs (triangle.dart:104-131); DiffuseAreaLight emits where
+    # dot(nn, w) > 0 (diffuse_area_light.dart): mirroring the parameterisation turns the light round
+    def floor_radiance(uv):
+        sb = host.SceneBuilder()
+        _plane(sb, material=sb.material((0.5, 0.5, 0.5)))
+        sb.mesh([[-1, 3, -1], [1, 3, -1], [1, 3, 1], [-1, 3, 1]], [[0, 1, 2], [0, 2, 3]], area_light=(10.0, 10.0, 10.0), nsamples=4, uv=uv)
+        cam = host.PerspectiveCamera(host.look_at((0.5, 1.0, -3.0), (0, 0, 0), (0, 1, 0)), fov=5.0)
+        o = _oracle(sb, cam, host.Film(4, 4), host.Sampler(kind=host.SAMPLER_LD, spp=16), host.Integrator(kind=host.INTEGRATOR_DIRECT))
+        o.render()
+        return o.film_read()["rgb"].mean()
+    default = floor_radiance(None)
+    same = floor_radiance([[0, 0], [1, 0], [1, 1], [0, 1]])
+    mirrored = floor_radiance([[1, 0], [0, 0], [0, 1], [1, 1]])
+    assert (default > 0.1) != (mirrored > 0.1) or (same > 0.1) != (mirrored > 0.1)
+    assert (same > 0.1) != (mirrored > 0.1)
+    assert min(same, mirrored) == 0.0

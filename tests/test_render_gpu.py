@@ -164,6 +164,48 @@ def test_cone_light_is_rejected():
         g.render(0, 1)
 
 
+def _smooth_room(which):
+    """cornell_synth plus smooth-shaded meshes: per-vertex N / S / uv through Triangle.getShadingGeometry (triangle.dart:271-364)."""
+    from tests.util import uv_sphere_mesh
+    sb, cam = (scenes.cornell_materials() if which == "lobes" else scenes.cornell_synth())
+    P, idx, N, S, UV = uv_sphere_mesh(10, 14, 1.0)
+    m = sb.material_lobes(host.plastic_lobes((0.3, 0.5, 0.7), 0.4, 0.1)) if which == "lobes" else sb.material((0.3, 0.5, 0.7))
+    # non-uniform scale + rotation: normals go through the inverse transpose, tangents through the matrix itself
+    sb.mesh(P, idx, material=m, o2w=host.mat_mul(host.mat_mul(host.translate(4, 2, -2), host.rotate(35, (1, 0.4, 0.2))), host.scale(3.0, 2.0, 2.5)), N=N, S=S, uv=UV)
+    sb.mesh(P, idx, material=m, o2w=host.mat_mul(host.translate(-5, 5, 3), host.scale(2.5, 2.5, 2.5)), N=N)          # normals only
+    sb.mesh(P, idx, material=m, o2w=host.mat_mul(host.translate(0, -7, -5), host.scale(2.0, 2.0, 2.0)), uv=UV)        # uvs only
+    sb.mesh(P, idx, material=m, o2w=host.mat_mul(host.translate(6, 7, 4), host.scale(1.5, 1.5, 1.5)), S=S, reverse=True)  # tangents only
+    return sb.arrays(), cam
+
+
+@pytest.mark.parametrize("which,integ", [
+    ("matte", host.Integrator(kind=host.INTEGRATOR_DIRECT)),
+    ("matte", host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=4)),
+    ("lobes", host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=4)),
+    ("lobes", host.Integrator(kind=host.INTEGRATOR_DIRECT, maxdepth=3)),
+    ("matte", host.Integrator(kind=host.INTEGRATOR_WHITTED, maxdepth=2)),
+])
+def test_smooth_shaded_meshes_match_oracle(which, integ):
+    arrays, cam = _smooth_room(which)
+    g, o, fg, fo = _render_both(arrays, cam, host.Film(80, 60), host.Sampler(kind=host.SAMPLER_LD, spp=4), integ)
+    err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
+    print("smooth room", which, integ.kind, "max rel err", err.max(), "q999", np.quantile(err, 0.999))
+    assert np.quantile(err, 0.999) <= 1e-3
+    assert abs(fg["rgb"].mean() - fo["rgb"].mean()) <= 2e-3 * fo["rgb"].mean()
+    if integ.kind == host.INTEGRATOR_DIRECT and which == "matte":
+        assert err.max() <= 1e-3
+        sg, so = g.render_stats(), o.render_stats()
+        assert sg["shadow_rays"] == so["shadow_rays"] and sg["closest_rays"] == so["closest_rays"]
+    # the attributes are in use: the same room without them renders differently
+    a2 = dict(arrays)
+    a2["mesh_shading"] = False
+    g2 = capi.Context(0)
+    host.upload_scene(g2, a2)
+    host.configure_render(g2, cam, host.Film(80, 60), host.Sampler(kind=host.SAMPLER_LD, spp=4), integ)
+    g2.render(0, 1)
+    assert np.abs(g2.film_read()["rgb"] - fg["rgb"]).max() > 1e-2
+
+
 # ---- path tracing ------------------------------------------------------------------------------------------
 def test_path_integrator_matches_oracle():
     arrays, cam = _cornell()

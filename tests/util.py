@@ -38,3 +38,28 @@ def mesh_refine_order(mesh_tri_counts, n_spheres_after=0):
         base += n
     order.extend(range(base, base + n_spheres_after))
     return np.asarray(order, dtype=np.uint32)
+
+
+def uv_sphere_mesh(stacks=12, slices=16, radius=1.0):
+    """A latitude/longitude sphere with per-vertex normals N (object space), tangents S and uvs: what a smooth-shaded
+    "trianglemesh" of the shipped scenes carries (triangle_mesh.dart:88-140)."""
+    P, N, S, UV, idx = [], [], [], [], []
+    for i in range(stacks + 1):
+        th = np.pi * i / stacks
+        for j in range(slices + 1):
+            ph = 2 * np.pi * j / slices
+            n = np.array([np.sin(th) * np.cos(ph), np.cos(th), np.sin(th) * np.sin(ph)])
+            P.append(radius * n)
+            N.append(n)
+            S.append([-np.sin(ph), 0.0, np.cos(ph)])
+            UV.append([j / slices, i / stacks])
+    w = slices + 1
+    for i in range(stacks):
+        for j in range(slices):
+            a, b, c, d = i * w + j, i * w + j + 1, (i + 1) * w + j, (i + 1) * w + j + 1
+            if i > 0:
+                idx.append([a, b, c])
+            if i < stacks - 1:
+                idx.append([b, d, c])
+    return (np.asarray(P, np.float32), np.asarray(idx, np.uint32), np.asarray(N, np.float32), np.asarray(S, np.float32),
+            np.asarray(UV, np.float32))
