@@ -38,6 +38,10 @@ typedef _SetTrianglesC = Int32 Function(_Ctx, _PF, Uint32, _PU, Uint32, _PI, _PI
 typedef _SetTrianglesD = int Function(_Ctx, _PF, int, _PU, int, _PI, _PI, _PB);
 typedef _SetQuadricsC = Int32 Function(_Ctx, Uint32, _PF, _PF, _PD, _PI, _PI, _PB);
 typedef _SetQuadricsD = int Function(_Ctx, int, _PF, _PF, _PD, _PI, _PI, _PB);
+typedef _SetKindQuadricsC = Int32 Function(_Ctx, Int32, Uint32, _PF, _PF, _PD, _PI, _PI, _PB);
+typedef _SetKindQuadricsD = int Function(_Ctx, int, int, _PF, _PF, _PD, _PI, _PI, _PB);
+typedef _SetMeshShadingC = Int32 Function(_Ctx, _PF, _PF, _PF, _PU, Uint32, _PF, _PF, _PB);
+typedef _SetMeshShadingD = int Function(_Ctx, _PF, _PF, _PF, _PU, int, _PF, _PF, _PB);
 typedef _SetOrderC = Int32 Function(_Ctx, _PU, Uint32);
 typedef _SetOrderD = int Function(_Ctx, _PU, int);
 typedef _BuildC = Int32 Function(_Ctx, Int32, Int32);
@@ -116,6 +120,12 @@ class Drt {
       check(lib.lookupFunction<_SetQuadricsC, _SetQuadricsD>('drt_set_spheres')(ctx, n, o2w, w2o, params, mat, light, rev));
   void setDisks(int n, _PF o2w, _PF w2o, _PD params, _PI mat, _PI light, _PB rev) =>
       check(lib.lookupFunction<_SetQuadricsC, _SetQuadricsD>('drt_set_disks')(ctx, n, o2w, w2o, params, mat, light, rev));
+  /// kind 2 cylinder, 3 cone, 4 paraboloid, 5 hyperboloid; params: n x 8 doubles (include/drt.h)
+  void setQuadrics(int kind, int n, _PF o2w, _PF w2o, _PD params, _PI mat, _PI light, _PB rev) =>
+      check(lib.lookupFunction<_SetKindQuadricsC, _SetKindQuadricsD>('drt_set_quadrics')(ctx, kind, n, o2w, w2o, params, mat, light, rev));
+  /// per-vertex N / S (object space) / uv, any may be nullptr; mesh index per triangle, per-mesh transforms and flags
+  void setMeshShading(_PF n, _PF s, _PF uv, _PU meshOfTri, int nMeshes, _PF o2w, _PF w2o, _PB flags) =>
+      check(lib.lookupFunction<_SetMeshShadingC, _SetMeshShadingD>('drt_set_mesh_shading')(ctx, n, s, uv, meshOfTri, nMeshes, o2w, w2o, flags));
   void setBuildOrder(_PU order, int n) => check(lib.lookupFunction<_SetOrderC, _SetOrderD>('drt_set_build_order')(ctx, order, n));
   void buildBvh(int split, int maxNodePrims) => check(lib.lookupFunction<_BuildC, _BuildD>('drt_build_bvh')(ctx, split, maxNodePrims));
   void setMaterials(int n, _PI kind, _PF kd, _PF sigma) =>

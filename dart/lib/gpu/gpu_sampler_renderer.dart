@@ -229,6 +229,7 @@ class GpuSamplerRenderer extends Renderer {
     // primitives arrive in the order BVHAccel's constructor refined them (bvh_accel.dart:46-52): that IS the build
     // order; ids are assigned per kind in upload order: triangles, then spheres, then disks.
     final tris = <GeometricPrimitive>[], sphs = <GeometricPrimitive>[], dsks = <GeometricPrimitive>[];
+    final quads = <GeometricPrimitive>[];  // cylinder / cone / paraboloid / hyperboloid: drt_set_quadrics, ids after the disks
     for (final Primitive p in bvh.primitives) {
       if (p is! GeometricPrimitive) {
         throw new GpuUnsupported('primitive ${p.runtimeType} (instancing / motion blur)');
@@ -240,6 +241,8 @@ class GpuSamplerRenderer extends Renderer {
         sphs.add(g);
       } else if (g.shape is Disk) {
         dsks.add(g);
+      } else if (g.shape is Cylinder || g.shape is Cone || g.shape is Paraboloid || g.shape is Hyperboloid) {
+        quads.add(g);
       } else {
         throw new GpuUnsupported('shape ${g.shape.runtimeType}');
       }
@@ -248,6 +251,7 @@ class GpuSamplerRenderer extends Renderer {
     for (int i = 0; i < tris.length; ++i) ids[tris[i]] = i;
     for (int i = 0; i < sphs.length; ++i) ids[sphs[i]] = tris.length + i;
     for (int i = 0; i < dsks.length; ++i) ids[dsks[i]] = tris.length + sphs.length + i;
+    for (int i = 0; i < quads.length; ++i) ids[quads[i]] = tris.length + sphs.length + dsks.length + i;
 
     // materials and area lights by identity
     final materials = <Material>[], lights = scene.lights;
@@ -262,15 +266,29 @@ class GpuSamplerRenderer extends Renderer {
     // triangles: three world-space float32 vertices each (TriangleMesh.point, triangle_mesh.dart:39-42); no sharing
     final P = <double>[], idx = <int>[], tm = <int>[], tl = <int>[], tr = <int>[];
     final triKey = new Map<TriangleMesh, Map<int, int>>.identity();
+    final meshes = <TriangleMesh>[], meshOfTri = <int>[];
+    final meshIndex = new Map<TriangleMesh, int>.identity();
+    final vN = <double>[], vS = <double>[], vUV = <double>[];
     for (int i = 0; i < tris.length; ++i) {
       final Triangle t = tris[i].shape;
-      if (t.mesh.n != null || t.mesh.s != null || t.mesh.uvs != null || t.mesh.alphaTexture != null) {
-        throw new GpuUnsupported('triangle meshes with normals, tangents, uvs or alpha textures');
+      if (t.mesh.alphaTexture != null) {
+        throw new GpuUnsupported('triangle meshes with alpha textures');
       }
+      // per-vertex N / S / uv (triangle_mesh.dart:24-28) travel as they are stored: object space; drt_set_mesh_shading
+      final TriangleMesh mesh = t.mesh;
+      final int mi = meshIndex.putIfAbsent(mesh, () {
+        meshes.add(mesh);
+        return meshes.length - 1;
+      });
+      meshOfTri.add(mi);
       for (int k = 0; k < 3; ++k) {
-        final Point p = t.mesh.point(t.mesh.vertexIndex[3 * t.index + k]);
+        final int v = mesh.vertexIndex[3 * t.index + k];
+        final Point p = mesh.point(v);
         P..add(p.x)..add(p.y)..add(p.z);
         idx.add(3 * i + k);
+        if (mesh.n != null) { vN..add(mesh.n[v].x)..add(mesh.n[v].y)..add(mesh.n[v].z); } else { vN..add(0.0)..add(0.0)..add(0.0); }
+        if (mesh.s != null) { vS..add(mesh.s[v].x)..add(mesh.s[v].y)..add(mesh.s[v].z); } else { vS..add(0.0)..add(0.0)..add(0.0); }
+        if (mesh.uvs != null) { vUV..add(mesh.uvs[2 * v])..add(mesh.uvs[2 * v + 1]); } else { vUV..add(0.0)..add(0.0); }
       }
       tm.add(matOf(tris[i]));
       tl.add(lightOf(tris[i]));
@@ -278,6 +296,17 @@ class GpuSamplerRenderer extends Renderer {
       triKey.putIfAbsent(t.mesh, () => <int, int>{})[t.index] = i;
     }
     drt.setTriangles(a.floats(P), P.length ~/ 3, a.uints(idx), tris.length, a.ints(tm), a.ints(tl), a.bytes(tr));
+    if (meshes.any((m) => m.n != null || m.s != null || m.uvs != null)) {
+      final mo2w = <double>[], mw2o = <double>[], flags = <int>[];
+      for (final m in meshes) {
+        mo2w.addAll(m.objectToWorld.m.data);
+        mw2o.addAll(m.worldToObject.m.data);
+        flags.add((m.n != null ? 1 : 0) | (m.s != null ? 2 : 0) | (m.uvs != null ? 4 : 0));
+      }
+      drt.setMeshShading(meshes.any((m) => m.n != null) ? a.floats(vN) : nullptr, meshes.any((m) => m.s != null) ? a.floats(vS) : nullptr,
+                         meshes.any((m) => m.uvs != null) ? a.floats(vUV) : nullptr, a.uints(meshOfTri), meshes.length,
+                         a.floats(mo2w), a.floats(mw2o), a.bytes(flags));
+    }
 
     void quadrics(List<GeometricPrimitive> prims, bool disk) {
       if (prims.isEmpty) {
@@ -306,6 +335,31 @@ class GpuSamplerRenderer extends Renderer {
     }
     quadrics(sphs, false);
     quadrics(dsks, true);
+    // the remaining quadrics, one drt_set_quadrics call each (ids in list order).  The fields hold what the constructors
+    // stored (cylinder.dart:24-31, cone.dart:23-27, paraboloid.dart:23-29, hyperboloid.dart:23-49): phiMax in radians, the
+    // hyperboloid's points after its p2.z == 0 swap — handing those back reproduces the same object
+    for (final g in quads) {
+      final prm = new List<double>.filled(8, 0.0);
+      int kind;
+      final Shape sh = g.shape;
+      if (sh is Cylinder) {
+        kind = 2;
+        prm[0] = sh.radius; prm[1] = sh.zmin; prm[2] = sh.zmax; prm[3] = Degrees(sh.phiMax);
+      } else if (sh is Cone) {
+        kind = 3;
+        prm[0] = sh.height; prm[1] = sh.radius; prm[2] = Degrees(sh.phiMax);
+      } else if (sh is Paraboloid) {
+        kind = 4;
+        prm[0] = sh.radius; prm[1] = sh.zmin; prm[2] = sh.zmax; prm[3] = Degrees(sh.phiMax);
+      } else {
+        final Hyperboloid hy = sh;
+        kind = 5;
+        prm[0] = hy.p1.x; prm[1] = hy.p1.y; prm[2] = hy.p1.z; prm[3] = hy.p2.x; prm[4] = hy.p2.y; prm[5] = hy.p2.z;
+        prm[6] = Degrees(hy.phiMax);
+      }
+      drt.setQuadrics(kind, 1, a.floats(sh.objectToWorld.m.data), a.floats(sh.worldToObject.m.data), a.doubles(prm),
+                      a.ints([matOf(g)]), a.ints([lightOf(g)]), a.bytes([sh.reverseOrientation ? 1 : 0]));
+    }
 
     final order = <int>[];
     for (final Primitive p in bvh.primitives) order.add(ids[p]);
