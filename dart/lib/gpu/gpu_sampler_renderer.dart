@@ -389,6 +389,7 @@ class GpuSamplerRenderer extends Renderer {
     final lk = <int>[], lL = <double>[], lpos = <double>[], lns = <int>[], so = <int>[0], sp = <int>[];
     final w2l = <double>[], cosines = <double>[];
     bool anySpot = false;
+    final infinite = <int>[];
     for (final Light l in lights) {
       lns.add(l.nSamples);
       w2l.addAll(l.worldToLight.m.data);
@@ -401,7 +402,7 @@ class GpuSamplerRenderer extends Renderer {
           if (s is Triangle) {
             sp.add(triKey[s.mesh][s.index]);
           } else {
-            final g = (sphs + dsks).firstWhere((q) => identical(q.shape, s));
+            final g = (sphs + dsks + quads).firstWhere((q) => identical(q.shape, s));
             sp.add(ids[g]);
           }
         }
@@ -421,6 +422,12 @@ class GpuSamplerRenderer extends Renderer {
         lL.addAll(_rgb(l.intensity));
         lpos..add(l.lightPos.x)..add(l.lightPos.y)..add(l.lightPos.z);
         cosines..add(l.cosTotalWidth)..add(l.cosFalloffStart);
+      } else if (l is InfiniteAreaLight) {
+        lk.add(4);
+        infinite.add(lk.length - 1);
+        lL.addAll(_rgb(l.L));
+        lpos.addAll([0.0, 0.0, 0.0]);
+        cosines.addAll([0.0, 0.0]);
       } else {
         throw new GpuUnsupported('light ${l.runtimeType}');
       }
@@ -429,6 +436,14 @@ class GpuSamplerRenderer extends Renderer {
     drt.setLights(lights.length, a.ints(lk), a.floats(lL), a.floats(lpos), a.ints(lns), a.uints(so), a.uints(sp));
     if (anySpot) {
       drt.setSpotParams(lights.length, a.floats(w2l), a.doubles(cosines));
+    }
+    for (final int i in infinite) {
+      // level 0 of the light's own MIPMap: already resampled to a power of two and multiplied by L by the reference's
+      // constructor (infinite_area_light.dart:43-60, mipmap.dart:72-139); drt_set_infinite_light rebuilds the rest
+      final InfiniteAreaLight l = lights[i];
+      final SpectrumImage level0 = l.radianceMap.pyramid[0];
+      drt.setInfiniteLight(i, level0.width, level0.height, a.floats(level0.data), a.floats(l.lightToWorld.m.data),
+                           a.floats(l.worldToLight.m.data));
     }
   }
 

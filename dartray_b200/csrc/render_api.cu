@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "drt_ctx.h"
+#include "env_map.h"
 #include "render_kernels.h"
 #include "shade_device.cuh"
 
@@ -24,6 +25,10 @@ struct HostLight {
   float w2l[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};  // spot lights (drt_set_spot_params)
   double cosTotalWidth = 0, cosFalloffStart = 0;
   bool haveSpot = false;
+  // infinite lights (drt_set_infinite_light): rows of lightToWorld's upper 3x3 (w2l holds worldToLight's) and the radiance map
+  float l2w[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  int mapW = 0, mapH = 0;
+  std::vector<float> texels;
 };
 
 struct ByteArena {  // one cudaMalloc per wavefront, carved into aligned arrays
@@ -68,7 +73,7 @@ struct RenderState {
   DevBuf<float> dLightCdf, dTable;
   DevBuf<uint32_t> dMeshOfTri, dTriIdx;
   DevBuf<GMesh> dMeshes;
-  DevBuf<float> dVertN, dVertS, dVertUV;
+  DevBuf<float> dVertN, dVertS, dVertUV, dEnv;
   DevBuf<DirectOffsets> dDirect;
   DevBuf<SampleArray> dArrays;
   DevBuf<double> dFilm;
@@ -103,7 +108,7 @@ void drtRenderStateDestroy(drt_ctx* c) {
   if (!r) return;
   r->dPrimToRec.release(); r->dPrimAttr.release(); r->dLightShapes.release(); r->dMaterials.release(); r->dLights.release();
   r->dLightCdf.release(); r->dTable.release(); r->dDirect.release(); r->dArrays.release();
-  r->dMeshOfTri.release(); r->dTriIdx.release(); r->dMeshes.release(); r->dVertN.release(); r->dVertS.release(); r->dVertUV.release();
+  r->dMeshOfTri.release(); r->dTriIdx.release(); r->dMeshes.release(); r->dVertN.release(); r->dVertS.release(); r->dVertUV.release(); r->dEnv.release();
   r->dFilm.release(); r->dCounters.release(); r->dRgb.release(); r->dXyz.release(); r->dWeight.release();
   if (r->wfMem) cudaFree(r->wfMem);
   delete r;
@@ -216,6 +221,8 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
     attr[i] = (uint32_t)m | ((uint32_t)(l + 1) << 16) | (rev ? 0x80000000u : 0u);
   }
   std::vector<GLight> gl(std::max(nLights, 1));
+  std::vector<float> env;  // radiance maps + sampling tables of the infinite lights
+  int nInfinite = 0;
   std::vector<GLightShape> shapes;
   std::vector<float> cdf;
   auto pushShape = [&](uint32_t sh, double area) {
@@ -252,6 +259,17 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
     GLight& g = gl[i];
     g.kind = hl.kind;
     if (hl.kind == 3 && !hl.haveSpot) return fail(c, DRT_E_STATE, "a spot light (kind 3) needs drt_set_spot_params after drt_set_lights");
+    std::memcpy(g.l2w, hl.l2w, sizeof(g.l2w));
+    g.mapW = g.mapH = 0;
+    g.envOffset = 0;
+    if (hl.kind == 4) {
+      if (hl.mapW == 0) return fail(c, DRT_E_STATE, "an infinite light (kind 4) needs drt_set_infinite_light after drt_set_lights");
+      g.mapW = hl.mapW;
+      g.mapH = hl.mapH;
+      g.envOffset = (uint32_t)env.size();
+      appendEnvTables(hl.mapW, hl.mapH, hl.texels.data(), hl.L, &env);
+      ++nInfinite;
+    }
     std::memcpy(g.w2l, hl.w2l, sizeof(g.w2l));
     g.cosTotalWidth = hl.cosTotalWidth;
     g.cosFalloffStart = hl.cosFalloffStart;
@@ -367,7 +385,14 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
     }
   }
   rs.ts = c->ts;
-  rs.extra = (rs.meshOfTri != nullptr || c->ts.quadMode == 2) ? 1 : 0;
+  rs.envData = nullptr;
+  rs.nInfinite = nInfinite;
+  if (!env.empty()) {
+    CK(c, r->dEnv.ensure(env.size()));
+    CK(c, cudaMemcpy(r->dEnv.p, env.data(), env.size() * 4, cudaMemcpyHostToDevice));
+    rs.envData = r->dEnv.p;
+  }
+  rs.extra = (rs.meshOfTri != nullptr || c->ts.quadMode == 2 || nInfinite > 0) ? 1 : 0;
   rs.ntris = nt;
   rs.nprims = np;
   rs.primToRec = r->dPrimToRec.p;
@@ -638,6 +663,10 @@ static int specularChains(drt_ctx* c, RenderState* r) {
       cur ^= 1;
       RK(traceQueue(c, false, wf.extO[cur], wf.extD[cur], wf.extRange[cur], wf.counts + cur, wf.extHit, wf.extT, st));
     }
+    if (rs.nInfinite > 0) {  // the new rays of this chain that escape: renderer.Li = sum of Le, times the chain weight
+      CK(c, STAGE(launchEscape)(rs, wf, cur, ESCAPE_WEIGHTED, sms, st));
+      c->launches++;
+    }
     uint32_t live = 0;
     CK(c, cudaMemcpyAsync(&live, wf.counts + cur, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
@@ -667,6 +696,10 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
   c->launches += 3;
   // camera rays: Scene.intersect (sampler_renderer.dart:84)
   RK(traceQueue(c, false, wf.extO[0], wf.extD[0], wf.extRange[0], wf.counts + Q_EXT0, wf.extHit, wf.extT, st));
+  if (rs.nInfinite > 0) {  // escaped camera rays see the infinite lights (sampler_renderer.dart:86-92), whatever the integrator
+    CK(c, STAGE(launchEscape)(rs, wf, 0, ESCAPE_CAMERA, sms, st));
+    c->launches++;
+  }
   r->stats.camera_samples += nSlots;
   r->stats.closest_rays += nSlots;
   if (p.integKind == 0) {
@@ -684,6 +717,10 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
       if (bounce == p.maxDepth) break;
       cur ^= 1;
       RK(traceQueue(c, false, wf.extO[cur], wf.extD[cur], wf.extRange[cur], wf.counts + cur, wf.extHit, wf.extT, st));
+      if (rs.nInfinite > 0 && rs.general) {  // path_integrator.dart:106-114: only after a specular bounce, which matte scenes never take
+        CK(c, STAGE(launchEscape)(rs, wf, cur, ESCAPE_PATH, sms, st));
+        c->launches++;
+      }
     }
   } else if (p.integKind == 1) {
     CK(c, STAGE(launchAoSetup)(p, rs, wf, sms, st));
@@ -834,7 +871,7 @@ int drt_set_lights(drt_ctx* c, uint32_t n, const int32_t* kind, const float* L, 
   for (uint32_t i = 0; i < n; ++i) {
     HostLight& l = ls[i];
     l.kind = kind[i];
-    if (l.kind < 0 || l.kind > 3) return fail(c, DRT_E_INVALID, "light kind must be 0 (diffuse area), 1 (point), 2 (distant) or 3 (spot)");
+    if (l.kind < 0 || l.kind > 4) return fail(c, DRT_E_INVALID, "light kind must be 0 (diffuse area), 1 (point), 2 (distant), 3 (spot) or 4 (infinite)");
     if (l.kind != 0 && !pos) return fail(c, DRT_E_INVALID, "point / distant / spot lights need the pos array");
     std::memcpy(l.L, L + 3 * i, 12);
     if (pos) std::memcpy(l.pos, pos + 3 * i, 12);
@@ -861,6 +898,28 @@ int drt_set_spot_params(drt_ctx* c, uint32_t n, const float* world_to_light, con
     l.cosFalloffStart = cos_total_falloff[2 * i + 1];
     l.haveSpot = true;
   }
+  r->sceneTablesValid = false;
+  return DRT_OK;
+}
+
+int drt_set_infinite_light(drt_ctx* c, uint32_t index, int width, int height, const float* rgb, const float* light_to_world,
+                           const float* world_to_light) {
+  if (!c) return DRT_E_INVALID;
+  RenderState* r = state(c);
+  if (index >= r->lights.size() || r->lights[index].kind != 4)
+    return fail(c, DRT_E_STATE, "drt_set_infinite_light: the light must have been declared with kind 4 by the last drt_set_lights");
+  if (!rgb || !light_to_world || !world_to_light) return fail(c, DRT_E_INVALID, "null infinite-light arrays");
+  if (width < 1 || height < 1 || (width & (width - 1)) || (height & (height - 1)) || (uint64_t)width * height > (1u << 26))
+    return fail(c, DRT_E_INVALID, "the radiance map must have power-of-two resolution (level 0 of the reference's MIPMap), at most 64 Mi texels");
+  HostLight& l = r->lights[index];
+  for (int row = 0; row < 3; ++row)
+    for (int col = 0; col < 3; ++col) {
+      l.l2w[3 * row + col] = light_to_world[4 * row + col];
+      l.w2l[3 * row + col] = world_to_light[4 * row + col];
+    }
+  l.mapW = width;
+  l.mapH = height;
+  l.texels.assign(rgb, rgb + 3 * (size_t)width * height);
   r->sceneTablesValid = false;
   return DRT_OK;
 }

@@ -525,6 +525,13 @@ __global__ void __launch_bounds__(128) resolveDirectKernel(RenderParams rp, Rend
           Li = Li * mks1(1.0);
           Ld = Ld + ld3(wf.pendMisF, cap, slot) * Li * wf.pendMisScale[slot];
         }
+      } else if (EXTRA && prim < 0 && rs.lights[light].kind == 4) {  // the BSDF-sampled ray escaped: Li = light.Le(ray), integrator.dart:172-174
+        const float4 d4 = wf.misD[mi];
+        Spec Li = infiniteLe(rs, rs.lights[light], V3{d4.x, d4.y, d4.z});
+        if (!IsBlack(Li)) {
+          Li = Li * mks1(1.0);
+          Ld = Ld + ld3(wf.pendMisF, cap, slot) * Li * wf.pendMisScale[slot];
+        }
       }
     }
     wf.shIdx[slot] = -1;
@@ -554,6 +561,35 @@ __global__ void __launch_bounds__(128) resolveDirectKernel(RenderParams rp, Rend
         st3(wf.Ld, cap, slot, acc);
       }
     }
+  }
+}
+
+// Rays of queue `cur` that escaped the scene pick up the infinite lights' Le (launched only when the scene has one):
+//   ESCAPE_CAMERA    Li = sum of lights.Le(ray)                          sampler_renderer.dart:86-92
+//   ESCAPE_PATH      L += pathThroughput * Le per light, after a specular bounce only   path_integrator.dart:106-114
+//   ESCAPE_WEIGHTED  the same sum through renderer.Li at the end of a specular chain, times the chain weight (integrator.dart:187-290)
+__global__ void __launch_bounds__(128) escapeKernel(RenderScene rs, Wavefront wf, int cur, int mode) {
+  const uint32_t n = wf.counts[cur], cap = wf.cap;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+    if (__float_as_int(wf.extHit[q].w) >= 0) continue;
+    const uint32_t slot = wf.extSlot[cur][q];
+    if (mode == ESCAPE_PATH && !wf.specBounce[slot]) continue;
+    const float4 d4 = wf.extD[cur][q];
+    const V3 d = V3{d4.x, d4.y, d4.z};
+    Spec L = ld3(wf.L, cap, slot);
+    if (mode == ESCAPE_PATH) {
+      const Spec T = ld3(wf.T, cap, slot);
+      for (int i = 0; i < rs.nLights; ++i)
+        if (rs.lights[i].kind == 4) L = L + T * infiniteLe(rs, rs.lights[i], d);
+    } else {
+      Spec Li = mks1(0.0);
+      for (int i = 0; i < rs.nLights; ++i)
+        if (rs.lights[i].kind == 4) Li = Li + infiniteLe(rs, rs.lights[i], d);
+      // T * Li + Lvi of SamplerRenderer.Li with T = 1, Lvi = 0, as the oracle writes it
+      Li = mks1(1.0) * Li + mks1(0.0);
+      L = (mode == ESCAPE_WEIGHTED) ? L + ld3(wf.pendT, cap, slot) * Li : Li;
+    }
+    st3(wf.L, cap, slot, L);
   }
 }
 
@@ -950,6 +986,11 @@ cudaError_t launchShadePath(const RenderParams& rp, const RenderScene& rs, const
 cudaError_t launchResolveDirect(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int cur, int mode,
                                 int nSamplesOfLight, int numSMs, cudaStream_t st) {
   resolveDirectKernel<DRT_EXTRA != 0><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, cur, mode, nSamplesOfLight);
+  return cudaGetLastError();
+}
+
+cudaError_t launchEscape(const RenderScene& rs, const Wavefront& wf, int cur, int mode, int numSMs, cudaStream_t st) {
+  escapeKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rs, wf, cur, mode);
   return cudaGetLastError();
 }
 

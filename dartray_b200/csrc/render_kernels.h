@@ -21,6 +21,7 @@ struct PixelBatch {
   uint32_t shard, nShards, blockPixels;
 };
 
+enum { ESCAPE_CAMERA = 0, ESCAPE_PATH = 1, ESCAPE_WEIGHTED = 2 };
 enum { Q_EXT0 = 0, Q_EXT1 = 1, Q_SHADOW = 2, Q_MIS = 3, Q_HITS = 4, Q_COUNT = 8 };
 
 // render_kernels.cu is compiled twice (shade_device.cuh, DRT_EXTRA): `plain` without per-vertex mesh attributes and the

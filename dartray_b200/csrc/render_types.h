@@ -28,7 +28,8 @@ static_assert(sizeof(GLobe) == 72, "GLobe layout");
 
 struct GLight {
   int32_t kind;  // 0 = DiffuseAreaLight (diffuse_area_light.dart), 1 = PointLight (point_light.dart),
-                 // 2 = DistantLight (distant_light.dart; pos = lightDir), 3 = SpotLight (spot_light.dart)
+                 // 2 = DistantLight (distant_light.dart; pos = lightDir), 3 = SpotLight (spot_light.dart),
+                 // 4 = InfiniteAreaLight (infinite_area_light.dart)
   float L[3];    // Lemit / intensity / radiance
   float pos[3];
   float w2l[9];  // spot: rows of worldToLight's upper 3x3 (Transform.transformVector, transform.dart:139-146)
@@ -37,6 +38,13 @@ struct GLight {
   uint32_t shapeOffset, nShapes;  // ShapeSet (shape_set.dart:26-50): slice of lightShapes / lightShapeAreas
   uint32_t cdfOffset;             // slice of lightCdf: nShapes + 1 floats (Distribution1D, montecarlo.dart:25-48)
   double area;
+  // InfiniteAreaLight: rows of lightToWorld's upper 3x3 (w2l above holds worldToLight's), the radiance map's resolution and
+  // where its tables start in RenderScene::envData (floats):
+  //   texels 3 x W x H | conditional func W x H | conditional cdf H x (W + 1) | conditional funcInt H |
+  //   marginal func H | marginal cdf H + 1 | marginal funcInt 1          (Distribution2D, montecarlo.dart:222-268)
+  float l2w[9];
+  int32_t mapW, mapH;
+  uint32_t envOffset;
 };
 
 // Per direct-lighting light: where its LightSampleOffsets / BSDFSampleOffsets live in a sample record
@@ -84,6 +92,8 @@ struct RenderScene {
   const uint32_t* triIdx;     // ntris x 3 vertex indices
   const GMesh* meshes;
   const float* vertN; const float* vertS; const float* vertUV;
+  const float* envData;  // radiance maps and sampling tables of the infinite lights (GLight::envOffset)
+  int32_t nInfinite;     // number of InfiniteAreaLights: escaped rays pick up their Le (sampler_renderer.dart:86-92)
   int32_t extra;  // 1: mesh attributes or quadrics of shape >= 2 are present (selects the kernels compiled with EXTRA)
 };
 

@@ -1198,6 +1198,114 @@ static __device__ inline V3 shapeSetSample(const RenderScene& rs, const GLight& 
   return RayAt(p, rd, thit);
 }
 
+// ---- InfiniteAreaLight (infinite_area_light.dart) ----------------------------------------------------------------------------
+// MIPMap.lookup with width 0 is triangle(0, s, t) (mipmap.dart:206-212,341-355; TEXTURE_REPEAT, Dart's % is never negative)
+static __device__ inline Spec envTexel(const float* tex, int W, int H, long long s, long long t) {
+  s = ((s % W) + W) % W;
+  t = ((t % H) + H) % H;
+  const float* q = tex + 3 * (size_t)(t * W + s);
+  return Spec{q[0], q[1], q[2]};
+}
+static __device__ __noinline__ void envRadianceCold(const RenderScene& rs, const GLight& l, double u, double v, Spec* out) {
+  const float* tex = rs.envData + l.envOffset;
+  const int W = l.mapW, H = l.mapH;
+  double s = u * W - 0.5, t = v * H - 0.5;
+  const long long s0 = (long long)floor(s), t0 = (long long)floor(t);
+  const double ds = s - s0, dt = t - t0;
+  Spec r = envTexel(tex, W, H, s0, t0) * ((1.0 - ds) * (1.0 - dt)) + envTexel(tex, W, H, s0, t0 + 1) * ((1.0 - ds) * dt) +
+           envTexel(tex, W, H, s0 + 1, t0) * (ds * (1.0 - dt)) + envTexel(tex, W, H, s0 + 1, t0 + 1) * (ds * dt);
+  *out = r * lightRadiance(l);  // _radiance = lookup * L (:240-242)
+}
+static __device__ inline double SphericalTheta(const V3& v) { return acos(clampD((double)v.z, -1.0, 1.0)); }  // vector.dart:185-187
+static __device__ inline double SphericalPhi(const V3& v) {                                                 // vector.dart:189-192
+  double p = atan2((double)v.y, (double)v.x);
+  return (p < 0.0) ? p + 2.0 * DRT_PI : p;
+}
+static __device__ inline V3 xf3(const float* m, const V3& w) {
+  return mkv((double)m[0] * w.x + (double)m[1] * w.y + (double)m[2] * w.z, (double)m[3] * w.x + (double)m[4] * w.y + (double)m[5] * w.z,
+             (double)m[6] * w.x + (double)m[7] * w.y + (double)m[8] * w.z);
+}
+// Light.Le(ray) of an infinite light (:86-91)
+static __device__ inline Spec infiniteLe(const RenderScene& rs, const GLight& l, const V3& d) {
+  const V3 wh = Normalize(xf3(l.w2l, d));
+  const double s = SphericalPhi(wh) * DRT_INV_TWOPI, t = SphericalTheta(wh) * DRT_INV_PI;
+  Spec r;
+  envRadianceCold(rs, l, s, t, &r);
+  return r;
+}
+// Distribution1D.sampleContinuous (montecarlo.dart:50-80) over float32 func / cdf tables
+static __device__ inline double dist1DSample(const float* func, const float* cdf, double funcInt, int count, double u, double* pdf, int* off) {
+  int lo = 0, hi = count + 1;  // upper_bound(cdf, u, last: count + 1)
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (u < (double)cdf[mid]) hi = mid;
+    else lo = mid + 1;
+  }
+  int offset = lo - 1 < 0 ? 0 : lo - 1;
+  if (offset == count) offset = count - 1;
+  if (off) *off = offset;
+  const double dc = (double)cdf[offset + 1] - (double)cdf[offset];
+  double du = 0.0;
+  if (dc != 0.0) du = (u - (double)cdf[offset]) / dc;
+  *pdf = (double)func[offset] / funcInt;
+  return (offset + du) / count;
+}
+struct EnvTables {
+  const float *condFunc, *condCdf, *condInt, *margFunc, *margCdf;
+  double margInt;
+};
+static __device__ inline EnvTables envTables(const RenderScene& rs, const GLight& l) {
+  const size_t W = l.mapW, H = l.mapH;
+  EnvTables t;
+  t.condFunc = rs.envData + l.envOffset + 3 * W * H;
+  t.condCdf = t.condFunc + W * H;
+  t.condInt = t.condCdf + H * (W + 1);
+  t.margFunc = t.condInt + H;
+  t.margCdf = t.margFunc + H;
+  t.margInt = (double)t.margCdf[H + 1];
+  return t;
+}
+// InfiniteAreaLight.sampleLAtPoint (:93-131): direction, pdf and radiance; false when the sample carries nothing
+static __device__ __noinline__ bool infiniteSampleCold(const RenderScene& rs, const GLight& l, double u0, double u1, V3* wi, double* pdf,
+                                                       Spec* Li) {
+  const EnvTables t = envTables(rs, l);
+  const int W = l.mapW, H = l.mapH;
+  double pdfs1, pdfs0;
+  int v;
+  const double uvv = dist1DSample(t.margFunc, t.margCdf, t.margInt, H, u1, &pdfs1, &v);
+  const double uvu = dist1DSample(t.condFunc + (size_t)v * W, t.condCdf + (size_t)v * (W + 1), (double)t.condInt[v], W, u0, &pdfs0, nullptr);
+  const double mapPdf = pdfs0 * pdfs1;
+  *pdf = 0.0;
+  if (mapPdf == 0.0) return false;
+  const double theta = uvv * DRT_PI, phi = uvu * 2.0 * DRT_PI;
+  const double costheta = cos(theta), sintheta = sin(theta), sinphi = sin(phi), cosphi = cos(phi);
+  *wi = xf3(l.l2w, mkv(sintheta * cosphi, sintheta * sinphi, costheta));
+  if (sintheta == 0.0) *pdf = 0.0;
+  else *pdf = mapPdf / (2.0 * DRT_PI * DRT_PI * sintheta);
+  envRadianceCold(rs, l, uvu, uvv, Li);
+  return true;
+}
+// InfiniteAreaLight.pdf (:244-259) with Distribution2D.pdf (montecarlo.dart:250-263)
+static __device__ __noinline__ double infinitePdfCold(const RenderScene& rs, const GLight& l, V3 w) {
+  const V3 wi = xf3(l.w2l, w);
+  const double theta = SphericalTheta(wi), phi = SphericalPhi(wi);
+  const double sintheta = sin(theta);
+  if (sintheta == 0.0) return 0.0;
+  const EnvTables t = envTables(rs, l);
+  const int W = l.mapW, H = l.mapH;
+  const double u = phi * DRT_INV_TWOPI, v = theta * DRT_INV_PI;
+  const int iu = (int)fmin(fmax(trunc(u * W), 0.0), (double)(W - 1)), iv = (int)fmin(fmax(trunc(v * H), 0.0), (double)(H - 1));
+  const double ci = (double)t.condInt[iv];
+  if (ci * t.margInt == 0.0) return 0.0;
+  const double p = ((double)t.condFunc[(size_t)iv * W + iu] * (double)t.margFunc[iv]) / (ci * t.margInt);
+  return p / (2.0 * DRT_PI * DRT_PI * sintheta);
+}
+// Light.pdf(p, wi) for the non-delta lights
+static __device__ inline double lightPdfAny(const RenderScene& rs, const GLight& l, const V3& p, const V3& wi) {
+  if (DRT_EXTRA && l.kind == 4) return infinitePdfCold(rs, l, wi);
+  return shapeSetPdf(rs, l, p, wi);
+}
+
 // What Integrator.EstimateDirect (integrator.dart:119-185) needs traced before it can finish: the
 // shadow ray of the light sample and the closest-hit ray of the BSDF sample, each with the
 // contribution it carries if the query comes out right.
@@ -1223,9 +1331,15 @@ static __device__ inline void estimateDirectSetup(const RenderScene& rs, int lig
   Spec Li;
   V3 segTo;
   double eps2;
-  const bool delta = l.kind != 0;  // isDeltaLight: point, distant, spot
-  const bool distant = l.kind == 2;
-  if (distant) {  // distant_light.dart:41-48: the shadow ray runs to infinity (visibility_tester.dart:31-33)
+  const bool infinite = DRT_EXTRA && l.kind == 4;
+  const bool delta = l.kind != 0 && !infinite;  // isDeltaLight: point, distant, spot
+  const bool distant = l.kind == 2 || infinite;  // the shadow ray runs to infinity (visibility_tester.dart:31-33)
+  if (infinite) {  // infinite_area_light.dart:93-131
+    segTo = p;
+    eps2 = 0.0;
+    Li = mks1(0.0);
+    infiniteSampleCold(rs, l, lu0, lu1, &wi, &lightPdf, &Li);
+  } else if (distant) {  // distant_light.dart:41-48
     wi = V3{l.pos[0], l.pos[1], l.pos[2]};
     lightPdf = 1.0;
     segTo = p;
@@ -1293,7 +1407,7 @@ static __device__ inline void estimateDirectSetup(const RenderScene& rs, int lig
     if (!IsBlack(f) && bPdf > 0.0) {
       double weight = 1.0;
       if ((sampledType & BSDF_SPECULAR) == 0) {
-        lightPdf = shapeSetPdf(rs, l, p, wi);
+        lightPdf = lightPdfAny(rs, l, p, wi);
         if (lightPdf == 0.0) return;
         weight = PowerHeuristic(1, bPdf, 1, lightPdf);
       }
@@ -1316,8 +1430,12 @@ static __device__ inline void whittedLightSetup(const RenderScene& rs, int light
   V3 wi, segTo = p;
   double lightPdf = 1.0, eps2 = 0.0;
   Spec Li;
-  const bool distant = l.kind == 2;
-  if (distant) {  // distant_light.dart:41-48
+  const bool infinite = DRT_EXTRA && l.kind == 4;
+  const bool distant = l.kind == 2 || infinite;
+  if (infinite) {  // infinite_area_light.dart:93-131
+    Li = mks1(0.0);
+    infiniteSampleCold(rs, l, lu0, lu1, &wi, &lightPdf, &Li);
+  } else if (distant) {  // distant_light.dart:41-48
     wi = V3{l.pos[0], l.pos[1], l.pos[2]};
     Li = lightRadiance(l);
   } else if (l.kind != 0) {  // point_light.dart:41-47, spot_light.dart:36-70

@@ -355,6 +355,15 @@ class SceneBuilder:
         self.lights.append(dict(kind=1, L=tuple(intensity), pos=tuple(pos), nsamples=1, shapes=[]))
         return len(self.lights) - 1
 
+    def infinite_light(self, L=(1.0, 1.0, 1.0), nsamples=1, light_to_world=None, texels=None) -> int:
+        """LightSource "infinite" (infinite_area_light.dart:37-69,308-316).  `texels`: level 0 of the light's radiance MIPMap as
+        the reference holds it — (h, w, 3) float32 at power-of-two resolution, already multiplied by L (:50-53) — or None for
+        the 1x1 white map of a scene without "mapname" (:66-68).  Radiance = lookup * L (:240-242)."""
+        l2w = np.eye(4, dtype=np.float32) if light_to_world is None else np.asarray(light_to_world, np.float32).reshape(4, 4)
+        tex = np.ones((1, 1, 3), np.float32) if texels is None else np.ascontiguousarray(texels, dtype=np.float32)
+        self.lights.append(dict(kind=4, L=tuple(L), pos=(0, 0, 0), nsamples=nsamples, shapes=[], l2w=l2w, texels=tex))
+        return len(self.lights) - 1
+
     def distant_light(self, frm, to, L) -> int:
         """DistantLight.Create (distant_light.dart:83-91) with an identity light-to-world: lightDir = normalize(from - to)."""
         d = (np.asarray(frm, np.float32).astype(np.float64) - np.asarray(to, np.float32).astype(np.float64)).astype(np.float32)
@@ -501,6 +510,7 @@ class SceneBuilder:
         for l in self.lights:
             shapes = [base[s[0]] + s[1] for s in l["shapes"]]
             lights.append(dict(kind=l["kind"], L=l["L"], pos=l["pos"], nsamples=l["nsamples"], shapes=shapes,
+                               l2w=l.get("l2w"), texels=l.get("texels"),
                                w2l=l.get("w2l", np.eye(4, dtype=np.float32).reshape(16)), cos=l.get("cos", (0.0, 0.0))))
         mats = self.materials or [(0, (0.5, 0.5, 0.5), 0.0)]
         general = any(m[0] == "lobes" for m in mats)
@@ -553,6 +563,7 @@ class SceneBuilder:
             light_w2l=np.asarray([l["w2l"] for l in lights], np.float32).reshape(-1, 16),
             light_cos=np.asarray([l["cos"] for l in lights], np.float64).reshape(-1, 2),
             light_has_spot=any(l["kind"] == 3 for l in lights),
+            light_infinite=[(i, l["l2w"], l["texels"]) for i, l in enumerate(lights) if l["kind"] == 4],
             light_shape_offsets=np.asarray(np.cumsum([0] + [len(l["shapes"]) for l in lights]), np.uint32),
             light_shape_prims=np.asarray([p for l in lights for p in l["shapes"]], np.uint32),
         )
@@ -589,6 +600,8 @@ def upload_scene(ctx, arrays: dict, split: int = 2, max_node_prims: int = 4):
                    a["light_shape_prims"])
     if a.get("light_has_spot"):
         ctx.set_spot_params(a["light_w2l"], a["light_cos"])
+    for i, l2w, tex in a.get("light_infinite", []):
+        ctx.set_infinite_light(i, tex, l2w, mat_inv(l2w))
 
 
 def configure_render(ctx, camera: PerspectiveCamera, film: Film, sampler: Sampler, integrator: Integrator):

@@ -232,6 +232,15 @@ int drt_set_lights(drt_ctx* ctx, uint32_t n, const int32_t* kind, const float* L
  * spot_light.dart:29-30). */
 int drt_set_spot_params(drt_ctx* ctx, uint32_t n, const float* world_to_light, const double* cos_total_falloff);
 
+/* Replaces InfiniteAreaLight construction (lib/lights/infinite_area_light.dart:37-69,276-316) for light `index`, which the last
+ * drt_set_lights declared with kind 4 (L = the light's L * scale, nsamples as given).  rgb: width x height RGB float32 texels,
+ * row-major — level 0 of the light's radiance MIPMap as the reference holds it (`radianceMap.pyramid[0]`): power-of-two
+ * resolution (the reference's constructor has resampled the image, mipmap.dart:72-139) and already multiplied by L (:50-53);
+ * a scene without "mapname" has the 1 x 1 white map (:66-68).  Radiance is lookup * L as the reference computes it (:240-242).
+ * The library builds the box pyramid and the Distribution2D the light is importance-sampled from. */
+int drt_set_infinite_light(drt_ctx* ctx, uint32_t index, int width, int height, const float* rgb, const float* light_to_world,
+                           const float* world_to_light);
+
 /* Replaces PerspectiveCamera (lib/cameras/perspective_camera.dart:46-57 + lib/core/
  * projective_camera.dart:34-53): the two float32 row-major matrices the camera holds
  * (rasterToCamera, cameraToWorld.startTransform) and its lens / shutter scalars. */

@@ -327,6 +327,18 @@ int orc_set_lights(orc_ctx* c, uint32_t n, const int32_t* kind, const float* L, 
   return 0;
 }
 
+// mirrors drt_set_infinite_light: light `index` (kind 4 in orc_set_lights) gets its transforms and radiance map — level 0 of
+// the reference's MIPMap, power-of-two resolution, RGB float32 (a 1x1 white texel when the scene names no map)
+int orc_set_infinite_light(orc_ctx* c, uint32_t index, int width, int height, const float* rgb, const float* l2w, const float* w2l) {
+  if (index >= c->rs.lights.size() || c->rs.lights[index].kind != 4) { c->err = "not an infinite light"; return -1; }
+  if (width < 1 || height < 1 || (width & (width - 1)) || (height & (height - 1))) { c->err = "map resolution must be a power of two"; return -1; }
+  Light& l = c->rs.lights[index];
+  l.lightToWorld = Transform(l2w, w2l);
+  l.worldToLight = Transform(w2l, l2w);
+  l.setRadianceMap(width, height, rgb);
+  return 0;
+}
+
 // mirrors drt_set_spot_params: worldToLight matrices and the two cosines of the spot lights set by orc_set_lights
 int orc_set_spot_params(orc_ctx* c, uint32_t n, const float* w2l, const double* cosines) {
   if (n != c->rs.lights.size()) return -1;

@@ -33,6 +33,106 @@ int Distribution1D::sampleDiscrete(double u) const {  // :82-92, upper_bound ove
   return std::max(0, ptr - 1);
 }
 
+double Distribution1D::sampleContinuous(double u, double* pdf, int* off) const {  // :50-80
+  int ptr = (int)(std::upper_bound(cdf.begin(), cdf.begin() + count + 1, u,
+                                   [](double v, float c) { return v < (double)c; }) - cdf.begin());
+  int offset = std::max(0, ptr - 1);
+  if (offset == count) offset = count - 1;
+  if (off) *off = offset;
+  double dc = (double)cdf[offset + 1] - (double)cdf[offset];
+  double du = 0.0;
+  if (dc != 0.0) du = (u - (double)cdf[offset]) / dc;
+  if (pdf) *pdf = (double)func[offset] / funcInt;
+  return (offset + du) / count;
+}
+
+void Distribution2D::init(const std::vector<float>& data, int nu, int nv) {
+  pConditionalV.assign(nv, Distribution1D());
+  std::vector<double> marginal(nv);
+  for (int v = 0; v < nv; ++v) {
+    std::vector<double> l(data.begin() + (size_t)v * nu, data.begin() + (size_t)v * nu + nu);
+    pConditionalV[v].init(l);
+    marginal[v] = f32(pConditionalV[v].funcInt);  // Float32List marginalFunc
+  }
+  pMarginal.init(marginal);
+}
+void Distribution2D::sampleContinuous(double u0, double u1, double uv[2], double* pdf) const {
+  double pdfs1, pdfs0;
+  int v;
+  uv[1] = pMarginal.sampleContinuous(u1, &pdfs1, &v);
+  uv[0] = pConditionalV[v].sampleContinuous(u0, &pdfs0, nullptr);
+  *pdf = pdfs0 * pdfs1;
+}
+double Distribution2D::pdf(double u, double v) const {
+  const int cu = pConditionalV[0].count, cv = pMarginal.count;
+  // (u * count).toInt().clamp(0, count - 1): toInt truncates toward zero (and throws on NaN / inf, which a sampled
+  // direction cannot produce here)
+  int iu = (int)std::min<double>(std::max<double>(std::trunc(u * cu), 0.0), cu - 1);
+  int iv = (int)std::min<double>(std::max<double>(std::trunc(v * cv), 0.0), cv - 1);
+  if (pConditionalV[iv].funcInt * pMarginal.funcInt == 0.0) return 0.0;
+  return ((double)pConditionalV[iv].func[iu] * (double)pMarginal.func[iv]) / (pConditionalV[iv].funcInt * pMarginal.funcInt);
+}
+
+static inline double Log2(double x) { return std::log(x) * (1.0 / std::log(2.0)); }  // common.dart:98-103
+
+void MipMap::init(int width, int height, const float* rgb) {
+  levels = 1 + (int)Log2(std::max(width, height));  // mipmap.dart:143
+  pyramid.assign(levels, {});
+  w.assign(levels, 1);
+  h.assign(levels, 1);
+  w[0] = width; h[0] = height;
+  pyramid[0].resize((size_t)width * height);
+  for (size_t i = 0; i < pyramid[0].size(); ++i) pyramid[0][i] = Spec(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+  for (int i = 1; i < levels; ++i) {  // :152-166
+    int sRes = std::max(1, w[i - 1] / 2), tRes = std::max(1, h[i - 1] / 2);
+    w[i] = sRes; h[i] = tRes;
+    pyramid[i].resize((size_t)sRes * tRes);
+    for (int t = 0, p = 0; t < tRes; ++t)
+      for (int s2 = 0; s2 < sRes; ++s2, ++p)
+        pyramid[i][p] = (texel(i - 1, 2 * s2, 2 * t) + texel(i - 1, 2 * s2 + 1, 2 * t) + texel(i - 1, 2 * s2, 2 * t + 1) +
+                         texel(i - 1, 2 * s2 + 1, 2 * t + 1)) * 0.25;
+  }
+}
+Spec MipMap::texel(int level, int64_t s, int64_t t) const {  // :183-204, TEXTURE_REPEAT; Dart's % is never negative
+  const int64_t W = w[level], H = h[level];
+  s = ((s % W) + W) % W;
+  t = ((t % H) + H) % H;
+  return pyramid[level][(size_t)(t * W + s)];
+}
+Spec MipMap::triangle(int level, double s, double t) const {  // :341-355
+  level = std::min(std::max(level, 0), levels - 1);
+  s = s * w[level] - 0.5;
+  t = t * h[level] - 0.5;
+  int64_t s0 = (int64_t)std::floor(s), t0 = (int64_t)std::floor(t);
+  double ds = s - s0, dt = t - t0;
+  return texel(level, s0, t0) * ((1.0 - ds) * (1.0 - dt)) + texel(level, s0, t0 + 1) * ((1.0 - ds) * dt) +
+         texel(level, s0 + 1, t0) * (ds * (1.0 - dt)) + texel(level, s0 + 1, t0 + 1) * (ds * dt);
+}
+Spec MipMap::lookup(double s, double t, double width) const {  // :206-222
+  double level = levels - 1 + Log2(std::fmax(width, 1.0e-8));
+  if (level < 0) return triangle(0, s, t);
+  if (level >= levels - 1) return texel(levels - 1, 0, 0);
+  int iLevel = (int)std::floor(level);
+  double delta = level - iLevel;
+  return triangle(iLevel, s, t) * (1.0 - delta) + triangle(iLevel + 1, s, t) * delta;
+}
+
+void Light::setRadianceMap(int width, int height, const float* rgb) {  // infinite_area_light.dart:276-306
+  radianceMap.init(width, height, rgb);
+  double filter = 1.0 / std::max(width, height);
+  std::vector<float> img((size_t)width * height);
+  for (int v = 0; v < height; ++v) {
+    double vp = (double)v / height;
+    double sinTheta = std::sin(kPi * (v + 0.5) / height);
+    for (int u = 0; u < width; ++u) {
+      double up = (double)u / width;
+      img[u + (size_t)v * width] = f32(radiance(up, vp, filter).luminance());
+      img[u + (size_t)v * width] = f32((double)img[u + (size_t)v * width] * sinTheta);
+    }
+  }
+  distribution.init(img, width, height);
+}
+
 static inline Vec UniformSampleSphere(double u1, double u2) {  // :113-120
   double z = 1.0 - 2.0 * u1;
   double r = std::sqrt(std::fmax(0.0, 1.0 - z * z));
@@ -858,6 +958,34 @@ struct Ctx {
     return pdf / l.area;
   }
 
+  // Light.Le(ray): zero for every light but the infinite one (light.dart:70-72, infinite_area_light.dart:86-91)
+  static double SphericalTheta(const Vec& v) { return std::acos(clampd((double)v.z, -1.0, 1.0)); }  // vector.dart:185-187
+  static double SphericalPhi(const Vec& v) {                                                       // vector.dart:189-192
+    double p = std::atan2((double)v.y, (double)v.x);
+    return (p < 0.0) ? p + 2.0 * kPi : p;
+  }
+  Spec lightLe(const Light& l, const Ray& r) const {
+    if (l.kind != 4) return Spec(0.0);
+    Vec wh = Normalize(l.worldToLight.vector(r.d));
+    double s = SphericalPhi(wh) * INV_TWOPI, t = SphericalTheta(wh) * INV_PI;
+    return l.radiance(s, t, 0.0);
+  }
+  Spec allLightsLe(const Ray& r) const {  // sampler_renderer.dart:88-92, path_integrator.dart:108-112
+    Spec L(0.0);
+    for (const Light& l : rs.lights) L = L + lightLe(l, r);
+    return L;
+  }
+  double lightPdf(const Light& l, const Vec& p, const Vec& w) const {
+    if (l.kind == 4) {  // infinite_area_light.dart:244-259
+      Vec wi = l.worldToLight.vector(w);
+      double theta = SphericalTheta(wi), phi = SphericalPhi(wi);
+      double sintheta = std::sin(theta);
+      if (sintheta == 0.0) return 0.0;
+      return l.distribution.pdf(phi * INV_TWOPI, theta * INV_PI) / (2.0 * kPi * kPi * sintheta);
+    }
+    return shapeSetPdf(l, p, w);
+  }
+
   struct Vis { Ray r; };
   static void setSegment(Vis* v, const Vec& p1, double eps1, const Vec& p2, double eps2, double time) {
     double dist = Distance(p1, p2);  // visibility_tester.dart:26-29
@@ -890,6 +1018,20 @@ struct Ctx {
       }
       return l.L * falloff / DistanceSquared(l.pos, p);
     }
+    if (l.kind == 4) {  // infinite_area_light.dart:93-131
+      double uv[2], mapPdf;
+      l.distribution.sampleContinuous(ls.u0, ls.u1, uv, &mapPdf);
+      *pdf = 0.0;
+      if (mapPdf == 0.0) return Spec(0.0);
+      double theta = uv[1] * kPi, phi = uv[0] * 2.0 * kPi;
+      double costheta = std::cos(theta), sintheta = std::sin(theta);
+      double sinphi = std::sin(phi), cosphi = std::cos(phi);
+      *wi = l.lightToWorld.vector(Vec(sintheta * cosphi, sintheta * sinphi, costheta));
+      if (sintheta == 0.0) *pdf = 0.0;
+      else *pdf = mapPdf / (2.0 * kPi * kPi * sintheta);
+      vis->r = Ray(p, *wi, pEps, kInf, time);  // visibility_tester.dart:31-33
+      return l.radiance(uv[0], uv[1], 0.0);
+    }
     Vec ns;  // diffuse_area_light.dart:59-70
     Vec ps = shapeSetSample(l, ls, &ns, p);
     *wi = Normalize(ps - p);
@@ -906,7 +1048,7 @@ struct Ctx {
     double lightPdf = 0.0, bsdfPdf = 0.0;
     Vis vis;
     Spec Li = sampleLAtPoint(light, p, rayEpsilon, lightSample, time, &wi, &lightPdf, &vis);
-    const bool delta = light.kind != 0;  // isDeltaLight: point, distant, spot
+    const bool delta = light.kind != 0 && light.kind != 4;  // isDeltaLight: point, distant, spot
     if (lightPdf > 0.0 && !Li.isBlack()) {
       Spec f = bsdf.f(wo, wi, flags);
       if (!f.isBlack() && !intersectP(vis.r)) {
@@ -927,7 +1069,7 @@ struct Ctx {
       if (!f.isBlack() && bsdfPdf > 0.0) {
         double weight = 1.0;
         if ((sampledType & BSDF_SPECULAR) == 0) {
-          lightPdf = shapeSetPdf(light, p, wi);
+          lightPdf = this->lightPdf(light, p, wi);
           if (lightPdf == 0.0) return Ld;
           weight = PowerHeuristic(1, bsdfPdf, 1, lightPdf);
         }
@@ -936,7 +1078,9 @@ struct Ctx {
         Ray ray(p, wi, rayEpsilon, kInf, time);
         if (intersect(ray, &lightIsect)) {
           if (g.lightOf[lightIsect.prim] == lightIndex) Li2 = isectLe(lightIsect, -wi);
-        }  // else Li = light.Le(ray) == 0 for area lights
+        } else {
+          Li2 = lightLe(light, ray);  // zero unless the light is infinite
+        }
         if (!Li2.isBlack()) {
           Li2 = Li2 * Spec(1.0);
           Ld = Ld + f * Li2 * (AbsDot(wi, n) * weight / bsdfPdf);
@@ -1010,7 +1154,11 @@ struct Ctx {
         pathThroughput = pathThroughput / continueProbability;
       }
       if (bounces == rs.integ.maxDepth) break;
-      if (!intersect(ray, &localIsect)) break;  // area lights: Light.Le(ray) == 0
+      if (!intersect(ray, &localIsect)) {  // path_integrator.dart:106-114
+        if (specularBounce)
+          for (const Light& lt : rs.lights) L = L + pathThroughput * lightLe(lt, ray);
+        break;
+      }
       // pathThroughput *= transmittance == 1
       pathThroughput = pathThroughput * Spec(1.0);
       isectP = localIsect;
@@ -1137,7 +1285,9 @@ struct Ctx {
         case 3: L = whittedLi(ray, isect, s, rng); break;
         default: L = directLi(ray, isect, s, rng); break;
       }
-    }  // else sum of lights[i].Le(ray) == 0 for area / point lights
+    } else {
+      L = allLightsLe(ray);  // sampler_renderer.dart:86-92
+    }
     // T * Li + Lvi with T = 1, Lvi = 0
     return Spec(1.0) * L + Spec(0.0);
   }

@@ -157,10 +157,32 @@ struct Distribution1D {  // montecarlo.dart:25-98
   int count = 0;
   void init(const std::vector<double>& f);
   int sampleDiscrete(double u) const;
+  double sampleContinuous(double u, double* pdf, int* off) const;  // :50-80
+};
+
+struct Distribution2D {  // montecarlo.dart:222-268
+  std::vector<Distribution1D> pConditionalV;
+  Distribution1D pMarginal;
+  void init(const std::vector<float>& data, int nu, int nv);
+  void sampleContinuous(double u0, double u1, double uv[2], double* pdf) const;
+  double pdf(double u, double v) const;
+};
+
+// lib/core/mipmap.dart restricted to what InfiniteAreaLight uses: TEXTURE_REPEAT, the box pyramid (:142-166), texel (:183-204),
+// triangle (:341-355) and the trilinear lookup (:206-222).  Level 0 arrives at power-of-two resolution: the reference's own
+// constructor has already resampled it (:72-139) when the Dart side reads `radianceMap.pyramid[0]`.
+struct MipMap {
+  int levels = 0;
+  std::vector<int> w, h;
+  std::vector<std::vector<Spec>> pyramid;
+  void init(int width, int height, const float* rgb);
+  Spec texel(int level, int64_t s, int64_t t) const;
+  Spec triangle(int level, double s, double t) const;
+  Spec lookup(double s, double t, double width) const;
 };
 
 struct Light {
-  int kind = 0;  // 0 = DiffuseAreaLight, 1 = PointLight, 2 = DistantLight, 3 = SpotLight
+  int kind = 0;  // 0 = DiffuseAreaLight, 1 = PointLight, 2 = DistantLight, 3 = SpotLight, 4 = InfiniteAreaLight
   Spec L;        // Lemit / intensity / radiance
   Vec pos;       // point / spot light position (world); distant light: lightDir (distant_light.dart:26)
   Transform worldToLight;                            // spot light (spot_light.dart:38-53)
@@ -170,6 +192,13 @@ struct Light {
   std::vector<double> areas;
   double area = 0;
   Distribution1D areaDistribution;
+  // InfiniteAreaLight (infinite_area_light.dart:37-69,276-306): worldToLight above + lightToWorld, the radiance map, its
+  // sampling distribution
+  Transform lightToWorld;
+  MipMap radianceMap;
+  Distribution2D distribution;
+  Spec radiance(double u, double v, double width) const { return radianceMap.lookup(u, v, width) * L; }  // :240-242
+  void setRadianceMap(int width, int height, const float* rgb);
 };
 
 struct Camera {  // perspective_camera.dart:46-57 + projective_camera.dart:34-53

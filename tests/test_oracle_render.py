@@ -249,3 +249,59 @@ def test_uv_orientation_decides_the_side_an_area_light_emits_to():
     assert (default > 0.1) != (mirrored > 0.1) or (same > 0.1) != (mirrored > 0.1)
     assert (same > 0.1) != (mirrored > 0.1)
     assert min(same, mirrored) == 0.0
+
+
+# ---- InfiniteAreaLight (infinite_area_light.dart) ----------------------------------------------------------------------
+def test_constant_infinite_light_closed_forms():
+    # an open matte plane under a constant sky: Lo = kd * L for direct lighting, every camera ray that escapes sees L, and a
+    # white furnace closed by the sky converges to L / (1 - rho) ... here with rho = kd and one bounce of sky light per vertex
+    kd, Lsky = 0.4, 2.0
+    sb = host.SceneBuilder()
+    _plane(sb, material=sb.material((kd, kd, kd)))
+    sb.infinite_light((Lsky, Lsky, Lsky), nsamples=4)
+    cam = host.PerspectiveCamera(host.look_at((0, 2, -4), (0, 0, 0), (0, 1, 0)), fov=10.0)
+    o = _oracle(sb, cam, host.Film(4, 4), host.Sampler(kind=host.SAMPLER_LD, spp=64), host.Integrator(kind=host.INTEGRATOR_DIRECT))
+    o.render()
+    assert o.film_read()["rgb"].mean() == pytest.approx(kd * Lsky, rel=1.5e-2)  # irradiance pi * L, BRDF kd / pi
+    # looking up at the sky: Li = sum of lights.Le(ray) (sampler_renderer.dart:86-92), exact up to the bilinear weights' rounding
+    cam = host.PerspectiveCamera(host.look_at((0, 2, -4), (0, 9, 0), (0, 0, 1)), fov=10.0)
+    o = _oracle(sb, cam, host.Film(4, 4), host.Sampler(kind=host.SAMPLER_LD, spp=4), host.Integrator(kind=host.INTEGRATOR_PATH))
+    o.render()
+    assert np.allclose(o.film_read()["rgb"], Lsky, rtol=1e-6)
+    # path tracing on the open plane: only direct light reaches it (the plane cannot see itself)
+    cam = host.PerspectiveCamera(host.look_at((0, 2, -4), (0, 0, 0), (0, 1, 0)), fov=10.0)
+    o = _oracle(sb, cam, host.Film(4, 4), host.Sampler(kind=host.SAMPLER_LD, spp=256), host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=3))
+    o.render()
+    assert o.film_read()["rgb"].mean() == pytest.approx(kd * Lsky, rel=1.5e-2)
+
+
+def test_infinite_light_map_is_importance_sampled_and_oriented():
+    # a lat-long map that is black except for one bright texel block near the zenith of the LIGHT's frame (+z, v = 0): with the
+    # light-to-world rotation that takes +z to +y the plane is lit from above; direct lighting (importance sampled through
+    # Distribution2D) and the path tracer's BSDF sampling must agree on the answer
+    w, h = 16, 8
+    tex = np.zeros((h, w, 3), np.float32)
+    tex[0:2, :, :] = 5.0  # theta in [0, pi / 4]: a polar cap
+    kd = 0.5
+    sb = host.SceneBuilder()
+    _plane(sb, material=sb.material((kd, kd, kd)))
+    sb.infinite_light((1.0, 1.0, 1.0), nsamples=8, light_to_world=host.rotate(-90, (1, 0, 0)), texels=tex)
+    cam = host.PerspectiveCamera(host.look_at((0, 2, -4), (0, 0, 0), (0, 1, 0)), fov=10.0)
+    res = {}
+    for name, integ, spp in (("direct", host.Integrator(kind=host.INTEGRATOR_DIRECT), 64),
+                             ("path", host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=2), 512)):
+        o = _oracle(sb, cam, host.Film(4, 4), host.Sampler(kind=host.SAMPLER_LD, spp=spp), integ)
+        o.render()
+        res[name] = o.film_read()["rgb"].mean()
+    # cap of half-angle pi / 4 with (bilinearly blurred) radiance 5: E ~ 5 * pi * sin^2(pi / 4) = 2.5 pi -> Lo ~ kd * 2.5; the
+    # blur across the cap's edge moves that by a few per cent, so pin the two estimators against each other tightly and the
+    # closed form loosely
+    assert res["direct"] == pytest.approx(res["path"], rel=3e-2)
+    assert res["direct"] == pytest.approx(kd * 2.5, rel=0.15)
+    # rotated the other way the cap is below the horizon: the plane is dark
+    sb2 = host.SceneBuilder()
+    _plane(sb2, material=sb2.material((kd, kd, kd)))
+    sb2.infinite_light((1.0, 1.0, 1.0), nsamples=8, light_to_world=host.rotate(90, (1, 0, 0)), texels=tex)
+    o = _oracle(sb2, cam, host.Film(4, 4), host.Sampler(kind=host.SAMPLER_LD, spp=16), host.Integrator(kind=host.INTEGRATOR_DIRECT))
+    o.render()
+    assert o.film_read()["rgb"].mean() < 1e-3 * res["direct"]

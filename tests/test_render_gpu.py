@@ -206,6 +206,67 @@ def test_smooth_shaded_meshes_match_oracle(which, integ):
     assert np.abs(g2.film_read()["rgb"] - fg["rgb"]).max() > 1e-2
 
 
+def _sky_scene(which, constant=False):
+    """Objects on a ground plane under an InfiniteAreaLight (infinite_area_light.dart): a procedural lat-long map with a
+    gradient and a bright patch (or the 1 x 1 constant map), rotated so that the map's pole is +y, plus a small quad light."""
+    sb = host.SceneBuilder()
+    lobes = which == "lobes"
+    mat = (lambda kd: sb.material_lobes(host.matte_lobes(kd, 0.0))) if lobes else (lambda kd: sb.material(kd))
+    ground = mat((0.5, 0.5, 0.45))
+    sb.mesh([[-30, 0, -30], [30, 0, -30], [30, 0, 30], [-30, 0, 30]], [[0, 2, 1], [0, 3, 2]], material=ground)
+    sb.sphere(host.translate(-2.5, 1.5, 0), radius=1.5, material=sb.material_lobes(host.glass_lobes(1.0, 1.0, 1.5)) if lobes else mat((0.7, 0.3, 0.3)))
+    sb.sphere(host.translate(2.5, 1.5, 1), radius=1.5, material=sb.material_lobes(host.mirror_lobes((0.9, 0.9, 0.9))) if lobes else mat((0.3, 0.7, 0.3)))
+    sb.cylinder(host.mat_mul(host.translate(0, 1.0, 3), host.rotate(90, (1, 0, 0))), radius=0.8, zmin=-1.0, zmax=1.0, material=mat((0.3, 0.3, 0.8)))
+    sb.mesh([[-1, 6, -1], [1, 6, -1], [1, 6, 1], [-1, 6, 1]], [[0, 1, 2], [0, 2, 3]], material=ground, area_light=(6.0, 6.0, 6.0), nsamples=2)
+    tex = None
+    if not constant:
+        w, h = 32, 16
+        v, u = np.meshgrid((np.arange(h) + 0.5) / h, (np.arange(w) + 0.5) / w, indexing="ij")
+        tex = np.stack([0.3 + 0.7 * (1 - v), 0.4 + 0.5 * (1 - v), 0.6 + 0.4 * u], axis=2).astype(np.float32)
+        tex[2:5, 5:9, :] = (30.0, 28.0, 20.0)  # a sun
+        tex[h // 2:, :, :] *= 0.2               # dim below the horizon
+    sb.infinite_light((0.8, 0.9, 1.0), nsamples=4, light_to_world=host.mat_mul(host.rotate(-90, (1, 0, 0)), host.rotate(40, (0, 0, 1))),
+                      texels=tex)
+    cam = host.PerspectiveCamera(host.look_at((0, 4, -12), (0, 1.5, 0), (0, 1, 0)), fov=40.0)
+    return sb.arrays(), cam
+
+
+@pytest.mark.parametrize("which,constant,integ", [
+    ("matte", False, host.Integrator(kind=host.INTEGRATOR_DIRECT)),
+    ("matte", True, host.Integrator(kind=host.INTEGRATOR_DIRECT, strategy=1)),
+    ("matte", False, host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=3)),
+    ("lobes", False, host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=5)),
+    ("lobes", False, host.Integrator(kind=host.INTEGRATOR_DIRECT, maxdepth=3)),
+    ("lobes", True, host.Integrator(kind=host.INTEGRATOR_WHITTED, maxdepth=3)),
+    ("matte", False, host.Integrator(kind=host.INTEGRATOR_AO, ao_nsamples=8)),
+])
+def test_infinite_light_matches_oracle(which, constant, integ):
+    arrays, cam = _sky_scene(which, constant)
+    g, o, fg, fo = _render_both(arrays, cam, host.Film(80, 60), host.Sampler(kind=host.SAMPLER_LD, spp=4), integ)
+    err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
+    print("sky scene", which, constant, integ.kind, "max rel err", err.max(), "q999", np.quantile(err, 0.999))
+    assert np.quantile(err, 0.999) <= 1e-3
+    assert abs(fg["rgb"].mean() - fo["rgb"].mean()) <= 2e-3 * fo["rgb"].mean()
+    sky = fo["rgb"][:10].mean()
+    assert sky > 0.05  # the escaped camera rays at the top of the frame see the map
+    if integ.kind in (host.INTEGRATOR_DIRECT, host.INTEGRATOR_AO) and which == "matte":
+        assert err.max() <= 1e-3
+        sg, so = g.render_stats(), o.render_stats()
+        assert sg["shadow_rays"] == so["shadow_rays"] and sg["closest_rays"] == so["closest_rays"]
+
+
+def test_infinite_light_needs_its_map():
+    arrays, cam = _sky_scene("matte")
+    arrays["light_infinite"] = []
+    g = capi.Context(0)
+    host.upload_scene(g, arrays)
+    host.configure_render(g, cam, host.Film(8, 8), host.Sampler(kind=host.SAMPLER_LD, spp=1), host.Integrator(kind=host.INTEGRATOR_DIRECT))
+    with pytest.raises(RuntimeError, match="drt_set_infinite_light"):
+        g.render(0, 1)
+    with pytest.raises(RuntimeError, match="power-of-two"):
+        g.set_infinite_light(1, np.ones((3, 5, 3), np.float32), np.eye(4), np.eye(4))
+
+
 # ---- path tracing ------------------------------------------------------------------------------------------
 def test_path_integrator_matches_oracle():
     arrays, cam = _cornell()
