@@ -505,7 +505,7 @@ static int prepare(drt_ctx* c, RenderState* r) {
   if (!r->haveCamera || !r->haveFilm) return fail(c, DRT_E_STATE, "drt_set_camera and drt_set_film must be called before rendering");
   CK(c, cudaSetDevice(c->device));
   RenderParams& p = r->rp;
-  p.nPixelSamples = p.samplerKind == 0 ? roundUpPow2(r->spp) : (p.samplerKind == 1 ? p.xs * p.ys : r->spp);
+  p.nPixelSamples = p.samplerKind == 0 ? roundUpPow2(r->spp) : (p.samplerKind == 1 ? p.xs * p.ys : (p.samplerKind == 3 ? 1 : r->spp));
   if (p.nPixelSamples < 1) return fail(c, DRT_E_INVALID, "sampler produces no samples per pixel");
   buildLayout(r);
   if (p.integKind == 2 && p.strategy == 0 && r->direct.size() != r->lights.size()) return fail(c, DRT_E_STATE, "light table out of date");
@@ -692,7 +692,7 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
   RenderCounters* rc = r->dCounters.p;
   CK(c, STAGE(launchSampler)(p, wf, r->dArrays.p, (int)r->arrays.size(), r->maxVals, r->maxOthers, pb, sms, st));
   CK(c, STAGE(launchResetCounts)(wf, 0xffu, st));
-  CK(c, STAGE(launchRaygen)(p, wf, pb, st));
+  CK(c, STAGE(launchRaygen)(p, wf, pb, rc, st));
   c->launches += 3;
   // camera rays: Scene.intersect (sampler_renderer.dart:84)
   RK(traceQueue(c, false, wf.extO[0], wf.extD[0], wf.extRange[0], wf.counts + Q_EXT0, wf.extHit, wf.extT, st));
@@ -700,8 +700,10 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
     CK(c, STAGE(launchEscape)(rs, wf, 0, ESCAPE_CAMERA, sms, st));
     c->launches++;
   }
-  r->stats.camera_samples += nSlots;
-  r->stats.closest_rays += nSlots;
+  if (p.samplerKind != 3) {  // halton: the accepted samples are counted on the device (raygenKernel)
+    r->stats.camera_samples += nSlots;
+    r->stats.closest_rays += nSlots;
+  }
   if (p.integKind == 0) {
     int cur = 0;
     for (int bounce = 0; bounce <= p.maxDepth; ++bounce) {
@@ -750,7 +752,13 @@ static int renderWindow(drt_ctx* c, int x, int y, int w, int h, uint32_t shard, 
   if (p.integKind >= 2 && r->hasSpecular && p.maxDepth - 1 > kMaxChainLevels - 1)
     return fail(c, DRT_E_UNSUPPORTED, "directlighting / whitted with specular BxDFs: maxdepth above 16 is not on the GPU path");
   if (w <= 0 || h <= 0) return DRT_OK;
-  const uint64_t total = (uint64_t)w * h;
+  uint64_t total = (uint64_t)w * h;
+  const bool halton = p.samplerKind == 3;
+  if (halton) {  // halton_sampler.dart:32-38: spp * delta^2 indices of the sequence take the place of the window's pixels
+    const uint64_t delta = (uint64_t)std::max(w, h);
+    total = (uint64_t)r->spp * delta * delta;
+    r->rp.winX = x; r->rp.winY = y; r->rp.winW = w; r->rp.winH = h;
+  }
   const uint32_t blockPixels = 1024;
   uint64_t mine = total;
   if (nShards > 1) {  // pixels of the blocks shard, shard + nShards, ...
@@ -778,6 +786,7 @@ static int renderWindow(drt_ctx* c, int x, int y, int w, int h, uint32_t shard, 
     for (uint64_t first = 0; first < mine; first += pixelsPerBatch) {
       PixelBatch pb;
       pb.x0 = x; pb.y0 = y; pb.w = w;
+      if (halton) { pb.x0 = 0; pb.y0 = 0; pb.w = 1 << 30; }  // pixelOf: (n mod 2^30, n / 2^30)
       pb.firstPixel = first;
       pb.nPixels = (uint32_t)std::min<uint64_t>(pixelsPerBatch, mine - first);
       pb.pass = (uint32_t)pass;
@@ -787,7 +796,8 @@ static int renderWindow(drt_ctx* c, int x, int y, int w, int h, uint32_t shard, 
   CK(c, cudaStreamSynchronize(c->stream));
   RenderCounters hc;
   CK(c, cudaMemcpy(&hc, r->dCounters.p, sizeof(hc), cudaMemcpyDeviceToHost));
-  r->stats.closest_rays += hc.closestRays;
+  r->stats.closest_rays += hc.closestRays + hc.cameraSamples;  // halton: one camera ray per accepted sample
+  r->stats.camera_samples += hc.cameraSamples;
   r->stats.shadow_rays += hc.shadowRays;
   r->stats.zeroed_samples += hc.zeroedSamples;
   CK(c, cudaMemset(r->dCounters.p, 0, sizeof(RenderCounters)));
@@ -960,7 +970,7 @@ int drt_set_film(drt_ctx* c, int xres, int yres, const double* crop, double xwid
 
 int drt_set_sampler(drt_ctx* c, int kind, int xs, int ys, int spp, int jitter, int pixel_order, int tile_size, uint64_t seed) {
   if (!c) return DRT_E_INVALID;
-  if (kind < 0 || kind > 2) return fail(c, DRT_E_INVALID, "sampler kind must be 0 (lowdiscrepancy), 1 (stratified) or 2 (random)");
+  if (kind < 0 || kind > 3) return fail(c, DRT_E_INVALID, "sampler kind must be 0 (lowdiscrepancy), 1 (stratified), 2 (random) or 3 (halton)");
   if (spp < 1 || xs < 1 || ys < 1) return fail(c, DRT_E_INVALID, "sample counts must be >= 1");
   RenderState* r = state(c);
   r->rp.samplerKind = kind; r->rp.xs = xs; r->rp.ys = ys; r->rp.jitter = jitter; r->rp.seed = seed;

@@ -288,13 +288,75 @@ __global__ void __launch_bounds__(128) samplerSeqKernel(RenderParams rp, Wavefro
   }
 }
 
+// Halton sampler (halton_sampler.dart:59-104): a "pixel" of the batch is one index n of the sequence (pixelOf returns
+// x = n mod 2^30, y = n / 2^30, which also key the sample's streams), one sample per index.  Image position from the radical
+// inverses in bases 3 and 2 scaled by delta = max(width, height); samples beyond the window's INCLUSIVE right / bottom are
+// rejected as written (camXY.x = NaN: raygen leaves them out of the ray queue, the film kernel skips them); lens and time from
+// bases 5, 7, 11 at n + 1 (currentSample has been incremented by then); integrator arrays by LatinHypercube.
+static __device__ inline double RadicalInverse(uint64_t n, int base) {  // montecarlo.dart:327-339: a truncated double product
+  double val = 0.0;
+  const double invBase = 1.0 / base;
+  double invBi = invBase;
+  while (n > 0) {
+    const int d_i = (int)(n % (uint64_t)base);
+    val += d_i * invBi;
+    n = (uint64_t)((double)n * invBase);
+    invBi *= invBase;
+  }
+  return val;
+}
+__global__ void __launch_bounds__(128) samplerHaltonKernel(RenderParams rp, Wavefront wf, const SampleArray* __restrict__ arrays,
+                                                           int nArrays, PixelBatch pb) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pb.nPixels) return;
+  int x, y;
+  pixelOf(pb, p, &x, &y);
+  const uint64_t n = ((uint64_t)(uint32_t)y << 30) | (uint32_t)x;
+  const uint32_t cap = wf.cap;
+  const double u = RadicalInverse(n, 3), v = RadicalInverse(n, 2);
+  const double lerpDelta = (double)max(rp.winW, rp.winH), left = rp.winX, top = rp.winY;
+  const double imageX = left * (1.0 - u) + (left + lerpDelta) * u, imageY = top * (1.0 - v) + (top + lerpDelta) * v;
+  if (imageX > rp.winX + rp.winW - 1 || imageY > rp.winY + rp.winH - 1) {
+    wf.camXY[p] = make_double2(CUDART_NAN, CUDART_NAN);
+    return;
+  }
+  wf.camXY[p] = make_double2(imageX, imageY);
+  wf.camLens[p] = make_double2(RadicalInverse(n + 1, 5), RadicalInverse(n + 1, 7));
+  wf.camTime[p] = (float)RadicalInverse(n + 1, 11);
+  Stream rng{streamKey(rp.seed, x, y, pb.pass, DRT_STREAM_PIXEL), 0};
+  for (int a = 3; a < nArrays; ++a) {  // LatinHypercube (montecarlo.dart:305-325)
+    const SampleArray A = arrays[a];
+    const uint32_t nS = (uint32_t)A.nSamples, nDim = (uint32_t)A.dims;
+    const double delta = 1.0 / nS;
+    float* vv = wf.vals + (size_t)A.dest * cap + p;
+    for (uint32_t s = 0; s < nS; ++s)
+      for (uint32_t j = 0; j < nDim; ++j) vv[(size_t)(nDim * s + j) * cap] = (float)fmin((s + rng.randomFloat()) * delta, DRT_ONE_MINUS_EPS);
+    for (uint32_t dd = 0; dd < nDim; ++dd)
+      for (uint32_t j = 0; j < nS; ++j) {
+        const uint32_t o = j + rng.randomUint() % (nS - j);
+        const float t = vv[(size_t)(nDim * j + dd) * cap];
+        vv[(size_t)(nDim * j + dd) * cap] = vv[(size_t)(nDim * o + dd) * cap];
+        vv[(size_t)(nDim * o + dd) * cap] = t;
+      }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Camera rays (perspective_camera.dart:93-132; ray differentials only feed texture filtering and are
 // not generated) + per-slot state reset.  Extension queue 0 = all slots in slot order.
-__global__ void __launch_bounds__(256) raygenKernel(RenderParams rp, Wavefront wf, PixelBatch pb, uint32_t nSlots) {
+__global__ void __launch_bounds__(256) raygenKernel(RenderParams rp, Wavefront wf, PixelBatch pb, uint32_t nSlots, RenderCounters* rc) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s == 0) wf.counts[Q_EXT0] = nSlots;
-  if (s >= nSlots) return;
+  uint32_t qi = s;  // position in extension queue 0
+  if (rp.samplerKind == 3) {  // halton: the rejected indices of the sequence never become rays (whole warps take this branch)
+    const bool accepted = s < nSlots && !isnan(wf.camXY[s].x);
+    qi = warpPush(&wf.counts[Q_EXT0], accepted);
+    const unsigned m = __ballot_sync(FULL, accepted);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&rc->cameraSamples, (unsigned long long)__popc(m));
+    if (!accepted) return;
+  } else {
+    if (s == 0) wf.counts[Q_EXT0] = nSlots;
+    if (s >= nSlots) return;
+  }
   const uint32_t n = (uint32_t)rp.nPixelSamples, cap = wf.cap;
   int x, y;
   pixelOf(pb, s / n, &x, &y);
@@ -324,10 +386,10 @@ __global__ void __launch_bounds__(256) raygenKernel(RenderParams rp, Wavefront w
     d = Normalize(Pfocus - o);
   }
   V3 wo = XfPoint(rp.cameraToWorld, o), wd = XfVector(rp.cameraToWorld, d);
-  wf.extO[0][s] = make_float4(wo.x, wo.y, wo.z, 0.f);
-  wf.extD[0][s] = make_float4(wd.x, wd.y, wd.z, CUDART_INF_F);
-  wf.extRange[0][s] = make_double2(0.0, CUDART_INF);
-  wf.extSlot[0][s] = s;
+  wf.extO[0][qi] = make_float4(wo.x, wo.y, wo.z, 0.f);
+  wf.extD[0][qi] = make_float4(wd.x, wd.y, wd.z, CUDART_INF_F);
+  wf.extRange[0][qi] = make_double2(0.0, CUDART_INF);
+  wf.extSlot[0][qi] = s;
   st3(wf.L, cap, s, Spec{0.f, 0.f, 0.f});
   st3(wf.T, cap, s, Spec{1.f, 1.f, 1.f});
   wf.shIdx[s] = -1;
@@ -866,6 +928,7 @@ __global__ void __launch_bounds__(128) directSampleKernel(RenderParams rp, Rende
 __global__ void __launch_bounds__(256) filmKernel(RenderParams rp, Wavefront wf, uint32_t nSlots, RenderCounters* rc) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nSlots) return;
+  if (rp.samplerKind == 3 && isnan(wf.camXY[s].x)) return;  // halton: a rejected index of the sequence
   Spec L = ld3(wf.L, wf.cap, s);
   const double lum = Luminance(L);
   if (isnan(L.r) || isnan(L.g) || isnan(L.b) || lum < -1e-5 || isinf(lum)) {
@@ -957,16 +1020,18 @@ cudaError_t launchSampler(const RenderParams& rp, const Wavefront& wf, const Sam
     uint64_t tasks = (uint64_t)pb.nPixels * nArrays;
     int grid = gridFor(tasks * G, block, numSMs, 16);
     samplerLDKernel<<<grid, block, smem, st>>>(rp, wf, dArrays, nArrays, maxVals, pb, G);
+  } else if (rp.samplerKind == 3) {
+    samplerHaltonKernel<<<(pb.nPixels + 127) / 128, 128, 0, st>>>(rp, wf, dArrays, nArrays, pb);
   } else {
     samplerSeqKernel<<<(pb.nPixels + 127) / 128, 128, 0, st>>>(rp, wf, dArrays, nArrays, pb);
   }
   return cudaGetLastError();
 }
 
-cudaError_t launchRaygen(const RenderParams& rp, const Wavefront& wf, const PixelBatch& pb, cudaStream_t st) {
+cudaError_t launchRaygen(const RenderParams& rp, const Wavefront& wf, const PixelBatch& pb, RenderCounters* rc, cudaStream_t st) {
   const uint32_t nSlots = pb.nPixels * (uint32_t)rp.nPixelSamples;
   if (nSlots == 0) return cudaSuccess;
-  raygenKernel<<<(nSlots + 255) / 256, 256, 0, st>>>(rp, wf, pb, nSlots);
+  raygenKernel<<<(nSlots + 255) / 256, 256, 0, st>>>(rp, wf, pb, nSlots, rc);
   return cudaGetLastError();
 }
 

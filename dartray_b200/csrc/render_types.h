@@ -108,7 +108,8 @@ struct RenderParams {
   const float* filterTable;  // 256 floats
   double* film;              // width*height x (X, Y, Z, weight)
   // sampler
-  int32_t samplerKind;  // 0 lowdiscrepancy, 1 stratified, 2 random
+  int32_t samplerKind;  // 0 lowdiscrepancy, 1 stratified, 2 random, 3 halton
+  int32_t winX, winY, winW, winH;  // halton: the sampler's window (halton_sampler.dart:32-38), set per render call
   int32_t xs, ys, jitter;
   int32_t nPixelSamples;  // samples per pixel visit
   uint64_t seed;
@@ -171,7 +172,7 @@ struct Wavefront {
 };
 
 struct RenderCounters {  // mirrors the reference's ray counters (stats.dart:541-555)
-  unsigned long long cameraSamples, closestRays, shadowRays, zeroedSamples;
+  unsigned long long cameraSamples, closestRays, shadowRays, zeroedSamples;  // cameraSamples: halton only (accepted samples)
 };
 
 }  // namespace drt

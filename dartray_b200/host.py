@@ -207,7 +207,7 @@ class Film:
         return left, top, width, height
 
 
-SAMPLER_LD, SAMPLER_STRATIFIED, SAMPLER_RANDOM = 0, 1, 2
+SAMPLER_LD, SAMPLER_STRATIFIED, SAMPLER_RANDOM, SAMPLER_HALTON = 0, 1, 2, 3
 INTEGRATOR_PATH, INTEGRATOR_AO, INTEGRATOR_DIRECT, INTEGRATOR_WHITTED = 0, 1, 2, 3
 RNG_SERIAL, RNG_KEYED = 0, 1
 

@@ -1356,6 +1356,20 @@ void GetSubWindow(int w, int h, int num, int count, int e[4]) {
   e[3] = std::min((int)std::floor(Lerp(ty1, 0, h)), h);
 }
 
+// montecarlo.dart:327-339: `n = (n * invBase).toInt()` is a double product truncated, not an integer division
+static double RadicalInverse(uint64_t n, int base) {
+  double val = 0.0;
+  const double invBase = 1.0 / base;
+  double invBi = invBase;
+  while (n > 0) {
+    const int d_i = (int)(n % (uint64_t)base);
+    val += d_i * invBi;
+    n = (uint64_t)((double)n * invBase);
+    invBi *= invBase;
+  }
+  return val;
+}
+
 // Samples of one pixel visit.  `pass` only matters for the random sampler (one visit per pass).
 // Serial mode draws everything from `serial`; keyed mode derives streams from (seed, x, y).
 int pixelSamples(const SamplerCfg& sc, const SampleLayout& layout, const Camera& cam, int x, int y, int pass, Rng* serial,
@@ -1400,6 +1414,27 @@ int pixelSamples(const SamplerCfg& sc, const SampleLayout& layout, const Camera&
   }
   KeyedRng k(sc.seed, x, y, (uint32_t)pass, kStreamPixel);
   Rng& rng = keyed ? (Rng&)k : *serial;
+  if (sc.kind == 3) {  // halton_sampler.dart:59-104: (x, y) carry the sequence index n = y * 2^30 + x, one sample per index
+    const uint64_t n = ((uint64_t)(uint32_t)y << 30) | (uint32_t)x;
+    const double u = RadicalInverse(n, 3), v = RadicalInverse(n, 2);
+    const double lerpDelta = (double)std::max(sc.winW, sc.winH);
+    const double left = sc.winX, top = sc.winY;
+    const double imageX = left * (1.0 - u) + (left + lerpDelta) * u;  // Lerp, common.dart:80-81
+    const double imageY = top * (1.0 - v) + (top + lerpDelta) * v;
+    // `right` and `bottom` are the INCLUSIVE last pixel coordinates (sampler.dart:53-55), so the last column and row of the
+    // window only receive samples on their left / top edge: as written
+    if (imageX > sc.winX + sc.winW - 1 || imageY > sc.winY + sc.winH - 1) { out.clear(); return 0; }
+    out.resize(1);
+    out[0].alloc(layout);
+    out[0].imageX = imageX;
+    out[0].imageY = imageY;
+    out[0].lensU = RadicalInverse(n + 1, 5);  // currentSample has been incremented by now (:82-89)
+    out[0].lensV = RadicalInverse(n + 1, 7);
+    out[0].time = Lerp(RadicalInverse(n + 1, 11), cam.shutterOpen, cam.shutterClose);
+    for (size_t j = 0; j < layout.n1D.size(); ++j) LatinHypercube(out[0].oneD[j].data(), layout.n1D[j], 1, rng);
+    for (size_t j = 0; j < layout.n2D.size(); ++j) LatinHypercube(out[0].twoD[j].data(), layout.n2D[j], 2, rng);
+    return 1;
+  }
   if (sc.kind == 1) {  // stratified_sampler.dart:67-124
     int n = sc.xs * sc.ys;
     out.resize(n);
@@ -1492,7 +1527,15 @@ void RenderScene::render(int taskNum, int taskCount, int nthreads) {
     x = ext[0] + e[0]; w = e[1] - e[0];
     y = ext[2] + e[2]; h = e[3] - e[2];
   }
-  std::vector<int32_t> px = pixelOrder(sampler, x, y, w, h);
+  std::vector<int32_t> px;
+  if (sampler.kind == 3) {  // halton_sampler.dart:32-38: spp * delta^2 sequence indices instead of pixels
+    sampler.winX = x; sampler.winY = y; sampler.winW = w; sampler.winH = h;
+    const uint64_t delta = (uint64_t)std::max(w, h), wanted = (uint64_t)sampler.spp * delta * delta;
+    px.reserve(2 * wanted);
+    for (uint64_t n = 0; n < wanted; ++n) { px.push_back((int32_t)(n & 0x3fffffffu)); px.push_back((int32_t)(n >> 30)); }
+  } else {
+    px = pixelOrder(sampler, x, y, w, h);
+  }
   const size_t nPix = px.size() / 2;
   const int passes = sampler.kind == 2 ? sampler.spp : 1;  // random sampler quirk: spp visits of spp samples
 

@@ -305,3 +305,44 @@ def test_infinite_light_map_is_importance_sampled_and_oriented():
     o = _oracle(sb2, cam, host.Film(4, 4), host.Sampler(kind=host.SAMPLER_LD, spp=16), host.Integrator(kind=host.INTEGRATOR_DIRECT))
     o.render()
     assert o.film_read()["rgb"].mean() < 1e-3 * res["direct"]
+
+
+# ---- HaltonSampler (halton_sampler.dart) --------------------------------------------------------------------------------
+def test_halton_sampler_radical_inverses_and_window():
+    # a white furnace-like flat field: every accepted sample returns the same radiance, so the box-filtered image is constant
+    # wherever samples land and the film weights count the samples: spp * delta^2 * (accepted area / delta^2)
+    sb = host.SceneBuilder()
+    sb.infinite_light((1.0, 1.0, 1.0))
+    cam = host.PerspectiveCamera(host.look_at((0, 0, -5), (0, 0, 0), (0, 1, 0)), fov=40.0)
+    spp, W, H = 4, 12, 8
+    o = _oracle(sb, cam, host.Film(W, H, filter="box", xwidth=0.5, ywidth=0.5), host.Sampler(kind=host.SAMPLER_HALTON, spp=spp),
+                host.Integrator(kind=host.INTEGRATOR_PATH))
+    o.render()
+    f = o.film_read()
+    st = o.render_stats()
+    # the sample window is [0, W] x [0, H] (box filter 0.5: image_film.dart:247-252) -> delta = W + 1 = 13, wanted = 4 * 169 indices;
+    # accepted: imageX <= W and imageY <= H - ... the INCLUSIVE right / bottom quirk (see the oracle): x <= 12, y <= 8
+    delta = W + 1
+    n = np.arange(spp * delta * delta)
+    def radical_inverse(n, base):
+        out = np.zeros(n.shape)
+        inv = 1.0 / base
+        f_ = inv
+        n = n.copy()
+        while n.any():
+            out += (n % base) * f_
+            n = (n * inv).astype(np.int64)  # the reference truncates a double product
+            f_ *= inv
+        return out
+    ix, iy = radical_inverse(n, 3) * delta, radical_inverse(n, 2) * delta
+    acc = (ix <= W) & (iy <= H)
+    assert st["camera_samples"] == int(acc.sum())
+    assert np.allclose(f["rgb"][f["weight"] > 0], 1.0, rtol=1e-6)
+    # per-pixel sample counts: box filter of half-width 0.5 -> the pixel whose centre is within 0.5 of the sample
+    cnt = np.zeros((H, W))
+    for x_, y_ in zip(ix[acc], iy[acc]):
+        dx, dy = x_ - 0.5, y_ - 0.5
+        for py in range(max(int(math.ceil(dy - 0.5)), 0), min(int(math.floor(dy + 0.5)), H - 1) + 1):
+            for px in range(max(int(math.ceil(dx - 0.5)), 0), min(int(math.floor(dx + 0.5)), W - 1) + 1):
+                cnt[py, px] += 1
+    assert np.array_equal(f["weight"], cnt.astype(np.float32))

@@ -267,6 +267,33 @@ def test_infinite_light_needs_its_map():
         g.set_infinite_light(1, np.ones((3, 5, 3), np.float32), np.eye(4), np.eye(4))
 
 
+@pytest.mark.parametrize("integ", [host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=4), host.Integrator(kind=host.INTEGRATOR_DIRECT),
+                                   host.Integrator(kind=host.INTEGRATOR_AO, ao_nsamples=8)])
+def test_halton_sampler_matches_oracle(integ):
+    """halton_sampler.dart: a global sequence scattered over the window with rejection, LatinHypercube integrator samples."""
+    arrays, cam = _cornell()
+    smp = host.Sampler(kind=host.SAMPLER_HALTON, spp=6, seed=3)
+    g, o, fg, fo = _render_both(arrays, cam, host.Film(72, 40), smp, integ)
+    sg, so = g.render_stats(), o.render_stats()
+    assert sg["camera_samples"] == so["camera_samples"] > 0  # the same indices of the sequence are accepted
+    assert np.array_equal(fg["weight"], fo["weight"])         # ... and land in the same pixels (box filter: sample counts)
+    err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
+    print("halton", integ.kind, "max rel err", err.max())
+    assert np.quantile(err, 0.999) <= 1e-3
+    if integ.kind != host.INTEGRATOR_PATH:
+        assert err.max() <= 1e-3 and sg["shadow_rays"] == so["shadow_rays"] and sg["closest_rays"] == so["closest_rays"]
+    # shards of the sequence tile it: the union of two shards is the whole render
+    films = []
+    for sh in range(2):
+        gs = capi.Context(0)
+        host.upload_scene(gs, arrays)
+        host.configure_render(gs, cam, host.Film(72, 40), smp, integ)
+        gs.render_shard(sh, 2)
+        films.append(gs.film_read())
+    assert np.array_equal(films[0]["weight"] + films[1]["weight"], fg["weight"])
+    assert np.allclose(films[0]["xyz"] + films[1]["xyz"], fg["xyz"], rtol=1e-5, atol=1e-6)  # xyz: the unnormalised sums
+
+
 # ---- path tracing ------------------------------------------------------------------------------------------
 def test_path_integrator_matches_oracle():
     arrays, cam = _cornell()
