@@ -425,7 +425,7 @@ def main():
         },
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-            "traffic": traffic, "kernel": "traceKernel<closest> on the incoherent set",
+            "traffic": traffic, "kernel": "traceFastKernel<closest, triangles-only leaf code> on the incoherent set",
             "algorithmic_bytes_per_launch": alg_bytes,
             "per_ray": {"nodes_visited": w["nodes_visited"] / w["rays"], "prims_tested": w["prims_tested"] / w["rays"],
                         "bytes": alg_bytes / w["rays"]},
