@@ -7,7 +7,7 @@ import pytest
 
 from dartray_b200 import capi, host, scenes
 from tests.oracle_lib import Oracle
-from tools.make_golden import FILM, RENDERS
+from tools.make_golden import FEATURES, FILM, RENDERS, feature_scene
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -91,6 +91,40 @@ def test_gpu_matches_cornell_path_golden():
     assert np.array_equal(f["weight"], g["path_weight"])
     err = np.abs(f["rgb"] - g["path_rgb"]) / np.maximum(np.abs(g["path_rgb"]), 1e-3)
     assert err.max() <= 1e-3
+
+
+def _feature_render(ctx, name):
+    arrays, cam, sampler, integ = feature_scene(name)
+    host.upload_scene(ctx, arrays)
+    host.configure_render(ctx, cam, host.Film(*FILM), sampler, integ)
+    ctx.render(0, 1)
+    return ctx
+
+
+@pytest.mark.parametrize("name", sorted(FEATURES))
+def test_oracle_reproduces_feature_golden(name):
+    g = np.load(os.path.join(GOLD, "render_features.npz"))
+    o = _feature_render(Oracle(), name)
+    f = o.film_read()
+    assert np.array_equal(f["weight"], g[name + "_weight"])
+    assert np.allclose(f["rgb"], g[name + "_rgb"], rtol=1e-6, atol=1e-7)  # libm pow / sin / cos / atan2
+    st = o.render_stats()
+    assert [st["camera_samples"], st["closest_rays"], st["shadow_rays"]] == g[name + "_rays"].tolist()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(FEATURES))
+def test_gpu_matches_feature_golden(name):
+    g = np.load(os.path.join(GOLD, "render_features.npz"))
+    c = _feature_render(capi.Context(0), name)
+    f = c.film_read()
+    assert np.array_equal(f["weight"], g[name + "_weight"])
+    ref = g[name + "_rgb"]
+    err = np.abs(f["rgb"] - ref) / np.maximum(np.abs(ref), 1e-3)
+    assert np.quantile(err, 0.995) <= 1e-3 and abs(f["rgb"].mean() - ref.mean()) <= 5e-3 * ref.mean()
+    assert c.render_stats()["camera_samples"] == g[name + "_rays"][0]
+    if name.endswith("direct"):
+        assert err.max() <= 1e-3
 
 
 def test_host_bvh_builder_reproduces_golden_topology(drt_lib):

@@ -93,10 +93,45 @@ def material_vectors():
                         path_rays=np.array([st["camera_samples"], st["closest_rays"], st["shadow_rays"]], np.int64))
 
 
+# Scenes of the widened path: every remaining quadric with a cylinder light; smooth-shaded meshes (per-vertex N / S /
+# uv) under BxDF lists; an environment-mapped InfiniteAreaLight with glass and mirror spheres; the halton sampler.
+FEATURES = {
+    "quadrics_direct": ("_quadric_room", (), host.Sampler(kind=host.SAMPLER_LD, spp=2, seed=5), host.Integrator(kind=host.INTEGRATOR_DIRECT)),
+    "smooth_path": ("_smooth_room", ("lobes",), host.Sampler(kind=host.SAMPLER_LD, spp=2, seed=5), host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=4)),
+    "sky_path": ("_sky_scene", ("lobes",), host.Sampler(kind=host.SAMPLER_LD, spp=2, seed=5), host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=4)),
+    "sky_direct": ("_sky_scene", ("matte",), host.Sampler(kind=host.SAMPLER_LD, spp=2, seed=5), host.Integrator(kind=host.INTEGRATOR_DIRECT)),
+    "halton_direct": ("_cornell", (), host.Sampler(kind=host.SAMPLER_HALTON, spp=3, seed=5), host.Integrator(kind=host.INTEGRATOR_DIRECT)),
+}
+
+
+def feature_scene(name):
+    import tests.test_render_gpu as T
+    fn, args, sampler, integ = FEATURES[name]
+    arrays, cam = getattr(T, fn)(*args)
+    return arrays, cam, sampler, integ
+
+
+def feature_vectors():
+    out = {}
+    for name in FEATURES:
+        arrays, cam, sampler, integ = feature_scene(name)
+        o = Oracle()
+        host.upload_scene(o, arrays)
+        host.configure_render(o, cam, host.Film(*FILM), sampler, integ)
+        o.render(0, 1, 1)
+        f = o.film_read()
+        st = o.render_stats()
+        out[f"{name}_rgb"] = f["rgb"]
+        out[f"{name}_weight"] = f["weight"]
+        out[f"{name}_rays"] = np.array([st["camera_samples"], st["closest_rays"], st["shadow_rays"]], np.int64)
+    np.savez_compressed(os.path.join(OUT, "render_features.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     trace_vectors()
     render_vectors()
     material_vectors()
+    feature_vectors()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
