@@ -493,6 +493,12 @@ class GpuSamplerRenderer extends Renderer {
     } else if (sampler is RandomSampler) {
       final RandomSampler s = sampler;
       drt.setSampler(2, 1, 1, s.samplesPerPixel, 1, order(s.pixels), 32, taskNum);
+    } else if (sampler is HaltonSampler) {
+      // wantedSamples = samplesPerPixel * max(width, height)^2 (halton_sampler.dart:32-38): the library derives it from spp
+      drt.setSampler(3, 1, 1, sampler.samplesPerPixel, 1, 1, 32, taskNum);
+    } else if (sampler is AdaptiveSampler) {
+      final AdaptiveSampler s = sampler;  // minSamples / maxSamples are already normalised (adaptive_sampler.dart:52-84)
+      drt.setSampler(4, s.minSamples, s.maxSamples, s.maxSamples, s.method, order(s.pixels), 32, taskNum);
     } else {
       throw new GpuUnsupported('sampler ${sampler.runtimeType}');
     }

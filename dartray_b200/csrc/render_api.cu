@@ -74,6 +74,7 @@ struct RenderState {
   DevBuf<uint32_t> dMeshOfTri, dTriIdx;
   DevBuf<GMesh> dMeshes;
   DevBuf<float> dVertN, dVertS, dVertUV, dEnv;
+  DevBuf<uint32_t> dAdaptList, dAdaptCount;  // adaptive sampler: pixels to supersample
   DevBuf<DirectOffsets> dDirect;
   DevBuf<SampleArray> dArrays;
   DevBuf<double> dFilm;
@@ -108,7 +109,7 @@ void drtRenderStateDestroy(drt_ctx* c) {
   if (!r) return;
   r->dPrimToRec.release(); r->dPrimAttr.release(); r->dLightShapes.release(); r->dMaterials.release(); r->dLights.release();
   r->dLightCdf.release(); r->dTable.release(); r->dDirect.release(); r->dArrays.release();
-  r->dMeshOfTri.release(); r->dTriIdx.release(); r->dMeshes.release(); r->dVertN.release(); r->dVertS.release(); r->dVertUV.release(); r->dEnv.release();
+  r->dMeshOfTri.release(); r->dTriIdx.release(); r->dMeshes.release(); r->dVertN.release(); r->dVertS.release(); r->dVertUV.release(); r->dEnv.release(); r->dAdaptList.release(); r->dAdaptCount.release();
   r->dFilm.release(); r->dCounters.release(); r->dRgb.release(); r->dXyz.release(); r->dWeight.release();
   if (r->wfMem) cudaFree(r->wfMem);
   delete r;
@@ -156,7 +157,7 @@ static void buildLayout(RenderState* r) {
     if (p.strategy == 0) {
       for (const HostLight& l : r->lights) {
         int n = l.nSamples;
-        if (p.samplerKind == 0) n = roundUpPow2(n);  // LowDiscrepancySampler.roundSize
+        if (p.samplerKind == 0 || p.samplerKind == 4) n = roundUpPow2(n);  // LowDiscrepancySampler / AdaptiveSampler.roundSize
         dn.push_back(n);
         dl.push_back(offsets(n));
         db.push_back(offsets(n));
@@ -435,6 +436,8 @@ static void carve(ByteArena& a, Wavefront& wf, uint32_t cap, uint32_t shCap, int
   wf.misHit = a.take<float4>(cap); wf.misT = a.take<double>(cap);
   wf.counts = a.take<uint32_t>(Q_COUNT);
   wf.hitList = a.take<uint32_t>(cap);
+  wf.camPrim = a.take<int32_t>(cap);
+  wf.adaptFlag = a.take<uint8_t>(cap);
   if (chains) {  // directlighting with specular BxDFs: counters per recursion level + a copy of the camera-ray queue
     wf.specCtr = a.take<uint32_t>(cap);
     wf.specCtrAt = a.take<uint32_t>((size_t)kMaxChainLevels * cap);
@@ -499,6 +502,17 @@ static void getSubWindow(int w, int h, int num, int count, int e[4]) {
   e[3] = std::min((int)std::floor(lerp(ty1, 0, h)), h);
 }
 
+// AdaptiveSampler's constructor (adaptive_sampler.dart:40-84): min / max swapped into order, rounded up to powers of two, at least
+// two initial samples, and more maximum than minimum samples
+static void adaptiveCounts(int mins, int maxs, int* mn, int* mx) {
+  if (mins > maxs) std::swap(mins, maxs);
+  int a = roundUpPow2(mins), b = roundUpPow2(maxs);
+  if (a < 2) a = 2;
+  if (a == b) b *= 2;
+  *mn = a;
+  *mx = b;
+}
+
 static int prepare(drt_ctx* c, RenderState* r) {
   if (c->device == DRT_DEVICE_NONE) return fail(c, DRT_E_NODEVICE, kNoDevice);
   if (!c->built) return fail(c, DRT_E_STATE, "drt_build_bvh must be called before rendering");
@@ -506,6 +520,12 @@ static int prepare(drt_ctx* c, RenderState* r) {
   CK(c, cudaSetDevice(c->device));
   RenderParams& p = r->rp;
   p.nPixelSamples = p.samplerKind == 0 ? roundUpPow2(r->spp) : (p.samplerKind == 1 ? p.xs * p.ys : (p.samplerKind == 3 ? 1 : r->spp));
+  if (p.samplerKind == 4) {  // the first visit of every pixel: minSamples (renderWindow switches to maxSamples for the second)
+    int mn, mx;
+    adaptiveCounts(p.xs, p.ys, &mn, &mx);
+    p.nPixelSamples = mn;
+    p.adaptiveMethod = p.jitter ? 1 : 0;
+  }
   if (p.nPixelSamples < 1) return fail(c, DRT_E_INVALID, "sampler produces no samples per pixel");
   buildLayout(r);
   if (p.integKind == 2 && p.strategy == 0 && r->direct.size() != r->lights.size()) return fail(c, DRT_E_STATE, "light table out of date");
@@ -522,7 +542,7 @@ static int prepare(drt_ctx* c, RenderState* r) {
   p.direct = r->dDirect.p;
   int rc = ensureFilm(c, r);
   if (rc != DRT_OK) return rc;
-  if (p.samplerKind == 0) {
+  if (p.samplerKind == 0 || p.samplerKind == 4) {
     size_t smem = 4 * (size_t)(r->maxVals | 1) * sizeof(float);  // G = 32: four tasks per block
     if (smem > 200 * 1024) return fail(c, DRT_E_INVALID, "lowdiscrepancy sampler: pixelsamples x light nsamples too large for one warp's shared memory");
   }
@@ -700,6 +720,10 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
     CK(c, STAGE(launchEscape)(rs, wf, 0, ESCAPE_CAMERA, sms, st));
     c->launches++;
   }
+  if (p.samplerKind == 4) {
+    CK(c, STAGE(launchSaveCameraPrims)(wf, nSlots, st));
+    c->launches++;
+  }
   if (p.samplerKind != 3) {  // halton: the accepted samples are counted on the device (raygenKernel)
     r->stats.camera_samples += nSlots;
     r->stats.closest_rays += nSlots;
@@ -740,7 +764,12 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
     RK(integratorStage(c, r, 0, false));
     if (wf.specCtr && r->hasSpecular) RK(specularChains(c, r));
   }
-  CK(c, STAGE(launchFilm)(p, wf, nSlots, rc, st));
+  const bool firstVisit = p.samplerKind == 4 && pb.pass == 0;
+  if (firstVisit) {  // reportResults (adaptive_sampler.dart:133-158): supersampled pixels drop this visit's samples
+    CK(c, STAGE(launchAdaptiveDecide)(p, wf, pb, r->dAdaptList.p, r->dAdaptCount.p, st));
+    c->launches++;
+  }
+  CK(c, STAGE(launchFilm)(p, wf, nSlots, firstVisit ? 1 : 0, rc, st));
   c->launches++;
   return DRT_OK;
 }
@@ -769,30 +798,60 @@ static int renderWindow(drt_ctx* c, int x, int y, int w, int h, uint32_t shard, 
   }
   uint64_t slots = r->batchSlots ? r->batchSlots : (1ull << 22);
   if (const char* e = std::getenv("DRT_BATCH_SLOTS")) slots = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10));
-  uint64_t pixelsPerBatch = std::max<uint64_t>(1, slots / (uint64_t)p.nPixelSamples);
-  pixelsPerBatch = std::min<uint64_t>(pixelsPerBatch, std::max<uint64_t>(mine, 1));
-  const uint64_t cap64 = pixelsPerBatch * (uint64_t)p.nPixelSamples;
-  if (cap64 > 0x7fffffffull) return fail(c, DRT_E_INVALID, "samples per pixel too large for one batch");
-  const uint32_t cap = (uint32_t)cap64;
-  uint32_t shCap = cap;
-  if (p.integKind == 1) {
-    const uint64_t nS = (uint64_t)roundUpPow2(p.aoSamples);
-    shCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(cap, std::max<uint64_t>(nS, 1ull << 24)), (uint64_t)cap * nS);
-    shCap = std::max<uint32_t>(shCap, (uint32_t)nS);
-  }
-  RK(ensureWavefront(c, r, cap, shCap));
-  const int passes = p.samplerKind == 2 ? r->spp : 1;  // random sampler: spp visits of spp samples (random_sampler.dart:47-88)
-  for (int pass = 0; pass < passes; ++pass)
-    for (uint64_t first = 0; first < mine; first += pixelsPerBatch) {
-      PixelBatch pb;
-      pb.x0 = x; pb.y0 = y; pb.w = w;
-      if (halton) { pb.x0 = 0; pb.y0 = 0; pb.w = 1 << 30; }  // pixelOf: (n mod 2^30, n / 2^30)
-      pb.firstPixel = first;
-      pb.nPixels = (uint32_t)std::min<uint64_t>(pixelsPerBatch, mine - first);
-      pb.pass = (uint32_t)pass;
-      pb.shard = shard; pb.nShards = nShards; pb.blockPixels = blockPixels;
-      RK(renderBatch(c, r, pb));
+  // One visit of `count` pixels (of this shard's part of the window, or of `list`) with the current p.nPixelSamples per pixel
+  auto runVisit = [&](uint64_t count, uint32_t visit, const uint32_t* list) -> int {
+    uint64_t pixelsPerBatch = std::max<uint64_t>(1, slots / (uint64_t)p.nPixelSamples);
+    pixelsPerBatch = std::min<uint64_t>(pixelsPerBatch, std::max<uint64_t>(count, 1));
+    const uint64_t cap64 = pixelsPerBatch * (uint64_t)p.nPixelSamples;
+    if (cap64 > 0x7fffffffull) return fail(c, DRT_E_INVALID, "samples per pixel too large for one batch");
+    const uint32_t cap = (uint32_t)cap64;
+    uint32_t shCap = cap;
+    if (p.integKind == 1) {
+      const uint64_t nS = (uint64_t)roundUpPow2(p.aoSamples);
+      shCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(cap, std::max<uint64_t>(nS, 1ull << 24)), (uint64_t)cap * nS);
+      shCap = std::max<uint32_t>(shCap, (uint32_t)nS);
     }
+    RK(ensureWavefront(c, r, cap, shCap));
+    const int passes = p.samplerKind == 2 ? r->spp : 1;  // random sampler: spp visits of spp samples (random_sampler.dart:47-88)
+    for (int pass = 0; pass < passes; ++pass)
+      for (uint64_t first = 0; first < count; first += pixelsPerBatch) {
+        PixelBatch pb;
+        pb.x0 = x; pb.y0 = y; pb.w = w;
+        if (halton) { pb.x0 = 0; pb.y0 = 0; pb.w = 1 << 30; }  // pixelOf: (n mod 2^30, n / 2^30)
+        pb.firstPixel = first;
+        pb.nPixels = (uint32_t)std::min<uint64_t>(pixelsPerBatch, count - first);
+        pb.pass = p.samplerKind == 4 ? visit : (uint32_t)pass;
+        pb.shard = shard; pb.nShards = nShards; pb.blockPixels = blockPixels;
+        pb.list = list;
+        RK(renderBatch(c, r, pb));
+      }
+    return DRT_OK;
+  };
+  if (p.samplerKind == 4) {  // adaptive_sampler.dart:101-158: every pixel with minSamples, the flagged ones again with maxSamples
+    if (total > 0xffffffffull) return fail(c, DRT_E_INVALID, "adaptive sampler: window too large");
+    CK(c, r->dAdaptList.ensure(std::max<uint64_t>(mine, 1)));
+    CK(c, r->dAdaptCount.ensure(1));
+    CK(c, cudaMemsetAsync(r->dAdaptCount.p, 0, sizeof(uint32_t), c->stream));
+    RK(runVisit(mine, 0, nullptr));
+    uint32_t nSuper = 0;
+    CK(c, cudaMemcpyAsync(&nSuper, r->dAdaptCount.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (nSuper > 0) {
+      int mn, mx;
+      adaptiveCounts(p.xs, p.ys, &mn, &mx);
+      r->rp.nPixelSamples = mx;
+      buildLayout(r);  // the sample arrays hold maxSamples values per pixel now
+      CK(c, r->dArrays.ensure(r->arrays.size()));
+      CK(c, cudaMemcpy(r->dArrays.p, r->arrays.data(), r->arrays.size() * sizeof(SampleArray), cudaMemcpyHostToDevice));
+      int rc2 = runVisit(nSuper, 1, r->dAdaptList.p);
+      r->rp.nPixelSamples = mn;
+      buildLayout(r);
+      CK(c, cudaMemcpy(r->dArrays.p, r->arrays.data(), r->arrays.size() * sizeof(SampleArray), cudaMemcpyHostToDevice));
+      if (rc2 != DRT_OK) return rc2;
+    }
+  } else {
+    RK(runVisit(mine, 0, nullptr));
+  }
   CK(c, cudaStreamSynchronize(c->stream));
   RenderCounters hc;
   CK(c, cudaMemcpy(&hc, r->dCounters.p, sizeof(hc), cudaMemcpyDeviceToHost));
@@ -970,7 +1029,8 @@ int drt_set_film(drt_ctx* c, int xres, int yres, const double* crop, double xwid
 
 int drt_set_sampler(drt_ctx* c, int kind, int xs, int ys, int spp, int jitter, int pixel_order, int tile_size, uint64_t seed) {
   if (!c) return DRT_E_INVALID;
-  if (kind < 0 || kind > 3) return fail(c, DRT_E_INVALID, "sampler kind must be 0 (lowdiscrepancy), 1 (stratified), 2 (random) or 3 (halton)");
+  if (kind < 0 || kind > 4)
+    return fail(c, DRT_E_INVALID, "sampler kind must be 0 (lowdiscrepancy), 1 (stratified), 2 (random), 3 (halton) or 4 (adaptive)");
   if (spp < 1 || xs < 1 || ys < 1) return fail(c, DRT_E_INVALID, "sample counts must be >= 1");
   RenderState* r = state(c);
   r->rp.samplerKind = kind; r->rp.xs = xs; r->rp.ys = ys; r->rp.jitter = jitter; r->rp.seed = seed;

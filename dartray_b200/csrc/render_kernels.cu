@@ -50,7 +50,8 @@ static __device__ __forceinline__ void stv3(float* a, uint32_t cap, uint32_t i, 
 
 static __device__ __forceinline__ void pixelOf(const PixelBatch& pb, uint32_t p, int* x, int* y) {
   uint64_t g = pb.firstPixel + p;
-  if (pb.nShards > 1) g = ((g / pb.blockPixels) * pb.nShards + pb.shard) * pb.blockPixels + (g % pb.blockPixels);
+  if (pb.list) g = pb.list[g];
+  else if (pb.nShards > 1) g = ((g / pb.blockPixels) * pb.nShards + pb.shard) * pb.blockPixels + (g % pb.blockPixels);
   *x = pb.x0 + (int)(g % (uint64_t)pb.w);
   *y = pb.y0 + (int)(g / (uint64_t)pb.w);
 }
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(128) samplerLDKernel(RenderParams rp, Wavefron
     const SampleArray A = arrays[valid ? task % nArrays : 0];
     int x, y;
     pixelOf(pb, p, &x, &y);
-    const uint64_t key = streamKey(rp.seed, x, y, 0, A.streamId);
+    const uint64_t key = streamKey(rp.seed, x, y, rp.samplerKind == 4 ? pb.pass : 0u, A.streamId);  // adaptive: the visit keys the draw
     const uint32_t nS = (uint32_t)A.nSamples, total = valid ? nS * nP : 0u, dims = (uint32_t)A.dims;
     const uint32_t s0 = drawUint(key, 1), s1 = dims == 2 ? drawUint(key, 2) : 0u;
     const uint64_t base = dims;  // draws consumed by the scrambles
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(128) samplerLDPermKernel(RenderParams rp, Wave
     const SampleArray A = arrays[valid ? task % nArrays : 0];
     int x, y;
     pixelOf(pb, p, &x, &y);
-    const uint64_t key = streamKey(rp.seed, x, y, 0, A.streamId);
+    const uint64_t key = streamKey(rp.seed, x, y, rp.samplerKind == 4 ? pb.pass : 0u, A.streamId);  // adaptive: the visit keys the draw
     const uint32_t dims = (uint32_t)A.dims;
     const uint32_t s0 = drawUint(key, 1), s1 = dims == 2 ? drawUint(key, 2) : 0u;
     // draws: dims scrambles, nP (unused: blocks of one sample are not shuffled, montecarlo.dart:528-530), then the nP swaps
@@ -925,9 +926,47 @@ __global__ void __launch_bounds__(128) directSampleKernel(RenderParams rp, Rende
 // SamplerRenderer's radiance checks (sampler_renderer.dart:181-193) + ImageFilm.addSample
 // (image_film.dart:99-150).  Accumulators are float64 and updated atomically, so the sums do not
 // depend on the order samples arrive in (the reference adds float32 in pixel order).
-__global__ void __launch_bounds__(256) filmKernel(RenderParams rp, Wavefront wf, uint32_t nSlots, RenderCounters* rc) {
+// Adaptive sampler: what SamplerRenderer's loop hands to reportResults (sampler_renderer.dart:173-207) — the radiance values
+// after the NaN / negative / infinite clean-up — and the camera rays' primitives.
+__global__ void saveCameraPrimsKernel(Wavefront wf, uint32_t nSlots) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nSlots) wf.camPrim[wf.extSlot[0][q]] = __float_as_int(wf.extHit[q].w);
+}
+__global__ void __launch_bounds__(128) adaptiveDecideKernel(RenderParams rp, Wavefront wf, PixelBatch pb, uint32_t* list, uint32_t* listCount) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pb.nPixels) return;
+  const uint32_t n = (uint32_t)rp.nPixelSamples, s0 = p * n;
+  bool needs = false;
+  if (rp.adaptiveMethod == 0) {  // adaptive_sampler.dart:163-171; an escaped ray compares as -1 (see the oracle)
+    for (uint32_t i = 0; i + 1 < n; ++i) needs = needs || wf.camPrim[s0 + i] != wf.camPrim[s0 + i + 1];
+  } else {  // :172-186
+    double Lavg = 0.0;
+    for (uint32_t i = 0; i < n; ++i) {
+      const Spec L = ld3(wf.L, wf.cap, s0 + i);
+      const double lum = Luminance(L);
+      const bool zeroed = isnan(L.r) || isnan(L.g) || isnan(L.b) || lum < -1e-5 || isinf(lum);
+      Lavg += zeroed ? 0.0 : lum;
+    }
+    Lavg /= n;
+    for (uint32_t i = 0; i < n; ++i) {
+      const Spec L = ld3(wf.L, wf.cap, s0 + i);
+      double lum = Luminance(L);
+      if (isnan(L.r) || isnan(L.g) || isnan(L.b) || lum < -1e-5 || isinf(lum)) lum = 0.0;
+      needs = needs || fabs(lum - Lavg) / Lavg > 0.5;
+    }
+  }
+  wf.adaptFlag[p] = needs ? 1 : 0;
+  if (needs) {
+    uint64_t g = pb.firstPixel + p;
+    if (pb.nShards > 1) g = ((g / pb.blockPixels) * pb.nShards + pb.shard) * pb.blockPixels + (g % pb.blockPixels);
+    list[atomicAdd(listCount, 1u)] = (uint32_t)g;
+  }
+}
+
+__global__ void __launch_bounds__(256) filmKernel(RenderParams rp, Wavefront wf, uint32_t nSlots, int skipFlagged, RenderCounters* rc) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nSlots) return;
+  if (skipFlagged && wf.adaptFlag[s / (uint32_t)rp.nPixelSamples]) return;  // adaptive: reportResults returned false (:148-151)
   if (rp.samplerKind == 3 && isnan(wf.camXY[s].x)) return;  // halton: a rejected index of the sequence
   Spec L = ld3(wf.L, wf.cap, s);
   const double lum = Luminance(L);
@@ -993,7 +1032,8 @@ static inline int gridFor(uint64_t n, int block, int numSMs, int perSm) {
 cudaError_t launchSampler(const RenderParams& rp, const Wavefront& wf, const SampleArray* dArrays, int nArrays, int maxVals,
                           int maxOthers, const PixelBatch& pb, int numSMs, cudaStream_t st) {
   if (pb.nPixels == 0) return cudaSuccess;
-  if (rp.samplerKind == 0 && rp.ldAllSingle && rp.nPixelSamples <= 2048) {
+  const bool ld = rp.samplerKind == 0 || rp.samplerKind == 4;  // adaptive draws LDPixelSample too
+  if (ld && rp.ldAllSingle && rp.nPixelSamples <= 2048) {
     const int block = 128;
     const int strideWords = rp.nPixelSamples | 1;  // two 16-bit arrays of nPixelSamples entries; odd word stride
     const size_t taskBytes = (size_t)strideWords * sizeof(float);
@@ -1004,7 +1044,7 @@ cudaError_t launchSampler(const RenderParams& rp, const Wavefront& wf, const Sam
     uint64_t tasks = (uint64_t)pb.nPixels * nArrays;
     int grid = gridFor(tasks * G, block, numSMs, 16);
     samplerLDPermKernel<<<grid, block, smem, st>>>(rp, wf, dArrays, nArrays, pb, G, strideWords);
-  } else if (rp.samplerKind == 0) {
+  } else if (ld) {
     const int block = 128;
     // lanes per (pixel, array) task: as few as shared memory allows (48 KB of arrays per block), because the
     // order-dependent shuffle runs on one lane per task
@@ -1116,9 +1156,22 @@ cudaError_t launchSpecularStep(const RenderParams& rp, const RenderScene& rs, co
   return cudaGetLastError();
 }
 
-cudaError_t launchFilm(const RenderParams& rp, const Wavefront& wf, uint32_t nSlots, RenderCounters* rc, cudaStream_t st) {
+cudaError_t launchSaveCameraPrims(const Wavefront& wf, uint32_t nSlots, cudaStream_t st) {
   if (nSlots == 0) return cudaSuccess;
-  filmKernel<<<(nSlots + 255) / 256, 256, 0, st>>>(rp, wf, nSlots, rc);
+  saveCameraPrimsKernel<<<(nSlots + 255) / 256, 256, 0, st>>>(wf, nSlots);
+  return cudaGetLastError();
+}
+
+cudaError_t launchAdaptiveDecide(const RenderParams& rp, const Wavefront& wf, const PixelBatch& pb, uint32_t* list, uint32_t* listCount,
+                                 cudaStream_t st) {
+  if (pb.nPixels == 0) return cudaSuccess;
+  adaptiveDecideKernel<<<(pb.nPixels + 127) / 128, 128, 0, st>>>(rp, wf, pb, list, listCount);
+  return cudaGetLastError();
+}
+
+cudaError_t launchFilm(const RenderParams& rp, const Wavefront& wf, uint32_t nSlots, int skipFlagged, RenderCounters* rc, cudaStream_t st) {
+  if (nSlots == 0) return cudaSuccess;
+  filmKernel<<<(nSlots + 255) / 256, 256, 0, st>>>(rp, wf, nSlots, skipFlagged, rc);
   return cudaGetLastError();
 }
 

@@ -19,6 +19,7 @@ struct PixelBatch {
   uint32_t nPixels;
   uint32_t pass;  // visit number (random sampler: one visit per pass, random_sampler.dart:47-88)
   uint32_t shard, nShards, blockPixels;
+  const uint32_t* list;  // adaptive sampler, second visit: the window-linear indices of the pixels to supersample (device), or null
 };
 
 enum { ESCAPE_CAMERA = 0, ESCAPE_PATH = 1, ESCAPE_WEIGHTED = 2 };

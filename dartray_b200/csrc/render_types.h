@@ -108,7 +108,8 @@ struct RenderParams {
   const float* filterTable;  // 256 floats
   double* film;              // width*height x (X, Y, Z, weight)
   // sampler
-  int32_t samplerKind;  // 0 lowdiscrepancy, 1 stratified, 2 random, 3 halton
+  int32_t samplerKind;  // 0 lowdiscrepancy, 1 stratified, 2 random, 3 halton, 4 adaptive (lowdiscrepancy samples, two visits)
+  int32_t adaptiveMethod;  // adaptive_sampler.dart:37-38: 0 compare shape ids, 1 contrast threshold
   int32_t winX, winY, winW, winH;  // halton: the sampler's window (halton_sampler.dart:32-38), set per render call
   int32_t xs, ys, jitter;
   int32_t nPixelSamples;  // samples per pixel visit
@@ -169,6 +170,8 @@ struct Wavefront {
   float4* misO; float4* misD; double2* misRange; float4* misHit; double* misT;
   uint32_t* counts;  // [0],[1] = extension queue sizes, [2] = shadow, [3] = MIS, [4] = hit list size
   uint32_t* hitList; // slots whose camera ray hit (AO / direct lighting)
+  int32_t* camPrim;  // adaptive sampler: primitive the slot's camera ray hit (-1: none)
+  uint8_t* adaptFlag;  // adaptive sampler, per pixel of the batch: 1 = supersample (the first visit's samples are dropped)
 };
 
 struct RenderCounters {  // mirrors the reference's ray counters (stats.dart:541-555)

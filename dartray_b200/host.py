@@ -207,7 +207,8 @@ class Film:
         return left, top, width, height
 
 
-SAMPLER_LD, SAMPLER_STRATIFIED, SAMPLER_RANDOM, SAMPLER_HALTON = 0, 1, 2, 3
+SAMPLER_LD, SAMPLER_STRATIFIED, SAMPLER_RANDOM, SAMPLER_HALTON, SAMPLER_ADAPTIVE = 0, 1, 2, 3, 4
+ADAPTIVE_SHAPE_ID, ADAPTIVE_CONTRAST = 0, 1  # adaptive_sampler.dart:37-38: the `method` (carried in Sampler.jitter)
 INTEGRATOR_PATH, INTEGRATOR_AO, INTEGRATOR_DIRECT, INTEGRATOR_WHITTED = 0, 1, 2, 3
 RNG_SERIAL, RNG_KEYED = 0, 1
 
@@ -216,9 +217,9 @@ RNG_SERIAL, RNG_KEYED = 0, 1
 class Sampler:
     kind: int = SAMPLER_LD
     spp: int = 4          # lowdiscrepancy / random: pixelsamples
-    xs: int = 2           # stratified: xsamples, ysamples
+    xs: int = 2           # stratified: xsamples, ysamples; adaptive: minsamples, maxsamples
     ys: int = 2
-    jitter: bool = True
+    jitter: bool = True   # adaptive: the method, ADAPTIVE_SHAPE_ID / ADAPTIVE_CONTRAST
     pixel_order: int = 1  # 0 linear, 1 tile (render_options.dart default 'tile')
     tile_size: int = 32
     seed: int = 0

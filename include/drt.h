@@ -263,7 +263,10 @@ int drt_set_film(drt_ctx* ctx, int32_t xres, int32_t yres, const double crop[4],
  * spp rounded up to a power of two), stratified (kind 1, lib/samplers/stratified_sampler.dart; xs x ys
  * strata, jitter), random (kind 2, lib/samplers/random_sampler.dart) and halton (kind 3,
  * lib/samplers/halton_sampler.dart: spp * max(w, h)^2 indices of one global sequence per sample window, samples outside the
- * window rejected as the reference rejects them; streams keyed by the index).  pixel_order / tile_size name
+ * window rejected as the reference rejects them; streams keyed by the index) and adaptive (kind 4,
+ * lib/samplers/adaptive_sampler.dart: xs = minsamples, ys = maxsamples, jitter = method (0 shape ids, 1 contrast); every pixel is
+ * rendered with minsamples lowdiscrepancy samples and, where reportResults asks for it, again with maxsamples, the first visit's
+ * samples being dropped).  pixel_order / tile_size name
  * the PixelSampler (0 linear, 1 tile: lib/pixel_samplers/*.dart); with per-pixel keyed streams the
  * visiting order does not change any sample, so they only document the request.  seed keys every
  * stream (the reference seeds its single RNG with the task number, sampler_renderer.dart:137). */

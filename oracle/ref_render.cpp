@@ -641,7 +641,7 @@ struct Ctx {
       if (ic.strategy == 0) {
         for (size_t i = 0; i < rs.lights.size(); ++i) {
           int n = rs.lights[i].nSamples;
-          if (rs.sampler.kind == 0) n = RoundUpPow2(n);  // sampler.roundSize
+          if (rs.sampler.kind == 0 || rs.sampler.kind == 4) n = RoundUpPow2(n);  // sampler.roundSize (LD and adaptive)
           dlLight.push_back(lightOffsets(n));
           dlBsdf.push_back(bsdfOffsets(n));
         }
@@ -1274,11 +1274,14 @@ struct Ctx {
   }
 
   // SamplerRenderer.Li (sampler_renderer.dart:67-98): also what the specular recursion calls
+  int32_t lastCameraPrim = -1;  // primitive the last camera ray hit (adaptive sampler, shapeid method)
   Spec LiRay(const Ray& rayIn, const SampleVals& s, Rng& rng) {
     Ray ray = rayIn;  // Scene.intersect shrinks ray.maxDistance to the hit (geometric_primitive.dart:47-61)
     Isect isect;
     Spec L(0.0);
-    if (intersect(ray, &isect)) {
+    const bool hit = intersect(ray, &isect);
+    if (rayIn.depth == 0) lastCameraPrim = hit ? isect.prim : -1;  // camera rays only: the recursion's rays have depth > 0
+    if (hit) {
       switch (rs.integ.kind) {
         case 0: L = pathLi(ray, isect, s, rng); break;
         case 1: L = aoLi(ray, isect, rng); break;
@@ -1370,19 +1373,55 @@ static double RadicalInverse(uint64_t n, int base) {
   return val;
 }
 
+// AdaptiveSampler's constructor (adaptive_sampler.dart:40-84): xs / ys carry minsamples / maxsamples
+void adaptiveCounts(const SamplerCfg& sc, int* mn, int* mx) {
+  int mins = sc.xs, maxs = sc.ys;
+  if (mins > maxs) std::swap(mins, maxs);
+  int a = RoundUpPow2(mins), b = RoundUpPow2(maxs);  // IsPowerOf2 ? itself : rounded up
+  if (a < 2) a = 2;
+  if (a == b) b *= 2;
+  *mn = a;
+  *mx = b;
+}
+// adaptive_sampler.dart:160-190.  `prims`: the camera ray's primitive id per sample, -1 for a miss — the reference compares
+// Intersection.shapeId / primitiveId, which for an escaped ray are whatever an EARLIER sample left in the reused Intersection
+// object (sampler_renderer.dart:147-176); that staleness only exists in a serial run and is not restated: a miss compares as -1.
+bool needsSupersampling(int method, const std::vector<Spec>& Ls, const std::vector<int32_t>& prims, int count) {
+  if (method == 0) {
+    for (int i = 0; i < count - 1; ++i)
+      if (prims[i] != prims[i + 1]) return true;
+    return false;
+  }
+  double Lavg = 0.0;
+  for (int i = 0; i < count; ++i) Lavg += Ls[i].luminance();
+  Lavg /= count;
+  const double maxContrast = 0.5;
+  for (int i = 0; i < count; ++i)
+    if (std::fabs(Ls[i].luminance() - Lavg) / Lavg > maxContrast) return true;
+  return false;
+}
+
 // Samples of one pixel visit.  `pass` only matters for the random sampler (one visit per pass).
 // Serial mode draws everything from `serial`; keyed mode derives streams from (seed, x, y).
 int pixelSamples(const SamplerCfg& sc, const SampleLayout& layout, const Camera& cam, int x, int y, int pass, Rng* serial,
                  std::vector<SampleVals>& out) {
   const bool keyed = sc.rngMode == 1;
-  if (sc.kind == 0) {  // low_discrepancy_sampler.dart:64-88 + montecarlo.dart:407-473
+  if (sc.kind == 0 || sc.kind == 4) {  // low_discrepancy_sampler.dart:64-88 + montecarlo.dart:407-473
+    // adaptive (adaptive_sampler.dart:101-131): the same LDPixelSample with minSamples (pass 0) or maxSamples (pass 1: the
+    // pixel is being supersampled); the keyed streams of the second visit carry the pass so that it is a fresh draw
     int n = RoundUpPow2(sc.spp);
+    if (sc.kind == 4) {
+      int mn, mx;
+      adaptiveCounts(sc, &mn, &mx);
+      n = pass == 0 ? mn : mx;
+    }
+    const uint32_t keyPass = sc.kind == 4 ? (uint32_t)pass : 0u;
     out.resize(n);
     for (auto& s : out) s.alloc(layout);
     uint32_t arr = 0;
     auto stream = [&](KeyedRng& k) -> Rng& {
       if (!keyed) return *serial;
-      k = KeyedRng(sc.seed, x, y, 0, arr);
+      k = KeyedRng(sc.seed, x, y, keyPass, arr);
       return k;
     };
     KeyedRng k;
@@ -1546,14 +1585,23 @@ void RenderScene::render(int taskNum, int taskCount, int nthreads) {
     std::vector<SampleVals> sv;
     for (int pass = 0; pass < passes; ++pass)
       for (size_t i = 0; i < nPix; ++i) {
-        int n = pixelSamples(sampler, c.layout, camera, px[2 * i], px[2 * i + 1], pass, &serial, sv);
-        std::vector<Spec> Ls(n);
-        for (int s = 0; s < n; ++s) {
-          KeyedRng k(sampler.seed, px[2 * i], px[2 * i + 1], (uint32_t)(pass * n + s), kStreamIntegrator);
-          Rng& rng = sampler.rngMode == 1 ? (Rng&)k : (Rng&)serial;
-          Ls[s] = c.Li(sv[s], rng);
+        // adaptive sampler: the pixel is visited with minSamples and, if reportResults asks for it, again with maxSamples,
+        // the first visit's samples being dropped (adaptive_sampler.dart:133-158, sampler_renderer.dart:199-207)
+        for (int visit = 0; visit < (sampler.kind == 4 ? 2 : 1); ++visit) {
+          const int ps = sampler.kind == 4 ? visit : pass;
+          int n = pixelSamples(sampler, c.layout, camera, px[2 * i], px[2 * i + 1], ps, &serial, sv);
+          std::vector<Spec> Ls(n);
+          std::vector<int32_t> prims(n);
+          for (int s = 0; s < n; ++s) {
+            KeyedRng k(sampler.seed, px[2 * i], px[2 * i + 1], (uint32_t)(ps * n + s), kStreamIntegrator);
+            Rng& rng = sampler.rngMode == 1 ? (Rng&)k : (Rng&)serial;
+            Ls[s] = c.Li(sv[s], rng);
+            prims[s] = c.lastCameraPrim;
+          }
+          if (sampler.kind == 4 && visit == 0 && needsSupersampling(sampler.jitter, Ls, prims, n)) continue;
+          for (int s = 0; s < n; ++s) film.addSample(sv[s].imageX, sv[s].imageY, Ls[s]);
+          break;
         }
-        for (int s = 0; s < n; ++s) film.addSample(sv[s].imageX, sv[s].imageY, Ls[s]);
       }
     stats = c.stats;
     return;
@@ -1571,11 +1619,19 @@ void RenderScene::render(int taskNum, int taskCount, int nthreads) {
       size_t b = nPix * t / nthreads, e = nPix * (t + 1) / nthreads;
       for (int pass = 0; pass < passes; ++pass)
         for (size_t i = b; i < e; ++i) {
-          int n = pixelSamples(sampler, c.layout, camera, px[2 * i], px[2 * i + 1], pass, nullptr, sv);
-          for (int s = 0; s < n; ++s) {
-            KeyedRng k(sampler.seed, px[2 * i], px[2 * i + 1], (uint32_t)(pass * n + s), kStreamIntegrator);
-            Spec L = c.Li(sv[s], k);
-            perThread[t].push_back({sv[s].imageX, sv[s].imageY, L});
+          for (int visit = 0; visit < (sampler.kind == 4 ? 2 : 1); ++visit) {
+            const int ps = sampler.kind == 4 ? visit : pass;
+            int n = pixelSamples(sampler, c.layout, camera, px[2 * i], px[2 * i + 1], ps, nullptr, sv);
+            std::vector<Spec> Ls(n);
+            std::vector<int32_t> prims(n);
+            for (int s = 0; s < n; ++s) {
+              KeyedRng k(sampler.seed, px[2 * i], px[2 * i + 1], (uint32_t)(ps * n + s), kStreamIntegrator);
+              Ls[s] = c.Li(sv[s], k);
+              prims[s] = c.lastCameraPrim;
+            }
+            if (sampler.kind == 4 && visit == 0 && needsSupersampling(sampler.jitter, Ls, prims, n)) continue;
+            for (int s = 0; s < n; ++s) perThread[t].push_back({sv[s].imageX, sv[s].imageY, Ls[s]});
+            break;
           }
         }
       st[t] = c.stats;

@@ -221,7 +221,7 @@ struct Film {  // image_film.dart:51-97
 };
 
 struct SamplerCfg {
-  int kind = 0;  // 0 lowdiscrepancy, 1 stratified, 2 random, 3 halton
+  int kind = 0;  // 0 lowdiscrepancy, 1 stratified, 2 random, 3 halton, 4 adaptive (xs = minsamples, ys = maxsamples, jitter = method)
   // halton: the sampler's window (left, top, width, height), filled in by render() (halton_sampler.dart:32-38)
   int winX = 0, winY = 0, winW = 0, winH = 0;
   int xs = 2, ys = 2;

@@ -346,3 +346,40 @@ def test_halton_sampler_radical_inverses_and_window():
             for px in range(max(int(math.ceil(dx - 0.5)), 0), min(int(math.floor(dx + 0.5)), W - 1) + 1):
                 cnt[py, px] += 1
     assert np.array_equal(f["weight"], cnt.astype(np.float32))
+
+
+# ---- AdaptiveSampler (adaptive_sampler.dart) -----------------------------------------------------------------------------
+def _adaptive_scene():
+    # a bright emitter quad in front of a black void: pixels inside the quad and pixels of the void are uniform, the pixels its
+    # outline crosses see both
+    sb = host.SceneBuilder()
+    sb.mesh([[-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0]], [[0, 2, 1], [0, 3, 2]], material=sb.material((0.5, 0.5, 0.5)),
+            area_light=(4.0, 4.0, 4.0))
+    cam = host.PerspectiveCamera(host.look_at((0.03, 0.02, -5), (0.03, 0.02, 0), (0, 1, 0)), fov=40.0)
+    return sb, cam
+
+
+@pytest.mark.parametrize("method", [host.ADAPTIVE_CONTRAST, host.ADAPTIVE_SHAPE_ID])
+def test_adaptive_sampler_supersamples_only_where_the_samples_disagree(method):
+    sb, cam = _adaptive_scene()
+    W = H = 24
+    smp = host.Sampler(kind=host.SAMPLER_ADAPTIVE, xs=3, ys=16, jitter=method)  # minsamples 3 -> 4, maxsamples 16
+    o = _oracle(sb, cam, host.Film(W, H, filter="box", xwidth=0.5, ywidth=0.5), smp, host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=1))
+    o.render()
+    f = o.film_read()
+    wt = f["weight"]
+    assert set(np.unique(wt)) == {4.0, 16.0}  # box filter of half-width 0.5: the weight is the pixel's own sample count
+    lit = f["rgb"][..., 0] > 0
+    inside = lit & np.roll(lit, 1, 0) & np.roll(lit, -1, 0) & np.roll(lit, 1, 1) & np.roll(lit, -1, 1)
+    outside = ~lit & ~np.roll(lit, 1, 0) & ~np.roll(lit, -1, 0) & ~np.roll(lit, 1, 1) & ~np.roll(lit, -1, 1)
+    assert inside.sum() > 20 and outside.sum() > 100
+    if method == host.ADAPTIVE_CONTRAST:
+        assert (wt[inside] == 4.0).all()        # uniform radiance 4: no contrast
+    else:
+        assert (wt[inside] == 4.0).mean() > 0.5  # shape ids: the quad is two triangles, its diagonal is supersampled too
+    assert (wt[outside] == 4.0).all()            # all misses: Lavg = 0 -> 0 / 0 = NaN > 0.5 is false; equal (absent) ids
+    edge = lit & ~inside
+    assert (wt[edge] == 16.0).mean() > 0.6       # the outline: radiance 4 and 0 in one pixel
+    # the sample window is one pixel wider and taller than the film (image_film.dart:247-252): 2 * 24 + 1 all-miss pixels more
+    assert o.render_stats()["camera_samples"] == int((wt == 4).sum() * 4 + (wt == 16).sum() * (4 + 16)) + (2 * W + 1) * 4
+    assert np.allclose(f["rgb"][inside], 4.0, rtol=1e-6)

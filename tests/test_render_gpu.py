@@ -294,6 +294,33 @@ def test_halton_sampler_matches_oracle(integ):
     assert np.allclose(films[0]["xyz"] + films[1]["xyz"], fg["xyz"], rtol=1e-5, atol=1e-6)  # xyz: the unnormalised sums
 
 
+@pytest.mark.parametrize("method,integ", [
+    (host.ADAPTIVE_CONTRAST, host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=3)),
+    (host.ADAPTIVE_CONTRAST, host.Integrator(kind=host.INTEGRATOR_DIRECT)),
+    (host.ADAPTIVE_SHAPE_ID, host.Integrator(kind=host.INTEGRATOR_DIRECT)),
+    (host.ADAPTIVE_SHAPE_ID, host.Integrator(kind=host.INTEGRATOR_AO, ao_nsamples=8)),
+])
+def test_adaptive_sampler_matches_oracle(method, integ):
+    """adaptive_sampler.dart: minSamples everywhere, maxSamples where reportResults asks (contrast or shape ids), the first
+    visit's samples dropped there."""
+    arrays, cam = _cornell()
+    smp = host.Sampler(kind=host.SAMPLER_ADAPTIVE, xs=2, ys=8, jitter=method, seed=9)
+    g, o, fg, fo = _render_both(arrays, cam, host.Film(64, 48), smp, integ)
+    # box filter: the weight is each pixel's own sample count, 2 or 8 — the same pixels are supersampled
+    same = fg["weight"] == fo["weight"]
+    print("adaptive", method, integ.kind, "supersampled", int((fo["weight"] == 8).sum()), "weights differing", int((~same).sum()))
+    assert set(np.unique(fo["weight"])) == {2.0, 8.0}
+    if method == host.ADAPTIVE_SHAPE_ID or integ.kind != host.INTEGRATOR_PATH:
+        assert same.all()
+        assert g.render_stats()["camera_samples"] == o.render_stats()["camera_samples"]
+    else:
+        assert (~same).mean() <= 2e-3  # a contrast ratio within rounding of 0.5 may fall either way
+    err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)[same]
+    assert np.quantile(err, 0.999) <= 1e-3
+    if integ.kind != host.INTEGRATOR_PATH:
+        assert err.max() <= 1e-3
+
+
 # ---- path tracing ------------------------------------------------------------------------------------------
 def test_path_integrator_matches_oracle():
     arrays, cam = _cornell()
