@@ -32,7 +32,10 @@ class _Lobe {
   int kind, fresnel = _FRESNEL_NOOP;
   Spectrum rgb, eta, k;
   double param = 0.0, ei = 1.0, et = 1.0;
-  _Lobe(this.kind, this.rgb, {this.fresnel: _FRESNEL_NOOP, this.eta, this.k, this.param: 0.0, this.ei: 1.0, this.et: 1.0});
+  int wrap = 0;     // drt_set_lobe_wrappers: bit 0 BRDFToBTDF, bit 1 ScaledBxDF
+  Spectrum scale;   // ScaledBxDF's s
+  _Lobe(this.kind, this.rgb, {this.fresnel: _FRESNEL_NOOP, this.eta, this.k, this.param: 0.0, this.ei: 1.0, this.et: 1.0,
+        this.wrap: 0, this.scale});
 }
 
 class _Arena {
@@ -177,6 +180,51 @@ class GpuSamplerRenderer extends Renderer {
       Spectrum kt = op * _const(m.Kt, 'uber Kt').clamp();
       if (!kt.isBlack()) {
         out.add(new _Lobe(_SPEC_TRANSMISSION, kt, fresnel: _FRESNEL_DIELECTRIC, ei: e, et: 1.0));
+      }
+    } else if (m is ShinyMetalMaterial) {  // shiny_metal_material.dart:42-64
+      noBump(m.bumpMap);
+      Spectrum spec = _const(m.Ks, 'shinymetal Ks').clamp(), r = _const(m.Kr, 'shinymetal Kr').clamp();
+      final Spectrum k = new Spectrum(0.0);
+      if (!spec.isBlack()) {
+        out.add(new _Lobe(_MICROFACET_BLINN, new Spectrum(1.0), fresnel: _FRESNEL_CONDUCTOR,
+                          eta: ShinyMetalMaterial.FresnelApproxEta(spec), k: k,
+                          param: _blinn(_constF(m.roughness, 'shinymetal roughness'))));
+      }
+      if (!r.isBlack()) {
+        out.add(new _Lobe(_SPEC_REFLECTION, new Spectrum(1.0), fresnel: _FRESNEL_CONDUCTOR,
+                          eta: ShinyMetalMaterial.FresnelApproxEta(r), k: k));
+      }
+    } else if (m is TranslucentMaterial) {  // translucent_material.dart:47-90: the transmissive halves are BRDFToBTDF wrappers
+      noBump(m.bumpMap);
+      Spectrum r = _const(m.reflect, 'translucent reflect').clamp(), t = _const(m.transmit, 'translucent transmit').clamp();
+      if (!(r.isBlack() && t.isBlack())) {
+        Spectrum kd = _const(m.Kd, 'translucent Kd').clamp();
+        if (!kd.isBlack()) {
+          if (!r.isBlack()) out.add(new _Lobe(_LAMBERTIAN, r * kd));
+          if (!t.isBlack()) out.add(new _Lobe(_LAMBERTIAN, t * kd, wrap: 1));
+        }
+        Spectrum ks = _const(m.Ks, 'translucent Ks').clamp();
+        if (!ks.isBlack()) {
+          final double e = _blinn(_constF(m.roughness, 'translucent roughness'));
+          if (!r.isBlack()) out.add(new _Lobe(_MICROFACET_BLINN, r * ks, fresnel: _FRESNEL_DIELECTRIC, ei: 1.5, et: 1.0, param: e));
+          if (!t.isBlack()) out.add(new _Lobe(_MICROFACET_BLINN, t * ks, fresnel: _FRESNEL_DIELECTRIC, ei: 1.5, et: 1.0, param: e, wrap: 1));
+        }
+      }
+    } else if (m is MixMaterial) {  // mix_material.dart:36-50: ScaledBxDF around every BxDF of both BSDFs, one level deep
+      Spectrum s1 = _const(m.scale, 'mix amount').clamp();
+      Spectrum s2 = (Spectrum.ONE - s1).clamp();
+      for (final pair in [[m.m1, s1], [m.m2, s2]]) {
+        for (final _Lobe l in _lobes(pair[0])) {
+          if ((l.wrap & 2) != 0) {
+            throw new GpuUnsupported('a mix of mix materials');
+          }
+          l.wrap |= 2;
+          l.scale = pair[1];
+          out.add(l);
+        }
+      }
+      if (out.length > 8) {
+        throw new GpuUnsupported('more than 8 BxDFs in one BSDF');
       }
     } else {
       throw new GpuUnsupported('material ${m.runtimeType}');
@@ -383,6 +431,16 @@ class GpuSamplerRenderer extends Renderer {
     if (materials.isNotEmpty) {
       drt.setMaterialLobes(materials.length, a.uints(offsets), a.ints(kind), a.floats(rgb), a.ints(fres), a.floats(eta),
                            a.floats(kk), a.doubles(scal));
+      final wraps = <int>[], scales = <double>[];
+      for (final ll in lobeLists) {
+        for (final l in ll) {
+          wraps.add(l.wrap);
+          scales.addAll(_rgb(l.scale == null ? new Spectrum(1.0) : l.scale));
+        }
+      }
+      if (wraps.any((w) => w != 0)) {
+        drt.setLobeWrappers(wraps.length, a.ints(wraps), a.floats(scales));
+      }
     }
 
     // lights

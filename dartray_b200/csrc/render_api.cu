@@ -917,6 +917,8 @@ int drt_set_material_lobes(drt_ctx* c, uint32_t n, const uint32_t* lobe_offsets,
       l.k[k] = fresnel_k ? fresnel_k[3 * j + k] : 0.f;
     }
     l.pad_ = 0.f;
+    l.wrap = 0;
+    l.scale[0] = l.scale[1] = l.scale[2] = 1.f;
     l.param = lobe_scalars[3 * j];
     l.ei = lobe_scalars[3 * j + 1];
     l.et = lobe_scalars[3 * j + 2];
@@ -927,6 +929,23 @@ int drt_set_material_lobes(drt_ctx* c, uint32_t n, const uint32_t* lobe_offsets,
   r->lobes.swap(ls);
   r->general = true;
   r->hasSpecular = spec;
+  r->sceneTablesValid = false;
+  return DRT_OK;
+}
+
+int drt_set_lobe_wrappers(drt_ctx* c, uint32_t n_lobes, const int32_t* wrap, const float* scale_rgb) {
+  if (!c) return DRT_E_INVALID;
+  RenderState* r = state(c);
+  if (!r->general || n_lobes != r->lobes.size())
+    return fail(c, DRT_E_STATE, "drt_set_lobe_wrappers: the lobe count must equal that of the last drt_set_material_lobes");
+  if (n_lobes && !wrap) return fail(c, DRT_E_INVALID, "null wrapper array");
+  for (uint32_t j = 0; j < n_lobes; ++j) {
+    if (wrap[j] < 0 || wrap[j] > 3) return fail(c, DRT_E_INVALID, "wrapper bits: 1 = BRDFToBTDF, 2 = ScaledBxDF");
+    if ((wrap[j] & 2) && !scale_rgb) return fail(c, DRT_E_INVALID, "ScaledBxDF needs the scale array");
+    GLobe& l = r->lobes[j];
+    l.wrap = wrap[j];
+    for (int k = 0; k < 3; ++k) l.scale[k] = (wrap[j] & 2) ? scale_rgb[3 * j + k] : 1.f;
+  }
   r->sceneTablesValid = false;
   return DRT_OK;
 }

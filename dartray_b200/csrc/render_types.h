@@ -21,10 +21,12 @@ struct GLobe {
   float rgb[3];
   float eta[3];
   float k[3];
-  float pad_;
+  int32_t wrap;  // bit 0: BRDFToBTDF(bxdf) (brdf_to_btdf.dart), bit 1: ScaledBxDF(.., scale) (scaled_bxdf.dart); drt_set_lobe_wrappers
   double param, ei, et;
+  float scale[3];
+  float pad_;
 };
-static_assert(sizeof(GLobe) == 72, "GLobe layout");
+static_assert(sizeof(GLobe) == 88, "GLobe layout");
 
 struct GLight {
   int32_t kind;  // 0 = DiffuseAreaLight (diffuse_area_light.dart), 1 = PointLight (point_light.dart),

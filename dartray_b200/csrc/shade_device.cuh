@@ -834,7 +834,11 @@ static __device__ inline int lobeType(int kind) {
                    : (kind == 2 ? (BSDF_REFLECTION | BSDF_GLOSSY)
                                 : (kind == 3 ? (BSDF_REFLECTION | BSDF_SPECULAR) : (BSDF_TRANSMISSION | BSDF_SPECULAR)));
 }
-static __device__ inline bool lobeMatches(const GLobe& l, int flags) { const int t = lobeType(l.kind); return (t & flags) == t; }
+static __device__ inline int lobeTypeOf(const GLobe& l) {  // brdf_to_btdf.dart:27-29 flips reflection <-> transmission
+  const int t = lobeType(l.kind);
+  return (l.wrap & 1) ? (t ^ (BSDF_REFLECTION | BSDF_TRANSMISSION)) : t;
+}
+static __device__ inline bool lobeMatches(const GLobe& l, int flags) { const int t = lobeTypeOf(l); return (t & flags) == t; }
 
 static __device__ inline Spec fresnelDielectric(double cosi, double eta_i, double eta_t) {  // fresnel_dielectric.dart:24-56
   if (!isnan(cosi)) cosi = clampD(cosi, -1.0, 1.0);
@@ -870,7 +874,7 @@ static __device__ inline double blinnPdfOf(double exponent, double costheta, dou
   if (woDotWh <= 0.0) pdf = 0.0;
   return pdf;
 }
-static __device__ inline Spec lobeF(const GLobe& l, const V3& wo, const V3& wi) {
+static __device__ inline Spec lobeBaseF(const GLobe& l, const V3& wo, const V3& wi) {
   const Spec R = Spec{l.rgb[0], l.rgb[1], l.rgb[2]};
   if (l.kind == 0) return R * DRT_INV_PI;  // lambertian.dart:35-37
   if (l.kind == 1) {                       // oren_nayar.dart:24-58
@@ -902,7 +906,7 @@ static __device__ inline Spec lobeF(const GLobe& l, const V3& wo, const V3& wi) 
   }
   return mks1(0.0);  // specular BxDFs: f == 0
 }
-static __device__ inline double lobePdf(const GLobe& l, const V3& wo, const V3& wi) {
+static __device__ inline double lobeBasePdf(const GLobe& l, const V3& wo, const V3& wi) {
   if (l.kind <= 1) return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * DRT_INV_PI : 0.0;  // bxdf.dart:84-88
   if (l.kind == 2) {                                                                     // microfacet.dart:68-73
     if (!SameHemisphere(wo, wi)) return 0.0;
@@ -912,12 +916,12 @@ static __device__ inline double lobePdf(const GLobe& l, const V3& wo, const V3& 
   return 0.0;
 }
 // *pdfOut is left untouched when the BxDF returns without setting it (specular_transmission.dart:52-54)
-static __device__ inline Spec lobeSampleF(const GLobe& l, const V3& wo, V3* wi, double u1, double u2, double* pdfOut) {
+static __device__ inline Spec lobeBaseSampleF(const GLobe& l, const V3& wo, V3* wi, double u1, double u2, double* pdfOut) {
   if (l.kind <= 1) {  // bxdf.dart:37-48
     *wi = CosineSampleHemisphere(u1, u2);
     if (wo.z < 0.0f) wi->z = (float)((double)wi->z * -1.0);
-    *pdfOut = lobePdf(l, wo, *wi);
-    return lobeF(l, wo, *wi);
+    *pdfOut = lobeBasePdf(l, wo, *wi);
+    return lobeBaseF(l, wo, *wi);
   }
   if (l.kind == 2) {  // microfacet.dart:59-66 + blinn.dart:36-60
     const double exponent = l.param;
@@ -929,7 +933,7 @@ static __device__ inline Spec lobeSampleF(const GLobe& l, const V3& wo, V3* wi, 
     *wi = -wo + wh * 2.0 * Dot(wo, wh);
     *pdfOut = blinnPdfOf(exponent, costheta, Dot(wo, wh));
     if (!SameHemisphere(wo, *wi)) return mks1(0.0);
-    return lobeF(l, wo, *wi);
+    return lobeBaseF(l, wo, *wi);
   }
   const Spec R = Spec{l.rgb[0], l.rgb[1], l.rgb[2]};
   if (l.kind == 3) {  // specular_reflection.dart:34-41
@@ -951,6 +955,24 @@ static __device__ inline Spec lobeSampleF(const GLobe& l, const V3& wo, V3* wi, 
   *pdfOut = 1.0;
   const Spec F = fresnelDielectric((double)wo.z, l.ei, l.et);
   return ((mks1(1.0) - F) * R) / AbsCosTheta(*wi);
+}
+
+// The BxDF the BSDF holds: the lobe itself, BRDFToBTDF(lobe) (brdf_to_btdf.dart:31-58: the other hemisphere of wi) and / or
+// ScaledBxDF(.., s) (scaled_bxdf.dart:24-52: s * f; it does not override pdf, so BxDF.pdf's cosine density answers, bxdf.dart:84-88)
+static __device__ inline V3 OtherHemisphere(const V3& w) { return V3{w.x, w.y, -w.z}; }
+static __device__ inline Spec lobeF(const GLobe& l, const V3& wo, const V3& wi) {
+  if (l.wrap == 0) return lobeBaseF(l, wo, wi);
+  const Spec r = lobeBaseF(l, wo, (l.wrap & 1) ? OtherHemisphere(wi) : wi);
+  return (l.wrap & 2) ? Spec{l.scale[0], l.scale[1], l.scale[2]} * r : r;
+}
+static __device__ inline double lobePdf(const GLobe& l, const V3& wo, const V3& wi) {
+  if (l.wrap & 2) return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * DRT_INV_PI : 0.0;
+  return lobeBasePdf(l, wo, (l.wrap & 1) ? OtherHemisphere(wi) : wi);
+}
+static __device__ inline Spec lobeSampleF(const GLobe& l, const V3& wo, V3* wi, double u1, double u2, double* pdfOut) {
+  const Spec r = lobeBaseSampleF(l, wo, wi, u1, u2, pdfOut);
+  if (l.wrap & 1) *wi = OtherHemisphere(*wi);
+  return (l.wrap & 2) ? Spec{l.scale[0], l.scale[1], l.scale[2]} * r : r;
 }
 
 static __device__ inline Spec bsdfF(const BsdfG& b, const V3& woW, const V3& wiW, int flags) {  // bsdf.dart:177-198
@@ -987,7 +1009,7 @@ static __device__ inline Spec bsdfSampleF(const BsdfG& b, const V3& woW, V3* wiW
   for (int i = 0; i < b.n; ++i)
     if (lobeMatches(b.lobes[i], flags) && count-- == 0) { chosen = i; break; }
   const GLobe lc = b.lobes[chosen];
-  const int type = lobeType(lc.kind);
+  const int type = lobeTypeOf(lc);
   const V3 wo = bsdfToLocal(b, woW);
   V3 wi = V3{0.f, 0.f, 0.f};
   Spec f = lobeSampleF(lc, wo, &wi, (double)u0, (double)u1, pdfOut);

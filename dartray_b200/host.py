@@ -263,9 +263,12 @@ def _black(s) -> bool:
     return not bool(np.any(s != 0))
 
 
-def _lobe(kind, rgb, fresnel=FRESNEL_NOOP, eta=(0, 0, 0), k=(0, 0, 0), param=0.0, ei=1.0, et=1.0) -> dict:
+WRAP_BTDF, WRAP_SCALED = 1, 2  # drt_set_lobe_wrappers: BRDFToBTDF(bxdf), ScaledBxDF(.., scale)
+
+
+def _lobe(kind, rgb, fresnel=FRESNEL_NOOP, eta=(0, 0, 0), k=(0, 0, 0), param=0.0, ei=1.0, et=1.0, wrap=0, scale=(1, 1, 1)) -> dict:
     return dict(kind=int(kind), rgb=_spec(rgb), fresnel=int(fresnel), eta=_spec(eta), k=_spec(k), param=float(param),
-                ei=float(ei), et=float(et))
+                ei=float(ei), et=float(et), wrap=int(wrap), scale=_spec(scale))
 
 
 def _blinn_exponent(roughness: float) -> float:  # 1 / roughness, then blinn.dart:24-28
@@ -301,6 +304,62 @@ def plastic_lobes(kd=0.25, ks=0.25, roughness=0.1) -> list:  # plastic_material.
         out.append(_lobe(LOBE_LAMBERTIAN, d))
     if not _black(sp):
         out.append(_lobe(LOBE_MICROFACET_BLINN, sp, FRESNEL_DIELECTRIC, param=_blinn_exponent(roughness), ei=1.5, et=1.0))
+    return out
+
+
+def _f32(a):
+    return np.asarray(a, np.float64).astype(np.float32)
+
+
+def shinymetal_lobes(ks=1.0, kr=1.0, roughness=0.1) -> list:  # shiny_metal_material.dart:42-76
+    out = []
+
+    def approx_eta(fr):  # FresnelApproxEta (:66-70): Spectrum operations round to float32 one by one
+        refl = np.clip(_clamp(fr).astype(np.float64), 0.0, 0.999).astype(np.float32)
+        sq = _f32(np.sqrt(refl.astype(np.float64)))
+        return _f32(_f32(1.0 + sq.astype(np.float64)).astype(np.float64) / _f32(1.0 - sq.astype(np.float64)).astype(np.float64))
+    sp, r = _clamp(ks), _clamp(kr)
+    if not _black(sp):
+        out.append(_lobe(LOBE_MICROFACET_BLINN, 1.0, FRESNEL_CONDUCTOR, eta=approx_eta(sp), k=(0, 0, 0), param=_blinn_exponent(roughness)))
+    if not _black(r):
+        out.append(_lobe(LOBE_SPECULAR_REFLECTION, 1.0, FRESNEL_CONDUCTOR, eta=approx_eta(r), k=(0, 0, 0)))
+    return out
+
+
+def translucent_lobes(kd=0.25, ks=0.25, reflect=0.5, transmit=0.5, roughness=0.1) -> list:  # translucent_material.dart:47-90
+    out, r, t = [], _clamp(reflect), _clamp(transmit)
+    if _black(r) and _black(t):
+        return out
+    d = _clamp(kd)
+    if not _black(d):
+        if not _black(r):
+            out.append(_lobe(LOBE_LAMBERTIAN, _mul(r, d)))
+        if not _black(t):
+            out.append(_lobe(LOBE_LAMBERTIAN, _mul(t, d), wrap=WRAP_BTDF))
+    sp = _clamp(ks)
+    if not _black(sp):
+        e = _blinn_exponent(roughness)
+        if not _black(r):
+            out.append(_lobe(LOBE_MICROFACET_BLINN, _mul(r, sp), FRESNEL_DIELECTRIC, param=e, ei=1.5, et=1.0))
+        if not _black(t):
+            out.append(_lobe(LOBE_MICROFACET_BLINN, _mul(t, sp), FRESNEL_DIELECTRIC, param=e, ei=1.5, et=1.0, wrap=WRAP_BTDF))
+    return out
+
+
+def mix_lobes(lobes1, lobes2, amount=0.5) -> list:  # mix_material.dart:36-50
+    s1 = _clamp(amount)
+    s2 = np.clip(_f32(1.0 - s1.astype(np.float64)).astype(np.float64), 0.0, np.inf).astype(np.float32)
+    out = []
+    for ll, sc in ((lobes1, s1), (lobes2, s2)):
+        for l in ll:
+            if l["wrap"] & WRAP_SCALED:
+                raise ValueError("a mix of mixes (ScaledBxDF of a ScaledBxDF) is not representable in drt_set_lobe_wrappers")
+            m = dict(l)
+            m["wrap"] = l["wrap"] | WRAP_SCALED
+            m["scale"] = sc
+            out.append(m)
+    if len(out) > 8:
+        raise ValueError("a BSDF holds at most 8 BxDFs (bsdf.dart:253)")
     return out
 
 
@@ -557,6 +616,8 @@ class SceneBuilder:
             lobe_eta=np.asarray([l["eta"] for l in lobes], np.float32).reshape(-1, 3),
             lobe_k=np.asarray([l["k"] for l in lobes], np.float32).reshape(-1, 3),
             lobe_scalars=np.asarray([(l["param"], l["ei"], l["et"]) for l in lobes], np.float64).reshape(-1, 3),
+            lobe_wrap=np.asarray([l.get("wrap", 0) for l in lobes], np.int32),
+            lobe_scale=np.asarray([l.get("scale", (1, 1, 1)) for l in lobes], np.float32).reshape(-1, 3),
             light_kind=np.asarray([l["kind"] for l in lights], np.int32),
             light_L=np.asarray([l["L"] for l in lights], np.float32).reshape(-1, 3),
             light_pos=np.asarray([l["pos"] for l in lights], np.float32).reshape(-1, 3),
@@ -595,6 +656,8 @@ def upload_scene(ctx, arrays: dict, split: int = 2, max_node_prims: int = 4):
     if a.get("mat_general"):
         ctx.set_material_lobes(a["mat_lobe_offsets"], a["lobe_kind"], a["lobe_rgb"], a["lobe_fresnel"], a["lobe_eta"], a["lobe_k"],
                                a["lobe_scalars"])
+        if "lobe_wrap" in a and a["lobe_wrap"].any():
+            ctx.set_lobe_wrappers(a["lobe_wrap"], a["lobe_scale"])
     else:
         ctx.set_materials(a["mat_kind"], a["mat_kd"], a["mat_sigma"])
     ctx.set_lights(a["light_kind"], a["light_L"], a["light_pos"], a["light_nsamples"], a["light_shape_offsets"],

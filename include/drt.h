@@ -215,6 +215,14 @@ int drt_set_material_lobes(drt_ctx* ctx, uint32_t n, const uint32_t* lobe_offset
                            const int32_t* fresnel_kind, const float* fresnel_eta, const float* fresnel_k,
                            const double* lobe_scalars);
 
+/* The two BxDF adapters of the reference around the lobes of the last drt_set_material_lobes, one entry per lobe in the same
+ * order: wrap bit 0 = BRDFToBTDF(bxdf) (lib/core/reflection/brdf_to_btdf.dart: TranslucentMaterial's transmissive Lambertian and
+ * Microfacet, translucent_material.dart:62-86), bit 1 = ScaledBxDF(.., scale) (scaled_bxdf.dart: MixMaterial scales the BxDFs of
+ * its first material by `amount` and those of the second by 1 - amount, mix_material.dart:36-50); scale_rgb: n_lobes x 3
+ * float32 (read where bit 1 is set).  As in the reference a ScaledBxDF answers pdf() with BxDF's cosine density
+ * (scaled_bxdf.dart has no pdf override, bxdf.dart:84-88).  One level: a mix of mixes is not representable. */
+int drt_set_lobe_wrappers(drt_ctx* ctx, uint32_t n_lobes, const int32_t* wrap, const float* scale_rgb);
+
 /* Replaces scene.lights: DiffuseAreaLight (kind 0, lib/lights/diffuse_area_light.dart:44-70; L = Lemit
  * x scale) and PointLight (kind 1, lib/lights/point_light.dart:41-47; L = intensity, pos = world
  * position); kinds 2 / 3: see drt_set_spot_params below.  nsamples: per light (NULL = 1).  The ShapeSet of light i (lib/core/light/

@@ -327,6 +327,20 @@ int orc_set_lights(orc_ctx* c, uint32_t n, const int32_t* kind, const float* L, 
   return 0;
 }
 
+// mirrors drt_set_lobe_wrappers: BRDFToBTDF / ScaledBxDF around the lobes of the last orc_set_material_lobes, in lobe order
+int orc_set_lobe_wrappers(orc_ctx* c, uint32_t nLobes, const int32_t* wrap, const float* scale) {
+  uint32_t k = 0;
+  for (Material& m : c->rs.materials)
+    for (Lobe& l : m.lobes) {
+      if (k >= nLobes) { c->err = "lobe count differs from the last orc_set_material_lobes"; return -1; }
+      l.wrap = wrap[k];
+      l.scale = Spec(scale[3 * k], scale[3 * k + 1], scale[3 * k + 2]);
+      ++k;
+    }
+  if (k != nLobes) { c->err = "lobe count differs from the last orc_set_material_lobes"; return -1; }
+  return 0;
+}
+
 // mirrors drt_set_infinite_light: light `index` (kind 4 in orc_set_lights) gets its transforms and radiance map — level 0 of
 // the reference's MIPMap, power-of-two resolution, RGB float32 (a 1x1 white texel when the scene names no map)
 int orc_set_infinite_light(orc_ctx* c, uint32_t index, int width, int height, const float* rgb, const float* l2w, const float* w2l) {

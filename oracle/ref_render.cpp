@@ -409,6 +409,7 @@ struct LobeEval {
       case 3: type = BSDF_REFLECTION | BSDF_SPECULAR; break;
       default: type = BSDF_TRANSMISSION | BSDF_SPECULAR; break;
     }
+    if (l.wrap & 1) type ^= (BSDF_REFLECTION | BSDF_TRANSMISSION);  // brdf_to_btdf.dart:27-29; ScaledBxDF keeps the type
   }
   bool matches(int flags) const { return (type & flags) == type; }  // bxdf.dart:31-33
 
@@ -470,7 +471,7 @@ struct LobeEval {
     return pdf;
   }
 
-  Spec f(const Vec& wo, const Vec& wi) const {
+  Spec baseF(const Vec& wo, const Vec& wi) const {
     switch (l.kind) {
       case 0: return l.R * INV_PI;  // lambertian.dart:35-37
       case 1: {                     // oren_nayar.dart:33-58
@@ -500,7 +501,7 @@ struct LobeEval {
       default: return Spec(0.0);  // specular_reflection.dart:30-32, specular_transmission.dart:33-35
     }
   }
-  double pdf(const Vec& wo, const Vec& wi) const {
+  double basePdf(const Vec& wo, const Vec& wi) const {
     switch (l.kind) {
       case 0:
       case 1: return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * INV_PI : 0.0;  // bxdf.dart:84-88
@@ -509,19 +510,19 @@ struct LobeEval {
     }
   }
   // pdf is untouched when a BxDF returns without setting it (specular_transmission.dart:52-54)
-  Spec sample_f(const Vec& wo, Vec* wi, double u1, double u2, double* pdfOut) const {
+  Spec baseSampleF(const Vec& wo, Vec* wi, double u1, double u2, double* pdfOut) const {
     switch (l.kind) {
       case 0:
       case 1: {  // bxdf.dart:37-48
         *wi = CosineSampleHemisphere(u1, u2);
         if (wo.z < 0.0f) wi->z = f32((double)wi->z * -1.0);
-        *pdfOut = pdf(wo, *wi);
-        return f(wo, *wi);
+        *pdfOut = basePdf(wo, *wi);
+        return baseF(wo, *wi);
       }
       case 2: {  // microfacet.dart:59-66
         *pdfOut = blinnSample(wo, wi, u1, u2);
         if (!SameHemisphere(wo, *wi)) return Spec(0.0);
-        return f(wo, *wi);
+        return baseF(wo, *wi);
       }
       case 3: {  // specular_reflection.dart:34-41
         *wi = Vec(-(double)wo.x, -(double)wo.y, wo.z);
@@ -545,6 +546,23 @@ struct LobeEval {
         return ((Spec(1.0) - F) * l.R) / AbsCosTheta(*wi);
       }
     }
+  }
+
+  // The BxDF the BSDF holds: the lobe itself, BRDFToBTDF(lobe) (brdf_to_btdf.dart:31-58: the other hemisphere of wi) and / or
+  // ScaledBxDF(.., s) (scaled_bxdf.dart:24-52: s * f; it does NOT override pdf, so BxDF.pdf's cosine density answers, bxdf.dart:84-88)
+  static Vec OtherHemisphere(const Vec& w) { return Vec(w.x, w.y, -(double)w.z); }
+  Spec f(const Vec& wo, const Vec& wi) const {
+    Spec r = baseF(wo, (l.wrap & 1) ? OtherHemisphere(wi) : wi);
+    return (l.wrap & 2) ? l.scale * r : r;
+  }
+  double pdf(const Vec& wo, const Vec& wi) const {
+    if (l.wrap & 2) return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * INV_PI : 0.0;
+    return basePdf(wo, (l.wrap & 1) ? OtherHemisphere(wi) : wi);
+  }
+  Spec sample_f(const Vec& wo, Vec* wi, double u1, double u2, double* pdfOut) const {
+    Spec r = baseSampleF(wo, wi, u1, u2, pdfOut);
+    if (l.wrap & 1) *wi = OtherHemisphere(*wi);
+    return (l.wrap & 2) ? l.scale * r : r;
   }
 };
 

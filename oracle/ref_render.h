@@ -143,6 +143,10 @@ struct Lobe {
   Spec eta, k;      // conductor
   double ei = 1.0, et = 1.0;  // FresnelDielectric / SpecularTransmission indices
   double param = 0.0;         // Blinn exponent (blinn.dart:24-28: clamped to 10000) | OrenNayar sigma in degrees
+  // wrappers (lib/core/reflection/brdf_to_btdf.dart, scaled_bxdf.dart): bit 0 = BRDFToBTDF(bxdf) (TranslucentMaterial),
+  // bit 1 = ScaledBxDF(<that>, scale) (MixMaterial)
+  int wrap = 0;
+  Spec scale = Spec(1.0);
 };
 
 struct Material {

@@ -59,6 +59,7 @@ def lib():
         L.orc_set_materials.argtypes = [vp, u32, vp, vp, vp]
         L.orc_set_material_lobes.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp]
         L.orc_set_spot_params.argtypes = [vp, u32, vp, vp]
+        L.orc_set_lobe_wrappers.argtypes = [vp, u32, vp, vp]
         L.orc_set_infinite_light.argtypes = [vp, u32, i32, i32, vp, vp, vp]
         L.orc_set_lights.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
         L.orc_set_camera.argtypes = [vp, vp, vp, dbl, dbl, dbl, dbl]
@@ -215,6 +216,11 @@ class Oracle:
         """worldToLight (n x 16) and (cosTotalWidth, cosFalloffStart) (n x 2) of the spot lights of the last set_lights."""
         w, cs = _arr(world_to_light, np.float32).reshape(-1, 16), _arr(cosines, np.float64).reshape(-1, 2)
         self._ck(self.L.orc_set_spot_params(self.h, w.shape[0], _p(w), _p(cs)))
+
+    def set_lobe_wrappers(self, wrap, scale):
+        """BRDFToBTDF (bit 0) / ScaledBxDF (bit 1, with its RGB scale) around the lobes of the last set_material_lobes."""
+        w, sc = _arr(wrap, np.int32), _arr(scale, np.float32).reshape(-1, 3)
+        self._ck(self.L.orc_set_lobe_wrappers(self.h, w.shape[0], _p(w), _p(sc)))
 
     def set_infinite_light(self, index, texels, light_to_world, world_to_light):
         """Radiance map (h x w x 3 float32, power-of-two resolution: level 0 of the reference's MIPMap) and transforms of light

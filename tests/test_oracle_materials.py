@@ -270,3 +270,67 @@ def test_whitted_point_light_and_mirror_recursion_match_closed_forms():
     o1 = _oracle(sb, cam, film, smp, host.Integrator(kind=host.INTEGRATOR_WHITTED, maxdepth=1))
     o1.render(0, 1, 1)
     assert np.all(_centre(o1, film) == 0)
+
+
+# ---- translucent / mix / shinymetal (BRDFToBTDF, ScaledBxDF, FresnelApproxEta) ---------------------------------------------
+def _sheet_radiance(lobes, light_y, integ=None, sky=None):
+    """Radiance leaving the centre of a horizontal sheet (normal +y) towards a camera ABOVE it, lit by a point light at height
+    light_y on the axis (negative: behind the sheet) or by a constant sky."""
+    sb = host.SceneBuilder()
+    m = sb.material_lobes(lobes)
+    sb.mesh([[-20, 0, -20], [20, 0, -20], [20, 0, 20], [-20, 0, 20]], [[0, 2, 1], [0, 3, 2]], material=m)
+    if sky is not None:
+        sb.infinite_light((sky, sky, sky), nsamples=4)
+    else:
+        sb.point_light((0.0, light_y, 0.0), (30.0, 30.0, 30.0))
+    cam = host.PerspectiveCamera(host.look_at((0.0, 6.0, 0.01), (0, 0, 0), (0, 0, 1)), fov=0.5)
+    o = Oracle()
+    host.upload_scene(o, sb.arrays())
+    host.configure_render(o, cam, host.Film(2, 2), host.Sampler(kind=host.SAMPLER_LD, spp=16),
+                          integ or host.Integrator(kind=host.INTEGRATOR_DIRECT, maxdepth=3))
+    o.render()
+    return o.film_read()["rgb"].mean(axis=(0, 1))
+
+
+def test_translucent_transmits_with_its_btdf_lobes():
+    # Lambertian(r * kd) towards the light's side, BRDFToBTDF(Lambertian(t * kd)) through the sheet (translucent_material.dart:62-70)
+    kd, r, t, I, h = 0.8, 0.6, 0.3, 30.0, 3.0
+    lobes = host.translucent_lobes(kd=kd, ks=0.0, reflect=r, transmit=t)
+    assert [l["wrap"] for l in lobes] == [0, host.WRAP_BTDF]
+    front = _sheet_radiance(lobes, +h)
+    back = _sheet_radiance(lobes, -h)
+    assert front == pytest.approx(r * kd / math.pi * I / (h * h), rel=1e-4)
+    assert back == pytest.approx(t * kd / math.pi * I / (h * h), rel=1e-4)
+    # the glossy pair: reflection only from the front, transmission only from behind, equal lobes up to reflect / transmit
+    g = host.translucent_lobes(kd=0.0, ks=0.5, reflect=0.5, transmit=0.25, roughness=0.3)
+    assert [l["wrap"] for l in g] == [0, host.WRAP_BTDF]
+    gf, gb = _sheet_radiance(g, +h), _sheet_radiance(g, -h)
+    assert gf[0] > 0 and gb[0] == pytest.approx(0.5 * gf[0], rel=1e-4)
+
+
+def test_mix_material_scales_both_bsdfs():
+    a, b, s, I, h = 0.9, 0.2, 0.3, 30.0, 3.0
+    lobes = host.mix_lobes(host.matte_lobes(a), host.matte_lobes(b), amount=s)
+    assert all(l["wrap"] == host.WRAP_SCALED for l in lobes)
+    L = _sheet_radiance(lobes, +h)
+    assert L == pytest.approx((s * a + (1 - s) * b) / math.pi * I / (h * h), rel=1e-4)
+    # amount 1 / 0 reduce to the single materials; a mix of mixes is refused
+    one = _sheet_radiance(host.mix_lobes(host.matte_lobes(a), host.matte_lobes(b), amount=1.0), +h)
+    assert one == pytest.approx(_sheet_radiance(host.matte_lobes(a), +h), rel=1e-6)
+    with pytest.raises(ValueError):
+        host.mix_lobes(lobes, host.matte_lobes(b))
+    # ScaledBxDF keeps BxDF.pdf's cosine density (scaled_bxdf.dart has no pdf override): a scaled glossy lobe under a sky is still
+    # an unbiased estimate as long as the light-sampling half carries it — compare a path-traced furnace against the unscaled lobe
+    gl = host.plastic_lobes(0.0, 0.6, 0.2)
+    half = host.mix_lobes(gl, gl, amount=0.5)
+    full = _sheet_radiance(gl, 0, host.Integrator(kind=host.INTEGRATOR_DIRECT), sky=1.0)
+    mixed = _sheet_radiance(half, 0, host.Integrator(kind=host.INTEGRATOR_DIRECT), sky=1.0)
+    assert mixed == pytest.approx(full, rel=0.1)
+
+
+def test_shinymetal_reflectance_at_normal_incidence():
+    # FresnelApproxEta (shiny_metal_material.dart:66-70) is built so that the conductor's normal-incidence reflectance is Kr:
+    # a mirror-like sheet seen head-on under a constant sky returns Kr * L (clamped at 0.999)
+    for kr in (0.2, 0.7, 1.0):
+        L = _sheet_radiance(host.shinymetal_lobes(ks=0.0, kr=kr), 0, host.Integrator(kind=host.INTEGRATOR_DIRECT, maxdepth=2), sky=2.0)
+        assert L == pytest.approx(min(kr, 0.999) * 2.0, rel=2e-3)

@@ -321,6 +321,39 @@ def test_adaptive_sampler_matches_oracle(method, integ):
         assert err.max() <= 1e-3
 
 
+def _wrapped_materials_room():
+    """cornell_synth with TranslucentMaterial, MixMaterial and ShinyMetalMaterial BSDFs (BRDFToBTDF / ScaledBxDF wrappers)."""
+    return scenes.cornell_synth({
+        "grey": host.mix_lobes(host.matte_lobes((0.7, 0.7, 0.65)), host.plastic_lobes((0.2, 0.3, 0.6), 0.4, 0.1), amount=(0.3, 0.5, 0.7)),
+        "red": host.shinymetal_lobes(ks=(0.8, 0.5, 0.3), kr=(0.2, 0.1, 0.1), roughness=0.15),
+        "box": host.translucent_lobes(kd=(0.6, 0.7, 0.5), ks=0.3, reflect=0.4, transmit=0.6, roughness=0.2),
+        "sphere": host.mix_lobes(host.glass_lobes(1.0, 1.0, 1.5), host.matte_lobes((0.8, 0.4, 0.2)), amount=0.6),
+    })
+
+
+@pytest.mark.parametrize("integ", [host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=5), host.Integrator(kind=host.INTEGRATOR_DIRECT, maxdepth=3),
+                                   host.Integrator(kind=host.INTEGRATOR_WHITTED, maxdepth=3)])
+def test_translucent_mix_and_shinymetal_match_oracle(integ):
+    sb, cam = _wrapped_materials_room()
+    arrays = sb.arrays()
+    assert (arrays["lobe_wrap"] & 1).any() and (arrays["lobe_wrap"] & 2).any()
+    g, o, fg, fo = _render_both(arrays, cam, host.Film(80, 60), host.Sampler(kind=host.SAMPLER_LD, spp=4), integ)
+    err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
+    print("wrapped materials", integ.kind, "max rel err", err.max(), "q999", np.quantile(err, 0.999))
+    assert np.quantile(err, 0.999) <= 1e-3
+    assert abs(fg["rgb"].mean() - fo["rgb"].mean()) <= 2e-3 * fo["rgb"].mean()
+    sg, so = g.render_stats(), o.render_stats()
+    assert abs(sg["closest_rays"] - so["closest_rays"]) <= 1e-3 * so["closest_rays"]
+    # the wrappers are in use: the same lobes without them render differently
+    a2 = dict(arrays)
+    a2["lobe_wrap"] = np.zeros_like(arrays["lobe_wrap"])
+    g2 = capi.Context(0)
+    host.upload_scene(g2, a2)
+    host.configure_render(g2, cam, host.Film(80, 60), host.Sampler(kind=host.SAMPLER_LD, spp=4), integ)
+    g2.render(0, 1)
+    assert np.abs(g2.film_read()["rgb"] - fg["rgb"]).max() > 1e-2
+
+
 # ---- path tracing ------------------------------------------------------------------------------------------
 def test_path_integrator_matches_oracle():
     arrays, cam = _cornell()
