@@ -447,7 +447,7 @@ class GpuSamplerRenderer extends Renderer {
     final lk = <int>[], lL = <double>[], lpos = <double>[], lns = <int>[], so = <int>[0], sp = <int>[];
     final w2l = <double>[], cosines = <double>[];
     bool anySpot = false;
-    final infinite = <int>[];
+    final infinite = <int>[], mapped = <int>[];
     for (final Light l in lights) {
       lns.add(l.nSamples);
       w2l.addAll(l.worldToLight.m.data);
@@ -480,6 +480,18 @@ class GpuSamplerRenderer extends Renderer {
         lL.addAll(_rgb(l.intensity));
         lpos..add(l.lightPos.x)..add(l.lightPos.y)..add(l.lightPos.z);
         cosines..add(l.cosTotalWidth)..add(l.cosFalloffStart);
+      } else if (l is ProjectionLight) {
+        lk.add(5);
+        mapped.add(lk.length - 1);
+        lL.addAll(_rgb(l.intensity));
+        lpos..add(l.lightPos.x)..add(l.lightPos.y)..add(l.lightPos.z);
+        cosines.addAll([0.0, 0.0]);
+      } else if (l is GoniometricLight) {
+        lk.add(6);
+        mapped.add(lk.length - 1);
+        lL.addAll(_rgb(l.intensity));
+        lpos..add(l.lightPos.x)..add(l.lightPos.y)..add(l.lightPos.z);
+        cosines.addAll([0.0, 0.0]);
       } else if (l is InfiniteAreaLight) {
         lk.add(4);
         infinite.add(lk.length - 1);
@@ -494,6 +506,19 @@ class GpuSamplerRenderer extends Renderer {
     drt.setLights(lights.length, a.ints(lk), a.floats(lL), a.floats(lpos), a.ints(lns), a.uints(so), a.uints(sp));
     if (anySpot) {
       drt.setSpotParams(lights.length, a.floats(w2l), a.doubles(cosines));
+    }
+    for (final int i in mapped) {  // projection / goniometric lights: level 0 of their MIPMap (or none) + their transforms
+      final Light l = lights[i];
+      final MIPMap map = l is ProjectionLight ? l.projectionMap : (l as GoniometricLight).mipmap;
+      final SpectrumImage level0 = map == null ? null : map.pyramid[0];
+      if (l is ProjectionLight) {
+        drt.setLightMap(i, level0 == null ? 0 : level0.width, level0 == null ? 0 : level0.height,
+                        level0 == null ? nullptr : a.floats(level0.data), a.floats(l.worldToLight.m.data),
+                        a.floats(l.lightProjection.m.data), a.doubles([l.screenX0, l.screenX1, l.screenY0, l.screenY1]), l.hither);
+      } else {
+        drt.setLightMap(i, level0 == null ? 0 : level0.width, level0 == null ? 0 : level0.height,
+                        level0 == null ? nullptr : a.floats(level0.data), a.floats(l.worldToLight.m.data), nullptr, nullptr, 0.0);
+      }
     }
     for (final int i in infinite) {
       // level 0 of the light's own MIPMap: already resampled to a power of two and multiplied by L by the reference's

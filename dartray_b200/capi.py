@@ -19,7 +19,7 @@ HIT_DTYPE = np.dtype([("t", np.float32), ("b1", np.float32), ("b2", np.float32),
 
 # every symbol include/drt.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
-    "drt_version", "drt_create", "drt_destroy", "drt_last_error", "drt_set_triangles", "drt_set_spheres", "drt_set_disks", "drt_set_quadrics", "drt_set_mesh_shading", "drt_set_infinite_light", "drt_set_lobe_wrappers",
+    "drt_version", "drt_create", "drt_destroy", "drt_last_error", "drt_set_triangles", "drt_set_spheres", "drt_set_disks", "drt_set_quadrics", "drt_set_mesh_shading", "drt_set_infinite_light", "drt_set_lobe_wrappers", "drt_set_light_map",
     "drt_set_build_order", "drt_build_bvh", "drt_bvh_info_get", "drt_bvh_export", "drt_trace_closest",
     "drt_trace_any", "drt_trace_closest_device", "drt_trace_any_device", "drt_set_counting", "drt_get_counters", "drt_set_kernel_variant",
     "drt_last_kernel_ms", "drt_kernel_launches",
@@ -95,6 +95,7 @@ def load():
     L.drt_set_materials.argtypes = [vp, u32, vp, vp, vp]
     L.drt_set_material_lobes.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp]
     L.drt_set_spot_params.argtypes = [vp, u32, vp, vp]
+    L.drt_set_light_map.argtypes = [vp, u32, i32, i32, vp, vp, vp, vp, C.c_double]
     L.drt_set_lobe_wrappers.argtypes = [vp, u32, vp, vp]
     L.drt_set_infinite_light.argtypes = [vp, u32, i32, i32, vp, vp, vp]
     L.drt_set_lights.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
@@ -281,6 +282,15 @@ class Context:
         """worldToLight (n x 16) and (cosTotalWidth, cosFalloffStart) (n x 2) of the spot lights of the last set_lights."""
         w, cs = _arr(world_to_light, np.float32).reshape(-1, 16), _arr(cosines, np.float64).reshape(-1, 2)
         self._ck(self.L.drt_set_spot_params(self.h, w.shape[0], _p(w), _p(cs)))
+
+    def set_light_map(self, index, texels, world_to_light, projection=None, screen=None, hither=1.0e-3):
+        """Map (h x w x 3 float32, power-of-two, or None) and transforms of a projection (kind 5) / goniometric (kind 6) light."""
+        t = _arr(texels, np.float32)
+        w2l = _arr(world_to_light, np.float32).reshape(16)
+        pr = _arr(projection, np.float32)
+        sc = _arr(screen, np.float64)
+        self._ck(self.L.drt_set_light_map(self.h, int(index), 0 if t is None else t.shape[1], 0 if t is None else t.shape[0], _p(t), _p(w2l),
+                                          _p(pr), _p(sc), float(hither)))
 
     def set_lobe_wrappers(self, wrap, scale):
         """BRDFToBTDF (bit 0) / ScaledBxDF (bit 1, with its RGB scale) around the lobes of the last set_material_lobes."""

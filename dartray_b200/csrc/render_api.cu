@@ -29,6 +29,10 @@ struct HostLight {
   float l2w[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   int mapW = 0, mapH = 0;
   std::vector<float> texels;
+  // projection / goniometric lights (drt_set_light_map)
+  bool haveMapParams = false;
+  float proj[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  double screen[4] = {-1, 1, -1, 1}, hither = 1.0e-3;
 };
 
 struct ByteArena {  // one cudaMalloc per wavefront, carved into aligned arrays
@@ -223,7 +227,7 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
   }
   std::vector<GLight> gl(std::max(nLights, 1));
   std::vector<float> env;  // radiance maps + sampling tables of the infinite lights
-  int nInfinite = 0;
+  int nInfinite = 0, nMapped = 0;
   std::vector<GLightShape> shapes;
   std::vector<float> cdf;
   auto pushShape = [&](uint32_t sh, double area) {
@@ -270,6 +274,17 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
       g.envOffset = (uint32_t)env.size();
       appendEnvTables(hl.mapW, hl.mapH, hl.texels.data(), hl.L, &env);
       ++nInfinite;
+    }
+    std::memcpy(g.proj, hl.proj, sizeof(g.proj));
+    std::memcpy(g.screen, hl.screen, sizeof(g.screen));
+    g.hither = hl.hither;
+    if (hl.kind >= 5) {
+      if (!hl.haveMapParams) return fail(c, DRT_E_STATE, "a projection / goniometric light (kind 5 / 6) needs drt_set_light_map after drt_set_lights");
+      g.mapW = hl.mapW;
+      g.mapH = hl.mapH;
+      g.envOffset = (uint32_t)env.size();
+      env.insert(env.end(), hl.texels.begin(), hl.texels.end());
+      ++nMapped;
     }
     std::memcpy(g.w2l, hl.w2l, sizeof(g.w2l));
     g.cosTotalWidth = hl.cosTotalWidth;
@@ -393,7 +408,7 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
     CK(c, cudaMemcpy(r->dEnv.p, env.data(), env.size() * 4, cudaMemcpyHostToDevice));
     rs.envData = r->dEnv.p;
   }
-  rs.extra = (rs.meshOfTri != nullptr || c->ts.quadMode == 2 || nInfinite > 0) ? 1 : 0;
+  rs.extra = (rs.meshOfTri != nullptr || c->ts.quadMode == 2 || nInfinite > 0 || nMapped > 0) ? 1 : 0;
   rs.ntris = nt;
   rs.nprims = np;
   rs.primToRec = r->dPrimToRec.p;
@@ -959,7 +974,8 @@ int drt_set_lights(drt_ctx* c, uint32_t n, const int32_t* kind, const float* L, 
   for (uint32_t i = 0; i < n; ++i) {
     HostLight& l = ls[i];
     l.kind = kind[i];
-    if (l.kind < 0 || l.kind > 4) return fail(c, DRT_E_INVALID, "light kind must be 0 (diffuse area), 1 (point), 2 (distant), 3 (spot) or 4 (infinite)");
+    if (l.kind < 0 || l.kind > 6)
+      return fail(c, DRT_E_INVALID, "light kind must be 0 (diffuse area), 1 (point), 2 (distant), 3 (spot), 4 (infinite), 5 (projection) or 6 (goniometric)");
     if (l.kind != 0 && !pos) return fail(c, DRT_E_INVALID, "point / distant / spot lights need the pos array");
     std::memcpy(l.L, L + 3 * i, 12);
     if (pos) std::memcpy(l.pos, pos + 3 * i, 12);
@@ -1008,6 +1024,37 @@ int drt_set_infinite_light(drt_ctx* c, uint32_t index, int width, int height, co
   l.mapW = width;
   l.mapH = height;
   l.texels.assign(rgb, rgb + 3 * (size_t)width * height);
+  r->sceneTablesValid = false;
+  return DRT_OK;
+}
+
+int drt_set_light_map(drt_ctx* c, uint32_t index, int width, int height, const float* rgb, const float* world_to_light,
+                      const float* light_projection, const double* screen_window, double hither) {
+  if (!c) return DRT_E_INVALID;
+  RenderState* r = state(c);
+  if (index >= r->lights.size() || (r->lights[index].kind != 5 && r->lights[index].kind != 6))
+    return fail(c, DRT_E_STATE, "drt_set_light_map: the light must have been declared with kind 5 or 6 by the last drt_set_lights");
+  if (!world_to_light) return fail(c, DRT_E_INVALID, "null world_to_light");
+  HostLight& l = r->lights[index];
+  if (l.kind == 5 && (!light_projection || !screen_window)) return fail(c, DRT_E_INVALID, "a projection light needs its projection and screen window");
+  if (rgb) {
+    if (width < 1 || height < 1 || (width & (width - 1)) || (height & (height - 1)) || (uint64_t)width * height > (1u << 26))
+      return fail(c, DRT_E_INVALID, "the map must have power-of-two resolution (level 0 of the reference's MIPMap), at most 64 Mi texels");
+    l.mapW = width;
+    l.mapH = height;
+    l.texels.assign(rgb, rgb + 3 * (size_t)width * height);
+  } else {
+    l.mapW = l.mapH = 0;
+    l.texels.clear();
+  }
+  for (int row = 0; row < 3; ++row)
+    for (int col = 0; col < 3; ++col) l.w2l[3 * row + col] = world_to_light[4 * row + col];
+  if (l.kind == 5) {
+    std::memcpy(l.proj, light_projection, sizeof(l.proj));
+    std::memcpy(l.screen, screen_window, sizeof(l.screen));
+    l.hither = hither;
+  }
+  l.haveMapParams = true;
   r->sceneTablesValid = false;
   return DRT_OK;
 }

@@ -31,7 +31,8 @@ static_assert(sizeof(GLobe) == 88, "GLobe layout");
 struct GLight {
   int32_t kind;  // 0 = DiffuseAreaLight (diffuse_area_light.dart), 1 = PointLight (point_light.dart),
                  // 2 = DistantLight (distant_light.dart; pos = lightDir), 3 = SpotLight (spot_light.dart),
-                 // 4 = InfiniteAreaLight (infinite_area_light.dart)
+                 // 4 = InfiniteAreaLight (infinite_area_light.dart), 5 = ProjectionLight (projection_light.dart),
+                 // 6 = GoniometricLight (goniometric_light.dart)
   float L[3];    // Lemit / intensity / radiance
   float pos[3];
   float w2l[9];  // spot: rows of worldToLight's upper 3x3 (Transform.transformVector, transform.dart:139-146)
@@ -45,8 +46,11 @@ struct GLight {
   //   texels 3 x W x H | conditional func W x H | conditional cdf H x (W + 1) | conditional funcInt H |
   //   marginal func H | marginal cdf H + 1 | marginal funcInt 1          (Distribution2D, montecarlo.dart:222-268)
   float l2w[9];
-  int32_t mapW, mapH;
+  int32_t mapW, mapH;  // projection / goniometric lights: their map (texels only at envOffset), 0 x 0 = no map
   uint32_t envOffset;
+  // ProjectionLight (projection_light.dart:38-100)
+  float proj[16];  // lightProjection
+  double screen[4], hither;
 };
 
 // Per direct-lighting light: where its LightSampleOffsets / BSDFSampleOffsets live in a sample record

@@ -1228,15 +1228,19 @@ static __device__ inline Spec envTexel(const float* tex, int W, int H, long long
   const float* q = tex + 3 * (size_t)(t * W + s);
   return Spec{q[0], q[1], q[2]};
 }
-static __device__ __noinline__ void envRadianceCold(const RenderScene& rs, const GLight& l, double u, double v, Spec* out) {
+static __device__ __noinline__ void mapLookupCold(const RenderScene& rs, const GLight& l, double u, double v, Spec* out) {
   const float* tex = rs.envData + l.envOffset;
   const int W = l.mapW, H = l.mapH;
   double s = u * W - 0.5, t = v * H - 0.5;
   const long long s0 = (long long)floor(s), t0 = (long long)floor(t);
   const double ds = s - s0, dt = t - t0;
-  Spec r = envTexel(tex, W, H, s0, t0) * ((1.0 - ds) * (1.0 - dt)) + envTexel(tex, W, H, s0, t0 + 1) * ((1.0 - ds) * dt) +
-           envTexel(tex, W, H, s0 + 1, t0) * (ds * (1.0 - dt)) + envTexel(tex, W, H, s0 + 1, t0 + 1) * (ds * dt);
-  *out = r * lightRadiance(l);  // _radiance = lookup * L (:240-242)
+  *out = envTexel(tex, W, H, s0, t0) * ((1.0 - ds) * (1.0 - dt)) + envTexel(tex, W, H, s0, t0 + 1) * ((1.0 - ds) * dt) +
+         envTexel(tex, W, H, s0 + 1, t0) * (ds * (1.0 - dt)) + envTexel(tex, W, H, s0 + 1, t0 + 1) * (ds * dt);
+}
+static __device__ inline void envRadianceCold(const RenderScene& rs, const GLight& l, double u, double v, Spec* out) {
+  Spec r;
+  mapLookupCold(rs, l, u, v, &r);
+  *out = r * lightRadiance(l);  // _radiance = lookup * L (infinite_area_light.dart:240-242)
 }
 static __device__ inline double SphericalTheta(const V3& v) { return acos(clampD((double)v.z, -1.0, 1.0)); }  // vector.dart:185-187
 static __device__ inline double SphericalPhi(const V3& v) {                                                 // vector.dart:189-192
@@ -1322,6 +1326,35 @@ static __device__ __noinline__ double infinitePdfCold(const RenderScene& rs, con
   const double p = ((double)t.condFunc[(size_t)iv * W + iu] * (double)t.margFunc[iv]) / (ci * t.margInt);
   return p / (2.0 * DRT_PI * DRT_PI * sintheta);
 }
+// ProjectionLight.projection(w) (projection_light.dart:115-139) / GoniometricLight.scale(w) (goniometric_light.dart:71-86) times
+// the intensity over the squared distance, as sampleLAtPoint writes it
+static __device__ __noinline__ void mappedPointLightCold(const RenderScene& rs, const GLight& l, V3 w, double dist2, Spec* out) {
+  const Spec I = lightRadiance(l);
+  if (l.kind == 5) {
+    const V3 wl = xf3(l.w2l, w);
+    Spec proj = mks1(0.0);
+    if (!((double)wl.z < l.hither)) {
+      const V3 Pl = XfPoint(l.proj, wl);
+      if (!((double)Pl.x < l.screen[0] || (double)Pl.x > l.screen[1] || (double)Pl.y < l.screen[2] || (double)Pl.y > l.screen[3])) {
+        if (l.mapW == 0) proj = mks1(1.0);
+        else mapLookupCold(rs, l, ((double)Pl.x - l.screen[0]) / (l.screen[1] - l.screen[0]),
+                           ((double)Pl.y - l.screen[2]) / (l.screen[3] - l.screen[2]), &proj);
+      }
+    }
+    *out = I * proj / dist2;
+    return;
+  }
+  V3 wp = Normalize(xf3(l.w2l, w));
+  const float tmp = wp.y;
+  wp.y = wp.z;
+  wp.z = tmp;
+  const double theta = SphericalTheta(wp), phi = SphericalPhi(wp);
+  if (l.mapW == 0) { *out = I * 1.0 / dist2; return; }
+  Spec sc;
+  mapLookupCold(rs, l, phi * DRT_INV_TWOPI, theta * DRT_INV_PI, &sc);
+  *out = I * sc / dist2;
+}
+
 // Light.pdf(p, wi) for the non-delta lights
 static __device__ inline double lightPdfAny(const RenderScene& rs, const GLight& l, const V3& p, const V3& wi) {
   if (DRT_EXTRA && l.kind == 4) return infinitePdfCold(rs, l, wi);
@@ -1375,6 +1408,8 @@ static __device__ inline void estimateDirectSetup(const RenderScene& rs, int lig
     eps2 = 0.0;
     if (l.kind == 1) {
       Li = lightRadiance(l) / DistanceSquared(pos, p);
+    } else if (DRT_EXTRA && l.kind >= 5) {
+      mappedPointLightCold(rs, l, -wi, DistanceSquared(pos, p), &Li);
     } else {
       const V3 w = -wi;
       const V3 wl = Normalize(mkv((double)l.w2l[0] * w.x + (double)l.w2l[1] * w.y + (double)l.w2l[2] * w.z,
@@ -1466,6 +1501,8 @@ static __device__ inline void whittedLightSetup(const RenderScene& rs, int light
     segTo = pos;
     if (l.kind == 1) {
       Li = lightRadiance(l) / DistanceSquared(pos, p);
+    } else if (DRT_EXTRA && l.kind >= 5) {
+      mappedPointLightCold(rs, l, -wi, DistanceSquared(pos, p), &Li);
     } else {
       const V3 wn = -wi;
       const V3 wl = Normalize(mkv((double)l.w2l[0] * wn.x + (double)l.w2l[1] * wn.y + (double)l.w2l[2] * wn.z,

@@ -424,6 +424,28 @@ class SceneBuilder:
         self.lights.append(dict(kind=4, L=tuple(L), pos=(0, 0, 0), nsamples=nsamples, shapes=[], l2w=l2w, texels=tex))
         return len(self.lights) - 1
 
+    def projection_light(self, I, fov=45.0, light_to_world=None, texels=None) -> int:
+        """LightSource "projection" (projection_light.dart:38-100,141-150): a point light at the light's origin whose intensity is
+        masked by a map projected along +z of the light's frame.  `texels`: level 0 of the map's MIPMap ((h, w, 3) float32,
+        power of two) or None."""
+        l2w = np.eye(4, dtype=np.float32) if light_to_world is None else np.asarray(light_to_world, np.float32).reshape(4, 4)
+        pos = transform_points(l2w, [[0.0, 0.0, 0.0]])[0]
+        aspect = 1.0 if texels is None else np.asarray(texels).shape[1] / np.asarray(texels).shape[0]
+        screen = (-aspect, aspect, -1.0, 1.0) if aspect > 1.0 else (-1.0, 1.0, -1.0 / aspect, 1.0 / aspect)
+        self.lights.append(dict(kind=5, L=tuple(I), pos=tuple(float(v) for v in pos), nsamples=1, shapes=[], w2l=mat_inv(l2w).reshape(16),
+                                texels=None if texels is None else np.ascontiguousarray(texels, dtype=np.float32),
+                                proj=perspective(fov, 1.0e-3, 1.0e30).reshape(16), screen=screen, hither=1.0e-3))
+        return len(self.lights) - 1
+
+    def goniometric_light(self, I, light_to_world=None, texels=None) -> int:
+        """LightSource "goniometric" (goniometric_light.dart:37-86,117-123): a point light scaled by a lat-long map of directions
+        (the light's y axis is the map's pole)."""
+        l2w = np.eye(4, dtype=np.float32) if light_to_world is None else np.asarray(light_to_world, np.float32).reshape(4, 4)
+        pos = transform_points(l2w, [[0.0, 0.0, 0.0]])[0]
+        self.lights.append(dict(kind=6, L=tuple(I), pos=tuple(float(v) for v in pos), nsamples=1, shapes=[], w2l=mat_inv(l2w).reshape(16),
+                                texels=None if texels is None else np.ascontiguousarray(texels, dtype=np.float32)))
+        return len(self.lights) - 1
+
     def distant_light(self, frm, to, L) -> int:
         """DistantLight.Create (distant_light.dart:83-91) with an identity light-to-world: lightDir = normalize(from - to)."""
         d = (np.asarray(frm, np.float32).astype(np.float64) - np.asarray(to, np.float32).astype(np.float64)).astype(np.float32)
@@ -570,7 +592,7 @@ class SceneBuilder:
         for l in self.lights:
             shapes = [base[s[0]] + s[1] for s in l["shapes"]]
             lights.append(dict(kind=l["kind"], L=l["L"], pos=l["pos"], nsamples=l["nsamples"], shapes=shapes,
-                               l2w=l.get("l2w"), texels=l.get("texels"),
+                               l2w=l.get("l2w"), texels=l.get("texels"), proj=l.get("proj"), screen=l.get("screen"), hither=l.get("hither", 1.0e-3),
                                w2l=l.get("w2l", np.eye(4, dtype=np.float32).reshape(16)), cos=l.get("cos", (0.0, 0.0))))
         mats = self.materials or [(0, (0.5, 0.5, 0.5), 0.0)]
         general = any(m[0] == "lobes" for m in mats)
@@ -626,6 +648,7 @@ class SceneBuilder:
             light_cos=np.asarray([l["cos"] for l in lights], np.float64).reshape(-1, 2),
             light_has_spot=any(l["kind"] == 3 for l in lights),
             light_infinite=[(i, l["l2w"], l["texels"]) for i, l in enumerate(lights) if l["kind"] == 4],
+            light_mapped=[(i, l["texels"], l["w2l"], l["proj"], l["screen"], l["hither"]) for i, l in enumerate(lights) if l["kind"] >= 5],
             light_shape_offsets=np.asarray(np.cumsum([0] + [len(l["shapes"]) for l in lights]), np.uint32),
             light_shape_prims=np.asarray([p for l in lights for p in l["shapes"]], np.uint32),
         )
@@ -666,6 +689,8 @@ def upload_scene(ctx, arrays: dict, split: int = 2, max_node_prims: int = 4):
         ctx.set_spot_params(a["light_w2l"], a["light_cos"])
     for i, l2w, tex in a.get("light_infinite", []):
         ctx.set_infinite_light(i, tex, l2w, mat_inv(l2w))
+    for i, tex, w2l, proj, screen, hither in a.get("light_mapped", []):
+        ctx.set_light_map(i, tex, w2l, proj, screen, hither)
 
 
 def configure_render(ctx, camera: PerspectiveCamera, film: Film, sampler: Sampler, integrator: Integrator):

@@ -249,6 +249,16 @@ int drt_set_spot_params(drt_ctx* ctx, uint32_t n, const float* world_to_light, c
 int drt_set_infinite_light(drt_ctx* ctx, uint32_t index, int width, int height, const float* rgb, const float* light_to_world,
                            const float* world_to_light);
 
+/* Replaces ProjectionLight (kind 5 of drt_set_lights; lib/lights/projection_light.dart:38-139) and GoniometricLight (kind 6;
+ * lib/lights/goniometric_light.dart:37-86) construction for light `index`: pos / L of drt_set_lights are lightPos / intensity.
+ * rgb: level 0 of the light's MIPMap (power-of-two resolution, row-major RGB float32) or NULL when the scene names no map
+ * (projection: 1 inside the screen window; goniometric: 1).  world_to_light: 16 floats.  Projection lights also pass
+ * light_projection (Transform.Perspective(fov, hither, yon), 16 floats), screen_window = screenX0, screenX1, screenY0,
+ * screenY1 and hither as the constructor left them; NULL / ignored for goniometric lights.  Both are delta lights: intensity *
+ * map lookup / distance^2. */
+int drt_set_light_map(drt_ctx* ctx, uint32_t index, int width, int height, const float* rgb, const float* world_to_light,
+                      const float* light_projection, const double* screen_window, double hither);
+
 /* Replaces PerspectiveCamera (lib/cameras/perspective_camera.dart:46-57 + lib/core/
  * projective_camera.dart:34-53): the two float32 row-major matrices the camera holds
  * (rasterToCamera, cameraToWorld.startTransform) and its lens / shutter scalars. */

@@ -327,6 +327,27 @@ int orc_set_lights(orc_ctx* c, uint32_t n, const int32_t* kind, const float* L, 
   return 0;
 }
 
+// mirrors drt_set_light_map: the map (level 0, power-of-two, or NULL) and transforms of a projection (kind 5) or goniometric
+// (kind 6) light
+int orc_set_light_map(orc_ctx* c, uint32_t index, int width, int height, const float* rgb, const float* w2l, const float* proj,
+                      const double* screen, double hither) {
+  if (index >= c->rs.lights.size() || (c->rs.lights[index].kind != 5 && c->rs.lights[index].kind != 6)) { c->err = "not a projection / goniometric light"; return -1; }
+  Light& l = c->rs.lights[index];
+  l.worldToLight = Transform(w2l, w2l);  // only m is used (vector)
+  if (rgb) {
+    if (width < 1 || height < 1 || (width & (width - 1)) || (height & (height - 1))) { c->err = "map resolution must be a power of two"; return -1; }
+    l.radianceMap.init(width, height, rgb);
+  } else {
+    l.radianceMap = MipMap();
+  }
+  if (l.kind == 5) {
+    l.lightProjection = Transform(proj, proj);
+    for (int k = 0; k < 4; ++k) l.screen[k] = screen[k];
+    l.hither = hither;
+  }
+  return 0;
+}
+
 // mirrors drt_set_lobe_wrappers: BRDFToBTDF / ScaledBxDF around the lobes of the last orc_set_material_lobes, in lobe order
 int orc_set_lobe_wrappers(orc_ctx* c, uint32_t nLobes, const int32_t* wrap, const float* scale) {
   uint32_t k = 0;

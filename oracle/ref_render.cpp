@@ -1036,6 +1036,32 @@ struct Ctx {
       }
       return l.L * falloff / DistanceSquared(l.pos, p);
     }
+    if (l.kind == 5) {  // projection_light.dart:102-109,115-139
+      *wi = Normalize(l.pos - p);
+      *pdf = 1.0;
+      setSegment(vis, p, pEps, l.pos, 0.0, time);
+      Vec wl = l.worldToLight.vector(-*wi);
+      Spec proj(0.0);
+      if (!(wl.z < l.hither)) {
+        Vec Pl = l.lightProjection.point(wl);
+        if (!(Pl.x < l.screen[0] || Pl.x > l.screen[1] || Pl.y < l.screen[2] || Pl.y > l.screen[3])) {
+          if (l.radianceMap.levels == 0) proj = Spec(1.0);
+          else proj = l.radianceMap.lookup(((double)Pl.x - l.screen[0]) / (l.screen[1] - l.screen[0]),
+                                           ((double)Pl.y - l.screen[2]) / (l.screen[3] - l.screen[2]), 0.0);
+        }
+      }
+      return l.L * proj / DistanceSquared(l.pos, p);
+    }
+    if (l.kind == 6) {  // goniometric_light.dart:58-86
+      *wi = Normalize(l.pos - p);
+      *pdf = 1.0;
+      setSegment(vis, p, pEps, l.pos, 0.0, time);
+      Vec wp = Normalize(l.worldToLight.vector(-*wi));
+      std::swap(wp.y, wp.z);
+      double theta = SphericalTheta(wp), phi = SphericalPhi(wp);
+      if (l.radianceMap.levels == 0) return l.L * 1.0 / DistanceSquared(l.pos, p);
+      return l.L * l.radianceMap.lookup(phi * INV_TWOPI, theta * INV_PI, 0.0) / DistanceSquared(l.pos, p);
+    }
     if (l.kind == 4) {  // infinite_area_light.dart:93-131
       double uv[2], mapPdf;
       l.distribution.sampleContinuous(ls.u0, ls.u1, uv, &mapPdf);

@@ -186,7 +186,8 @@ struct MipMap {
 };
 
 struct Light {
-  int kind = 0;  // 0 = DiffuseAreaLight, 1 = PointLight, 2 = DistantLight, 3 = SpotLight, 4 = InfiniteAreaLight
+  int kind = 0;  // 0 = DiffuseAreaLight, 1 = PointLight, 2 = DistantLight, 3 = SpotLight, 4 = InfiniteAreaLight,
+                 // 5 = ProjectionLight (projection_light.dart), 6 = GoniometricLight (goniometric_light.dart)
   Spec L;        // Lemit / intensity / radiance
   Vec pos;       // point / spot light position (world); distant light: lightDir (distant_light.dart:26)
   Transform worldToLight;                            // spot light (spot_light.dart:38-53)
@@ -203,6 +204,10 @@ struct Light {
   Distribution2D distribution;
   Spec radiance(double u, double v, double width) const { return radianceMap.lookup(u, v, width) * L; }  // :240-242
   void setRadianceMap(int width, int height, const float* rgb);
+  // ProjectionLight (projection_light.dart:38-100): lightProjection, the screen window and hither; both it and the
+  // GoniometricLight look their map up at width 0 (radianceMap above; levels == 0: no map -> 1)
+  Transform lightProjection;
+  double screen[4] = {-1, 1, -1, 1}, hither = 1.0e-3;
 };
 
 struct Camera {  // perspective_camera.dart:46-57 + projective_camera.dart:34-53

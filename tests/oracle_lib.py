@@ -59,6 +59,7 @@ def lib():
         L.orc_set_materials.argtypes = [vp, u32, vp, vp, vp]
         L.orc_set_material_lobes.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp]
         L.orc_set_spot_params.argtypes = [vp, u32, vp, vp]
+        L.orc_set_light_map.argtypes = [vp, u32, i32, i32, vp, vp, vp, vp, dbl]
         L.orc_set_lobe_wrappers.argtypes = [vp, u32, vp, vp]
         L.orc_set_infinite_light.argtypes = [vp, u32, i32, i32, vp, vp, vp]
         L.orc_set_lights.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
@@ -216,6 +217,15 @@ class Oracle:
         """worldToLight (n x 16) and (cosTotalWidth, cosFalloffStart) (n x 2) of the spot lights of the last set_lights."""
         w, cs = _arr(world_to_light, np.float32).reshape(-1, 16), _arr(cosines, np.float64).reshape(-1, 2)
         self._ck(self.L.orc_set_spot_params(self.h, w.shape[0], _p(w), _p(cs)))
+
+    def set_light_map(self, index, texels, world_to_light, projection=None, screen=None, hither=1.0e-3):
+        """Map (h x w x 3 float32, power-of-two, or None) and transforms of a projection (kind 5) / goniometric (kind 6) light."""
+        t = _arr(texels, np.float32)
+        w2l = _arr(world_to_light, np.float32).reshape(16)
+        pr = _arr(projection, np.float32)
+        sc = _arr(screen, np.float64)
+        self._ck(self.L.orc_set_light_map(self.h, int(index), 0 if t is None else t.shape[1], 0 if t is None else t.shape[0], _p(t), _p(w2l),
+                                          _p(pr), _p(sc), float(hither)))
 
     def set_lobe_wrappers(self, wrap, scale):
         """BRDFToBTDF (bit 0) / ScaledBxDF (bit 1, with its RGB scale) around the lobes of the last set_material_lobes."""

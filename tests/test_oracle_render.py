@@ -383,3 +383,62 @@ def test_adaptive_sampler_supersamples_only_where_the_samples_disagree(method):
     # the sample window is one pixel wider and taller than the film (image_film.dart:247-252): 2 * 24 + 1 all-miss pixels more
     assert o.render_stats()["camera_samples"] == int((wt == 4).sum() * 4 + (wt == 16).sum() * (4 + 16)) + (2 * W + 1) * 4
     assert np.allclose(f["rgb"][inside], 4.0, rtol=1e-6)
+
+
+# ---- ProjectionLight / GoniometricLight (projection_light.dart, goniometric_light.dart) -----------------------------------
+def _floor_under(light_fn, look=(0.0, 0.0, 0.0)):
+    kd = 0.5
+    sb = host.SceneBuilder()
+    _plane(sb, material=sb.material((kd, kd, kd)))
+    light_fn(sb)
+    cam = host.PerspectiveCamera(host.look_at((look[0] + 0.01, 3.0, look[2] - 0.01), look, (0, 0, 1)), fov=0.5)
+    o = _oracle(sb, cam, host.Film(2, 2), host.Sampler(kind=host.SAMPLER_STRATIFIED, xs=1, ys=1, jitter=False),
+                host.Integrator(kind=host.INTEGRATOR_DIRECT))
+    o.render()
+    return o.film_read()["rgb"].mean(axis=(0, 1)), kd
+
+
+def test_projection_light_window_and_map():
+    I, h = 40.0, 4.0
+    down = host.mat_mul(host.translate(0, h, 0), host.rotate(90, (1, 0, 0)))  # the light's +z points at the floor
+    # no map: a point light inside the projected square (fov 60 -> half-width h * tan(30 deg) on the floor), nothing outside
+    L, kd = _floor_under(lambda sb: sb.projection_light((I, I, I), fov=60.0, light_to_world=down))
+    assert L[0] == pytest.approx(kd / math.pi * I / (h * h), rel=1e-4)
+    edge = h * math.tan(math.radians(30.0))
+    x_in, x_out = 0.9 * edge, 1.1 * edge
+    L_in, _ = _floor_under(lambda sb: sb.projection_light((I, I, I), fov=60.0, light_to_world=down), look=(x_in, 0.0, 0.0))
+    L_out, _ = _floor_under(lambda sb: sb.projection_light((I, I, I), fov=60.0, light_to_world=down), look=(x_out, 0.0, 0.0))
+    d2 = h * h + x_in * x_in
+    assert L_in[0] == pytest.approx(kd / math.pi * I * (h / math.sqrt(d2)) / d2, rel=1e-3) and L_out[0] == 0.0
+    # a uniform map scales it; a two-colour map (left half red, right half blue) colours the two sides of the axis
+    L_half, _ = _floor_under(lambda sb: sb.projection_light((I, I, I), fov=60.0, light_to_world=down, texels=np.full((4, 4, 3), 0.5, np.float32)))
+    assert L_half[0] == pytest.approx(0.5 * L[0], rel=1e-5)
+    tex = np.zeros((8, 8, 3), np.float32)
+    tex[:, :4, 0] = 1.0
+    tex[:, 4:, 2] = 1.0
+    a, _ = _floor_under(lambda sb: sb.projection_light((I, I, I), fov=60.0, light_to_world=down, texels=tex), look=(0.5 * edge, 0.0, 0.0))
+    b, _ = _floor_under(lambda sb: sb.projection_light((I, I, I), fov=60.0, light_to_world=down, texels=tex), look=(-0.5 * edge, 0.0, 0.0))
+    e = 1e-3  # the bilinear lookup leaves a trace of the other half
+    assert (a[0] > e) != (b[0] > e) and (a[2] > e) != (b[2] > e) and (a[0] > e) == (b[2] > e)
+
+
+def test_goniometric_light_scales_a_point_light_by_direction():
+    I, h = 40.0, 4.0
+    at = host.translate(0, h, 0)
+    plain, kd = _floor_under(lambda sb: sb.goniometric_light((I, I, I), light_to_world=at))
+    assert plain[0] == pytest.approx(kd / math.pi * I / (h * h), rel=1e-4)  # no map: a point light
+    quarter, _ = _floor_under(lambda sb: sb.goniometric_light((I, I, I), light_to_world=at, texels=np.full((2, 4, 3), 0.25, np.float32)))
+    assert quarter[0] == pytest.approx(0.25 * plain[0], rel=1e-5)
+    # the map's pole is the light's +y (the y / z swap of :74-76): rows near t = 1 face the floor below the light
+    tex = np.zeros((16, 8, 3), np.float32)
+    tex[8:] = 1.0
+    tex2 = np.zeros((16, 8, 3), np.float32)
+    tex2[:8] = 1.0
+    off = (2.0, 0.0, 0.0)  # 27 degrees off the nadir: t = 0.85, rows 13 / 14
+    ref, _ = _floor_under(lambda sb: sb.goniometric_light((I, I, I), light_to_world=at), look=off)
+    below, _ = _floor_under(lambda sb: sb.goniometric_light((I, I, I), light_to_world=at, texels=tex), look=off)
+    dark, _ = _floor_under(lambda sb: sb.goniometric_light((I, I, I), light_to_world=at, texels=tex2), look=off)
+    assert below[0] == pytest.approx(ref[0], rel=1e-5) and dark[0] == 0.0
+    # exactly at the nadir t = 1: the bilinear lookup blends the last row with row 0 (TEXTURE_REPEAT, mipmap.dart:183-204,341-355)
+    nadir, _ = _floor_under(lambda sb: sb.goniometric_light((I, I, I), light_to_world=at, texels=tex))
+    assert nadir[0] == pytest.approx(0.5 * plain[0], rel=5e-2)  # the camera looks a hair off the axis

@@ -354,6 +354,37 @@ def test_translucent_mix_and_shinymetal_match_oracle(integ):
     assert np.abs(g2.film_read()["rgb"] - fg["rgb"]).max() > 1e-2
 
 
+@pytest.mark.parametrize("integ", [host.Integrator(kind=host.INTEGRATOR_DIRECT), host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=3),
+                                   host.Integrator(kind=host.INTEGRATOR_WHITTED, maxdepth=2)])
+def test_projection_and_goniometric_lights_match_oracle(integ):
+    """projection_light.dart / goniometric_light.dart: point lights scaled by a map lookup (drt_set_light_map)."""
+    sb, cam = scenes.cornell_synth()
+    w, h = 16, 8
+    v, u = np.meshgrid((np.arange(h) + 0.5) / h, (np.arange(w) + 0.5) / w, indexing="ij")
+    stripes = np.stack([0.5 + 0.5 * np.sin(12 * u), 0.5 + 0.5 * np.cos(9 * v), 0.3 + 0.7 * u * v], axis=2).astype(np.float32)
+    sb.projection_light((300.0, 280.0, 250.0), fov=50.0, texels=stripes,
+                        light_to_world=host.mat_mul(host.translate(-3, 6, -6), host.rotate(60, (1, 0.2, 0))))
+    sb.projection_light((150.0, 150.0, 150.0), fov=30.0, light_to_world=host.mat_mul(host.translate(5, 8, -2), host.rotate(80, (1, 0, 0.3))))
+    sb.goniometric_light((120.0, 140.0, 160.0), texels=stripes[:, ::-1].copy(), light_to_world=host.mat_mul(host.translate(0, 2, -4), host.rotate(30, (0, 0, 1))))
+    sb.goniometric_light((40.0, 40.0, 40.0), light_to_world=host.translate(-6, -6, -3))
+    arrays = sb.arrays()
+    g, o, fg, fo = _render_both(arrays, cam, host.Film(80, 60), host.Sampler(kind=host.SAMPLER_LD, spp=4), integ)
+    err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
+    print("mapped lights", integ.kind, "max rel err", err.max())
+    assert np.quantile(err, 0.999) <= 1e-3
+    if integ.kind == host.INTEGRATOR_DIRECT:
+        assert err.max() <= 1e-3
+        sg, so = g.render_stats(), o.render_stats()
+        assert sg["shadow_rays"] == so["shadow_rays"] and sg["closest_rays"] == so["closest_rays"]
+    # a projection / goniometric light without its drt_set_light_map is refused
+    arrays["light_mapped"] = []
+    g2 = capi.Context(0)
+    host.upload_scene(g2, arrays)
+    host.configure_render(g2, cam, host.Film(8, 8), host.Sampler(kind=host.SAMPLER_LD, spp=1), integ)
+    with pytest.raises(RuntimeError, match="drt_set_light_map"):
+        g2.render(0, 1)
+
+
 # ---- path tracing ------------------------------------------------------------------------------------------
 def test_path_integrator_matches_oracle():
     arrays, cam = _cornell()
