@@ -25,7 +25,7 @@ class GpuUnsupported implements Exception {
   String toString() => 'not on the GPU path: $what';
 }
 
-const int _LAMBERTIAN = 0, _OREN_NAYAR = 1, _MICROFACET_BLINN = 2, _SPEC_REFLECTION = 3, _SPEC_TRANSMISSION = 4;
+const int _LAMBERTIAN = 0, _OREN_NAYAR = 1, _MICROFACET_BLINN = 2, _SPEC_REFLECTION = 3, _SPEC_TRANSMISSION = 4, _FRESNEL_BLEND = 5;
 const int _FRESNEL_NOOP = 0, _FRESNEL_DIELECTRIC = 1, _FRESNEL_CONDUCTOR = 2;
 
 class _Lobe {
@@ -180,6 +180,13 @@ class GpuSamplerRenderer extends Renderer {
       Spectrum kt = op * _const(m.Kt, 'uber Kt').clamp();
       if (!kt.isBlack()) {
         out.add(new _Lobe(_SPEC_TRANSMISSION, kt, fresnel: _FRESNEL_DIELECTRIC, ei: e, et: 1.0));
+      }
+    } else if (m is SubstrateMaterial) {  // substrate_material.dart:46-68: one FresnelBlend over an Anisotropic distribution
+      noBump(m.bumpMap);
+      Spectrum d = _const(m.Kd, 'substrate Kd').clamp(), sp = _const(m.Ks, 'substrate Ks').clamp();
+      if (!d.isBlack() || !sp.isBlack()) {
+        out.add(new _Lobe(_FRESNEL_BLEND, d, eta: sp, param: _blinn(_constF(m.nu, 'substrate uroughness')),
+                          ei: _blinn(_constF(m.nv, 'substrate vroughness'))));  // Rs in the eta slot; anisotropic.dart:30-37 clamps like Blinn
       }
     } else if (m is ShinyMetalMaterial) {  // shiny_metal_material.dart:42-64
       noBump(m.bumpMap);

@@ -57,7 +57,7 @@ struct RenderState {
   // host-side description
   std::vector<GMaterial> materials{GMaterial{{0.5f, 0.5f, 0.5f}, 0.f}};
   // general materials (drt_set_material_lobes): BxDF lists; empty when every material is matte
-  bool general = false, hasSpecular = false;
+  bool general = false, hasSpecular = false, hasBlend = false;  // hasBlend: a FresnelBlend lobe (kind 5) -> the `extra` kernels
   std::vector<uint2> matLobes;
   std::vector<GLobe> lobes;
   std::vector<HostLight> lights;
@@ -408,7 +408,7 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
     CK(c, cudaMemcpy(r->dEnv.p, env.data(), env.size() * 4, cudaMemcpyHostToDevice));
     rs.envData = r->dEnv.p;
   }
-  rs.extra = (rs.meshOfTri != nullptr || c->ts.quadMode == 2 || nInfinite > 0 || nMapped > 0) ? 1 : 0;
+  rs.extra = (rs.meshOfTri != nullptr || c->ts.quadMode == 2 || nInfinite > 0 || nMapped > 0 || (r->general && r->hasBlend)) ? 1 : 0;
   rs.ntris = nt;
   rs.nprims = np;
   rs.primToRec = r->dPrimToRec.p;
@@ -897,7 +897,7 @@ int drt_set_materials(drt_ctx* c, uint32_t n, const int32_t* kind, const float* 
     if (kind && kind[i] != 0) return fail(c, DRT_E_INVALID, "only material kind 0 (matte) is on the GPU path");
     r->materials[i] = GMaterial{{kd[3 * i], kd[3 * i + 1], kd[3 * i + 2]}, sigma ? sigma[i] : 0.f};
   }
-  r->general = r->hasSpecular = false;
+  r->general = r->hasSpecular = r->hasBlend = false;
   r->matLobes.clear();
   r->lobes.clear();
   r->sceneTablesValid = false;
@@ -914,7 +914,7 @@ int drt_set_material_lobes(drt_ctx* c, uint32_t n, const uint32_t* lobe_offsets,
   RenderState* r = state(c);
   std::vector<uint2> ml(n);
   std::vector<GLobe> ls(nl);
-  bool spec = false;
+  bool spec = false, blend = false;
   for (uint32_t i = 0; i < n; ++i) {
     if (lobe_offsets[i + 1] < lobe_offsets[i] || lobe_offsets[i + 1] - lobe_offsets[i] > 8)
       return fail(c, DRT_E_INVALID, "a BSDF holds at most 8 BxDFs (bsdf.dart:253) and the offsets must not decrease");
@@ -924,7 +924,9 @@ int drt_set_material_lobes(drt_ctx* c, uint32_t n, const uint32_t* lobe_offsets,
     GLobe& l = ls[j];
     l.kind = lobe_kind[j];
     l.fresnel = fresnel_kind ? fresnel_kind[j] : 0;
-    if (l.kind < 0 || l.kind > 4 || l.fresnel < 0 || l.fresnel > 2) return fail(c, DRT_E_INVALID, "unknown BxDF or Fresnel kind");
+    if (l.kind < 0 || l.kind > 5 || l.fresnel < 0 || l.fresnel > 2) return fail(c, DRT_E_INVALID, "unknown BxDF or Fresnel kind");
+    if (l.kind == 5 && !fresnel_eta) return fail(c, DRT_E_INVALID, "FresnelBlend (kind 5) carries Rs in the eta array");
+    blend = blend || l.kind == 5;
     if (l.fresnel == 2 && (!fresnel_eta || !fresnel_k)) return fail(c, DRT_E_INVALID, "FresnelConductor needs eta and k");
     for (int k = 0; k < 3; ++k) {
       l.rgb[k] = lobe_rgb[3 * j + k];
@@ -937,13 +939,14 @@ int drt_set_material_lobes(drt_ctx* c, uint32_t n, const uint32_t* lobe_offsets,
     l.param = lobe_scalars[3 * j];
     l.ei = lobe_scalars[3 * j + 1];
     l.et = lobe_scalars[3 * j + 2];
-    spec = spec || l.kind >= 3;
+    spec = spec || l.kind == 3 || l.kind == 4;
   }
   r->materials.assign(n, GMaterial{{0.f, 0.f, 0.f}, 0.f});  // the single-lobe table is not read when `general` is set
   r->matLobes.swap(ml);
   r->lobes.swap(ls);
   r->general = true;
   r->hasSpecular = spec;
+  r->hasBlend = blend;
   r->sceneTablesValid = false;
   return DRT_OK;
 }

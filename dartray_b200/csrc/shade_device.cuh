@@ -831,7 +831,7 @@ static __device__ inline bool SameHemisphere(const V3& w, const V3& wp) { return
 
 static __device__ inline int lobeType(int kind) {
   return kind <= 1 ? (BSDF_REFLECTION | BSDF_DIFFUSE)
-                   : (kind == 2 ? (BSDF_REFLECTION | BSDF_GLOSSY)
+                   : ((kind == 2 || kind == 5) ? (BSDF_REFLECTION | BSDF_GLOSSY)
                                 : (kind == 3 ? (BSDF_REFLECTION | BSDF_SPECULAR) : (BSDF_TRANSMISSION | BSDF_SPECULAR)));
 }
 static __device__ inline int lobeTypeOf(const GLobe& l) {  // brdf_to_btdf.dart:27-29 flips reflection <-> transmission
@@ -874,7 +874,84 @@ static __device__ inline double blinnPdfOf(double exponent, double costheta, dou
   if (woDotWh <= 0.0) pdf = 0.0;
   return pdf;
 }
+// FresnelBlend (fresnel_blend.dart:24-90) over an Anisotropic distribution (anisotropic.dart:27-121): lobe kind 5 with Rd = rgb,
+// Rs = eta, ex = param, ey = ei.  SubstrateMaterial's only BxDF; kept out of line (rare, pow / atan / tan heavy).
+static __device__ inline double anisoPdfOf(const GLobe& l, const V3& wo, const V3& wh) {
+  const double costhetah = AbsCosTheta(wh), ds = 1.0 - costhetah * costhetah;
+  double p = 0.0;
+  if (ds > 0.0 && Dot(wo, wh) > 0.0) {
+    const double e = (l.param * wh.x * wh.x + l.ei * wh.y * wh.y) / ds;
+    const double dd = sqrt((l.param + 1.0) * (l.ei + 1.0)) * DRT_INV_TWOPI * pow(costhetah, e);
+    p = dd / (4.0 * Dot(wo, wh));
+  }
+  return p;
+}
+static __device__ __noinline__ void blendFCold(const GLobe& l, V3 wo, V3 wi, Spec* out) {
+  const Spec ONE = mks1(1.0), Rd = Spec{l.rgb[0], l.rgb[1], l.rgb[2]}, Rs = Spec{l.eta[0], l.eta[1], l.eta[2]};
+  const Spec diffuse = Rd * ((28.0 / (23.0 * DRT_PI))) * (ONE - Rs) *
+                       ((1.0 - pow(1.0 - 0.5 * AbsCosTheta(wi), 5.0)) * (1.0 - pow(1.0 - 0.5 * AbsCosTheta(wo), 5.0)));
+  V3 wh = wi + wo;
+  if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) { *out = mks1(0.0); return; }
+  wh = Normalize(wh);
+  const double costhetah = fabs((double)wh.z), d1 = 1.0 - costhetah * costhetah;
+  double D = 0.0;
+  if (d1 != 0.0) {
+    const double e = (l.param * wh.x * wh.x + l.ei * wh.y * wh.y) / d1;
+    D = sqrt((l.param + 2.0) * (l.ei + 2.0)) * DRT_INV_TWOPI * pow(costhetah, e);
+  }
+  const double a = D / (4.0 * AbsDot(wi, wh) * dartMax(AbsCosTheta(wi), AbsCosTheta(wo)));
+  const Spec b = Rs + (ONE - Rs) * (pow(1.0 - Dot(wi, wh), 5.0));
+  *out = diffuse + b * a;
+}
+static __device__ __noinline__ double blendPdfCold(const GLobe& l, V3 wo, V3 wi) {
+  if (!SameHemisphere(wo, wi)) return 0.0;
+  return 0.5 * (AbsCosTheta(wi) * DRT_INV_PI + anisoPdfOf(l, wo, Normalize(wo + wi)));
+}
+static __device__ inline void anisoFirstQuadrant(const GLobe& l, double u1, double u2, double* phi, double* costheta) {
+  const double ex = l.param, ey = l.ei;
+  if (ex == ey) *phi = DRT_PI * u1 * 0.5;
+  else *phi = atan(sqrt((ex + 1.0) / (ey + 1.0)) * tan(DRT_PI * u1 * 0.5));
+  const double cosphi = cos(*phi), sinphi = sin(*phi);
+  *costheta = pow(u2, 1.0 / (ex * cosphi * cosphi + ey * sinphi * sinphi + 1.0));
+}
+static __device__ __noinline__ void blendSampleCold(const GLobe& l, V3 wo, double u1, double u2, V3* wiOut, double* pdfOut, Spec* fOut) {
+  V3 wi;
+  if (u1 < 0.5) {
+    u1 = 2.0 * u1;
+    wi = CosineSampleHemisphere(u1, u2);
+    if (wo.z < 0.0f) wi.z = (float)((double)wi.z * -1.0);
+  } else {
+    u1 = 2.0 * (u1 - 0.5);
+    double phi, cosTheta;
+    if (u1 < 0.25) {
+      anisoFirstQuadrant(l, 4.0 * u1, u2, &phi, &cosTheta);
+    } else if (u1 < 0.5) {
+      u1 = 4.0 * (0.5 - u1);
+      anisoFirstQuadrant(l, u1, u2, &phi, &cosTheta);
+      phi = DRT_PI - phi;
+    } else if (u1 < 0.75) {
+      u1 = 4.0 * (u1 - 0.5);
+      anisoFirstQuadrant(l, u1, u2, &phi, &cosTheta);
+      phi += DRT_PI;
+    } else {
+      u1 = 4.0 * (1.0 - u1);
+      anisoFirstQuadrant(l, u1, u2, &phi, &cosTheta);
+      phi = 2.0 * DRT_PI - phi;
+    }
+    const double sintheta = sqrt(dartMax(0.0, 1.0 - cosTheta * cosTheta));
+    V3 wh = mkv(sintheta * cos(phi), sintheta * sin(phi), cosTheta);
+    if (!SameHemisphere(wo, wh)) wh = -wh;
+    wi = -wo + wh * 2.0 * Dot(wo, wh);
+    *pdfOut = anisoPdfOf(l, wo, wh);
+    if (!SameHemisphere(wo, wi)) { *wiOut = wi; *fOut = mks1(0.0); return; }
+  }
+  *wiOut = wi;
+  *pdfOut = blendPdfCold(l, wo, wi);
+  blendFCold(l, wo, wi, fOut);
+}
+
 static __device__ inline Spec lobeBaseF(const GLobe& l, const V3& wo, const V3& wi) {
+  if (DRT_EXTRA && l.kind == 5) { Spec r; blendFCold(l, wo, wi, &r); return r; }
   const Spec R = Spec{l.rgb[0], l.rgb[1], l.rgb[2]};
   if (l.kind == 0) return R * DRT_INV_PI;  // lambertian.dart:35-37
   if (l.kind == 1) {                       // oren_nayar.dart:24-58
@@ -907,6 +984,7 @@ static __device__ inline Spec lobeBaseF(const GLobe& l, const V3& wo, const V3& 
   return mks1(0.0);  // specular BxDFs: f == 0
 }
 static __device__ inline double lobeBasePdf(const GLobe& l, const V3& wo, const V3& wi) {
+  if (DRT_EXTRA && l.kind == 5) return blendPdfCold(l, wo, wi);
   if (l.kind <= 1) return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * DRT_INV_PI : 0.0;  // bxdf.dart:84-88
   if (l.kind == 2) {                                                                     // microfacet.dart:68-73
     if (!SameHemisphere(wo, wi)) return 0.0;
@@ -917,6 +995,15 @@ static __device__ inline double lobeBasePdf(const GLobe& l, const V3& wo, const 
 }
 // *pdfOut is left untouched when the BxDF returns without setting it (specular_transmission.dart:52-54)
 static __device__ inline Spec lobeBaseSampleF(const GLobe& l, const V3& wo, V3* wi, double u1, double u2, double* pdfOut) {
+  if (DRT_EXTRA && l.kind == 5) {
+    V3 w;
+    Spec f;
+    double p = *pdfOut;
+    blendSampleCold(l, wo, u1, u2, &w, &p, &f);
+    *wi = w;
+    *pdfOut = p;
+    return f;
+  }
   if (l.kind <= 1) {  // bxdf.dart:37-48
     *wi = CosineSampleHemisphere(u1, u2);
     if (wo.z < 0.0f) wi->z = (float)((double)wi->z * -1.0);

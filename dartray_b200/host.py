@@ -243,7 +243,7 @@ class Integrator:
 # The Dart shim does the same flattening when it walks GeometricPrimitive.material: every Material.getBSDF below only
 # evaluates constant textures, so the BxDF list of a material is a constant of the scene.  Spectrum arithmetic is
 # float32 storage / float64 expressions like RGBColor (rgb_color.dart:142-169).
-LOBE_LAMBERTIAN, LOBE_OREN_NAYAR, LOBE_MICROFACET_BLINN, LOBE_SPECULAR_REFLECTION, LOBE_SPECULAR_TRANSMISSION = range(5)
+LOBE_LAMBERTIAN, LOBE_OREN_NAYAR, LOBE_MICROFACET_BLINN, LOBE_SPECULAR_REFLECTION, LOBE_SPECULAR_TRANSMISSION, LOBE_FRESNEL_BLEND = range(6)
 FRESNEL_NOOP, FRESNEL_DIELECTRIC, FRESNEL_CONDUCTOR = range(3)
 
 
@@ -361,6 +361,15 @@ def mix_lobes(lobes1, lobes2, amount=0.5) -> list:  # mix_material.dart:36-50
     if len(out) > 8:
         raise ValueError("a BSDF holds at most 8 BxDFs (bsdf.dart:253)")
     return out
+
+
+def substrate_lobes(kd=0.5, ks=0.5, uroughness=0.1, vroughness=0.1) -> list:  # substrate_material.dart:46-68
+    d, sp = _clamp(kd), _clamp(ks)
+    if _black(d) and _black(sp):
+        return []
+    # FresnelBlend(d, s, Anisotropic(1 / u, 1 / v)): Rs travels in the eta slot, the two exponents (clamped as anisotropic.dart:30-37
+    # clamps them, the same rule as Blinn's) in param / ei
+    return [_lobe(LOBE_FRESNEL_BLEND, d, eta=sp, param=_blinn_exponent(uroughness), ei=_blinn_exponent(vroughness))]
 
 
 def metal_lobes(eta, k, roughness=0.01) -> list:  # metal_material.dart:26-46 (eta / k given as RGB)

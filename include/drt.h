@@ -199,11 +199,15 @@ int drt_set_materials(drt_ctx* ctx, uint32_t n, const int32_t* kind, const float
 /* Materials as ordered BxDF lists: what Material.getBSDF builds with constant textures, for the materials whose
  * getBSDF only adds these BxDFs: matte (lib/materials/matte_material.dart:41-65), mirror
  * (mirror_material.dart:26-43), glass (glass_material.dart:26-52), plastic (plastic_material.dart:26-53), metal
- * (metal_material.dart:26-46), uber (uber_material.dart:27-75).  Material i owns lobes [lobe_offsets[i],
+ * (metal_material.dart:26-46), uber (uber_material.dart:27-75), shinymetal (shiny_metal_material.dart:42-76), substrate, and —
+ * with drt_set_lobe_wrappers — translucent and mix.  Material i owns lobes [lobe_offsets[i],
  * lobe_offsets[i + 1]) in the order of its bsdf.add calls (BSDF.sample_f picks by position, bsdf.dart:68-79; at most 8,
  * bsdf.dart:253).  Per lobe:
  *   lobe_kind     0 Lambertian (lambertian.dart), 1 OrenNayar (oren_nayar.dart), 2 Microfacet with a Blinn distribution
- *                 (microfacet.dart, blinn.dart), 3 SpecularReflection, 4 SpecularTransmission
+ *                 (microfacet.dart, blinn.dart), 3 SpecularReflection, 4 SpecularTransmission, 5 FresnelBlend over an
+ *                 Anisotropic distribution (fresnel_blend.dart, anisotropic.dart: SubstrateMaterial, substrate_material.dart:46-68)
+ *                 with Rd in lobe_rgb, Rs in fresnel_eta and the exponents 1 / uroughness, 1 / vroughness (clamped to 10000 as
+ *                 anisotropic.dart:30-37 clamps them) in lobe_scalars[0] and [1]
  *   lobe_rgb      R / T of the BxDF, already clamped and multiplied as the material does (n_lobes x 3)
  *   fresnel_kind  0 FresnelNoOp, 1 FresnelDielectric(ei, et), 2 FresnelConductor(eta, k) (fresnel_*.dart); NULL = all 0
  *   fresnel_eta, fresnel_k   conductor spectra as RGB (n_lobes x 3; NULL when no lobe uses a conductor)

@@ -407,6 +407,7 @@ struct LobeEval {
       }
       case 2: type = BSDF_REFLECTION | BSDF_GLOSSY; break;
       case 3: type = BSDF_REFLECTION | BSDF_SPECULAR; break;
+      case 5: type = BSDF_REFLECTION | BSDF_GLOSSY; break;
       default: type = BSDF_TRANSMISSION | BSDF_SPECULAR; break;
     }
     if (l.wrap & 1) type ^= (BSDF_REFLECTION | BSDF_TRANSMISSION);  // brdf_to_btdf.dart:27-29; ScaledBxDF keeps the type
@@ -471,6 +472,75 @@ struct LobeEval {
     return pdf;
   }
 
+  // anisotropic.dart:27-121 (ex = l.param, ey = l.ei, both already clamped to 10000 by the constructor, :30-37)
+  double anisoD(const Vec& wh) const {
+    double costhetah = std::fabs((double)wh.z);
+    double d = 1.0 - costhetah * costhetah;
+    if (d == 0.0) return 0.0;
+    double e = (l.param * wh.x * wh.x + l.ei * wh.y * wh.y) / d;
+    return std::sqrt((l.param + 2.0) * (l.ei + 2.0)) * INV_TWOPI * std::pow(costhetah, e);
+  }
+  double anisoPdfOf(const Vec& wo, const Vec& wh) const {
+    double costhetah = AbsCosTheta(wh);
+    double ds = 1.0 - costhetah * costhetah;
+    double p = 0.0;
+    if (ds > 0.0 && Dot(wo, wh) > 0.0) {
+      double e = (l.param * wh.x * wh.x + l.ei * wh.y * wh.y) / ds;
+      double d = std::sqrt((l.param + 1.0) * (l.ei + 1.0)) * INV_TWOPI * std::pow(costhetah, e);
+      p = d / (4.0 * Dot(wo, wh));
+    }
+    return p;
+  }
+  double anisoPdf(const Vec& wo, const Vec& wi) const { return anisoPdfOf(wo, Normalize(wo + wi)); }
+  void anisoFirstQuadrant(double u1, double u2, double* phi, double* costheta) const {
+    const double ex = l.param, ey = l.ei;
+    if (ex == ey) *phi = kPi * u1 * 0.5;
+    else *phi = std::atan(std::sqrt((ex + 1.0) / (ey + 1.0)) * std::tan(kPi * u1 * 0.5));
+    double cosphi = std::cos(*phi), sinphi = std::sin(*phi);
+    *costheta = std::pow(u2, 1.0 / (ex * cosphi * cosphi + ey * sinphi * sinphi + 1.0));
+  }
+  double anisoSample(const Vec& wo, Vec* wi, double u1, double u2) const {
+    double phi, cosTheta;
+    if (u1 < 0.25) {
+      anisoFirstQuadrant(4.0 * u1, u2, &phi, &cosTheta);
+    } else if (u1 < 0.5) {
+      u1 = 4.0 * (0.5 - u1);
+      anisoFirstQuadrant(u1, u2, &phi, &cosTheta);
+      phi = kPi - phi;
+    } else if (u1 < 0.75) {
+      u1 = 4.0 * (u1 - 0.5);
+      anisoFirstQuadrant(u1, u2, &phi, &cosTheta);
+      phi += kPi;
+    } else {
+      u1 = 4.0 * (1.0 - u1);
+      anisoFirstQuadrant(u1, u2, &phi, &cosTheta);
+      phi = 2.0 * kPi - phi;
+    }
+    double sintheta = std::sqrt(dmax(0.0, 1.0 - cosTheta * cosTheta));
+    Vec wh = SphericalDirection(sintheta, cosTheta, phi);
+    if (!SameHemisphere(wo, wh)) wh = -wh;
+    *wi = -wo + wh * 2.0 * Dot(wo, wh);
+    return anisoPdfOf(wo, wh);
+  }
+  // fresnel_blend.dart:30-58
+  Spec blendF(const Vec& wo, const Vec& wi) const {
+    const Spec ONE(1.0);
+    const Spec& Rd = l.R;
+    const Spec& Rs = l.eta;
+    Spec diffuse = Rd * ((28.0 / (23.0 * kPi))) * (ONE - Rs) *
+                   ((1.0 - std::pow(1.0 - 0.5 * AbsCosTheta(wi), 5)) * (1.0 - std::pow(1.0 - 0.5 * AbsCosTheta(wo), 5)));
+    Vec wh = wi + wo;
+    if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return Spec(0.0);
+    wh = Normalize(wh);
+    double a = anisoD(wh) / (4.0 * AbsDot(wi, wh) * dmax(AbsCosTheta(wi), AbsCosTheta(wo)));
+    Spec b = Rs + (ONE - Rs) * (std::pow(1.0 - Dot(wi, wh), 5.0));
+    return diffuse + b * a;
+  }
+  double blendPdf(const Vec& wo, const Vec& wi) const {  // :84-90
+    if (!SameHemisphere(wo, wi)) return 0.0;
+    return 0.5 * (AbsCosTheta(wi) * INV_PI + anisoPdf(wo, wi));
+  }
+
   Spec baseF(const Vec& wo, const Vec& wi) const {
     switch (l.kind) {
       case 0: return l.R * INV_PI;  // lambertian.dart:35-37
@@ -498,6 +568,7 @@ struct LobeEval {
         double G = dmin(1.0, dmin((2.0 * NdotWh * NdotWo / WOdotWh), (2.0 * NdotWh * NdotWi / WOdotWh)));
         return l.R * (blinnD(wh) * G) * F / (4.0 * cosThetaI * cosThetaO);
       }
+      case 5: return blendF(wo, wi);
       default: return Spec(0.0);  // specular_reflection.dart:30-32, specular_transmission.dart:33-35
     }
   }
@@ -506,6 +577,7 @@ struct LobeEval {
       case 0:
       case 1: return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * INV_PI : 0.0;  // bxdf.dart:84-88
       case 2: return SameHemisphere(wo, wi) ? blinnPdf(wo, wi) : 0.0;          // microfacet.dart:68-73
+      case 5: return blendPdf(wo, wi);
       default: return 0.0;
     }
   }
@@ -523,6 +595,19 @@ struct LobeEval {
         *pdfOut = blinnSample(wo, wi, u1, u2);
         if (!SameHemisphere(wo, *wi)) return Spec(0.0);
         return baseF(wo, *wi);
+      }
+      case 5: {  // fresnel_blend.dart:60-82
+        if (u1 < 0.5) {
+          u1 = 2.0 * u1;
+          *wi = CosineSampleHemisphere(u1, u2);
+          if (wo.z < 0.0f) wi->z = f32((double)wi->z * -1.0);
+        } else {
+          u1 = 2.0 * (u1 - 0.5);
+          *pdfOut = anisoSample(wo, wi, u1, u2);
+          if (!SameHemisphere(wo, *wi)) return Spec(0.0);
+        }
+        *pdfOut = blendPdf(wo, *wi);
+        return blendF(wo, *wi);
       }
       case 3: {  // specular_reflection.dart:34-41
         *wi = Vec(-(double)wo.x, -(double)wo.y, wo.z);

@@ -137,7 +137,8 @@ static const uint32_t kStreamIntegrator = 0x80000000u;
 //   metal    metal_material.dart:26-46      Microfacet(1, FresnelConductor(eta, k), Blinn(1/roughness))
 //   uber     uber_material.dart:27-75       SpecularTransmission(1-op, 1, 1) + Lambertian + Microfacet + SpecularReflection + SpecularTransmission
 struct Lobe {
-  int kind = 0;     // 0 Lambertian, 1 OrenNayar, 2 Microfacet(Blinn), 3 SpecularReflection, 4 SpecularTransmission
+  int kind = 0;     // 0 Lambertian, 1 OrenNayar, 2 Microfacet(Blinn), 3 SpecularReflection, 4 SpecularTransmission,
+                    // 5 FresnelBlend(Rd = R, Rs = eta, Anisotropic(ex = param, ey = ei)) (fresnel_blend.dart, anisotropic.dart)
   Spec R;           // R / T of the BxDF (already clamped by the material)
   int fresnel = 0;  // 0 FresnelNoOp, 1 FresnelDielectric(ei, et), 2 FresnelConductor(eta, k)
   Spec eta, k;      // conductor

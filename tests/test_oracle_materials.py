@@ -334,3 +334,39 @@ def test_shinymetal_reflectance_at_normal_incidence():
     for kr in (0.2, 0.7, 1.0):
         L = _sheet_radiance(host.shinymetal_lobes(ks=0.0, kr=kr), 0, host.Integrator(kind=host.INTEGRATOR_DIRECT, maxdepth=2), sky=2.0)
         assert L == pytest.approx(min(kr, 0.999) * 2.0, rel=2e-3)
+
+
+def test_substrate_fresnel_blend_albedo_matches_numeric_quadrature():
+    # FresnelBlend over an Anisotropic distribution (fresnel_blend.dart:30-58, anisotropic.dart:39-50): the radiance of a substrate
+    # sheet under a constant unit sky is its directional albedo, which a brute-force quadrature of f * cos reproduces; the render
+    # gets there through sample_f / pdf (cosine + anisotropic half-vector sampling) and the sky's light sampling with MIS
+    Rd, Rs, ex, ey = np.array([0.5, 0.3, 0.2]), np.array([0.05, 0.1, 0.3]), 1.0 / 0.2, 1.0 / 0.05
+    lobes = host.substrate_lobes(kd=Rd, ks=Rs, uroughness=0.2, vroughness=0.05)
+    assert len(lobes) == 1 and lobes[0]["kind"] == host.LOBE_FRESNEL_BLEND
+    L = _sheet_radiance(lobes, 0, host.Integrator(kind=host.INTEGRATOR_DIRECT), sky=1.0)
+
+    # camera of _sheet_radiance: at (0, 6, 0.01) looking at the origin -> wo in the sheet's shading frame
+    wo_w = np.array([0.0, 6.0, 0.01])
+    wo_w /= np.linalg.norm(wo_w)
+    # shading frame of the quad [[-20,0,-20],[20,0,-20],[20,0,20],[-20,0,20]] with indices (0,2,1),(0,3,2) and default uvs:
+    # sn = normalize(dpdu), nn = +y; the albedo of this lobe depends on the azimuth of wo only through ex != ey, and wo is 0.1
+    # degrees off the normal, so any in-plane orientation of the frame gives the same number to the test's tolerance
+    wo = np.array([wo_w[2], wo_w[0], wo_w[1]])
+    n_th, n_ph = 400, 800
+    th = (np.arange(n_th) + 0.5) / n_th * (np.pi / 2)
+    ph = (np.arange(n_ph) + 0.5) / n_ph * (2 * np.pi)
+    T, P = np.meshgrid(th, ph, indexing="ij")
+    wi = np.stack([np.sin(T) * np.cos(P), np.sin(T) * np.sin(P), np.cos(T)], axis=-1)
+    wh = wi + wo
+    wh /= np.linalg.norm(wh, axis=-1, keepdims=True)
+    cos_h = np.abs(wh[..., 2])
+    d = 1 - cos_h ** 2
+    e = (ex * wh[..., 0] ** 2 + ey * wh[..., 1] ** 2) / np.maximum(d, 1e-300)
+    D = np.where(d == 0, 0.0, np.sqrt((ex + 2) * (ey + 2)) / (2 * np.pi) * cos_h ** e)
+    wi_h = np.abs((wi * wh).sum(-1))
+    a = D / (4 * wi_h * np.maximum(wi[..., 2], wo[2]))
+    schlick = Rs + (1 - Rs) * ((1 - (wi * wh).sum(-1)) ** 5)[..., None]
+    diffuse = Rd * (28 / (23 * np.pi)) * (1 - Rs) * ((1 - (1 - 0.5 * wi[..., 2]) ** 5) * (1 - (1 - 0.5 * wo[2]) ** 5))[..., None]
+    f = diffuse + schlick * a[..., None]
+    rho = (f * (wi[..., 2] * np.sin(T))[..., None]).sum(axis=(0, 1)) * (np.pi / 2 / n_th) * (2 * np.pi / n_ph)
+    assert np.allclose(L, rho, rtol=3e-2), (L, rho)

@@ -322,10 +322,12 @@ def test_adaptive_sampler_matches_oracle(method, integ):
 
 
 def _wrapped_materials_room():
-    """cornell_synth with TranslucentMaterial, MixMaterial and ShinyMetalMaterial BSDFs (BRDFToBTDF / ScaledBxDF wrappers)."""
+    """cornell_synth with TranslucentMaterial, MixMaterial, ShinyMetalMaterial and SubstrateMaterial BSDFs (BRDFToBTDF / ScaledBxDF
+    wrappers, FresnelBlend over an Anisotropic distribution)."""
     return scenes.cornell_synth({
         "grey": host.mix_lobes(host.matte_lobes((0.7, 0.7, 0.65)), host.plastic_lobes((0.2, 0.3, 0.6), 0.4, 0.1), amount=(0.3, 0.5, 0.7)),
         "red": host.shinymetal_lobes(ks=(0.8, 0.5, 0.3), kr=(0.2, 0.1, 0.1), roughness=0.15),
+        "green": host.substrate_lobes(kd=(0.2, 0.5, 0.2), ks=(0.1, 0.15, 0.1), uroughness=0.3, vroughness=0.05),
         "box": host.translucent_lobes(kd=(0.6, 0.7, 0.5), ks=0.3, reflect=0.4, transmit=0.6, roughness=0.2),
         "sphere": host.mix_lobes(host.glass_lobes(1.0, 1.0, 1.5), host.matte_lobes((0.8, 0.4, 0.2)), amount=0.6),
     })
