@@ -40,6 +40,8 @@ typedef _SetQuadricsC = Int32 Function(_Ctx, Uint32, _PF, _PF, _PD, _PI, _PI, _P
 typedef _SetQuadricsD = int Function(_Ctx, int, _PF, _PF, _PD, _PI, _PI, _PB);
 typedef _SetKindQuadricsC = Int32 Function(_Ctx, Int32, Uint32, _PF, _PF, _PD, _PI, _PI, _PB);
 typedef _SetKindQuadricsD = int Function(_Ctx, int, int, _PF, _PF, _PD, _PI, _PI, _PB);
+typedef _SetTableC = Int32 Function(_Ctx, _PD, Uint32);
+typedef _SetTableD = int Function(_Ctx, _PD, int);
 typedef _SetLightMapC = Int32 Function(_Ctx, Uint32, Int32, Int32, _PF, _PF, _PF, _PD, Double);
 typedef _SetLightMapD = int Function(_Ctx, int, int, int, _PF, _PF, _PF, _PD, double);
 typedef _SetWrappersC = Int32 Function(_Ctx, Uint32, _PI, _PF);
@@ -141,6 +143,8 @@ class Drt {
   void setLights(int n, _PI kind, _PF L, _PF pos, _PI nsamples, _PU shapeOffsets, _PU shapePrims) =>
       check(lib.lookupFunction<_SetLightsC, _SetLightsD>('drt_set_lights')(ctx, n, kind, L, pos, nsamples, shapeOffsets, shapePrims));
   void setSpotParams(int n, _PF w2l, _PD cosines) => check(lib.lookupFunction<_SetSpotC, _SetSpotD>('drt_set_spot_params')(ctx, n, w2l, cosines));
+  void setSampleTable(_PD table, int nEntries) =>
+      check(lib.lookupFunction<_SetTableC, _SetTableD>('drt_set_sample_table')(ctx, table, nEntries));
   void setLightMap(int index, int width, int height, _PF rgb, _PF w2l, _PF projection, _PD screen, double hither) =>
       check(lib.lookupFunction<_SetLightMapC, _SetLightMapD>('drt_set_light_map')(ctx, index, width, height, rgb, w2l, projection, screen, hither));
   void setLobeWrappers(int nLobes, _PI wrap, _PF scaleRgb) =>

@@ -586,6 +586,10 @@ class GpuSamplerRenderer extends Renderer {
     } else if (sampler is HaltonSampler) {
       // wantedSamples = samplesPerPixel * max(width, height)^2 (halton_sampler.dart:32-38): the library derives it from spp
       drt.setSampler(3, 1, 1, sampler.samplesPerPixel, 1, 1, 32, taskNum);
+    } else if (sampler is BestCandidateSampler) {
+      // the 4096 x 5 pattern is data of the reference (best_candidate_sampler.dart:163-4258): hand it over
+      drt.setSampleTable(a.doubles(BestCandidateSampler.SAMPLE_TABLE), BestCandidateSampler.SAMPLE_TABLE_SIZE);
+      drt.setSampler(5, 1, 1, sampler.samplesPerPixel, 1, 1, 32, taskNum);
     } else if (sampler is AdaptiveSampler) {
       final AdaptiveSampler s = sampler;  // minSamples / maxSamples are already normalised (adaptive_sampler.dart:52-84)
       drt.setSampler(4, s.minSamples, s.maxSamples, s.maxSamples, s.method, order(s.pixels), 32, taskNum);

@@ -19,7 +19,7 @@ HIT_DTYPE = np.dtype([("t", np.float32), ("b1", np.float32), ("b2", np.float32),
 
 # every symbol include/drt.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
-    "drt_version", "drt_create", "drt_destroy", "drt_last_error", "drt_set_triangles", "drt_set_spheres", "drt_set_disks", "drt_set_quadrics", "drt_set_mesh_shading", "drt_set_infinite_light", "drt_set_lobe_wrappers", "drt_set_light_map",
+    "drt_version", "drt_create", "drt_destroy", "drt_last_error", "drt_set_triangles", "drt_set_spheres", "drt_set_disks", "drt_set_quadrics", "drt_set_mesh_shading", "drt_set_infinite_light", "drt_set_lobe_wrappers", "drt_set_light_map", "drt_set_sample_table",
     "drt_set_build_order", "drt_build_bvh", "drt_bvh_info_get", "drt_bvh_export", "drt_trace_closest",
     "drt_trace_any", "drt_trace_closest_device", "drt_trace_any_device", "drt_set_counting", "drt_get_counters", "drt_set_kernel_variant",
     "drt_last_kernel_ms", "drt_kernel_launches",
@@ -95,6 +95,7 @@ def load():
     L.drt_set_materials.argtypes = [vp, u32, vp, vp, vp]
     L.drt_set_material_lobes.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp]
     L.drt_set_spot_params.argtypes = [vp, u32, vp, vp]
+    L.drt_set_sample_table.argtypes = [vp, vp, u32]
     L.drt_set_light_map.argtypes = [vp, u32, i32, i32, vp, vp, vp, vp, C.c_double]
     L.drt_set_lobe_wrappers.argtypes = [vp, u32, vp, vp]
     L.drt_set_infinite_light.argtypes = [vp, u32, i32, i32, vp, vp, vp]
@@ -321,6 +322,11 @@ class Context:
             raise ValueError("the GPU path replays keyed (counter-based) sample streams only; the reference's single "
                              "serial RNG stream cannot be evaluated in parallel")
         self._ck(self.L.drt_set_sampler(self.h, kind, xs, ys, spp, jitter, pixel_order, tile_size, seed))
+
+    def set_sample_table(self, table):
+        """The bestcandidate sampler's 4096 x 5 pattern (doubles)."""
+        t = _arr(table, np.float64).reshape(-1, 5)
+        self._ck(self.L.drt_set_sample_table(self.h, _p(t), t.shape[0]))
 
     def set_integrator(self, kind, maxdepth, strategy, ao_nsamples, ao_mindist, ao_maxdist):
         self._ck(self.L.drt_set_integrator(self.h, kind, maxdepth, strategy, ao_nsamples, ao_mindist, ao_maxdist))

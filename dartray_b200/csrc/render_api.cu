@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "drt_ctx.h"
+#include "dart_random.h"
 #include "env_map.h"
 #include "render_kernels.h"
 #include "shade_device.cuh"
@@ -79,6 +80,8 @@ struct RenderState {
   DevBuf<GMesh> dMeshes;
   DevBuf<float> dVertN, dVertS, dVertUV, dEnv;
   DevBuf<uint32_t> dAdaptList, dAdaptCount;  // adaptive sampler: pixels to supersample
+  std::vector<double> sampleTable;           // bestcandidate sampler: the 4096 x 5 pattern (drt_set_sample_table)
+  DevBuf<double> dBcTable, dBcShifts;
   DevBuf<DirectOffsets> dDirect;
   DevBuf<SampleArray> dArrays;
   DevBuf<double> dFilm;
@@ -113,7 +116,7 @@ void drtRenderStateDestroy(drt_ctx* c) {
   if (!r) return;
   r->dPrimToRec.release(); r->dPrimAttr.release(); r->dLightShapes.release(); r->dMaterials.release(); r->dLights.release();
   r->dLightCdf.release(); r->dTable.release(); r->dDirect.release(); r->dArrays.release();
-  r->dMeshOfTri.release(); r->dTriIdx.release(); r->dMeshes.release(); r->dVertN.release(); r->dVertS.release(); r->dVertUV.release(); r->dEnv.release(); r->dAdaptList.release(); r->dAdaptCount.release();
+  r->dMeshOfTri.release(); r->dTriIdx.release(); r->dMeshes.release(); r->dVertN.release(); r->dVertS.release(); r->dVertUV.release(); r->dEnv.release(); r->dAdaptList.release(); r->dAdaptCount.release(); r->dBcTable.release(); r->dBcShifts.release();
   r->dFilm.release(); r->dCounters.release(); r->dRgb.release(); r->dXyz.release(); r->dWeight.release();
   if (r->wfMem) cudaFree(r->wfMem);
   delete r;
@@ -161,7 +164,7 @@ static void buildLayout(RenderState* r) {
     if (p.strategy == 0) {
       for (const HostLight& l : r->lights) {
         int n = l.nSamples;
-        if (p.samplerKind == 0 || p.samplerKind == 4) n = roundUpPow2(n);  // LowDiscrepancySampler / AdaptiveSampler.roundSize
+        if (p.samplerKind == 0 || p.samplerKind >= 4) n = roundUpPow2(n);  // LowDiscrepancy / Adaptive / BestCandidate Sampler.roundSize
         dn.push_back(n);
         dl.push_back(offsets(n));
         db.push_back(offsets(n));
@@ -534,7 +537,9 @@ static int prepare(drt_ctx* c, RenderState* r) {
   if (!r->haveCamera || !r->haveFilm) return fail(c, DRT_E_STATE, "drt_set_camera and drt_set_film must be called before rendering");
   CK(c, cudaSetDevice(c->device));
   RenderParams& p = r->rp;
-  p.nPixelSamples = p.samplerKind == 0 ? roundUpPow2(r->spp) : (p.samplerKind == 1 ? p.xs * p.ys : (p.samplerKind == 3 ? 1 : r->spp));
+  p.nPixelSamples = p.samplerKind == 0 ? roundUpPow2(r->spp) : (p.samplerKind == 1 ? p.xs * p.ys : ((p.samplerKind == 3 || p.samplerKind == 5) ? 1 : r->spp));
+  if (p.samplerKind == 5 && r->sampleTable.size() != 5 * 4096)
+    return fail(c, DRT_E_STATE, "the bestcandidate sampler (kind 5) needs drt_set_sample_table");
   if (p.samplerKind == 4) {  // the first visit of every pixel: minSamples (renderWindow switches to maxSamples for the second)
     int mn, mx;
     adaptiveCounts(p.xs, p.ys, &mn, &mx);
@@ -557,7 +562,7 @@ static int prepare(drt_ctx* c, RenderState* r) {
   p.direct = r->dDirect.p;
   int rc = ensureFilm(c, r);
   if (rc != DRT_OK) return rc;
-  if (p.samplerKind == 0 || p.samplerKind == 4) {
+  if (p.samplerKind == 0 || p.samplerKind >= 4) {
     size_t smem = 4 * (size_t)(r->maxVals | 1) * sizeof(float);  // G = 32: four tasks per block
     if (smem > 200 * 1024) return fail(c, DRT_E_INVALID, "lowdiscrepancy sampler: pixelsamples x light nsamples too large for one warp's shared memory");
   }
@@ -739,7 +744,7 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
     CK(c, STAGE(launchSaveCameraPrims)(wf, nSlots, st));
     c->launches++;
   }
-  if (p.samplerKind != 3) {  // halton: the accepted samples are counted on the device (raygenKernel)
+  if (p.samplerKind != 3 && p.samplerKind != 5) {  // halton / bestcandidate: the accepted samples are counted on the device (raygenKernel)
     r->stats.camera_samples += nSlots;
     r->stats.closest_rays += nSlots;
   }
@@ -797,8 +802,29 @@ static int renderWindow(drt_ctx* c, int x, int y, int w, int h, uint32_t shard, 
     return fail(c, DRT_E_UNSUPPORTED, "directlighting / whitted with specular BxDFs: maxdepth above 16 is not on the GPU path");
   if (w <= 0 || h <= 0) return DRT_OK;
   uint64_t total = (uint64_t)w * h;
-  const bool halton = p.samplerKind == 3;
-  if (halton) {  // halton_sampler.dart:32-38: spp * delta^2 indices of the sequence take the place of the window's pixels
+  const bool halton = p.samplerKind == 3 || p.samplerKind == 5;  // a global sequence of sample indices instead of pixels
+  if (p.samplerKind == 5) {  // best_candidate_sampler.dart:36-52: every entry of the pattern in every tile the window touches
+    const double tableWidth = 64 / std::sqrt((double)r->spp);
+    const int xs0 = (int)std::floor(x / tableWidth), xs1 = (int)std::floor((x + w - 1) / tableWidth);
+    const int ys0 = (int)std::floor(y / tableWidth), ys1 = (int)std::floor((y + h - 1) / tableWidth);
+    const int nx = xs1 - xs0 + 1, ny = ys1 - ys0 + 1;
+    total = (uint64_t)nx * ny * 4096;
+    std::vector<double> shifts(3 * (size_t)nx * ny);
+    for (int ty = 0; ty < ny; ++ty)
+      for (int tx = 0; tx < nx; ++tx) {
+        DartRandom tileRng((int64_t)(xs0 + tx) + ((int64_t)(ys0 + ty) << 8));  // :44-47,91-94
+        for (int k = 0; k < 3; ++k) shifts[3 * ((size_t)ty * nx + tx) + k] = tileRng.nextDouble();
+      }
+    CK(c, r->dBcTable.ensure(r->sampleTable.size()));
+    CK(c, r->dBcShifts.ensure(shifts.size()));
+    CK(c, cudaMemcpy(r->dBcTable.p, r->sampleTable.data(), r->sampleTable.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpy(r->dBcShifts.p, shifts.data(), shifts.size() * sizeof(double), cudaMemcpyHostToDevice));
+    r->rp.bcTable = r->dBcTable.p;
+    r->rp.bcTileShifts = r->dBcShifts.p;
+    r->rp.bcXTileStart = xs0; r->rp.bcYTileStart = ys0; r->rp.bcTilesX = nx;
+    r->rp.bcTableWidth = tableWidth;
+    r->rp.winX = x; r->rp.winY = y; r->rp.winW = w; r->rp.winH = h;
+  } else if (halton) {  // halton_sampler.dart:32-38: spp * delta^2 indices of the sequence take the place of the window's pixels
     const uint64_t delta = (uint64_t)std::max(w, h);
     total = (uint64_t)r->spp * delta * delta;
     r->rp.winX = x; r->rp.winY = y; r->rp.winW = w; r->rp.winH = h;
@@ -1098,12 +1124,19 @@ int drt_set_film(drt_ctx* c, int xres, int yres, const double* crop, double xwid
 
 int drt_set_sampler(drt_ctx* c, int kind, int xs, int ys, int spp, int jitter, int pixel_order, int tile_size, uint64_t seed) {
   if (!c) return DRT_E_INVALID;
-  if (kind < 0 || kind > 4)
-    return fail(c, DRT_E_INVALID, "sampler kind must be 0 (lowdiscrepancy), 1 (stratified), 2 (random), 3 (halton) or 4 (adaptive)");
+  if (kind < 0 || kind > 5)
+    return fail(c, DRT_E_INVALID, "sampler kind must be 0 (lowdiscrepancy), 1 (stratified), 2 (random), 3 (halton), 4 (adaptive) or 5 (bestcandidate)");
   if (spp < 1 || xs < 1 || ys < 1) return fail(c, DRT_E_INVALID, "sample counts must be >= 1");
   RenderState* r = state(c);
   r->rp.samplerKind = kind; r->rp.xs = xs; r->rp.ys = ys; r->rp.jitter = jitter; r->rp.seed = seed;
   r->spp = spp; r->pixelOrder = pixel_order; r->tileSize = tile_size;
+  return DRT_OK;
+}
+
+int drt_set_sample_table(drt_ctx* c, const double* table, uint32_t n_entries) {
+  if (!c) return DRT_E_INVALID;
+  if (!table || n_entries != 4096) return fail(c, DRT_E_INVALID, "the bestcandidate pattern holds 4096 entries of 5 values (best_candidate_sampler.dart:32-34)");
+  state(c)->sampleTable.assign(table, table + 5 * (size_t)n_entries);
   return DRT_OK;
 }
 

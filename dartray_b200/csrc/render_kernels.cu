@@ -342,13 +342,39 @@ __global__ void __launch_bounds__(128) samplerHaltonKernel(RenderParams rp, Wave
   }
 }
 
+// Best-candidate sampler (best_candidate_sampler.dart:74-132): like halton a "pixel" of the batch is one index
+// n = tile * 4096 + tableOffset.  The lowdiscrepancy kernels have already written the integrator arrays of the index (one pixel
+// sample each, LDShuffleScrambled1D / 2D, :125-131); this kernel sets the camera sample from the pattern and rejects — as
+// written, both coordinates against left and right (:117-118).
+__global__ void __launch_bounds__(128) samplerBestCandidateKernel(RenderParams rp, Wavefront wf, PixelBatch pb) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pb.nPixels) return;
+  int x, y;
+  pixelOf(pb, p, &x, &y);
+  const uint64_t n = ((uint64_t)(uint32_t)y << 30) | (uint32_t)x;
+  const uint64_t tile = n / 4096;
+  const double* T = rp.bcTable + (size_t)(n % 4096) * 5;
+  const double* so = rp.bcTileShifts + 3 * tile;
+  const int xTile = rp.bcXTileStart + (int)(tile % (uint64_t)rp.bcTilesX), yTile = rp.bcYTileStart + (int)(tile / (uint64_t)rp.bcTilesX);
+  const double imageX = (xTile + T[0]) * rp.bcTableWidth, imageY = (yTile + T[1]) * rp.bcTableWidth;
+  const int left = rp.winX, right = rp.winX + rp.winW - 1;
+  if (imageX < left || imageX > right || imageY < left || imageY > right) {
+    wf.camXY[p] = make_double2(CUDART_NAN, CUDART_NAN);
+    return;
+  }
+  const double t = so[0] + T[2], lu = so[1] + T[3], lv = so[2] + T[4];
+  wf.camXY[p] = make_double2(imageX, imageY);
+  wf.camLens[p] = make_double2(lu > 1 ? (lu - 1) : lu, lv > 1 ? (lv - 1) : lv);
+  wf.camTime[p] = (float)(t > 1 ? (t - 1) : t);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Camera rays (perspective_camera.dart:93-132; ray differentials only feed texture filtering and are
 // not generated) + per-slot state reset.  Extension queue 0 = all slots in slot order.
 __global__ void __launch_bounds__(256) raygenKernel(RenderParams rp, Wavefront wf, PixelBatch pb, uint32_t nSlots, RenderCounters* rc) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t qi = s;  // position in extension queue 0
-  if (rp.samplerKind == 3) {  // halton: the rejected indices of the sequence never become rays (whole warps take this branch)
+  if (rp.samplerKind == 3 || rp.samplerKind == 5) {  // halton / bestcandidate: rejected indices never become rays (warp-uniform branch)
     const bool accepted = s < nSlots && !isnan(wf.camXY[s].x);
     qi = warpPush(&wf.counts[Q_EXT0], accepted);
     const unsigned m = __ballot_sync(FULL, accepted);
@@ -967,7 +993,7 @@ __global__ void __launch_bounds__(256) filmKernel(RenderParams rp, Wavefront wf,
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nSlots) return;
   if (skipFlagged && wf.adaptFlag[s / (uint32_t)rp.nPixelSamples]) return;  // adaptive: reportResults returned false (:148-151)
-  if (rp.samplerKind == 3 && isnan(wf.camXY[s].x)) return;  // halton: a rejected index of the sequence
+  if ((rp.samplerKind == 3 || rp.samplerKind == 5) && isnan(wf.camXY[s].x)) return;  // halton / bestcandidate: a rejected index
   Spec L = ld3(wf.L, wf.cap, s);
   const double lum = Luminance(L);
   if (isnan(L.r) || isnan(L.g) || isnan(L.b) || lum < -1e-5 || isinf(lum)) {
@@ -1032,7 +1058,8 @@ static inline int gridFor(uint64_t n, int block, int numSMs, int perSm) {
 cudaError_t launchSampler(const RenderParams& rp, const Wavefront& wf, const SampleArray* dArrays, int nArrays, int maxVals,
                           int maxOthers, const PixelBatch& pb, int numSMs, cudaStream_t st) {
   if (pb.nPixels == 0) return cudaSuccess;
-  const bool ld = rp.samplerKind == 0 || rp.samplerKind == 4;  // adaptive draws LDPixelSample too
+  const bool ld = rp.samplerKind == 0 || rp.samplerKind == 4 || rp.samplerKind == 5;  // adaptive draws LDPixelSample too; bestcandidate
+                                                                                      // its integrator arrays (one pixel sample)
   if (ld && rp.ldAllSingle && rp.nPixelSamples <= 2048) {
     const int block = 128;
     const int strideWords = rp.nPixelSamples | 1;  // two 16-bit arrays of nPixelSamples entries; odd word stride
@@ -1065,6 +1092,8 @@ cudaError_t launchSampler(const RenderParams& rp, const Wavefront& wf, const Sam
   } else {
     samplerSeqKernel<<<(pb.nPixels + 127) / 128, 128, 0, st>>>(rp, wf, dArrays, nArrays, pb);
   }
+  // bestcandidate: the camera sample comes from the pattern, after the lowdiscrepancy kernel wrote the integrator arrays
+  if (rp.samplerKind == 5) samplerBestCandidateKernel<<<(pb.nPixels + 127) / 128, 128, 0, st>>>(rp, wf, pb);
   return cudaGetLastError();
 }
 

@@ -114,7 +114,14 @@ struct RenderParams {
   const float* filterTable;  // 256 floats
   double* film;              // width*height x (X, Y, Z, weight)
   // sampler
-  int32_t samplerKind;  // 0 lowdiscrepancy, 1 stratified, 2 random, 3 halton, 4 adaptive (lowdiscrepancy samples, two visits)
+  int32_t samplerKind;  // 0 lowdiscrepancy, 1 stratified, 2 random, 3 halton, 4 adaptive (lowdiscrepancy samples, two visits),
+                        // 5 bestcandidate
+  // bestcandidate (best_candidate_sampler.dart:36-52): the 4096 x 5 pattern, the three shifts of every tile the window touches,
+  // the tile grid and the table's width in pixels
+  const double* bcTable;
+  const double* bcTileShifts;
+  int32_t bcXTileStart, bcYTileStart, bcTilesX;
+  double bcTableWidth;
   int32_t adaptiveMethod;  // adaptive_sampler.dart:37-38: 0 compare shape ids, 1 contrast threshold
   int32_t winX, winY, winW, winH;  // halton: the sampler's window (halton_sampler.dart:32-38), set per render call
   int32_t xs, ys, jitter;

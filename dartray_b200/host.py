@@ -207,7 +207,7 @@ class Film:
         return left, top, width, height
 
 
-SAMPLER_LD, SAMPLER_STRATIFIED, SAMPLER_RANDOM, SAMPLER_HALTON, SAMPLER_ADAPTIVE = 0, 1, 2, 3, 4
+SAMPLER_LD, SAMPLER_STRATIFIED, SAMPLER_RANDOM, SAMPLER_HALTON, SAMPLER_ADAPTIVE, SAMPLER_BEST_CANDIDATE = 0, 1, 2, 3, 4, 5
 ADAPTIVE_SHAPE_ID, ADAPTIVE_CONTRAST = 0, 1  # adaptive_sampler.dart:37-38: the `method` (carried in Sampler.jitter)
 INTEGRATOR_PATH, INTEGRATOR_AO, INTEGRATOR_DIRECT, INTEGRATOR_WHITTED = 0, 1, 2, 3
 RNG_SERIAL, RNG_KEYED = 0, 1
@@ -224,6 +224,7 @@ class Sampler:
     tile_size: int = 32
     seed: int = 0
     rng_mode: int = RNG_KEYED
+    sample_table: object = None  # bestcandidate: the 4096 x 5 pattern (best_candidate_sampler.dart:163-4258), handed over by the caller
 
 
 @dataclass
@@ -710,5 +711,7 @@ def configure_render(ctx, camera: PerspectiveCamera, film: Film, sampler: Sample
     ctx.set_film(film.xres, film.yres, film.crop, xw, yw, table)
     ctx.set_sampler(sampler.kind, sampler.xs, sampler.ys, sampler.spp, int(sampler.jitter), sampler.pixel_order,
                     sampler.tile_size, sampler.seed, sampler.rng_mode)
+    if getattr(sampler, "sample_table", None) is not None:
+        ctx.set_sample_table(sampler.sample_table)
     ctx.set_integrator(integrator.kind, integrator.maxdepth, integrator.strategy, integrator.ao_nsamples,
                        integrator.ao_mindist, integrator.ao_maxdist)

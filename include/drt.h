@@ -288,12 +288,20 @@ int drt_set_film(drt_ctx* ctx, int32_t xres, int32_t yres, const double crop[4],
  * window rejected as the reference rejects them; streams keyed by the index) and adaptive (kind 4,
  * lib/samplers/adaptive_sampler.dart: xs = minsamples, ys = maxsamples, jitter = method (0 shape ids, 1 contrast); every pixel is
  * rendered with minsamples lowdiscrepancy samples and, where reportResults asks for it, again with maxsamples, the first visit's
- * samples being dropped).  pixel_order / tile_size name
+ * samples being dropped) and bestcandidate (kind 5, needs drt_set_sample_table).  pixel_order / tile_size name
  * the PixelSampler (0 linear, 1 tile: lib/pixel_samplers/*.dart); with per-pixel keyed streams the
  * visiting order does not change any sample, so they only document the request.  seed keys every
  * stream (the reference seeds its single RNG with the task number, sampler_renderer.dart:137). */
 int drt_set_sampler(drt_ctx* ctx, int32_t kind, int32_t xs, int32_t ys, int32_t spp, int32_t jitter, int32_t pixel_order,
                     int32_t tile_size, uint64_t seed);
+
+/* The pattern of the bestcandidate sampler (kind 5 of drt_set_sampler; lib/samplers/best_candidate_sampler.dart:32-132): the
+ * 4096 x 5 doubles of its _SAMPLE_TABLE (imageX, imageY, time, lensU, lensV per entry, :163-4258), which is data of the
+ * reference and therefore travels through the ABI instead of living in this library.  The sampler walks every entry of the
+ * pattern in every table tile the sample window touches (tile width 64 / sqrt(pixelsamples) pixels), shifts time / lens by the
+ * tile's three random offsets — drawn, as in the reference, from a dart:math Random seeded with xTile + (yTile << 8) — rejects
+ * samples outside the window exactly as :117-118 does, and draws the integrator arrays with LDShuffleScrambled1D / 2D. */
+int drt_set_sample_table(drt_ctx* ctx, const double* table_4096x5, uint32_t n_entries);
 
 /* Replaces the SurfaceIntegrator plugins path (kind 0, lib/surface_integrators/path_integrator.dart;
  * maxdepth), ambientocclusion (kind 1, ambient_occlusion_integrator.dart; nsamples rounded up to a

@@ -416,6 +416,13 @@ int orc_set_sampler(orc_ctx* c, int kind, int xs, int ys, int spp, int jitter, i
   return 0;
 }
 
+// mirrors drt_set_sample_table: the bestcandidate sampler's 4096 x 5 pattern
+int orc_set_sample_table(orc_ctx* c, const double* table, uint32_t nEntries) {
+  if (nEntries != 4096 || !table) { c->err = "the sample table holds 4096 x 5 values"; return -1; }
+  c->rs.sampler.sampleTable.assign(table, table + 5 * (size_t)nEntries);
+  return 0;
+}
+
 int orc_set_integrator(orc_ctx* c, int kind, int maxDepth, int strategy, int aoSamples, double aoMin, double aoMax) {
   IntegratorCfg& i = c->rs.integ;
   i.kind = kind; i.maxDepth = maxDepth; i.strategy = strategy; i.aoSamples = aoSamples; i.aoMinDist = aoMin; i.aoMaxDist = aoMax;

@@ -744,7 +744,7 @@ struct Ctx {
       if (ic.strategy == 0) {
         for (size_t i = 0; i < rs.lights.size(); ++i) {
           int n = rs.lights[i].nSamples;
-          if (rs.sampler.kind == 0 || rs.sampler.kind == 4) n = RoundUpPow2(n);  // sampler.roundSize (LD and adaptive)
+          if (rs.sampler.kind == 0 || rs.sampler.kind >= 4) n = RoundUpPow2(n);  // sampler.roundSize (LD, adaptive, bestcandidate)
           dlLight.push_back(lightOffsets(n));
           dlBsdf.push_back(bsdfOffsets(n));
         }
@@ -1582,6 +1582,44 @@ int pixelSamples(const SamplerCfg& sc, const SampleLayout& layout, const Camera&
   }
   KeyedRng k(sc.seed, x, y, (uint32_t)pass, kStreamPixel);
   Rng& rng = keyed ? (Rng&)k : *serial;
+  if (sc.kind == 5) {  // best_candidate_sampler.dart:36-52,74-132: (x, y) carry n = (tile index) * 4096 + tableOffset
+    const uint64_t n = ((uint64_t)(uint32_t)y << 30) | (uint32_t)x;
+    const double tableWidth = 64 / std::sqrt((double)sc.spp);
+    const int right = sc.winX + sc.winW - 1, bottom = sc.winY + sc.winH - 1;
+    const int xTileStart = (int)std::floor(sc.winX / tableWidth), xTileEnd = (int)std::floor(right / tableWidth);
+    const int yTileStart = (int)std::floor(sc.winY / tableWidth);
+    (void)bottom;
+    const int nx = xTileEnd - xTileStart + 1;
+    const uint64_t tile = n / 4096;
+    const int to = (int)(n % 4096) * 5;
+    const int xTile = xTileStart + (int)(tile % (uint64_t)nx), yTile = yTileStart + (int)(tile / (uint64_t)nx);
+    DartRandom tileRng((int64_t)xTile + ((int64_t)yTile << 8));  // the tile's own RNG (:44-47,91-94): not the shared stream
+    double so[3];
+    for (int i = 0; i < 3; ++i) so[i] = tileRng.randomFloat();
+    auto WRAP = [](double v) { return v > 1 ? (v - 1) : v; };
+    const double* T = sc.sampleTable.data();
+    const double imageX = (xTile + T[to]) * tableWidth, imageY = (yTile + T[to + 1]) * tableWidth;
+    // as written (:117-118): BOTH coordinates are compared with left and right
+    if (imageX < sc.winX || imageX > right || imageY < sc.winX || imageY > right) { out.clear(); return 0; }
+    out.resize(1);
+    out[0].alloc(layout);
+    out[0].imageX = imageX;
+    out[0].imageY = imageY;
+    out[0].time = Lerp(WRAP(so[0] + T[to + 2]), cam.shutterOpen, cam.shutterClose);
+    out[0].lensU = WRAP(so[1] + T[to + 3]);
+    out[0].lensV = WRAP(so[2] + T[to + 4]);
+    // integrator samples: LDShuffleScrambled1D / 2D with one pixel sample (:125-131); keyed like the lowdiscrepancy arrays
+    uint32_t arr = 3;
+    auto stream = [&](KeyedRng& kk) -> Rng& {
+      if (!keyed) return *serial;
+      kk = KeyedRng(sc.seed, x, y, 0, arr);
+      return kk;
+    };
+    KeyedRng kk;
+    for (size_t i = 0; i < layout.n1D.size(); ++i) { LDShuffleScrambled1D(layout.n1D[i], 1, out[0].oneD[i].data(), stream(kk)); arr++; }
+    for (size_t i = 0; i < layout.n2D.size(); ++i) { LDShuffleScrambled2D(layout.n2D[i], 1, out[0].twoD[i].data(), stream(kk)); arr++; }
+    return 1;
+  }
   if (sc.kind == 3) {  // halton_sampler.dart:59-104: (x, y) carry the sequence index n = y * 2^30 + x, one sample per index
     const uint64_t n = ((uint64_t)(uint32_t)y << 30) | (uint32_t)x;
     const double u = RadicalInverse(n, 3), v = RadicalInverse(n, 2);
@@ -1696,7 +1734,15 @@ void RenderScene::render(int taskNum, int taskCount, int nthreads) {
     y = ext[2] + e[2]; h = e[3] - e[2];
   }
   std::vector<int32_t> px;
-  if (sampler.kind == 3) {  // halton_sampler.dart:32-38: spp * delta^2 sequence indices instead of pixels
+  if (sampler.kind == 5) {  // best_candidate_sampler.dart:38-44: every table entry of every tile the window touches
+    sampler.winX = x; sampler.winY = y; sampler.winW = w; sampler.winH = h;
+    const double tableWidth = 64 / std::sqrt((double)sampler.spp);
+    const int64_t nx = (int64_t)std::floor((x + w - 1) / tableWidth) - (int64_t)std::floor(x / tableWidth) + 1;
+    const int64_t ny = (int64_t)std::floor((y + h - 1) / tableWidth) - (int64_t)std::floor(y / tableWidth) + 1;
+    const uint64_t wanted = (uint64_t)(nx * ny) * 4096;
+    px.reserve(2 * wanted);
+    for (uint64_t n = 0; n < wanted; ++n) { px.push_back((int32_t)(n & 0x3fffffffu)); px.push_back((int32_t)(n >> 30)); }
+  } else if (sampler.kind == 3) {  // halton_sampler.dart:32-38: spp * delta^2 sequence indices instead of pixels
     sampler.winX = x; sampler.winY = y; sampler.winW = w; sampler.winH = h;
     const uint64_t delta = (uint64_t)std::max(w, h), wanted = (uint64_t)sampler.spp * delta * delta;
     px.reserve(2 * wanted);

@@ -231,7 +231,9 @@ struct Film {  // image_film.dart:51-97
 };
 
 struct SamplerCfg {
-  int kind = 0;  // 0 lowdiscrepancy, 1 stratified, 2 random, 3 halton, 4 adaptive (xs = minsamples, ys = maxsamples, jitter = method)
+  int kind = 0;  // 0 lowdiscrepancy, 1 stratified, 2 random, 3 halton, 4 adaptive (xs = minsamples, ys = maxsamples, jitter = method),
+                 // 5 bestcandidate (best_candidate_sampler.dart; its 4096 x 5 pattern arrives through orc_set_sample_table)
+  std::vector<double> sampleTable;  // bestcandidate: _SAMPLE_TABLE (best_candidate_sampler.dart:163-4258), handed over by the caller
   // halton: the sampler's window (left, top, width, height), filled in by render() (halton_sampler.dart:32-38)
   int winX = 0, winY = 0, winW = 0, winH = 0;
   int xs = 2, ys = 2;

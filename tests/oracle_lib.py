@@ -59,6 +59,7 @@ def lib():
         L.orc_set_materials.argtypes = [vp, u32, vp, vp, vp]
         L.orc_set_material_lobes.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp]
         L.orc_set_spot_params.argtypes = [vp, u32, vp, vp]
+        L.orc_set_sample_table.argtypes = [vp, vp, u32]
         L.orc_set_light_map.argtypes = [vp, u32, i32, i32, vp, vp, vp, vp, dbl]
         L.orc_set_lobe_wrappers.argtypes = [vp, u32, vp, vp]
         L.orc_set_infinite_light.argtypes = [vp, u32, i32, i32, vp, vp, vp]
@@ -253,6 +254,11 @@ class Oracle:
 
     def set_sampler(self, kind, xs, ys, spp, jitter, pixel_order, tile_size, seed, rng_mode):
         self._ck(self.L.orc_set_sampler(self.h, kind, xs, ys, spp, jitter, pixel_order, tile_size, seed, rng_mode))
+
+    def set_sample_table(self, table):
+        """The bestcandidate sampler's 4096 x 5 pattern (doubles)."""
+        t = _arr(table, np.float64).reshape(-1, 5)
+        self._ck(self.L.orc_set_sample_table(self.h, _p(t), t.shape[0]))
 
     def set_integrator(self, kind, maxdepth, strategy, ao_nsamples, ao_mindist, ao_maxdist):
         self._ck(self.L.orc_set_integrator(self.h, kind, maxdepth, strategy, ao_nsamples, ao_mindist, ao_maxdist))

@@ -442,3 +442,39 @@ def test_goniometric_light_scales_a_point_light_by_direction():
     # exactly at the nadir t = 1: the bilinear lookup blends the last row with row 0 (TEXTURE_REPEAT, mipmap.dart:183-204,341-355)
     nadir, _ = _floor_under(lambda sb: sb.goniometric_light((I, I, I), light_to_world=at, texels=tex))
     assert nadir[0] == pytest.approx(0.5 * plain[0], rel=5e-2)  # the camera looks a hair off the axis
+
+
+# ---- BestCandidateSampler (best_candidate_sampler.dart) -------------------------------------------------------------------
+@pytest.mark.parametrize("W,H", [(24, 12), (12, 24)])
+def test_best_candidate_sampler_places_the_pattern_and_rejects_as_written(W, H):
+    from tests.util import synthetic_sample_table
+    table = synthetic_sample_table()
+    sb = host.SceneBuilder()
+    sb.infinite_light((1.0, 1.0, 1.0))
+    cam = host.PerspectiveCamera(host.look_at((0, 0, -5), (0, 0, 0), (0, 1, 0)), fov=40.0)
+    spp = 4
+    smp = host.Sampler(kind=host.SAMPLER_BEST_CANDIDATE, spp=spp, sample_table=table)
+    o = _oracle(sb, cam, host.Film(W, H, filter="box", xwidth=0.5, ywidth=0.5), smp, host.Integrator(kind=host.INTEGRATOR_PATH))
+    o.render()
+    f, st = o.film_read(), o.render_stats()
+    # window [0, W] x [0, H] (box filter 0.5), right = W inclusive; tiles of 64 / sqrt(4) = 32 pixels
+    tw = 64 / math.sqrt(spp)
+    nx, ny = int(W // tw) + 1, int(H // tw) + 1
+    pts = []
+    for ty in range(ny):
+        for tx in range(nx):
+            pts.append(np.stack([(tx + table[:, 0]) * tw, (ty + table[:, 1]) * tw], axis=1))
+    pts = np.concatenate(pts)
+    # :117-118 compares BOTH coordinates with left and right: a wide window keeps samples below its bottom edge (they miss the
+    # film), a tall one loses everything below y = right
+    acc = (pts[:, 0] >= 0) & (pts[:, 0] <= W) & (pts[:, 1] >= 0) & (pts[:, 1] <= W)
+    assert st["camera_samples"] == int(acc.sum())
+    cnt = np.zeros((H, W))
+    for x_, y_ in pts[acc]:
+        dx, dy = x_ - 0.5, y_ - 0.5
+        for py in range(max(int(math.ceil(dy - 0.5)), 0), min(int(math.floor(dy + 0.5)), H - 1) + 1):
+            for px in range(max(int(math.ceil(dx - 0.5)), 0), min(int(math.floor(dx + 0.5)), W - 1) + 1):
+                cnt[py, px] += 1
+    assert np.array_equal(f["weight"], cnt.astype(np.float32))
+    if H > W:
+        assert (f["weight"][W + 1:] == 0).all() and (f["weight"][:W - 1] > 0).any()

@@ -387,6 +387,31 @@ def test_projection_and_goniometric_lights_match_oracle(integ):
         g2.render(0, 1)
 
 
+@pytest.mark.parametrize("integ", [host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=4), host.Integrator(kind=host.INTEGRATOR_DIRECT)])
+def test_best_candidate_sampler_matches_oracle(integ):
+    """best_candidate_sampler.dart: the pattern table through drt_set_sample_table, per-tile shifts from dart:math Random."""
+    from tests.util import synthetic_sample_table
+    arrays, cam = _cornell()
+    sb2 = None
+    smp = host.Sampler(kind=host.SAMPLER_BEST_CANDIDATE, spp=5, seed=2, sample_table=synthetic_sample_table())
+    cam.lens_radius, cam.focal_distance = 0.3, 30.0  # lens samples come from the pattern + the tile's shifts
+    g, o, fg, fo = _render_both(arrays, cam, host.Film(80, 60), smp, integ)
+    sg, so = g.render_stats(), o.render_stats()
+    assert sg["camera_samples"] == so["camera_samples"] > 0
+    assert np.array_equal(fg["weight"], fo["weight"])
+    err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
+    print("bestcandidate", integ.kind, "max rel err", err.max())
+    assert np.quantile(err, 0.999) <= 1e-3
+    if integ.kind == host.INTEGRATOR_DIRECT:
+        assert err.max() <= 1e-3 and sg["shadow_rays"] == so["shadow_rays"]
+    # without its table the sampler is refused
+    g2 = capi.Context(0)
+    host.upload_scene(g2, arrays)
+    host.configure_render(g2, cam, host.Film(8, 8), host.Sampler(kind=host.SAMPLER_BEST_CANDIDATE, spp=4), integ)
+    with pytest.raises(RuntimeError, match="drt_set_sample_table"):
+        g2.render(0, 1)
+
+
 # ---- path tracing ------------------------------------------------------------------------------------------
 def test_path_integrator_matches_oracle():
     arrays, cam = _cornell()

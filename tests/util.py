@@ -63,3 +63,13 @@ def uv_sphere_mesh(stacks=12, slices=16, radius=1.0):
                 idx.append([b, d, c])
     return (np.asarray(P, np.float32), np.asarray(idx, np.uint32), np.asarray(N, np.float32), np.asarray(S, np.float32),
             np.asarray(UV, np.float32))
+
+
+def synthetic_sample_table(seed=7):
+    """A stand-in for BestCandidateSampler's _SAMPLE_TABLE (best_candidate_sampler.dart:163-4258): 4096 x 5 doubles, image
+    positions from a jittered 64 x 64 grid in shuffled order, time / lens uniform.  The reference's own table is data of the
+    reference and is handed over by the caller (drt_set_sample_table); the tests only need its shape."""
+    rng = np.random.default_rng(seed)
+    g = (np.stack(np.meshgrid(np.arange(64), np.arange(64), indexing="ij"), -1).reshape(-1, 2) + rng.uniform(0.05, 0.95, (4096, 2))) / 64.0
+    rng.shuffle(g)
+    return np.concatenate([g, rng.uniform(0, 1, (4096, 3))], axis=1).astype(np.float64)
