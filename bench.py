@@ -195,9 +195,16 @@ def render_legs(ctx_soup, rank, world, barrier):
         l0 = ctx.kernel_launches
         barrier()
         t0 = time.perf_counter()
-        distributed.render_sharded(ctx, rank, world)
+        parts = distributed.render_sharded(ctx, rank, world)
+        t_done = time.perf_counter() - t0
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        # where the time goes: this rank's render, its film sum (which also waits for the slowest rank), its own total
+        pr = torch.tensor([parts["render_s"], parts["film_sum_s"], t_done], dtype=torch.float64, device=dev)
+        pr_min = pr.clone()
+        if world > 1:
+            dist.all_reduce(pr, op=dist.ReduceOp.MAX)
+            dist.all_reduce(pr_min, op=dist.ReduceOp.MIN)
         st = ctx.render_stats()
         cnt = torch.tensor([st["camera_samples"], st["closest_rays"], st["shadow_rays"]], dtype=torch.float64, device=dev)
         if world > 1:
@@ -208,7 +215,9 @@ def render_legs(ctx_soup, rank, world, barrier):
         rgb = ctx.film_read()["rgb"]
         out[name] = {"seconds": sec, "camera_samples": int(samples), "samples_per_s": samples / sec,
                      "mrays_per_s": (closest + shadow) / sec / 1e6, "closest_rays": int(closest), "shadow_rays": int(shadow),
-                     "launches_rank0": int(ctx.kernel_launches - l0), "mean_rgb": [float(v) for v in rgb.mean(axis=(0, 1))]}
+                     "launches_rank0": int(ctx.kernel_launches - l0), "mean_rgb": [float(v) for v in rgb.mean(axis=(0, 1))],
+                     "per_rank": {"render_s_max": float(pr[0]), "render_s_min": float(pr_min[0]), "film_sum_s_max": float(pr[1]),
+                                  "film_sum_s_min": float(pr_min[1]), "render_plus_sum_s_max": float(pr[2])}}
     out["ao"]["config"] = (f"BASELINE.json configs[2]: soup_1m, {RENDER_RES[0]}x{RENDER_RES[1]}, 1 camera sample/pixel at the "
                            f"pixel centre, {AO_RAYS} AO rays per hit")
     out["path"]["config"] = (f"BASELINE.json configs[3]: cornell_synth, {RENDER_RES[0]}x{RENDER_RES[1]}, lowdiscrepancy "

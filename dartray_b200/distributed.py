@@ -61,9 +61,14 @@ def sum_films(film, group=None):
 def render_sharded(ctx, rank: int, world: int, group=None):
     """Render this rank's shard and sum the films; afterwards every rank's `ctx.film_read()` returns the
     whole image."""
+    import time
+
     import torch
-    ctx.render_shard(rank, world)
+    t0 = time.perf_counter()
+    ctx.render_shard(rank, world)  # blocking: returns when this rank's film is complete
+    t1 = time.perf_counter()
     if world > 1:
         film = film_tensor(ctx)
         sum_films(film, group)
         torch.cuda.synchronize(ctx.device)
+    return {"render_s": t1 - t0, "film_sum_s": time.perf_counter() - t1}

@@ -321,7 +321,8 @@ int drt_render(drt_ctx* ctx, int32_t task_num, int32_t task_count);
  * exactly the sample set of drt_render(0, 1). */
 int drt_render_shard(drt_ctx* ctx, int32_t shard, int32_t n_shards);
 
-/* Camera samples in flight per wavefront batch (0 = default 4 Mi). */
+/* Camera samples in flight per wavefront batch (0 = default 16 Mi, about 10 GB of device memory for the largest renders; a
+ * render with fewer samples allocates only what it needs). */
 int drt_set_batch_slots(drt_ctx* ctx, uint64_t slots);
 
 int drt_film_clear(drt_ctx* ctx);

@@ -412,6 +412,39 @@ def test_best_candidate_sampler_matches_oracle(integ):
         g2.render(0, 1)
 
 
+@pytest.mark.parametrize("smp", [
+    host.Sampler(kind=host.SAMPLER_ADAPTIVE, xs=2, ys=8, jitter=host.ADAPTIVE_CONTRAST, seed=4),
+    host.Sampler(kind=host.SAMPLER_BEST_CANDIDATE, spp=4, seed=4),
+    host.Sampler(kind=host.SAMPLER_HALTON, spp=3, seed=4),
+])
+def test_shards_and_tasks_of_the_sequence_samplers_tile_the_render(smp):
+    """drt_render_shard splits the pixel list / the sample sequence in blocks; drt_render(task, count) gives every task its own
+    sampler over its sub-window, as the reference does (dartray.dart:1009-1023)."""
+    from tests.util import synthetic_sample_table
+    if smp.kind == host.SAMPLER_BEST_CANDIDATE:
+        smp.sample_table = synthetic_sample_table()
+    arrays, cam = _cornell()
+    integ = host.Integrator(kind=host.INTEGRATOR_DIRECT)
+    film = host.Film(96, 64)
+
+    def render(fn):
+        c = capi.Context(0)
+        host.upload_scene(c, arrays)
+        host.configure_render(c, cam, film, smp, integ)
+        fn(c)
+        return c.film_read(), c.render_stats()
+    whole, st = render(lambda c: c.render(0, 1))
+    parts = [render(lambda c, k=k: c.render_shard(k, 3)) for k in range(3)]
+    assert np.array_equal(sum(p[0]["weight"] for p in parts), whole["weight"])
+    assert np.allclose(sum(p[0]["xyz"] for p in parts), whole["xyz"], rtol=1e-5, atol=1e-6)
+    assert sum(p[1]["camera_samples"] for p in parts) == st["camera_samples"]
+    # tasks: GPU == oracle task by task (each task is its own sampler window)
+    for task in ((0, 2), (1, 2)):
+        g, o, fg, fo = _render_both(arrays, cam, film, smp, integ, task=task)
+        assert np.array_equal(fg["weight"], fo["weight"])
+        assert _rel_err(fg["rgb"], fo["rgb"]).max() <= 1e-3
+
+
 # ---- path tracing ------------------------------------------------------------------------------------------
 def test_path_integrator_matches_oracle():
     arrays, cam = _cornell()
