@@ -187,9 +187,10 @@ def render_legs(ctx_soup, rank, world, barrier):
     legs = [("ao", ctx_soup, cam_soup, ao_s, ao_i), ("path", ctx_c, cam_cornell, pt_s, pt_i)]
     for name, ctx, cam, smp, integ in legs:
         film = host.Film(*RENDER_RES)
-        warm = host.Sampler(kind=smp.kind, spp=min(smp.spp, 16), xs=smp.xs, ys=smp.ys, jitter=smp.jitter)
-        host.configure_render(ctx, cam, film, warm, integ)
-        distributed.render_sharded(ctx, rank, world)  # warm-up: allocations, first launches, NCCL channel
+        # warm-up: one untimed render of the SAME configuration, so that the wavefront allocation (up to ~10 GB, sized by the
+        # batch), the first launches and the NCCL channel are outside the timed region, as they are for every later frame
+        host.configure_render(ctx, cam, film, smp, integ)
+        distributed.render_sharded(ctx, rank, world)
         host.configure_render(ctx, cam, film, smp, integ)
         ctx.film_clear()
         l0 = ctx.kernel_launches
