@@ -356,10 +356,8 @@ def test_translucent_mix_and_shinymetal_match_oracle(integ):
     assert np.abs(g2.film_read()["rgb"] - fg["rgb"]).max() > 1e-2
 
 
-@pytest.mark.parametrize("integ", [host.Integrator(kind=host.INTEGRATOR_DIRECT), host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=3),
-                                   host.Integrator(kind=host.INTEGRATOR_WHITTED, maxdepth=2)])
-def test_projection_and_goniometric_lights_match_oracle(integ):
-    """projection_light.dart / goniometric_light.dart: point lights scaled by a map lookup (drt_set_light_map)."""
+def _mapped_lights_room():
+    """cornell_synth lit by projection and goniometric lights, with and without maps (drt_set_light_map)."""
     sb, cam = scenes.cornell_synth()
     w, h = 16, 8
     v, u = np.meshgrid((np.arange(h) + 0.5) / h, (np.arange(w) + 0.5) / w, indexing="ij")
@@ -369,7 +367,19 @@ def test_projection_and_goniometric_lights_match_oracle(integ):
     sb.projection_light((150.0, 150.0, 150.0), fov=30.0, light_to_world=host.mat_mul(host.translate(5, 8, -2), host.rotate(80, (1, 0, 0.3))))
     sb.goniometric_light((120.0, 140.0, 160.0), texels=stripes[:, ::-1].copy(), light_to_world=host.mat_mul(host.translate(0, 2, -4), host.rotate(30, (0, 0, 1))))
     sb.goniometric_light((40.0, 40.0, 40.0), light_to_world=host.translate(-6, -6, -3))
-    arrays = sb.arrays()
+    return sb.arrays(), cam
+
+
+def _wrapped_room_arrays():
+    sb, cam = _wrapped_materials_room()
+    return sb.arrays(), cam
+
+
+@pytest.mark.parametrize("integ", [host.Integrator(kind=host.INTEGRATOR_DIRECT), host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=3),
+                                   host.Integrator(kind=host.INTEGRATOR_WHITTED, maxdepth=2)])
+def test_projection_and_goniometric_lights_match_oracle(integ):
+    """projection_light.dart / goniometric_light.dart: point lights scaled by a map lookup (drt_set_light_map)."""
+    arrays, cam = _mapped_lights_room()
     g, o, fg, fo = _render_both(arrays, cam, host.Film(80, 60), host.Sampler(kind=host.SAMPLER_LD, spp=4), integ)
     err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
     print("mapped lights", integ.kind, "max rel err", err.max())

@@ -101,6 +101,12 @@ FEATURES = {
     "sky_path": ("_sky_scene", ("lobes",), host.Sampler(kind=host.SAMPLER_LD, spp=2, seed=5), host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=4)),
     "sky_direct": ("_sky_scene", ("matte",), host.Sampler(kind=host.SAMPLER_LD, spp=2, seed=5), host.Integrator(kind=host.INTEGRATOR_DIRECT)),
     "halton_direct": ("_cornell", (), host.Sampler(kind=host.SAMPLER_HALTON, spp=3, seed=5), host.Integrator(kind=host.INTEGRATOR_DIRECT)),
+    "adaptive_direct": ("_cornell", (), host.Sampler(kind=host.SAMPLER_ADAPTIVE, xs=2, ys=8, jitter=host.ADAPTIVE_CONTRAST, seed=5),
+                        host.Integrator(kind=host.INTEGRATOR_DIRECT)),
+    "bestcandidate_direct": ("_cornell", (), host.Sampler(kind=host.SAMPLER_BEST_CANDIDATE, spp=4, seed=5), host.Integrator(kind=host.INTEGRATOR_DIRECT)),
+    "mapped_lights_direct": ("_mapped_lights_room", (), host.Sampler(kind=host.SAMPLER_LD, spp=2, seed=5), host.Integrator(kind=host.INTEGRATOR_DIRECT)),
+    "wrapped_materials_path": ("_wrapped_room_arrays", (), host.Sampler(kind=host.SAMPLER_LD, spp=2, seed=5),
+                               host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=4)),
 }
 
 
@@ -108,6 +114,9 @@ def feature_scene(name):
     import tests.test_render_gpu as T
     fn, args, sampler, integ = FEATURES[name]
     arrays, cam = getattr(T, fn)(*args)
+    if sampler.kind == host.SAMPLER_BEST_CANDIDATE:
+        from tests.util import synthetic_sample_table
+        sampler.sample_table = synthetic_sample_table()
     return arrays, cam, sampler, integ
 
 
