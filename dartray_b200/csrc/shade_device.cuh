@@ -1062,29 +1062,32 @@ static __device__ inline Spec lobeSampleF(const GLobe& l, const V3& wo, V3* wi, 
   return (l.wrap & 2) ? Spec{l.scale[0], l.scale[1], l.scale[2]} * r : r;
 }
 
-static __device__ inline Spec bsdfF(const BsdfG& b, const V3& woW, const V3& wiW, int flags) {  // bsdf.dart:177-198
+// The three BSDF entry points of a BxDF list are OUT OF LINE: inlined at their five call sites they made shadePathKernel<GENERAL>
+// 23.5 K instructions, and ncu showed the kernel waiting for instruction fetch (stall no_instruction 59 per issue, issue active
+// 6 %: profiles/r01n_summary.md).  One copy of each keeps the divergent warps inside the instruction cache.
+static __device__ __noinline__ Spec bsdfF(const BsdfG& b, const V3& woW, const V3& wiW, int flags) {  // bsdf.dart:177-198
   const V3 wi = bsdfToLocal(b, wiW), wo = bsdfToLocal(b, woW);
   if (Dot(wiW, b.ng) * Dot(woW, b.ng) > 0) flags &= ~BSDF_TRANSMISSION;
   else flags &= ~BSDF_REFLECTION;
   Spec r = mks1(0.0);
   for (int i = 0; i < b.n; ++i) {
-    const GLobe l = b.lobes[i];
+    const GLobe& l = b.lobes[i];
     if (lobeMatches(l, flags)) r = r + lobeF(l, wo, wi);
   }
   return r;
 }
-static __device__ inline double bsdfPdf(const BsdfG& b, const V3& woW, const V3& wiW, int flags) {  // bsdf.dart:128-146
+static __device__ __noinline__ double bsdfPdf(const BsdfG& b, const V3& woW, const V3& wiW, int flags) {  // bsdf.dart:128-146
   if (b.n == 0) return 0.0;
   const V3 wo = bsdfToLocal(b, woW), wi = bsdfToLocal(b, wiW);
   double p = 0.0;
   int matching = 0;
   for (int i = 0; i < b.n; ++i) {
-    const GLobe l = b.lobes[i];
+    const GLobe& l = b.lobes[i];
     if (lobeMatches(l, flags)) { ++matching; p += lobePdf(l, wo, wi); }
   }
   return matching > 0 ? p / matching : 0.0;
 }
-static __device__ inline Spec bsdfSampleF(const BsdfG& b, const V3& woW, V3* wiW, float u0, float u1, double comp, double* pdfOut,
+static __device__ __noinline__ Spec bsdfSampleF(const BsdfG& b, const V3& woW, V3* wiW, float u0, float u1, double comp, double* pdfOut,
                                           int flags, int* sampledType) {  // bsdf.dart:53-126
   *sampledType = 0;
   *pdfOut = 0.0;
@@ -1095,7 +1098,7 @@ static __device__ inline Spec bsdfSampleF(const BsdfG& b, const V3& woW, V3* wiW
   int chosen = 0, count = which;
   for (int i = 0; i < b.n; ++i)
     if (lobeMatches(b.lobes[i], flags) && count-- == 0) { chosen = i; break; }
-  const GLobe lc = b.lobes[chosen];
+  const GLobe& lc = b.lobes[chosen];
   const int type = lobeTypeOf(lc);
   const V3 wo = bsdfToLocal(b, woW);
   V3 wi = V3{0.f, 0.f, 0.f};
@@ -1105,7 +1108,7 @@ static __device__ inline Spec bsdfSampleF(const BsdfG& b, const V3& woW, V3* wiW
   *wiW = bsdfToWorld(b, wi);
   if (!((type & BSDF_SPECULAR) != 0) && matching > 1)
     for (int i = 0; i < b.n; ++i) {
-      const GLobe l = b.lobes[i];
+      const GLobe& l = b.lobes[i];
       if (i != chosen && lobeMatches(l, flags)) *pdfOut += lobePdf(l, wo, wi);
     }
   if (matching > 1) *pdfOut /= matching;
@@ -1114,7 +1117,7 @@ static __device__ inline Spec bsdfSampleF(const BsdfG& b, const V3& woW, V3* wiW
     if (Dot(*wiW, b.ng) * Dot(woW, b.ng) > 0) flags &= ~BSDF_TRANSMISSION;
     else flags &= ~BSDF_REFLECTION;
     for (int i = 0; i < b.n; ++i) {
-      const GLobe l = b.lobes[i];
+      const GLobe& l = b.lobes[i];
       if (lobeMatches(l, flags)) f = f + lobeF(l, wo, wi);
     }
   }

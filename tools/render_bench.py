@@ -3,6 +3,7 @@
   python tools/render_bench.py ao      [xres yres spp ao_nsamples]     config 3 (soup_1m, AO)
   python tools/render_bench.py path    [xres yres spp]                 config 4 (cornell_synth, path maxdepth 5)
   python tools/render_bench.py soup    [xres yres spp n_spheres]       config 5 style (soup, path)
+  python tools/render_bench.py materials | sky [xres yres spp]         BxDF-list materials / environment-lit scene (path)
 """
 import json
 import os
@@ -21,6 +22,23 @@ def main():
         sb, cam = scenes.soup_render_scene(512)
         sampler = host.Sampler(kind=host.SAMPLER_STRATIFIED, xs=spp, ys=1, jitter=False)
         integ = host.Integrator(kind=host.INTEGRATOR_AO, ao_nsamples=ns)
+    elif what in ("materials", "sky"):  # BxDF-list materials (cornell_materials) / the environment-lit scene of the GPU tests
+        xres, yres, spp = a[:3] if len(a) >= 3 else (1920, 1080, 64)
+        if what == "materials":
+            sb, cam = scenes.cornell_materials()
+        else:
+            from tests.test_render_gpu import _sky_scene
+
+            class _SB:  # upload_scene only needs arrays()
+                def __init__(self, arr):
+                    self._a = arr
+
+                def arrays(self):
+                    return self._a
+            arr, cam = _sky_scene("lobes")
+            sb = _SB(arr)
+        sampler = host.Sampler(kind=host.SAMPLER_LD, spp=spp)
+        integ = host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=5)
     elif what == "path":
         xres, yres, spp = a[:3] if len(a) >= 3 else (1920, 1080, 16)
         sb, cam = scenes.cornell_synth()
