@@ -418,6 +418,7 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
   rs.primAttr = r->dPrimAttr.p;
   rs.materials = r->dMaterials.p;
   rs.general = r->general ? 1 : 0;
+  rs.nMaterials = nMat;
   rs.matLobes = r->dMatLobes.p;
   rs.lobes = r->dLobes.p;
   rs.lights = r->dLights.p;
@@ -454,6 +455,8 @@ static void carve(ByteArena& a, Wavefront& wf, uint32_t cap, uint32_t shCap, int
   wf.misHit = a.take<float4>(cap); wf.misT = a.take<double>(cap);
   wf.counts = a.take<uint32_t>(Q_COUNT);
   wf.hitList = a.take<uint32_t>(cap);
+  wf.shadeOrder = a.take<uint32_t>(cap);
+  wf.matHist = a.take<uint32_t>(1024);
   wf.camPrim = a.take<int32_t>(cap);
   wf.adaptFlag = a.take<uint8_t>(cap);
   if (chains) {  // directlighting with specular BxDFs: counters per recursion level + a copy of the camera-ray queue

@@ -467,19 +467,51 @@ static __device__ __forceinline__ void pushDirectWork(const Wavefront& wf, uint3
 #define DRT_SHADE_MIN_BLOCKS 4  // 128 registers: 16 warps/SM; 321 vs 277 Msamples/s at 2 (tools/shade_sweep.sh)
 #endif
 // GENERAL = false: every material is matte (one diffuse BxDF, never a specular bounce); true: BxDF lists.
-// EXTRA: see hitGeometry (shade_device.cuh).
+// Counting sort of extension queue `cur` by material (BxDF-list scenes): histogram, one-block exclusive scan, scatter.
+#define DRT_SORT_MAX_MATERIALS 1023
+static __device__ __forceinline__ uint32_t shadeKey(const RenderScene& rs, const Wavefront& wf, uint32_t q) {
+  const int prim = __float_as_int(wf.extHit[q].w);
+  return prim < 0 ? (uint32_t)rs.nMaterials : (uint32_t)primMaterial(rs, (uint32_t)prim);
+}
+__global__ void __launch_bounds__(256) matHistKernel(RenderScene rs, Wavefront wf, int cur) {
+  __shared__ uint32_t h[DRT_SORT_MAX_MATERIALS + 1];
+  const uint32_t n = wf.counts[cur], bins = (uint32_t)rs.nMaterials + 1;
+  for (uint32_t b = threadIdx.x; b < bins; b += blockDim.x) h[b] = 0;
+  __syncthreads();
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) atomicAdd(&h[shadeKey(rs, wf, q)], 1u);
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < bins; b += blockDim.x)
+    if (h[b]) atomicAdd(&wf.matHist[b], h[b]);
+}
+__global__ void matScanKernel(RenderScene rs, Wavefront wf) {  // one thread: at most 1024 bins
+  uint32_t acc = 0;
+  for (int b = 0; b <= rs.nMaterials; ++b) {
+    const uint32_t c = wf.matHist[b];
+    wf.matHist[b] = acc;
+    acc += c;
+  }
+}
+__global__ void __launch_bounds__(256) matScatterKernel(RenderScene rs, Wavefront wf, int cur) {
+  const uint32_t n = wf.counts[cur];
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
+    wf.shadeOrder[atomicAdd(&wf.matHist[shadeKey(rs, wf, q)], 1u)] = q;
+}
+
+// EXTRA: see hitGeometry (shade_device.cuh).  SORTED: work item i of the launch is queue entry shadeOrder[i].
 template <bool GENERAL, bool EXTRA>
 __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(RenderParams rp, RenderScene rs, Wavefront wf, int bounce, int cur,
-                                                       RenderCounters* rc) {
+                                                       RenderCounters* rc, int sortedOrder) {
   const uint32_t n = wf.counts[cur], cap = wf.cap;
   const int nxt = cur ^ 1;
   unsigned long long nShadow = 0, nClosest = 0;
+  const bool sorted = GENERAL && sortedOrder != 0;
   for (uint32_t q0 = blockIdx.x * blockDim.x; q0 < n; q0 += gridDim.x * blockDim.x) {
-    const uint32_t q = q0 + threadIdx.x;
+    uint32_t q = q0 + threadIdx.x;
     bool valid = q < n;
     uint32_t slot = 0;
     int prim = -1;
     if (valid) {
+      if (sorted) q = wf.shadeOrder[q];
       slot = wf.extSlot[cur][q];
       prim = __float_as_int(wf.extHit[q].w);
       wf.shIdx[slot] = -1;
@@ -1112,8 +1144,21 @@ cudaError_t launchResetCounts(const Wavefront& wf, unsigned mask, cudaStream_t s
 cudaError_t launchShadePath(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int bounce, int cur,
                             RenderCounters* rc, int numSMs, cudaStream_t st) {
   const int grid = gridFor(wf.cap, 128, numSMs, 8);
-  if (rs.general) shadePathKernel<true, DRT_EXTRA != 0><<<grid, 128, 0, st>>>(rp, rs, wf, bounce, cur, rc);
-  else shadePathKernel<false, DRT_EXTRA != 0><<<grid, 128, 0, st>>>(rp, rs, wf, bounce, cur, rc);
+  if (rs.general) {
+    // material-coherent warps: sort the queue by material first (skipped for a single material or more than the sort's bins)
+    const int sorted = (rs.nMaterials > 1 && rs.nMaterials <= DRT_SORT_MAX_MATERIALS) ? 1 : 0;
+    if (sorted) {
+      cudaError_t e = cudaMemsetAsync(wf.matHist, 0, (size_t)(rs.nMaterials + 1) * sizeof(uint32_t), st);
+      if (e != cudaSuccess) return e;
+      const int g2 = gridFor(wf.cap, 256, numSMs, 4);
+      matHistKernel<<<g2, 256, 0, st>>>(rs, wf, cur);
+      matScanKernel<<<1, 1, 0, st>>>(rs, wf);
+      matScatterKernel<<<g2, 256, 0, st>>>(rs, wf, cur);
+    }
+    shadePathKernel<true, DRT_EXTRA != 0><<<grid, 128, 0, st>>>(rp, rs, wf, bounce, cur, rc, sorted);
+  } else {
+    shadePathKernel<false, DRT_EXTRA != 0><<<grid, 128, 0, st>>>(rp, rs, wf, bounce, cur, rc, 0);
+  }
   return cudaGetLastError();
 }
 

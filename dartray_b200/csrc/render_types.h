@@ -87,6 +87,7 @@ struct RenderScene {
   const GMaterial* materials;
   // general materials (any BxDF list): material m owns lobes [matLobes[m].x, matLobes[m].x + matLobes[m].y)
   int32_t general;  // 0: every material is matte and the shading kernels take the single-lobe path
+  int32_t nMaterials;
   const uint2* matLobes;
   const GLobe* lobes;
   const GLight* lights;
@@ -183,6 +184,10 @@ struct Wavefront {
   float4* misO; float4* misD; double2* misRange; float4* misHit; double* misT;
   uint32_t* counts;  // [0],[1] = extension queue sizes, [2] = shadow, [3] = MIS, [4] = hit list size
   uint32_t* hitList; // slots whose camera ray hit (AO / direct lighting)
+  // BxDF-list scenes: the extension queue is shaded in material order (a warp then runs one BxDF list instead of up to 32):
+  // shadeOrder[i] = queue index, built per bounce by a counting sort over matHist (nMaterials + 1 bins, misses last)
+  uint32_t* shadeOrder;
+  uint32_t* matHist;
   int32_t* camPrim;  // adaptive sampler: primitive the slot's camera ray hit (-1: none)
   uint8_t* adaptFlag;  // adaptive sampler, per pixel of the batch: 1 = supersample (the first visit's samples are dropped)
 };
