@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "render_kernels.h"
 #include "shade_device.cuh"
@@ -1146,7 +1147,10 @@ cudaError_t launchShadePath(const RenderParams& rp, const RenderScene& rs, const
   const int grid = gridFor(wf.cap, 128, numSMs, 8);
   if (rs.general) {
     // material-coherent warps: sort the queue by material first (skipped for a single material or more than the sort's bins)
-    const int sorted = (rs.nMaterials > 1 && rs.nMaterials <= DRT_SORT_MAX_MATERIALS) ? 1 : 0;
+    // (measured: the same order makes directSampleKernel slower, 64 -> 74 ms on cornell_materials at 16 spp — that kernel is not
+    // fetch-bound and pays for the scattered queue reads — so only the path vertex kernel uses it; DRT_NO_MATERIAL_SORT turns it off)
+    static const bool sortOff = std::getenv("DRT_NO_MATERIAL_SORT") != nullptr;
+    const int sorted = (!sortOff && rs.nMaterials > 1 && rs.nMaterials <= DRT_SORT_MAX_MATERIALS) ? 1 : 0;
     if (sorted) {
       cudaError_t e = cudaMemsetAsync(wf.matHist, 0, (size_t)(rs.nMaterials + 1) * sizeof(uint32_t), st);
       if (e != cudaSuccess) return e;
