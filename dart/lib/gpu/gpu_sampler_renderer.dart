@@ -95,17 +95,36 @@ class GpuSamplerRenderer extends Renderer {
   Spectrum transmittance(Scene scene, RayDifferential ray, Sample sample, RNG rng) => new Spectrum(1.0);
 
   // ---- materials: Material.getBSDF with constant textures, as ordered BxDF lists ------------------------
-  static Spectrum _const(Texture t, String what) {
+  // ConstantTexture, and ScaleTexture / MixTexture trees over constants (textures/scale_texture.dart:26-34,
+  // textures/mix_texture.dart:26-31): none of them reads the hit, so evaluating them once with no DifferentialGeometry gives the
+  // value every Material.getBSDF call would see — through the reference's own operators, so the float32 stores are the reference's.
+  static dynamic _fold(Texture t, String what) {
     if (t is ConstantTexture) {
-      return t.value is Spectrum ? new Spectrum.from(t.value) : new Spectrum(t.value.toDouble());
+      return t.value;
+    }
+    if (t is ScaleTexture) {
+      _fold(t.tex1, what);
+      _fold(t.tex2, what);
+      return t.evaluate(null);
+    }
+    if (t is MixTexture) {
+      _fold(t.tex1, what);
+      _fold(t.tex2, what);
+      _fold(t.amount, what);
+      return t.evaluate(null);
     }
     throw new GpuUnsupported('$what is not a constant texture');
   }
+  static Spectrum _const(Texture t, String what) {
+    final v = _fold(t, what);
+    return v is Spectrum ? new Spectrum.from(v) : new Spectrum(v.toDouble());
+  }
   static double _constF(Texture t, String what) {
-    if (t is ConstantTexture) {
-      return t.value.toDouble();
+    final v = _fold(t, what);
+    if (v is num) {
+      return v.toDouble();
     }
-    throw new GpuUnsupported('$what is not a constant texture');
+    throw new GpuUnsupported('$what is a spectrum texture where a float texture is expected');
   }
   static double _blinn(double roughness) {  // 1 / roughness, then blinn.dart:24-28
     double e = 1.0 / roughness;

@@ -264,6 +264,97 @@ def _black(s) -> bool:
     return not bool(np.any(s != 0))
 
 
+# ---- textures: the constant-valued subset, folded on the host -----------------------------------------------------
+# Material.getBSDF evaluates its textures per hit; ConstantTexture (core/texture/constant_texture.dart:23-37) ignores the hit, and so
+# do ScaleTexture (textures/scale_texture.dart:26-34) and MixTexture (textures/mix_texture.dart:26-31) over constant inputs, so a tree
+# of these three folds to one value when the scene is flattened.  Float textures are Dart doubles; spectrum textures round to float32
+# after every operator like RGBColor (rgb_color.dart:136-151).  Anything that reads the hit point (imagemap, checkerboard, ...) is not
+# on the GPU path yet: GpuUnsupported, as the Dart shim raises it (dart/lib/gpu/gpu_sampler_renderer.dart).
+class GpuUnsupported(ValueError):
+    pass
+
+
+class Texture:
+    def evaluate(self):
+        raise GpuUnsupported(f"{type(self).__name__} is not a constant texture")
+
+
+def _is_num(v) -> bool:
+    return isinstance(v, (int, float, np.floating, np.integer))
+
+
+def _tex_value(v):
+    """One texture value as the reference holds it: a double, or a float32 RGB spectrum."""
+    return float(v) if _is_num(v) else np.asarray(v, np.float64).reshape(3).astype(np.float32)
+
+
+def _tex_mul(a, b):  # RGBColor.operator* with a num or a spectrum; double * double for float textures
+    if _is_num(a) and _is_num(b):
+        return a * b
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64)).astype(np.float32)
+
+
+class ConstantTexture(Texture):
+    def __init__(self, value=1.0):
+        self.value = _tex_value(value)
+
+    def evaluate(self):
+        return self.value
+
+
+class ScaleTexture(Texture):
+    def __init__(self, tex1=1.0, tex2=1.0):
+        self.tex1, self.tex2 = as_texture(tex1), as_texture(tex2)
+
+    def evaluate(self):
+        t1, t2 = self.tex1.evaluate(), self.tex2.evaluate()
+        return _tex_mul(t2, t1) if _is_num(t1) else _tex_mul(t1, t2)
+
+
+class MixTexture(Texture):
+    def __init__(self, tex1=0.0, tex2=1.0, amount=0.5):
+        self.tex1, self.tex2, self.amount = as_texture(tex1), as_texture(tex2), as_texture(amount)
+
+    def evaluate(self):
+        t1, t2, amt = self.tex1.evaluate(), self.tex2.evaluate(), self.amount.evaluate()
+        if not _is_num(amt):
+            raise ValueError("MixTexture amount is a float texture (mix_texture.dart:33-45)")
+        a, b = _tex_mul(t1, 1.0 - amt), _tex_mul(t2, amt)
+        if _is_num(a) and _is_num(b):
+            return a + b
+        if _is_num(a) or _is_num(b):
+            raise ValueError("MixTexture mixes two float or two spectrum textures")
+        return (a.astype(np.float64) + b.astype(np.float64)).astype(np.float32)
+
+
+class OpaqueTexture(Texture):
+    """Stands for a texture plugin that reads the hit point (imagemap, checkerboard, bilerp, ...): evaluate() raises."""
+
+    def __init__(self, plugin: str):
+        self.plugin = plugin
+
+    def evaluate(self):
+        raise GpuUnsupported(f"texture '{self.plugin}' is not a constant texture")
+
+
+def as_texture(v) -> Texture:
+    return v if isinstance(v, Texture) else ConstantTexture(v)
+
+
+def fold_texture(v):
+    """The value a material parameter takes at every hit: numbers and RGB triples pass through, texture trees fold."""
+    return v.evaluate() if isinstance(v, Texture) else v
+
+
+def _folds_textures(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        return fn(*[fold_texture(a) for a in args], **{k: fold_texture(v) for k, v in kw.items()})
+    return wrapper
+
+
 WRAP_BTDF, WRAP_SCALED = 1, 2  # drt_set_lobe_wrappers: BRDFToBTDF(bxdf), ScaledBxDF(.., scale)
 
 
@@ -278,6 +369,7 @@ def _blinn_exponent(roughness: float) -> float:  # 1 / roughness, then blinn.dar
     return 10000.0 if (e > 10000.0 or math.isnan(e)) else e
 
 
+@_folds_textures
 def matte_lobes(kd=0.5, sigma=0.0) -> list:  # matte_material.dart:41-65
     r, sig = _clamp(kd), min(max(float(sigma), 0.0), 90.0)
     if _black(r):
@@ -285,11 +377,13 @@ def matte_lobes(kd=0.5, sigma=0.0) -> list:  # matte_material.dart:41-65
     return [_lobe(LOBE_LAMBERTIAN, r)] if sig == 0.0 else [_lobe(LOBE_OREN_NAYAR, r, param=sig)]
 
 
+@_folds_textures
 def mirror_lobes(kr=0.9) -> list:  # mirror_material.dart:26-43
     r = _clamp(kr)
     return [] if _black(r) else [_lobe(LOBE_SPECULAR_REFLECTION, r, FRESNEL_NOOP)]
 
 
+@_folds_textures
 def glass_lobes(kr=1.0, kt=1.0, index=1.5) -> list:  # glass_material.dart:26-52
     out, r, t = [], _clamp(kr), _clamp(kt)
     if not _black(r):
@@ -299,6 +393,7 @@ def glass_lobes(kr=1.0, kt=1.0, index=1.5) -> list:  # glass_material.dart:26-52
     return out
 
 
+@_folds_textures
 def plastic_lobes(kd=0.25, ks=0.25, roughness=0.1) -> list:  # plastic_material.dart:26-53
     out, d, sp = [], _clamp(kd), _clamp(ks)
     if not _black(d):
@@ -312,6 +407,7 @@ def _f32(a):
     return np.asarray(a, np.float64).astype(np.float32)
 
 
+@_folds_textures
 def shinymetal_lobes(ks=1.0, kr=1.0, roughness=0.1) -> list:  # shiny_metal_material.dart:42-76
     out = []
 
@@ -327,6 +423,7 @@ def shinymetal_lobes(ks=1.0, kr=1.0, roughness=0.1) -> list:  # shiny_metal_mate
     return out
 
 
+@_folds_textures
 def translucent_lobes(kd=0.25, ks=0.25, reflect=0.5, transmit=0.5, roughness=0.1) -> list:  # translucent_material.dart:47-90
     out, r, t = [], _clamp(reflect), _clamp(transmit)
     if _black(r) and _black(t):
@@ -348,7 +445,7 @@ def translucent_lobes(kd=0.25, ks=0.25, reflect=0.5, transmit=0.5, roughness=0.1
 
 
 def mix_lobes(lobes1, lobes2, amount=0.5) -> list:  # mix_material.dart:36-50
-    s1 = _clamp(amount)
+    s1 = _clamp(fold_texture(amount))
     s2 = np.clip(_f32(1.0 - s1.astype(np.float64)).astype(np.float64), 0.0, np.inf).astype(np.float32)
     out = []
     for ll, sc in ((lobes1, s1), (lobes2, s2)):
@@ -364,6 +461,7 @@ def mix_lobes(lobes1, lobes2, amount=0.5) -> list:  # mix_material.dart:36-50
     return out
 
 
+@_folds_textures
 def substrate_lobes(kd=0.5, ks=0.5, uroughness=0.1, vroughness=0.1) -> list:  # substrate_material.dart:46-68
     d, sp = _clamp(kd), _clamp(ks)
     if _black(d) and _black(sp):
@@ -373,10 +471,12 @@ def substrate_lobes(kd=0.5, ks=0.5, uroughness=0.1, vroughness=0.1) -> list:  # 
     return [_lobe(LOBE_FRESNEL_BLEND, d, eta=sp, param=_blinn_exponent(uroughness), ei=_blinn_exponent(vroughness))]
 
 
+@_folds_textures
 def metal_lobes(eta, k, roughness=0.01) -> list:  # metal_material.dart:26-46 (eta / k given as RGB)
     return [_lobe(LOBE_MICROFACET_BLINN, 1.0, FRESNEL_CONDUCTOR, eta=eta, k=k, param=_blinn_exponent(roughness))]
 
 
+@_folds_textures
 def uber_lobes(kd=0.25, ks=0.25, kr=0.0, kt=0.0, roughness=0.1, index=1.5, opacity=1.0) -> list:  # uber_material.dart:27-75
     out, op = [], _clamp(opacity)
     if not bool(np.all(op == 1.0)):
@@ -413,7 +513,8 @@ class SceneBuilder:
         self._nverts = 0
 
     def material(self, kd, sigma=0.0) -> int:
-        self.materials.append((0, tuple(float(v) for v in kd), float(sigma)))
+        kd, sigma = fold_texture(kd), fold_texture(sigma)  # constant Kd / sigma textures (matte_material.dart:41-65)
+        self.materials.append((0, tuple(float(v) for v in np.broadcast_to(np.asarray(kd, np.float64), (3,))), float(sigma)))
         return len(self.materials) - 1
 
     def material_lobes(self, lobes: list) -> int:
