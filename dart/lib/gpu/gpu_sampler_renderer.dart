@@ -346,7 +346,11 @@ class GpuSamplerRenderer extends Renderer {
     for (int i = 0; i < tris.length; ++i) {
       final Triangle t = tris[i].shape;
       if (t.mesh.alphaTexture != null) {
-        throw new GpuUnsupported('triangle meshes with alpha textures');
+        // Triangle.intersect / intersectP drop a hit only where alpha evaluates to exactly 0 (triangle.dart:139-151,196-237):
+        // a constant-valued alpha other than 0 changes nothing
+        if (_constF(t.mesh.alphaTexture, 'a mesh alpha texture') == 0.0) {
+          throw new GpuUnsupported('a triangle mesh whose alpha texture is 0 everywhere');
+        }
       }
       // per-vertex N / S / uv (triangle_mesh.dart:24-28) travel as they are stored: object space; drt_set_mesh_shading
       final TriangleMesh mesh = t.mesh;

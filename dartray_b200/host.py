@@ -591,11 +591,20 @@ class SceneBuilder:
         self.lights.append(dict(kind=0, L=tuple(L), pos=(0, 0, 0), nsamples=nsamples, shapes=[]))
         return len(self.lights) - 1
 
-    def mesh(self, P, idx, material=0, o2w=None, area_light=None, nsamples=1, reverse=False, N=None, S=None, uv=None) -> int:
+    def mesh(self, P, idx, material=0, o2w=None, area_light=None, nsamples=1, reverse=False, N=None, S=None, uv=None, alpha=None) -> int:
         """Shape "trianglemesh": vertices go to world space at construction (triangle_mesh.dart:24-37).
         `area_light` = emitted radiance: one DiffuseAreaLight per shape (dartray.dart:378-467).
         N / S / uv: the per-vertex "normal N" / "vector S" / "float uv" parameters (triangle_mesh.dart:88-140), kept in object
-        space as the reference keeps them; Triangle.getShadingGeometry transforms them per hit (triangle.dart:271-364)."""
+        space as the reference keeps them; Triangle.getShadingGeometry transforms them per hit (triangle.dart:271-364).
+        alpha: the mesh's float "alpha" texture (triangle_mesh.dart:176-192).  Triangle.intersect / intersectP drop a hit only where
+        it evaluates to exactly 0 (triangle.dart:139-151,196-237), so a constant-valued texture other than 0 changes nothing and is
+        accepted; a mesh that is transparent everywhere, or an alpha that reads the hit point, is not on the GPU path."""
+        if alpha is not None:
+            a = fold_texture(alpha)
+            if not _is_num(a):
+                raise ValueError("alpha is a float texture (triangle_mesh.dart:176-192)")
+            if a == 0.0:
+                raise GpuUnsupported("a triangle mesh whose alpha texture is 0 everywhere")
         P = np.asarray(P, dtype=np.float32).reshape(-1, 3)
         nv = P.shape[0]
         m2w = np.eye(4, dtype=np.float32) if o2w is None else np.asarray(o2w, dtype=np.float32).reshape(4, 4)

@@ -82,3 +82,20 @@ def test_textures_that_read_the_hit_are_refused():
         H.ScaleTexture(H.OpaqueTexture("checkerboard"), 0.5).evaluate()
     with pytest.raises(ValueError):
         H.MixTexture(0.1, (0.1, 0.2, 0.3), 0.5).evaluate()
+
+
+def test_constant_mesh_alpha_other_than_zero_is_accepted():
+    # Triangle.intersect drops a hit only where alpha == 0.0 (triangle.dart:139-151): a constant 0.5 changes nothing
+    P, idx = [(0, 0, 0), (1, 0, 0), (0, 1, 0)], [(0, 1, 2)]
+    a, b = H.SceneBuilder(), H.SceneBuilder()
+    a.material((0.5, 0.5, 0.5)); b.material((0.5, 0.5, 0.5))
+    a.mesh(P, idx)
+    b.mesh(P, idx, alpha=H.ScaleTexture(0.5, H.ConstantTexture(1.0)))
+    aa, bb = a.arrays(), b.arrays()
+    assert aa.keys() == bb.keys()
+    for k in aa:
+        assert np.array_equal(np.asarray(aa[k]), np.asarray(bb[k])), k
+    with pytest.raises(H.GpuUnsupported):
+        H.SceneBuilder().mesh(P, idx, alpha=H.MixTexture(0.0, 1.0, 0.0))  # folds to 0: transparent everywhere
+    with pytest.raises(H.GpuUnsupported):
+        H.SceneBuilder().mesh(P, idx, alpha=H.OpaqueTexture("imagemap"))
