@@ -474,12 +474,25 @@ static __device__ __forceinline__ uint32_t shadeKey(const RenderScene& rs, const
   const int prim = __float_as_int(wf.extHit[q].w);
   return prim < 0 ? (uint32_t)rs.nMaterials : (uint32_t)primMaterial(rs, (uint32_t)prim);
 }
+// Both passes aggregate per warp first (__match_any_sync on the key): a scene has a handful of materials, so per-entry atomics
+// would all land on the same few counters.  AGG = false keeps the per-entry atomics (DRT_SORT_PLAIN_ATOMICS, for A/B runs).
+template <bool AGG>
 __global__ void __launch_bounds__(256) matHistKernel(RenderScene rs, Wavefront wf, int cur) {
   __shared__ uint32_t h[DRT_SORT_MAX_MATERIALS + 1];
-  const uint32_t n = wf.counts[cur], bins = (uint32_t)rs.nMaterials + 1;
+  const uint32_t n = wf.counts[cur], bins = (uint32_t)rs.nMaterials + 1, lane = threadIdx.x & 31u;
   for (uint32_t b = threadIdx.x; b < bins; b += blockDim.x) h[b] = 0;
   __syncthreads();
-  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) atomicAdd(&h[shadeKey(rs, wf, q)], 1u);
+  for (uint32_t q0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); q0 < n; q0 += gridDim.x * blockDim.x) {  // warp-uniform trip count
+    const uint32_t q = q0 + lane;
+    const bool v = q < n;
+    const uint32_t key = v ? shadeKey(rs, wf, q) : 0xffffffffu;
+    if (AGG) {
+      const uint32_t peers = __match_any_sync(FULL, key);
+      if (v && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&h[key], (uint32_t)__popc(peers));
+    } else if (v) {
+      atomicAdd(&h[key], 1u);
+    }
+  }
   __syncthreads();
   for (uint32_t b = threadIdx.x; b < bins; b += blockDim.x)
     if (h[b]) atomicAdd(&wf.matHist[b], h[b]);
@@ -492,10 +505,24 @@ __global__ void matScanKernel(RenderScene rs, Wavefront wf) {  // one thread: at
     acc += c;
   }
 }
+template <bool AGG>
 __global__ void __launch_bounds__(256) matScatterKernel(RenderScene rs, Wavefront wf, int cur) {
-  const uint32_t n = wf.counts[cur];
-  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
-    wf.shadeOrder[atomicAdd(&wf.matHist[shadeKey(rs, wf, q)], 1u)] = q;
+  const uint32_t n = wf.counts[cur], lane = threadIdx.x & 31u;
+  for (uint32_t q0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); q0 < n; q0 += gridDim.x * blockDim.x) {
+    const uint32_t q = q0 + lane;
+    const bool v = q < n;
+    const uint32_t key = v ? shadeKey(rs, wf, q) : 0xffffffffu;
+    if (AGG) {  // one atomic per (warp, material): the leader reserves the run, the lanes take consecutive places in lane order
+      const uint32_t peers = __match_any_sync(FULL, key);
+      const int leader = __ffs(peers) - 1;
+      uint32_t base = 0;
+      if (v && (int)lane == leader) base = atomicAdd(&wf.matHist[key], (uint32_t)__popc(peers));
+      base = __shfl_sync(FULL, base, leader);
+      if (v) wf.shadeOrder[base + __popc(peers & ((1u << lane) - 1u))] = q;
+    } else if (v) {
+      wf.shadeOrder[atomicAdd(&wf.matHist[key], 1u)] = q;
+    }
+  }
 }
 
 // EXTRA: see hitGeometry (shade_device.cuh).  SORTED: work item i of the launch is queue entry shadeOrder[i].
@@ -1155,9 +1182,12 @@ cudaError_t launchShadePath(const RenderParams& rp, const RenderScene& rs, const
       cudaError_t e = cudaMemsetAsync(wf.matHist, 0, (size_t)(rs.nMaterials + 1) * sizeof(uint32_t), st);
       if (e != cudaSuccess) return e;
       const int g2 = gridFor(wf.cap, 256, numSMs, 4);
-      matHistKernel<<<g2, 256, 0, st>>>(rs, wf, cur);
+      static const bool plainAtomics = std::getenv("DRT_SORT_PLAIN_ATOMICS") != nullptr;
+      if (plainAtomics) matHistKernel<false><<<g2, 256, 0, st>>>(rs, wf, cur);
+      else matHistKernel<true><<<g2, 256, 0, st>>>(rs, wf, cur);
       matScanKernel<<<1, 1, 0, st>>>(rs, wf);
-      matScatterKernel<<<g2, 256, 0, st>>>(rs, wf, cur);
+      if (plainAtomics) matScatterKernel<false><<<g2, 256, 0, st>>>(rs, wf, cur);
+      else matScatterKernel<true><<<g2, 256, 0, st>>>(rs, wf, cur);
     }
     shadePathKernel<true, DRT_EXTRA != 0><<<grid, 128, 0, st>>>(rp, rs, wf, bounce, cur, rc, sorted);
   } else {
