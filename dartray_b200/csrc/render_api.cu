@@ -604,11 +604,19 @@ static int directStage(drt_ctx* c, RenderState* r, int cur, bool weighted) {
   if (rs.nLights <= 0) return DRT_OK;
   const bool one = p.strategy != 0;
   const int nL = one ? 1 : rs.nLights;
+  // BxDF-list scenes: one material sort of the queue serves every (light, sample) launch below (64 -> 46.5 ms on cornell_materials,
+  // 1080p x 16 spp; DRT_NO_DIRECT_SORT keeps the queue order for A/B runs)
+  int sorted = 0;
+  static const bool directSort = std::getenv("DRT_NO_DIRECT_SORT") == nullptr;
+  if (directSort) {
+    CK(c, STAGE(launchMaterialSort)(rs, wf, cur, sms, &sorted, st));
+    if (sorted) c->launches += 3;
+  }
   for (int li = 0; li < nL; ++li) {
     const int nS = one ? 1 : r->direct[li].nSamples;
     for (int j = 0; j < nS; ++j) {
       CK(c, STAGE(launchResetCounts)(wf, (1u << Q_SHADOW) | (1u << Q_MIS), st));
-      CK(c, STAGE(launchDirectSample)(p, rs, wf, one ? -1 : li, j, cur, rc, sms, st));
+      CK(c, STAGE(launchDirectSample)(p, rs, wf, one ? -1 : li, j, cur, rc, sorted, sms, st));
       RK(traceQueue(c, true, wf.shO, wf.shD, wf.shRange, wf.counts + Q_SHADOW, wf.shOcc, nullptr, st));
       RK(traceQueue(c, false, wf.misO, wf.misD, wf.misRange, wf.counts + Q_MIS, wf.misHit, wf.misT, st));
       int mode = RESOLVE_DIRECT | (weighted ? RESOLVE_WEIGHTED : 0);
@@ -642,9 +650,15 @@ static int whittedStage(drt_ctx* c, RenderState* r, int cur, bool weighted) {
   RenderCounters* rc = r->dCounters.p;
   CK(c, STAGE(launchWhittedSetup)(p, rs, wf, cur, weighted ? 1 : 0, sms, st));
   c->launches++;
+  int sorted = 0;  // material order measured no gain here (33.7 vs 34.1 ms, cornell_materials 1080p x 16 spp): off unless DRT_WHITTED_SORT is set
+  static const bool whittedSort = std::getenv("DRT_WHITTED_SORT") != nullptr;
+  if (whittedSort && rs.nLights > 0) {
+    CK(c, STAGE(launchMaterialSort)(rs, wf, cur, sms, &sorted, st));
+    if (sorted) c->launches += 3;
+  }
   for (int li = 0; li < rs.nLights; ++li) {
     CK(c, STAGE(launchResetCounts)(wf, (1u << Q_SHADOW) | (1u << Q_MIS), st));
-    CK(c, STAGE(launchWhittedSample)(p, rs, wf, li, cur, rc, sms, st));
+    CK(c, STAGE(launchWhittedSample)(p, rs, wf, li, cur, rc, sorted, sms, st));
     RK(traceQueue(c, true, wf.shO, wf.shD, wf.shRange, wf.counts + Q_SHADOW, wf.shOcc, nullptr, st));
     CK(c, STAGE(launchResolveDirect)(p, rs, wf, cur, RESOLVE_DIRECT | RESOLVE_WHITTED | (weighted ? RESOLVE_WEIGHTED : 0), 1, sms, st));
     c->launches += 3;

@@ -854,15 +854,17 @@ __global__ void __launch_bounds__(128) whittedSetupKernel(RenderParams rp, Rende
 
 template <bool GENERAL>
 __global__ void __launch_bounds__(128) whittedSampleKernel(RenderParams rp, RenderScene rs, Wavefront wf, int light, int cur,
-                                                           RenderCounters* rc) {
+                                                           RenderCounters* rc, int sortedOrder) {
   const uint32_t n = wf.counts[cur];
   unsigned long long nShadow = 0;
+  const bool sorted = GENERAL && sortedOrder != 0;
   for (uint32_t q0 = blockIdx.x * blockDim.x; q0 < n; q0 += gridDim.x * blockDim.x) {
-    const uint32_t q = q0 + threadIdx.x;
+    uint32_t q = q0 + threadIdx.x;
     bool valid = q < n;
     uint32_t slot = 0;
     int prim = -1;
     if (valid) {
+      if (sorted) q = wf.shadeOrder[q];
       slot = wf.extSlot[cur][q];
       prim = __float_as_int(wf.extHit[q].w);
       valid = prim >= 0;
@@ -955,15 +957,17 @@ __global__ void __launch_bounds__(128) specularStepKernel(RenderParams rp, Rende
 
 template <bool GENERAL>
 __global__ void __launch_bounds__(128) directSampleKernel(RenderParams rp, RenderScene rs, Wavefront wf, int light, int j, int cur,
-                                                          RenderCounters* rc) {
+                                                          RenderCounters* rc, int sortedOrder) {
   const uint32_t n = wf.counts[cur];
   unsigned long long nShadow = 0, nClosest = 0;
+  const bool sorted = GENERAL && sortedOrder != 0;
   for (uint32_t q0 = blockIdx.x * blockDim.x; q0 < n; q0 += gridDim.x * blockDim.x) {
-    const uint32_t q = q0 + threadIdx.x;
+    uint32_t q = q0 + threadIdx.x;
     bool valid = q < n;
     uint32_t slot = 0;
     int prim = -1;
     if (valid) {
+      if (sorted) q = wf.shadeOrder[q];
       slot = wf.extSlot[cur][q];
       prim = __float_as_int(wf.extHit[q].w);
       valid = prim >= 0;
@@ -1169,26 +1173,34 @@ cudaError_t launchResetCounts(const Wavefront& wf, unsigned mask, cudaStream_t s
   return cudaGetLastError();
 }
 
+// Counting sort of extension queue `cur` by material into wf.shadeOrder; *sorted = 0 when the scene has one material or more than
+// the sort's bins (the shading kernels then walk the queue as it is).  DRT_NO_MATERIAL_SORT turns it off.
+cudaError_t launchMaterialSort(const RenderScene& rs, const Wavefront& wf, int cur, int numSMs, int* sorted, cudaStream_t st) {
+  static const bool sortOff = std::getenv("DRT_NO_MATERIAL_SORT") != nullptr;
+  *sorted = (!sortOff && rs.general && rs.nMaterials > 1 && rs.nMaterials <= DRT_SORT_MAX_MATERIALS) ? 1 : 0;
+  if (!*sorted) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(wf.matHist, 0, (size_t)(rs.nMaterials + 1) * sizeof(uint32_t), st);
+  if (e != cudaSuccess) return e;
+  const int g2 = gridFor(wf.cap, 256, numSMs, 4);
+  static const bool plainAtomics = std::getenv("DRT_SORT_PLAIN_ATOMICS") != nullptr;
+  if (plainAtomics) matHistKernel<false><<<g2, 256, 0, st>>>(rs, wf, cur);
+  else matHistKernel<true><<<g2, 256, 0, st>>>(rs, wf, cur);
+  matScanKernel<<<1, 1, 0, st>>>(rs, wf);
+  if (plainAtomics) matScatterKernel<false><<<g2, 256, 0, st>>>(rs, wf, cur);
+  else matScatterKernel<true><<<g2, 256, 0, st>>>(rs, wf, cur);
+  return cudaGetLastError();
+}
+
 cudaError_t launchShadePath(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int bounce, int cur,
                             RenderCounters* rc, int numSMs, cudaStream_t st) {
   const int grid = gridFor(wf.cap, 128, numSMs, 8);
   if (rs.general) {
     // material-coherent warps: sort the queue by material first (skipped for a single material or more than the sort's bins)
-    // (measured: the same order makes directSampleKernel slower, 64 -> 74 ms on cornell_materials at 16 spp — that kernel is not
-    // fetch-bound and pays for the scattered queue reads — so only the path vertex kernel uses it; DRT_NO_MATERIAL_SORT turns it off)
-    static const bool sortOff = std::getenv("DRT_NO_MATERIAL_SORT") != nullptr;
-    const int sorted = (!sortOff && rs.nMaterials > 1 && rs.nMaterials <= DRT_SORT_MAX_MATERIALS) ? 1 : 0;
-    if (sorted) {
-      cudaError_t e = cudaMemsetAsync(wf.matHist, 0, (size_t)(rs.nMaterials + 1) * sizeof(uint32_t), st);
-      if (e != cudaSuccess) return e;
-      const int g2 = gridFor(wf.cap, 256, numSMs, 4);
-      static const bool plainAtomics = std::getenv("DRT_SORT_PLAIN_ATOMICS") != nullptr;
-      if (plainAtomics) matHistKernel<false><<<g2, 256, 0, st>>>(rs, wf, cur);
-      else matHistKernel<true><<<g2, 256, 0, st>>>(rs, wf, cur);
-      matScanKernel<<<1, 1, 0, st>>>(rs, wf);
-      if (plainAtomics) matScatterKernel<false><<<g2, 256, 0, st>>>(rs, wf, cur);
-      else matScatterKernel<true><<<g2, 256, 0, st>>>(rs, wf, cur);
-    }
+    // (directSampleKernel walks the same order since the sort's atomics are warp-aggregated: 64 -> 46.5 ms on cornell_materials at
+    // 16 spp; with one atomic per entry the sort cost more than it saved there, 64 -> 74 ms)
+    int sorted = 0;
+    cudaError_t e = launchMaterialSort(rs, wf, cur, numSMs, &sorted, st);
+    if (e != cudaSuccess) return e;
     shadePathKernel<true, DRT_EXTRA != 0><<<grid, 128, 0, st>>>(rp, rs, wf, bounce, cur, rc, sorted);
   } else {
     shadePathKernel<false, DRT_EXTRA != 0><<<grid, 128, 0, st>>>(rp, rs, wf, bounce, cur, rc, 0);
@@ -1239,9 +1251,9 @@ cudaError_t launchDirectSetup(const RenderParams& rp, const RenderScene& rs, con
 }
 
 cudaError_t launchDirectSample(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int light, int j, int cur,
-                               RenderCounters* rc, int numSMs, cudaStream_t st) {
-  if (rs.general) directSampleKernel<true><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, j, cur, rc);
-  else directSampleKernel<false><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, j, cur, rc);
+                               RenderCounters* rc, int sorted, int numSMs, cudaStream_t st) {
+  if (rs.general) directSampleKernel<true><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, j, cur, rc, sorted);
+  else directSampleKernel<false><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, j, cur, rc, 0);
   return cudaGetLastError();
 }
 
@@ -1252,9 +1264,9 @@ cudaError_t launchWhittedSetup(const RenderParams& rp, const RenderScene& rs, co
 }
 
 cudaError_t launchWhittedSample(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int light, int cur,
-                                RenderCounters* rc, int numSMs, cudaStream_t st) {
-  if (rs.general) whittedSampleKernel<true><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, cur, rc);
-  else whittedSampleKernel<false><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, cur, rc);
+                                RenderCounters* rc, int sorted, int numSMs, cudaStream_t st) {
+  if (rs.general) whittedSampleKernel<true><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, cur, rc, sorted);
+  else whittedSampleKernel<false><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, cur, rc, 0);
   return cudaGetLastError();
 }
 

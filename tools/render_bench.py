@@ -49,6 +49,8 @@ def main():
         sb, cam = scenes.soup_render_scene(nsph)
         sampler = host.Sampler(kind=host.SAMPLER_LD, spp=spp)
         integ = host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=5)
+    if os.environ.get("INTEG") == "whitted":
+        integ = host.Integrator(kind=host.INTEGRATOR_WHITTED, maxdepth=3)
     if os.environ.get("INTEG") == "direct":  # the same scene through the directlighting integrator (strategy all)
         integ = host.Integrator(kind=host.INTEGRATOR_DIRECT, maxdepth=3)
     ctx = capi.Context(0)
