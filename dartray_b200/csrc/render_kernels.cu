@@ -1053,27 +1053,62 @@ __global__ void __launch_bounds__(128) adaptiveDecideKernel(RenderParams rp, Wav
   }
 }
 
+// WARPSUM: when all 32 samples of a warp fall on ONE pixel (the usual case: a pixel's samples are consecutive slots and a box filter
+// of half a pixel covers one pixel), the warp adds its terms with a butterfly and lane 0 issues the four atomics instead of 128 on the
+// same four addresses.  The terms are float32 values times the filter weight, summed in f64 — exact for unit weights — so the film
+// does not depend on the grouping.
+template <bool WARPSUM>
 __global__ void __launch_bounds__(256) filmKernel(RenderParams rp, Wavefront wf, uint32_t nSlots, int skipFlagged, RenderCounters* rc) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nSlots) return;
-  if (skipFlagged && wf.adaptFlag[s / (uint32_t)rp.nPixelSamples]) return;  // adaptive: reportResults returned false (:148-151)
-  if ((rp.samplerKind == 3 || rp.samplerKind == 5) && isnan(wf.camXY[s].x)) return;  // halton / bestcandidate: a rejected index
-  Spec L = ld3(wf.L, wf.cap, s);
-  const double lum = Luminance(L);
-  if (isnan(L.r) || isnan(L.g) || isnan(L.b) || lum < -1e-5 || isinf(lum)) {
-    L = Spec{0.f, 0.f, 0.f};
-    atomicAdd(&rc->zeroedSamples, 1ull);
+  bool live = s < nSlots;
+  if (live && skipFlagged && wf.adaptFlag[s / (uint32_t)rp.nPixelSamples]) live = false;  // adaptive: reportResults returned false (:148-151)
+  if (live && (rp.samplerKind == 3 || rp.samplerKind == 5) && isnan(wf.camXY[s].x)) live = false;  // halton / bestcandidate: a rejected index
+  int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
+  float X = 0.f, Y = 0.f, Z = 0.f;
+  double dimageX = 0.0, dimageY = 0.0;
+  if (live) {
+    Spec L = ld3(wf.L, wf.cap, s);
+    const double lum = Luminance(L);
+    if (isnan(L.r) || isnan(L.g) || isnan(L.b) || lum < -1e-5 || isinf(lum)) {
+      L = Spec{0.f, 0.f, 0.f};
+      atomicAdd(&rc->zeroedSamples, 1ull);
+    }
+    const double2 im = wf.camXY[s];
+    dimageX = im.x - 0.5; dimageY = im.y - 0.5;
+    x0 = (int)ceil(dimageX - rp.xWidth); x1 = (int)floor(dimageX + rp.xWidth);
+    y0 = (int)ceil(dimageY - rp.yWidth); y1 = (int)floor(dimageY + rp.yWidth);
+    x0 = max(x0, rp.left); x1 = min(x1, rp.left + rp.width - 1);
+    y0 = max(y0, rp.top); y1 = min(y1, rp.top + rp.height - 1);
+    if ((x1 - x0) < 0 || (y1 - y0) < 0) live = false;
+    const double r = L.r, g = L.g, b = L.b;  // RGBColor.toXYZ -> XYZColor (float32), spectrum.dart:293-297
+    X = (float)(0.412453 * r + 0.357580 * g + 0.180423 * b); Y = (float)(0.212671 * r + 0.715160 * g + 0.072169 * b);
+    Z = (float)(0.019334 * r + 0.119193 * g + 0.950227 * b);
   }
-  const double2 im = wf.camXY[s];
-  const double dimageX = im.x - 0.5, dimageY = im.y - 0.5;
-  int x0 = (int)ceil(dimageX - rp.xWidth), x1 = (int)floor(dimageX + rp.xWidth);
-  int y0 = (int)ceil(dimageY - rp.yWidth), y1 = (int)floor(dimageY + rp.yWidth);
-  x0 = max(x0, rp.left); x1 = min(x1, rp.left + rp.width - 1);
-  y0 = max(y0, rp.top); y1 = min(y1, rp.top + rp.height - 1);
-  if ((x1 - x0) < 0 || (y1 - y0) < 0) return;
-  const double r = L.r, g = L.g, b = L.b;  // RGBColor.toXYZ -> XYZColor (float32), spectrum.dart:293-297
-  const float X = (float)(0.412453 * r + 0.357580 * g + 0.180423 * b), Y = (float)(0.212671 * r + 0.715160 * g + 0.072169 * b),
-              Z = (float)(0.019334 * r + 0.119193 * g + 0.950227 * b);
+  if (WARPSUM) {
+    // one pixel for the whole warp?  (every lane live, a one-pixel footprint, the same pixel as lane 0)
+    const int px0 = __shfl_sync(FULL, x0, 0), py0 = __shfl_sync(FULL, y0, 0);
+    const bool same = live && x0 == x1 && y0 == y1 && x0 == px0 && y0 == py0;
+    if (__all_sync(FULL, same)) {
+      const double fy = fabs((y0 - dimageY) * rp.invYWidth * 16), fx = fabs((x0 - dimageX) * rp.invXWidth * 16);
+      const double wt = rp.filterTable[min((int)floor(fy), 15) * 16 + min((int)floor(fx), 15)];
+      double a0 = wt * X, a1 = wt * Y, a2 = wt * Z, a3 = wt;
+      for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(FULL, a0, o);
+        a1 += __shfl_xor_sync(FULL, a1, o);
+        a2 += __shfl_xor_sync(FULL, a2, o);
+        a3 += __shfl_xor_sync(FULL, a3, o);
+      }
+      if ((threadIdx.x & 31) == 0) {
+        double* px = rp.film + 4 * ((size_t)(y0 - rp.top) * rp.width + (x0 - rp.left));
+        atomicAdd(px + 0, a0);
+        atomicAdd(px + 1, a1);
+        atomicAdd(px + 2, a2);
+        atomicAdd(px + 3, a3);
+      }
+      return;
+    }
+  }
+  if (!live) return;
   for (int y = y0; y <= y1; ++y) {
     const double fy = fabs((y - dimageY) * rp.invYWidth * 16);
     const int iy = min((int)floor(fy), 15);
@@ -1291,7 +1326,9 @@ cudaError_t launchAdaptiveDecide(const RenderParams& rp, const Wavefront& wf, co
 
 cudaError_t launchFilm(const RenderParams& rp, const Wavefront& wf, uint32_t nSlots, int skipFlagged, RenderCounters* rc, cudaStream_t st) {
   if (nSlots == 0) return cudaSuccess;
-  filmKernel<<<(nSlots + 255) / 256, 256, 0, st>>>(rp, wf, nSlots, skipFlagged, rc);
+  static const bool perSample = std::getenv("DRT_FILM_PLAIN_ATOMICS") != nullptr;  // A/B knob: four atomics per (sample, pixel)
+  if (perSample) filmKernel<false><<<(nSlots + 255) / 256, 256, 0, st>>>(rp, wf, nSlots, skipFlagged, rc);
+  else filmKernel<true><<<(nSlots + 255) / 256, 256, 0, st>>>(rp, wf, nSlots, skipFlagged, rc);
   return cudaGetLastError();
 }
 
