@@ -1,6 +1,12 @@
-"""In-tree build of libdartray_gpu.so for sm_100a (nvcc cross-compiles without a GPU)."""
+"""In-tree build of libdartray_gpu.so for sm_100a (nvcc cross-compiles without a GPU).
+
+Every translation unit is compiled to an object file on its own (in parallel, only when it or a header
+changed) and the objects are linked into the shared library; no relocatable device code is needed, each
+.cu launches only its own kernels.
+"""
 from __future__ import annotations
 
+import concurrent.futures
 import os
 import shutil
 import subprocess
@@ -8,42 +14,88 @@ import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
+OBJ = os.path.join(PKG, "_obj")
 LIB = os.path.join(PKG, "libdartray_gpu.so")
 
-NVCC_FLAGS = [
+COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     # Dart doubles never contract a*b+c; the kernels call fma()/fmaf() explicitly where it is safe.
     "-fmad=false",
     "-Xcompiler", "-fPIC,-pthread,-ffp-contract=off",
-    "-shared", "-cudart", "static",
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-Xcompiler", "-pthread"]
 
 
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp")))
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB):
+def _headers():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".inc"))]
+    return hs + [os.path.join(PKG, "..", "include", "drt.h"), __file__]
+
+
+def _obj_of(src: str) -> str:
+    return os.path.join(OBJ, os.path.basename(src) + ".o")
+
+
+def _stale_obj(src: str, hdr_time: float, extra_key: str) -> bool:
+    o = _obj_of(src)
+    if not os.path.exists(o):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(PKG, "..", "include", "drt.h"), __file__]
-    return any(os.path.getmtime(d) > t for d in deps)
+    key = o + ".flags"
+    if not os.path.exists(key) or open(key).read() != extra_key:
+        return True
+    t = os.path.getmtime(o)
+    # render_kernels_plain.cu includes render_kernels.cu
+    deps = [src] + ([os.path.join(CSRC, "render_kernels.cu")] if src.endswith("render_kernels_plain.cu") else [])
+    return any(os.path.getmtime(d) > t for d in deps) or hdr_time > t
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
-        return LIB
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
-    return LIB
+def build(force: bool = False, verbose: bool = False, defines: tuple = (), lib: str = LIB) -> str:
+    """Builds (if stale) and returns the path of the shared library.  `defines` (e.g. ("DRT_MIN_BLOCKS=4",)) and a
+    different `lib` path give A/B variants for one gpurun call; objects of variant builds live in their own directory."""
+    global OBJ
+    extra_key = " ".join(sorted(defines))
+    obj_dir = OBJ if not defines else OBJ + "_" + "".join(ch if ch.isalnum() else "_" for ch in extra_key)
+    saved, OBJ = OBJ, obj_dir
+    try:
+        os.makedirs(OBJ, exist_ok=True)
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        hdr_time = max(os.path.getmtime(h) for h in _headers())
+        todo = [s for s in sources() if force or _stale_obj(s, hdr_time, extra_key)]
+        dflags = [f"-D{d}" for d in defines]
+
+        def compile_one(src):
+            cmd = [nvcc] + COMPILE_FLAGS + dflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", _obj_of(src), src]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+            with open(_obj_of(src) + ".flags", "w") as f:
+                f.write(extra_key)
+            return res.stderr
+
+        if todo:
+            with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 4)) as ex:
+                for log in ex.map(compile_one, todo):
+                    if verbose:
+                        print(log)
+        objs = [_obj_of(s) for s in sources()]
+        if todo or not os.path.exists(lib) or any(os.path.getmtime(o) > os.path.getmtime(lib) for o in objs):
+            cmd = [nvcc] + LINK_FLAGS + ["-o", lib] + objs
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        return lib
+    finally:
+        OBJ = saved
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = tuple(a[2:] for a in sys.argv[1:] if a.startswith("-D"))
+    out = LIB
+    for a in sys.argv[1:]:
+        if a.startswith("--out="):
+            out = a[6:]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, lib=out))
