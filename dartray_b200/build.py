@@ -53,10 +53,16 @@ def _stale_obj(src: str, hdr_time: float, extra_key: str) -> bool:
     return any(os.path.getmtime(d) > t for d in deps) or hdr_time > t
 
 
-def build(force: bool = False, verbose: bool = False, defines: tuple = (), lib: str = LIB) -> str:
+def build(force: bool = False, verbose: bool = False, defines: tuple = (), lib: str = LIB, only: tuple = ()) -> str:
     """Builds (if stale) and returns the path of the shared library.  `defines` (e.g. ("DRT_MIN_BLOCKS=4",)) and a
-    different `lib` path give A/B variants for one gpurun call; objects of variant builds live in their own directory."""
+    different `lib` path give A/B variants for one gpurun call; objects of variant builds live in their own directory.
+    `only`: file names the defines apply to — the other objects are taken from the default build."""
     global OBJ
+    if defines and only:
+        build()  # the shared objects
+        base_objs = {s: _obj_of(s) for s in sources() if os.path.basename(s) not in only}
+    else:
+        base_objs = {}
     extra_key = " ".join(sorted(defines))
     obj_dir = OBJ if not defines else OBJ + "_" + "".join(ch if ch.isalnum() else "_" for ch in extra_key)
     saved, OBJ = OBJ, obj_dir
@@ -64,7 +70,7 @@ def build(force: bool = False, verbose: bool = False, defines: tuple = (), lib: 
         os.makedirs(OBJ, exist_ok=True)
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
         hdr_time = max(os.path.getmtime(h) for h in _headers())
-        todo = [s for s in sources() if force or _stale_obj(s, hdr_time, extra_key)]
+        todo = [s for s in sources() if s not in base_objs and (force or _stale_obj(s, hdr_time, extra_key))]
         dflags = [f"-D{d}" for d in defines]
 
         def compile_one(src):
@@ -81,7 +87,7 @@ def build(force: bool = False, verbose: bool = False, defines: tuple = (), lib: 
                 for log in ex.map(compile_one, todo):
                     if verbose:
                         print(log)
-        objs = [_obj_of(s) for s in sources()]
+        objs = [base_objs.get(s) or _obj_of(s) for s in sources()]
         if todo or not os.path.exists(lib) or any(os.path.getmtime(o) > os.path.getmtime(lib) for o in objs):
             cmd = [nvcc] + LINK_FLAGS + ["-o", lib] + objs
             res = subprocess.run(cmd, capture_output=True, text=True)
@@ -98,4 +104,5 @@ if __name__ == "__main__":
     for a in sys.argv[1:]:
         if a.startswith("--out="):
             out = a[6:]
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, lib=out))
+    only = tuple(a[7:] for a in sys.argv[1:] if a.startswith("--only="))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, lib=out, only=only))

@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libdartray_gpu.so")
+# DRT_LIB_PATH: an A/B build of the same library (tools/trace_ab.sh); the default is the in-tree build
+LIB_PATH = os.environ.get("DRT_LIB_PATH") or os.path.join(PKG, "libdartray_gpu.so")
 
 DEVICE_NONE = -1
 SPLIT_MIDDLE, SPLIT_EQUAL_COUNTS, SPLIT_SAH = 0, 1, 2

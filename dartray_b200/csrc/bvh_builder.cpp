@@ -311,7 +311,65 @@ struct Flattener {
     }
     g.orderLut = (int32_t)lut;
     out->wide[my] = g;
+    if (out->wideQ.size() <= (size_t)my) out->wideQ.resize((size_t)my + 1);
+    if (!quantiseNode(g, &out->wideQ[my])) out->wideQOk = false;
     return my;
+  }
+
+  // GNode4 -> GNode4Q: an 8-bit grid per axis, origin just below the node's box, step 2^e.  Every inequality the
+  // traversal kernel relies on is CHECKED here with the decode expression the device uses (binary64, exact).
+  static bool quantiseNode(const GNode4& g, GNode4Q* q) {
+    std::memset(q, 0, sizeof(*q));
+    for (int k = 0; k < 4; ++k) q->ref[k] = g.ref[k];
+    q->orderLut = (uint32_t)g.orderLut;
+    const double guard = DRT_Q_GUARD;
+    uint32_t scaleHi[3] = {0, 0, 0};
+    uint8_t qb[3][4][2];
+    for (int a = 0; a < 3; ++a) {
+      double lo = std::numeric_limits<double>::infinity(), hi = -lo;
+      for (int k = 0; k < 4; ++k) {
+        if (g.ref[k] == DRT_REF_EMPTY) continue;
+        lo = std::min(lo, (double)g.box[k][2 * a]);
+        hi = std::max(hi, (double)g.box[k][2 * a + 1]);
+      }
+      if (!(lo <= hi) || !(std::fabs(lo) <= DRT_Q_COORD_MAX) || !(std::fabs(hi) <= DRT_Q_COORD_MAX)) return false;
+      int e = DRT_Q_EXP_MIN;
+      {
+        double ext = std::max(hi - lo, (double)std::fabs((float)lo) * 1.2e-7);
+        if (ext > 0.0) e = std::max(e, (int)std::ceil(std::log2(ext / 250.0)) - 1);
+      }
+      for (;; ++e) {
+        if (e > DRT_Q_EXP_MAX) return false;
+        const double s = std::ldexp(1.0, e);
+        float O = (float)(lo - 2.0 * guard * s);
+        while (!(lo - (double)O >= guard * s)) O = std::nextafterf(O, -std::numeric_limits<float>::infinity());
+        if (!(std::fabs((double)O) <= DRT_Q_COORD_MAX)) return false;
+        bool fits = true;
+        for (int k = 0; k < 4 && fits; ++k) {
+          if (g.ref[k] == DRT_REF_EMPTY) { qb[a][k][0] = 255; qb[a][k][1] = 0; continue; }
+          const double blo = g.box[k][2 * a], bhi = g.box[k][2 * a + 1];
+          double ql = std::floor((blo - (double)O) / s - guard), qh = std::ceil((bhi - (double)O) / s + guard);
+          while (ql >= 0.0 && !((double)O + ql * s <= blo - guard * s)) ql -= 1.0;
+          while (qh <= 255.0 && !((double)O + qh * s >= bhi + guard * s)) qh += 1.0;
+          if (ql < 0.0 || qh > 255.0) { fits = false; break; }
+          qb[a][k][0] = (uint8_t)ql;
+          qb[a][k][1] = (uint8_t)qh;
+        }
+        if (!fits) continue;
+        q->origin[a] = O;
+        const float sp = std::ldexp(1.0f, e + 15);  // what the kernel multiplies by: 1 + q * 2^-15 is a float32 built by PRMT
+        uint32_t bits;
+        std::memcpy(&bits, &sp, 4);
+        scaleHi[a] = bits >> 16;  // a power of two: the low mantissa half is zero
+        break;
+      }
+      for (int j = 0; j < 2; ++j)
+        q->q[a][j] = (uint32_t)qb[a][2 * j][0] | ((uint32_t)qb[a][2 * j][1] << 8) | ((uint32_t)qb[a][2 * j + 1][0] << 16) |
+                     ((uint32_t)qb[a][2 * j + 1][1] << 24);
+    }
+    q->scaleXY = scaleHi[0] | (scaleHi[1] << 16);
+    q->scaleZ = scaleHi[2];
+    return true;
   }
 
   // GPU layout: interior nodes in DFS order, leaf records in DFS (left-first) order.
@@ -387,6 +445,7 @@ bool buildBvh(const std::vector<PrimBounds>& bounds, const std::vector<uint32_t>
   out->nodes.reserve(arena.pool.size() / 2 + 1);
   out->rootRef = fl.emit(root, 0, refIndexOf);
   out->wide.reserve(arena.pool.size() / 3 + 1);
+  out->wideQ.reserve(arena.pool.size() / 3 + 1);
   out->wideRootRef = fl.emitWide(root, refIndexOf);
   std::memcpy(out->rootMin, arena.pool[root].box.lo, 12);
   std::memcpy(out->rootMax, arena.pool[root].box.hi, 12);

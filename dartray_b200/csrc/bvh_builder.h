@@ -26,6 +26,8 @@ struct RefNode {  // the reference's _LinearBVHNode numbering, for drt_bvh_expor
 struct BuiltBvh {
   std::vector<GNode> nodes;            // interior nodes, DFS order
   std::vector<GNode4> wide;            // two-level collapsed nodes, DFS order
+  std::vector<GNode4Q> wideQ;          // wide[i] with quantised boxes (same indices, same references)
+  bool wideQOk = true;                 // false: some node cannot be quantised (non-finite or > 2^62 coordinates)
   int32_t wideRootRef = 0;
   std::vector<uint32_t> leafPrimIds;   // primitive ids in GPU leaf order (DFS, left first)
   std::vector<uint32_t> leafCounts;    // for record i: count of its leaf if i is the leaf's first record, else 0

@@ -53,7 +53,7 @@ drt_ctx* drt_create(int device_id) {
   c->device = device_id;
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
-      (e = c->dCounters.ensure(1)) != cudaSuccess || (e = c->dNextRay.ensure(1 + drt_ctx::kPipe)) != cudaSuccess ||
+      (e = c->dCounters.ensure(1)) != cudaSuccess || (e = c->dNextRay.ensure(1 + drt_ctx::kPipe + drt_ctx::kRing)) != cudaSuccess ||
       (e = cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, device_id)) != cudaSuccess) {
     g_createError = cudaGetErrorString(e);
     delete c;
@@ -61,6 +61,8 @@ drt_ctx* drt_create(int device_id) {
   }
   for (int i = 0; i < drt_ctx::kPipe && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking);
   for (int i = 0; i < 2 * drt_ctx::kMaxChunks && e == cudaSuccess; ++i) e = cudaEventCreate(&c->chunkEv[i]);
+  for (int i = 0; i < drt_ctx::kRing && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ringEv[i], cudaEventDisableTiming);
+  c->fastV1 = std::getenv("DRT_TRACE_V1") != nullptr;
   if (e != cudaSuccess) {
     g_createError = cudaGetErrorString(e);
     drt_destroy(c);
@@ -74,13 +76,14 @@ void drt_destroy(drt_ctx* c) {
   if (c->device == DRT_DEVICE_NONE) { drtRenderStateDestroy(c); delete c; return; }
   cudaSetDevice(c->device);
   drtRenderStateDestroy(c);
-  c->dNodes.release(); c->dWide.release(); c->dPrims.release(); c->dSpheres.release(); c->dCounters.release(); c->dNextRay.release();
+  c->dNodes.release(); c->dWide.release(); c->dWideQ.release(); c->dPrims.release(); c->dSpheres.release(); c->dCounters.release(); c->dNextRay.release();
   c->dRayO.release(); c->dRayD.release(); c->dHits.release(); c->dOcc.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
   for (int i = 0; i < drt_ctx::kPipe; ++i) if (c->pipe[i]) cudaStreamDestroy(c->pipe[i]);
   for (int i = 0; i < 2 * drt_ctx::kMaxChunks; ++i) if (c->chunkEv[i]) cudaEventDestroy(c->chunkEv[i]);
+  for (int i = 0; i < drt_ctx::kRing; ++i) if (c->ringEv[i]) cudaEventDestroy(c->ringEv[i]);
   delete c;
 }
 
@@ -370,6 +373,12 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
   CK(c, c->dWide.ensure(std::max<size_t>(1, B.wide.size())));
   if (!B.wide.empty())
     CK(c, cudaMemcpy(c->dWide.p, B.wide.data(), B.wide.size() * sizeof(GNode4), cudaMemcpyHostToDevice));
+  c->wideQOk = B.wideQOk && B.wideQ.size() == B.wide.size();
+  if (c->wideQOk) {
+    CK(c, c->dWideQ.ensure(std::max<size_t>(1, B.wideQ.size())));
+    if (!B.wideQ.empty())
+      CK(c, cudaMemcpy(c->dWideQ.p, B.wideQ.data(), B.wideQ.size() * sizeof(GNode4Q), cudaMemcpyHostToDevice));
+  }
   CK(c, c->dPrims.ensure(prims.size()));
   CK(c, c->dSpheres.ensure(std::max<size_t>(1, gs.size())));
   if (!B.nodes.empty())
@@ -378,6 +387,7 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
   if (!gs.empty()) CK(c, cudaMemcpy(c->dSpheres.p, gs.data(), gs.size() * sizeof(GSphere), cudaMemcpyHostToDevice));
   c->ts.nodes = c->dNodes.p;
   c->ts.wide = c->dWide.p;
+  c->ts.wideQ = (c->wideQOk && !c->fastV1) ? c->dWideQ.p : nullptr;
   c->ts.wideRootRef = B.wideRootRef;
   c->ts.prims = c->dPrims.p;
   c->ts.spheres = c->dSpheres.p;
@@ -392,7 +402,8 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
   c->info.n_leaves = B.nLeaves;
   c->info.max_leaf_prims = B.maxLeafPrims;
   c->info.max_depth = B.maxDepth;
-  c->info.device_bytes = B.wide.size() * sizeof(GNode4) + prims.size() * sizeof(GPrim) + gs.size() * sizeof(GSphere);
+  c->info.device_bytes = (c->ts.wideQ ? B.wideQ.size() * sizeof(GNode4Q) : B.wide.size() * sizeof(GNode4)) +
+                         prims.size() * sizeof(GPrim) + gs.size() * sizeof(GSphere);
   c->info.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   c->built = true;
   return DRT_OK;
@@ -421,17 +432,30 @@ int drt_bvh_export(const drt_ctx* c, float* bounds, int32_t* offset, int32_t* np
 }
 
 
+// counterSlot < 0: a launch on a caller's stream (drt_trace_*_device) — takes the next slot of the counter ring.
 static int traceDevice(drt_ctx* c, bool any, const void* o, const void* d, uint64_t n, void* out, cudaStream_t st,
-                       int counterSlot = 0) {
+                       int counterSlot = -1) {
   if (c->device == DRT_DEVICE_NONE) return fail(c, DRT_E_NODEVICE, kNoDevice);
   if (!c->built) return fail(c, DRT_E_STATE, "drt_build_bvh must be called before tracing");
   if (n && (!o || !d || !out)) return fail(c, DRT_E_INVALID, "null ray or output buffer");
+  CK(c, cudaSetDevice(c->device));
+  int ring = -1;
+  if (counterSlot < 0) {
+    ring = c->ringNext;
+    c->ringNext = (c->ringNext + 1) % drt_ctx::kRing;
+    counterSlot = 1 + drt_ctx::kPipe + ring;
+    if (c->ringUsed[ring]) CK(c, cudaStreamWaitEvent(st, c->ringEv[ring], 0));  // the slot's previous launch, maybe on another stream
+  }
   if (c->counting || c->exactWalk) {
     // reference-walk kernel: the slab test in f64 for every node; also the counting variant
     if (c->counting) CK(c, cudaMemsetAsync(c->dCounters.p, 0, sizeof(DeviceCounters), st));
     CK(c, launchTrace(c->ts, any, c->counting, o, d, n, out, c->dCounters.p, st));
   } else {
     CK(c, launchTraceFast(c->ts, any, o, d, n, out, c->dNextRay.p + counterSlot, c->numSMs, st));
+  }
+  if (ring >= 0) {
+    CK(c, cudaEventRecord(c->ringEv[ring], st));
+    c->ringUsed[ring] = true;
   }
   if (n) c->launches++;
   return DRT_OK;
@@ -503,8 +527,11 @@ int drt_set_counting(drt_ctx* c, int enabled) {
 
 int drt_set_kernel_variant(drt_ctx* c, int variant) {
   if (!c) return DRT_E_INVALID;
-  if (variant != DRT_KERNEL_FAST && variant != DRT_KERNEL_EXACT_WALK) return fail(c, DRT_E_INVALID, "unknown kernel variant");
+  if (variant != DRT_KERNEL_FAST && variant != DRT_KERNEL_EXACT_WALK && variant != DRT_KERNEL_FAST_V1)
+    return fail(c, DRT_E_INVALID, "unknown kernel variant");
   c->exactWalk = variant == DRT_KERNEL_EXACT_WALK;
+  c->fastV1 = variant == DRT_KERNEL_FAST_V1 || std::getenv("DRT_TRACE_V1") != nullptr;
+  c->ts.wideQ = (c->built && c->wideQOk && !c->fastV1) ? c->dWideQ.p : nullptr;
   return DRT_OK;
 }
 

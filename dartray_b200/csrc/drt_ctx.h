@@ -66,10 +66,20 @@ struct drt_ctx {
   drt_bvh_info info{};
   DevBuf<GNode> dNodes;
   DevBuf<GNode4> dWide;
+  DevBuf<GNode4Q> dWideQ;
+  bool wideQOk = false;  // the scene's wide nodes could be quantised (bvh_builder.cpp quantiseNode)
+  bool fastV1 = false;   // DRT_KERNEL_FAST_V1 / env DRT_TRACE_V1: the float32-box kernel of trace_fast.cu
   DevBuf<GPrim> dPrims;
   DevBuf<GSphere> dSpheres;
   DevBuf<DeviceCounters> dCounters;
+  // work counters of the persistent traversal kernels: slot 0 = the renderer (ctx stream), 1..kPipe = the host-buffer
+  // pipeline streams, then a ring for drt_trace_*_device launches on caller streams (each launch takes the next slot and
+  // waits for the slot's previous user, so concurrent launches never share a counter)
+  static const int kRing = 32;
   DevBuf<unsigned long long> dNextRay;
+  cudaEvent_t ringEv[kRing] = {};
+  bool ringUsed[kRing] = {};
+  int ringNext = 0;
   int numSMs = 148;
   TraceScene ts{};
   // ray staging for host-buffer calls

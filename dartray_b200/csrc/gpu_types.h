@@ -55,6 +55,30 @@ struct alignas(16) GNode4 {
 };
 static_assert(sizeof(GNode4) == 128, "GNode4 must be 128 bytes");
 
+// Quantised wide node = 64 bytes = two 256-bit loads (half the L1TEX wavefronts of GNode4): the same four slots, each box on
+// an 8-bit grid local to the node.  Plane position = origin[a] + q * 2^e[a] (exact in binary64); the builder
+// (bvh_builder.cpp, quantiseNode) guarantees  decoded lo <= true lo - g * 2^e  and  decoded hi >= true hi + g * 2^e  with
+// g = 2^-6 of a grid step, which pays for the float32 evaluation error of the traversal kernel (trace_fast2.cu).  The
+// boxes are only ever CONSERVATIVE: every leaf-box decision is made exactly, in binary64 on the box rebuilt from the
+// leaf's primitives, in the leaf phase.
+//   words 0-2  origin.xyz (float32)
+//   word  3    high halves of the float32 values 2^(e+15): x in bits 0-15, y in bits 16-31
+//   word  4    the same for z in bits 0-15
+//   word  5    orderLut (as GNode4)
+//   words 6-11 qx[2], qy[2], qz[2]: bytes (lo, hi) of slot 2j, (lo, hi) of slot 2j+1; an EMPTY slot is (255, 0)
+//   words 12-15 the four child references (as GNode4)
+struct alignas(32) GNode4Q {
+  float origin[3];
+  uint32_t scaleXY, scaleZ, orderLut;
+  uint32_t q[3][2];
+  int32_t ref[4];
+};
+static_assert(sizeof(GNode4Q) == 64, "GNode4Q must be 64 bytes");
+#define DRT_Q_GUARD 0.015625   // g: 2^-6 grid steps
+#define DRT_Q_EXP_MIN (-60)    // grid step 2^e, e in [DRT_Q_EXP_MIN, DRT_Q_EXP_MAX]
+#define DRT_Q_EXP_MAX 62
+#define DRT_Q_COORD_MAX 4.611686018427388e18  // 2^62: |coordinate| bound of a quantisable scene and of a "fast" ray origin
+
 // One leaf primitive record = 48 bytes = three 128-bit loads, stored in leaf order.
 // Triangle: the three ORIGINAL float32 world-space vertices (triangle.dart:47-50 reads exactly
 // these; edges are formed in f64 on the fly so the arithmetic matches the reference bit for bit).
@@ -87,7 +111,8 @@ struct alignas(16) GSphere {
 
 struct TraceScene {
   const GNode* nodes;    // binary layout (exact-walk / counting kernel)
-  const GNode4* wide;    // collapsed layout (production kernel)
+  const GNode4* wide;    // collapsed layout, float32 boxes (v1 production kernel; fallback)
+  const GNode4Q* wideQ;  // the same nodes with quantised boxes (v2 production kernel); nullptr when a node is not quantisable
   int32_t wideRootRef;
   const GPrim* prims;
   const GSphere* spheres;

@@ -471,6 +471,7 @@ static cudaError_t launchOne(const TraceScene& sc, bool any, const float4* o, co
 
 cudaError_t launchTraceFast(const TraceScene& sc, bool any, const void* rayO, const void* rayD, uint64_t n, void* out,
                             unsigned long long* nextRay, int numSMs, cudaStream_t stream, const TraceExtras* extras) {
+  if (sc.wideQ) return launchTraceQ(sc, any, rayO, rayD, n, out, nextRay, numSMs, stream, extras);
   TraceExtras ex{};
   if (extras) ex = *extras;
   const float4* o = static_cast<const float4*>(rayO);

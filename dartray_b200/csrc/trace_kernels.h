@@ -30,4 +30,9 @@ cudaError_t launchTraceFast(const TraceScene& sc, bool any, const void* rayO, co
                             unsigned long long* nextRay, int numSMs, cudaStream_t stream,
                             const TraceExtras* extras = nullptr);
 
+// Second generation (trace_fast2.cu): quantised 64-byte wide nodes, postponed leaves, every leaf box decided exactly in
+// the leaf phase.  launchTraceFast forwards here whenever the scene carries quantised nodes (TraceScene::wideQ).
+cudaError_t launchTraceQ(const TraceScene& sc, bool any, const void* rayO, const void* rayD, uint64_t n, void* out,
+                         unsigned long long* nextRay, int numSMs, cudaStream_t stream, const TraceExtras* extras = nullptr);
+
 }  // namespace drt

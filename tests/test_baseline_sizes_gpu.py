@@ -1,0 +1,170 @@
+"""Per-pixel parity at the BASELINE.json sizes.
+
+The CPU oracle cannot render a whole 1080p / 4K film in seconds, but it does not have to: sample streams are keyed by the
+ABSOLUTE pixel (seed, x, y, ...), and with the box filter of width 0.5 a pixel only receives its own samples, so the
+oracle rendering a CROP WINDOW of the same film (ImageFilm's cropwindow, image_film.dart:67-70) reproduces exactly the
+pixels the GPU computed inside the full-size render.  The GPU renders the whole film at the BASELINE size; the oracle
+renders windows of it; every pixel of every window is compared at the north_star tolerance (deterministic integrators
+1e-3 relative, path tracing well inside 3 sigma of the per-pixel Monte Carlo noise — the streams are replayed, so the
+observed difference is float rounding)."""
+import os
+
+import numpy as np
+import pytest
+
+from dartray_b200 import capi, host, scenes
+from tests.oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+NT = os.cpu_count() or 8
+
+
+def _crop(film_w, film_h, x0, y0, w, h):
+    """Crop-window fractions whose extent (image_film.dart:67-70) is exactly the pixels [x0, x0 + w) x [y0, y0 + h)."""
+    c = ((x0 - 0.5) / film_w, (x0 + w - 0.5) / film_w, (y0 - 0.5) / film_h, (y0 + h - 0.5) / film_h)
+    f = host.Film(film_w, film_h, crop=c)
+    assert f.extent() == (x0, y0, w, h), (f.extent(), (x0, y0, w, h))
+    return c
+
+
+def _rel_err(a, b, floor=1e-4):
+    return np.abs(a - b) / np.maximum(np.abs(b), floor)
+
+
+def test_config3_ambient_occlusion_1080p_matches_the_oracle_per_pixel_on_crop_windows():
+    """AO, 1920x1080, one camera sample per pixel centre, 64 AO rays, soup_1m; per pixel <= 1e-3
+    relative (ambient_occlusion_integrator.dart:28-53) and identical shadow-ray counts."""
+    P, idx = scenes.soup(512)
+    assert idx.shape[0] == 1_015_810
+    cam = host.PerspectiveCamera(host.look_at((0, 0, -4), (0, 0, 0), (0, 1, 0)), fov=40.0)
+    smp = host.Sampler(kind=host.SAMPLER_STRATIFIED, xs=1, ys=1, jitter=False)
+    integ = host.Integrator(kind=host.INTEGRATOR_AO, ao_nsamples=64)
+    g, o = capi.Context(0), Oracle()
+    for c in (g, o):
+        c.set_triangles(P, idx)
+        c.build_bvh(capi.SPLIT_SAH, 4)
+    host.configure_render(g, cam, host.Film(1920, 1080), smp, integ)
+    g.film_clear()
+    g.render()
+    full = g.film_read()
+    assert full["rgb"].shape == (1080, 1920, 3) and (full["weight"] == 1.0).all()
+    windows = [(840, 472, 240, 135), (0, 0, 240, 135), (1680, 945, 240, 135), (300, 600, 240, 135)]
+    worst, off_by_one = 0.0, 0
+    for (x0, y0, w, h) in windows:
+        film = host.Film(1920, 1080, crop=_crop(1920, 1080, x0, y0, w, h))
+        host.configure_render(o, cam, film, smp, integ)
+        o.film_clear()
+        o.render(0, 1, NT)
+        fo = o.film_read()
+        assert fo["rgb"].shape == (h, w, 3)
+        a = full["rgb"][y0:y0 + h, x0:x0 + w]
+        err = _rel_err(a, fo["rgb"])
+        worst = max(worst, float(err.max()))
+        off_by_one += int((np.abs(a - fo["rgb"]).max(axis=2) > 0.5 / 64).sum())
+        assert err.max() <= 1e-3, (x0, y0, float(err.max()))
+        # the same window on the GPU: identical ray counts (every camera ray that hits spawns exactly 64 shadow rays)
+        host.configure_render(g, cam, film, smp, integ)
+        g.film_clear()
+        g.render()
+        sg, so = g.render_stats(), o.render_stats()
+        assert sg["camera_samples"] == so["camera_samples"]
+        assert sg["closest_rays"] == so["closest_rays"]
+        assert sg["shadow_rays"] == so["shadow_rays"]
+        assert np.array_equal(g.film_read()["rgb"], a)  # a window of the film is the film
+    print(f"config 3: {len(windows)} windows of 240x135, max rel err {worst:.3e}, pixels off by a 1/64 step: {off_by_one}")
+    assert off_by_one == 0
+
+
+def test_config4_path_tracing_1080p_256spp_matches_the_oracle_per_pixel_on_a_480x270_window():
+    """cornell_synth, 1920x1080, lowdiscrepancy 256 spp, path maxdepth 5, box filter; per-pixel mean
+    within 3 sigma of the oracle's per-pixel Monte Carlo noise on a 480x270 window, image mean within 0.5 %.
+    With replayed streams the two renders differ by float rounding only; both bounds are asserted."""
+    sb, cam = scenes.cornell_synth()
+    arrays = sb.arrays()
+    g, o = capi.Context(0), Oracle()
+    for c in (g, o):
+        host.upload_scene(c, arrays)
+    smp = host.Sampler(kind=host.SAMPLER_LD, spp=256)
+    integ = host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=5)
+    host.configure_render(g, cam, host.Film(1920, 1080), smp, integ)
+    g.film_clear()
+    g.render()
+    full = g.film_read()
+    assert np.isfinite(full["rgb"]).all()
+    x0, y0, w, h = 720, 405, 480, 270
+    film = host.Film(1920, 1080, crop=_crop(1920, 1080, x0, y0, w, h))
+    host.configure_render(o, cam, film, smp, integ)
+    o.film_clear()
+    o.render(0, 1, NT)
+    fo = o.film_read()
+    a, b = full["rgb"][y0:y0 + h, x0:x0 + w].astype(np.float64), fo["rgb"].astype(np.float64)
+    assert np.array_equal(full["weight"][y0:y0 + h, x0:x0 + w], fo["weight"])
+    err = _rel_err(a, b, floor=1e-3)
+    print(f"config 4: 480x270 window at 256 spp, max rel err {err.max():.3e}, mean gpu {a.mean():.6f} oracle {b.mean():.6f}")
+    assert err.max() <= 1e-3
+    assert abs(a.mean() - b.mean()) <= 5e-3 * b.mean()
+    # 3 sigma, sigma from the oracle's own samples of a pixel (sampler_renderer.dart:161-197: one L per camera sample):
+    # the estimator's standard error is std(L) / sqrt(spp); checked on a lattice of pixels of the window
+    host.configure_render(g, cam, film, smp, integ)
+    g.film_clear()
+    g.render()
+    sg, so = g.render_stats(), o.render_stats()
+    for k in ("camera_samples", "closest_rays", "shadow_rays"):
+        assert sg[k] == so[k], k
+    lum = lambda rgb: 0.212671 * rgb[..., 0] + 0.715160 * rgb[..., 1] + 0.072169 * rgb[..., 2]
+    # per-pixel noise estimate from the spread of the image itself at that pixel's neighbourhood is not the estimator's
+    # sigma; use the window's two half-sample renders instead: 128 spp with seed 1 and seed 2 give two independent
+    # estimates whose difference has variance 2 sigma_128^2 = 4 sigma_256^2
+    halves = []
+    for seed in (1, 2):
+        host.configure_render(o, cam, film, host.Sampler(kind=host.SAMPLER_LD, spp=128, seed=seed), integ)
+        o.film_clear()
+        o.render(0, 1, NT)
+        halves.append(lum(o.film_read()["rgb"].astype(np.float64)))
+    sigma256 = np.sqrt(np.maximum(((halves[0] - halves[1]) ** 2), 0.0)) / 2.0
+    # smooth the one-sample variance estimate over 9x9 pixels
+    k = 9
+    pad = np.pad(sigma256 ** 2, k // 2, mode="edge")
+    var = np.zeros_like(sigma256)
+    for dy in range(k):
+        for dx in range(k):
+            var += pad[dy:dy + h, dx:dx + w]
+    sigma = np.sqrt(var / (k * k))
+    lit = sigma > 1e-4 * lum(b).mean()
+    assert (np.abs(lum(a) - lum(b))[lit] <= 3.0 * sigma[lit]).all()
+    # ... and the independent 2 x 128 spp estimate brackets the 256 spp image like Monte Carlo noise should
+    z = (lum(b) - 0.5 * (halves[0] + halves[1]))[lit] / (np.sqrt(2.0) * sigma[lit])
+    assert np.mean(np.abs(z) > 3.0) < 0.02
+
+
+def test_config5_soup_10m_4k_path_matches_the_oracle_per_pixel_on_crop_windows():
+    """~10 M triangles (soup_10m), 3840x2160, path maxdepth 5; parity on 240x135 windows of the 4K film
+    at 64 spp (the oracle cannot afford more), per pixel <= 1e-3 relative with identical ray counts."""
+    sb, cam = scenes.soup_render_scene(5120)
+    arrays = sb.arrays()
+    g, o = capi.Context(0), Oracle()
+    for c in (g, o):
+        host.upload_scene(c, arrays)
+    info = g.bvh_info()
+    assert info["n_prims"] == 10_158_084
+    smp = host.Sampler(kind=host.SAMPLER_LD, spp=64)
+    integ = host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=5)
+    worst = 0.0
+    for (x0, y0) in [(1800, 1012), (400, 300)]:
+        film = host.Film(3840, 2160, crop=_crop(3840, 2160, x0, y0, 240, 135))
+        for c in (g, o):
+            host.configure_render(c, cam, film, smp, integ)
+            c.film_clear()
+        g.render()
+        o.render(0, 1, NT)
+        a, b = g.film_read()["rgb"], o.film_read()["rgb"]
+        assert a.shape == (135, 240, 3)
+        err = _rel_err(a, b, floor=1e-3)
+        worst = max(worst, float(err.max()))
+        assert err.max() <= 1e-3, (x0, y0, float(err.max()))
+        sg, so = g.render_stats(), o.render_stats()
+        for k in ("camera_samples", "closest_rays", "shadow_rays"):
+            assert sg[k] == so[k], k
+    print(f"config 5: soup_10m ({info['n_prims']} primitives, {info['device_bytes'] / 1e6:.0f} MB on the device), 4K film, "
+          f"2 windows of 240x135 at 64 spp, max rel err {worst:.3e}")
