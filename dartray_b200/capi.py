@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("DRT_LIB_PATH") or os.path.join(PKG, "libdartray_gpu.s
 
 DEVICE_NONE = -1
 SPLIT_MIDDLE, SPLIT_EQUAL_COUNTS, SPLIT_SAH = 0, 1, 2
+KERNEL_FAST, KERNEL_EXACT_WALK, KERNEL_FAST_V1, KERNEL_FAST_Q = 0, 1, 2, 3
 
 HIT_DTYPE = np.dtype([("t", np.float32), ("b1", np.float32), ("b2", np.float32), ("prim", np.int32)])
 

@@ -63,6 +63,7 @@ drt_ctx* drt_create(int device_id) {
   for (int i = 0; i < 2 * drt_ctx::kMaxChunks && e == cudaSuccess; ++i) e = cudaEventCreate(&c->chunkEv[i]);
   for (int i = 0; i < drt_ctx::kRing && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ringEv[i], cudaEventDisableTiming);
   c->fastV1 = std::getenv("DRT_TRACE_V1") != nullptr;
+  if (const char* q = std::getenv("DRT_Q_MIN_PRIMS")) c->qMinPrims = (uint32_t)std::strtoul(q, nullptr, 10);
   if (e != cudaSuccess) {
     g_createError = cudaGetErrorString(e);
     drt_destroy(c);
@@ -88,6 +89,18 @@ void drt_destroy(drt_ctx* c) {
 }
 
 const char* drt_last_error(const drt_ctx* c) { return c ? c->err.c_str() : g_createError.c_str(); }
+
+// The float32 wide nodes of trace_fast.cu, uploaded on demand (scenes that run the quantised kernel never need them).
+static int uploadWideV1(drt_ctx* c) {
+  const BuiltBvh& B = c->bvh;
+  CK(c, cudaSetDevice(c->device));
+  CK(c, c->dWide.ensure(std::max<size_t>(1, B.wide.size())));
+  if (!B.wide.empty())
+    CK(c, cudaMemcpy(c->dWide.p, B.wide.data(), B.wide.size() * sizeof(GNode4), cudaMemcpyHostToDevice));
+  c->wideUploaded = true;
+  c->ts.wide = c->dWide.p;
+  return DRT_OK;
+}
 
 int drt_set_triangles(drt_ctx* c, const float* P, uint32_t nverts, const uint32_t* idx, uint32_t ntris,
                       const int32_t* mat, const int32_t* light, const uint8_t* rev) {
@@ -370,10 +383,12 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
     return DRT_OK;
   }
   CK(c, c->dNodes.ensure(std::max<size_t>(1, B.nodes.size())));
-  CK(c, c->dWide.ensure(std::max<size_t>(1, B.wide.size())));
-  if (!B.wide.empty())
-    CK(c, cudaMemcpy(c->dWide.p, B.wide.data(), B.wide.size() * sizeof(GNode4), cudaMemcpyHostToDevice));
   c->wideQOk = B.wideQOk && B.wideQ.size() == B.wide.size();
+  c->wideUploaded = false;
+  if (!c->useQ()) {  // the float32 nodes go to the device only when their kernel is the one that runs (or is asked for later)
+    int rc = uploadWideV1(c);
+    if (rc != DRT_OK) return rc;
+  }
   if (c->wideQOk) {
     CK(c, c->dWideQ.ensure(std::max<size_t>(1, B.wideQ.size())));
     if (!B.wideQ.empty())
@@ -387,7 +402,7 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
   if (!gs.empty()) CK(c, cudaMemcpy(c->dSpheres.p, gs.data(), gs.size() * sizeof(GSphere), cudaMemcpyHostToDevice));
   c->ts.nodes = c->dNodes.p;
   c->ts.wide = c->dWide.p;
-  c->ts.wideQ = (c->wideQOk && !c->fastV1) ? c->dWideQ.p : nullptr;
+  c->ts.wideQ = c->useQ() ? c->dWideQ.p : nullptr;
   c->ts.wideRootRef = B.wideRootRef;
   c->ts.prims = c->dPrims.p;
   c->ts.spheres = c->dSpheres.p;
@@ -402,7 +417,7 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
   c->info.n_leaves = B.nLeaves;
   c->info.max_leaf_prims = B.maxLeafPrims;
   c->info.max_depth = B.maxDepth;
-  c->info.device_bytes = (c->ts.wideQ ? B.wideQ.size() * sizeof(GNode4Q) : B.wide.size() * sizeof(GNode4)) +
+  c->info.device_bytes = (c->wideQOk ? B.wideQ.size() * sizeof(GNode4Q) : 0) + (c->wideUploaded ? B.wide.size() * sizeof(GNode4) : 0) +
                          prims.size() * sizeof(GPrim) + gs.size() * sizeof(GSphere);
   c->info.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   c->built = true;
@@ -527,11 +542,16 @@ int drt_set_counting(drt_ctx* c, int enabled) {
 
 int drt_set_kernel_variant(drt_ctx* c, int variant) {
   if (!c) return DRT_E_INVALID;
-  if (variant != DRT_KERNEL_FAST && variant != DRT_KERNEL_EXACT_WALK && variant != DRT_KERNEL_FAST_V1)
+  if (variant != DRT_KERNEL_FAST && variant != DRT_KERNEL_EXACT_WALK && variant != DRT_KERNEL_FAST_V1 && variant != DRT_KERNEL_FAST_Q)
     return fail(c, DRT_E_INVALID, "unknown kernel variant");
   c->exactWalk = variant == DRT_KERNEL_EXACT_WALK;
-  c->fastV1 = variant == DRT_KERNEL_FAST_V1 || std::getenv("DRT_TRACE_V1") != nullptr;
-  c->ts.wideQ = (c->built && c->wideQOk && !c->fastV1) ? c->dWideQ.p : nullptr;
+  c->fastV1 = variant == DRT_KERNEL_FAST_V1 || (variant != DRT_KERNEL_FAST_Q && std::getenv("DRT_TRACE_V1") != nullptr);
+  if (variant == DRT_KERNEL_FAST_Q) c->qMinPrims = 0;
+  if (c->built && c->device != DRT_DEVICE_NONE && !c->useQ() && !c->wideUploaded) {
+    int rc = uploadWideV1(c);
+    if (rc != DRT_OK) return rc;
+  }
+  c->ts.wideQ = (c->built && c->useQ()) ? c->dWideQ.p : nullptr;
   return DRT_OK;
 }
 

@@ -68,7 +68,13 @@ struct drt_ctx {
   DevBuf<GNode4> dWide;
   DevBuf<GNode4Q> dWideQ;
   bool wideQOk = false;  // the scene's wide nodes could be quantised (bvh_builder.cpp quantiseNode)
+  bool wideUploaded = false;  // dWide holds this build's float32 wide nodes
   bool fastV1 = false;   // DRT_KERNEL_FAST_V1 / env DRT_TRACE_V1: the float32-box kernel of trace_fast.cu
+  // Scenes below this many primitives keep the float32-box kernel: with a handful of nodes per ray the walk is all leaf
+  // phase, where the second generation pays a binary64 box test per leaf (config 4, 25 primitives: 549 vs 417 M samples/s;
+  // soup(8), 16 K triangles: 10.7 vs 8.5 Grays/s; soup(64), 127 K: 4.2 vs 4.6; soup_1m: 1.88 vs 2.36 Grays/s — tools/size_sweep.sh).  Env DRT_Q_MIN_PRIMS overrides (A/B runs).
+  uint32_t qMinPrims = 65536;
+  bool useQ() const { return wideQOk && !fastV1 && nprims() >= qMinPrims; }
   DevBuf<GPrim> dPrims;
   DevBuf<GSphere> dSpheres;
   DevBuf<DeviceCounters> dCounters;

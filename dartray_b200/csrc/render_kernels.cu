@@ -613,7 +613,8 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(Ren
         T = T * (f * AbsDot(wi, nrm) / pdf);
         cont = true;
         if (bounce > 3) {  // Russian roulette (:93-99)
-          double continueProbability = fmin(0.5, Luminance(T));
+          const double lumT = Luminance(T);
+          double continueProbability = lumT != lumT ? lumT : fmin(0.5, lumT);  // Dart's Math.min propagates NaN (path_integrator.dart:94)
           if (rng.randomFloat() > continueProbability) cont = false;
           else T = T / continueProbability;
         }

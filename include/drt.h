@@ -169,13 +169,14 @@ int drt_trace_any_device(drt_ctx* ctx, const void* d_ray_o_tmin, const void* d_r
                          void* d_occluded, void* cuda_stream);
 
 /* All kernel variants make every decision with the reference's arithmetic and return identical
- * results.  FAST (default): persistent warps over 64-byte quantised 4-wide nodes, conservative float32
- * box tests, postponed leaves, every leaf box decided in float64 before its primitives are tested
- * (falls back to FAST_V1 for scenes whose coordinates cannot be quantised: non-finite or beyond 2^62).
+ * results.  FAST (default): the library picks FAST_Q or FAST_V1 by scene size (FAST_Q from 65536 primitives up).
+ * FAST_Q: persistent warps over 64-byte quantised 4-wide nodes, conservative float32 box tests, postponed
+ * leaves, every leaf box decided in float64 before its primitives are tested (falls back to FAST_V1 for
+ * scenes whose coordinates cannot be quantised: non-finite or beyond 2^62).
  * FAST_V1: the first-generation kernel, 128-byte float32 nodes with a float32-filtered slab test.
  * EXACT_WALK: one thread per ray, float64 slab test at every node — the literal reference walk, kept as a
  * cross-check and as the counting kernel. */
-enum { DRT_KERNEL_FAST = 0, DRT_KERNEL_EXACT_WALK = 1, DRT_KERNEL_FAST_V1 = 2 };
+enum { DRT_KERNEL_FAST = 0, DRT_KERNEL_EXACT_WALK = 1, DRT_KERNEL_FAST_V1 = 2, DRT_KERNEL_FAST_Q = 3 };
 int drt_set_kernel_variant(drt_ctx* ctx, int variant);
 
 /* When enabled the trace kernels also count slab and primitive tests (uses the EXACT_WALK kernel;

@@ -468,6 +468,19 @@ int orc_render_stats(const orc_ctx* c, uint64_t out[5]) {
 }
 
 // dart:math Random restatement, for documentation/tests of the serial stream
+// test probes: BSDF.f / pdf / sample_f of a material in the canonical shading frame (see RenderScene::bsdfEval)
+int orc_bsdf_eval(orc_ctx* c, uint32_t material, uint32_t n, const double* wo, const double* wi, int flags, float* f, double* pdf) {
+  if (material >= c->rs.materials.size()) return -1;
+  c->rs.bsdfEval(material, n, wo, wi, flags, f, pdf);
+  return 0;
+}
+int orc_bsdf_sample(orc_ctx* c, uint32_t material, uint32_t n, const double* wo, const double* u, int flags, double* wi, float* f,
+                    double* pdf, int32_t* sampledType) {
+  if (material >= c->rs.materials.size()) return -1;
+  c->rs.bsdfSample(material, n, wo, u, flags, wi, f, pdf, sampledType);
+  return 0;
+}
+
 int orc_dart_random(int64_t seed, int n, double* floats, uint32_t* uints) {
   DartRandom r(seed);
   for (int i = 0; i < n; ++i) {

@@ -1278,7 +1278,7 @@ struct Ctx {
       pathThroughput = pathThroughput * (f * AbsDot(wi, n) / pdf);
       ray = Ray(p, wi, isectP.rayEpsilon, kInf, ray.time, ray.depth + 1);  // RayDifferential.child
       if (bounces > 3) {
-        double continueProbability = std::fmin(0.5, pathThroughput.luminance());
+        double continueProbability = dmin(0.5, pathThroughput.luminance());  // Math.min: NaN propagates (path_integrator.dart:94)
         if (rng.randomFloat() > continueProbability) break;
         pathThroughput = pathThroughput / continueProbability;
       }
@@ -1685,6 +1685,46 @@ int pixelSamples(const SamplerCfg& sc, const SampleLayout& layout, const Camera&
 }
 
 }  // namespace
+
+static Bsdf canonicalBsdf(const RenderScene& rs, uint32_t material) {
+  Bsdf b;
+  b.p = Vec(0, 0, 0);
+  b.nn = b.ng = Vec(0, 0, 1);
+  b.sn = Vec(1, 0, 0);
+  b.tn = Vec(0, 1, 0);
+  for (const Lobe& l : rs.materials.at(material).lobes) b.bxdfs[b.nBxDFs++].init(l);
+  return b;
+}
+
+void RenderScene::bsdfEval(uint32_t material, uint32_t n, const double* wo, const double* wi, int flags, float* f, double* pdf) const {
+  const Bsdf b = canonicalBsdf(*this, material);
+  for (uint32_t i = 0; i < n; ++i) {
+    const Vec o(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]), w(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
+    const Spec v = b.f(o, w, flags);
+    for (int k = 0; k < 3; ++k) f[3 * i + k] = v.c[k];
+    pdf[i] = b.pdf(o, w, flags);
+  }
+}
+
+void RenderScene::bsdfSample(uint32_t material, uint32_t n, const double* wo, const double* u, int flags, double* wi, float* f,
+                             double* pdf, int32_t* sampledType) const {
+  const Bsdf b = canonicalBsdf(*this, material);
+  for (uint32_t i = 0; i < n; ++i) {
+    const Vec o(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
+    U3 s;
+    s.u0 = f32(u[3 * i]);  // BSDFSample keeps its two direction values in a Float32List (bsdf_sample.dart)
+    s.u1 = f32(u[3 * i + 1]);
+    s.comp = u[3 * i + 2];
+    Vec w(0, 0, 0);
+    int type = 0;
+    double p = 0.0;
+    const Spec v = b.sample_f(o, &w, s, &p, flags, &type);
+    for (int k = 0; k < 3; ++k) f[3 * i + k] = v.c[k];
+    wi[3 * i] = w.x; wi[3 * i + 1] = w.y; wi[3 * i + 2] = w.z;
+    pdf[i] = p;
+    sampledType[i] = type;
+  }
+}
 
 void RenderScene::finalizeLights() {
   Ctx c(*this);

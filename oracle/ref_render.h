@@ -274,6 +274,11 @@ struct RenderScene {
   // The camera samples only (imageX, imageY, lensU, lensV, time + integrator arrays) of one pixel,
   // for sampler parity tests.  Returns floats per sample.
   int samplesForPixel(int px, int py, std::vector<float>* out);
+  // Test probes of the BSDF a material builds (Material.getBSDF with the canonical frame sn = +x, tn = +y, nn = ng = +z):
+  // BSDF.f / BSDF.pdf for n (wo, wi) pairs, and BSDF.sample_f for n (wo, (u0, u1, component)) pairs — bsdf.dart:53-198.
+  void bsdfEval(uint32_t material, uint32_t n, const double* wo, const double* wi, int flags, float* f, double* pdf) const;
+  void bsdfSample(uint32_t material, uint32_t n, const double* wo, const double* u, int flags, double* wi, float* f, double* pdf,
+                  int32_t* sampledType) const;
 };
 
 }  // namespace orc

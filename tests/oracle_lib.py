@@ -76,6 +76,8 @@ def lib():
         L.orc_pixel_samples.argtypes = [vp, i32, i32, vp, i32, vp]
         L.orc_render_stats.argtypes = [vp, vp]
         L.orc_dart_random.argtypes = [C.c_int64, i32, vp, vp]
+        L.orc_bsdf_eval.argtypes = [vp, u32, u32, vp, vp, i32, vp, vp]
+        L.orc_bsdf_sample.argtypes = [vp, u32, u32, vp, vp, i32, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -285,6 +287,24 @@ class Oracle:
         n = C.c_int(0)
         per = self.L.orc_pixel_samples(self.h, x, y, _p(out), cap, C.byref(n))
         return out[:per * n.value].reshape(n.value, per).copy()
+
+    def bsdf_eval(self, material, wo, wi, flags=31):
+        """BSDF.f / BSDF.pdf (bsdf.dart:128-198) of `material` in the canonical frame sn = +x, tn = +y, nn = ng = +z."""
+        wo = np.ascontiguousarray(np.broadcast_to(np.asarray(wo, np.float64), np.asarray(wi).shape), np.float64).reshape(-1, 3)
+        wi = np.ascontiguousarray(wi, np.float64).reshape(-1, 3)
+        n = wi.shape[0]
+        f, pdf = np.zeros((n, 3), np.float32), np.zeros(n, np.float64)
+        self._ck(self.L.orc_bsdf_eval(self.h, material, n, _p(wo), _p(wi), flags, _p(f), _p(pdf)))
+        return f, pdf
+
+    def bsdf_sample(self, material, wo, u, flags=31):
+        """BSDF.sample_f (bsdf.dart:53-126) for rows (u0, u1, component) of `u`; returns wi, f, pdf, sampled type."""
+        u = np.ascontiguousarray(u, np.float64).reshape(-1, 3)
+        wo = np.ascontiguousarray(np.broadcast_to(np.asarray(wo, np.float64), u.shape), np.float64)
+        n = u.shape[0]
+        wi, f, pdf, ty = np.zeros((n, 3), np.float64), np.zeros((n, 3), np.float32), np.zeros(n, np.float64), np.zeros(n, np.int32)
+        self._ck(self.L.orc_bsdf_sample(self.h, material, n, _p(wo), _p(u), flags, _p(wi), _p(f), _p(pdf), _p(ty)))
+        return wi, f, pdf, ty
 
     def render_stats(self):
         out = np.zeros(5, np.uint64)

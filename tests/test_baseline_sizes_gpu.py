@@ -110,8 +110,13 @@ def test_config4_path_tracing_1080p_256spp_matches_the_oracle_per_pixel_on_a_480
     g.film_clear()
     g.render()
     sg, so = g.render_stats(), o.render_stats()
-    for k in ("camera_samples", "closest_rays", "shadow_rays"):
-        assert sg[k] == so[k], k
+    print("config 4 window ray counts: gpu", {k: sg[k] for k in ("camera_samples", "closest_rays", "shadow_rays")},
+          "oracle", {k: so[k] for k in ("camera_samples", "closest_rays", "shadow_rays")})
+    assert sg["camera_samples"] == so["camera_samples"]
+    # 33 M paths of up to 6 vertices: CUDA's and glibc's sin / cos / atan2 differ in the last place now and then
+    # (SURVEY 8c), which moves a sampled direction by one ulp and, a few times in 10^8 rays, a grazing hit with it
+    for k in ("closest_rays", "shadow_rays"):
+        assert abs(int(sg[k]) - int(so[k])) <= 1e-6 * so[k], (k, sg[k], so[k])
     lum = lambda rgb: 0.212671 * rgb[..., 0] + 0.715160 * rgb[..., 1] + 0.072169 * rgb[..., 2]
     # per-pixel noise estimate from the spread of the image itself at that pixel's neighbourhood is not the estimator's
     # sigma; use the window's two half-sample renders instead: 128 spp with seed 1 and seed 2 give two independent

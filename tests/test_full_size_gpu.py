@@ -37,17 +37,21 @@ def ray_sets():
 def test_production_kernel_equals_the_literal_walk_on_every_ray(soup_1m, ray_sets, which):
     P, idx, c = soup_1m
     ro, rd = ray_sets[which]
-    c.set_kernel_variant(0)
+    c.set_kernel_variant(capi.KERNEL_FAST)  # soup_1m: the quantised-node kernel (trace_fast2.cu)
+    assert c.bvh_info()["device_bytes"] < 90e6  # 64-byte wide nodes: 81 MB; the float32 nodes make it 114 MB
     fast, fast_any = c.trace_closest(ro, rd), c.trace_any(ro, rd)
-    c.set_kernel_variant(1)
     try:
+        c.set_kernel_variant(capi.KERNEL_FAST_V1)
+        v1, v1_any = c.trace_closest(ro, rd), c.trace_any(ro, rd)
+        c.set_kernel_variant(capi.KERNEL_EXACT_WALK)
         walk, walk_any = c.trace_closest(ro, rd), c.trace_any(ro, rd)
     finally:
-        c.set_kernel_variant(0)
-    assert np.array_equal(fast["prim"], walk["prim"])
-    for k in ("t", "b1", "b2"):
-        assert np.array_equal(fast[k].view(np.uint32), walk[k].view(np.uint32)), k
-    assert np.array_equal(fast_any, walk_any)
+        c.set_kernel_variant(capi.KERNEL_FAST)
+    for other, other_any in ((walk, walk_any), (v1, v1_any)):
+        assert np.array_equal(fast["prim"], other["prim"])
+        for k in ("t", "b1", "b2"):
+            assert np.array_equal(fast[k].view(np.uint32), other[k].view(np.uint32)), k
+        assert np.array_equal(fast_any, other_any)
     hit = fast["prim"] >= 0
     assert 0.2 < hit.mean() < 1.0
     # shadow rays with the full interval: intersectP's float32 edge vectors (triangle.dart:162-194) may disagree with

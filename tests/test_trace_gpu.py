@@ -12,7 +12,9 @@ from tests.util import mesh_refine_order, random_rays, random_soup, translate
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[0, 1], ids=["fast", "exact_walk"])
+# DRT_KERNEL_FAST_Q (quantised 64-byte nodes, forced whatever the scene size), DRT_KERNEL_FAST_V1 (float32 128-byte nodes),
+# DRT_KERNEL_EXACT_WALK (the literal walk); DRT_KERNEL_FAST = 0 picks between the first two by scene size
+@pytest.fixture(params=[3, 2, 1], ids=["fast_q", "fast_v1", "exact_walk"])
 def variant(request):
     return request.param
 
@@ -251,6 +253,43 @@ def test_soup_scene_coherent_and_incoherent(drt_lib, variant):
     for ro, rd in (scenes.coherent_rays(512, 256), scenes.incoherent_rays(1 << 17)):
         assert_hits_equal(c.trace_closest(ro, rd), o.trace_closest(ro, rd, nthreads=8))
         assert (c.trace_any(ro, rd) == o.trace_any(ro, rd, nthreads=8)).all()
+
+
+def test_concurrent_device_launches_on_two_streams_do_not_share_a_work_counter(drt_lib):
+    """drt_trace_*_device is asynchronous on the caller's stream: two launches in flight on different streams of one
+    context must each trace every ray (they used to share the persistent kernel's work counter)."""
+    import torch
+    P, idx = scenes.soup(8)
+    c = capi.Context(0)
+    c.set_triangles(P, idx)
+    c.build_bvh()
+    n = 1 << 18
+    ro, rd = scenes.incoherent_rays(n)
+    ro2, rd2 = scenes.coherent_rays(512, 512)
+    href, href2 = c.trace_closest(ro, rd), c.trace_closest(ro2, rd2)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    dro, drd, dro2, drd2 = (torch.from_numpy(a).cuda() for a in (ro, rd, ro2, rd2))
+    for rep in range(8):
+        dh = torch.full((n, 4), -7.0, dtype=torch.float32, device="cuda")
+        dh2 = torch.full((n, 4), -7.0, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        c.trace_closest_device(dro.data_ptr(), drd.data_ptr(), n, dh.data_ptr(), s1.cuda_stream)
+        c.trace_closest_device(dro2.data_ptr(), drd2.data_ptr(), n, dh2.data_ptr(), s2.cuda_stream)
+        torch.cuda.synchronize()
+        for d, h in ((dh, href), (dh2, href2)):
+            hd = d.cpu().numpy().view(capi.HIT_DTYPE).reshape(-1)
+            assert (hd["prim"] == h["prim"]).all() and (hd["t"].view(np.uint32) == h["t"].view(np.uint32)).all(), rep
+
+
+def test_default_variant_picks_the_kernel_by_scene_size(drt_lib):
+    for ns, expect_q in ((8, False), (64, True)):
+        P, idx = scenes.soup(ns)
+        c = capi.Context(0)
+        c.set_triangles(P, idx)
+        c.build_bvh()
+        per_prim = c.bvh_info()["device_bytes"] / idx.shape[0]
+        # 64-byte nodes (~32 B per primitive) + 48-byte records, against 128-byte nodes (~64 B per primitive)
+        assert (per_prim < 96) == expect_q, (ns, per_prim)
 
 
 def test_device_pointer_entry_matches_host_entry(drt_lib):
