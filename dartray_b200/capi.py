@@ -27,7 +27,7 @@ SYMBOLS = [
     "drt_last_kernel_ms", "drt_kernel_launches",
     "drt_set_materials", "drt_set_material_lobes", "drt_set_lights", "drt_set_spot_params", "drt_set_camera", "drt_set_camera_kind", "drt_set_film", "drt_set_sampler", "drt_set_integrator",
     "drt_render", "drt_render_shard", "drt_set_batch_slots", "drt_film_clear", "drt_film_size", "drt_film_read",
-    "drt_film_device", "drt_pixel_samples", "drt_render_stats_get",
+    "drt_film_device", "drt_pixel_samples", "drt_render_stats_get", "drt_set_render_profiling", "drt_render_profile_get",
 ]
 
 
@@ -46,6 +46,14 @@ class BvhInfo(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("nodes_visited", C.c_uint64), ("prims_tested", C.c_uint64),
                 ("hits", C.c_uint64)]
+
+
+class RenderProfile(C.Structure):
+    _fields_ = [("ms", C.c_double * 7), ("launches", C.c_uint64 * 7), ("closest", Counters), ("any", Counters)]
+
+
+PROFILE_TIME, PROFILE_WORK = 1, 2
+PROFILE_CLASSES = ["trace_closest", "trace_any", "integrator", "sampler", "resolve", "film", "other"]
 
 
 class RenderStats(C.Structure):
@@ -116,6 +124,8 @@ def load():
     L.drt_film_device.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     L.drt_pixel_samples.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32), C.POINTER(i32)]
     L.drt_render_stats_get.argtypes = [vp, C.POINTER(RenderStats)]
+    L.drt_set_render_profiling.argtypes = [vp, i32]
+    L.drt_render_profile_get.argtypes = [vp, C.POINTER(RenderProfile)]
     _lib = L
     return L
 
@@ -367,6 +377,18 @@ class Context:
         n, per = C.c_int32(0), C.c_int32(0)
         self._ck(self.L.drt_pixel_samples(self.h, x, y, _p(out), cap, C.byref(n), C.byref(per)))
         return out[:per.value * n.value].reshape(n.value, per.value).copy()
+
+    def set_render_profiling(self, flags: int):
+        """PROFILE_TIME: CUDA-event spans per kernel class; PROFILE_WORK: reference-walk counters of every traced queue."""
+        self._ck(self.L.drt_set_render_profiling(self.h, flags))
+
+    def render_profile(self) -> dict:
+        p = RenderProfile()
+        self._ck(self.L.drt_render_profile_get(self.h, C.byref(p)))
+        cnt = lambda c: {k: int(getattr(c, k)) for k, _ in Counters._fields_}
+        return {"ms": dict(zip(PROFILE_CLASSES, [float(v) for v in p.ms])),
+                "launches": dict(zip(PROFILE_CLASSES, [int(v) for v in p.launches])),
+                "closest": cnt(p.closest), "any": cnt(p.any)}
 
     def render_stats(self) -> dict:
         s = RenderStats()

@@ -88,6 +88,13 @@ struct RenderState {
   DevBuf<RenderCounters> dCounters;
   DevBuf<float> dRgb, dXyz, dWeight;
   size_t filmPixels = 0;
+  // drt_set_render_profiling: one event after every launch (class of the launch it follows), spans summed after the render
+  int profFlags = 0;
+  std::vector<cudaEvent_t> profEv;
+  std::vector<int> profCls;
+  size_t profUsed = 0;
+  drt_render_profile prof{};
+  DevBuf<DeviceCounters> dWork;  // [0] closest, [1] any
   bool sceneTablesValid = false;
   uint64_t buildSerial = 0;
   // sample layout
@@ -117,7 +124,8 @@ void drtRenderStateDestroy(drt_ctx* c) {
   r->dPrimToRec.release(); r->dPrimAttr.release(); r->dLightShapes.release(); r->dMaterials.release(); r->dLights.release();
   r->dLightCdf.release(); r->dTable.release(); r->dDirect.release(); r->dArrays.release();
   r->dMeshOfTri.release(); r->dTriIdx.release(); r->dMeshes.release(); r->dVertN.release(); r->dVertS.release(); r->dVertUV.release(); r->dEnv.release(); r->dAdaptList.release(); r->dAdaptCount.release(); r->dBcTable.release(); r->dBcShifts.release();
-  r->dFilm.release(); r->dCounters.release(); r->dRgb.release(); r->dXyz.release(); r->dWeight.release();
+  r->dFilm.release(); r->dCounters.release(); r->dRgb.release(); r->dXyz.release(); r->dWeight.release(); r->dWork.release();
+  for (cudaEvent_t e : r->profEv) cudaEventDestroy(e);
   if (r->wfMem) cudaFree(r->wfMem);
   delete r;
   c->render = nullptr;
@@ -572,6 +580,45 @@ static int prepare(drt_ctx* c, RenderState* r) {
   return DRT_OK;
 }
 
+// Records the end of the launch(es) just enqueued; cls = DRT_PK_*, -1 = start of a render (nothing before it is counted).
+static void profMark(drt_ctx* c, int cls) {
+  RenderState* r = c->render;
+  if (!r || !(r->profFlags & DRT_PROFILE_TIME)) return;
+  if (r->profUsed == r->profEv.size()) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    r->profEv.push_back(e);
+    r->profCls.push_back(0);
+  }
+  r->profCls[r->profUsed] = cls;
+  cudaEventRecord(r->profEv[r->profUsed++], c->stream);
+}
+
+static int profCollect(drt_ctx* c) {  // after the render's stream synchronize
+  RenderState* r = c->render;
+  if (r->profFlags & DRT_PROFILE_TIME) {
+    for (size_t i = 1; i < r->profUsed; ++i) {
+      if (r->profCls[i] < 0) continue;
+      float ms = 0.f;
+      CK(c, cudaEventElapsedTime(&ms, r->profEv[i - 1], r->profEv[i]));
+      r->prof.ms[r->profCls[i]] += ms;
+      r->prof.launches[r->profCls[i]]++;
+    }
+    r->profUsed = 0;
+  }
+  if (r->profFlags & DRT_PROFILE_WORK) {
+    DeviceCounters h[2];
+    CK(c, cudaMemcpy(h, r->dWork.p, sizeof(h), cudaMemcpyDeviceToHost));
+    CK(c, cudaMemset(r->dWork.p, 0, sizeof(h)));
+    drt_counters* dst[2] = {&r->prof.closest, &r->prof.any};
+    for (int k = 0; k < 2; ++k) {
+      dst[k]->rays += h[k].rays; dst[k]->nodes_visited += h[k].nodes_visited;
+      dst[k]->prims_tested += h[k].prims_tested; dst[k]->hits += h[k].hits;
+    }
+  }
+  return DRT_OK;
+}
+
 static int traceQueue(drt_ctx* c, bool any, const float4* o, const float4* d, const double2* range, const uint32_t* nDev, void* out,
                       double* tOut, cudaStream_t st) {
   TraceExtras ex;
@@ -580,6 +627,15 @@ static int traceQueue(drt_ctx* c, bool any, const float4* o, const float4* d, co
   ex.tOut = tOut;
   CK(c, launchTraceFast(c->ts, any, o, d, 0, out, c->dNextRay.p, c->numSMs, st, &ex));
   c->launches++;
+  profMark(c, any ? DRT_PK_TRACE_ANY : DRT_PK_TRACE_CLOSEST);
+  RenderState* r = c->render;
+  if (r && (r->profFlags & DRT_PROFILE_WORK)) {  // the reference's walk over the same queue, counting only
+    uint32_t n = 0;
+    CK(c, cudaMemcpyAsync(&n, nDev, sizeof(n), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    CK(c, launchTrace(c->ts, any, true, o, d, n, nullptr, r->dWork.p + (any ? 1 : 0), st, range, nDev));
+    profMark(c, -1);
+  }
   return DRT_OK;
 }
 
@@ -599,7 +655,7 @@ static int directStage(drt_ctx* c, RenderState* r, int cur, bool weighted) {
   cudaStream_t st = c->stream;
   const int sms = c->numSMs;
   RenderCounters* rc = r->dCounters.p;
-  CK(c, STAGE(launchDirectSetup)(p, rs, wf, cur, weighted ? 1 : 0, sms, st));
+  CK(c, STAGE(launchDirectSetup)(p, rs, wf, cur, weighted ? 1 : 0, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
   c->launches++;
   if (rs.nLights <= 0) return DRT_OK;
   const bool one = p.strategy != 0;
@@ -609,14 +665,14 @@ static int directStage(drt_ctx* c, RenderState* r, int cur, bool weighted) {
   int sorted = 0;
   static const bool directSort = std::getenv("DRT_NO_DIRECT_SORT") == nullptr;
   if (directSort) {
-    CK(c, STAGE(launchMaterialSort)(rs, wf, cur, sms, &sorted, st));
+    CK(c, STAGE(launchMaterialSort)(rs, wf, cur, sms, &sorted, st)); profMark(c, DRT_PK_OTHER);
     if (sorted) c->launches += 3;
   }
   for (int li = 0; li < nL; ++li) {
     const int nS = one ? 1 : r->direct[li].nSamples;
     for (int j = 0; j < nS; ++j) {
-      CK(c, STAGE(launchResetCounts)(wf, (1u << Q_SHADOW) | (1u << Q_MIS), st));
-      CK(c, STAGE(launchDirectSample)(p, rs, wf, one ? -1 : li, j, cur, rc, sorted, sms, st));
+      CK(c, STAGE(launchResetCounts)(wf, (1u << Q_SHADOW) | (1u << Q_MIS), st)); profMark(c, DRT_PK_OTHER);
+      CK(c, STAGE(launchDirectSample)(p, rs, wf, one ? -1 : li, j, cur, rc, sorted, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
       RK(traceQueue(c, true, wf.shO, wf.shD, wf.shRange, wf.counts + Q_SHADOW, wf.shOcc, nullptr, st));
       RK(traceQueue(c, false, wf.misO, wf.misD, wf.misRange, wf.counts + Q_MIS, wf.misHit, wf.misT, st));
       int mode = RESOLVE_DIRECT | (weighted ? RESOLVE_WEIGHTED : 0);
@@ -626,7 +682,7 @@ static int directStage(drt_ctx* c, RenderState* r, int cur, bool weighted) {
         if (j == nS - 1) mode |= RESOLVE_LAST_OF_LIGHT;
         if (j == nS - 1 && li == nL - 1) mode |= RESOLVE_FINAL;
       }
-      CK(c, STAGE(launchResolveDirect)(p, rs, wf, cur, mode, nS, sms, st));
+      CK(c, STAGE(launchResolveDirect)(p, rs, wf, cur, mode, nS, sms, st)); profMark(c, DRT_PK_RESOLVE);
       c->launches += 3;
     }
   }
@@ -648,19 +704,19 @@ static int whittedStage(drt_ctx* c, RenderState* r, int cur, bool weighted) {
   cudaStream_t st = c->stream;
   const int sms = c->numSMs;
   RenderCounters* rc = r->dCounters.p;
-  CK(c, STAGE(launchWhittedSetup)(p, rs, wf, cur, weighted ? 1 : 0, sms, st));
+  CK(c, STAGE(launchWhittedSetup)(p, rs, wf, cur, weighted ? 1 : 0, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
   c->launches++;
   int sorted = 0;  // material order measured no gain here (33.7 vs 34.1 ms, cornell_materials 1080p x 16 spp): off unless DRT_WHITTED_SORT is set
   static const bool whittedSort = std::getenv("DRT_WHITTED_SORT") != nullptr;
   if (whittedSort && rs.nLights > 0) {
-    CK(c, STAGE(launchMaterialSort)(rs, wf, cur, sms, &sorted, st));
+    CK(c, STAGE(launchMaterialSort)(rs, wf, cur, sms, &sorted, st)); profMark(c, DRT_PK_OTHER);
     if (sorted) c->launches += 3;
   }
   for (int li = 0; li < rs.nLights; ++li) {
-    CK(c, STAGE(launchResetCounts)(wf, (1u << Q_SHADOW) | (1u << Q_MIS), st));
-    CK(c, STAGE(launchWhittedSample)(p, rs, wf, li, cur, rc, sorted, sms, st));
+    CK(c, STAGE(launchResetCounts)(wf, (1u << Q_SHADOW) | (1u << Q_MIS), st)); profMark(c, DRT_PK_OTHER);
+    CK(c, STAGE(launchWhittedSample)(p, rs, wf, li, cur, rc, sorted, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
     RK(traceQueue(c, true, wf.shO, wf.shD, wf.shRange, wf.counts + Q_SHADOW, wf.shOcc, nullptr, st));
-    CK(c, STAGE(launchResolveDirect)(p, rs, wf, cur, RESOLVE_DIRECT | RESOLVE_WHITTED | (weighted ? RESOLVE_WEIGHTED : 0), 1, sms, st));
+    CK(c, STAGE(launchResolveDirect)(p, rs, wf, cur, RESOLVE_DIRECT | RESOLVE_WHITTED | (weighted ? RESOLVE_WEIGHTED : 0), 1, sms, st)); profMark(c, DRT_PK_RESOLVE);
     c->launches += 3;
   }
   return DRT_OK;
@@ -714,14 +770,14 @@ static int specularChains(drt_ctx* c, RenderState* r) {
     CK(c, cudaMemcpyAsync(wf.counts + Q_EXT0, &n0, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     int cur = 0;
     for (int k = 1; k <= len + 1; ++k) {
-      CK(c, STAGE(launchResetCounts)(wf, 1u << (cur ^ 1), st));
-      CK(c, STAGE(launchSpecularStep)(p, rs, wf, cur, kFlags[chain[k - 1]], k, k == len + 1 ? 1 : 0, rc, sms, st));
+      CK(c, STAGE(launchResetCounts)(wf, 1u << (cur ^ 1), st)); profMark(c, DRT_PK_OTHER);
+      CK(c, STAGE(launchSpecularStep)(p, rs, wf, cur, kFlags[chain[k - 1]], k, k == len + 1 ? 1 : 0, rc, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
       c->launches += 2;
       cur ^= 1;
       RK(traceQueue(c, false, wf.extO[cur], wf.extD[cur], wf.extRange[cur], wf.counts + cur, wf.extHit, wf.extT, st));
     }
     if (rs.nInfinite > 0) {  // the new rays of this chain that escape: renderer.Li = sum of Le, times the chain weight
-      CK(c, STAGE(launchEscape)(rs, wf, cur, ESCAPE_WEIGHTED, sms, st));
+      CK(c, STAGE(launchEscape)(rs, wf, cur, ESCAPE_WEIGHTED, sms, st)); profMark(c, DRT_PK_OTHER);
       c->launches++;
     }
     uint32_t live = 0;
@@ -747,18 +803,18 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
   const int sms = c->numSMs;
   const uint32_t nSlots = pb.nPixels * (uint32_t)p.nPixelSamples;
   RenderCounters* rc = r->dCounters.p;
-  CK(c, STAGE(launchSampler)(p, wf, r->dArrays.p, (int)r->arrays.size(), r->maxVals, r->maxOthers, pb, sms, st));
-  CK(c, STAGE(launchResetCounts)(wf, 0xffu, st));
-  CK(c, STAGE(launchRaygen)(p, wf, pb, rc, st));
+  CK(c, STAGE(launchSampler)(p, wf, r->dArrays.p, (int)r->arrays.size(), r->maxVals, r->maxOthers, pb, sms, st)); profMark(c, DRT_PK_SAMPLER);
+  CK(c, STAGE(launchResetCounts)(wf, 0xffu, st)); profMark(c, DRT_PK_OTHER);
+  CK(c, STAGE(launchRaygen)(p, wf, pb, rc, st)); profMark(c, DRT_PK_SAMPLER);
   c->launches += 3;
   // camera rays: Scene.intersect (sampler_renderer.dart:84)
   RK(traceQueue(c, false, wf.extO[0], wf.extD[0], wf.extRange[0], wf.counts + Q_EXT0, wf.extHit, wf.extT, st));
   if (rs.nInfinite > 0) {  // escaped camera rays see the infinite lights (sampler_renderer.dart:86-92), whatever the integrator
-    CK(c, STAGE(launchEscape)(rs, wf, 0, ESCAPE_CAMERA, sms, st));
+    CK(c, STAGE(launchEscape)(rs, wf, 0, ESCAPE_CAMERA, sms, st)); profMark(c, DRT_PK_OTHER);
     c->launches++;
   }
   if (p.samplerKind == 4) {
-    CK(c, STAGE(launchSaveCameraPrims)(wf, nSlots, st));
+    CK(c, STAGE(launchSaveCameraPrims)(wf, nSlots, st)); profMark(c, DRT_PK_OTHER);
     c->launches++;
   }
   if (p.samplerKind != 3 && p.samplerKind != 5) {  // halton / bestcandidate: the accepted samples are counted on the device (raygenKernel)
@@ -768,32 +824,32 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
   if (p.integKind == 0) {
     int cur = 0;
     for (int bounce = 0; bounce <= p.maxDepth; ++bounce) {
-      CK(c, STAGE(launchResetCounts)(wf, (1u << (cur ^ 1)) | (1u << Q_SHADOW) | (1u << Q_MIS), st));
-      CK(c, STAGE(launchShadePath)(p, rs, wf, bounce, cur, rc, sms, st));
+      CK(c, STAGE(launchResetCounts)(wf, (1u << (cur ^ 1)) | (1u << Q_SHADOW) | (1u << Q_MIS), st)); profMark(c, DRT_PK_OTHER);
+      CK(c, STAGE(launchShadePath)(p, rs, wf, bounce, cur, rc, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
       c->launches += 2;
       if (rs.nLights > 0) {
         RK(traceQueue(c, true, wf.shO, wf.shD, wf.shRange, wf.counts + Q_SHADOW, wf.shOcc, nullptr, st));
         RK(traceQueue(c, false, wf.misO, wf.misD, wf.misRange, wf.counts + Q_MIS, wf.misHit, wf.misT, st));
-        CK(c, STAGE(launchResolveDirect)(p, rs, wf, cur, RESOLVE_PATH, 1, sms, st));
+        CK(c, STAGE(launchResolveDirect)(p, rs, wf, cur, RESOLVE_PATH, 1, sms, st)); profMark(c, DRT_PK_RESOLVE);
         c->launches++;
       }
       if (bounce == p.maxDepth) break;
       cur ^= 1;
       RK(traceQueue(c, false, wf.extO[cur], wf.extD[cur], wf.extRange[cur], wf.counts + cur, wf.extHit, wf.extT, st));
       if (rs.nInfinite > 0 && rs.general) {  // path_integrator.dart:106-114: only after a specular bounce, which matte scenes never take
-        CK(c, STAGE(launchEscape)(rs, wf, cur, ESCAPE_PATH, sms, st));
+        CK(c, STAGE(launchEscape)(rs, wf, cur, ESCAPE_PATH, sms, st)); profMark(c, DRT_PK_OTHER);
         c->launches++;
       }
     }
   } else if (p.integKind == 1) {
-    CK(c, STAGE(launchAoSetup)(p, rs, wf, sms, st));
+    CK(c, STAGE(launchAoSetup)(p, rs, wf, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
     c->launches++;
     const int nS = roundUpPow2(p.aoSamples);
     const uint32_t hitsPerChunk = std::max<uint32_t>(1, r->shCap / (uint32_t)nS);
     for (uint32_t first = 0; first < nSlots; first += hitsPerChunk) {
-      CK(c, STAGE(launchAoGen)(p, wf, first, hitsPerChunk, sms, st));
+      CK(c, STAGE(launchAoGen)(p, wf, first, hitsPerChunk, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
       RK(traceQueue(c, true, wf.shO, wf.shD, wf.shRange, wf.counts + Q_SHADOW, wf.shOcc, nullptr, st));
-      CK(c, STAGE(launchAoCount)(p, wf, first, hitsPerChunk, rc, sms, st));
+      CK(c, STAGE(launchAoCount)(p, wf, first, hitsPerChunk, rc, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
       c->launches += 2;
     }
   } else {  // directlighting / whitted: the integrator at the camera vertices, then its specular recursion
@@ -803,10 +859,10 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
   }
   const bool firstVisit = p.samplerKind == 4 && pb.pass == 0;
   if (firstVisit) {  // reportResults (adaptive_sampler.dart:133-158): supersampled pixels drop this visit's samples
-    CK(c, STAGE(launchAdaptiveDecide)(p, wf, pb, r->dAdaptList.p, r->dAdaptCount.p, st));
+    CK(c, STAGE(launchAdaptiveDecide)(p, wf, pb, r->dAdaptList.p, r->dAdaptCount.p, st)); profMark(c, DRT_PK_OTHER);
     c->launches++;
   }
-  CK(c, STAGE(launchFilm)(p, wf, nSlots, firstVisit ? 1 : 0, rc, st));
+  CK(c, STAGE(launchFilm)(p, wf, nSlots, firstVisit ? 1 : 0, rc, st)); profMark(c, DRT_PK_FILM);
   c->launches++;
   return DRT_OK;
 }
@@ -859,6 +915,12 @@ static int renderWindow(drt_ctx* c, int x, int y, int w, int h, uint32_t shard, 
   uint64_t slots = r->batchSlots ? r->batchSlots : (1ull << 24);
   if (const char* e = std::getenv("DRT_BATCH_SLOTS")) slots = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10));
   // One visit of `count` pixels (of this shard's part of the window, or of `list`) with the current p.nPixelSamples per pixel
+  if (r->profFlags & DRT_PROFILE_WORK) {
+    const bool fresh = r->dWork.p == nullptr;
+    CK(c, r->dWork.ensure(2));
+    if (fresh) CK(c, cudaMemset(r->dWork.p, 0, 2 * sizeof(DeviceCounters)));
+  }
+  profMark(c, -1);
   auto runVisit = [&](uint64_t count, uint32_t visit, const uint32_t* list) -> int {
     uint64_t pixelsPerBatch = std::max<uint64_t>(1, slots / (uint64_t)p.nPixelSamples);
     pixelsPerBatch = std::min<uint64_t>(pixelsPerBatch, std::max<uint64_t>(count, 1));
@@ -920,6 +982,7 @@ static int renderWindow(drt_ctx* c, int x, int y, int w, int h, uint32_t shard, 
   r->stats.shadow_rays += hc.shadowRays;
   r->stats.zeroed_samples += hc.zeroedSamples;
   CK(c, cudaMemset(r->dCounters.p, 0, sizeof(RenderCounters)));
+  if (r->profFlags) RK(profCollect(c));
   return DRT_OK;
 }
 
@@ -1212,6 +1275,7 @@ int drt_film_clear(drt_ctx* c) {
   r->filmPixels = 0;
   int rc = ensureFilm(c, r);
   r->stats = drt_render_stats{};
+  r->prof = drt_render_profile{};
   return rc;
 }
 
@@ -1263,7 +1327,7 @@ int drt_pixel_samples(drt_ctx* c, int x, int y, float* out, int cap, int32_t* n_
   const uint32_t n = (uint32_t)p.nPixelSamples;
   RK(ensureWavefront(c, r, n, n));
   PixelBatch pb{x, y, 1, 0, 1, 0, 0, 1, 1024};
-  CK(c, STAGE(launchSampler)(p, r->wf, r->dArrays.p, (int)r->arrays.size(), r->maxVals, r->maxOthers, pb, c->numSMs, c->stream));
+  CK(c, STAGE(launchSampler)(p, r->wf, r->dArrays.p, (int)r->arrays.size(), r->maxVals, r->maxOthers, pb, c->numSMs, c->stream)); profMark(c, DRT_PK_SAMPLER);
   c->launches++;
   std::vector<double2> xy(n), lens(n);
   std::vector<float> tm(n), vals((size_t)std::max(p.nVals, 1) * n);
@@ -1284,6 +1348,19 @@ int drt_pixel_samples(drt_ctx* c, int x, int y, float* out, int cap, int32_t* n_
       if ((size_t)i * per + k < (size_t)cap) out[(size_t)i * per + k] = rec[k];
   }
   if (floats_per_sample) *floats_per_sample = per;
+  return DRT_OK;
+}
+
+int drt_set_render_profiling(drt_ctx* c, int flags) {
+  if (!c) return DRT_E_INVALID;
+  if (flags & ~(DRT_PROFILE_TIME | DRT_PROFILE_WORK)) return fail(c, DRT_E_INVALID, "unknown profiling flags");
+  state(c)->profFlags = flags;
+  return DRT_OK;
+}
+
+int drt_render_profile_get(drt_ctx* c, drt_render_profile* out) {
+  if (!c || !out) return DRT_E_INVALID;
+  *out = state(c)->prof;
   return DRT_OK;
 }
 

@@ -24,8 +24,10 @@ namespace drt {
 template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(128) traceKernel(TraceScene sc, const float4* __restrict__ rayO,
                                                    const float4* __restrict__ rayD, uint64_t n, drt_hit_rec* hits,
-                                                   uint8_t* occluded, DeviceCounters* counters) {
+                                                   uint8_t* occluded, DeviceCounters* counters, const double2* __restrict__ range,
+                                                   const uint32_t* __restrict__ nDev) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (nDev) n = *nDev;  // a wavefront queue of the renderer: the count lives in device memory
   unsigned long long nodesVisited = 0, primsTested = 0;
   bool found = false;
   HitState hit;
@@ -33,6 +35,7 @@ __global__ void __launch_bounds__(128) traceKernel(TraceScene sc, const float4* 
   if (i < n && !sc.empty) {
     RayState r;
     initRay(r, rayO[i], rayD[i]);
+    if (range) { r.mint = range[i].x; r.maxt = range[i].y; }  // renderer rays: f64 minDistance / maxDistance
     int32_t stackRef[DRT_STACK];
     double stackT[DRT_STACK];
     int sp = 0;
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(128) traceKernel(TraceScene sc, const float4* 
       }
     }
   }
-  if (i < n) {
+  if (i < n && (ANY ? (occluded != nullptr) : (hits != nullptr))) {  // null output: count only
     if (ANY) {
       occluded[i] = found ? 1 : 0;
     } else {
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(128) traceKernel(TraceScene sc, const float4* 
 }
 
 cudaError_t launchTrace(const TraceScene& sc, bool any, bool count, const void* rayO, const void* rayD, uint64_t n,
-                        void* out, DeviceCounters* counters, cudaStream_t stream) {
+                        void* out, DeviceCounters* counters, cudaStream_t stream, const double2* range, const uint32_t* nDev) {
   if (n == 0) return cudaSuccess;
   const int block = 128;
   uint64_t grid64 = (n + block - 1) / block;
@@ -161,11 +164,11 @@ cudaError_t launchTrace(const TraceScene& sc, bool any, bool count, const void* 
   const float4* o = static_cast<const float4*>(rayO);
   const float4* d = static_cast<const float4*>(rayD);
   if (any) {
-    if (count) traceKernel<true, true><<<grid, block, 0, stream>>>(sc, o, d, n, nullptr, (uint8_t*)out, counters);
-    else traceKernel<true, false><<<grid, block, 0, stream>>>(sc, o, d, n, nullptr, (uint8_t*)out, counters);
+    if (count) traceKernel<true, true><<<grid, block, 0, stream>>>(sc, o, d, n, nullptr, (uint8_t*)out, counters, range, nDev);
+    else traceKernel<true, false><<<grid, block, 0, stream>>>(sc, o, d, n, nullptr, (uint8_t*)out, counters, range, nDev);
   } else {
-    if (count) traceKernel<false, true><<<grid, block, 0, stream>>>(sc, o, d, n, (drt_hit_rec*)out, nullptr, counters);
-    else traceKernel<false, false><<<grid, block, 0, stream>>>(sc, o, d, n, (drt_hit_rec*)out, nullptr, counters);
+    if (count) traceKernel<false, true><<<grid, block, 0, stream>>>(sc, o, d, n, (drt_hit_rec*)out, nullptr, counters, range, nDev);
+    else traceKernel<false, false><<<grid, block, 0, stream>>>(sc, o, d, n, (drt_hit_rec*)out, nullptr, counters, range, nDev);
   }
   return cudaGetLastError();
 }

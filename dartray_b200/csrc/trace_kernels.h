@@ -14,8 +14,11 @@ struct drt_hit_rec {  // == drt_hit of include/drt.h
 
 // Launches the closest-hit (any = false) or any-hit (any = true) traversal for n rays whose two
 // float4 arrays live in device memory.  `out` is drt_hit_rec[n] or uint8_t[n].
+// `range` / `nDev`: the renderer's per-ray f64 intervals and device-resident ray count (n is then the queue capacity);
+// out == nullptr with count = true only counts.
 cudaError_t launchTrace(const TraceScene& sc, bool any, bool count, const void* rayO, const void* rayD, uint64_t n,
-                        void* out, DeviceCounters* counters, cudaStream_t stream);
+                        void* out, DeviceCounters* counters, cudaStream_t stream, const double2* range = nullptr,
+                        const uint32_t* nDev = nullptr);
 
 // Optional inputs/outputs of the production kernel used by the wavefront renderer.
 struct TraceExtras {

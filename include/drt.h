@@ -354,6 +354,24 @@ typedef struct drt_render_stats {
 } drt_render_stats;
 int drt_render_stats_get(drt_ctx* ctx, drt_render_stats* out);
 
+/* Where a render's GPU time and algorithmic work go (SURVEY 8d "per-sample work"; the reference keeps the same kind of
+ * tallies in lib/core/stats.dart:527-640).  drt_set_render_profiling flags: DRT_PROFILE_TIME = record a CUDA event after
+ * every kernel the following renders launch on the context's stream and accumulate the spans per kernel class;
+ * DRT_PROFILE_WORK = also run, for every ray queue the renders trace, the counting walk of the reference's tree
+ * (bvh_accel.dart:125/131/187/193: every slab test and every primitive test; slow, results unchanged).
+ * drt_render_profile_get returns what accumulated since the last drt_film_clear. */
+enum { DRT_PROFILE_TIME = 1, DRT_PROFILE_WORK = 2 };
+enum { DRT_PK_TRACE_CLOSEST = 0, DRT_PK_TRACE_ANY = 1, DRT_PK_INTEGRATOR = 2, DRT_PK_SAMPLER = 3, DRT_PK_RESOLVE = 4,
+       DRT_PK_FILM = 5, DRT_PK_OTHER = 6, DRT_PK_COUNT = 7 };
+typedef struct drt_render_profile {
+  double ms[DRT_PK_COUNT];         /* device time per kernel class (launch-to-launch spans on the render stream) */
+  uint64_t launches[DRT_PK_COUNT];
+  drt_counters closest;            /* reference work of the closest-hit rays (Scene.intersect) */
+  drt_counters any;                /* reference work of the shadow rays (Scene.intersectP) */
+} drt_render_profile;
+int drt_set_render_profiling(drt_ctx* ctx, int flags);
+int drt_render_profile_get(drt_ctx* ctx, drt_render_profile* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -726,3 +726,33 @@ def test_render_errors():
         g.set_integrator(5, 5, 0, 1, 0.0, 1.0)
     with pytest.raises(capi.DrtError):
         g.set_materials(np.array([3], np.int32), np.ones((1, 3), np.float32), np.zeros(1, np.float32))
+
+
+# ---- drt_render_profile: event spans per kernel class, reference-walk work of every traced queue --------------------------------
+def test_render_profile_counts_the_reference_work_of_every_ray():
+    arrays, cam = _cornell()
+    g, o = _pair(arrays)
+    film, smp = host.Film(64, 48), host.Sampler(kind=host.SAMPLER_LD, spp=4)
+    integ = host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=5)
+    for c in (g, o):
+        host.configure_render(c, cam, film, smp, integ)
+    g.set_render_profiling(capi.PROFILE_TIME | capi.PROFILE_WORK)
+    g.film_clear()
+    g.render()
+    o.render(0, 1, 8)
+    prof, sg, so = g.render_profile(), g.render_stats(), o.render_stats()
+    # the counting walk saw exactly the rays the render traced ...
+    assert prof["closest"]["rays"] == sg["closest_rays"] == so["closest_rays"]
+    assert prof["any"]["rays"] == sg["shadow_rays"] == so["shadow_rays"]
+    # ... and did the slab / primitive tests the oracle's walk did (bvh_accel.dart:125/131/187/193)
+    assert prof["closest"]["nodes_visited"] + prof["any"]["nodes_visited"] == so["nodes_visited"]
+    assert prof["closest"]["prims_tested"] + prof["any"]["prims_tested"] == so["prims_tested"]
+    # every class that launched took time; the picture is unchanged by profiling
+    for k in ("trace_closest", "trace_any", "integrator", "sampler", "resolve", "film"):
+        assert prof["launches"][k] > 0 and prof["ms"][k] > 0.0, k
+    a = g.film_read()["rgb"]
+    g.set_render_profiling(0)
+    g.film_clear()
+    g.render()
+    assert np.array_equal(a, g.film_read()["rgb"])
+    assert g.render_profile()["launches"]["film"] == 0  # cleared by drt_film_clear, nothing recorded with profiling off
