@@ -36,21 +36,52 @@ def peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
-def other_bounds(alg_bytes, fp_ops, ms):
-    """SURVEY 8d asks for both candidate rooflines: the same algorithmic work against the L2 read bandwidth at the BVH's
-    working-set size and against the FP32 FMA rate, both measured on this pool's B200 by tools/microbench.cu
-    (profiles/r01_microbench.json).  The HBM figure above is the one the contract's `peak` names."""
-    try:
-        mb = json.load(open(os.path.join(ROOT, "profiles", "r01_microbench.json")))
-    except Exception:
-        return None
-    l2 = mb["l2_read_gb_per_s"]["114MB"]
-    fp = 2.0 * mb["fp32_fma_per_s"]
+def microbench():
+    """FP32 FMA rate and L2-resident read bandwidth by working-set size, measured on this pool's B200 by tools/microbench.cu
+    (MEASURED_PEAKS.json holds neither): the newest profiles/r0N_microbench.json."""
+    for name in ("r02_microbench.json", "r01_microbench.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name))), f"profiles/{name}"
+        except Exception:
+            continue
+    return None, None
+
+
+def l2_peak(working_set_bytes):
+    """Measured L2 read bandwidth (GB/s) at the scene's working-set size: linear interpolation between the measured sizes."""
+    mb, src = microbench()
+    if mb is None:
+        return None, None
+    pts = sorted((float(k[:-2]), v) for k, v in mb["l2_read_gb_per_s"].items())  # "64MB" -> (64 MiB, GB/s)
+    x = working_set_bytes / 2.0 ** 20
+    if x <= pts[0][0]:
+        return pts[0][1], src
+    for (x0, y0), (x1, y1) in zip(pts, pts[1:]):
+        if x <= x1:
+            return y0 + (y1 - y0) * (x - x0) / (x1 - x0), src
+    return pts[-1][1], src
+
+
+def roofline_block(alg_bytes, fp_ops, ms, working_set_bytes, hbm_gbs, peak_src):
+    """The contract's roofline object for a kernel whose working set is L2-resident: SURVEY 8d asks for both candidate
+    rooflines (memory and FP32 issue) and to call the one that binds the bound.  ncu (profiles/r02_summary.md) shows DRAM
+    at ~4 % of its peak and the L2 hit rate above 80 % for the 1 M-triangle BVH, so the memory roofline of this kernel is
+    the L2's, measured at the working-set size; the HBM-copy and FP32 figures are kept beside it."""
     t = ms * 1e-3
-    return {"l2": {"achieved": alg_bytes / t / 1e9, "peak": l2, "unit": "GB/s", "frac": alg_bytes / t / 1e9 / l2,
-                   "note": "L2 read bandwidth over a 114 MB working set (the soup_1m BVH)"},
-            "fp32": {"achieved": fp_ops / t / 1e12, "peak": fp / 1e12, "unit": "TFLOP/s", "frac": fp_ops / t / fp,
-                     "note": "20 x nodes + 51 x prims reference operations per ray (SURVEY 8d) against the FP32 FMA rate"}}
+    achieved = alg_bytes / t / 1e9
+    mb, mb_src = microbench()
+    l2, _ = l2_peak(working_set_bytes)
+    out = {"bound": "l2" if l2 else "hbm", "achieved": achieved, "peak": l2 or hbm_gbs, "unit": "GB/s",
+           "frac": achieved / (l2 or hbm_gbs),
+           "peak_source": (f"L2 read bandwidth at a {working_set_bytes / 2.0 ** 20:.0f} MiB working set, tools/microbench.cu ({mb_src})"
+                           if l2 else peak_src),
+           "hbm": {"achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "peak_source": peak_src,
+                   "note": "the same algorithmic bytes against the HBM copy peak: the working set is L2-resident, HBM is nearly idle"}}
+    if mb is not None:
+        fp = 2.0 * mb["fp32_fma_per_s"]
+        out["fp32"] = {"achieved": fp_ops / t / 1e12, "peak": fp / 1e12, "unit": "TFLOP/s", "frac": fp_ops / t / fp,
+                       "note": "20 x nodes + 51 x prims reference operations per ray (SURVEY 8d) against the measured FP32 FMA rate"}
+    return out
 
 
 class ClockSampler(threading.Thread):
@@ -143,8 +174,8 @@ def run_cpu_step(orc, cs, is_, threads):
     return (cs[0].shape[0] + 2 * is_[0].shape[0]), dt
 
 
-def config_dict(n_gpus):
-    return {
+def config_dict(n_gpus, sample=None):
+    d = {
         "workload": "soup_1m ray cast: 1,015,810-triangle procedural mesh, SAH BVH (maxnodeprims 4); per step "
                     "8,388,608 coherent closest-hit + 8,388,608 incoherent closest-hit + 8,388,608 incoherent "
                     "any-hit (shadow) rays per GPU",
@@ -153,6 +184,9 @@ def config_dict(n_gpus):
         "parallelism": f"rays sharded, BVH replicated x{n_gpus}",
         "l2": "L2 flushed (256 MiB write) between timed steps; ray buffers (268 MB/launch) exceed the 126 MB L2",
     }
+    if sample:
+        d["sample"] = sample  # the CPU arm times a bounded sample of the step, not the whole step
+    return d
 
 
 # ---- render legs (BASELINE.json configs[2] and configs[3]) ------------------------------------------------
@@ -169,7 +203,7 @@ def render_configs():
     return ao, path
 
 
-def render_legs(ctx_soup, rank, world, barrier):
+def render_legs(ctx_soup, soup_mesh, rank, world, barrier):
     """configs[2]: ambient occlusion on soup_1m; configs[3]: cornell_synth path tracing, 256 spp.  Pixels are
     sharded over the ranks (interleaved 1024-pixel blocks), the films summed with NCCL; timed as the blocking
     C-ABI call (wall clock between barriers, max over ranks)."""
@@ -184,6 +218,7 @@ def render_legs(ctx_soup, rank, world, barrier):
     sb, cam_cornell = scenes.cornell_synth()
     ctx_c = capi.Context(ctx_soup.device)
     host.upload_scene(ctx_c, sb.arrays())
+    arrays_of = {"ao": None, "path": sb.arrays()}  # ao: the bare soup_1m mesh the ray-cast step uses
     legs = [("ao", ctx_soup, cam_soup, ao_s, ao_i), ("path", ctx_c, cam_cornell, pt_s, pt_i)]
     for name, ctx, cam, smp, integ in legs:
         film = host.Film(*RENDER_RES)
@@ -219,6 +254,80 @@ def render_legs(ctx_soup, rank, world, barrier):
                      "launches_rank0": int(ctx.kernel_launches - l0), "mean_rgb": [float(v) for v in rgb.mean(axis=(0, 1))],
                      "per_rank": {"render_s_max": float(pr[0]), "render_s_min": float(pr_min[0]), "film_sum_s_max": float(pr[1]),
                                   "film_sum_s_min": float(pr_min[1]), "render_plus_sum_s_max": float(pr[2])}}
+        # ---- roofline of the leg (rank 0's shard; untimed extra passes) ------------------------------------------------
+        # (1) device time per kernel class: CUDA events after every launch of one more render of the same configuration
+        ctx.set_render_profiling(capi.PROFILE_TIME)
+        ctx.film_clear()
+        ctx.render_shard(rank, world)
+        prof = ctx.render_profile()
+        my_samples = ctx.render_stats()["camera_samples"]
+        # (2) reference work of the rays (slab and primitive tests of the reference's walk over its binary BVH),
+        # counted by the counting kernel on every queue; the path leg counts a 16 spp render of the same film (1/16 of the
+        # rays, the per-sample work is what scales)
+        work_smp = smp if name == "ao" else host.Sampler(kind=host.SAMPLER_LD, spp=16)
+        host.configure_render(ctx, cam, film, work_smp, integ)
+        ctx.set_render_profiling(capi.PROFILE_WORK)
+        ctx.film_clear()
+        ctx.render_shard(rank, world)
+        wk, wst = ctx.render_profile(), ctx.render_stats()
+        ctx.set_render_profiling(0)
+        floats_per_sample = int(ctx.pixel_samples(RENDER_RES[0] // 2, RENDER_RES[1] // 2).shape[1])
+        host.configure_render(ctx, cam, film, smp, integ)
+        ws = max(1, wst["camera_samples"])
+        b_closest = 32 * wk["closest"]["nodes_visited"] + 36 * wk["closest"]["prims_tested"] + 48 * wk["closest"]["rays"]
+        b_any = 32 * wk["any"]["nodes_visited"] + 36 * wk["any"]["prims_tested"] + 33 * wk["any"]["rays"]
+        ops = 20 * (wk["closest"]["nodes_visited"] + wk["any"]["nodes_visited"]) + 51 * (wk["closest"]["prims_tested"] + wk["any"]["prims_tested"])
+        per_sample_bytes = (b_closest + b_any) / ws + 4 * floats_per_sample + 16
+        ms_all = sum(prof["ms"].values())
+        dom = max(prof["ms"], key=prof["ms"].get)
+        pk, pk_src = peaks()
+        wset = ctx.bvh_info()["device_bytes"]
+        rl = roofline_block(per_sample_bytes * my_samples, ops / ws * my_samples, ms_all, wset, pk["hbm_gbs"], pk_src)
+        rl.update({
+            "kernel": f"whole leg ({len([k for k, v in prof['launches'].items() if v])} kernel classes, {sum(prof['launches'].values())} launches); dominant class: {dom}",
+            "per_sample": {"bytes": per_sample_bytes, "traversal_bytes": (b_closest + b_any) / ws, "sampler_bytes": 4 * floats_per_sample,
+                           "film_bytes": 16, "fp_ops": ops / ws,
+                           "closest_rays": wk["closest"]["rays"] / ws, "shadow_rays": wk["any"]["rays"] / ws,
+                           "nodes_visited": (wk["closest"]["nodes_visited"] + wk["any"]["nodes_visited"]) / ws,
+                           "prims_tested": (wk["closest"]["prims_tested"] + wk["any"]["prims_tested"]) / ws},
+            "device_ms_by_class": prof["ms"], "launches_by_class": prof["launches"],
+            "share_by_class": {k: v / ms_all for k, v in prof["ms"].items()},
+            "work_counted_on": f"{wst['camera_samples']} camera samples ({'the timed configuration' if name == 'ao' else '16 spp of the same film'}), rank 0's shard",
+            "traffic": None,
+        })
+        # the traversal kernels on their own: reference bytes of the class's rays over the class's device time
+        scale = my_samples / ws
+        trav = {}
+        for cls, b in (("trace_closest", b_closest), ("trace_any", b_any)):
+            if prof["ms"][cls] > 0:
+                l2, _ = l2_peak(wset)
+                a = b * scale / (prof["ms"][cls] * 1e-3) / 1e9
+                trav[cls] = {"achieved": a, "unit": "GB/s", "frac_l2": a / l2 if l2 else None, "frac_hbm": a / pk["hbm_gbs"],
+                             "mrays_per_s": wk["closest" if cls == "trace_closest" else "any"]["rays"] * scale / prof["ms"][cls] / 1e3}
+        rl["traversal"] = trav
+        out[name]["roofline"] = rl
+        # ---- end to end through the C ABI from host arrays: scene upload (+ BVH build) + render + film read-back ------------
+        arrays = arrays_of[name]
+        barrier()
+        t0 = time.perf_counter()
+        ctx2 = capi.Context(ctx.device)
+        if arrays is None:
+            ctx2.set_triangles(*soup_mesh)
+            ctx2.build_bvh(capi.SPLIT_SAH, 4)
+        else:
+            host.upload_scene(ctx2, arrays)
+        host.configure_render(ctx2, cam, film, smp, integ)
+        t_up = time.perf_counter() - t0
+        distributed.render_sharded(ctx2, rank, world)
+        img = ctx2.film_read()["rgb"]
+        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        h2d = int(sum(v.nbytes for v in (arrays.values() if arrays is not None else soup_mesh) if isinstance(v, np.ndarray)))
+        out[name]["e2e"] = {"seconds": float(t_e2e.item()), "value": samples / float(t_e2e.item()), "unit": "camera samples/s",
+                            "upload_and_build_seconds_rank0": t_up, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(img.nbytes),
+                            "what": "fresh context: drt_set_* scene arrays from host memory, drt_build_bvh, drt_render_shard, film sum, drt_film_read"}
+        del ctx2
     out["ao"]["config"] = (f"BASELINE.json configs[2]: soup_1m, {RENDER_RES[0]}x{RENDER_RES[1]}, 1 camera sample/pixel at the "
                            f"pixel centre, {AO_RAYS} AO rays per hit")
     out["path"]["config"] = (f"BASELINE.json configs[3]: cornell_synth, {RENDER_RES[0]}x{RENDER_RES[1]}, lowdiscrepancy "
@@ -271,7 +380,7 @@ def reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus),
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus, sample),
         "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample,
                          "note": "C++ restatement of the DartRay CPU path (oracle/), not the Dart VM: no Dart SDK in the image",
                          "render": cpu_render_sample(threads)},
@@ -409,7 +518,7 @@ def main():
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_val = world * rays_per_step * e2e_steps / float(e2e_t.item()) / 1e6
 
-    render = None if args.no_render else render_legs(ctx, rank, world, barrier)
+    render = None if args.no_render else render_legs(ctx, (P, idx), rank, world, barrier)
 
     if rank != 0:
         if world > 1:
@@ -420,10 +529,13 @@ def main():
     w = work[1]
     alg_bytes = 32 * w["nodes_visited"] + 36 * w["prims_tested"] + 48 * w["rays"]
     achieved = alg_bytes / (per_kind_ms[1] * 1e-3) / 1e9
-    traffic = None
+    # dram__bytes_read + dram__bytes_write of this launch from the round's `ncu --set full` capture (tools/capture_round.sh
+    # writes the file next to the ncu metrics it was read from)
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
     line = {
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -433,18 +545,17 @@ def main():
             "incoherent_any_mrays": n_inc / per_kind_ms[2] / 1e3, "ms": per_kind_ms,
             "wall_s_timed_region": t_wall,
         },
-        "roofline": {
-            "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-            "traffic": traffic, "kernel": "traceFastKernel<closest, triangles-only leaf code> on the incoherent set",
-            "algorithmic_bytes_per_launch": alg_bytes,
-            "per_ray": {"nodes_visited": w["nodes_visited"] / w["rays"], "prims_tested": w["prims_tested"] / w["rays"],
-                        "bytes": alg_bytes / w["rays"]},
-            "fp_ops_per_launch": 20 * w["nodes_visited"] + 51 * w["prims_tested"],
-            "other_bounds": other_bounds(alg_bytes, 20 * w["nodes_visited"] + 51 * w["prims_tested"], per_kind_ms[1]),
-            "peak_source": pk_src,
-            "note": "algorithmic bytes = 32*nodes + 36*prims + 48 per ray on the reference BVH (SURVEY 8d); the working "
-                    "set (114 MB) is L2-resident, so this can exceed the HBM copy peak",
-        },
+        "roofline": dict(
+            roofline_block(alg_bytes, 20 * w["nodes_visited"] + 51 * w["prims_tested"], per_kind_ms[1], info["device_bytes"],
+                           pk["hbm_gbs"], pk_src),
+            traffic=traffic, traffic_source=traffic_src,
+            kernel="traceQKernel<closest, triangles-only leaf code> on the incoherent set (trace_fast2.cu)",
+            algorithmic_bytes_per_launch=alg_bytes,
+            per_ray={"nodes_visited": w["nodes_visited"] / w["rays"], "prims_tested": w["prims_tested"] / w["rays"],
+                     "bytes": alg_bytes / w["rays"]},
+            fp_ops_per_launch=20 * w["nodes_visited"] + 51 * w["prims_tested"],
+            note="algorithmic bytes = 32*nodes + 36*prims + 48 per ray on the REFERENCE binary BVH (SURVEY 8d), whatever the "
+                 "kernel's own node format fetches"),
         "e2e": {"value": e2e_val, "unit": "Mrays/s",
                 "h2d_bytes_per_step": 32 * (n_coh + 2 * n_inc), "d2h_bytes_per_step": 16 * (n_coh + n_inc) + n_inc},
         "gpu_launches": int(gpu_launches),

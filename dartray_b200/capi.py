@@ -21,7 +21,7 @@ HIT_DTYPE = np.dtype([("t", np.float32), ("b1", np.float32), ("b2", np.float32),
 
 # every symbol include/drt.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
-    "drt_version", "drt_create", "drt_destroy", "drt_last_error", "drt_set_triangles", "drt_set_spheres", "drt_set_disks", "drt_set_quadrics", "drt_set_mesh_shading", "drt_set_infinite_light", "drt_set_lobe_wrappers", "drt_set_light_map", "drt_set_sample_table",
+    "drt_version", "drt_create", "drt_create_multi", "drt_device_count", "drt_destroy", "drt_last_error", "drt_set_triangles", "drt_set_spheres", "drt_set_disks", "drt_set_quadrics", "drt_set_mesh_shading", "drt_set_infinite_light", "drt_set_lobe_wrappers", "drt_set_light_map", "drt_set_sample_table",
     "drt_set_build_order", "drt_build_bvh", "drt_bvh_info_get", "drt_bvh_export", "drt_trace_closest",
     "drt_trace_any", "drt_trace_closest_device", "drt_trace_any_device", "drt_set_counting", "drt_get_counters", "drt_set_kernel_variant",
     "drt_last_kernel_ms", "drt_kernel_launches",
@@ -78,6 +78,9 @@ def load():
     L.drt_version.restype = i32
     L.drt_create.restype = vp
     L.drt_create.argtypes = [i32]
+    L.drt_create_multi.restype = vp
+    L.drt_create_multi.argtypes = [vp, i32]
+    L.drt_device_count.argtypes = [vp]
     L.drt_destroy.argtypes = [vp]
     L.drt_last_error.restype = C.c_char_p
     L.drt_last_error.argtypes = [vp]
@@ -139,14 +142,26 @@ def _arr(a, dtype):
 
 
 class Context:
-    """One drt_ctx: a scene resident on one CUDA device."""
+    """One drt_ctx: a scene resident on one CUDA device, or — `device` a list of ids — on several (drt_create_multi:
+    one BVH build, renders split over the devices, films summed into the first device's)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
         self.L = load()
-        self.h = self.L.drt_create(device)
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int * len(device))(*device)
+            self.h = self.L.drt_create_multi(ids, len(device))
+            self.devices = list(device)
+            device = device[0] if device else -1
+        else:
+            self.h = self.L.drt_create(device)
+            self.devices = [device]
         if not self.h:
             raise DrtError(-4, self.L.drt_last_error(None).decode())
         self.device = device
+
+    @property
+    def device_count(self) -> int:
+        return int(self.L.drt_device_count(self.h))
 
     def close(self):
         if getattr(self, "h", None):
@@ -354,6 +369,7 @@ class Context:
 
     def film_clear(self):
         self._ck(self.L.drt_film_clear(self.h))
+        self._film_is_summed = False  # distributed.render_sharded
 
     def film_size(self):
         out = np.zeros(4, np.int32)

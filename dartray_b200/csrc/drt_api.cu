@@ -13,6 +13,8 @@
 
 #include "drt_ctx.h"
 
+#include <thread>
+
 namespace {
 thread_local std::string g_createError;
 }
@@ -72,8 +74,32 @@ drt_ctx* drt_create(int device_id) {
   return c;
 }
 
+drt_ctx* drt_create_multi(const int* device_ids, int n_devices) {
+  if (!device_ids || n_devices < 1) { g_createError = "drt_create_multi needs at least one device id"; return nullptr; }
+  for (int i = 0; i < n_devices; ++i)
+    for (int j = 0; j < i; ++j)
+      if (device_ids[i] == device_ids[j] && !std::getenv("DRT_ALLOW_DUPLICATE_DEVICES")) {
+        // (the env knob lets a one-GPU box exercise the whole multi-device path: two contexts of one device)
+        g_createError = "drt_create_multi: a device id is listed twice";
+        return nullptr;
+      }
+  drt_ctx* c = drt_create(device_ids[0]);
+  if (!c) return nullptr;
+  for (int i = 1; i < n_devices; ++i) {
+    drt_ctx* p = drt_create(device_ids[i]);
+    if (!p) { drt_destroy(c); return nullptr; }
+    p->owner = c;
+    c->peers.push_back(p);
+  }
+  return c;
+}
+
+int drt_device_count(const drt_ctx* c) { return c ? 1 + (int)c->peers.size() : 0; }
+
 void drt_destroy(drt_ctx* c) {
   if (!c) return;
+  for (drt_ctx* p : c->peers) drt_destroy(p);
+  c->peers.clear();
   if (c->device == DRT_DEVICE_NONE) { drtRenderStateDestroy(c); delete c; return; }
   cudaSetDevice(c->device);
   drtRenderStateDestroy(c);
@@ -92,7 +118,7 @@ const char* drt_last_error(const drt_ctx* c) { return c ? c->err.c_str() : g_cre
 
 // The float32 wide nodes of trace_fast.cu, uploaded on demand (scenes that run the quantised kernel never need them).
 static int uploadWideV1(drt_ctx* c) {
-  const BuiltBvh& B = c->bvh;
+  const BuiltBvh& B = c->hostBvh();
   CK(c, cudaSetDevice(c->device));
   CK(c, c->dWide.ensure(std::max<size_t>(1, B.wide.size())));
   if (!B.wide.empty())
@@ -104,6 +130,7 @@ static int uploadWideV1(drt_ctx* c) {
 
 int drt_set_triangles(drt_ctx* c, const float* P, uint32_t nverts, const uint32_t* idx, uint32_t ntris,
                       const int32_t* mat, const int32_t* light, const uint8_t* rev) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_triangles(p_, P, nverts, idx, ntris, mat, light, rev));
   if (!c) return DRT_E_INVALID;
   if ((ntris && (!P || !idx)) || (ntris && !nverts)) return fail(c, DRT_E_INVALID, "null triangle arrays");
   for (uint64_t i = 0; i < (uint64_t)ntris * 3; ++i)
@@ -124,6 +151,7 @@ int drt_set_triangles(drt_ctx* c, const float* P, uint32_t nverts, const uint32_
 
 int drt_set_mesh_shading(drt_ctx* c, const float* N, const float* S, const float* uv, const uint32_t* meshOfTri, uint32_t nmeshes,
                          const float* o2w, const float* w2o, const uint8_t* flags) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_mesh_shading(p_, N, S, uv, meshOfTri, nmeshes, o2w, w2o, flags));
   if (!c) return DRT_E_INVALID;
   c->vertN.clear(); c->vertS.clear(); c->vertUV.clear(); c->meshOfTri.clear();
   c->meshO2W.clear(); c->meshW2O.clear(); c->meshFlags.clear();
@@ -147,6 +175,7 @@ int drt_set_mesh_shading(drt_ctx* c, const float* N, const float* S, const float
 
 int drt_set_spheres(drt_ctx* c, uint32_t n, const float* o2w, const float* w2o, const double* prm, const int32_t* mat,
                     const int32_t* light, const uint8_t* rev) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_spheres(p_, n, o2w, w2o, prm, mat, light, rev));
   if (!c) return DRT_E_INVALID;
   if (n && (!o2w || !w2o || !prm)) return fail(c, DRT_E_INVALID, "null sphere arrays");
   c->spheres.resize(n);
@@ -169,6 +198,7 @@ int drt_set_spheres(drt_ctx* c, uint32_t n, const float* o2w, const float* w2o, 
 
 int drt_set_disks(drt_ctx* c, uint32_t n, const float* o2w, const float* w2o, const double* prm, const int32_t* mat,
                   const int32_t* light, const uint8_t* rev) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_disks(p_, n, o2w, w2o, prm, mat, light, rev));
   if (!c) return DRT_E_INVALID;
   if (n && (!o2w || !w2o || !prm)) return fail(c, DRT_E_INVALID, "null disk arrays");
   for (uint32_t i = 0; i < n; ++i) {  // appended to the quadric range, after the spheres
@@ -189,6 +219,7 @@ int drt_set_disks(drt_ctx* c, uint32_t n, const float* o2w, const float* w2o, co
 
 int drt_set_quadrics(drt_ctx* c, int kind, uint32_t n, const float* o2w, const float* w2o, const double* prm, const int32_t* mat,
                      const int32_t* light, const uint8_t* rev) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_quadrics(p_, kind, n, o2w, w2o, prm, mat, light, rev));
   if (!c) return DRT_E_INVALID;
   if (kind < DRT_QUADRIC_CYLINDER || kind > DRT_QUADRIC_HYPERBOLOID) return fail(c, DRT_E_INVALID, "unknown quadric kind");
   if (n && (!o2w || !w2o || !prm)) return fail(c, DRT_E_INVALID, "null quadric arrays");
@@ -208,6 +239,7 @@ int drt_set_quadrics(drt_ctx* c, int kind, uint32_t n, const float* o2w, const f
 }
 
 int drt_set_build_order(drt_ctx* c, const uint32_t* ids, uint32_t n) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_build_order(p_, ids, n));
   if (!c) return DRT_E_INVALID;
   if (!ids) c->order.clear();
   else c->order.assign(ids, ids + n);
@@ -267,6 +299,52 @@ static void quadricSetup(const HostSphere& s, GSphere* gp) {
   g.phiMax = (3.141592653589793 / 180.0) * clampd(pm, 0.0, 360.0);
 }
 
+// Device half of drt_build_bvh: the built tree's arrays go to c's device.  B / prims / gs may belong to another context (the
+// owner of a multi-device context builds once on the host and every device uploads the same arrays).
+static int uploadBuilt(drt_ctx* c, const BuiltBvh& B, const std::vector<GPrim>& prims, const std::vector<GSphere>& gs, uint32_t np) {
+  CK(c, cudaSetDevice(c->device));
+  CK(c, c->dNodes.ensure(std::max<size_t>(1, B.nodes.size())));
+  c->wideQOk = B.wideQOk && B.wideQ.size() == B.wide.size();
+  c->wideUploaded = false;
+  if (!c->useQ()) {  // the float32 nodes go to the device only when their kernel is the one that runs (or is asked for later)
+    int rc = uploadWideV1(c);
+    if (rc != DRT_OK) return rc;
+  }
+  if (c->wideQOk) {
+    CK(c, c->dWideQ.ensure(std::max<size_t>(1, B.wideQ.size())));
+    if (!B.wideQ.empty())
+      CK(c, cudaMemcpy(c->dWideQ.p, B.wideQ.data(), B.wideQ.size() * sizeof(GNode4Q), cudaMemcpyHostToDevice));
+  }
+  CK(c, c->dPrims.ensure(prims.size()));
+  CK(c, c->dSpheres.ensure(std::max<size_t>(1, gs.size())));
+  if (!B.nodes.empty())
+    CK(c, cudaMemcpy(c->dNodes.p, B.nodes.data(), B.nodes.size() * sizeof(GNode), cudaMemcpyHostToDevice));
+  CK(c, cudaMemcpy(c->dPrims.p, prims.data(), prims.size() * sizeof(GPrim), cudaMemcpyHostToDevice));
+  if (!gs.empty()) CK(c, cudaMemcpy(c->dSpheres.p, gs.data(), gs.size() * sizeof(GSphere), cudaMemcpyHostToDevice));
+  c->ts.nodes = c->dNodes.p;
+  c->ts.wide = c->dWide.p;
+  c->ts.wideQ = c->useQ() ? c->dWideQ.p : nullptr;
+  c->ts.wideRootRef = B.wideRootRef;
+  c->ts.prims = c->dPrims.p;
+  c->ts.spheres = c->dSpheres.p;
+  std::memcpy(c->ts.rootMin, B.rootMin, 12);
+  std::memcpy(c->ts.rootMax, B.rootMax, 12);
+  c->ts.rootRef = B.rootRef;
+  c->ts.empty = 0;
+  c->ts.quadMode = 0;
+  for (const HostSphere& hs : c->spheres) c->ts.quadMode = std::max(c->ts.quadMode, hs.shape >= 2 ? 2 : 1);
+  c->info.n_nodes = (uint32_t)B.refNodes.size();
+  c->info.n_prims = np;
+  c->info.n_leaves = B.nLeaves;
+  c->info.max_leaf_prims = B.maxLeafPrims;
+  c->info.max_depth = B.maxDepth;
+  c->info.device_bytes = (c->wideQOk ? B.wideQ.size() * sizeof(GNode4Q) : 0) + (c->wideUploaded ? B.wide.size() * sizeof(GNode4) : 0) +
+                         prims.size() * sizeof(GPrim) + gs.size() * sizeof(GSphere);
+  c->built = true;
+  return DRT_OK;
+}
+
+
 int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
   if (!c) return DRT_E_INVALID;
   if (split < 0 || split > 2) return fail(c, DRT_E_INVALID, "split method must be 0 (middle), 1 (equal) or 2 (sah)");
@@ -282,6 +360,7 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
   if (np == 0) {  // bvh_accel.dart:50-53: nodes == null, every query misses
     c->ts.empty = 1;
     c->built = true;
+    for (drt_ctx* p_ : c->peers) { p_->ts = TraceScene{}; p_->ts.empty = 1; p_->built = true; p_->buildSerial++; }
     return DRT_OK;
   }
   std::vector<uint32_t> order = c->order;
@@ -382,45 +461,27 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
     c->built = true;
     return DRT_OK;
   }
-  CK(c, c->dNodes.ensure(std::max<size_t>(1, B.nodes.size())));
-  c->wideQOk = B.wideQOk && B.wideQ.size() == B.wide.size();
-  c->wideUploaded = false;
-  if (!c->useQ()) {  // the float32 nodes go to the device only when their kernel is the one that runs (or is asked for later)
-    int rc = uploadWideV1(c);
-    if (rc != DRT_OK) return rc;
+  int rc = uploadBuilt(c, B, prims, gs, np);
+  if (rc != DRT_OK) return rc;
+  // a multi-device context: the same arrays to every other device, one host thread each
+  if (!c->peers.empty()) {
+    std::vector<int> rcs(c->peers.size(), DRT_OK);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < c->peers.size(); ++i)
+      th.emplace_back([&, i] {
+        drt_ctx* p_ = c->peers[i];
+        p_->built = false;
+        p_->buildSerial++;
+        p_->ts = TraceScene{};
+        p_->info = drt_bvh_info{};
+        rcs[i] = uploadBuilt(p_, B, prims, gs, np);
+      });
+    for (auto& t : th) t.join();
+    for (size_t i = 0; i < rcs.size(); ++i)
+      if (rcs[i] != DRT_OK) { c->err = "device " + std::to_string(c->peers[i]->device) + ": " + c->peers[i]->err; return rcs[i]; }
   }
-  if (c->wideQOk) {
-    CK(c, c->dWideQ.ensure(std::max<size_t>(1, B.wideQ.size())));
-    if (!B.wideQ.empty())
-      CK(c, cudaMemcpy(c->dWideQ.p, B.wideQ.data(), B.wideQ.size() * sizeof(GNode4Q), cudaMemcpyHostToDevice));
-  }
-  CK(c, c->dPrims.ensure(prims.size()));
-  CK(c, c->dSpheres.ensure(std::max<size_t>(1, gs.size())));
-  if (!B.nodes.empty())
-    CK(c, cudaMemcpy(c->dNodes.p, B.nodes.data(), B.nodes.size() * sizeof(GNode), cudaMemcpyHostToDevice));
-  CK(c, cudaMemcpy(c->dPrims.p, prims.data(), prims.size() * sizeof(GPrim), cudaMemcpyHostToDevice));
-  if (!gs.empty()) CK(c, cudaMemcpy(c->dSpheres.p, gs.data(), gs.size() * sizeof(GSphere), cudaMemcpyHostToDevice));
-  c->ts.nodes = c->dNodes.p;
-  c->ts.wide = c->dWide.p;
-  c->ts.wideQ = c->useQ() ? c->dWideQ.p : nullptr;
-  c->ts.wideRootRef = B.wideRootRef;
-  c->ts.prims = c->dPrims.p;
-  c->ts.spheres = c->dSpheres.p;
-  std::memcpy(c->ts.rootMin, B.rootMin, 12);
-  std::memcpy(c->ts.rootMax, B.rootMax, 12);
-  c->ts.rootRef = B.rootRef;
-  c->ts.empty = 0;
-  c->ts.quadMode = 0;
-  for (const HostSphere& hs : c->spheres) c->ts.quadMode = std::max(c->ts.quadMode, hs.shape >= 2 ? 2 : 1);
-  c->info.n_nodes = (uint32_t)B.refNodes.size();
-  c->info.n_prims = np;
-  c->info.n_leaves = B.nLeaves;
-  c->info.max_leaf_prims = B.maxLeafPrims;
-  c->info.max_depth = B.maxDepth;
-  c->info.device_bytes = (c->wideQOk ? B.wideQ.size() * sizeof(GNode4Q) : 0) + (c->wideUploaded ? B.wide.size() * sizeof(GNode4) : 0) +
-                         prims.size() * sizeof(GPrim) + gs.size() * sizeof(GSphere);
   c->info.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  c->built = true;
+  for (drt_ctx* p_ : c->peers) p_->info.build_seconds = c->info.build_seconds;
   return DRT_OK;
 }
 
@@ -434,7 +495,7 @@ int drt_bvh_info_get(const drt_ctx* c, drt_bvh_info* out) {
 int drt_bvh_export(const drt_ctx* c, float* bounds, int32_t* offset, int32_t* nprims, int32_t* axis, uint32_t* ordered) {
   if (!c) return DRT_E_INVALID;
   if (!c->built) return DRT_E_STATE;
-  const BuiltBvh& B = c->bvh;
+  const BuiltBvh& B = c->hostBvh();
   for (size_t i = 0; i < B.refNodes.size(); ++i) {
     const RefNode& n = B.refNodes[i];
     if (bounds) { std::memcpy(bounds + 6 * i, n.bmin, 12); std::memcpy(bounds + 6 * i + 3, n.bmax, 12); }
@@ -541,6 +602,7 @@ int drt_set_counting(drt_ctx* c, int enabled) {
 }
 
 int drt_set_kernel_variant(drt_ctx* c, int variant) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_kernel_variant(p_, variant));
   if (!c) return DRT_E_INVALID;
   if (variant != DRT_KERNEL_FAST && variant != DRT_KERNEL_EXACT_WALK && variant != DRT_KERNEL_FAST_V1 && variant != DRT_KERNEL_FAST_Q)
     return fail(c, DRT_E_INVALID, "unknown kernel variant");

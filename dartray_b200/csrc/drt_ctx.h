@@ -110,6 +110,14 @@ struct drt_ctx {
 
   struct RenderState* render = nullptr;  // render_api.cu
 
+  // drt_create_multi: this context drives device_ids[0]; `peers` are the contexts of the other devices (owned: destroyed with
+  // this one).  Every scene / camera / film / sampler setter is applied to the peers too; the BVH is built once, here, and its
+  // arrays uploaded to every device; renders are split over all devices and the films summed into this one's.
+  std::vector<drt_ctx*> peers;
+  drt_ctx* owner = nullptr;  // set on a peer: the context that holds the host copy of the built BVH
+  bool peerAccessTried = false;
+  const BuiltBvh& hostBvh() const { return owner ? owner->bvh : bvh; }
+
   uint32_t ntris() const { return (uint32_t)(idx.size() / 3); }
   uint32_t nprims() const { return ntris() + (uint32_t)spheres.size(); }
 };
@@ -121,6 +129,19 @@ struct drt_ctx {
       (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                  \
       return e__ == cudaErrorMemoryAllocation ? DRT_E_NOMEM : DRT_E_CUDA;                \
     }                                                                                    \
+  } while (0)
+
+// First line of every setter: apply the call to the other devices of a multi-device context (`p_` names the peer).
+#define DRT_FORWARD_TO_PEERS(ctx, call)                                                              \
+  do {                                                                                               \
+    if (ctx)                                                                                         \
+      for (drt_ctx* p_ : (ctx)->peers) {                                                             \
+        int rc_ = (call);                                                                            \
+        if (rc_ != DRT_OK) {                                                                         \
+          (ctx)->err = "device " + std::to_string(p_->device) + ": " + p_->err;                      \
+          return rc_;                                                                                \
+        }                                                                                            \
+      }                                                                                              \
   } while (0)
 
 static inline int fail(drt_ctx* c, int code, const char* msg) {

@@ -11,6 +11,8 @@
 #include <vector>
 
 #include "drt_ctx.h"
+
+#include <thread>
 #include "dart_random.h"
 #include "env_map.h"
 #include "render_kernels.h"
@@ -226,7 +228,7 @@ static void buildLayout(RenderState* r) {
 static int uploadSceneTables(drt_ctx* c, RenderState* r) {
   const uint32_t nt = c->ntris(), np = c->nprims();
   std::vector<uint32_t> primToRec(std::max<uint32_t>(np, 1), 0), attr(std::max<uint32_t>(np, 1), 0);
-  for (size_t i = 0; i < c->bvh.leafPrimIds.size(); ++i) primToRec[c->bvh.leafPrimIds[i]] = (uint32_t)i;
+  for (size_t i = 0; i < c->hostBvh().leafPrimIds.size(); ++i) primToRec[c->hostBvh().leafPrimIds[i]] = (uint32_t)i;
   const int nMat = (int)r->materials.size(), nLights = (int)r->lights.size();
   for (uint32_t i = 0; i < np; ++i) {
     int m = i < nt ? c->matOf[i] : c->sphMat[i - nt], l = i < nt ? c->lightOf[i] : c->sphLight[i - nt];
@@ -986,6 +988,96 @@ static int renderWindow(drt_ctx* c, int x, int y, int w, int h, uint32_t shard, 
   return DRT_OK;
 }
 
+// ---- multi-device contexts (drt_create_multi) ------------------------------------------------------------------------------
+// What lib/dartray_web/render_manager.dart:100-141 does with one isolate per image region and a copy of each region's pixels:
+// here one GPU per set of interleaved pixel blocks, and a SUM of the films (filter footprints cross block borders).
+struct FilmPtrs {
+  const double* src[15];
+};
+
+// dst += sum of the peers' films, read through peer-mapped pointers over NVLink (one pass, no staging copy)
+__global__ void filmSumKernel(double* __restrict__ dst, FilmPtrs peers, int nPeers, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double v = dst[i];
+    for (int k = 0; k < nPeers; ++k) v += peers.src[k][i];
+    dst[i] = v;
+  }
+}
+
+static int reduceFilms(drt_ctx* c) {
+  RenderState* r = state(c);
+  const size_t n = 4 * r->filmPixels;
+  if (n == 0) return DRT_OK;
+  CK(c, cudaSetDevice(c->device));
+  bool direct = true;
+  for (drt_ctx* p : c->peers) {
+    if (4 * state(p)->filmPixels != n) return fail(c, DRT_E_STATE, "multi-device render: the devices' films differ in size");
+    int can = 1;
+    if (p->device != c->device) CK(c, cudaDeviceCanAccessPeer(&can, c->device, p->device));
+    if (!can) direct = false;
+  }
+  if (direct && !c->peerAccessTried) {
+    for (drt_ctx* p : c->peers) {
+      if (p->device == c->device) continue;
+      cudaError_t e = cudaDeviceEnablePeerAccess(p->device, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (e != cudaSuccess) { cudaGetLastError(); direct = false; }
+    }
+    c->peerAccessTried = true;
+  }
+  const int grid = c->numSMs * 8;
+  if (direct) {
+    for (size_t first = 0; first < c->peers.size(); first += 15) {
+      FilmPtrs fp{};
+      const int cnt = (int)std::min<size_t>(15, c->peers.size() - first);
+      for (int k = 0; k < cnt; ++k) fp.src[k] = state(c->peers[first + k])->dFilm.p;
+      filmSumKernel<<<grid, 256, 0, c->stream>>>(r->dFilm.p, fp, cnt, n);
+      CK(c, cudaGetLastError());
+      c->launches++;
+    }
+  } else {  // no peer mapping between these devices: copy each film over and add it
+    DevBuf<double> stage;
+    CK(c, stage.ensure(n));
+    for (drt_ctx* p : c->peers) {
+      CK(c, cudaMemcpyPeerAsync(stage.p, c->device, state(p)->dFilm.p, p->device, n * sizeof(double), c->stream));
+      FilmPtrs fp{};
+      fp.src[0] = stage.p;
+      filmSumKernel<<<grid, 256, 0, c->stream>>>(r->dFilm.p, fp, 1, n);
+      CK(c, cudaGetLastError());
+      c->launches++;
+    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    stage.release();
+  }
+  CK(c, cudaStreamSynchronize(c->stream));
+  // the peers' films hold only what they rendered since the last sum: a later render into the same film adds its own delta
+  for (drt_ctx* p : c->peers) {
+    CK(c, cudaSetDevice(p->device));
+    CK(c, cudaMemset(state(p)->dFilm.p, 0, n * sizeof(double)));
+  }
+  CK(c, cudaSetDevice(c->device));
+  return DRT_OK;
+}
+
+static int renderWindow(drt_ctx* c, int x, int y, int w, int h, uint32_t shard, uint32_t nShards);
+
+// One render call of a multi-device context: device k renders shard (shard * D + k) of (nShards * D) of the window — the
+// interleaved 1024-pixel blocks of drt_render_shard, so that the union of the devices' samples is exactly the one-device
+// sample set (streams are keyed by pixel) — each on its own host thread; then the films are summed into this device's.
+static int renderMulti(drt_ctx* c, int x, int y, int w, int h, uint32_t shard, uint32_t nShards) {
+  const uint32_t D = 1 + (uint32_t)c->peers.size();
+  std::vector<int> rcs(D, DRT_OK);
+  std::vector<std::thread> th;
+  for (uint32_t k = 1; k < D; ++k)
+    th.emplace_back([&, k] { rcs[k] = renderWindow(c->peers[k - 1], x, y, w, h, shard * D + k, nShards * D); });
+  rcs[0] = renderWindow(c, x, y, w, h, shard * D, nShards * D);
+  for (auto& t : th) t.join();
+  for (uint32_t k = 1; k < D; ++k)
+    if (rcs[k] != DRT_OK) { c->err = "device " + std::to_string(c->peers[k - 1]->device) + ": " + c->peers[k - 1]->err; return rcs[k]; }
+  if (rcs[0] != DRT_OK) return rcs[0];
+  return reduceFilms(c);
+}
+
 static void sampleExtent(const RenderParams& p, int e[4]) {  // image_film.dart:247-252
   e[0] = (int)std::floor(p.left + 0.5 - p.xWidth);
   e[1] = (int)std::ceil(p.left + 0.5 + p.width + p.xWidth);
@@ -996,6 +1088,7 @@ static void sampleExtent(const RenderParams& p, int e[4]) {  // image_film.dart:
 extern "C" {
 
 int drt_set_materials(drt_ctx* c, uint32_t n, const int32_t* kind, const float* kd, const float* sigma) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_materials(p_, n, kind, kd, sigma));
   if (!c) return DRT_E_INVALID;
   if (n && !kd) return fail(c, DRT_E_INVALID, "null Kd array");
   RenderState* r = state(c);
@@ -1015,6 +1108,7 @@ int drt_set_materials(drt_ctx* c, uint32_t n, const int32_t* kind, const float* 
 int drt_set_material_lobes(drt_ctx* c, uint32_t n, const uint32_t* lobe_offsets, const int32_t* lobe_kind, const float* lobe_rgb,
                            const int32_t* fresnel_kind, const float* fresnel_eta, const float* fresnel_k,
                            const double* lobe_scalars) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_material_lobes(p_, n, lobe_offsets, lobe_kind, lobe_rgb, fresnel_kind, fresnel_eta, fresnel_k, lobe_scalars));
   if (!c) return DRT_E_INVALID;
   if (n == 0 || !lobe_offsets) return fail(c, DRT_E_INVALID, "drt_set_material_lobes needs at least one material and its offsets");
   const uint32_t nl = lobe_offsets[n];
@@ -1060,6 +1154,7 @@ int drt_set_material_lobes(drt_ctx* c, uint32_t n, const uint32_t* lobe_offsets,
 }
 
 int drt_set_lobe_wrappers(drt_ctx* c, uint32_t n_lobes, const int32_t* wrap, const float* scale_rgb) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_lobe_wrappers(p_, n_lobes, wrap, scale_rgb));
   if (!c) return DRT_E_INVALID;
   RenderState* r = state(c);
   if (!r->general || n_lobes != r->lobes.size())
@@ -1078,6 +1173,7 @@ int drt_set_lobe_wrappers(drt_ctx* c, uint32_t n_lobes, const int32_t* wrap, con
 
 int drt_set_lights(drt_ctx* c, uint32_t n, const int32_t* kind, const float* L, const float* pos, const int32_t* nsamples,
                    const uint32_t* shape_offsets, const uint32_t* shape_prims) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_lights(p_, n, kind, L, pos, nsamples, shape_offsets, shape_prims));
   if (!c) return DRT_E_INVALID;
   if (n && (!kind || !L)) return fail(c, DRT_E_INVALID, "null light arrays");
   RenderState* r = state(c);
@@ -1100,6 +1196,7 @@ int drt_set_lights(drt_ctx* c, uint32_t n, const int32_t* kind, const float* L, 
 }
 
 int drt_set_spot_params(drt_ctx* c, uint32_t n, const float* world_to_light, const double* cos_total_falloff) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_spot_params(p_, n, world_to_light, cos_total_falloff));
   if (!c) return DRT_E_INVALID;
   RenderState* r = state(c);
   if (n != r->lights.size()) return fail(c, DRT_E_STATE, "drt_set_spot_params: n must equal the light count of the last drt_set_lights");
@@ -1119,6 +1216,7 @@ int drt_set_spot_params(drt_ctx* c, uint32_t n, const float* world_to_light, con
 
 int drt_set_infinite_light(drt_ctx* c, uint32_t index, int width, int height, const float* rgb, const float* light_to_world,
                            const float* world_to_light) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_infinite_light(p_, index, width, height, rgb, light_to_world, world_to_light));
   if (!c) return DRT_E_INVALID;
   RenderState* r = state(c);
   if (index >= r->lights.size() || r->lights[index].kind != 4)
@@ -1141,6 +1239,7 @@ int drt_set_infinite_light(drt_ctx* c, uint32_t index, int width, int height, co
 
 int drt_set_light_map(drt_ctx* c, uint32_t index, int width, int height, const float* rgb, const float* world_to_light,
                       const float* light_projection, const double* screen_window, double hither) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_light_map(p_, index, width, height, rgb, world_to_light, light_projection, screen_window, hither));
   if (!c) return DRT_E_INVALID;
   RenderState* r = state(c);
   if (index >= r->lights.size() || (r->lights[index].kind != 5 && r->lights[index].kind != 6))
@@ -1172,6 +1271,7 @@ int drt_set_light_map(drt_ctx* c, uint32_t index, int width, int height, const f
 
 int drt_set_camera(drt_ctx* c, const float* raster_to_camera, const float* camera_to_world, double lens_radius,
                    double focal_distance, double shutter_open, double shutter_close) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_camera(p_, raster_to_camera, camera_to_world, lens_radius, focal_distance, shutter_open, shutter_close));
   if (!c) return DRT_E_INVALID;
   if (!raster_to_camera || !camera_to_world) return fail(c, DRT_E_INVALID, "null camera matrix");
   RenderState* r = state(c);
@@ -1184,6 +1284,7 @@ int drt_set_camera(drt_ctx* c, const float* raster_to_camera, const float* camer
 }
 
 int drt_set_camera_kind(drt_ctx* c, int kind) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_camera_kind(p_, kind));
   if (!c) return DRT_E_INVALID;
   if (kind < 0 || kind > 2) return fail(c, DRT_E_INVALID, "camera kind must be 0 (perspective), 1 (orthographic) or 2 (environment)");
   state(c)->rp.cameraKind = kind;
@@ -1191,6 +1292,7 @@ int drt_set_camera_kind(drt_ctx* c, int kind) {
 }
 
 int drt_set_film(drt_ctx* c, int xres, int yres, const double* crop, double xwidth, double ywidth, const float* table) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_film(p_, xres, yres, crop, xwidth, ywidth, table));
   if (!c) return DRT_E_INVALID;
   if (xres < 1 || yres < 1 || !(xwidth > 0.0) || !(ywidth > 0.0) || !table) return fail(c, DRT_E_INVALID, "bad film parameters");
   RenderState* r = state(c);
@@ -1205,6 +1307,7 @@ int drt_set_film(drt_ctx* c, int xres, int yres, const double* crop, double xwid
 }
 
 int drt_set_sampler(drt_ctx* c, int kind, int xs, int ys, int spp, int jitter, int pixel_order, int tile_size, uint64_t seed) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_sampler(p_, kind, xs, ys, spp, jitter, pixel_order, tile_size, seed));
   if (!c) return DRT_E_INVALID;
   if (kind < 0 || kind > 5)
     return fail(c, DRT_E_INVALID, "sampler kind must be 0 (lowdiscrepancy), 1 (stratified), 2 (random), 3 (halton), 4 (adaptive) or 5 (bestcandidate)");
@@ -1216,6 +1319,7 @@ int drt_set_sampler(drt_ctx* c, int kind, int xs, int ys, int spp, int jitter, i
 }
 
 int drt_set_sample_table(drt_ctx* c, const double* table, uint32_t n_entries) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_sample_table(p_, table, n_entries));
   if (!c) return DRT_E_INVALID;
   if (!table || n_entries != 4096) return fail(c, DRT_E_INVALID, "the bestcandidate pattern holds 4096 entries of 5 values (best_candidate_sampler.dart:32-34)");
   state(c)->sampleTable.assign(table, table + 5 * (size_t)n_entries);
@@ -1223,6 +1327,7 @@ int drt_set_sample_table(drt_ctx* c, const double* table, uint32_t n_entries) {
 }
 
 int drt_set_integrator(drt_ctx* c, int kind, int maxdepth, int strategy, int ao_nsamples, double ao_mindist, double ao_maxdist) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_integrator(p_, kind, maxdepth, strategy, ao_nsamples, ao_mindist, ao_maxdist));
   if (!c) return DRT_E_INVALID;
   if (kind < 0 || kind > 3)
     return fail(c, DRT_E_INVALID, "integrator kind must be 0 (path), 1 (ambientocclusion), 2 (directlighting) or 3 (whitted)");
@@ -1234,6 +1339,7 @@ int drt_set_integrator(drt_ctx* c, int kind, int maxdepth, int strategy, int ao_
 }
 
 int drt_set_batch_slots(drt_ctx* c, uint64_t slots) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_batch_slots(p_, slots));
   if (!c) return DRT_E_INVALID;
   state(c)->batchSlots = slots;
   return DRT_OK;
@@ -1253,6 +1359,7 @@ int drt_render(drt_ctx* c, int task_num, int task_count) {
     x = ext[0] + e[0]; w = e[1] - e[0];
     y = ext[2] + e[2]; h = e[3] - e[2];
   }
+  if (!c->peers.empty()) return renderMulti(c, x, y, w, h, 0, 1);
   return renderWindow(c, x, y, w, h, 0, 1);
 }
 
@@ -1263,10 +1370,12 @@ int drt_render_shard(drt_ctx* c, int shard, int n_shards) {
   if (!r->haveFilm) return fail(c, DRT_E_STATE, "drt_set_film must be called before rendering");
   int ext[4];
   sampleExtent(r->rp, ext);
+  if (!c->peers.empty()) return renderMulti(c, ext[0], ext[2], ext[1] - ext[0], ext[3] - ext[2], (uint32_t)shard, (uint32_t)n_shards);
   return renderWindow(c, ext[0], ext[2], ext[1] - ext[0], ext[3] - ext[2], (uint32_t)shard, (uint32_t)n_shards);
 }
 
 int drt_film_clear(drt_ctx* c) {
+  DRT_FORWARD_TO_PEERS(c, drt_film_clear(p_));
   if (!c) return DRT_E_INVALID;
   RenderState* r = state(c);
   if (c->device == DRT_DEVICE_NONE) return fail(c, DRT_E_NODEVICE, kNoDevice);
@@ -1367,6 +1476,11 @@ int drt_render_profile_get(drt_ctx* c, drt_render_profile* out) {
 int drt_render_stats_get(drt_ctx* c, drt_render_stats* out) {
   if (!c || !out) return DRT_E_INVALID;
   *out = state(c)->stats;
+  for (drt_ctx* p : c->peers) {  // a multi-device context reports the rays of all its devices
+    const drt_render_stats& s = state(p)->stats;
+    out->camera_samples += s.camera_samples; out->closest_rays += s.closest_rays;
+    out->shadow_rays += s.shadow_rays; out->zeroed_samples += s.zeroed_samples;
+  }
   return DRT_OK;
 }
 

@@ -60,10 +60,16 @@ def sum_films(film, group=None):
 
 def render_sharded(ctx, rank: int, world: int, group=None):
     """Render this rank's shard and sum the films; afterwards every rank's `ctx.film_read()` returns the
-    whole image."""
+    whole image.
+
+    The sum is in place: after it every rank's film holds the contributions of ALL ranks, so a second sharded render into
+    the same film would count the earlier passes `world` times.  Progressive multi-pass use therefore has to call
+    `ctx.film_clear()` between passes (and accumulate the passes outside); this is checked."""
     import time
 
     import torch
+    if world > 1 and getattr(ctx, "_film_is_summed", False):
+        raise RuntimeError("render_sharded: the film already holds an all-reduced image; call ctx.film_clear() before the next pass")
     t0 = time.perf_counter()
     ctx.render_shard(rank, world)  # blocking: returns when this rank's film is complete
     t1 = time.perf_counter()
@@ -71,4 +77,5 @@ def render_sharded(ctx, rank: int, world: int, group=None):
         film = film_tensor(ctx)
         sum_films(film, group)
         torch.cuda.synchronize(ctx.device)
+        ctx._film_is_summed = True
     return {"render_s": t1 - t0, "film_sum_s": time.perf_counter() - t1}

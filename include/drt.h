@@ -82,6 +82,17 @@ int drt_version(void);
  * reference's constructor); every query on it fails with DRT_E_NODEVICE. */
 #define DRT_DEVICE_NONE (-1)
 drt_ctx* drt_create(int device_id);
+/* One context over several GPUs of the box: what lib/dartray_web/render_manager.dart:100-141 does with one isolate (and one
+ * private copy of the scene) per image region, and what `taskNum / taskCount` (lib/dartray/dartray.dart:1009-1023) express.
+ * Every drt_set_* call and drt_film_clear is applied to all devices; drt_build_bvh builds the tree ONCE on the host and uploads
+ * its arrays to every device (one host thread per device); drt_render / drt_render_shard split their window over the devices
+ * in interleaved 1024-pixel blocks (keyed sample streams: the union is exactly the one-device sample set), each device driven
+ * by its own host thread, and the per-device films are then summed into the first device's over NVLink — one kernel reading
+ * the peers' films through peer-mapped pointers (a staged cudaMemcpyPeer where peer mapping is unavailable) — so that
+ * drt_film_read / drt_film_device return the whole image and drt_render_stats_get the rays of all devices.  Ray queries
+ * (drt_trace_*) and drt_pixel_samples run on the first device.  SURVEY 8b proposed this signature for drt_create. */
+drt_ctx* drt_create_multi(const int* device_ids, int n_devices);
+int drt_device_count(const drt_ctx* ctx);
 void drt_destroy(drt_ctx* ctx);
 const char* drt_last_error(const drt_ctx* ctx);
 

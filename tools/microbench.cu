@@ -51,7 +51,7 @@ int main() {
   runFma<float>("fp32_fma");
   runFma<double>("fp64_fma");
   int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  for (size_t mb : {32, 64, 96, 114}) {
+  for (size_t mb : {32, 48, 64, 78, 96, 114}) {  // MiB; 78 MiB = the soup_1m BVH with 64-byte quantised nodes, 114 with the float32 nodes
     size_t n = mb * 1024 * 1024 / 16;
     float4 *in, *out; cudaMalloc(&in, n * 16); cudaMalloc(&out, 16);
     cudaMemset(in, 0, n * 16);
