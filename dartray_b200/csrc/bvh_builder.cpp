@@ -3,8 +3,14 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <new>
+#include <atomic>
 #include <future>
+#include <thread>
 #include <limits>
 
 namespace drt {
@@ -40,23 +46,41 @@ struct TNode {
   int32_t left = -1, right = -1;  // pool indices; -1 -> leaf
   uint32_t first = 0, count = 0;  // leaf: range in the builder's PrimRef array
   int32_t axis = 0;
+  // subtree totals, filled when the children return: they fix every output offset, so the flattening passes below can
+  // write disjoint ranges of pre-sized arrays from concurrent tasks
+  uint32_t nNodes = 1, nPrims = 0, nInterior = 0, nWide = 0, nLeaves = 1, maxLeaf = 0, depthBelow = 0;
 };
 
+// The node pool: 2n slots, handed out by primitive count (TreeBuilder::build).  Raw storage: a slot is constructed by the task
+// that builds its node (value-initialising 1.5 GB up front for 10 M primitives cost half a second, serially).
+struct NodePool {
+  TNode* p = nullptr;
+  size_t n = 0;
+  explicit NodePool(size_t count) : p(static_cast<TNode*>(std::malloc(std::max<size_t>(count, 1) * sizeof(TNode)))), n(count) {}
+  ~NodePool() { std::free(p); }
+  NodePool(const NodePool&) = delete;
+  NodePool& operator=(const NodePool&) = delete;
+  TNode& operator[](size_t i) { return p[i]; }
+  const TNode& operator[](size_t i) const { return p[i]; }
+  size_t size() const { return n; }
+};
 struct Arena {
-  std::vector<TNode> pool;
+  NodePool pool;
+  explicit Arena(size_t count) : pool(count) {}
 };
 
 class TreeBuilder {
  public:
   TreeBuilder(std::vector<PrimRef>& refs, int split, int maxPrims) : refs_(refs), split_(split), maxPrims_(maxPrims) {}
 
-  // Builds [start, end) into `arena`, returns the node's index in that arena.
-  int32_t build(Arena& arena, uint32_t start, uint32_t end, int depth) {
-    int32_t me = (int32_t)arena.pool.size();
-    arena.pool.emplace_back();
+  // Builds [start, end) into pool slot `me`.  The subtree of a node over n primitives owns the slots [me, me + 2n - 1): its first
+  // child sits at me + 1, its second at me + 2 * (primitives of the first) — fixed by the split alone, so subtrees can be
+  // built by concurrent tasks straight into the one pre-sized pool and the result does not depend on thread timing.
+  int32_t build(Arena& arena, int32_t me, uint32_t start, uint32_t end, int depth) {
     Box box;
     box.clear();
     for (uint32_t i = start; i < end; ++i) box.grow(refs_[i].lo, refs_[i].hi);
+    new (&arena.pool[me]) TNode();
     arena.pool[me].box = box;
     uint32_t n = end - start;
     if (n == 1) return makeLeaf(arena, me, start, end);
@@ -123,23 +147,38 @@ class TreeBuilder {
       sortByCentroid(start, end, dim);
     }
 
-    // Large subtrees are built concurrently; each child uses a private arena that is spliced in
-    // afterwards, so the result does not depend on thread timing.
+    // Large subtrees are built concurrently (at most a few tasks per hardware thread in flight).
     int32_t l, r;
-    if (n >= (1u << 16) && depth < 4) {
-      Arena right;
-      auto fut = std::async(std::launch::async, [&] { return build(right, mid, end, depth + 1); });
-      l = build(arena, start, mid, depth + 1);
-      int32_t rLocal = fut.get();
-      r = splice(arena, right, rLocal);
+    const int32_t lSlot = me + 1, rSlot = me + 2 * (int32_t)(mid - start);
+    if (n >= (1u << 14) && liveTasks_.load(std::memory_order_relaxed) < maxTasks_) {
+      liveTasks_.fetch_add(1, std::memory_order_relaxed);
+      auto fut = std::async(std::launch::async, [&] {
+        int32_t v = build(arena, rSlot, mid, end, depth + 1);
+        liveTasks_.fetch_sub(1, std::memory_order_relaxed);
+        return v;
+      });
+      l = build(arena, lSlot, start, mid, depth + 1);
+      r = fut.get();
     } else {
-      l = build(arena, start, mid, depth + 1);
-      r = build(arena, mid, end, depth + 1);
+      l = build(arena, lSlot, start, mid, depth + 1);
+      r = build(arena, rSlot, mid, end, depth + 1);
     }
     TNode& node = arena.pool[me];
     node.left = l;
     node.right = r;
     node.axis = dim;
+    {
+      const TNode &a = arena.pool[l], &b = arena.pool[r];
+      node.nNodes = 1 + a.nNodes + b.nNodes;
+      node.nPrims = a.nPrims + b.nPrims;
+      node.nInterior = 1 + a.nInterior + b.nInterior;
+      node.nLeaves = a.nLeaves + b.nLeaves;
+      node.maxLeaf = std::max(a.maxLeaf, b.maxLeaf);
+      node.depthBelow = 1 + std::max(a.depthBelow, b.depthBelow);
+      // wide nodes of the two-level collapse rooted here (Flattener::emitWide): this one + those rooted at the grandchildren
+      auto under = [&](const TNode& side) { return side.left < 0 ? 0u : arena.pool[side.left].nWide + arena.pool[side.right].nWide; };
+      node.nWide = 1 + under(a) + under(b);
+    }
     // bvh_accel.dart:521 — union of the children's boxes (equals `box`: min/max are exact)
     return me;
   }
@@ -147,6 +186,8 @@ class TreeBuilder {
  private:
   std::vector<PrimRef>& refs_;
   int split_, maxPrims_;
+  std::atomic<int> liveTasks_{0};
+  const int maxTasks_ = 4 * (int)std::max(1u, std::thread::hardware_concurrency());
 
   static int maxExtent(const Box& b) {  // bbox.dart:174-183 on the float32 diagonal
     float dx = (float)((double)b.hi[0] - b.lo[0]), dy = (float)((double)b.hi[1] - b.lo[1]),
@@ -159,6 +200,7 @@ class TreeBuilder {
   int32_t makeLeaf(Arena& arena, int32_t me, uint32_t start, uint32_t end) {
     arena.pool[me].first = start;
     arena.pool[me].count = end - start;
+    arena.pool[me].nPrims = arena.pool[me].maxLeaf = end - start;
     return me;
   }
 
@@ -200,27 +242,30 @@ class TreeBuilder {
       refs_[j] = el;
     }
   }
-
-  static int32_t splice(Arena& dst, Arena& src, int32_t srcRoot) {
-    int32_t base = (int32_t)dst.pool.size();
-    for (TNode n : src.pool) {
-      if (n.left >= 0) { n.left += base; n.right += base; }
-      dst.pool.push_back(n);
-    }
-    return srcRoot + base;
-  }
 };
 
 struct Flattener {
-  const std::vector<TNode>& pool;
+  const NodePool& pool;
   const std::vector<PrimRef>& refs;
   BuiltBvh* out;
 
-  // Reference numbering: depth first, first child at n+1 (bvh_accel.dart:419-437).
-  int32_t numberRef(int32_t t, std::vector<int32_t>& refIndexOf) {
-    int32_t my = (int32_t)out->refNodes.size();
+  // Two subtrees at once when they are big enough to pay for a task.
+  template <class FA, class FB>
+  static void both(bool parallel, FA&& fa, FB&& fb) {
+    if (parallel) {
+      auto fut = std::async(std::launch::async, [&] { fa(); });
+      fb();
+      fut.get();
+    } else {
+      fa();
+      fb();
+    }
+  }
+  static constexpr uint32_t kTaskNodes = 1u << 15;
+
+  // Reference numbering: depth first, first child at n+1 (bvh_accel.dart:419-437).  Node t gets index `my`.
+  void numberRef(int32_t t, int32_t my, std::vector<int32_t>& refIndexOf) {
     refIndexOf[t] = my;
-    out->refNodes.emplace_back();
     const TNode& n = pool[t];
     RefNode rn;
     std::memcpy(rn.bmin, n.box.lo, 12);
@@ -231,37 +276,34 @@ struct Flattener {
     if (n.left >= 0) {
       rn.axis = n.axis;
       rn.nPrimitives = 0;
+      const int32_t second = my + 1 + (int32_t)pool[n.left].nNodes;
+      rn.offset = second;
       out->refNodes[my] = rn;
-      numberRef(n.left, refIndexOf);
-      int32_t second = numberRef(n.right, refIndexOf);
-      out->refNodes[my].offset = second;
+      both(n.nNodes >= kTaskNodes, [&] { numberRef(n.left, my + 1, refIndexOf); }, [&] { numberRef(n.right, second, refIndexOf); });
     } else {
       out->refNodes[my] = rn;
     }
-    return my;
   }
 
   // The reference appends a leaf's primitives to `orderedPrims` when the leaf is created and
-  // builds the SECOND child first (bvh_accel.dart:407-411) -> right-first leaf order.
-  void orderRef(int32_t t, const std::vector<int32_t>& refIndexOf) {
+  // builds the SECOND child first (bvh_accel.dart:407-411) -> right-first leaf order.  `off`: first slot of t's primitives.
+  void orderRef(int32_t t, uint32_t off, const std::vector<int32_t>& refIndexOf) {
     const TNode& n = pool[t];
     if (n.left < 0) {
-      out->refNodes[refIndexOf[t]].offset = (int32_t)out->refOrdered.size();
-      for (uint32_t i = 0; i < n.count; ++i) out->refOrdered.push_back(refs[n.first + i].id);
+      out->refNodes[refIndexOf[t]].offset = (int32_t)off;
+      for (uint32_t i = 0; i < n.count; ++i) out->refOrdered[off + i] = refs[n.first + i].id;
       return;
     }
-    orderRef(n.right, refIndexOf);
-    orderRef(n.left, refIndexOf);
+    both(n.nNodes >= kTaskNodes, [&] { orderRef(n.right, off, refIndexOf); },
+         [&] { orderRef(n.left, off + pool[n.right].nPrims, refIndexOf); });
   }
 
   // Wide layout: collapse P with its two children (see GNode4).  Must run AFTER emit(): it reuses
   // the leaf references recorded there so both layouts index the same GPrim[] order.
   std::vector<int32_t> leafRefOf;  // per pool node: leaf reference (leaves only)
-  int32_t emitWide(int32_t t, const std::vector<int32_t>& refIndexOf) {
+  int32_t emitWide(int32_t t, int32_t my) {
     const TNode& n = pool[t];
     if (n.left < 0) return leafRefOf[t];
-    int32_t my = (int32_t)out->wide.size();
-    out->wide.emplace_back();
     GNode4 g;
     std::memset(&g, 0, sizeof(g));
     for (int k = 0; k < 4; ++k) {
@@ -269,7 +311,6 @@ struct Flattener {
       for (int a = 0; a < 6; ++a) g.box[k][a] = 0.f;
     }
     g.axisP = n.axis;
-    (void)refIndexOf;
     // Slot order = any-hit visiting order (that kernel walks the slots as stored: its answer does not depend on
     // the order): the larger box first, inside each side and between the sides.  A swap is recorded in bit 2 of
     // the axis field, which the closest-hit kernel XORs into dirIsNeg[axis] to recover the reference's order.
@@ -278,6 +319,8 @@ struct Flattener {
       std::swap(sides[0], sides[1]);
       g.axisP |= 4;
     }
+    int32_t slotKid[4] = {-1, -1, -1, -1}, slotBase[4] = {0, 0, 0, 0};
+    int32_t next = my + 1;  // the kids' wide subtrees follow in slot order
     for (int sIdx = 0; sIdx < 2; ++sIdx) {
       const TNode& side = pool[sides[sIdx]];
       int base = 2 * sIdx;
@@ -299,8 +342,14 @@ struct Flattener {
           g.box[base + k][2 * a] = c.box.lo[a];
           g.box[base + k][2 * a + 1] = c.box.hi[a];
         }
-        g.ref[base + k] = emitWide(kids[k], refIndexOf);
+        slotKid[base + k] = kids[k];
+        slotBase[base + k] = next;
+        if (c.left >= 0) next += (int32_t)c.nWide;
       }
+    }
+    {
+      auto run = [&](int k) { if (slotKid[k] >= 0) g.ref[k] = emitWide(slotKid[k], slotBase[k]); };
+      both(n.nNodes >= kTaskNodes, [&] { run(0); run(1); }, [&] { run(2); run(3); });
     }
     // visiting decisions of the closest-hit walk for each of the 8 dirIsNeg octants, 3 bits each:
     // bit 0 = slots 2,3 before 0,1; bit 1 = slot 1 before 0; bit 2 = slot 3 before 2
@@ -311,9 +360,24 @@ struct Flattener {
     }
     g.orderLut = (int32_t)lut;
     out->wide[my] = g;
-    if (out->wideQ.size() <= (size_t)my) out->wideQ.resize((size_t)my + 1);
-    if (!quantiseNode(g, &out->wideQ[my])) out->wideQOk = false;
     return my;
+  }
+
+  // wide[i] -> wideQ[i] for every node, in parallel (the nodes are independent)
+  void quantiseAll() {
+    const size_t n = out->wide.size();
+    out->wideQ.resize(n);
+    const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    std::vector<std::thread> th;
+    std::atomic<bool> ok{true};
+    for (unsigned t = 0; t < nt; ++t)
+      th.emplace_back([&, t] {
+        const size_t a = n * t / nt, b = n * (t + 1) / nt;
+        for (size_t i = a; i < b; ++i)
+          if (!quantiseNode(out->wide[i], &out->wideQ[i])) ok.store(false, std::memory_order_relaxed);
+      });
+    for (auto& x : th) x.join();
+    out->wideQOk = ok.load();
   }
 
   // GNode4 -> GNode4Q: an 8-bit grid per axis, origin just below the node's box, step 2^e.  Every inequality the
@@ -336,7 +400,11 @@ struct Flattener {
       int e = DRT_Q_EXP_MIN;
       {
         double ext = std::max(hi - lo, (double)std::fabs((float)lo) * 1.2e-7);
-        if (ext > 0.0) e = std::max(e, (int)std::ceil(std::log2(ext / 250.0)) - 1);
+        if (ext > 0.0) {  // a starting exponent a little below log2(ext / 255); the loop below raises it until everything fits
+          int ex = 0;
+          std::frexp(ext, &ex);  // ext = m * 2^ex, m in [0.5, 1)
+          e = std::max(e, ex - 10);
+        }
       }
       for (;; ++e) {
         if (e > DRT_Q_EXP_MAX) return false;
@@ -373,24 +441,20 @@ struct Flattener {
   }
 
   // GPU layout: interior nodes in DFS order, leaf records in DFS (left-first) order.
-  int32_t emit(int32_t t, uint32_t depth, const std::vector<int32_t>& refIndexOf) {
+  // `my`: index of t among the interior nodes (DFS order); `off`: first leaf record of t's primitives.
+  int32_t emit(int32_t t, int32_t my, uint32_t off, const std::vector<int32_t>& refIndexOf) {
     const TNode& n = pool[t];
-    if (depth > out->maxDepth) out->maxDepth = depth;
     if (n.left < 0) {
-      uint32_t off = (uint32_t)out->leafPrimIds.size();
       for (uint32_t i = 0; i < n.count; ++i) {
-        out->leafPrimIds.push_back(refs[n.first + i].id);
-        out->leafCounts.push_back(i == 0 ? n.count : 0);
+        out->leafPrimIds[off + i] = refs[n.first + i].id;
+        out->leafCounts[off + i] = i == 0 ? n.count : 0;
       }
-      out->nLeaves++;
-      if (n.count > out->maxLeafPrims) out->maxLeafPrims = n.count;
       leafRefOf[t] = makeLeafRef(off, n.count);
       return leafRefOf[t];
     }
-    int32_t my = (int32_t)out->nodes.size();
-    out->nodes.emplace_back();
-    int32_t r0 = emit(n.left, depth + 1, refIndexOf);
-    int32_t r1 = emit(n.right, depth + 1, refIndexOf);
+    int32_t r0 = 0, r1 = 0;
+    both(n.nNodes >= kTaskNodes, [&] { r0 = emit(n.left, my + 1, off, refIndexOf); },
+         [&] { r1 = emit(n.right, my + 1 + (int32_t)pool[n.left].nInterior, off + pool[n.left].nPrims, refIndexOf); });
     GNode g;
     const TNode &a = pool[n.left], &b = pool[n.right];
     std::memcpy(g.c0min, a.box.lo, 12);
@@ -428,25 +492,44 @@ bool buildBvh(const std::vector<PrimBounds>& bounds, const std::vector<uint32_t>
     }
     r.id = order[i];
   }
-  Arena arena;
-  arena.pool.reserve(2 * n);
+  const bool timing = std::getenv("DRT_BUILD_TIMING") != nullptr;
+  auto tPrev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[drt build] %-28s %.3f s\n", what, std::chrono::duration<double>(now - tPrev).count());
+    tPrev = now;
+  };
+  lap("primitive references");
+  Arena arena(2 * n);  // slot ranges by primitive count (TreeBuilder::build); unused slots are never touched
+  if (!arena.pool.p) { *err = "out of host memory for the BVH build"; return false; }
   TreeBuilder tb(refs, splitMethod, maxPrims);
-  int32_t root = tb.build(arena, 0, (uint32_t)n, 0);
+  int32_t root = tb.build(arena, 0, 0, (uint32_t)n, 0);
+  lap("tree (SAH recursion)");
 
   Flattener fl{arena.pool, refs, out, {}};
+  const TNode& rt = arena.pool[root];
   fl.leafRefOf.assign(arena.pool.size(), 0);
   std::vector<int32_t> refIndexOf(arena.pool.size(), -1);
-  out->refNodes.reserve(arena.pool.size());
-  fl.numberRef(root, refIndexOf);
-  out->refOrdered.reserve(n);
-  fl.orderRef(root, refIndexOf);
-  out->leafPrimIds.reserve(n);
-  out->leafCounts.reserve(n);
-  out->nodes.reserve(arena.pool.size() / 2 + 1);
-  out->rootRef = fl.emit(root, 0, refIndexOf);
-  out->wide.reserve(arena.pool.size() / 3 + 1);
-  out->wideQ.reserve(arena.pool.size() / 3 + 1);
-  out->wideRootRef = fl.emitWide(root, refIndexOf);
+  out->refNodes.resize(rt.nNodes);
+  fl.numberRef(root, 0, refIndexOf);
+  lap("reference numbering");
+  out->refOrdered.resize(n);
+  fl.orderRef(root, 0, refIndexOf);
+  lap("reference primitive order");
+  out->leafPrimIds.resize(n);
+  out->leafCounts.resize(n);
+  out->nodes.resize(rt.nInterior);
+  out->nLeaves = rt.nLeaves;
+  out->maxLeafPrims = rt.maxLeaf;
+  out->maxDepth = rt.depthBelow;
+  out->rootRef = fl.emit(root, 0, 0, refIndexOf);
+  lap("binary GPU layout");
+  out->wide.resize(rt.left < 0 ? 0 : rt.nWide);
+  out->wideRootRef = fl.emitWide(root, 0);
+  lap("wide layout");
+  fl.quantiseAll();
+  lap("quantised wide nodes");
   std::memcpy(out->rootMin, arena.pool[root].box.lo, 12);
   std::memcpy(out->rootMax, arena.pool[root].box.hi, 12);
   if (out->maxDepth >= 64) {
