@@ -304,7 +304,7 @@ int drt_set_film(drt_ctx* ctx, int32_t xres, int32_t yres, const double crop[4],
  * lib/samplers/adaptive_sampler.dart: xs = minsamples, ys = maxsamples, jitter = method (0 shape ids, 1 contrast); every pixel is
  * rendered with minsamples lowdiscrepancy samples and, where reportResults asks for it, again with maxsamples, the first visit's
  * samples being dropped) and bestcandidate (kind 5, needs drt_set_sample_table).  pixel_order / tile_size name
- * the PixelSampler (0 linear, 1 tile: lib/pixel_samplers/*.dart); with per-pixel keyed streams the
+ * the PixelSampler (0 linear, 1 tile: lib/pixel_samplers/{linear,tile}_pixel_sampler.dart); with per-pixel keyed streams the
  * visiting order does not change any sample, so they only document the request.  seed keys every
  * stream (the reference seeds its single RNG with the task number, sampler_renderer.dart:137). */
 int drt_set_sampler(drt_ctx* ctx, int32_t kind, int32_t xs, int32_t ys, int32_t spp, int32_t jitter, int32_t pixel_order,
