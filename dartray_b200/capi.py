@@ -25,7 +25,7 @@ SYMBOLS = [
     "drt_set_build_order", "drt_build_bvh", "drt_bvh_info_get", "drt_bvh_export", "drt_trace_closest",
     "drt_trace_any", "drt_trace_closest_device", "drt_trace_any_device", "drt_set_counting", "drt_get_counters", "drt_set_kernel_variant",
     "drt_last_kernel_ms", "drt_kernel_launches",
-    "drt_set_materials", "drt_set_material_lobes", "drt_set_lights", "drt_set_spot_params", "drt_set_camera", "drt_set_camera_kind", "drt_set_film", "drt_set_sampler", "drt_set_integrator",
+    "drt_set_materials", "drt_set_material_lobes", "drt_set_lights", "drt_set_spot_params", "drt_set_volumes", "drt_set_volume_integrator", "drt_set_camera", "drt_set_camera_kind", "drt_set_film", "drt_set_sampler", "drt_set_integrator",
     "drt_render", "drt_render_shard", "drt_set_batch_slots", "drt_film_clear", "drt_film_size", "drt_film_read",
     "drt_film_device", "drt_pixel_samples", "drt_render_stats_get", "drt_set_render_profiling", "drt_render_profile_get",
 ]
@@ -127,6 +127,8 @@ def load():
     L.drt_film_device.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     L.drt_pixel_samples.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32), C.POINTER(i32)]
     L.drt_render_stats_get.argtypes = [vp, C.POINTER(RenderStats)]
+    L.drt_set_volumes.argtypes = [vp, u32] + [vp] * 13
+    L.drt_set_volume_integrator.argtypes = [vp, i32, dbl]
     L.drt_set_render_profiling.argtypes = [vp, i32]
     L.drt_render_profile_get.argtypes = [vp, C.POINTER(RenderProfile)]
     _lib = L
@@ -393,6 +395,15 @@ class Context:
         n, per = C.c_int32(0), C.c_int32(0)
         self._ck(self.L.drt_pixel_samples(self.h, x, y, _p(out), cap, C.byref(n), C.byref(per)))
         return out[:per.value * n.value].reshape(n.value, per.value).copy()
+
+    def set_volumes(self, v: dict):
+        """v: host.pack_volumes(...) — the flat arrays of drt_set_volumes."""
+        self._ck(self.L.drt_set_volumes(self.h, v["n"], _p(v["kind"]), _p(v["sigma_a"]), _p(v["sigma_s"]), _p(v["le"]), _p(v["g"]),
+                                        _p(v["p0p1"]), _p(v["v2w"]), _p(v["w2v"]), _p(v["ab"]), _p(v["up"]), _p(v["dims"]),
+                                        _p(v["density_offsets"]), _p(v["density"])))
+
+    def set_volume_integrator(self, kind: int, step_size: float):
+        self._ck(self.L.drt_set_volume_integrator(self.h, kind, float(step_size)))
 
     def set_render_profiling(self, flags: int):
         """PROFILE_TIME: CUDA-event spans per kernel class; PROFILE_WORK: reference-walk counters of every traced queue."""

@@ -64,6 +64,15 @@ struct RenderState {
   std::vector<uint2> matLobes;
   std::vector<GLobe> lobes;
   std::vector<HostLight> lights;
+  // participating media (drt_set_volumes / drt_set_volume_integrator)
+  std::vector<GVolume> volumes;
+  std::vector<double> volDensity;
+  int volIntegrator = 0;
+  double volStep = 1.0;
+  std::vector<float> volV2W;     // n x 16: volumeToWorld, for the regions' world bound
+  uint32_t volMaxSteps = 0;      // single scattering: bound on a camera ray's march steps (regions' bound diagonal / stepsize)
+  DevBuf<GVolume> dVolumes;
+  DevBuf<double> dVolDensity;
   bool haveCamera = false, haveFilm = false;
   RenderParams rp{};
   double crop[4] = {0, 1, 0, 1};
@@ -127,6 +136,7 @@ void drtRenderStateDestroy(drt_ctx* c) {
   r->dLightCdf.release(); r->dTable.release(); r->dDirect.release(); r->dArrays.release();
   r->dMeshOfTri.release(); r->dTriIdx.release(); r->dMeshes.release(); r->dVertN.release(); r->dVertS.release(); r->dVertUV.release(); r->dEnv.release(); r->dAdaptList.release(); r->dAdaptCount.release(); r->dBcTable.release(); r->dBcShifts.release();
   r->dFilm.release(); r->dCounters.release(); r->dRgb.release(); r->dXyz.release(); r->dWeight.release(); r->dWork.release();
+  r->dVolumes.release(); r->dVolDensity.release();
   for (cudaEvent_t e : r->profEv) cudaEventDestroy(e);
   if (r->wfMem) cudaFree(r->wfMem);
   delete r;
@@ -186,7 +196,7 @@ static void buildLayout(RenderState* r) {
       db.push_back(offsets(1));
     }
   }
-  n1D.push_back(1);
+  n1D.push_back(1);  // volume integrator: tau sample, scatter sample (emission_integrator.dart:26-29)
   n1D.push_back(1);
   std::vector<int> v1(n1D.size()), v2(n2D.size());
   int v = 0;
@@ -203,6 +213,8 @@ static void buildLayout(RenderState* r) {
     }
   }
   p.dlLightNum = dlNum >= 0 ? v1[dlNum] : 0;
+  p.pTauSample = v1[n1D.size() - 2];
+  p.pScatterSample = v1[n1D.size() - 1];
   r->direct.clear();
   for (size_t i = 0; i < dl.size(); ++i)
     r->direct.push_back(DirectOffsets{dn[i], v1[dl[i].comp1D], v2[dl[i].pos2D], v1[db[i].comp1D], v2[db[i].pos2D]});
@@ -421,7 +433,22 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
     CK(c, cudaMemcpy(r->dEnv.p, env.data(), env.size() * 4, cudaMemcpyHostToDevice));
     rs.envData = r->dEnv.p;
   }
-  rs.extra = (rs.meshOfTri != nullptr || c->ts.quadMode == 2 || nInfinite > 0 || nMapped > 0 || (r->general && r->hasBlend)) ? 1 : 0;
+  rs.volumes = nullptr;
+  rs.volDensity = nullptr;
+  rs.nVolumes = (int32_t)r->volumes.size();
+  rs.volIntegrator = r->volIntegrator;
+  rs.volStep = r->volStep;
+  if (!r->volumes.empty()) {
+    CK(c, r->dVolumes.ensure(r->volumes.size()));
+    CK(c, cudaMemcpy(r->dVolumes.p, r->volumes.data(), r->volumes.size() * sizeof(GVolume), cudaMemcpyHostToDevice));
+    CK(c, r->dVolDensity.ensure(std::max<size_t>(1, r->volDensity.size())));
+    if (!r->volDensity.empty())
+      CK(c, cudaMemcpy(r->dVolDensity.p, r->volDensity.data(), r->volDensity.size() * sizeof(double), cudaMemcpyHostToDevice));
+    rs.volumes = r->dVolumes.p;
+    rs.volDensity = r->dVolDensity.p;
+  }
+  rs.extra = (rs.meshOfTri != nullptr || c->ts.quadMode == 2 || nInfinite > 0 || nMapped > 0 || (r->general && r->hasBlend) ||
+              rs.nVolumes > 0) ? 1 : 0;
   rs.ntris = nt;
   rs.nprims = np;
   rs.primToRec = r->dPrimToRec.p;
@@ -442,8 +469,18 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
 
 static const int kMaxChainLevels = 16;  // specular recursion depth the chain evaluation covers (maxdepth <= 17)
 
-static void carve(ByteArena& a, Wavefront& wf, uint32_t cap, uint32_t shCap, int nVals, bool chains) {
+static void carve(ByteArena& a, Wavefront& wf, uint32_t cap, uint32_t shCap, int nVals, bool chains, bool volumes, uint32_t volMaxSteps) {
   wf.cap = cap;
+  wf.volScratch = nullptr;
+  wf.volMaxSteps = volMaxSteps;
+  if (volumes) {
+    wf.trCtr = a.take<uint32_t>(cap);
+    wf.volT = a.take<float>(3 * (size_t)cap); wf.volL = a.take<float>(3 * (size_t)cap);
+    if (volMaxSteps) wf.volScratch = a.take<float>(4 * (size_t)volMaxSteps * cap);
+  } else {
+    wf.trCtr = nullptr;
+    wf.volT = wf.volL = nullptr;
+  }
   wf.pixX = a.take<int32_t>(cap); wf.pixY = a.take<int32_t>(cap); wf.sampleIdx = a.take<uint32_t>(cap);
   wf.camXY = a.take<double2>(cap); wf.camLens = a.take<double2>(cap); wf.camTime = a.take<float>(cap);
   wf.vals = a.take<float>((size_t)std::max(nVals, 1) * cap);
@@ -485,7 +522,9 @@ static int ensureWavefront(drt_ctx* c, RenderState* r, uint32_t cap, uint32_t sh
   const bool chains = (r->rp.integKind == 2 && r->hasSpecular && r->rp.maxDepth > 1) || r->rp.integKind == 3;
   ByteArena probe;
   Wavefront tmp{};
-  carve(probe, tmp, cap, shCap, r->rp.nVals, chains);
+  const bool volumes = !r->volumes.empty();
+  const uint32_t volMaxSteps = (volumes && r->volIntegrator == 1) ? r->volMaxSteps : 0;
+  carve(probe, tmp, cap, shCap, r->rp.nVals, chains, volumes, volMaxSteps);
   size_t need = probe.used + 256;
   if (need > r->wfBytes) {
     if (r->wfMem) cudaFree(r->wfMem);
@@ -497,7 +536,7 @@ static int ensureWavefront(drt_ctx* c, RenderState* r, uint32_t cap, uint32_t sh
   ByteArena a;
   a.base = r->wfMem;
   a.size = r->wfBytes;
-  carve(a, r->wf, cap, shCap, r->rp.nVals, chains);
+  carve(a, r->wf, cap, shCap, r->rp.nVals, chains, volumes, volMaxSteps);
   r->shCap = shCap;
   return DRT_OK;
 }
@@ -576,9 +615,36 @@ static int prepare(drt_ctx* c, RenderState* r) {
   int rc = ensureFilm(c, r);
   if (rc != DRT_OK) return rc;
   if (p.samplerKind == 0 || p.samplerKind >= 4) {
-    size_t smem = 4 * (size_t)(r->maxVals | 1) * sizeof(float);  // G = 32: four tasks per block
+    size_t maxVals = (size_t)r->maxVals;
+    if (p.samplerKind == 4) {  // the second visit of a supersampled pixel uses the maxSamples layout: check THAT one before any work
+      int mn, mx;
+      adaptiveCounts(p.xs, p.ys, &mn, &mx);
+      maxVals = maxVals / (size_t)mn * (size_t)mx;
+    }
+    size_t smem = 4 * (size_t)(maxVals | 1) * sizeof(float);  // G = 32: four tasks per block
     if (smem > 200 * 1024) return fail(c, DRT_E_INVALID, "lowdiscrepancy sampler: pixelsamples x light nsamples too large for one warp's shared memory");
   }
+  if (!r->volumes.empty() && r->volIntegrator == 1) {
+    // a camera ray (unit direction: every camera normalises it) spends at most the diagonal of the regions' world bound inside them
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (size_t i = 0; i < r->volumes.size(); ++i) {
+      const GVolume& v = r->volumes[i];
+      for (int k = 0; k < 8; ++k) {
+        const V3 q = XfPoint(&r->volV2W[16 * i], V3{(k & 1) ? v.hi[0] : v.lo[0], (k & 2) ? v.hi[1] : v.lo[1], (k & 4) ? v.hi[2] : v.lo[2]});
+        const double qq[3] = {q.x, q.y, q.z};
+        for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], qq[a]); hi[a] = std::max(hi[a], qq[a]); }
+      }
+    }
+    const double diag = std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2]));
+    const double steps = std::ceil(diag * 1.001 / r->volStep) + 2.0;
+    if (!(steps <= 65536.0)) return fail(c, DRT_E_UNSUPPORTED, "single-scattering volume integrator: more than 65536 steps across the volume regions");
+    r->volMaxSteps = (uint32_t)steps;
+  }
+  if (!r->volumes.empty() && p.integKind >= 2 && r->hasSpecular && p.maxDepth > 1)
+    return fail(c, DRT_E_UNSUPPORTED, "participating media with the specular recursion of directlighting / whitted (renderer.Li along every "
+                                      "reflected ray, integrator.dart:187-290) is not on the GPU path");
+  if (!r->volumes.empty() && (p.samplerKind == 3 || p.samplerKind == 4 || p.samplerKind == 5))
+    return fail(c, DRT_E_UNSUPPORTED, "participating media with the halton / adaptive / bestcandidate samplers is not on the GPU path");
   return DRT_OK;
 }
 
@@ -819,6 +885,11 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
     CK(c, STAGE(launchSaveCameraPrims)(wf, nSlots, st)); profMark(c, DRT_PK_OTHER);
     c->launches++;
   }
+  if (rs.nVolumes > 0) {  // VolumeIntegrator.Li along the camera rays (sampler_renderer.dart:93-95): T and Lvi per slot
+    CK(c, cudaMemsetAsync(wf.trCtr, 0, (size_t)wf.cap * sizeof(uint32_t), st));
+    CK(c, drt::extra::launchVolumeLi(p, rs, wf, rc, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
+    c->launches++;
+  }
   if (p.samplerKind != 3 && p.samplerKind != 5) {  // halton / bestcandidate: the accepted samples are counted on the device (raygenKernel)
     r->stats.camera_samples += nSlots;
     r->stats.closest_rays += nSlots;
@@ -862,6 +933,10 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
   const bool firstVisit = p.samplerKind == 4 && pb.pass == 0;
   if (firstVisit) {  // reportResults (adaptive_sampler.dart:133-158): supersampled pixels drop this visit's samples
     CK(c, STAGE(launchAdaptiveDecide)(p, wf, pb, r->dAdaptList.p, r->dAdaptCount.p, st)); profMark(c, DRT_PK_OTHER);
+    c->launches++;
+  }
+  if (rs.nVolumes > 0) {  // T * Li + Lvi (sampler_renderer.dart:97)
+    CK(c, drt::extra::launchVolumeCombine(wf, nSlots, st)); profMark(c, DRT_PK_OTHER);
     c->launches++;
   }
   CK(c, STAGE(launchFilm)(p, wf, nSlots, firstVisit ? 1 : 0, rc, st)); profMark(c, DRT_PK_FILM);
@@ -916,6 +991,8 @@ static int renderWindow(drt_ctx* c, int x, int y, int w, int h, uint32_t shard, 
   // 4 / 8 / 16 / 32 Mi slots (tools/batch_sweep.sh) — fewer, longer launches per bounce
   uint64_t slots = r->batchSlots ? r->batchSlots : (1ull << 24);
   if (const char* e = std::getenv("DRT_BATCH_SLOTS")) slots = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10));
+  if (!r->volumes.empty() && r->volIntegrator == 1)  // the march's sample arrays: 16 bytes x steps per slot, at most ~8 GB
+    slots = std::max<uint64_t>(4096, std::min<uint64_t>(slots, (8ull << 30) / (16ull * std::max<uint32_t>(r->volMaxSteps, 1))));
   // One visit of `count` pixels (of this shard's part of the window, or of `list`) with the current p.nPixelSamples per pixel
   if (r->profFlags & DRT_PROFILE_WORK) {
     const bool fresh = r->dWork.p == nullptr;
@@ -1265,6 +1342,71 @@ int drt_set_light_map(drt_ctx* c, uint32_t index, int width, int height, const f
     l.hither = hither;
   }
   l.haveMapParams = true;
+  r->sceneTablesValid = false;
+  return DRT_OK;
+}
+
+int drt_set_volumes(drt_ctx* c, uint32_t n, const int32_t* kind, const float* sigma_a, const float* sigma_s, const float* le, const double* g,
+                    const float* p0_p1, const float* volume_to_world, const float* world_to_volume, const double* exp_a_b,
+                    const float* up_dir, const int32_t* grid_dims, const uint64_t* density_offsets, const double* density) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_volumes(p_, n, kind, sigma_a, sigma_s, le, g, p0_p1, volume_to_world, world_to_volume, exp_a_b, up_dir,
+                                          grid_dims, density_offsets, density));
+  if (!c) return DRT_E_INVALID;
+  if (n && (!kind || !sigma_a || !sigma_s || !le || !g || !p0_p1 || !world_to_volume)) return fail(c, DRT_E_INVALID, "null volume arrays");
+  RenderState* r = state(c);
+  std::vector<GVolume> vols(n);
+  std::vector<double> dens;
+  for (uint32_t i = 0; i < n; ++i) {
+    GVolume& v = vols[i];
+    std::memset(&v, 0, sizeof(v));
+    v.kind = kind[i];
+    if (v.kind < 0 || v.kind > 2) return fail(c, DRT_E_INVALID, "volume kind must be 0 (homogeneous), 1 (exponential) or 2 (volumegrid)");
+    for (int k = 0; k < 3; ++k) {
+      v.sigA[k] = sigma_a[3 * i + k];
+      v.sigS[k] = sigma_s[3 * i + k];
+      v.sigT[k] = (float)((double)v.sigA[k] + (double)v.sigS[k]);  // the Spectrum sig_a + sig_s
+      v.le[k] = le[3 * i + k];
+      // BBox(p0, p1): component-wise min / max (bbox.dart:35-41)
+      v.lo[k] = std::fmin(p0_p1[6 * i + k], p0_p1[6 * i + 3 + k]);
+      v.hi[k] = std::fmax(p0_p1[6 * i + k], p0_p1[6 * i + 3 + k]);
+    }
+    std::memcpy(v.w2v, world_to_volume + 16 * i, 64);
+    v.g = g[i];
+    v.a = v.b = 1.0;
+    v.nx = v.ny = v.nz = 1;
+    if (v.kind == 1) {
+      if (!exp_a_b || !up_dir) return fail(c, DRT_E_INVALID, "exponential volume needs a, b and updir");
+      v.a = exp_a_b[2 * i];
+      v.b = exp_a_b[2 * i + 1];
+      const V3 up = Normalize(V3{up_dir[3 * i], up_dir[3 * i + 1], up_dir[3 * i + 2]});  // exponential_density_region.dart:29
+      v.up[0] = up.x; v.up[1] = up.y; v.up[2] = up.z;
+    }
+    if (v.kind == 2) {
+      if (!grid_dims || !density_offsets || !density) return fail(c, DRT_E_INVALID, "volumegrid needs nx, ny, nz and the density values");
+      v.nx = grid_dims[3 * i]; v.ny = grid_dims[3 * i + 1]; v.nz = grid_dims[3 * i + 2];
+      const uint64_t cnt = density_offsets[i + 1] - density_offsets[i];
+      if (v.nx < 1 || v.ny < 1 || v.nz < 1 || cnt != (uint64_t)v.nx * v.ny * v.nz)
+        return fail(c, DRT_E_INVALID, "volumegrid: the number of density values is not nx * ny * nz (volume_grid.dart:95-99)");
+      v.densityOffset = (uint32_t)dens.size();
+      dens.insert(dens.end(), density + density_offsets[i], density + density_offsets[i + 1]);
+    }
+  }
+  r->volumes.swap(vols);
+  r->volDensity.swap(dens);
+  r->volV2W.assign(volume_to_world ? volume_to_world : world_to_volume, (volume_to_world ? volume_to_world : world_to_volume) + 16 * (size_t)n);
+  if (!volume_to_world && n) return fail(c, DRT_E_INVALID, "null volume_to_world");
+  r->sceneTablesValid = false;
+  return DRT_OK;
+}
+
+int drt_set_volume_integrator(drt_ctx* c, int32_t kind, double step_size) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_volume_integrator(p_, kind, step_size));
+  if (!c) return DRT_E_INVALID;
+  if (kind < 0 || kind > 1) return fail(c, DRT_E_INVALID, "volume integrator must be 0 (emission) or 1 (single)");
+  if (!(step_size > 0.0)) return fail(c, DRT_E_INVALID, "stepsize must be positive");
+  RenderState* r = state(c);
+  r->volIntegrator = kind;
+  r->volStep = step_size;
   r->sceneTablesValid = false;
   return DRT_OK;
 }

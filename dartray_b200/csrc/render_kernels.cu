@@ -21,6 +21,8 @@
 
 #include "render_kernels.h"
 #include "shade_device.cuh"
+#include "trace_device.cuh"
+#include "volume_device.cuh"
 
 #ifndef DRT_RK_NS
 #define DRT_RK_NS extra  // this file as it stands; render_kernels_plain.cu includes it again with DRT_EXTRA = 0 / plain
@@ -558,6 +560,14 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(Ren
       ShapeHit h;
       hitGeometry<EXTRA>(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
       Spec T = ld3(wf.T, cap, slot);
+      if (EXTRA && rs.nVolumes > 0 && bounce > 0) {  // pathThroughput *= renderer.transmittance(ray) once the ray found this vertex (:116)
+        uint32_t ctr = wf.trCtr[slot];
+        Spec tr;
+        volTransmittanceDrawCold(rs, streamKey(rp.seed, wf.pixX[slot], wf.pixY[slot], wf.sampleIdx[slot], DRT_STREAM_TRANSMITTANCE), &ctr, o, d,
+                                 wf.extRange[cur][q].x, wf.extT[q], &tr);
+        wf.trCtr[slot] = ctr;
+        T = T * tr;
+      }
       const V3 wo = -d;
       // emitted light at the first vertex or after a specular bounce (:46-48); matte BSDFs never set specularBounce
       if (bounce == 0 || (GENERAL && wf.specBounce[slot])) {
@@ -661,7 +671,25 @@ __global__ void __launch_bounds__(128) resolveDirectKernel(RenderParams rp, Rend
       continue;
     }
     Spec Ld = mks1(0.0);
-    if (si >= 0 && !wf.shOcc[si]) Ld = Ld + ld3(wf.pendSh, cap, slot);
+    const bool media = EXTRA && rs.nVolumes > 0;  // Li *= transmittance along the unoccluded shadow ray (integrator.dart:137)
+    uint64_t trKey = 0;
+    uint32_t trCtr = 0;
+    if (media) {
+      trKey = streamKey(rp.seed, wf.pixX[slot], wf.pixY[slot], wf.sampleIdx[slot], DRT_STREAM_TRANSMITTANCE);
+      trCtr = wf.trCtr[slot];
+    }
+    if (si >= 0 && !wf.shOcc[si]) {
+      Spec c = ld3(wf.pendSh, cap, slot);
+      if (media) {
+        const float4 so = wf.shO[si], sd = wf.shD[si];
+        const double2 sr = wf.shRange[si];
+        Spec tr;
+        if (mode & 64) volTransmittanceSampleCold(rs, (double)val(wf, rp.pTauSample, slot), V3{so.x, so.y, so.z}, V3{sd.x, sd.y, sd.z}, sr.x, sr.y, &tr);
+        else volTransmittanceDrawCold(rs, trKey, &trCtr, V3{so.x, so.y, so.z}, V3{sd.x, sd.y, sd.z}, sr.x, sr.y, &tr);
+        c = c * tr;  // every factor of the contribution is a product with Li: the order of the float32 roundings is Li's first
+      }
+      Ld = Ld + c;
+    }
     if (mi >= 0) {
       const int prim = __float_as_int(wf.misHit[mi].w);
       const int light = wf.misLight[slot];
@@ -672,20 +700,30 @@ __global__ void __launch_bounds__(128) resolveDirectKernel(RenderParams rp, Rend
         hitGeometry<EXTRA>(rs, (uint32_t)prim, o, wi, wf.misT[mi], &h);
         Spec Li = areaL(rs.lights[light], h.nn, -wi);  // Intersection.Le, intersection.dart:62-65
         if (!IsBlack(Li)) {
-          Li = Li * mks1(1.0);
+          if (media) {  // renderer.transmittance along the ray up to the light's surface (integrator.dart:178)
+            Spec tr;
+            volTransmittanceDrawCold(rs, trKey, &trCtr, o, wi, wf.misRange[mi].x, wf.misT[mi], &tr);
+            Li = Li * tr;
+          }
           Ld = Ld + ld3(wf.pendMisF, cap, slot) * Li * wf.pendMisScale[slot];
         }
       } else if (EXTRA && prim < 0 && rs.lights[light].kind == 4) {  // the BSDF-sampled ray escaped: Li = light.Le(ray), integrator.dart:172-174
         const float4 d4 = wf.misD[mi];
         Spec Li = infiniteLe(rs, rs.lights[light], V3{d4.x, d4.y, d4.z});
         if (!IsBlack(Li)) {
-          Li = Li * mks1(1.0);
+          if (media) {
+            const float4 o4 = wf.misO[mi];
+            Spec tr;
+            volTransmittanceDrawCold(rs, trKey, &trCtr, V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, wf.misRange[mi].x, CUDART_INF, &tr);
+            Li = Li * tr;
+          }
           Ld = Ld + ld3(wf.pendMisF, cap, slot) * Li * wf.pendMisScale[slot];
         }
       }
     }
     wf.shIdx[slot] = -1;
     wf.misIdx[slot] = -1;
+    if (media) wf.trCtr[slot] = trCtr;
     if (!direct) {  // path: L += pathThroughput * (EstimateDirect * nLights)
       Spec L = ld3(wf.L, cap, slot);
       L = L + ld3(wf.pendT, cap, slot) * (Ld * (double)rs.nLights);
@@ -1054,6 +1092,188 @@ __global__ void __launch_bounds__(128) adaptiveDecideKernel(RenderParams rp, Wav
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Participating media: VolumeIntegrator.Li along the camera rays (sampler_renderer.dart:93-97).
+#if DRT_EXTRA
+// Light.sampleLAtPoint as the single-scattering integrator calls it (single_scatter_integrator.dart:105-109): Li, wi, pdf and the
+// VisibilityTester's ray.  Same light code as estimateDirectSetup (shade_device.cuh), without a BSDF.
+static __device__ __noinline__ void volLightSampleCold(const RenderScene& rs, int lightIndex, V3 p, float lu0, float lu1, double lcomp, Spec* LiOut,
+                                                       V3* wiOut, double* pdfOut, V3* shD, double* shMax) {
+  const GLight l = rs.lights[lightIndex];
+  V3 wi, segTo = p;
+  double lightPdf = 1.0, eps2 = 0.0;
+  Spec Li = mks1(0.0);
+  const bool infinite = l.kind == 4;
+  const bool distant = l.kind == 2 || infinite;
+  if (infinite) {
+    infiniteSampleCold(rs, l, lu0, lu1, &wi, &lightPdf, &Li);
+  } else if (distant) {
+    wi = V3{l.pos[0], l.pos[1], l.pos[2]};
+    Li = lightRadiance(l);
+  } else if (l.kind != 0) {
+    const V3 pos = V3{l.pos[0], l.pos[1], l.pos[2]};
+    wi = Normalize(pos - p);
+    segTo = pos;
+    if (l.kind == 1) {
+      Li = lightRadiance(l) / DistanceSquared(pos, p);
+    } else if (l.kind >= 5) {
+      mappedPointLightCold(rs, l, -wi, DistanceSquared(pos, p), &Li);
+    } else {  // spot_light.dart:36-70
+      const V3 wn = -wi;
+      const V3 wl = Normalize(mkv((double)l.w2l[0] * wn.x + (double)l.w2l[1] * wn.y + (double)l.w2l[2] * wn.z,
+                                  (double)l.w2l[3] * wn.x + (double)l.w2l[4] * wn.y + (double)l.w2l[5] * wn.z,
+                                  (double)l.w2l[6] * wn.x + (double)l.w2l[7] * wn.y + (double)l.w2l[8] * wn.z));
+      const double costheta = wl.z;
+      double falloff;
+      if (costheta < l.cosTotalWidth) falloff = 0.0;
+      else if (costheta > l.cosFalloffStart) falloff = 1.0;
+      else {
+        const double dl = (costheta - l.cosTotalWidth) / (l.cosFalloffStart - l.cosTotalWidth);
+        falloff = dl * dl * dl * dl;
+      }
+      Li = lightRadiance(l) * falloff / DistanceSquared(pos, p);
+    }
+  } else {  // diffuse_area_light.dart:59-70
+    V3 ns;
+    const V3 ps = shapeSetSample(rs, l, p, lu0, lu1, lcomp, &ns);
+    wi = Normalize(ps - p);
+    lightPdf = shapeSetPdf(rs, l, p, wi);
+    segTo = ps;
+    eps2 = 1.0e-3;
+    Li = areaL(l, ns, -wi);
+  }
+  *LiOut = Li;
+  *wiOut = wi;
+  *pdfOut = lightPdf;
+  if (distant) {
+    *shD = wi;
+    *shMax = CUDART_INF;
+  } else {
+    const double dist = Distance(p, segTo);  // visibility_tester.dart:26-29 with eps1 = 0
+    *shD = (segTo - p) / dist;
+    *shMax = dist * (1.0 - eps2);
+  }
+}
+
+// Shuffle (montecarlo.dart:294-303) of `count` entries of `dims` floats each, entry i at a[(dims * i + j) * stride]
+static __device__ inline void volShuffle(float* a, size_t stride, int count, int dims, Stream& rng) {
+  for (int i = 0; i < count; ++i) {
+    const int other = i + (int)(rng.randomUint() % (uint32_t)(count - i));
+    for (int j = 0; j < dims; ++j) {
+      const float t = a[(size_t)(dims * i + j) * stride];
+      a[(size_t)(dims * i + j) * stride] = a[(size_t)(dims * other + j) * stride];
+      a[(size_t)(dims * other + j) * stride] = t;
+    }
+  }
+}
+
+// EmissionIntegrator.Li (emission_integrator.dart:31-83) / SingleScatteringIntegrator.Li (single_scatter_integrator.dart:52-133): one
+// thread marches one camera ray.  The single-scattering shadow rays are traced in place (anyHitWalk: the reference's walk for one
+// ray); their sample arrays (LDShuffleScrambled1D / 2D over the march's steps) live in a per-slot scratch column.
+__global__ void __launch_bounds__(128) volumeLiKernel(RenderParams rp, RenderScene rs, Wavefront wf, RenderCounters* rc) {
+  const uint32_t n = wf.counts[Q_EXT0], cap = wf.cap;
+  unsigned long long nShadow = 0;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+    const uint32_t slot = wf.extSlot[0][q];
+    const float4 o4 = wf.extO[0][q], d4 = wf.extD[0][q];
+    const bool hit = __float_as_int(wf.extHit[q].w) >= 0;
+    VRay ray{V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, wf.extRange[0][q].x, hit ? wf.extT[q] : CUDART_INF};
+    double t0 = 0.0, t1 = 0.0;
+    Spec Tr = mks1(1.0), Lv = mks1(0.0);
+    if (volIntersectP(rs, ray, &t0, &t1) && (t1 - t0) != 0.0) {
+      Stream rng{streamKey(rp.seed, wf.pixX[slot], wf.pixY[slot], wf.sampleIdx[slot], DRT_STREAM_VOLUME_LI), 0};
+      uint64_t trKey = streamKey(rp.seed, wf.pixX[slot], wf.pixY[slot], wf.sampleIdx[slot], DRT_STREAM_TRANSMITTANCE);
+      uint32_t trCtr = wf.trCtr[slot];
+      const double stepSize = rs.volStep;
+      const bool single = rs.volIntegrator == 1;
+      int nSamples = (int)ceil((t1 - t0) / stepSize);
+      const double step = (t1 - t0) / nSamples;
+      V3 p = VRayAt(ray, t0), pPrev;
+      const V3 w = -ray.d;
+      t0 += (double)val(wf, rp.pScatterSample, slot) * step;
+      float* aNum = nullptr; float* aComp = nullptr; float* aPos = nullptr;
+      bool overflow = false;
+      if (single) {
+        if (nSamples > (int)wf.volMaxSteps) { overflow = true; nSamples = 0; }  // the host sized the scratch from the regions' bound
+        aNum = wf.volScratch + slot;
+        aComp = aNum + (size_t)wf.volMaxSteps * cap;
+        aPos = aComp + (size_t)wf.volMaxSteps * cap;
+        {  // LDShuffleScrambled1D(1, nSamples, lightNum, rng): montecarlo.dart:524-536
+          const uint32_t sc = rng.randomUint();
+          for (int i = 0; i < nSamples; ++i) aNum[(size_t)i * cap] = (float)VanDerCorput((uint32_t)i, sc);
+          for (int i = 0; i < nSamples; ++i) rng.randomUint();  // Shuffle of one element per block: a draw, no move
+          volShuffle(aNum, cap, nSamples, 1, rng);
+        }
+        {
+          const uint32_t sc = rng.randomUint();
+          for (int i = 0; i < nSamples; ++i) aComp[(size_t)i * cap] = (float)VanDerCorput((uint32_t)i, sc);
+          for (int i = 0; i < nSamples; ++i) rng.randomUint();
+          volShuffle(aComp, cap, nSamples, 1, rng);
+        }
+        {  // LDShuffleScrambled2D: montecarlo.dart:539-551
+          const uint32_t s0 = rng.randomUint(), s1 = rng.randomUint();
+          for (int i = 0; i < nSamples; ++i) {
+            aPos[(size_t)(2 * i) * cap] = (float)VanDerCorput((uint32_t)i, s0);
+            aPos[(size_t)(2 * i + 1) * cap] = (float)Sobol2((uint32_t)i, s1);
+          }
+          for (int i = 0; i < nSamples; ++i) rng.randomUint();
+          volShuffle(aPos, cap, nSamples, 2, rng);
+        }
+      }
+      for (int i = 0; i < nSamples; ++i, t0 += step) {
+        pPrev = p;
+        p = VRayAt(ray, t0);
+        VRay tauRay{pPrev, p - pPrev, 0.0, 1.0};
+        const Spec stepTau = volTau(rs, tauRay, 0.5 * stepSize, rng.randomFloat());
+        Tr = Tr * expNeg(stepTau);
+        if (Luminance(Tr) < 1.0e-3) {  // possibly terminate the march
+          const double continueProb = 0.5;
+          if (rng.randomFloat() > continueProb) {
+            Tr = mks1(0.0);
+            break;
+          }
+          Tr = Tr / continueProb;
+        }
+        Lv = Lv + Tr * volCoeff(rs, p, VOL_LVE);
+        if (single) {
+          const Spec ss = volCoeff(rs, p, VOL_SIG_S);
+          if (!IsBlack(ss) && rs.nLights > 0) {
+            const int ln = min((int)floor((double)aNum[(size_t)i * cap] * rs.nLights), rs.nLights - 1);
+            Spec L;
+            V3 wo, shD;
+            double pdf = 0.0, shMax = 0.0;
+            volLightSampleCold(rs, ln, p, aPos[(size_t)(2 * i) * cap], aPos[(size_t)(2 * i + 1) * cap], (double)aComp[(size_t)i * cap], &L, &wo,
+                               &pdf, &shD, &shMax);
+            if (!IsBlack(L) && pdf > 0.0) {
+              ++nShadow;
+              if (!anyHitWalk(rs.ts, make_float4(p.x, p.y, p.z, 0.f), make_float4(shD.x, shD.y, shD.z, 0.f), 0.0, shMax)) {
+                Spec tr;
+                volTransmittanceDrawCold(rs, trKey, &trCtr, p, shD, 0.0, shMax, &tr);
+                const Spec Ld = L * tr;
+                Lv = Lv + Tr * ss * volPhase(rs, p, w, -wo) * Ld * (double)rs.nLights / pdf;
+              }
+            }
+          }
+        }
+      }
+      if (overflow) { Tr = mks1(CUDART_NAN); }  // cannot happen with a host bound that holds; visible (zeroed sample counter) if it does
+      Lv = Lv * step;
+      wf.trCtr[slot] = trCtr;
+    }
+    st3(wf.volT, cap, slot, Tr);
+    st3(wf.volL, cap, slot, Lv);
+  }
+  for (int o = 16; o > 0; o >>= 1) nShadow += __shfl_down_sync(FULL, nShadow, o);
+  if ((threadIdx.x & 31) == 0 && nShadow) atomicAdd(&rc->shadowRays, nShadow);
+}
+
+__global__ void __launch_bounds__(256) volumeCombineKernel(Wavefront wf, uint32_t nSlots) {  // T * Li + Lvi
+  const uint32_t cap = wf.cap;
+  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < nSlots; slot += gridDim.x * blockDim.x)
+    st3(wf.L, cap, slot, ld3(wf.volT, cap, slot) * ld3(wf.L, cap, slot) + ld3(wf.volL, cap, slot));
+}
+#endif  // DRT_EXTRA
+
 // WARPSUM: when all 32 samples of a warp fall on ONE pixel (the usual case: a pixel's samples are consecutive slots and a box filter
 // of half a pixel covers one pixel), the warp adds its terms with a butterfly and lane 0 issues the four atomics instead of 128 on the
 // same four addresses.  The terms are float32 values times the filter weight, summed in f64 — exact for unit weights — so the film
@@ -1331,6 +1551,27 @@ cudaError_t launchFilm(const RenderParams& rp, const Wavefront& wf, uint32_t nSl
   if (perSample) filmKernel<false><<<(nSlots + 255) / 256, 256, 0, st>>>(rp, wf, nSlots, skipFlagged, rc);
   else filmKernel<true><<<(nSlots + 255) / 256, 256, 0, st>>>(rp, wf, nSlots, skipFlagged, rc);
   return cudaGetLastError();
+}
+
+cudaError_t launchVolumeLi(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, RenderCounters* rc, int numSMs, cudaStream_t st) {
+#if DRT_EXTRA
+  volumeLiKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, rc);
+  return cudaGetLastError();
+#else
+  (void)rp; (void)rs; (void)wf; (void)rc; (void)numSMs; (void)st;
+  return cudaErrorNotSupported;
+#endif
+}
+
+cudaError_t launchVolumeCombine(const Wavefront& wf, uint32_t nSlots, cudaStream_t st) {
+#if DRT_EXTRA
+  if (nSlots == 0) return cudaSuccess;
+  volumeCombineKernel<<<(nSlots + 255) / 256, 256, 0, st>>>(wf, nSlots);
+  return cudaGetLastError();
+#else
+  (void)wf; (void)nSlots; (void)st;
+  return cudaErrorNotSupported;
+#endif
 }
 
 cudaError_t launchFilmConvert(const RenderParams& rp, float* rgb, float* xyz, float* weight, cudaStream_t st) {

@@ -79,6 +79,17 @@ struct GMesh {
   float pad_;
 };
 
+// One VolumeRegion (lib/volume_regions/*.dart): kind 0 homogeneous, 1 exponential density, 2 volumegrid.
+struct GVolume {
+  int32_t kind, nx, ny, nz;
+  float sigA[3], sigS[3], sigT[3], le[3];  // sigT = the Spectrum sig_a + sig_s
+  float lo[3], hi[3];                      // extent = BBox(p0, p1) in volume space
+  float w2v[16];                           // worldToVolume
+  double g, a, b;
+  float up[3];                             // normalised up direction (exponential)
+  uint32_t densityOffset;                  // first value of the grid in RenderScene::volDensity
+};
+
 struct RenderScene {
   TraceScene ts;
   uint32_t ntris, nprims;
@@ -102,6 +113,12 @@ struct RenderScene {
   const float* envData;  // radiance maps and sampling tables of the infinite lights (GLight::envOffset)
   int32_t nInfinite;     // number of InfiniteAreaLights: escaped rays pick up their Le (sampler_renderer.dart:86-92)
   int32_t extra;  // 1: mesh attributes or quadrics of shape >= 2 are present (selects the kernels compiled with EXTRA)
+  // participating media (scene.volumeRegion + the volume integrator; nVolumes == 0: none, transmittance == 1 without a draw)
+  const GVolume* volumes;
+  int32_t nVolumes;
+  const double* volDensity;
+  int32_t volIntegrator;  // 0 emission, 1 single
+  double volStep;
 };
 
 struct RenderParams {
@@ -136,6 +153,8 @@ struct RenderParams {
   double aoMinDist, aoMaxDist;
   // path_integrator.dart:124-131: value indices for bounces 0..2
   int32_t pLightComp[3], pLightPos[3], pLightNum[3], pBsdfComp[3], pBsdfPos[3], pPathComp[3], pPathPos[3];
+  // volume integrator's two one-D samples (emission_integrator.dart:26-29): value indices
+  int32_t pTauSample, pScatterSample;
   // direct lighting, strategy "one": light number value; per-light offsets in `direct`
   int32_t dlLightNum;
   const DirectOffsets* direct;
@@ -188,6 +207,11 @@ struct Wavefront {
   // shadeOrder[i] = queue index, built per bounce by a counting sort over matHist (nMaterials + 1 bins, misses last)
   uint32_t* shadeOrder;
   uint32_t* matHist;
+  // participating media: position of the slot's transmittance stream; T and Lvi of the camera ray (sampler_renderer.dart:93-97)
+  uint32_t* trCtr;
+  float* volT; float* volL;  // 3 x cap each
+  float* volScratch;         // single scattering: 4 x volMaxSteps x cap (lightNum, lightComp, lightPos x 2 per step), [value][slot]
+  uint32_t volMaxSteps;
   int32_t* camPrim;  // adaptive sampler: primitive the slot's camera ray hit (-1: none)
   uint8_t* adaptFlag;  // adaptive sampler, per pixel of the batch: 1 = supersample (the first visit's samples are dropped)
 };

@@ -116,6 +116,8 @@ static DRT_HD inline uint64_t streamKey(uint64_t seed, int32_t x, int32_t y, uin
 }
 #define DRT_STREAM_PIXEL 4095u
 #define DRT_STREAM_INTEGRATOR 0x80000000u
+#define DRT_STREAM_TRANSMITTANCE 0x80000001u  // the draws of VolumeIntegrator.transmittance inside the surface integrator, in call order
+#define DRT_STREAM_VOLUME_LI 0x80000002u      // the draws of VolumeIntegrator.Li along the camera ray
 // d-th draw of a stream, d = 1, 2, ...
 static DRT_HD inline uint64_t draw64(uint64_t key, uint64_t d) { return mix64(key + d * 0x9E3779B97F4A7C15ull); }
 static DRT_HD inline double drawFloat(uint64_t key, uint64_t d) { return (double)(draw64(key, d) >> 11) * (1.0 / 9007199254740992.0); }

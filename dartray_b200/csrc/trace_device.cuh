@@ -289,4 +289,57 @@ static __device__ __forceinline__ void initRay(RayState& r, const float4 o, cons
 
 static __device__ __forceinline__ float4 ldg4(const void* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// BVHAccel.intersectP (bvh_accel.dart:167-226) for ONE ray inside another kernel: the literal walk of traceKernel<ANY = true>
+// (trace_kernels.cu) over the binary nodes, f64 slab test at every node.  For stages that trace a few rays per thread in a
+// data-dependent loop (the single-scattering volume integrator's shadow rays), where a wavefront queue per step would cost a
+// launch per step; the batched kernels of trace_fast*.cu remain the production path.
+static __device__ __noinline__ bool anyHitWalk(const TraceScene& sc, float4 o4, float4 d4, double mint, double maxt) {
+  if (sc.empty) return false;
+  RayState r;
+  initRay(r, o4, d4);
+  r.mint = mint;
+  r.maxt = maxt;
+  int32_t stackRef[DRT_STACK];
+  int sp = 0;
+  int32_t cur = 0;
+  {
+    double tmin, tmax;
+    if (!(slabs(r, sc.rootMin[0], sc.rootMin[1], sc.rootMin[2], sc.rootMax[0], sc.rootMax[1], sc.rootMax[2], &tmin, &tmax) &&
+          (tmin < r.maxt) && (tmax > r.mint)))
+      return false;
+    cur = sc.rootRef;
+  }
+  for (;;) {
+    if (cur >= 0) {
+      const GNode* nd = sc.nodes + cur;
+      float4 q0 = ldg4(&nd->c0min[0]), q1 = ldg4(&nd->c0max[1]), q2 = ldg4(&nd->c1min[2]);
+      int4 q3 = __ldg(reinterpret_cast<const int4*>(&nd->ref0));
+      const int neg = q3.z == 0 ? r.negx : (q3.z == 1 ? r.negy : r.negz);
+      double tmin0, tmax0, tmin1, tmax1;
+      const bool h0 = slabs(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tmin0, &tmax0) && (tmin0 < r.maxt) && (tmax0 > r.mint);
+      const bool h1 = slabs(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tmin1, &tmax1) && (tmin1 < r.maxt) && (tmax1 > r.mint);
+      const int32_t nearRef = neg ? q3.y : q3.x, farRef = neg ? q3.x : q3.y;
+      const bool hn = neg ? h1 : h0, hf = neg ? h0 : h1;
+      if (hf) stackRef[sp++] = farRef;  // maxDistance never shrinks in intersectP: the pop-time test cannot change
+      if (hn) { cur = nearRef; continue; }
+    } else {
+      uint32_t off = refLeafOffset(cur), cnt = refLeafCountField(cur);
+      const GPrim* pr = sc.prims + off;
+      if (cnt == 15u) cnt = (uint32_t)__ldg(&pr->leafCount);
+      for (uint32_t k = 0; k < cnt; ++k) {
+        float4 a = ldg4(&pr[k].p1[0]), b = ldg4(&pr[k].p2[0]), c = ldg4(&pr[k].p3[0]);
+        const int kind = __float_as_int(c.w);
+        if ((kind & 1) == 0) {
+          if (triangleAny(r, a, b, c)) return true;
+        } else {
+          double th;
+          if (sphereTest<true>(sc.spheres[kind >> 1], r, true, &th, nullptr, nullptr)) return true;
+        }
+      }
+    }
+    if (sp == 0) return false;
+    cur = stackRef[--sp];
+  }
+}
+
 }  // namespace drt

@@ -522,6 +522,29 @@ class SceneBuilder:
         self.materials.append(("lobes", list(lobes)))
         return len(self.materials) - 1
 
+    # -- participating media (lib/volume_regions/*.dart, Volume "homogeneous" | "exponential" | "volumegrid") ------------------
+    def volume(self, kind="homogeneous", sigma_a=0.0, sigma_s=0.0, g=0.0, le=0.0, p0=(0, 0, 0), p1=(1, 1, 1), volume_to_world=None,
+               a=1.0, b=1.0, updir=(0, 1, 0), density=None) -> int:
+        """One VolumeRegion with the reference's parameter names and defaults (homogenous_volume_region.dart:75-87,
+        exponential_density_region.dart:52-66, volume_grid.dart:75-102).  `density`: (nz, ny, nx) array for "volumegrid"."""
+        kinds = {"homogeneous": 0, "exponential": 1, "volumegrid": 2}
+        rgb = lambda v: tuple(float(x) for x in np.broadcast_to(np.asarray(fold_texture(v), np.float64), (3,)))
+        v2w = np.eye(4, dtype=np.float32) if volume_to_world is None else np.asarray(volume_to_world, np.float32).reshape(4, 4)
+        d = None
+        if kinds[kind] == 2:
+            d = np.ascontiguousarray(density, np.float64)
+            if d.ndim != 3:
+                raise ValueError("volumegrid: density must be a (nz, ny, nx) array")
+        if not hasattr(self, "volumes"):
+            self.volumes = []
+        self.volumes.append(dict(kind=kinds[kind], sigma_a=rgb(sigma_a), sigma_s=rgb(sigma_s), le=rgb(le), g=float(g), p0=tuple(p0),
+                                 p1=tuple(p1), v2w=v2w, a=float(a), b=float(b), up=tuple(updir), density=d))
+        return len(self.volumes) - 1
+
+    def volume_integrator(self, kind="emission", stepsize=1.0):
+        """VolumeIntegrator "emission" (the default, render_options.dart:24-39) | "single"; `stepsize` as in the scene file."""
+        self.vol_integrator = ({"emission": 0, "single": 1}[kind], float(stepsize))
+
     def point_light(self, pos, intensity) -> int:
         self.lights.append(dict(kind=1, L=tuple(intensity), pos=tuple(pos), nsamples=1, shapes=[]))
         return len(self.lights) - 1
@@ -771,7 +794,32 @@ class SceneBuilder:
             light_mapped=[(i, l["texels"], l["w2l"], l["proj"], l["screen"], l["hither"]) for i, l in enumerate(lights) if l["kind"] >= 5],
             light_shape_offsets=np.asarray(np.cumsum([0] + [len(l["shapes"]) for l in lights]), np.uint32),
             light_shape_prims=np.asarray([p for l in lights for p in l["shapes"]], np.uint32),
+            volumes=list(getattr(self, "volumes", [])),
+            vol_integrator=getattr(self, "vol_integrator", (0, 1.0)),
         )
+
+
+def pack_volumes(volumes: list) -> dict:
+    """The flat arrays of drt_set_volumes for a list of SceneBuilder.volume() entries."""
+    n = len(volumes)
+    f32 = lambda rows, w: np.ascontiguousarray(np.asarray(rows, np.float32).reshape(n, w)) if n else np.zeros((0, w), np.float32)
+    dens, off = [], [0]
+    for v in volumes:
+        if v["density"] is not None:
+            dens.append(v["density"].reshape(-1))
+        off.append(off[-1] + (v["density"].size if v["density"] is not None else 0))
+    return dict(
+        n=n, kind=np.asarray([v["kind"] for v in volumes], np.int32),
+        sigma_a=f32([v["sigma_a"] for v in volumes], 3), sigma_s=f32([v["sigma_s"] for v in volumes], 3), le=f32([v["le"] for v in volumes], 3),
+        g=np.asarray([v["g"] for v in volumes], np.float64),
+        p0p1=f32([tuple(v["p0"]) + tuple(v["p1"]) for v in volumes], 6),
+        v2w=f32([v["v2w"].reshape(16) for v in volumes], 16), w2v=f32([mat_inv(v["v2w"]).reshape(16) for v in volumes], 16),
+        ab=np.ascontiguousarray(np.asarray([(v["a"], v["b"]) for v in volumes], np.float64).reshape(n, 2)),
+        up=f32([v["up"] for v in volumes], 3),
+        dims=np.ascontiguousarray(np.asarray([(v["density"].shape[2], v["density"].shape[1], v["density"].shape[0]) if v["density"] is not None
+                                              else (1, 1, 1) for v in volumes], np.int32).reshape(n, 3)),
+        density_offsets=np.asarray(off, np.uint64),
+        density=np.concatenate(dens).astype(np.float64) if dens else np.zeros(1, np.float64))
 
 
 def upload_scene(ctx, arrays: dict, split: int = 2, max_node_prims: int = 4):
@@ -811,6 +859,8 @@ def upload_scene(ctx, arrays: dict, split: int = 2, max_node_prims: int = 4):
         ctx.set_infinite_light(i, tex, l2w, mat_inv(l2w))
     for i, tex, w2l, proj, screen, hither in a.get("light_mapped", []):
         ctx.set_light_map(i, tex, w2l, proj, screen, hither)
+    ctx.set_volumes(pack_volumes(a.get("volumes") or []))
+    ctx.set_volume_integrator(*a.get("vol_integrator", (0, 1.0)))
 
 
 def configure_render(ctx, camera: PerspectiveCamera, film: Film, sampler: Sampler, integrator: Integrator):

@@ -278,6 +278,27 @@ int drt_set_infinite_light(drt_ctx* ctx, uint32_t index, int width, int height, 
 int drt_set_light_map(drt_ctx* ctx, uint32_t index, int width, int height, const float* rgb, const float* world_to_light,
                       const float* light_projection, const double* screen_window, double hither);
 
+/* Participating media.  Replaces the VolumeRegion plugins (lib/volume_regions/homogenous_volume_region.dart:24-95,
+ * exponential_density_region.dart:22-72, volume_grid.dart:22-109 over lib/core/volume/density_region.dart:22-86; several regions
+ * = AggregateVolume, lib/core/volume/aggregate_volume.dart:23-103, as DartRay.worldEnd builds it, lib/dartray/dartray.dart:604-612).
+ * kind: 0 homogeneous, 1 exponential, 2 volumegrid.  sigma_a / sigma_s / le: n x 3; g: n; p0_p1: n x 6 (the extent's two corners
+ * in volume space); volume_to_world / world_to_volume: n x 16 row-major; exp_a_b: n x 2 and up_dir: n x 3 (exponential: density =
+ * a * exp(-b * height along normalize(up)); may be NULL without such a region); grid_dims: n x 3 (nx, ny, nz) and density values
+ * [density_offsets[i], density_offsets[i+1]) of region i, z-major as the scene file lists them (volumegrid; may be NULL without one).
+ * n = 0 removes the volume: every transmittance is 1 and no random number is drawn for it, as in the reference. */
+int drt_set_volumes(drt_ctx* ctx, uint32_t n, const int32_t* kind, const float* sigma_a_rgb, const float* sigma_s_rgb, const float* le_rgb,
+                    const double* g, const float* p0_p1, const float* volume_to_world, const float* world_to_volume,
+                    const double* exp_a_b, const float* up_dir, const int32_t* grid_dims, const uint64_t* density_offsets,
+                    const double* density);
+/* Replaces the VolumeIntegrator plugins: 0 = emission (the default of a scene without a VolumeIntegrator statement,
+ * lib/dartray/render_options.dart:24-39; lib/volume_integrators/emission_integrator.dart:22-112), 1 = single
+ * (single_scatter_integrator.dart:24-140).  Both march the camera ray through the regions in steps of `step_size`
+ * (SamplerRenderer.Li returns T * Li + Lvi, lib/renderers/sampler_renderer.dart:67-98) and give the surface integrators their
+ * transmittance() (integrator.dart:137,178, path_integrator.dart:116, whitted_integrator.dart:58).  Not on the GPU path (the call
+ * that starts the render returns DRT_E_UNSUPPORTED): media together with the specular recursion of directlighting / whitted, or with
+ * the halton / adaptive / bestcandidate samplers. */
+int drt_set_volume_integrator(drt_ctx* ctx, int32_t kind, double step_size);
+
 /* Replaces PerspectiveCamera (lib/cameras/perspective_camera.dart:46-57 + lib/core/
  * projective_camera.dart:34-53): the two float32 row-major matrices the camera holds
  * (rasterToCamera, cameraToWorld.startTransform) and its lens / shutter scalars. */

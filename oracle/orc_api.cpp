@@ -468,6 +468,43 @@ int orc_render_stats(const orc_ctx* c, uint64_t out[5]) {
 }
 
 // dart:math Random restatement, for documentation/tests of the serial stream
+// VolumeRegion plugins + the volume integrator; same arrays as drt_set_volumes / drt_set_volume_integrator (include/drt.h)
+int orc_set_volumes(orc_ctx* c, uint32_t n, const int32_t* kind, const float* sigA, const float* sigS, const float* le, const double* g,
+                    const float* p0p1, const float* v2w, const float* w2v, const double* ab, const float* up, const int32_t* dims,
+                    const uint64_t* densOff, const double* dens) {
+  c->rs.volume.regions.clear();
+  for (uint32_t i = 0; i < n; ++i) {
+    VolumeRegionCfg v;
+    v.kind = kind[i];
+    if (v.kind < 0 || v.kind > 2) return -1;
+    v.sigA = Spec(sigA[3 * i], sigA[3 * i + 1], sigA[3 * i + 2]);
+    v.sigS = Spec(sigS[3 * i], sigS[3 * i + 1], sigS[3 * i + 2]);
+    v.le = Spec(le[3 * i], le[3 * i + 1], le[3 * i + 2]);
+    v.g = g[i];
+    v.p0 = Vec(p0p1[6 * i], p0p1[6 * i + 1], p0p1[6 * i + 2]);
+    v.p1 = Vec(p0p1[6 * i + 3], p0p1[6 * i + 4], p0p1[6 * i + 5]);
+    v.worldToVolume = Transform(w2v + 16 * i, v2w + 16 * i);
+    if (v.kind == 1) {
+      v.a = ab[2 * i];
+      v.b = ab[2 * i + 1];
+      v.upDir = Normalize(Vec(up[3 * i], up[3 * i + 1], up[3 * i + 2]));  // exponential_density_region.dart:29
+    }
+    if (v.kind == 2) {
+      v.nx = dims[3 * i]; v.ny = dims[3 * i + 1]; v.nz = dims[3 * i + 2];
+      if (v.nx < 1 || v.ny < 1 || v.nz < 1 || densOff[i + 1] - densOff[i] != (uint64_t)v.nx * v.ny * v.nz) return -1;
+      v.density.assign(dens + densOff[i], dens + densOff[i + 1]);
+    }
+    c->rs.volume.regions.push_back(v);
+  }
+  return 0;
+}
+int orc_set_volume_integrator(orc_ctx* c, int kind, double stepSize) {
+  if (kind < 0 || kind > 1) return -1;
+  c->rs.volume.integrator = kind;
+  c->rs.volume.stepSize = stepSize;
+  return 0;
+}
+
 // test probes: BSDF.f / pdf / sample_f of a material in the canonical shading frame (see RenderScene::bsdfEval)
 int orc_bsdf_eval(orc_ctx* c, uint32_t material, uint32_t n, const double* wo, const double* wi, int flags, float* f, double* pdf) {
   if (material >= c->rs.materials.size()) return -1;

@@ -755,9 +755,240 @@ struct Ctx {
         dlBsdf.push_back(bsdfOffsets(1));
       }
     }
-    // volume integrator "emission" (render_options.dart:24-39 default), emission_integrator.dart:26-29
-    layout.add1D(1);
-    layout.add1D(1);
+    // volume integrator (emission by default, render_options.dart:24-39): emission_integrator.dart:26-29,
+    // single_scatter_integrator.dart:47-50
+    tauSampleOffset = layout.add1D(1);
+    scatterSampleOffset = layout.add1D(1);
+  }
+
+  // ---- participating media (lib/core/volume/*.dart, lib/volume_regions/*.dart, lib/volume_integrators/*.dart) ----------------
+  int tauSampleOffset = -1, scatterSampleOffset = -1;
+  Rng* trRng = nullptr;   // transmittance() draws; set per camera sample (keyed: kStreamTransmittance; serial: the one RNG)
+  Rng* volRng = nullptr;  // volume Li draws (keyed: kStreamVolumeLi)
+  bool hasVolume() const { return !rs.volume.regions.empty(); }
+
+  static bool boxIntersectP(const Vec& pMin, const Vec& pMax, const Ray& ray, double* hitt0, double* hitt1) {  // bbox.dart:81-114
+    double t0 = ray.mint, t1 = ray.maxt;
+    const float o[3] = {ray.o.x, ray.o.y, ray.o.z}, d[3] = {ray.d.x, ray.d.y, ray.d.z};
+    const float lo[3] = {pMin.x, pMin.y, pMin.z}, hi[3] = {pMax.x, pMax.y, pMax.z};
+    for (int i = 0; i < 3; ++i) {
+      double invRayDir = 1.0 / (double)d[i];
+      double tNear = ((double)lo[i] - (double)o[i]) * invRayDir;
+      double tFar = ((double)hi[i] - (double)o[i]) * invRayDir;
+      if (tNear > tFar) std::swap(tNear, tFar);
+      t0 = tNear > t0 ? tNear : t0;
+      t1 = tFar < t1 ? tFar : t1;
+      if (t0 > t1) return false;
+    }
+    *hitt0 = t0;
+    *hitt1 = t1;
+    return true;
+  }
+  static bool boxInside(const Vec& pMin, const Vec& pMax, const Vec& pt) {  // bbox.dart:123-127
+    return pt.x >= pMin.x && pt.x <= pMax.x && pt.y >= pMin.y && pt.y <= pMax.y && pt.z >= pMin.z && pt.z <= pMax.z;
+  }
+  static void extentOf(const VolumeRegionCfg& v, Vec* pMin, Vec* pMax) {
+    BBox b(v.p0, v.p1);
+    *pMin = b.pMin;
+    *pMax = b.pMax;
+  }
+  bool regionIntersectP(const VolumeRegionCfg& v, const Ray& r, double* t0, double* t1) const {
+    Ray ray = v.worldToVolume.ray(r);  // homogenous_volume_region.dart:32-35
+    Vec lo, hi;
+    extentOf(v, &lo, &hi);
+    return boxIntersectP(lo, hi, ray, t0, t1);
+  }
+  double regionDensity(const VolumeRegionCfg& v, const Vec& Pobj) const {
+    Vec lo, hi;
+    extentOf(v, &lo, &hi);
+    if (!boxInside(lo, hi, Pobj)) return 0.0;
+    if (v.kind == 0) return 1.0;
+    if (v.kind == 1) {  // exponential_density_region.dart:42-50
+      double height = Dot(Pobj - lo, v.upDir);
+      return v.a * std::exp(-v.b * height);
+    }
+    // volume_grid.dart:39-66
+    Vec vox(((double)Pobj.x - lo.x) / ((double)hi.x - lo.x), ((double)Pobj.y - lo.y) / ((double)hi.y - lo.y),
+            ((double)Pobj.z - lo.z) / ((double)hi.z - lo.z));  // bbox.dart:193-197, a float32 Vector
+    vox.x = f32((double)vox.x * v.nx - 0.5);
+    vox.y = f32((double)vox.y * v.ny - 0.5);
+    vox.z = f32((double)vox.z * v.nz - 0.5);
+    int vx = (int)std::floor((double)vox.x), vy = (int)std::floor((double)vox.y), vz = (int)std::floor((double)vox.z);
+    double dx = (double)vox.x - vx, dy = (double)vox.y - vy, dz = (double)vox.z - vz;
+    auto D = [&](int x, int y, int z) {
+      x = std::min(std::max(x, 0), v.nx - 1);
+      y = std::min(std::max(y, 0), v.ny - 1);
+      z = std::min(std::max(z, 0), v.nz - 1);
+      return v.density[(size_t)z * v.nx * v.ny + (size_t)y * v.nx + x];
+    };
+    double d00 = Lerp(dx, D(vx, vy, vz), D(vx + 1, vy, vz));
+    double d10 = Lerp(dx, D(vx, vy + 1, vz), D(vx + 1, vy + 1, vz));
+    double d01 = Lerp(dx, D(vx, vy, vz + 1), D(vx + 1, vy, vz + 1));
+    double d11 = Lerp(dx, D(vx, vy + 1, vz + 1), D(vx + 1, vy + 1, vz + 1));
+    double d0 = Lerp(dy, d00, d10), d1 = Lerp(dy, d01, d11);
+    return Lerp(dz, d0, d1);
+  }
+  // sigma_a / sigma_s / sigma_t / Lve at a world point: homogenous_volume_region.dart:37-56, density_region.dart:33-47
+  enum { kSigA, kSigS, kSigT, kLve };
+  Spec regionCoeff(const VolumeRegionCfg& v, const Vec& p, int which) const {
+    const Spec c = which == kSigA ? v.sigA : which == kSigS ? v.sigS : which == kSigT ? (v.sigA + v.sigS) : v.le;
+    const Vec q = v.worldToVolume.point(p);
+    if (v.kind == 0) {
+      Vec lo, hi;
+      extentOf(v, &lo, &hi);
+      return boxInside(lo, hi, q) ? c : Spec(0.0);
+    }
+    return c * regionDensity(v, q);
+  }
+  double regionPhase(const VolumeRegionCfg& v, const Vec& p, const Vec& w, const Vec& wp) const {
+    if (v.kind == 0) {  // homogenous_volume_region.dart:58-63
+      Vec lo, hi;
+      extentOf(v, &lo, &hi);
+      if (!boxInside(lo, hi, v.worldToVolume.point(p))) return 0.0;
+    }
+    double costheta = Dot(w, wp);  // PhaseHG, volume.dart:84-88
+    return 1.0 / (4.0 * kPi) * (1.0 - v.g * v.g) / std::pow(1.0 + v.g * v.g - 2.0 * v.g * costheta, 1.5);
+  }
+  Spec regionTau(const VolumeRegionCfg& v, const Ray& r, double stepSize, double u) const {
+    double t0 = 0.0, t1 = 0.0;
+    if (v.kind == 0) {  // homogenous_volume_region.dart:65-73: analytic, step and offset unused
+      if (!regionIntersectP(v, r, &t0, &t1)) return Spec(0.0);
+      return (v.sigA + v.sigS) * Distance(r.at(t0), r.at(t1));
+    }
+    // density_region.dart:53-77
+    double length = Length(r.d);
+    if (length == 0.0) return Spec(0.0);
+    Ray rn(r.o, r.d / length, r.mint * length, r.maxt * length, r.time);
+    if (!regionIntersectP(v, rn, &t0, &t1)) return Spec(0.0);
+    Spec tau(0.0);
+    t0 += u * stepSize;
+    while (t0 < t1) {
+      tau = tau + regionCoeff(v, rn.at(t0), kSigT);
+      t0 += stepSize;
+    }
+    return tau * stepSize;
+  }
+  // the scene's volumeRegion: the region itself, or an AggregateVolume over all of them (aggregate_volume.dart:23-103)
+  bool volIntersectP(const Ray& ray, double* t0, double* t1) const {
+    const auto& R = rs.volume.regions;
+    if (R.size() == 1) return regionIntersectP(R[0], ray, t0, t1);
+    *t0 = kInf;
+    *t1 = -kInf;
+    for (const VolumeRegionCfg& v : R) {
+      double a = 0.0, b = 0.0;
+      if (regionIntersectP(v, ray, &a, &b)) { *t0 = dmin(*t0, a); *t1 = dmax(*t1, b); }
+    }
+    return *t0 < *t1;
+  }
+  Spec volCoeff(const Vec& p, int which) const {
+    const auto& R = rs.volume.regions;
+    if (R.size() == 1) return regionCoeff(R[0], p, which);
+    Spec s(0.0);
+    for (const VolumeRegionCfg& v : R) s = s + regionCoeff(v, p, which);
+    return s;
+  }
+  double volPhase(const Vec& p, const Vec& w, const Vec& wp) const {
+    const auto& R = rs.volume.regions;
+    if (R.size() == 1) return regionPhase(R[0], p, w, wp);
+    double ph = 0.0, sumWt = 0.0;  // aggregate_volume.dart:71-80
+    for (const VolumeRegionCfg& v : R) {
+      double wt = regionCoeff(v, p, kSigS).luminance();
+      sumWt += wt;
+      ph += wt * regionPhase(v, p, w, wp);
+    }
+    return ph / sumWt;
+  }
+  Spec volTau(const Ray& ray, double step, double offset) const {
+    const auto& R = rs.volume.regions;
+    if (R.size() == 1) return regionTau(R[0], ray, step, offset);
+    Spec t(0.0);
+    for (const VolumeRegionCfg& v : R) t = t + regionTau(v, ray, step, offset);
+    return t;
+  }
+  static Spec expNeg(const Spec& tau) { return Spec(std::exp(-(double)tau.c[0]), std::exp(-(double)tau.c[1]), std::exp(-(double)tau.c[2])); }
+
+  // EmissionIntegrator.transmittance == SingleScatteringIntegrator.transmittance (emission_integrator.dart:85-105,
+  // single_scatter_integrator.dart:26-45): with a Sample the step is stepSize and the offset the tau sample; without, 4 x stepSize
+  // and a draw.  No volume region: 1, and NO draw.
+  Spec transmittance(const Ray& ray, const SampleVals* sample) {
+    if (!hasVolume()) return Spec(1.0);
+    double step, offset;
+    if (sample) {
+      step = rs.volume.stepSize;
+      offset = sample->oneD[tauSampleOffset][0];
+    } else {
+      step = 4.0 * rs.volume.stepSize;
+      offset = trRng->randomFloat();
+    }
+    return expNeg(volTau(ray, step, offset));
+  }
+
+  // EmissionIntegrator.Li (emission_integrator.dart:31-83) / SingleScatteringIntegrator.Li (single_scatter_integrator.dart:52-133)
+  Spec volumeLi(const Ray& ray, const SampleVals& sample, Spec* T) {
+    double t0 = 0.0, t1 = 0.0;
+    if (!hasVolume() || !volIntersectP(ray, &t0, &t1) || (t1 - t0) == 0.0) {
+      *T = Spec(1.0);
+      return Spec(0.0);
+    }
+    Rng& rng = *volRng;
+    const double stepSize = rs.volume.stepSize;
+    const bool single = rs.volume.integrator == 1;
+    Spec Lv(0.0);
+    int nSamples = (int)std::ceil((t1 - t0) / stepSize);
+    double step = (t1 - t0) / nSamples;
+    Spec Tr(1.0);
+    Vec p = ray.at(t0), pPrev;
+    Vec w = -ray.d;
+    t0 += (double)sample.oneD[scatterSampleOffset][0] * step;
+    std::vector<float> lightNum, lightComp, lightPos;
+    if (single) {
+      lightNum.assign(nSamples, 0.f);
+      LDShuffleScrambled1D(1, nSamples, lightNum.data(), rng);
+      lightComp.assign(nSamples, 0.f);
+      LDShuffleScrambled1D(1, nSamples, lightComp.data(), rng);
+      lightPos.assign(2 * (size_t)nSamples, 0.f);
+      LDShuffleScrambled2D(1, nSamples, lightPos.data(), rng);
+    }
+    int sampOffset = 0;
+    for (int i = 0; i < nSamples; ++i, t0 += step) {
+      pPrev = p;
+      p = ray.at(t0);
+      Ray tauRay(pPrev, p - pPrev, 0.0, 1.0, ray.time, ray.depth);
+      Spec stepTau = volTau(tauRay, 0.5 * stepSize, rng.randomFloat());
+      Tr = Tr * expNeg(stepTau);
+      if (Tr.luminance() < 1.0e-3) {  // possibly terminate the march
+        const double continueProb = 0.5;
+        if (rng.randomFloat() > continueProb) {
+          Tr = Spec(0.0);
+          break;
+        }
+        Tr = Tr / continueProb;
+      }
+      Lv = Lv + Tr * volCoeff(p, kLve);
+      if (single) {
+        Spec ss = volCoeff(p, kSigS);
+        if (!ss.isBlack() && !rs.lights.empty()) {
+          int nLights = (int)rs.lights.size();
+          int ln = std::min((int)std::floor((double)lightNum[sampOffset] * nLights), nLights - 1);
+          const Light& light = rs.lights[ln];
+          double pdf = 0.0;
+          Vis vis;
+          Vec wo;
+          U3 ls;  // LightSample(lightComp, lightPos0, lightPos1): light_sample.dart:28-36
+          ls.comp = lightComp[sampOffset];
+          ls.u0 = lightPos[2 * (size_t)sampOffset];
+          ls.u1 = lightPos[2 * (size_t)sampOffset + 1];
+          Spec L = sampleLAtPoint(light, p, 0.0, ls, ray.time, &wo, &pdf, &vis);
+          if (!L.isBlack() && pdf > 0.0 && !intersectP(vis.r)) {
+            Spec Ld = L * transmittance(vis.r, nullptr);
+            Lv = Lv + Tr * ss * volPhase(p, w, -wo) * Ld * (double)nLights / pdf;
+          }
+        }
+        ++sampOffset;
+      }
+    }
+    *T = Tr;
+    return Lv * step;
   }
 
   // ---- scene queries with stats ----
@@ -1181,8 +1412,7 @@ struct Ctx {
     if (lightPdf > 0.0 && !Li.isBlack()) {
       Spec f = bsdf.f(wo, wi, flags);
       if (!f.isBlack() && !intersectP(vis.r)) {
-        // Li *= transmittance == 1
-        Li = Li * Spec(1.0);
+        Li = Li * transmittance(vis.r, nullptr);  // integrator.dart:137
         if (delta) {
           Ld = Ld + f * Li * (AbsDot(wi, n) / lightPdf);
         } else {
@@ -1211,7 +1441,7 @@ struct Ctx {
           Li2 = lightLe(light, ray);  // zero unless the light is infinite
         }
         if (!Li2.isBlack()) {
-          Li2 = Li2 * Spec(1.0);
+          Li2 = Li2 * transmittance(ray, nullptr);  // integrator.dart:178 (the ray ends at the light's surface, or never)
           Ld = Ld + f * Li2 * (AbsDot(wi, n) * weight / bsdfPdf);
         }
       }
@@ -1288,8 +1518,7 @@ struct Ctx {
           for (const Light& lt : rs.lights) L = L + pathThroughput * lightLe(lt, ray);
         break;
       }
-      // pathThroughput *= transmittance == 1
-      pathThroughput = pathThroughput * Spec(1.0);
+      pathThroughput = pathThroughput * transmittance(ray, nullptr);  // path_integrator.dart:116
       isectP = localIsect;
     }
     return L;
@@ -1344,7 +1573,7 @@ struct Ctx {
       Spec Li = sampleLAtPoint(rs.lights[i], p, isect.rayEpsilon, U3::random(rng), ray.time, &wi, &pdf, &vis);
       if (Li.isBlack() || pdf == 0.0) continue;
       Spec f = bsdf.f(wo, wi, BSDF_ALL);
-      if (!f.isBlack() && !intersectP(vis.r)) L = L + f * Li * AbsDot(wi, n) * Spec(1.0) / pdf;
+      if (!f.isBlack() && !intersectP(vis.r)) L = L + f * Li * AbsDot(wi, n) * transmittance(vis.r, &sample) / pdf;  // whitted_integrator.dart:56-58
     }
     if (ray.depth + 1 < rs.integ.maxDepth) {
       L = L + specularBranch(ray, bsdf, isect, sample, rng, BSDF_REFLECTION | BSDF_SPECULAR);
@@ -1420,8 +1649,10 @@ struct Ctx {
     } else {
       L = allLightsLe(ray);  // sampler_renderer.dart:86-92
     }
-    // T * Li + Lvi with T = 1, Lvi = 0
-    return Spec(1.0) * L + Spec(0.0);
+    // T * Li + Lvi (sampler_renderer.dart:93-97); `ray` ends at the surface hit
+    Spec T(1.0);
+    Spec Lvi = volumeLi(ray, s, &T);
+    return T * L + Lvi;
   }
 
   // sampler_renderer.dart:173-193
@@ -1809,7 +2040,11 @@ void RenderScene::render(int taskNum, int taskCount, int nthreads) {
           std::vector<int32_t> prims(n);
           for (int s = 0; s < n; ++s) {
             KeyedRng k(sampler.seed, px[2 * i], px[2 * i + 1], (uint32_t)(ps * n + s), kStreamIntegrator);
+            KeyedRng kt(sampler.seed, px[2 * i], px[2 * i + 1], (uint32_t)(ps * n + s), kStreamTransmittance);
+            KeyedRng kv(sampler.seed, px[2 * i], px[2 * i + 1], (uint32_t)(ps * n + s), kStreamVolumeLi);
             Rng& rng = sampler.rngMode == 1 ? (Rng&)k : (Rng&)serial;
+            c.trRng = sampler.rngMode == 1 ? (Rng*)&kt : (Rng*)&serial;
+            c.volRng = sampler.rngMode == 1 ? (Rng*)&kv : (Rng*)&serial;
             Ls[s] = c.Li(sv[s], rng);
             prims[s] = c.lastCameraPrim;
           }
@@ -1841,6 +2076,10 @@ void RenderScene::render(int taskNum, int taskCount, int nthreads) {
             std::vector<int32_t> prims(n);
             for (int s = 0; s < n; ++s) {
               KeyedRng k(sampler.seed, px[2 * i], px[2 * i + 1], (uint32_t)(ps * n + s), kStreamIntegrator);
+              KeyedRng kt(sampler.seed, px[2 * i], px[2 * i + 1], (uint32_t)(ps * n + s), kStreamTransmittance);
+              KeyedRng kv(sampler.seed, px[2 * i], px[2 * i + 1], (uint32_t)(ps * n + s), kStreamVolumeLi);
+              c.trRng = &kt;
+              c.volRng = &kv;
               Ls[s] = c.Li(sv[s], k);
               prims[s] = c.lastCameraPrim;
             }

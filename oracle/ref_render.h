@@ -125,6 +125,11 @@ struct KeyedRng : Rng {
 };
 static const uint32_t kStreamPixel = 4095;          // stratified / random sampler: one stream per pixel
 static const uint32_t kStreamIntegrator = 0x80000000u;
+// keyed mode with participating media: the draws the volume integrator's transmittance() makes inside the surface integrator
+// (one per call, in call order) and the draws of its Li() have their own per-camera-sample streams, so that the wavefront can
+// run the camera rays' volume integration and the surface integrator's bounces in either order.  Serial mode: the one RNG.
+static const uint32_t kStreamTransmittance = 0x80000001u;
+static const uint32_t kStreamVolumeLi = 0x80000002u;
 
 // ---- scene description beyond geometry ----------------------------------------------------------------
 // One BxDF of a material's BSDF with constant textures.  The materials of lib/materials/*.dart decompose into
@@ -253,6 +258,24 @@ struct IntegratorCfg {
   double aoMinDist = 1e-4, aoMaxDist = kInf;
 };
 
+// VolumeRegion plugins (lib/volume_regions/*.dart) and the volume integrator (lib/volume_integrators/*.dart)
+struct VolumeRegionCfg {
+  int kind = 0;  // 0 homogeneous, 1 exponential, 2 volumegrid
+  Spec sigA, sigS, le;
+  double g = 0.0;
+  Vec p0, p1;            // extent = BBox(p0, p1) in volume space
+  Transform worldToVolume;
+  double a = 1.0, b = 1.0;  // exponential: density = a * exp(-b * height)
+  Vec upDir;                // normalised (exponential_density_region.dart:29)
+  int nx = 1, ny = 1, nz = 1;
+  std::vector<double> density;  // volumegrid: Float64List, z-major (volume_grid.dart:73)
+};
+struct VolumeCfg {
+  std::vector<VolumeRegionCfg> regions;  // > 1: AggregateVolume (dartray.dart:604-612)
+  int integrator = 0;                    // 0 emission (the default, render_options.dart:24-39), 1 single
+  double stepSize = 1.0;
+};
+
 struct RenderStats {
   uint64_t cameraSamples = 0, closestRays = 0, shadowRays = 0, nodesVisited = 0, primsTested = 0;
 };
@@ -265,6 +288,7 @@ struct RenderScene {
   Film film;
   SamplerCfg sampler;
   IntegratorCfg integ;
+  VolumeCfg volume;
   RenderStats stats;
 
   void finalizeLights();

@@ -76,6 +76,8 @@ def lib():
         L.orc_pixel_samples.argtypes = [vp, i32, i32, vp, i32, vp]
         L.orc_render_stats.argtypes = [vp, vp]
         L.orc_dart_random.argtypes = [C.c_int64, i32, vp, vp]
+        L.orc_set_volumes.argtypes = [vp, u32] + [vp] * 13
+        L.orc_set_volume_integrator.argtypes = [vp, i32, dbl]
         L.orc_bsdf_eval.argtypes = [vp, u32, u32, vp, vp, i32, vp, vp]
         L.orc_bsdf_sample.argtypes = [vp, u32, u32, vp, vp, i32, vp, vp, vp, vp]
         _lib = L
@@ -264,6 +266,16 @@ class Oracle:
 
     def set_integrator(self, kind, maxdepth, strategy, ao_nsamples, ao_mindist, ao_maxdist):
         self._ck(self.L.orc_set_integrator(self.h, kind, maxdepth, strategy, ao_nsamples, ao_mindist, ao_maxdist))
+
+    def set_volumes(self, v):
+        """v: the dict host.pack_volumes() returns (same arrays as Context.set_volumes)."""
+        self._keep_vol = v
+        self._ck(self.L.orc_set_volumes(self.h, v["n"], _p(v["kind"]), _p(v["sigma_a"]), _p(v["sigma_s"]), _p(v["le"]), _p(v["g"]),
+                                        _p(v["p0p1"]), _p(v["v2w"]), _p(v["w2v"]), _p(v["ab"]), _p(v["up"]), _p(v["dims"]),
+                                        _p(v["density_offsets"]), _p(v["density"])))
+
+    def set_volume_integrator(self, kind, step_size):
+        self._ck(self.L.orc_set_volume_integrator(self.h, kind, float(step_size)))
 
     def render(self, task_num=0, task_count=1, nthreads=8):
         self._ck(self.L.orc_render(self.h, task_num, task_count, nthreads))
