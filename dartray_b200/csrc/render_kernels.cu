@@ -1182,8 +1182,6 @@ __global__ void __launch_bounds__(128) volumeLiKernel(RenderParams rp, RenderSce
     Spec Tr = mks1(1.0), Lv = mks1(0.0);
     if (volIntersectP(rs, ray, &t0, &t1) && (t1 - t0) != 0.0) {
       Stream rng{streamKey(rp.seed, wf.pixX[slot], wf.pixY[slot], wf.sampleIdx[slot], DRT_STREAM_VOLUME_LI), 0};
-      uint64_t trKey = streamKey(rp.seed, wf.pixX[slot], wf.pixY[slot], wf.sampleIdx[slot], DRT_STREAM_TRANSMITTANCE);
-      uint32_t trCtr = wf.trCtr[slot];
       const double stepSize = rs.volStep;
       const bool single = rs.volIntegrator == 1;
       int nSamples = (int)ceil((t1 - t0) / stepSize);
@@ -1247,9 +1245,9 @@ __global__ void __launch_bounds__(128) volumeLiKernel(RenderParams rp, RenderSce
             if (!IsBlack(L) && pdf > 0.0) {
               ++nShadow;
               if (!anyHitWalk(rs.ts, make_float4(p.x, p.y, p.z, 0.f), make_float4(shD.x, shD.y, shD.z, 0.f), 0.0, shMax)) {
-                Spec tr;
-                volTransmittanceDrawCold(rs, trKey, &trCtr, p, shD, 0.0, shMax, &tr);
-                const Spec Ld = L * tr;
+                // vis.transmittance(scene, renderer, null, rng): step 4 x stepSize, the offset drawn from this march's own stream
+                VRay sray{p, shD, 0.0, shMax};
+                const Spec Ld = L * expNeg(volTau(rs, sray, 4.0 * stepSize, rng.randomFloat()));
                 Lv = Lv + Tr * ss * volPhase(rs, p, w, -wo) * Ld * (double)rs.nLights / pdf;
               }
             }
@@ -1258,7 +1256,6 @@ __global__ void __launch_bounds__(128) volumeLiKernel(RenderParams rp, RenderSce
       }
       if (overflow) { Tr = mks1(CUDART_NAN); }  // cannot happen with a host bound that holds; visible (zeroed sample counter) if it does
       Lv = Lv * step;
-      wf.trCtr[slot] = trCtr;
     }
     st3(wf.volT, cap, slot, Tr);
     st3(wf.volL, cap, slot, Lv);

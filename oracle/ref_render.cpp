@@ -910,7 +910,9 @@ struct Ctx {
   // EmissionIntegrator.transmittance == SingleScatteringIntegrator.transmittance (emission_integrator.dart:85-105,
   // single_scatter_integrator.dart:26-45): with a Sample the step is stepSize and the offset the tau sample; without, 4 x stepSize
   // and a draw.  No volume region: 1, and NO draw.
-  Spec transmittance(const Ray& ray, const SampleVals* sample) {
+  // `rng`: where the sample-less call draws its offset — the transmittance stream for the surface integrators' calls, the volume
+  // Li stream for the calls SingleScatteringIntegrator.Li makes itself (keyed mode; serial mode has one RNG for everything).
+  Spec transmittance(const Ray& ray, const SampleVals* sample, Rng* rng = nullptr) {
     if (!hasVolume()) return Spec(1.0);
     double step, offset;
     if (sample) {
@@ -918,7 +920,7 @@ struct Ctx {
       offset = sample->oneD[tauSampleOffset][0];
     } else {
       step = 4.0 * rs.volume.stepSize;
-      offset = trRng->randomFloat();
+      offset = (rng ? rng : trRng)->randomFloat();
     }
     return expNeg(volTau(ray, step, offset));
   }
@@ -980,7 +982,7 @@ struct Ctx {
           ls.u1 = lightPos[2 * (size_t)sampOffset + 1];
           Spec L = sampleLAtPoint(light, p, 0.0, ls, ray.time, &wo, &pdf, &vis);
           if (!L.isBlack() && pdf > 0.0 && !intersectP(vis.r)) {
-            Spec Ld = L * transmittance(vis.r, nullptr);
+            Spec Ld = L * transmittance(vis.r, nullptr, volRng);
             Lv = Lv + Tr * ss * volPhase(p, w, -wo) * Ld * (double)nLights / pdf;
           }
         }

@@ -126,8 +126,9 @@ struct KeyedRng : Rng {
 static const uint32_t kStreamPixel = 4095;          // stratified / random sampler: one stream per pixel
 static const uint32_t kStreamIntegrator = 0x80000000u;
 // keyed mode with participating media: the draws the volume integrator's transmittance() makes inside the surface integrator
-// (one per call, in call order) and the draws of its Li() have their own per-camera-sample streams, so that the wavefront can
-// run the camera rays' volume integration and the surface integrator's bounces in either order.  Serial mode: the one RNG.
+// (one per call, in call order) and the draws of its Li() — its own transmittance() calls along the single-scattering shadow rays
+// included — have their own per-camera-sample streams, so that the wavefront can run the camera rays' volume integration and the
+// surface integrator's bounces in either order.  Serial mode: the one RNG.
 static const uint32_t kStreamTransmittance = 0x80000001u;
 static const uint32_t kStreamVolumeLi = 0x80000002u;
 

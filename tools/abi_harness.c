@@ -56,16 +56,16 @@ int main(int argc, char** argv) {
   drt_ctx* ctx = drt_create((int)num("device", 0));
   if (!ctx) { fprintf(stderr, "drt_create: %s\n", drt_last_error(NULL)); return 3; }
 
-  /* _flattenScene: triangles, then disks / spheres (gpu_sampler_renderer.dart:376-445) */
+  /* _flattenScene: triangles, spheres, then disks — ids follow in that order (gpu_sampler_renderer.dart:376-445) */
   CK(drt_set_triangles(ctx, (const float*)ptr("P"), (uint32_t)count("P", 12), (const uint32_t*)ptr("idx"), (uint32_t)count("idx", 12),
                        (const int32_t*)ptr("tri_mat"), (const int32_t*)ptr("tri_light"), (const uint8_t*)ptr("tri_rev")));
+  CK(drt_set_spheres(ctx, (uint32_t)count("sph_params", 32), (const float*)ptr("sph_o2w"), (const float*)ptr("sph_w2o"),
+                     (const double*)ptr("sph_params"), (const int32_t*)ptr("sph_mat"), (const int32_t*)ptr("sph_light"),
+                     (const uint8_t*)ptr("sph_rev")));
   if (count("dsk_params", 32))
     CK(drt_set_disks(ctx, (uint32_t)count("dsk_params", 32), (const float*)ptr("dsk_o2w"), (const float*)ptr("dsk_w2o"),
                      (const double*)ptr("dsk_params"), (const int32_t*)ptr("dsk_mat"), (const int32_t*)ptr("dsk_light"),
                      (const uint8_t*)ptr("dsk_rev")));
-  CK(drt_set_spheres(ctx, (uint32_t)count("sph_params", 32), (const float*)ptr("sph_o2w"), (const float*)ptr("sph_w2o"),
-                     (const double*)ptr("sph_params"), (const int32_t*)ptr("sph_mat"), (const int32_t*)ptr("sph_light"),
-                     (const uint8_t*)ptr("sph_rev")));
   CK(drt_set_build_order(ctx, (const uint32_t*)ptr("order"), (uint32_t)count("order", 4)));
   CK(drt_build_bvh(ctx, (int)num("bvh", 0), (int)num("bvh", 1)));
   drt_bvh_info info;
