@@ -232,11 +232,17 @@ __global__ void __launch_bounds__(DRT_Q_BLOCK, DRT_Q_MIN_BLOCKS)
       if (ex.tOut) ex.tOut[rayIdx_] = hprim_ >= 0 ? r.maxt : CUDART_INF;                                     \
     }                                                                                                        \
   } while (0)
+#ifdef DRT_Q_PREFETCH_LEAF  // start the postponed leaf's first record towards L1: the leaf phase comes a few node steps later
+#define PREFETCH_LEAF(refv) asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.prims + refLeafOffset(refv)))
+#else
+#define PREFETCH_LEAF(refv)
+#endif
 #define ENQUEUE_LEAF(refv)                        \
   do {                                            \
     if (npend == 0) pend0 = (refv);               \
     else pend1 = (refv);                          \
     ++npend;                                      \
+    PREFETCH_LEAF(refv);                          \
   } while (0)
 
   for (;;) {
@@ -395,7 +401,11 @@ __global__ void __launch_bounds__(DRT_Q_BLOCK, DRT_Q_MIN_BLOCKS)
 #pragma unroll
     for (int step_ = 0; step_ < DRT_Q_STEPS; ++step_) {
     if (alive && cur == DRT_REF_NONE) {
+#ifdef DRT_Q_SINGLE_POP
+      for (int once_ = 0; once_ < 1; ++once_) {  // one entry per step: a culled or leaf entry costs the lane this step, not the warp a loop trip
+#else
       for (;;) {
+#endif
         if (npend == DRT_PEND || sp == 0) break;
         --sp;
         const uint2 e_ = sp < DRT_SMEM_STACK ? lds64(smBase + (unsigned)sp * DRT_Q_STRIDE) : deepStack[sp - DRT_SMEM_STACK];
@@ -499,6 +509,12 @@ __global__ void __launch_bounds__(DRT_Q_BLOCK, DRT_Q_MIN_BLOCKS)
         STACK_STORE(sp, s1, u1); sp += p1;
       }
       cur = v0 ? s0 : (v1 ? s1 : (v2 ? s2 : (v3 ? s3 : DRT_REF_NONE)));
+#ifdef DRT_Q_PREFETCH_TOP  // the entry that pops next (the second passing child): towards L1 while the first child's subtree is walked
+      if (p1 | p2 | p3) {
+        const int32_t nxt_ = p1 ? s1 : (p2 ? s2 : s3);
+        if (nxt_ >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.wideQ + nxt_));
+      }
+#endif
       if (cur < 0) {  // a leaf: postpone it (the lane walked, so its queue had room)
         ENQUEUE_LEAF(cur);
         cur = DRT_REF_NONE;

@@ -310,3 +310,42 @@ def test_device_pointer_entry_matches_host_entry(drt_lib):
     hd = dh.cpu().numpy().view(capi.HIT_DTYPE).reshape(-1)
     assert (hd["prim"] == href["prim"]).all() and (hd["t"].view(np.uint32) == href["t"].view(np.uint32)).all()
     assert (docc.cpu().numpy() == c.trace_any(ro, rd)).all()
+
+
+# ---- the quantised-node kernel at the edges of its float32 preconditions (trace_fast2.cu header) -------------------------------
+@pytest.mark.parametrize("scale,offset", [(1.0e-20, 0.0), (1.0e15, 0.0), (1.0, 3.0e6), (1.0e-3, -7.5e4), (3.0e17, 1.0e18)],
+                         ids=["tiny", "huge", "far_small", "far_tiny", "near_2^62"])
+def test_quantised_nodes_at_extreme_coordinates(drt_lib, variant, scale, offset):
+    """Grid steps clamp at 2^-60, coordinates approach the 2^62 bound, boxes shrink to a few ulps of their position: the node
+    boxes stay conservative (the builder checks every inequality in binary64) and every leaf decision is the reference's."""
+    P, idx = random_soup(3000, seed=11)
+    P = (P.astype(np.float64) * scale + offset).astype(np.float32)
+    o, c = make_pair(P, idx, variant=variant)
+    ro, rd = random_rays(30000, seed=12)
+    ro[:, :3] = (ro[:, :3].astype(np.float64) * scale + offset).astype(np.float32)
+    assert_hits_equal(c.trace_closest(ro, rd), o.trace_closest(ro, rd, nthreads=8))
+    assert (c.trace_any(ro, rd) == o.trace_any(ro, rd, nthreads=8)).all()
+    hit = c.trace_closest(ro, rd)["prim"] >= 0
+    assert scale * 1e3 < abs(offset) or hit.mean() > 0.05  # far-away flat soups may be missed by most rays; the others are hit
+
+
+def test_quantised_nodes_with_unnormalised_and_degenerate_directions(drt_lib, variant):
+    """Directions scaled by 1e-25 / 1e25 (|invDir| leaves [2^-60, 2^40]: the binary64 path on the decoded boxes), axis-parallel rays
+    (infinite invDir), rays from beyond 2^62 and rays starting exactly on box planes."""
+    P, idx = random_soup(2000, seed=21)
+    o, c = make_pair(P, idx, variant=variant)
+    ro, rd = random_rays(20000, seed=22)
+    rd2 = rd.copy()
+    rd2[0::4, :3] *= np.float32(1e-25)
+    rd2[1::4, :3] *= np.float32(1e25)
+    rd2[2::8, 0] = 0.0                      # parallel to the yz plane
+    rd2[6::8, 1:3] = 0.0                    # along x
+    rd2[:, 3] = np.inf
+    ro2 = ro.copy()
+    ro2[3::16, :3] *= np.float32(1e19)      # beyond the 2^62 origin bound
+    # origins exactly on triangle vertices' coordinates: on leaf / node box planes
+    k = np.arange(5, ro2.shape[0], 16)
+    ro2[k, 0] = P[idx[k % idx.shape[0], 0], 0]
+    for a, b in ((ro2, rd2), (ro, rd2)):
+        assert_hits_equal(c.trace_closest(a, b), o.trace_closest(a, b, nthreads=8))
+        assert (c.trace_any(a, b) == o.trace_any(a, b, nthreads=8)).all()
