@@ -251,7 +251,9 @@ int drt_set_build_order(drt_ctx* c, const uint32_t* ids, uint32_t n) {
 // hyperboloid.dart:23-49 (Points are float32, the expressions f64).  The object bound of each is
 // (-radius, -radius, zmin) .. (radius, radius, zmax) with the record's radius / zmin / zmax (cone: 0 .. height;
 // hyperboloid: rmax).
-static void quadricSetup(const HostSphere& s, GSphere* gp) {
+// Returns false for a hyperboloid whose implicit coefficients never become finite (hyperboloid.dart:40-48 loops until they do:
+// p1 == p2, non-finite points, ...): an ABI entry point must not hang where the reference's constructor would.
+static bool quadricSetup(const HostSphere& s, GSphere* gp) {
   GSphere& g = *gp;
   const double* prm = s.prm;
   double pm = 360.0;
@@ -281,7 +283,9 @@ static void quadricSetup(const HostSphere& s, GSphere* gp) {
       for (int k = 0; k < 3; ++k) std::swap(p1[k], p2[k]);
     float pp[3] = {p1[0], p1[1], p1[2]};
     double a, cc;
+    int tries = 0;
     do {
+      if (++tries > 4096) return false;
       for (int k = 0; k < 3; ++k) {
         float dk = (float)((double)p2[k] - (double)p1[k]);  // Vector p2 - p1
         float d2 = (float)((double)dk * 2.0);               // * 2.0
@@ -297,6 +301,7 @@ static void quadricSetup(const HostSphere& s, GSphere* gp) {
     g.hc = cc;
   }
   g.phiMax = (3.141592653589793 / 180.0) * clampd(pm, 0.0, 360.0);
+  return true;
 }
 
 // Device half of drt_build_bvh: the built tree's arrays go to c's device.  B / prims / gs may belong to another context (the
@@ -406,7 +411,7 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
       g.zmin = g.zmax = s.height;
       g.thetaMin = g.thetaMax = 0.0;
     } else if (s.shape >= 2) {
-      quadricSetup(s, &g);
+      if (!quadricSetup(s, &g)) return fail(c, DRT_E_INVALID, "hyperboloid: degenerate points (the implicit form has no finite coefficients)");
     } else {
       g.zmin = clampd(std::fmin(s.zmin, s.zmax), -s.radius, s.radius);
       g.zmax = clampd(std::fmax(s.zmin, s.zmax), -s.radius, s.radius);

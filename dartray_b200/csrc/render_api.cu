@@ -246,7 +246,7 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
     int m = i < nt ? c->matOf[i] : c->sphMat[i - nt], l = i < nt ? c->lightOf[i] : c->sphLight[i - nt];
     int rev = i < nt ? c->revOf[i] : c->sphRev[i - nt];
     if (m < 0 || m >= nMat) return fail(c, DRT_E_INVALID, "a primitive refers to a material index that drt_set_materials did not define");
-    if (l >= nLights) return fail(c, DRT_E_INVALID, "a primitive refers to a light index that drt_set_lights did not define");
+    if (l >= nLights || l < -1) return fail(c, DRT_E_INVALID, "a primitive refers to a light index that drt_set_lights did not define");
     if (m > 0xffff || l + 1 > 0x7fff) return fail(c, DRT_E_INVALID, "too many materials (65535) or lights (32766)");
     attr[i] = (uint32_t)m | ((uint32_t)(l + 1) << 16) | (rev ? 0x80000000u : 0u);
   }
@@ -325,6 +325,10 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
     std::vector<double> a;
     for (uint32_t sh : hl.shapes) {
       if (sh >= np) return fail(c, DRT_E_INVALID, "light shape id out of range");
+      // the MIS test `lightIsect.primitive.getAreaLight() == light` (integrator.dart:170) reads the primitive's own light index:
+      // a shape listed under light i has to carry i, or the BSDF-sampled half of the estimate silently never matches
+      if ((sh < nt ? c->lightOf[sh] : c->sphLight[sh - nt]) != i)
+        return fail(c, DRT_E_INVALID, "a light's shape list names a primitive whose light index is another light (or none)");
       double area;
       if (sh < nt) {  // triangle.dart:265-269
         TriVerts t;
