@@ -300,10 +300,12 @@ struct Flattener {
 
   // Wide layout: collapse P with its two children (see GNode4).  Must run AFTER emit(): it reuses
   // the leaf references recorded there so both layouts index the same GPrim[] order.
-  std::vector<int32_t> leafRefOf;  // per pool node: leaf reference (leaves only)
+  // A leaf's records start at its range in the builder's PrimRef array: the in-place partitions leave that array in leaf
+  // (depth-first, first child first) order, which is the order of the GPrim records.
+  int32_t leafRefOf(int32_t t) const { return makeLeafRef(pool[t].first, pool[t].count); }
   int32_t emitWide(int32_t t, int32_t my) {
     const TNode& n = pool[t];
-    if (n.left < 0) return leafRefOf[t];
+    if (n.left < 0) return leafRefOf(t);
     GNode4 g;
     std::memset(&g, 0, sizeof(g));
     for (int k = 0; k < 4; ++k) {
@@ -441,20 +443,19 @@ struct Flattener {
   }
 
   // GPU layout: interior nodes in DFS order, leaf records in DFS (left-first) order.
-  // `my`: index of t among the interior nodes (DFS order); `off`: first leaf record of t's primitives.
-  int32_t emit(int32_t t, int32_t my, uint32_t off, const std::vector<int32_t>& refIndexOf) {
+  // `my`: index of t among the interior nodes (DFS order).
+  int32_t emit(int32_t t, int32_t my, const std::vector<int32_t>& refIndexOf) {
     const TNode& n = pool[t];
     if (n.left < 0) {
       for (uint32_t i = 0; i < n.count; ++i) {
-        out->leafPrimIds[off + i] = refs[n.first + i].id;
-        out->leafCounts[off + i] = i == 0 ? n.count : 0;
+        out->leafPrimIds[n.first + i] = refs[n.first + i].id;
+        out->leafCounts[n.first + i] = i == 0 ? n.count : 0;
       }
-      leafRefOf[t] = makeLeafRef(off, n.count);
-      return leafRefOf[t];
+      return leafRefOf(t);
     }
     int32_t r0 = 0, r1 = 0;
-    both(n.nNodes >= kTaskNodes, [&] { r0 = emit(n.left, my + 1, off, refIndexOf); },
-         [&] { r1 = emit(n.right, my + 1 + (int32_t)pool[n.left].nInterior, off + pool[n.left].nPrims, refIndexOf); });
+    both(n.nNodes >= kTaskNodes, [&] { r0 = emit(n.left, my + 1, refIndexOf); },
+         [&] { r1 = emit(n.right, my + 1 + (int32_t)pool[n.left].nInterior, refIndexOf); });
     GNode g;
     const TNode &a = pool[n.left], &b = pool[n.right];
     std::memcpy(g.c0min, a.box.lo, 12);
@@ -480,17 +481,25 @@ bool buildBvh(const std::vector<PrimBounds>& bounds, const std::vector<uint32_t>
   if (n >= (1u << 26)) { *err = "too many primitives for the 26-bit leaf offset"; return false; }
   int maxPrims = std::min(255, maxPrimsInNode);  // bvh_accel.dart:44
   std::vector<PrimRef> refs(n);
-  for (size_t i = 0; i < n; ++i) {
-    const PrimBounds& b = bounds[order[i]];
-    PrimRef& r = refs[i];
-    std::memcpy(r.lo, b.bmin, 12);
-    std::memcpy(r.hi, b.bmax, 12);
-    // bbox.dart:68: (pMin * 0.5) + (pMax * 0.5), each Point operation rounds to float32
-    for (int a = 0; a < 3; ++a) {
-      float h0 = (float)((double)b.bmin[a] * 0.5), h1 = (float)((double)b.bmax[a] * 0.5);
-      r.cen[a] = (float)((double)h0 + (double)h1);
-    }
-    r.id = order[i];
+  {
+    const unsigned nt = n < (1u << 16) ? 1u : std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+      th.emplace_back([&, t] {
+        for (size_t i = n * t / nt; i < n * (t + 1) / nt; ++i) {
+          const PrimBounds& b = bounds[order[i]];
+          PrimRef& r = refs[i];
+          std::memcpy(r.lo, b.bmin, 12);
+          std::memcpy(r.hi, b.bmax, 12);
+          // bbox.dart:68: (pMin * 0.5) + (pMax * 0.5), each Point operation rounds to float32
+          for (int a = 0; a < 3; ++a) {
+            float h0 = (float)((double)b.bmin[a] * 0.5), h1 = (float)((double)b.bmax[a] * 0.5);
+            r.cen[a] = (float)((double)h0 + (double)h1);
+          }
+          r.id = order[i];
+        }
+      });
+    for (auto& x : th) x.join();
   }
   const bool timing = std::getenv("DRT_BUILD_TIMING") != nullptr;
   auto tPrev = std::chrono::steady_clock::now();
@@ -507,29 +516,31 @@ bool buildBvh(const std::vector<PrimBounds>& bounds, const std::vector<uint32_t>
   int32_t root = tb.build(arena, 0, 0, (uint32_t)n, 0);
   lap("tree (SAH recursion)");
 
-  Flattener fl{arena.pool, refs, out, {}};
+  Flattener fl{arena.pool, refs, out};
   const TNode& rt = arena.pool[root];
-  fl.leafRefOf.assign(arena.pool.size(), 0);
-  std::vector<int32_t> refIndexOf(arena.pool.size(), -1);
-  out->refNodes.resize(rt.nNodes);
-  fl.numberRef(root, 0, refIndexOf);
-  lap("reference numbering");
-  out->refOrdered.resize(n);
-  fl.orderRef(root, 0, refIndexOf);
-  lap("reference primitive order");
-  out->leafPrimIds.resize(n);
-  out->leafCounts.resize(n);
-  out->nodes.resize(rt.nInterior);
   out->nLeaves = rt.nLeaves;
   out->maxLeafPrims = rt.maxLeaf;
   out->maxDepth = rt.depthBelow;
-  out->rootRef = fl.emit(root, 0, 0, refIndexOf);
-  lap("binary GPU layout");
+  // two independent chains over the finished tree: (reference numbering -> reference primitive order -> binary GPU layout) on a
+  // second thread, (wide layout -> quantised nodes) here
+  std::thread binaryChain([&] {
+    std::vector<int32_t> refIndexOf(arena.pool.size(), -1);
+    out->refNodes.resize(rt.nNodes);
+    fl.numberRef(root, 0, refIndexOf);
+    out->refOrdered.resize(n);
+    fl.orderRef(root, 0, refIndexOf);
+    out->leafPrimIds.resize(n);
+    out->leafCounts.resize(n);
+    out->nodes.resize(rt.nInterior);
+    out->rootRef = fl.emit(root, 0, refIndexOf);
+  });
   out->wide.resize(rt.left < 0 ? 0 : rt.nWide);
   out->wideRootRef = fl.emitWide(root, 0);
   lap("wide layout");
   fl.quantiseAll();
   lap("quantised wide nodes");
+  binaryChain.join();
+  lap("reference numbering + binary layout (second thread)");
   std::memcpy(out->rootMin, arena.pool[root].box.lo, 12);
   std::memcpy(out->rootMax, arena.pool[root].box.hi, 12);
   if (out->maxDepth >= 64) {

@@ -30,6 +30,16 @@ static void xformPoint(const float* m, const float p[3], float out[3]) {
   out[0] = ox; out[1] = oy; out[2] = oz;
 }
 
+// Splits [0, n) over the host threads (scene set-up loops over millions of primitives).
+template <class F>
+static void parallelFor(size_t n, F&& f) {
+  const unsigned nt = n < (1u << 16) ? 1u : std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+  if (nt == 1) { f((size_t)0, n); return; }
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t] { f(n * t / nt, n * (t + 1) / nt); });
+  for (auto& x : th) x.join();
+}
+
 static double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 extern "C" {
@@ -382,15 +392,17 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
   }
   // world bounds: triangle.dart:39-42, sphere.dart:34-37 + shape.dart:38-40
   std::vector<PrimBounds> bounds(np);
-  for (uint32_t t = 0; t < nt; ++t) {
-    PrimBounds& b = bounds[t];
-    for (int a = 0; a < 3; ++a) {
-      float v0 = c->P[3 * (size_t)c->idx[3 * (size_t)t] + a], v1 = c->P[3 * (size_t)c->idx[3 * (size_t)t + 1] + a],
-            v2 = c->P[3 * (size_t)c->idx[3 * (size_t)t + 2] + a];
-      b.bmin[a] = std::fmin(std::fmin(v0, v1), v2);
-      b.bmax[a] = std::fmax(std::fmax(v0, v1), v2);
+  parallelFor(nt, [&](size_t t0, size_t t1) {
+    for (size_t t = t0; t < t1; ++t) {
+      PrimBounds& b = bounds[t];
+      for (int a = 0; a < 3; ++a) {
+        float v0 = c->P[3 * (size_t)c->idx[3 * t] + a], v1 = c->P[3 * (size_t)c->idx[3 * t + 1] + a],
+              v2 = c->P[3 * (size_t)c->idx[3 * t + 2] + a];
+        b.bmin[a] = std::fmin(std::fmin(v0, v1), v2);
+        b.bmax[a] = std::fmax(std::fmax(v0, v1), v2);
+      }
     }
-  }
+  });
   std::vector<GSphere> gs(c->spheres.size());
   for (size_t i = 0; i < c->spheres.size(); ++i) {
     const HostSphere& s = c->spheres[i];
@@ -437,24 +449,26 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
 
   // leaf records
   std::vector<GPrim> prims(B.leafPrimIds.size());
-  for (size_t i = 0; i < prims.size(); ++i) {
-    uint32_t id = B.leafPrimIds[i];
-    GPrim& g = prims[i];
-    std::memset(&g, 0, sizeof(g));
-    g.primId = (int32_t)id;
-    g.leafCount = (int32_t)B.leafCounts[i];
-    if (id < nt) {
-      const float* a = &c->P[3 * (size_t)c->idx[3 * (size_t)id]];
-      const float* b = &c->P[3 * (size_t)c->idx[3 * (size_t)id + 1]];
-      const float* d = &c->P[3 * (size_t)c->idx[3 * (size_t)id + 2]];
-      std::memcpy(g.p1, a, 12);
-      std::memcpy(g.p2, b, 12);
-      std::memcpy(g.p3, d, 12);
-      g.kindSphere = 0;
-    } else {
-      g.kindSphere = (int32_t)(((id - nt) << 1) | 1u);
+  parallelFor(prims.size(), [&](size_t i0, size_t i1) {
+    for (size_t i = i0; i < i1; ++i) {
+      uint32_t id = B.leafPrimIds[i];
+      GPrim& g = prims[i];
+      std::memset(&g, 0, sizeof(g));
+      g.primId = (int32_t)id;
+      g.leafCount = (int32_t)B.leafCounts[i];
+      if (id < nt) {
+        const float* a = &c->P[3 * (size_t)c->idx[3 * (size_t)id]];
+        const float* b = &c->P[3 * (size_t)c->idx[3 * (size_t)id + 1]];
+        const float* d = &c->P[3 * (size_t)c->idx[3 * (size_t)id + 2]];
+        std::memcpy(g.p1, a, 12);
+        std::memcpy(g.p2, b, 12);
+        std::memcpy(g.p3, d, 12);
+        g.kindSphere = 0;
+      } else {
+        g.kindSphere = (int32_t)(((id - nt) << 1) | 1u);
+      }
     }
-  }
+  });
   if (hostOnly) {
     c->info.n_nodes = (uint32_t)B.refNodes.size();
     c->info.n_prims = np;
