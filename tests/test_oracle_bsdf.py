@@ -315,3 +315,42 @@ def test_conductor_fresnel_known_values(zoo):
     wo = np.array([math.sqrt(1 - c * c), 0.0, c])
     f, _ = o.bsdf_eval(ids["blinn_conductor"], wo, wo * [-1, -1, 1])
     assert np.allclose(f[0], (e + 2) / (2 * np.pi) * np_conductor(np.array([c]), ETA, KK)[0] / (4 * c * c), rtol=2e-6)
+
+
+# ---- closed-box furnace through the integrators: pathLi / EstimateDirect against the numpy albedo -------------------------------
+def _furnace_first_bounce(lobes, integ, spp=1024, radius=5.0):
+    """A closed emissive sphere (Le = 1) seen from its centre: every direction of the hemisphere above any surface point sees the
+    emitter, so the radiance after ONE bounce of direct lighting is  Le + Le * rho_hd(wo),  rho_hd(wo) = int f(wo, wi) |cos| dwi.
+    The integrators get there by light sampling of the sphere (sphere.dart:247-311) + BSDF sampling with the power heuristic
+    (integrator.dart:119-185); the albedo on the right comes from the numpy restatements above."""
+    sb = host.SceneBuilder()
+    sb.sphere(host.translate(0, 0, 0), radius=radius, material=sb.material_lobes(lobes), area_light=(1.0, 1.0, 1.0), reverse=True)
+    cam = host.PerspectiveCamera(host.look_at((0, 0, 0), (0, 0, 1), (0, 1, 0)), fov=1.0)  # from the centre: wo = the normal
+    o = Oracle()
+    host.upload_scene(o, sb.arrays())
+    host.configure_render(o, cam, host.Film(2, 2), host.Sampler(kind=host.SAMPLER_LD, spp=spp), integ)
+    o.render(0, 1, 8)
+    return o.film_read()["rgb"].astype(np.float64).mean(axis=(0, 1))
+
+
+def _np_albedo(f_of_wi, n_th=600, n_ph=1200):
+    wi, dw = _hemi_grid(n_th, n_ph)
+    wo = np.broadcast_to(np.array([0.0, 0.0, 1.0]), wi.shape).copy()
+    return (f_of_wi(wo, wi) * (wi[:, 2] * dw)[:, None]).sum(axis=0)
+
+
+@pytest.mark.parametrize("integ", [host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=0), host.Integrator(kind=host.INTEGRATOR_DIRECT, maxdepth=1)],
+                         ids=["path_depth0", "directlighting"])
+def test_furnace_first_bounce_equals_one_plus_the_numpy_albedo(integ):
+    cases = {
+        "lambert": (host.matte_lobes(KD), lambda wo, wi: np.broadcast_to(KD.astype(np.float64) / np.pi, wi.shape)),
+        "oren_nayar": (host.matte_lobes(KD, 35.0), lambda wo, wi: np_oren_nayar(wo, wi, KD, 35.0)),
+        "plastic": (host.plastic_lobes(KD, KS, 0.15),
+                    lambda wo, wi: KD.astype(np.float64) / np.pi + np_blinn_microfacet(wo, wi, KS, 1.0 / 0.15, lambda c: np_dielectric(c, 1.5, 1.0))),
+        "metal": (host.metal_lobes(ETA, KK, 0.08),
+                  lambda wo, wi: np_blinn_microfacet(wo, wi, 1.0, host.metal_lobes(ETA, KK, 0.08)[0]["param"], lambda c: np_conductor(c, ETA, KK))),
+    }
+    for name, (lobes, f) in cases.items():
+        got = _furnace_first_bounce(lobes, integ)
+        expect = 1.0 + _np_albedo(f)
+        assert np.allclose(got, expect, rtol=1.5e-2), (name, got, expect)
