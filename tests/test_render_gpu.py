@@ -160,6 +160,13 @@ def test_cone_light_is_rejected():
     g = capi.Context(0)
     host.upload_scene(g, a)
     host.configure_render(g, cam, host.Film(8, 8), host.Sampler(kind=host.SAMPLER_LD, spp=1), host.Integrator(kind=host.INTEGRATOR_DIRECT))
+    # a shape listed under a light has to carry that light's index itself (the MIS test reads it, integrator.dart:170)
+    with pytest.raises(RuntimeError, match="whose light index is another light"):
+        g.render(0, 1)
+    a["quad_light"] = np.asarray([0], np.int32)
+    g = capi.Context(0)
+    host.upload_scene(g, a)
+    host.configure_render(g, cam, host.Film(8, 8), host.Sampler(kind=host.SAMPLER_LD, spp=1), host.Integrator(kind=host.INTEGRATOR_DIRECT))
     with pytest.raises(RuntimeError, match="area lights"):  # the scene tables are validated when the render starts
         g.render(0, 1)
 
