@@ -316,8 +316,16 @@ static bool quadricSetup(const HostSphere& s, GSphere* gp) {
 
 // Device half of drt_build_bvh: the built tree's arrays go to c's device.  B / prims / gs may belong to another context (the
 // owner of a multi-device context builds once on the host and every device uploads the same arrays).
-static int uploadBuilt(drt_ctx* c, const BuiltBvh& B, const std::vector<GPrim>& prims, const std::vector<GSphere>& gs, uint32_t np) {
+// `src`: a context of ANOTHER device that already holds this build: the arrays then come over NVLink from its memory
+// (cudaMemcpyPeer) instead of over PCIe from pageable host memory — soup_10m on 8 GPUs: 1.2 s of host uploads -> one upload.
+static int uploadBuilt(drt_ctx* c, const BuiltBvh& B, const std::vector<GPrim>& prims, const std::vector<GSphere>& gs, uint32_t np,
+                       const drt_ctx* src = nullptr) {
   CK(c, cudaSetDevice(c->device));
+  auto put = [&](void* dst, const void* host, const void* peer, size_t bytes) -> cudaError_t {
+    if (bytes == 0) return cudaSuccess;
+    if (src && peer && src->device != c->device) return cudaMemcpyPeer(dst, c->device, peer, src->device, bytes);
+    return cudaMemcpy(dst, host, bytes, cudaMemcpyHostToDevice);
+  };
   CK(c, c->dNodes.ensure(std::max<size_t>(1, B.nodes.size())));
   c->wideQOk = B.wideQOk && B.wideQ.size() == B.wide.size();
   c->wideUploaded = false;
@@ -327,15 +335,13 @@ static int uploadBuilt(drt_ctx* c, const BuiltBvh& B, const std::vector<GPrim>& 
   }
   if (c->wideQOk) {
     CK(c, c->dWideQ.ensure(std::max<size_t>(1, B.wideQ.size())));
-    if (!B.wideQ.empty())
-      CK(c, cudaMemcpy(c->dWideQ.p, B.wideQ.data(), B.wideQ.size() * sizeof(GNode4Q), cudaMemcpyHostToDevice));
+    CK(c, put(c->dWideQ.p, B.wideQ.data(), src ? src->dWideQ.p : nullptr, B.wideQ.size() * sizeof(GNode4Q)));
   }
   CK(c, c->dPrims.ensure(prims.size()));
   CK(c, c->dSpheres.ensure(std::max<size_t>(1, gs.size())));
-  if (!B.nodes.empty())
-    CK(c, cudaMemcpy(c->dNodes.p, B.nodes.data(), B.nodes.size() * sizeof(GNode), cudaMemcpyHostToDevice));
-  CK(c, cudaMemcpy(c->dPrims.p, prims.data(), prims.size() * sizeof(GPrim), cudaMemcpyHostToDevice));
-  if (!gs.empty()) CK(c, cudaMemcpy(c->dSpheres.p, gs.data(), gs.size() * sizeof(GSphere), cudaMemcpyHostToDevice));
+  CK(c, put(c->dNodes.p, B.nodes.data(), src ? src->dNodes.p : nullptr, B.nodes.size() * sizeof(GNode)));
+  CK(c, put(c->dPrims.p, prims.data(), src ? src->dPrims.p : nullptr, prims.size() * sizeof(GPrim)));
+  CK(c, put(c->dSpheres.p, gs.data(), src ? src->dSpheres.p : nullptr, gs.size() * sizeof(GSphere)));
   c->ts.nodes = c->dNodes.p;
   c->ts.wide = c->dWide.p;
   c->ts.wideQ = c->useQ() ? c->dWideQ.p : nullptr;
@@ -493,7 +499,7 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
         p_->buildSerial++;
         p_->ts = TraceScene{};
         p_->info = drt_bvh_info{};
-        rcs[i] = uploadBuilt(p_, B, prims, gs, np);
+        rcs[i] = uploadBuilt(p_, B, prims, gs, np, c);
       });
     for (auto& t : th) t.join();
     for (size_t i = 0; i < rcs.size(); ++i)
