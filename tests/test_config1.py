@@ -55,7 +55,7 @@ def test_config1_real_scene_with_disk_light_gpu_matches_oracle():
     rgb, ref = g.film_read()["rgb"], o.film_read()["rgb"]
     err = np.abs(rgb - ref) / np.maximum(np.abs(ref), 1e-3)
     assert abs(rgb.mean() - ref.mean()) <= 1e-4 * ref.mean()
-    assert np.quantile(err, 0.9999) <= 1e-3
+    assert err.max() <= 1e-3
     sg, so = g.render_stats(), o.render_stats()
     assert abs(sg["shadow_rays"] - so["shadow_rays"]) <= 1e-4 * so["shadow_rays"]
 
@@ -70,4 +70,4 @@ def test_config1_gpu_matches_the_keyed_oracle():
     rgb, ref = g.film_read()["rgb"], _oracle(host.RNG_KEYED)
     err = np.abs(rgb - ref) / np.maximum(np.abs(ref), 1e-3)
     assert abs(rgb.mean() - ref.mean()) <= 1e-4 * ref.mean()
-    assert np.quantile(err, 0.9999) <= 1e-3
+    assert err.max() <= 1e-3

@@ -143,7 +143,7 @@ def test_quadrics_path_and_ao_match_oracle():
                                 host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=4))
     err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
     print("quadric room path max rel err", err.max())
-    assert np.quantile(err, 0.999) <= 1e-3
+    assert err.max() <= 1e-3
     assert abs(fg["rgb"].mean() - fo["rgb"].mean()) <= 5e-3 * fo["rgb"].mean()
     g, o, fg, fo = _render_both(arrays, cam, host.Film(64, 48), host.Sampler(kind=host.SAMPLER_LD, spp=1),
                                 host.Integrator(kind=host.INTEGRATOR_AO, ao_nsamples=16, ao_maxdist=6.0))
@@ -197,7 +197,7 @@ def test_smooth_shaded_meshes_match_oracle(which, integ):
     g, o, fg, fo = _render_both(arrays, cam, host.Film(80, 60), host.Sampler(kind=host.SAMPLER_LD, spp=4), integ)
     err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
     print("smooth room", which, integ.kind, "max rel err", err.max(), "q999", np.quantile(err, 0.999))
-    assert np.quantile(err, 0.999) <= 1e-3
+    assert err.max() <= 1e-3
     assert abs(fg["rgb"].mean() - fo["rgb"].mean()) <= 2e-3 * fo["rgb"].mean()
     if integ.kind == host.INTEGRATOR_DIRECT and which == "matte":
         assert err.max() <= 1e-3
@@ -252,7 +252,7 @@ def test_infinite_light_matches_oracle(which, constant, integ):
     g, o, fg, fo = _render_both(arrays, cam, host.Film(80, 60), host.Sampler(kind=host.SAMPLER_LD, spp=4), integ)
     err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
     print("sky scene", which, constant, integ.kind, "max rel err", err.max(), "q999", np.quantile(err, 0.999))
-    assert np.quantile(err, 0.999) <= 1e-3
+    assert err.max() <= 1e-3
     assert abs(fg["rgb"].mean() - fo["rgb"].mean()) <= 2e-3 * fo["rgb"].mean()
     sky = fo["rgb"][:10].mean()
     assert sky > 0.05  # the escaped camera rays at the top of the frame see the map
@@ -286,7 +286,7 @@ def test_halton_sampler_matches_oracle(integ):
     assert np.array_equal(fg["weight"], fo["weight"])         # ... and land in the same pixels (box filter: sample counts)
     err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
     print("halton", integ.kind, "max rel err", err.max())
-    assert np.quantile(err, 0.999) <= 1e-3
+    assert err.max() <= 1e-3
     if integ.kind != host.INTEGRATOR_PATH:
         assert err.max() <= 1e-3 and sg["shadow_rays"] == so["shadow_rays"] and sg["closest_rays"] == so["closest_rays"]
     # shards of the sequence tile it: the union of two shards is the whole render
@@ -323,7 +323,7 @@ def test_adaptive_sampler_matches_oracle(method, integ):
     else:
         assert (~same).mean() <= 2e-3  # a contrast ratio within rounding of 0.5 may fall either way
     err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)[same]
-    assert np.quantile(err, 0.999) <= 1e-3
+    assert err.max() <= 1e-3
     if integ.kind != host.INTEGRATOR_PATH:
         assert err.max() <= 1e-3
 
@@ -349,7 +349,7 @@ def test_translucent_mix_and_shinymetal_match_oracle(integ):
     g, o, fg, fo = _render_both(arrays, cam, host.Film(80, 60), host.Sampler(kind=host.SAMPLER_LD, spp=4), integ)
     err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
     print("wrapped materials", integ.kind, "max rel err", err.max(), "q999", np.quantile(err, 0.999))
-    assert np.quantile(err, 0.999) <= 1e-3
+    assert err.max() <= 1e-3
     assert abs(fg["rgb"].mean() - fo["rgb"].mean()) <= 2e-3 * fo["rgb"].mean()
     sg, so = g.render_stats(), o.render_stats()
     assert abs(sg["closest_rays"] - so["closest_rays"]) <= 1e-3 * so["closest_rays"]
@@ -390,7 +390,7 @@ def test_projection_and_goniometric_lights_match_oracle(integ):
     g, o, fg, fo = _render_both(arrays, cam, host.Film(80, 60), host.Sampler(kind=host.SAMPLER_LD, spp=4), integ)
     err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
     print("mapped lights", integ.kind, "max rel err", err.max())
-    assert np.quantile(err, 0.999) <= 1e-3
+    assert err.max() <= 1e-3
     if integ.kind == host.INTEGRATOR_DIRECT:
         assert err.max() <= 1e-3
         sg, so = g.render_stats(), o.render_stats()
@@ -418,7 +418,7 @@ def test_best_candidate_sampler_matches_oracle(integ):
     assert np.array_equal(fg["weight"], fo["weight"])
     err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
     print("bestcandidate", integ.kind, "max rel err", err.max())
-    assert np.quantile(err, 0.999) <= 1e-3
+    assert err.max() <= 1e-3
     if integ.kind == host.INTEGRATOR_DIRECT:
         assert err.max() <= 1e-3 and sg["shadow_rays"] == so["shadow_rays"]
     # without its table the sampler is refused
@@ -473,7 +473,7 @@ def test_path_integrator_matches_oracle():
     sigma = fo["rgb"].std() / math.sqrt(16)
     assert np.abs(fg["rgb"] - fo["rgb"]).max() <= 3 * sigma
     assert abs(fg["rgb"].mean() - fo["rgb"].mean()) <= 5e-3 * fo["rgb"].mean()
-    assert np.quantile(err, 0.999) <= 1e-3
+    assert err.max() <= 1e-3
     sg, so = g.render_stats(), o.render_stats()
     assert abs(sg["closest_rays"] - so["closest_rays"]) <= 1e-3 * so["closest_rays"]
     assert abs(sg["shadow_rays"] - so["shadow_rays"]) <= 1e-3 * so["shadow_rays"]
@@ -484,7 +484,7 @@ def test_path_deep_bounces_use_the_integrator_stream():
     g, o, fg, fo = _render_both(arrays, cam, host.Film(40, 30), host.Sampler(kind=host.SAMPLER_RANDOM, spp=2),
                                 host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=9))
     err = _rel_err(fg["rgb"], fo["rgb"], floor=1e-3)
-    assert np.quantile(err, 0.999) <= 1e-3
+    assert err.max() <= 1e-3
     assert abs(fg["rgb"].mean() - fo["rgb"].mean()) <= 5e-3 * fo["rgb"].mean()
 
 
@@ -512,10 +512,10 @@ def test_path_integrator_with_bxdf_lists_matches_oracle(which):
     assert np.isfinite(fg["rgb"]).all()
     # north_star: per-pixel mean within 3 sigma of the Monte Carlo noise; replayed streams do far better
     sigma = fo["rgb"].std() / math.sqrt(spp)
-    assert np.quantile(np.abs(fg["rgb"] - fo["rgb"]), 0.999) <= 3 * sigma
+    assert np.abs(fg["rgb"] - fo["rgb"]).max() <= 3 * sigma
     assert abs(fg["rgb"].mean() - fo["rgb"].mean()) <= 5e-3 * fo["rgb"].mean()
-    # libm pow / sin / cos differ from CUDA's in the last ulp and a specular path can amplify that: allow 1 % of the pixels
-    assert np.quantile(err, 0.99) <= 1e-3
+    # every pixel, not a quantile: the replayed streams agree to ~2e-6 on a B200 (profiles/r02p_pytest_gpu.log)
+    assert err.max() <= 1e-3
     sg, so = g.render_stats(), o.render_stats()
     assert abs(sg["closest_rays"] - so["closest_rays"]) <= 2e-3 * so["closest_rays"]
     assert abs(sg["shadow_rays"] - so["shadow_rays"]) <= 2e-3 * so["shadow_rays"]
