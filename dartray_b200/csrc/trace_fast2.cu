@@ -73,6 +73,11 @@ namespace drt {
 #endif
 #define DRT_PEND (ANY ? DRT_PEND_ANY : DRT_PEND_CLOSEST)
 
+#ifndef DRT_Q_LAZY_BOX
+#define DRT_Q_LAZY_BOX 0  // 1: the leaf's f64 box test only once a triangle of the leaf reports a hit.  REJECTED on measurement
+                         // (profiles/r02q_trace_ab.log: 4.45 vs 3.59 ms): the box test with `tmin < maxDistance` is what culls most
+                         // leaves a conservative walk reaches, far cheaper than the f64 triangle tests it saves
+#endif
 #ifndef DRT_Q_STEPS
 #define DRT_Q_STEPS 3  // pop + node steps per round of refill / leaf-phase checks (1 / 2 / 3: 4.01 / 3.63 / 3.56 ms)
 #endif
@@ -341,24 +346,55 @@ __global__ void __launch_bounds__(DRT_Q_BLOCK, DRT_Q_MIN_BLOCKS)
             if (cnt == 15u) cnt = (uint32_t)__float_as_int(b.w);
             // the reference's own slab test of this leaf node (bvh_accel.dart:125 / 187), on the box rebuilt from its
             // primitives (triangle.dart:39-42 / the quadric's world bound), with the maxDistance of this moment
-            float lo0 = CUDART_INF_F, lo1 = CUDART_INF_F, lo2 = CUDART_INF_F, hi0 = -CUDART_INF_F, hi1 = -CUDART_INF_F,
-                  hi2 = -CUDART_INF_F;
-            for (uint32_t k = 0; k < cnt; ++k) {
-              float4 a2 = a, b2 = b, c2 = c;
-              if (k) { a2 = ldg4(&pr[k].p1[0]); b2 = ldg4(&pr[k].p2[0]); c2 = ldg4(&pr[k].p3[0]); }
-              const int kind = __float_as_int(c2.w);
-              if (QUAD == 0 || (kind & 1) == 0) {
-                lo0 = fminf(lo0, fminf(a2.x, fminf(b2.x, c2.x))); hi0 = fmaxf(hi0, fmaxf(a2.x, fmaxf(b2.x, c2.x)));
-                lo1 = fminf(lo1, fminf(a2.y, fminf(b2.y, c2.y))); hi1 = fmaxf(hi1, fmaxf(a2.y, fmaxf(b2.y, c2.y)));
-                lo2 = fminf(lo2, fminf(a2.z, fminf(b2.z, c2.z))); hi2 = fmaxf(hi2, fmaxf(a2.z, fmaxf(b2.z, c2.z)));
-              } else {
-                const GSphere& s = sc.spheres[kind >> 1];
-                lo0 = fminf(lo0, s.wmin[0]); hi0 = fmaxf(hi0, s.wmax[0]);
-                lo1 = fminf(lo1, s.wmin[1]); hi1 = fmaxf(hi1, s.wmax[1]);
-                lo2 = fminf(lo2, s.wmin[2]); hi2 = fmaxf(hi2, s.wmax[2]);
-              }
+#define DRT_LEAF_BOX(okVar, maxtArg)                                                                                       \
+            {                                                                                                              \
+              float lo0 = CUDART_INF_F, lo1 = CUDART_INF_F, lo2 = CUDART_INF_F, hi0 = -CUDART_INF_F, hi1 = -CUDART_INF_F,  \
+                    hi2 = -CUDART_INF_F;                                                                                   \
+              for (uint32_t k2 = 0; k2 < cnt; ++k2) {                                                                      \
+                const float4 a2 = ldg4(&pr[k2].p1[0]), b2 = ldg4(&pr[k2].p2[0]), c2 = ldg4(&pr[k2].p3[0]);                 \
+                const int kind2 = __float_as_int(c2.w);                                                                    \
+                if (QUAD == 0 || (kind2 & 1) == 0) {                                                                       \
+                  lo0 = fminf(lo0, fminf(a2.x, fminf(b2.x, c2.x))); hi0 = fmaxf(hi0, fmaxf(a2.x, fmaxf(b2.x, c2.x)));      \
+                  lo1 = fminf(lo1, fminf(a2.y, fminf(b2.y, c2.y))); hi1 = fmaxf(hi1, fmaxf(a2.y, fmaxf(b2.y, c2.y)));      \
+                  lo2 = fminf(lo2, fminf(a2.z, fminf(b2.z, c2.z))); hi2 = fmaxf(hi2, fmaxf(a2.z, fmaxf(b2.z, c2.z)));      \
+                } else {                                                                                                   \
+                  const GSphere& s2 = sc.spheres[kind2 >> 1];                                                              \
+                  lo0 = fminf(lo0, s2.wmin[0]); hi0 = fmaxf(hi0, s2.wmax[0]);                                              \
+                  lo1 = fminf(lo1, s2.wmin[1]); hi1 = fmaxf(hi1, s2.wmax[1]);                                              \
+                  lo2 = fminf(lo2, s2.wmin[2]); hi2 = fmaxf(hi2, s2.wmax[2]);                                              \
+                }                                                                                                          \
+              }                                                                                                            \
+              okVar = (slabExactQ(-nox, -noy, -r.noz, ixf, iyf, r.iz, rs.mint, (maxtArg), lo0, lo1, lo2, hi0, hi1, hi2) >> 32) != 0ull; \
             }
-            const bool boxOk = (slabExactQ(-nox, -noy, -r.noz, ixf, iyf, r.iz, rs.mint, rs.maxt, lo0, lo1, lo2, hi0, hi1, hi2) >> 32) != 0ull;
+            if (QUAD == 0 && DRT_Q_LAZY_BOX) {
+              // Triangles only: the box test decides nothing unless a triangle of the leaf reports a hit (a miss changes no
+              // state), so it is evaluated at the FIRST hit, with the maxDistance the ray had when the reference would have
+              // reached the leaf — which is still rs.maxt's value then, no hit of this leaf having been taken before.  A
+              // failing box drops the hit and the rest of the leaf, as if the reference had not entered it.
+              const double maxtEntry = rs.maxt;
+              bool boxKnown = false;
+              for (uint32_t k = 0; k < cnt && !stop; ++k) {
+                if (k) { a = ldg4(&pr[k].p1[0]); b = ldg4(&pr[k].p2[0]); c = ldg4(&pr[k].p3[0]); }
+                HitState h;
+                const bool hit = ANY ? triangleAny(rs, a, b, c) : triangleClosest(rs, a, b, c, &h);
+                if (hit) {
+                  if (!boxKnown) {
+                    bool boxOk;
+                    DRT_LEAF_BOX(boxOk, maxtEntry);
+                    if (!boxOk) { rs.maxt = maxtEntry; break; }
+                    boxKnown = true;
+                  }
+                  if (ANY) { found = true; stop = true; }
+                  else {
+                    COLD_ST(6, __float_as_uint(__double2float_rn(h.b1))); COLD_ST(7, __float_as_uint(__double2float_rn(h.b2)));
+                    COLD_ST(8, (uint32_t)h.prim);
+                  }
+                }
+              }
+              continue;
+            }
+            bool boxOk;
+            DRT_LEAF_BOX(boxOk, rs.maxt);
             for (uint32_t k = 0; boxOk && k < cnt && !stop; ++k) {
               if (k) { a = ldg4(&pr[k].p1[0]); b = ldg4(&pr[k].p2[0]); c = ldg4(&pr[k].p3[0]); }
               const int kind = __float_as_int(c.w);
@@ -385,6 +421,7 @@ __global__ void __launch_bounds__(DRT_Q_BLOCK, DRT_Q_MIN_BLOCKS)
               }
             }
           }
+#undef DRT_LEAF_BOX
           npend = 0;
           if (!ANY && rs.maxt != r.maxt) {
             r.maxt = rs.maxt;
