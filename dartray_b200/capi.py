@@ -25,7 +25,7 @@ SYMBOLS = [
     "drt_set_build_order", "drt_build_bvh", "drt_bvh_info_get", "drt_bvh_export", "drt_trace_closest",
     "drt_trace_any", "drt_trace_closest_device", "drt_trace_any_device", "drt_set_counting", "drt_get_counters", "drt_set_kernel_variant",
     "drt_last_kernel_ms", "drt_kernel_launches",
-    "drt_set_materials", "drt_set_material_lobes", "drt_set_lights", "drt_set_spot_params", "drt_set_volumes", "drt_set_volume_integrator", "drt_set_camera", "drt_set_camera_kind", "drt_set_film", "drt_set_sampler", "drt_set_integrator",
+    "drt_set_materials", "drt_set_material_lobes", "drt_set_textures", "drt_set_material_programs", "drt_set_lights", "drt_set_spot_params", "drt_set_volumes", "drt_set_volume_integrator", "drt_set_camera", "drt_set_camera_kind", "drt_set_film", "drt_set_sampler", "drt_set_integrator",
     "drt_render", "drt_render_shard", "drt_set_batch_slots", "drt_film_clear", "drt_film_size", "drt_film_read",
     "drt_film_device", "drt_pixel_samples", "drt_render_stats_get", "drt_set_render_profiling", "drt_render_profile_get",
 ]
@@ -111,6 +111,8 @@ def load():
     L.drt_set_sample_table.argtypes = [vp, vp, u32]
     L.drt_set_light_map.argtypes = [vp, u32, i32, i32, vp, vp, vp, vp, C.c_double]
     L.drt_set_lobe_wrappers.argtypes = [vp, u32, vp, vp]
+    L.drt_set_textures.argtypes = [vp, u32, vp, vp, u64]
+    L.drt_set_material_programs.argtypes = [vp, u32, vp]
     L.drt_set_infinite_light.argtypes = [vp, u32, i32, i32, vp, vp, vp]
     L.drt_set_lights.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
     L.drt_set_camera.argtypes = [vp, vp, vp, dbl, dbl, dbl, dbl]
@@ -326,6 +328,17 @@ class Context:
         """BRDFToBTDF (bit 0) / ScaledBxDF (bit 1, with its RGB scale) around the lobes of the last set_material_lobes."""
         w, sc = _arr(wrap, np.int32), _arr(scale, np.float32).reshape(-1, 3)
         self._ck(self.L.drt_set_lobe_wrappers(self.h, w.shape[0], _p(w), _p(sc)))
+
+    def set_textures(self, nodes, texels):
+        """Texture nodes (host.TEX_DTYPE records = drt_texture) and the level-0 texels of their images."""
+        from . import host
+        n, t = np.ascontiguousarray(nodes, host.TEX_DTYPE), _arr(texels, np.float32)
+        self._ck(self.L.drt_set_textures(self.h, n.shape[0], _p(n), _p(t), t.size))
+
+    def set_material_programs(self, programs):
+        from . import host
+        pr = np.ascontiguousarray(programs, host.PROG_DTYPE)
+        self._ck(self.L.drt_set_material_programs(self.h, pr.shape[0], _p(pr)))
 
     def set_infinite_light(self, index, texels, light_to_world, world_to_light):
         """Radiance map (h x w x 3 float32, power-of-two resolution: level 0 of the reference's MIPMap) and transforms of light

@@ -337,6 +337,179 @@ class OpaqueTexture(Texture):
         raise GpuUnsupported(f"texture '{self.plugin}' is not a constant texture")
 
 
+# ---- textures that read the hit point (drt_set_textures, include/drt.h) ---------------------------------
+# numpy twins of the C structs drt_texture / drt_material_program
+TEX_DTYPE = np.dtype([("kind", "i4"), ("spectrum", "i4"), ("tex1", "i4"), ("tex2", "i4"), ("amount", "i4"), ("mapping", "i4"),
+                      ("image_width", "i4"), ("image_height", "i4"), ("image_channels", "i4"), ("image_wrap", "i4"),
+                      ("image_trilinear", "i4"), ("aa_method", "i4"), ("image_offset", "u8"), ("value", "f8", (3,)),
+                      ("value2", "f8", (9,)), ("su", "f8"), ("sv", "f8"), ("du", "f8"), ("dv", "f8"), ("max_anisotropy", "f8"),
+                      ("world_to_texture", "f4", (16,)), ("v1", "f4", (3,)), ("v2", "f4", (3,))], align=True)
+PROG_DTYPE = np.dtype([("kind", "i4"), ("tex", "i4", (8,)), ("bump", "i4"), ("m1", "i4"), ("m2", "i4")], align=True)
+assert TEX_DTYPE.itemsize == 280 and PROG_DTYPE.itemsize == 48
+WRAP_REPEAT, WRAP_BLACK, WRAP_CLAMP = 0, 1, 2  # mipmap.dart:24-26
+
+
+@dataclass
+class UVMapping:  # lib/core/texture/uv_mapping_2d.dart
+    su: float = 1.0
+    sv: float = 1.0
+    du: float = 0.0
+    dv: float = 0.0
+    kind = 0
+
+
+@dataclass
+class SphericalMapping:  # spherical_mapping_2d.dart (Transform.Inverse(tex2world))
+    world_to_texture: np.ndarray = field(default_factory=lambda: np.eye(4, dtype=np.float32))
+    kind = 1
+
+
+@dataclass
+class CylindricalMapping(SphericalMapping):  # cylindrical_mapping_2d.dart
+    kind = 2
+
+
+@dataclass
+class PlanarMapping:  # planar_mapping_2d.dart
+    v1: tuple = (1.0, 0.0, 0.0)
+    v2: tuple = (0.0, 1.0, 0.0)
+    ds: float = 0.0
+    dt: float = 0.0
+    kind = 3
+
+
+class HitPointTexture(Texture):
+    """A texture whose value depends on the DifferentialGeometry: it cannot fold (evaluate() raises GpuUnsupported, which sends
+    the material to SceneBuilder.material_program instead of the *_lobes functions)."""
+
+
+class ImageTexture(HitPointTexture):
+    """image_texture.dart.  `texels`: level 0 of the MIPMap as its constructor left it — (H, W) for a float texture, (H, W, 3) for a
+    spectrum texture, power-of-two resolution, scale / gamma already applied (image_texture.dart:52-58)."""
+
+    def __init__(self, texels, mapping=None, trilinear=False, max_anisotropy=8.0, wrap=WRAP_REPEAT):
+        self.texels = np.ascontiguousarray(texels, np.float32)
+        h, w = self.texels.shape[:2]
+        if (w & (w - 1)) or (h & (h - 1)):
+            raise ValueError("level 0 must have power-of-two resolution (the reference resamples at load, mipmap.dart:72-139)")
+        self.mapping, self.trilinear, self.max_anisotropy, self.wrap = mapping or UVMapping(), trilinear, max_anisotropy, wrap
+
+
+class CheckerboardTexture(HitPointTexture):  # checkerboard_texture.dart, dimension 2
+    def __init__(self, tex1=1.0, tex2=0.0, mapping=None, aa="closedform"):
+        self.tex1, self.tex2, self.mapping = as_texture(tex1), as_texture(tex2), mapping or UVMapping()
+        self.aa = {"none": 0, "closedform": 1}[aa]
+
+
+class UVTexture(HitPointTexture):  # uv_texture.dart
+    def __init__(self, mapping=None):
+        self.mapping = mapping or UVMapping()
+
+
+class BilerpTexture(HitPointTexture):  # bilerp_texture.dart
+    def __init__(self, v00=0.0, v01=1.0, v10=0.0, v11=1.0, mapping=None):
+        self.v, self.mapping = (v00, v01, v10, v11), mapping or UVMapping()
+
+
+def is_constant_texture(v) -> bool:
+    if not isinstance(v, Texture):
+        return True
+    try:
+        v.evaluate()
+        return True
+    except GpuUnsupported:
+        return False
+
+
+class TextureTable:
+    """Flattens texture trees into the node array of drt_set_textures (children before parents, one node per (object, type))."""
+
+    def __init__(self):
+        self.nodes, self.texels, self._ids, self._ntex = [], [], {}, 0
+
+    def _mapping(self, n, m):
+        n["mapping"] = m.kind
+        if m.kind == 0:
+            n["su"], n["sv"], n["du"], n["dv"] = m.su, m.sv, m.du, m.dv
+        elif m.kind in (1, 2):
+            n["world_to_texture"] = _m(m.world_to_texture).reshape(16)
+        else:
+            n["v1"], n["v2"], n["du"], n["dv"] = m.v1, m.v2, m.ds, m.dt
+
+    def add(self, v, spectrum: bool) -> int:
+        key = (id(v), spectrum) if isinstance(v, Texture) else None
+        if key in self._ids:
+            return self._ids[key]
+        n = np.zeros((), TEX_DTYPE)
+        n["spectrum"] = int(spectrum)
+        n["tex1"] = n["tex2"] = n["amount"] = -1
+        n["su"] = n["sv"] = 1.0
+        n["max_anisotropy"] = 8.0
+        n["world_to_texture"] = np.eye(4, dtype=np.float32).reshape(16)
+
+        def const(val):
+            n["kind"] = 0
+            n["value"] = np.broadcast_to(np.asarray(val, np.float64), (3,)) if spectrum else (float(np.asarray(val).reshape(-1)[0]), 0, 0)
+
+        if not isinstance(v, Texture):
+            const(v)
+        elif is_constant_texture(v):
+            const(v.evaluate())  # a constant tree folds here exactly as fold_texture folds it
+        elif isinstance(v, ScaleTexture):
+            n["kind"], n["tex1"], n["tex2"] = 1, self.add(v.tex1, spectrum), self.add(v.tex2, spectrum)
+        elif isinstance(v, MixTexture):
+            n["kind"], n["tex1"], n["tex2"], n["amount"] = 2, self.add(v.tex1, spectrum), self.add(v.tex2, spectrum), self.add(v.amount, False)
+        elif isinstance(v, ImageTexture):
+            ch = 3 if v.texels.ndim == 3 else 1
+            if ch != (3 if spectrum else 1):
+                raise ValueError("a spectrum parameter needs an (H, W, 3) image, a float parameter an (H, W) image (image_texture.dart:38-42)")
+            n["kind"], n["image_height"], n["image_width"], n["image_channels"] = 3, v.texels.shape[0], v.texels.shape[1], ch
+            n["image_wrap"], n["image_trilinear"], n["max_anisotropy"] = v.wrap, int(v.trilinear), v.max_anisotropy
+            n["image_offset"] = self._ntex
+            self.texels.append(v.texels.reshape(-1))
+            self._ntex += v.texels.size
+            self._mapping(n, v.mapping)
+        elif isinstance(v, CheckerboardTexture):
+            n["kind"], n["tex1"], n["tex2"], n["aa_method"] = 4, self.add(v.tex1, spectrum), self.add(v.tex2, spectrum), v.aa
+            self._mapping(n, v.mapping)
+        elif isinstance(v, UVTexture):
+            if not spectrum:
+                raise GpuUnsupported("'uv' has no float form (uv_texture.dart:39-41)")
+            n["kind"] = 5
+            self._mapping(n, v.mapping)
+        elif isinstance(v, BilerpTexture):
+            n["kind"] = 6
+            vals = [np.broadcast_to(np.asarray(x, np.float64), (3,)) for x in v.v]
+            n["value"], n["value2"] = vals[0], np.concatenate(vals[1:])
+            self._mapping(n, v.mapping)
+        else:
+            raise GpuUnsupported(f"texture {type(v).__name__} is not on the GPU path")
+        self.nodes.append(n)
+        if key:
+            self._ids[key] = len(self.nodes) - 1
+        return len(self.nodes) - 1
+
+    def arrays(self):
+        nodes = np.asarray(self.nodes, TEX_DTYPE) if self.nodes else np.zeros(0, TEX_DTYPE)
+        return nodes, (np.concatenate(self.texels) if self.texels else np.zeros(0, np.float32))
+
+
+# parameter slots of drt_material_program per material plugin: (name, is spectrum, default) in tex[] order (include/drt.h)
+PROGRAM_PARAMS = {
+    "matte": (0, (("kd", True, 0.5), ("sigma", False, 0.0))),
+    "mirror": (1, (("kr", True, 0.9),)),
+    "glass": (2, (("kr", True, 1.0), ("kt", True, 1.0), ("index", False, 1.5))),
+    "plastic": (3, (("kd", True, 0.25), ("ks", True, 0.25), ("roughness", False, 0.1))),
+    "metal": (4, (("eta", True, None), ("k", True, None), ("roughness", False, 0.01))),
+    "shinymetal": (5, (("ks", True, 1.0), ("kr", True, 1.0), ("roughness", False, 0.1))),
+    "substrate": (6, (("kd", True, 0.5), ("ks", True, 0.5), ("uroughness", False, 0.1), ("vroughness", False, 0.1))),
+    "translucent": (7, (("kd", True, 0.25), ("ks", True, 0.25), ("reflect", True, 0.5), ("transmit", True, 0.5), ("roughness", False, 0.1))),
+    "uber": (8, (("kd", True, 0.25), ("ks", True, 0.25), ("kr", True, 0.0), ("kt", True, 0.0), ("roughness", False, 0.1),
+                 ("opacity", True, 1.0), ("index", False, 1.5))),
+    "mix": (9, (("amount", True, 0.5),)),
+}
+
+
 def as_texture(v) -> Texture:
     return v if isinstance(v, Texture) else ConstantTexture(v)
 
@@ -520,6 +693,25 @@ class SceneBuilder:
     def material_lobes(self, lobes: list) -> int:
         """A material given as its ordered BxDF list (mirror_lobes, glass_lobes, plastic_lobes, metal_lobes, uber_lobes ...)."""
         self.materials.append(("lobes", list(lobes)))
+        return len(self.materials) - 1
+
+    def material_program(self, plugin: str, bumpmap=None, m1=None, m2=None, **params) -> int:
+        """A material whose parameters are textures that read the hit point, or that carries a bump map (`plugin` and the parameter
+        names are the reference's, lower case: material_program("uber", kd=ImageTexture(...), ks=0.05, bumpmap=...)); "mix" takes
+        the two material indices m1 / m2 and `amount`."""
+        kind, slots = PROGRAM_PARAMS[plugin]
+        unknown = set(params) - {n for n, _, _ in slots}
+        if unknown:
+            raise ValueError(f"{plugin} has no parameter {sorted(unknown)}")
+        vals = []
+        for name, spectrum, default in slots:
+            v = params.get(name, default)
+            if v is None:
+                raise ValueError(f"{plugin} needs {name}")
+            vals.append((v, spectrum))
+        if kind == 9 and (m1 is None or m2 is None):
+            raise ValueError("mix needs m1 and m2")
+        self.materials.append(("program", kind, vals, bumpmap, m1, m2))
         return len(self.materials) - 1
 
     # -- participating media (lib/volume_regions/*.dart, Volume "homogeneous" | "exponential" | "volumegrid") ------------------
@@ -738,8 +930,25 @@ class SceneBuilder:
                                l2w=l.get("l2w"), texels=l.get("texels"), proj=l.get("proj"), screen=l.get("screen"), hither=l.get("hither", 1.0e-3),
                                w2l=l.get("w2l", np.eye(4, dtype=np.float32).reshape(16)), cos=l.get("cos", (0.0, 0.0))))
         mats = self.materials or [(0, (0.5, 0.5, 0.5), 0.0)]
-        general = any(m[0] == "lobes" for m in mats)
-        lobe_lists = [m[1] if m[0] == "lobes" else matte_lobes(m[1], m[2]) for m in mats]
+        general = any(m[0] in ("lobes", "program") for m in mats)
+        lobe_lists = [m[1] if m[0] == "lobes" else ([] if m[0] == "program" else matte_lobes(m[1], m[2])) for m in mats]
+        table, programs = TextureTable(), np.zeros(len(mats), PROG_DTYPE)
+        programs["kind"], programs["tex"], programs["bump"], programs["m1"], programs["m2"] = -1, -1, -1, -1, -1
+        for i, m in enumerate(mats):
+            if m[0] != "program":
+                continue
+            programs[i]["kind"] = m[1]
+            for j, (v, spectrum) in enumerate(m[2]):
+                programs[i]["tex"][j] = table.add(v, spectrum)
+            if m[3] is not None:
+                programs[i]["bump"] = table.add(m[3], False)
+            if m[1] == 9:
+                programs[i]["m1"], programs[i]["m2"] = m[4], m[5]
+                for sub in (m[4], m[5]):
+                    if mats[sub][0] == "program" and mats[sub][1] == 9:
+                        raise ValueError("a mix of mixes (ScaledBxDF of a ScaledBxDF) is not representable")
+        tex_nodes, tex_texels = table.arrays()
+        has_programs = any(m[0] == "program" for m in mats)
         lobes = [l for ll in lobe_lists for l in ll]
         if general:  # the matte-only entry point cannot carry these: upload_scene uses drt_set_material_lobes instead
             mats = [(0, (0.0, 0.0, 0.0), 0.0) for _ in mats]
@@ -774,6 +983,7 @@ class SceneBuilder:
             mat_kind=np.asarray([m[0] for m in mats], np.int32), mat_kd=np.asarray([m[1] for m in mats], np.float32),
             mat_sigma=np.asarray([m[2] for m in mats], np.float32),
             mat_general=general,
+            mat_programs=programs if has_programs else None, tex_nodes=tex_nodes, tex_texels=tex_texels,
             mat_lobe_offsets=np.asarray(np.cumsum([0] + [len(ll) for ll in lobe_lists]), np.uint32),
             lobe_kind=np.asarray([l["kind"] for l in lobes], np.int32),
             lobe_rgb=np.asarray([l["rgb"] for l in lobes], np.float32).reshape(-1, 3),
@@ -851,6 +1061,9 @@ def upload_scene(ctx, arrays: dict, split: int = 2, max_node_prims: int = 4):
             ctx.set_lobe_wrappers(a["lobe_wrap"], a["lobe_scale"])
     else:
         ctx.set_materials(a["mat_kind"], a["mat_kd"], a["mat_sigma"])
+    if a.get("mat_programs") is not None:
+        ctx.set_textures(a["tex_nodes"], a["tex_texels"])
+        ctx.set_material_programs(a["mat_programs"])
     ctx.set_lights(a["light_kind"], a["light_L"], a["light_pos"], a["light_nsamples"], a["light_shape_offsets"],
                    a["light_shape_prims"])
     if a.get("light_has_spot"):

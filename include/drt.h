@@ -242,6 +242,59 @@ int drt_set_material_lobes(drt_ctx* ctx, uint32_t n, const uint32_t* lobe_offset
  * (scaled_bxdf.dart has no pdf override, bxdf.dart:84-88).  One level: a mix of mixes is not representable. */
 int drt_set_lobe_wrappers(drt_ctx* ctx, uint32_t n_lobes, const int32_t* wrap, const float* scale_rgb);
 
+/* Textures that read the hit point.  One node per Texture object of the scene (lib/core/texture.dart); children are
+ * referenced by node index.  Replaces what Texture.evaluate(dg) does for:
+ *   kind 0 ConstantTexture (lib/core/texture/constant_texture.dart)            value
+ *   kind 1 ScaleTexture    (lib/textures/scale_texture.dart:26-33)              tex1, tex2
+ *   kind 2 MixTexture      (lib/textures/mix_texture.dart:26-31)                tex1, tex2, amount (a float texture)
+ *   kind 3 ImageTexture    (lib/textures/image_texture.dart:76-86)              mapping + image_*: MIPMap.lookup2, i.e. the
+ *          trilinear lookup (lib/core/mipmap.dart:206-222) or the EWA filter (:224-339) over the box pyramid (:142-166)
+ *   kind 4 CheckerboardTexture, dimension 2 (checkerboard_texture.dart:29-75)   mapping, tex1, tex2, aa_method (0 none, 1 closedform)
+ *   kind 5 UVTexture       (uv_texture.dart:26-37)                              mapping
+ *   kind 6 BilerpTexture   (bilerp_texture.dart:26-40)                          mapping, value = v00, value2 = v01, v10, v11
+ * spectrum: 0 = Texture<double> (values are Dart doubles; value[0]), 1 = Texture<Spectrum> (float32 RGB per operation).
+ * mapping: 0 UVMapping2D (lib/core/texture/uv_mapping_2d.dart; su, sv, du, dv), 1 SphericalMapping2D, 2 CylindricalMapping2D
+ * (world_to_texture, row-major), 3 PlanarMapping2D (v1, v2, du = ds, dv = dt).
+ * Images: `texels` holds every image's level 0 AS THE REFERENCE'S MIPMap CONSTRUCTOR LEFT IT (pyramid[0]: scale / gamma applied,
+ * float images converted, resampled to power-of-two resolution, mipmap.dart:72-139) — image_channels (1 or 3) floats per texel
+ * from float offset image_offset; the library rebuilds the pyramid, including what SpectrumImage's shared return object does to
+ * the spectrum levels (see oracle/ref_texture.cpp).  image_wrap: 0 repeat, 1 black, 2 clamp. */
+typedef struct drt_texture {
+  int32_t kind, spectrum;
+  int32_t tex1, tex2, amount; /* child node indices, -1 = none */
+  int32_t mapping;
+  int32_t image_width, image_height, image_channels, image_wrap, image_trilinear;
+  int32_t aa_method;
+  uint64_t image_offset;
+  double value[3];
+  double value2[9];
+  double su, sv, du, dv;
+  double max_anisotropy;
+  float world_to_texture[16];
+  float v1[3], v2[3];
+} drt_texture;
+int drt_set_textures(drt_ctx* ctx, uint32_t n, const drt_texture* nodes, const float* texels, uint64_t n_texel_floats);
+
+/* Materials whose parameters are textures, or that carry a bump map (Material.Bump, lib/core/material.dart:35-88): one entry per
+ * material of the last drt_set_material_lobes / drt_set_materials.  kind -1 keeps the material's flattened lobe list.  Otherwise
+ * the library evaluates the textures at every hit (after DifferentialGeometry.computeDifferentials with the camera ray's
+ * differentials, differential_geometry.dart:122-205, perspective_camera.dart:122-128, sampler_renderer.dart:166) and builds
+ * the BSDF the material's getBSDF builds; tex[] by kind (node indices into drt_set_textures; every parameter is a node,
+ * constants included):
+ *   0 matte        Kd, sigma                         5 shinymetal   Ks, Kr, roughness
+ *   1 mirror       Kr                                6 substrate    Kd, Ks, uroughness, vroughness
+ *   2 glass        Kr, Kt, index                     7 translucent  Kd, Ks, reflect, transmit, roughness
+ *   3 plastic      Kd, Ks, roughness                 8 uber         Kd, Ks, Kr, Kt, roughness, opacity, index
+ *   4 metal        eta, k, roughness                 9 mix          amount; m1 / m2 = material indices (one level)
+ * bump: a float texture node or -1.  n == 0 removes the programs. */
+typedef struct drt_material_program {
+  int32_t kind;
+  int32_t tex[8];
+  int32_t bump;
+  int32_t m1, m2;
+} drt_material_program;
+int drt_set_material_programs(drt_ctx* ctx, uint32_t n, const drt_material_program* programs);
+
 /* Replaces scene.lights: DiffuseAreaLight (kind 0, lib/lights/diffuse_area_light.dart:44-70; L = Lemit
  * x scale) and PointLight (kind 1, lib/lights/point_light.dart:41-47; L = intensity, pos = world
  * position); kinds 2 / 3: see drt_set_spot_params below.  nsamples: per light (NULL = 1).  The ShapeSet of light i (lib/core/light/

@@ -9,6 +9,7 @@
 #include <string>
 #include <thread>
 
+#include "../include/drt.h"  // the plain-data structs drt_texture / drt_material_program only
 #include "ref_render.h"
 #include "ref_scene.h"
 
@@ -360,6 +361,91 @@ int orc_set_lobe_wrappers(orc_ctx* c, uint32_t nLobes, const int32_t* wrap, cons
     }
   if (k != nLobes) { c->err = "lobe count differs from the last orc_set_material_lobes"; return -1; }
   return 0;
+}
+
+// mirrors drt_set_textures (include/drt.h)
+int orc_set_textures(orc_ctx* c, uint32_t n, const drt_texture* nodes, const float* texels, uint64_t nTexelFloats) {
+  TextureSet& ts = c->rs.textures;
+  ts.nodes.clear();
+  ts.images.clear();
+  for (uint32_t i = 0; i < n; ++i) {
+    const drt_texture& d = nodes[i];
+    TextureNode t;
+    t.kind = d.kind; t.spectrum = d.spectrum;
+    t.tex1 = d.tex1; t.tex2 = d.tex2; t.amount = d.amount;
+    for (int k = 0; k < 3; ++k) t.value[k] = d.value[k];
+    for (int k = 0; k < 9; ++k) t.value2[k] = d.value2[k];
+    t.mapping = d.mapping;
+    t.su = d.su; t.sv = d.sv; t.du = d.du; t.dv = d.dv;
+    t.worldToTexture = Transform(d.world_to_texture, d.world_to_texture);  // only m is used (transformPoint)
+    t.v1 = Vec(d.v1[0], d.v1[1], d.v1[2]);
+    t.v2 = Vec(d.v2[0], d.v2[1], d.v2[2]);
+    t.aaMethod = d.aa_method;
+    for (int child : {d.tex1, d.tex2, d.amount})
+      if (child >= (int)i) { c->err = "a texture node may only reference earlier nodes"; return -1; }
+    if (d.kind == 3) {
+      const int W = d.image_width, H = d.image_height, ch = d.image_channels;
+      if (W < 1 || H < 1 || (W & (W - 1)) || (H & (H - 1)) || (ch != 1 && ch != 3)) { c->err = "image: power-of-two resolution, 1 or 3 channels"; return -1; }
+      if (ch != (d.spectrum ? 3 : 1)) { c->err = "image channels must match the texture's type"; return -1; }
+      if (d.image_offset + (uint64_t)W * H * ch > nTexelFloats) { c->err = "image beyond the texel array"; return -1; }
+      t.image = (int)ts.images.size();
+      ts.images.emplace_back();
+      ts.images.back().init(W, H, ch, texels + d.image_offset, d.image_wrap, d.image_trilinear != 0, d.max_anisotropy);
+    }
+    ts.nodes.push_back(t);
+  }
+  return 0;
+}
+
+// mirrors drt_set_material_programs
+int orc_set_material_programs(orc_ctx* c, uint32_t n, const drt_material_program* programs) {
+  c->rs.programs.clear();
+  if (n == 0) return 0;
+  if (n != c->rs.materials.size()) { c->err = "one program per material"; return -1; }
+  for (uint32_t i = 0; i < n; ++i) {
+    MaterialProgram p;
+    p.kind = programs[i].kind;
+    for (int k = 0; k < 8; ++k) p.tex[k] = programs[i].tex[k];
+    p.bump = programs[i].bump;
+    p.m1 = programs[i].m1; p.m2 = programs[i].m2;
+    c->rs.programs.push_back(p);
+  }
+  return 0;
+}
+
+// Test probes: Texture.evaluate at n DifferentialGeometry records (p 3, u, v, dudx, dvdx, dudy, dvdy, dpdx 3, dpdy 3 = 15 doubles
+// each; Points / Vectors are rounded to float32 as their Dart objects would hold them) -> 3 doubles per record (a float
+// texture: the value in [0]); and MIPMap.lookup2 of image texture `node` at n (s, t, ds0, dt0, ds1, dt1) records.
+int orc_texture_eval(orc_ctx* c, int32_t node, uint32_t n, const double* dgs, double* out) {
+  const TextureSet& ts = c->rs.textures;
+  if (node < 0 || (size_t)node >= ts.nodes.size()) return -1;
+  for (uint32_t i = 0; i < n; ++i) {
+    const double* q = dgs + 15 * (size_t)i;
+    DG dg;
+    dg.p = Vec(q[0], q[1], q[2]);
+    dg.u = q[3]; dg.v = q[4]; dg.dudx = q[5]; dg.dvdx = q[6]; dg.dudy = q[7]; dg.dvdy = q[8];
+    dg.dpdx = Vec(q[9], q[10], q[11]);
+    dg.dpdy = Vec(q[12], q[13], q[14]);
+    if (ts.nodes[(size_t)node].spectrum) {
+      float v[3];
+      ts.evalSpec(node, dg, v);
+      out[3 * i] = v[0]; out[3 * i + 1] = v[1]; out[3 * i + 2] = v[2];
+    } else {
+      out[3 * i] = ts.evalFloat(node, dg);
+      out[3 * i + 1] = out[3 * i + 2] = 0.0;
+    }
+  }
+  return 0;
+}
+int orc_image_level(orc_ctx* c, int32_t node, int32_t level, int32_t* w, int32_t* h, float* out) {
+  const TextureSet& ts = c->rs.textures;
+  if (node < 0 || (size_t)node >= ts.nodes.size() || ts.nodes[(size_t)node].image < 0) return -1;
+  const TexImage& im = ts.images[(size_t)ts.nodes[(size_t)node].image];
+  if (level < 0) return im.levels;
+  if (level >= im.levels) return -1;
+  *w = im.w[level]; *h = im.h[level];
+  if (out) std::copy(im.data[level].begin(), im.data[level].end(), out);
+  return im.levels;
 }
 
 // mirrors drt_set_infinite_light: light `index` (kind 4 in orc_set_lights) gets its transforms and radiance map — level 0 of

@@ -319,10 +319,7 @@ void Film::writeImage(float* rgb) const {  // :268-299 (OutputImage.rgb is a Flo
 // shading geometry
 namespace {
 
-struct DG {  // the part of DifferentialGeometry the matte path uses
-  Vec p, nn, dpdu, dpdv;
-  double u = 0.0, v = 0.0;  // triangles: the interpolated (tu, tv) of triangle.dart:134-136 (getShadingGeometry reads them)
-};
+// struct DG: the whole DifferentialGeometry, ref_texture.h
 
 struct Isect {
   DG dg;
@@ -653,6 +650,11 @@ struct LobeEval {
 
 struct Bsdf {  // bsdf.dart:41-255
   Vec p, nn, ng, sn, tn;
+  DG dgs;            // bsdf.dgShading
+  double eta = 1.0;  // bsdf.eta (glass: index, translucent: 1.5)
+  Vec dpdx, dpdy;    // isect.dg.dpdx / dpdy after Intersection.getBSDF's computeDifferentials
+  bool framed = false;
+  Lobe lobes[8];     // what the BxDFs were built from (MixMaterial re-wraps them)
   int nBxDFs = 0;
   LobeEval bxdfs[8];
   Vec worldToLocal(const Vec& v) const { return Vec(Dot(v, sn), Dot(v, tn), Dot(v, nn)); }
@@ -1014,6 +1016,23 @@ struct Ctx {
     return hit;
   }
 
+  // dndu / dndv from the fundamental forms (sphere.dart:138-153 and the same block in the other quadrics).  `perFactor`: the
+  // sphere multiplies dpdu by (f F - e G) and then by invEGF2 (two float32 Vectors), the others by their product.
+  static void weingarten(const Vec& dpdu, const Vec& dpdv, const Vec& d2Pduu, const Vec& d2Pduv, const Vec& d2Pdvv, bool perFactor,
+                         Vec* dndu, Vec* dndv) {
+    double E = Dot(dpdu, dpdu), F = Dot(dpdu, dpdv), G = Dot(dpdv, dpdv);
+    Vec N = Normalize(Cross(dpdu, dpdv));
+    double e = Dot(N, d2Pduu), f = Dot(N, d2Pduv), gg = Dot(N, d2Pdvv);
+    double invEGF2 = 1.0 / (E * G - F * F);
+    if (perFactor) {
+      *dndu = dpdu * (f * F - e * G) * invEGF2 + dpdv * (e * F - f * E) * invEGF2;
+      *dndv = dpdu * (gg * F - f * G) * invEGF2 + dpdv * (f * F - gg * E) * invEGF2;
+    } else {
+      *dndu = dpdu * ((f * F - e * G) * invEGF2) + dpdv * ((e * F - f * E) * invEGF2);
+      *dndv = dpdu * ((gg * F - f * G) * invEGF2) + dpdv * ((f * F - gg * E) * invEGF2);
+    }
+  }
+
   // dg.set(...) of triangle.dart:100-154 / sphere.dart:118-160 + differential_geometry.dart:77-99.
   // `rayAtHit` is the ray the shape test ran on (its maxt already holds tHit for closest-hit queries).
   void shapeDG(uint32_t prim, const Ray& ray, const Hit& h, DG* dg) const {
@@ -1062,9 +1081,27 @@ struct Ctx {
         dpdv = Vec(((double)s.hp2.x - s.hp1.x) * cosphi - ((double)s.hp2.y - s.hp1.y) * sinphi,
                    ((double)s.hp2.x - s.hp1.x) * sinphi + ((double)s.hp2.y - s.hp1.y) * cosphi, (double)s.hp2.z - s.hp1.z);
       }
+      // second derivatives and the Weingarten equations (cylinder.dart:114-135, cone.dart:109-131, paraboloid.dart:111-137,
+      // hyperboloid.dart:138-157)
+      Vec d2Pduu = Vec(phit.x, phit.y, 0.0) * (-s.phiMax * s.phiMax), d2Pduv, d2Pdvv;
+      if (s.shape == 3) {
+        double v = (double)phit.z / s.height;
+        d2Pduv = Vec(phit.y, -(double)phit.x, 0.0) * (s.phiMax / (1.0 - v));
+      } else if (s.shape == 4) {
+        d2Pduv = Vec(-(double)phit.y / (2.0 * phit.z), (double)phit.x / (2.0 * phit.z), 0.0) * (s.zmax - s.zmin) * s.phiMax;
+        d2Pdvv = Vec((double)phit.x / (4.0 * phit.z * phit.z), (double)phit.y / (4.0 * phit.z * phit.z), 0.0) *
+                 (-(s.zmax - s.zmin) * (s.zmax - s.zmin));
+      } else if (s.shape == 5) {
+        d2Pduv = Vec(-(double)dpdv.y, dpdv.x, 0.0) * s.phiMax;
+      }
+      Vec dndu, dndv;
+      weingarten(dpdu, dpdv, d2Pduu, d2Pduv, d2Pdvv, false, &dndu, &dndv);
       dg->p = s.o2w.point(phit);
       dg->dpdu = s.o2w.vector(dpdu);
       dg->dpdv = s.o2w.vector(dpdv);
+      dg->dndu = s.o2w.normal(dndu);
+      dg->dndv = s.o2w.normal(dndv);
+      dg->u = h.b1; dg->v = h.b2;
     } else if (g.spheres[prim - g.ntris()].shape == 1) {  // disk.dart:69-97
       const Sphere& s = g.spheres[prim - g.ntris()];
       Vec phit = h.phitObj;
@@ -1078,6 +1115,9 @@ struct Ctx {
       dg->p = s.o2w.point(phit);
       dg->dpdu = s.o2w.vector(dpdu);
       dg->dpdv = s.o2w.vector(dpdv);
+      dg->dndu = s.o2w.normal(Vec());  // disk.dart:81-82
+      dg->dndv = s.o2w.normal(Vec());
+      dg->u = h.b1; dg->v = h.b2;
     } else {
       const Sphere& s = g.spheres[prim - g.ntris()];
       Vec phit = h.phitObj;
@@ -1089,11 +1129,21 @@ struct Ctx {
       (void)phi;
       Vec dpdu(-s.phiMax * phit.y, s.phiMax * phit.x, 0.0);
       Vec dpdv = Vec(phit.z * cosphi, phit.z * sinphi, -s.radius * std::sin(theta)) * (s.thetaMax - s.thetaMin);
+      // sphere.dart:131-153 (this file multiplies the vectors factor by factor)
+      Vec d2Pduu = Vec(phit.x, phit.y, 0.0) * -s.phiMax * s.phiMax;
+      Vec d2Pduv = Vec(-sinphi, cosphi, 0.0) * (s.thetaMax - s.thetaMin) * phit.z * s.phiMax;
+      Vec d2Pdvv = Vec(phit.x, phit.y, phit.z) * -(s.thetaMax - s.thetaMin) * (s.thetaMax - s.thetaMin);
+      Vec dndu, dndv;
+      weingarten(dpdu, dpdv, d2Pduu, d2Pduv, d2Pdvv, true, &dndu, &dndv);
       dg->p = s.o2w.point(phit);
       dg->dpdu = s.o2w.vector(dpdu);
       dg->dpdv = s.o2w.vector(dpdv);
+      dg->dndu = s.o2w.normal(dndu);
+      dg->dndv = s.o2w.normal(dndv);
+      dg->u = h.b1; dg->v = h.b2;
     }
     dg->nn = Normalize(Cross(dg->dpdu, dg->dpdv));
+    dg->reverse = g.reverseOf[prim] != 0;
     if (g.reverseOf[prim]) dg->nn = dg->nn * -1.0;  // transformSwapsHandedness is never set (shape.dart:30)
   }
   void fillIsect(const Ray& ray, const Hit& h, Isect* is) const {
@@ -1113,14 +1163,165 @@ struct Ctx {
     return true;
   }
 
-  // ---- BSDF (intersection.dart:44-50 -> geometric_primitive.dart:71-75 -> matte_material.dart:41-65) ----
-  Bsdf getBSDF(const Isect& is) const {
+  // ---- BSDF (intersection.dart:44-50 -> geometric_primitive.dart:71-75 -> the material's getBSDF) ----
+  static Spec specOf(const float v[3]) { Spec r; r.c[0] = v[0]; r.c[1] = v[1]; r.c[2] = v[2]; return r; }
+  static Spec clampS(const Spec& a, double lo = 0.0, double hi = kInf) {  // rgb_color.dart:189-192
+    auto cl = [&](float x) { double v = x; return v < lo ? lo : (v > hi ? hi : v); };
+    return Spec(cl(a.c[0]), cl(a.c[1]), cl(a.c[2]));
+  }
+  static double blinnExp(double rough) {  // 1 / roughness, then blinn.dart:24-28
+    double e = 1.0 / rough;
+    return (e > 10000.0 || std::isnan(e)) ? 10000.0 : e;
+  }
+  static Spec approxEta(const Spec& fr) {  // shiny_metal_material.dart:75-79
+    Spec refl = clampS(fr, 0.0, 0.999);
+    Spec sq(std::sqrt((double)refl.c[0]), std::sqrt((double)refl.c[1]), std::sqrt((double)refl.c[2]));
+    return (Spec(1.0) + sq) / (Spec(1.0) - sq);
+  }
+  Spec texS(int id, const DG& dg) const { float v[3]; rs.textures.evalSpec(id, dg, v); return specOf(v); }
+  double texF(int id, const DG& dg) const { return rs.textures.evalFloat(id, dg); }
+  static void addLobe(Bsdf* b, const Lobe& l) { b->bxdfs[b->nBxDFs++].init(l); b->lobes[b->nBxDFs - 1] = l; }
+  static Lobe mkLobe(int kind, const Spec& R, int fresnel = 0, double param = 0.0, double ei = 1.0, double et = 1.0) {
+    Lobe l; l.kind = kind; l.R = R; l.fresnel = fresnel; l.param = param; l.ei = ei; l.et = et; return l;
+  }
+  // new BSDF(dgs, dgGeom.nn, eta): bsdf.dart:45-51
+  static void frameBsdf(Bsdf* b, const DG& dgs, const Vec& ng, double eta) {
+    b->dgs = dgs; b->eta = eta;
+    b->p = dgs.p; b->ng = ng; b->nn = dgs.nn;
+    b->sn = Normalize(dgs.dpdu);
+    b->tn = Cross(b->nn, b->sn);
+    b->nBxDFs = 0;
+    b->framed = true;
+  }
+  // Material.getBSDF(dgGeom, dgShading) of material `mat` into *b (lib/materials/*.dart)
+  void materialBSDF(uint32_t mat, const DG& dgGeom, const DG& dgShading, Bsdf* b) const {
+    static const Material kDefault = Material::matte(Spec(0.5), 0.0);  // no material table: the default matte, Kd = 0.5
+    const MaterialProgram* prog = (mat < rs.programs.size() && rs.programs[mat].kind >= 0) ? &rs.programs[mat] : nullptr;
+    if (!prog) {  // constant parameters, no bump map: the lobe list flattened by the caller
+      frameBsdf(b, dgShading, dgGeom.nn, 1.0);
+      const Material& m = rs.materials.empty() ? kDefault : rs.materials[mat];
+      for (const Lobe& l : m.lobes) addLobe(b, l);
+      return;
+    }
+    const int* t = prog->tex;
+    if (prog->kind == 9) {  // mix_material.dart:36-50
+      materialBSDF((uint32_t)prog->m1, dgGeom, dgShading, b);
+      Bsdf b2;
+      materialBSDF((uint32_t)prog->m2, dgGeom, dgShading, &b2);
+      Spec s1 = clampS(texS(t[0], dgShading));
+      Spec s2 = clampS(Spec(1.0) - s1);
+      const int n1 = b->nBxDFs, n2 = b2.nBxDFs;
+      Lobe all[8];
+      int n = 0;
+      for (int i = 0; i < n1 && n < 8; ++i) { all[n] = b->lobes[i]; all[n].wrap |= 2; all[n].scale = s1; ++n; }
+      for (int i = 0; i < n2 && n < 8; ++i) { all[n] = b2.lobes[i]; all[n].wrap |= 2; all[n].scale = s2; ++n; }
+      b->nBxDFs = 0;
+      for (int i = 0; i < n; ++i) addLobe(b, all[i]);
+      return;
+    }
+    DG dgs = dgShading;
+    if (prog->bump >= 0) Bump(rs.textures, prog->bump, dgGeom, dgShading, &dgs);
+    switch (prog->kind) {
+      case 0: {  // matte_material.dart:41-65
+        frameBsdf(b, dgs, dgGeom.nn, 1.0);
+        Spec r = clampS(texS(t[0], dgs));
+        double sig = clampd(texF(t[1], dgs), 0.0, 90.0);
+        if (!r.isBlack()) addLobe(b, sig == 0.0 ? mkLobe(0, r) : mkLobe(1, r, 0, sig));
+        break;
+      }
+      case 1: {  // mirror_material.dart:38-55
+        frameBsdf(b, dgs, dgGeom.nn, 1.0);
+        Spec R = clampS(texS(t[0], dgs));
+        if (!R.isBlack()) addLobe(b, mkLobe(3, R, 0));
+        break;
+      }
+      case 2: {  // glass_material.dart:44-70
+        double ior = texF(t[2], dgs);
+        frameBsdf(b, dgs, dgGeom.nn, ior);
+        Spec R = clampS(texS(t[0], dgs)), T = clampS(texS(t[1], dgs));
+        if (!R.isBlack()) addLobe(b, mkLobe(3, R, 1, 0.0, 1.0, ior));
+        if (!T.isBlack()) addLobe(b, mkLobe(4, T, 1, 0.0, 1.0, ior));
+        break;
+      }
+      case 3: {  // plastic_material.dart:43-72
+        frameBsdf(b, dgs, dgGeom.nn, 1.0);
+        Spec kd = clampS(texS(t[0], dgs));
+        if (!kd.isBlack()) addLobe(b, mkLobe(0, kd));
+        Spec ks = clampS(texS(t[1], dgs));
+        if (!ks.isBlack()) addLobe(b, mkLobe(2, ks, 1, blinnExp(texF(t[2], dgs)), 1.5, 1.0));
+        break;
+      }
+      case 4: {  // metal_material.dart:44-64
+        frameBsdf(b, dgs, dgGeom.nn, 1.0);
+        double rough = texF(t[2], dgs);
+        Lobe l = mkLobe(2, Spec(1.0), 2, blinnExp(rough));
+        l.eta = texS(t[0], dgs);
+        l.k = texS(t[1], dgs);
+        addLobe(b, l);
+        break;
+      }
+      case 5: {  // shiny_metal_material.dart:44-73
+        frameBsdf(b, dgs, dgGeom.nn, 1.0);
+        Spec spec = clampS(texS(t[0], dgs));
+        double rough = texF(t[2], dgs);
+        Spec R = clampS(texS(t[1], dgs));
+        if (!spec.isBlack()) { Lobe l = mkLobe(2, Spec(1.0), 2, blinnExp(rough)); l.eta = approxEta(spec); l.k = Spec(0.0); addLobe(b, l); }
+        if (!R.isBlack()) { Lobe l = mkLobe(3, Spec(1.0), 2); l.eta = approxEta(R); l.k = Spec(0.0); addLobe(b, l); }
+        break;
+      }
+      case 6: {  // substrate_material.dart:48-70: FresnelBlend(d, s, Anisotropic(1 / u, 1 / v))
+        frameBsdf(b, dgs, dgGeom.nn, 1.0);
+        Spec d = clampS(texS(t[0], dgs)), sp = clampS(texS(t[1], dgs));
+        double u = texF(t[2], dgs), v = texF(t[3], dgs);
+        if (!d.isBlack() || !sp.isBlack()) { Lobe l = mkLobe(5, d, 0, blinnExp(u), blinnExp(v)); l.eta = sp; addLobe(b, l); }
+        break;
+      }
+      case 7: {  // translucent_material.dart:47-103
+        frameBsdf(b, dgs, dgGeom.nn, 1.5);
+        Spec r = clampS(texS(t[2], dgs)), tr = clampS(texS(t[3], dgs));
+        if (r.isBlack() && tr.isBlack()) break;
+        Spec kd = clampS(texS(t[0], dgs));
+        if (!kd.isBlack()) {
+          if (!r.isBlack()) addLobe(b, mkLobe(0, r * kd));
+          if (!tr.isBlack()) { Lobe l = mkLobe(0, tr * kd); l.wrap = 1; addLobe(b, l); }
+        }
+        Spec ks = clampS(texS(t[1], dgs));
+        if (!ks.isBlack()) {
+          double e = blinnExp(texF(t[4], dgs));
+          if (!r.isBlack()) addLobe(b, mkLobe(2, r * ks, 1, e, 1.5, 1.0));
+          if (!tr.isBlack()) { Lobe l = mkLobe(2, tr * ks, 1, e, 1.5, 1.0); l.wrap = 1; addLobe(b, l); }
+        }
+        break;
+      }
+      default: {  // 8 uber_material.dart:56-104
+        frameBsdf(b, dgs, dgGeom.nn, 1.0);
+        Spec op = clampS(texS(t[5], dgs));
+        if (!(op.c[0] == 1.f && op.c[1] == 1.f && op.c[2] == 1.f)) {
+          Spec neg(-(double)op.c[0], -(double)op.c[1], -(double)op.c[2]);
+          addLobe(b, mkLobe(4, neg + Spec(1.0), 1, 0.0, 1.0, 1.0));
+        }
+        Spec kd = op * clampS(texS(t[0], dgs));
+        if (!kd.isBlack()) addLobe(b, mkLobe(0, kd));
+        double e = texF(t[6], dgs);
+        Spec ks = op * clampS(texS(t[1], dgs));
+        if (!ks.isBlack()) addLobe(b, mkLobe(2, ks, 1, blinnExp(texF(t[4], dgs)), e, 1.0));
+        Spec kr = op * clampS(texS(t[2], dgs));
+        if (!kr.isBlack()) addLobe(b, mkLobe(3, kr, 1, 0.0, e, 1.0));
+        Spec kt = op * clampS(texS(t[3], dgs));
+        if (!kt.isBlack()) addLobe(b, mkLobe(4, kt, 1, 0.0, e, 1.0));
+        break;
+      }
+    }
+  }
+
+  // Intersection.getBSDF(ray): computeDifferentials, Shape.getShadingGeometry, Material.getBSDF.  `rd` null: a ray without
+  // differentials (RayDifferential.child, ray_differential.dart:42-44)
+  Bsdf getBSDF(const Isect& is, const RayDiff* rd = nullptr) const {
     Bsdf b;
-    const DG& dg = is.dg;
-    b.p = dg.p;
-    b.nn = dg.nn;  // dgShading == dg: no per-vertex normals (triangle.dart:273-276), quadrics (shape.dart:73-77)
-    b.ng = dg.nn;
-    Vec ss = dg.dpdu;
+    DG dg = is.dg;
+    computeDifferentials(&dg, rd ? *rd : RayDiff());
+    b.dpdx = dg.dpdx; b.dpdy = dg.dpdy;
+    DG dgs = dg;  // dgShading == dg: no per-vertex normals (triangle.dart:273-276), quadrics (shape.dart:73-77)
     const Scene::MeshInfo* mesh = (uint32_t)is.prim < g.ntris() ? g.meshOf((uint32_t)is.prim) : nullptr;
     if (mesh && (mesh->hasN || mesh->hasS)) {  // Triangle.getShadingGeometry, triangle.dart:271-364
       const uint32_t tri = (uint32_t)is.prim;
@@ -1142,7 +1343,7 @@ struct Ctx {
         const float* q = &a[3 * (size_t)g.idx[3 * (size_t)tri + k]];
         return Vec(q[0], q[1], q[2]);
       };
-      Vec ns, ts;
+      Vec ns, ss, ts;
       if (mesh->hasN) ns = Normalize(mesh->o2w.normal(((vert(g.vertN, 0) * bx) + (vert(g.vertN, 1) * by)) + (vert(g.vertN, 2) * bz)));
       else ns = dg.nn;
       if (mesh->hasS) ss = Normalize(mesh->o2w.vector(((vert(g.vertS, 0) * bx) + (vert(g.vertS, 1) * by)) + (vert(g.vertS, 2) * bz)));
@@ -1154,17 +1355,27 @@ struct Ctx {
       } else {
         CoordinateSystem(ns, &ss, &ts);
       }
-      // dgShading.set(dg.p, ss, ts, ...): nn = normalize(cross(dpdu, dpdv)), flipped by reverseOrientation
-      // (differential_geometry.dart:77-99)
-      b.nn = Normalize(Cross(ss, ts));
-      if (g.reverseOf[is.prim]) b.nn = b.nn * -1.0;
+      Vec dndu, dndv;  // :328-351
+      if (mesh->hasN) {
+        double du1 = uv[0] - uv[4], du2 = uv[2] - uv[4], dv1 = uv[1] - uv[5], dv2 = uv[3] - uv[5];
+        Vec dn1 = vert(g.vertN, 0) - vert(g.vertN, 2), dn2 = vert(g.vertN, 1) - vert(g.vertN, 2);
+        double determinant = du1 * dv2 - dv1 * du2;
+        if (determinant != 0.0) {
+          double invdet = 1.0 / determinant;
+          dndu = (dn1 * dv2 - dn2 * dv1) * invdet;
+          dndv = (dn1 * -du2 + dn2 * du1) * invdet;
+        }
+      }
+      // dgShading.set(dg.p, ss, ts, o2w(dndu), o2w(dndv), dg.u, dg.v, dg.shape): nn = normalize(cross(dpdu, dpdv)), flipped by
+      // reverseOrientation (differential_geometry.dart:77-99); the differentials are copied over (:354-363)
+      dgs.dpdu = ss;
+      dgs.dpdv = ts;
+      dgs.dndu = mesh->o2w.normal(dndu);
+      dgs.dndv = mesh->o2w.normal(dndv);
+      dgs.nn = Normalize(Cross(ss, ts));
+      if (g.reverseOf[is.prim]) dgs.nn = dgs.nn * -1.0;
     }
-    b.sn = Normalize(ss);
-    b.tn = Cross(b.nn, b.sn);
-    // no material table: every primitive is the default matte, Kd = 0.5 (matte_material.dart:67-72), as in drt_create
-    static const Material kDefault = Material::matte(Spec(0.5), 0.0);
-    const Material& m = rs.materials.empty() ? kDefault : rs.materials[g.materialOf[is.prim]];
-    for (const Lobe& l : m.lobes) b.bxdfs[b.nBxDFs++].init(l);
+    materialBSDF(rs.materials.empty() ? 0u : (uint32_t)g.materialOf[is.prim], dg, dgs, &b);
     return b;
   }
 
@@ -1486,14 +1697,15 @@ struct Ctx {
   }
 
   // path_integrator.dart:29-122
-  Spec pathLi(const Ray& r, const Isect& isect, const SampleVals& sample, Rng& rng) {
+  Spec pathLi(const Ray& r, const Isect& isect, const SampleVals& sample, Rng& rng, const RayDiff* rd = nullptr) {
     Spec pathThroughput(1.0), L(0.0);
     Ray ray = r;
     bool specularBounce = false;
     Isect isectP = isect, localIsect;
     for (int bounces = 0;; ++bounces) {
       if (bounces == 0 || specularBounce) L = L + pathThroughput * isectLe(isectP, -ray.d);
-      Bsdf bsdf = getBSDF(isectP);
+      // the rays after the first are RayDifferential.child: no differentials (path_integrator.dart:100)
+      Bsdf bsdf = getBSDF(isectP, bounces == 0 ? rd : nullptr);
       Vec p = bsdf.p, n = bsdf.nn, wo = -ray.d;
       if (bounces < 3)
         L = L + pathThroughput * UniformSampleOneLight(p, n, wo, isectP.rayEpsilon, ray.time, bsdf, sample, rng,
@@ -1527,8 +1739,8 @@ struct Ctx {
   }
 
   // ambient_occlusion_integrator.dart:28-53
-  Spec aoLi(const Ray& ray, const Isect& isect, Rng& rng) {
-    Bsdf bsdf = getBSDF(isect);
+  Spec aoLi(const Ray& ray, const Isect& isect, Rng& rng, const RayDiff* rd = nullptr) {
+    Bsdf bsdf = getBSDF(isect, rd);
     Vec p = bsdf.p;
     Vec n = FaceForward(isect.dg.nn, -ray.d);
     int nSamples = RoundUpPow2(rs.integ.aoSamples);
@@ -1545,9 +1757,9 @@ struct Ctx {
   }
 
   // direct_lighting_integrator.dart:30-68
-  Spec directLi(const Ray& ray, const Isect& isect, const SampleVals& sample, Rng& rng) {
+  Spec directLi(const Ray& ray, const Isect& isect, const SampleVals& sample, Rng& rng, const RayDiff* rd = nullptr) {
     Spec L(0.0);
-    Bsdf bsdf = getBSDF(isect);
+    Bsdf bsdf = getBSDF(isect, rd);
     Vec wo = -ray.d, p = bsdf.p, n = bsdf.nn;
     L = L + isectLe(isect, wo);
     if (!rs.lights.empty()) {
@@ -1555,17 +1767,17 @@ struct Ctx {
       else L = L + UniformSampleOneLight(p, n, wo, isect.rayEpsilon, ray.time, bsdf, sample, rng, dlLightNum, &dlLight[0], &dlBsdf[0]);
     }
     if (ray.depth + 1 < rs.integ.maxDepth) {
-      L = L + specularBranch(ray, bsdf, isect, sample, rng, BSDF_REFLECTION | BSDF_SPECULAR);
-      L = L + specularBranch(ray, bsdf, isect, sample, rng, BSDF_TRANSMISSION | BSDF_SPECULAR);
+      L = L + specularBranch(ray, bsdf, isect, sample, rng, BSDF_REFLECTION | BSDF_SPECULAR, rd);
+      L = L + specularBranch(ray, bsdf, isect, sample, rng, BSDF_TRANSMISSION | BSDF_SPECULAR, rd);
     }
     return L;
   }
 
   // whitted_integrator.dart:26-78: emitted light, one LightSample.random(rng) per light (no multiple importance
   // sampling, every BxDF), then the specular recursion
-  Spec whittedLi(const Ray& ray, const Isect& isect, const SampleVals& sample, Rng& rng) {
+  Spec whittedLi(const Ray& ray, const Isect& isect, const SampleVals& sample, Rng& rng, const RayDiff* rd = nullptr) {
     Spec L(0.0);
-    Bsdf bsdf = getBSDF(isect);
+    Bsdf bsdf = getBSDF(isect, rd);
     Vec p = bsdf.p, n = bsdf.nn, wo = -ray.d;
     L = L + isectLe(isect, wo);
     for (size_t i = 0; i < rs.lights.size(); ++i) {
@@ -1578,15 +1790,16 @@ struct Ctx {
       if (!f.isBlack() && !intersectP(vis.r)) L = L + f * Li * AbsDot(wi, n) * transmittance(vis.r, &sample) / pdf;  // whitted_integrator.dart:56-58
     }
     if (ray.depth + 1 < rs.integ.maxDepth) {
-      L = L + specularBranch(ray, bsdf, isect, sample, rng, BSDF_REFLECTION | BSDF_SPECULAR);
-      L = L + specularBranch(ray, bsdf, isect, sample, rng, BSDF_TRANSMISSION | BSDF_SPECULAR);
+      L = L + specularBranch(ray, bsdf, isect, sample, rng, BSDF_REFLECTION | BSDF_SPECULAR, rd);
+      L = L + specularBranch(ray, bsdf, isect, sample, rng, BSDF_TRANSMISSION | BSDF_SPECULAR, rd);
     }
     return L;
   }
 
-  // Integrator.SpecularReflect / SpecularTransmit (integrator.dart:187-290) without the ray differentials (they only
-  // feed texture filtering): one BSDFSample.random(rng) is drawn whether or not the BSDF has such a component.
-  Spec specularBranch(const Ray& ray, const Bsdf& bsdf, const Isect& isect, const SampleVals& sample, Rng& rng, int flags) {
+  // Integrator.SpecularReflect / SpecularTransmit (integrator.dart:187-290): one BSDFSample.random(rng) is drawn whether or
+  // not the BSDF has such a component; the child ray carries differentials when its parent does.
+  Spec specularBranch(const Ray& ray, const Bsdf& bsdf, const Isect& isect, const SampleVals& sample, Rng& rng, int flags,
+                      const RayDiff* rdIn = nullptr) {
     Vec wo = -ray.d, wi;
     double pdf = 0.0;
     Vec p = bsdf.p, n = bsdf.nn;
@@ -1595,22 +1808,56 @@ struct Ctx {
     Spec L(0.0);
     if (pdf > 0.0 && !f.isBlack() && AbsDot(wi, n) != 0.0) {
       Ray rd(p, wi, isect.rayEpsilon, kInf, ray.time, ray.depth + 1);  // RayDifferential.child
-      Spec Li = LiRay(rd, sample, rng);
+      RayDiff cd;
+      if (rdIn && rdIn->has) {
+        const DG& ds = bsdf.dgs;
+        cd.has = true;
+        cd.rxo = p + bsdf.dpdx;
+        cd.ryo = p + bsdf.dpdy;
+        Vec dndx = ds.dndu * ds.dudx + ds.dndv * ds.dvdx;
+        Vec dndy = ds.dndu * ds.dudy + ds.dndv * ds.dvdy;
+        Vec dwodx = -rdIn->rxd - wo, dwody = -rdIn->ryd - wo;
+        double dDNdx = Dot(dwodx, n) + Dot(wo, dndx), dDNdy = Dot(dwody, n) + Dot(wo, dndy);
+        if (flags & BSDF_REFLECTION) {  // :203-221
+          cd.rxd = wi - dwodx + (dndx * Dot(wo, n) + n * dDNdx) * 2.0;
+          cd.ryd = wi - dwody + (dndy * Dot(wo, n) + n * dDNdy) * 2.0;
+        } else {  // :250-280
+          double eta = bsdf.eta;
+          Vec w = -wo;
+          if (Dot(wo, n) < 0.0) eta = 1.0 / eta;
+          double mu = eta * Dot(w, n) - Dot(wi, n);
+          double dmudx = (eta - (eta * eta * Dot(w, n)) / Dot(wi, n)) * dDNdx;
+          double dmudy = (eta - (eta * eta * Dot(w, n)) / Dot(wi, n)) * dDNdy;
+          cd.rxd = wi + dwodx * eta - (dndx * mu + n * dmudx);
+          cd.ryd = wi + dwody * eta - (dndy * mu + n * dmudy);
+        }
+      }
+      Spec Li = LiRay(rd, sample, rng, cd.has ? &cd : nullptr);
       L = f * Li * (AbsDot(wi, n) / pdf);
     }
     return L;
   }
 
-  // perspective_camera.dart:93-132 (the differential rays only feed texture filtering: not computed)
-  Ray cameraRay(const SampleVals& s) const {
+  // Camera.generateRayDifferential: perspective_camera.dart:93-132, orthographic_camera.dart:86-117, and the generic one-pixel
+  // shifts of camera.dart:37-62 for the environment camera.  `rd` null: the main ray only.
+  Ray cameraRay(const SampleVals& s, RayDiff* rd = nullptr) const {
     const Camera& c = rs.camera;
     if (c.kind == 2) {  // environment_camera.dart:42-52
-      double theta = kPi * s.imageY / rs.film.yres;
-      double phi = 2 * kPi * s.imageX / rs.film.xres;
-      Ray er(Vec(), Vec(std::sin(theta) * std::cos(phi), std::cos(theta), std::sin(theta) * std::sin(phi)), 0.0, kInf);
-      er.time = s.time;
-      Ray ew = c.cameraToWorld.ray(er);
-      ew.time = s.time;
+      auto gen = [&](double imageX, double imageY) {
+        double theta = kPi * imageY / rs.film.yres;
+        double phi = 2 * kPi * imageX / rs.film.xres;
+        Ray er(Vec(), Vec(std::sin(theta) * std::cos(phi), std::cos(theta), std::sin(theta) * std::sin(phi)), 0.0, kInf);
+        er.time = s.time;
+        Ray ew = c.cameraToWorld.ray(er);
+        ew.time = s.time;
+        return ew;
+      };
+      Ray ew = gen(s.imageX, s.imageY);
+      if (rd) {  // camera.dart:40-58: sshift.imageX++, then imageX--, imageY++ (Dart doubles)
+        Ray rx = gen(s.imageX + 1.0, s.imageY), ry = gen((s.imageX + 1.0) - 1.0, s.imageY + 1.0);
+        rd->has = true;
+        rd->rxo = rx.o; rd->rxd = rx.d; rd->ryo = ry.o; rd->ryd = ry.d;
+      }
       return ew;
     }
     Vec Pras(s.imageX, s.imageY, 0.0);
@@ -1630,12 +1877,42 @@ struct Ctx {
     ray.time = s.time;
     Ray w = c.cameraToWorld.ray(ray);
     w.time = s.time;
+    if (rd) {
+      rd->has = true;
+      if (c.kind == 0) {  // perspective_camera.dart:50-56,122-128: the offsets ignore the lens; transformRayDifferential
+        Vec dxCamera = c.rasterToCamera.point(Vec(1.0, 0.0, 0.0)) - c.rasterToCamera.point(Vec(0.0, 0.0, 0.0));
+        Vec dyCamera = c.rasterToCamera.point(Vec(0.0, 1.0, 0.0)) - c.rasterToCamera.point(Vec(0.0, 0.0, 0.0));
+        rd->rxo = c.cameraToWorld.point(ray.o);
+        rd->ryo = c.cameraToWorld.point(ray.o);
+        rd->rxd = c.cameraToWorld.vector(Normalize(Pcamera + dxCamera));
+        rd->ryd = c.cameraToWorld.vector(Normalize(Pcamera + dyCamera));
+      } else {
+        // orthographic_camera.dart:111-115 AS WRITTEN: rxOrigin / ryOrigin are built in camera space and the call that follows is
+        // transformRay, not transformRayDifferential, so they STAY in camera space; rxDirection and ryDirection are the very
+        // object ray.direction is, which transformRay overwrites in place: they end up as the world-space direction.
+        Vec dxCamera = c.rasterToCamera.vector(Vec(1.0, 0.0, 0.0)), dyCamera = c.rasterToCamera.vector(Vec(0.0, 1.0, 0.0));
+        rd->rxo = ray.o + dxCamera;
+        rd->ryo = ray.o + dyCamera;
+        rd->rxd = w.d;
+        rd->ryd = w.d;
+      }
+    }
     return w;
+  }
+  // Sampler.samplesPerPixel as each sampler's constructor hands it to the base class (lib/samplers/*.dart)
+  int samplesPerPixel() const {
+    const SamplerCfg& sc = rs.sampler;
+    switch (sc.kind) {
+      case 0: return RoundUpPow2(sc.spp);
+      case 1: return sc.xs * sc.ys;
+      case 4: return RoundUpPow2(std::max(sc.xs, sc.ys));
+      default: return sc.spp;
+    }
   }
 
   // SamplerRenderer.Li (sampler_renderer.dart:67-98): also what the specular recursion calls
   int32_t lastCameraPrim = -1;  // primitive the last camera ray hit (adaptive sampler, shapeid method)
-  Spec LiRay(const Ray& rayIn, const SampleVals& s, Rng& rng) {
+  Spec LiRay(const Ray& rayIn, const SampleVals& s, Rng& rng, const RayDiff* rd = nullptr) {
     Ray ray = rayIn;  // Scene.intersect shrinks ray.maxDistance to the hit (geometric_primitive.dart:47-61)
     Isect isect;
     Spec L(0.0);
@@ -1643,10 +1920,10 @@ struct Ctx {
     if (rayIn.depth == 0) lastCameraPrim = hit ? isect.prim : -1;  // camera rays only: the recursion's rays have depth > 0
     if (hit) {
       switch (rs.integ.kind) {
-        case 0: L = pathLi(ray, isect, s, rng); break;
-        case 1: L = aoLi(ray, isect, rng); break;
-        case 3: L = whittedLi(ray, isect, s, rng); break;
-        default: L = directLi(ray, isect, s, rng); break;
+        case 0: L = pathLi(ray, isect, s, rng, rd); break;
+        case 1: L = aoLi(ray, isect, rng, rd); break;
+        case 3: L = whittedLi(ray, isect, s, rng, rd); break;
+        default: L = directLi(ray, isect, s, rng, rd); break;
       }
     } else {
       L = allLightsLe(ray);  // sampler_renderer.dart:86-92
@@ -1659,9 +1936,12 @@ struct Ctx {
 
   // sampler_renderer.dart:173-193
   Spec Li(const SampleVals& s, Rng& rng) {
-    Ray ray = cameraRay(s);
+    RayDiff rd;
+    const bool textured = !rs.programs.empty();  // the differentials only feed texture filtering and bump mapping
+    Ray ray = cameraRay(s, textured ? &rd : nullptr);
+    if (textured) rd.scale(ray.o, ray.d, 1.0 / std::sqrt((double)samplesPerPixel()));  // sampler_renderer.dart:166
     stats.cameraSamples++;
-    Spec L = LiRay(ray, s, rng);
+    Spec L = LiRay(ray, s, rng, textured ? &rd : nullptr);
     L = L * 1.0;  // rayWeight
     if (L.hasNaNs()) L = Spec(0.0);
     else if (L.luminance() < -1e-5) L = Spec(0.0);

@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "ref_scene.h"
+#include "ref_texture.h"
 
 namespace orc {
 
@@ -284,6 +285,9 @@ struct RenderStats {
 struct RenderScene {
   Scene* geom = nullptr;
   std::vector<Material> materials;
+  // textures that read the hit point and the materials built from them (ref_texture.h); programs is empty or one per material
+  TextureSet textures;
+  std::vector<MaterialProgram> programs;
   std::vector<Light> lights;
   Camera camera;
   Film film;

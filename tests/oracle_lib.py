@@ -63,6 +63,10 @@ def lib():
         L.orc_set_light_map.argtypes = [vp, u32, i32, i32, vp, vp, vp, vp, dbl]
         L.orc_set_lobe_wrappers.argtypes = [vp, u32, vp, vp]
         L.orc_set_infinite_light.argtypes = [vp, u32, i32, i32, vp, vp, vp]
+        L.orc_set_textures.argtypes = [vp, u32, vp, vp, u64]
+        L.orc_set_material_programs.argtypes = [vp, u32, vp]
+        L.orc_texture_eval.argtypes = [vp, i32, u32, vp, vp]
+        L.orc_image_level.argtypes = [vp, i32, i32, vp, vp, vp]
         L.orc_set_lights.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
         L.orc_set_camera.argtypes = [vp, vp, vp, dbl, dbl, dbl, dbl]
         L.orc_set_camera_kind.argtypes = [vp, i32]
@@ -236,6 +240,36 @@ class Oracle:
         """BRDFToBTDF (bit 0) / ScaledBxDF (bit 1, with its RGB scale) around the lobes of the last set_material_lobes."""
         w, sc = _arr(wrap, np.int32), _arr(scale, np.float32).reshape(-1, 3)
         self._ck(self.L.orc_set_lobe_wrappers(self.h, w.shape[0], _p(w), _p(sc)))
+
+    def set_textures(self, nodes, texels):
+        """Texture nodes (host.TEX_DTYPE records = drt_texture) and the level-0 texels of their images."""
+        from dartray_b200 import host
+        n, t = np.ascontiguousarray(nodes, host.TEX_DTYPE), _arr(texels, np.float32)
+        self._ck(self.L.orc_set_textures(self.h, n.shape[0], _p(n), _p(t), t.size))
+
+    def set_material_programs(self, programs):
+        from dartray_b200 import host
+        pr = np.ascontiguousarray(programs, host.PROG_DTYPE)
+        self._ck(self.L.orc_set_material_programs(self.h, pr.shape[0], _p(pr)))
+
+    def texture_eval(self, node, dgs):
+        """Texture.evaluate of node at n DifferentialGeometry records (p 3, u, v, dudx, dvdx, dudy, dvdy, dpdx 3, dpdy 3)."""
+        d = _arr(dgs, np.float64).reshape(-1, 15)
+        out = np.zeros((d.shape[0], 3), np.float64)
+        self._ck(self.L.orc_texture_eval(self.h, node, d.shape[0], _p(d), _p(out)))
+        return out
+
+    def image_levels(self, node, channels):
+        """The MIPMap pyramid the oracle built for image texture `node`: list of (h, w) or (h, w, 3) float32 arrays."""
+        w, h = C.c_int32(0), C.c_int32(0)
+        n = self.L.orc_image_level(self.h, node, -1, None, None, None)
+        out = []
+        for lv in range(n):
+            self.L.orc_image_level(self.h, node, lv, C.byref(w), C.byref(h), None)
+            buf = np.zeros(w.value * h.value * channels, np.float32)
+            self.L.orc_image_level(self.h, node, lv, C.byref(w), C.byref(h), _p(buf))
+            out.append(buf.reshape((h.value, w.value) if channels == 1 else (h.value, w.value, 3)))
+        return out
 
     def set_infinite_light(self, index, texels, light_to_world, world_to_light):
         """Radiance map (h x w x 3 float32, power-of-two resolution: level 0 of the reference's MIPMap) and transforms of light
