@@ -16,6 +16,7 @@
 #include "dart_random.h"
 #include "env_map.h"
 #include "render_kernels.h"
+#include "texture_kernels.h"
 #include "shade_device.cuh"
 
 namespace {
@@ -73,6 +74,14 @@ struct RenderState {
   uint32_t volMaxSteps = 0;      // single scattering: bound on a camera ray's march steps (regions' bound diagonal / stepsize)
   DevBuf<GVolume> dVolumes;
   DevBuf<double> dVolDensity;
+  // textures that read the hit point, and the materials built from them (drt_set_textures / drt_set_material_programs)
+  std::vector<GTex> textures;
+  std::vector<float> texData;
+  std::vector<GProgram> programs;
+  bool programsMaySpecular = false;
+  DevBuf<GTex> dTextures;
+  DevBuf<float> dTexData;
+  DevBuf<GProgram> dPrograms;
   bool haveCamera = false, haveFilm = false;
   RenderParams rp{};
   double crop[4] = {0, 1, 0, 1};
@@ -137,6 +146,7 @@ void drtRenderStateDestroy(drt_ctx* c) {
   r->dMeshOfTri.release(); r->dTriIdx.release(); r->dMeshes.release(); r->dVertN.release(); r->dVertS.release(); r->dVertUV.release(); r->dEnv.release(); r->dAdaptList.release(); r->dAdaptCount.release(); r->dBcTable.release(); r->dBcShifts.release();
   r->dFilm.release(); r->dCounters.release(); r->dRgb.release(); r->dXyz.release(); r->dWeight.release(); r->dWork.release();
   r->dVolumes.release(); r->dVolDensity.release();
+  r->dTextures.release(); r->dTexData.release(); r->dPrograms.release();
   for (cudaEvent_t e : r->profEv) cudaEventDestroy(e);
   if (r->wfMem) cudaFree(r->wfMem);
   delete r;
@@ -451,8 +461,59 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
     rs.volumes = r->dVolumes.p;
     rs.volDensity = r->dVolDensity.p;
   }
+  rs.textures = nullptr;
+  rs.texData = nullptr;
+  rs.programs = nullptr;
+  rs.nPrograms = 0;
+  if (!r->programs.empty()) {
+    if ((int)r->programs.size() != nMat) return fail(c, DRT_E_INVALID, "drt_set_material_programs: one entry per material of the material table");
+    if (!r->general) return fail(c, DRT_E_STATE, "material programs go with drt_set_material_lobes (an empty lobe list for a program's material)");
+    // which parameter of which plugin is a spectrum texture (the tex[] order documented in include/drt.h)
+    static const int kSlots[10] = {2, 1, 3, 3, 3, 3, 4, 5, 7, 1};
+    static const unsigned kSpectrumMask[10] = {0x1, 0x1, 0x3, 0x3, 0x3, 0x3, 0x3, 0xf, 0x2f, 0x1};
+    const int nTex = (int)r->textures.size();
+    r->programsMaySpecular = false;
+    for (int m = 0; m < nMat; ++m) {
+      const GProgram& pr = r->programs[m];
+      if (pr.kind < 0) continue;
+      if (pr.kind > 9) return fail(c, DRT_E_INVALID, "material program kind out of range");
+      for (int k = 0; k < kSlots[pr.kind]; ++k) {
+        if (pr.tex[k] < 0 || pr.tex[k] >= nTex) return fail(c, DRT_E_INVALID, "a material program names a texture node drt_set_textures did not define");
+        if (r->textures[pr.tex[k]].spectrum != (int)((kSpectrumMask[pr.kind] >> k) & 1u))
+          return fail(c, DRT_E_INVALID, "a material program binds a float texture to a spectrum parameter or the reverse");
+      }
+      if (pr.bump >= nTex || (pr.bump >= 0 && r->textures[pr.bump].spectrum != 0)) return fail(c, DRT_E_INVALID, "bumpmap must be a float texture node");
+      if (pr.kind == 9) {
+        for (int sub : {pr.m1, pr.m2}) {
+          if (sub < 0 || sub >= nMat || sub == m) return fail(c, DRT_E_INVALID, "mix: m1 / m2 must be other materials of the table");
+          if (r->programs[sub].kind == 9) return fail(c, DRT_E_UNSUPPORTED, "a mix of mixes (ScaledBxDF of a ScaledBxDF) is not representable");
+        }
+      }
+      // can this program add a specular BxDF at some hit?  (a constant-valued parameter decides it for good)
+      auto constantIs = [&](int id, float v) {
+        const GTex& t = r->textures[id];
+        return t.kind == 0 && (float)t.value[0] == v && (float)t.value[1] == v && (float)t.value[2] == v;
+      };
+      bool spec = false;
+      if (pr.kind == 1) spec = !constantIs(pr.tex[0], 0.f);                                     // mirror: Kr
+      else if (pr.kind == 2) spec = !constantIs(pr.tex[0], 0.f) || !constantIs(pr.tex[1], 0.f);  // glass: Kr, Kt
+      else if (pr.kind == 5) spec = !constantIs(pr.tex[1], 0.f);                                 // shinymetal: Kr
+      else if (pr.kind == 8) spec = !constantIs(pr.tex[2], 0.f) || !constantIs(pr.tex[3], 0.f) || !constantIs(pr.tex[5], 1.f);  // uber: Kr, Kt, opacity
+      if (spec) r->programsMaySpecular = true;  // mix: its two materials are entries of the same table
+    }
+    CK(c, r->dTextures.ensure(std::max<size_t>(1, r->textures.size())));
+    if (!r->textures.empty()) CK(c, cudaMemcpy(r->dTextures.p, r->textures.data(), r->textures.size() * sizeof(GTex), cudaMemcpyHostToDevice));
+    CK(c, r->dTexData.ensure(std::max<size_t>(128, r->texData.size())));
+    if (!r->texData.empty()) CK(c, cudaMemcpy(r->dTexData.p, r->texData.data(), r->texData.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(c, r->dPrograms.ensure(r->programs.size()));
+    CK(c, cudaMemcpy(r->dPrograms.p, r->programs.data(), r->programs.size() * sizeof(GProgram), cudaMemcpyHostToDevice));
+    rs.textures = r->dTextures.p;
+    rs.texData = r->dTexData.p;
+    rs.programs = r->dPrograms.p;
+    rs.nPrograms = nMat;
+  }
   rs.extra = (rs.meshOfTri != nullptr || c->ts.quadMode == 2 || nInfinite > 0 || nMapped > 0 || (r->general && r->hasBlend) ||
-              rs.nVolumes > 0) ? 1 : 0;
+              rs.nVolumes > 0 || rs.nPrograms > 0) ? 1 : 0;
   rs.ntris = nt;
   rs.nprims = np;
   rs.primToRec = r->dPrimToRec.p;
@@ -473,8 +534,16 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
 
 static const int kMaxChainLevels = 16;  // specular recursion depth the chain evaluation covers (maxdepth <= 17)
 
-static void carve(ByteArena& a, Wavefront& wf, uint32_t cap, uint32_t shCap, int nVals, bool chains, bool volumes, uint32_t volMaxSteps) {
+static void carve(ByteArena& a, Wavefront& wf, uint32_t cap, uint32_t shCap, int nVals, bool chains, bool volumes, uint32_t volMaxSteps,
+                  bool programs) {
   wf.cap = cap;
+  if (programs) {  // the BSDF the texture pass builds per slot: 8 lobes (bsdf.dart:253) + the shading frame
+    wf.hitLobes = a.take<GLobe>(8 * (size_t)cap);
+    wf.hitCount = a.take<int32_t>(cap);
+    wf.hitFrame = a.take<float>(6 * (size_t)cap);
+  } else {
+    wf.hitLobes = nullptr; wf.hitCount = nullptr; wf.hitFrame = nullptr;
+  }
   wf.volScratch = nullptr;
   wf.volMaxSteps = volMaxSteps;
   if (volumes) {
@@ -528,7 +597,8 @@ static int ensureWavefront(drt_ctx* c, RenderState* r, uint32_t cap, uint32_t sh
   Wavefront tmp{};
   const bool volumes = !r->volumes.empty();
   const uint32_t volMaxSteps = (volumes && r->volIntegrator == 1) ? r->volMaxSteps : 0;
-  carve(probe, tmp, cap, shCap, r->rp.nVals, chains, volumes, volMaxSteps);
+  const bool programs = !r->programs.empty();
+  carve(probe, tmp, cap, shCap, r->rp.nVals, chains, volumes, volMaxSteps, programs);
   size_t need = probe.used + 256;
   if (need > r->wfBytes) {
     if (r->wfMem) cudaFree(r->wfMem);
@@ -540,7 +610,7 @@ static int ensureWavefront(drt_ctx* c, RenderState* r, uint32_t cap, uint32_t sh
   ByteArena a;
   a.base = r->wfMem;
   a.size = r->wfBytes;
-  carve(a, r->wf, cap, shCap, r->rp.nVals, chains, volumes, volMaxSteps);
+  carve(a, r->wf, cap, shCap, r->rp.nVals, chains, volumes, volMaxSteps, programs);
   r->shCap = shCap;
   return DRT_OK;
 }
@@ -647,6 +717,16 @@ static int prepare(drt_ctx* c, RenderState* r) {
   if (!r->volumes.empty() && p.integKind >= 2 && r->hasSpecular && p.maxDepth > 1)
     return fail(c, DRT_E_UNSUPPORTED, "participating media with the specular recursion of directlighting / whitted (renderer.Li along every "
                                       "reflected ray, integrator.dart:187-290) is not on the GPU path");
+  {  // Sampler.samplesPerPixel as each sampler's constructor hands it to the base class (lib/samplers/*.dart)
+    int sppBase = r->spp;
+    if (p.samplerKind == 0) sppBase = roundUpPow2(r->spp);
+    else if (p.samplerKind == 1) sppBase = p.xs * p.ys;
+    else if (p.samplerKind == 4) sppBase = roundUpPow2(std::max(p.xs, p.ys));
+    p.diffScale = 1.0 / std::sqrt((double)sppBase);  // sampler_renderer.dart:166
+  }
+  if (!r->programs.empty() && p.integKind >= 2 && (r->hasSpecular || r->programsMaySpecular) && p.maxDepth > 1)
+    return fail(c, DRT_E_UNSUPPORTED, "textured / bump-mapped materials with the specular recursion of directlighting / whitted (ray "
+                                      "differentials through SpecularReflect / SpecularTransmit, integrator.dart:203-280) are not on the GPU path");
   if (!r->volumes.empty() && (p.samplerKind == 3 || p.samplerKind == 4 || p.samplerKind == 5))
     return fail(c, DRT_E_UNSUPPORTED, "participating media with the halton / adaptive / bestcandidate samplers is not on the GPU path");
   return DRT_OK;
@@ -727,6 +807,10 @@ static int directStage(drt_ctx* c, RenderState* r, int cur, bool weighted) {
   cudaStream_t st = c->stream;
   const int sms = c->numSMs;
   RenderCounters* rc = r->dCounters.p;
+  if (rs.nPrograms > 0) {  // camera vertices only: prepare() rejects programs together with the specular recursion
+    CK(c, launchTexturePass(p, rs, wf, cur, weighted ? 0 : 1, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
+    c->launches++;
+  }
   CK(c, STAGE(launchDirectSetup)(p, rs, wf, cur, weighted ? 1 : 0, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
   c->launches++;
   if (rs.nLights <= 0) return DRT_OK;
@@ -776,6 +860,10 @@ static int whittedStage(drt_ctx* c, RenderState* r, int cur, bool weighted) {
   cudaStream_t st = c->stream;
   const int sms = c->numSMs;
   RenderCounters* rc = r->dCounters.p;
+  if (rs.nPrograms > 0) {
+    CK(c, launchTexturePass(p, rs, wf, cur, weighted ? 0 : 1, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
+    c->launches++;
+  }
   CK(c, STAGE(launchWhittedSetup)(p, rs, wf, cur, weighted ? 1 : 0, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
   c->launches++;
   int sorted = 0;  // material order measured no gain here (33.7 vs 34.1 ms, cornell_materials 1080p x 16 spp): off unless DRT_WHITTED_SORT is set
@@ -902,6 +990,10 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
     int cur = 0;
     for (int bounce = 0; bounce <= p.maxDepth; ++bounce) {
       CK(c, STAGE(launchResetCounts)(wf, (1u << (cur ^ 1)) | (1u << Q_SHADOW) | (1u << Q_MIS), st)); profMark(c, DRT_PK_OTHER);
+      if (rs.nPrograms > 0) {  // only the camera ray carries differentials: the later rays are RayDifferential.child (path_integrator.dart:100)
+        CK(c, launchTexturePass(p, rs, wf, cur, bounce == 0 ? 1 : 0, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
+        c->launches++;
+      }
       CK(c, STAGE(launchShadePath)(p, rs, wf, bounce, cur, rc, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
       c->launches += 2;
       if (rs.nLights > 0) {
@@ -994,6 +1086,7 @@ static int renderWindow(drt_ctx* c, int x, int y, int w, int h, uint32_t shard, 
   // 16 Mi camera samples in flight (~10 GB of wavefront state): measured on B200, config 4 takes 1063 / 1022 / 1002 / 991 ms at
   // 4 / 8 / 16 / 32 Mi slots (tools/batch_sweep.sh) — fewer, longer launches per bounce
   uint64_t slots = r->batchSlots ? r->batchSlots : (1ull << 24);
+  if (!r->programs.empty()) slots = std::min<uint64_t>(slots, 1ull << 21);  // 8 x 88 B of per-slot BSDF records (texture pass): 1.5 GB
   if (const char* e = std::getenv("DRT_BATCH_SLOTS")) slots = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10));
   if (!r->volumes.empty() && r->volIntegrator == 1)  // the march's sample arrays: 16 bytes x steps per slot, at most ~8 GB
     slots = std::max<uint64_t>(4096, std::min<uint64_t>(slots, (8ull << 30) / (16ull * std::max<uint32_t>(r->volMaxSteps, 1))));
@@ -1249,6 +1342,40 @@ int drt_set_lobe_wrappers(drt_ctx* c, uint32_t n_lobes, const int32_t* wrap, con
     for (int k = 0; k < 3; ++k) l.scale[k] = (wrap[j] & 2) ? scale_rgb[3 * j + k] : 1.f;
   }
   r->sceneTablesValid = false;
+  return DRT_OK;
+}
+
+int drt_set_textures(drt_ctx* c, uint32_t n, const drt_texture* nodes, const float* texels, uint64_t n_texel_floats) {
+  if (!c) return DRT_E_INVALID;
+  if (n > 0 && !nodes) return fail(c, DRT_E_INVALID, "drt_set_textures: nodes is NULL");
+  if (n_texel_floats > 0 && !texels) return fail(c, DRT_E_INVALID, "drt_set_textures: texels is NULL");
+  RenderState* r = state(c);
+  std::vector<GTex> tex;
+  std::vector<float> data;
+  std::string err;
+  if (!buildTextureTables(n, nodes, texels, n_texel_floats, &tex, &data, &err)) {
+    return fail(c, DRT_E_INVALID, ("drt_set_textures: " + err).c_str());
+  }
+  r->textures.swap(tex);
+  r->texData.swap(data);
+  r->sceneTablesValid = false;
+  return DRT_OK;
+}
+
+int drt_set_material_programs(drt_ctx* c, uint32_t n, const drt_material_program* programs) {
+  if (!c) return DRT_E_INVALID;
+  if (n > 0 && !programs) return fail(c, DRT_E_INVALID, "drt_set_material_programs: programs is NULL");
+  RenderState* r = state(c);
+  r->programs.resize(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    GProgram& g = r->programs[i];
+    g.kind = programs[i].kind;
+    for (int k = 0; k < 8; ++k) g.tex[k] = programs[i].tex[k];
+    g.bump = programs[i].bump;
+    g.m1 = programs[i].m1;
+    g.m2 = programs[i].m2;
+  }
+  r->sceneTablesValid = false;  // validated against the material and texture tables when the render starts
   return DRT_OK;
 }
 

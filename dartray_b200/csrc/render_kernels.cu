@@ -578,7 +578,8 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(Ren
           st3(wf.L, cap, slot, L);
         }
       }
-      const typename BsdfOf<GENERAL>::type bsdf = makeBsdfT<GENERAL, EXTRA>(rs, (uint32_t)prim, h, o, d);
+      typename BsdfOf<GENERAL>::type bsdf = makeBsdfT<GENERAL, EXTRA>(rs, (uint32_t)prim, h, o, d);
+      if (GENERAL && EXTRA) applyHitBsdf(rs, wf, slot, &bsdf);
       p = h.p;
       rayEps = h.rayEps;
       const V3 nrm = bsdf.nn;
@@ -917,7 +918,8 @@ __global__ void __launch_bounds__(128) whittedSampleKernel(RenderParams rp, Rend
       const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
       ShapeHit h;
       hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
-      const typename BsdfOf<GENERAL>::type bsdf = makeBsdfT<GENERAL>(rs, (uint32_t)prim, h, o, d);
+      typename BsdfOf<GENERAL>::type bsdf = makeBsdfT<GENERAL>(rs, (uint32_t)prim, h, o, d);
+      if (GENERAL) applyHitBsdf(rs, wf, slot, &bsdf);
       p = h.p;
       rayEps = h.rayEps;
       Stream rng{integratorKey(rp, wf, slot), (uint64_t)wf.aoScramble[slot] + 3ull * (uint64_t)light};
@@ -967,7 +969,8 @@ __global__ void __launch_bounds__(128) specularStepKernel(RenderParams rp, Rende
         const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
         ShapeHit h;
         hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
-        const BsdfG bsdf = makeBsdfG(rs, (uint32_t)prim, h, o, d);
+        BsdfG bsdf = makeBsdfG(rs, (uint32_t)prim, h, o, d);
+        applyHitBsdf(rs, wf, slot, &bsdf);
         double pdf = 0.0;
         int type = 0;
         const Spec f = bsdfSampleF(bsdf, -d, &wi, u0, u1, comp, &pdf, flags, &type);
@@ -1021,7 +1024,8 @@ __global__ void __launch_bounds__(128) directSampleKernel(RenderParams rp, Rende
       const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
       ShapeHit h;
       hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
-      const typename BsdfOf<GENERAL>::type bsdf = makeBsdfT<GENERAL>(rs, (uint32_t)prim, h, o, d);
+      typename BsdfOf<GENERAL>::type bsdf = makeBsdfT<GENERAL>(rs, (uint32_t)prim, h, o, d);
+      if (GENERAL) applyHitBsdf(rs, wf, slot, &bsdf);
       p = h.p;
       rayEps = h.rayEps;
       DirectOffsets off;

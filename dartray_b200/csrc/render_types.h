@@ -90,6 +90,23 @@ struct GVolume {
   uint32_t densityOffset;                  // first value of the grid in RenderScene::volDensity
 };
 
+// One texture node.  Image levels live in RenderScene::texData (floats): level l of the image at levelOffset[l], w >> l x h >> l
+// (at least 1) texels of `channels` floats; texData[0..127] is MIPMap.weightLut (mipmap.dart:168-176).
+struct GTex {
+  int32_t kind, spectrum, tex1, tex2, amount, mapping;
+  int32_t w, h, channels, wrap, trilinear, aa, levels, pad_;
+  uint32_t levelOffset[16];
+  double value[3], value2[9];
+  double su, sv, du, dv, maxAniso;
+  float w2t[16];
+  float v1[3], v2[3];
+};
+struct GProgram {
+  int32_t kind;
+  int32_t tex[8];
+  int32_t bump, m1, m2;
+};
+
 struct RenderScene {
   TraceScene ts;
   uint32_t ntris, nprims;
@@ -119,6 +136,12 @@ struct RenderScene {
   const double* volDensity;
   int32_t volIntegrator;  // 0 emission, 1 single
   double volStep;
+  // textures that read the hit point and the materials built from them (drt_set_textures / drt_set_material_programs):
+  // evaluated by the texture pass (texture_kernels.cu) into Wavefront::hitLobes before a queue is shaded
+  const GTex* textures;
+  const float* texData;
+  const GProgram* programs;  // nPrograms == 0 or one per material
+  int32_t nPrograms;
 };
 
 struct RenderParams {
@@ -145,6 +168,7 @@ struct RenderParams {
   int32_t xs, ys, jitter;
   int32_t nPixelSamples;  // samples per pixel visit
   uint64_t seed;
+  double diffScale;  // 1 / sqrt(sampler.samplesPerPixel): RayDifferential.scaleDifferentials, sampler_renderer.dart:166
   int32_t nVals;  // integrator values per sample (sum n1D + 2 sum n2D)
   int32_t ldAllSingle;  // lowdiscrepancy: every array holds one value per camera sample (path / AO): index-shuffle fast path
   // integrator
@@ -212,6 +236,11 @@ struct Wavefront {
   float* volT; float* volL;  // 3 x cap each
   float* volScratch;         // single scattering: 4 x volMaxSteps x cap (lightNum, lightComp, lightPos x 2 per step), [value][slot]
   uint32_t volMaxSteps;
+  // per slot, textured scenes only: the BSDF the texture pass built for the slot's current vertex (<= 8 lobes, bsdf.dart:253;
+  // frame = dgShading.nn, normalize(dgShading.dpdu) after bump mapping); hitCount < 0: the material has no program
+  GLobe* hitLobes;
+  int32_t* hitCount;
+  float* hitFrame;  // 6 x cap
   int32_t* camPrim;  // adaptive sampler: primitive the slot's camera ray hit (-1: none)
   uint8_t* adaptFlag;  // adaptive sampler, per pixel of the batch: 1 = supersample (the first visit's samples are dropped)
 };

@@ -1148,6 +1148,24 @@ static __device__ inline typename BsdfOf<GENERAL>::type makeBsdfT(const RenderSc
   return MakeBsdf<GENERAL, EXTRA>::make(rs, prim, h, o, d);
 }
 
+// Materials with a program (drt_set_material_programs: textures that read the hit point, bump maps): the BSDF the texture pass
+// (texture_kernels.cu) built for the slot's current vertex replaces the flattened one — frame = dgShading after Material.Bump
+// (bsdf.dart:45-51), lobes as the material's getBSDF added them.  ng stays the geometric normal.
+static __device__ inline void applyHitBsdf(const RenderScene& rs, const Wavefront& wf, uint32_t slot, BsdfG* b) {
+#if DRT_EXTRA
+  if (rs.nPrograms <= 0) return;
+  const int n = wf.hitCount[slot];
+  if (n < 0) return;
+  const size_t cap = wf.cap;
+  b->nn = V3{wf.hitFrame[slot], wf.hitFrame[cap + slot], wf.hitFrame[2 * cap + slot]};
+  b->sn = V3{wf.hitFrame[3 * cap + slot], wf.hitFrame[4 * cap + slot], wf.hitFrame[5 * cap + slot]};
+  b->tn = Cross(b->nn, b->sn);
+  b->lobes = wf.hitLobes + (size_t)slot * 8;
+  b->n = n;
+#endif
+}
+static __device__ inline void applyHitBsdf(const RenderScene&, const Wavefront&, uint32_t, Bsdf*) {}
+
 // ---- lights (diffuse_area_light.dart:44-70, shape_set.dart:43-96, shape.dart:100-121,
 // triangle.dart:265-269,366-383, sphere.dart:243-311, point_light.dart:41-47) --------------------------
 static __device__ inline Spec lightRadiance(const GLight& l) { return Spec{l.L[0], l.L[1], l.L[2]}; }

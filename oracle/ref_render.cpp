@@ -1064,6 +1064,8 @@ struct Ctx {
       dg->p = ray.at(h.t);
       dg->dpdu = dpdu;
       dg->dpdv = dpdv;
+      dg->dndu = Vec();  // dg.set(..., Normal.ZERO, Normal.ZERO, ...), triangle.dart:150
+      dg->dndv = Vec();
     } else if (g.spheres[prim - g.ntris()].shape >= 2) {
       const Sphere& s = g.spheres[prim - g.ntris()];
       Vec phit = h.phitObj;

@@ -81,7 +81,7 @@ def test_gpu_matches_cornell_materials_golden():
     assert np.array_equal(f["weight"], g["path_weight"])
     err = np.abs(f["rgb"] - g["path_rgb"]) / np.maximum(np.abs(g["path_rgb"]), 1e-3)
     print("golden cornell_materials max rel err", err.max())
-    assert np.quantile(err, 0.99) <= 1e-3 and abs(f["rgb"].mean() - g["path_rgb"].mean()) <= 5e-3 * g["path_rgb"].mean()
+    assert err.max() <= 1e-3 and abs(f["rgb"].mean() - g["path_rgb"].mean()) <= 5e-3 * g["path_rgb"].mean()
 
 
 @pytest.mark.gpu
@@ -123,7 +123,7 @@ def test_gpu_matches_feature_golden(name):
     ref = g[name + "_rgb"]
     err = np.abs(f["rgb"] - ref) / np.maximum(np.abs(ref), 1e-3)
     print("golden", name, "max rel err", err.max())
-    assert np.quantile(err, 0.995) <= 1e-3 and abs(f["rgb"].mean() - ref.mean()) <= 5e-3 * ref.mean()
+    assert err.max() <= 1e-3 and abs(f["rgb"].mean() - ref.mean()) <= 5e-3 * ref.mean()
     assert c.render_stats()["camera_samples"] == g[name + "_rays"][0]
     if name.endswith("direct"):
         assert err.max() <= 1e-3
