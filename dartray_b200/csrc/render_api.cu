@@ -469,14 +469,14 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
     if ((int)r->programs.size() != nMat) return fail(c, DRT_E_INVALID, "drt_set_material_programs: one entry per material of the material table");
     if (!r->general) return fail(c, DRT_E_STATE, "material programs go with drt_set_material_lobes (an empty lobe list for a program's material)");
     // which parameter of which plugin is a spectrum texture (the tex[] order documented in include/drt.h)
-    static const int kSlots[10] = {2, 1, 3, 3, 3, 3, 4, 5, 7, 1};
-    static const unsigned kSpectrumMask[10] = {0x1, 0x1, 0x3, 0x3, 0x3, 0x3, 0x3, 0xf, 0x2f, 0x1};
+    static const int kSlots[11] = {2, 1, 3, 3, 3, 3, 4, 5, 7, 1, 2};
+    static const unsigned kSpectrumMask[11] = {0x1, 0x1, 0x3, 0x3, 0x3, 0x3, 0x3, 0xf, 0x2f, 0x1, 0x1};
     const int nTex = (int)r->textures.size();
     r->programsMaySpecular = false;
     for (int m = 0; m < nMat; ++m) {
       const GProgram& pr = r->programs[m];
       if (pr.kind < 0) continue;
-      if (pr.kind > 9) return fail(c, DRT_E_INVALID, "material program kind out of range");
+      if (pr.kind > 10) return fail(c, DRT_E_INVALID, "material program kind out of range");
       for (int k = 0; k < kSlots[pr.kind]; ++k) {
         if (pr.tex[k] < 0 || pr.tex[k] >= nTex) return fail(c, DRT_E_INVALID, "a material program names a texture node drt_set_textures did not define");
         if (r->textures[pr.tex[k]].spectrum != (int)((kSpectrumMask[pr.kind] >> k) & 1u))
@@ -495,7 +495,7 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
         return t.kind == 0 && (float)t.value[0] == v && (float)t.value[1] == v && (float)t.value[2] == v;
       };
       bool spec = false;
-      if (pr.kind == 1) spec = !constantIs(pr.tex[0], 0.f);                                     // mirror: Kr
+      if (pr.kind == 1 || pr.kind == 10) spec = !constantIs(pr.tex[0], 0.f);                    // mirror, subsurface: Kr
       else if (pr.kind == 2) spec = !constantIs(pr.tex[0], 0.f) || !constantIs(pr.tex[1], 0.f);  // glass: Kr, Kt
       else if (pr.kind == 5) spec = !constantIs(pr.tex[1], 0.f);                                 // shinymetal: Kr
       else if (pr.kind == 8) spec = !constantIs(pr.tex[2], 0.f) || !constantIs(pr.tex[3], 0.f) || !constantIs(pr.tex[5], 1.f);  // uber: Kr, Kt, opacity

@@ -6,7 +6,8 @@
 //   full dg of every shape (u, v, dndu, dndv)   lib/shapes/{triangle,sphere,disk,cylinder,cone,paraboloid,hyperboloid}.dart
 //   Triangle.getShadingGeometry                 lib/shapes/triangle.dart:271-364
 //   MIPMap.lookup2 / lookup / EWA / triangle    lib/core/mipmap.dart:183-355
-//   the texture mappings and textures           lib/core/texture/*.dart, lib/textures/{scale,mix,image,checkerboard,uv,bilerp}_texture.dart
+//   the texture mappings and textures           lib/core/texture/*.dart, lib/textures/*.dart (every texture plugin), Noise / FBm /
+//                                               Turbulence lib/core/texture.dart:40-140
 //   Material.Bump                               lib/core/material.dart:35-88
 //   the materials' getBSDF                      lib/materials/*.dart
 // Arithmetic model as everywhere in the shading code (shade_device.cuh header): float32 objects, binary64 expressions.
@@ -547,6 +548,98 @@ static __device__ inline double checkerWeight(const GTex& n, const ST& m, bool* 
   return area2;
 }
 
+// ---- Perlin noise (lib/core/texture.dart:40-140) ----------------------------------------------------------------------------------
+// Ken Perlin's published permutation (the table of his 2002 reference implementation), which texture.dart:142-203 holds twice over
+static __device__ const uint8_t kNoisePerm[256] = {
+    151, 160, 137, 91, 90, 15, 131, 13, 201, 95, 96, 53, 194, 233, 7, 225, 140, 36, 103, 30, 69, 142, 8, 99, 37, 240, 21, 10, 23, 190, 6, 148,
+    247, 120, 234, 75, 0, 26, 197, 62, 94, 252, 219, 203, 117, 35, 11, 32, 57, 177, 33, 88, 237, 149, 56, 87, 174, 20, 125, 136, 171, 168, 68, 175,
+    74, 165, 71, 134, 139, 48, 27, 166, 77, 146, 158, 231, 83, 111, 229, 122, 60, 211, 133, 230, 220, 105, 92, 41, 55, 46, 245, 40, 244, 102, 143, 54,
+    65, 25, 63, 161, 1, 216, 80, 73, 209, 76, 132, 187, 208, 89, 18, 169, 200, 196, 135, 130, 116, 188, 159, 86, 164, 100, 109, 198, 173, 186, 3, 64,
+    52, 217, 226, 250, 124, 123, 5, 202, 38, 147, 118, 126, 255, 82, 85, 212, 207, 206, 59, 227, 47, 16, 58, 17, 182, 189, 28, 42, 223, 183, 170, 213,
+    119, 248, 152, 2, 44, 154, 163, 70, 221, 153, 101, 155, 167, 43, 172, 9, 129, 22, 39, 253, 19, 98, 108, 110, 79, 113, 224, 232, 178, 185, 112, 104,
+    218, 246, 97, 228, 251, 34, 242, 193, 238, 210, 144, 12, 191, 179, 162, 241, 81, 51, 145, 235, 249, 14, 239, 107, 49, 192, 214, 31, 181, 199, 106, 157,
+    184, 84, 204, 176, 115, 121, 50, 45, 127, 4, 150, 254, 138, 236, 205, 93, 222, 114, 67, 29, 24, 72, 243, 141, 128, 195, 78, 66, 215, 61, 156, 180};
+static __device__ inline int noiseP(int i) { return kNoisePerm[i & 255]; }  // _NOISE_PERM has 512 entries: the second half repeats the first
+static __device__ inline double noiseGrad(int x, int y, int z, double dx, double dy, double dz) {  // :119-125
+  int h = noiseP(noiseP(noiseP(x) + y) + z);
+  h &= 15;
+  const double u = (h < 8 || h == 12 || h == 13) ? dx : dy;
+  const double v = (h < 4 || h == 12 || h == 13) ? dy : dz;
+  return ((h & 1) != 0 ? -u : u) + ((h & 2) != 0 ? -v : v);
+}
+static __device__ inline double noiseWeight(double t) {  // :128-132
+  const double t3 = t * t * t, t4 = t3 * t;
+  return 6.0 * t4 * t - 15.0 * t4 + 10.0 * t3;
+}
+static __device__ __noinline__ double NoiseCold(double x, double y, double z) {  // :40-77
+  int ix = (int)floor(x), iy = (int)floor(y), iz = (int)floor(z);
+  const double dx = x - ix, dy = y - iy, dz = z - iz;
+  ix &= 255; iy &= 255; iz &= 255;
+  const double w000 = noiseGrad(ix, iy, iz, dx, dy, dz), w100 = noiseGrad(ix + 1, iy, iz, dx - 1, dy, dz);
+  const double w010 = noiseGrad(ix, iy + 1, iz, dx, dy - 1, dz), w110 = noiseGrad(ix + 1, iy + 1, iz, dx - 1, dy - 1, dz);
+  const double w001 = noiseGrad(ix, iy, iz + 1, dx, dy, dz - 1), w101 = noiseGrad(ix + 1, iy, iz + 1, dx - 1, dy, dz - 1);
+  const double w011 = noiseGrad(ix, iy + 1, iz + 1, dx, dy - 1, dz - 1), w111 = noiseGrad(ix + 1, iy + 1, iz + 1, dx - 1, dy - 1, dz - 1);
+  const double wx = noiseWeight(dx), wy = noiseWeight(dy), wz = noiseWeight(dz);
+  const double x00 = LerpD(wx, w000, w100), x10 = LerpD(wx, w010, w110), x01 = LerpD(wx, w001, w101), x11 = LerpD(wx, w011, w111);
+  const double y0 = LerpD(wy, x00, x10), y1 = LerpD(wy, x01, x11);
+  return LerpD(wz, y0, y1);
+}
+static __device__ inline double NoisePoint(const V3& p) { return NoiseCold((double)p.x, (double)p.y, (double)p.z); }
+static __device__ inline double SmoothStep(double mn, double mx, double value) {  // common.dart:131-134
+  const double v = clampD((value - mn) / (mx - mn), 0.0, 1.0);
+  return v * v * (-2.0 * v + 3.0);
+}
+// FBm (:81-102) and Turbulence (:104-129): `turbulence` sums |noise| and adds 0.2 per octave that was cut
+static __device__ __noinline__ double fbmCold(V3 Pt, V3 dpdx, V3 dpdy, double omega, int maxOctaves, bool turbulence) {
+  const double s2 = fmax(LengthSquared(dpdx), LengthSquared(dpdy));
+  const double foctaves = fmin((double)maxOctaves, fmax(0.0, -1.0 - 0.5 * Log2d(s2)));
+  const int octaves = (int)floor(foctaves);
+  double sum = 0.0, lambda = 1.0, o = 1.0;
+  for (int i = 0; i < octaves; ++i) {
+    const double nz = NoisePoint(Pt * lambda);
+    sum += o * (turbulence ? fabs(nz) : nz);
+    lambda *= 1.99;
+    o *= omega;
+  }
+  const double partialOctave = foctaves - octaves;
+  const double nz = NoisePoint(Pt * lambda);
+  sum += o * SmoothStep(0.3, 0.7, partialOctave) * (turbulence ? fabs(nz) : nz);
+  if (turbulence) sum += (maxOctaves - foctaves) * 0.2;
+  return sum;
+}
+// IdentityMapping3D.map (identity_mapping_3d.dart:25-29)
+static __device__ inline V3 map3D(const GTex& n, const FullDG& dg, V3* dpdx, V3* dpdy) {
+  *dpdx = XfVector(n.w2t, dg.dpdx);
+  *dpdy = XfVector(n.w2t, dg.dpdy);
+  return XfPoint(n.w2t, dg.p);
+}
+// 7 fbm (fbm_texture.dart:26-32), 8 wrinkled (wrinkled_texture.dart:26-32), 9 windy (windy_texture.dart:26-38)
+static __device__ inline double noiseScalar(const GTex& n, const FullDG& dg) {
+  V3 dpdx, dpdy;
+  const V3 Pt = map3D(n, dg, &dpdx, &dpdy);
+  if (n.kind == 7) return fbmCold(Pt, dpdx, dpdy, n.value[0], n.aa, false);
+  if (n.kind == 8) return fbmCold(Pt, dpdx, dpdy, n.value[0], n.aa, true);
+  const double windStrength = fbmCold(Pt * 0.1, dpdx * 0.1, dpdy * 0.1, 0.5, 3, false);
+  const double waveHeight = fbmCold(Pt, dpdx, dpdy, 0.5, 6, false);
+  return fabs(windStrength) * waveHeight;
+}
+static __device__ inline bool insideDot(double s, double t) {  // dots_texture.dart:26-52
+  const int sCell = (int)floor(s + 0.5), tCell = (int)floor(t + 0.5);
+  if (NoiseCold(sCell + 0.5, tCell + 0.5, 0.5) > 0) {
+    const double radius = 0.35, maxShift = 0.5 - radius;
+    const double sCenter = sCell + maxShift * NoiseCold(sCell + 1.5, tCell + 2.8, 0.5);
+    const double tCenter = tCell + maxShift * NoiseCold(sCell + 4.5, tCell + 9.8, 0.5);
+    const double ds = s - sCenter, dt = t - tCenter;
+    if (ds * ds + dt * dt < radius * radius) return true;
+  }
+  return false;
+}
+static __device__ inline bool checker3D(const GTex& n, const FullDG& dg) {  // checkerboard_3d_texture.dart:26-35: true = tex1
+  V3 dpdx, dpdy;
+  const V3 p = map3D(n, dg, &dpdx, &dpdy);
+  return dartModLL((long long)floor((double)p.x) + (long long)floor((double)p.y) + (long long)floor((double)p.z), 2) == 0;
+}
+
 // ---- Texture.evaluate (recursive over the node table: depth bounded by the host, children precede parents) ------------------
 static __device__ double texEvalF(const TexCtx& c, int id, const FullDG& dg);
 static __device__ void texEvalS(const TexCtx& c, int id, const FullDG& dg, Spec* out);
@@ -586,6 +679,13 @@ static __device__ __noinline__ double texEvalF(const TexCtx& c, int id, const Fu
       const double s = m.s, t = m.t;
       return n.value[0] * ((1.0 - s) * (1 - t)) + n.value2[0] * (1.0 - s) * t + n.value2[3] * s * (1.0 - t) + n.value2[6] * s * t;
     }
+    case 7: case 8: case 9: return noiseScalar(n, dg);
+    case 11: {  // DotsTexture(mapping, outsideDot = tex1, insideDot = tex2)
+      ST m;
+      mapSTCold(n, dg, &m);
+      return texEvalF(c, insideDot(m.s, m.t) ? n.tex2 : n.tex1, dg);
+    }
+    case 12: return texEvalF(c, checker3D(n, dg) ? n.tex1 : n.tex2, dg);
     default: return 0.0;
   }
 }
@@ -647,6 +747,37 @@ static __device__ __noinline__ void texEvalS(const TexCtx& c, int id, const Full
       *out = v00 * ((1.0 - s) * (1 - t)) + v01 * (1.0 - s) * t + v10 * s * (1.0 - t) + v11 * s * t;
       return;
     }
+    case 7: case 8: case 9: *out = mks1(noiseScalar(n, dg)); return;  // new Spectrum(n)
+    case 10: {  // marble_texture.dart:27-66
+      V3 dpdx, dpdy;
+      V3 Pt = map3D(n, dg, &dpdx, &dpdy);
+      const double scale = n.value[1], variation = n.value[2];
+      Pt = Pt * scale;
+      const double marble = (double)Pt.y + variation * fbmCold(Pt, dpdx * scale, dpdy * scale, n.value[0], n.aa, false);
+      double t = 0.5 + 0.5 * sin(marble);
+      const double cs[27] = {0.58, 0.58, 0.6, 0.58, 0.58, 0.6, 0.58, 0.58, 0.6, 0.5, 0.5, 0.5, 0.6, 0.59, 0.58,
+                             0.58, 0.58, 0.6, 0.58, 0.58, 0.6, 0.2, 0.2, 0.33, 0.58, 0.58, 0.6};
+      const int NSEG = 9 - 3;
+      const int first = (int)floor(t * NSEG);
+      t = (t * NSEG - first);
+      const int ci = first * 3;
+      const Spec c0 = mks(cs[ci], cs[ci + 1], cs[ci + 2]), c1 = mks(cs[ci + 3], cs[ci + 4], cs[ci + 5]), c2 = mks(cs[ci + 6], cs[ci + 7], cs[ci + 8]),
+                 c3 = mks(cs[ci + 9], cs[ci + 10], cs[ci + 11]);
+      Spec s0 = c0 * (1.0 - t) + c1 * t;
+      Spec s1 = c1 * (1.0 - t) + c2 * t;
+      const Spec s2 = c2 * (1.0 - t) + c3 * t;
+      s0 = s0 * (1.0 - t) + s1 * t;
+      s1 = s1 * (1.0 - t) + s2 * t;
+      *out = (s0 * (1.0 - t) + s1 * t) * 1.5;
+      return;
+    }
+    case 11: {
+      ST m;
+      mapSTCold(n, dg, &m);
+      texEvalS(c, insideDot(m.s, m.t) ? n.tex2 : n.tex1, dg, out);
+      return;
+    }
+    case 12: texEvalS(c, checker3D(n, dg) ? n.tex1 : n.tex2, dg, out); return;
     default: *out = Spec{0.f, 0.f, 0.f};
   }
 }
@@ -803,6 +934,12 @@ static __device__ __noinline__ void materialBsdfCold(const RenderScene& rs, cons
         if (!IsBlack(r)) add(mkLobe(2, r * ks, 1, e, 1.5, 1.0));
         if (!IsBlack(tr)) { GLobe l = mkLobe(2, tr * ks, 1, e, 1.5, 1.0); l.wrap = 1; add(l); }
       }
+      break;
+    }
+    case 10: {  // subsurface_material.dart:52-69, kd_subsurface_material.dart:48-67 (the BSSRDF is the dipole integrator's)
+      const Spec R = clampS(S(t[0], dgs));
+      const double e = texEvalF(c, t[1], dgs);
+      if (!IsBlack(R)) add(mkLobe(3, R, 1, 0.0, 1.0, e));
       break;
     }
     default: {  // 8 uber_material.dart:56-104

@@ -44,16 +44,17 @@ bool buildTextureTables(uint32_t n, const drt_texture* nodes, const float* texel
     t.maxAniso = d.max_anisotropy;
     for (int k = 0; k < 16; ++k) t.w2t[k] = d.world_to_texture[k];
     for (int k = 0; k < 3; ++k) { t.v1[k] = d.v1[k]; t.v2[k] = d.v2[k]; }
-    if (d.kind < 0 || d.kind > 6 || d.mapping < 0 || d.mapping > 3) { *err = "texture kind / mapping out of range"; return false; }
+    if (d.kind < 0 || d.kind > 12 || d.mapping < 0 || d.mapping > 4) { *err = "texture kind / mapping out of range"; return false; }
     for (int child : {d.tex1, d.tex2, d.amount})
       if (child >= (int)i) { *err = "a texture node may only reference earlier nodes"; return false; }
-    const bool two = d.kind == 1 || d.kind == 2 || d.kind == 4;
+    const bool two = d.kind == 1 || d.kind == 2 || d.kind == 4 || d.kind == 11 || d.kind == 12;
     if (two && (d.tex1 < 0 || d.tex2 < 0 || nodes[d.tex1].spectrum != d.spectrum || nodes[d.tex2].spectrum != d.spectrum)) {
-      *err = "scale / mix / checkerboard need two children of their own type";
+      *err = "scale / mix / checkerboard / dots need two children of their own type";
       return false;
     }
     if (d.kind == 2 && (d.amount < 0 || nodes[d.amount].spectrum != 0)) { *err = "mix needs a float texture as amount"; return false; }
-    if (d.kind == 5 && !d.spectrum) { *err = "'uv' has no float form (uv_texture.dart:39-41)"; return false; }
+    if ((d.kind == 5 || d.kind == 10) && !d.spectrum) { *err = "'uv' and 'marble' have no float form (uv_texture.dart:39-41, marble_texture.dart:68-70)"; return false; }
+    if ((d.kind == 7 || d.kind == 8 || d.kind == 10) && (d.aa_method < 0 || d.aa_method > 64)) { *err = "noise texture: octaves out of range"; return false; }
     if (d.kind == 3) {
       const int W = d.image_width, H = d.image_height, ch = d.image_channels;
       if (W < 1 || H < 1 || (W & (W - 1)) || (H & (H - 1)) || W > 32768 || H > 32768 || (ch != 1 && ch != 3)) {

@@ -411,6 +411,50 @@ class BilerpTexture(HitPointTexture):  # bilerp_texture.dart
         self.v, self.mapping = (v00, v01, v10, v11), mapping or UVMapping()
 
 
+class _Noise3D(HitPointTexture):
+    """Textures over IdentityMapping3D (identity_mapping_3d.dart): `mapping_transform` is the Transform the mapping holds — the
+    plugins' Create functions hand it tex2world as it is."""
+    kind = 7
+
+    def __init__(self, octaves=8, roughness=0.5, mapping_transform=None):
+        self.octaves, self.roughness = int(octaves), float(roughness)
+        self.w2t = np.eye(4, dtype=np.float32) if mapping_transform is None else mapping_transform
+
+
+class FBmTexture(_Noise3D):  # fbm_texture.dart
+    kind = 7
+
+
+class WrinkledTexture(_Noise3D):  # wrinkled_texture.dart
+    kind = 8
+
+
+class WindyTexture(_Noise3D):  # windy_texture.dart
+    kind = 9
+
+    def __init__(self, mapping_transform=None):
+        super().__init__(0, 0.0, mapping_transform)
+
+
+class MarbleTexture(_Noise3D):  # marble_texture.dart (spectrum only)
+    kind = 10
+
+    def __init__(self, octaves=8, roughness=0.5, scale=1.0, variation=0.2, mapping_transform=None):
+        super().__init__(octaves, roughness, mapping_transform)
+        self.scale, self.variation = float(scale), float(variation)
+
+
+class DotsTexture(HitPointTexture):  # dots_texture.dart
+    def __init__(self, inside=1.0, outside=0.0, mapping=None):
+        self.inside, self.outside, self.mapping = as_texture(inside), as_texture(outside), mapping or UVMapping()
+
+
+class Checkerboard3DTexture(HitPointTexture):  # checkerboard_3d_texture.dart
+    def __init__(self, tex1=1.0, tex2=0.0, mapping_transform=None):
+        self.tex1, self.tex2 = as_texture(tex1), as_texture(tex2)
+        self.w2t = np.eye(4, dtype=np.float32) if mapping_transform is None else mapping_transform
+
+
 def is_constant_texture(v) -> bool:
     if not isinstance(v, Texture):
         return True
@@ -477,6 +521,18 @@ class TextureTable:
                 raise GpuUnsupported("'uv' has no float form (uv_texture.dart:39-41)")
             n["kind"] = 5
             self._mapping(n, v.mapping)
+        elif isinstance(v, _Noise3D):
+            if v.kind == 10 and not spectrum:
+                raise GpuUnsupported("'marble' has no float form (marble_texture.dart:68-70)")
+            n["kind"], n["aa_method"], n["mapping"] = v.kind, v.octaves, 4
+            n["value"] = (v.roughness, getattr(v, "scale", 0.0), getattr(v, "variation", 0.0))
+            n["world_to_texture"] = _m(v.w2t).reshape(16)
+        elif isinstance(v, DotsTexture):
+            n["kind"], n["tex1"], n["tex2"] = 11, self.add(v.outside, spectrum), self.add(v.inside, spectrum)
+            self._mapping(n, v.mapping)
+        elif isinstance(v, Checkerboard3DTexture):
+            n["kind"], n["tex1"], n["tex2"], n["mapping"] = 12, self.add(v.tex1, spectrum), self.add(v.tex2, spectrum), 4
+            n["world_to_texture"] = _m(v.w2t).reshape(16)
         elif isinstance(v, BilerpTexture):
             n["kind"] = 6
             vals = [np.broadcast_to(np.asarray(x, np.float64), (3,)) for x in v.v]
@@ -507,6 +563,8 @@ PROGRAM_PARAMS = {
     "uber": (8, (("kd", True, 0.25), ("ks", True, 0.25), ("kr", True, 0.0), ("kt", True, 0.0), ("roughness", False, 0.1),
                  ("opacity", True, 1.0), ("index", False, 1.5))),
     "mix": (9, (("amount", True, 0.5),)),
+    "subsurface": (10, (("kr", True, 1.0), ("index", False, 1.3))),
+    "kdsubsurface": (10, (("kr", True, 1.0), ("index", False, 1.3))),
 }
 
 
@@ -647,6 +705,14 @@ def substrate_lobes(kd=0.5, ks=0.5, uroughness=0.1, vroughness=0.1) -> list:  # 
 @_folds_textures
 def metal_lobes(eta, k, roughness=0.01) -> list:  # metal_material.dart:26-46 (eta / k given as RGB)
     return [_lobe(LOBE_MICROFACET_BLINN, 1.0, FRESNEL_CONDUCTOR, eta=eta, k=k, param=_blinn_exponent(roughness))]
+
+
+@_folds_textures
+def subsurface_lobes(kr=1.0, index=1.3) -> list:  # subsurface_material.dart:52-69, kd_subsurface_material.dart:48-67
+    """The BSDF of both subsurface materials is one SpecularReflection(Kr, FresnelDielectric(1, index)); their BSSRDF is read by the
+    dipole integrator only, which is not on the path."""
+    r = _clamp(kr)
+    return [] if _black(r) else [_lobe(LOBE_SPECULAR_REFLECTION, r, FRESNEL_DIELECTRIC, ei=1.0, et=index)]
 
 
 @_folds_textures

@@ -252,6 +252,13 @@ int drt_set_lobe_wrappers(drt_ctx* ctx, uint32_t n_lobes, const int32_t* wrap, c
  *   kind 4 CheckerboardTexture, dimension 2 (checkerboard_texture.dart:29-75)   mapping, tex1, tex2, aa_method (0 none, 1 closedform)
  *   kind 5 UVTexture       (uv_texture.dart:26-37)                              mapping
  *   kind 6 BilerpTexture   (bilerp_texture.dart:26-40)                          mapping, value = v00, value2 = v01, v10, v11
+ *   kind 7 FBmTexture / 8 WrinkledTexture (fbm_texture.dart, wrinkled_texture.dart)   world_to_texture, aa_method = octaves, value[0] = roughness
+ *   kind 9 WindyTexture    (windy_texture.dart:26-38)                           world_to_texture
+ *   kind 10 MarbleTexture  (marble_texture.dart:27-66; spectrum only)           world_to_texture, aa_method = octaves, value = roughness, scale, variation
+ *   kind 11 DotsTexture    (dots_texture.dart:26-52)                            mapping, tex1 = outside, tex2 = inside
+ *   kind 12 CheckerboardTexture, dimension 3 (checkerboard_3d_texture.dart)     world_to_texture, tex1, tex2
+ *   (7-10, 12 go through IdentityMapping3D, identity_mapping_3d.dart: world_to_texture is the Transform the mapping holds — the
+ *   plugins hand it tex2world as it is; Noise / FBm / Turbulence: lib/core/texture.dart:40-140)
  * spectrum: 0 = Texture<double> (values are Dart doubles; value[0]), 1 = Texture<Spectrum> (float32 RGB per operation).
  * mapping: 0 UVMapping2D (lib/core/texture/uv_mapping_2d.dart; su, sv, du, dv), 1 SphericalMapping2D, 2 CylindricalMapping2D
  * (world_to_texture, row-major), 3 PlanarMapping2D (v1, v2, du = ds, dv = dt).
@@ -286,6 +293,8 @@ int drt_set_textures(drt_ctx* ctx, uint32_t n, const drt_texture* nodes, const f
  *   2 glass        Kr, Kt, index                     7 translucent  Kd, Ks, reflect, transmit, roughness
  *   3 plastic      Kd, Ks, roughness                 8 uber         Kd, Ks, Kr, Kt, roughness, opacity, index
  *   4 metal        eta, k, roughness                 9 mix          amount; m1 / m2 = material indices (one level)
+ *   10 subsurface / kdsubsurface   Kr, index  (their BSDF is SpecularReflection(Kr, FresnelDielectric(1, index)),
+ *      subsurface_material.dart:52-69; the BSSRDF belongs to the dipole integrator, which is not on the path)
  * bump: a float texture node or -1.  n == 0 removes the programs. */
 typedef struct drt_material_program {
   int32_t kind;

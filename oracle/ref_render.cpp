@@ -1295,6 +1295,13 @@ struct Ctx {
         }
         break;
       }
+      case 10: {  // subsurface_material.dart:52-69, kd_subsurface_material.dart:48-67 (the BSSRDF is the dipole integrator's)
+        frameBsdf(b, dgs, dgGeom.nn, 1.0);
+        Spec R = clampS(texS(t[0], dgs));
+        double e = texF(t[1], dgs);
+        if (!R.isBlack()) addLobe(b, mkLobe(3, R, 1, 0.0, 1.0, e));
+        break;
+      }
       default: {  // 8 uber_material.dart:56-104
         frameBsdf(b, dgs, dgGeom.nn, 1.0);
         Spec op = clampS(texS(t[5], dgs));

@@ -363,6 +363,114 @@ double checkerWeight(const TextureNode& n, const ST& m, bool* single) {
 }
 }  // namespace
 
+// ---- Perlin noise (lib/core/texture.dart:40-140) ----------------------------------------------------------------------------------
+namespace {
+// Ken Perlin's published permutation (the table of his 2002 reference implementation), which texture.dart:142-203 holds twice over
+const uint8_t kNoisePerm[256] = {
+    151, 160, 137, 91, 90, 15, 131, 13, 201, 95, 96, 53, 194, 233, 7, 225, 140, 36, 103, 30, 69, 142, 8, 99, 37, 240, 21, 10, 23, 190, 6, 148,
+    247, 120, 234, 75, 0, 26, 197, 62, 94, 252, 219, 203, 117, 35, 11, 32, 57, 177, 33, 88, 237, 149, 56, 87, 174, 20, 125, 136, 171, 168, 68, 175,
+    74, 165, 71, 134, 139, 48, 27, 166, 77, 146, 158, 231, 83, 111, 229, 122, 60, 211, 133, 230, 220, 105, 92, 41, 55, 46, 245, 40, 244, 102, 143, 54,
+    65, 25, 63, 161, 1, 216, 80, 73, 209, 76, 132, 187, 208, 89, 18, 169, 200, 196, 135, 130, 116, 188, 159, 86, 164, 100, 109, 198, 173, 186, 3, 64,
+    52, 217, 226, 250, 124, 123, 5, 202, 38, 147, 118, 126, 255, 82, 85, 212, 207, 206, 59, 227, 47, 16, 58, 17, 182, 189, 28, 42, 223, 183, 170, 213,
+    119, 248, 152, 2, 44, 154, 163, 70, 221, 153, 101, 155, 167, 43, 172, 9, 129, 22, 39, 253, 19, 98, 108, 110, 79, 113, 224, 232, 178, 185, 112, 104,
+    218, 246, 97, 228, 251, 34, 242, 193, 238, 210, 144, 12, 191, 179, 162, 241, 81, 51, 145, 235, 249, 14, 239, 107, 49, 192, 214, 31, 181, 199, 106, 157,
+    184, 84, 204, 176, 115, 121, 50, 45, 127, 4, 150, 254, 138, 236, 205, 93, 222, 114, 67, 29, 24, 72, 243, 141, 128, 195, 78, 66, 215, 61, 156, 180};
+inline int P(int i) { return kNoisePerm[i & 255]; }  // _NOISE_PERM has 512 entries: the second half repeats the first
+inline double Grad(int x, int y, int z, double dx, double dy, double dz) {  // :119-125
+  int h = P(P(P(x) + y) + z);
+  h &= 15;
+  double u = (h < 8 || h == 12 || h == 13) ? dx : dy;
+  double v = (h < 4 || h == 12 || h == 13) ? dy : dz;
+  return ((h & 1) != 0 ? -u : u) + ((h & 2) != 0 ? -v : v);
+}
+inline double NoiseWeight(double t) {  // :128-132
+  double t3 = t * t * t, t4 = t3 * t;
+  return 6.0 * t4 * t - 15.0 * t4 + 10.0 * t3;
+}
+inline double LerpN(double t, double a, double b) { return (1.0 - t) * a + t * b; }  // common.dart:80-81
+double Noise(double x, double y = 0.5, double z = 0.5) {  // :40-77
+  int ix = (int)std::floor(x), iy = (int)std::floor(y), iz = (int)std::floor(z);
+  double dx = x - ix, dy = y - iy, dz = z - iz;
+  ix &= 255; iy &= 255; iz &= 255;
+  double w000 = Grad(ix, iy, iz, dx, dy, dz), w100 = Grad(ix + 1, iy, iz, dx - 1, dy, dz);
+  double w010 = Grad(ix, iy + 1, iz, dx, dy - 1, dz), w110 = Grad(ix + 1, iy + 1, iz, dx - 1, dy - 1, dz);
+  double w001 = Grad(ix, iy, iz + 1, dx, dy, dz - 1), w101 = Grad(ix + 1, iy, iz + 1, dx - 1, dy, dz - 1);
+  double w011 = Grad(ix, iy + 1, iz + 1, dx, dy - 1, dz - 1), w111 = Grad(ix + 1, iy + 1, iz + 1, dx - 1, dy - 1, dz - 1);
+  double wx = NoiseWeight(dx), wy = NoiseWeight(dy), wz = NoiseWeight(dz);
+  double x00 = LerpN(wx, w000, w100), x10 = LerpN(wx, w010, w110), x01 = LerpN(wx, w001, w101), x11 = LerpN(wx, w011, w111);
+  double y0 = LerpN(wy, x00, x10), y1 = LerpN(wy, x01, x11);
+  return LerpN(wz, y0, y1);
+}
+inline double NoisePoint(const Vec& p) { return Noise(p.x, p.y, p.z); }
+inline double SmoothStep(double mn, double mx, double value) {  // common.dart:131-134
+  double v = clampd((value - mn) / (mx - mn), 0.0, 1.0);
+  return v * v * (-2.0 * v + 3.0);
+}
+double FBm(const Vec& Pt, const Vec& dpdx, const Vec& dpdy, double omega, int maxOctaves) {  // :81-102
+  double s2 = std::fmax(LengthSquared(dpdx), LengthSquared(dpdy));
+  double log2_s2 = Log2d(s2);
+  double foctaves = std::fmin((double)maxOctaves, std::fmax(0.0, -1.0 - 0.5 * log2_s2));
+  int octaves = (int)std::floor(foctaves);
+  double sum = 0.0, lambda = 1.0, o = 1.0;
+  for (int i = 0; i < octaves; ++i) {
+    sum += o * NoisePoint(Pt * lambda);
+    lambda *= 1.99;
+    o *= omega;
+  }
+  double partialOctave = foctaves - octaves;
+  sum += o * SmoothStep(0.3, 0.7, partialOctave) * NoisePoint(Pt * lambda);
+  return sum;
+}
+double Turbulence(const Vec& Pt, const Vec& dpdx, const Vec& dpdy, double omega, int maxOctaves) {  // :104-129
+  double s2 = std::fmax(LengthSquared(dpdx), LengthSquared(dpdy));
+  double foctaves = std::fmin((double)maxOctaves, std::fmax(0.0, -1.0 - 0.5 * Log2d(s2)));
+  int octaves = (int)std::floor(foctaves);
+  double sum = 0.0, lambda = 1.0, o = 1.0;
+  for (int i = 0; i < octaves; ++i) {
+    sum += o * std::fabs(NoisePoint(Pt * lambda));
+    lambda *= 1.99;
+    o *= omega;
+  }
+  double partialOctave = foctaves - octaves;
+  sum += o * SmoothStep(0.3, 0.7, partialOctave) * std::fabs(NoisePoint(Pt * lambda));
+  sum += (maxOctaves - foctaves) * 0.2;
+  return sum;
+}
+// IdentityMapping3D.map (identity_mapping_3d.dart:25-29)
+inline Vec map3D(const TextureNode& n, const DG& dg, Vec* dpdx, Vec* dpdy) {
+  *dpdx = n.worldToTexture.vector(dg.dpdx);
+  *dpdy = n.worldToTexture.vector(dg.dpdy);
+  return n.worldToTexture.point(dg.p);
+}
+// the scalar of the noise textures: 7 fbm (fbm_texture.dart:26-32), 8 wrinkled (wrinkled_texture.dart:26-32), 9 windy (windy_texture.dart:26-38)
+double noiseScalar(const TextureNode& n, const DG& dg) {
+  Vec dpdx, dpdy;
+  Vec Pt = map3D(n, dg, &dpdx, &dpdy);
+  if (n.kind == 7) return FBm(Pt, dpdx, dpdy, n.value[0], n.aaMethod);
+  if (n.kind == 8) return Turbulence(Pt, dpdx, dpdy, n.value[0], n.aaMethod);
+  double windStrength = FBm(Pt * 0.1, dpdx * 0.1, dpdy * 0.1, 0.5, 3);
+  double waveHeight = FBm(Pt, dpdx, dpdy, 0.5, 6);
+  return std::fabs(windStrength) * waveHeight;
+}
+// dots_texture.dart:26-52: true = inside a dot
+bool insideDot(double s, double t) {
+  int sCell = (int)std::floor(s + 0.5), tCell = (int)std::floor(t + 0.5);
+  if (Noise(sCell + 0.5, tCell + 0.5) > 0) {
+    double radius = 0.35, maxShift = 0.5 - radius;
+    double sCenter = sCell + maxShift * Noise(sCell + 1.5, tCell + 2.8);
+    double tCenter = tCell + maxShift * Noise(sCell + 4.5, tCell + 9.8);
+    double ds = s - sCenter, dt = t - tCenter;
+    if (ds * ds + dt * dt < radius * radius) return true;
+  }
+  return false;
+}
+bool checker3D(const TextureNode& n, const DG& dg) {  // checkerboard_3d_texture.dart:26-35: true = tex1
+  Vec dpdx, dpdy;
+  Vec p = map3D(n, dg, &dpdx, &dpdy);
+  return dartMod((int64_t)std::floor((double)p.x) + (int64_t)std::floor((double)p.y) + (int64_t)std::floor((double)p.z), 2) == 0;
+}
+}  // namespace
+
 // ---- textures -----------------------------------------------------------------------------------------------
 double TextureSet::evalFloat(int id, const DG& dg) const {
   const TextureNode& n = nodes[(size_t)id];
@@ -391,6 +499,12 @@ double TextureSet::evalFloat(int id, const DG& dg) const {
       const double s = m.s, t = m.t;
       return n.value[0] * ((1.0 - s) * (1 - t)) + n.value2[0] * (1.0 - s) * t + n.value2[3] * s * (1.0 - t) + n.value2[6] * s * t;
     }
+    case 7: case 8: case 9: return noiseScalar(n, dg);
+    case 11: {  // DotsTexture(mapping, outsideDot = tex1, insideDot = tex2)
+      const ST m = mapST(n, dg);
+      return evalFloat(insideDot(m.s, m.t) ? n.tex2 : n.tex1, dg);
+    }
+    case 12: return evalFloat(checker3D(n, dg) ? n.tex1 : n.tex2, dg);
     default: return 0.0;
   }
 }
@@ -456,6 +570,39 @@ void TextureSet::evalSpec(int id, const DG& dg, float out[3]) const {
       addS(a, c, out);
       return;
     }
+    case 7: case 8: case 9: {  // new Spectrum(n)
+      out[0] = out[1] = out[2] = f32(noiseScalar(n, dg));
+      return;
+    }
+    case 10: {  // marble_texture.dart:27-66
+      Vec dpdx, dpdy;
+      Vec Pt = map3D(n, dg, &dpdx, &dpdy);
+      const double scale = n.value[1], variation = n.value[2];
+      Pt = Pt * scale;
+      double marble = (double)Pt.y + variation * FBm(Pt, dpdx * scale, dpdy * scale, n.value[0], n.aaMethod);
+      double t = 0.5 + 0.5 * std::sin(marble);
+      static const double c[27] = {0.58, 0.58, 0.6, 0.58, 0.58, 0.6, 0.58, 0.58, 0.6, 0.5, 0.5, 0.5, 0.6, 0.59, 0.58,
+                                   0.58, 0.58, 0.6, 0.58, 0.58, 0.6, 0.2, 0.2, 0.33, 0.58, 0.58, 0.6};
+      const int NSEG = 9 - 3;
+      int first = (int)std::floor(t * NSEG);
+      t = (t * NSEG - first);
+      const int ci = first * 3;
+      float c0[3], c1[3], c2[3], c3[3], s0[3], s1[3], s2[3], a[3], b[3];
+      for (int k = 0; k < 3; ++k) { c0[k] = f32(c[ci + k]); c1[k] = f32(c[ci + 3 + k]); c2[k] = f32(c[ci + 6 + k]); c3[k] = f32(c[ci + 9 + k]); }
+      auto bez = [&](const float* x, const float* y, float* o) { mulS(x, 1.0 - t, a); mulS(y, t, b); addS(a, b, o); };
+      bez(c0, c1, s0); bez(c1, c2, s1); bez(c2, c3, s2);
+      float r0[3], r1[3], r[3];
+      bez(s0, s1, r0); bez(s1, s2, r1);
+      bez(r0, r1, r);
+      mulS(r, 1.5, out);
+      return;
+    }
+    case 11: {
+      const ST m = mapST(n, dg);
+      evalSpec(insideDot(m.s, m.t) ? n.tex2 : n.tex1, dg, out);
+      return;
+    }
+    case 12: evalSpec(checker3D(n, dg) ? n.tex1 : n.tex2, dg, out); return;
     default:
       out[0] = out[1] = out[2] = 0.f;
   }

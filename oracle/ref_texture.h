@@ -7,7 +7,9 @@
 //                               lookup2 / EWA :224-339, triangle :341-355)
 //   texture mappings            lib/core/texture/{uv,spherical,cylindrical,planar}_mapping_2d.dart
 //   textures                    lib/core/texture/constant_texture.dart, lib/textures/{scale,mix,image}_texture.dart,
-//                               checkerboard_texture.dart, uv_texture.dart, bilerp_texture.dart
+//                               checkerboard_texture.dart, uv_texture.dart, bilerp_texture.dart, and the noise textures
+//                               {fbm,wrinkled,windy,marble,dots}_texture.dart, checkerboard_3d_texture.dart over Noise / FBm /
+//                               Turbulence (lib/core/texture.dart:40-140) and IdentityMapping3D
 //   Material.Bump               lib/core/material.dart:35-88
 //   the materials' getBSDF      lib/materials/{matte,mirror,glass,plastic,metal,shiny_metal,substrate,translucent,uber,mix}
 //                               _material.dart with textures that read the hit point
@@ -64,7 +66,8 @@ struct TexImage {
 };
 
 struct TextureNode {
-  int kind = 0;       // 0 constant, 1 scale, 2 mix, 3 imagemap, 4 checkerboard (2D), 5 uv, 6 bilerp
+  int kind = 0;       // 0 constant, 1 scale, 2 mix, 3 imagemap, 4 checkerboard (2D), 5 uv, 6 bilerp, 7 fbm, 8 wrinkled, 9 windy,
+                      // 10 marble, 11 dots, 12 checkerboard (3D): aaMethod = octaves, value = (roughness, scale, variation)
   int spectrum = 0;   // 0: Texture<double>, 1: Texture<Spectrum>
   int tex1 = -1, tex2 = -1, amount = -1;
   double value[3] = {0, 0, 0};  // constant; bilerp: v00 (then value2: v01, v10, v11)
@@ -83,6 +86,7 @@ struct TextureNode {
 //   2 glass        Kr, Kt, index                     7 translucent  Kd, Ks, reflect, transmit, roughness
 //   3 plastic      Kd, Ks, roughness                 8 uber         Kd, Ks, Kr, Kt, roughness, opacity, index
 //   4 metal        eta, k, roughness                 9 mix          amount; m1 / m2 = material indices
+//   10 subsurface / kdsubsurface   Kr, index
 // kind -1: the material keeps its flattened lobe list (constant parameters, no bump map).
 struct MaterialProgram {
   int kind = -1;

@@ -320,6 +320,8 @@ PROGRAM_CASES = {
     "substrate": (host.substrate_lobes, dict(kd=(0.5, 0.3, 0.2), ks=0.4, uroughness=0.05, vroughness=0.2)),
     "translucent": (host.translucent_lobes, dict(kd=0.4, ks=0.3, reflect=(0.6, 0.5, 0.4), transmit=0.3, roughness=0.1)),
     "uber": (host.uber_lobes, dict(kd=(0.4, 0.3, 0.2), ks=0.2, kr=0.1, kt=0.15, roughness=0.07, index=1.3, opacity=0.8)),
+    "subsurface": (host.subsurface_lobes, dict(kr=(0.9, 0.8, 0.7), index=1.4)),
+    "kdsubsurface": (host.subsurface_lobes, dict(kr=0.8, index=1.25)),
 }
 
 
@@ -426,3 +428,120 @@ def test_camera_ray_differentials_size_the_texture_filter():
     # the footprint at the frame centre is exact; off centre the perspective foreshortening of the differentials is second order
     assert np.abs(img[inner] - want[inner]).max() < 0.02, np.abs(img[inner] - want[inner]).max()
     assert img[inner].std() > 0.05  # the checks are resolved, not averaged away
+
+
+# ---- the noise textures (lib/core/texture.dart:40-140 and lib/textures/{fbm,wrinkled,windy,marble,dots}_texture.dart) ------------
+# Ken Perlin's published permutation table (his 2002 reference implementation), typed here independently of the C++ sides
+PERLIN = [151, 160, 137, 91, 90, 15, 131, 13, 201, 95, 96, 53, 194, 233, 7, 225, 140, 36, 103, 30, 69, 142, 8, 99, 37, 240, 21, 10, 23, 190, 6,
+          148, 247, 120, 234, 75, 0, 26, 197, 62, 94, 252, 219, 203, 117, 35, 11, 32, 57, 177, 33, 88, 237, 149, 56, 87, 174, 20, 125, 136, 171,
+          168, 68, 175, 74, 165, 71, 134, 139, 48, 27, 166, 77, 146, 158, 231, 83, 111, 229, 122, 60, 211, 133, 230, 220, 105, 92, 41, 55, 46,
+          245, 40, 244, 102, 143, 54, 65, 25, 63, 161, 1, 216, 80, 73, 209, 76, 132, 187, 208, 89, 18, 169, 200, 196, 135, 130, 116, 188, 159,
+          86, 164, 100, 109, 198, 173, 186, 3, 64, 52, 217, 226, 250, 124, 123, 5, 202, 38, 147, 118, 126, 255, 82, 85, 212, 207, 206, 59, 227,
+          47, 16, 58, 17, 182, 189, 28, 42, 223, 183, 170, 213, 119, 248, 152, 2, 44, 154, 163, 70, 221, 153, 101, 155, 167, 43, 172, 9, 129,
+          22, 39, 253, 19, 98, 108, 110, 79, 113, 224, 232, 178, 185, 112, 104, 218, 246, 97, 228, 251, 34, 242, 193, 238, 210, 144, 12, 191,
+          179, 162, 241, 81, 51, 145, 235, 249, 14, 239, 107, 49, 192, 214, 31, 181, 199, 106, 157, 184, 84, 204, 176, 115, 121, 50, 45, 127,
+          4, 150, 254, 138, 236, 205, 93, 222, 114, 67, 29, 24, 72, 243, 141, 128, 195, 78, 66, 215, 61, 156, 180] * 2
+
+
+def _noise(x, y=0.5, z=0.5):
+    ix, iy, iz = math.floor(x), math.floor(y), math.floor(z)
+    dx, dy, dz = x - ix, y - iy, z - iz
+    ix, iy, iz = ix & 255, iy & 255, iz & 255
+
+    def grad(X, Y, Z, a, b, c):
+        h = PERLIN[PERLIN[PERLIN[X] + Y] + Z] & 15
+        u = a if (h < 8 or h in (12, 13)) else b
+        v = b if (h < 4 or h in (12, 13)) else c
+        return (-u if h & 1 else u) + (-v if h & 2 else v)
+
+    def wgt(t):
+        return 6 * t ** 5 - 15 * t ** 4 + 10 * t ** 3
+    lerp = lambda t, a, b: (1 - t) * a + t * b  # noqa: E731
+    wx, wy, wz = wgt(dx), wgt(dy), wgt(dz)
+    x00 = lerp(wx, grad(ix, iy, iz, dx, dy, dz), grad(ix + 1, iy, iz, dx - 1, dy, dz))
+    x10 = lerp(wx, grad(ix, iy + 1, iz, dx, dy - 1, dz), grad(ix + 1, iy + 1, iz, dx - 1, dy - 1, dz))
+    x01 = lerp(wx, grad(ix, iy, iz + 1, dx, dy, dz - 1), grad(ix + 1, iy, iz + 1, dx - 1, dy, dz - 1))
+    x11 = lerp(wx, grad(ix, iy + 1, iz + 1, dx, dy - 1, dz - 1), grad(ix + 1, iy + 1, iz + 1, dx - 1, dy - 1, dz - 1))
+    return lerp(wz, lerp(wy, x00, x10), lerp(wy, x01, x11))
+
+
+def _f32v(v):
+    return np.asarray(v, np.float64).astype(np.float32).astype(np.float64)
+
+
+def _fbm(P, dpdx, dpdy, omega, max_oct, turbulence=False):
+    s2 = max(float(dpdx @ dpdx), float(dpdy @ dpdy))
+    l2 = math.log(s2) / math.log(2.0) if s2 > 0 else -math.inf
+    foct = min(float(max_oct), max(0.0, -1.0 - 0.5 * l2))
+    octv = math.floor(foct)
+    total, lam, o = 0.0, 1.0, 1.0
+    f = abs if turbulence else (lambda q: q)
+    for _ in range(octv):
+        total += o * f(_noise(*_f32v(P * lam)))  # P * lambda is a new float32 Point
+        lam *= 1.99
+        o *= omega
+    v = min(max((foct - octv - 0.3) / (0.7 - 0.3), 0.0), 1.0)
+    total += o * (v * v * (-2.0 * v + 3.0)) * f(_noise(*_f32v(P * lam)))
+    if turbulence:
+        total += (max_oct - foct) * 0.2
+    return total
+
+
+def test_perlin_noise_has_the_properties_of_the_published_function():
+    """Independent of any table copy: gradient noise vanishes on the integer lattice, is bounded, and has period 256."""
+    for x, y, z in RNG.integers(-300, 300, (50, 3)):
+        assert _noise(float(x), float(y), float(z)) == 0.0
+    pts = RNG.uniform(-40, 40, (300, 3))
+    vals = np.array([_noise(*q) for q in pts])
+    assert np.abs(vals).max() <= 1.5 and vals.std() > 0.1
+    for q in pts[:40]:
+        assert _noise(q[0] + 256.0, q[1], q[2] - 256.0) == pytest.approx(_noise(*q), abs=1e-9)
+
+
+def test_noise_textures_match_the_numpy_restatement():
+    """fbm / wrinkled / windy / marble over IdentityMapping3D, dots over a 2D mapping, the 3D checkerboard."""
+    xf = host.mat_mul(host.scale(1.7, 0.9, 1.3), host.rotate(20.0, (0, 1, 1)))
+    fbm, wr, wi = host.FBmTexture(6, 0.6, xf), host.WrinkledTexture(5, 0.45, xf), host.WindyTexture(xf)
+    mar = host.MarbleTexture(7, 0.55, 2.5, 0.3, xf)
+    dots = host.DotsTexture(0.9, 0.1, host.UVMapping(7.0, 5.0, 0.3, 0.1))
+    ch3 = host.Checkerboard3DTexture(0.8, 0.25, xf)
+    o, ids = _oracle_with([fbm, fbm, wr, wi, mar, dots, ch3], [False, True, False, False, True, False, False])
+    n = 60
+    p = _f32v(RNG.uniform(-3, 3, (n, 3)))
+    dpx, dpy = _f32v(RNG.normal(size=(n, 3)) * 10.0 ** RNG.uniform(-4, -0.5, (n, 1))), _f32v(RNG.normal(size=(n, 3)) * 0.01)
+    dpx[:5] = 0.0
+    dpy[:5] = 0.0  # no differentials: every octave
+    u, v = RNG.random(n), RNG.random(n)
+    dg = _dg(n, u, v, p, dpdx=dpx, dpdy=dpy)
+    M = host._m(xf).astype(np.float64)
+    xp = lambda q: _f32v(M[:3, :3] @ q + M[:3, 3])  # noqa: E731
+    xv = lambda q: _f32v(M[:3, :3] @ q)  # noqa: E731
+    g_fbm, g_fbms, g_wr, g_wi = (o.texture_eval(i, dg) for i in ids[:4])
+    g_mar, g_dots, g_ch3 = (o.texture_eval(i, dg) for i in ids[4:])
+    spline = np.array([[0.58, 0.58, 0.6], [0.58, 0.58, 0.6], [0.58, 0.58, 0.6], [0.5, 0.5, 0.5], [0.6, 0.59, 0.58], [0.58, 0.58, 0.6],
+                       [0.58, 0.58, 0.6], [0.2, 0.2, 0.33], [0.58, 0.58, 0.6]])
+    for i in range(n):
+        P, dx, dy = xp(p[i]), xv(dpx[i]), xv(dpy[i])
+        want = _fbm(P, dx, dy, 0.6, 6)
+        assert g_fbm[i, 0] == pytest.approx(want, rel=1e-9, abs=1e-12)
+        assert np.allclose(g_fbms[i], np.float32(want), rtol=1e-7)  # new Spectrum(n)
+        assert g_wr[i, 0] == pytest.approx(_fbm(P, dx, dy, 0.45, 5, True), rel=1e-9, abs=1e-12)
+        wind = abs(_fbm(_f32v(P * 0.1), _f32v(dx * 0.1), _f32v(dy * 0.1), 0.5, 3)) * _fbm(P, dx, dy, 0.5, 6)
+        assert g_wi[i, 0] == pytest.approx(wind, rel=1e-9, abs=1e-12)
+        Ps = _f32v(P * 2.5)
+        t = 0.5 + 0.5 * math.sin(Ps[1] + 0.3 * _fbm(Ps, _f32v(dx * 2.5), _f32v(dy * 2.5), 0.55, 7))
+        first = math.floor(t * 6)
+        t = t * 6 - first
+        c0, c1, c2, c3 = spline[first:first + 4]
+        s0, s1, s2 = c0 * (1 - t) + c1 * t, c1 * (1 - t) + c2 * t, c2 * (1 - t) + c3 * t
+        s0, s1 = s0 * (1 - t) + s1 * t, s1 * (1 - t) + s2 * t
+        assert np.allclose(g_mar[i], (s0 * (1 - t) + s1 * t) * 1.5, rtol=2e-6)
+        s, tt = 7.0 * u[i] + 0.3, 5.0 * v[i] + 0.1
+        sc, tc = math.floor(s + 0.5), math.floor(tt + 0.5)
+        inside = False
+        if _noise(sc + 0.5, tc + 0.5) > 0:
+            cs, ct = sc + 0.15 * _noise(sc + 1.5, tc + 2.8), tc + 0.15 * _noise(sc + 4.5, tc + 9.8)
+            inside = (s - cs) ** 2 + (tt - ct) ** 2 < 0.35 * 0.35
+        assert g_dots[i, 0] == (0.9 if inside else 0.1)
+        assert g_ch3[i, 0] == (0.8 if (math.floor(P[0]) + math.floor(P[1]) + math.floor(P[2])) % 2 == 0 else 0.25)
+    assert 0 < (g_dots[:, 0] == 0.9).sum() < n  # both branches were taken

@@ -117,6 +117,7 @@ PLUGINS = {
     "translucent": dict(kd=host.ImageTexture(IMG_RGB), ks=0.2, reflect=host.UVTexture(), transmit=0.4, roughness=0.1),
     "uber": dict(kd=host.ImageTexture(IMG_RGB), ks=0.2, kr=host.CheckerboardTexture(0.3, 0.0, host.UVMapping(5.0, 5.0)), kt=0.1, roughness=0.07,
                  index=1.3, opacity=host.MixTexture((1.0, 1.0, 1.0), (0.5, 0.6, 0.7), host.ImageTexture(IMG_F))),
+    "subsurface": dict(kr=host.ImageTexture(IMG_RGB), index=host.BilerpTexture(1.2, 1.3, 1.4, 1.5)),
 }
 
 
@@ -218,3 +219,27 @@ def test_invalid_texture_tables_are_rejected():
     nodes["kind"], nodes["tex1"] = 1, 0
     with pytest.raises(RuntimeError, match="earlier nodes"):
         g.set_textures(nodes, np.zeros(0, np.float32))
+
+
+NOISE_XF = host.mat_mul(host.scale(2.5, 2.0, 3.0), host.rotate(20.0, (0, 1, 1)))
+NOISE_CASES = {
+    "marble_fbm_bump": ("matte", dict(kd=host.MarbleTexture(6, 0.5, 3.0, 0.4, NOISE_XF), bumpmap=host.ScaleTexture(host.FBmTexture(5, 0.6, NOISE_XF), 0.05))),
+    "wrinkled_windy": ("plastic", dict(kd=host.ScaleTexture(host.WrinkledTexture(4, 0.5, NOISE_XF), (0.8, 0.6, 0.4)), ks=host.MixTexture((0.05, 0.05, 0.05), (0.4, 0.4, 0.4), host.WindyTexture(NOISE_XF)), roughness=0.1)),
+    "dots_checker3d": ("uber", dict(kd=host.DotsTexture((0.9, 0.2, 0.1), (0.2, 0.3, 0.8), host.UVMapping(9.0, 9.0)), ks=0.1,
+                                    roughness=host.Checkerboard3DTexture(0.05, 0.3, NOISE_XF))),
+}
+
+
+@pytest.mark.parametrize("case", sorted(NOISE_CASES))
+def test_noise_textures(case):
+    """fbm / wrinkled / windy / marble (Perlin noise over IdentityMapping3D, octaves cut by the screen-space footprint), dots and the
+    3D checkerboard, on every shape, camera vertices with differentials and later bounces without."""
+    plugin, params = NOISE_CASES[case]
+
+    def mats(sb, name):
+        if not hasattr(sb, "_m"):
+            sb._m = sb.material_program(plugin, **params)
+        return sb._m
+    sb = _scene(mats)
+    g, o, fg, fo = _both(sb, CAM, host.Film(64, 48), host.Sampler(kind=host.SAMPLER_LD, spp=4), host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=3))
+    _check(g, o, fg, fo, case)
