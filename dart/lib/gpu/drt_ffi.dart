@@ -44,6 +44,10 @@ typedef _SetTableC = Int32 Function(_Ctx, _PD, Uint32);
 typedef _SetTableD = int Function(_Ctx, _PD, int);
 typedef _SetLightMapC = Int32 Function(_Ctx, Uint32, Int32, Int32, _PF, _PF, _PF, _PD, Double);
 typedef _SetLightMapD = int Function(_Ctx, int, int, int, _PF, _PF, _PF, _PD, double);
+typedef _SetTexturesC = Int32 Function(_Ctx, Uint32, _PB, _PF, Uint64);
+typedef _SetTexturesD = int Function(_Ctx, int, _PB, _PF, int);
+typedef _SetProgramsC = Int32 Function(_Ctx, Uint32, _PI);
+typedef _SetProgramsD = int Function(_Ctx, int, _PI);
 typedef _SetWrappersC = Int32 Function(_Ctx, Uint32, _PI, _PF);
 typedef _SetWrappersD = int Function(_Ctx, int, _PI, _PF);
 typedef _SetInfiniteC = Int32 Function(_Ctx, Uint32, Int32, Int32, _PF, _PF, _PF);
@@ -149,6 +153,11 @@ class Drt {
       check(lib.lookupFunction<_SetLightMapC, _SetLightMapD>('drt_set_light_map')(ctx, index, width, height, rgb, w2l, projection, screen, hither));
   void setLobeWrappers(int nLobes, _PI wrap, _PF scaleRgb) =>
       check(lib.lookupFunction<_SetWrappersC, _SetWrappersD>('drt_set_lobe_wrappers')(ctx, nLobes, wrap, scaleRgb));
+  // textures that read the hit point / materials bound to them (drt_texture, drt_material_program records packed by _Arena)
+  void setTextures(_PB nodes, int n, _PF texels, int nTexelFloats) =>
+      check(lib.lookupFunction<_SetTexturesC, _SetTexturesD>('drt_set_textures')(ctx, n, nodes, texels, nTexelFloats));
+  void setMaterialPrograms(_PI programs, int n) =>
+      check(lib.lookupFunction<_SetProgramsC, _SetProgramsD>('drt_set_material_programs')(ctx, n, programs));
   void setInfiniteLight(int index, int width, int height, _PF rgb, _PF l2w, _PF w2l) =>
       check(lib.lookupFunction<_SetInfiniteC, _SetInfiniteD>('drt_set_infinite_light')(ctx, index, width, height, rgb, l2w, w2l));
   void setCamera(_PF rasterToCamera, _PF cameraToWorld, double lensRadius, double focalDistance, double open, double close) =>

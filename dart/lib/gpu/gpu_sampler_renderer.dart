@@ -17,6 +17,8 @@ import 'package:ffi/ffi.dart';
 import 'package:dartray/dartray_core.dart';
 import 'drt_ffi.dart';
 
+part 'gpu_textures.dart';
+
 /// Thrown by the flattener when the scene uses something the GPU path does not cover; the caller then
 /// keeps the stock SamplerRenderer (see `makeRenderer` at the bottom).
 class GpuUnsupported implements Exception {
@@ -69,6 +71,42 @@ class _Arena {
     p.asTypedList(v.length).setAll(0, v);
     _owned.add(p);
     return p;
+  }
+  // drt_texture records (include/drt.h: 280 bytes each, natural C alignment — the layout host.TEX_DTYPE asserts in Python)
+  Pointer<Uint8> textures(List<_TexNode> nodes) {
+    final p = calloc<Uint8>(Math.max(nodes.length, 1) * 280);
+    final bd = p.asTypedList(nodes.length * 280).buffer.asByteData();
+    for (int i = 0; i < nodes.length; ++i) {
+      final n = nodes[i];
+      final int o = i * 280;
+      final ints = [n.kind, n.spectrum, n.tex1, n.tex2, n.amount, n.mapping, n.imageWidth, n.imageHeight, n.imageChannels, n.imageWrap,
+                    n.imageTrilinear, n.aaMethod];
+      for (int k = 0; k < 12; ++k) bd.setInt32(o + 4 * k, ints[k], Endian.host);
+      bd.setUint64(o + 48, n.imageOffset, Endian.host);
+      for (int k = 0; k < 3; ++k) bd.setFloat64(o + 56 + 8 * k, n.value[k], Endian.host);
+      for (int k = 0; k < 9; ++k) bd.setFloat64(o + 80 + 8 * k, n.value2[k], Endian.host);
+      final d = [n.su, n.sv, n.du, n.dv, n.maxAnisotropy];
+      for (int k = 0; k < 5; ++k) bd.setFloat64(o + 152 + 8 * k, d[k], Endian.host);
+      for (int k = 0; k < 16; ++k) bd.setFloat32(o + 192 + 4 * k, n.worldToTexture[k], Endian.host);
+      for (int k = 0; k < 3; ++k) {
+        bd.setFloat32(o + 256 + 4 * k, n.v1[k], Endian.host);
+        bd.setFloat32(o + 268 + 4 * k, n.v2[k], Endian.host);
+      }
+    }
+    _owned.add(p);
+    return p;
+  }
+  // drt_material_program records (48 bytes: kind, tex[8], bump, m1, m2); materials without a program get kind -1
+  Pointer<Int32> programs(int nMaterials, Map<int, _Program> progs) {
+    final v = new List<int>.filled(12 * nMaterials, -1);
+    progs.forEach((i, pr) {
+      v[12 * i] = pr.kind;
+      for (int k = 0; k < 8; ++k) v[12 * i + 1 + k] = pr.tex[k];
+      v[12 * i + 9] = pr.bump;
+      v[12 * i + 10] = pr.m1;
+      v[12 * i + 11] = pr.m2;
+    });
+    return ints(v);
   }
   void free() {
     for (final p in _owned) {
@@ -444,8 +482,27 @@ class GpuSamplerRenderer extends Renderer {
     drt.setBuildOrder(a.uints(order), order.length);
     drt.buildBvh(bvh.splitMethod, bvh.maxPrimsInNode);
 
-    // materials
-    final lobeLists = materials.map(_lobes).toList();
+    // materials: constant parameters flatten into BxDF lists (_lobes); a material with a texture that reads the hit point or with
+    // a bump map becomes a program (gpu_textures.dart) and owns an empty list.  A MixMaterial's two materials join the table.
+    final flattener = new TextureFlattener();
+    final programs = <int, _Program>{};
+    int indexOfMaterial(Material sub) {
+      int i = materials.indexOf(sub);
+      if (i < 0) {
+        materials.add(sub);
+        i = materials.length - 1;
+      }
+      return i;
+    }
+    final lobeLists = <List<_Lobe>>[];
+    for (int i = 0; i < materials.length; ++i) {  // the list may grow while a mix is flattened
+      try {
+        lobeLists.add(_lobes(materials[i]));
+      } on GpuUnsupported {
+        programs[i] = flattener.program(materials[i], indexOfMaterial);  // throws GpuUnsupported itself for what it cannot take
+        lobeLists.add(<_Lobe>[]);
+      }
+    }
     final offsets = <int>[0], kind = <int>[], fres = <int>[], rgb = <double>[], eta = <double>[], kk = <double>[], scal = <double>[];
     for (final ll in lobeLists) {
       for (final l in ll) {
@@ -470,6 +527,10 @@ class GpuSamplerRenderer extends Renderer {
       }
       if (wraps.any((w) => w != 0)) {
         drt.setLobeWrappers(wraps.length, a.ints(wraps), a.floats(scales));
+      }
+      if (programs.isNotEmpty) {
+        drt.setTextures(a.textures(flattener.nodes), flattener.nodes.length, a.floats(flattener.texels), flattener.texels.length);
+        drt.setMaterialPrograms(a.programs(materials.length, programs), materials.length);
       }
     }
 

@@ -37,12 +37,24 @@ def _write_blob(path, entries):
             f.write(data)
 
 
+def _textured_cornell():
+    """cornell-path.pbrt with bump-sphere.pbrt's material on the sphere and an image texture on the back wall's material."""
+    sb, cam = scenes.cornell_path()
+    rng = np.random.default_rng(5)
+    kd = host.ScaleTexture(host.ImageTexture(rng.random((16, 16, 3)).astype(np.float32)), (0.8, 0.7, 0.4))
+    bump = host.ScaleTexture(host.ImageTexture(rng.random((8, 8)).astype(np.float32), host.UVMapping(4.0, 4.0)), -0.1)
+    m = sb.material_program("uber", kd=kd, ks=0.05, roughness=0.01, bumpmap=bump)
+    sb.sph = [(s[0], s[1], s[2], m, s[4], s[5]) for s in sb.sph]
+    return sb, cam
+
+
 @pytest.mark.gpu
-def test_c_client_renders_the_film_the_ctypes_client_renders(drt_lib, tmp_path):
+@pytest.mark.parametrize("textured", [False, True], ids=["matte", "textured"])
+def test_c_client_renders_the_film_the_ctypes_client_renders(drt_lib, tmp_path, textured):
     exe = _build(tmp_path)
-    sb, cam = scenes.cornell_path()  # the shipped scene: 22 triangles, a sphere, the DISK area light (cornell-path.pbrt)
+    sb, cam = _textured_cornell() if textured else scenes.cornell_path()  # the shipped scene: 22 triangles, a sphere, the DISK area light
     a = sb.arrays()
-    assert not a.get("mat_general")
+    assert bool(a.get("mat_general")) == textured
     film, smp = host.Film(96, 72), host.Sampler(kind=host.SAMPLER_LD, spp=4)
     integ = host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=5)
     xw, yw, table = film.table()
@@ -51,6 +63,9 @@ def test_c_client_renders_the_film_the_ctypes_client_renders(drt_lib, tmp_path):
                                  "sph_rev", "dsk_o2w", "dsk_w2o", "dsk_params", "dsk_mat", "dsk_light", "dsk_rev", "order", "mat_kind",
                                  "mat_kd", "mat_sigma", "light_kind", "light_L", "light_pos", "light_nsamples", "light_shape_offsets",
                                  "light_shape_prims")}
+    if textured:  # the records go to the C client as raw bytes: its compiler's struct layout reads them
+        entries.update({k: a[k] for k in ("mat_lobe_offsets", "lobe_kind", "lobe_rgb", "lobe_fresnel", "lobe_eta", "lobe_k", "lobe_scalars",
+                                          "tex_nodes", "tex_texels", "mat_programs")})
     entries.update({
         "device": d(0), "bvh": d(2, 4),
         "raster_to_camera": np.asarray(cam.raster_to_camera(film.xres, film.yres), np.float32),

@@ -15,6 +15,10 @@
 
 #include "drt.h"
 
+/* the plain-data records of the texture ABI, as a C compiler lays them out (host.TEX_DTYPE / PROG_DTYPE assert the same in Python) */
+typedef char drt_texture_is_280_bytes[sizeof(drt_texture) == 280 ? 1 : -1];
+typedef char drt_material_program_is_48_bytes[sizeof(drt_material_program) == 48 ? 1 : -1];
+
 typedef struct { char name[32]; int64_t nbytes; void* data; } blob;
 static blob* g_blobs;
 static int g_nblobs;
@@ -71,9 +75,22 @@ int main(int argc, char** argv) {
   drt_bvh_info info;
   CK(drt_bvh_info_get(ctx, &info));
 
-  /* materials as matte table (drt_set_materials) */
-  CK(drt_set_materials(ctx, (uint32_t)count("mat_kind", 4), (const int32_t*)ptr("mat_kind"), (const float*)ptr("mat_kd"),
-                       (const float*)ptr("mat_sigma")));
+  /* materials: the matte table (drt_set_materials), or BxDF lists plus the texture nodes and material programs of a scene whose
+   * materials read the hit point (gpu_sampler_renderer.dart: the materials block; gpu_textures.dart) */
+  if (find("mat_lobe_offsets")) {
+    CK(drt_set_material_lobes(ctx, (uint32_t)count("mat_lobe_offsets", 4) - 1, (const uint32_t*)ptr("mat_lobe_offsets"),
+                              (const int32_t*)ptr("lobe_kind"), (const float*)ptr("lobe_rgb"), (const int32_t*)ptr("lobe_fresnel"),
+                              (const float*)ptr("lobe_eta"), (const float*)ptr("lobe_k"), (const double*)ptr("lobe_scalars")));
+    if (find("tex_nodes")) {
+      CK(drt_set_textures(ctx, (uint32_t)count("tex_nodes", sizeof(drt_texture)), (const drt_texture*)ptr("tex_nodes"),
+                          (const float*)ptr("tex_texels"), (uint64_t)count("tex_texels", 4)));
+      CK(drt_set_material_programs(ctx, (uint32_t)count("mat_programs", sizeof(drt_material_program)),
+                                   (const drt_material_program*)ptr("mat_programs")));
+    }
+  } else {
+    CK(drt_set_materials(ctx, (uint32_t)count("mat_kind", 4), (const int32_t*)ptr("mat_kind"), (const float*)ptr("mat_kd"),
+                         (const float*)ptr("mat_sigma")));
+  }
   CK(drt_set_lights(ctx, (uint32_t)count("light_kind", 4), (const int32_t*)ptr("light_kind"), (const float*)ptr("light_L"),
                     (const float*)ptr("light_pos"), (const int32_t*)ptr("light_nsamples"), (const uint32_t*)ptr("light_shape_offsets"),
                     (const uint32_t*)ptr("light_shape_prims")));
