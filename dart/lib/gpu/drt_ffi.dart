@@ -46,6 +46,8 @@ typedef _SetLightMapC = Int32 Function(_Ctx, Uint32, Int32, Int32, _PF, _PF, _PF
 typedef _SetLightMapD = int Function(_Ctx, int, int, int, _PF, _PF, _PF, _PD, double);
 typedef _SetTexturesC = Int32 Function(_Ctx, Uint32, _PB, _PF, Uint64);
 typedef _SetTexturesD = int Function(_Ctx, int, _PB, _PF, int);
+typedef _SetMeasuredC = Int32 Function(_Ctx, Uint32, _PI, _PI, Pointer<Uint64>, _PF, Uint64);
+typedef _SetMeasuredD = int Function(_Ctx, int, _PI, _PI, Pointer<Uint64>, _PF, int);
 typedef _SetProgramsC = Int32 Function(_Ctx, Uint32, _PI);
 typedef _SetProgramsD = int Function(_Ctx, int, _PI);
 typedef _SetWrappersC = Int32 Function(_Ctx, Uint32, _PI, _PF);
@@ -156,6 +158,8 @@ class Drt {
   // textures that read the hit point / materials bound to them (drt_texture, drt_material_program records packed by _Arena)
   void setTextures(_PB nodes, int n, _PF texels, int nTexelFloats) =>
       check(lib.lookupFunction<_SetTexturesC, _SetTexturesD>('drt_set_textures')(ctx, n, nodes, texels, nTexelFloats));
+  void setMeasured(int n, _PI kind, _PI dims, Pointer<Uint64> offsets, _PF data, int nFloats) =>
+      check(lib.lookupFunction<_SetMeasuredC, _SetMeasuredD>('drt_set_measured')(ctx, n, kind, dims, offsets, data, nFloats));
   void setMaterialPrograms(_PI programs, int n) =>
       check(lib.lookupFunction<_SetProgramsC, _SetProgramsD>('drt_set_material_programs')(ctx, n, programs));
   void setInfiniteLight(int index, int width, int height, _PF rgb, _PF l2w, _PF w2l) =>

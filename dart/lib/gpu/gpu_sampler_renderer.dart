@@ -66,6 +66,12 @@ class _Arena {
     _owned.add(p);
     return p;
   }
+  Pointer<Uint64> uint64s(List<int> v) {
+    final p = calloc<Uint64>(Math.max(v.length, 1));
+    p.asTypedList(v.length).setAll(0, v);
+    _owned.add(p);
+    return p;
+  }
   Pointer<Uint8> bytes(List<int> v) {
     final p = calloc<Uint8>(Math.max(v.length, 1));
     p.asTypedList(v.length).setAll(0, v);
@@ -527,6 +533,11 @@ class GpuSamplerRenderer extends Renderer {
       }
       if (wraps.any((w) => w != 0)) {
         drt.setLobeWrappers(wraps.length, a.ints(wraps), a.floats(scales));
+      }
+      if (flattener.measuredTables.isNotEmpty) {
+        final mt = flattener.measuredTables;
+        drt.setMeasured(mt.length, a.ints([for (final t in mt) t.kind]), a.ints([for (final t in mt) ...t.dims]),
+                        a.uint64s([for (final t in mt) t.offset]), a.floats(flattener.measuredData), flattener.measuredData.length);
       }
       if (programs.isNotEmpty) {
         drt.setTextures(a.textures(flattener.nodes), flattener.nodes.length, a.floats(flattener.texels), flattener.texels.length);

@@ -22,9 +22,43 @@ class _Program {  // one drt_material_program
   List<int> tex = new List<int>.filled(8, -1);
 }
 
+class _MeasuredTable {  // one table of drt_set_measured
+  int kind = 0;  // 0 regular halfangle (.merl), 1 irregular isotropic (.brdf)
+  List<int> dims = [0, 0, 0];
+  int offset = 0;
+}
+
 class TextureFlattener {
   final List<_TexNode> nodes = [];
   final List<double> texels = [];
+  // MeasuredMaterial data (measured_material.dart:76-205), shared between materials that loaded the same file
+  final List<_MeasuredTable> measuredTables = [];
+  final List<double> measuredData = [];
+  final Map<Object, int> _measuredIds = {};
+
+  int _measured(MeasuredMaterial m) {
+    final Object key = m.regularHalfangleData != null ? m.regularHalfangleData : m.thetaPhiData;
+    if (key == null) throw new GpuUnsupported('measured material without loaded data');
+    if (_measuredIds.containsKey(key)) return _measuredIds[key];
+    final t = new _MeasuredTable()..offset = measuredData.length;
+    if (m.regularHalfangleData != null) {
+      t.kind = 0;
+      t.dims = [m.nThetaH, m.nThetaD, m.nPhiD];
+      measuredData.addAll(m.regularHalfangleData);
+    } else {
+      // the samples the KdTree holds (kdtree.dart:35-57: nodeData is a permutation of the list it was built from); the library visits
+      // the ones inside the search radius in this order, the reference in the order its tree yields them — the sum is the same set's
+      final List samples = m.thetaPhiData.nodeData;
+      t.kind = 1;
+      t.dims = [samples.length, 0, 0];
+      for (final IrregIsotropicBRDFSample s in samples) {
+        measuredData..add(s.p.x)..add(s.p.y)..add(s.p.z);
+        measuredData.addAll(GpuSamplerRenderer._rgb(s.v));
+      }
+    }
+    measuredTables.add(t);
+    return _measuredIds[key] = measuredTables.length - 1;
+  }
   final Map<Texture, Map<bool, int>> _ids = {};
 
   void _map2D(_TexNode n, TextureMapping2D m) {
@@ -115,7 +149,10 @@ class TextureFlattener {
     else if (m is UberMaterial) slots(8, [m.Kd, m.Ks, m.Kr, m.Kt, m.roughness, m.opacity, m.eta], [S, S, S, S, F, S, F], m.bumpMap);
     else if (m is SubsurfaceMaterial) slots(10, [m.Kr, m.eta], [S, F], m.bumpMap);
     else if (m is KdSubsurfaceMaterial) slots(10, [m.Kr, m.eta], [S, F], m.bumpMap);
-    else if (m is MixMaterial) {
+    else if (m is MeasuredMaterial) {
+      slots(11, [], [], m.bumpMap);
+      p.m1 = _measured(m);
+    } else if (m is MixMaterial) {
       slots(9, [m.scale], [S], null);
       p.m1 = indexOf(m.m1);
       p.m2 = indexOf(m.m2);

@@ -25,7 +25,7 @@ SYMBOLS = [
     "drt_set_build_order", "drt_build_bvh", "drt_bvh_info_get", "drt_bvh_export", "drt_trace_closest",
     "drt_trace_any", "drt_trace_closest_device", "drt_trace_any_device", "drt_set_counting", "drt_get_counters", "drt_set_kernel_variant",
     "drt_last_kernel_ms", "drt_kernel_launches",
-    "drt_set_materials", "drt_set_material_lobes", "drt_set_textures", "drt_set_material_programs", "drt_set_lights", "drt_set_spot_params", "drt_set_volumes", "drt_set_volume_integrator", "drt_set_camera", "drt_set_camera_kind", "drt_set_film", "drt_set_sampler", "drt_set_integrator",
+    "drt_set_materials", "drt_set_material_lobes", "drt_set_measured", "drt_set_textures", "drt_set_material_programs", "drt_set_lights", "drt_set_spot_params", "drt_set_volumes", "drt_set_volume_integrator", "drt_set_camera", "drt_set_camera_kind", "drt_set_film", "drt_set_sampler", "drt_set_integrator",
     "drt_render", "drt_render_shard", "drt_set_batch_slots", "drt_film_clear", "drt_film_size", "drt_film_read",
     "drt_film_device", "drt_pixel_samples", "drt_render_stats_get", "drt_set_render_profiling", "drt_render_profile_get",
 ]
@@ -112,6 +112,7 @@ def load():
     L.drt_set_light_map.argtypes = [vp, u32, i32, i32, vp, vp, vp, vp, C.c_double]
     L.drt_set_lobe_wrappers.argtypes = [vp, u32, vp, vp]
     L.drt_set_textures.argtypes = [vp, u32, vp, vp, u64]
+    L.drt_set_measured.argtypes = [vp, u32, vp, vp, vp, vp, u64]
     L.drt_set_material_programs.argtypes = [vp, u32, vp]
     L.drt_set_infinite_light.argtypes = [vp, u32, i32, i32, vp, vp, vp]
     L.drt_set_lights.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
@@ -328,6 +329,22 @@ class Context:
         """BRDFToBTDF (bit 0) / ScaledBxDF (bit 1, with its RGB scale) around the lobes of the last set_material_lobes."""
         w, sc = _arr(wrap, np.int32), _arr(scale, np.float32).reshape(-1, 3)
         self._ck(self.L.drt_set_lobe_wrappers(self.h, w.shape[0], _p(w), _p(sc)))
+
+    def set_measured(self, tables):
+        """MeasuredMaterial data (measured_material.dart:76-205): list of (kind, array) — kind 0 = RegularHalfangleBRDF table
+        (nThetaH x nThetaD x nPhiD x 3 float32), kind 1 = IrregIsotropicBRDFSamples (n x 6 float32: BRDFRemap point, RGB)."""
+        kinds = np.array([k for k, _ in tables], np.int32)
+        dims = np.zeros((len(tables), 3), np.int32)
+        offs = np.zeros(len(tables), np.uint64)
+        chunks, pos = [], 0
+        for i, (k, a) in enumerate(tables):
+            a = np.ascontiguousarray(a, np.float32)
+            dims[i] = a.shape[:3] if k == 0 else (a.shape[0], 0, 0)
+            offs[i] = pos
+            pos += a.size
+            chunks.append(a.ravel())
+        data = np.concatenate(chunks) if chunks else np.zeros(0, np.float32)
+        self._ck(self.L.drt_set_measured(self.h, len(tables), _p(kinds), _p(dims), _p(offs), _p(data), data.size))
 
     def set_textures(self, nodes, texels):
         """Texture nodes (host.TEX_DTYPE records = drt_texture) and the level-0 texels of their images."""

@@ -79,6 +79,11 @@ struct RenderState {
   std::vector<float> texData;
   std::vector<GProgram> programs;
   bool programsMaySpecular = false;
+  // MeasuredMaterial tables (drt_set_measured): descriptors with data == offset into measuredData until they are uploaded
+  std::vector<GMeasured> measured;
+  std::vector<uint64_t> measuredOffsets;
+  std::vector<float> measuredData;
+  bool hasMeasured = false;
   DevBuf<GTex> dTextures;
   DevBuf<float> dTexData;
   DevBuf<GProgram> dPrograms;
@@ -94,6 +99,8 @@ struct RenderState {
   DevBuf<GMaterial> dMaterials;
   DevBuf<uint2> dMatLobes;
   DevBuf<GLobe> dLobes;
+  DevBuf<GMeasured> dMeasured;
+  DevBuf<float> dMeasuredData;
   DevBuf<GLight> dLights;
   DevBuf<float> dLightCdf, dTable;
   DevBuf<uint32_t> dMeshOfTri, dTriIdx;
@@ -398,7 +405,30 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
   CK(c, r->dMatLobes.ensure(std::max<size_t>(1, r->matLobes.size())));
   CK(c, r->dLobes.ensure(std::max<size_t>(1, r->lobes.size())));
   if (!r->matLobes.empty()) CK(c, cudaMemcpy(r->dMatLobes.p, r->matLobes.data(), r->matLobes.size() * sizeof(uint2), cudaMemcpyHostToDevice));
-  if (!r->lobes.empty()) CK(c, cudaMemcpy(r->dLobes.p, r->lobes.data(), r->lobes.size() * sizeof(GLobe), cudaMemcpyHostToDevice));
+  // MeasuredMaterial tables; lobes of kind 6 / 7 get their table's device address and dimensions written into them (render_types.h)
+  std::vector<GMeasured> gmeas(r->measured);
+  if (!gmeas.empty()) {
+    CK(c, r->dMeasuredData.ensure(std::max<size_t>(1, r->measuredData.size())));
+    CK(c, cudaMemcpy(r->dMeasuredData.p, r->measuredData.data(), r->measuredData.size() * sizeof(float), cudaMemcpyHostToDevice));
+    for (size_t i = 0; i < gmeas.size(); ++i) gmeas[i].data = r->dMeasuredData.p + r->measuredOffsets[i];
+    CK(c, r->dMeasured.ensure(gmeas.size()));
+    CK(c, cudaMemcpy(r->dMeasured.p, gmeas.data(), gmeas.size() * sizeof(GMeasured), cudaMemcpyHostToDevice));
+  }
+  if (!r->lobes.empty()) {
+    std::vector<GLobe> ls(r->lobes);
+    for (GLobe& l : ls) {
+      if (l.kind != 6 && l.kind != 7) continue;
+      const double ti = l.param;
+      if (!(ti >= 0.0) || ti >= (double)gmeas.size() || ti != std::floor(ti))
+        return fail(c, DRT_E_INVALID, "a measured BxDF (lobe kind 6 / 7) names a table drt_set_measured did not define");
+      const GMeasured& tb = gmeas[(size_t)ti];
+      if (tb.kind != l.kind - 6) return fail(c, DRT_E_INVALID, "lobe kind 6 needs a regular-halfangle table, kind 7 an irregular-isotropic one");
+      const long long bits = (long long)(uintptr_t)tb.data;
+      std::memcpy(&l.et, &bits, 8);
+      for (int k = 0; k < 3; ++k) std::memcpy(&l.k[k], &tb.dims[k], 4);
+    }
+    CK(c, cudaMemcpy(r->dLobes.p, ls.data(), ls.size() * sizeof(GLobe), cudaMemcpyHostToDevice));
+  }
   CK(c, cudaMemcpy(r->dLights.p, gl.data(), gl.size() * sizeof(GLight), cudaMemcpyHostToDevice));
   if (!shapes.empty()) CK(c, cudaMemcpy(r->dLightShapes.p, shapes.data(), shapes.size() * sizeof(GLightShape), cudaMemcpyHostToDevice));
   if (!cdf.empty()) CK(c, cudaMemcpy(r->dLightCdf.p, cdf.data(), cdf.size() * 4, cudaMemcpyHostToDevice));
@@ -469,14 +499,16 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
     if ((int)r->programs.size() != nMat) return fail(c, DRT_E_INVALID, "drt_set_material_programs: one entry per material of the material table");
     if (!r->general) return fail(c, DRT_E_STATE, "material programs go with drt_set_material_lobes (an empty lobe list for a program's material)");
     // which parameter of which plugin is a spectrum texture (the tex[] order documented in include/drt.h)
-    static const int kSlots[11] = {2, 1, 3, 3, 3, 3, 4, 5, 7, 1, 2};
-    static const unsigned kSpectrumMask[11] = {0x1, 0x1, 0x3, 0x3, 0x3, 0x3, 0x3, 0xf, 0x2f, 0x1, 0x1};
+    static const int kSlots[12] = {2, 1, 3, 3, 3, 3, 4, 5, 7, 1, 2, 0};
+    static const unsigned kSpectrumMask[12] = {0x1, 0x1, 0x3, 0x3, 0x3, 0x3, 0x3, 0xf, 0x2f, 0x1, 0x1, 0x0};
     const int nTex = (int)r->textures.size();
     r->programsMaySpecular = false;
     for (int m = 0; m < nMat; ++m) {
       const GProgram& pr = r->programs[m];
       if (pr.kind < 0) continue;
-      if (pr.kind > 10) return fail(c, DRT_E_INVALID, "material program kind out of range");
+      if (pr.kind > 11) return fail(c, DRT_E_INVALID, "material program kind out of range");
+      if (pr.kind == 11 && (pr.m1 < 0 || pr.m1 >= (int)gmeas.size()))
+        return fail(c, DRT_E_INVALID, "measured: m1 must name a table of drt_set_measured");
       for (int k = 0; k < kSlots[pr.kind]; ++k) {
         if (pr.tex[k] < 0 || pr.tex[k] >= nTex) return fail(c, DRT_E_INVALID, "a material program names a texture node drt_set_textures did not define");
         if (r->textures[pr.tex[k]].spectrum != (int)((kSpectrumMask[pr.kind] >> k) & 1u))
@@ -512,7 +544,9 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
     rs.programs = r->dPrograms.p;
     rs.nPrograms = nMat;
   }
-  rs.extra = (rs.meshOfTri != nullptr || c->ts.quadMode == 2 || nInfinite > 0 || nMapped > 0 || (r->general && r->hasBlend) ||
+  rs.measured = gmeas.empty() ? nullptr : r->dMeasured.p;
+  rs.nMeasured = (int32_t)gmeas.size();
+  rs.extra = (rs.meshOfTri != nullptr || c->ts.quadMode == 2 || nInfinite > 0 || nMapped > 0 || (r->general && (r->hasBlend || r->hasMeasured)) ||
               rs.nVolumes > 0 || rs.nPrograms > 0) ? 1 : 0;
   rs.ntris = nt;
   rs.nprims = np;
@@ -1290,7 +1324,7 @@ int drt_set_material_lobes(drt_ctx* c, uint32_t n, const uint32_t* lobe_offsets,
   RenderState* r = state(c);
   std::vector<uint2> ml(n);
   std::vector<GLobe> ls(nl);
-  bool spec = false, blend = false;
+  bool spec = false, blend = false, measuredLobe = false;
   for (uint32_t i = 0; i < n; ++i) {
     if (lobe_offsets[i + 1] < lobe_offsets[i] || lobe_offsets[i + 1] - lobe_offsets[i] > 8)
       return fail(c, DRT_E_INVALID, "a BSDF holds at most 8 BxDFs (bsdf.dart:253) and the offsets must not decrease");
@@ -1300,7 +1334,8 @@ int drt_set_material_lobes(drt_ctx* c, uint32_t n, const uint32_t* lobe_offsets,
     GLobe& l = ls[j];
     l.kind = lobe_kind[j];
     l.fresnel = fresnel_kind ? fresnel_kind[j] : 0;
-    if (l.kind < 0 || l.kind > 5 || l.fresnel < 0 || l.fresnel > 2) return fail(c, DRT_E_INVALID, "unknown BxDF or Fresnel kind");
+    if (l.kind < 0 || l.kind > 7 || l.fresnel < 0 || l.fresnel > 2) return fail(c, DRT_E_INVALID, "unknown BxDF or Fresnel kind");
+    measuredLobe = measuredLobe || l.kind >= 6;
     if (l.kind == 5 && !fresnel_eta) return fail(c, DRT_E_INVALID, "FresnelBlend (kind 5) carries Rs in the eta array");
     blend = blend || l.kind == 5;
     if (l.fresnel == 2 && (!fresnel_eta || !fresnel_k)) return fail(c, DRT_E_INVALID, "FresnelConductor needs eta and k");
@@ -1323,6 +1358,31 @@ int drt_set_material_lobes(drt_ctx* c, uint32_t n, const uint32_t* lobe_offsets,
   r->general = true;
   r->hasSpecular = spec;
   r->hasBlend = blend;
+  r->hasMeasured = measuredLobe;
+  r->sceneTablesValid = false;
+  return DRT_OK;
+}
+
+int drt_set_measured(drt_ctx* c, uint32_t n_tables, const int32_t* kind, const int32_t* dims, const uint64_t* offsets, const float* data,
+                     uint64_t n_floats) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_measured(p_, n_tables, kind, dims, offsets, data, n_floats));
+  if (!c) return DRT_E_INVALID;
+  if (n_tables && (!kind || !dims || !offsets || !data)) return fail(c, DRT_E_INVALID, "drt_set_measured: null arrays");
+  RenderState* r = state(c);
+  std::vector<GMeasured> ms(n_tables);
+  for (uint32_t i = 0; i < n_tables; ++i) {
+    GMeasured& m = ms[i];
+    m.data = nullptr;
+    m.kind = kind[i];
+    for (int k = 0; k < 3; ++k) m.dims[k] = dims[3 * i + k];
+    if (m.kind != 0 && m.kind != 1) return fail(c, DRT_E_INVALID, "measured table kind: 0 = regular halfangle (.merl), 1 = irregular isotropic (.brdf)");
+    if (m.dims[0] < 1 || (m.kind == 0 && (m.dims[1] < 1 || m.dims[2] < 1))) return fail(c, DRT_E_INVALID, "measured table dimensions must be positive");
+    const uint64_t need = m.kind == 0 ? 3ull * (uint64_t)m.dims[0] * (uint64_t)m.dims[1] * (uint64_t)m.dims[2] : 6ull * (uint64_t)m.dims[0];
+    if (offsets[i] > n_floats || need > n_floats - offsets[i]) return fail(c, DRT_E_INVALID, "a measured table reaches beyond the data array");
+  }
+  r->measured.swap(ms);
+  r->measuredOffsets.assign(offsets, offsets + n_tables);
+  r->measuredData.assign(data, data + (n_tables ? n_floats : 0));
   r->sceneTablesValid = false;
   return DRT_OK;
 }

@@ -27,6 +27,16 @@ struct GLobe {
   float pad_;
 };
 static_assert(sizeof(GLobe) == 88, "GLobe layout");
+// Lobe kinds 6 RegularHalfangleBRDF / 7 IrregularIsotropicBRDF (regular_halfangle_brdf.dart, irregular_isotropic_brdf.dart: the two BxDFs
+// of MeasuredMaterial): `param` is the table index the caller gave (drt_set_measured); when the scene tables are uploaded the library
+// writes where the table lives INTO the lobe — the bits of the device pointer in `et`, the three dimensions as int bits in `k` — so
+// the BxDF code needs nothing but the lobe, like every other kind (texture-pass lobes copy the same fields from GMeasured).
+struct GMeasured {
+  const float* data;  // kind 0: nThetaH x nThetaD x nPhiD cells of RGB; kind 1: n samples of (BRDFRemap point, RGB)
+  int32_t dims[3];
+  int32_t kind;
+};
+static_assert(sizeof(GMeasured) == 24, "GMeasured layout");
 
 struct GLight {
   int32_t kind;  // 0 = DiffuseAreaLight (diffuse_area_light.dart), 1 = PointLight (point_light.dart),
@@ -142,6 +152,8 @@ struct RenderScene {
   const float* texData;
   const GProgram* programs;  // nPrograms == 0 or one per material
   int32_t nPrograms;
+  const GMeasured* measured;  // drt_set_measured (material program kind 11 reads it; flattened lobes carry their table themselves)
+  int32_t nMeasured;
 };
 
 struct RenderParams {

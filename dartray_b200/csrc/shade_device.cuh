@@ -833,7 +833,7 @@ static __device__ inline bool SameHemisphere(const V3& w, const V3& wp) { return
 
 static __device__ inline int lobeType(int kind) {
   return kind <= 1 ? (BSDF_REFLECTION | BSDF_DIFFUSE)
-                   : ((kind == 2 || kind == 5) ? (BSDF_REFLECTION | BSDF_GLOSSY)
+                   : ((kind == 2 || kind >= 5) ? (BSDF_REFLECTION | BSDF_GLOSSY)
                                 : (kind == 3 ? (BSDF_REFLECTION | BSDF_SPECULAR) : (BSDF_TRANSMISSION | BSDF_SPECULAR)));
 }
 static __device__ inline int lobeTypeOf(const GLobe& l) {  // brdf_to_btdf.dart:27-29 flips reflection <-> transmission
@@ -952,8 +952,84 @@ static __device__ __noinline__ void blendSampleCold(const GLobe& l, V3 wo, doubl
   blendFCold(l, wo, wi, fOut);
 }
 
+// MeasuredMaterial's two BxDFs (lobe kinds 6 / 7; render_types.h GMeasured: the table's device pointer travels in the bits of `et`,
+// its dimensions in the bits of `k`).  Both keep BxDF's cosine sampling and density (bxdf.dart:37-48,84-88).  Out of line: rare.
+static __device__ inline const float* measuredData(const GLobe& l) { return (const float*)(uintptr_t)__double_as_longlong(l.et); }
+static __device__ inline double SphericalPhi(const V3& v) {  // vector.dart:189-192
+  const double p = atan2((double)v.y, (double)v.x);
+  return p < 0.0 ? p + 2.0 * DRT_PI : p;
+}
+// regular_halfangle_brdf.dart:27-75.  REMAP(V, MAX, COUNT) => ((V / MAX).toInt() * COUNT).clamp(0, COUNT - 1) AS WRITTEN: the quotient is
+// truncated BEFORE it is multiplied, so an index is 0 until V / MAX reaches 1
+static __device__ inline int measuredRemap(double v, double mx, int count) {
+  const long long q = (long long)trunc(v / mx) * count;
+  return (int)(q < 0 ? 0 : (q > count - 1 ? count - 1 : q));
+}
+static __device__ __noinline__ void regularHalfangleFCold(const GLobe& l, V3 wo, V3 wi, Spec* out) {
+  const int nThetaH = __float_as_int(l.k[0]), nThetaD = __float_as_int(l.k[1]), nPhiD = __float_as_int(l.k[2]);
+  V3 wh = wo + wi;
+  if (wh.z < 0.0f) { wo = -wo; wi = -wi; wh = -wh; }
+  if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) { *out = mks1(0.0); return; }
+  wh = Normalize(wh);
+  const double whTheta = acos(clampD((double)wh.z, -1.0, 1.0));
+  const double whCosPhi = CosPhi(wh), whSinPhi = SinPhi(wh), whCosTheta = (double)wh.z, whSinTheta = SinTheta(wh);
+  const V3 whx = mkv(whCosPhi * whCosTheta, whSinPhi * whCosTheta, -whSinTheta);
+  const V3 why = mkv(-whSinPhi, whCosPhi, 0.0);
+  const V3 wd = mkv(Dot(wi, whx), Dot(wi, why), Dot(wi, wh));
+  const double wdTheta = acos(clampD((double)wd.z, -1.0, 1.0));
+  double wdPhi = SphericalPhi(wd);
+  if (wdPhi > DRT_PI) wdPhi -= DRT_PI;
+  const int whThetaIndex = measuredRemap(sqrt(dartMax(0.0, whTheta / (DRT_PI / 2.0))), 1.0, nThetaH);
+  const int wdThetaIndex = measuredRemap(wdTheta, DRT_PI / 2.0, nThetaD);
+  const int wdPhiIndex = measuredRemap(wdPhi, DRT_PI, nPhiD);
+  const size_t index = (size_t)wdPhiIndex + (size_t)nPhiD * ((size_t)wdThetaIndex + (size_t)whThetaIndex * nThetaD);
+  const float* brdf = measuredData(l);
+  *out = Spec{__ldg(brdf + 3 * index), __ldg(brdf + 3 * index + 1), __ldg(brdf + 3 * index + 2)};
+}
+// irregular_isotropic_brdf.dart:36-62 over BRDFRemap (brdf_remap.dart:23-47).  KdTree.lookup (kdtree.dart:86-112) hands proc() exactly
+// the samples with DistanceSquared(sample.p, m) < maxDist2, in an order that depends on object hash codes (kdtree.dart:120-124): the
+// reference does not fix the order of its float32 sums, the oracle visits the samples in file order, and so does this loop.
+static __device__ __noinline__ void irregularIsotropicFCold(const GLobe& l, V3 wo, V3 wi, Spec* out) {
+  const int n = __float_as_int(l.k[0]);
+  const float* data = measuredData(l);
+  const double cosi = (double)wi.z, coso = (double)wo.z, sini = SinTheta(wi), sino = SinTheta(wo);
+  double dphi = SphericalPhi(wi) - SphericalPhi(wo);
+  if (dphi < 0.0) dphi += 2.0 * DRT_PI;
+  if (dphi > 2.0 * DRT_PI) dphi -= 2.0 * DRT_PI;
+  if (dphi > DRT_PI) dphi = 2.0 * DRT_PI - dphi;
+  const V3 m = mkv(sini * sino, dphi / DRT_PI, cosi * coso);
+  double lastMaxDist2 = 0.001;
+  for (;;) {
+    Spec v = mks1(0.0);
+    double sumWeights = 0.0;
+    int nFound = 0;
+    for (int i = 0; i < n; ++i) {
+      const float* q = data + 6 * (size_t)i;
+      const V3 sp = V3{__ldg(q), __ldg(q + 1), __ldg(q + 2)};
+      const double d2 = DistanceSquared(sp, m);
+      if (d2 < lastMaxDist2) {
+        const double weight = exp(-100.0 * d2);
+        v = v + Spec{__ldg(q + 3), __ldg(q + 4), __ldg(q + 5)} * weight;
+        sumWeights += weight;
+        ++nFound;
+      }
+    }
+    if (nFound > 2 || lastMaxDist2 > 1.5) {
+      *out = mks(clampD((double)v.r, 0.0, CUDART_INF), clampD((double)v.g, 0.0, CUDART_INF), clampD((double)v.b, 0.0, CUDART_INF)) / sumWeights;
+      return;
+    }
+    lastMaxDist2 *= 2.0;
+  }
+}
+
 static __device__ inline Spec lobeBaseF(const GLobe& l, const V3& wo, const V3& wi) {
-  if (DRT_EXTRA && l.kind == 5) { Spec r; blendFCold(l, wo, wi, &r); return r; }
+  if (DRT_EXTRA && l.kind >= 5) {
+    Spec r;
+    if (l.kind == 5) blendFCold(l, wo, wi, &r);
+    else if (l.kind == 6) regularHalfangleFCold(l, wo, wi, &r);
+    else irregularIsotropicFCold(l, wo, wi, &r);
+    return r;
+  }
   const Spec R = Spec{l.rgb[0], l.rgb[1], l.rgb[2]};
   if (l.kind == 0) return R * DRT_INV_PI;  // lambertian.dart:35-37
   if (l.kind == 1) {                       // oren_nayar.dart:24-58
@@ -987,7 +1063,7 @@ static __device__ inline Spec lobeBaseF(const GLobe& l, const V3& wo, const V3& 
 }
 static __device__ inline double lobeBasePdf(const GLobe& l, const V3& wo, const V3& wi) {
   if (DRT_EXTRA && l.kind == 5) return blendPdfCold(l, wo, wi);
-  if (l.kind <= 1) return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * DRT_INV_PI : 0.0;  // bxdf.dart:84-88
+  if (l.kind <= 1 || l.kind >= 6) return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * DRT_INV_PI : 0.0;  // bxdf.dart:84-88
   if (l.kind == 2) {                                                                     // microfacet.dart:68-73
     if (!SameHemisphere(wo, wi)) return 0.0;
     const V3 wh = Normalize(wo + wi);
@@ -1006,7 +1082,7 @@ static __device__ inline Spec lobeBaseSampleF(const GLobe& l, const V3& wo, V3* 
     *pdfOut = p;
     return f;
   }
-  if (l.kind <= 1) {  // bxdf.dart:37-48
+  if (l.kind <= 1 || l.kind >= 6) {  // bxdf.dart:37-48
     *wi = CosineSampleHemisphere(u1, u2);
     if (wo.z < 0.0f) wi->z = (float)((double)wi->z * -1.0);
     *pdfOut = lobeBasePdf(l, wo, *wi);
@@ -1353,10 +1429,6 @@ static __device__ inline void envRadianceCold(const RenderScene& rs, const GLigh
   *out = r * lightRadiance(l);  // _radiance = lookup * L (infinite_area_light.dart:240-242)
 }
 static __device__ inline double SphericalTheta(const V3& v) { return acos(clampD((double)v.z, -1.0, 1.0)); }  // vector.dart:185-187
-static __device__ inline double SphericalPhi(const V3& v) {                                                 // vector.dart:189-192
-  double p = atan2((double)v.y, (double)v.x);
-  return (p < 0.0) ? p + 2.0 * DRT_PI : p;
-}
 static __device__ inline V3 xf3(const float* m, const V3& w) {
   return mkv((double)m[0] * w.x + (double)m[1] * w.y + (double)m[2] * w.z, (double)m[3] * w.x + (double)m[4] * w.y + (double)m[5] * w.z,
              (double)m[6] * w.x + (double)m[7] * w.y + (double)m[8] * w.z);

@@ -936,6 +936,14 @@ static __device__ __noinline__ void materialBsdfCold(const RenderScene& rs, cons
       }
       break;
     }
+    case 11: {  // measured_material.dart:219-238: m1 = table of drt_set_measured (its kind picks the BxDF)
+      const GMeasured tb = rs.measured[pr.m1];
+      GLobe l = mkLobe(tb.kind == 0 ? 6 : 7, mks1(1.0), 0, (double)pr.m1);
+      l.et = __longlong_as_double((long long)(uintptr_t)tb.data);
+      for (int k = 0; k < 3; ++k) l.k[k] = __int_as_float(tb.dims[k]);
+      add(l);
+      break;
+    }
     case 10: {  // subsurface_material.dart:52-69, kd_subsurface_material.dart:48-67 (the BSSRDF is the dipole integrator's)
       const Spec R = clampS(S(t[0], dgs));
       const double e = texEvalF(c, t[1], dgs);

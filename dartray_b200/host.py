@@ -245,6 +245,8 @@ class Integrator:
 # evaluates constant textures, so the BxDF list of a material is a constant of the scene.  Spectrum arithmetic is
 # float32 storage / float64 expressions like RGBColor (rgb_color.dart:142-169).
 LOBE_LAMBERTIAN, LOBE_OREN_NAYAR, LOBE_MICROFACET_BLINN, LOBE_SPECULAR_REFLECTION, LOBE_SPECULAR_TRANSMISSION, LOBE_FRESNEL_BLEND = range(6)
+LOBE_REGULAR_HALFANGLE, LOBE_IRREGULAR_ISOTROPIC = 6, 7  # MeasuredMaterial's BxDFs: param = table index (drt_set_measured)
+MEASURED_REGULAR_HALFANGLE, MEASURED_IRREGULAR_ISOTROPIC = 0, 1
 FRESNEL_NOOP, FRESNEL_DIELECTRIC, FRESNEL_CONDUCTOR = range(3)
 
 
@@ -565,6 +567,7 @@ PROGRAM_PARAMS = {
     "mix": (9, (("amount", True, 0.5),)),
     "subsurface": (10, (("kr", True, 1.0), ("index", False, 1.3))),
     "kdsubsurface": (10, (("kr", True, 1.0), ("index", False, 1.3))),
+    "measured": (11, ()),  # m1 = SceneBuilder.measured_table(...)
 }
 
 
@@ -715,6 +718,46 @@ def subsurface_lobes(kr=1.0, index=1.3) -> list:  # subsurface_material.dart:52-
     return [] if _black(r) else [_lobe(LOBE_SPECULAR_REFLECTION, r, FRESNEL_DIELECTRIC, ei=1.0, et=index)]
 
 
+def measured_lobes(table: int, table_kind: int) -> list:  # measured_material.dart:219-238
+    """MeasuredMaterial.getBSDF without a bump map: one RegularHalfangleBRDF or IrregularIsotropicBRDF over table `table`."""
+    return [_lobe(LOBE_REGULAR_HALFANGLE if table_kind == MEASURED_REGULAR_HALFANGLE else LOBE_IRREGULAR_ISOTROPIC, 1.0, param=table)]
+
+
+def merl_table(data: bytes) -> np.ndarray:  # measured_material.dart:160-202
+    """regularHalfangleData of a .merl file: three little-endian int32 dimensions, then one plane of float64 per colour channel; every
+    value is rounded to float32 (the Float32List `tmp`), scaled by (1, 1.15, 1.66) / 1500 in binary64 and clamped below at 0."""
+    dims = np.frombuffer(data, "<i4", 3)
+    n = int(dims[0]) * int(dims[1]) * int(dims[2])
+    if n != 90 * 90 * 180:
+        raise ValueError("Dimensions don't match")
+    raw = np.frombuffer(data, "<f8", 3 * n, 12).reshape(3, n).astype(np.float32).astype(np.float64)
+    scales = np.array([1.0 / 1500.0, 1.15 / 1500.0, 1.66 / 1500.0])
+    out = np.maximum(0.0, raw * scales[:, None]).astype(np.float32)
+    return np.ascontiguousarray(out.T).reshape(90, 90, 180, 3)
+
+
+def brdf_remap(wo, wi) -> np.ndarray:  # brdf_remap.dart:23-47 (float32 Vector components in, float32 Point out)
+    wo, wi = np.asarray(wo, np.float32).astype(np.float64), np.asarray(wi, np.float32).astype(np.float64)
+    cosi, coso = wi[..., 2], wo[..., 2]
+    sini, sino = np.sqrt(np.maximum(0.0, 1.0 - cosi * cosi)), np.sqrt(np.maximum(0.0, 1.0 - coso * coso))
+    phi = lambda v: np.where(np.arctan2(v[..., 1], v[..., 0]) < 0.0, np.arctan2(v[..., 1], v[..., 0]) + 2.0 * np.pi, np.arctan2(v[..., 1], v[..., 0]))
+    dphi = phi(wi) - phi(wo)
+    dphi = np.where(dphi < 0.0, dphi + 2.0 * np.pi, dphi)
+    dphi = np.where(dphi > 2.0 * np.pi, dphi - 2.0 * np.pi, dphi)
+    dphi = np.where(dphi > np.pi, 2.0 * np.pi - dphi, dphi)
+    return np.stack([sini * sino, dphi / np.pi, cosi * coso], -1).astype(np.float32)
+
+
+def brdf_samples(thetai, phii, thetao, phio, rgb) -> np.ndarray:  # measured_material.dart:117-131
+    """The IrregIsotropicBRDFSamples of a .brdf file's measurements: the four angles of every measurement and its value ALREADY
+    converted to RGB (Spectrum.fromSampled stays with the caller) -> n x 6 float32 (BRDFRemap point, RGB) in file order."""
+    def sph(theta, phi):  # Vector.SphericalDirection(sin(theta), cos(theta), phi)
+        st, ct, ph = np.sin(np.asarray(theta, np.float64)), np.cos(np.asarray(theta, np.float64)), np.asarray(phi, np.float64)
+        return np.stack([st * np.cos(ph), st * np.sin(ph), ct], -1).astype(np.float32)
+    p = brdf_remap(sph(thetao, phio), sph(thetai, phii))
+    return np.concatenate([p, np.asarray(rgb, np.float32).reshape(-1, 3)], 1)
+
+
 @_folds_textures
 def uber_lobes(kd=0.25, ks=0.25, kr=0.0, kt=0.0, roughness=0.1, index=1.5, opacity=1.0) -> list:  # uber_material.dart:27-75
     out, op = [], _clamp(opacity)
@@ -761,6 +804,18 @@ class SceneBuilder:
         self.materials.append(("lobes", list(lobes)))
         return len(self.materials) - 1
 
+    def measured_table(self, kind: int, data) -> int:
+        """Data of one MeasuredMaterial file (drt_set_measured): kind MEASURED_REGULAR_HALFANGLE with an (nThetaH, nThetaD, nPhiD, 3)
+        array (merl_table) or MEASURED_IRREGULAR_ISOTROPIC with an (n, 6) array (brdf_samples).  Returns the table index that
+        measured_lobes / material_program("measured", m1=...) take."""
+        if not hasattr(self, "measured"):
+            self.measured = []
+        a = np.ascontiguousarray(data, np.float32)
+        if (kind == MEASURED_REGULAR_HALFANGLE and (a.ndim != 4 or a.shape[3] != 3)) or (kind == MEASURED_IRREGULAR_ISOTROPIC and (a.ndim != 2 or a.shape[1] != 6)):
+            raise ValueError("measured table shape")
+        self.measured.append((int(kind), a))
+        return len(self.measured) - 1
+
     def material_program(self, plugin: str, bumpmap=None, m1=None, m2=None, **params) -> int:
         """A material whose parameters are textures that read the hit point, or that carries a bump map (`plugin` and the parameter
         names are the reference's, lower case: material_program("uber", kd=ImageTexture(...), ks=0.05, bumpmap=...)); "mix" takes
@@ -777,6 +832,8 @@ class SceneBuilder:
             vals.append((v, spectrum))
         if kind == 9 and (m1 is None or m2 is None):
             raise ValueError("mix needs m1 and m2")
+        if kind == 11 and m1 is None:
+            raise ValueError("measured needs m1 = the index measured_table() returned")
         self.materials.append(("program", kind, vals, bumpmap, m1, m2))
         return len(self.materials) - 1
 
@@ -1008,6 +1065,8 @@ class SceneBuilder:
                 programs[i]["tex"][j] = table.add(v, spectrum)
             if m[3] is not None:
                 programs[i]["bump"] = table.add(m[3], False)
+            if m[1] == 11:
+                programs[i]["m1"], programs[i]["m2"] = m[4], 0
             if m[1] == 9:
                 programs[i]["m1"], programs[i]["m2"] = m[4], m[5]
                 for sub in (m[4], m[5]):
@@ -1050,6 +1109,7 @@ class SceneBuilder:
             mat_sigma=np.asarray([m[2] for m in mats], np.float32),
             mat_general=general,
             mat_programs=programs if has_programs else None, tex_nodes=tex_nodes, tex_texels=tex_texels,
+            measured=list(getattr(self, "measured", [])),
             mat_lobe_offsets=np.asarray(np.cumsum([0] + [len(ll) for ll in lobe_lists]), np.uint32),
             lobe_kind=np.asarray([l["kind"] for l in lobes], np.int32),
             lobe_rgb=np.asarray([l["rgb"] for l in lobes], np.float32).reshape(-1, 3),
@@ -1120,6 +1180,8 @@ def upload_scene(ctx, arrays: dict, split: int = 2, max_node_prims: int = 4):
         i = j
     ctx.set_build_order(a["order"])
     ctx.build_bvh(split, max_node_prims)
+    if a.get("measured"):
+        ctx.set_measured(a["measured"])
     if a.get("mat_general"):
         ctx.set_material_lobes(a["mat_lobe_offsets"], a["lobe_kind"], a["lobe_rgb"], a["lobe_fresnel"], a["lobe_eta"], a["lobe_k"],
                                a["lobe_scalars"])

@@ -227,12 +227,25 @@ int drt_set_materials(drt_ctx* ctx, uint32_t n, const int32_t* kind, const float
  *   fresnel_kind  0 FresnelNoOp, 1 FresnelDielectric(ei, et), 2 FresnelConductor(eta, k) (fresnel_*.dart); NULL = all 0
  *   fresnel_eta, fresnel_k   conductor spectra as RGB (n_lobes x 3; NULL when no lobe uses a conductor)
  *   lobe_scalars  n_lobes x 3 doubles: {Blinn exponent after blinn.dart:24-28 | OrenNayar sigma in degrees, ei, et}
+ *   lobe_kind 6 RegularHalfangleBRDF (regular_halfangle_brdf.dart) / 7 IrregularIsotropicBRDF (irregular_isotropic_brdf.dart), the
+ *                 BxDFs of MeasuredMaterial: lobe_scalars[0] = index of the table given to drt_set_measured
  * Every integrator takes every combination; directlighting evaluates its SpecularReflect / SpecularTransmit recursion
  * (lib/core/integrator.dart:187-290) chain by chain up to maxdepth 17 (DRT_E_UNSUPPORTED beyond).  Replaces a previous
  * drt_set_materials and vice versa. */
 int drt_set_material_lobes(drt_ctx* ctx, uint32_t n, const uint32_t* lobe_offsets, const int32_t* lobe_kind, const float* lobe_rgb,
                            const int32_t* fresnel_kind, const float* fresnel_eta, const float* fresnel_k,
                            const double* lobe_scalars);
+
+/* The data a MeasuredMaterial holds once its file is loaded (lib/materials/measured_material.dart:76-205; loading and the
+ * spectrum -> RGB conversion of .brdf files stay with the caller).  Table i = data[offsets[i] ...]:
+ *   kind 0  regularHalfangleData of a .merl file: dims = (nThetaH, nThetaD, nPhiD) = (90, 90, 180) in the reference, 3 floats (RGB)
+ *           per cell with the phi difference as the minor index (regular_halfangle_brdf.dart:66-71)
+ *   kind 1  the IrregIsotropicBRDFSamples of a .brdf file: dims[0] samples of 6 floats, the BRDFRemap point (brdf_remap.dart:23-47)
+ *           then the sample's RGB value; the reference finds the samples around a query through a KdTree (kdtree.dart:86-112),
+ *           which visits exactly those closer than the search radius — here they are visited in the order given
+ * Referenced by lobe kinds 6 / 7 of drt_set_material_lobes and by material program kind 11.  n_tables == 0 removes them. */
+int drt_set_measured(drt_ctx* ctx, uint32_t n_tables, const int32_t* kind, const int32_t* dims, const uint64_t* offsets,
+                     const float* data, uint64_t n_floats);
 
 /* The two BxDF adapters of the reference around the lobes of the last drt_set_material_lobes, one entry per lobe in the same
  * order: wrap bit 0 = BRDFToBTDF(bxdf) (lib/core/reflection/brdf_to_btdf.dart: TranslucentMaterial's transmissive Lambertian and
@@ -295,6 +308,8 @@ int drt_set_textures(drt_ctx* ctx, uint32_t n, const drt_texture* nodes, const f
  *   4 metal        eta, k, roughness                 9 mix          amount; m1 / m2 = material indices (one level)
  *   10 subsurface / kdsubsurface   Kr, index  (their BSDF is SpecularReflection(Kr, FresnelDielectric(1, index)),
  *      subsurface_material.dart:52-69; the BSSRDF belongs to the dipole integrator, which is not on the path)
+ *   11 measured    no textures; m1 = table of drt_set_measured (measured_material.dart:219-238: the table's kind picks
+ *      RegularHalfangleBRDF or IrregularIsotropicBRDF)
  * bump: a float texture node or -1.  n == 0 removes the programs. */
 typedef struct drt_material_program {
   int32_t kind;

@@ -363,6 +363,23 @@ int orc_set_lobe_wrappers(orc_ctx* c, uint32_t nLobes, const int32_t* wrap, cons
   return 0;
 }
 
+// mirrors drt_set_measured: the tables a MeasuredMaterial holds after loading its file (measured_material.dart:76-205)
+int orc_set_measured(orc_ctx* c, uint32_t n, const int32_t* kind, const int32_t* dims, const uint64_t* offsets, const float* data,
+                     uint64_t nFloats) {
+  c->rs.measured.assign(n, MeasuredTable());
+  for (uint32_t i = 0; i < n; ++i) {
+    MeasuredTable& t = c->rs.measured[i];
+    t.kind = kind[i];
+    for (int k = 0; k < 3; ++k) t.dims[k] = dims[3 * i + k];
+    if (t.kind != 0 && t.kind != 1) { c->err = "measured table kind must be 0 (regular halfangle) or 1 (irregular isotropic)"; return -1; }
+    if (t.dims[0] < 1 || (t.kind == 0 && (t.dims[1] < 1 || t.dims[2] < 1))) { c->err = "measured table dimensions"; return -1; }
+    const uint64_t need = t.kind == 0 ? 3ull * t.dims[0] * t.dims[1] * t.dims[2] : 6ull * t.dims[0];
+    if (offsets[i] + need > nFloats) { c->err = "measured table beyond the data array"; return -1; }
+    t.data.assign(data + offsets[i], data + offsets[i] + need);
+  }
+  return 0;
+}
+
 // mirrors drt_set_textures (include/drt.h)
 int orc_set_textures(orc_ctx* c, uint32_t n, const drt_texture* nodes, const float* texels, uint64_t nTexelFloats) {
   TextureSet& ts = c->rs.textures;

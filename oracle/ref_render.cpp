@@ -404,7 +404,7 @@ struct LobeEval {
       }
       case 2: type = BSDF_REFLECTION | BSDF_GLOSSY; break;
       case 3: type = BSDF_REFLECTION | BSDF_SPECULAR; break;
-      case 5: type = BSDF_REFLECTION | BSDF_GLOSSY; break;
+      case 5: case 6: case 7: type = BSDF_REFLECTION | BSDF_GLOSSY; break;
       default: type = BSDF_TRANSMISSION | BSDF_SPECULAR; break;
     }
     if (l.wrap & 1) type ^= (BSDF_REFLECTION | BSDF_TRANSMISSION);  // brdf_to_btdf.dart:27-29; ScaledBxDF keeps the type
@@ -538,6 +538,75 @@ struct LobeEval {
     return 0.5 * (AbsCosTheta(wi) * INV_PI + anisoPdf(wo, wi));
   }
 
+  // regular_halfangle_brdf.dart:27-75
+  Spec regularHalfangleF(const Vec& WO, const Vec& WI) const {
+    const MeasuredTable& tb = *l.measured;
+    Vec wo = WO, wi = WI;
+    Vec wh = wo + wi;
+    if (wh.z < 0.0f) { wo = -wo; wi = -wi; wh = -wh; }
+    if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return Spec(0.0);
+    wh = Normalize(wh);
+    double whTheta = std::acos(clampd((double)wh.z, -1.0, 1.0));  // SphericalTheta
+    double whCosPhi = CosPhi(wh), whSinPhi = SinPhi(wh), whCosTheta = CosTheta(wh), whSinTheta = SinTheta(wh);
+    Vec whx(whCosPhi * whCosTheta, whSinPhi * whCosTheta, -whSinTheta);
+    Vec why(-whSinPhi, whCosPhi, 0.0);
+    Vec wd(Dot(wi, whx), Dot(wi, why), Dot(wi, wh));
+    double wdTheta = std::acos(clampd((double)wd.z, -1.0, 1.0));
+    double wdPhi = std::atan2((double)wd.y, (double)wd.x);  // SphericalPhi, vector.dart:189-192
+    if (wdPhi < 0.0) wdPhi += 2.0 * kPi;
+    if (wdPhi > kPi) wdPhi -= kPi;
+    // REMAP(V, MAX, COUNT) => ((V / MAX).toInt() * COUNT).clamp(0, COUNT - 1) AS WRITTEN: the truncation comes BEFORE the multiplication,
+    // so every index is 0 except where V / MAX reaches 1 (toInt of a NaN throws in Dart: not a value the BRDF is evaluated at)
+    auto REMAP = [](double V, double MAX, int COUNT) {
+      long long q = (long long)std::trunc(V / MAX) * COUNT;
+      return (int)std::min<long long>(std::max<long long>(q, 0), COUNT - 1);
+    };
+    int whThetaIndex = REMAP(std::sqrt(std::fmax(0.0, whTheta / (kPi / 2.0))), 1.0, tb.dims[0]);
+    int wdThetaIndex = REMAP(wdTheta, kPi / 2.0, tb.dims[1]);
+    int wdPhiIndex = REMAP(wdPhi, kPi, tb.dims[2]);
+    size_t index = (size_t)wdPhiIndex + (size_t)tb.dims[2] * ((size_t)wdThetaIndex + (size_t)whThetaIndex * tb.dims[1]);
+    return Spec(tb.data[3 * index], tb.data[3 * index + 1], tb.data[3 * index + 2]);
+  }
+  // brdf_remap.dart:23-47
+  static Vec BRDFRemap(const Vec& wo, const Vec& wi) {
+    double cosi = CosTheta(wi), coso = CosTheta(wo), sini = SinTheta(wi), sino = SinTheta(wo);
+    auto sphPhi = [](const Vec& v) { double p = std::atan2((double)v.y, (double)v.x); return p < 0.0 ? p + 2.0 * kPi : p; };
+    double dphi = sphPhi(wi) - sphPhi(wo);
+    if (dphi < 0.0) dphi += 2.0 * kPi;
+    if (dphi > 2.0 * kPi) dphi -= 2.0 * kPi;
+    if (dphi > kPi) dphi = 2.0 * kPi - dphi;
+    return Vec(sini * sino, dphi / kPi, cosi * coso);
+  }
+  // irregular_isotropic_brdf.dart:36-62.  KdTree.lookup (kdtree.dart:86-112) hands proc() exactly the samples with
+  // DistanceSquared(sample.p, m) < maxDist2; in which order depends on nth_element and on object hash codes (kdtree.dart:120-124), so
+  // the reference itself does not fix the order of the float32 sums: here the samples are visited in file order.
+  Spec irregularIsotropicF(const Vec& wo, const Vec& wi) const {
+    const MeasuredTable& tb = *l.measured;
+    Vec m = BRDFRemap(wo, wi);
+    double lastMaxDist2 = 0.001;
+    for (;;) {
+      Spec v(0.0);
+      double sumWeights = 0.0;
+      int nFound = 0;
+      for (int i = 0; i < tb.dims[0]; ++i) {
+        const float* q = &tb.data[6 * (size_t)i];
+        Vec sp;
+        sp.x = q[0]; sp.y = q[1]; sp.z = q[2];
+        double d2 = DistanceSquared(sp, m);
+        if (d2 < lastMaxDist2) {
+          double weight = std::exp(-100.0 * d2);
+          Spec sv;
+          sv.c[0] = q[3]; sv.c[1] = q[4]; sv.c[2] = q[5];
+          v = v + sv * weight;
+          sumWeights += weight;
+          ++nFound;
+        }
+      }
+      if (nFound > 2 || lastMaxDist2 > 1.5) return Spec(clampd(v.c[0], 0.0, kInf), clampd(v.c[1], 0.0, kInf), clampd(v.c[2], 0.0, kInf)) / sumWeights;
+      lastMaxDist2 *= 2.0;
+    }
+  }
+
   Spec baseF(const Vec& wo, const Vec& wi) const {
     switch (l.kind) {
       case 0: return l.R * INV_PI;  // lambertian.dart:35-37
@@ -566,13 +635,17 @@ struct LobeEval {
         return l.R * (blinnD(wh) * G) * F / (4.0 * cosThetaI * cosThetaO);
       }
       case 5: return blendF(wo, wi);
+      case 6: return regularHalfangleF(wo, wi);
+      case 7: return irregularIsotropicF(wo, wi);
       default: return Spec(0.0);  // specular_reflection.dart:30-32, specular_transmission.dart:33-35
     }
   }
   double basePdf(const Vec& wo, const Vec& wi) const {
     switch (l.kind) {
       case 0:
-      case 1: return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * INV_PI : 0.0;  // bxdf.dart:84-88
+      case 1:
+      case 6:
+      case 7: return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * INV_PI : 0.0;  // bxdf.dart:84-88
       case 2: return SameHemisphere(wo, wi) ? blinnPdf(wo, wi) : 0.0;          // microfacet.dart:68-73
       case 5: return blendPdf(wo, wi);
       default: return 0.0;
@@ -582,7 +655,9 @@ struct LobeEval {
   Spec baseSampleF(const Vec& wo, Vec* wi, double u1, double u2, double* pdfOut) const {
     switch (l.kind) {
       case 0:
-      case 1: {  // bxdf.dart:37-48
+      case 1:
+      case 6:
+      case 7: {  // bxdf.dart:37-48
         *wi = CosineSampleHemisphere(u1, u2);
         if (wo.z < 0.0f) wi->z = f32((double)wi->z * -1.0);
         *pdfOut = basePdf(wo, *wi);
@@ -1182,7 +1257,12 @@ struct Ctx {
   }
   Spec texS(int id, const DG& dg) const { float v[3]; rs.textures.evalSpec(id, dg, v); return specOf(v); }
   double texF(int id, const DG& dg) const { return rs.textures.evalFloat(id, dg); }
-  static void addLobe(Bsdf* b, const Lobe& l) { b->bxdfs[b->nBxDFs++].init(l); b->lobes[b->nBxDFs - 1] = l; }
+  void addLobe(Bsdf* b, const Lobe& lobe) const {
+    Lobe l = lobe;
+    if (l.kind == 6 || l.kind == 7) l.measured = &rs.measured[(size_t)l.param];
+    b->bxdfs[b->nBxDFs++].init(l);
+    b->lobes[b->nBxDFs - 1] = l;
+  }
   static Lobe mkLobe(int kind, const Spec& R, int fresnel = 0, double param = 0.0, double ei = 1.0, double et = 1.0) {
     Lobe l; l.kind = kind; l.R = R; l.fresnel = fresnel; l.param = param; l.ei = ei; l.et = et; return l;
   }
@@ -1293,6 +1373,11 @@ struct Ctx {
           if (!r.isBlack()) addLobe(b, mkLobe(2, r * ks, 1, e, 1.5, 1.0));
           if (!tr.isBlack()) { Lobe l = mkLobe(2, tr * ks, 1, e, 1.5, 1.0); l.wrap = 1; addLobe(b, l); }
         }
+        break;
+      }
+      case 11: {  // measured_material.dart:219-238 (m1 = table index; regularHalfangleData or thetaPhiData picks the BxDF)
+        frameBsdf(b, dgs, dgGeom.nn, 1.0);
+        addLobe(b, mkLobe(rs.measured.at((size_t)prog->m1).kind == 0 ? 6 : 7, Spec(1.0), 0, (double)prog->m1));
         break;
       }
       case 10: {  // subsurface_material.dart:52-69, kd_subsurface_material.dart:48-67 (the BSSRDF is the dipole integrator's)
@@ -2214,7 +2299,10 @@ static Bsdf canonicalBsdf(const RenderScene& rs, uint32_t material) {
   b.nn = b.ng = Vec(0, 0, 1);
   b.sn = Vec(1, 0, 0);
   b.tn = Vec(0, 1, 0);
-  for (const Lobe& l : rs.materials.at(material).lobes) b.bxdfs[b.nBxDFs++].init(l);
+  for (Lobe l : rs.materials.at(material).lobes) {
+    if (l.kind == 6 || l.kind == 7) l.measured = &rs.measured.at((size_t)l.param);
+    b.bxdfs[b.nBxDFs++].init(l);
+  }
   return b;
 }
 

@@ -143,6 +143,14 @@ static const uint32_t kStreamVolumeLi = 0x80000002u;
 //   plastic  plastic_material.dart:26-53    Lambertian(Kd) + Microfacet(Ks, FresnelDielectric(1.5, 1), Blinn(1/roughness))
 //   metal    metal_material.dart:26-46      Microfacet(1, FresnelConductor(eta, k), Blinn(1/roughness))
 //   uber     uber_material.dart:27-75       SpecularTransmission(1-op, 1, 1) + Lambertian + Microfacet + SpecularReflection + SpecularTransmission
+// MeasuredMaterial's data (measured_material.dart:76-205): kind 0 = RegularHalfangleBRDF table (3 floats per cell, dims = nThetaH,
+// nThetaD, nPhiD), kind 1 = the IrregIsotropicBRDFSamples of a .brdf file (dims[0] samples of 6 floats: BRDFRemap point, RGB value)
+struct MeasuredTable {
+  int kind = 0;
+  int dims[3] = {0, 0, 0};
+  std::vector<float> data;
+};
+
 struct Lobe {
   int kind = 0;     // 0 Lambertian, 1 OrenNayar, 2 Microfacet(Blinn), 3 SpecularReflection, 4 SpecularTransmission,
                     // 5 FresnelBlend(Rd = R, Rs = eta, Anisotropic(ex = param, ey = ei)) (fresnel_blend.dart, anisotropic.dart)
@@ -155,6 +163,9 @@ struct Lobe {
   // bit 1 = ScaledBxDF(<that>, scale) (MixMaterial)
   int wrap = 0;
   Spec scale = Spec(1.0);
+  // kinds 6 RegularHalfangleBRDF / 7 IrregularIsotropicBRDF (regular_halfangle_brdf.dart, irregular_isotropic_brdf.dart): param = index
+  // of the table in RenderScene::measured; the pointer is resolved when the BSDF is built
+  const MeasuredTable* measured = nullptr;
 };
 
 struct Material {
@@ -288,6 +299,7 @@ struct RenderScene {
   // textures that read the hit point and the materials built from them (ref_texture.h); programs is empty or one per material
   TextureSet textures;
   std::vector<MaterialProgram> programs;
+  std::vector<MeasuredTable> measured;
   std::vector<Light> lights;
   Camera camera;
   Film film;

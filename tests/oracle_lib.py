@@ -64,6 +64,7 @@ def lib():
         L.orc_set_lobe_wrappers.argtypes = [vp, u32, vp, vp]
         L.orc_set_infinite_light.argtypes = [vp, u32, i32, i32, vp, vp, vp]
         L.orc_set_textures.argtypes = [vp, u32, vp, vp, u64]
+        L.orc_set_measured.argtypes = [vp, u32, vp, vp, vp, vp, u64]
         L.orc_set_material_programs.argtypes = [vp, u32, vp]
         L.orc_texture_eval.argtypes = [vp, i32, u32, vp, vp]
         L.orc_image_level.argtypes = [vp, i32, i32, vp, vp, vp]
@@ -240,6 +241,22 @@ class Oracle:
         """BRDFToBTDF (bit 0) / ScaledBxDF (bit 1, with its RGB scale) around the lobes of the last set_material_lobes."""
         w, sc = _arr(wrap, np.int32), _arr(scale, np.float32).reshape(-1, 3)
         self._ck(self.L.orc_set_lobe_wrappers(self.h, w.shape[0], _p(w), _p(sc)))
+
+    def set_measured(self, tables):
+        """MeasuredMaterial data (measured_material.dart:76-205): list of (kind, array) — kind 0 = RegularHalfangleBRDF table
+        (nThetaH x nThetaD x nPhiD x 3 float32), kind 1 = IrregIsotropicBRDFSamples (n x 6 float32: BRDFRemap point, RGB)."""
+        kinds = np.array([k for k, _ in tables], np.int32)
+        dims = np.zeros((len(tables), 3), np.int32)
+        offs = np.zeros(len(tables), np.uint64)
+        chunks, pos = [], 0
+        for i, (k, a) in enumerate(tables):
+            a = np.ascontiguousarray(a, np.float32)
+            dims[i] = a.shape[:3] if k == 0 else (a.shape[0], 0, 0)
+            offs[i] = pos
+            pos += a.size
+            chunks.append(a.ravel())
+        data = np.concatenate(chunks) if chunks else np.zeros(0, np.float32)
+        self._ck(self.L.orc_set_measured(self.h, len(tables), _p(kinds), _p(dims), _p(offs), _p(data), data.size))
 
     def set_textures(self, nodes, texels):
         """Texture nodes (host.TEX_DTYPE records = drt_texture) and the level-0 texels of their images."""

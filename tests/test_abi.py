@@ -107,7 +107,15 @@ def test_argument_errors_of_the_widened_scene_and_render_entries(drt_lib):
         ctx.set_lobe_wrappers([2, 8], np.ones((2, 3), np.float32))
     ctx.set_lobe_wrappers([l["wrap"] for l in lobes], [l["scale"] for l in lobes])
     with pytest.raises(capi.DrtError, match="BxDF"):
-        ctx.set_material_lobes([0, 1], [6], [[1, 1, 1]], [0], [[0, 0, 0]], [[0, 0, 0]], [(0, 1, 1)])
+        ctx.set_material_lobes([0, 1], [8], [[1, 1, 1]], [0], [[0, 0, 0]], [[0, 0, 0]], [(0, 1, 1)])
+    # MeasuredMaterial tables
+    with pytest.raises(capi.DrtError, match="beyond the data"):
+        ctx.L.drt_set_measured.restype = int
+        ctx._ck(ctx.L.drt_set_measured(ctx.h, 1, np.array([0], np.int32).ctypes.data, np.array([90, 90, 180], np.int32).ctypes.data,
+                                       np.array([0], np.uint64).ctypes.data, np.zeros(8, np.float32).ctypes.data, 8))
+    with pytest.raises(capi.DrtError, match="table kind"):
+        ctx.set_measured([(3, np.zeros((2, 6), np.float32))])
+    ctx.set_measured([(0, np.zeros((2, 2, 2, 3), np.float32)), (1, np.zeros((5, 6), np.float32))])
     # samplers
     with pytest.raises(capi.DrtError, match="sampler kind"):
         ctx.set_sampler(6, 1, 1, 4, 1, 1, 32, 0)
