@@ -22,7 +22,7 @@ HIT_DTYPE = np.dtype([("t", np.float32), ("b1", np.float32), ("b2", np.float32),
 # every symbol include/drt.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
     "drt_version", "drt_create", "drt_create_multi", "drt_device_count", "drt_destroy", "drt_last_error", "drt_set_triangles", "drt_set_spheres", "drt_set_disks", "drt_set_quadrics", "drt_set_mesh_shading", "drt_set_infinite_light", "drt_set_lobe_wrappers", "drt_set_light_map", "drt_set_sample_table",
-    "drt_set_build_order", "drt_build_bvh", "drt_bvh_info_get", "drt_bvh_export", "drt_trace_closest",
+    "drt_set_instances", "drt_set_ray_times", "drt_set_build_order", "drt_build_bvh", "drt_bvh_info_get", "drt_bvh_export", "drt_trace_closest",
     "drt_trace_any", "drt_trace_closest_device", "drt_trace_any_device", "drt_set_counting", "drt_get_counters", "drt_set_kernel_variant",
     "drt_last_kernel_ms", "drt_kernel_launches",
     "drt_set_materials", "drt_set_material_lobes", "drt_set_measured", "drt_set_textures", "drt_set_material_programs", "drt_set_lights", "drt_set_spot_params", "drt_set_volumes", "drt_set_volume_integrator", "drt_set_camera", "drt_set_camera_kind", "drt_set_film", "drt_set_sampler", "drt_set_integrator",
@@ -113,6 +113,8 @@ def load():
     L.drt_set_lobe_wrappers.argtypes = [vp, u32, vp, vp]
     L.drt_set_textures.argtypes = [vp, u32, vp, vp, u64]
     L.drt_set_measured.argtypes = [vp, u32, vp, vp, vp, vp, u64]
+    L.drt_set_instances.argtypes = [vp, u32, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp, vp]
+    L.drt_set_ray_times.argtypes = [vp, vp, u64]
     L.drt_set_material_programs.argtypes = [vp, u32, vp]
     L.drt_set_infinite_light.argtypes = [vp, u32, i32, i32, vp, vp, vp]
     L.drt_set_lights.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
@@ -329,6 +331,23 @@ class Context:
         """BRDFToBTDF (bit 0) / ScaledBxDF (bit 1, with its RGB scale) around the lobes of the last set_material_lobes."""
         w, sc = _arr(wrap, np.int32), _arr(scale, np.float32).reshape(-1, 3)
         self._ck(self.L.drt_set_lobe_wrappers(self.h, w.shape[0], _p(w), _p(sc)))
+
+    def set_instances(self, object_offsets, object_prims, object_split, object_max_node_prims, instance_object, start_m, start_minv,
+                      end_m, end_minv, times):
+        """TransformedPrimitives (transformed_primitive.dart): objects (prim lists + nested accelerator parameters) and instances
+        (object, world-to-primitive m / mInv at the start and end time, n x 2 times).  Before set_build_order / build_bvh."""
+        oo, op = _arr(object_offsets, np.uint32), _arr(object_prims, np.uint32)
+        os_, om = _arr(object_split, np.int32), _arr(object_max_node_prims, np.int32)
+        io = _arr(instance_object, np.uint32)
+        m = [_arr(x, np.float32).reshape(-1, 16) for x in (start_m, start_minv, end_m, end_minv)]
+        tm = _arr(times, np.float64).reshape(-1, 2)
+        self._ck(self.L.drt_set_instances(self.h, oo.shape[0] - 1, _p(oo), _p(op), _p(os_), _p(om), io.shape[0], _p(io), _p(m[0]), _p(m[1]),
+                                          _p(m[2]), _p(m[3]), _p(tm)))
+
+    def set_ray_times(self, times):
+        """Ray i of the following trace_* calls travels at times[i] (None: every ray at time 0)."""
+        t = _arr(times, np.float64)
+        self._ck(self.L.drt_set_ray_times(self.h, _p(t), 0 if t is None else t.size))
 
     def set_measured(self, tables):
         """MeasuredMaterial data (measured_material.dart:76-205): list of (kind, array) — kind 0 = RegularHalfangleBRDF table

@@ -248,6 +248,47 @@ int drt_set_quadrics(drt_ctx* c, int kind, uint32_t n, const float* o2w, const f
   return DRT_OK;
 }
 
+int drt_set_instances(drt_ctx* c, uint32_t n_objects, const uint32_t* object_offsets, const uint32_t* object_prims,
+                      const int32_t* object_split, const int32_t* object_max_node_prims, uint32_t n_instances,
+                      const uint32_t* instance_object, const float* start_m, const float* start_minv, const float* end_m,
+                      const float* end_minv, const double* times) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_instances(p_, n_objects, object_offsets, object_prims, object_split, object_max_node_prims, n_instances,
+                                            instance_object, start_m, start_minv, end_m, end_minv, times));
+  if (!c) return DRT_E_INVALID;
+  if (n_objects && (!object_offsets || !object_prims)) return fail(c, DRT_E_INVALID, "drt_set_instances: null object arrays");
+  if (n_instances && (!instance_object || !start_m || !start_minv || !end_m || !end_minv))
+    return fail(c, DRT_E_INVALID, "drt_set_instances: null instance arrays");
+  if (n_instances && !n_objects) return fail(c, DRT_E_INVALID, "drt_set_instances: instances without objects");
+  std::vector<drt_ctx::HostObject> objs(n_objects);
+  for (uint32_t i = 0; i < n_objects; ++i) {
+    if (object_offsets[i + 1] <= object_offsets[i]) return fail(c, DRT_E_INVALID, "an object holds at least one primitive (dartray.dart:514-516)");
+    objs[i].order.assign(object_prims + object_offsets[i], object_prims + object_offsets[i + 1]);
+    objs[i].split = object_split ? object_split[i] : 2;
+    objs[i].maxPrims = object_max_node_prims ? object_max_node_prims[i] : 1;  // BVHAccel's constructor defaults (bvh_accel.dart:41)
+    if (objs[i].split < 0 || objs[i].split > 2 || objs[i].maxPrims < 1) return fail(c, DRT_E_INVALID, "object accelerator parameters out of range");
+  }
+  std::vector<GInstance> insts(n_instances);
+  for (uint32_t i = 0; i < n_instances; ++i) {
+    if (instance_object[i] >= n_objects) return fail(c, DRT_E_INVALID, "an instance names an object that was not defined");
+    std::memset(&insts[i], 0, sizeof(GInstance));
+    animInit(&insts[i], start_m + 16 * (size_t)i, start_minv + 16 * (size_t)i, end_m + 16 * (size_t)i, end_minv + 16 * (size_t)i,
+             times ? times[2 * i] : 0.0, times ? times[2 * i + 1] : 1.0);
+    insts[i].object = (int32_t)instance_object[i];
+  }
+  c->objects.swap(objs);
+  c->instances.swap(insts);
+  c->built = false;
+  return DRT_OK;
+}
+
+int drt_set_ray_times(drt_ctx* c, const double* times, uint64_t n) {
+  if (!c) return DRT_E_INVALID;
+  if (times) c->rayTimes.assign(times, times + n);
+  else c->rayTimes.clear();
+  c->rayTimesDirty = true;
+  return DRT_OK;
+}
+
 int drt_set_build_order(drt_ctx* c, const uint32_t* ids, uint32_t n) {
   DRT_FORWARD_TO_PEERS(c, drt_set_build_order(p_, ids, n));
   if (!c) return DRT_E_INVALID;
@@ -318,7 +359,8 @@ static bool quadricSetup(const HostSphere& s, GSphere* gp) {
 // owner of a multi-device context builds once on the host and every device uploads the same arrays).
 // `src`: a context of ANOTHER device that already holds this build: the arrays then come over NVLink from its memory
 // (cudaMemcpyPeer) instead of over PCIe from pageable host memory — soup_10m on 8 GPUs: 1.2 s of host uploads -> one upload.
-static int uploadBuilt(drt_ctx* c, const BuiltBvh& B, const std::vector<GPrim>& prims, const std::vector<GSphere>& gs, uint32_t np,
+static int uploadBuilt(drt_ctx* c, const BuiltBvh& B, const std::vector<GNode>& nodes, const std::vector<GPrim>& prims,
+                       const std::vector<GSphere>& gs, const std::vector<GObject>& gobjs, const std::vector<GInstance>& ginsts, uint32_t np,
                        const drt_ctx* src = nullptr) {
   CK(c, cudaSetDevice(c->device));
   auto put = [&](void* dst, const void* host, const void* peer, size_t bytes) -> cudaError_t {
@@ -326,7 +368,7 @@ static int uploadBuilt(drt_ctx* c, const BuiltBvh& B, const std::vector<GPrim>& 
     if (src && peer && src->device != c->device) return cudaMemcpyPeer(dst, c->device, peer, src->device, bytes);
     return cudaMemcpy(dst, host, bytes, cudaMemcpyHostToDevice);
   };
-  CK(c, c->dNodes.ensure(std::max<size_t>(1, B.nodes.size())));
+  CK(c, c->dNodes.ensure(std::max<size_t>(1, nodes.size())));
   c->wideQOk = B.wideQOk && B.wideQ.size() == B.wide.size();
   c->wideUploaded = false;
   if (!c->useQ()) {  // the float32 nodes go to the device only when their kernel is the one that runs (or is asked for later)
@@ -339,7 +381,14 @@ static int uploadBuilt(drt_ctx* c, const BuiltBvh& B, const std::vector<GPrim>& 
   }
   CK(c, c->dPrims.ensure(prims.size()));
   CK(c, c->dSpheres.ensure(std::max<size_t>(1, gs.size())));
-  CK(c, put(c->dNodes.p, B.nodes.data(), src ? src->dNodes.p : nullptr, B.nodes.size() * sizeof(GNode)));
+  CK(c, put(c->dNodes.p, nodes.data(), src ? src->dNodes.p : nullptr, nodes.size() * sizeof(GNode)));
+  c->ts.instances = nullptr; c->ts.objects = nullptr; c->ts.nInstances = 0;
+  if (!ginsts.empty()) {
+    CK(c, c->dInstances.ensure(ginsts.size()));
+    CK(c, c->dObjects.ensure(gobjs.size()));
+    CK(c, cudaMemcpy(c->dInstances.p, ginsts.data(), ginsts.size() * sizeof(GInstance), cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpy(c->dObjects.p, gobjs.data(), gobjs.size() * sizeof(GObject), cudaMemcpyHostToDevice));
+  }
   CK(c, put(c->dPrims.p, prims.data(), src ? src->dPrims.p : nullptr, prims.size() * sizeof(GPrim)));
   CK(c, put(c->dSpheres.p, gs.data(), src ? src->dSpheres.p : nullptr, gs.size() * sizeof(GSphere)));
   c->ts.nodes = c->dNodes.p;
@@ -354,6 +403,12 @@ static int uploadBuilt(drt_ctx* c, const BuiltBvh& B, const std::vector<GPrim>& 
   c->ts.empty = 0;
   c->ts.quadMode = 0;
   for (const HostSphere& hs : c->spheres) c->ts.quadMode = std::max(c->ts.quadMode, hs.shape >= 2 ? 2 : 1);
+  if (!ginsts.empty()) {
+    c->ts.instances = c->dInstances.p;
+    c->ts.objects = c->dObjects.p;
+    c->ts.nInstances = (int32_t)ginsts.size();
+    c->ts.quadMode = 2;
+  }
   c->info.n_nodes = (uint32_t)B.refNodes.size();
   c->info.n_prims = np;
   c->info.n_leaves = B.nLeaves;
@@ -378,6 +433,7 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
   c->buildSerial++;
   c->ts = TraceScene{};
   c->info = drt_bvh_info{};
+  const uint32_t ninst = (uint32_t)c->instances.size();
   if (np == 0) {  // bvh_accel.dart:50-53: nodes == null, every query misses
     c->ts.empty = 1;
     c->built = true;
@@ -388,16 +444,31 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
   if (order.empty()) {
     order.resize(np);
     for (uint32_t i = 0; i < np; ++i) order[i] = i;
-  } else {
+    if (ninst) return fail(c, DRT_E_INVALID, "a scene with instances needs the top-level build order (drt_set_build_order)");
+  } else if (ninst == 0) {
     if (order.size() != np) return fail(c, DRT_E_INVALID, "build order length != primitive count");
     std::vector<uint8_t> seen(np, 0);
     for (uint32_t id : order) {
       if (id >= np || seen[id]) return fail(c, DRT_E_INVALID, "build order is not a permutation of the primitive ids");
       seen[id] = 1;
     }
+  } else {
+    // every geometric primitive belongs to the top level or to exactly one object; every instance is a top-level primitive
+    std::vector<uint8_t> seen(np + ninst, 0);
+    for (const drt_ctx::HostObject& ob : c->objects)
+      for (uint32_t id : ob.order) {
+        if (id >= np || seen[id]) return fail(c, DRT_E_INVALID, "object primitive ids must be distinct geometric primitives");
+        seen[id] = 1;
+      }
+    for (uint32_t id : order) {
+      if (id >= np + ninst || seen[id]) return fail(c, DRT_E_INVALID, "build order: ids of top-level primitives and instances, each once, none owned by an object");
+      seen[id] = 1;
+    }
+    for (uint32_t id = 0; id < np + ninst; ++id)
+      if (!seen[id]) return fail(c, DRT_E_INVALID, "a primitive or instance is neither in an object nor in the build order");
   }
   // world bounds: triangle.dart:39-42, sphere.dart:34-37 + shape.dart:38-40
-  std::vector<PrimBounds> bounds(np);
+  std::vector<PrimBounds> bounds(np + ninst);
   parallelFor(nt, [&](size_t t0, size_t t1) {
     for (size_t t = t0; t < t1; ++t) {
       PrimBounds& b = bounds[t];
@@ -409,7 +480,7 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
       }
     }
   });
-  std::vector<GSphere> gs(c->spheres.size());
+  std::vector<GSphere> gs(c->spheres.size() + ninst);
   for (size_t i = 0; i < c->spheres.size(); ++i) {
     const HostSphere& s = c->spheres[i];
     GSphere& g = gs[i];
@@ -419,7 +490,7 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
     std::memcpy(g.o2wRow3, s.o2w + 12, 16);
     g.radius = s.radius;  // sphere.dart:24-32
     g.shape = s.shape;
-    g.pad_ = 0.f;
+    g.instance = -1;
     g.height = s.height;
     g.innerRadius = s.innerRadius;
     g.phiMax = (3.141592653589793 / 180.0) * clampd(s.phiMaxDeg, 0.0, 360.0);
@@ -450,18 +521,65 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
     std::memcpy(g.wmax, b.bmax, 12);
   }
   std::string err;
+  // the objects TransformedPrimitives wrap: their own accelerators first (an instance's world bound needs its object's),
+  // binary nodes and leaf records collected behind the top level's (references rebased below)
+  std::vector<BuiltBvh> objBvh(c->objects.size());
+  std::vector<GObject> gobjs(c->objects.size());
+  for (size_t k = 0; k < c->objects.size(); ++k) {
+    const drt_ctx::HostObject& ob = c->objects[k];
+    if (!buildBvh(bounds, ob.order, ob.split, ob.maxPrims, &objBvh[k], &err)) return fail(c, DRT_E_INVALID, err.c_str());
+    GObject& g = gobjs[k];
+    std::memcpy(g.rootMin, objBvh[k].rootMin, 12);
+    std::memcpy(g.rootMax, objBvh[k].rootMax, 12);
+    g.single = ob.order.size() == 1 ? 1 : 0;
+    if (g.single) {  // primitive.worldBound() of the GeometricPrimitive itself
+      std::memcpy(g.rootMin, bounds[ob.order[0]].bmin, 12);
+      std::memcpy(g.rootMax, bounds[ob.order[0]].bmax, 12);
+    }
+    g.rootRef = objBvh[k].rootRef;
+  }
+  for (uint32_t i = 0; i < ninst; ++i) {  // TransformedPrimitive.worldBound (transformed_primitive.dart:76-78)
+    const GInstance& in = c->instances[i];
+    const GObject& ob = gobjs[(size_t)in.object];
+    PrimBounds& b = bounds[np + i];
+    animMotionBounds(in, ob.rootMin, ob.rootMax, b.bmin, b.bmax);
+    GSphere& g = gs[c->spheres.size() + i];
+    std::memset(&g, 0, sizeof(g));
+    g.shape = 6;
+    g.instance = (int32_t)i;
+    std::memcpy(g.wmin, b.bmin, 12);
+    std::memcpy(g.wmax, b.bmax, 12);
+  }
   if (!buildBvh(bounds, order, split, maxPrims, &c->bvh, &err)) return fail(c, DRT_E_INVALID, err.c_str());
   const BuiltBvh& B = c->bvh;
+  std::vector<GNode> nodes(B.nodes);
+  c->recPrimIds = B.leafPrimIds;
+  std::vector<uint32_t> recCounts(B.leafCounts);
+  for (size_t k = 0; k < objBvh.size(); ++k) {
+    const BuiltBvh& O = objBvh[k];
+    const int32_t nodeBase = (int32_t)nodes.size();
+    const uint32_t recBase = (uint32_t)c->recPrimIds.size();
+    auto rebase = [&](int32_t ref) -> int32_t {
+      if (ref == DRT_REF_EMPTY) return ref;
+      if (ref >= 0) return ref + nodeBase;
+      const uint32_t bits = (uint32_t)~ref;
+      return (int32_t)~((((bits >> 5) + recBase) << 5) | (bits & 31u));
+    };
+    for (GNode n : O.nodes) { n.ref0 = rebase(n.ref0); n.ref1 = rebase(n.ref1); nodes.push_back(n); }
+    gobjs[k].rootRef = rebase(O.rootRef);
+    c->recPrimIds.insert(c->recPrimIds.end(), O.leafPrimIds.begin(), O.leafPrimIds.end());
+    recCounts.insert(recCounts.end(), O.leafCounts.begin(), O.leafCounts.end());
+  }
 
   // leaf records
-  std::vector<GPrim> prims(B.leafPrimIds.size());
+  std::vector<GPrim> prims(c->recPrimIds.size());
   parallelFor(prims.size(), [&](size_t i0, size_t i1) {
     for (size_t i = i0; i < i1; ++i) {
-      uint32_t id = B.leafPrimIds[i];
+      uint32_t id = c->recPrimIds[i];
       GPrim& g = prims[i];
       std::memset(&g, 0, sizeof(g));
       g.primId = (int32_t)id;
-      g.leafCount = (int32_t)B.leafCounts[i];
+      g.leafCount = (int32_t)recCounts[i];
       if (id < nt) {
         const float* a = &c->P[3 * (size_t)c->idx[3 * (size_t)id]];
         const float* b = &c->P[3 * (size_t)c->idx[3 * (size_t)id + 1]];
@@ -470,7 +588,7 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
         std::memcpy(g.p2, b, 12);
         std::memcpy(g.p3, d, 12);
         g.kindSphere = 0;
-      } else {
+      } else {  // quadrics, then the instances' stand-in records (GSphere::shape 6)
         g.kindSphere = (int32_t)(((id - nt) << 1) | 1u);
       }
     }
@@ -486,7 +604,7 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
     c->built = true;
     return DRT_OK;
   }
-  int rc = uploadBuilt(c, B, prims, gs, np);
+  int rc = uploadBuilt(c, B, nodes, prims, gs, gobjs, c->instances, np);
   if (rc != DRT_OK) return rc;
   // a multi-device context: the same arrays to every other device, one host thread each
   if (!c->peers.empty()) {
@@ -499,7 +617,8 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
         p_->buildSerial++;
         p_->ts = TraceScene{};
         p_->info = drt_bvh_info{};
-        rcs[i] = uploadBuilt(p_, B, prims, gs, np, c);
+        p_->recPrimIds = c->recPrimIds;
+        rcs[i] = uploadBuilt(p_, B, nodes, prims, gs, gobjs, c->instances, np, c);
       });
     for (auto& t : th) t.join();
     for (size_t i = 0; i < rcs.size(); ++i)
@@ -535,7 +654,7 @@ int drt_bvh_export(const drt_ctx* c, float* bounds, int32_t* offset, int32_t* np
 
 // counterSlot < 0: a launch on a caller's stream (drt_trace_*_device) — takes the next slot of the counter ring.
 static int traceDevice(drt_ctx* c, bool any, const void* o, const void* d, uint64_t n, void* out, cudaStream_t st,
-                       int counterSlot = -1) {
+                       int counterSlot = -1, uint64_t firstRay = 0) {
   if (c->device == DRT_DEVICE_NONE) return fail(c, DRT_E_NODEVICE, kNoDevice);
   if (!c->built) return fail(c, DRT_E_STATE, "drt_build_bvh must be called before tracing");
   if (n && (!o || !d || !out)) return fail(c, DRT_E_INVALID, "null ray or output buffer");
@@ -547,10 +666,21 @@ static int traceDevice(drt_ctx* c, bool any, const void* o, const void* d, uint6
     counterSlot = 1 + drt_ctx::kPipe + ring;
     if (c->ringUsed[ring]) CK(c, cudaStreamWaitEvent(st, c->ringEv[ring], 0));  // the slot's previous launch, maybe on another stream
   }
-  if (c->counting || c->exactWalk) {
-    // reference-walk kernel: the slab test in f64 for every node; also the counting variant
+  if (c->counting || c->exactWalk || c->ts.nInstances > 0) {
+    // reference-walk kernel: the slab test in f64 for every node; also the counting variant, and the kernel that descends into
+    // TransformedPrimitives
     if (c->counting) CK(c, cudaMemsetAsync(c->dCounters.p, 0, sizeof(DeviceCounters), st));
-    CK(c, launchTrace(c->ts, any, c->counting, o, d, n, out, c->dCounters.p, st));
+    ExactExtras xx{};
+    if (c->ts.nInstances > 0 && !c->rayTimes.empty()) {
+      if (firstRay + n > c->rayTimes.size()) return fail(c, DRT_E_INVALID, "drt_set_ray_times gave fewer times than this call has rays");
+      if (c->rayTimesDirty) {
+        CK(c, c->dRayTimes.ensure(c->rayTimes.size()));
+        CK(c, cudaMemcpy(c->dRayTimes.p, c->rayTimes.data(), c->rayTimes.size() * sizeof(double), cudaMemcpyHostToDevice));
+        c->rayTimesDirty = false;
+      }
+      xx.times = c->dRayTimes.p + firstRay;
+    }
+    CK(c, launchTrace(c->ts, any, c->counting, o, d, n, out, c->dCounters.p, st, nullptr, nullptr, &xx));
   } else {
     CK(c, launchTraceFast(c->ts, any, o, d, n, out, c->dNextRay.p + counterSlot, c->numSMs, st));
   }
@@ -589,7 +719,7 @@ static int traceHost(drt_ctx* c, bool any, const float* o, const float* d, uint6
     CK(c, cudaMemcpyAsync(c->dRayO.p + first, o + 4 * first, m * 16, cudaMemcpyHostToDevice, st));
     CK(c, cudaMemcpyAsync(c->dRayD.p + first, d + 4 * first, m * 16, cudaMemcpyHostToDevice, st));
     CK(c, cudaEventRecord(c->chunkEv[2 * nChunks], st));
-    int rc = traceDevice(c, any, c->dRayO.p + first, c->dRayD.p + first, m, (char*)dout + first * outSize, st, 1 + slot);
+    int rc = traceDevice(c, any, c->dRayO.p + first, c->dRayD.p + first, m, (char*)dout + first * outSize, st, 1 + slot, first);
     if (rc != DRT_OK) return rc;
     CK(c, cudaEventRecord(c->chunkEv[2 * nChunks + 1], st));
     CK(c, cudaMemcpyAsync((char*)out + first * outSize, (char*)dout + first * outSize, m * outSize, cudaMemcpyDeviceToHost, st));

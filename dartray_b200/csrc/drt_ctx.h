@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/drt.h"
+#include "anim_transform.h"
 #include "bvh_builder.h"
 #include "gpu_types.h"
 #include "render_types.h"
@@ -107,6 +108,22 @@ struct drt_ctx {
   std::vector<uint32_t> meshOfTri;
   std::vector<float> meshO2W, meshW2O;  // nmeshes x 16
   std::vector<uint8_t> meshFlags;
+
+  // drt_set_instances: TransformedPrimitives (transformed_primitive.dart).  objects = the aggregates they wrap (primitive ids in the
+  // refined order handed to the nested accelerator + its parameters), instances = AnimatedTransform after its constructor + object
+  struct HostObject {
+    std::vector<uint32_t> order;
+    int split = 2, maxPrims = 1;
+  };
+  std::vector<HostObject> objects;
+  std::vector<GInstance> instances;
+  std::vector<uint32_t> recPrimIds;  // primitive id of every GPrim record on the device (the top level's, then the objects')
+  DevBuf<GInstance> dInstances;
+  DevBuf<GObject> dObjects;
+  // drt_set_ray_times: times of the rays of the host-buffer / device-buffer trace calls (scenes with instances; empty: time 0)
+  std::vector<double> rayTimes;
+  DevBuf<double> dRayTimes;
+  bool rayTimesDirty = false;
 
   struct RenderState* render = nullptr;  // render_api.cu
 

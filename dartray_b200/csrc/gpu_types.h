@@ -102,12 +102,15 @@ struct alignas(16) GSphere {
   float o2wRow3[4];
   double radius, zmin, zmax, phiMax, thetaMin, thetaMax;
   float wmin[3], wmax[3];  // world bound (sphere.dart:34-37 + shape.dart:38-40), = the leaf box of a 1-sphere leaf
-  int32_t shape;           // 0 sphere, 1 disk, 2 cylinder, 3 cone, 4 paraboloid, 5 hyperboloid
-  float pad_;
+  int32_t shape;           // 0 sphere, 1 disk, 2 cylinder, 3 cone, 4 paraboloid, 5 hyperboloid, 6 a TransformedPrimitive (instance)
+  int32_t instance;        // shape 6: index into TraceScene::instances (wmin / wmax hold its world bound)
   double height, innerRadius;  // disk (both), cone (height)
   float hp1[3], hp2[3];        // hyperboloid.dart:24: the two Points after the constructor's swap (:36-39)
   double ha, hc;               // hyperboloid.dart:40-48 implicit coefficients; `radius` holds rmax
 };
+
+struct GInstance;  // anim_transform.h
+struct GObject;
 
 struct TraceScene {
   const GNode* nodes;    // binary layout (exact-walk / counting kernel)
@@ -120,6 +123,12 @@ struct TraceScene {
   int32_t rootRef;
   int32_t empty;  // 1 -> no primitives (bvh_accel.dart:102-104)
   int32_t quadMode;  // which leaf code the scene needs: 0 triangles only, 1 + spheres / disks, 2 + the other quadrics
+  // TransformedPrimitives (transformed_primitive.dart): a top-level leaf record of kind "quadric" whose GSphere has shape 6 stands
+  // for instance GSphere::instance; the objects' binary nodes / leaf records sit behind the top level's in `nodes` / `prims`.
+  // Scenes with instances run the literal walk (traceKernel), which descends into the object with the transformed ray.
+  const GInstance* instances;
+  const GObject* objects;
+  int32_t nInstances;
 };
 
 struct DeviceCounters {

@@ -257,7 +257,9 @@ static void buildLayout(RenderState* r) {
 static int uploadSceneTables(drt_ctx* c, RenderState* r) {
   const uint32_t nt = c->ntris(), np = c->nprims();
   std::vector<uint32_t> primToRec(std::max<uint32_t>(np, 1), 0), attr(std::max<uint32_t>(np, 1), 0);
-  for (size_t i = 0; i < c->hostBvh().leafPrimIds.size(); ++i) primToRec[c->hostBvh().leafPrimIds[i]] = (uint32_t)i;
+  const std::vector<uint32_t>& recIds = (c->owner ? c->owner : c)->recPrimIds;  // the top level's records, then the objects'; instance stand-ins skipped
+  for (size_t i = 0; i < recIds.size(); ++i)
+    if (recIds[i] < np) primToRec[recIds[i]] = (uint32_t)i;
   const int nMat = (int)r->materials.size(), nLights = (int)r->lights.size();
   for (uint32_t i = 0; i < np; ++i) {
     int m = i < nt ? c->matOf[i] : c->sphMat[i - nt], l = i < nt ? c->lightOf[i] : c->sphLight[i - nt];
@@ -546,7 +548,7 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
   }
   rs.measured = gmeas.empty() ? nullptr : r->dMeasured.p;
   rs.nMeasured = (int32_t)gmeas.size();
-  rs.extra = (rs.meshOfTri != nullptr || c->ts.quadMode == 2 || nInfinite > 0 || nMapped > 0 || (r->general && (r->hasBlend || r->hasMeasured)) ||
+  rs.extra = (rs.meshOfTri != nullptr || c->ts.quadMode == 2 || c->ts.nInstances > 0 || nInfinite > 0 || nMapped > 0 || (r->general && (r->hasBlend || r->hasMeasured)) ||
               rs.nVolumes > 0 || rs.nPrograms > 0) ? 1 : 0;
   rs.ntris = nt;
   rs.nprims = np;
@@ -569,8 +571,14 @@ static int uploadSceneTables(drt_ctx* c, RenderState* r) {
 static const int kMaxChainLevels = 16;  // specular recursion depth the chain evaluation covers (maxdepth <= 17)
 
 static void carve(ByteArena& a, Wavefront& wf, uint32_t cap, uint32_t shCap, int nVals, bool chains, bool volumes, uint32_t volMaxSteps,
-                  bool programs) {
+                  bool programs, bool instances) {
   wf.cap = cap;
+  wf.slotTime = nullptr; wf.extInst = wf.misInst = wf.bakInst = nullptr;
+  if (instances) {
+    wf.slotTime = a.take<double>(cap);
+    wf.extInst = a.take<int32_t>(cap); wf.misInst = a.take<int32_t>(cap);
+    if (chains) wf.bakInst = a.take<int32_t>(cap);
+  }
   if (programs) {  // the BSDF the texture pass builds per slot: 8 lobes (bsdf.dart:253) + the shading frame
     wf.hitLobes = a.take<GLobe>(8 * (size_t)cap);
     wf.hitCount = a.take<int32_t>(cap);
@@ -632,7 +640,8 @@ static int ensureWavefront(drt_ctx* c, RenderState* r, uint32_t cap, uint32_t sh
   const bool volumes = !r->volumes.empty();
   const uint32_t volMaxSteps = (volumes && r->volIntegrator == 1) ? r->volMaxSteps : 0;
   const bool programs = !r->programs.empty();
-  carve(probe, tmp, cap, shCap, r->rp.nVals, chains, volumes, volMaxSteps, programs);
+  const bool instances = c->ts.nInstances > 0;
+  carve(probe, tmp, cap, shCap, r->rp.nVals, chains, volumes, volMaxSteps, programs, instances);
   size_t need = probe.used + 256;
   if (need > r->wfBytes) {
     if (r->wfMem) cudaFree(r->wfMem);
@@ -644,7 +653,7 @@ static int ensureWavefront(drt_ctx* c, RenderState* r, uint32_t cap, uint32_t sh
   ByteArena a;
   a.base = r->wfMem;
   a.size = r->wfBytes;
-  carve(a, r->wf, cap, shCap, r->rp.nVals, chains, volumes, volMaxSteps, programs);
+  carve(a, r->wf, cap, shCap, r->rp.nVals, chains, volumes, volMaxSteps, programs, instances);
   r->shCap = shCap;
   return DRT_OK;
 }
@@ -714,6 +723,24 @@ static int prepare(drt_ctx* c, RenderState* r) {
     if (rc != DRT_OK) return rc;
   }
   r->rs.ts = c->ts;
+  if (c->ts.nInstances > 0) {  // TransformedPrimitives: what the renderer carries for them so far
+    if (!r->volumes.empty()) return fail(c, DRT_E_UNSUPPORTED, "participating media together with instances / animated shapes");
+    if (!r->programs.empty())
+      return fail(c, DRT_E_UNSUPPORTED, "textured / bump-mapped materials together with instances / animated shapes");
+    if (p.samplerKind == 2 || p.samplerKind == 3 || p.samplerKind == 5)
+      return fail(c, DRT_E_UNSUPPORTED, "instances / animated shapes with the random / halton / bestcandidate samplers (their time samples "
+                                        "are binary64 values; the wavefront keeps float32 ones)");
+    std::vector<uint8_t> inObject(c->nprims(), 0);
+    for (const drt_ctx::HostObject& ob : c->objects)
+      for (uint32_t id : ob.order) inObject[id] = 1;
+    for (uint32_t id = 0; id < c->nprims(); ++id) {
+      if (!inObject[id]) continue;
+      const int32_t light = id < c->ntris() ? (c->lightOf.empty() ? -1 : c->lightOf[id]) : (c->sphLight.empty() ? -1 : c->sphLight[id - c->ntris()]);
+      if (light >= 0) return fail(c, DRT_E_UNSUPPORTED, "an area light on an instanced / animated shape (the reference drops it with a warning, dartray.dart:407-410)");
+      if (id < c->ntris() && !c->meshOfTri.empty() && (c->meshFlags[c->meshOfTri[id]] & 3u))
+        return fail(c, DRT_E_UNSUPPORTED, "per-vertex N / S on a mesh inside an instanced / animated object");
+    }
+  }
   CK(c, r->dArrays.ensure(r->arrays.size()));
   CK(c, cudaMemcpy(r->dArrays.p, r->arrays.data(), r->arrays.size() * sizeof(SampleArray), cudaMemcpyHostToDevice));
   CK(c, r->dDirect.ensure(std::max<size_t>(1, r->direct.size())));
@@ -807,6 +834,21 @@ static int profCollect(drt_ctx* c) {  // after the render's stream synchronize
 
 static int traceQueue(drt_ctx* c, bool any, const float4* o, const float4* d, const double2* range, const uint32_t* nDev, void* out,
                       double* tOut, cudaStream_t st) {
+  if (c->ts.nInstances > 0) {
+    // scenes with TransformedPrimitives: the literal walk, which descends into the objects at each ray's time.  One thread per
+    // queue slot (the live count is on the device; the surplus threads leave at once).
+    const Wavefront& wf = c->render->wf;
+    ExactExtras xx;
+    xx.times = wf.slotTime;
+    xx.timesBySlot = 1;
+    xx.tOut = tOut;
+    xx.instOut = any ? nullptr : (out == (void*)wf.misHit ? wf.misInst : wf.extInst);
+    const uint64_t capQ = (o == wf.shO) ? c->render->shCap : wf.cap;
+    CK(c, launchTrace(c->ts, any, false, o, d, capQ, out, nullptr, st, range, nDev, &xx));
+    c->launches++;
+    profMark(c, any ? DRT_PK_TRACE_ANY : DRT_PK_TRACE_CLOSEST);
+    return DRT_OK;
+  }
   TraceExtras ex;
   ex.nDev = nDev;
   ex.range = range;
@@ -937,6 +979,7 @@ static int specularChains(drt_ctx* c, RenderState* r) {
   CK(c, cudaMemcpyAsync(wf.bakSlot, wf.extSlot[0], cap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
   CK(c, cudaMemcpyAsync(wf.bakHit, wf.extHit, cap * sizeof(float4), cudaMemcpyDeviceToDevice, st));
   CK(c, cudaMemcpyAsync(wf.bakT, wf.extT, cap * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (wf.bakInst) CK(c, cudaMemcpyAsync(wf.bakInst, wf.extInst, cap * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   uint32_t n0 = 0;
   CK(c, cudaMemcpyAsync(&n0, wf.counts + Q_EXT0, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   CK(c, cudaStreamSynchronize(st));
@@ -961,6 +1004,7 @@ static int specularChains(drt_ctx* c, RenderState* r) {
     CK(c, cudaMemcpyAsync(wf.extSlot[0], wf.bakSlot, n0 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     CK(c, cudaMemcpyAsync(wf.extHit, wf.bakHit, n0 * sizeof(float4), cudaMemcpyDeviceToDevice, st));
     CK(c, cudaMemcpyAsync(wf.extT, wf.bakT, n0 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (wf.bakInst) CK(c, cudaMemcpyAsync(wf.extInst, wf.bakInst, n0 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     CK(c, cudaMemcpyAsync(wf.counts + Q_EXT0, &n0, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     int cur = 0;
     for (int k = 1; k <= len + 1; ++k) {

@@ -371,6 +371,13 @@ __global__ void __launch_bounds__(128) samplerBestCandidateKernel(RenderParams r
   wf.camTime[p] = (float)(t > 1 ? (t - 1) : t);
 }
 
+// The fourth lane of a renderer ray's origin: scenes with TransformedPrimitives carry the wavefront slot there (the traversal looks the
+// ray's time up in Wavefront::slotTime — every ray a camera sample spawns inherits its time, ray.dart:59); the interval itself always
+// travels in the f64 range arrays.
+static __device__ __forceinline__ float rayLaneW(const Wavefront& wf, uint32_t slot, float informational) {
+  return wf.slotTime ? __uint_as_float(slot) : informational;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Camera rays (perspective_camera.dart:93-132; ray differentials only feed texture filtering and are
 // not generated) + per-slot state reset.  Extension queue 0 = all slots in slot order.
@@ -416,7 +423,8 @@ __global__ void __launch_bounds__(256) raygenKernel(RenderParams rp, Wavefront w
     d = Normalize(Pfocus - o);
   }
   V3 wo = XfPoint(rp.cameraToWorld, o), wd = XfVector(rp.cameraToWorld, d);
-  wf.extO[0][qi] = make_float4(wo.x, wo.y, wo.z, 0.f);
+  if (wf.slotTime) wf.slotTime[s] = LerpD((double)wf.camTime[s], rp.shutterOpen, rp.shutterClose);  // the samplers' Lerp(time sample, shutterOpen, shutterClose)
+  wf.extO[0][qi] = make_float4(wo.x, wo.y, wo.z, rayLaneW(wf, s, 0.f));
   wf.extD[0][qi] = make_float4(wd.x, wd.y, wd.z, CUDART_INF_F);
   wf.extRange[0][qi] = make_double2(0.0, CUDART_INF);
   wf.extSlot[0][qi] = s;
@@ -445,13 +453,13 @@ static __device__ __forceinline__ void pushDirectWork(const Wavefront& wf, uint3
   const uint32_t mi = warpPush(&wf.counts[Q_MIS], wantMis);
   const uint32_t cap = wf.cap;
   if (wantSh) {
-    wf.shO[si] = make_float4(w.shO.x, w.shO.y, w.shO.z, (float)w.shMin);
+    wf.shO[si] = make_float4(w.shO.x, w.shO.y, w.shO.z, rayLaneW(wf, slot, (float)w.shMin));
     wf.shD[si] = make_float4(w.shD.x, w.shD.y, w.shD.z, (float)w.shMax);
     wf.shRange[si] = make_double2(w.shMin, w.shMax);
     st3(wf.pendSh, cap, slot, w.shContribution);
   }
   if (wantMis) {
-    wf.misO[mi] = make_float4(p.x, p.y, p.z, (float)rayEps);
+    wf.misO[mi] = make_float4(p.x, p.y, p.z, rayLaneW(wf, slot, (float)rayEps));
     wf.misD[mi] = make_float4(w.misD.x, w.misD.y, w.misD.z, CUDART_INF_F);
     wf.misRange[mi] = make_double2(rayEps, CUDART_INF);
     st3(wf.pendMisF, cap, slot, w.misF);
@@ -558,7 +566,7 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(Ren
       const float4 o4 = wf.extO[cur][q], d4 = wf.extD[cur][q];
       const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
       ShapeHit h;
-      hitGeometry<EXTRA>(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
+      hitGeometryQ<EXTRA>(rs, wf, q, slot, (uint32_t)prim, o, d, wf.extT[q], &h);
       Spec T = ld3(wf.T, cap, slot);
       if (EXTRA && rs.nVolumes > 0 && bounce > 0) {  // pathThroughput *= renderer.transmittance(ray) once the ray found this vertex (:116)
         uint32_t ctr = wf.trCtr[slot];
@@ -636,7 +644,7 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(Ren
     pushDirectWork(wf, slot, valid, dw, p, rayEps, lightNum);
     const uint32_t ei = warpPush(&wf.counts[nxt], cont);
     if (cont) {
-      wf.extO[nxt][ei] = make_float4(p.x, p.y, p.z, (float)rayEps);
+      wf.extO[nxt][ei] = make_float4(p.x, p.y, p.z, rayLaneW(wf, slot, (float)rayEps));
       wf.extD[nxt][ei] = make_float4(wi.x, wi.y, wi.z, CUDART_INF_F);
       wf.extRange[nxt][ei] = make_double2(rayEps, CUDART_INF);
       wf.extSlot[nxt][ei] = slot;
@@ -798,7 +806,7 @@ __global__ void __launch_bounds__(128) aoSetupKernel(RenderParams rp, RenderScen
         const float4 o4 = wf.extO[0][q], d4 = wf.extD[0][q];
         const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
         ShapeHit h;
-        hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
+        hitGeometryQ(rs, wf, q, slot, (uint32_t)prim, o, d, wf.extT[q], &h);
         stv3(wf.hitP, cap, slot, h.p);
         stv3(wf.hitN, cap, slot, FaceForward(h.nn, -d));
         Stream rng{integratorKey(rp, wf, slot), 0};
@@ -825,7 +833,8 @@ __global__ void __launch_bounds__(256) aoGenKernel(RenderParams rp, Wavefront wf
     V3 w = UniformSampleSphere(u0, u1);
     const V3 nrm = ldv3(wf.hitN, cap, slot), p = ldv3(wf.hitP, cap, slot);
     if (Dot(w, nrm) < 0.0) w = -w;
-    wf.shO[r] = make_float4(p.x, p.y, p.z, (float)rp.aoMinDist);
+    // new Ray(p, w, minDist, maxDist) (ambient_occlusion_integrator.dart:45): no time argument, the ray travels at time 0
+    wf.shO[r] = make_float4(p.x, p.y, p.z, wf.slotTime ? __uint_as_float(0xffffffffu) : (float)rp.aoMinDist);
     wf.shD[r] = make_float4(w.x, w.y, w.z, (float)rp.aoMaxDist);
     wf.shRange[r] = make_double2(rp.aoMinDist, rp.aoMaxDist);
   }
@@ -917,7 +926,7 @@ __global__ void __launch_bounds__(128) whittedSampleKernel(RenderParams rp, Rend
       const float4 o4 = wf.extO[cur][q], d4 = wf.extD[cur][q];
       const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
       ShapeHit h;
-      hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
+      hitGeometryQ(rs, wf, q, slot, (uint32_t)prim, o, d, wf.extT[q], &h);
       typename BsdfOf<GENERAL>::type bsdf = makeBsdfT<GENERAL>(rs, (uint32_t)prim, h, o, d);
       if (GENERAL) applyHitBsdf(rs, wf, slot, &bsdf);
       p = h.p;
@@ -968,7 +977,7 @@ __global__ void __launch_bounds__(128) specularStepKernel(RenderParams rp, Rende
         const float4 o4 = wf.extO[cur][q], d4 = wf.extD[cur][q];
         const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
         ShapeHit h;
-        hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
+        hitGeometryQ(rs, wf, q, slot, (uint32_t)prim, o, d, wf.extT[q], &h);
         BsdfG bsdf = makeBsdfG(rs, (uint32_t)prim, h, o, d);
         applyHitBsdf(rs, wf, slot, &bsdf);
         double pdf = 0.0;
@@ -986,7 +995,7 @@ __global__ void __launch_bounds__(128) specularStepKernel(RenderParams rp, Rende
     }
     const uint32_t ei = warpPush(&wf.counts[nxt], cont);
     if (cont) {
-      wf.extO[nxt][ei] = make_float4(p.x, p.y, p.z, (float)rayEps);
+      wf.extO[nxt][ei] = make_float4(p.x, p.y, p.z, rayLaneW(wf, slot, (float)rayEps));
       wf.extD[nxt][ei] = make_float4(wi.x, wi.y, wi.z, CUDART_INF_F);
       wf.extRange[nxt][ei] = make_double2(rayEps, CUDART_INF);
       wf.extSlot[nxt][ei] = slot;
@@ -1023,7 +1032,7 @@ __global__ void __launch_bounds__(128) directSampleKernel(RenderParams rp, Rende
       const float4 o4 = wf.extO[cur][q], d4 = wf.extD[cur][q];
       const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
       ShapeHit h;
-      hitGeometry(rs, (uint32_t)prim, o, d, wf.extT[q], &h);
+      hitGeometryQ(rs, wf, q, slot, (uint32_t)prim, o, d, wf.extT[q], &h);
       typename BsdfOf<GENERAL>::type bsdf = makeBsdfT<GENERAL>(rs, (uint32_t)prim, h, o, d);
       if (GENERAL) applyHitBsdf(rs, wf, slot, &bsdf);
       p = h.p;

@@ -253,6 +253,11 @@ struct Wavefront {
   GLobe* hitLobes;
   int32_t* hitCount;
   float* hitFrame;  // 6 x cap
+  // scenes with TransformedPrimitives only (null otherwise): Ray.time of every ray the slot's camera sample spawns (camera_sample.dart:33,
+  // ray.dart:59; the traversal reads it through the slot id the rays carry in the bits of rayO.w), and the instance each closest hit of
+  // the extension / MIS queue came through (-1: a top-level primitive)
+  double* slotTime;
+  int32_t* extInst; int32_t* misInst; int32_t* bakInst;
   int32_t* camPrim;  // adaptive sampler: primitive the slot's camera ray hit (-1: none)
   uint8_t* adaptFlag;  // adaptive sampler, per pixel of the batch: 1 = supersample (the first visit's samples are dropped)
 };

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdint>
 
+#include "anim_transform.h"
 #include "gpu_types.h"
 #include "render_types.h"
 
@@ -624,6 +625,39 @@ static __device__ inline void hitGeometry(const RenderScene& rs, uint32_t prim, 
     h->rayEps = 5.0e-4 * t;  // sphere.dart:164, disk.dart:100
   }
   h->nn = shapeNormal(h->dpdu, dpdv, primReverse(rs, prim));
+}
+
+// A hit that came through a TransformedPrimitive (transformed_primitive.dart:30-58): the shape saw the ray in primitive space
+// (worldToPrimitive.interpolate(ray.time) applied to it), so its differential geometry is rebuilt there and moved to world space
+// with Inverse(w2p) — p as a point, nn as a normal (then normalised), dpdu as a vector — unless w2p is the identity.
+static __device__ __noinline__ void instanceHitCold(const RenderScene& rs, uint32_t prim, int inst, double time, V3 o, V3 d, double t,
+                                                    ShapeHit* out) {
+  M4 m, inv;
+  animInterpolate(rs.ts.instances[inst], time, &m, &inv);
+  const V3 o2 = XfPoint(m.d, o), d2 = XfVector(m.d, d);
+  ShapeHit h;
+  hitGeometry<true>(rs, prim, o2, d2, t, &h);
+  if (!m4IsIdentity(m)) {
+    h.p = XfPoint(inv.d, h.p);
+    h.nn = Normalize(XfNormal(m.d, h.nn));  // p2w = Transform(inv, m): its transformNormal reads ITS inverse, m
+    h.dpdu = XfVector(inv.d, h.dpdu);
+  }
+  *out = h;
+}
+// hitGeometry for entry q of the extension queue (slot = its wavefront slot): Wavefront::extInst names the instance, if any
+template <bool EXTRA = (DRT_EXTRA != 0)>
+static __device__ inline void hitGeometryQ(const RenderScene& rs, const Wavefront& wf, uint32_t q, uint32_t slot, uint32_t prim, const V3& o,
+                                           const V3& d, double t, ShapeHit* h) {
+  if (DRT_EXTRA && EXTRA && wf.extInst) {
+    const int inst = wf.extInst[q];
+    if (inst >= 0) {
+      ShapeHit tmp;
+      instanceHitCold(rs, prim, inst, wf.slotTime[slot], o, d, t, &tmp);
+      *h = tmp;
+      return;
+    }
+  }
+  hitGeometry<EXTRA>(rs, prim, o, d, t, h);
 }
 
 // Shape.intersect on one shape with an explicit interval (ShapeSet / Shape.pdf2 use it directly,

@@ -6,6 +6,7 @@
 
 #include <cstdint>
 
+#include "anim_transform.h"
 #include "gpu_types.h"
 
 namespace drt {
@@ -44,6 +45,7 @@ static __device__ __forceinline__ bool slabs(const RayState& r, float lox, float
 struct HitState {
   double t, b1, b2;
   int prim;
+  int inst;  // the TransformedPrimitive the hit came through (only the literal walk of trace_kernels.cu sets and reads it)
 };
 
 // triangle.dart:52-98, all f64 on the float32 vertices; updates r.maxt like
@@ -340,6 +342,110 @@ static __device__ __noinline__ bool anyHitWalk(const TraceScene& sc, float4 o4, 
     if (sp == 0) return false;
     cur = stackRef[--sp];
   }
+}
+
+// ---- TransformedPrimitive (lib/core/primitive/transformed_primitive.dart:30-62) -------------------------------------------------
+// Transform.transformRay (transform.dart:180-196): the origin as a Point (homogeneous divide when w != 1), the direction as a
+// Vector, both float32; the interval is kept.  invDir / dirIsNeg as the nested BVHAccel.intersect derives them (bvh_accel.dart:109-115).
+static __device__ inline void transformRayState(const M4& m, const RayState& r, RayState* o) {
+  double x = rf((double)m.d[0] * r.ox + (double)m.d[1] * r.oy + (double)m.d[2] * r.oz + (double)m.d[3]);
+  double y = rf((double)m.d[4] * r.ox + (double)m.d[5] * r.oy + (double)m.d[6] * r.oz + (double)m.d[7]);
+  double z = rf((double)m.d[8] * r.ox + (double)m.d[9] * r.oy + (double)m.d[10] * r.oz + (double)m.d[11]);
+  const double w = (double)m.d[12] * r.ox + (double)m.d[13] * r.oy + (double)m.d[14] * r.oz + (double)m.d[15];
+  if (w != 1.0) { x = rf(x / w); y = rf(y / w); z = rf(z / w); }
+  o->ox = x; o->oy = y; o->oz = z;
+  o->dx = rf((double)m.d[0] * r.dx + (double)m.d[1] * r.dy + (double)m.d[2] * r.dz);
+  o->dy = rf((double)m.d[4] * r.dx + (double)m.d[5] * r.dy + (double)m.d[6] * r.dz);
+  o->dz = rf((double)m.d[8] * r.dx + (double)m.d[9] * r.dy + (double)m.d[10] * r.dz);
+  o->mint = r.mint; o->maxt = r.maxt;
+  const float ixf = __double2float_rn(1.0 / o->dx), iyf = __double2float_rn(1.0 / o->dy), izf = __double2float_rn(1.0 / o->dz);
+  o->ix = ixf; o->iy = iyf; o->iz = izf;
+  o->negx = ixf < 0.f; o->negy = iyf < 0.f; o->negz = izf < 0.f;
+}
+
+// The primitives of one leaf against a ray in the space the leaf lives in (triangles and quadrics: an object holds no instance)
+template <bool ANY>
+static __device__ inline bool objectLeaf(const TraceScene& sc, int32_t leaf, RayState& r, HitState* hit) {
+  uint32_t off = refLeafOffset(leaf), cnt = refLeafCountField(leaf);
+  const GPrim* pr = sc.prims + off;
+  if (cnt == 15u) cnt = (uint32_t)__ldg(&pr->leafCount);
+  bool found = false;
+  for (uint32_t k = 0; k < cnt; ++k) {
+    const float4 a = ldg4(&pr[k].p1[0]), b = ldg4(&pr[k].p2[0]), c = ldg4(&pr[k].p3[0]);
+    const int kind = __float_as_int(c.w);
+    if ((kind & 1) == 0) {
+      if (ANY) { if (triangleAny(r, a, b, c)) return true; }
+      else if (triangleClosest(r, a, b, c, hit)) found = true;
+    } else {
+      const GSphere& s = sc.spheres[kind >> 1];
+      double th, u, v;
+      if (ANY) { if (sphereTest<true>(s, r, true, &th, nullptr, nullptr)) return true; }
+      else if (sphereTest<true>(s, r, false, &th, &u, &v)) {
+        hit->t = th; hit->b1 = u; hit->b2 = v; hit->prim = __float_as_int(a.w);
+        r.maxt = th;
+        found = true;
+      }
+    }
+  }
+  return found;
+}
+
+// BVHAccel.intersect / intersectP of the object's own accelerator (bvh_accel.dart:101-226): the literal walk of traceKernel
+template <bool ANY>
+static __device__ bool objectWalk(const TraceScene& sc, const GObject& ob, RayState& r, HitState* hit) {
+  if (ob.single) return objectLeaf<ANY>(sc, ob.rootRef, r, hit);  // one GeometricPrimitive: no accelerator, no box
+  {
+    double tmin, tmax;
+    if (!(slabs(r, ob.rootMin[0], ob.rootMin[1], ob.rootMin[2], ob.rootMax[0], ob.rootMax[1], ob.rootMax[2], &tmin, &tmax) &&
+          (tmin < r.maxt) && (tmax > r.mint)))
+      return false;
+  }
+  int32_t stackRef[DRT_STACK];
+  double stackT[DRT_STACK];
+  int sp = 0;
+  int32_t cur = ob.rootRef;
+  bool found = false;
+  for (;;) {
+    if (cur >= 0) {
+      const GNode* nd = sc.nodes + cur;
+      const float4 q0 = ldg4(&nd->c0min[0]), q1 = ldg4(&nd->c0max[1]), q2 = ldg4(&nd->c1min[2]);
+      const int4 q3 = __ldg(reinterpret_cast<const int4*>(&nd->ref0));
+      const int neg = q3.z == 0 ? r.negx : (q3.z == 1 ? r.negy : r.negz);
+      double tmin0, tmax0, tmin1, tmax1;
+      const bool h0 = slabs(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tmin0, &tmax0) && (tmax0 > r.mint);
+      const bool h1 = slabs(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tmin1, &tmax1) && (tmax1 > r.mint);
+      const int32_t nearRef = neg ? q3.y : q3.x, farRef = neg ? q3.x : q3.y;
+      const bool hn = neg ? h1 : h0, hf = neg ? h0 : h1;
+      const double tn = neg ? tmin1 : tmin0, tf = neg ? tmin0 : tmin1;
+      if (hf && tf < r.maxt) { stackRef[sp] = farRef; stackT[sp] = tf; sp++; }  // re-tested against maxDistance when popped
+      if (hn && tn < r.maxt) { cur = nearRef; continue; }
+    } else {
+      if (objectLeaf<ANY>(sc, cur, r, hit)) {
+        if (ANY) return true;
+        found = true;
+      }
+    }
+    bool have = false;
+    while (sp > 0) {
+      --sp;
+      if (stackT[sp] < r.maxt) { cur = stackRef[sp]; have = true; break; }
+    }
+    if (!have) return found;
+  }
+}
+
+// TransformedPrimitive.intersect / intersectP for the ray `r` (world space) at `time`: interpolate, transform the ray, query the
+// object.  A closest hit leaves t / b1 / b2 / prim in *hit; the caller sets r.maxDistance = t (transformed_primitive.dart:39).
+static __device__ __noinline__ bool instanceTestCold(const TraceScene& sc, int inst, bool any, const RayState* rWorld, double time,
+                                                     HitState* hit) {
+  const GInstance& in = sc.instances[inst];
+  M4 m, inv;
+  animInterpolate(in, time, &m, &inv);
+  RayState r;
+  transformRayState(m, *rWorld, &r);
+  const GObject& ob = sc.objects[in.object];
+  if (any) return objectWalk<true>(sc, ob, r, hit);
+  return objectWalk<false>(sc, ob, r, hit);
 }
 
 }  // namespace drt

@@ -25,16 +25,24 @@ template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(128) traceKernel(TraceScene sc, const float4* __restrict__ rayO,
                                                    const float4* __restrict__ rayD, uint64_t n, drt_hit_rec* hits,
                                                    uint8_t* occluded, DeviceCounters* counters, const double2* __restrict__ range,
-                                                   const uint32_t* __restrict__ nDev) {
+                                                   const uint32_t* __restrict__ nDev, ExactExtras xx) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (nDev) n = *nDev;  // a wavefront queue of the renderer: the count lives in device memory
   unsigned long long nodesVisited = 0, primsTested = 0;
   bool found = false;
   HitState hit;
-  hit.t = CUDART_INF; hit.b1 = 0.0; hit.b2 = 0.0; hit.prim = -1;
+  hit.t = CUDART_INF; hit.b1 = 0.0; hit.b2 = 0.0; hit.prim = -1; hit.inst = -1;
   if (i < n && !sc.empty) {
     RayState r;
     initRay(r, rayO[i], rayD[i]);
+    // the ray's time (scenes with TransformedPrimitives): per ray, or per wavefront slot with the slot id in the bits of rayO.w
+    // (slot id 0xffffffff: a ray built without a time, i.e. at time 0 — the ambient-occlusion rays, ambient_occlusion_integrator.dart:45)
+    double time = 0.0;
+    if (xx.times) {
+      const uint32_t ti = xx.timesBySlot ? __float_as_uint(rayO[i].w) : (uint32_t)i;
+      if (!xx.timesBySlot) time = xx.times[i];
+      else if (ti != 0xffffffffu) time = xx.times[ti];
+    }
     if (range) { r.mint = range[i].x; r.maxt = range[i].y; }  // renderer rays: f64 minDistance / maxDistance
     int32_t stackRef[DRT_STACK];
     double stackT[DRT_STACK];
@@ -95,15 +103,23 @@ __global__ void __launch_bounds__(128) traceKernel(TraceScene sc, const float4* 
             if (ANY) {
               if (triangleAny(r, a, b, c)) { found = true; break; }
             } else {
-              if (triangleClosest(r, a, b, c, &hit)) found = true;
+              if (triangleClosest(r, a, b, c, &hit)) { found = true; hit.inst = -1; }
             }
           } else {
             const GSphere& s = sc.spheres[kind >> 1];
             double th, u, v;
-            if (ANY) {
+            if (s.shape == 6) {  // a TransformedPrimitive: the object's own accelerator sees the transformed ray
+              HitState ih;
+              if (instanceTestCold(sc, s.instance, ANY, &r, time, &ih)) {
+                found = true;
+                if (ANY) break;
+                hit.t = ih.t; hit.b1 = ih.b1; hit.b2 = ih.b2; hit.prim = ih.prim; hit.inst = s.instance;
+                r.maxt = ih.t;
+              }
+            } else if (ANY) {
               if (sphereTest<true>(s, r, true, &th, nullptr, nullptr)) { found = true; break; }
             } else if (sphereTest<true>(s, r, false, &th, &u, &v)) {
-              hit.t = th; hit.b1 = u; hit.b2 = v; hit.prim = __float_as_int(a.w);
+              hit.t = th; hit.b1 = u; hit.b2 = v; hit.prim = __float_as_int(a.w); hit.inst = -1;
               r.maxt = th;
               found = true;
             }
@@ -134,6 +150,8 @@ __global__ void __launch_bounds__(128) traceKernel(TraceScene sc, const float4* 
       o.b2 = __double2float_rn(hit.b2);
       o.prim = hit.prim;
       reinterpret_cast<float4*>(hits)[i] = make_float4(o.t, o.b1, o.b2, __int_as_float(o.prim));
+      if (xx.tOut) xx.tOut[i] = found ? hit.t : CUDART_INF;
+      if (xx.instOut) xx.instOut[i] = found ? hit.inst : -1;
     }
   }
   if (COUNT) {
@@ -155,8 +173,11 @@ __global__ void __launch_bounds__(128) traceKernel(TraceScene sc, const float4* 
 }
 
 cudaError_t launchTrace(const TraceScene& sc, bool any, bool count, const void* rayO, const void* rayD, uint64_t n,
-                        void* out, DeviceCounters* counters, cudaStream_t stream, const double2* range, const uint32_t* nDev) {
+                        void* out, DeviceCounters* counters, cudaStream_t stream, const double2* range, const uint32_t* nDev,
+                        const ExactExtras* extras) {
   if (n == 0) return cudaSuccess;
+  ExactExtras xx{};
+  if (extras) xx = *extras;
   const int block = 128;
   uint64_t grid64 = (n + block - 1) / block;
   if (grid64 > 0x7fffffffull) return cudaErrorInvalidValue;
@@ -164,11 +185,11 @@ cudaError_t launchTrace(const TraceScene& sc, bool any, bool count, const void* 
   const float4* o = static_cast<const float4*>(rayO);
   const float4* d = static_cast<const float4*>(rayD);
   if (any) {
-    if (count) traceKernel<true, true><<<grid, block, 0, stream>>>(sc, o, d, n, nullptr, (uint8_t*)out, counters, range, nDev);
-    else traceKernel<true, false><<<grid, block, 0, stream>>>(sc, o, d, n, nullptr, (uint8_t*)out, counters, range, nDev);
+    if (count) traceKernel<true, true><<<grid, block, 0, stream>>>(sc, o, d, n, nullptr, (uint8_t*)out, counters, range, nDev, xx);
+    else traceKernel<true, false><<<grid, block, 0, stream>>>(sc, o, d, n, nullptr, (uint8_t*)out, counters, range, nDev, xx);
   } else {
-    if (count) traceKernel<false, true><<<grid, block, 0, stream>>>(sc, o, d, n, (drt_hit_rec*)out, nullptr, counters, range, nDev);
-    else traceKernel<false, false><<<grid, block, 0, stream>>>(sc, o, d, n, (drt_hit_rec*)out, nullptr, counters, range, nDev);
+    if (count) traceKernel<false, true><<<grid, block, 0, stream>>>(sc, o, d, n, (drt_hit_rec*)out, nullptr, counters, range, nDev, xx);
+    else traceKernel<false, false><<<grid, block, 0, stream>>>(sc, o, d, n, (drt_hit_rec*)out, nullptr, counters, range, nDev, xx);
   }
   return cudaGetLastError();
 }

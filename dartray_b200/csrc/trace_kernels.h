@@ -16,9 +16,16 @@ struct drt_hit_rec {  // == drt_hit of include/drt.h
 // float4 arrays live in device memory.  `out` is drt_hit_rec[n] or uint8_t[n].
 // `range` / `nDev`: the renderer's per-ray f64 intervals and device-resident ray count (n is then the queue capacity);
 // out == nullptr with count = true only counts.
+// `extras`: what scenes with TransformedPrimitives add — the rays' times, the f64 tHit and the instance of each closest hit.
+struct ExactExtras {
+  const double* times = nullptr;  // ray times: indexed by the ray, or (timesBySlot) by the wavefront slot id carried in the bits of rayO.w
+  int32_t timesBySlot = 0;
+  double* tOut = nullptr;         // closest hit: tHit in f64 (+inf on a miss)
+  int32_t* instOut = nullptr;     // closest hit: index of the TransformedPrimitive the hit came through, -1 for a top-level primitive
+};
 cudaError_t launchTrace(const TraceScene& sc, bool any, bool count, const void* rayO, const void* rayD, uint64_t n,
                         void* out, DeviceCounters* counters, cudaStream_t stream, const double2* range = nullptr,
-                        const uint32_t* nDev = nullptr);
+                        const uint32_t* nDev = nullptr, const ExactExtras* extras = nullptr);
 
 // Optional inputs/outputs of the production kernel used by the wavefront renderer.
 struct TraceExtras {

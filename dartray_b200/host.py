@@ -792,6 +792,11 @@ class SceneBuilder:
         self.materials = []  # (kind, kd, sigma)
         self.lights = []  # dict(kind, L, pos, nsamples, shapes=[("tri"|"sph", local ids...)])
         self._order = []  # ("mesh", first_tri, ntris) | ("sphere", sphere_index)
+        # TransformedPrimitives (transformed_primitive.dart): objects = the aggregates they wrap (each an order list like _order plus the
+        # nested accelerator's parameters), instances = (object, world-to-primitive m / mInv at the start and end time, the two times)
+        self._top_order = self._order
+        self.objects = []
+        self.instances = []
         self._nverts = 0
 
     def material(self, kd, sigma=0.0) -> int:
@@ -815,6 +820,44 @@ class SceneBuilder:
             raise ValueError("measured table shape")
         self.measured.append((int(kind), a))
         return len(self.measured) - 1
+
+    # -- TransformedPrimitive: object instancing and animated shapes (dartray.dart:404-452,480-546) -------------------------------
+    def begin_object(self) -> None:
+        """ObjectBegin: the shapes added until end_object() go into the object, not into the scene.  Their transforms stay their own
+        (a shape inside an object is built with the CTM of its definition, dartray.dart:378-403)."""
+        if self._order is not self._top_order:
+            raise ValueError("ObjectBegin inside an object")
+        self._order = []
+
+    def end_object(self, split: int = 2, max_node_prims: int = 4) -> int:
+        """ObjectEnd; returns the object index for instance().  split / max_node_prims: the accelerator objectInstance() builds
+        over the object's primitives when it has more than one (the scene's own accelerator parameters, dartray.dart:520-536)."""
+        if self._order is self._top_order:
+            raise ValueError("ObjectEnd without ObjectBegin")
+        if not self._order:
+            raise ValueError("an empty object cannot be instanced (dartray.dart:514-516 returns)")
+        self.objects.append((self._order, int(split), int(max_node_prims)))
+        self._order = self._top_order
+        return len(self.objects) - 1
+
+    def instance(self, obj: int, instance_to_world, instance_to_world_end=None, start_time: float = 0.0, end_time: float = 1.0) -> int:
+        """ObjectInstance under the CTM `instance_to_world` (and, inside an ActiveTransform / TransformTimes block, the end-time CTM):
+        TransformedPrimitive(object, AnimatedTransform(Inverse(ctm0), t0, Inverse(ctm1), t1)) (dartray.dart:537-546)."""
+        m0 = np.asarray(instance_to_world, np.float32).reshape(4, 4)
+        m1 = m0 if instance_to_world_end is None else np.asarray(instance_to_world_end, np.float32).reshape(4, 4)
+        # Transform.Inverse swaps m and mInv (transform.dart:58-60): world-to-primitive = (mInv, m) of the CTM
+        self.instances.append((int(obj), mat_inv(m0), m0, mat_inv(m1), m1, float(start_time), float(end_time)))
+        self._top_order.append(("instance", len(self.instances) - 1))
+        return len(self.instances) - 1
+
+    def animated(self, add_shape, o2w_start, o2w_end, start_time: float = 0.0, end_time: float = 1.0, max_node_prims: int = 1) -> int:
+        """DartRay.shape for an animated CTM (dartray.dart:404-452): the shape is built under the IDENTITY transform — call
+        `add_shape(sb)` to add it, without an o2w — wrapped in a BVHAccel with the constructor's defaults (maxPrims 1, sah) when it
+        refines into more than one primitive, and instanced with AnimatedTransform(Inverse(ctm0), Inverse(ctm1))."""
+        self.begin_object()
+        add_shape(self)
+        obj = self.end_object(split=2, max_node_prims=max_node_prims)
+        return self.instance(obj, o2w_start, o2w_end, start_time, end_time)
 
     def material_program(self, plugin: str, bumpmap=None, m1=None, m2=None, **params) -> int:
         """A material whose parameters are textures that read the hit point, or that carries a bump map (`plugin` and the parameter
@@ -1035,16 +1078,26 @@ class SceneBuilder:
         P = np.concatenate(self.P) if self.P else np.zeros((0, 3), np.float32)
         idx = np.concatenate(self.idx) if self.idx else np.zeros((0, 3), np.uint32)
         # refined order handed to BVHAccel: Primitive.fullyRefine is LIFO per primitive (primitive.dart:71-84)
-        order = []
-        for item in self._order:
-            if item[0] == "mesh":
-                order += list(range(item[1] + item[2] - 1, item[1] - 1, -1))
-            elif item[0] == "sphere":
-                order.append(ntris + item[1])
-            elif item[0] == "disk":
-                order.append(ntris + nsph + item[1])
-            else:
-                order.append(ntris + nsph + ndsk + item[1])
+        if self._order is not self._top_order:
+            raise ValueError("ObjectBegin without ObjectEnd")
+        nprims = ntris + nsph + ndsk + len(self.quad)
+
+        def refine(items):
+            order = []
+            for item in items:
+                if item[0] == "mesh":
+                    order += list(range(item[1] + item[2] - 1, item[1] - 1, -1))
+                elif item[0] == "sphere":
+                    order.append(ntris + item[1])
+                elif item[0] == "disk":
+                    order.append(ntris + nsph + item[1])
+                elif item[0] == "instance":
+                    order.append(nprims + item[1])
+                else:
+                    order.append(ntris + nsph + ndsk + item[1])
+            return order
+        order = refine(self._top_order)
+        object_orders = [refine(o[0]) for o in self.objects]
         lights = []
         base = {"tri": 0, "sph": ntris, "dsk": ntris + nsph, "quad": ntris + nsph + ndsk}
         for l in self.lights:
@@ -1110,6 +1163,16 @@ class SceneBuilder:
             mat_general=general,
             mat_programs=programs if has_programs else None, tex_nodes=tex_nodes, tex_texels=tex_texels,
             measured=list(getattr(self, "measured", [])),
+            object_offsets=np.asarray(np.cumsum([0] + [len(o) for o in object_orders]), np.uint32),
+            object_prims=np.asarray([p for o in object_orders for p in o], np.uint32),
+            object_split=np.asarray([o[1] for o in self.objects], np.int32),
+            object_max_node_prims=np.asarray([o[2] for o in self.objects], np.int32),
+            instance_object=np.asarray([i[0] for i in self.instances], np.uint32),
+            instance_start_m=np.asarray([i[1] for i in self.instances], np.float32).reshape(-1, 16),
+            instance_start_minv=np.asarray([i[2] for i in self.instances], np.float32).reshape(-1, 16),
+            instance_end_m=np.asarray([i[3] for i in self.instances], np.float32).reshape(-1, 16),
+            instance_end_minv=np.asarray([i[4] for i in self.instances], np.float32).reshape(-1, 16),
+            instance_times=np.asarray([(i[5], i[6]) for i in self.instances], np.float64).reshape(-1, 2),
             mat_lobe_offsets=np.asarray(np.cumsum([0] + [len(ll) for ll in lobe_lists]), np.uint32),
             lobe_kind=np.asarray([l["kind"] for l in lobes], np.int32),
             lobe_rgb=np.asarray([l["rgb"] for l in lobes], np.float32).reshape(-1, 3),
@@ -1178,6 +1241,9 @@ def upload_scene(ctx, arrays: dict, split: int = 2, max_node_prims: int = 4):
         ctx.set_quadrics(int(qk[i]), a["quad_o2w"][i:j], a["quad_w2o"][i:j], a["quad_params"][i:j], a["quad_mat"][i:j],
                          a["quad_light"][i:j], a["quad_rev"][i:j])
         i = j
+    if a.get("instance_object") is not None and a["instance_object"].shape[0]:
+        ctx.set_instances(a["object_offsets"], a["object_prims"], a["object_split"], a["object_max_node_prims"], a["instance_object"],
+                          a["instance_start_m"], a["instance_start_minv"], a["instance_end_m"], a["instance_end_minv"], a["instance_times"])
     ctx.set_build_order(a["order"])
     ctx.build_bvh(split, max_node_prims)
     if a.get("measured"):

@@ -144,6 +144,33 @@ int drt_set_quadrics(drt_ctx* ctx, int kind, uint32_t n, const float* o2w, const
                      const int32_t* material_of_quadric, const int32_t* light_of_quadric,
                      const uint8_t* reverse_orientation_of_quadric);
 
+/* TransformedPrimitives (lib/core/primitive/transformed_primitive.dart:26-82): what DartRay.shape builds for a shape under an
+ * animated CTM (lib/dartray/dartray.dart:404-452) and DartRay.objectInstance for an ObjectInstance (:505-546).
+ *   objects    the `primitive` each one wraps: object i owns the geometric primitives object_prims[object_offsets[i] ..
+ *              object_offsets[i + 1]) in the refined order its accelerator sees (one entry: the GeometricPrimitive itself, no
+ *              accelerator); more than one: a BVHAccel with object_split / object_max_node_prims (NULL: sah, 1 — the constructor
+ *              defaults an animated shape gets, bvh_accel.dart:41; an ObjectInstance uses the scene's accelerator parameters)
+ *   instances  instance j wraps object instance_object[j] with AnimatedTransform(start, times[2j], end, times[2j + 1])
+ *              (lib/core/animated_transform.dart:35-43): start / end are WORLD-TO-PRIMITIVE Transforms (m and mInv, row-major) —
+ *              Inverse(CTM[0]), Inverse(CTM[1]); times NULL = (0, 1).  The library runs the constructor's Decompose and, per ray,
+ *              worldToPrimitive.interpolate(ray.time) (:61-136) with the reference's float32 / binary64 arithmetic, and
+ *              motionBounds (:183-200) for the world bound.
+ * Primitive ids: instance j is top-level primitive n_triangles + n_quadrics + j in drt_set_build_order; object primitives are
+ * geometric primitives that the build order leaves out (their shapes keep the transforms they were built with: identity for an
+ * animated shape).  Hits report the geometric primitive.  The ray's time: the camera sample's time inside drt_render (every ray
+ * a sample spawns inherits it, ray.dart:59); drt_set_ray_times for the drt_trace_* calls.  Scenes with instances are traced by
+ * the literal-walk kernel (one thread per ray descends into the object with the transformed ray).  Area lights cannot be
+ * instanced (dartray.dart:407-410,455-458 drop them with a warning); meshes inside objects carry no per-vertex N / S here.
+ * Call before drt_set_build_order / drt_build_bvh.  n_instances == 0 removes them. */
+int drt_set_instances(drt_ctx* ctx, uint32_t n_objects, const uint32_t* object_offsets, const uint32_t* object_prims,
+                      const int32_t* object_split, const int32_t* object_max_node_prims, uint32_t n_instances,
+                      const uint32_t* instance_object, const float* start_m, const float* start_minv, const float* end_m,
+                      const float* end_minv, const double* times);
+
+/* Ray i of the following drt_trace_* calls travels at times[i] (Ray.time, lib/core/ray.dart:37-38; read by TransformedPrimitives
+ * only).  NULL: every ray at time 0. */
+int drt_set_ray_times(drt_ctx* ctx, const double* times, uint64_t n);
+
 /* Order in which BVHAccel sees the refined primitives (a permutation of primitive ids).  The
  * reference's Primitive.fullyRefine is LIFO (lib/core/primitive.dart:71-84), so a mesh's triangles
  * reach the builder in reverse order; the build's partition steps depend on it.  NULL = identity. */

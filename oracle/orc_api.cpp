@@ -21,6 +21,7 @@ struct orc_ctx {
   Counters counters;
   std::string err;
   double buildSeconds = 0;
+  std::vector<double> rayTimes;  // orc_set_ray_times
 };
 
 struct orc_hit {
@@ -155,9 +156,67 @@ int orc_set_build_order(orc_ctx* c, const uint32_t* ids, uint32_t n) {
   return 0;
 }
 
+// mirrors drt_set_instances (include/drt.h): objects = the aggregates TransformedPrimitives wrap, instances = the TransformedPrimitives
+int orc_set_instances(orc_ctx* c, uint32_t nObjects, const uint32_t* objectOffsets, const uint32_t* objectPrims, const int32_t* objectSplit,
+                      const int32_t* objectMaxPrims, uint32_t nInstances, const uint32_t* instanceObject, const float* startM,
+                      const float* startMInv, const float* endM, const float* endMInv, const double* times) {
+  Scene& s = c->scene;
+  std::vector<Scene::Object> objs(nObjects);
+  for (uint32_t i = 0; i < nObjects; ++i) {
+    if (objectOffsets[i + 1] <= objectOffsets[i]) { c->err = "an object holds at least one primitive"; return -1; }
+    objs[i].order.assign(objectPrims + objectOffsets[i], objectPrims + objectOffsets[i + 1]);
+    for (uint32_t id : objs[i].order)
+      if (id >= s.nprims()) { c->err = "object primitive id out of range"; return -1; }
+    objs[i].split = objectSplit ? objectSplit[i] : 2;
+    objs[i].maxPrims = objectMaxPrims ? objectMaxPrims[i] : 1;
+  }
+  std::vector<Scene::Instance> insts(nInstances);
+  for (uint32_t i = 0; i < nInstances; ++i) {
+    if (instanceObject[i] >= nObjects) { c->err = "instance names an object that was not defined"; return -1; }
+    insts[i].object = instanceObject[i];
+    insts[i].worldToPrimitive.init(Transform(startM + 16 * i, startMInv + 16 * i), times ? times[2 * i] : 0.0,
+                                   Transform(endM + 16 * i, endMInv + 16 * i), times ? times[2 * i + 1] : 1.0);
+  }
+  s.setInstances(std::move(objs), std::move(insts));
+  return 0;
+}
+
+// times of the rays of the following orc_trace_* calls (ray i travels at times[i]; NULL: every ray at time 0)
+int orc_set_ray_times(orc_ctx* c, const double* times, uint64_t n) {
+  if (times) c->rayTimes.assign(times, times + n);
+  else c->rayTimes.clear();
+  return 0;
+}
+
+// AnimatedTransform probes for the tests: Decompose of instance `inst`'s two transforms (T 2 x 3, R 2 x 4 as x y z w, S 2 x 16),
+// interpolate(time) (m, mInv) and the instance's world bound
+int orc_instance_probe(const orc_ctx* c, uint32_t inst, double time, double* T, double* R, float* S, float* m, float* mInv, float* bound,
+                       int32_t* animated) {
+  const Scene& s = c->scene;
+  if (inst >= s.instances.size()) return -1;
+  const AnimatedTransform& a = s.instances[inst].worldToPrimitive;
+  for (int k = 0; k < 2; ++k) {
+    if (T) { T[3 * k] = a.T[k].x; T[3 * k + 1] = a.T[k].y; T[3 * k + 2] = a.T[k].z; }
+    if (R) { R[4 * k] = a.R[k].v.x; R[4 * k + 1] = a.R[k].v.y; R[4 * k + 2] = a.R[k].v.z; R[4 * k + 3] = a.R[k].w; }
+    if (S) std::memcpy(S + 16 * k, a.S[k].d, 64);
+  }
+  const Transform t = a.interpolate(time);
+  if (m) std::memcpy(m, t.m, 64);
+  if (mInv) std::memcpy(mInv, t.mInv, 64);
+  const BBox& b = s.instances[inst].bound;
+  if (bound) { bound[0] = b.pMin.x; bound[1] = b.pMin.y; bound[2] = b.pMin.z; bound[3] = b.pMax.x; bound[4] = b.pMax.y; bound[5] = b.pMax.z; }
+  if (animated) *animated = a.actuallyAnimated ? 1 : 0;
+  return 0;
+}
+
 int orc_build_bvh(orc_ctx* c, int split, int maxPrims) {
   Scene& s = c->scene;
-  if (!s.buildOrder.empty() && s.buildOrder.size() != s.nprims()) { c->err = "build order size mismatch"; return -1; }
+  if (s.instances.empty() && !s.buildOrder.empty() && s.buildOrder.size() != s.nprims()) { c->err = "build order size mismatch"; return -1; }
+  if (!s.instances.empty()) {  // the top-level order names geometric primitives outside every object and the instances
+    if (s.buildOrder.empty()) { c->err = "a scene with instances needs the top-level build order"; return -1; }
+    for (uint32_t id : s.buildOrder)
+      if (id >= s.nprims() + s.instances.size()) { c->err = "build order id out of range"; return -1; }
+  }
   auto t0 = std::chrono::steady_clock::now();
   s.buildBVH(split, maxPrims);
   c->buildSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -210,6 +269,7 @@ int orc_trace_closest(orc_ctx* c, const float* o, const float* d, uint64_t n, or
     Counters cc;
     for (uint64_t i = b; i < e; ++i) {
       Ray r = makeRay(o + 4 * i, d + 4 * i);
+      if (i < c->rayTimes.size()) r.time = c->rayTimes[i];
       Hit hit;
       bool h = s.intersect(r, &hit, &cc);
       storeHit(&hits[i], h, hit);
@@ -230,6 +290,7 @@ int orc_trace_any(orc_ctx* c, const float* o, const float* d, uint64_t n, uint8_
     Counters cc;
     for (uint64_t i = b; i < e; ++i) {
       Ray r = makeRay(o + 4 * i, d + 4 * i);
+      if (i < c->rayTimes.size()) r.time = c->rayTimes[i];
       occluded[i] = s.intersectP(r, &cc) ? 1 : 0;
     }
     cc.rays = e - b;
@@ -247,6 +308,7 @@ int orc_trace_closest_brute(orc_ctx* c, const float* o, const float* d, uint64_t
   parallelFor(n, nthreads, [&](int, uint64_t b, uint64_t e) {
     for (uint64_t i = b; i < e; ++i) {
       Ray r = makeRay(o + 4 * i, d + 4 * i);
+      if (i < c->rayTimes.size()) r.time = c->rayTimes[i];
       Hit hit;
       int ties = 0;
       double sec = kInf;
@@ -264,6 +326,7 @@ int orc_trace_any_brute(orc_ctx* c, const float* o, const float* d, uint64_t n, 
   parallelFor(n, nthreads, [&](int, uint64_t b, uint64_t e) {
     for (uint64_t i = b; i < e; ++i) {
       Ray r = makeRay(o + 4 * i, d + 4 * i);
+      if (i < c->rayTimes.size()) r.time = c->rayTimes[i];
       uint8_t occ = 0;
       for (uint32_t p = 0; p < s.nprims() && !occ; ++p) occ = s.primIntersectP(p, r) ? 1 : 0;
       occluded[i] = occ;

@@ -325,6 +325,8 @@ struct Isect {
   DG dg;
   int32_t prim = -1;
   double rayEpsilon = 0;
+  int32_t inst = -1;  // the TransformedPrimitive the hit came through and its worldToPrimitive at the ray's time
+  Transform w2p;
 };
 
 struct SampleLayout {
@@ -1226,8 +1228,27 @@ struct Ctx {
   void fillIsect(const Ray& ray, const Hit& h, Isect* is) const {
     is->prim = h.prim;
     is->rayEpsilon = h.rayEpsilon;
+    is->inst = h.inst;
     // the shape computed dg.p with the ray it was given; maxt == tHit after a closest-hit query
-    shapeDG((uint32_t)h.prim, ray, h, &is->dg);
+    if (h.inst < 0) {
+      shapeDG((uint32_t)h.prim, ray, h, &is->dg);
+      return;
+    }
+    // transformed_primitive.dart:30-58: the shape saw the ray in primitive space; its differential geometry goes back to world space
+    const Transform w2p = g.instances[(size_t)h.inst].worldToPrimitive.interpolate(ray.time);
+    const Ray r2(w2p.point(ray.o), w2p.vector(ray.d), ray.mint, ray.maxt, ray.time, ray.depth);
+    shapeDG((uint32_t)h.prim, r2, h, &is->dg);
+    is->w2p = w2p;
+    if (!XfIsIdentity(w2p)) {
+      const Transform p2w = XfInverse(w2p);
+      DG& dg = is->dg;
+      dg.p = p2w.point(dg.p);
+      dg.nn = Normalize(p2w.normal(dg.nn));
+      dg.dpdu = p2w.vector(dg.dpdu);
+      dg.dpdv = p2w.vector(dg.dpdv);
+      dg.dndu = p2w.normal(dg.dndu);
+      dg.dndv = p2w.normal(dg.dndv);
+    }
   }
 
   // Shape.intersect without the GeometricPrimitive side effect (ray.maxDistance unchanged)
@@ -1419,6 +1440,9 @@ struct Ctx {
     const Scene::MeshInfo* mesh = (uint32_t)is.prim < g.ntris() ? g.meshOf((uint32_t)is.prim) : nullptr;
     if (mesh && (mesh->hasN || mesh->hasS)) {  // Triangle.getShadingGeometry, triangle.dart:271-364
       const uint32_t tri = (uint32_t)is.prim;
+      // obj2world: the Intersection's objectToWorld — the shape's, or through a TransformedPrimitive Inverse(worldToObject * w2p)
+      // (transformed_primitive.dart:44-45); the dndu / dndv of :354-355 use the SHAPE's own objectToWorld either way
+      const Transform obj2world = is.inst >= 0 && !XfIsIdentity(is.w2p) ? XfInverse(XfMul(XfInverse(mesh->o2w), is.w2p)) : mesh->o2w;
       double uv[6];
       g.triUVs(tri, uv);
       double A0 = uv[2] - uv[0], A1 = uv[4] - uv[0], A2 = uv[3] - uv[1], A3 = uv[5] - uv[1];
@@ -1438,9 +1462,9 @@ struct Ctx {
         return Vec(q[0], q[1], q[2]);
       };
       Vec ns, ss, ts;
-      if (mesh->hasN) ns = Normalize(mesh->o2w.normal(((vert(g.vertN, 0) * bx) + (vert(g.vertN, 1) * by)) + (vert(g.vertN, 2) * bz)));
+      if (mesh->hasN) ns = Normalize(obj2world.normal(((vert(g.vertN, 0) * bx) + (vert(g.vertN, 1) * by)) + (vert(g.vertN, 2) * bz)));
       else ns = dg.nn;
-      if (mesh->hasS) ss = Normalize(mesh->o2w.vector(((vert(g.vertS, 0) * bx) + (vert(g.vertS, 1) * by)) + (vert(g.vertS, 2) * bz)));
+      if (mesh->hasS) ss = Normalize(obj2world.vector(((vert(g.vertS, 0) * bx) + (vert(g.vertS, 1) * by)) + (vert(g.vertS, 2) * bz)));
       else ss = Normalize(dg.dpdu);
       ts = Cross(ss, ns);
       if (LengthSquared(ts) > 0.0) {

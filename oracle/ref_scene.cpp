@@ -418,29 +418,39 @@ struct Builder {
 
 }  // namespace
 
-void Scene::buildBVH(int split, int maxPrims) {
-  splitMethod = split;
-  maxPrimsInNode = std::min(255, maxPrims);  // :44
-  nodes.clear();
-  ordered.clear();
-  uint32_t n = nprims();
+void Scene::buildInto(const std::vector<uint32_t>& order, int split, int maxPrims, std::vector<uint32_t>* orderedOut,
+                      std::vector<LinearNode>* nodesOut) const {
+  nodesOut->clear();
+  orderedOut->clear();
+  const uint32_t n = (uint32_t)order.size();
   if (n == 0) return;
-  Builder b{*this, splitMethod, maxPrimsInNode, {}, {}, {}, 0};
+  Builder b{*this, split, std::min(255, maxPrims), {}, {}, {}, 0};  // :44
   b.buildData.resize(n);
   for (uint32_t i = 0; i < n; ++i) {  // :59-65
-    uint32_t prim = buildOrder.empty() ? i : buildOrder[i];
+    const uint32_t prim = order[i];
     b.buildData[i].primitiveNumber = prim;
     b.buildData[i].bounds = primBound(prim);
     b.buildData[i].centroid = b.buildData[i].bounds.center();
   }
   b.ordered.reserve(n);
   BuildNode* root = b.recursiveBuild(0, (int)n);
-  nodes.resize(b.totalNodes);
+  nodesOut->resize(b.totalNodes);
   int off = 0;
-  b.flatten(root, nodes, &off);
+  b.flatten(root, *nodesOut, &off);
   assert(off == b.totalNodes);
-  ordered.swap(b.ordered);
+  orderedOut->swap(b.ordered);
   for (BuildNode* p : b.pool) delete p;
+}
+
+void Scene::buildBVH(int split, int maxPrims) {
+  splitMethod = split;
+  maxPrimsInNode = std::min(255, maxPrims);  // :44
+  std::vector<uint32_t> order = buildOrder;
+  if (order.empty()) {  // upload order; with instances the caller always gives the top-level order
+    order.resize(nprims());
+    for (uint32_t i = 0; i < nprims(); ++i) order[i] = i;
+  }
+  buildInto(order, splitMethod, maxPrimsInNode, &ordered, &nodes);
 }
 
 // lib/accelerators/bvh_accel.dart:439-472
@@ -461,7 +471,8 @@ static inline bool slab(const BBox& bounds, const Ray& ray, const Vec& invDir, c
 }
 
 // lib/accelerators/bvh_accel.dart:101-165
-bool Scene::intersect(Ray& ray, Hit* hit, Counters* c) const {
+bool Scene::intersect(Ray& ray, Hit* hit, Counters* c) const { return walk(nodes, ordered, ray, hit, c); }
+bool Scene::walk(const std::vector<LinearNode>& nodes, const std::vector<uint32_t>& ordered, Ray& ray, Hit* hit, Counters* c) const {
   if (nodes.empty()) return false;
   bool any = false;
   Vec invDir(1.0 / (double)ray.d.x, 1.0 / (double)ray.d.y, 1.0 / (double)ray.d.z);  // f32-rounded, :109-111
@@ -475,7 +486,7 @@ bool Scene::intersect(Ray& ray, Hit* hit, Counters* c) const {
       if (node.nPrimitives > 0) {
         for (int i = 0; i < node.nPrimitives; ++i) {
           if (c) c->prims_tested++;
-          if (primIntersect(ordered[node.offset + i], ray, hit)) any = true;
+          if (primIntersect(ordered[node.offset + i], ray, hit, c)) any = true;
         }
         if (todoOffset == 0) break;
         nodeNum = todo[--todoOffset];
@@ -497,7 +508,8 @@ bool Scene::intersect(Ray& ray, Hit* hit, Counters* c) const {
 }
 
 // lib/accelerators/bvh_accel.dart:167-226
-bool Scene::intersectP(const Ray& ray, Counters* c) const {
+bool Scene::intersectP(const Ray& ray, Counters* c) const { return walkP(nodes, ordered, ray, c); }
+bool Scene::walkP(const std::vector<LinearNode>& nodes, const std::vector<uint32_t>& ordered, const Ray& ray, Counters* c) const {
   if (nodes.empty()) return false;
   Vec invDir(1.0 / (double)ray.d.x, 1.0 / (double)ray.d.y, 1.0 / (double)ray.d.z);
   int dirIsNeg[3] = {invDir.x < 0 ? 1 : 0, invDir.y < 0 ? 1 : 0, invDir.z < 0 ? 1 : 0};
@@ -510,7 +522,7 @@ bool Scene::intersectP(const Ray& ray, Counters* c) const {
       if (node.nPrimitives > 0) {
         for (int i = 0; i < node.nPrimitives; ++i) {
           if (c) c->prims_tested++;
-          if (primIntersectP(ordered[node.offset + i], ray)) return true;
+          if (primIntersectP(ordered[node.offset + i], ray, c)) return true;
         }
         if (todoOffset == 0) break;
         nodeNum = todo[--todoOffset];
@@ -531,20 +543,63 @@ bool Scene::intersectP(const Ray& ray, Counters* c) const {
   return false;
 }
 
+// transformed_primitive.dart:30-58.  The Intersection's differential geometry is moved to world space by the renderer side
+// (ref_render.cpp fillIsect), which repeats interpolate(r.time) for the instance the hit names.
+bool Scene::instanceIntersect(uint32_t inst, Ray& r, Hit* hit, Counters* c) const {
+  const Instance& in = instances[inst];
+  const Object& ob = objects[in.object];
+  const Transform w2p = in.worldToPrimitive.interpolate(r.time);
+  Ray ray(w2p.point(r.o), w2p.vector(r.d), r.mint, r.maxt, r.time, r.depth);  // transform.dart:180-196
+  bool h;
+  if (ob.order.size() == 1) {
+    if (c) c->prims_tested++;
+    h = primIntersect(ob.order[0], ray, hit);
+  } else {
+    h = walk(ob.nodes, ob.ordered, ray, hit, c);
+  }
+  if (!h) return false;
+  r.maxt = ray.maxt;
+  hit->inst = (int32_t)inst;
+  return true;
+}
+// transformed_primitive.dart:60-62 over AnimatedTransform.transformRay (animated_transform.dart:138-154: the same three cases)
+bool Scene::instanceIntersectP(uint32_t inst, const Ray& r, Counters* c) const {
+  const Instance& in = instances[inst];
+  const Object& ob = objects[in.object];
+  const Transform w2p = in.worldToPrimitive.interpolate(r.time);
+  const Ray ray(w2p.point(r.o), w2p.vector(r.d), r.mint, r.maxt, r.time, r.depth);
+  if (ob.order.size() == 1) {
+    if (c) c->prims_tested++;
+    return primIntersectP(ob.order[0], ray);
+  }
+  return walkP(ob.nodes, ob.ordered, ray, c);
+}
+
+void Scene::setInstances(std::vector<Object>&& objs, std::vector<Instance>&& insts) {
+  objects = std::move(objs);
+  instances = std::move(insts);
+  for (Object& ob : objects)
+    if (ob.order.size() > 1) buildInto(ob.order, ob.split, ob.maxPrims, &ob.ordered, &ob.nodes);
+  for (Instance& in : instances) in.bound = in.worldToPrimitive.motionBounds(objects[in.object].worldBound(*this), true);
+}
+
 // Exhaustive differential check in the style of aggregate_test_renderer.dart:82-96:
 // every primitive in upload order, same shrinking ray.maxDistance.  Also reports how
 // many primitives hit at exactly the winning t (tie set size) and the runner-up t.
 bool Scene::intersectBrute(Ray& ray, Hit* hit, int* nTies, double* secondT) const {
   bool any = false;
   const double mint = ray.mint, maxt0 = ray.maxt;
-  uint32_t n = nprims();
-  for (uint32_t p = 0; p < n; ++p)
+  // the top-level primitives in upload order (with instances: the geometric primitives the build order names, then the instances)
+  std::vector<uint32_t> top = buildOrder;
+  if (top.empty()) { top.resize(nprims()); for (uint32_t i = 0; i < nprims(); ++i) top[i] = i; }
+  std::sort(top.begin(), top.end());
+  for (uint32_t p : top)
     if (primIntersect(p, ray, hit)) any = true;
   if (nTies || secondT) {
     int ties = 0;
     double second = kInf;
     if (any) {
-      for (uint32_t p = 0; p < n; ++p) {
+      for (uint32_t p : top) {
         Ray r2 = ray;
         r2.mint = mint;
         r2.maxt = maxt0;

@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <vector>
 
+#include "ref_anim.h"
 #include "ref_core.h"
 
 namespace orc {
@@ -118,6 +119,7 @@ struct Hit {
   double rayEpsilon = 0.0;
   Vec phitObj;       // sphere: object-space hit point after the 1e-5*r nudge
   double phi = 0.0;  // sphere
+  int32_t inst = -1;  // TransformedPrimitive the hit came through (transformed_primitive.dart:30-62), -1: a top-level primitive
 };
 
 // lib/core/common.dart:140-167
@@ -189,6 +191,30 @@ struct Scene {
   std::vector<uint32_t> ordered;  // primitives after the build (ids in upload numbering)
   std::vector<LinearNode> nodes;
 
+  // TransformedPrimitive (lib/core/primitive/transformed_primitive.dart): what DartRay.shape builds for an animated shape
+  // (dartray.dart:404-452) and DartRay.objectInstance for an instance (:505-546).  An Object is the `primitive` it wraps: one
+  // GeometricPrimitive, or the BVHAccel over the refined primitives of the shape / the instance's primitive list (built with the
+  // caller's split method and maxnodeprims: BVHAccel's defaults for an animated shape, the scene's accelerator for an instance).
+  // Object primitives are geometric primitives of this scene (ids < nprims()) that the top-level build order leaves out; an
+  // instance is a top-level primitive with id nprims() + its index.
+  struct Object {
+    std::vector<uint32_t> order;  // refined order handed to the nested BVHAccel (one entry: the primitive itself)
+    int split = 2, maxPrims = 1;
+    std::vector<uint32_t> ordered;
+    std::vector<LinearNode> nodes;
+    BBox worldBound(const Scene& sc) const {  // bvh_accel.dart:93-95 / geometric_primitive.dart:35-37
+      if (order.size() == 1) return sc.primBound(order[0]);
+      return nodes.empty() ? BBox() : nodes[0].bounds;
+    }
+  };
+  struct Instance {
+    uint32_t object = 0;
+    AnimatedTransform worldToPrimitive;
+    BBox bound;  // worldToPrimitive.motionBounds(primitive.worldBound(), true), transformed_primitive.dart:76-78
+  };
+  std::vector<Object> objects;
+  std::vector<Instance> instances;
+
   uint32_t ntris() const { return (uint32_t)(idx.size() / 3); }
   uint32_t nprims() const { return ntris() + (uint32_t)spheres.size(); }
 
@@ -206,6 +232,7 @@ struct Scene {
       triVerts(prim, &p1, &p2, &p3);
       return UnionPoint(BBox(p1, p2), p3);
     }
+    if (prim >= nprims()) return instances[prim - nprims()].bound;
     return spheres[prim - ntris()].worldBound();
   }
 
@@ -214,17 +241,26 @@ struct Scene {
   bool triIntersectP(uint32_t tri, const Ray& ray) const;      // triangle.dart:162-240
   bool sphIntersect(const Sphere& s, Ray& r, Hit* hit) const;  // sphere.dart:39-167
   bool sphIntersectP(const Sphere& s, const Ray& r) const;     // sphere.dart:169-241
-  bool primIntersect(uint32_t prim, Ray& ray, Hit* hit) const {
+  bool primIntersect(uint32_t prim, Ray& ray, Hit* hit, Counters* c = nullptr) const {
+    if (prim >= nprims()) return instanceIntersect(prim - nprims(), ray, hit, c);
     bool h = prim < ntris() ? triIntersect(prim, ray, hit) : sphIntersect(spheres[prim - ntris()], ray, hit);
-    if (h) hit->prim = (int32_t)prim;
+    if (h) { hit->prim = (int32_t)prim; hit->inst = -1; }
     return h;
   }
-  bool primIntersectP(uint32_t prim, const Ray& ray) const {
+  bool primIntersectP(uint32_t prim, const Ray& ray, Counters* c = nullptr) const {
+    if (prim >= nprims()) return instanceIntersectP(prim - nprims(), ray, c);
     return prim < ntris() ? triIntersectP(prim, ray) : sphIntersectP(spheres[prim - ntris()], ray);
   }
+  bool instanceIntersect(uint32_t inst, Ray& r, Hit* hit, Counters* c) const;   // transformed_primitive.dart:30-58
+  bool instanceIntersectP(uint32_t inst, const Ray& r, Counters* c) const;     // transformed_primitive.dart:60-62
+  void setInstances(std::vector<Object>&& objs, std::vector<Instance>&& insts);  // builds the nested accelerators and the bounds
 
   // ---- BVH ---------------------------------------------------------------
   void buildBVH(int split, int maxPrims);                       // bvh_accel.dart:41-91
+  void buildInto(const std::vector<uint32_t>& order, int split, int maxPrims, std::vector<uint32_t>* ordered,
+                 std::vector<LinearNode>* nodes) const;
+  bool walk(const std::vector<LinearNode>& nodes, const std::vector<uint32_t>& ordered, Ray& ray, Hit* hit, Counters* c) const;
+  bool walkP(const std::vector<LinearNode>& nodes, const std::vector<uint32_t>& ordered, const Ray& ray, Counters* c) const;
   bool intersect(Ray& ray, Hit* hit, Counters* c) const;        // bvh_accel.dart:101-165
   bool intersectP(const Ray& ray, Counters* c) const;           // bvh_accel.dart:167-226
   // exhaustive loop in upload order (the pattern of aggregate_test_renderer.dart:82-96)

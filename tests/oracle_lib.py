@@ -65,6 +65,9 @@ def lib():
         L.orc_set_infinite_light.argtypes = [vp, u32, i32, i32, vp, vp, vp]
         L.orc_set_textures.argtypes = [vp, u32, vp, vp, u64]
         L.orc_set_measured.argtypes = [vp, u32, vp, vp, vp, vp, u64]
+        L.orc_set_instances.argtypes = [vp, u32, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp, vp]
+        L.orc_set_ray_times.argtypes = [vp, vp, u64]
+        L.orc_instance_probe.argtypes = [vp, u32, dbl, vp, vp, vp, vp, vp, vp, vp]
         L.orc_set_material_programs.argtypes = [vp, u32, vp]
         L.orc_texture_eval.argtypes = [vp, i32, u32, vp, vp]
         L.orc_image_level.argtypes = [vp, i32, i32, vp, vp, vp]
@@ -241,6 +244,31 @@ class Oracle:
         """BRDFToBTDF (bit 0) / ScaledBxDF (bit 1, with its RGB scale) around the lobes of the last set_material_lobes."""
         w, sc = _arr(wrap, np.int32), _arr(scale, np.float32).reshape(-1, 3)
         self._ck(self.L.orc_set_lobe_wrappers(self.h, w.shape[0], _p(w), _p(sc)))
+
+    def set_instances(self, object_offsets, object_prims, object_split, object_max_node_prims, instance_object, start_m, start_minv,
+                      end_m, end_minv, times):
+        """TransformedPrimitives (transformed_primitive.dart): objects (prim lists + nested accelerator parameters) and instances
+        (object, world-to-primitive m / mInv at the start and end time, n x 2 times).  Before set_build_order / build_bvh."""
+        oo, op = _arr(object_offsets, np.uint32), _arr(object_prims, np.uint32)
+        os_, om = _arr(object_split, np.int32), _arr(object_max_node_prims, np.int32)
+        io = _arr(instance_object, np.uint32)
+        m = [_arr(x, np.float32).reshape(-1, 16) for x in (start_m, start_minv, end_m, end_minv)]
+        tm = _arr(times, np.float64).reshape(-1, 2)
+        self._ck(self.L.orc_set_instances(self.h, oo.shape[0] - 1, _p(oo), _p(op), _p(os_), _p(om), io.shape[0], _p(io), _p(m[0]), _p(m[1]),
+                                          _p(m[2]), _p(m[3]), _p(tm)))
+
+    def set_ray_times(self, times):
+        """Ray i of the following trace_* calls travels at times[i] (None: every ray at time 0)."""
+        t = _arr(times, np.float64)
+        self._ck(self.L.orc_set_ray_times(self.h, _p(t), 0 if t is None else t.size))
+
+    def instance_probe(self, inst, time=0.0):
+        """Decompose / interpolate(time) / world bound of instance `inst`'s AnimatedTransform."""
+        T, R, S = np.zeros((2, 3)), np.zeros((2, 4)), np.zeros((2, 16), np.float32)
+        m, minv, bound = np.zeros(16, np.float32), np.zeros(16, np.float32), np.zeros(6, np.float32)
+        an = C.c_int32(0)
+        self._ck(self.L.orc_instance_probe(self.h, inst, float(time), _p(T), _p(R), _p(S), _p(m), _p(minv), _p(bound), C.byref(an)))
+        return dict(T=T, R=R, S=S.reshape(2, 4, 4), m=m.reshape(4, 4), minv=minv.reshape(4, 4), bound=bound, animated=bool(an.value))
 
     def set_measured(self, tables):
         """MeasuredMaterial data (measured_material.dart:76-205): list of (kind, array) — kind 0 = RegularHalfangleBRDF table
