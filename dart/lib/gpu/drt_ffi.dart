@@ -56,6 +56,8 @@ typedef _SetInfiniteC = Int32 Function(_Ctx, Uint32, Int32, Int32, _PF, _PF, _PF
 typedef _SetInfiniteD = int Function(_Ctx, int, int, int, _PF, _PF, _PF);
 typedef _SetMeshShadingC = Int32 Function(_Ctx, _PF, _PF, _PF, _PU, Uint32, _PF, _PF, _PB);
 typedef _SetMeshShadingD = int Function(_Ctx, _PF, _PF, _PF, _PU, int, _PF, _PF, _PB);
+typedef _SetInstancesC = Int32 Function(_Ctx, Uint32, _PU, _PU, _PI, _PI, Uint32, _PU, _PF, _PF, _PF, _PF, _PD);
+typedef _SetInstancesD = int Function(_Ctx, int, _PU, _PU, _PI, _PI, int, _PU, _PF, _PF, _PF, _PF, _PD);
 typedef _SetOrderC = Int32 Function(_Ctx, _PU, Uint32);
 typedef _SetOrderD = int Function(_Ctx, _PU, int);
 typedef _BuildC = Int32 Function(_Ctx, Int32, Int32);
@@ -140,6 +142,11 @@ class Drt {
   /// per-vertex N / S (object space) / uv, any may be nullptr; mesh index per triangle, per-mesh transforms and flags
   void setMeshShading(_PF n, _PF s, _PF uv, _PU meshOfTri, int nMeshes, _PF o2w, _PF w2o, _PB flags) =>
       check(lib.lookupFunction<_SetMeshShadingC, _SetMeshShadingD>('drt_set_mesh_shading')(ctx, n, s, uv, meshOfTri, nMeshes, o2w, w2o, flags));
+  // TransformedPrimitives: objects (primitive lists + nested accelerator parameters) and instances (AnimatedTransform start / end)
+  void setInstances(int nObjects, _PU offsets, _PU prims, _PI split, _PI maxPrims, int nInstances, _PU object, _PF m0, _PF i0, _PF m1,
+                    _PF i1, _PD times) =>
+      check(lib.lookupFunction<_SetInstancesC, _SetInstancesD>('drt_set_instances')(ctx, nObjects, offsets, prims, split, maxPrims,
+                                                                                      nInstances, object, m0, i0, m1, i1, times));
   void setBuildOrder(_PU order, int n) => check(lib.lookupFunction<_SetOrderC, _SetOrderD>('drt_set_build_order')(ctx, order, n));
   void buildBvh(int split, int maxNodePrims) => check(lib.lookupFunction<_BuildC, _BuildD>('drt_build_bvh')(ctx, split, maxNodePrims));
   void setMaterials(int n, _PI kind, _PF kd, _PF sigma) =>

@@ -348,9 +348,32 @@ class GpuSamplerRenderer extends Renderer {
     // order; ids are assigned per kind in upload order: triangles, then spheres, then disks.
     final tris = <GeometricPrimitive>[], sphs = <GeometricPrimitive>[], dsks = <GeometricPrimitive>[];
     final quads = <GeometricPrimitive>[];  // cylinder / cone / paraboloid / hyperboloid: drt_set_quadrics, ids after the disks
+    // TransformedPrimitives (animated shapes, object instances: transformed_primitive.dart): the primitive each one wraps is an
+    // "object" — a GeometricPrimitive, or a BVHAccel whose refined primitives join the lists above — shared by identity between
+    // the instances of one ObjectBegin block (drt_set_instances)
+    final instances = <TransformedPrimitive>[];
+    final objects = <Primitive>[];
+    final objectIndex = new Map<Primitive, int>.identity();
+    final allGeometric = <Primitive>[];
     for (final Primitive p in bvh.primitives) {
+      if (p is TransformedPrimitive) {
+        instances.add(p);
+        if (!objectIndex.containsKey(p.primitive)) {
+          objectIndex[p.primitive] = objects.length;
+          objects.add(p.primitive);
+          if (p.primitive is BVHAccel) {
+            allGeometric.addAll((p.primitive as BVHAccel).primitives);
+          } else {
+            allGeometric.add(p.primitive);
+          }
+        }
+      } else {
+        allGeometric.add(p);
+      }
+    }
+    for (final Primitive p in allGeometric) {
       if (p is! GeometricPrimitive) {
-        throw new GpuUnsupported('primitive ${p.runtimeType} (instancing / motion blur)');
+        throw new GpuUnsupported('primitive ${p.runtimeType} (an instance inside an object, or an accelerator other than bvh inside one)');
       }
       final GeometricPrimitive g = p;
       if (g.shape is Triangle) {
@@ -483,8 +506,35 @@ class GpuSamplerRenderer extends Renderer {
                       a.ints([matOf(g)]), a.ints([lightOf(g)]), a.bytes([sh.reverseOrientation ? 1 : 0]));
     }
 
+    final int nGeometric = tris.length + sphs.length + dsks.length + quads.length;
+    if (instances.isNotEmpty) {
+      final offsets = <int>[0], prims = <int>[], split = <int>[], maxPrims = <int>[];
+      for (final Primitive ob in objects) {
+        if (ob is BVHAccel) {
+          for (final Primitive q in ob.primitives) prims.add(ids[q]);  // the order its constructor refined them in
+          split.add(ob.splitMethod);
+          maxPrims.add(ob.maxPrimsInNode);
+        } else {
+          prims.add(ids[ob]);
+          split.add(2);
+          maxPrims.add(1);
+        }
+        offsets.add(prims.length);
+      }
+      final ob = <int>[], m0 = <double>[], i0 = <double>[], m1 = <double>[], i1 = <double>[], tt = <double>[];
+      for (final TransformedPrimitive t in instances) {
+        final AnimatedTransform w2p = t.worldToPrimitive;
+        ob.add(objectIndex[t.primitive]);
+        m0.addAll(w2p.startTransform.m.data); i0.addAll(w2p.startTransform.mInv.data);
+        m1.addAll(w2p.endTransform.m.data); i1.addAll(w2p.endTransform.mInv.data);
+        tt..add(w2p.startTime)..add(w2p.endTime);
+      }
+      drt.setInstances(objects.length, a.uints(offsets), a.uints(prims), a.ints(split), a.ints(maxPrims), instances.length, a.uints(ob),
+                       a.floats(m0), a.floats(i0), a.floats(m1), a.floats(i1), a.doubles(tt));
+    }
     final order = <int>[];
-    for (final Primitive p in bvh.primitives) order.add(ids[p]);
+    int nextInstance = 0;
+    for (final Primitive p in bvh.primitives) order.add(p is TransformedPrimitive ? nGeometric + (nextInstance++) : ids[p]);
     drt.setBuildOrder(a.uints(order), order.length);
     drt.buildBvh(bvh.splitMethod, bvh.maxPrimsInNode);
 
