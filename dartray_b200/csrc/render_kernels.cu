@@ -480,22 +480,36 @@ static __device__ __forceinline__ void pushDirectWork(const Wavefront& wf, uint3
 // GENERAL = false: every material is matte (one diffuse BxDF, never a specular bounce); true: BxDF lists.
 // Counting sort of extension queue `cur` by material (BxDF-list scenes): histogram, one-block exclusive scan, scatter.
 #define DRT_SORT_MAX_MATERIALS 1023
-static __device__ __forceinline__ uint32_t shadeKey(const RenderScene& rs, const Wavefront& wf, uint32_t q) {
+// keyMode 0: the material (BxDF-list scenes: a warp evaluates one BxDF list).  keyMode 1 (matte-only scenes): the SHAPE CLASS of the
+// hit — triangle, then the quadric kinds — so that a warp rebuilds one kind of differential geometry; in both modes the rays that
+// missed sort last, so the warps of the shading kernel are full of live vertices (a quarter of config 4's lanes idled on misses:
+// profiles/r02u_shade_lines.txt shows at most 25 of 32 threads per instruction).
+#define DRT_SHAPE_CLASSES 7  // triangle + GSphere::shape 0..5
+static __device__ __forceinline__ uint32_t sortBins(const RenderScene& rs, int keyMode) {
+  return keyMode ? (uint32_t)DRT_SHAPE_CLASSES + 1u : (uint32_t)rs.nMaterials + 1u;
+}
+static __device__ __forceinline__ uint32_t shadeKey(const RenderScene& rs, const Wavefront& wf, uint32_t q, int keyMode) {
   const int prim = __float_as_int(wf.extHit[q].w);
+  if (keyMode) {
+    if (prim < 0) return (uint32_t)DRT_SHAPE_CLASSES;
+    if ((uint32_t)prim < rs.ntris) return 0u;
+    const int sh = rs.ts.spheres[(uint32_t)prim - rs.ntris].shape;
+    return 1u + (uint32_t)(sh < 0 ? 0 : (sh > 5 ? 5 : sh));
+  }
   return prim < 0 ? (uint32_t)rs.nMaterials : (uint32_t)primMaterial(rs, (uint32_t)prim);
 }
 // Both passes aggregate per warp first (__match_any_sync on the key): a scene has a handful of materials, so per-entry atomics
 // would all land on the same few counters.  AGG = false keeps the per-entry atomics (DRT_SORT_PLAIN_ATOMICS, for A/B runs).
 template <bool AGG>
-__global__ void __launch_bounds__(256) matHistKernel(RenderScene rs, Wavefront wf, int cur) {
+__global__ void __launch_bounds__(256) matHistKernel(RenderScene rs, Wavefront wf, int cur, int keyMode) {
   __shared__ uint32_t h[DRT_SORT_MAX_MATERIALS + 1];
-  const uint32_t n = wf.counts[cur], bins = (uint32_t)rs.nMaterials + 1, lane = threadIdx.x & 31u;
+  const uint32_t n = wf.counts[cur], bins = sortBins(rs, keyMode), lane = threadIdx.x & 31u;
   for (uint32_t b = threadIdx.x; b < bins; b += blockDim.x) h[b] = 0;
   __syncthreads();
   for (uint32_t q0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); q0 < n; q0 += gridDim.x * blockDim.x) {  // warp-uniform trip count
     const uint32_t q = q0 + lane;
     const bool v = q < n;
-    const uint32_t key = v ? shadeKey(rs, wf, q) : 0xffffffffu;
+    const uint32_t key = v ? shadeKey(rs, wf, q, keyMode) : 0xffffffffu;
     if (AGG) {
       const uint32_t peers = __match_any_sync(FULL, key);
       if (v && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&h[key], (uint32_t)__popc(peers));
@@ -507,21 +521,22 @@ __global__ void __launch_bounds__(256) matHistKernel(RenderScene rs, Wavefront w
   for (uint32_t b = threadIdx.x; b < bins; b += blockDim.x)
     if (h[b]) atomicAdd(&wf.matHist[b], h[b]);
 }
-__global__ void matScanKernel(RenderScene rs, Wavefront wf) {  // one thread: at most 1024 bins
+__global__ void matScanKernel(RenderScene rs, Wavefront wf, int keyMode) {  // one thread: at most 1024 bins
   uint32_t acc = 0;
-  for (int b = 0; b <= rs.nMaterials; ++b) {
+  const int bins = (int)sortBins(rs, keyMode);
+  for (int b = 0; b < bins; ++b) {
     const uint32_t c = wf.matHist[b];
     wf.matHist[b] = acc;
     acc += c;
   }
 }
 template <bool AGG>
-__global__ void __launch_bounds__(256) matScatterKernel(RenderScene rs, Wavefront wf, int cur) {
+__global__ void __launch_bounds__(256) matScatterKernel(RenderScene rs, Wavefront wf, int cur, int keyMode) {
   const uint32_t n = wf.counts[cur], lane = threadIdx.x & 31u;
   for (uint32_t q0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); q0 < n; q0 += gridDim.x * blockDim.x) {
     const uint32_t q = q0 + lane;
     const bool v = q < n;
-    const uint32_t key = v ? shadeKey(rs, wf, q) : 0xffffffffu;
+    const uint32_t key = v ? shadeKey(rs, wf, q, keyMode) : 0xffffffffu;
     if (AGG) {  // one atomic per (warp, material): the leader reserves the run, the lanes take consecutive places in lane order
       const uint32_t peers = __match_any_sync(FULL, key);
       const int leader = __ffs(peers) - 1;
@@ -542,7 +557,7 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(Ren
   const uint32_t n = wf.counts[cur], cap = wf.cap;
   const int nxt = cur ^ 1;
   unsigned long long nShadow = 0, nClosest = 0;
-  const bool sorted = GENERAL && sortedOrder != 0;
+  const bool sorted = sortedOrder != 0;
   for (uint32_t q0 = blockIdx.x * blockDim.x; q0 < n; q0 += gridDim.x * blockDim.x) {
     uint32_t q = q0 + threadIdx.x;
     bool valid = q < n;
@@ -556,6 +571,7 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(Ren
       wf.misIdx[slot] = -1;
       valid = prim >= 0;  // miss: the path ends; area/point lights add no Le along escaping rays
     }
+    if (sorted && !__any_sync(FULL, valid)) continue;  // the misses sort last: their warps have nothing to shade or to push
     DirectWork dw;
     dw.hasShadow = dw.hasMis = false;
     bool cont = false;
@@ -1441,20 +1457,24 @@ cudaError_t launchResetCounts(const Wavefront& wf, unsigned mask, cudaStream_t s
 
 // Counting sort of extension queue `cur` by material into wf.shadeOrder; *sorted = 0 when the scene has one material or more than
 // the sort's bins (the shading kernels then walk the queue as it is).  DRT_NO_MATERIAL_SORT turns it off.
+static cudaError_t launchQueueSort(const RenderScene& rs, const Wavefront& wf, int cur, int keyMode, int numSMs, cudaStream_t st) {
+  const size_t bins = keyMode ? (size_t)DRT_SHAPE_CLASSES + 1 : (size_t)rs.nMaterials + 1;
+  cudaError_t e = cudaMemsetAsync(wf.matHist, 0, bins * sizeof(uint32_t), st);
+  if (e != cudaSuccess) return e;
+  const int g2 = gridFor(wf.cap, 256, numSMs, 4);
+  static const bool plainAtomics = std::getenv("DRT_SORT_PLAIN_ATOMICS") != nullptr;
+  if (plainAtomics) matHistKernel<false><<<g2, 256, 0, st>>>(rs, wf, cur, keyMode);
+  else matHistKernel<true><<<g2, 256, 0, st>>>(rs, wf, cur, keyMode);
+  matScanKernel<<<1, 1, 0, st>>>(rs, wf, keyMode);
+  if (plainAtomics) matScatterKernel<false><<<g2, 256, 0, st>>>(rs, wf, cur, keyMode);
+  else matScatterKernel<true><<<g2, 256, 0, st>>>(rs, wf, cur, keyMode);
+  return cudaGetLastError();
+}
 cudaError_t launchMaterialSort(const RenderScene& rs, const Wavefront& wf, int cur, int numSMs, int* sorted, cudaStream_t st) {
   static const bool sortOff = std::getenv("DRT_NO_MATERIAL_SORT") != nullptr;
   *sorted = (!sortOff && rs.general && rs.nMaterials > 1 && rs.nMaterials <= DRT_SORT_MAX_MATERIALS) ? 1 : 0;
   if (!*sorted) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(wf.matHist, 0, (size_t)(rs.nMaterials + 1) * sizeof(uint32_t), st);
-  if (e != cudaSuccess) return e;
-  const int g2 = gridFor(wf.cap, 256, numSMs, 4);
-  static const bool plainAtomics = std::getenv("DRT_SORT_PLAIN_ATOMICS") != nullptr;
-  if (plainAtomics) matHistKernel<false><<<g2, 256, 0, st>>>(rs, wf, cur);
-  else matHistKernel<true><<<g2, 256, 0, st>>>(rs, wf, cur);
-  matScanKernel<<<1, 1, 0, st>>>(rs, wf);
-  if (plainAtomics) matScatterKernel<false><<<g2, 256, 0, st>>>(rs, wf, cur);
-  else matScatterKernel<true><<<g2, 256, 0, st>>>(rs, wf, cur);
-  return cudaGetLastError();
+  return launchQueueSort(rs, wf, cur, 0, numSMs, st);
 }
 
 cudaError_t launchShadePath(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int bounce, int cur,
@@ -1469,7 +1489,17 @@ cudaError_t launchShadePath(const RenderParams& rp, const RenderScene& rs, const
     if (e != cudaSuccess) return e;
     shadePathKernel<true, DRT_EXTRA != 0><<<grid, 128, 0, st>>>(rp, rs, wf, bounce, cur, rc, sorted);
   } else {
-    shadePathKernel<false, DRT_EXTRA != 0><<<grid, 128, 0, st>>>(rp, rs, wf, bounce, cur, rc, 0);
+    // matte-only scenes: DRT_SHAPE_SORT=1 walks the queue in shape-class order, misses last (full, type-coherent warps).  Measured on
+    // B200 (profiles/r02v_shape_sort_ab.log, r02x_path_*.csv): the kernel itself gains 11 % (22 % on the bounces that have misses:
+    // 25.9 instead of 18.9 threads per instruction), but the three sort passes (3.0 ms per 12 launches) and the less coalesced
+    // shadow / MIS queues in resolveDirectKernel (+1.4 ms) take it back: config 4 0.986 s against 0.978 s.  Off by default.
+    static const bool shapeSortOn = std::getenv("DRT_SHAPE_SORT") != nullptr;
+    const int sorted = shapeSortOn ? 1 : 0;
+    if (sorted) {
+      cudaError_t e = launchQueueSort(rs, wf, cur, 1, numSMs, st);
+      if (e != cudaSuccess) return e;
+    }
+    shadePathKernel<false, DRT_EXTRA != 0><<<grid, 128, 0, st>>>(rp, rs, wf, bounce, cur, rc, sorted);
   }
   return cudaGetLastError();
 }

@@ -33,8 +33,32 @@ struct V3 {
   float x, y, z;
 };
 static DRT_HD inline V3 mkv(double x, double y, double z) { return V3{(float)x, (float)y, (float)z}; }
+// ONE operation on two float32 operands, evaluated in binary64 and rounded to float32 — what `new Vector(a.x + b.x, ...)` does —
+// equals the float32 operation itself: double rounding is innocuous for +, -, *, / when the wide format has >= 2 * 24 + 2 bits
+// (Figueroa).  The float32 forms save two widening and one narrowing conversion per component (the XU pipe was the busiest pipe of
+// shadePathKernel) — tried as an A/B build, see below.  Longer expressions (Dot, Cross, a * double) keep their binary64 evaluation.
+#ifndef DRT_F32_SINGLE_OPS
+#define DRT_F32_SINGLE_OPS 0  // measured on B200 (profiles/r02t_f32ops_ab.log): config 4 0.9715 s with the float32 forms, 0.9690 s
+                             // without; cornell_materials 0.405 vs 0.399 s — no gain (results identical, 122 GPU tests green), off
+#endif
+#if DRT_F32_SINGLE_OPS
+#ifdef __CUDA_ARCH__
+#define DRT_FADD(a, b) __fadd_rn((a), (b))
+#define DRT_FSUB(a, b) __fsub_rn((a), (b))
+#define DRT_FMUL(a, b) __fmul_rn((a), (b))
+#define DRT_FDIV(a, b) __fdiv_rn((a), (b))
+#else
+#define DRT_FADD(a, b) ((a) + (b))
+#define DRT_FSUB(a, b) ((a) - (b))
+#define DRT_FMUL(a, b) ((a) * (b))
+#define DRT_FDIV(a, b) ((a) / (b))
+#endif
+static DRT_HD inline V3 operator+(const V3& a, const V3& b) { return V3{DRT_FADD(a.x, b.x), DRT_FADD(a.y, b.y), DRT_FADD(a.z, b.z)}; }
+static DRT_HD inline V3 operator-(const V3& a, const V3& b) { return V3{DRT_FSUB(a.x, b.x), DRT_FSUB(a.y, b.y), DRT_FSUB(a.z, b.z)}; }
+#else
 static DRT_HD inline V3 operator+(const V3& a, const V3& b) { return mkv((double)a.x + b.x, (double)a.y + b.y, (double)a.z + b.z); }
 static DRT_HD inline V3 operator-(const V3& a, const V3& b) { return mkv((double)a.x - b.x, (double)a.y - b.y, (double)a.z - b.z); }
+#endif
 static DRT_HD inline V3 operator*(const V3& a, double f) { return mkv((double)a.x * f, (double)a.y * f, (double)a.z * f); }
 static DRT_HD inline V3 operator/(const V3& a, double f) { return mkv((double)a.x / f, (double)a.y / f, (double)a.z / f); }
 static DRT_HD inline V3 operator-(const V3& a) { return V3{-a.x, -a.y, -a.z}; }
@@ -95,8 +119,13 @@ struct Spec {
 };
 static DRT_HD inline Spec mks(double r, double g, double b) { return Spec{(float)r, (float)g, (float)b}; }
 static DRT_HD inline Spec mks1(double v) { return Spec{(float)v, (float)v, (float)v}; }
+#if DRT_F32_SINGLE_OPS
+static DRT_HD inline Spec operator+(const Spec& a, const Spec& b) { return Spec{DRT_FADD(a.r, b.r), DRT_FADD(a.g, b.g), DRT_FADD(a.b, b.b)}; }
+static DRT_HD inline Spec operator*(const Spec& a, const Spec& b) { return Spec{DRT_FMUL(a.r, b.r), DRT_FMUL(a.g, b.g), DRT_FMUL(a.b, b.b)}; }
+#else
 static DRT_HD inline Spec operator+(const Spec& a, const Spec& b) { return mks((double)a.r + b.r, (double)a.g + b.g, (double)a.b + b.b); }
 static DRT_HD inline Spec operator*(const Spec& a, const Spec& b) { return mks((double)a.r * b.r, (double)a.g * b.g, (double)a.b * b.b); }
+#endif
 static DRT_HD inline Spec operator*(const Spec& a, double s) { return mks((double)a.r * s, (double)a.g * s, (double)a.b * s); }
 static DRT_HD inline Spec operator/(const Spec& a, double s) { return mks((double)a.r / s, (double)a.g / s, (double)a.b / s); }
 static DRT_HD inline bool IsBlack(const Spec& s) { return !(s.r != 0.f || s.g != 0.f || s.b != 0.f); }
@@ -861,8 +890,13 @@ static __device__ inline BsdfG makeBsdfG(const RenderScene& rs, uint32_t prim, c
 // dart:math min / max: NaN when either argument is NaN
 static __device__ inline double dartMin(double a, double b) { return (isnan(a) || isnan(b)) ? CUDART_NAN : (a < b ? a : b); }
 static __device__ inline double dartMax(double a, double b) { return (isnan(a) || isnan(b)) ? CUDART_NAN : (a > b ? a : b); }
+#if DRT_F32_SINGLE_OPS
+static __device__ inline Spec operator-(const Spec& a, const Spec& b) { return Spec{DRT_FSUB(a.r, b.r), DRT_FSUB(a.g, b.g), DRT_FSUB(a.b, b.b)}; }
+static __device__ inline Spec operator/(const Spec& a, const Spec& b) { return Spec{DRT_FDIV(a.r, b.r), DRT_FDIV(a.g, b.g), DRT_FDIV(a.b, b.b)}; }
+#else
 static __device__ inline Spec operator-(const Spec& a, const Spec& b) { return mks((double)a.r - b.r, (double)a.g - b.g, (double)a.b - b.b); }
 static __device__ inline Spec operator/(const Spec& a, const Spec& b) { return mks((double)a.r / b.r, (double)a.g / b.g, (double)a.b / b.b); }
+#endif
 static __device__ inline bool SameHemisphere(const V3& w, const V3& wp) { return (double)w.z * wp.z > 0.0; }  // vector.dart:194-196
 
 static __device__ inline int lobeType(int kind) {

@@ -78,6 +78,12 @@ namespace drt {
                          // (profiles/r02q_trace_ab.log: 4.45 vs 3.59 ms): the box test with `tmin < maxDistance` is what culls most
                          // leaves a conservative walk reaches, far cheaper than the f64 triangle tests it saves
 #endif
+#ifndef DRT_Q_LEAF_PRE
+#define DRT_Q_LEAF_PRE 0  // 1: a conservative float32 slab test on the leaf's own (unquantised) box in front of the binary64 one (a leaf
+                         // it rejects would fail the reference's test too, so only the survivors pay for f64).  Exact (full-size tests
+                         // green) but REJECTED on measurement (profiles/r02s_trace_ab.log: incoherent closest 3.70 vs 3.58 ms, any hit
+                         // 2.11 vs 2.13): the leaf phase waits for its loads, not for the binary64 pipe
+#endif
 #ifndef DRT_Q_STEPS
 #define DRT_Q_STEPS 3  // pop + node steps per round of refill / leaf-phase checks (1 / 2 / 3: 4.01 / 3.63 / 3.56 ms)
 #endif
@@ -394,6 +400,25 @@ __global__ void __launch_bounds__(DRT_Q_BLOCK, DRT_Q_MIN_BLOCKS)
               continue;
             }
             bool boxOk;
+#if DRT_Q_LEAF_PRE
+            if (QUAD == 0 && cnt == 1u && !(r.flags & 8u)) {
+              // one triangle (the usual leaf: ranges of <= 4 primitives are always split): its box in float32.  t' = fl(fl(b - o) *
+              // invDir) = t (1 + e), |e| <= 2^-23, against the reference's binary64 t; DRT_EPS2 = 2^-21 covers it.  Every comparison
+              // is written so that a NaN (0 * inf cannot occur here: slow rays skip this) never rejects.
+              const float bx0 = fminf(a.x, fminf(b.x, c.x)), bx1 = fmaxf(a.x, fmaxf(b.x, c.x));
+              const float by0 = fminf(a.y, fminf(b.y, c.y)), by1 = fmaxf(a.y, fmaxf(b.y, c.y));
+              const float bz0 = fminf(a.z, fminf(b.z, c.z)), bz1 = fmaxf(a.z, fmaxf(b.z, c.z));
+              const float tx0 = __fmul_rn(__fadd_rn(bx0, nox), ixf), tx1 = __fmul_rn(__fadd_rn(bx1, nox), ixf);
+              const float ty0 = __fmul_rn(__fadd_rn(by0, noy), iyf), ty1 = __fmul_rn(__fadd_rn(by1, noy), iyf);
+              const float tz0 = __fmul_rn(__fadd_rn(bz0, r.noz), r.iz), tz1 = __fmul_rn(__fadd_rn(bz1, r.noz), r.iz);
+              const float N_ = max3(fminf(tx0, tx1), fminf(ty0, ty1), fminf(tz0, tz1));
+              const float F_ = min3(fmaxf(tx0, tx1), fmaxf(ty0, ty1), fmaxf(tz0, tz1));
+              // the absolute 1e-36 pays for products that fall into the float32 denormal range, where the relative margin vanishes
+              const float Nlo_ = fmaf(-DRT_EPS2, fabsf(N_), N_) - 1.0e-36f, Fhi_ = fmaf(DRT_EPS2, fabsf(F_), F_) + 1.0e-36f;
+              const float mh_ = j == 0 ? r.maxtHi : __double2float_ru(rs.maxt);  // the first leaf of the queue may have shortened the ray
+              if (Nlo_ > Fhi_ || Nlo_ >= mh_ || Fhi_ < r.mintLo) continue;
+            }
+#endif
             DRT_LEAF_BOX(boxOk, rs.maxt);
             for (uint32_t k = 0; boxOk && k < cnt && !stop; ++k) {
               if (k) { a = ldg4(&pr[k].p1[0]); b = ldg4(&pr[k].p2[0]); c = ldg4(&pr[k].p3[0]); }
