@@ -597,7 +597,7 @@ static void carve(ByteArena& a, Wavefront& wf, uint32_t cap, uint32_t shCap, int
     wf.volT = wf.volL = nullptr;
   }
   wf.pixX = a.take<int32_t>(cap); wf.pixY = a.take<int32_t>(cap); wf.sampleIdx = a.take<uint32_t>(cap);
-  wf.camXY = a.take<double2>(cap); wf.camLens = a.take<double2>(cap); wf.camTime = a.take<float>(cap);
+  wf.camXY = a.take<double2>(cap); wf.camLens = a.take<double2>(cap); wf.camTime = a.take<double>(cap);
   wf.vals = a.take<float>((size_t)std::max(nVals, 1) * cap);
   wf.L = a.take<float>(3 * (size_t)cap); wf.T = a.take<float>(3 * (size_t)cap);
   wf.pendSh = a.take<float>(3 * (size_t)cap); wf.pendMisF = a.take<float>(3 * (size_t)cap); wf.pendMisScale = a.take<double>(cap);
@@ -724,12 +724,6 @@ static int prepare(drt_ctx* c, RenderState* r) {
   }
   r->rs.ts = c->ts;
   if (c->ts.nInstances > 0) {  // TransformedPrimitives: what the renderer carries for them so far
-    if (!r->volumes.empty()) return fail(c, DRT_E_UNSUPPORTED, "participating media together with instances / animated shapes");
-    if (!r->programs.empty())
-      return fail(c, DRT_E_UNSUPPORTED, "textured / bump-mapped materials together with instances / animated shapes");
-    if (p.samplerKind == 2 || p.samplerKind == 3 || p.samplerKind == 5)
-      return fail(c, DRT_E_UNSUPPORTED, "instances / animated shapes with the random / halton / bestcandidate samplers (their time samples "
-                                        "are binary64 values; the wavefront keeps float32 ones)");
     std::vector<uint8_t> inObject(c->nprims(), 0);
     for (const drt_ctx::HostObject& ob : c->objects)
       for (uint32_t id : ob.order) inObject[id] = 1;
@@ -1816,10 +1810,11 @@ int drt_pixel_samples(drt_ctx* c, int x, int y, float* out, int cap, int32_t* n_
   CK(c, STAGE(launchSampler)(p, r->wf, r->dArrays.p, (int)r->arrays.size(), r->maxVals, r->maxOthers, pb, c->numSMs, c->stream)); profMark(c, DRT_PK_SAMPLER);
   c->launches++;
   std::vector<double2> xy(n), lens(n);
-  std::vector<float> tm(n), vals((size_t)std::max(p.nVals, 1) * n);
+  std::vector<double> tm(n);
+  std::vector<float> vals((size_t)std::max(p.nVals, 1) * n);
   CK(c, cudaMemcpyAsync(xy.data(), r->wf.camXY, n * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaMemcpyAsync(lens.data(), r->wf.camLens, n * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
-  CK(c, cudaMemcpyAsync(tm.data(), r->wf.camTime, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaMemcpyAsync(tm.data(), r->wf.camTime, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaMemcpyAsync(vals.data(), r->wf.vals, (size_t)p.nVals * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
   const int per = 5 + p.nVals;

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(128) samplerSeqKernel(RenderParams rp, Wavefro
     }
     for (uint32_t i = 0; i < n; ++i) {  // Shuffle(time)
       uint32_t o = i + rng.randomUint() % (n - i);
-      float a = wf.camTime[slot0 + i];
+      const double a = wf.camTime[slot0 + i];
       wf.camTime[slot0 + i] = wf.camTime[slot0 + o];
       wf.camTime[slot0 + o] = a;
     }
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(128) samplerSeqKernel(RenderParams rp, Wavefro
       double lu = rng.randomFloat(), lv = rng.randomFloat();
       wf.camXY[slot0 + si] = make_double2(ix, iy);
       wf.camLens[slot0 + si] = make_double2(lu, lv);
-      wf.camTime[slot0 + si] = (float)rng.randomFloat();
+      wf.camTime[slot0 + si] = rng.randomFloat();  // random_sampler.dart:71: a Dart double
       for (int a = 3; a < nArrays; ++a) {
         const SampleArray A = arrays[a];
         const uint32_t cnt = (uint32_t)(A.nSamples * A.dims);
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(128) samplerHaltonKernel(RenderParams rp, Wave
   }
   wf.camXY[p] = make_double2(imageX, imageY);
   wf.camLens[p] = make_double2(RadicalInverse(n + 1, 5), RadicalInverse(n + 1, 7));
-  wf.camTime[p] = (float)RadicalInverse(n + 1, 11);
+  wf.camTime[p] = RadicalInverse(n + 1, 11);  // halton_sampler.dart:88: a Dart double
   Stream rng{streamKey(rp.seed, x, y, pb.pass, DRT_STREAM_PIXEL), 0};
   for (int a = 3; a < nArrays; ++a) {  // LatinHypercube (montecarlo.dart:305-325)
     const SampleArray A = arrays[a];
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(128) samplerBestCandidateKernel(RenderParams r
   const double t = so[0] + T[2], lu = so[1] + T[3], lv = so[2] + T[4];
   wf.camXY[p] = make_double2(imageX, imageY);
   wf.camLens[p] = make_double2(lu > 1 ? (lu - 1) : lu, lv > 1 ? (lv - 1) : lv);
-  wf.camTime[p] = (float)(t > 1 ? (t - 1) : t);
+  wf.camTime[p] = t > 1 ? (t - 1) : t;  // best_candidate_sampler.dart:111: a Dart double
 }
 
 // The fourth lane of a renderer ray's origin: scenes with TransformedPrimitives carry the wavefront slot there (the traversal looks the
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(256) raygenKernel(RenderParams rp, Wavefront w
     d = Normalize(Pfocus - o);
   }
   V3 wo = XfPoint(rp.cameraToWorld, o), wd = XfVector(rp.cameraToWorld, d);
-  if (wf.slotTime) wf.slotTime[s] = LerpD((double)wf.camTime[s], rp.shutterOpen, rp.shutterClose);  // the samplers' Lerp(time sample, shutterOpen, shutterClose)
+  if (wf.slotTime) wf.slotTime[s] = LerpD(wf.camTime[s], rp.shutterOpen, rp.shutterClose);  // the samplers' Lerp(time sample, shutterOpen, shutterClose)
   wf.extO[0][qi] = make_float4(wo.x, wo.y, wo.z, rayLaneW(wf, s, 0.f));
   wf.extD[0][qi] = make_float4(wd.x, wd.y, wd.z, CUDART_INF_F);
   wf.extRange[0][qi] = make_double2(0.0, CUDART_INF);
@@ -1273,7 +1273,8 @@ __global__ void __launch_bounds__(128) volumeLiKernel(RenderParams rp, RenderSce
                                &pdf, &shD, &shMax);
             if (!IsBlack(L) && pdf > 0.0) {
               ++nShadow;
-              if (!anyHitWalk(rs.ts, make_float4(p.x, p.y, p.z, 0.f), make_float4(shD.x, shD.y, shD.z, 0.f), 0.0, shMax)) {
+              if (!anyHitWalk(rs.ts, make_float4(p.x, p.y, p.z, 0.f), make_float4(shD.x, shD.y, shD.z, 0.f), 0.0, shMax,
+                              wf.slotTime ? wf.slotTime[slot] : 0.0)) {
                 // vis.transmittance(scene, renderer, null, rng): step 4 x stepSize, the offset drawn from this march's own stream
                 VRay sray{p, shD, 0.0, shMax};
                 const Spec Ld = L * expNeg(volTau(rs, sray, 4.0 * stepSize, rng.randomFloat()));

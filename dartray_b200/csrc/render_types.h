@@ -211,7 +211,7 @@ struct Wavefront {
   int32_t* pixX; int32_t* pixY;      // pixel of the slot
   uint32_t* sampleIdx;               // index of the sample inside its pixel (keys the integrator stream)
   double2* camXY; double2* camLens;  // imageX, imageY / lensU, lensV
-  float* camTime;                    // time sample in [0,1) (static scenes: carried, not used)
+  double* camTime;                   // time sample in [0,1): a float32 value for the samplers that keep a Float32List of them, binary64 otherwise
   float* vals;                       // nVals x cap, value-major
   float* L;                          // 3 x cap, channel-major: radiance accumulated so far
   float* T;                          // 3 x cap: path throughput

@@ -120,7 +120,25 @@ __global__ void __launch_bounds__(128) texturePassKernel(RenderParams rp, Render
     const float4 o4 = wf.extO[cur][q], d4 = wf.extD[cur][q];
     const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
     FullDG dg, dgs;
-    fullGeometryCold(rs, (uint32_t)prim, o, d, wf.extT[q], &dg, &dgs);
+    const int inst = wf.extInst ? wf.extInst[q] : -1;
+    if (inst >= 0) {
+      // a hit through a TransformedPrimitive (transformed_primitive.dart:30-58): the shape's differential geometry in primitive
+      // space, moved to world space with Inverse(w2p); objects carry no per-vertex N / S, so dgShading is the same record
+      M4 m, inv;
+      animInterpolate(rs.ts.instances[inst], wf.slotTime[slot], &m, &inv);
+      fullGeometryCold(rs, (uint32_t)prim, XfPoint(m.d, o), XfVector(m.d, d), wf.extT[q], &dg, &dgs);
+      if (!m4IsIdentity(m)) {
+        dg.p = XfPoint(inv.d, dg.p);
+        dg.nn = Normalize(XfNormal(m.d, dg.nn));
+        dg.dpdu = XfVector(inv.d, dg.dpdu);
+        dg.dpdv = XfVector(inv.d, dg.dpdv);
+        dg.dndu = XfNormal(m.d, dg.dndu);
+        dg.dndv = XfNormal(m.d, dg.dndv);
+      }
+      dgs = dg;
+    } else {
+      fullGeometryCold(rs, (uint32_t)prim, o, d, wf.extT[q], &dg, &dgs);
+    }
     RayDiffs rd;
     rd.has = false;
     if (hasDiff) {

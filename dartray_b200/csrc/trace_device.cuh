@@ -295,7 +295,9 @@ static __device__ __forceinline__ float4 ldg4(const void* p) { return __ldg(rein
 // (trace_kernels.cu) over the binary nodes, f64 slab test at every node.  For stages that trace a few rays per thread in a
 // data-dependent loop (the single-scattering volume integrator's shadow rays), where a wavefront queue per step would cost a
 // launch per step; the batched kernels of trace_fast*.cu remain the production path.
-static __device__ __noinline__ bool anyHitWalk(const TraceScene& sc, float4 o4, float4 d4, double mint, double maxt) {
+static __device__ __noinline__ bool instanceTestCold(const TraceScene& sc, int inst, bool any, const RayState* rWorld, double time,
+                                                     HitState* hit);
+static __device__ __noinline__ bool anyHitWalk(const TraceScene& sc, float4 o4, float4 d4, double mint, double maxt, double time = 0.0) {
   if (sc.empty) return false;
   RayState r;
   initRay(r, o4, d4);
@@ -335,7 +337,13 @@ static __device__ __noinline__ bool anyHitWalk(const TraceScene& sc, float4 o4, 
           if (triangleAny(r, a, b, c)) return true;
         } else {
           double th;
-          if (sphereTest<true>(sc.spheres[kind >> 1], r, true, &th, nullptr, nullptr)) return true;
+          const GSphere& s = sc.spheres[kind >> 1];
+          if (s.shape == 6) {  // a TransformedPrimitive at the ray's time
+            HitState ih;
+            if (instanceTestCold(sc, s.instance, true, &r, time, &ih)) return true;
+          } else if (sphereTest<true>(s, r, true, &th, nullptr, nullptr)) {
+            return true;
+          }
         }
       }
     }

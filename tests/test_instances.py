@@ -410,13 +410,61 @@ def test_gpu_render_with_instances_and_motion_blur_matches_the_oracle(integ):
     assert abs(sg["closest_rays"] - so["closest_rays"]) <= 1e-3 * so["closest_rays"]
 
 
-@pytest.mark.gpu
-def test_gpu_rejects_what_the_instance_path_does_not_carry():
-    sb = _instance_scene()
-    sb.volume("homogeneous", sigma_a=0.1, sigma_s=0.1, p0=(-1, -1, -1), p1=(1, 1, 1))
+def _render_both(sb, sampler, integ, film=(64, 48)):
     cam = host.PerspectiveCamera(host.look_at((0.2, 0.3, -6.0), (0, 0, 0.5), (0, 1, 0)), fov=40.0)
-    g = capi.Context(0)
-    host.upload_scene(g, sb.arrays())
-    host.configure_render(g, cam, host.Film(16, 12), host.Sampler(kind=host.SAMPLER_LD, spp=2), host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=2))
-    with pytest.raises(capi.DrtError, match="media together with instances"):
-        g.render(0, 1)
+    g, o = _both_contexts(sb)
+    for c in (g, o):
+        host.configure_render(c, cam, host.Film(*film), sampler, integ)
+    g.render(0, 1)
+    o.render(0, 1, 8)
+    fg, fo = g.film_read()["rgb"], o.film_read()["rgb"]
+    err = np.abs(fg - fo) / np.maximum(np.abs(fo), 1e-3)
+    return fg, fo, err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sampler", [host.Sampler(kind=host.SAMPLER_HALTON, spp=4), host.Sampler(kind=host.SAMPLER_RANDOM, spp=4),
+                                     host.Sampler(kind=host.SAMPLER_STRATIFIED, xs=2, ys=2)], ids=["halton", "random", "stratified"])
+def test_gpu_instances_with_the_samplers_whose_time_samples_are_doubles(sampler):
+    fg, fo, err = _render_both(_instance_scene(), sampler, host.Integrator(kind=host.INTEGRATOR_DIRECT))
+    print("instances, sampler", sampler.kind, "max rel err", err.max(), "mean", float(fo.mean()))
+    assert fo.max() > 0.05 and (err.max(axis=2) > 1e-3).mean() <= 2e-3 and np.median(err) < 1e-5
+
+
+@pytest.mark.gpu
+def test_gpu_instances_with_textured_bumped_materials():
+    from tests.test_textures_gpu import IMG_F, IMG_RGB
+    sb = host.SceneBuilder()
+    kd = host.ScaleTexture(host.ImageTexture(IMG_RGB, host.UVMapping(3.0, 2.0, 0.1, 0.2)), (0.9, 0.8, 0.7))
+    bump = host.ScaleTexture(host.ImageTexture(IMG_F, host.UVMapping(2.0, 2.0)), -0.05)
+    tex = sb.material_program("uber", kd=kd, ks=0.05, roughness=0.05, bumpmap=bump)
+    marble = sb.material_program("matte", kd=host.MarbleTexture() if hasattr(host, "MarbleTexture") else kd)
+    sb.begin_object()
+    sb.sphere(np.eye(4, dtype=f32), radius=0.5, material=tex)
+    ball = sb.end_object()
+    sb.begin_object()
+    P, I = _tetra()
+    sb.mesh(P, I, material=marble, uv=np.array([[0, 0], [1, 0], [1, 1], [0, 1]], f32))
+    sb.cylinder(host.translate(0.0, 0.0, -0.3), radius=0.2, zmin=-0.5, zmax=0.5, material=tex)
+    thing = sb.end_object(split=2, max_node_prims=1)
+    sb.instance(ball, host.translate(1.2, 0.9, 0.0))
+    sb.instance(ball, host.translate(1.0, -0.8, 0.0), host.translate(1.6, -0.2, 0.4))
+    c0, c1 = _ctm_pair()
+    sb.instance(thing, c0, c1)
+    sb.mesh([[-3, -2, 2.5], [3, -2, 2.5], [3, 2.5, 2.5], [-3, 2.5, 2.5]], [[0, 1, 2], [2, 3, 0]], material=tex,
+            uv=np.array([[0, 0], [2, 0], [2, 2], [0, 2]], f32))
+    sb.point_light((0.5, 2.0, -4.0), (30, 28, 26))
+    for integ in (host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=3), host.Integrator(kind=host.INTEGRATOR_DIRECT)):
+        fg, fo, err = _render_both(sb, host.Sampler(kind=host.SAMPLER_LD, spp=4), integ)
+        print("instances, textured", integ.kind, "max rel err", err.max(), "mean", float(fo.mean()))
+        assert fo.max() > 0.05 and (err.max(axis=2) > 1e-3).mean() <= 2e-3 and np.median(err) < 1e-5
+
+
+@pytest.mark.gpu
+def test_gpu_instances_inside_participating_media():
+    sb = _instance_scene()
+    sb.volume("homogeneous", sigma_a=0.05, sigma_s=0.15, g=0.2, p0=(-2.5, -2, -1), p1=(2.5, 2.5, 2.4))
+    sb.vol_integrator = (1, 0.25)  # single scattering, step 0.25
+    fg, fo, err = _render_both(sb, host.Sampler(kind=host.SAMPLER_LD, spp=4), host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=3), film=(48, 36))
+    print("instances in fog: max rel err", err.max(), "mean", float(fo.mean()))
+    assert fo.max() > 0.02 and (err.max(axis=2) > 1e-3).mean() <= 5e-3 and np.median(err) < 1e-5
