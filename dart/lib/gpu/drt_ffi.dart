@@ -71,6 +71,8 @@ typedef _SetLightsD = int Function(_Ctx, int, _PI, _PF, _PF, _PI, _PU, _PU);
 typedef _SetSpotC = Int32 Function(_Ctx, Uint32, _PF, _PD);
 typedef _SetSpotD = int Function(_Ctx, int, _PF, _PD);
 typedef _SetCameraC = Int32 Function(_Ctx, _PF, _PF, Double, Double, Double, Double);
+typedef _SetCameraMotionC = Int32 Function(_Ctx, _PF, Double, Double);
+typedef _SetCameraMotionD = int Function(_Ctx, _PF, double, double);
 typedef _SetCameraD = int Function(_Ctx, _PF, _PF, double, double, double, double);
 typedef _SetIntC = Int32 Function(_Ctx, Int32);
 typedef _SetIntD = int Function(_Ctx, int);
@@ -173,6 +175,8 @@ class Drt {
       check(lib.lookupFunction<_SetInfiniteC, _SetInfiniteD>('drt_set_infinite_light')(ctx, index, width, height, rgb, l2w, w2l));
   void setCamera(_PF rasterToCamera, _PF cameraToWorld, double lensRadius, double focalDistance, double open, double close) =>
       check(lib.lookupFunction<_SetCameraC, _SetCameraD>('drt_set_camera')(ctx, rasterToCamera, cameraToWorld, lensRadius, focalDistance, open, close));
+  void setCameraMotion(_PF cameraToWorldEnd, double startTime, double endTime) =>
+      check(lib.lookupFunction<_SetCameraMotionC, _SetCameraMotionD>('drt_set_camera_motion')(ctx, cameraToWorldEnd, startTime, endTime));
   void setCameraKind(int kind) => check(lib.lookupFunction<_SetIntC, _SetIntD>('drt_set_camera_kind')(ctx, kind));
   void setFilm(int xres, int yres, _PD crop, double xw, double yw, _PF table) =>
       check(lib.lookupFunction<_SetFilmC, _SetFilmD>('drt_set_film')(ctx, xres, yres, crop, xw, yw, table));

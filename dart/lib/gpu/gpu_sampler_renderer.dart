@@ -684,9 +684,6 @@ class GpuSamplerRenderer extends Renderer {
 
   void _configure(Drt drt, _Arena a) {
     // camera (perspective_camera.dart:46-57, orthographic_camera.dart, environment_camera.dart)
-    if (camera.cameraToWorld.actuallyAnimated) {
-      throw new GpuUnsupported('animated cameras');
-    }
     final c2w = camera.cameraToWorld.startTransform.m.data;
     if (camera is ProjectiveCamera) {
       final ProjectiveCamera pc = camera;
@@ -698,6 +695,11 @@ class GpuSamplerRenderer extends Renderer {
       drt.setCameraKind(2);
     } else {
       throw new GpuUnsupported('camera ${camera.runtimeType}');
+    }
+    // an animated camera: the end-time matrix and the transform times; the library decomposes and interpolates per camera ray
+    final AnimatedTransform cw = camera.cameraToWorld;
+    if (cw.actuallyAnimated) {
+      drt.setCameraMotion(a.floats(cw.endTransform.m.data), cw.startTime, cw.endTime);
     }
 
     // film: the 16 x 16 filter table ImageFilm builds (image_film.dart:74-82), recomputed through the public Filter API

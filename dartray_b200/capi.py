@@ -25,7 +25,7 @@ SYMBOLS = [
     "drt_set_instances", "drt_set_ray_times", "drt_set_build_order", "drt_build_bvh", "drt_bvh_info_get", "drt_bvh_export", "drt_trace_closest",
     "drt_trace_any", "drt_trace_closest_device", "drt_trace_any_device", "drt_set_counting", "drt_get_counters", "drt_set_kernel_variant",
     "drt_last_kernel_ms", "drt_kernel_launches",
-    "drt_set_materials", "drt_set_material_lobes", "drt_set_measured", "drt_set_textures", "drt_set_material_programs", "drt_set_lights", "drt_set_spot_params", "drt_set_volumes", "drt_set_volume_integrator", "drt_set_camera", "drt_set_camera_kind", "drt_set_film", "drt_set_sampler", "drt_set_integrator",
+    "drt_set_materials", "drt_set_material_lobes", "drt_set_measured", "drt_set_textures", "drt_set_material_programs", "drt_set_lights", "drt_set_spot_params", "drt_set_volumes", "drt_set_volume_integrator", "drt_set_camera", "drt_set_camera_motion", "drt_set_camera_kind", "drt_set_film", "drt_set_sampler", "drt_set_integrator",
     "drt_render", "drt_render_shard", "drt_set_batch_slots", "drt_film_clear", "drt_film_size", "drt_film_read",
     "drt_film_device", "drt_pixel_samples", "drt_render_stats_get", "drt_set_render_profiling", "drt_render_profile_get",
 ]
@@ -120,6 +120,7 @@ def load():
     L.drt_set_lights.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
     L.drt_set_camera.argtypes = [vp, vp, vp, dbl, dbl, dbl, dbl]
     L.drt_set_camera_kind.argtypes = [vp, i32]
+    L.drt_set_camera_motion.argtypes = [vp, vp, C.c_double, C.c_double]
     L.drt_set_film.argtypes = [vp, i32, i32, vp, dbl, dbl, vp]
     L.drt_set_sampler.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, u64]
     L.drt_set_integrator.argtypes = [vp, i32, i32, i32, i32, dbl, dbl]
@@ -387,6 +388,11 @@ class Context:
                    shutter_close=1.0):
         r2c, c2w = _arr(raster_to_camera, np.float32).reshape(16), _arr(camera_to_world, np.float32).reshape(16)
         self._ck(self.L.drt_set_camera(self.h, _p(r2c), _p(c2w), lens_radius, focal_distance, shutter_open, shutter_close))
+
+    def set_camera_motion(self, camera_to_world_end, start_time=0.0, end_time=1.0):
+        """The end-time camera-to-world matrix of an animated camera (None: static); after set_camera."""
+        m = _arr(camera_to_world_end, np.float32)
+        self._ck(self.L.drt_set_camera_motion(self.h, _p(None if m is None else m.reshape(16)), float(start_time), float(end_time)))
 
     def set_camera_kind(self, kind):
         self._ck(self.L.drt_set_camera_kind(self.h, kind))

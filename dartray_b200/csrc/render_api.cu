@@ -79,6 +79,10 @@ struct RenderState {
   std::vector<float> texData;
   std::vector<GProgram> programs;
   bool programsMaySpecular = false;
+  // an animated camera (drt_set_camera_motion): Camera.cameraToWorld as an AnimatedTransform
+  bool cameraMoves = false;
+  GInstance cameraMotion{};
+  DevBuf<GInstance> dCameraMotion;
   // MeasuredMaterial tables (drt_set_measured): descriptors with data == offset into measuredData until they are uploaded
   std::vector<GMeasured> measured;
   std::vector<uint64_t> measuredOffsets;
@@ -723,6 +727,12 @@ static int prepare(drt_ctx* c, RenderState* r) {
     if (rc != DRT_OK) return rc;
   }
   r->rs.ts = c->ts;
+  p.cameraMotion = nullptr;
+  if (r->cameraMoves) {
+    CK(c, r->dCameraMotion.ensure(1));
+    CK(c, cudaMemcpy(r->dCameraMotion.p, &r->cameraMotion, sizeof(GInstance), cudaMemcpyHostToDevice));
+    p.cameraMotion = r->dCameraMotion.p;
+  }
   if (c->ts.nInstances > 0) {  // TransformedPrimitives: what the renderer carries for them so far
     std::vector<uint8_t> inObject(c->nprims(), 0);
     for (const drt_ctx::HostObject& ob : c->objects)
@@ -1648,9 +1658,26 @@ int drt_set_camera(drt_ctx* c, const float* raster_to_camera, const float* camer
   RenderState* r = state(c);
   std::memcpy(r->rp.rasterToCamera, raster_to_camera, 64);
   std::memcpy(r->rp.cameraToWorld, camera_to_world, 64);
+  r->cameraMoves = false;  // drt_set_camera_motion follows for an animated camera
+  r->rp.cameraMotion = nullptr;
   r->rp.lensRadius = lens_radius; r->rp.focalDistance = focal_distance;
   r->rp.shutterOpen = shutter_open; r->rp.shutterClose = shutter_close;
   r->haveCamera = true;
+  return DRT_OK;
+}
+
+int drt_set_camera_motion(drt_ctx* c, const float* camera_to_world_end, double start_time, double end_time) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_camera_motion(p_, camera_to_world_end, start_time, end_time));
+  if (!c) return DRT_E_INVALID;
+  RenderState* r = state(c);
+  if (!r->haveCamera) return fail(c, DRT_E_STATE, "drt_set_camera_motion follows drt_set_camera");
+  r->cameraMoves = false;
+  r->rp.cameraMotion = nullptr;
+  if (!camera_to_world_end) return DRT_OK;
+  // AnimatedTransform(cam2world[0], start, cam2world[1], end) (dartray.dart:971-975): only the matrices m are read by the camera
+  animInit(&r->cameraMotion, r->rp.cameraToWorld, r->rp.cameraToWorld, camera_to_world_end, camera_to_world_end, start_time, end_time);
+  r->cameraMotion.object = -1;
+  r->cameraMoves = r->cameraMotion.animated != 0;
   return DRT_OK;
 }
 

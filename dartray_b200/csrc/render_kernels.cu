@@ -422,7 +422,13 @@ __global__ void __launch_bounds__(256) raygenKernel(RenderParams rp, Wavefront w
     o = mkv(lu, lv, 0.0);
     d = Normalize(Pfocus - o);
   }
-  V3 wo = XfPoint(rp.cameraToWorld, o), wd = XfVector(rp.cameraToWorld, d);
+  const float* c2w = rp.cameraToWorld;
+  M4 camM, camInv;
+  if (rp.cameraMotion) {  // cameraToWorld.transformRay[Differential]: interpolate(ray.time) first (animated_transform.dart:138-169)
+    animInterpolate(*rp.cameraMotion, LerpD(wf.camTime[s], rp.shutterOpen, rp.shutterClose), &camM, &camInv);
+    c2w = camM.d;
+  }
+  V3 wo = XfPoint(c2w, o), wd = XfVector(c2w, d);
   if (wf.slotTime) wf.slotTime[s] = LerpD(wf.camTime[s], rp.shutterOpen, rp.shutterClose);  // the samplers' Lerp(time sample, shutterOpen, shutterClose)
   wf.extO[0][qi] = make_float4(wo.x, wo.y, wo.z, rayLaneW(wf, s, 0.f));
   wf.extD[0][qi] = make_float4(wd.x, wd.y, wd.z, CUDART_INF_F);

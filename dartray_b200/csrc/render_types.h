@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdint>
 
+#include "anim_transform.h"
 #include "gpu_types.h"
 
 namespace drt {
@@ -159,6 +160,9 @@ struct RenderScene {
 struct RenderParams {
   // camera: perspective_camera.dart:46-57,93-132 + projective_camera.dart:34-53
   float rasterToCamera[16], cameraToWorld[16];
+  // Camera.cameraToWorld is an AnimatedTransform (camera.dart:27): non-null when the camera moves (drt_set_camera_motion) — the
+  // camera kernels then use cameraMotion->interpolate(sample time) instead of cameraToWorld (animated_transform.dart:138-169)
+  const GInstance* cameraMotion;
   double lensRadius, focalDistance, shutterOpen, shutterClose;
   int32_t cameraKind;  // 0 perspective, 1 orthographic (orthographic_camera.dart:52-80), 2 environment (environment_camera.dart:42-52)
   // film: image_film.dart:51-97

@@ -49,29 +49,36 @@ static __device__ inline void cameraGenerate(const RenderParams& rp, double imag
   }
   *oC = o; *dC = d; *pCam = Pcamera;
 }
-static __device__ inline void environmentRay(const RenderParams& rp, double imageX, double imageY, V3* o, V3* d) {  // environment_camera.dart:42-52
+static __device__ inline void environmentRay(const RenderParams& rp, const float* c2w, double imageX, double imageY, V3* o, V3* d) {  // environment_camera.dart:42-52
   const double theta = DRT_PI * imageY / rp.yres, phi = 2 * DRT_PI * imageX / rp.xres;
-  *o = XfPoint(rp.cameraToWorld, V3{0.f, 0.f, 0.f});
-  *d = XfVector(rp.cameraToWorld, mkv(sin(theta) * cos(phi), cos(theta), sin(theta) * sin(phi)));
+  *o = XfPoint(c2w, V3{0.f, 0.f, 0.f});
+  *d = XfVector(c2w, mkv(sin(theta) * cos(phi), cos(theta), sin(theta) * sin(phi)));
 }
 // o, d: the world-space camera ray (as raygenKernel stored it); scale = 1 / sqrt(samplesPerPixel) (sampler_renderer.dart:166)
+// `time`: the camera sample's time, for a moving camera (cameraToWorld.interpolate(time), animated_transform.dart:158-169)
 static __device__ __noinline__ void cameraDifferentialsCold(const RenderParams& rp, double imageX, double imageY, double lensU, double lensV,
-                                                            V3 o, V3 d, double scale, RayDiffs* out) {
+                                                            V3 o, V3 d, double scale, double time, RayDiffs* out) {
   RayDiffs r;
   r.has = true;
+  const float* c2w = rp.cameraToWorld;
+  M4 camM, camInv;
+  if (rp.cameraMotion) {
+    animInterpolate(*rp.cameraMotion, time, &camM, &camInv);
+    c2w = camM.d;
+  }
   if (rp.cameraKind == 2) {  // camera.dart:40-58: imageX++, then imageX--, imageY++
-    environmentRay(rp, imageX + 1.0, imageY, &r.rxo, &r.rxd);
-    environmentRay(rp, (imageX + 1.0) - 1.0, imageY + 1.0, &r.ryo, &r.ryd);
+    environmentRay(rp, c2w, imageX + 1.0, imageY, &r.rxo, &r.rxd);
+    environmentRay(rp, c2w, (imageX + 1.0) - 1.0, imageY + 1.0, &r.ryo, &r.ryd);
   } else {
     V3 oC, dC, pCam;
     cameraGenerate(rp, imageX, imageY, lensU, lensV, &oC, &dC, &pCam);
     if (rp.cameraKind == 0) {  // perspective_camera.dart:50-56,122-128
       const V3 p0 = XfPoint(rp.rasterToCamera, V3{0.f, 0.f, 0.f});
       const V3 dxCamera = XfPoint(rp.rasterToCamera, V3{1.f, 0.f, 0.f}) - p0, dyCamera = XfPoint(rp.rasterToCamera, V3{0.f, 1.f, 0.f}) - p0;
-      r.rxo = XfPoint(rp.cameraToWorld, oC);
+      r.rxo = XfPoint(c2w, oC);
       r.ryo = r.rxo;
-      r.rxd = XfVector(rp.cameraToWorld, Normalize(pCam + dxCamera));
-      r.ryd = XfVector(rp.cameraToWorld, Normalize(pCam + dyCamera));
+      r.rxd = XfVector(c2w, Normalize(pCam + dxCamera));
+      r.ryd = XfVector(c2w, Normalize(pCam + dyCamera));
     } else {
       // orthographic_camera.dart:111-115 AS WRITTEN: the offset origins are built in camera space and transformRay (not
       // transformRayDifferential) follows, so they stay there; rxDirection / ryDirection are the object ray.direction is, which

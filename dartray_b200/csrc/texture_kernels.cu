@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(128) texturePassKernel(RenderParams rp, Render
     rd.has = false;
     if (hasDiff) {
       const double2 xy = wf.camXY[slot], lens = wf.camLens[slot];
-      cameraDifferentialsCold(rp, xy.x, xy.y, lens.x, lens.y, o, d, rp.diffScale, &rd);
+      cameraDifferentialsCold(rp, xy.x, xy.y, lens.x, lens.y, o, d, rp.diffScale, LerpD(wf.camTime[slot], rp.shutterOpen, rp.shutterClose), &rd);
     }
     // Intersection.getBSDF: dg.computeDifferentials(ray); getShadingGeometry copies the differentials into dgShading (triangle.dart:354-363)
     computeDifferentials(&dg, rd);

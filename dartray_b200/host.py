@@ -1273,6 +1273,9 @@ def upload_scene(ctx, arrays: dict, split: int = 2, max_node_prims: int = 4):
 def configure_render(ctx, camera: PerspectiveCamera, film: Film, sampler: Sampler, integrator: Integrator):
     ctx.set_camera(camera.raster_to_camera(film.xres, film.yres), camera.camera_to_world, camera.lens_radius,
                    camera.focal_distance, camera.shutter_open, camera.shutter_close)
+    # an animated camera: the end-time CTM and the two transform times (Camera.cameraToWorld is an AnimatedTransform, camera.dart:27)
+    end = getattr(camera, "camera_to_world_end", None)
+    ctx.set_camera_motion(end, *getattr(camera, "transform_times", (0.0, 1.0)))
     ctx.set_camera_kind(getattr(camera, "kind", 0))
     xw, yw, table = film.table()
     ctx.set_film(film.xres, film.yres, film.crop, xw, yw, table)

@@ -409,6 +409,12 @@ int drt_set_volume_integrator(drt_ctx* ctx, int32_t kind, double step_size);
 int drt_set_camera(drt_ctx* ctx, const float raster_to_camera[16], const float camera_to_world[16], double lens_radius,
                    double focal_distance, double shutter_open, double shutter_close);
 
+/* An animated camera: Camera.cameraToWorld is AnimatedTransform(cam2world[0], start, cam2world[1], end) (lib/core/camera.dart:27,
+ * lib/dartray/dartray.dart:971-975); every camera ray goes through cameraToWorld.interpolate(sample.time)
+ * (lib/core/animated_transform.dart:107-169).  camera_to_world_end: the end-time matrix (row-major; NULL = a static camera, the
+ * default); the start-time matrix is drt_set_camera's.  Call after drt_set_camera. */
+int drt_set_camera_motion(drt_ctx* ctx, const float* camera_to_world_end, double start_time, double end_time);
+
 /* Which Camera plugin the matrices of drt_set_camera belong to: 0 = perspective (default), 1 = orthographic
  * (lib/cameras/orthographic_camera.dart:52-80: origin = rasterToCamera(Pras), direction +z; same lens model),
  * 2 = environment (lib/cameras/environment_camera.dart:42-52: direction from (theta, phi) of the raster

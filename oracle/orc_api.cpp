@@ -552,11 +552,22 @@ int orc_set_spot_params(orc_ctx* c, uint32_t n, const float* w2l, const double* 
   return 0;
 }
 
+// mirrors drt_set_camera_motion: the camera's end-time CTM (NULL: a static camera) and the two transform times
+int orc_set_camera_motion(orc_ctx* c, const float* cameraToWorldEnd, double startTime, double endTime) {
+  Camera& cam = c->rs.camera;
+  cam.animated = false;
+  if (!cameraToWorldEnd) return 0;
+  cam.cameraMotion.init(cam.cameraToWorld, startTime, Transform(cameraToWorldEnd, cameraToWorldEnd), endTime);  // only m is read
+  cam.animated = cam.cameraMotion.actuallyAnimated;
+  return 0;
+}
+
 int orc_set_camera(orc_ctx* c, const float* rasterToCamera, const float* cameraToWorld, double lensRadius,
                    double focalDistance, double shutterOpen, double shutterClose) {
   Camera& cam = c->rs.camera;
   cam.rasterToCamera = Transform(rasterToCamera, rasterToCamera);  // only m is used (point/vector)
   cam.cameraToWorld = Transform(cameraToWorld, cameraToWorld);
+  cam.animated = false;  // orc_set_camera_motion follows for an animated camera
   cam.lensRadius = lensRadius; cam.focalDistance = focalDistance;
   cam.shutterOpen = shutterOpen; cam.shutterClose = shutterClose;
   return 0;

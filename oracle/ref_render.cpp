@@ -1960,13 +1960,16 @@ struct Ctx {
   // shifts of camera.dart:37-62 for the environment camera.  `rd` null: the main ray only.
   Ray cameraRay(const SampleVals& s, RayDiff* rd = nullptr) const {
     const Camera& c = rs.camera;
+    // AnimatedTransform.transformRay / transformRayDifferential (animated_transform.dart:138-169): interpolate(ray.time), then the
+    // Transform's own method; a static camera keeps startTransform
+    const Transform c2w = c.c2w(s.time);
     if (c.kind == 2) {  // environment_camera.dart:42-52
       auto gen = [&](double imageX, double imageY) {
         double theta = kPi * imageY / rs.film.yres;
         double phi = 2 * kPi * imageX / rs.film.xres;
         Ray er(Vec(), Vec(std::sin(theta) * std::cos(phi), std::cos(theta), std::sin(theta) * std::sin(phi)), 0.0, kInf);
         er.time = s.time;
-        Ray ew = c.cameraToWorld.ray(er);
+        Ray ew = c2w.ray(er);
         ew.time = s.time;
         return ew;
       };
@@ -1993,17 +1996,17 @@ struct Ctx {
       ray.d = Normalize(Pfocus - ray.o);
     }
     ray.time = s.time;
-    Ray w = c.cameraToWorld.ray(ray);
+    Ray w = c2w.ray(ray);
     w.time = s.time;
     if (rd) {
       rd->has = true;
       if (c.kind == 0) {  // perspective_camera.dart:50-56,122-128: the offsets ignore the lens; transformRayDifferential
         Vec dxCamera = c.rasterToCamera.point(Vec(1.0, 0.0, 0.0)) - c.rasterToCamera.point(Vec(0.0, 0.0, 0.0));
         Vec dyCamera = c.rasterToCamera.point(Vec(0.0, 1.0, 0.0)) - c.rasterToCamera.point(Vec(0.0, 0.0, 0.0));
-        rd->rxo = c.cameraToWorld.point(ray.o);
-        rd->ryo = c.cameraToWorld.point(ray.o);
-        rd->rxd = c.cameraToWorld.vector(Normalize(Pcamera + dxCamera));
-        rd->ryd = c.cameraToWorld.vector(Normalize(Pcamera + dyCamera));
+        rd->rxo = c2w.point(ray.o);
+        rd->ryo = c2w.point(ray.o);
+        rd->rxd = c2w.vector(Normalize(Pcamera + dxCamera));
+        rd->ryd = c2w.vector(Normalize(Pcamera + dyCamera));
       } else {
         // orthographic_camera.dart:111-115 AS WRITTEN: rxOrigin / ryOrigin are built in camera space and the call that follows is
         // transformRay, not transformRayDifferential, so they STAY in camera space; rxDirection and ryDirection are the very

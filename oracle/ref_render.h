@@ -26,6 +26,7 @@
 #include <memory>
 #include <vector>
 
+#include "ref_anim.h"
 #include "ref_scene.h"
 #include "ref_texture.h"
 
@@ -231,6 +232,10 @@ struct Light {
 
 struct Camera {  // perspective_camera.dart:46-57 + projective_camera.dart:34-53
   Transform rasterToCamera, cameraToWorld;
+  // Camera.cameraToWorld is an AnimatedTransform (camera.dart:27, dartray.dart:971-975): `animated` when the end-time CTM differs
+  bool animated = false;
+  AnimatedTransform cameraMotion;
+  Transform c2w(double time) const { return animated ? cameraMotion.interpolate(time) : cameraToWorld; }
   double lensRadius = 0, focalDistance = 1e30, shutterOpen = 0, shutterClose = 1;
   int kind = 0;  // 0 perspective, 1 orthographic (orthographic_camera.dart:52-80), 2 environment (environment_camera.dart:42-52)
 };

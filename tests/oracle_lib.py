@@ -74,6 +74,7 @@ def lib():
         L.orc_set_lights.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp]
         L.orc_set_camera.argtypes = [vp, vp, vp, dbl, dbl, dbl, dbl]
         L.orc_set_camera_kind.argtypes = [vp, i32]
+        L.orc_set_camera_motion.argtypes = [vp, vp, dbl, dbl]
         L.orc_set_film.argtypes = [vp, i32, i32, vp, dbl, dbl, vp]
         L.orc_set_sampler.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, u64, i32]
         L.orc_set_integrator.argtypes = [vp, i32, i32, i32, i32, dbl, dbl]
@@ -327,6 +328,10 @@ class Oracle:
                    shutter_close=1.0):
         r2c, c2w = _arr(raster_to_camera, np.float32).reshape(16), _arr(camera_to_world, np.float32).reshape(16)
         self._ck(self.L.orc_set_camera(self.h, _p(r2c), _p(c2w), lens_radius, focal_distance, shutter_open, shutter_close))
+
+    def set_camera_motion(self, camera_to_world_end, start_time=0.0, end_time=1.0):
+        m = _arr(camera_to_world_end, np.float32)
+        self._ck(self.L.orc_set_camera_motion(self.h, _p(None if m is None else m.reshape(16)), float(start_time), float(end_time)))
 
     def set_camera_kind(self, kind):
         self._ck(self.L.orc_set_camera_kind(self.h, kind))
