@@ -838,7 +838,8 @@ static int profCollect(drt_ctx* c) {  // after the render's stream synchronize
 
 static int traceQueue(drt_ctx* c, bool any, const float4* o, const float4* d, const double2* range, const uint32_t* nDev, void* out,
                       double* tOut, cudaStream_t st) {
-  if (c->ts.nInstances > 0) {
+  static const bool exactEnv = std::getenv("DRT_RENDER_EXACT_WALK") != nullptr;  // A/B: the literal walk for every renderer queue
+  if (c->ts.nInstances > 0 || exactEnv) {
     // scenes with TransformedPrimitives: the literal walk, which descends into the objects at each ray's time.  One thread per
     // queue slot (the live count is on the device; the surplus threads leave at once).
     const Wavefront& wf = c->render->wf;

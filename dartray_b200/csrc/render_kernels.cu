@@ -491,6 +491,9 @@ static __device__ __forceinline__ void pushDirectWork(const Wavefront& wf, uint3
 // missed sort last, so the warps of the shading kernel are full of live vertices (a quarter of config 4's lanes idled on misses:
 // profiles/r02u_shade_lines.txt shows at most 25 of 32 threads per instruction).
 #define DRT_SHAPE_CLASSES 7  // triangle + GSphere::shape 0..5
+#ifndef DRT_SHAPE_SORT_BUILD
+#define DRT_SHAPE_SORT_BUILD 0  // 1: the matte-only path kernel can walk the queue in shape-class order (env DRT_SHAPE_SORT=1); see launchShadePath
+#endif
 static __device__ __forceinline__ uint32_t sortBins(const RenderScene& rs, int keyMode) {
   return keyMode ? (uint32_t)DRT_SHAPE_CLASSES + 1u : (uint32_t)rs.nMaterials + 1u;
 }
@@ -557,13 +560,20 @@ __global__ void __launch_bounds__(256) matScatterKernel(RenderScene rs, Wavefron
 }
 
 // EXTRA: see hitGeometry (shade_device.cuh).  SORTED: work item i of the launch is queue entry shadeOrder[i].
-template <bool GENERAL, bool EXTRA>
-__global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(RenderParams rp, RenderScene rs, Wavefront wf, int bounce, int cur,
+// PART: 0 the whole vertex in one kernel; 1 / 2 the same work as two launches — emitted light + the direct-lighting set-up (shadow and
+// MIS rays), then the next direction + Russian roulette + the extension ray — each recomputing the cheap hit geometry / BSDF frame.
+// Smaller kernels (the single one is 11.5 K instructions: ncu shows `no_instruction` stalls of 2.3 warps per issue) with fewer live
+// registers; the per-slot draws keep their positions in the integrator stream, so the results are the single kernel's.
+#ifndef DRT_SHADE_SPLIT_MIN_BLOCKS
+#define DRT_SHADE_SPLIT_MIN_BLOCKS 5
+#endif
+template <bool GENERAL, bool EXTRA, int PART>
+__global__ void __launch_bounds__(128, PART == 0 ? DRT_SHADE_MIN_BLOCKS : DRT_SHADE_SPLIT_MIN_BLOCKS) shadePathKernel(RenderParams rp, RenderScene rs, Wavefront wf, int bounce, int cur,
                                                        RenderCounters* rc, int sortedOrder) {
   const uint32_t n = wf.counts[cur], cap = wf.cap;
   const int nxt = cur ^ 1;
   unsigned long long nShadow = 0, nClosest = 0;
-  const bool sorted = sortedOrder != 0;
+  const bool sorted = (GENERAL || DRT_SHAPE_SORT_BUILD) && sortedOrder != 0;
   for (uint32_t q0 = blockIdx.x * blockDim.x; q0 < n; q0 += gridDim.x * blockDim.x) {
     uint32_t q = q0 + threadIdx.x;
     bool valid = q < n;
@@ -573,11 +583,13 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(Ren
       if (sorted) q = wf.shadeOrder[q];
       slot = wf.extSlot[cur][q];
       prim = __float_as_int(wf.extHit[q].w);
-      wf.shIdx[slot] = -1;
-      wf.misIdx[slot] = -1;
+      if (PART != 2) {
+        wf.shIdx[slot] = -1;
+        wf.misIdx[slot] = -1;
+      }
       valid = prim >= 0;  // miss: the path ends; area/point lights add no Le along escaping rays
     }
-    if (sorted && !__any_sync(FULL, valid)) continue;  // the misses sort last: their warps have nothing to shade or to push
+    if (DRT_SHAPE_SORT_BUILD && sorted && !__any_sync(FULL, valid)) continue;  // the misses sort last: their warps have nothing to shade or to push
     DirectWork dw;
     dw.hasShadow = dw.hasMis = false;
     bool cont = false;
@@ -600,7 +612,7 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(Ren
       }
       const V3 wo = -d;
       // emitted light at the first vertex or after a specular bounce (:46-48); matte BSDFs never set specularBounce
-      if (bounce == 0 || (GENERAL && wf.specBounce[slot])) {
+      if (PART != 2 && (bounce == 0 || (GENERAL && wf.specBounce[slot]))) {
         const int li = primLight(rs, (uint32_t)prim);
         if (li >= 0) {
           Spec L = ld3(wf.L, cap, slot);
@@ -619,7 +631,9 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(Ren
         rng.ctr = (uint64_t)(bounce - 3) * per + (uint64_t)(bounce - 4);
       }
       // direct lighting: UniformSampleOneLight (integrator.dart:79-117)
-      if (rs.nLights > 0) {
+      if (PART == 2) {
+        if (rs.nLights > 0 && bounce >= 3) rng.ctr += 7;  // the draws the direct-lighting launch consumed: light number, LightSample, BSDFSample
+      } else if (rs.nLights > 0) {
         float lu0, lu1, bu0, bu1;
         double lcomp, bcomp;
         if (bounce < 3) {
@@ -638,6 +652,7 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(Ren
         st3(wf.pendT, cap, slot, T);
       }
       // next direction (:63-92)
+      if (PART != 1) {
       float pu0, pu1;
       double pcomp;
       if (bounce < 3) {
@@ -662,9 +677,10 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MIN_BLOCKS) shadePathKernel(Ren
         if (bounce == rp.maxDepth) cont = false;
         if (cont) st3(wf.T, cap, slot, T);
       }
+      }  // PART != 1
     }
-    pushDirectWork(wf, slot, valid, dw, p, rayEps, lightNum);
-    const uint32_t ei = warpPush(&wf.counts[nxt], cont);
+    if (PART != 2) pushDirectWork(wf, slot, valid, dw, p, rayEps, lightNum);
+    const uint32_t ei = PART == 1 ? 0u : warpPush(&wf.counts[nxt], cont);
     if (cont) {
       wf.extO[nxt][ei] = make_float4(p.x, p.y, p.z, rayLaneW(wf, slot, (float)rayEps));
       wf.extD[nxt][ei] = make_float4(wi.x, wi.y, wi.z, CUDART_INF_F);
@@ -1494,19 +1510,28 @@ cudaError_t launchShadePath(const RenderParams& rp, const RenderScene& rs, const
     int sorted = 0;
     cudaError_t e = launchMaterialSort(rs, wf, cur, numSMs, &sorted, st);
     if (e != cudaSuccess) return e;
-    shadePathKernel<true, DRT_EXTRA != 0><<<grid, 128, 0, st>>>(rp, rs, wf, bounce, cur, rc, sorted);
+    shadePathKernel<true, DRT_EXTRA != 0, 0><<<grid, 128, 0, st>>>(rp, rs, wf, bounce, cur, rc, sorted);
   } else {
     // matte-only scenes: DRT_SHAPE_SORT=1 walks the queue in shape-class order, misses last (full, type-coherent warps).  Measured on
     // B200 (profiles/r02v_shape_sort_ab.log, r02x_path_*.csv): the kernel itself gains 11 % (22 % on the bounces that have misses:
     // 25.9 instead of 18.9 threads per instruction), but the three sort passes (3.0 ms per 12 launches) and the less coalesced
     // shadow / MIS queues in resolveDirectKernel (+1.4 ms) take it back: config 4 0.986 s against 0.978 s.  Off by default.
-    static const bool shapeSortOn = std::getenv("DRT_SHAPE_SORT") != nullptr;
+    static const bool shapeSortOn = DRT_SHAPE_SORT_BUILD && std::getenv("DRT_SHAPE_SORT") != nullptr;
     const int sorted = shapeSortOn ? 1 : 0;
     if (sorted) {
       cudaError_t e = launchQueueSort(rs, wf, cur, 1, numSMs, st);
       if (e != cudaSuccess) return e;
     }
-    shadePathKernel<false, DRT_EXTRA != 0><<<grid, 128, 0, st>>>(rp, rs, wf, bounce, cur, rc, sorted);
+    // DRT_SHADE_SPLIT=1 (scenes without media): the vertex as two smaller launches, see shadePathKernel.  Measured on B200 (config 4,
+    // profiles/r02y_shade_split_ab.log): 96 registers each instead of 128, and SLOWER, 1.085 s against 0.986 s — the two launches read
+    // the queue and rebuild the hit geometry twice, and the extra warps do not buy that back.  Off by default.
+    static const bool split = std::getenv("DRT_SHADE_SPLIT") != nullptr;
+    if (split && rs.nVolumes == 0) {
+      shadePathKernel<false, DRT_EXTRA != 0, 1><<<grid, 128, 0, st>>>(rp, rs, wf, bounce, cur, rc, sorted);
+      shadePathKernel<false, DRT_EXTRA != 0, 2><<<grid, 128, 0, st>>>(rp, rs, wf, bounce, cur, rc, sorted);
+    } else {
+      shadePathKernel<false, DRT_EXTRA != 0, 0><<<grid, 128, 0, st>>>(rp, rs, wf, bounce, cur, rc, sorted);
+    }
   }
   return cudaGetLastError();
 }
