@@ -218,10 +218,15 @@ def render_legs(ctx_soup, soup_mesh, rank, world, barrier):
     sb, cam_cornell = scenes.cornell_synth()
     ctx_c = capi.Context(ctx_soup.device)
     host.upload_scene(ctx_c, sb.arrays())
-    arrays_of = {"ao": None, "path": sb.arrays()}  # ao: the bare soup_1m mesh the ray-cast step uses
-    legs = [("ao", ctx_soup, cam_soup, ao_s, ao_i), ("path", ctx_c, cam_cornell, pt_s, pt_i)]
-    for name, ctx, cam, smp, integ in legs:
+    arrays_of = {"ao": None, "path": sb.arrays(), "path_f32": sb.arrays()}  # ao: the bare soup_1m mesh the ray-cast step uses
+    # configs[3] twice: with the binary64 shading kernels that replay the reference's arithmetic (per-sample parity ~1e-6) and with
+    # drt_set_shading_precision(DRT_PRECISION_F32), which north_star's 3-sigma bar for the path tracer admits (tests/test_precision_gpu.py)
+    legs = [("ao", ctx_soup, cam_soup, ao_s, ao_i, None), ("path", ctx_c, cam_cornell, pt_s, pt_i, capi.PRECISION_F64),
+            ("path_f32", ctx_c, cam_cornell, pt_s, pt_i, capi.PRECISION_F32)]
+    for name, ctx, cam, smp, integ, precision in legs:
         film = host.Film(*RENDER_RES)
+        if precision is not None:
+            ctx.set_shading_precision(precision)
         # warm-up: one untimed render of the SAME configuration, so that the wavefront allocation (up to ~10 GB, sized by the
         # batch), the first launches and the NCCL channel are outside the timed region, as they are for every later frame
         host.configure_render(ctx, cam, film, smp, integ)
@@ -317,6 +322,8 @@ def render_legs(ctx_soup, soup_mesh, rank, world, barrier):
         else:
             host.upload_scene(ctx2, arrays)
         host.configure_render(ctx2, cam, film, smp, integ)
+        if precision is not None:
+            ctx2.set_shading_precision(precision)
         t_up = time.perf_counter() - t0
         distributed.render_sharded(ctx2, rank, world)
         img = ctx2.film_read()["rgb"]
@@ -332,7 +339,11 @@ def render_legs(ctx_soup, soup_mesh, rank, world, barrier):
                            f"pixel centre, {AO_RAYS} AO rays per hit")
     out["path"]["config"] = (f"BASELINE.json configs[3]: cornell_synth, {RENDER_RES[0]}x{RENDER_RES[1]}, lowdiscrepancy "
                              f"{PATH_SPP} spp, path maxdepth 5, box filter; pixel blocks sharded over {world} GPU(s), film "
-                             "summed with NCCL")
+                             "summed with NCCL; shading kernels in binary64 (DRT_PRECISION_F64: the reference's arithmetic, "
+                             "per-sample parity ~1e-6)")
+    out["path_f32"]["config"] = out["path"]["config"].replace(
+        "binary64 (DRT_PRECISION_F64: the reference's arithmetic, per-sample parity ~1e-6)",
+        "float32 (DRT_PRECISION_F32: per-pixel means within 3 sigma, tests/test_precision_gpu.py)")
     out["timing"] = "wall clock of the blocking drt_render_shard + film all-reduce, between barriers, max over ranks"
     return out
 

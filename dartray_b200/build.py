@@ -12,6 +12,11 @@ import shutil
 import subprocess
 import sys
 
+try:
+    from . import gen_f32
+except ImportError:  # run as a script
+    import gen_f32
+
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "_obj")
@@ -24,6 +29,19 @@ COMPILE_FLAGS = [
     "-fmad=false",
     "-Xcompiler", "-fPIC,-pthread,-ffp-contract=off",
 ]
+# render_kernels_f32.cu (the float32 shading build, gen_f32.py): no bit replay to protect, so contraction and the fast division /
+# square root / sincos are on.  DRT_F32_FLAGS overrides the extra flags for A/B builds.
+F32_UNIT = "render_kernels_f32.cu"
+F32_FLAGS = os.environ.get("DRT_F32_FLAGS", "-use_fast_math").split()
+
+
+def _flags_for(src: str) -> list:
+    flags = list(COMPILE_FLAGS) + ["-I", CSRC]
+    if os.path.basename(src) == F32_UNIT:
+        flags = [f for f in flags if f != "-fmad=false"] + F32_FLAGS
+    return flags
+
+
 LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-Xcompiler", "-pthread"]
 
 
@@ -49,7 +67,7 @@ def _stale_obj(src: str, hdr_time: float, extra_key: str) -> bool:
         return True
     t = os.path.getmtime(o)
     # render_kernels_plain.cu includes render_kernels.cu
-    deps = [src] + ([os.path.join(CSRC, "render_kernels.cu")] if src.endswith("render_kernels_plain.cu") else [])
+    deps = [src] + ([os.path.join(CSRC, "render_kernels.cu")] if src.endswith(("render_kernels_plain.cu", F32_UNIT)) else [])
     return any(os.path.getmtime(d) > t for d in deps) or hdr_time > t
 
 
@@ -63,8 +81,9 @@ def build(force: bool = False, verbose: bool = False, defines: tuple = (), lib: 
         base_objs = {s: _obj_of(s) for s in sources() if os.path.basename(s) not in only}
     else:
         base_objs = {}
-    extra_key = " ".join(sorted(defines))
-    obj_dir = OBJ if not defines else OBJ + "_" + "".join(ch if ch.isalnum() else "_" for ch in extra_key)
+    extra_key = " ".join(sorted(defines)) + " | " + " ".join(F32_FLAGS)
+    gen_f32.generate()
+    obj_dir = OBJ if not defines else OBJ + "_" + "".join(ch if ch.isalnum() else "_" for ch in " ".join(sorted(defines)))
     saved, OBJ = OBJ, obj_dir
     try:
         os.makedirs(OBJ, exist_ok=True)
@@ -74,7 +93,7 @@ def build(force: bool = False, verbose: bool = False, defines: tuple = (), lib: 
         dflags = [f"-D{d}" for d in defines]
 
         def compile_one(src):
-            cmd = [nvcc] + COMPILE_FLAGS + dflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", _obj_of(src), src]
+            cmd = [nvcc] + _flags_for(src) + dflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", _obj_of(src), src]
             res = subprocess.run(cmd, capture_output=True, text=True)
             if res.returncode != 0:
                 raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

@@ -25,7 +25,7 @@ SYMBOLS = [
     "drt_set_instances", "drt_set_ray_times", "drt_set_build_order", "drt_build_bvh", "drt_bvh_info_get", "drt_bvh_export", "drt_trace_closest",
     "drt_trace_any", "drt_trace_closest_device", "drt_trace_any_device", "drt_set_counting", "drt_get_counters", "drt_set_kernel_variant",
     "drt_last_kernel_ms", "drt_kernel_launches",
-    "drt_set_materials", "drt_set_material_lobes", "drt_set_measured", "drt_set_textures", "drt_set_material_programs", "drt_set_lights", "drt_set_spot_params", "drt_set_volumes", "drt_set_volume_integrator", "drt_set_camera", "drt_set_camera_motion", "drt_set_camera_kind", "drt_set_film", "drt_set_sampler", "drt_set_integrator",
+    "drt_set_materials", "drt_set_material_lobes", "drt_set_measured", "drt_set_textures", "drt_set_material_programs", "drt_set_lights", "drt_set_spot_params", "drt_set_volumes", "drt_set_volume_integrator", "drt_set_shading_precision", "drt_set_camera", "drt_set_camera_motion", "drt_set_camera_kind", "drt_set_film", "drt_set_sampler", "drt_set_integrator",
     "drt_render", "drt_render_shard", "drt_set_batch_slots", "drt_film_clear", "drt_film_size", "drt_film_read",
     "drt_film_device", "drt_pixel_samples", "drt_render_stats_get", "drt_set_render_profiling", "drt_render_profile_get",
 ]
@@ -53,6 +53,7 @@ class RenderProfile(C.Structure):
 
 
 PROFILE_TIME, PROFILE_WORK = 1, 2
+PRECISION_F64, PRECISION_F32 = 0, 1
 PROFILE_CLASSES = ["trace_closest", "trace_any", "integrator", "sampler", "resolve", "film", "other"]
 
 
@@ -135,6 +136,7 @@ def load():
     L.drt_render_stats_get.argtypes = [vp, C.POINTER(RenderStats)]
     L.drt_set_volumes.argtypes = [vp, u32] + [vp] * 13
     L.drt_set_volume_integrator.argtypes = [vp, i32, dbl]
+    L.drt_set_shading_precision.argtypes = [vp, i32]
     L.drt_set_render_profiling.argtypes = [vp, i32]
     L.drt_render_profile_get.argtypes = [vp, C.POINTER(RenderProfile)]
     _lib = L
@@ -459,6 +461,10 @@ class Context:
 
     def set_volume_integrator(self, kind: int, step_size: float):
         self._ck(self.L.drt_set_volume_integrator(self.h, kind, float(step_size)))
+
+    def set_shading_precision(self, precision: int):
+        """PRECISION_F64 (0, default): the reference's arithmetic; PRECISION_F32 (1): float32 path-vertex kernels (3-sigma parity)."""
+        self._ck(self.L.drt_set_shading_precision(self.h, int(precision)))
 
     def set_render_profiling(self, flags: int):
         """PROFILE_TIME: CUDA-event spans per kernel class; PROFILE_WORK: reference-walk counters of every traced queue."""

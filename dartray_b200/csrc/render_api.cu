@@ -70,6 +70,9 @@ struct RenderState {
   std::vector<double> volDensity;
   int volIntegrator = 0;
   double volStep = 1.0;
+  // drt_set_shading_precision: DRT_PRECISION_F32 runs the path integrator's vertex / resolve kernels from the float32 build
+  // (render_kernels_f32.cu) on scenes that build serves: matte materials, no per-vertex attributes, no media, no texture programs
+  int shadingPrecision = 0;
   std::vector<float> volV2W;     // n x 16: volumeToWorld, for the regions' world bound
   uint32_t volMaxSteps = 0;      // single scattering: bound on a camera ray's march steps (regions' bound diagonal / stepsize)
   DevBuf<GVolume> dVolumes;
@@ -1071,18 +1074,23 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
   }
   if (p.integKind == 0) {
     int cur = 0;
+    // float32 shading (drt_set_shading_precision; env DRT_SHADE_F32=1 / 0 overrides for A/B runs): same queues, same sample values, same
+    // binary64 traversal — only the arithmetic of the vertex and resolve kernels changes
+    static const char* f32Env = std::getenv("DRT_SHADE_F32");
+    const bool wantF32 = f32Env ? f32Env[0] == '1' : r->shadingPrecision == DRT_PRECISION_F32;
+    const bool f32 = wantF32 && !rs.extra && !rs.general && rs.nVolumes == 0 && rs.nPrograms == 0;
     for (int bounce = 0; bounce <= p.maxDepth; ++bounce) {
       CK(c, STAGE(launchResetCounts)(wf, (1u << (cur ^ 1)) | (1u << Q_SHADOW) | (1u << Q_MIS), st)); profMark(c, DRT_PK_OTHER);
       if (rs.nPrograms > 0) {  // only the camera ray carries differentials: the later rays are RayDifferential.child (path_integrator.dart:100)
         CK(c, launchTexturePass(p, rs, wf, cur, bounce == 0 ? 1 : 0, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
         c->launches++;
       }
-      CK(c, STAGE(launchShadePath)(p, rs, wf, bounce, cur, rc, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
+      CK(c, (f32 ? drt::plainf::launchShadePath : STAGE(launchShadePath))(p, rs, wf, bounce, cur, rc, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
       c->launches += 2;
       if (rs.nLights > 0) {
         RK(traceQueue(c, true, wf.shO, wf.shD, wf.shRange, wf.counts + Q_SHADOW, wf.shOcc, nullptr, st));
         RK(traceQueue(c, false, wf.misO, wf.misD, wf.misRange, wf.counts + Q_MIS, wf.misHit, wf.misT, st));
-        CK(c, STAGE(launchResolveDirect)(p, rs, wf, cur, RESOLVE_PATH, 1, sms, st)); profMark(c, DRT_PK_RESOLVE);
+        CK(c, (f32 ? drt::plainf::launchResolveDirect : STAGE(launchResolveDirect))(p, rs, wf, cur, RESOLVE_PATH, 1, sms, st)); profMark(c, DRT_PK_RESOLVE);
         c->launches++;
       }
       if (bounce == p.maxDepth) break;
@@ -1648,6 +1656,14 @@ int drt_set_volume_integrator(drt_ctx* c, int32_t kind, double step_size) {
   r->volIntegrator = kind;
   r->volStep = step_size;
   r->sceneTablesValid = false;
+  return DRT_OK;
+}
+
+int drt_set_shading_precision(drt_ctx* c, int32_t precision) {
+  DRT_FORWARD_TO_PEERS(c, drt_set_shading_precision(p_, precision));
+  if (!c) return DRT_E_INVALID;
+  if (precision != DRT_PRECISION_F64 && precision != DRT_PRECISION_F32) return fail(c, DRT_E_INVALID, "precision must be DRT_PRECISION_F64 or DRT_PRECISION_F32");
+  state(c)->shadingPrecision = precision;
   return DRT_OK;
 }
 

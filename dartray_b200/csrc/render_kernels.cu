@@ -59,6 +59,7 @@ static __device__ __forceinline__ void pixelOf(const PixelBatch& pb, uint32_t p,
   *y = pb.y0 + (int)(g / (uint64_t)pb.w);
 }
 
+#ifndef DRT_PATH_ONLY  // the float32 path build (render_kernels_f32.cu) takes the path-vertex and resolve kernels only
 // ---------------------------------------------------------------------------------------------------
 // Low-discrepancy sampler: one group of G lanes (G = 1..32, a power of two chosen so that a block's
 // arrays fit in shared memory) per (pixel, array).  LDShuffleScrambled1D/2D (montecarlo.dart:524-551):
@@ -371,6 +372,7 @@ __global__ void __launch_bounds__(128) samplerBestCandidateKernel(RenderParams r
   wf.camTime[p] = t > 1 ? (t - 1) : t;  // best_candidate_sampler.dart:111: a Dart double
 }
 
+#endif  // DRT_PATH_ONLY
 // The fourth lane of a renderer ray's origin: scenes with TransformedPrimitives carry the wavefront slot there (the traversal looks the
 // ray's time up in Wavefront::slotTime — every ray a camera sample spawns inherits its time, ray.dart:59); the interval itself always
 // travels in the f64 range arrays.
@@ -378,6 +380,7 @@ static __device__ __forceinline__ float rayLaneW(const Wavefront& wf, uint32_t s
   return wf.slotTime ? __uint_as_float(slot) : informational;
 }
 
+#ifndef DRT_PATH_ONLY  // the float32 path build (render_kernels_f32.cu) takes the path-vertex and resolve kernels only
 // ---------------------------------------------------------------------------------------------------
 // Camera rays (perspective_camera.dart:93-132; ray differentials only feed texture filtering and are
 // not generated) + per-slot state reset.  Extension queue 0 = all slots in slot order.
@@ -444,6 +447,7 @@ __global__ void resetCountsKernel(Wavefront wf, unsigned mask) {
   if (threadIdx.x < Q_COUNT && ((mask >> threadIdx.x) & 1u)) wf.counts[threadIdx.x] = 0;
 }
 
+#endif  // DRT_PATH_ONLY
 // Sample-record access helpers (Sample.oneD / twoD, sample.dart:23-79)
 static __device__ __forceinline__ float val(const Wavefront& wf, int v, uint32_t slot) { return wf.vals[(size_t)v * wf.cap + slot]; }
 
@@ -828,6 +832,7 @@ __global__ void __launch_bounds__(128) escapeKernel(RenderScene rs, Wavefront wf
   }
 }
 
+#ifndef DRT_PATH_ONLY  // the float32 path build (render_kernels_f32.cu) takes the path-vertex and resolve kernels only
 // ---------------------------------------------------------------------------------------------------
 // Ambient occlusion (ambient_occlusion_integrator.dart:28-53)
 __global__ void __launch_bounds__(128) aoSetupKernel(RenderParams rp, RenderScene rs, Wavefront wf) {
@@ -1416,6 +1421,7 @@ __global__ void filmConvertKernel(RenderParams rp, float* rgb, float* xyz, float
   }
 }
 
+#endif  // DRT_PATH_ONLY
 // ---------------------------------------------------------------------------------------------------
 static inline int gridFor(uint64_t n, int block, int numSMs, int perSm) {
   uint64_t want = (n + block - 1) / block;
@@ -1424,6 +1430,7 @@ static inline int gridFor(uint64_t n, int block, int numSMs, int perSm) {
   return (int)(want < cap ? want : cap);
 }
 
+#ifndef DRT_PATH_ONLY  // the float32 path build (render_kernels_f32.cu) takes the path-vertex and resolve kernels only
 cudaError_t launchSampler(const RenderParams& rp, const Wavefront& wf, const SampleArray* dArrays, int nArrays, int maxVals,
                           int maxOthers, const PixelBatch& pb, int numSMs, cudaStream_t st) {
   if (pb.nPixels == 0) return cudaSuccess;
@@ -1478,6 +1485,7 @@ cudaError_t launchResetCounts(const Wavefront& wf, unsigned mask, cudaStream_t s
   return cudaGetLastError();
 }
 
+#endif  // DRT_PATH_ONLY
 // Counting sort of extension queue `cur` by material into wf.shadeOrder; *sorted = 0 when the scene has one material or more than
 // the sort's bins (the shading kernels then walk the queue as it is).  DRT_NO_MATERIAL_SORT turns it off.
 static cudaError_t launchQueueSort(const RenderScene& rs, const Wavefront& wf, int cur, int keyMode, int numSMs, cudaStream_t st) {
@@ -1542,6 +1550,7 @@ cudaError_t launchResolveDirect(const RenderParams& rp, const RenderScene& rs, c
   return cudaGetLastError();
 }
 
+#ifndef DRT_PATH_ONLY  // the float32 path build (render_kernels_f32.cu) takes the path-vertex and resolve kernels only
 cudaError_t launchEscape(const RenderScene& rs, const Wavefront& wf, int cur, int mode, int numSMs, cudaStream_t st) {
   escapeKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rs, wf, cur, mode);
   return cudaGetLastError();
@@ -1652,5 +1661,6 @@ cudaError_t launchFilmConvert(const RenderParams& rp, float* rgb, float* xyz, fl
   return cudaGetLastError();
 }
 
+#endif  // DRT_PATH_ONLY
 }  // namespace DRT_RK_NS
 }  // namespace drt

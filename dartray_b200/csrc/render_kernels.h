@@ -34,6 +34,10 @@ namespace plain {
 namespace extra {
 #include "render_launchers.inc"
 }
+// float32 arithmetic (render_kernels_f32.cu): launchShadePath and launchResolveDirect only are defined
+namespace plainf {
+#include "render_launchers.inc"
+}
 
 // resolve mode bits: 1 = direct-lighting integrator (0 = path), 2 = first sample of a light, 4 = last sample of a
 // light, 8 = last light (add the sum to L), 16 = strategy "one", 32 = the vertices belong to a specular chain: weight the

@@ -150,7 +150,11 @@ static DRT_HD inline uint64_t streamKey(uint64_t seed, int32_t x, int32_t y, uin
 #define DRT_STREAM_VOLUME_LI 0x80000002u      // the draws of VolumeIntegrator.Li along the camera ray
 // d-th draw of a stream, d = 1, 2, ...
 static DRT_HD inline uint64_t draw64(uint64_t key, uint64_t d) { return mix64(key + d * 0x9E3779B97F4A7C15ull); }
+#if DRT_REAL32  // the float32 build (gen_f32.py): 24 bits, so that the draw stays below 1
+static DRT_HD inline double drawFloat(uint64_t key, uint64_t d) { return (double)(uint32_t)(draw64(key, d) >> 40) * 5.9604644775390625e-8; }
+#else
 static DRT_HD inline double drawFloat(uint64_t key, uint64_t d) { return (double)(draw64(key, d) >> 11) * (1.0 / 9007199254740992.0); }
+#endif
 static DRT_HD inline uint32_t drawUint(uint64_t key, uint64_t d) { return (uint32_t)(draw64(key, d) >> 32) % 0xffffffffu; }
 
 struct Stream {

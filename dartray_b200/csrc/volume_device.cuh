@@ -59,7 +59,7 @@ static __device__ inline double regionDensity(const RenderScene& rs, const GVolu
   vox.z = (float)((double)vox.z * v.nz - 0.5);
   const int vx = (int)floor((double)vox.x), vy = (int)floor((double)vox.y), vz = (int)floor((double)vox.z);
   const double dx = (double)vox.x - vx, dy = (double)vox.y - vy, dz = (double)vox.z - vz;
-  const double* dens = rs.volDensity + v.densityOffset;
+  const auto* dens = rs.volDensity + v.densityOffset;  // binary64 storage in either build
   auto D = [&](int x, int y, int z) {
     x = min(max(x, 0), v.nx - 1);
     y = min(max(y, 0), v.ny - 1);

@@ -403,6 +403,18 @@ int drt_set_volumes(drt_ctx* ctx, uint32_t n, const int32_t* kind, const float* 
  * the halton / adaptive / bestcandidate samplers. */
 int drt_set_volume_integrator(drt_ctx* ctx, int32_t kind, double step_size);
 
+/* Arithmetic of the path integrator's shading kernels.  DRT_PRECISION_F64 (the default) evaluates every expression the way the Dart VM
+ * does — float32 objects, binary64 expressions (lib/core/vector.dart:26-74, rgb_color.dart:23-169) — and reproduces the reference's
+ * radiance per camera sample to ~1e-6.  DRT_PRECISION_F32 runs PathIntegrator.Li's vertex code (lib/surface_integrators/
+ * path_integrator.dart:44-119, lib/core/integrator.dart:79-185) in float32 throughout: the same samples, queues and binary64
+ * traversal, but a sample's radiance now agrees with the reference's only within float32 rounding (and a vertex that lies within
+ * rounding of an edge may take the other branch), which is inside what the Monte Carlo estimate itself promises — per-pixel means
+ * within 3 sigma.  It applies to the path integrator on scenes whose materials are all matte, without per-vertex mesh attributes,
+ * texture programs or media; every other render keeps the binary64 kernels whatever this is set to. */
+#define DRT_PRECISION_F64 0
+#define DRT_PRECISION_F32 1
+int drt_set_shading_precision(drt_ctx* ctx, int32_t precision);
+
 /* Replaces PerspectiveCamera (lib/cameras/perspective_camera.dart:46-57 + lib/core/
  * projective_camera.dart:34-53): the two float32 row-major matrices the camera holds
  * (rasterToCamera, cameraToWorld.startTransform) and its lens / shutter scalars. */
