@@ -76,6 +76,7 @@ drt_ctx* drt_create(int device_id) {
   for (int i = 0; i < drt_ctx::kRing && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ringEv[i], cudaEventDisableTiming);
   c->fastV1 = std::getenv("DRT_TRACE_V1") != nullptr;
   if (const char* q = std::getenv("DRT_Q_MIN_PRIMS")) c->qMinPrims = (uint32_t)std::strtoul(q, nullptr, 10);
+  c->smallOff = std::getenv("DRT_NO_SMALL") != nullptr;
   if (e != cudaSuccess) {
     g_createError = cudaGetErrorString(e);
     drt_destroy(c);
@@ -355,6 +356,68 @@ static bool quadricSetup(const HostSphere& s, GSphere* gp) {
   return true;
 }
 
+// Leaf lists of a small scene (GSmallScene, gpu_types.h): the leaves in storage order with their boxes, and for each dirIsNeg octant
+// the order in which the reference's walk reaches them (bvh_accel.dart:147-153: the second child first when the ray's direction is
+// negative along the node's split axis).  Returns false when the scene is not small.
+static bool buildSmallScene(const BuiltBvh& B, const std::vector<GNode>& nodes, const std::vector<GPrim>& prims, const std::vector<GSphere>& gs,
+                            GSmallScene* out) {
+  if (B.nLeaves == 0 || B.nLeaves > DRT_SMALL_MAX_LEAVES) return false;
+  std::memset(out, 0, sizeof(*out));
+  std::vector<int32_t> walk[8];
+  for (int oct = 0; oct < 8; ++oct) {
+    std::vector<int32_t> todo{B.rootRef};
+    while (!todo.empty()) {
+      const int32_t ref = todo.back();
+      todo.pop_back();
+      if (ref == DRT_REF_EMPTY) continue;
+      if (ref < 0) { walk[oct].push_back(ref); continue; }
+      if ((size_t)ref >= nodes.size()) return false;
+      const GNode& n = nodes[(size_t)ref];
+      const bool neg = ((oct >> (n.axis & 3)) & 1) != 0;
+      todo.push_back(neg ? n.ref0 : n.ref1);  // the far child waits on the stack
+      todo.push_back(neg ? n.ref1 : n.ref0);
+    }
+    if (walk[oct].size() != B.nLeaves) return false;
+  }
+  out->nLeaves = (int32_t)B.nLeaves;
+  for (uint32_t l = 0; l < B.nLeaves; ++l) {
+    const int32_t ref = walk[0][l];
+    GSmallLeaf& L = out->leaf[l];
+    L.ref = ref;
+    const uint32_t off = refLeafOffset(ref);
+    uint32_t cnt = refLeafCountField(ref);
+    if (off >= prims.size()) return false;
+    if (cnt == 15u) cnt = (uint32_t)prims[off].leafCount;
+    if (cnt == 0 || off + cnt > prims.size()) return false;
+    for (int a = 0; a < 3; ++a) { L.lo[a] = INFINITY; L.hi[a] = -INFINITY; }
+    for (uint32_t k = 0; k < cnt; ++k) {  // the box the traversal kernels rebuild from a leaf's records (trace_fast.cu, leaf phase)
+      const GPrim& pr = prims[off + k];
+      if ((pr.kindSphere & 1) == 0) {
+        for (int a = 0; a < 3; ++a) {
+          L.lo[a] = std::fmin(L.lo[a], std::fmin(pr.p1[a], std::fmin(pr.p2[a], pr.p3[a])));
+          L.hi[a] = std::fmax(L.hi[a], std::fmax(pr.p1[a], std::fmax(pr.p2[a], pr.p3[a])));
+        }
+      } else {
+        const size_t si = (size_t)(pr.kindSphere >> 1);
+        if (si >= gs.size()) return false;
+        for (int a = 0; a < 3; ++a) {
+          L.lo[a] = std::fmin(L.lo[a], gs[si].wmin[a]);
+          L.hi[a] = std::fmax(L.hi[a], gs[si].wmax[a]);
+        }
+      }
+    }
+  }
+  for (int oct = 0; oct < 8; ++oct)
+    for (uint32_t k = 0; k < B.nLeaves; ++k) {
+      uint32_t l = 0;
+      while (l < B.nLeaves && walk[0][l] != walk[oct][k]) ++l;
+      if (l == B.nLeaves) return false;
+      out->order[oct][k] = (uint8_t)l;
+      out->position[oct][l] = (uint8_t)k;
+    }
+  return true;
+}
+
 // Device half of drt_build_bvh: the built tree's arrays go to c's device.  B / prims / gs may belong to another context (the
 // owner of a multi-device context builds once on the host and every device uploads the same arrays).
 // `src`: a context of ANOTHER device that already holds this build: the arrays then come over NVLink from its memory
@@ -391,9 +454,19 @@ static int uploadBuilt(drt_ctx* c, const BuiltBvh& B, const std::vector<GNode>& 
   }
   CK(c, put(c->dPrims.p, prims.data(), src ? src->dPrims.p : nullptr, prims.size() * sizeof(GPrim)));
   CK(c, put(c->dSpheres.p, gs.data(), src ? src->dSpheres.p : nullptr, gs.size() * sizeof(GSphere)));
+  c->smallOk = false;
+  if (ginsts.empty()) {
+    GSmallScene small;
+    if (buildSmallScene(B, nodes, prims, gs, &small)) {
+      CK(c, c->dSmall.ensure(1));
+      CK(c, cudaMemcpy(c->dSmall.p, &small, sizeof(small), cudaMemcpyHostToDevice));
+      c->smallOk = true;
+    }
+  }
   c->ts.nodes = c->dNodes.p;
   c->ts.wide = c->dWide.p;
   c->ts.wideQ = c->useQ() ? c->dWideQ.p : nullptr;
+  c->ts.small = c->useSmall() ? c->dSmall.p : nullptr;
   c->ts.wideRootRef = B.wideRootRef;
   c->ts.prims = c->dPrims.p;
   c->ts.spheres = c->dSpheres.p;
@@ -764,11 +837,13 @@ int drt_set_kernel_variant(drt_ctx* c, int variant) {
   c->exactWalk = variant == DRT_KERNEL_EXACT_WALK;
   c->fastV1 = variant == DRT_KERNEL_FAST_V1 || (variant != DRT_KERNEL_FAST_Q && std::getenv("DRT_TRACE_V1") != nullptr);
   if (variant == DRT_KERNEL_FAST_Q) c->qMinPrims = 0;
+  c->variantForced = variant != DRT_KERNEL_FAST;
   if (c->built && c->device != DRT_DEVICE_NONE && !c->useQ() && !c->wideUploaded) {
     int rc = uploadWideV1(c);
     if (rc != DRT_OK) return rc;
   }
   c->ts.wideQ = (c->built && c->useQ()) ? c->dWideQ.p : nullptr;
+  c->ts.small = (c->built && c->useSmall()) ? c->dSmall.p : nullptr;
   return DRT_OK;
 }
 

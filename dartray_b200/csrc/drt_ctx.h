@@ -76,6 +76,11 @@ struct drt_ctx {
   // soup(8), 16 K triangles: 10.7 vs 8.5 Grays/s; soup(64), 127 K: 4.2 vs 4.6; soup_1m: 1.88 vs 2.36 Grays/s — tools/size_sweep.sh).  Env DRT_Q_MIN_PRIMS overrides (A/B runs).
   uint32_t qMinPrims = 65536;
   bool useQ() const { return wideQOk && !fastV1 && nprims() >= qMinPrims; }
+  // Scenes of <= DRT_SMALL_MAX_LEAVES leaves without instances: the leaf-list kernel (traceSmallKernel) unless a variant is forced
+  // (drt_set_kernel_variant other than DRT_KERNEL_FAST) or env DRT_NO_SMALL is set (A/B runs)
+  DevBuf<GSmallScene> dSmall;
+  bool smallOk = false, variantForced = false, smallOff = false;
+  bool useSmall() const { return smallOk && !variantForced && !fastV1 && !smallOff; }
   DevBuf<GPrim> dPrims;
   DevBuf<GSphere> dSpheres;
   DevBuf<DeviceCounters> dCounters;

@@ -109,6 +109,24 @@ struct alignas(16) GSphere {
   double ha, hc;               // hyperboloid.dart:40-48 implicit coefficients; `radius` holds rmax
 };
 
+// Scenes of at most DRT_SMALL_MAX_LEAVES leaves (BASELINE.json config 4: 25 primitives) skip the tree: the reference's walk visits
+// the leaves in an order that depends on the ray's dirIsNeg octant only (bvh_accel.dart:147-153), tests a leaf's primitives iff the
+// leaf's own box test passes at that moment, and every interior test is implied by a leaf's (trace_fast.cu, argument (1)).  So the
+// small-scene kernel (traceSmallKernel, trace_fast.cu) walks the octant's leaf list and decides every leaf box exactly.
+#define DRT_SMALL_MAX_LEAVES 64
+struct alignas(16) GSmallLeaf {
+  float lo[3];
+  int32_t ref;   // the leaf reference (offset / count of its GPrim records)
+  float hi[3];   // box = union of the primitives' world bounds: what the reference's leaf node holds (bvh_accel.dart:262-281)
+  int32_t pad;
+};
+struct alignas(16) GSmallScene {
+  int32_t nLeaves, pad[3];
+  GSmallLeaf leaf[DRT_SMALL_MAX_LEAVES];         // in storage (depth-first, first child first) order
+  uint8_t order[8][DRT_SMALL_MAX_LEAVES];        // order[octant][k] = k-th leaf the reference's walk reaches for rays of that octant
+  uint8_t position[8][DRT_SMALL_MAX_LEAVES];     // the inverse: position[octant][leaf]
+};
+
 struct GInstance;  // anim_transform.h
 struct GObject;
 
@@ -126,6 +144,7 @@ struct TraceScene {
   // TransformedPrimitives (transformed_primitive.dart): a top-level leaf record of kind "quadric" whose GSphere has shape 6 stands
   // for instance GSphere::instance; the objects' binary nodes / leaf records sit behind the top level's in `nodes` / `prims`.
   // Scenes with instances run the literal walk (traceKernel), which descends into the object with the transformed ray.
+  const GSmallScene* small;  // leaf lists of a scene with <= DRT_SMALL_MAX_LEAVES leaves and no instances, else nullptr
   const GInstance* instances;
   const GObject* objects;
   int32_t nInstances;

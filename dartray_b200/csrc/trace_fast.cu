@@ -441,6 +441,155 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
 #undef RETIRE
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Small scenes (<= DRT_SMALL_MAX_LEAVES leaves, no instances: BASELINE.json config 4 has 25 primitives in 11 leaves): no tree, no
+// stack, no persistent warps.  By argument (1) above the reference's answer is fixed by (a) the ORDER in which its walk reaches the
+// leaves, which depends on the ray's dirIsNeg octant only (bvh_accel.dart:147-153) and is tabulated by the host (GSmallScene::order),
+// and (b) each leaf's own box decision at the moment it is reached, every interior test being implied by it.  One thread per ray:
+//   pass 1  the float32 filter of every leaf box, the leaves read in storage order (one shared-memory broadcast per leaf for the whole
+//           warp, no divergence); survivors are marked in a 64-bit mask at their POSITION in the octant's visiting order;
+//   pass 2  the marked leaves in that order: the filter again with the ray's maxDistance of this moment, the reference's binary64 slab
+//           test where the filter cannot prove the decision, then the reference's primitive tests (trace_device.cuh).
+// A leaf dropped in pass 1 fails the reference's test at any later moment too (maxDistance only shrinks), so the two passes test the
+// primitives of exactly the leaves the reference enters, in its order, with its maxDistance.  "Slow" rays (non-finite origin or
+// invDir) mark every leaf and decide each box in binary64.  Any hit: the order is immaterial, octant 0's is used.
+#ifndef DRT_SMALL_BLOCK
+#define DRT_SMALL_BLOCK 256
+#endif
+#ifndef DRT_SMALL_MIN_BLOCKS
+#define DRT_SMALL_MIN_BLOCKS 3
+#endif
+template <bool ANY, int QUAD>
+__global__ void __launch_bounds__(DRT_SMALL_BLOCK, DRT_SMALL_MIN_BLOCKS)
+    traceSmallKernel(TraceScene sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD, uint32_t n,
+                     float4* __restrict__ hits, uint8_t* __restrict__ occluded, TraceExtras ex) {
+  __shared__ GSmallScene sm;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(sc.small);
+    uint4* dst = reinterpret_cast<uint4*>(&sm);
+    for (unsigned i = threadIdx.x; i < sizeof(GSmallScene) / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  if (ex.nDev) n = *ex.nDev;
+  const int nLeaves = sm.nLeaves;
+  for (uint32_t rayIdx = blockIdx.x * blockDim.x + threadIdx.x; rayIdx < n; rayIdx += gridDim.x * blockDim.x) {
+    const float4 o = __ldg(rayO + rayIdx), d = __ldg(rayD + rayIdx);
+    const float ix = __frcp_rn(d.x), iy = __frcp_rn(d.y), iz = __frcp_rn(d.z);  // invDir, see traceFastKernel
+    FastRay r;
+    r.ox2 = pack2(o.x, o.x); r.oy2 = pack2(o.y, o.y); r.oz2 = pack2(o.z, o.z);
+    r.ix2 = pack2(ix, ix); r.iy2 = pack2(iy, iy); r.iz2 = pack2(iz, iz);
+    if (ex.range) {
+      const double2 mm = __ldg(ex.range + rayIdx);
+      r.mint = mm.x; r.mintLo = __double2float_rd(mm.x); r.mintHi = __double2float_ru(mm.x);
+      r.maxt = mm.y; r.maxtLo = __double2float_rd(mm.y); r.maxtHi = __double2float_ru(mm.y);
+    } else {
+      r.mint = o.w; r.mintLo = r.mintHi = o.w;
+      r.maxt = d.w; r.maxtLo = r.maxtHi = d.w;
+    }
+    const bool slow = !(fabsf(o.x) <= 3.0e38f) || !(fabsf(o.y) <= 3.0e38f) || !(fabsf(o.z) <= 3.0e38f) ||
+                      !(fabsf(ix) <= 3.0e38f) || !(fabsf(iy) <= 3.0e38f) || !(fabsf(iz) <= 3.0e38f);
+    const unsigned oct = ANY ? 0u : ((ix < 0.f ? 1u : 0u) | (iy < 0.f ? 2u : 0u) | (iz < 0.f ? 4u : 0u));
+    r.negMask = oct;
+    unsigned long long mask = 0ull;
+    if (slow || sc.empty) {
+      mask = sc.empty ? 0ull : (nLeaves >= 64 ? ~0ull : ((1ull << nLeaves) - 1ull));
+    } else {
+      for (int l = 0; l < nLeaves; ++l) {
+        const GSmallLeaf& L = sm.leaf[l];
+        float tm;
+        const int c = slabFilter(r, pack2(L.lo[0], L.hi[0]), pack2(L.lo[1], L.hi[1]), pack2(L.lo[2], L.hi[2]), &tm);
+        if (c) mask |= 1ull << sm.position[oct][l];
+      }
+    }
+    RayState rs;
+    rs.ox = o.x; rs.oy = o.y; rs.oz = o.z;
+    rs.dx = d.x; rs.dy = d.y; rs.dz = d.z;
+    rs.mint = r.mint; rs.maxt = r.maxt;
+    bool found = false;
+    float hb1 = 0.f, hb2 = 0.f;
+    int hprim = -1;
+    while (mask) {
+      const int j = __ffsll((long long)mask) - 1;
+      mask &= mask - 1ull;
+      const GSmallLeaf& L = sm.leaf[sm.order[oct][j]];
+      const float lo0 = L.lo[0], lo1 = L.lo[1], lo2 = L.lo[2], hi0 = L.hi[0], hi1 = L.hi[1], hi2 = L.hi[2];
+      const int32_t ref = L.ref;
+      int c = 2;
+      float tm;
+      if (!slow) c = slabFilter(r, pack2(lo0, hi0), pack2(lo1, hi1), pack2(lo2, hi2), &tm);
+      if (c == 0) continue;
+      if (c == 2 && !slabExact(o.x, o.y, o.z, ix, iy, iz, r.mint, r.maxt, lo0, lo1, lo2, hi0, hi1, hi2, &tm)) continue;
+      const uint32_t off = refLeafOffset(ref);
+      uint32_t cnt = refLeafCountField(ref);
+      const GPrim* pr = sc.prims + off;
+      if (cnt == 15u) cnt = (uint32_t)__ldg(&pr->leafCount);
+      bool stop = false;
+      for (uint32_t k = 0; k < cnt && !stop; ++k) {
+        const float4 a = ldg4(&pr[k].p1[0]), b = ldg4(&pr[k].p2[0]), cc = ldg4(&pr[k].p3[0]);
+        const int kind = __float_as_int(cc.w);
+        if (QUAD == 0 || (kind & 1) == 0) {
+          if (ANY) {
+            if (triangleAny(rs, a, b, cc)) { found = true; stop = true; }
+          } else {
+            HitState h;
+            if (triangleClosest(rs, a, b, cc, &h)) {
+              found = true;
+              hb1 = __double2float_rn(h.b1); hb2 = __double2float_rn(h.b2); hprim = h.prim;
+            }
+          }
+        } else {
+          const GSphere& s = sc.spheres[kind >> 1];
+          double th, u, v;
+          if (ANY) {
+            if (sphereTest<QUAD == 2>(s, rs, true, &th, nullptr, nullptr)) { found = true; stop = true; }
+          } else if (sphereTest<QUAD == 2>(s, rs, false, &th, &u, &v)) {
+            found = true;
+            hb1 = __double2float_rn(u); hb2 = __double2float_rn(v); hprim = __float_as_int(a.w);
+            rs.maxt = th;
+          }
+        }
+      }
+      if (ANY) {
+        if (found) break;
+      } else if (rs.maxt != r.maxt) {
+        r.maxt = rs.maxt;
+        r.maxtLo = __double2float_rd(rs.maxt);
+        r.maxtHi = __double2float_ru(rs.maxt);
+      }
+    }
+    if (ANY) {
+      occluded[rayIdx] = found ? 1 : 0;
+    } else {
+      hits[rayIdx] = make_float4(found ? __double2float_rn(r.maxt) : CUDART_INF_F, hb1, hb2, __int_as_float(hprim));
+      if (ex.tOut) ex.tOut[rayIdx] = found ? r.maxt : CUDART_INF;
+    }
+  }
+}
+
+static cudaError_t launchSmall(const TraceScene& sc, bool any, const float4* o, const float4* d, uint32_t n, bool nUnknown, void* out,
+                               int numSMs, cudaStream_t stream, const TraceExtras& ex) {
+  typedef void (*KernelFn)(TraceScene, const float4*, const float4*, uint32_t, float4*, uint8_t*, TraceExtras);
+  static const KernelFn kKernels[6] = {traceSmallKernel<false, 0>, traceSmallKernel<false, 1>, traceSmallKernel<false, 2>,
+                                       traceSmallKernel<true, 0>,  traceSmallKernel<true, 1>,  traceSmallKernel<true, 2>};
+  const int variant = (any ? 3 : 0) + (sc.quadMode < 0 ? 0 : (sc.quadMode > 2 ? 2 : sc.quadMode));
+  const KernelFn kernel = kKernels[variant];
+  static int perSm[6] = {0, 0, 0, 0, 0, 0};
+  if (!perSm[variant]) {
+    int b = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, DRT_SMALL_BLOCK, 0);
+    if (e != cudaSuccess) return e;
+    perSm[variant] = b > 0 ? b : 1;
+  }
+  const uint64_t resident = (uint64_t)numSMs * perSm[variant];
+  const uint64_t wanted = nUnknown ? resident : ((uint64_t)n + DRT_SMALL_BLOCK - 1) / DRT_SMALL_BLOCK;
+  const uint64_t cap = resident * 8;  // a few waves of blocks: the tail of one wave overlaps the head of the next
+  dim3 grid((unsigned)(wanted < 1 ? 1 : (wanted < cap ? wanted : cap)));
+  if (nUnknown) grid.x = (unsigned)cap;
+  if (any) kernel<<<grid, DRT_SMALL_BLOCK, 0, stream>>>(sc, o, d, n, nullptr, (uint8_t*)out, ex);
+  else kernel<<<grid, DRT_SMALL_BLOCK, 0, stream>>>(sc, o, d, n, (float4*)out, nullptr, ex);
+  return cudaGetLastError();
+}
+
 static cudaError_t launchOne(const TraceScene& sc, bool any, const float4* o, const float4* d, uint32_t n, bool nUnknown, void* out,
                              unsigned long long* nextRay, int numSMs, cudaStream_t stream, const TraceExtras& ex) {
   cudaError_t e = cudaMemsetAsync(nextRay, 0, sizeof(unsigned long long), stream);
@@ -471,11 +620,25 @@ static cudaError_t launchOne(const TraceScene& sc, bool any, const float4* o, co
 
 cudaError_t launchTraceFast(const TraceScene& sc, bool any, const void* rayO, const void* rayD, uint64_t n, void* out,
                             unsigned long long* nextRay, int numSMs, cudaStream_t stream, const TraceExtras* extras) {
-  if (sc.wideQ) return launchTraceQ(sc, any, rayO, rayD, n, out, nextRay, numSMs, stream, extras);
+  if (sc.wideQ && !sc.small) return launchTraceQ(sc, any, rayO, rayD, n, out, nextRay, numSMs, stream, extras);
   TraceExtras ex{};
   if (extras) ex = *extras;
   const float4* o = static_cast<const float4*>(rayO);
   const float4* d = static_cast<const float4*>(rayD);
+  if (sc.small) {  // a handful of leaves: the leaf-list kernel
+    if (ex.nDev) return launchSmall(sc, any, o, d, 0, true, out, numSMs, stream, ex);
+    const uint64_t kMaxS = 1ull << 30;
+    for (uint64_t first = 0; first < n; first += kMaxS) {
+      const uint32_t m = (uint32_t)(n - first < kMaxS ? n - first : kMaxS);
+      TraceExtras e2 = ex;
+      if (e2.range) e2.range += first;
+      if (e2.tOut) e2.tOut += first;
+      void* o2 = any ? (void*)((uint8_t*)out + first) : (void*)((float4*)out + first);
+      cudaError_t e = launchSmall(sc, any, o + first, d + first, m, false, o2, numSMs, stream, e2);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
   if (ex.nDev) return launchOne(sc, any, o, d, 0, true, out, nextRay, numSMs, stream, ex);  // count lives on the device (< 2^31)
   const uint64_t kMax = 1ull << 30;  // rays per launch: 32-bit ray indices inside the kernel
   for (uint64_t first = 0; first < n; first += kMax) {
