@@ -82,6 +82,8 @@ typedef _SetSamplerC = Int32 Function(_Ctx, Int32, Int32, Int32, Int32, Int32, I
 typedef _SetSamplerD = int Function(_Ctx, int, int, int, int, int, int, int, int);
 typedef _SetIntegratorC = Int32 Function(_Ctx, Int32, Int32, Int32, Int32, Double, Double);
 typedef _SetIntegratorD = int Function(_Ctx, int, int, int, int, double, double);
+typedef _SetPrecisionC = Int32 Function(_Ctx, Int32);
+typedef _SetPrecisionD = int Function(_Ctx, int);
 typedef _RenderC = Int32 Function(_Ctx, Int32, Int32);
 typedef _RenderD = int Function(_Ctx, int, int);
 typedef _FilmReadC = Int32 Function(_Ctx, _PF, _PF, _PF);
@@ -184,6 +186,10 @@ class Drt {
       check(lib.lookupFunction<_SetSamplerC, _SetSamplerD>('drt_set_sampler')(ctx, kind, xs, ys, spp, jitter, pixelOrder, tileSize, seed));
   void setIntegrator(int kind, int maxDepth, int strategy, int aoSamples, double aoMin, double aoMax) =>
       check(lib.lookupFunction<_SetIntegratorC, _SetIntegratorD>('drt_set_integrator')(ctx, kind, maxDepth, strategy, aoSamples, aoMin, aoMax));
+  /// drt_set_shading_precision: 0 = DRT_PRECISION_F64 (the Dart VM's arithmetic, the default), 1 = DRT_PRECISION_F32 (path integrator
+  /// only; per-pixel means within 3 sigma).
+  void setShadingPrecision(int precision) =>
+      check(lib.lookupFunction<_SetPrecisionC, _SetPrecisionD>('drt_set_shading_precision')(ctx, precision));
   void render(int taskNum, int taskCount) => check(lib.lookupFunction<_RenderC, _RenderD>('drt_render')(ctx, taskNum, taskCount));
   void filmSize(_PI out4) => check(lib.lookupFunction<_FilmSizeC, _FilmSizeD>('drt_film_size')(ctx, out4));
   void filmRead(_PF rgb, _PF xyz, _PF weight) => check(lib.lookupFunction<_FilmReadC, _FilmReadD>('drt_film_read')(ctx, rgb, xyz, weight));

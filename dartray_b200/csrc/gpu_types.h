@@ -113,7 +113,7 @@ struct alignas(16) GSphere {
 // the leaves in an order that depends on the ray's dirIsNeg octant only (bvh_accel.dart:147-153), tests a leaf's primitives iff the
 // leaf's own box test passes at that moment, and every interior test is implied by a leaf's (trace_fast.cu, argument (1)).  So the
 // small-scene kernel (traceSmallKernel, trace_fast.cu) walks the octant's leaf list and decides every leaf box exactly.
-#define DRT_SMALL_MAX_LEAVES 64
+#define DRT_SMALL_MAX_LEAVES 32
 struct alignas(16) GSmallLeaf {
   float lo[3];
   int32_t ref;   // the leaf reference (offset / count of its GPrim records)

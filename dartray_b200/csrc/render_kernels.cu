@@ -149,13 +149,39 @@ __global__ void __launch_bounds__(128) samplerLDKernel(RenderParams rp, Wavefron
 // is counter-based), one lane per group applies the swaps to a 16-bit permutation in shared memory (the only
 // order-dependent part: four shared-memory accesses per step), then the whole warp evaluates VanDerCorput / Sobol2 at
 // the permuted indices and stores full lines.  Shared memory per task: 4 bytes per pixel sample.
+// Bit-identical short forms of montecarlo.dart:486-504 for this kernel: the (0,2)-sequence values are k * 2^-24 with k < 2^24, exact in
+// float32 (the reference's min with OneMinusEpsilon = 1 - 2^-24 never binds), VanDerCorput's five swap steps are one bit reversal,
+// and Sobol2's direction numbers XOR linearly, so two 256-entry tables (sobolLo / sobolHi, built per block) replace its loop.
+static __device__ __forceinline__ float vdcValue(uint32_t n, uint32_t scramble) {
+  return (float)((__brev(n) ^ scramble) >> 8) * 5.9604644775390625e-8f;
+}
+static __device__ __forceinline__ uint32_t sobolBits(uint32_t n) {  // Sobol2's XOR of direction numbers for the set bits of n
+  uint32_t s = 0u;
+  for (uint32_t v = 1u << 31; n != 0; n >>= 1, v ^= v >> 1)
+    if (n & 0x1) s ^= v;
+  return s;
+}
+// PT: the type of a permutation entry — uint8_t when nPixelSamples <= 256 (half the shared memory per task, so twice the tasks per
+// block run the order-dependent swaps at once), uint16_t otherwise.
+template <typename PT>
 __global__ void __launch_bounds__(128) samplerLDPermKernel(RenderParams rp, Wavefront wf, const SampleArray* __restrict__ arrays,
                                                            int nArrays, PixelBatch pb, int G, int strideWords) {
   extern __shared__ float smem[];
+  __shared__ uint32_t sobolLo[256], sobolHi[256];
+  // x % d for the swap targets, d = nP - i: Lemire's exact remainder with M = floor((2^64 - 1) / d) + 1 (d = 1: M wraps to 0 and
+  // the remainder is 0), tabulated per block when nP <= 256
+  __shared__ unsigned long long modM[256];
   const uint32_t groupsPerBlock = blockDim.x / G, grp = threadIdx.x / G, gl = threadIdx.x % G;
   const uint32_t nP = (uint32_t)rp.nPixelSamples;
-  uint16_t* tgt = reinterpret_cast<uint16_t*>(smem + (size_t)grp * strideWords);
-  uint16_t* perm = tgt + nP;
+  const bool fastMod = nP <= 256u;
+  for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) {
+    sobolLo[i] = sobolBits(i);
+    sobolHi[i] = sobolBits(i << 8);
+    modM[i] = (fastMod && i < nP) ? (~0ull / (unsigned long long)(nP - i) + 1ull) : 0ull;
+  }
+  __syncthreads();
+  PT* tgt = reinterpret_cast<PT*>(smem + (size_t)grp * strideWords);
+  PT* perm = tgt + nP;
   const uint64_t nTasks = (uint64_t)pb.nPixels * nArrays;
   const uint32_t lane = threadIdx.x & 31u, groupsPerWarp = 32u / (uint32_t)G;
   for (uint64_t t0 = (uint64_t)blockIdx.x * groupsPerBlock; t0 < nTasks; t0 += (uint64_t)gridDim.x * groupsPerBlock) {
@@ -172,14 +198,18 @@ __global__ void __launch_bounds__(128) samplerLDPermKernel(RenderParams rp, Wave
     const uint64_t base = (uint64_t)dims + nP;
     if (valid)
       for (uint32_t i = gl; i < nP; i += G) {
-        tgt[i] = (uint16_t)(i + drawUint(key, base + i + 1) % (nP - i));
-        perm[i] = (uint16_t)i;
+        const uint32_t u = drawUint(key, base + i + 1);
+        uint32_t rem;
+        if (fastMod) rem = (uint32_t)__umul64hi(modM[i] * (unsigned long long)u, (unsigned long long)(nP - i));
+        else rem = u % (nP - i);
+        tgt[i] = (PT)(i + rem);
+        perm[i] = (PT)i;
       }
     __syncwarp();
     if (gl == 0 && valid)
       for (uint32_t i = 0; i < nP; ++i) {  // Shuffle (montecarlo.dart:294-303) on the indices
         const uint32_t o = tgt[i];
-        const uint16_t a = perm[i];
+        const PT a = perm[i];
         perm[i] = perm[o];
         perm[o] = a;
       }
@@ -193,11 +223,11 @@ __global__ void __launch_bounds__(128) samplerLDPermKernel(RenderParams rp, Wave
       const uint32_t s0_ = __shfl_sync(FULL, s0, src), s1_ = __shfl_sync(FULL, s1, src);
       const int x_ = __shfl_sync(FULL, x, src), y_ = __shfl_sync(FULL, y, src);
       if (!v_) continue;
-      const uint16_t* pm = reinterpret_cast<const uint16_t*>(smem + (size_t)((threadIdx.x >> 5) * groupsPerWarp + gi) * strideWords) + nP;
+      const PT* pm = reinterpret_cast<const PT*>(smem + (size_t)((threadIdx.x >> 5) * groupsPerWarp + gi) * strideWords) + nP;
       for (uint32_t i = lane; i < nP; i += 32u) {
         const uint32_t e = pm[i];
-        const float v0 = (float)VanDerCorput(e, s0_);
-        const float v1 = dims_ == 2 ? (float)Sobol2(e, s1_) : 0.f;
+        const float v0 = vdcValue(e, s0_);
+        const float v1 = dims_ == 2 ? (float)((s1_ ^ sobolLo[e & 255u] ^ sobolHi[(e >> 8) & 255u]) >> 8) * 5.9604644775390625e-8f : 0.f;
         if (dest_ >= 0) {
           wf.vals[(size_t)dest_ * wf.cap + slot0_ + i] = v0;
           if (dims_ == 2) wf.vals[(size_t)(dest_ + 1) * wf.cap + slot0_ + i] = v1;
@@ -1438,15 +1468,19 @@ cudaError_t launchSampler(const RenderParams& rp, const Wavefront& wf, const Sam
                                                                                       // its integrator arrays (one pixel sample)
   if (ld && rp.ldAllSingle && rp.nPixelSamples <= 2048) {
     const int block = 128;
-    const int strideWords = rp.nPixelSamples | 1;  // two 16-bit arrays of nPixelSamples entries; odd word stride
+    const bool bytes = rp.nPixelSamples <= 256;  // permutation entries of 8 bits: half the shared memory per task
+    // two arrays of nPixelSamples entries of 16 (8) bits; odd word stride
+    const int strideWords = (bytes ? (rp.nPixelSamples + 1) / 2 : rp.nPixelSamples) | 1;
     const size_t taskBytes = (size_t)strideWords * sizeof(float);
-    int tasksPerBlock = (int)std::min<size_t>(block, std::max<size_t>(4, (48 * 1024) / taskBytes));
+    const size_t budget = 48 * 1024 - 4 * 1024;  // the kernel's own tables (Sobol, remainders) take 4 KB of the static 48 KB
+    int tasksPerBlock = (int)std::min<size_t>(block, std::max<size_t>(4, budget / taskBytes));
     int G = 1;
     while (block / G > tasksPerBlock) G <<= 1;
     const size_t smem = (size_t)(block / G) * taskBytes;
     uint64_t tasks = (uint64_t)pb.nPixels * nArrays;
     int grid = gridFor(tasks * G, block, numSMs, 16);
-    samplerLDPermKernel<<<grid, block, smem, st>>>(rp, wf, dArrays, nArrays, pb, G, strideWords);
+    if (bytes) samplerLDPermKernel<uint8_t><<<grid, block, smem, st>>>(rp, wf, dArrays, nArrays, pb, G, strideWords);
+    else samplerLDPermKernel<uint16_t><<<grid, block, smem, st>>>(rp, wf, dArrays, nArrays, pb, G, strideWords);
   } else if (ld) {
     const int block = 128;
     // lanes per (pixel, array) task: as few as shared memory allows (48 KB of arrays per block), because the

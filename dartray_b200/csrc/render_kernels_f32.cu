@@ -9,5 +9,8 @@
 #define DRT_REAL32 1
 // CTAs of 128 threads per SM the path-vertex kernel is compiled for.  Measured on B200 (config 4, profiles/r02z_f32_ab.log):
 // 4 (128 registers) 0.6647 s, 5 (96) 0.6899 s, 6 (80) 0.7036 s, 8 (64 registers) 0.6599 s; the binary64 kernel: 0.9709 s
-#define DRT_SHADE_MIN_BLOCKS 8
+#ifndef DRT_SHADE_MIN_BLOCKS_F32
+#define DRT_SHADE_MIN_BLOCKS_F32 8
+#endif
+#define DRT_SHADE_MIN_BLOCKS DRT_SHADE_MIN_BLOCKS_F32
 #include "_gen/render_kernels_f32.inc"

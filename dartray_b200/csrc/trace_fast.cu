@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
 // leaves, which depends on the ray's dirIsNeg octant only (bvh_accel.dart:147-153) and is tabulated by the host (GSmallScene::order),
 // and (b) each leaf's own box decision at the moment it is reached, every interior test being implied by it.  One thread per ray:
 //   pass 1  the float32 filter of every leaf box, the leaves read in storage order (one shared-memory broadcast per leaf for the whole
-//           warp, no divergence); survivors are marked in a 64-bit mask at their POSITION in the octant's visiting order;
+//           warp, no divergence); survivors are marked in a 32-bit mask at their POSITION in the octant's visiting order;
 //   pass 2  the marked leaves in that order: the filter again with the ray's maxDistance of this moment, the reference's binary64 slab
 //           test where the filter cannot prove the decision, then the reference's primitive tests (trace_device.cuh).
 // A leaf dropped in pass 1 fails the reference's test at any later moment too (maxDistance only shrinks), so the two passes test the
@@ -458,6 +458,9 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
 #endif
 #ifndef DRT_SMALL_MIN_BLOCKS
 #define DRT_SMALL_MIN_BLOCKS 3
+#endif
+#ifndef DRT_SMALL_QUAD_BATCH
+#define DRT_SMALL_QUAD_BATCH 8  // lanes waiting at a quadric before the warp runs the quadric test
 #endif
 template <bool ANY, int QUAD>
 __global__ void __launch_bounds__(DRT_SMALL_BLOCK, DRT_SMALL_MIN_BLOCKS)
@@ -472,13 +475,17 @@ __global__ void __launch_bounds__(DRT_SMALL_BLOCK, DRT_SMALL_MIN_BLOCKS)
   __syncthreads();
   if (ex.nDev) n = *ex.nDev;
   const int nLeaves = sm.nLeaves;
-  for (uint32_t rayIdx = blockIdx.x * blockDim.x + threadIdx.x; rayIdx < n; rayIdx += gridDim.x * blockDim.x) {
-    const float4 o = __ldg(rayO + rayIdx), d = __ldg(rayD + rayIdx);
+  // the loop runs the same number of trips for every lane of a warp (a lane beyond n idles): the leaf loop below votes
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const uint32_t rayIdx = base + threadIdx.x;
+    const bool valid = rayIdx < n;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(1.f, 1.f, 1.f, 0.f);
+    if (valid) { o = __ldg(rayO + rayIdx); d = __ldg(rayD + rayIdx); }
     const float ix = __frcp_rn(d.x), iy = __frcp_rn(d.y), iz = __frcp_rn(d.z);  // invDir, see traceFastKernel
     FastRay r;
     r.ox2 = pack2(o.x, o.x); r.oy2 = pack2(o.y, o.y); r.oz2 = pack2(o.z, o.z);
     r.ix2 = pack2(ix, ix); r.iy2 = pack2(iy, iy); r.iz2 = pack2(iz, iz);
-    if (ex.range) {
+    if (valid && ex.range) {
       const double2 mm = __ldg(ex.range + rayIdx);
       r.mint = mm.x; r.mintLo = __double2float_rd(mm.x); r.mintHi = __double2float_ru(mm.x);
       r.maxt = mm.y; r.maxtLo = __double2float_rd(mm.y); r.maxtHi = __double2float_ru(mm.y);
@@ -490,15 +497,18 @@ __global__ void __launch_bounds__(DRT_SMALL_BLOCK, DRT_SMALL_MIN_BLOCKS)
                       !(fabsf(ix) <= 3.0e38f) || !(fabsf(iy) <= 3.0e38f) || !(fabsf(iz) <= 3.0e38f);
     const unsigned oct = ANY ? 0u : ((ix < 0.f ? 1u : 0u) | (iy < 0.f ? 2u : 0u) | (iz < 0.f ? 4u : 0u));
     r.negMask = oct;
-    unsigned long long mask = 0ull;
-    if (slow || sc.empty) {
-      mask = sc.empty ? 0ull : (nLeaves >= 64 ? ~0ull : ((1ull << nLeaves) - 1ull));
+    // ---- pass 1: which leaves can the reference enter at all (storage order: one broadcast per leaf) --------------------
+    unsigned mask = 0u;
+    if (!valid || sc.empty) {
+      mask = 0u;
+    } else if (slow) {
+      mask = nLeaves >= 32 ? 0xffffffffu : ((1u << nLeaves) - 1u);
     } else {
       for (int l = 0; l < nLeaves; ++l) {
         const GSmallLeaf& L = sm.leaf[l];
         float tm;
         const int c = slabFilter(r, pack2(L.lo[0], L.hi[0]), pack2(L.lo[1], L.hi[1]), pack2(L.lo[2], L.hi[2]), &tm);
-        if (c) mask |= 1ull << sm.position[oct][l];
+        if (c) mask |= 1u << sm.position[oct][l];
       }
     }
     RayState rs;
@@ -508,28 +518,45 @@ __global__ void __launch_bounds__(DRT_SMALL_BLOCK, DRT_SMALL_MIN_BLOCKS)
     bool found = false;
     float hb1 = 0.f, hb2 = 0.f;
     int hprim = -1;
-    while (mask) {
-      const int j = __ffsll((long long)mask) - 1;
-      mask &= mask - 1ull;
-      const GSmallLeaf& L = sm.leaf[sm.order[oct][j]];
-      const float lo0 = L.lo[0], lo1 = L.lo[1], lo2 = L.lo[2], hi0 = L.hi[0], hi1 = L.hi[1], hi2 = L.hi[2];
-      const int32_t ref = L.ref;
-      int c = 2;
-      float tm;
-      if (!slow) c = slabFilter(r, pack2(lo0, hi0), pack2(lo1, hi1), pack2(lo2, hi2), &tm);
-      if (c == 0) continue;
-      if (c == 2 && !slabExact(o.x, o.y, o.z, ix, iy, iz, r.mint, r.maxt, lo0, lo1, lo2, hi0, hi1, hi2, &tm)) continue;
-      const uint32_t off = refLeafOffset(ref);
-      uint32_t cnt = refLeafCountField(ref);
-      const GPrim* pr = sc.prims + off;
-      if (cnt == 15u) cnt = (uint32_t)__ldg(&pr->leafCount);
-      bool stop = false;
-      for (uint32_t k = 0; k < cnt && !stop; ++k) {
+    // ---- pass 2: the marked leaves in the octant's order.  Every trip of the warp-uniform loop first gives each lane that has
+    //      finished its leaf the next one it may enter (filter with the maxDistance of this moment, binary64 where undecided), then
+    //      tests ONE primitive per lane, so that the long binary64 primitive tests run with as many lanes as have work ------------
+    const GPrim* pr = sc.prims;
+    uint32_t k = 0, cnt = 0;
+    for (;;) {
+      if (k >= cnt && !(ANY && found)) {
+        while (mask) {
+          const int j = __ffs((int)mask) - 1;
+          mask &= mask - 1u;
+          const GSmallLeaf& L = sm.leaf[sm.order[oct][j]];
+          const float lo0 = L.lo[0], lo1 = L.lo[1], lo2 = L.lo[2], hi0 = L.hi[0], hi1 = L.hi[1], hi2 = L.hi[2];
+          const int32_t ref = L.ref;
+          int c = 2;
+          float tm;
+          if (!slow) c = slabFilter(r, pack2(lo0, hi0), pack2(lo1, hi1), pack2(lo2, hi2), &tm);
+          if (c == 0) continue;
+          if (c == 2 && !slabExact(o.x, o.y, o.z, ix, iy, iz, r.mint, r.maxt, lo0, lo1, lo2, hi0, hi1, hi2, &tm)) continue;
+          pr = sc.prims + refLeafOffset(ref);
+          cnt = refLeafCountField(ref);
+          if (cnt == 15u) cnt = (uint32_t)__ldg(&pr->leafCount);
+          k = 0;
+          break;
+        }
+      }
+      __syncwarp();
+      const bool work = k < cnt && !(ANY && found);
+      if (!__any_sync(FULL_MASK, work)) break;
+      // triangles at once; a lane whose next primitive is a quadric (a long, rarely taken path: a handful of lanes per warp reach
+      // the sphere's leaf in a given trip) waits until DRT_SMALL_QUAD_BATCH lanes do, or nobody has a triangle left to test
+      bool atQuad = false;
+      int quadIdx = 0, quadPrim = 0;
+      if (work) {
         const float4 a = ldg4(&pr[k].p1[0]), b = ldg4(&pr[k].p2[0]), cc = ldg4(&pr[k].p3[0]);
         const int kind = __float_as_int(cc.w);
         if (QUAD == 0 || (kind & 1) == 0) {
+          ++k;
           if (ANY) {
-            if (triangleAny(rs, a, b, cc)) { found = true; stop = true; }
+            if (triangleAny(rs, a, b, cc)) found = true;
           } else {
             HitState h;
             if (triangleClosest(rs, a, b, cc, &h)) {
@@ -538,30 +565,39 @@ __global__ void __launch_bounds__(DRT_SMALL_BLOCK, DRT_SMALL_MIN_BLOCKS)
             }
           }
         } else {
-          const GSphere& s = sc.spheres[kind >> 1];
+          atQuad = true;
+          quadIdx = kind >> 1;
+          quadPrim = __float_as_int(a.w);
+        }
+      }
+      if (QUAD != 0) {
+        const unsigned qb = __ballot_sync(FULL_MASK, atQuad), tb = __ballot_sync(FULL_MASK, work && !atQuad);
+        if (atQuad && (__popc(qb) >= DRT_SMALL_QUAD_BATCH || tb == 0u)) {
+          ++k;
+          const GSphere& s = sc.spheres[quadIdx];
           double th, u, v;
           if (ANY) {
-            if (sphereTest<QUAD == 2>(s, rs, true, &th, nullptr, nullptr)) { found = true; stop = true; }
+            if (sphereTest<QUAD == 2>(s, rs, true, &th, nullptr, nullptr)) found = true;
           } else if (sphereTest<QUAD == 2>(s, rs, false, &th, &u, &v)) {
             found = true;
-            hb1 = __double2float_rn(u); hb2 = __double2float_rn(v); hprim = __float_as_int(a.w);
+            hb1 = __double2float_rn(u); hb2 = __double2float_rn(v); hprim = quadPrim;
             rs.maxt = th;
           }
         }
       }
-      if (ANY) {
-        if (found) break;
-      } else if (rs.maxt != r.maxt) {
+      if (!ANY && rs.maxt != r.maxt) {
         r.maxt = rs.maxt;
         r.maxtLo = __double2float_rd(rs.maxt);
         r.maxtHi = __double2float_ru(rs.maxt);
       }
     }
-    if (ANY) {
-      occluded[rayIdx] = found ? 1 : 0;
-    } else {
-      hits[rayIdx] = make_float4(found ? __double2float_rn(r.maxt) : CUDART_INF_F, hb1, hb2, __int_as_float(hprim));
-      if (ex.tOut) ex.tOut[rayIdx] = found ? r.maxt : CUDART_INF;
+    if (valid) {
+      if (ANY) {
+        occluded[rayIdx] = found ? 1 : 0;
+      } else {
+        hits[rayIdx] = make_float4(found ? __double2float_rn(r.maxt) : CUDART_INF_F, hb1, hb2, __int_as_float(hprim));
+        if (ex.tOut) ex.tOut[rayIdx] = found ? r.maxt : CUDART_INF;
+      }
     }
   }
 }
