@@ -861,6 +861,7 @@ static int traceQueue(drt_ctx* c, bool any, const float4* o, const float4* d, co
   ex.nDev = nDev;
   ex.range = range;
   ex.tOut = tOut;
+  ex.noUV = 1;  // the shading stages read the primitive and tHit only
   CK(c, launchTraceFast(c->ts, any, o, d, 0, out, c->dNextRay.p, c->numSMs, st, &ex));
   c->launches++;
   profMark(c, any ? DRT_PK_TRACE_ANY : DRT_PK_TRACE_CLOSEST);

@@ -217,8 +217,13 @@ static __device__ bool sphereTest(const GSphere& s, const RayState& r, bool shad
     double px = rf(ox + rf(dx * thit)), py = rf(oy + rf(dy * thit));
     double dist2 = px * px + py * py;
     if (dist2 > s.radius * s.radius || dist2 < s.innerRadius * s.innerRadius) return false;
-    double phi = atan2(py, px);
-    if (phi < 0) phi += 2.0 * 3.141592653589793;
+    // phi <= fl(2 pi) whatever the hit point (atan2 >= -pi; a negative value gets 2.0 * pi added): with phiMax at its full-circle
+    // value the cut below never fires, and a caller that does not ask for (u, v) needs no atan2 at all
+    double phi = 0.0;
+    if (uOut || !(s.phiMax >= 6.283185307179586)) {
+      phi = atan2(py, px);
+      if (phi < 0) phi += 2.0 * 3.141592653589793;
+    }
     if (phi > s.phiMax) return false;
     *thitOut = thit;
     if (uOut) {
@@ -256,16 +261,22 @@ static __device__ bool sphereTest(const GSphere& s, const RayState& r, bool shad
   // ray.pointAt: origin + (direction * t), two float32 roundings (ray.dart:70-71)
   double px = rf(ox + rf(dx * thit)), py = rf(oy + rf(dy * thit)), pz = rf(oz + rf(dz * thit));
   if (px == 0.0 && py == 0.0) px = rf(1.0e-5 * s.radius);
-  double phi = atan2(py, px);
-  if (phi < 0.0) phi += 2.0 * 3.141592653589793;
+  const bool needPhi = uOut || !(s.phiMax >= 6.283185307179586);  // see the disk above
+  double phi = 0.0;
+  if (needPhi) {
+    phi = atan2(py, px);
+    if (phi < 0.0) phi += 2.0 * 3.141592653589793;
+  }
   if ((s.zmin > -s.radius && pz < s.zmin) || (s.zmax < s.radius && pz > s.zmax) || phi > s.phiMax) {
     if (!shadow && thit == t1) return false;
     if (t1 > r.maxt) return false;
     thit = t1;
     px = rf(ox + rf(dx * thit)); py = rf(oy + rf(dy * thit)); pz = rf(oz + rf(dz * thit));
     if (px == 0.0 && py == 0.0) px = rf(1.0e-5 * s.radius);
-    phi = atan2(py, px);
-    if (phi < 0.0) phi += 2.0 * 3.141592653589793;
+    if (needPhi) {
+      phi = atan2(py, px);
+      if (phi < 0.0) phi += 2.0 * 3.141592653589793;
+    }
     if ((s.zmin > -s.radius && pz < s.zmin) || (s.zmax < s.radius && pz > s.zmax) || phi > s.phiMax) return false;
   }
   *thitOut = thit;

@@ -414,9 +414,9 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
             double th, u, v;
             if (ANY) {
               if (sphereTest<QUAD == 2>(s, rs, true, &th, nullptr, nullptr)) { found = true; stop = true; }
-            } else if (sphereTest<QUAD == 2>(s, rs, false, &th, &u, &v)) {
+            } else if (sphereTest<QUAD == 2>(s, rs, false, &th, ex.noUV ? nullptr : &u, &v)) {
               found = true;
-              hb1 = __double2float_rn(u); hb2 = __double2float_rn(v); hprim = __float_as_int(a.w);
+              hb1 = ex.noUV ? 0.f : __double2float_rn(u); hb2 = ex.noUV ? 0.f : __double2float_rn(v); hprim = __float_as_int(a.w);
               rs.maxt = th;
             }
           }
@@ -457,10 +457,11 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
 #define DRT_SMALL_BLOCK 256
 #endif
 #ifndef DRT_SMALL_MIN_BLOCKS
-#define DRT_SMALL_MIN_BLOCKS 3
+#define DRT_SMALL_MIN_BLOCKS 4  // 64 registers.  Config 4 on B200 (profiles/r02z5_variants_ab.log): 3 (80 registers) 0.5648 s, 4 0.5552 s
 #endif
 #ifndef DRT_SMALL_QUAD_BATCH
-#define DRT_SMALL_QUAD_BATCH 8  // lanes waiting at a quadric before the warp runs the quadric test
+#define DRT_SMALL_QUAD_BATCH 1  // lanes waiting at a quadric before the warp runs the quadric test.  Measured (same log): 1 (no
+                                // waiting) 0.5478 s, 8 0.5648 s, 16 0.5645 s — the waiting lanes' extra trips cost more than the fuller test
 #endif
 template <bool ANY, int QUAD>
 __global__ void __launch_bounds__(DRT_SMALL_BLOCK, DRT_SMALL_MIN_BLOCKS)
@@ -578,9 +579,9 @@ __global__ void __launch_bounds__(DRT_SMALL_BLOCK, DRT_SMALL_MIN_BLOCKS)
           double th, u, v;
           if (ANY) {
             if (sphereTest<QUAD == 2>(s, rs, true, &th, nullptr, nullptr)) found = true;
-          } else if (sphereTest<QUAD == 2>(s, rs, false, &th, &u, &v)) {
+          } else if (sphereTest<QUAD == 2>(s, rs, false, &th, ex.noUV ? nullptr : &u, &v)) {
             found = true;
-            hb1 = __double2float_rn(u); hb2 = __double2float_rn(v); hprim = quadPrim;
+            hb1 = ex.noUV ? 0.f : __double2float_rn(u); hb2 = ex.noUV ? 0.f : __double2float_rn(v); hprim = quadPrim;
             rs.maxt = th;
           }
         }

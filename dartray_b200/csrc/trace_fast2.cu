@@ -438,8 +438,8 @@ __global__ void __launch_bounds__(DRT_Q_BLOCK, DRT_Q_MIN_BLOCKS)
                 double th, u, v;
                 if (ANY) {
                   if (sphereTest<QUAD == 2>(s, rs, true, &th, nullptr, nullptr)) { found = true; stop = true; }
-                } else if (sphereTest<QUAD == 2>(s, rs, false, &th, &u, &v)) {
-                  COLD_ST(6, __float_as_uint(__double2float_rn(u))); COLD_ST(7, __float_as_uint(__double2float_rn(v)));
+                } else if (sphereTest<QUAD == 2>(s, rs, false, &th, ex.noUV ? nullptr : &u, &v)) {
+                  COLD_ST(6, ex.noUV ? 0u : __float_as_uint(__double2float_rn(u))); COLD_ST(7, ex.noUV ? 0u : __float_as_uint(__double2float_rn(v)));
                   COLD_ST(8, (uint32_t)__float_as_int(a.w));
                   rs.maxt = th;
                 }

@@ -32,6 +32,8 @@ struct TraceExtras {
   const uint32_t* nDev = nullptr;  // ray count in device memory (overrides n)
   const double2* range = nullptr;  // per ray (minDistance, maxDistance) in f64 instead of the float4 .w lanes
   double* tOut = nullptr;          // closest hit: tHit in f64 (+inf on a miss)
+  int32_t noUV = 0;                // closest hit: the caller reads only t and the primitive (the renderer rebuilds the hit geometry
+                                   // from t): a quadric's (u, v) — an atan2 and an acos in binary64 — are not computed, b1 = b2 = 0
 };
 
 // Production path: persistent warps, while-while traversal, float32-filtered slab test with exact
