@@ -71,7 +71,8 @@ struct RenderState {
   int volIntegrator = 0;
   double volStep = 1.0;
   // drt_set_shading_precision: DRT_PRECISION_F32 runs the path integrator's vertex / resolve kernels from the float32 build
-  // (render_kernels_f32.cu) on scenes that build serves: matte materials, no per-vertex attributes, no media, no texture programs
+  // (render_kernels_f32.cu) on scenes that build serves: no per-vertex attributes or rarer quadrics, no FresnelBlend lobe, no media, no
+  // texture programs
   int shadingPrecision = 0;
   std::vector<float> volV2W;     // n x 16: volumeToWorld, for the regions' world bound
   uint32_t volMaxSteps = 0;      // single scattering: bound on a camera ray's march steps (regions' bound diagonal / stepsize)
@@ -1079,7 +1080,7 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
     // binary64 traversal — only the arithmetic of the vertex and resolve kernels changes
     static const char* f32Env = std::getenv("DRT_SHADE_F32");
     const bool wantF32 = f32Env ? f32Env[0] == '1' : r->shadingPrecision == DRT_PRECISION_F32;
-    const bool f32 = wantF32 && !rs.extra && !rs.general && rs.nVolumes == 0 && rs.nPrograms == 0;
+    const bool f32 = wantF32 && !rs.extra && rs.nVolumes == 0 && rs.nPrograms == 0;
     for (int bounce = 0; bounce <= p.maxDepth; ++bounce) {
       CK(c, STAGE(launchResetCounts)(wf, (1u << (cur ^ 1)) | (1u << Q_SHADOW) | (1u << Q_MIS), st)); profMark(c, DRT_PK_OTHER);
       if (rs.nPrograms > 0) {  // only the camera ray carries differentials: the later rays are RayDifferential.child (path_integrator.dart:100)

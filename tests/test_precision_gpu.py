@@ -140,3 +140,43 @@ def test_f32_path_config4_1080p_256spp_within_3_sigma_of_the_binary64_film_and_o
     zw = np.abs(aw - bo)[litw] / sw[litw]
     print(f"f32 path vs oracle on a 240x135 window of the 1080p film: max |d| / sigma {zw.max():.3e}")
     assert zw.max() <= 3.0
+
+
+def test_f32_path_on_bxdf_list_materials_within_3_sigma_of_the_oracle():
+    """cornell_materials (plastic, OrenNayar matte, metal, uber, glass: BxDF lists with specular bounces), 160x90, lowdiscrepancy 64 spp:
+    the float32 kernels against the oracle.  A specular choice that flips at a float32 rounding replaces one sample's radiance by
+    another valid sample's, so the bound is the Monte Carlo one, with sigma from two independent 32-spp oracle renders."""
+    sb, cam = scenes.cornell_materials()
+    arrays = sb.arrays()
+    g, o = capi.Context(0), Oracle()
+    for c in (g, o):
+        host.upload_scene(c, arrays)
+    film = host.Film(160, 90)
+    smp = host.Sampler(kind=host.SAMPLER_LD, spp=64)
+    integ = host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=5)
+    f32, s32 = _render(g, cam, film, smp, integ, capi.PRECISION_F32)
+    f64, s64 = _render(g, cam, film, smp, integ, capi.PRECISION_F64)
+    host.configure_render(o, cam, film, smp, integ)
+    o.film_clear()
+    o.render(0, 1, NT)
+    fo, so = o.film_read(), o.render_stats()
+    assert np.isfinite(f32["rgb"]).all()
+    assert not np.array_equal(f32["rgb"], f64["rgb"])
+    halves = []
+    for seed in (1, 2):
+        host.configure_render(o, cam, film, host.Sampler(kind=host.SAMPLER_LD, spp=32, seed=seed), integ)
+        o.film_clear()
+        o.render(0, 1, NT)
+        halves.append(_lum(o.film_read()["rgb"]))
+    sigma = np.sqrt(_smooth(((halves[0] - halves[1]) ** 2) / 4.0))
+    a, b = _lum(f32["rgb"]), _lum(fo["rgb"])
+    lit = sigma > 1e-4 * b.mean()
+    z = np.abs(a - b)[lit] / sigma[lit]
+    rel = np.abs(f32["rgb"].astype(np.float64) - fo["rgb"]) / np.maximum(np.abs(fo["rgb"]), 1e-3)
+    print(f"f32 path vs oracle, cornell_materials 160x90 x 64 spp: max |d| / sigma {z.max():.3e}, pixels above 1 sigma {int((z > 1).sum())}, "
+          f"max rel err {rel.max():.3e}, 99.9 % rel err {np.quantile(rel, 0.999):.3e}, mean f32 {a.mean():.6f} oracle {b.mean():.6f}")
+    assert z.max() <= 3.0
+    assert abs(a.mean() - b.mean()) <= 5e-3 * b.mean()
+    assert s32["camera_samples"] == so["camera_samples"]
+    for k in ("closest_rays", "shadow_rays"):
+        assert abs(int(s32[k]) - int(so[k])) <= 1e-3 * so[k], (k, s32[k], so[k])
