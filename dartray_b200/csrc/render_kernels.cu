@@ -495,13 +495,17 @@ static __device__ __forceinline__ void pushDirectWork(const Wavefront& wf, uint3
   if (wantSh) {
     wf.shO[si] = make_float4(w.shO.x, w.shO.y, w.shO.z, rayLaneW(wf, slot, (float)w.shMin));
     wf.shD[si] = make_float4(w.shD.x, w.shD.y, w.shD.z, (float)w.shMax);
+#if !DRT_REAL32  // the float32 build's intervals ARE float32 values: they travel in the .w lanes of the ray records alone
     wf.shRange[si] = make_double2(w.shMin, w.shMax);
+#endif
     st3(wf.pendSh, cap, slot, w.shContribution);
   }
   if (wantMis) {
     wf.misO[mi] = make_float4(p.x, p.y, p.z, rayLaneW(wf, slot, (float)rayEps));
     wf.misD[mi] = make_float4(w.misD.x, w.misD.y, w.misD.z, CUDART_INF_F);
+#if !DRT_REAL32  // the float32 build's intervals ARE float32 values: they travel in the .w lanes of the ray records alone
     wf.misRange[mi] = make_double2(rayEps, CUDART_INF);
+#endif
     st3(wf.pendMisF, cap, slot, w.misF);
     wf.pendMisScale[slot] = w.misScale;
     wf.misLight[slot] = lightNum;
@@ -718,7 +722,9 @@ __global__ void __launch_bounds__(128, PART == 0 ? DRT_SHADE_MIN_BLOCKS : DRT_SH
     if (cont) {
       wf.extO[nxt][ei] = make_float4(p.x, p.y, p.z, rayLaneW(wf, slot, (float)rayEps));
       wf.extD[nxt][ei] = make_float4(wi.x, wi.y, wi.z, CUDART_INF_F);
+#if !DRT_REAL32  // the float32 build's intervals ARE float32 values: they travel in the .w lanes of the ray records alone
       wf.extRange[nxt][ei] = make_double2(rayEps, CUDART_INF);
+#endif
       wf.extSlot[nxt][ei] = slot;
     }
     nShadow += (valid && dw.hasShadow) ? 1 : 0;
