@@ -1092,13 +1092,13 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
       if (rs.nLights > 0) {
         // float32 shading: minDistance / maxDistance are the float32 values in the ray records' .w lanes (no binary64 range arrays)
         RK(traceQueue(c, true, wf.shO, wf.shD, f32 ? nullptr : wf.shRange, wf.counts + Q_SHADOW, wf.shOcc, nullptr, st));
-        RK(traceQueue(c, false, wf.misO, wf.misD, f32 ? nullptr : wf.misRange, wf.counts + Q_MIS, wf.misHit, wf.misT, st));
+        RK(traceQueue(c, false, wf.misO, wf.misD, f32 ? nullptr : wf.misRange, wf.counts + Q_MIS, wf.misHit, f32 ? nullptr : wf.misT, st));
         CK(c, (f32 ? drt::plainf::launchResolveDirect : STAGE(launchResolveDirect))(p, rs, wf, cur, RESOLVE_PATH, 1, sms, st)); profMark(c, DRT_PK_RESOLVE);
         c->launches++;
       }
       if (bounce == p.maxDepth) break;
       cur ^= 1;
-      RK(traceQueue(c, false, wf.extO[cur], wf.extD[cur], f32 ? nullptr : wf.extRange[cur], wf.counts + cur, wf.extHit, wf.extT, st));
+      RK(traceQueue(c, false, wf.extO[cur], wf.extD[cur], f32 ? nullptr : wf.extRange[cur], wf.counts + cur, wf.extHit, f32 ? nullptr : wf.extT, st));
       if (rs.nInfinite > 0 && rs.general) {  // path_integrator.dart:106-114: only after a specular bounce, which matte scenes never take
         CK(c, STAGE(launchEscape)(rs, wf, cur, ESCAPE_PATH, sms, st)); profMark(c, DRT_PK_OTHER);
         c->launches++;

@@ -516,6 +516,16 @@ static __device__ __forceinline__ void pushDirectWork(const Wavefront& wf, uint3
   }
 }
 
+// tHit of a traced queue entry: the binary64 build reads the traversal kernels' f64 output (ray.maxDistance after the hit, ray.dart:36);
+// the float32 build would round it to float32 first, which is what the hit record's first lane already holds — its trace calls ask
+// for no f64 array at all (render_api.cu)
+#if DRT_REAL32
+#define DRT_EXT_THIT(wf, q) ((wf).extHit[q].x)
+#define DRT_MIS_THIT(wf, mi) ((wf).misHit[mi].x)
+#else
+#define DRT_EXT_THIT(wf, q) ((wf).extT[q])
+#define DRT_MIS_THIT(wf, mi) ((wf).misT[mi])
+#endif
 // ---------------------------------------------------------------------------------------------------
 // Path integrator, one vertex (path_integrator.dart:44-119 loop body for `bounces` = bounce).
 #ifndef DRT_SHADE_MIN_BLOCKS
@@ -638,7 +648,7 @@ __global__ void __launch_bounds__(128, PART == 0 ? DRT_SHADE_MIN_BLOCKS : DRT_SH
       const float4 o4 = wf.extO[cur][q], d4 = wf.extD[cur][q];
       const V3 o = V3{o4.x, o4.y, o4.z}, d = V3{d4.x, d4.y, d4.z};
       ShapeHit h;
-      hitGeometryQ<EXTRA>(rs, wf, q, slot, (uint32_t)prim, o, d, wf.extT[q], &h);
+      hitGeometryQ<EXTRA>(rs, wf, q, slot, (uint32_t)prim, o, d, DRT_EXT_THIT(wf, q), &h);
       Spec T = ld3(wf.T, cap, slot);
       if (EXTRA && rs.nVolumes > 0 && bounce > 0) {  // pathThroughput *= renderer.transmittance(ray) once the ray found this vertex (:116)
         uint32_t ctr = wf.trCtr[slot];
@@ -784,7 +794,7 @@ __global__ void __launch_bounds__(128) resolveDirectKernel(RenderParams rp, Rend
         const float4 o4 = wf.misO[mi], d4 = wf.misD[mi];
         const V3 o = V3{o4.x, o4.y, o4.z}, wi = V3{d4.x, d4.y, d4.z};
         ShapeHit h;
-        hitGeometry<EXTRA>(rs, (uint32_t)prim, o, wi, wf.misT[mi], &h);
+        hitGeometry<EXTRA>(rs, (uint32_t)prim, o, wi, DRT_MIS_THIT(wf, mi), &h);
         Spec Li = areaL(rs.lights[light], h.nn, -wi);  // Intersection.Le, intersection.dart:62-65
         if (!IsBlack(Li)) {
           if (media) {  // renderer.transmittance along the ray up to the light's surface (integrator.dart:178)
