@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 
 # DRT_KERNEL_FAST_Q (quantised 64-byte nodes, forced whatever the scene size), DRT_KERNEL_FAST_V1 (float32 128-byte nodes),
 # DRT_KERNEL_EXACT_WALK (the literal walk); DRT_KERNEL_FAST = 0 picks between the first two by scene size
-@pytest.fixture(params=[3, 2, 1], ids=["fast_q", "fast_v1", "exact_walk"])
+# by scene size — and runs the leaf-list kernel (traceSmallKernel) on scenes of <= 32 leaves
+@pytest.fixture(params=[3, 2, 1, 0], ids=["fast_q", "fast_v1", "exact_walk", "default"])
 def variant(request):
     return request.param
 
@@ -206,6 +207,65 @@ def test_counters_match_reference_work(drt_lib):
     co = o.counters()
     assert cg["nodes_visited"] == co["nodes_visited"] and cg["prims_tested"] == co["prims_tested"]
     c.set_counting(False)
+
+
+def test_small_scene_with_every_shape_kind_runs_the_leaf_list_kernel(drt_lib):
+    """<= 32 leaves: the default variant is traceSmallKernel (trace_fast.cu).  24 triangles, a full and a clipped sphere, two disks
+    (one an annulus with a phi cut) and the four other quadrics; random, bounded, axis-parallel, far-away and on-surface rays; every
+    split method (the visiting-order tables follow the tree).  Bit-exact against the oracle like the tree kernels."""
+    from tests.test_oracle_trace import quadric_zoo
+    P, idx = random_soup(24, seed=77)
+    mats = [translate(0.3, 0.1, -0.2), translate(-0.4, 0.2, 0.5)]
+    sph = (np.stack([m[0] for m in mats]), np.stack([m[1] for m in mats]), [[0.25, -0.25, 0.25, 360.0], [0.4, -0.1, 0.3, 200.0]])
+    dm = [host.mat_mul(host.translate(0.1, -0.3, 0.2), host.rotate(35.0, (1.0, 0.3, 0.2))), host.translate(-0.5, 0.5, -0.4)]
+    dsk = (np.stack([m.reshape(16) for m in dm]), np.stack([host.mat_inv(m).reshape(16) for m in dm]),
+           [[0.0, 0.6, 0.0, 360.0], [0.1, 0.5, 0.2, 250.0]])
+    rng = np.random.default_rng(78)
+    for split in (0, 1, 2):
+        for with_quadrics in (False, True):
+            o, c = Oracle(), capi.Context(0)
+            for x in (o, c):
+                x.set_triangles(P, idx)
+                x.set_spheres(*sph)
+                x.set_disks(*dsk)
+                if with_quadrics:
+                    for kind, prm, m in quadric_zoo(host):
+                        x.set_quadrics(kind, m.reshape(16), host.mat_inv(m).reshape(16), [prm])
+                x.build_bvh(split, 4)
+            assert c.bvh_info()["n_leaves"] <= 32
+            sets = [random_rays(60000, seed=79 + split), random_rays(60000, seed=90 + split, tmin=0.4, tmax=1.9)]
+            ro, rd = random_rays(6000, seed=95)
+            rd = rd.copy()
+            rd[:2000, 0] = 0.0   # zero direction components: inf / NaN in the slab test, "slow" rays
+            rd[2000:4000, :2] = 0.0
+            rd[4000:5000, 1] = -0.0
+            ro = ro.copy()
+            ro[5000:5500, :3] *= 1.0e6      # far away
+            ro[5500:5750, :3] = 3.0e38      # at the edge of the float32 filter's preconditions: products overflow, the filter says "undecided"
+            ro[5750:6000, :3] = 3.2e38      # beyond them: "slow" rays, every box in binary64
+            sets.append((ro, rd))
+            n = 20000  # rays that start on a triangle of the soup (secondary-ray style, tmin = 1e-3)
+            tri = P[idx[rng.integers(0, idx.shape[0], n)]]
+            b = rng.uniform(0, 1, (n, 2)).astype(np.float32)
+            flip = b.sum(axis=1) > 1
+            b[flip] = 1 - b[flip]
+            org = (tri[:, 0] * (1 - b[:, :1] - b[:, 1:]) + tri[:, 1] * b[:, :1] + tri[:, 2] * b[:, 1:]).astype(np.float32)
+            d2 = rng.normal(size=(n, 3))
+            d2 = (d2 / np.linalg.norm(d2, axis=1, keepdims=True)).astype(np.float32)
+            sets.append(scenes.pack_rays(org, d2, 1e-3, np.inf))
+            for ro, rd in sets:
+                hg, ho = c.trace_closest(ro, rd), o.trace_closest(ro, rd, nthreads=8)
+                assert (hg["prim"] == ho["prim"]).all(), (split, with_quadrics, int((hg["prim"] != ho["prim"]).sum()))
+                same_t = (hg["t"].view(np.uint32) == ho["t"].view(np.uint32)) | (np.isnan(hg["t"]) & np.isnan(ho["t"]))
+                assert same_t.all()
+                np.testing.assert_allclose(hg["b1"], ho["b1"], rtol=1e-6, atol=1e-7)
+                np.testing.assert_allclose(hg["b2"], ho["b2"], rtol=1e-6, atol=1e-7)
+                assert (c.trace_any(ro, rd) == o.trace_any(ro, rd, nthreads=8)).all()
+            assert (ho["prim"] >= 0).sum() > 1000
+            # the same rays through the forced tree kernel: identical records
+            c.set_kernel_variant(2)
+            ht = c.trace_closest(ro, rd)
+            assert hg.tobytes() == ht.tobytes() or (np.isnan(hg["t"]).any() and (hg["prim"] == ht["prim"]).all())
 
 
 def test_axis_aligned_walls_and_rays(drt_lib, variant):
