@@ -1488,13 +1488,21 @@ cudaError_t launchSampler(const RenderParams& rp, const Wavefront& wf, const Sam
     // two arrays of nPixelSamples entries of 16 (8) bits; odd word stride
     const int strideWords = (bytes ? (rp.nPixelSamples + 1) / 2 : rp.nPixelSamples) | 1;
     const size_t taskBytes = (size_t)strideWords * sizeof(float);
-    const size_t budget = 48 * 1024 - 4 * 1024;  // the kernel's own tables (Sobol, remainders) take 4 KB of the static 48 KB
+    // shared memory per block for the tasks' permutation arrays: the kernel's own tables (Sobol, remainders) take 4 KB of the 48 KB
+    // a block gets without opting in; env DRT_SAMPLER_SMEM_KB asks for more (fewer lanes per task, fewer blocks per SM) for A/B runs
+    static const size_t budgetKb = std::getenv("DRT_SAMPLER_SMEM_KB") ? (size_t)std::atoi(std::getenv("DRT_SAMPLER_SMEM_KB")) : 48;
+    const size_t budget = std::min<size_t>(std::max<size_t>(budgetKb, 16), 200) * 1024 - 4 * 1024;
     int tasksPerBlock = (int)std::min<size_t>(block, std::max<size_t>(4, budget / taskBytes));
     int G = 1;
     while (block / G > tasksPerBlock) G <<= 1;
     const size_t smem = (size_t)(block / G) * taskBytes;
     uint64_t tasks = (uint64_t)pb.nPixels * nArrays;
     int grid = gridFor(tasks * G, block, numSMs, 16);
+    if (smem + 4 * 1024 > 48 * 1024) {
+      cudaError_t e = bytes ? cudaFuncSetAttribute(samplerLDPermKernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(samplerLDPermKernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
     if (bytes) samplerLDPermKernel<uint8_t><<<grid, block, smem, st>>>(rp, wf, dArrays, nArrays, pb, G, strideWords);
     else samplerLDPermKernel<uint16_t><<<grid, block, smem, st>>>(rp, wf, dArrays, nArrays, pb, G, strideWords);
   } else if (ld) {
