@@ -31,13 +31,13 @@ COMPILE_FLAGS = [
 ]
 # render_kernels_f32.cu (the float32 shading build, gen_f32.py): no bit replay to protect, so contraction and the fast division /
 # square root / sincos are on.  DRT_F32_FLAGS overrides the extra flags for A/B builds.
-F32_UNIT = "render_kernels_f32.cu"
+F32_UNITS = ("render_kernels_f32.cu", "render_kernels_f32x.cu")
 F32_FLAGS = os.environ.get("DRT_F32_FLAGS", "-use_fast_math").split()
 
 
 def _flags_for(src: str) -> list:
     flags = list(COMPILE_FLAGS) + ["-I", CSRC]
-    if os.path.basename(src) == F32_UNIT:
+    if os.path.basename(src) in F32_UNITS:
         flags = [f for f in flags if f != "-fmad=false"] + F32_FLAGS
     return flags
 
@@ -67,7 +67,7 @@ def _stale_obj(src: str, hdr_time: float, extra_key: str) -> bool:
         return True
     t = os.path.getmtime(o)
     # render_kernels_plain.cu includes render_kernels.cu
-    deps = [src] + ([os.path.join(CSRC, "render_kernels.cu")] if src.endswith(("render_kernels_plain.cu", F32_UNIT)) else [])
+    deps = [src] + ([os.path.join(CSRC, "render_kernels.cu")] if src.endswith(("render_kernels_plain.cu",) + F32_UNITS) else [])
     return any(os.path.getmtime(d) > t for d in deps) or hdr_time > t
 
 

@@ -71,8 +71,7 @@ struct RenderState {
   int volIntegrator = 0;
   double volStep = 1.0;
   // drt_set_shading_precision: DRT_PRECISION_F32 runs the path integrator's vertex / resolve kernels from the float32 build
-  // (render_kernels_f32.cu) on scenes that build serves: no per-vertex attributes or rarer quadrics, no FresnelBlend lobe, no media, no
-  // texture programs
+  // (render_kernels_f32.cu / render_kernels_f32x.cu) on scenes without media, texture programs or instances
   int shadingPrecision = 0;
   std::vector<float> volV2W;     // n x 16: volumeToWorld, for the regions' world bound
   uint32_t volMaxSteps = 0;      // single scattering: bound on a camera ray's march steps (regions' bound diagonal / stepsize)
@@ -1080,20 +1079,22 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
     // binary64 traversal — only the arithmetic of the vertex and resolve kernels changes
     static const char* f32Env = std::getenv("DRT_SHADE_F32");
     const bool wantF32 = f32Env ? f32Env[0] == '1' : r->shadingPrecision == DRT_PRECISION_F32;
-    const bool f32 = wantF32 && !rs.extra && rs.nVolumes == 0 && rs.nPrograms == 0;
+    const bool f32 = wantF32 && rs.nVolumes == 0 && rs.nPrograms == 0 && c->ts.nInstances == 0 && wf.slotTime == nullptr;
+    const auto shadeF32 = rs.extra ? drt::extraf::launchShadePath : drt::plainf::launchShadePath;
+    const auto resolveF32 = rs.extra ? drt::extraf::launchResolveDirect : drt::plainf::launchResolveDirect;
     for (int bounce = 0; bounce <= p.maxDepth; ++bounce) {
       CK(c, STAGE(launchResetCounts)(wf, (1u << (cur ^ 1)) | (1u << Q_SHADOW) | (1u << Q_MIS), st)); profMark(c, DRT_PK_OTHER);
       if (rs.nPrograms > 0) {  // only the camera ray carries differentials: the later rays are RayDifferential.child (path_integrator.dart:100)
         CK(c, launchTexturePass(p, rs, wf, cur, bounce == 0 ? 1 : 0, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
         c->launches++;
       }
-      CK(c, (f32 ? drt::plainf::launchShadePath : STAGE(launchShadePath))(p, rs, wf, bounce, cur, rc, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
+      CK(c, (f32 ? shadeF32 : STAGE(launchShadePath))(p, rs, wf, bounce, cur, rc, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
       c->launches += 2;
       if (rs.nLights > 0) {
         // float32 shading: minDistance / maxDistance are the float32 values in the ray records' .w lanes (no binary64 range arrays)
         RK(traceQueue(c, true, wf.shO, wf.shD, f32 ? nullptr : wf.shRange, wf.counts + Q_SHADOW, wf.shOcc, nullptr, st));
         RK(traceQueue(c, false, wf.misO, wf.misD, f32 ? nullptr : wf.misRange, wf.counts + Q_MIS, wf.misHit, f32 ? nullptr : wf.misT, st));
-        CK(c, (f32 ? drt::plainf::launchResolveDirect : STAGE(launchResolveDirect))(p, rs, wf, cur, RESOLVE_PATH, 1, sms, st)); profMark(c, DRT_PK_RESOLVE);
+        CK(c, (f32 ? resolveF32 : STAGE(launchResolveDirect))(p, rs, wf, cur, RESOLVE_PATH, 1, sms, st)); profMark(c, DRT_PK_RESOLVE);
         c->launches++;
       }
       if (bounce == p.maxDepth) break;

@@ -38,6 +38,9 @@ namespace extra {
 namespace plainf {
 #include "render_launchers.inc"
 }
+namespace extraf {  // the same two launchers from the `extra` build (render_kernels_f32x.cu)
+#include "render_launchers.inc"
+}
 
 // resolve mode bits: 1 = direct-lighting integrator (0 = path), 2 = first sample of a light, 4 = last sample of a
 // light, 8 = last light (add the sum to L), 16 = strategy "one", 32 = the vertices belong to a specular chain: weight the

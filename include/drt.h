@@ -409,9 +409,8 @@ int drt_set_volume_integrator(drt_ctx* ctx, int32_t kind, double step_size);
  * path_integrator.dart:44-119, lib/core/integrator.dart:79-185) in float32 throughout: the same samples, queues and binary64
  * traversal, but a sample's radiance now agrees with the reference's only within float32 rounding (and a vertex that lies within
  * rounding of an edge may take the other branch), which is inside what the Monte Carlo estimate itself promises — per-pixel means
- * within 3 sigma.  It applies to the path integrator on scenes without per-vertex mesh attributes, cylinder / cone / paraboloid /
- * hyperboloid shapes, FresnelBlend (substrate) lobes, texture programs or media; every other render keeps the binary64 kernels
- * whatever this is set to. */
+ * within 3 sigma.  It applies to the path integrator on scenes without texture programs, media or object instances; every other
+ * render keeps the binary64 kernels whatever this is set to. */
 #define DRT_PRECISION_F64 0
 #define DRT_PRECISION_F32 1
 int drt_set_shading_precision(drt_ctx* ctx, int32_t precision);

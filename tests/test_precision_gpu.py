@@ -180,3 +180,57 @@ def test_f32_path_on_bxdf_list_materials_within_3_sigma_of_the_oracle():
     assert s32["camera_samples"] == so["camera_samples"]
     for k in ("closest_rays", "shadow_rays"):
         assert abs(int(s32[k]) - int(so[k])) <= 1e-3 * so[k], (k, s32[k], so[k])
+
+
+def _f32_against_oracle(arrays, cam, film, spp, what, count_tol=1e-3):
+    """float32 path render against the oracle: per-pixel |d| <= 3 sigma (sigma from two independent half-size oracle renders), image
+    mean within 0.5 %, ray counts within count_tol; the float32 film must differ from the binary64 one (the switch took effect)."""
+    g, o = capi.Context(0), Oracle()
+    for c in (g, o):
+        host.upload_scene(c, arrays)
+    smp = host.Sampler(kind=host.SAMPLER_LD, spp=spp)
+    integ = host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=5)
+    f32, s32 = _render(g, cam, film, smp, integ, capi.PRECISION_F32)
+    f64, _ = _render(g, cam, film, smp, integ, capi.PRECISION_F64)
+    host.configure_render(o, cam, film, smp, integ)
+    o.film_clear()
+    o.render(0, 1, NT)
+    fo, so = o.film_read(), o.render_stats()
+    assert np.isfinite(f32["rgb"]).all()
+    assert not np.array_equal(f32["rgb"], f64["rgb"])
+    e64 = np.abs(f64["rgb"].astype(np.float64) - fo["rgb"]) / np.maximum(np.abs(fo["rgb"]), 1e-3)
+    halves = []
+    for seed in (1, 2):
+        host.configure_render(o, cam, film, host.Sampler(kind=host.SAMPLER_LD, spp=spp // 2, seed=seed), integ)
+        o.film_clear()
+        o.render(0, 1, NT)
+        halves.append(_lum(o.film_read()["rgb"]))
+    sigma = np.sqrt(_smooth(((halves[0] - halves[1]) ** 2) / 4.0))
+    a, b = _lum(f32["rgb"]), _lum(fo["rgb"])
+    lit = sigma > 1e-4 * b.mean()
+    z = np.abs(a - b)[lit] / sigma[lit]
+    rel = np.abs(f32["rgb"].astype(np.float64) - fo["rgb"]) / np.maximum(np.abs(fo["rgb"]), 1e-3)
+    print(f"f32 path vs oracle, {what}: max |d| / sigma {z.max():.3e}, pixels above 1 sigma {int((z > 1).sum())}, max rel err {rel.max():.3e}, "
+          f"99.9 % {np.quantile(rel, 0.999):.3e} (binary64 kernels: max rel err {e64.max():.1e}), mean f32 {a.mean():.6f} oracle {b.mean():.6f}")
+    assert z.max() <= 3.0
+    assert abs(a.mean() - b.mean()) <= 5e-3 * b.mean()
+    assert s32["camera_samples"] == so["camera_samples"]
+    for k in ("closest_rays", "shadow_rays"):
+        assert abs(int(s32[k]) - int(so[k])) <= count_tol * so[k], (k, s32[k], so[k])
+
+
+@pytest.mark.parametrize("which", ["matte", "lobes"])
+def test_f32_path_with_per_vertex_mesh_attributes(which):
+    """The `extra` build in float32 (render_kernels_f32x.cu): smooth-shaded meshes (per-vertex N / S / uv, triangle.dart:100-160)."""
+    from tests.test_render_gpu import _smooth_room
+    arrays, cam = _smooth_room(which)
+    _f32_against_oracle(arrays, cam, host.Film(96, 72), 64, f"smooth room ({which})")
+
+
+@pytest.mark.parametrize("which", ["matte", "lobes"])
+def test_f32_path_under_an_infinite_light_with_a_cylinder_glass_and_mirror(which):
+    """The `extra` build in float32 on the environment-lit scene of the render tests: InfiniteAreaLight importance sampling, a cylinder,
+    glass and mirror spheres (specular bounces pick up Le of escaped rays through the binary64 escape kernel)."""
+    from tests.test_render_gpu import _sky_scene
+    arrays, cam = _sky_scene(which)
+    _f32_against_oracle(arrays, cam, host.Film(96, 72), 64, f"sky scene ({which})")
