@@ -73,6 +73,8 @@ struct RenderState {
   // drt_set_shading_precision: DRT_PRECISION_F32 runs the path integrator's vertex / resolve kernels from the float32 build
   // (render_kernels_f32.cu / render_kernels_f32x.cu) on scenes without media, texture programs or instances
   int shadingPrecision = 0;
+  bool f32Trace = false;  // set while the path integrator's queues of a float32 render are traced: small scenes then run the float32
+                          // leaf-list kernel (trace_small_f32.cu); env DRT_F32_TRACE=0 keeps the binary64 traversal (A/B runs)
   std::vector<float> volV2W;     // n x 16: volumeToWorld, for the regions' world bound
   uint32_t volMaxSteps = 0;      // single scattering: bound on a camera ray's march steps (regions' bound diagonal / stepsize)
   DevBuf<GVolume> dVolumes;
@@ -862,7 +864,8 @@ static int traceQueue(drt_ctx* c, bool any, const float4* o, const float4* d, co
   ex.range = range;
   ex.tOut = tOut;
   ex.noUV = 1;  // the shading stages read the primitive and tHit only
-  CK(c, launchTraceFast(c->ts, any, o, d, 0, out, c->dNextRay.p, c->numSMs, st, &ex));
+  if (c->render && c->render->f32Trace && c->render->rp.integKind == 0 && c->ts.small) CK(c, launchTraceSmallF32(c->ts, any, o, d, out, c->numSMs, st, ex));
+  else CK(c, launchTraceFast(c->ts, any, o, d, 0, out, c->dNextRay.p, c->numSMs, st, &ex));
   c->launches++;
   profMark(c, any ? DRT_PK_TRACE_ANY : DRT_PK_TRACE_CLOSEST);
   RenderState* r = c->render;
@@ -1080,6 +1083,8 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
     static const char* f32Env = std::getenv("DRT_SHADE_F32");
     const bool wantF32 = f32Env ? f32Env[0] == '1' : r->shadingPrecision == DRT_PRECISION_F32;
     const bool f32 = wantF32 && rs.nVolumes == 0 && rs.nPrograms == 0 && c->ts.nInstances == 0 && wf.slotTime == nullptr;
+    static const bool f32TraceOff = std::getenv("DRT_F32_TRACE") != nullptr && std::getenv("DRT_F32_TRACE")[0] == '0';
+    r->f32Trace = f32 && !f32TraceOff;
     const auto shadeF32 = rs.extra ? drt::extraf::launchShadePath : drt::plainf::launchShadePath;
     const auto resolveF32 = rs.extra ? drt::extraf::launchResolveDirect : drt::plainf::launchResolveDirect;
     for (int bounce = 0; bounce <= p.maxDepth; ++bounce) {
@@ -1105,6 +1110,7 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
         c->launches++;
       }
     }
+    r->f32Trace = false;
   } else if (p.integKind == 1) {
     CK(c, STAGE(launchAoSetup)(p, rs, wf, sms, st)); profMark(c, DRT_PK_INTEGRATOR);
     c->launches++;
