@@ -176,6 +176,7 @@ static __device__ __noinline__ unsigned long long slabExactQ(float ox, float oy,
   return ((unsigned long long)(ok ? 1u : 0u) << 32) | (unsigned long long)__float_as_uint(__double2float_rn(tmin));
 }
 
+// f32-keep-begin (gen_f32.py: the decode of a quantised box stays binary64 in the float32 unit too — a float32 decode could shrink it)
 // One slot of a quantised node for a "slow" ray (zero / tiny / huge direction components, far-away origins; rare and
 // warp-divergent): the reference's own binary64 decision on the DECODED box, which contains the true box, so that a box
 // the reference enters is entered (for zero direction components: origin strictly inside the true slab -> strictly
@@ -193,6 +194,8 @@ static __device__ __noinline__ unsigned long long slowSlotQ(float ox, float oy, 
   const float hiz = __double2float_ru((double)Oz + (double)((bz >> 8) & 255u) * ((double)sz * k));
   return slabExactQ(ox, oy, oz, ix, iy, iz, mint, maxt, lox, loy, loz, hix, hiy, hiz);
 }
+
+// f32-keep-end
 
 // QUAD: the leaf code the scene needs (TraceScene::quadMode): 0 triangles only, 1 + spheres / disks, 2 + the remaining quadrics.
 template <bool ANY, int QUAD>

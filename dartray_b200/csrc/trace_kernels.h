@@ -51,6 +51,8 @@ cudaError_t launchTraceQ(const TraceScene& sc, bool any, const void* rayO, const
 // queues run on a small scene under DRT_PRECISION_F32.  Box filter, triangle and quadric tests in float32; the visiting order is the
 // reference's, the decisions are float32 ones (a hit within rounding of an edge or of the interval's end may differ), which is the
 // tolerance that mode states.  Needs TraceScene::small and a device-resident ray count (ex.nDev).
+cudaError_t launchTraceQF32(const TraceScene& sc, bool any, const void* rayO, const void* rayD, uint64_t n, void* out,
+                            unsigned long long* nextRay, int numSMs, cudaStream_t stream, const TraceExtras* extras);  // trace_q_f32.cu
 cudaError_t launchTraceSmallF32(const TraceScene& sc, bool any, const void* rayO, const void* rayD, void* out, int numSMs, cudaStream_t stream,
                                 const TraceExtras& ex);
 

@@ -234,3 +234,11 @@ def test_f32_path_under_an_infinite_light_with_a_cylinder_glass_and_mirror(which
     from tests.test_render_gpu import _sky_scene
     arrays, cam = _sky_scene(which)
     _f32_against_oracle(arrays, cam, host.Film(96, 72), 64, f"sky scene ({which})")
+
+
+def test_f32_path_on_a_127k_triangle_scene_runs_the_float32_leaf_phase_of_the_quantised_kernel():
+    """soup(64) (127 K triangles: the quantised-node kernel) lit by its area light, 96x54 x 64 spp: under DRT_PRECISION_F32 the path
+    integrator's queues run traceQKernel with a float32 leaf phase (trace_q_f32.cu)."""
+    sb, cam = scenes.soup_render_scene(64)
+    arrays = sb.arrays()
+    _f32_against_oracle(arrays, cam, host.Film(96, 54), 64, "soup(64) 127 K triangles")
