@@ -409,8 +409,9 @@ int drt_set_volume_integrator(drt_ctx* ctx, int32_t kind, double step_size);
  * path_integrator.dart:44-119, lib/core/integrator.dart:79-185) in float32 throughout: the same samples, queues and binary64
  * camera rays, but a sample's radiance now agrees with the reference's only within float32 rounding (the integrator's rays are
  * intersected in float32 too, so a hit within rounding of an edge may go the other way), which is inside what the Monte Carlo
- * estimate itself promises — per-pixel means within 3 sigma.  drt_trace_* are not affected.  It applies to the path integrator on scenes without texture programs, media or object instances; every other
- * render keeps the binary64 kernels whatever this is set to. */
+ * estimate itself promises — per-pixel means within 3 sigma.  drt_trace_* are not affected.  It applies to the path integrator on
+ * scenes without texture programs, media or object instances; every other render keeps the binary64 kernels whatever this is set
+ * to. */
 #define DRT_PRECISION_F64 0
 #define DRT_PRECISION_F32 1
 int drt_set_shading_precision(drt_ctx* ctx, int32_t precision);
