@@ -31,7 +31,7 @@ COMPILE_FLAGS = [
 ]
 # render_kernels_f32.cu (the float32 shading build, gen_f32.py): no bit replay to protect, so contraction and the fast division /
 # square root / sincos are on.  DRT_F32_FLAGS overrides the extra flags for A/B builds.
-F32_UNITS = ("render_kernels_f32.cu", "render_kernels_f32x.cu", "trace_small_f32.cu", "trace_q_f32.cu")
+F32_UNITS = ("render_kernels_f32.cu", "render_kernels_f32x.cu", "trace_fast_f32.cu", "trace_q_f32.cu")
 F32_FLAGS = os.environ.get("DRT_F32_FLAGS", "-use_fast_math").split()
 
 

@@ -73,9 +73,8 @@ struct RenderState {
   // drt_set_shading_precision: DRT_PRECISION_F32 runs the path integrator's vertex / resolve kernels from the float32 build
   // (render_kernels_f32.cu / render_kernels_f32x.cu) on scenes without media, texture programs or instances
   int shadingPrecision = 0;
-  bool f32Trace = false;  // set while the path integrator's queues of a float32 render are traced: small scenes then run the float32
-                          // leaf-list kernel (trace_small_f32.cu), scenes on quantised nodes traceQKernel with a float32 leaf phase
-                          // (trace_q_f32.cu); env DRT_F32_TRACE=0 keeps the binary64 traversal (A/B runs)
+  bool f32Trace = false;  // set while the path integrator's queues of a float32 render are traced: they run the float32 builds of the
+                          // traversal kernels (trace_fast_f32.cu, trace_q_f32.cu); env DRT_F32_TRACE=0 keeps the binary64 traversal (A/B runs)
   std::vector<float> volV2W;     // n x 16: volumeToWorld, for the regions' world bound
   uint32_t volMaxSteps = 0;      // single scattering: bound on a camera ray's march steps (regions' bound diagonal / stepsize)
   DevBuf<GVolume> dVolumes;
@@ -866,8 +865,7 @@ static int traceQueue(drt_ctx* c, bool any, const float4* o, const float4* d, co
   ex.tOut = tOut;
   ex.noUV = 1;  // the shading stages read the primitive and tHit only
   const bool f32Q = c->render && c->render->f32Trace && c->render->rp.integKind == 0;
-  if (f32Q && c->ts.small) CK(c, launchTraceSmallF32(c->ts, any, o, d, out, c->numSMs, st, ex));
-  else if (f32Q && c->ts.wideQ) CK(c, launchTraceQF32(c->ts, any, o, d, 0, out, c->dNextRay.p, c->numSMs, st, &ex));
+  if (f32Q) CK(c, launchTraceFastF32(c->ts, any, o, d, 0, out, c->dNextRay.p, c->numSMs, st, &ex));
   else CK(c, launchTraceFast(c->ts, any, o, d, 0, out, c->dNextRay.p, c->numSMs, st, &ex));
   c->launches++;
   profMark(c, any ? DRT_PK_TRACE_ANY : DRT_PK_TRACE_CLOSEST);

@@ -131,7 +131,6 @@ static __device__ __noinline__ bool slabExact(float ox, float oy, float oz, floa
   return (tmin < maxt) && (tmax > mint);
 }
 
-#ifndef DRT_SMALL_ONLY  // the float32 small-scene unit (trace_small_f32.cu) takes the leaf-list kernel only
 // One slot of a wide node for a regular ray: conservative for interior children, exact-or-marked for leaf children.
 // Returns the reference to visit (a leaf reference possibly marked "undecided") or DRT_REF_EMPTY.
 static __device__ __forceinline__ int32_t testSlot(const FastRay& r, int32_t ref, const float2 bx, const float2 by,
@@ -442,8 +441,6 @@ __global__ void __launch_bounds__(128, DRT_MIN_BLOCKS)
 #undef RETIRE
 }
 
-#endif  // DRT_SMALL_ONLY
-
 // ---------------------------------------------------------------------------------------------------------------------
 // Small scenes (<= DRT_SMALL_MAX_LEAVES leaves, no instances: BASELINE.json config 4 has 25 primitives in 11 leaves): no tree, no
 // stack, no persistent warps.  By argument (1) above the reference's answer is fixed by (a) the ORDER in which its walk reaches the
@@ -630,7 +627,6 @@ static cudaError_t launchSmall(const TraceScene& sc, bool any, const float4* o, 
   return cudaGetLastError();
 }
 
-#ifndef DRT_SMALL_ONLY
 static cudaError_t launchOne(const TraceScene& sc, bool any, const float4* o, const float4* d, uint32_t n, bool nUnknown, void* out,
                              unsigned long long* nextRay, int numSMs, cudaStream_t stream, const TraceExtras& ex) {
   cudaError_t e = cudaMemsetAsync(nextRay, 0, sizeof(unsigned long long), stream);
@@ -693,15 +689,5 @@ cudaError_t launchTraceFast(const TraceScene& sc, bool any, const void* rayO, co
   }
   return cudaSuccess;
 }
-
-#endif  // DRT_SMALL_ONLY
-
-#ifdef DRT_SMALL_ONLY
-// The renderer's queues under DRT_PRECISION_F32 on a small scene: the ray count lives on the device
-cudaError_t launchTraceSmallF32(const TraceScene& sc, bool any, const void* rayO, const void* rayD, void* out, int numSMs, cudaStream_t stream,
-                                const TraceExtras& ex) {
-  return launchSmall(sc, any, static_cast<const float4*>(rayO), static_cast<const float4*>(rayD), 0, true, out, numSMs, stream, ex);
-}
-#endif
 
 }  // namespace drt

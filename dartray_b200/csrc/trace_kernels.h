@@ -47,13 +47,11 @@ cudaError_t launchTraceFast(const TraceScene& sc, bool any, const void* rayO, co
 cudaError_t launchTraceQ(const TraceScene& sc, bool any, const void* rayO, const void* rayD, uint64_t n, void* out,
                          unsigned long long* nextRay, int numSMs, cudaStream_t stream, const TraceExtras* extras = nullptr);
 
-// Float32 leaf-list kernel (trace_small_f32.cu: trace_fast.cu's traceSmallKernel lowered by gen_f32.py): what the path integrator's
-// queues run on a small scene under DRT_PRECISION_F32.  Box filter, triangle and quadric tests in float32; the visiting order is the
-// reference's, the decisions are float32 ones (a hit within rounding of an edge or of the interval's end may differ), which is the
-// tolerance that mode states.  Needs TraceScene::small and a device-resident ray count (ex.nDev).
-cudaError_t launchTraceQF32(const TraceScene& sc, bool any, const void* rayO, const void* rayD, uint64_t n, void* out,
-                            unsigned long long* nextRay, int numSMs, cudaStream_t stream, const TraceExtras* extras);  // trace_q_f32.cu
-cudaError_t launchTraceSmallF32(const TraceScene& sc, bool any, const void* rayO, const void* rayD, void* out, int numSMs, cudaStream_t stream,
-                                const TraceExtras& ex);
+// Float32 builds of the production kernels (trace_fast_f32.cu, trace_q_f32.cu: trace_fast.cu / trace_fast2.cu lowered by gen_f32.py): what
+// the path integrator's ray queues run under DRT_PRECISION_F32.  Box filter, leaf box, triangle and quadric tests in float32; the
+// visiting order is the reference's, the decisions are float32 ones (a hit within rounding of an edge or of the interval's end may
+// differ), which is the tolerance that mode states.  Same kernel choice by scene as launchTraceFast.
+cudaError_t launchTraceFastF32(const TraceScene& sc, bool any, const void* rayO, const void* rayD, uint64_t n, void* out,
+                               unsigned long long* nextRay, int numSMs, cudaStream_t stream, const TraceExtras* extras);
 
 }  // namespace drt

@@ -242,3 +242,10 @@ def test_f32_path_on_a_127k_triangle_scene_runs_the_float32_leaf_phase_of_the_qu
     sb, cam = scenes.soup_render_scene(64)
     arrays = sb.arrays()
     _f32_against_oracle(arrays, cam, host.Film(96, 54), 64, "soup(64) 127 K triangles")
+
+
+def test_f32_path_on_a_16k_triangle_scene_runs_the_float32_tree_kernel():
+    """soup(8) (16 K triangles: below the quantised kernel's threshold, above the leaf-list kernel's): the float32 build of
+    traceFastKernel (trace_fast_f32.cu)."""
+    sb, cam = scenes.soup_render_scene(8)
+    _f32_against_oracle(sb.arrays(), cam, host.Film(96, 54), 64, "soup(8) 16 K triangles")
