@@ -612,6 +612,10 @@ __global__ void __launch_bounds__(256) matScatterKernel(RenderScene rs, Wavefron
 // MIS rays), then the next direction + Russian roulette + the extension ray — each recomputing the cheap hit geometry / BSDF frame.
 // Smaller kernels (the single one is 11.5 K instructions: ncu shows `no_instruction` stalls of 2.3 warps per issue) with fewer live
 // registers; the per-slot draws keep their positions in the integrator stream, so the results are the single kernel's.
+#ifndef DRT_SHADE_PREFETCH
+#define DRT_SHADE_PREFETCH 0  // 1: prefetch the thread's next queue entry.  Measured on B200 with the float32 kernel (config 4,
+                              // profiles/r02z11_prefetch_ab.log): 0.4716 s against 0.4672 s — rejected, off
+#endif
 #ifndef DRT_SHADE_SPLIT_MIN_BLOCKS
 #define DRT_SHADE_SPLIT_MIN_BLOCKS 5
 #endif
@@ -625,6 +629,17 @@ __global__ void __launch_bounds__(128, PART == 0 ? DRT_SHADE_MIN_BLOCKS : DRT_SH
   for (uint32_t q0 = blockIdx.x * blockDim.x; q0 < n; q0 += gridDim.x * blockDim.x) {
     uint32_t q = q0 + threadIdx.x;
     bool valid = q < n;
+#if DRT_SHADE_PREFETCH  // the queue entry this thread shades in its NEXT trip, on its way to L1 while this one is shaded (A/B knob)
+    {
+      const uint32_t qn = q + gridDim.x * blockDim.x;
+      if (qn < n && !sorted) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(wf.extSlot[cur] + qn));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(wf.extHit + qn));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(wf.extO[cur] + qn));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(wf.extD[cur] + qn));
+      }
+    }
+#endif
     uint32_t slot = 0;
     int prim = -1;
     if (valid) {
