@@ -6,3 +6,6 @@ compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test
 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_precision_gpu.py tests/test_trace_gpu.py -m gpu -q -x -k "bxdf_list or (default and known_answer)" > gpurun_out/r02final_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"
 compute-sanitizer --tool synccheck --error-exitcode 7 python -m pytest tests/test_precision_gpu.py tests/test_trace_gpu.py -m gpu -q -x -k "bxdf_list or (default and axis_aligned)" > gpurun_out/r02final_sanitizer_synccheck.log 2>&1; echo "synccheck rc=$?"
 for f in gpurun_out/r02final_sanitizer_*.log; do tail -n 4 $f; done
+# the float32 traversal units (lowered trace_fast.cu / trace_fast2.cu) through the float32 path render
+compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_precision_gpu.py -m gpu -q -x -k "16k or bxdf_list or (mesh_attributes and matte)" > gpurun_out/r02final_sanitizer_memcheck_f32trace.log 2>&1; echo "memcheck f32 trace rc=$?"
+compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_precision_gpu.py -m gpu -q -x -k "16k" > gpurun_out/r02final_sanitizer_racecheck_f32trace.log 2>&1; echo "racecheck f32 trace rc=$?"
