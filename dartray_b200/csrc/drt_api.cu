@@ -623,14 +623,31 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
     std::memcpy(g.wmin, b.bmin, 12);
     std::memcpy(g.wmax, b.bmax, 12);
   }
+  static const bool phaseTiming = std::getenv("DRT_BUILD_TIMING") != nullptr;
+  auto tPhase = std::chrono::steady_clock::now();
+  auto phase = [&](const char* what) {
+    if (!phaseTiming) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[drt build] %-28s %.3f s\n", what, std::chrono::duration<double>(now - tPhase).count());
+    tPhase = now;
+  };
+  phase("(api) bounds, quadrics, objects");
   if (!buildBvh(bounds, order, split, maxPrims, &c->bvh, &err)) return fail(c, DRT_E_INVALID, err.c_str());
+  phase("(api) buildBvh");
   const BuiltBvh& B = c->bvh;
-  std::vector<GNode> nodes(B.nodes);
+  // the top level's binary nodes and leaf counts are used in place unless objects append theirs (soup_10m: 650 MB not copied)
+  std::vector<GNode> nodesOwned;
+  std::vector<uint32_t> recCountsOwned;
+  if (!objBvh.empty()) {
+    nodesOwned = B.nodes;
+    recCountsOwned = B.leafCounts;
+  }
+  std::vector<GNode>& nodesMut = nodesOwned;
+  std::vector<uint32_t>& recCountsMut = recCountsOwned;
   c->recPrimIds = B.leafPrimIds;
-  std::vector<uint32_t> recCounts(B.leafCounts);
   for (size_t k = 0; k < objBvh.size(); ++k) {
     const BuiltBvh& O = objBvh[k];
-    const int32_t nodeBase = (int32_t)nodes.size();
+    const int32_t nodeBase = (int32_t)nodesMut.size();
     const uint32_t recBase = (uint32_t)c->recPrimIds.size();
     auto rebase = [&](int32_t ref) -> int32_t {
       if (ref == DRT_REF_EMPTY) return ref;
@@ -638,12 +655,15 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
       const uint32_t bits = (uint32_t)~ref;
       return (int32_t)~((((bits >> 5) + recBase) << 5) | (bits & 31u));
     };
-    for (GNode n : O.nodes) { n.ref0 = rebase(n.ref0); n.ref1 = rebase(n.ref1); nodes.push_back(n); }
+    for (GNode n : O.nodes) { n.ref0 = rebase(n.ref0); n.ref1 = rebase(n.ref1); nodesMut.push_back(n); }
     gobjs[k].rootRef = rebase(O.rootRef);
     c->recPrimIds.insert(c->recPrimIds.end(), O.leafPrimIds.begin(), O.leafPrimIds.end());
-    recCounts.insert(recCounts.end(), O.leafCounts.begin(), O.leafCounts.end());
+    recCountsMut.insert(recCountsMut.end(), O.leafCounts.begin(), O.leafCounts.end());
   }
+  const std::vector<GNode>& nodes = objBvh.empty() ? B.nodes : nodesOwned;
+  const std::vector<uint32_t>& recCounts = objBvh.empty() ? B.leafCounts : recCountsOwned;
 
+  phase("(api) node / record copies");
   // leaf records
   std::vector<GPrim> prims(c->recPrimIds.size());
   parallelFor(prims.size(), [&](size_t i0, size_t i1) {
@@ -666,6 +686,7 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
       }
     }
   });
+  phase("(api) leaf records");
   if (hostOnly) {
     c->info.n_nodes = (uint32_t)B.refNodes.size();
     c->info.n_prims = np;
@@ -679,6 +700,7 @@ int drt_build_bvh(drt_ctx* c, int split, int maxPrims) {
   }
   int rc = uploadBuilt(c, B, nodes, prims, gs, gobjs, c->instances, np);
   if (rc != DRT_OK) return rc;
+  phase("(api) upload, first device");
   // a multi-device context: the same arrays to every other device, one host thread each
   if (!c->peers.empty()) {
     std::vector<int> rcs(c->peers.size(), DRT_OK);
