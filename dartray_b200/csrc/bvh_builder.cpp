@@ -263,43 +263,55 @@ struct Flattener {
   }
   static constexpr uint32_t kTaskNodes = 1u << 15;
 
-  // Reference numbering: depth first, first child at n+1 (bvh_accel.dart:419-437).  Node t gets index `my`.
-  void numberRef(int32_t t, int32_t my, std::vector<int32_t>& refIndexOf) {
-    refIndexOf[t] = my;
+  // One pass over the finished tree writes the three things that are numbered differently:
+  //  * the reference numbering: depth first, first child at n+1, second child after the first one's subtree (bvh_accel.dart:419-437);
+  //    node t gets index `myRef`;
+  //  * the reference's `primitives` order: it appends a leaf's primitives when the leaf is created and builds the SECOND child first
+  //    (bvh_accel.dart:407-411) -> right-first leaf order; `off` is the first slot of t's primitives;
+  //  * the binary GPU layout: interior nodes in DFS order (`my`: index of t among them), leaf records in DFS (left-first) order, which
+  //    is the order the in-place partitions left the PrimRef array in.
+  // Every index follows from the subtree totals, so the two subtrees of a node are independent tasks.
+  void emitBinary(int32_t t, int32_t my, int32_t myRef, uint32_t off) {
     const TNode& n = pool[t];
     RefNode rn;
     std::memcpy(rn.bmin, n.box.lo, 12);
     std::memcpy(rn.bmax, n.box.hi, 12);
     rn.axis = 0;
-    rn.offset = 0;
-    rn.nPrimitives = (int32_t)n.count;
-    if (n.left >= 0) {
-      rn.axis = n.axis;
-      rn.nPrimitives = 0;
-      const int32_t second = my + 1 + (int32_t)pool[n.left].nNodes;
-      rn.offset = second;
-      out->refNodes[my] = rn;
-      both(n.nNodes >= kTaskNodes, [&] { numberRef(n.left, my + 1, refIndexOf); }, [&] { numberRef(n.right, second, refIndexOf); });
-    } else {
-      out->refNodes[my] = rn;
-    }
-  }
-
-  // The reference appends a leaf's primitives to `orderedPrims` when the leaf is created and
-  // builds the SECOND child first (bvh_accel.dart:407-411) -> right-first leaf order.  `off`: first slot of t's primitives.
-  void orderRef(int32_t t, uint32_t off, const std::vector<int32_t>& refIndexOf) {
-    const TNode& n = pool[t];
     if (n.left < 0) {
-      out->refNodes[refIndexOf[t]].offset = (int32_t)off;
-      for (uint32_t i = 0; i < n.count; ++i) out->refOrdered[off + i] = refs[n.first + i].id;
+      rn.nPrimitives = (int32_t)n.count;
+      rn.offset = (int32_t)off;
+      out->refNodes[myRef] = rn;
+      for (uint32_t i = 0; i < n.count; ++i) {
+        const uint32_t id = refs[n.first + i].id;
+        out->refOrdered[off + i] = id;
+        out->leafPrimIds[n.first + i] = id;
+        out->leafCounts[n.first + i] = i == 0 ? n.count : 0;
+      }
       return;
     }
-    both(n.nNodes >= kTaskNodes, [&] { orderRef(n.right, off, refIndexOf); },
-         [&] { orderRef(n.left, off + pool[n.right].nPrims, refIndexOf); });
+    const TNode &a = pool[n.left], &b = pool[n.right];
+    const int32_t secondRef = myRef + 1 + (int32_t)a.nNodes;
+    rn.axis = n.axis;
+    rn.nPrimitives = 0;
+    rn.offset = secondRef;
+    out->refNodes[myRef] = rn;
+    const int32_t myLeft = my + 1, myRight = my + 1 + (int32_t)a.nInterior;
+    GNode g;
+    std::memcpy(g.c0min, a.box.lo, 12);
+    std::memcpy(g.c0max, a.box.hi, 12);
+    std::memcpy(g.c1min, b.box.lo, 12);
+    std::memcpy(g.c1max, b.box.hi, 12);
+    g.ref0 = a.left < 0 ? leafRefOf(n.left) : myLeft;
+    g.ref1 = b.left < 0 ? leafRefOf(n.right) : myRight;
+    g.axis = n.axis;
+    g.refNode = myRef;
+    out->nodes[my] = g;
+    both(n.nNodes >= kTaskNodes, [&] { emitBinary(n.left, myLeft, myRef + 1, off + b.nPrims); },
+         [&] { emitBinary(n.right, myRight, secondRef, off); });
   }
 
-  // Wide layout: collapse P with its two children (see GNode4).  Must run AFTER emit(): it reuses
-  // the leaf references recorded there so both layouts index the same GPrim[] order.
+  // Wide layout: collapse P with its two children (see GNode4).  Independent of emitBinary(): both derive a leaf's reference from
+  // its range in the PrimRef array, so the two layouts index the same GPrim[] order.
   // A leaf's records start at its range in the builder's PrimRef array: the in-place partitions leave that array in leaf
   // (depth-first, first child first) order, which is the order of the GPrim records.
   int32_t leafRefOf(int32_t t) const { return makeLeafRef(pool[t].first, pool[t].count); }
@@ -428,33 +440,6 @@ struct Flattener {
     return true;
   }
 
-  // GPU layout: interior nodes in DFS order, leaf records in DFS (left-first) order.
-  // `my`: index of t among the interior nodes (DFS order).
-  int32_t emit(int32_t t, int32_t my, const std::vector<int32_t>& refIndexOf) {
-    const TNode& n = pool[t];
-    if (n.left < 0) {
-      for (uint32_t i = 0; i < n.count; ++i) {
-        out->leafPrimIds[n.first + i] = refs[n.first + i].id;
-        out->leafCounts[n.first + i] = i == 0 ? n.count : 0;
-      }
-      return leafRefOf(t);
-    }
-    int32_t r0 = 0, r1 = 0;
-    both(n.nNodes >= kTaskNodes, [&] { r0 = emit(n.left, my + 1, refIndexOf); },
-         [&] { r1 = emit(n.right, my + 1 + (int32_t)pool[n.left].nInterior, refIndexOf); });
-    GNode g;
-    const TNode &a = pool[n.left], &b = pool[n.right];
-    std::memcpy(g.c0min, a.box.lo, 12);
-    std::memcpy(g.c0max, a.box.hi, 12);
-    std::memcpy(g.c1min, b.box.lo, 12);
-    std::memcpy(g.c1max, b.box.hi, 12);
-    g.ref0 = r0;
-    g.ref1 = r1;
-    g.axis = n.axis;
-    g.refNode = refIndexOf[t];
-    out->nodes[my] = g;
-    return my;
-  }
 };
 
 }  // namespace
@@ -507,18 +492,16 @@ bool buildBvh(const std::vector<PrimBounds>& bounds, const std::vector<uint32_t>
   out->nLeaves = rt.nLeaves;
   out->maxLeafPrims = rt.maxLeaf;
   out->maxDepth = rt.depthBelow;
-  // two independent chains over the finished tree: (reference numbering -> reference primitive order -> binary GPU layout) on a
-  // second thread, (wide layout -> quantised nodes) here
+  // two independent passes over the finished tree: reference numbering + reference primitive order + binary GPU layout (emitBinary)
+  // on a second thread, wide layout + quantised nodes here
   std::thread binaryChain([&] {
-    std::vector<int32_t> refIndexOf(arena.pool.size(), -1);
     out->refNodes.resize(rt.nNodes);
-    fl.numberRef(root, 0, refIndexOf);
     out->refOrdered.resize(n);
-    fl.orderRef(root, 0, refIndexOf);
     out->leafPrimIds.resize(n);
     out->leafCounts.resize(n);
     out->nodes.resize(rt.nInterior);
-    out->rootRef = fl.emit(root, 0, refIndexOf);
+    fl.emitBinary(root, 0, 0, 0);
+    out->rootRef = rt.left < 0 ? fl.leafRefOf(root) : 0;
   });
   out->wide.resize(rt.left < 0 ? 0 : rt.nWide);
   out->wideQ.resize(out->wide.size());
