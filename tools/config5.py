@@ -85,6 +85,7 @@ def main():
             "busy_seconds_per_gpu": [float(x) for x in g[:, 0]],
             "imbalance_max_over_mean": float(g[:, 0].max() / g[:, 0].mean()),
             "mean_rgb": [float(x) for x in ctx.film_read()["rgb"].mean(axis=(0, 1))],
+            "shading": "float32 (DRT_SHADE_F32=1)" if os.environ.get("DRT_SHADE_F32") == "1" else "binary64",
         }
         if args.crop_parity:
             from tests.oracle_lib import Oracle
