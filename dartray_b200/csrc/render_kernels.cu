@@ -924,35 +924,58 @@ __global__ void __launch_bounds__(128) aoSetupKernel(RenderParams rp, RenderScen
   }
 }
 
+// Where the AO rays of a chunk sit in the shadow queue.  The reference's order — hit after hit, sample after sample — puts the 2^k
+// samples of ONE hit side by side, and a (0,2)-sequence spreads consecutive samples over the whole hemisphere: a warp of the any-hit
+// kernel then holds 32 rays of one origin pointing everywhere.  The occlusion count of a hit does not depend on the order its rays are
+// traced in, so the queue is laid out for the traversal instead: the first 2^k points of the scrambled (0,2)-sequence form a
+// (0, k, 2)-net (montecarlo.dart:486-504: base-2 digit scrambling keeps the property), i.e. every cell of the 2^a x 2^b grid over
+// [0,1)^2, a + b = k, holds exactly one sample of a hit — its cell number is a bijection of the sample index.  Blocks of 32
+// consecutive hits (neighbouring pixels) are transposed: 32 consecutive queue entries = the SAME cell of 32 neighbouring hits, rays of
+// nearby origins and directions.  The last, partial block of a chunk keeps the plain layout.  DRT_AO_PLAIN_ORDER=1 keeps it everywhere
+// (A/B runs).
+static __device__ __forceinline__ uint32_t aoCell(uint32_t i, uint32_t s0, uint32_t s1, int k) {
+  const int a = (k + 1) >> 1, b = k >> 1;
+  const uint32_t v0 = __brev(i) ^ s0, v1 = sobolBits(i) ^ s1;  // the integers VanDerCorput / Sobol2 turn into [0, 1) values
+  const uint32_t cx = a ? v0 >> (32 - a) : 0u, cy = b ? v1 >> (32 - b) : 0u;
+  return (cx << b) | cy;
+}
+static __device__ __forceinline__ uint64_t aoRayPos(uint32_t hI, uint32_t cell, uint32_t hitsHere, uint32_t nS, int plain) {
+  const uint32_t B = hI >> 5;
+  if (plain || ((B + 1u) << 5) > hitsHere) return (uint64_t)hI * nS + cell;
+  return (((uint64_t)B * nS + cell) << 5) + (hI & 31u);
+}
+
 // AO rays of hits [firstHit, firstHit + maxHits) of the hit list, nSamples each, into the shadow queue
-__global__ void __launch_bounds__(256) aoGenKernel(RenderParams rp, Wavefront wf, uint32_t firstHit, uint32_t maxHits, int nS) {
+__global__ void __launch_bounds__(256) aoGenKernel(RenderParams rp, Wavefront wf, uint32_t firstHit, uint32_t maxHits, int nS, int plain) {
   const uint32_t nHits = wf.counts[Q_HITS], cap = wf.cap;
   const uint32_t hitsHere = nHits > firstHit ? min(nHits - firstHit, maxHits) : 0u;
   const uint64_t nRays = (uint64_t)hitsHere * nS;
   if (blockIdx.x == 0 && threadIdx.x == 0) wf.counts[Q_SHADOW] = (uint32_t)nRays;
   for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nRays; r += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t slot = wf.hitList[firstHit + (uint32_t)(r / nS)];
+    const uint32_t hI = (uint32_t)(r / nS);
+    const uint32_t slot = wf.hitList[firstHit + hI];
     const uint32_t i = (uint32_t)(r % nS);
-    const double u0 = VanDerCorput(i, wf.aoScramble[slot]), u1 = Sobol2(i, wf.aoScramble[cap + slot]);
+    const uint32_t s0 = wf.aoScramble[slot], s1 = wf.aoScramble[cap + slot];
+    const double u0 = VanDerCorput(i, s0), u1 = Sobol2(i, s1);
     V3 w = UniformSampleSphere(u0, u1);
     const V3 nrm = ldv3(wf.hitN, cap, slot), p = ldv3(wf.hitP, cap, slot);
     if (Dot(w, nrm) < 0.0) w = -w;
+    const uint64_t at = aoRayPos(hI, plain ? i : aoCell(i, s0, s1, 31 - __clz(nS)), hitsHere, (uint32_t)nS, plain);
     // new Ray(p, w, minDist, maxDist) (ambient_occlusion_integrator.dart:45): no time argument, the ray travels at time 0
-    wf.shO[r] = make_float4(p.x, p.y, p.z, wf.slotTime ? __uint_as_float(0xffffffffu) : (float)rp.aoMinDist);
-    wf.shD[r] = make_float4(w.x, w.y, w.z, (float)rp.aoMaxDist);
-    wf.shRange[r] = make_double2(rp.aoMinDist, rp.aoMaxDist);
+    wf.shO[at] = make_float4(p.x, p.y, p.z, wf.slotTime ? __uint_as_float(0xffffffffu) : (float)rp.aoMinDist);
+    wf.shD[at] = make_float4(w.x, w.y, w.z, (float)rp.aoMaxDist);
+    wf.shRange[at] = make_double2(rp.aoMinDist, rp.aoMaxDist);
   }
 }
 
 __global__ void __launch_bounds__(256) aoCountKernel(RenderParams rp, Wavefront wf, uint32_t firstHit, uint32_t maxHits, int nS,
-                                                     RenderCounters* rc) {
+                                                     RenderCounters* rc, int plain) {
   const uint32_t nHits = wf.counts[Q_HITS], cap = wf.cap;
   const uint32_t hitsHere = nHits > firstHit ? min(nHits - firstHit, maxHits) : 0u;
   for (uint32_t hI = blockIdx.x * blockDim.x + threadIdx.x; hI < hitsHere; hI += gridDim.x * blockDim.x) {
     const uint32_t slot = wf.hitList[firstHit + hI];
-    const uint8_t* occ = wf.shOcc + (size_t)hI * nS;
     int nClear = 0;
-    for (int i = 0; i < nS; ++i) nClear += occ[i] ? 0 : 1;
+    for (int c = 0; c < nS; ++c) nClear += wf.shOcc[aoRayPos(hI, (uint32_t)c, hitsHere, (uint32_t)nS, plain)] ? 0 : 1;
     st3(wf.L, cap, slot, mks1((double)nClear / nS));
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&rc->shadowRays, (unsigned long long)hitsHere * nS);
@@ -1643,14 +1666,16 @@ static inline int roundUpPow2(int v) {  // common.dart:117-125
 cudaError_t launchAoGen(const RenderParams& rp, const Wavefront& wf, uint32_t firstHit, uint32_t maxHits, int numSMs,
                         cudaStream_t st) {
   const int nS = roundUpPow2(rp.aoSamples);
-  aoGenKernel<<<gridFor((uint64_t)maxHits * nS, 256, numSMs, 8), 256, 0, st>>>(rp, wf, firstHit, maxHits, nS);
+  static const int plain = std::getenv("DRT_AO_PLAIN_ORDER") != nullptr ? 1 : 0;
+  aoGenKernel<<<gridFor((uint64_t)maxHits * nS, 256, numSMs, 8), 256, 0, st>>>(rp, wf, firstHit, maxHits, nS, plain);
   return cudaGetLastError();
 }
 
 cudaError_t launchAoCount(const RenderParams& rp, const Wavefront& wf, uint32_t firstHit, uint32_t maxHits, RenderCounters* rc,
                           int numSMs, cudaStream_t st) {
   const int nS = roundUpPow2(rp.aoSamples);
-  aoCountKernel<<<gridFor(maxHits, 256, numSMs, 8), 256, 0, st>>>(rp, wf, firstHit, maxHits, nS, rc);
+  static const int plain = std::getenv("DRT_AO_PLAIN_ORDER") != nullptr ? 1 : 0;
+  aoCountKernel<<<gridFor(maxHits, 256, numSMs, 8), 256, 0, st>>>(rp, wf, firstHit, maxHits, nS, rc, plain);
   return cudaGetLastError();
 }
 

@@ -85,6 +85,19 @@ def test_ambient_occlusion_matches_oracle_per_pixel():
     assert sg["shadow_rays"] == so["shadow_rays"]
 
 
+@pytest.mark.parametrize("ns", [1, 2, 4, 13, 64, 128])
+def test_ambient_occlusion_ray_queue_layout_keeps_every_sample(ns):
+    """The AO rays are queued by (0,2)-net cell and hit block, not in the reference's order (render_kernels.cu: aoRayPos): every sample
+    of every hit must still be traced exactly once — the film equals the oracle's BIT FOR BIT (an occlusion count over 2^k rays) for
+    sample counts that exercise every split of the cell grid (13 rounds up to 16), odd film sizes (a partial last block of hits)."""
+    arrays, cam = _cornell()
+    g, o, fg, fo = _render_both(arrays, cam, host.Film(61, 37), host.Sampler(kind=host.SAMPLER_LD, spp=1),
+                                host.Integrator(kind=host.INTEGRATOR_AO, ao_nsamples=ns))
+    assert np.array_equal(fg["rgb"], fo["rgb"]), int((fg["rgb"] != fo["rgb"]).any(axis=2).sum())
+    sg, so = g.render_stats(), o.render_stats()
+    assert sg["shadow_rays"] == so["shadow_rays"]
+
+
 @pytest.mark.parametrize("strategy", [0, 1])
 def test_direct_lighting_matches_oracle_per_pixel(strategy):
     sb, cam = scenes.cornell_synth()

@@ -51,6 +51,8 @@ def main():
         integ = host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=5)
     if os.environ.get("INTEG") == "whitted":
         integ = host.Integrator(kind=host.INTEGRATOR_WHITTED, maxdepth=3)
+    if os.environ.get("INTEG") == "ao":  # the same scene through the ambient-occlusion integrator, 64 rays per hit
+        integ = host.Integrator(kind=host.INTEGRATOR_AO, ao_nsamples=64)
     if os.environ.get("INTEG") == "direct":  # the same scene through the directlighting integrator (strategy all)
         integ = host.Integrator(kind=host.INTEGRATOR_DIRECT, maxdepth=3)
     ctx = capi.Context(0)
