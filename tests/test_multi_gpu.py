@@ -69,6 +69,25 @@ def test_multi_device_film_equals_the_one_device_film_config4():
     assert np.array_equal(f3["weight"], f1["weight"]) and np.allclose(f3["rgb"], f1["rgb"], rtol=1e-6, atol=1e-7)
 
 
+def test_multi_device_context_forwards_the_shading_precision():
+    """drt_set_shading_precision on a multi-device context reaches every device: the float32 film of the devices together equals the
+    float32 film of one device bit for bit (same kernels, keyed streams), and differs from the binary64 film."""
+    ids = _devices()
+    sb, cam = scenes.cornell_synth()
+    arrays = sb.arrays()
+    film, smp = host.Film(480, 270), host.Sampler(kind=host.SAMPLER_LD, spp=16)
+    integ = host.Integrator(kind=host.INTEGRATOR_PATH, maxdepth=5)
+    one, multi = capi.Context(ids[0]), capi.Context(ids)
+    f64, _ = _render(one, arrays, cam, film, smp, integ)
+    for c in (one, multi):
+        c.set_shading_precision(capi.PRECISION_F32)
+    f1, s1 = _render(one, arrays, cam, film, smp, integ)
+    fm, sm = _render(multi, arrays, cam, film, smp, integ)
+    assert s1 == sm
+    assert np.array_equal(f1["rgb"], fm["rgb"]) and np.array_equal(f1["weight"], fm["weight"])
+    assert not np.array_equal(f1["rgb"], f64["rgb"])
+
+
 def test_multi_device_filter_footprints_cross_block_borders():
     """A wide gaussian filter spreads every sample over pixels of other devices' blocks: the SUM of the films (not a copy of
     regions) keeps those contributions; AO on a mesh with per-device BVH copies."""
