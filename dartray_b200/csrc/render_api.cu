@@ -1079,8 +1079,9 @@ static int renderBatch(drt_ctx* c, RenderState* r, const PixelBatch& pb) {
   }
   if (p.integKind == 0) {
     int cur = 0;
-    // float32 shading (drt_set_shading_precision; env DRT_SHADE_F32=1 / 0 overrides for A/B runs): same queues, same sample values, same
-    // binary64 traversal — only the arithmetic of the vertex and resolve kernels changes
+    // float32 shading (drt_set_shading_precision; env DRT_SHADE_F32=1 / 0 overrides for A/B runs): same queues, same sample values, the
+    // camera rays traced in binary64 as always; the vertex / resolve kernels and the traversal of the integrator's own ray queues run
+    // their float32 builds
     static const char* f32Env = std::getenv("DRT_SHADE_F32");
     const bool wantF32 = f32Env ? f32Env[0] == '1' : r->shadingPrecision == DRT_PRECISION_F32;
     const bool f32 = wantF32 && rs.nVolumes == 0 && rs.nPrograms == 0 && c->ts.nInstances == 0 && wf.slotTime == nullptr;
