@@ -35,3 +35,10 @@ def test_generated_sources_hold_no_binary64_arithmetic_types():
         assert not re.search(r"\bdouble\b", code), path
         assert os.path.basename(path).endswith(("_f32.cuh", "_f32.inc"))
     assert "f32-keep-begin" in open(os.path.join(gen_f32.GEN, "trace_fast2_f32.inc")).read()
+
+
+def test_assignment_to_a_narrowed_member_is_refused():
+    import pytest
+    with pytest.raises(ValueError):
+        gen_f32.lower("g.radius = 2.0;")
+    assert "==" in gen_f32.lower("if (s.radius == 0.0) return;")
