@@ -612,6 +612,12 @@ __global__ void __launch_bounds__(256) matScatterKernel(RenderScene rs, Wavefron
 // MIS rays), then the next direction + Russian roulette + the extension ray — each recomputing the cheap hit geometry / BSDF frame.
 // Smaller kernels (the single one is 11.5 K instructions: ncu shows `no_instruction` stalls of 2.3 warps per issue) with fewer live
 // registers; the per-slot draws keep their positions in the integrator stream, so the results are the single kernel's.
+#ifndef DRT_SHADE_NOLOOP
+#define DRT_SHADE_NOLOOP 0  // 1 (timing experiment, ray statistics not counted): one queue entry per thread instead of the grid-stride
+                             // loop, tried because the looped float32 kernel spills its hoisted array addresses at entry (52 STL, ncu: as
+                             // many local-memory sectors as global ones).  Measured on B200 (profiles/r02z13_noloop_ab.log): 0.5822 s against
+                             // 0.4658 s — 131 K short CTAs cost far more than the spills.  Rejected, off
+#endif
 #ifndef DRT_SHADE_PREFETCH
 #define DRT_SHADE_PREFETCH 0  // 1: prefetch the thread's next queue entry.  Measured on B200 with the float32 kernel (config 4,
                               // profiles/r02z11_prefetch_ab.log): 0.4716 s against 0.4672 s — rejected, off
@@ -626,7 +632,11 @@ __global__ void __launch_bounds__(128, PART == 0 ? DRT_SHADE_MIN_BLOCKS : DRT_SH
   const int nxt = cur ^ 1;
   unsigned long long nShadow = 0, nClosest = 0;
   const bool sorted = (GENERAL || DRT_SHAPE_SORT_BUILD) && sortedOrder != 0;
+#if DRT_SHADE_NOLOOP  // EXPERIMENT (timing only: the ray statistics are not counted): one queue entry per thread, no grid-stride loop
+  for (uint32_t q0 = blockIdx.x * blockDim.x; q0 < n; q0 = 0xffffffffu) {
+#else
   for (uint32_t q0 = blockIdx.x * blockDim.x; q0 < n; q0 += gridDim.x * blockDim.x) {
+#endif
     uint32_t q = q0 + threadIdx.x;
     bool valid = q < n;
 #if DRT_SHADE_PREFETCH  // the queue entry this thread shades in its NEXT trip, on its way to L1 while this one is shaded (A/B knob)
@@ -752,9 +762,14 @@ __global__ void __launch_bounds__(128, PART == 0 ? DRT_SHADE_MIN_BLOCKS : DRT_SH
 #endif
       wf.extSlot[nxt][ei] = slot;
     }
+#if !DRT_SHADE_NOLOOP
     nShadow += (valid && dw.hasShadow) ? 1 : 0;
     nClosest += ((valid && dw.hasMis) ? 1 : 0) + (cont ? 1 : 0);
+#endif
   }
+#if DRT_SHADE_NOLOOP
+  return;
+#endif
   // ray statistics (stats.dart:541-555): one atomic per warp
   for (int o = 16; o > 0; o >>= 1) {
     nShadow += __shfl_down_sync(FULL, nShadow, o);
@@ -1606,7 +1621,7 @@ cudaError_t launchMaterialSort(const RenderScene& rs, const Wavefront& wf, int c
 
 cudaError_t launchShadePath(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int bounce, int cur,
                             RenderCounters* rc, int numSMs, cudaStream_t st) {
-  const int grid = gridFor(wf.cap, 128, numSMs, 8);
+  const int grid = DRT_SHADE_NOLOOP ? (int)((wf.cap + 127u) / 128u) : gridFor(wf.cap, 128, numSMs, 8);
   if (rs.general) {
     // material-coherent warps: sort the queue by material first (skipped for a single material or more than the sort's bins)
     // (directSampleKernel walks the same order since the sort's atomics are warp-aggregated: 64 -> 46.5 ms on cornell_materials at
