@@ -46,6 +46,23 @@ static __device__ __forceinline__ uint32_t warpPush(uint32_t* counter, bool want
   return base + __popc(m & ((1u << lane) - 1u));
 }
 
+// Two appends at once: lane 0 issues both atomics before either result is awaited (two warpPush calls in a row wait for the first
+// counter's round trip to L2 before the second atomic leaves).
+static __device__ __forceinline__ void warpPush2(uint32_t* counterA, bool wantA, uint32_t* counterB, bool wantB, uint32_t* atA, uint32_t* atB) {
+  const unsigned mA = __ballot_sync(FULL, wantA), mB = __ballot_sync(FULL, wantB);
+  const unsigned lane = threadIdx.x & 31u;
+  uint32_t baseA = 0, baseB = 0;
+  if (lane == 0) {
+    if (mA) baseA = atomicAdd(counterA, (uint32_t)__popc(mA));
+    if (mB) baseB = atomicAdd(counterB, (uint32_t)__popc(mB));
+  }
+  baseA = __shfl_sync(FULL, baseA, 0);
+  baseB = __shfl_sync(FULL, baseB, 0);
+  const unsigned lt = (1u << lane) - 1u;
+  *atA = baseA + __popc(mA & lt);
+  *atB = baseB + __popc(mB & lt);
+}
+
 static __device__ __forceinline__ Spec ld3(const float* a, uint32_t cap, uint32_t i) { return Spec{a[i], a[cap + i], a[2 * cap + i]}; }
 static __device__ __forceinline__ void st3(float* a, uint32_t cap, uint32_t i, const Spec& s) { a[i] = s.r; a[cap + i] = s.g; a[2 * cap + i] = s.b; }
 static __device__ __forceinline__ V3 ldv3(const float* a, uint32_t cap, uint32_t i) { return V3{a[i], a[cap + i], a[2 * cap + i]}; }
@@ -489,8 +506,8 @@ static __device__ __forceinline__ uint64_t integratorKey(const RenderParams& rp,
 static __device__ __forceinline__ void pushDirectWork(const Wavefront& wf, uint32_t slot, bool valid, const DirectWork& w,
                                                       const V3& p, double rayEps, int lightNum) {
   const bool wantSh = valid && w.hasShadow, wantMis = valid && w.hasMis;
-  const uint32_t si = warpPush(&wf.counts[Q_SHADOW], wantSh);
-  const uint32_t mi = warpPush(&wf.counts[Q_MIS], wantMis);
+  uint32_t si, mi;
+  warpPush2(&wf.counts[Q_SHADOW], wantSh, &wf.counts[Q_MIS], wantMis, &si, &mi);
   const uint32_t cap = wf.cap;
   if (wantSh) {
     wf.shO[si] = make_float4(w.shO.x, w.shO.y, w.shO.z, rayLaneW(wf, slot, (float)w.shMin));

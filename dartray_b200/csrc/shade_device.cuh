@@ -155,7 +155,10 @@ static DRT_HD inline double drawFloat(uint64_t key, uint64_t d) { return (double
 #else
 static DRT_HD inline double drawFloat(uint64_t key, uint64_t d) { return (double)(draw64(key, d) >> 11) * (1.0 / 9007199254740992.0); }
 #endif
-static DRT_HD inline uint32_t drawUint(uint64_t key, uint64_t d) { return (uint32_t)(draw64(key, d) >> 32) % 0xffffffffu; }
+static DRT_HD inline uint32_t drawUint(uint64_t key, uint64_t d) {  // (draw >> 32) % 0xffffffff: the value itself unless it is 2^32 - 1
+  const uint32_t x = (uint32_t)(draw64(key, d) >> 32);
+  return x == 0xffffffffu ? 0u : x;
+}
 
 struct Stream {
   uint64_t key;
