@@ -631,8 +631,8 @@ __global__ void __launch_bounds__(256) matScatterKernel(RenderScene rs, Wavefron
 // registers; the per-slot draws keep their positions in the integrator stream, so the results are the single kernel's.
 #ifndef DRT_SHADE_NOLOOP
 #define DRT_SHADE_NOLOOP 0  // 1 (timing experiment, ray statistics not counted): one queue entry per thread instead of the grid-stride
-                             // loop, tried because the looped float32 kernel spills its hoisted array addresses at entry (52 STL, ncu: as
-                             // many local-memory sectors as global ones).  Measured on B200 (profiles/r02z13_noloop_ab.log): 0.5822 s against
+                             // loop, tried because the float32 kernel moves as many local-memory sectors as global ones (ncu; a 712-byte
+                             // frame, the RenderScene parameter copied to the stack at entry for the out-of-line callees).  Measured on B200 (profiles/r02z13_noloop_ab.log): 0.5822 s against
                              // 0.4658 s — 131 K short CTAs cost far more than the spills.  Rejected, off
 #endif
 #ifndef DRT_SHADE_PREFETCH
