@@ -965,7 +965,7 @@ __global__ void __launch_bounds__(128) aoSetupKernel(RenderParams rp, RenderScen
 // consecutive hits (neighbouring pixels) are transposed: 32 consecutive queue entries = the SAME cell of 32 neighbouring hits, rays of
 // nearby origins and directions.  The last, partial block of a chunk keeps the plain layout.  DRT_AO_PLAIN_ORDER=1 keeps it everywhere
 // (A/B runs).
-static __device__ __forceinline__ uint32_t aoCell(uint32_t i, uint32_t s0, uint32_t s1, int k) {
+static __device__ __forceinline__ __attribute__((unused)) uint32_t aoCell(uint32_t i, uint32_t s0, uint32_t s1, int k) {
   const int a = (k + 1) >> 1, b = k >> 1;
   const uint32_t v0 = __brev(i) ^ s0, v1 = sobolBits(i) ^ s1;  // the integers VanDerCorput / Sobol2 turn into [0, 1) values
   const uint32_t cx = a ? v0 >> (32 - a) : 0u, cy = b ? v1 >> (32 - b) : 0u;
@@ -977,26 +977,55 @@ static __device__ __forceinline__ uint64_t aoRayPos(uint32_t hI, uint32_t cell, 
   return (((uint64_t)B * nS + cell) << 5) + (hI & 31u);
 }
 
-// AO rays of hits [firstHit, firstHit + maxHits) of the hit list, nSamples each, into the shadow queue
+// AO rays of hits [firstHit, firstHit + maxHits) of the hit list, nSamples each, into the shadow queue.  One thread per QUEUE ENTRY, so
+// that the ray records are written coalesced: in the transposed part of the queue entry r is cell (r / 32) % nS of hit 32 * block +
+// r % 32, and the sample index that falls into that cell follows from the two generator matrices — the low a bits of i from the
+// cell's x (the van der Corput digits are the reversed index), the high b bits through the inverse of the linear map
+// x -> top b bits of Sobol2's direction-number sum of (x << a), tabulated per block (aoCell is the forward map; the films of
+// tests/test_render_gpu.py::test_ambient_occlusion_ray_queue_layout_keeps_every_sample are bit-identical to the oracle's only if
+// the two agree for every sample).
+#define DRT_AO_MAX_B 10  // cells grids up to 2^11 x 2^10 (nSamples <= 2^21); beyond that the plain layout
 __global__ void __launch_bounds__(256) aoGenKernel(RenderParams rp, Wavefront wf, uint32_t firstHit, uint32_t maxHits, int nS, int plain) {
+  __shared__ uint16_t invHi[1 << DRT_AO_MAX_B];
   const uint32_t nHits = wf.counts[Q_HITS], cap = wf.cap;
   const uint32_t hitsHere = nHits > firstHit ? min(nHits - firstHit, maxHits) : 0u;
   const uint64_t nRays = (uint64_t)hitsHere * nS;
+  const int k = 31 - __clz(nS), a = (k + 1) >> 1, b = k >> 1;
+  if (!plain) {
+    for (uint32_t x = threadIdx.x; x < (1u << b); x += blockDim.x) invHi[b ? sobolBits(x << a) >> (32 - b) : 0u] = (uint16_t)x;
+    __syncthreads();
+  }
+  const uint64_t nTransposed = plain ? 0ull : (uint64_t)(hitsHere >> 5) * 32ull * (uint64_t)nS;
   if (blockIdx.x == 0 && threadIdx.x == 0) wf.counts[Q_SHADOW] = (uint32_t)nRays;
   for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nRays; r += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t hI = (uint32_t)(r / nS);
-    const uint32_t slot = wf.hitList[firstHit + hI];
-    const uint32_t i = (uint32_t)(r % nS);
-    const uint32_t s0 = wf.aoScramble[slot], s1 = wf.aoScramble[cap + slot];
+    uint32_t hI, i, slot, s0, s1;
+    if (r < nTransposed) {
+      const uint64_t g = r >> 5;
+      const uint32_t cell = (uint32_t)(g % (uint32_t)nS);
+      hI = (uint32_t)(g / (uint32_t)nS) * 32u + (uint32_t)(r & 31u);
+      slot = wf.hitList[firstHit + hI];
+      s0 = wf.aoScramble[slot]; s1 = wf.aoScramble[cap + slot];
+      const uint32_t cx = cell >> b, cy = cell & ((1u << b) - 1u);
+      const uint32_t iLo = a ? __brev(cx ^ (s0 >> (32 - a))) >> (32 - a) : 0u;
+      const uint32_t tgt = b ? (cy ^ ((sobolBits(iLo) ^ s1) >> (32 - b))) : 0u;
+      i = iLo | ((uint32_t)invHi[tgt] << a);
+#ifdef DRT_AO_SELFCHECK  // the inverse against the forward map
+      if (aoCell(i, s0, s1, k) != cell) __trap();
+#endif
+    } else {
+      hI = (uint32_t)(r / nS);
+      i = (uint32_t)(r % nS);
+      slot = wf.hitList[firstHit + hI];
+      s0 = wf.aoScramble[slot]; s1 = wf.aoScramble[cap + slot];
+    }
     const double u0 = VanDerCorput(i, s0), u1 = Sobol2(i, s1);
     V3 w = UniformSampleSphere(u0, u1);
     const V3 nrm = ldv3(wf.hitN, cap, slot), p = ldv3(wf.hitP, cap, slot);
     if (Dot(w, nrm) < 0.0) w = -w;
-    const uint64_t at = aoRayPos(hI, plain ? i : aoCell(i, s0, s1, 31 - __clz(nS)), hitsHere, (uint32_t)nS, plain);
     // new Ray(p, w, minDist, maxDist) (ambient_occlusion_integrator.dart:45): no time argument, the ray travels at time 0
-    wf.shO[at] = make_float4(p.x, p.y, p.z, wf.slotTime ? __uint_as_float(0xffffffffu) : (float)rp.aoMinDist);
-    wf.shD[at] = make_float4(w.x, w.y, w.z, (float)rp.aoMaxDist);
-    wf.shRange[at] = make_double2(rp.aoMinDist, rp.aoMaxDist);
+    wf.shO[r] = make_float4(p.x, p.y, p.z, wf.slotTime ? __uint_as_float(0xffffffffu) : (float)rp.aoMinDist);
+    wf.shD[r] = make_float4(w.x, w.y, w.z, (float)rp.aoMaxDist);
+    wf.shRange[r] = make_double2(rp.aoMinDist, rp.aoMaxDist);
   }
 }
 
@@ -1698,7 +1727,8 @@ static inline int roundUpPow2(int v) {  // common.dart:117-125
 cudaError_t launchAoGen(const RenderParams& rp, const Wavefront& wf, uint32_t firstHit, uint32_t maxHits, int numSMs,
                         cudaStream_t st) {
   const int nS = roundUpPow2(rp.aoSamples);
-  static const int plain = std::getenv("DRT_AO_PLAIN_ORDER") != nullptr ? 1 : 0;
+  static const int plainEnv = std::getenv("DRT_AO_PLAIN_ORDER") != nullptr ? 1 : 0;
+  const int plain = (plainEnv || (31 - __builtin_clz((unsigned)nS)) / 2 > DRT_AO_MAX_B) ? 1 : 0;
   aoGenKernel<<<gridFor((uint64_t)maxHits * nS, 256, numSMs, 8), 256, 0, st>>>(rp, wf, firstHit, maxHits, nS, plain);
   return cudaGetLastError();
 }
@@ -1706,7 +1736,8 @@ cudaError_t launchAoGen(const RenderParams& rp, const Wavefront& wf, uint32_t fi
 cudaError_t launchAoCount(const RenderParams& rp, const Wavefront& wf, uint32_t firstHit, uint32_t maxHits, RenderCounters* rc,
                           int numSMs, cudaStream_t st) {
   const int nS = roundUpPow2(rp.aoSamples);
-  static const int plain = std::getenv("DRT_AO_PLAIN_ORDER") != nullptr ? 1 : 0;
+  static const int plainEnv = std::getenv("DRT_AO_PLAIN_ORDER") != nullptr ? 1 : 0;
+  const int plain = (plainEnv || (31 - __builtin_clz((unsigned)nS)) / 2 > DRT_AO_MAX_B) ? 1 : 0;
   aoCountKernel<<<gridFor(maxHits, 256, numSMs, 8), 256, 0, st>>>(rp, wf, firstHit, maxHits, nS, rc, plain);
   return cudaGetLastError();
 }
