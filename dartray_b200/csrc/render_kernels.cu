@@ -961,20 +961,25 @@ __global__ void __launch_bounds__(128) aoSetupKernel(RenderParams rp, RenderScen
 // kernel then holds 32 rays of one origin pointing everywhere.  The occlusion count of a hit does not depend on the order its rays are
 // traced in, so the queue is laid out for the traversal instead: the first 2^k points of the scrambled (0,2)-sequence form a
 // (0, k, 2)-net (montecarlo.dart:486-504: base-2 digit scrambling keeps the property), i.e. every cell of the 2^a x 2^b grid over
-// [0,1)^2, a + b = k, holds exactly one sample of a hit — its cell number is a bijection of the sample index.  Blocks of 32
-// consecutive hits (neighbouring pixels) are transposed: 32 consecutive queue entries = the SAME cell of 32 neighbouring hits, rays of
-// nearby origins and directions.  The last, partial block of a chunk keeps the plain layout.  DRT_AO_PLAIN_ORDER=1 keeps it everywhere
-// (A/B runs).
+// [0,1)^2, a + b = k, holds exactly one sample of a hit — its cell number is a bijection of the sample index.  Blocks of 2^16
+// consecutive hits (neighbouring pixels) are transposed: consecutive queue entries = the SAME cell of consecutive hits, rays of
+// nearby origins and directions.  DRT_AO_PLAIN_ORDER=1 keeps the reference's order (A/B runs).
 static __device__ __forceinline__ __attribute__((unused)) uint32_t aoCell(uint32_t i, uint32_t s0, uint32_t s1, int k) {
   const int a = (k + 1) >> 1, b = k >> 1;
   const uint32_t v0 = __brev(i) ^ s0, v1 = sobolBits(i) ^ s1;  // the integers VanDerCorput / Sobol2 turn into [0, 1) values
   const uint32_t cx = a ? v0 >> (32 - a) : 0u, cy = b ? v1 >> (32 - b) : 0u;
   return (cx << b) | cy;
 }
+#ifndef DRT_AO_BLOCK_LOG2
+#define DRT_AO_BLOCK_LOG2 16  // hits per transposed block.  Measured on B200 (profiles/r02z15 - r02z17_ao_block_ab.log; config 3 / AO on the
+                              // Cornell scene): 2^5 19.12 / 34.4 ms, 2^8 18.98 / 33.5, 2^13 18.89 / 33.0, 2^16 18.85 / 32.3, 2^20 18.96 / 33.0
+#endif
+#define DRT_AO_BLOCK (1u << DRT_AO_BLOCK_LOG2)
 static __device__ __forceinline__ uint64_t aoRayPos(uint32_t hI, uint32_t cell, uint32_t hitsHere, uint32_t nS, int plain) {
-  const uint32_t B = hI >> 5;
-  if (plain || ((B + 1u) << 5) > hitsHere) return (uint64_t)hI * nS + cell;
-  return (((uint64_t)B * nS + cell) << 5) + (hI & 31u);
+  if (plain) return (uint64_t)hI * nS + cell;
+  const uint32_t B = hI >> DRT_AO_BLOCK_LOG2, first = B << DRT_AO_BLOCK_LOG2;
+  const uint32_t m = min(DRT_AO_BLOCK, hitsHere - first);  // the last block of a chunk is shorter
+  return (uint64_t)first * nS + (uint64_t)cell * m + (hI - first);
 }
 
 // AO rays of hits [firstHit, firstHit + maxHits) of the hit list, nSamples each, into the shadow queue.  One thread per QUEUE ENTRY, so
@@ -995,14 +1000,16 @@ __global__ void __launch_bounds__(256) aoGenKernel(RenderParams rp, Wavefront wf
     for (uint32_t x = threadIdx.x; x < (1u << b); x += blockDim.x) invHi[b ? sobolBits(x << a) >> (32 - b) : 0u] = (uint16_t)x;
     __syncthreads();
   }
-  const uint64_t nTransposed = plain ? 0ull : (uint64_t)(hitsHere >> 5) * 32ull * (uint64_t)nS;
+  const uint64_t blockRays = (uint64_t)DRT_AO_BLOCK * (uint64_t)nS;
   if (blockIdx.x == 0 && threadIdx.x == 0) wf.counts[Q_SHADOW] = (uint32_t)nRays;
   for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nRays; r += (uint64_t)gridDim.x * blockDim.x) {
     uint32_t hI, i, slot, s0, s1;
-    if (r < nTransposed) {
-      const uint64_t g = r >> 5;
-      const uint32_t cell = (uint32_t)(g % (uint32_t)nS);
-      hI = (uint32_t)(g / (uint32_t)nS) * 32u + (uint32_t)(r & 31u);
+    if (!plain) {
+      const uint32_t B = (uint32_t)(r / blockRays), first = B << DRT_AO_BLOCK_LOG2;
+      const uint32_t m = min(DRT_AO_BLOCK, hitsHere - first);
+      const uint64_t rem = r - (uint64_t)first * nS;
+      const uint32_t cell = (uint32_t)(rem / m);
+      hI = first + (uint32_t)(rem - (uint64_t)cell * m);
       slot = wf.hitList[firstHit + hI];
       s0 = wf.aoScramble[slot]; s1 = wf.aoScramble[cap + slot];
       const uint32_t cx = cell >> b, cy = cell & ((1u << b) - 1u);
