@@ -1674,7 +1674,17 @@ cudaError_t launchMaterialSort(const RenderScene& rs, const Wavefront& wf, int c
 
 cudaError_t launchShadePath(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int bounce, int cur,
                             RenderCounters* rc, int numSMs, cudaStream_t st) {
-  const int grid = DRT_SHADE_NOLOOP ? (int)((wf.cap + 127u) / 128u) : gridFor(wf.cap, 128, numSMs, 8);
+  // one resident wave of the grid-stride kernel: a grid that is not a multiple of what fits (e.g. 8 CTAs per SM asked for, 7 resident)
+  // ends in a partial second wave
+  static int perSm[2] = {0, 0};
+  if (!perSm[0]) {
+    int b = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, shadePathKernel<false, DRT_EXTRA != 0, 0>, 128, 0) != cudaSuccess || b < 1) b = 8;
+    perSm[0] = b;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, shadePathKernel<true, DRT_EXTRA != 0, 0>, 128, 0) != cudaSuccess || b < 1) b = 8;
+    perSm[1] = b;
+  }
+  const int grid = DRT_SHADE_NOLOOP ? (int)((wf.cap + 127u) / 128u) : gridFor(wf.cap, 128, numSMs, perSm[rs.general ? 1 : 0]);
   if (rs.general) {
     // material-coherent warps: sort the queue by material first (skipped for a single material or more than the sort's bins)
     // (directSampleKernel walks the same order since the sort's atomics are warp-aggregated: 64 -> 46.5 ms on cornell_materials at
