@@ -1720,7 +1720,13 @@ cudaError_t launchShadePath(const RenderParams& rp, const RenderScene& rs, const
 
 cudaError_t launchResolveDirect(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int cur, int mode,
                                 int nSamplesOfLight, int numSMs, cudaStream_t st) {
-  resolveDirectKernel<DRT_EXTRA != 0><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, cur, mode, nSamplesOfLight);
+  static int perSm = 0;  // one resident wave, as many CTAs as fit (the kernel waits on memory: more warps in flight)
+  if (!perSm) {
+    int b = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, resolveDirectKernel<DRT_EXTRA != 0>, 128, 0) != cudaSuccess || b < 1) b = 8;
+    perSm = b;
+  }
+  resolveDirectKernel<DRT_EXTRA != 0><<<gridFor(wf.cap, 128, numSMs, perSm), 128, 0, st>>>(rp, rs, wf, cur, mode, nSamplesOfLight);
   return cudaGetLastError();
 }
 
