@@ -1575,6 +1575,24 @@ __global__ void filmConvertKernel(RenderParams rp, float* rgb, float* xyz, float
 
 #endif  // DRT_PATH_ONLY
 // ---------------------------------------------------------------------------------------------------
+// Grid of a grid-stride kernel: one resident wave — as many CTAs per SM as the occupancy API says fit (cached per kernel).  A fixed
+// "8 per SM" was a partial second wave for kernels of which 5 - 7 fit and half the machine's warps for kernels of which 16 fit.
+template <class K>
+static inline int residentGrid(K kernel, uint64_t n, int block, int numSMs) {
+  static int perSm = 0;  // one instance per kernel type AND per call site's function pointer type; keyed below by the pointer itself
+  static const void* cachedFor = nullptr;
+  if (cachedFor != (const void*)kernel) {
+    int b = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, block, 0) != cudaSuccess || b < 1) b = 8;
+    perSm = b;
+    cachedFor = (const void*)kernel;
+  }
+  uint64_t want = (n + block - 1) / block;
+  uint64_t cap = (uint64_t)numSMs * perSm;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
 static inline int gridFor(uint64_t n, int block, int numSMs, int perSm) {
   uint64_t want = (n + block - 1) / block;
   uint64_t cap = (uint64_t)numSMs * perSm;
@@ -1732,12 +1750,12 @@ cudaError_t launchResolveDirect(const RenderParams& rp, const RenderScene& rs, c
 
 #ifndef DRT_PATH_ONLY  // the float32 path build (render_kernels_f32.cu) takes the path-vertex and resolve kernels only
 cudaError_t launchEscape(const RenderScene& rs, const Wavefront& wf, int cur, int mode, int numSMs, cudaStream_t st) {
-  escapeKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rs, wf, cur, mode);
+  escapeKernel<<<residentGrid(escapeKernel, wf.cap, 128, numSMs), 128, 0, st>>>(rs, wf, cur, mode);
   return cudaGetLastError();
 }
 
 cudaError_t launchAoSetup(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int numSMs, cudaStream_t st) {
-  aoSetupKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf);
+  aoSetupKernel<<<residentGrid(aoSetupKernel, wf.cap, 128, numSMs), 128, 0, st>>>(rp, rs, wf);
   return cudaGetLastError();
 }
 
@@ -1767,33 +1785,33 @@ cudaError_t launchAoCount(const RenderParams& rp, const Wavefront& wf, uint32_t 
 
 cudaError_t launchDirectSetup(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int cur, int weighted, int numSMs,
                               cudaStream_t st) {
-  directSetupKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, cur, weighted);
+  directSetupKernel<<<residentGrid(directSetupKernel, wf.cap, 128, numSMs), 128, 0, st>>>(rp, rs, wf, cur, weighted);
   return cudaGetLastError();
 }
 
 cudaError_t launchDirectSample(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int light, int j, int cur,
                                RenderCounters* rc, int sorted, int numSMs, cudaStream_t st) {
-  if (rs.general) directSampleKernel<true><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, j, cur, rc, sorted);
-  else directSampleKernel<false><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, j, cur, rc, 0);
+  if (rs.general) directSampleKernel<true><<<residentGrid(directSampleKernel<true>, wf.cap, 128, numSMs), 128, 0, st>>>(rp, rs, wf, light, j, cur, rc, sorted);
+  else directSampleKernel<false><<<residentGrid(directSampleKernel<false>, wf.cap, 128, numSMs), 128, 0, st>>>(rp, rs, wf, light, j, cur, rc, 0);
   return cudaGetLastError();
 }
 
 cudaError_t launchWhittedSetup(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int cur, int weighted, int numSMs,
                                cudaStream_t st) {
-  whittedSetupKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, cur, weighted);
+  whittedSetupKernel<<<residentGrid(whittedSetupKernel, wf.cap, 128, numSMs), 128, 0, st>>>(rp, rs, wf, cur, weighted);
   return cudaGetLastError();
 }
 
 cudaError_t launchWhittedSample(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int light, int cur,
                                 RenderCounters* rc, int sorted, int numSMs, cudaStream_t st) {
-  if (rs.general) whittedSampleKernel<true><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, cur, rc, sorted);
-  else whittedSampleKernel<false><<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, light, cur, rc, 0);
+  if (rs.general) whittedSampleKernel<true><<<residentGrid(whittedSampleKernel<true>, wf.cap, 128, numSMs), 128, 0, st>>>(rp, rs, wf, light, cur, rc, sorted);
+  else whittedSampleKernel<false><<<residentGrid(whittedSampleKernel<false>, wf.cap, 128, numSMs), 128, 0, st>>>(rp, rs, wf, light, cur, rc, 0);
   return cudaGetLastError();
 }
 
 cudaError_t launchSpecularStep(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, int cur, int flags, int level,
                                int isNew, RenderCounters* rc, int numSMs, cudaStream_t st) {
-  specularStepKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, cur, flags, level, isNew, rc);
+  specularStepKernel<<<residentGrid(specularStepKernel, wf.cap, 128, numSMs), 128, 0, st>>>(rp, rs, wf, cur, flags, level, isNew, rc);
   return cudaGetLastError();
 }
 
@@ -1820,7 +1838,7 @@ cudaError_t launchFilm(const RenderParams& rp, const Wavefront& wf, uint32_t nSl
 
 cudaError_t launchVolumeLi(const RenderParams& rp, const RenderScene& rs, const Wavefront& wf, RenderCounters* rc, int numSMs, cudaStream_t st) {
 #if DRT_EXTRA
-  volumeLiKernel<<<gridFor(wf.cap, 128, numSMs, 8), 128, 0, st>>>(rp, rs, wf, rc);
+  volumeLiKernel<<<residentGrid(volumeLiKernel, wf.cap, 128, numSMs), 128, 0, st>>>(rp, rs, wf, rc);
   return cudaGetLastError();
 #else
   (void)rp; (void)rs; (void)wf; (void)rc; (void)numSMs; (void)st;
