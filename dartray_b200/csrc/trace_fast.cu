@@ -25,6 +25,8 @@
 #include <math_constants.h>
 
 #include <cstdint>
+#include <cstdlib>
+#include <algorithm>
 
 #include "gpu_types.h"
 #include "trace_device.cuh"
@@ -619,7 +621,9 @@ static cudaError_t launchSmall(const TraceScene& sc, bool any, const float4* o, 
   }
   const uint64_t resident = (uint64_t)numSMs * perSm[variant];
   const uint64_t wanted = nUnknown ? resident : ((uint64_t)n + DRT_SMALL_BLOCK - 1) / DRT_SMALL_BLOCK;
-  const uint64_t cap = resident * 8;  // a few waves of blocks: the tail of one wave overlaps the head of the next
+  static const int waves = std::getenv("DRT_SMALL_WAVES") ? std::max(1, std::atoi(std::getenv("DRT_SMALL_WAVES"))) : 8;  // A/B knob: config 4
+  // with 1 / 2 / 4 / 8 / 16 / 32 waves 0.4629 / 0.4551 / 0.4500 / 0.4484 / 0.4487 / 0.4526 s (profiles/r02z22_small_waves_ab.log)
+  const uint64_t cap = resident * (uint64_t)waves;  // a few waves of blocks: the tail of one wave overlaps the head of the next
   dim3 grid((unsigned)(wanted < 1 ? 1 : (wanted < cap ? wanted : cap)));
   if (nUnknown) grid.x = (unsigned)cap;
   if (any) kernel<<<grid, DRT_SMALL_BLOCK, 0, stream>>>(sc, o, d, n, nullptr, (uint8_t*)out, ex);
